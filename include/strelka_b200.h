@@ -1,0 +1,326 @@
+/*
+ * strelka_b200.h -- C ABI of the B200-native Strelka2 per-locus scoring hot path.
+ *
+ * This is the drop-in boundary.  The reference (Illumina/strelka,
+ * paths relative to /root/reference/src/c++/lib/) has no FFI of its own; each entry point
+ * below names the reference call site whose work it takes over.  INTEGRATION.md shows the
+ * C++ shim a reference maintainer adds at each of those call sites.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every input/output buffer is HOST memory owned by the
+ *     caller for the duration of the call (pinned memory from sx_host_alloc() makes the
+ *     transfers true DMA).  `*_dev` variants take DEVICE pointers (inputs already in HBM).
+ *   - return value 0 == SX_OK, negative == failure; sx_last_error(ctx) gives the text.
+ *     The library never calls exit() and never falls back to a CPU implementation: without
+ *     a usable CUDA device sx_create() fails with SX_ERR_CUDA.
+ *   - one sx_ctx per (GPU, host thread).  No process globals: unlike the reference's
+ *     function-local static caches (strelka_common/position_snp_call_grid_lhood_cached.cpp:136,
+ *     applications/strelka/position_somatic_snv_strand_grid_lhood_cached.cpp:46,139) a ctx is
+ *     re-entrant.
+ */
+#ifndef STRELKA_B200_H
+#define STRELKA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SX_ABI_VERSION 1
+
+enum {
+    SX_OK = 0,
+    SX_ERR_CUDA = -1,        /* CUDA runtime/driver failure (incl. "no device") */
+    SX_ERR_ARG = -2,         /* NULL / inconsistent argument */
+    SX_ERR_ALIGNMENT = -3,   /* a region slice violates the 16-byte staging alignment rule */
+    SX_ERR_UNSUPPORTED = -4, /* option combination outside the accelerated path */
+    SX_ERR_RANGE = -5,       /* value outside the reference's own asserted range (e.g. qscore > 70) */
+    SX_ERR_NOMEM = -6,
+    SX_ERR_NCCL = -7
+};
+
+typedef struct sx_ctx sx_ctx;
+
+/* ------------------------------------------------------------------------------------------
+ * Options snapshot: every option field the hot-path functions read.
+ *   blt_options            blt_common/blt_shared.hh:82-128
+ *   starling_options       applications/starling/starling_shared.hh:34-39 (ssd 0.35/0.6, min_vexp 0.25)
+ *   strelka_options        applications/strelka/strelka_shared.hh:126-151
+ * sx_default_params() fills the reference defaults for the germline (starling2) caller and the
+ * workflow defaults of configureStrelkaSomaticWorkflow.py.ini for the somatic one.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sx_params {
+    /* germline site model */
+    double bsnp_diploid_theta;           /* 0.001 */
+    double bsnp_ssd_no_mismatch;         /* 0.35  (0 disables dependent error probs) */
+    double bsnp_ssd_one_mismatch;        /* 0.6 */
+    int32_t is_min_vexp;                 /* 1 */
+    int32_t is_bsnp_diploid;             /* 1 for starling; is_dependent_eprob() needs it (blt_shared.hh:76-81) */
+    double min_vexp;                     /* 0.25 */
+    double hetVariantFrequencyExtension; /* 0; >0 (RNA mode) -> SX_ERR_UNSUPPORTED */
+    /* somatic site model */
+    double somatic_snv_rate;                         /* 1e-4  */
+    double shared_site_error_rate;                   /* 5e-10 */
+    double shared_site_error_strand_bias_fraction;   /* 0 */
+    double ssnv_contam_tolerance;                    /* 0.15 */
+    /* runtime knobs (not reference options) */
+    int32_t pipeline_chunks;   /* host-buffer entry points split a batch into this many H2D/compute/D2H chunks; 0 = auto */
+    int32_t reserved;
+} sx_params;
+
+void sx_default_params(sx_params* p);
+
+int sx_create(int cuda_device, const sx_params* p, sx_ctx** out);
+void sx_destroy(sx_ctx* ctx);
+const char* sx_last_error(const sx_ctx* ctx); /* valid until the next call on ctx; ctx may be NULL for create errors */
+int sx_abi_version(void);
+
+/* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) */
+void* sx_host_alloc(size_t bytes);
+void sx_host_free(void* p);
+/* device memory helpers for the *_dev entry points (cudaMalloc/cudaFree/cudaMemcpy on ctx's device) */
+void* sx_dev_alloc(sx_ctx* ctx, size_t bytes);
+void sx_dev_free(sx_ctx* ctx, void* p);
+int sx_memcpy_h2d(sx_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int sx_memcpy_d2h(sx_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int sx_synchronize(sx_ctx* ctx);
+
+/* ==========================================================================================
+ * K1  score_alignments
+ *   replaces the loop  for (cal : candAlignments) scoreCandidateAlignment(opt,indelBuffer,rseg,cal,ref)
+ *   starling_common/starling_read_align.cpp:1568-1571 calling
+ *   starling_common/starling_read_align_score.cpp:260-499.
+ *
+ * A batch is a list of REGIONS (the reads buffered around one candidate locus / realignment
+ * window).  Each region owns a slice of the reference, a contiguous run of reads and the
+ * contiguous run of candidate alignments of those reads.
+ *
+ * Staging rule (the kernel moves each region into shared memory with TMA bulk copies):
+ *   region.seq_off, region.qual_off, region.ref_off and the first insert-pool byte of a region
+ *   are multiples of 16; the first segment index of a region is a multiple of 4; every pool is
+ *   allocated with SX_POOL_SLACK spare bytes after its last used byte.  Violations return
+ *   SX_ERR_ALIGNMENT.  The C++ host mirror (strelka_b200/host/sx_read_align.hh) builds
+ *   conforming batches from reference-shaped objects.
+ * ======================================================================================== */
+#define SX_POOL_SLACK 64
+
+/* flattened path segment kinds (host flattens ALIGNPATH::align_t + IndelKey lookups, see
+ * starling_read_align_score.cpp:306-499 and INTEGRATION.md) */
+enum {
+    SX_SEG_MATCH = 0,    /* MATCH / SEQ_MATCH: read base vs reference base; advances read and ref */
+    SX_SEG_INSERT = 1,   /* INSERT, the insert half of a swap, or SEQ_MISMATCH: read base vs next bases of the
+                            alignment's insert-pool slice (already tail-adjusted for leading-edge insertions,
+                            score.cpp:334-338,394-398); advances read only */
+    SX_SEG_REFSKIP = 2,  /* DELETE / SKIP / delete half of a swap / ref half of SEQ_MISMATCH: advances ref only */
+    SX_SEG_SOFTCLIP = 3, /* adds len*ln(0.25) (score.cpp:453-454); advances read */
+    SX_SEG_HARDCLIP = 4  /* no-op */
+};
+#define SX_SEGF_NONCANDIDATE 0x1 /* add ln(1e-5) after this segment (score.cpp:473-485) */
+
+typedef struct sx_aln_seg {
+    uint16_t len;
+    uint8_t kind;
+    uint8_t flags;
+} sx_aln_seg;
+
+typedef struct sx_aln {
+    uint32_t read;    /* read index in the batch */
+    int32_t ref_pos;  /* cal.al.pos: contig coordinate of the first reference base of the path */
+    uint32_t seg_off; /* index of first segment in seg pool; segments end at the next alignment's seg_off */
+    uint32_t ins_off; /* byte offset of this alignment's inserted bases in the insert pool */
+} sx_aln;
+
+typedef struct sx_region {
+    uint64_t seq_off;    /* byte offset in seq4 pool of the region's first read (multiple of 16) */
+    uint64_t qual_off;   /* byte offset in qual pool (multiple of 16) */
+    uint64_t ref_off;    /* byte offset in ref pool (multiple of 16) */
+    uint32_t read_begin; /* first read; reads end at next region's read_begin */
+    uint32_t aln_begin;  /* first alignment; ends at next region's aln_begin */
+    int32_t ref_begin;   /* contig coordinate of ref pool byte ref_off */
+    uint32_t ref_len;    /* bases available; positions outside read as 'N' (reference_contig_segment::get_base) */
+} sx_region;
+
+typedef struct sx_align_batch {
+    uint32_t n_regions;
+    uint32_t n_reads;
+    uint32_t n_alns;
+    uint32_t n_segs;
+    const sx_region* regions;  /* [n_regions + 1]; entry n_regions is a sentinel carrying the end offsets */
+    const uint16_t* read_len;  /* [n_reads] */
+    const uint8_t* seq4;       /* BAM-native 4-bit packed bases ('=':0 A:1 C:2 G:4 T:8 N:15, high nibble first,
+                                  htsapi/bam_seq.hh:38-47); within a region reads are packed back to back,
+                                  each read starting on a byte boundary */
+    const uint8_t* qual;       /* 1 byte per base, reads back to back within a region; values <= 70 */
+    const char* ref;           /* ASCII reference bases */
+    const sx_aln* alns;        /* [n_alns + 1], sorted by region; sentinel carries end offsets */
+    const sx_aln_seg* segs;    /* [n_segs] */
+    const char* ins;           /* ASCII inserted bases */
+    uint64_t seq4_bytes, qual_bytes, ref_bytes, ins_bytes; /* used bytes of each pool (without slack) */
+} sx_align_batch;
+
+/* lnp_out[n_alns] <- ln P(read | alignment path); bit-identical to the reference's double. */
+int sx_score_alignments(sx_ctx* ctx, const sx_align_batch* batch_host, double* lnp_out_host);
+/* same, every pointer inside *batch_dev and lnp_out_dev is a DEVICE pointer (the struct itself is host) */
+int sx_score_alignments_dev(sx_ctx* ctx, const sx_align_batch* batch_dev, double* lnp_out_dev);
+/* cell updates in a batch = sum over alignments of read bases in MATCH/INSERT segments (SURVEY 8a GCUPS def.) */
+uint64_t sx_align_batch_cells(const sx_align_batch* batch_host);
+
+/* K1 epilogue (starling_read_align.cpp:1535-1593): per read, the maximum path score and the index of the first
+ * alignment attaining it in batch order; ties are resolved by the caller with isFirstCandidateAlignmentPreferred
+ * (:1352) among alignments whose score equals max.  max_aln[n_reads] (UINT32_MAX for a read without alignments). */
+int sx_read_max_dev(sx_ctx* ctx, const sx_align_batch* batch_dev, const double* lnp_dev,
+                    double* max_lnp_dev, uint32_t* max_aln_dev);
+
+/* ==========================================================================================
+ * K3  global_align
+ *   replaces _aligner.align(hap.begin,end, ref.begin,end, result)
+ *   starling_common/ActiveRegionProcessor.cpp:591 -> alignment/GlobalAlignerImpl.hh:36-228,
+ *   alignment/SingleRefAlignerSharedImpl.hh:80-170 (traceback, '='/'X' expansion).
+ * ======================================================================================== */
+typedef struct sx_ga_scores { /* alignment/AlignmentScores.hh:24-53 */
+    int32_t match, mismatch, open, extend, offEdge, insertDelete;
+    int32_t isAllowEdgeInsertion, isRequireEdgeDeletion;
+} sx_ga_scores;
+
+/* the scores ActiveRegionDetector constructs its aligner with (ActiveRegionDetector.hh:62-66, .cpp:41) */
+void sx_ga_active_region_scores(sx_ga_scores* s);
+
+typedef struct sx_ga_batch {
+    uint32_t n;
+    const char* query;         /* ASCII pool */
+    const char* ref;           /* ASCII pool */
+    const uint32_t* query_off; /* [n+1] */
+    const uint32_t* ref_off;   /* [n+1] */
+    uint32_t max_ops;          /* capacity (in ops) of each result's cigar slot */
+} sx_ga_batch;
+
+/* cigar op = (len << 4) | code with BAM codes M0 I1 D2 N3 S4 H5 P6 =7 X8 */
+typedef struct sx_ga_result {
+    int32_t score;
+    int32_t beginPos;
+    uint32_t n_ops; /* > max_ops: overflow, cigar truncated */
+    uint32_t status; /* 0 ok; 1 cigar overflow; 2 problem too large for the kernel's shared-memory tile */
+} sx_ga_result;
+
+#define SX_GA_MAX_QUERY 1023
+#define SX_GA_MAX_CELLS (200 * 1024) /* (Q+1)*(R+1) pointer bytes must fit one CTA's shared memory */
+
+int sx_global_align(sx_ctx* ctx, const sx_ga_scores* scores, const sx_ga_batch* batch_host,
+                    sx_ga_result* res_host /*[n]*/, uint32_t* cigar_host /*[n*max_ops]*/);
+int sx_global_align_dev(sx_ctx* ctx, const sx_ga_scores* scores, const sx_ga_batch* batch_dev,
+                        sx_ga_result* res_dev, uint32_t* cigar_dev);
+
+/* ==========================================================================================
+ * K2a  site_gl_germline
+ *   replaces CleanPileupFilter + CleanPileupErrorProb + position_snp_call_pprob_digt:
+ *   starling_common/PileupCleaner.cpp:30-75, blt_common/adjust_joint_eprob.cpp:60-243,
+ *   blt_common/position_snp_call_pprob_digt.cpp:326-539, called from
+ *   applications/starling/starling_pos_processor.cpp:178,254-267.
+ *
+ * A pileup batch is CSR over sites.  `calls` uses the reference's own 16-bit base_call layout
+ * (blt_common/snp_pos_info.hh:109-118): bits 0-5 qscore, 6-9 base_id (A0 C1 G2 T3), 10 is_fwd_strand,
+ * 11 is_neighbor_mismatch, 12 is_call_filter, 13 is_tier_specific_call_filter.
+ * ======================================================================================== */
+#define SX_CALL(q, base_id, fwd, nbr_mm, filt, tfilt) \
+    ((uint16_t)(((q) & 63) | (((base_id) & 15) << 6) | (((fwd) & 1) << 10) | (((nbr_mm) & 1) << 11) | (((filt) & 1) << 12) | (((tfilt) & 1) << 13)))
+
+typedef struct sx_pileup_batch {
+    uint32_t n_sites;
+    const uint32_t* site_off;   /* [n_sites+1] offsets into calls */
+    const uint16_t* calls;      /* snp_pos_info::calls of every site, in pileup order */
+    const uint32_t* t2_off;     /* [n_sites+1] offsets into t2_calls, or NULL (no tier2 data) */
+    const uint16_t* t2_calls;   /* snp_pos_info::tier2_calls */
+    const char* ref_base;       /* [n_sites] 'A','C','G','T' or 'N' */
+    const uint8_t* ploidy;      /* [n_sites] 2 (diploid) or 1 (haploid); NULL = all 2 */
+} sx_pileup_batch;
+
+typedef struct sx_digt_result_set { /* diploid_genotype::result_set, position_snp_call_pprob_digt.hh:72-90 */
+    double ref_pprob;
+    uint32_t max_gt;
+    int32_t snp_qphred;
+    int32_t max_gt_qphred;
+    int32_t pad;
+} sx_digt_result_set;
+
+typedef struct sx_digt_result { /* diploid_genotype, position_snp_call_pprob_digt.hh:39-110 */
+    sx_digt_result_set genome;
+    sx_digt_result_set poly;
+    double strand_bias;
+    float lhood[10];          /* ln P(pileup | gt), DIGT order AA CC GG TT AC AG AT CG CT GT (blt_util/digt.hh) */
+    uint32_t phredLoghood[10];
+    uint32_t ref_gt;
+    uint32_t is_computed;     /* 0: early return (ref 'N', or all-ref site without is_always_test): fields are the reset() values */
+    uint32_t n_used_calls;    /* calls left after CleanPileupFilter */
+    uint32_t pad;
+} sx_digt_result;
+
+int sx_site_gl_germline(sx_ctx* ctx, const sx_pileup_batch* batch_host, int is_always_test,
+                        sx_digt_result* out_host /*[n_sites]*/);
+int sx_site_gl_germline_dev(sx_ctx* ctx, const sx_pileup_batch* batch_dev, int is_always_test,
+                            sx_digt_result* out_dev);
+/* the dependent error probs alone (adjust_joint_eprob), one float per *cleaned* call, CSR by out_off[n_sites+1] */
+int sx_dependent_eprob(sx_ctx* ctx, const sx_pileup_batch* batch_host, uint32_t* out_off_host, float* de_host);
+
+/* ==========================================================================================
+ * K2b  site_gl_somatic
+ *   replaces sscaller_strand_grid().position_somatic_snv_call(nepi,tepi,nepi_t2,tepi_t2,false,sgtg)
+ *   applications/strelka/strelka_pos_processor.cpp:213-219 ->
+ *   applications/strelka/position_somatic_snv_strand_grid.cpp:228-363,
+ *   position_somatic_snv_strand_grid_lhood_cached.cpp:41-234, qscore_calculator.cpp:47-209.
+ * ======================================================================================== */
+typedef struct sx_ssnv_result { /* somatic_snv_genotype_grid + snv_result_set */
+    float normal_lhood[30];  /* tier selected by snv_from_ntype_tier; DIGT_GRID order (strelka_digt_states.hh:89-98); 21..29 unused (0) */
+    float tumor_lhood[30];
+    float strandBias;
+    uint32_t ref_gt;
+    uint32_t is_computed;        /* 0: early return; nothing below is meaningful */
+    uint32_t snv_tier;
+    uint32_t snv_from_ntype_tier;
+    uint32_t ntype;              /* NTYPE: REF 0, HOM 1, HET 2, CONFLICT 3 */
+    uint32_t max_gt;
+    int32_t qphred;              /* QSS */
+    int32_t from_ntype_qphred;   /* QSS_NT */
+    uint32_t normal_alt_id;
+    uint32_t tumor_alt_id;
+    uint32_t pad;
+} sx_ssnv_result;
+
+/* normal and tumor must have the same n_sites and ref_base; is_forced_output may be NULL (all 0);
+ * tier2 evaluation happens when both batches carry t2_off */
+int sx_site_gl_somatic(sx_ctx* ctx, const sx_pileup_batch* normal_host, const sx_pileup_batch* tumor_host,
+                       const uint8_t* is_forced_output_host, sx_ssnv_result* out_host /*[n_sites]*/);
+int sx_site_gl_somatic_dev(sx_ctx* ctx, const sx_pileup_batch* normal_dev, const sx_pileup_batch* tumor_dev,
+                           const uint8_t* is_forced_output_dev, sx_ssnv_result* out_dev);
+
+/* ==========================================================================================
+ * Multi-GPU: regions shard across ranks with no data-path collective; one gather of fixed-size
+ * call records at the end (the in-memory analogue of concatIndexVcf,
+ * src/python/lib/strelkaSharedWorkflow.py:126-136).  The NCCL communicator is created from an
+ * id the caller distributes out of band (torch.distributed / MPI / file).
+ * ======================================================================================== */
+#define SX_NCCL_ID_BYTES 128
+int sx_comm_get_unique_id(void* id_out /*[SX_NCCL_ID_BYTES]*/);
+int sx_comm_init(sx_ctx* ctx, const void* id, int rank, int world_size);
+/* every rank contributes `bytes` from local_dev; rank `root` receives world_size*bytes in all_dev (ncclGather
+ * semantics via grouped send/recv); blocks until complete */
+int sx_gather_records(sx_ctx* ctx, const void* local_dev, size_t bytes, void* all_dev, int root);
+
+/* ------------------------------------------------------------------------------------------
+ * Instrumentation: device time (ms, CUDA events on the launching stream) and launch count of
+ * the kernels run by the most recent entry-point call on ctx.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sx_timing {
+    float kernel_ms;     /* sum over this call's kernels */
+    float h2d_ms, d2h_ms;
+    uint32_t launches;   /* kernels launched by this call */
+    uint32_t pad;
+} sx_timing;
+int sx_last_timing(const sx_ctx* ctx, sx_timing* out);
+uint64_t sx_total_launches(const sx_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STRELKA_B200_H */
