@@ -1,0 +1,202 @@
+"""ctypes view of include/strelka_b200.h (the C ABI) and the loader of libstrelka_b200.so.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no CPU
+fallback: if the library is missing, ``load()`` raises, and without a CUDA device ``sx_create`` fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libstrelka_b200.so")
+
+SX_OK = 0
+SX_ERR_CUDA, SX_ERR_ARG, SX_ERR_ALIGNMENT, SX_ERR_UNSUPPORTED, SX_ERR_RANGE, SX_ERR_NOMEM, SX_ERR_NCCL = -1, -2, -3, -4, -5, -6, -7
+SX_POOL_SLACK = 64
+SX_SEG_MATCH, SX_SEG_INSERT, SX_SEG_REFSKIP, SX_SEG_SOFTCLIP, SX_SEG_HARDCLIP = 0, 1, 2, 3, 4
+SX_SEGF_NONCANDIDATE = 1
+SX_NCCL_ID_BYTES = 128
+
+
+class SxParams(C.Structure):
+    _fields_ = [
+        ("bsnp_diploid_theta", C.c_double),
+        ("bsnp_ssd_no_mismatch", C.c_double),
+        ("bsnp_ssd_one_mismatch", C.c_double),
+        ("is_min_vexp", C.c_int32),
+        ("is_bsnp_diploid", C.c_int32),
+        ("min_vexp", C.c_double),
+        ("hetVariantFrequencyExtension", C.c_double),
+        ("somatic_snv_rate", C.c_double),
+        ("shared_site_error_rate", C.c_double),
+        ("shared_site_error_strand_bias_fraction", C.c_double),
+        ("ssnv_contam_tolerance", C.c_double),
+        ("pipeline_chunks", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+def default_params() -> SxParams:
+    """Reference defaults: starling_options (starling_shared.hh:34-39) + configureStrelkaSomaticWorkflow.py.ini."""
+    return SxParams(0.001, 0.35, 0.6, 1, 1, 0.25, 0.0, 1e-4, 5e-10, 0.0, 0.15, 0, 0)
+
+
+# numpy mirrors of the POD arrays (layout == C structs; checked against sizeof in tests/test_abi.py)
+ALN_SEG_DT = np.dtype([("len", "<u2"), ("kind", "u1"), ("flags", "u1")])
+ALN_DT = np.dtype([("read", "<u4"), ("ref_pos", "<i4"), ("seg_off", "<u4"), ("ins_off", "<u4")])
+REGION_DT = np.dtype(
+    [("seq_off", "<u8"), ("qual_off", "<u8"), ("ref_off", "<u8"), ("read_begin", "<u4"), ("aln_begin", "<u4"), ("ref_begin", "<i4"), ("ref_len", "<u4")]
+)
+GA_RESULT_DT = np.dtype([("score", "<i4"), ("beginPos", "<i4"), ("n_ops", "<u4"), ("status", "<u4")])
+DIGT_RS_DT = np.dtype([("ref_pprob", "<f8"), ("max_gt", "<u4"), ("snp_qphred", "<i4"), ("max_gt_qphred", "<i4"), ("pad", "<i4")])
+DIGT_RESULT_DT = np.dtype(
+    [
+        ("genome", DIGT_RS_DT),
+        ("poly", DIGT_RS_DT),
+        ("strand_bias", "<f8"),
+        ("lhood", "<f4", (10,)),
+        ("phredLoghood", "<u4", (10,)),
+        ("ref_gt", "<u4"),
+        ("is_computed", "<u4"),
+        ("n_used_calls", "<u4"),
+        ("pad", "<u4"),
+    ]
+)
+SSNV_RESULT_DT = np.dtype(
+    [
+        ("normal_lhood", "<f4", (30,)),
+        ("tumor_lhood", "<f4", (30,)),
+        ("strandBias", "<f4"),
+        ("ref_gt", "<u4"),
+        ("is_computed", "<u4"),
+        ("snv_tier", "<u4"),
+        ("snv_from_ntype_tier", "<u4"),
+        ("ntype", "<u4"),
+        ("max_gt", "<u4"),
+        ("qphred", "<i4"),
+        ("from_ntype_qphred", "<i4"),
+        ("normal_alt_id", "<u4"),
+        ("tumor_alt_id", "<u4"),
+        ("pad", "<u4"),
+    ]
+)
+
+
+class SxAlignBatch(C.Structure):
+    _fields_ = [
+        ("n_regions", C.c_uint32),
+        ("n_reads", C.c_uint32),
+        ("n_alns", C.c_uint32),
+        ("n_segs", C.c_uint32),
+        ("regions", C.c_void_p),
+        ("read_len", C.c_void_p),
+        ("seq4", C.c_void_p),
+        ("qual", C.c_void_p),
+        ("ref", C.c_void_p),
+        ("alns", C.c_void_p),
+        ("segs", C.c_void_p),
+        ("ins", C.c_void_p),
+        ("seq4_bytes", C.c_uint64),
+        ("qual_bytes", C.c_uint64),
+        ("ref_bytes", C.c_uint64),
+        ("ins_bytes", C.c_uint64),
+    ]
+
+
+class SxGaScores(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("match", "mismatch", "open", "extend", "offEdge", "insertDelete", "isAllowEdgeInsertion", "isRequireEdgeDeletion")]
+
+
+class SxGaBatch(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint32),
+        ("query", C.c_void_p),
+        ("ref", C.c_void_p),
+        ("query_off", C.c_void_p),
+        ("ref_off", C.c_void_p),
+        ("max_ops", C.c_uint32),
+    ]
+
+
+class SxPileupBatch(C.Structure):
+    _fields_ = [
+        ("n_sites", C.c_uint32),
+        ("site_off", C.c_void_p),
+        ("calls", C.c_void_p),
+        ("t2_off", C.c_void_p),
+        ("t2_calls", C.c_void_p),
+        ("ref_base", C.c_void_p),
+        ("ploidy", C.c_void_p),
+    ]
+
+
+class SxTiming(C.Structure):
+    _fields_ = [("kernel_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("launches", C.c_uint32), ("pad", C.c_uint32)]
+
+
+# every symbol include/strelka_b200.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = [
+    ("sx_default_params", None, [C.POINTER(SxParams)]),
+    ("sx_create", C.c_int, [C.c_int, C.POINTER(SxParams), C.POINTER(_P)]),
+    ("sx_destroy", None, [_P]),
+    ("sx_last_error", C.c_char_p, [_P]),
+    ("sx_abi_version", C.c_int, []),
+    ("sx_host_alloc", _P, [C.c_size_t]),
+    ("sx_host_free", None, [_P]),
+    ("sx_dev_alloc", _P, [_P, C.c_size_t]),
+    ("sx_dev_free", None, [_P, _P]),
+    ("sx_memcpy_h2d", C.c_int, [_P, _P, _P, C.c_size_t]),
+    ("sx_memcpy_d2h", C.c_int, [_P, _P, _P, C.c_size_t]),
+    ("sx_synchronize", C.c_int, [_P]),
+    ("sx_score_alignments", C.c_int, [_P, C.POINTER(SxAlignBatch), _P]),
+    ("sx_score_alignments_dev", C.c_int, [_P, C.POINTER(SxAlignBatch), _P]),
+    ("sx_align_batch_cells", C.c_uint64, [C.POINTER(SxAlignBatch)]),
+    ("sx_read_max_dev", C.c_int, [_P, C.POINTER(SxAlignBatch), _P, _P, _P]),
+    ("sx_ga_active_region_scores", None, [C.POINTER(SxGaScores)]),
+    ("sx_global_align", C.c_int, [_P, C.POINTER(SxGaScores), C.POINTER(SxGaBatch), _P, _P]),
+    ("sx_global_align_dev", C.c_int, [_P, C.POINTER(SxGaScores), C.POINTER(SxGaBatch), _P, _P]),
+    ("sx_site_gl_germline", C.c_int, [_P, C.POINTER(SxPileupBatch), C.c_int, _P]),
+    ("sx_site_gl_germline_dev", C.c_int, [_P, C.POINTER(SxPileupBatch), C.c_int, _P]),
+    ("sx_dependent_eprob", C.c_int, [_P, C.POINTER(SxPileupBatch), _P, _P]),
+    ("sx_site_gl_somatic", C.c_int, [_P, C.POINTER(SxPileupBatch), C.POINTER(SxPileupBatch), _P, _P]),
+    ("sx_site_gl_somatic_dev", C.c_int, [_P, C.POINTER(SxPileupBatch), C.POINTER(SxPileupBatch), _P, _P]),
+    ("sx_comm_get_unique_id", C.c_int, [_P]),
+    ("sx_comm_init", C.c_int, [_P, _P, C.c_int, C.c_int]),
+    ("sx_gather_records", C.c_int, [_P, _P, C.c_size_t, _P, C.c_int]),
+    ("sx_last_timing", C.c_int, [_P, C.POINTER(SxTiming)]),
+    ("sx_total_launches", C.c_uint64, [_P]),
+]
+
+_lib = None
+
+
+def load(path: str | None = None) -> C.CDLL:
+    """Load libstrelka_b200.so and bind every declared symbol.  Raises if the library is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"{p} not found: the CUDA extension has not been built (run `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "strelka_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError here == ABI symbol missing
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def ptr(a: np.ndarray | None) -> int | None:
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data

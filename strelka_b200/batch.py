@@ -1,0 +1,331 @@
+"""Host-side construction of the flattened batches the C ABI consumes.
+
+This is the Python twin of the C++ host mirror in ``strelka_b200/host`` (used by tests and bench.py): it takes
+reference-shaped objects -- a candidate alignment as (pos, CIGAR path, indel keys with candidacy), a pileup as a list of
+``base_call`` fields -- and produces ``sx_align_batch`` / ``sx_pileup_batch`` arrays that obey the staging rules of
+``include/strelka_b200.h``.
+
+The flattening of a candidate alignment follows the segment walk of ``scoreCandidateAlignment``
+(/root/reference/src/c++/lib/starling_common/starling_read_align_score.cpp:289-499) exactly; what is resolved here is
+everything that function looks up in host-only containers (``getMatchingIndelKey`` :172-224, ``getInsertSeq`` :229-256,
+``IndelBuffer::isCandidateIndel`` :473-475, the leading-edge insert-sequence tail rule :334-338 / :394-398).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _abi as A
+
+# INDEL::index_t  (starling_common/indel_core.hh:57-66)
+INDEL_NONE, INDEL_INDEL, INDEL_MISMATCH, INDEL_BP_LEFT, INDEL_BP_RIGHT = 0, 1, 2, 3, 4
+
+BAM_CODE = {"=": 0, "A": 1, "C": 2, "G": 4, "T": 8, "N": 15}  # htsapi/bam_seq.hh:38-47
+
+
+def codes_of(seq: str) -> np.ndarray:
+    return np.array([BAM_CODE.get(c, 15) for c in seq], dtype=np.uint8)
+
+
+@dataclass
+class IndelKeySpec:
+    """IndelKey (starling_common/IndelKey.hh:39-193) + its candidacy in the IndelBuffer."""
+
+    pos: int
+    type: int = INDEL_INDEL
+    delete_length: int = 0
+    insert_seq: str = ""
+    is_candidate: bool = True
+
+
+@dataclass
+class CandidateAlignmentSpec:
+    """CandidateAlignment (starling_common/CandidateAlignment.hh:36-83) for read index ``read`` of its region."""
+
+    read: int
+    pos: int
+    path: List[Tuple[str, int]]  # [('M', 70), ('I', 5), ...]  ALIGNPATH types as CIGAR chars
+    indels: List[IndelKeySpec] = field(default_factory=list)
+    leading: int = -1  # index into indels of cal.leading_indel_key, or -1
+    trailing: int = -1
+
+
+@dataclass
+class RegionSpec:
+    ref: str
+    ref_begin: int
+    reads: List[Tuple[np.ndarray, np.ndarray]]  # (4-bit codes, quals) per read
+    alns: List[CandidateAlignmentSpec]
+
+
+def parse_cigar(s: str) -> List[Tuple[str, int]]:
+    out, n = [], ""
+    for ch in s:
+        if ch.isdigit():
+            n += ch
+        else:
+            out.append((ch, int(n)))
+            n = ""
+    return out
+
+
+_ALIGN_MATCH = ("M", "=", "X")
+
+
+def flatten_alignment(cal: CandidateAlignmentSpec) -> Tuple[List[Tuple[int, int, int]], bytes]:
+    """-> ([(len, kind, flags)], insert bytes) following score.cpp:289-499."""
+    path = cal.path
+    aps = len(path)
+    first = last = aps
+    seen = False
+    for i, (t, _) in enumerate(path):  # get_match_edge_segments, blt_util/align_path.cpp:736-752
+        if t in _ALIGN_MATCH:
+            if not seen:
+                first = i
+            seen = True
+            last = i
+    segs: List[Tuple[int, int, int]] = []
+    ins = bytearray()
+    ref_head = cal.pos
+    i = 0
+
+    def matching_key(ref_head_pos: int, dl: int, il: int, path_index: int) -> IndelKeySpec:
+        if path_index < first:
+            if cal.leading < 0:
+                raise ValueError("leading edge indel without leading_indel_key")
+            return cal.indels[cal.leading]
+        if path_index > last:
+            if cal.trailing < 0:
+                raise ValueError("trailing edge indel without trailing_indel_key")
+            return cal.indels[cal.trailing]
+        for k, key in enumerate(cal.indels):
+            if k in (cal.leading, cal.trailing):
+                continue
+            if key.pos == ref_head_pos and key.type in (INDEL_INDEL, INDEL_MISMATCH) and key.delete_length == dl and len(key.insert_seq) == il:
+                return key
+        raise ValueError(f"no indel key matches path segment {path_index} at ref pos {ref_head_pos} (del {dl}, ins {il})")
+
+    def emit_insert(key: IndelKeySpec, seg_len_for_head: int, il: int, path_index: int, flags: int) -> None:
+        head = 0
+        if path_index < first:
+            head = len(key.insert_seq) - seg_len_for_head
+        for k in range(il):
+            p = head + k
+            ins.append(ord(key.insert_seq[p]) if 0 <= p < len(key.insert_seq) else ord("N"))
+        segs.append((il, A.SX_SEG_INSERT, flags))
+
+    while i < aps:
+        t, ln = path[i]
+        # is_segment_swap_start, blt_util/align_path.cpp:868-895
+        j, has_i, has_d = i, False, False
+        while j < aps and path[j][0] in ("I", "D"):
+            has_i |= path[j][0] == "I"
+            has_d |= path[j][0] == "D"
+            j += 1
+        is_swap = has_i and has_d
+        n_seg = 1
+        if is_swap or t == "X":
+            if t == "X":
+                dl = il = ln
+            else:
+                n_seg = j - i
+                il = sum(l for tt, l in path[i:j] if tt == "I")
+                dl = sum(l for tt, l in path[i:j] if tt == "D")
+            key = matching_key(ref_head, dl, il, i)
+            fl = 0 if key.is_candidate else A.SX_SEGF_NONCANDIDATE
+            emit_insert(key, ln, il, i, fl)
+            segs.append((dl, A.SX_SEG_REFSKIP, 0))
+            ref_head += dl
+        elif t in ("M", "="):
+            segs.append((ln, A.SX_SEG_MATCH, 0))
+            ref_head += ln
+        elif t == "I":
+            key = matching_key(ref_head, 0, ln, i)
+            fl = 0 if key.is_candidate else A.SX_SEGF_NONCANDIDATE
+            emit_insert(key, ln, ln, i, fl)
+        elif t in ("D", "N"):
+            fl = 0
+            if t == "D":
+                key = matching_key(ref_head, ln, 0, i)
+                fl = 0 if key.is_candidate else A.SX_SEGF_NONCANDIDATE
+            segs.append((ln, A.SX_SEG_REFSKIP, fl))
+            ref_head += ln
+        elif t == "S":
+            segs.append((ln, A.SX_SEG_SOFTCLIP, 0))
+        elif t == "H":
+            segs.append((ln, A.SX_SEG_HARDCLIP, 0))
+        else:
+            raise ValueError(f"Can't handle cigar code: {t}")  # blt_exception at score.cpp:461-466
+        i += n_seg
+    return segs, bytes(ins)
+
+
+def _pad16(n: int) -> int:
+    return (n + 15) & ~15
+
+
+class AlignBatch:
+    """Owns the numpy pools of one sx_align_batch and exposes the ctypes struct (``.c``)."""
+
+    def __init__(self, regions, read_len, seq4, qual, ref, alns, segs, ins, used):
+        self.regions, self.read_len, self.seq4, self.qual, self.ref = regions, read_len, seq4, qual, ref
+        self.alns, self.segs, self.ins = alns, segs, ins
+        self.n_regions = len(regions) - 1
+        self.n_reads = len(read_len)
+        self.n_alns = len(alns) - 1
+        self.n_segs = int(alns["seg_off"][-1])
+        self.used = used
+        self.c = A.SxAlignBatch(
+            self.n_regions, self.n_reads, self.n_alns, self.n_segs,
+            A.ptr(regions), A.ptr(read_len), A.ptr(seq4), A.ptr(qual), A.ptr(ref), A.ptr(alns), A.ptr(segs), A.ptr(ins),
+            used["seq4"], used["qual"], used["ref"], used["ins"],
+        )
+
+    def cells(self) -> int:
+        """SURVEY 8a cell-update count: read bases in MATCH/INSERT segments over all alignments."""
+        s = self.segs[: self.n_segs]
+        m = (s["kind"] == A.SX_SEG_MATCH) | (s["kind"] == A.SX_SEG_INSERT)
+        return int(s["len"][m].astype(np.int64).sum())
+
+    def algorithmic_bytes(self) -> int:
+        """SURVEY 8d K1 bytes: each read once (packed bases + quals), headers, segments, inserted bases, ref windows, 8 B out/aln."""
+        return int(
+            self.used["seq4"] + self.used["qual"] + self.used["ref"] + self.used["ins"]
+            + self.n_alns * (A.ALN_DT.itemsize + 8) + self.n_segs * A.ALN_SEG_DT.itemsize
+            + self.n_reads * 2 + self.n_regions * A.REGION_DT.itemsize
+        )
+
+
+def build_align_batch(regions: Sequence[RegionSpec]) -> AlignBatch:
+    reg = np.zeros(len(regions) + 1, dtype=A.REGION_DT)
+    read_len: List[int] = []
+    seq4 = bytearray()
+    qual = bytearray()
+    ref = bytearray()
+    ins = bytearray()
+    alns: List[Tuple[int, int, int, int]] = []
+    segs: List[Tuple[int, int, int]] = []
+    for ri, r in enumerate(regions):
+        for pool in (seq4, qual, ref, ins):
+            pool.extend(b"\0" * (_pad16(len(pool)) - len(pool)))
+        while len(segs) % 4:
+            segs.append((0, A.SX_SEG_HARDCLIP, 0))  # no-op pad, absorbed by the previous region's last alignment
+        reg[ri] = (len(seq4), len(qual), len(ref), len(read_len), len(alns), r.ref_begin, len(r.ref))
+        ref.extend(r.ref.encode())
+        rbase = len(read_len)
+        for codes, q in r.reads:
+            n = len(codes)
+            assert len(q) == n
+            read_len.append(n)
+            c = np.asarray(codes, dtype=np.uint8)
+            if n & 1:
+                c = np.concatenate([c, np.zeros(1, np.uint8)])
+            seq4.extend(((c[0::2] << 4) | c[1::2]).astype(np.uint8).tobytes())
+            qual.extend(np.asarray(q, dtype=np.uint8).tobytes())
+        order = sorted(range(len(r.alns)), key=lambda k: r.alns[k].read)
+        assert order == list(range(len(r.alns))), "alignments of a region must be sorted by read"
+        for cal in r.alns:
+            s, ib = flatten_alignment(cal)
+            alns.append((rbase + cal.read, cal.pos, len(segs), len(ins)))
+            segs.extend(s)
+            ins.extend(ib)
+    for pool in (seq4, qual, ref, ins):
+        pool.extend(b"\0" * (_pad16(len(pool)) - len(pool)))
+    while len(segs) % 4:
+        segs.append((0, A.SX_SEG_HARDCLIP, 0))
+    used = {"seq4": len(seq4), "qual": len(qual), "ref": len(ref), "ins": len(ins)}
+    reg[len(regions)] = (len(seq4), len(qual), len(ref), len(read_len), len(alns), 0, 0)
+    alns.append((len(read_len), 0, len(segs), len(ins)))
+    slack = b"\0" * A.SX_POOL_SLACK
+    aln_arr = np.array(alns, dtype=A.ALN_DT)
+    seg_arr = np.zeros(len(segs) + 16, dtype=A.ALN_SEG_DT)
+    if segs:
+        seg_arr[: len(segs)] = np.array(segs, dtype=A.ALN_SEG_DT)
+    seg_arr["kind"][len(segs):] = A.SX_SEG_HARDCLIP
+    return AlignBatch(
+        reg,
+        np.array(read_len, dtype=np.uint16),
+        np.frombuffer(bytes(seq4) + slack, dtype=np.uint8).copy(),
+        np.frombuffer(bytes(qual) + slack, dtype=np.uint8).copy(),
+        np.frombuffer(bytes(ref) + slack, dtype=np.uint8).copy(),
+        aln_arr,
+        seg_arr,
+        np.frombuffer(bytes(ins) + slack, dtype=np.uint8).copy(),
+        used,
+    )
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# pileups
+# ------------------------------------------------------------------------------------------------------------------
+def pack_call(q, base_id, fwd, nbr_mm=0, filt=0, tfilt=0):
+    """base_call bit layout, blt_common/snp_pos_info.hh:109-118 (works on scalars and numpy arrays)."""
+    return (
+        (np.asarray(q, dtype=np.uint16) & 63)
+        | ((np.asarray(base_id, dtype=np.uint16) & 15) << 6)
+        | ((np.asarray(fwd, dtype=np.uint16) & 1) << 10)
+        | ((np.asarray(nbr_mm, dtype=np.uint16) & 1) << 11)
+        | ((np.asarray(filt, dtype=np.uint16) & 1) << 12)
+        | ((np.asarray(tfilt, dtype=np.uint16) & 1) << 13)
+    ).astype(np.uint16)
+
+
+class PileupBatch:
+    def __init__(self, site_off, calls, ref_base, ploidy=None, t2_off=None, t2_calls=None):
+        self.site_off = np.ascontiguousarray(site_off, dtype=np.uint32)
+        self.calls = np.ascontiguousarray(calls, dtype=np.uint16)
+        self.ref_base = np.ascontiguousarray(ref_base, dtype=np.uint8)
+        self.ploidy = None if ploidy is None else np.ascontiguousarray(ploidy, dtype=np.uint8)
+        self.t2_off = None if t2_off is None else np.ascontiguousarray(t2_off, dtype=np.uint32)
+        self.t2_calls = None if t2_calls is None else np.ascontiguousarray(t2_calls, dtype=np.uint16)
+        if self.calls.size == 0:
+            self.calls = np.zeros(1, np.uint16)
+        if self.t2_calls is not None and self.t2_calls.size == 0:
+            self.t2_calls = np.zeros(1, np.uint16)
+        self.n_sites = len(self.site_off) - 1
+        assert len(self.ref_base) == self.n_sites
+        self.c = A.SxPileupBatch(
+            self.n_sites, A.ptr(self.site_off), A.ptr(self.calls), A.ptr(self.t2_off), A.ptr(self.t2_calls), A.ptr(self.ref_base), A.ptr(self.ploidy)
+        )
+
+    @property
+    def n_calls(self) -> int:
+        return int(self.site_off[-1])
+
+    @staticmethod
+    def from_sites(sites: Sequence[Sequence[int]], ref_bases: str, ploidy=None, t2_sites=None) -> "PileupBatch":
+        off = np.zeros(len(sites) + 1, np.uint32)
+        off[1:] = np.cumsum([len(s) for s in sites])
+        calls = np.array([c for s in sites for c in s], dtype=np.uint16)
+        t2_off = t2_calls = None
+        if t2_sites is not None:
+            t2_off = np.zeros(len(sites) + 1, np.uint32)
+            t2_off[1:] = np.cumsum([len(s) for s in t2_sites])
+            t2_calls = np.array([c for s in t2_sites for c in s], dtype=np.uint16)
+        return PileupBatch(off, calls, np.frombuffer(ref_bases.encode(), dtype=np.uint8), ploidy, t2_off, t2_calls)
+
+
+class GaBatch:
+    def __init__(self, queries: Sequence[str], refs: Sequence[str], max_ops: int = 64):
+        assert len(queries) == len(refs)
+        self.n = len(queries)
+        self.query = np.frombuffer(("".join(queries) + "\0" * 16).encode(), dtype=np.uint8).copy()
+        self.ref = np.frombuffer(("".join(refs) + "\0" * 16).encode(), dtype=np.uint8).copy()
+        self.query_off = np.zeros(self.n + 1, np.uint32)
+        self.query_off[1:] = np.cumsum([len(q) for q in queries])
+        self.ref_off = np.zeros(self.n + 1, np.uint32)
+        self.ref_off[1:] = np.cumsum([len(r) for r in refs])
+        self.max_ops = max_ops
+        self.c = A.SxGaBatch(self.n, A.ptr(self.query), A.ptr(self.ref), A.ptr(self.query_off), A.ptr(self.ref_off), max_ops)
+
+    def cells(self) -> int:
+        q = np.diff(self.query_off).astype(np.int64)
+        r = np.diff(self.ref_off).astype(np.int64)
+        return int((q * r).sum()) * 3
+
+
+def cigar_string(ops: np.ndarray) -> str:
+    return "".join(f"{int(o) >> 4}{'MIDNSHP=X'[int(o) & 15]}" for o in ops)

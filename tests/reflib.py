@@ -1,0 +1,184 @@
+"""Loaders for the two CPU checkers (TEST INFRASTRUCTURE):
+   oracle/liboracle.so          -- our restatement (travels as source, built by __graft_entry__.build())
+   oracle/_ref/libstrelka_ref.so -- the reference's own code behind a C shim (built here from /root/reference)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from strelka_b200 import _abi as A
+from strelka_b200 import batch as B
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libstrelka_ref.so")
+
+_P = C.c_void_p
+_oracle = None
+_ref = None
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def oracle() -> C.CDLL:
+    global _oracle
+    if _oracle is None:
+        if not os.path.exists(ORACLE_SO):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
+        lib = C.CDLL(ORACLE_SO)
+        lib.ox_score_alignments.argtypes = [C.POINTER(A.SxAlignBatch), _P]
+        lib.ox_score_alignments_range.argtypes = [C.POINTER(A.SxAlignBatch), C.c_uint32, C.c_uint32, _P]
+        lib.ox_global_align.argtypes = [C.POINTER(A.SxGaScores), C.POINTER(A.SxGaBatch), _P, _P]
+        lib.ox_site_gl_germline.argtypes = [C.POINTER(A.SxParams), C.POINTER(A.SxPileupBatch), C.c_int, _P]
+        lib.ox_site_gl_germline_range.argtypes = [C.POINTER(A.SxParams), C.POINTER(A.SxPileupBatch), C.c_int, C.c_uint32, C.c_uint32, _P]
+        lib.ox_dependent_eprob.argtypes = [C.POINTER(A.SxParams), C.POINTER(A.SxPileupBatch), _P, _P]
+        lib.ox_site_gl_somatic.argtypes = [C.POINTER(A.SxParams), C.POINTER(A.SxPileupBatch), C.POINTER(A.SxPileupBatch), _P, _P]
+        lib.ox_site_gl_somatic_range.argtypes = [C.POINTER(A.SxParams), C.POINTER(A.SxPileupBatch), C.POINTER(A.SxPileupBatch), _P, C.c_uint32, C.c_uint32, _P]
+        lib.ox_logf_restated.argtypes = [C.c_float]
+        lib.ox_logf_restated.restype = C.c_float
+        lib.ox_powf_restated.argtypes = [C.c_float, C.c_float]
+        lib.ox_powf_restated.restype = C.c_float
+        lib.ox_sort_restated.argtypes = [_P, C.c_uint32, _P]
+        lib.ox_sort_std.argtypes = [_P, C.c_uint32, _P]
+        _oracle = lib
+    return _oracle
+
+
+def ref() -> C.CDLL:
+    global _ref
+    if _ref is None:
+        lib = C.CDLL(REF_SO)
+        lib.ref_getLogSum_float.argtypes = [C.c_float, C.c_float]
+        lib.ref_getLogSum_float.restype = C.c_float
+        _ref = lib
+    return _ref
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# oracle wrappers
+# ---------------------------------------------------------------------------------------------------------------------
+def ox_score(batch: B.AlignBatch) -> np.ndarray:
+    out = np.zeros(batch.n_alns, np.float64)
+    rc = oracle().ox_score_alignments(C.byref(batch.c), A.ptr(out))
+    assert rc == 0, rc
+    return out
+
+
+def ox_global_align(scores: A.SxGaScores, gb: B.GaBatch):
+    res = np.zeros(gb.n, A.GA_RESULT_DT)
+    cig = np.zeros((gb.n, gb.max_ops), np.uint32)
+    rc = oracle().ox_global_align(C.byref(scores), C.byref(gb.c), A.ptr(res), A.ptr(cig))
+    assert rc == 0, rc
+    return res, cig
+
+
+def ox_germline(params: A.SxParams, pb: B.PileupBatch, is_always_test: bool) -> np.ndarray:
+    out = np.zeros(pb.n_sites, A.DIGT_RESULT_DT)
+    rc = oracle().ox_site_gl_germline(C.byref(params), C.byref(pb.c), int(is_always_test), A.ptr(out))
+    assert rc == 0, rc
+    return out
+
+
+def ox_dependent_eprob(params: A.SxParams, pb: B.PileupBatch):
+    off = np.zeros(pb.n_sites + 1, np.uint32)
+    de = np.zeros(max(1, pb.n_calls), np.float32)
+    rc = oracle().ox_dependent_eprob(C.byref(params), C.byref(pb.c), A.ptr(off), A.ptr(de))
+    assert rc == 0, rc
+    return off, de[: off[-1]]
+
+
+def ox_somatic(params: A.SxParams, npb: B.PileupBatch, tpb: B.PileupBatch, forced=None) -> np.ndarray:
+    out = np.zeros(npb.n_sites, A.SSNV_RESULT_DT)
+    f = None if forced is None else np.ascontiguousarray(forced, np.uint8)
+    rc = oracle().ox_site_gl_somatic(C.byref(params), C.byref(npb.c), C.byref(tpb.c), A.ptr(f), A.ptr(out))
+    assert rc == 0, rc
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference wrappers
+# ---------------------------------------------------------------------------------------------------------------------
+def _err():
+    return C.create_string_buffer(1024)
+
+
+def ref_score_region(r: B.RegionSpec) -> np.ndarray:
+    """scoreCandidateAlignment (reference code) on every candidate alignment of one region."""
+    read_off = np.zeros(len(r.reads) + 1, np.int32)
+    read_off[1:] = np.cumsum([len(c) for c, _ in r.reads])
+    codes = np.concatenate([np.asarray(c, np.uint8) for c, _ in r.reads]) if r.reads else np.zeros(0, np.uint8)
+    quals = np.concatenate([np.asarray(q, np.uint8) for _, q in r.reads]) if r.reads else np.zeros(0, np.uint8)
+    n = len(r.alns)
+    aln_read = np.array([a.read for a in r.alns], np.int32)
+    aln_pos = np.array([a.pos for a in r.alns], np.int32)
+    path_off = np.zeros(n + 1, np.int32)
+    path_off[1:] = np.cumsum([len(a.path) for a in r.alns])
+    path_type = "".join(t for a in r.alns for t, _ in a.path).encode()
+    path_len = np.array([l for a in r.alns for _, l in a.path], np.int32)
+    indel_off = np.zeros(n + 1, np.int32)
+    indel_off[1:] = np.cumsum([len(a.indels) for a in r.alns])
+    keys = [k for a in r.alns for k in a.indels]
+    ipos = np.array([k.pos for k in keys], np.int32)
+    ityp = np.array([k.type for k in keys], np.int32)
+    idel = np.array([k.delete_length for k in keys], np.int32)
+    iins_off = np.zeros(len(keys) + 1, np.int32)
+    iins_off[1:] = np.cumsum([len(k.insert_seq) for k in keys])
+    ins_pool = "".join(k.insert_seq for k in keys).encode()
+    icand = np.array([1 if k.is_candidate else 0 for k in keys], np.uint8)
+    lead = np.array([a.leading for a in r.alns], np.int32)
+    trail = np.array([a.trailing for a in r.alns], np.int32)
+    out = np.zeros(n, np.float64)
+    err = _err()
+    rc = ref().ref_score_alignments(
+        r.ref.encode(), len(r.ref), r.ref_begin, len(r.reads), _P(A.ptr(codes)), _P(A.ptr(quals)), _P(A.ptr(read_off)), n,
+        _P(A.ptr(aln_read)), _P(A.ptr(aln_pos)), _P(A.ptr(path_off)), path_type, _P(A.ptr(path_len)), _P(A.ptr(indel_off)), _P(A.ptr(ipos)),
+        _P(A.ptr(ityp)), _P(A.ptr(idel)), _P(A.ptr(iins_off)), ins_pool, _P(A.ptr(icand)), _P(A.ptr(lead)), _P(A.ptr(trail)), _P(A.ptr(out)), err, 1024,
+    )
+    if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    return out
+
+
+def ref_global_align(scores: A.SxGaScores, gb: B.GaBatch, use_short: bool = False):
+    res = np.zeros(gb.n, A.GA_RESULT_DT)
+    cig = np.zeros((gb.n, gb.max_ops), np.uint32)
+    err = _err()
+    rc = ref().ref_global_align(C.byref(scores), C.byref(gb.c), int(use_short), _P(A.ptr(res)), _P(A.ptr(cig)), err, 1024)
+    if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    return res, cig
+
+
+def ref_germline(params: A.SxParams, pb: B.PileupBatch, is_always_test: bool) -> np.ndarray:
+    out = np.zeros(pb.n_sites, A.DIGT_RESULT_DT)
+    err = _err()
+    rc = ref().ref_site_gl_germline(C.byref(params), C.byref(pb.c), int(is_always_test), _P(A.ptr(out)), err, 1024)
+    if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    return out
+
+
+def ref_dependent_eprob(params: A.SxParams, pb: B.PileupBatch):
+    off = np.zeros(pb.n_sites + 1, np.uint32)
+    de = np.zeros(max(1, pb.n_calls), np.float32)
+    err = _err()
+    rc = ref().ref_dependent_eprob(C.byref(params), C.byref(pb.c), _P(A.ptr(off)), _P(A.ptr(de)), err, 1024)
+    if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    return off, de[: off[-1]]
+
+
+def ref_somatic(params: A.SxParams, npb: B.PileupBatch, tpb: B.PileupBatch, forced=None) -> np.ndarray:
+    out = np.zeros(npb.n_sites, A.SSNV_RESULT_DT)
+    f = None if forced is None else np.ascontiguousarray(forced, np.uint8)
+    err = _err()
+    rc = ref().ref_site_gl_somatic(C.byref(params), C.byref(npb.c), C.byref(tpb.c), _P(A.ptr(f)), _P(A.ptr(out)), err, 1024)
+    if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    return out

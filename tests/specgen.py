@@ -1,0 +1,297 @@
+"""Seeded generators of reference-shaped test inputs (candidate alignments, pileups, haplotype/reference pairs)."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+from strelka_b200 import batch as B
+
+BASES = "ACGT"
+CODE_OF = {"A": 1, "C": 2, "G": 4, "T": 8, "N": 15, "=": 0}
+QUALS = np.array([0, 2, 3, 11, 17, 25, 30, 37, 40, 41, 60, 70], dtype=np.uint8)
+QUAL_P = np.array([0.01, 0.02, 0.02, 0.05, 0.05, 0.1, 0.1, 0.45, 0.1, 0.05, 0.03, 0.02])
+
+
+def rand_seq(rng: np.random.Generator, n: int, n_frac: float = 0.0) -> str:
+    s = rng.integers(0, 4, n)
+    out = np.array(list(BASES))[s]
+    if n_frac > 0:
+        out[rng.random(n) < n_frac] = "N"
+    return "".join(out)
+
+
+def random_region(rng: np.random.Generator, n_reads: int = 6, alns_per_read: Tuple[int, int] = (1, 4), read_len: Tuple[int, int] = (30, 150),
+                  ref_len: int = 400, ref_begin: int = 1000, weird: bool = True) -> B.RegionSpec:
+    """One region with randomly shaped candidate alignments: plain matches, internal insertions / deletions / swaps /
+    SEQ_MISMATCH blocks, leading- and trailing-edge insertions with longer key sequences, soft/hard clips, skips, N and '='
+    read codes, alignments hanging off either end of the held reference, candidate and non-candidate indels."""
+    ref = rand_seq(rng, ref_len, 0.01 if weird else 0.0)
+    reads = []
+    alns: List[B.CandidateAlignmentSpec] = []
+    # candidacy must be a function of the indel key within a region (one IndelBuffer)
+    cand_of = {}
+
+    def candidacy(pos, typ, dl, ins):
+        k = (pos, typ, dl, ins)
+        if k not in cand_of:
+            cand_of[k] = bool(rng.random() < 0.7)
+        return cand_of[k]
+
+    for r in range(n_reads):
+        L = int(rng.integers(read_len[0], read_len[1] + 1))
+        na = int(rng.integers(alns_per_read[0], alns_per_read[1] + 1))
+        read_bases: List[str] = ["A"] * L
+        first = True
+        for _ in range(na):
+            # build a path consuming exactly L read bases
+            remaining = L
+            path: List[Tuple[str, int]] = []
+            indels: List[B.IndelKeySpec] = []
+            leading = trailing = -1
+            pos = int(rng.integers(ref_begin - 20, ref_begin + ref_len - L // 2))
+            ref_head = pos
+            expected: List[str] = []  # the base each read position is compared against ('?' = none)
+
+            def ref_at(p):
+                q = p - ref_begin
+                return ref[q] if 0 <= q < ref_len else "N"
+
+            if weird and rng.random() < 0.1:
+                path.append(("H", int(rng.integers(1, 5))))
+            if weird and rng.random() < 0.2 and remaining > 20:
+                n = int(rng.integers(1, 8))
+                path.append(("S", n))
+                expected += ["?"] * n
+                remaining -= n
+            if weird and rng.random() < 0.15 and remaining > 20:
+                n = int(rng.integers(1, 6))
+                full = rand_seq(rng, n + int(rng.integers(0, 4)))  # key sequence may be longer than the observed tail
+                indels.append(B.IndelKeySpec(ref_head, B.INDEL_INDEL, 0, full, candidacy(ref_head, 1, 0, full)))
+                leading = len(indels) - 1
+                path.append(("I", n))
+                expected += list(full[len(full) - n:])
+                remaining -= n
+            tail_budget = 0
+            want_trailing_ins = weird and rng.random() < 0.15 and remaining > 30
+            want_trailing_clip = weird and rng.random() < 0.2 and remaining > 30
+            if want_trailing_ins:
+                tail_budget += 5
+            if want_trailing_clip:
+                tail_budget += 7
+            # internal structure: M (event M)*
+            n_events = int(rng.integers(0, 4)) if remaining > 40 else 0
+            body = remaining - tail_budget
+            for e in range(n_events + 1):
+                last_block = e == n_events
+                m = body if last_block else int(rng.integers(3, max(4, body // (n_events + 1 - e))))
+                m = max(1, min(m, body))
+                mt = "=" if (weird and rng.random() < 0.1) else "M"
+                path.append((mt, m))
+                expected += [ref_at(ref_head + k) for k in range(m)]
+                ref_head += m
+                body -= m
+                if last_block or body < 8:
+                    if not last_block:
+                        # fold what is left into a final match block
+                        path.append(("M", body))
+                        expected += [ref_at(ref_head + k) for k in range(body)]
+                        ref_head += body
+                        body = 0
+                    break
+                ev = rng.random()
+                if ev < 0.3:  # insertion
+                    n = int(rng.integers(1, min(6, body - 3) + 1))
+                    s = rand_seq(rng, n)
+                    indels.append(B.IndelKeySpec(ref_head, B.INDEL_INDEL, 0, s, candidacy(ref_head, 1, 0, s)))
+                    path.append(("I", n))
+                    expected += list(s)
+                    body -= n
+                elif ev < 0.6:  # deletion
+                    n = int(rng.integers(1, 12))
+                    indels.append(B.IndelKeySpec(ref_head, B.INDEL_INDEL, n, "", candidacy(ref_head, 1, n, "")))
+                    path.append(("D", n))
+                    ref_head += n
+                elif ev < 0.75:  # swap, either order
+                    ni = int(rng.integers(1, min(5, body - 3) + 1))
+                    nd = int(rng.integers(1, 8))
+                    s = rand_seq(rng, ni)
+                    # complex (insert+delete) alleles are never candidates: IndelBuffer.cpp:118-129 sets doNotGenotype
+                    indels.append(B.IndelKeySpec(ref_head, B.INDEL_INDEL, nd, s, False))
+                    if rng.random() < 0.5:
+                        path += [("I", ni), ("D", nd)]
+                    else:
+                        path += [("D", nd), ("I", ni)]
+                    expected += list(s)
+                    ref_head += nd
+                    body -= ni
+                elif ev < 0.9 and weird:  # SEQ_MISMATCH block with a MISMATCH key
+                    n = int(rng.integers(1, min(4, body - 3) + 1))
+                    s = rand_seq(rng, n)
+                    indels.append(B.IndelKeySpec(ref_head, B.INDEL_MISMATCH, n, s, candidacy(ref_head, 2, n, s)))
+                    path.append(("X", n))
+                    expected += list(s)
+                    ref_head += n
+                    body -= n
+                else:  # skip
+                    n = int(rng.integers(1, 30))
+                    path.append(("N", n))
+                    ref_head += n
+            remaining = tail_budget
+            if want_trailing_ins:
+                n = int(rng.integers(1, 6))
+                full = rand_seq(rng, n + int(rng.integers(0, 4)))
+                indels.append(B.IndelKeySpec(ref_head, B.INDEL_INDEL, 0, full, candidacy(ref_head, 1, 0, full)))
+                trailing = len(indels) - 1
+                path.append(("I", n))
+                expected += list(full[:n])
+                remaining -= n
+            if remaining > 0:
+                if want_trailing_clip:
+                    path.append(("S", remaining))
+                    expected += ["?"] * remaining
+                else:
+                    # give the spare bases back to the last match block is awkward after a trailing insert: soft-clip them
+                    path.append(("S", remaining))
+                    expected += ["?"] * remaining
+                remaining = 0
+            if weird and rng.random() < 0.05:
+                path.append(("H", 3))
+            assert len(expected) == L, (len(expected), L, path)
+            if first:
+                # derive the read from the first alignment's expectation, with sequencing noise
+                for k in range(L):
+                    e = expected[k]
+                    b = e if e in BASES else BASES[int(rng.integers(0, 4))]
+                    if rng.random() < 0.05:
+                        b = BASES[int(rng.integers(0, 4))]
+                    read_bases[k] = b
+                first = False
+            # merge adjacent same-type segments the generator may have produced
+            merged: List[Tuple[str, int]] = []
+            for t, l in path:
+                if merged and merged[-1][0] == t and t in ("M", "=", "S"):
+                    merged[-1] = (t, merged[-1][1] + l)
+                else:
+                    merged.append((t, l))
+            alns.append(B.CandidateAlignmentSpec(r, pos, merged, indels, leading, trailing))
+        codes = np.array([CODE_OF[b] for b in read_bases], dtype=np.uint8)
+        if weird:
+            z = rng.random(L)
+            codes[z < 0.02] = 15  # N
+            codes[(z >= 0.02) & (z < 0.03)] = 0  # '='
+            codes[(z >= 0.03) & (z < 0.035)] = 3  # an IUPAC ambiguity nibble: matches nothing
+        quals = rng.choice(QUALS, size=L, p=QUAL_P).astype(np.uint8)
+        reads.append((codes, quals))
+    return B.RegionSpec(ref, ref_begin, reads, alns)
+
+
+def simple_region(rng: np.random.Generator, n_reads: int = 30, n_haps: int = 4, read_len: int = 150, ref_len: int = 420, ref_begin: int = 100000) -> B.RegionSpec:
+    """A cfg2-shaped candidate locus: `n_haps` haplotypes (reference + alt indel alleles at one locus), every read scored
+    against every haplotype."""
+    ref = rand_seq(rng, ref_len)
+    locus = ref_begin + ref_len // 2
+    haps = [None]
+    for _ in range(n_haps - 1):
+        if rng.random() < 0.5:
+            n = int(min(20, rng.geometric(0.4)))
+            haps.append(("I", rand_seq(rng, n)))
+        else:
+            haps.append(("D", int(min(20, rng.geometric(0.4)))))
+    reads, alns = [], []
+    for r in range(n_reads):
+        start = int(rng.integers(locus - read_len + 10, locus - 10))
+        h = haps[int(rng.integers(0, n_haps))]
+        # read sequence from haplotype h
+        left = locus - start
+        if h is None:
+            s = ref[start - ref_begin: start - ref_begin + read_len]
+        elif h[0] == "I":
+            s = (ref[start - ref_begin: locus - ref_begin] + h[1] + ref[locus - ref_begin:])[:read_len]
+        else:
+            s = (ref[start - ref_begin: locus - ref_begin] + ref[locus - ref_begin + h[1]:])[:read_len]
+        s = s.ljust(read_len, "A")
+        q = rng.choice(np.array([11, 25, 37], np.uint8), size=read_len, p=[0.03, 0.07, 0.90])
+        bases = np.array(list(s))
+        err = rng.random(read_len) < 10.0 ** (-q / 10.0)
+        bases[err] = np.array(list(BASES))[rng.integers(0, 4, int(err.sum()))]
+        reads.append((np.array([CODE_OF[b] for b in bases], np.uint8), q.astype(np.uint8)))
+        for hh in haps:
+            if hh is None:
+                alns.append(B.CandidateAlignmentSpec(r, start, [("M", read_len)], []))
+            elif hh[0] == "I":
+                n = min(len(hh[1]), read_len - left)
+                rest = read_len - left - n
+                key = B.IndelKeySpec(locus, B.INDEL_INDEL, 0, hh[1], True)
+                if rest > 0:
+                    alns.append(B.CandidateAlignmentSpec(r, start, [("M", left), ("I", n), ("M", rest)], [key]))
+                else:
+                    alns.append(B.CandidateAlignmentSpec(r, start, [("M", left), ("I", n)], [key], trailing=0))
+            else:
+                key = B.IndelKeySpec(locus, B.INDEL_INDEL, hh[1], "", True)
+                alns.append(B.CandidateAlignmentSpec(r, start, [("M", left), ("D", hh[1]), ("M", read_len - left)], [key]))
+    return B.RegionSpec(ref, ref_begin, reads, alns)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# pileups
+# ------------------------------------------------------------------------------------------------------------------
+def random_pileups(rng: np.random.Generator, n_sites: int, depth: float = 30.0, alt_frac_choices=(0.0, 0.0, 0.0, 0.02, 0.1, 0.25, 0.5, 1.0),
+                   filt_frac: float = 0.05, with_tier2: bool = False, n_ref_frac: float = 0.01, max_depth: int = 250):
+    """-> PileupBatch.  Each site: Poisson depth, a minor allele at a random fraction, strand split, phred mix, a few filtered calls."""
+    sites, t2, refs = [], [], []
+    for _ in range(n_sites):
+        n = int(min(max_depth, rng.poisson(depth)))
+        ref_id = int(rng.integers(0, 4))
+        alt_id = (ref_id + int(rng.integers(1, 4))) % 4
+        af = float(rng.choice(alt_frac_choices))
+        q = rng.choice(np.array([2, 3, 11, 17, 25, 30, 37, 40, 41, 60], np.uint8), size=n, p=[0.01, 0.01, 0.04, 0.04, 0.1, 0.1, 0.5, 0.1, 0.07, 0.03])
+        base = np.where(rng.random(n) < af, alt_id, ref_id)
+        err = rng.random(n) < 0.01
+        base[err] = rng.integers(0, 4, int(err.sum()))
+        fwd = rng.random(n) < 0.5
+        nbr = rng.random(n) < 0.1
+        filt = rng.random(n) < filt_frac
+        tfilt = filt & (rng.random(n) < 0.5)
+        sites.append(list(B.pack_call(q, base, fwd, nbr, filt, tfilt)))
+        refs.append("N" if rng.random() < n_ref_frac else BASES[ref_id])
+        if with_tier2:
+            m = int(rng.poisson(depth * 0.1))
+            q2 = rng.choice(np.array([11, 25, 37], np.uint8), size=m)
+            b2 = np.where(rng.random(m) < af, alt_id, ref_id)
+            t2.append(list(B.pack_call(q2, b2, rng.random(m) < 0.5, 0, rng.random(m) < 0.3, 0)))
+    return B.PileupBatch.from_sites(sites, "".join(refs), None, t2 if with_tier2 else None)
+
+
+def random_ga_problems(rng: np.random.Generator, n: int, qlen=(5, 120), rlen=(5, 150), n_frac=0.0):
+    qs, rs = [], []
+    for _ in range(n):
+        R = int(rng.integers(rlen[0], rlen[1] + 1))
+        r = rand_seq(rng, R, n_frac)
+        mode = rng.random()
+        if mode < 0.7:
+            # haplotype-like query: the reference with a few edits
+            q = list(r)
+            for _ in range(int(rng.integers(0, 5))):
+                if not q:
+                    break
+                p = int(rng.integers(0, len(q)))
+                e = rng.random()
+                if e < 0.4:
+                    q[p] = BASES[int(rng.integers(0, 4))]
+                elif e < 0.7:
+                    del q[p: p + int(rng.integers(1, 8))]
+                else:
+                    q[p:p] = list(rand_seq(rng, int(rng.integers(1, 8))))
+            q = "".join(q)
+            if rng.random() < 0.2:
+                q = rand_seq(rng, int(rng.integers(1, 6))) + q
+            if rng.random() < 0.2:
+                q = q + rand_seq(rng, int(rng.integers(1, 6)))
+            if not q:
+                q = "A"
+        else:
+            q = rand_seq(rng, int(rng.integers(qlen[0], qlen[1] + 1)), n_frac)
+        qs.append(q)
+        rs.append(r)
+    return qs, rs

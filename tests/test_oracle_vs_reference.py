@@ -1,0 +1,93 @@
+"""Pins oracle/strelka_oracle.cpp (the travelling CPU checker) against the reference's own code
+(oracle/_ref/libstrelka_ref.so = /root/reference compiled by oracle/build_ref.sh).  CPU only."""
+import numpy as np
+import pytest
+
+import reflib
+import specgen
+from strelka_b200 import _abi as A
+from strelka_b200 import batch as B
+
+pytestmark = pytest.mark.ref
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_score_alignments_bit_exact(seed):
+    rng = np.random.default_rng(seed)
+    regions = [specgen.random_region(rng, n_reads=int(rng.integers(1, 8))) for _ in range(12)]
+    regions.append(specgen.simple_region(rng, n_reads=10))
+    batch = B.build_align_batch(regions)
+    got = reflib.ox_score(batch)
+    want = np.concatenate([reflib.ref_score_region(r) for r in regions])
+    assert got.shape == want.shape
+    # bit-exact: compare the raw IEEE-754 words
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    assert np.all(want <= 0)
+
+
+def _ga_scores(match, mismatch, open_, extend, off_edge, ins_del=0, allow_edge_ins=False, require_edge_del=False):
+    return A.SxGaScores(match, mismatch, open_, extend, off_edge, ins_del, int(allow_edge_ins), int(require_edge_del))
+
+
+@pytest.mark.parametrize("flags", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("seed", range(3))
+def test_global_align_bit_exact(seed, flags):
+    rng = np.random.default_rng(100 + seed)
+    qs, rs = specgen.random_ga_problems(rng, 150, n_frac=0.01)
+    gb = B.GaBatch(qs, rs, max_ops=400)
+    for sc in (_ga_scores(1, -4, -5, -1, -100, -5, *flags), _ga_scores(2, -4, -5, -1, -1, 0, *flags)):
+        r_res, r_cig = reflib.ref_global_align(sc, gb)
+        o_res, o_cig = reflib.ox_global_align(sc, gb)
+        assert np.array_equal(r_res, o_res)
+        assert np.array_equal(r_cig, o_cig)
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("always", [True, False])
+def test_site_gl_germline(seed, always):
+    rng = np.random.default_rng(200 + seed)
+    pb = specgen.random_pileups(rng, 400, depth=[8.0, 30.0, 60.0, 120.0][seed])
+    p = A.default_params()
+    want = reflib.ref_germline(p, pb, always)
+    got = reflib.ox_germline(p, pb, always)
+    for f in ("ref_gt", "is_computed", "n_used_calls", "phredLoghood", "strand_bias"):
+        assert np.array_equal(want[f], got[f]), f
+    for rs in ("genome", "poly"):
+        for f in ("max_gt", "snp_qphred", "max_gt_qphred", "ref_pprob"):
+            assert np.array_equal(want[rs][f], got[rs][f]), (rs, f)
+    assert np.array_equal(want["lhood"].view(np.uint32), got["lhood"].view(np.uint32))
+    ro, rde = reflib.ref_dependent_eprob(p, pb)
+    oo, ode = reflib.ox_dependent_eprob(p, pb)
+    assert np.array_equal(ro, oo) and np.array_equal(rde.view(np.uint32), ode.view(np.uint32))
+
+
+def test_site_gl_germline_haploid_and_nodep():
+    rng = np.random.default_rng(7)
+    pb0 = specgen.random_pileups(rng, 300, depth=25.0)
+    pl = rng.integers(1, 3, pb0.n_sites).astype(np.uint8)
+    pb = B.PileupBatch(pb0.site_off, pb0.calls, pb0.ref_base, pl)
+    for p in (A.default_params(), A.SxParams(0.001, 0.0, 0.0, 0, 1, 0.0, 0.0, 1e-4, 5e-10, 0.0, 0.15, 0, 0)):
+        want = reflib.ref_germline(p, pb, True)
+        got = reflib.ox_germline(p, pb, True)
+        assert want.tobytes() == got.tobytes()
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("tier2", [False, True])
+def test_site_gl_somatic(seed, tier2):
+    rng = np.random.default_rng(300 + seed)
+    n = 300
+    npb = specgen.random_pileups(rng, n, depth=30.0, with_tier2=tier2, alt_frac_choices=(0.0, 0.0, 0.0, 0.0, 0.02, 0.5))
+    tpb0 = specgen.random_pileups(rng, n, depth=60.0, with_tier2=tier2, alt_frac_choices=(0.0, 0.0, 0.05, 0.1, 0.2, 0.4))
+    # same reference base at a site in both samples
+    tpb = B.PileupBatch(tpb0.site_off, tpb0.calls, npb.ref_base, None, tpb0.t2_off, tpb0.t2_calls)
+    forced = (rng.random(n) < 0.2).astype(np.uint8)
+    p = A.default_params()
+    want = reflib.ref_somatic(p, npb, tpb, forced)
+    got = reflib.ox_somatic(p, npb, tpb, forced)
+    assert np.array_equal(want["is_computed"], got["is_computed"])
+    m = want["is_computed"] == 1
+    assert m.sum() > 10
+    for f in ("ref_gt", "snv_tier", "snv_from_ntype_tier", "ntype", "max_gt", "qphred", "from_ntype_qphred", "normal_alt_id", "tumor_alt_id"):
+        assert np.array_equal(want[f][m], got[f][m]), f
+    assert np.array_equal(want["strandBias"][m].view(np.uint32), got["strandBias"][m].view(np.uint32))
