@@ -138,6 +138,8 @@ typedef struct sx_region {
     uint64_t ref_off;    /* byte offset in ref pool (multiple of 16) */
     uint32_t read_begin; /* first read; reads end at next region's read_begin */
     uint32_t aln_begin;  /* first alignment; ends at next region's aln_begin */
+    uint32_t seg_begin;  /* == alns[aln_begin].seg_off rounded down to the region's first (possibly pad) segment; multiple of 4 */
+    uint32_t ins_begin;  /* first insert-pool byte of the region; multiple of 16 */
     int32_t ref_begin;   /* contig coordinate of ref pool byte ref_off */
     uint32_t ref_len;    /* bases available; positions outside read as 'N' (reference_contig_segment::get_base) */
 } sx_region;

@@ -48,7 +48,8 @@ def default_params() -> SxParams:
 ALN_SEG_DT = np.dtype([("len", "<u2"), ("kind", "u1"), ("flags", "u1")])
 ALN_DT = np.dtype([("read", "<u4"), ("ref_pos", "<i4"), ("seg_off", "<u4"), ("ins_off", "<u4")])
 REGION_DT = np.dtype(
-    [("seq_off", "<u8"), ("qual_off", "<u8"), ("ref_off", "<u8"), ("read_begin", "<u4"), ("aln_begin", "<u4"), ("ref_begin", "<i4"), ("ref_len", "<u4")]
+    [("seq_off", "<u8"), ("qual_off", "<u8"), ("ref_off", "<u8"), ("read_begin", "<u4"), ("aln_begin", "<u4"), ("seg_begin", "<u4"), ("ins_begin", "<u4"),
+     ("ref_begin", "<i4"), ("ref_len", "<u4")]
 )
 GA_RESULT_DT = np.dtype([("score", "<i4"), ("beginPos", "<i4"), ("n_ops", "<u4"), ("status", "<u4")])
 DIGT_RS_DT = np.dtype([("ref_pprob", "<f8"), ("max_gt", "<u4"), ("snp_qphred", "<i4"), ("max_gt_qphred", "<i4"), ("pad", "<i4")])

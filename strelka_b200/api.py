@@ -1,0 +1,191 @@
+"""Python face of the C ABI (ctypes): what tests and bench.py call.  It adds nothing to the data path -- every method is one
+``sx_*`` call on libstrelka_b200.so with numpy (host) buffers or raw device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _abi as A
+from . import batch as B
+
+
+class SxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"strelka_b200 error {code}: {msg}")
+        self.code = code
+
+
+class DeviceArray:
+    """A cudaMalloc'd buffer owned by a Context (freed on close or __del__)."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        self.ptr = ctx.lib.sx_dev_alloc(ctx.h, max(1, self.nbytes))
+        if not self.ptr:
+            raise SxError(A.SX_ERR_NOMEM, ctx.last_error())
+
+    def upload(self, a: np.ndarray) -> "DeviceArray":
+        a = np.ascontiguousarray(a)
+        assert a.nbytes <= self.nbytes
+        self.ctx._chk(self.ctx.lib.sx_memcpy_h2d(self.ctx.h, self.ptr, a.ctypes.data, a.nbytes))
+        return self
+
+    def download(self, dtype, count: int) -> np.ndarray:
+        out = np.empty(count, dtype=dtype)
+        self.ctx._chk(self.ctx.lib.sx_memcpy_d2h(self.ctx.h, out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr and self.ctx.h:
+            self.ctx.lib.sx_dev_free(self.ctx.h, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DevAlignBatch:
+    """sx_align_batch whose pools live in HBM (inputs resident before the timed region)."""
+
+    def __init__(self, ctx: "Context", hb: B.AlignBatch):
+        self.host = hb
+        self.bufs = {}
+        for name in ("regions", "read_len", "seq4", "qual", "ref", "alns", "segs", "ins"):
+            arr = getattr(hb, name)
+            self.bufs[name] = DeviceArray(ctx, arr.nbytes + 64).upload(arr)
+        self.c = A.SxAlignBatch(
+            hb.n_regions, hb.n_reads, hb.n_alns, hb.n_segs,
+            self.bufs["regions"].ptr, self.bufs["read_len"].ptr, self.bufs["seq4"].ptr, self.bufs["qual"].ptr, self.bufs["ref"].ptr,
+            self.bufs["alns"].ptr, self.bufs["segs"].ptr, self.bufs["ins"].ptr,
+            hb.used["seq4"], hb.used["qual"], hb.used["ref"], hb.used["ins"],
+        )
+        self.out = DeviceArray(ctx, hb.n_alns * 8)
+
+
+class DevPileupBatch:
+    def __init__(self, ctx: "Context", hb: B.PileupBatch):
+        self.host = hb
+        self.bufs = {}
+        ptrs = {}
+        for name in ("site_off", "calls", "t2_off", "t2_calls", "ref_base", "ploidy"):
+            arr = getattr(hb, name)
+            if arr is None:
+                ptrs[name] = None
+            else:
+                self.bufs[name] = DeviceArray(ctx, arr.nbytes + 64).upload(arr)
+                ptrs[name] = self.bufs[name].ptr
+        self.c = A.SxPileupBatch(hb.n_sites, ptrs["site_off"], ptrs["calls"], ptrs["t2_off"], ptrs["t2_calls"], ptrs["ref_base"], ptrs["ploidy"])
+
+
+class DevGaBatch:
+    def __init__(self, ctx: "Context", hb: B.GaBatch):
+        self.host = hb
+        self.bufs = {n: DeviceArray(ctx, getattr(hb, n).nbytes + 64).upload(getattr(hb, n)) for n in ("query", "ref", "query_off", "ref_off")}
+        self.c = A.SxGaBatch(hb.n, self.bufs["query"].ptr, self.bufs["ref"].ptr, self.bufs["query_off"].ptr, self.bufs["ref_off"].ptr, hb.max_ops)
+        self.res = DeviceArray(ctx, hb.n * A.GA_RESULT_DT.itemsize)
+        self.cigar = DeviceArray(ctx, hb.n * hb.max_ops * 4 + 16)
+
+
+class Context:
+    """One sx_ctx (one GPU, one host thread)."""
+
+    def __init__(self, device: int = 0, params: Optional[A.SxParams] = None):
+        self.lib = A.load()
+        self.params = params or A.default_params()
+        h = C.c_void_p()
+        rc = self.lib.sx_create(device, C.byref(self.params), C.byref(h))
+        if rc != 0:
+            raise SxError(rc, (self.lib.sx_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def last_error(self) -> str:
+        return (self.lib.sx_last_error(self.h) or b"").decode()
+
+    def _chk(self, rc: int):
+        if rc != 0:
+            raise SxError(rc, self.last_error())
+
+    def timing(self) -> A.SxTiming:
+        t = A.SxTiming()
+        self.lib.sx_last_timing(self.h, C.byref(t))
+        return t
+
+    def total_launches(self) -> int:
+        return int(self.lib.sx_total_launches(self.h))
+
+    def synchronize(self):
+        self._chk(self.lib.sx_synchronize(self.h))
+
+    # ---- K1
+    def score_alignments(self, batch: B.AlignBatch, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.zeros(batch.n_alns, np.float64)
+        self._chk(self.lib.sx_score_alignments(self.h, C.byref(batch.c), out.ctypes.data))
+        return out
+
+    def score_alignments_dev(self, db: DevAlignBatch) -> None:
+        self._chk(self.lib.sx_score_alignments_dev(self.h, C.byref(db.c), db.out.ptr))
+
+    def read_max_dev(self, db: DevAlignBatch, max_lnp: DeviceArray, max_aln: DeviceArray) -> None:
+        self._chk(self.lib.sx_read_max_dev(self.h, C.byref(db.c), db.out.ptr, max_lnp.ptr, max_aln.ptr))
+
+    # ---- K3
+    def global_align(self, scores: A.SxGaScores, gb: B.GaBatch) -> Tuple[np.ndarray, np.ndarray]:
+        res = np.zeros(gb.n, A.GA_RESULT_DT)
+        cig = np.zeros((gb.n, gb.max_ops), np.uint32)
+        self._chk(self.lib.sx_global_align(self.h, C.byref(scores), C.byref(gb.c), res.ctypes.data, cig.ctypes.data))
+        return res, cig
+
+    def global_align_dev(self, scores: A.SxGaScores, db: DevGaBatch) -> None:
+        self._chk(self.lib.sx_global_align_dev(self.h, C.byref(scores), C.byref(db.c), db.res.ptr, db.cigar.ptr))
+
+    def active_region_scores(self) -> A.SxGaScores:
+        s = A.SxGaScores()
+        self.lib.sx_ga_active_region_scores(C.byref(s))
+        return s
+
+    # ---- K2a
+    def site_gl_germline(self, pb: B.PileupBatch, is_always_test: bool = True, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.zeros(pb.n_sites, A.DIGT_RESULT_DT)
+        self._chk(self.lib.sx_site_gl_germline(self.h, C.byref(pb.c), int(is_always_test), out.ctypes.data))
+        return out
+
+    def site_gl_germline_dev(self, db: DevPileupBatch, out: DeviceArray, is_always_test: bool = True) -> None:
+        self._chk(self.lib.sx_site_gl_germline_dev(self.h, C.byref(db.c), int(is_always_test), out.ptr))
+
+    def dependent_eprob(self, pb: B.PileupBatch) -> Tuple[np.ndarray, np.ndarray]:
+        off = np.zeros(pb.n_sites + 1, np.uint32)
+        de = np.zeros(max(1, pb.n_calls), np.float32)
+        self._chk(self.lib.sx_dependent_eprob(self.h, C.byref(pb.c), off.ctypes.data, de.ctypes.data))
+        return off, de[: off[-1]]
+
+    # ---- K2b
+    def site_gl_somatic(self, npb: B.PileupBatch, tpb: B.PileupBatch, forced: Optional[np.ndarray] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.zeros(npb.n_sites, A.SSNV_RESULT_DT)
+        f = None if forced is None else np.ascontiguousarray(forced, np.uint8)
+        self._chk(self.lib.sx_site_gl_somatic(self.h, C.byref(npb.c), C.byref(tpb.c), A.ptr(f), out.ctypes.data))
+        return out
+
+    def site_gl_somatic_dev(self, dn: DevPileupBatch, dt: DevPileupBatch, forced: Optional[DeviceArray], out: DeviceArray) -> None:
+        self._chk(self.lib.sx_site_gl_somatic_dev(self.h, C.byref(dn.c), C.byref(dt.c), forced.ptr if forced else None, out.ptr))

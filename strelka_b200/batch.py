@@ -213,7 +213,7 @@ def build_align_batch(regions: Sequence[RegionSpec]) -> AlignBatch:
             pool.extend(b"\0" * (_pad16(len(pool)) - len(pool)))
         while len(segs) % 4:
             segs.append((0, A.SX_SEG_HARDCLIP, 0))  # no-op pad, absorbed by the previous region's last alignment
-        reg[ri] = (len(seq4), len(qual), len(ref), len(read_len), len(alns), r.ref_begin, len(r.ref))
+        reg[ri] = (len(seq4), len(qual), len(ref), len(read_len), len(alns), len(segs), len(ins), r.ref_begin, len(r.ref))
         ref.extend(r.ref.encode())
         rbase = len(read_len)
         for codes, q in r.reads:
@@ -237,7 +237,7 @@ def build_align_batch(regions: Sequence[RegionSpec]) -> AlignBatch:
     while len(segs) % 4:
         segs.append((0, A.SX_SEG_HARDCLIP, 0))
     used = {"seq4": len(seq4), "qual": len(qual), "ref": len(ref), "ins": len(ins)}
-    reg[len(regions)] = (len(seq4), len(qual), len(ref), len(read_len), len(alns), 0, 0)
+    reg[len(regions)] = (len(seq4), len(qual), len(ref), len(read_len), len(alns), len(segs), len(ins), 0, 0)
     alns.append((len(read_len), 0, len(segs), len(ins)))
     slack = b"\0" * A.SX_POOL_SLACK
     aln_arr = np.array(alns, dtype=A.ALN_DT)

@@ -1,0 +1,597 @@
+// k1_score.cu -- K1 score_alignments: ln P(read | one candidate alignment path) for every (read, alignment) pair.
+//
+// Replaces scoreCandidateAlignment  (/root/reference/src/c++/lib/starling_common/starling_read_align_score.cpp:260-499,
+// scoreMatchSegment :142-170, scoreInsertSegment :108-137) over the loop at starling_read_align.cpp:1568-1571.
+//
+// Bit-exactness contract: the reference accumulates one running double per path, term by term in read order
+// (score.cpp:104-106 explains why: equal scores must stay exactly equal so ambiguous alignments tie).  A reduction tree
+// would reorder the additions, so each (read, alignment) pair is summed by ONE thread in read order with __dadd_rn; the
+// parallelism is across pairs.  The addends come from a 143-row table built on the host with the host libm
+// (sx_context.cu), so there is no transcendental on the device.
+//
+// Data movement: one CTA per region.  Every pool slice of the region (packed bases, qualities, reference window,
+// alignment headers, segments, inserted bases, the term table) is pulled into shared memory by TMA bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx) issued by one thread; each read is then expanded ONCE into a 16-bit
+// (table-row | one-hot base) entry that all of its H alignments share, so HBM sees every read byte exactly once.
+#include "sx_internal.h"
+
+#include <algorithm>
+
+namespace
+{
+constexpr int K1_THREADS = 128;
+constexpr int K1_TAB_BYTES = SX_K1_ROWS * 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier.  16-byte aligned src/dst/size.
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__host__ __device__ __forceinline__ uint32_t pad16(uint32_t x) { return (x + 15u) & ~15u; }
+
+struct k1_layout
+{
+    uint32_t tab, alns, segs, ref, ins, seq, qual, rlen, boff, soff, ent, total;
+    uint32_t n_reads, n_alns, seg_bytes, ref_bytes, ins_bytes, seq_bytes, qual_bytes;
+};
+
+__host__ __device__ __forceinline__ k1_layout k1_make_layout(const sx_region& r0, const sx_region& r1)
+{
+    k1_layout L;
+    L.n_reads = r1.read_begin - r0.read_begin;
+    L.n_alns = r1.aln_begin - r0.aln_begin;
+    L.seg_bytes = pad16((r1.seg_begin - r0.seg_begin) * 4u);
+    L.ref_bytes = pad16(r0.ref_len);
+    L.ins_bytes = pad16(r1.ins_begin - r0.ins_begin);
+    L.seq_bytes = pad16(static_cast<uint32_t>(r1.seq_off - r0.seq_off));
+    L.qual_bytes = pad16(static_cast<uint32_t>(r1.qual_off - r0.qual_off));
+    uint32_t o = 16; // mbarrier
+    L.tab = o;
+    o += K1_TAB_BYTES;
+    L.alns = o;
+    o += (L.n_alns + 1) * 16u;
+    L.segs = o;
+    o += L.seg_bytes;
+    L.ref = o;
+    o += L.ref_bytes;
+    L.ins = o;
+    o += L.ins_bytes;
+    L.seq = o;
+    o += L.seq_bytes;
+    L.qual = o;
+    o += L.qual_bytes;
+    L.rlen = o;
+    o += pad16(L.n_reads * 2u);
+    L.boff = o;
+    o += pad16((L.n_reads + 1) * 4u);
+    L.soff = o;
+    o += pad16((L.n_reads + 1) * 4u);
+    L.ent = o;
+    o += L.qual_bytes * 2u;
+    L.total = o;
+    return L;
+}
+
+// reference base (ASCII) -> one-hot nibble; everything that is not ACGT (N, '=', IUPAC) -> 0, which ANDs to "mismatch" with every
+// read nibble.  (get_bam_seq_code maps such characters to ANY=15; a read nibble of 15 never reaches the compare, and 15 equals no
+// other read nibble, so "never matches" is the same relation.)
+__device__ __forceinline__ uint8_t onehot_of_char(uint8_t c)
+{
+    return c == 'A' ? 1 : c == 'C' ? 2 : c == 'G' ? 4 : c == 'T' ? 8 : 0;
+}
+
+__global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* __restrict__ regions, const uint16_t* __restrict__ read_len,
+                                                              const uint8_t* __restrict__ seq4, const uint8_t* __restrict__ qual,
+                                                              const char* __restrict__ ref, const sx_aln* __restrict__ alns,
+                                                              const sx_aln_seg* __restrict__ segs, const char* __restrict__ ins,
+                                                              const sx_tables* __restrict__ tables, uint32_t region_begin, double* __restrict__ lnp_out,
+                                                              int* __restrict__ status, uint32_t smem_bytes)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t ri = region_begin + blockIdx.x;
+    const sx_region r0 = regions[ri];
+    const sx_region r1 = regions[ri + 1];
+    const k1_layout L = k1_make_layout(r0, r1);
+    if (L.n_alns == 0) return;
+    if (L.total > smem_bytes)
+    {
+        if (threadIdx.x == 0) atomicOr(status, 2);
+        return;
+    }
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    const double* tab = reinterpret_cast<const double*>(smem + L.tab);
+    const uint4* alns_s = reinterpret_cast<const uint4*>(smem + L.alns);
+    const uint32_t* segs_s = reinterpret_cast<const uint32_t*>(smem + L.segs);
+    uint8_t* ref_s = smem + L.ref;
+    uint8_t* ins_s = smem + L.ins;
+    const uint8_t* seq_s = smem + L.seq;
+    const uint8_t* qual_s = smem + L.qual;
+    uint16_t* rlen_s = reinterpret_cast<uint16_t*>(smem + L.rlen);
+    uint32_t* boff_s = reinterpret_cast<uint32_t*>(smem + L.boff);
+    uint32_t* soff_s = reinterpret_cast<uint32_t*>(smem + L.soff);
+    uint16_t* ent_s = reinterpret_cast<uint16_t*>(smem + L.ent);
+
+    if (threadIdx.x == 0)
+    {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t tx = K1_TAB_BYTES + (L.n_alns + 1) * 16u + L.seg_bytes + L.ref_bytes + L.ins_bytes + L.seq_bytes + L.qual_bytes;
+        mbar_expect_tx(bar, tx);
+        tma_bulk_g2s(smem + L.tab, tables->k1_tab, K1_TAB_BYTES, bar);
+        tma_bulk_g2s(smem + L.alns, alns + r0.aln_begin, (L.n_alns + 1) * 16u, bar);
+        if (L.seg_bytes) tma_bulk_g2s(smem + L.segs, segs + r0.seg_begin, L.seg_bytes, bar);
+        if (L.ref_bytes) tma_bulk_g2s(smem + L.ref, ref + r0.ref_off, L.ref_bytes, bar);
+        if (L.ins_bytes) tma_bulk_g2s(smem + L.ins, ins + r0.ins_begin, L.ins_bytes, bar);
+        if (L.seq_bytes) tma_bulk_g2s(smem + L.seq, seq4 + r0.seq_off, L.seq_bytes, bar);
+        if (L.qual_bytes) tma_bulk_g2s(smem + L.qual, qual + r0.qual_off, L.qual_bytes, bar);
+    }
+    // read lengths: tiny, plain coalesced loads (their offset has no 16-byte alignment guarantee)
+    for (uint32_t r = threadIdx.x; r < L.n_reads; r += K1_THREADS) rlen_s[r] = read_len[r0.read_begin + r];
+    __syncthreads(); // rlen visible, mbarrier initialised
+    // per-read base / packed-byte offsets: warp 0, shuffle scan
+    if (threadIdx.x < 32)
+    {
+        uint32_t carry_b = 0, carry_s = 0;
+        for (uint32_t base = 0; base < L.n_reads; base += 32)
+        {
+            const uint32_t r = base + threadIdx.x;
+            const uint32_t len = r < L.n_reads ? rlen_s[r] : 0;
+            uint32_t xb = len, xs = (len + 1) >> 1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const uint32_t yb = __shfl_up_sync(0xffffffffu, xb, d);
+                const uint32_t ys = __shfl_up_sync(0xffffffffu, xs, d);
+                if (threadIdx.x >= d)
+                {
+                    xb += yb;
+                    xs += ys;
+                }
+            }
+            if (r < L.n_reads)
+            {
+                boff_s[r] = carry_b + xb - len;
+                soff_s[r] = carry_s + xs - ((len + 1) >> 1);
+            }
+            carry_b += __shfl_sync(0xffffffffu, xb, 31);
+            carry_s += __shfl_sync(0xffffffffu, xs, 31);
+        }
+        if (threadIdx.x == 0)
+        {
+            boff_s[L.n_reads] = carry_b;
+            soff_s[L.n_reads] = carry_s;
+        }
+    }
+    mbar_wait(bar, 0);
+    __syncthreads();
+    if (boff_s[L.n_reads] > L.qual_bytes || soff_s[L.n_reads] > L.seq_bytes)
+    {
+        if (threadIdx.x == 0) atomicOr(status, 2);
+        return;
+    }
+    // expand each read once: entry = (table row << 4) | one-hot base
+    {
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        bool bad_q = false;
+        for (uint32_t r = warp; r < L.n_reads; r += K1_THREADS / 32)
+        {
+            const uint32_t len = rlen_s[r];
+            const uint8_t* sq = seq_s + soff_s[r];
+            const uint8_t* ql = qual_s + boff_s[r];
+            uint16_t* en = ent_s + boff_s[r];
+            for (uint32_t i = lane; i < len; i += 32)
+            {
+                const uint32_t code = (sq[i >> 1] >> ((~i & 1u) << 2)) & 15u; // bam_seq::get_code, high nibble first
+                uint32_t q = ql[i];
+                if (q > SX_MAX_QSCORE)
+                {
+                    if (code != 15u) bad_q = true; // the reference only looks at the quality of non-N bases (score.cpp:125-126,158-159)
+                    q = SX_MAX_QSCORE;
+                }
+                uint32_t row, nib;
+                if (code == 15u) { row = SX_K1_ROW_ZERO; nib = 0; }            // BAM_BASE::ANY: skipped (adds +0.0)
+                else if (code == 0u) { row = SX_K1_ROW_EQ + q; nib = 0; }      // BAM_BASE::REF: always "is_ref"
+                else { row = q; nib = (code == 1u || code == 2u || code == 4u || code == 8u) ? code : 0u; }
+                en[i] = static_cast<uint16_t>((row << 4) | nib);
+            }
+        }
+        if (bad_q) atomicOr(status, 1);
+        for (uint32_t i = threadIdx.x; i < L.ref_bytes; i += K1_THREADS) ref_s[i] = onehot_of_char(ref_s[i]);
+        for (uint32_t i = threadIdx.x; i < L.ins_bytes; i += K1_THREADS) ins_s[i] = onehot_of_char(ins_s[i]);
+    }
+    __syncthreads();
+
+    const double softclip = tables->k1_softclip;
+    const double noncand = tables->k1_noncand;
+    const unsigned char* tabb = reinterpret_cast<const unsigned char*>(tab);
+    const int ref_len = static_cast<int>(r0.ref_len);
+
+    for (uint32_t a = threadIdx.x; a < L.n_alns; a += K1_THREADS)
+    {
+        const uint4 h = alns_s[a];
+        const uint32_t rl = h.x - r0.read_begin;
+        if (rl >= L.n_reads)
+        {
+            atomicOr(status, 2);
+            continue;
+        }
+        const uint16_t* ent = ent_s + boff_s[rl];
+        int read_left = static_cast<int>(boff_s[rl + 1] - boff_s[rl]);
+        int refp = static_cast<int>(h.y) - r0.ref_begin;
+        const uint8_t* insp = ins_s + (h.w - r0.ins_begin);
+        uint32_t s = h.z - r0.seg_begin;
+        const uint32_t s_end = alns_s[a + 1].z - r0.seg_begin;
+        double lnp = 0.0;
+        int rem = 0;
+        bool pend = false;
+        const uint8_t* cp = ref_s;
+        for (;;)
+        {
+            bool done = false;
+            while (rem == 0)
+            {
+                if (pend)
+                {
+                    lnp = __dadd_rn(lnp, noncand);
+                    pend = false;
+                }
+                if (s == s_end)
+                {
+                    done = true;
+                    break;
+                }
+                const uint32_t seg = segs_s[s++];
+                const int len = static_cast<int>(seg & 0xffffu);
+                const uint32_t kind = (seg >> 16) & 0xffu;
+                pend = (seg >> 24) & SX_SEGF_NONCANDIDATE;
+                if (kind == SX_SEG_MATCH || kind == SX_SEG_INSERT || kind == SX_SEG_SOFTCLIP)
+                {
+                    if (len > read_left)
+                    {
+                        atomicOr(status, 8);
+                        done = true;
+                        break;
+                    }
+                    read_left -= len;
+                }
+                if (kind == SX_SEG_MATCH)
+                {
+                    if (refp >= 0 && refp + len <= ref_len)
+                    {
+                        cp = ref_s + refp;
+                        rem = len;
+                    }
+                    else
+                    {
+                        // part of the segment lies outside the held reference window: those positions read as 'N'
+                        for (int i = 0; i < len; ++i)
+                        {
+                            const uint32_t e = ent[i];
+                            const int p = refp + i;
+                            const uint32_t c = (p >= 0 && p < ref_len) ? ref_s[p] : 0u;
+                            const uint32_t off = (e & 0xfff0u) + ((e & c) ? 8u : 0u);
+                            lnp = __dadd_rn(lnp, *reinterpret_cast<const double*>(tabb + off));
+                        }
+                        ent += len;
+                    }
+                    refp += len;
+                }
+                else if (kind == SX_SEG_INSERT)
+                {
+                    cp = insp;
+                    insp += len;
+                    rem = len;
+                }
+                else if (kind == SX_SEG_REFSKIP)
+                {
+                    refp += len;
+                }
+                else if (kind == SX_SEG_SOFTCLIP)
+                {
+                    lnp = __dadd_rn(lnp, __dmul_rn(static_cast<double>(static_cast<unsigned>(len)), softclip));
+                    ent += len;
+                }
+                else if (kind != SX_SEG_HARDCLIP)
+                {
+                    atomicOr(status, 4);
+                }
+            }
+            if (done) break;
+            if (rem >= 8)
+            {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                {
+                    const uint32_t e = ent[k];
+                    const uint32_t c = cp[k];
+                    const uint32_t off = (e & 0xfff0u) + ((e & c) ? 8u : 0u);
+                    lnp = __dadd_rn(lnp, *reinterpret_cast<const double*>(tabb + off));
+                }
+                ent += 8;
+                cp += 8;
+                rem -= 8;
+            }
+            else
+            {
+                const int n = rem;
+#pragma unroll
+                for (int k = 0; k < 7; ++k)
+                {
+                    if (k < n)
+                    {
+                        const uint32_t e = ent[k];
+                        const uint32_t c = cp[k];
+                        const uint32_t off = (e & 0xfff0u) + ((e & c) ? 8u : 0u);
+                        lnp = __dadd_rn(lnp, *reinterpret_cast<const double*>(tabb + off));
+                    }
+                }
+                ent += n;
+                cp += n;
+                rem = 0;
+            }
+        }
+        lnp_out[r0.aln_begin + a] = lnp;
+    }
+}
+
+// max shared-memory footprint over regions [begin, end) (device-resident batches: the region table is not on the host)
+__global__ void k1_smem_need_kernel(const sx_region* __restrict__ regions, uint32_t begin, uint32_t end, uint32_t* __restrict__ out)
+{
+    uint32_t m = 0;
+    for (uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x)
+    {
+        const k1_layout L = k1_make_layout(regions[i], regions[i + 1]);
+        m = max(m, L.total);
+    }
+    for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// per-read max over its alignments (first max in batch order), one thread per read; alignments are sorted by read
+__global__ void k1_read_max_kernel(const sx_aln* __restrict__ alns, uint32_t n_alns, uint32_t n_reads, const double* __restrict__ lnp,
+                                   double* __restrict__ max_lnp, uint32_t* __restrict__ max_aln)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    // lower bound of r in alns[].read
+    uint32_t lo = 0, hi = n_alns;
+    while (lo < hi)
+    {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (alns[mid].read < r) lo = mid + 1;
+        else hi = mid;
+    }
+    double best = 0;
+    uint32_t besta = 0xffffffffu;
+    for (uint32_t a = lo; a < n_alns && alns[a].read == r; ++a)
+    {
+        const double v = lnp[a];
+        if (besta == 0xffffffffu || v > best)
+        {
+            best = v;
+            besta = a;
+        }
+    }
+    max_lnp[r] = best;
+    max_aln[r] = besta;
+}
+
+int k1_smem_need_dev(sx_ctx* ctx, const sx_region* regions_dev, uint32_t begin, uint32_t end, uint32_t* need)
+{
+    uint32_t* d = nullptr;
+    int rc = sx_ensure(ctx, 20, sizeof(uint32_t), reinterpret_cast<void**>(&d));
+    if (rc) return rc;
+    SX_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(uint32_t), ctx->s_compute));
+    const uint32_t n = end - begin;
+    const int blocks = static_cast<int>(std::min<uint32_t>((n + 255) / 256, 1184));
+    k1_smem_need_kernel<<<blocks, 256, 0, ctx->s_compute>>>(regions_dev, begin, end, d);
+    SX_CUDA(ctx, cudaMemcpyAsync(need, d, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_compute));
+    SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    return SX_OK;
+}
+} // namespace
+
+size_t sx_k1_region_smem(const sx_region* r0, const sx_region* r1, const sx_aln*)
+{
+    return k1_make_layout(*r0, *r1).total;
+}
+
+int sx_k1_launch(sx_ctx* ctx, const sx_align_batch* d, uint32_t region_begin, uint32_t region_end, double* lnp_dev, size_t smem_bytes, cudaStream_t st)
+{
+    if (region_end <= region_begin) return SX_OK;
+    if (smem_bytes > ctx->smem_optin)
+        return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments: a region needs %zu bytes of shared memory (limit %zu); split it into smaller regions", smem_bytes,
+                       ctx->smem_optin);
+    static thread_local size_t attr_set = 0;
+    if (smem_bytes > 48 * 1024 && smem_bytes > attr_set)
+    {
+        SX_CUDA(ctx, cudaFuncSetAttribute(k1_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+        attr_set = ctx->smem_optin;
+    }
+    k1_score_kernel<<<region_end - region_begin, K1_THREADS, smem_bytes, st>>>(d->regions, d->read_len, d->seq4, d->qual, d->ref, d->alns, d->segs, d->ins,
+                                                                              ctx->d_tables, region_begin, lnp_dev, ctx->d_status, static_cast<uint32_t>(smem_bytes));
+    SX_CUDA(ctx, cudaGetLastError());
+    return SX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// entry points
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" uint64_t sx_align_batch_cells(const sx_align_batch* b)
+{
+    uint64_t n = 0;
+    for (uint32_t i = 0; i < b->n_segs; ++i)
+        if (b->segs[i].kind == SX_SEG_MATCH || b->segs[i].kind == SX_SEG_INSERT) n += b->segs[i].len;
+    return n;
+}
+
+static int validate_host_batch(sx_ctx* ctx, const sx_align_batch* b, size_t* max_smem)
+{
+    if (!b || !b->regions || !b->alns || (b->n_reads && !b->read_len)) return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments: NULL batch array");
+    size_t m = 0;
+    for (uint32_t i = 0; i < b->n_regions; ++i)
+    {
+        const sx_region& r = b->regions[i];
+        const sx_region& n = b->regions[i + 1];
+        if ((r.seq_off | r.qual_off | r.ref_off | r.ins_begin) & 15u || (r.seg_begin & 3u))
+            return sx_fail(ctx, SX_ERR_ALIGNMENT, "sx_score_alignments: region %u violates the 16-byte staging rule (seq_off %llu qual_off %llu ref_off %llu ins_begin %u seg_begin %u)", i,
+                           (unsigned long long)r.seq_off, (unsigned long long)r.qual_off, (unsigned long long)r.ref_off, r.ins_begin, r.seg_begin);
+        if (n.read_begin < r.read_begin || n.aln_begin < r.aln_begin || n.seg_begin < r.seg_begin || n.ins_begin < r.ins_begin || n.seq_off < r.seq_off ||
+            n.qual_off < r.qual_off)
+            return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments: region table is not monotone at region %u", i);
+        m = std::max(m, sx_k1_region_smem(&r, &n, b->alns));
+    }
+    if (b->n_regions)
+    {
+        const sx_region& e = b->regions[b->n_regions];
+        if (e.read_begin != b->n_reads || e.aln_begin != b->n_alns) return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments: sentinel region does not close the batch");
+    }
+    *max_smem = m;
+    return SX_OK;
+}
+
+extern "C" int sx_score_alignments_dev(sx_ctx* ctx, const sx_align_batch* d, double* lnp_out_dev)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    if (!d || !lnp_out_dev) return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments_dev: NULL argument");
+    if (d->n_regions == 0) return SX_OK;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    sx_kernel_timer t(ctx);
+    uint32_t need = 0;
+    int rc = k1_smem_need_dev(ctx, d->regions, 0, d->n_regions, &need);
+    if (rc) return rc;
+    rc = sx_k1_launch(ctx, d, 0, d->n_regions, lnp_out_dev, need, ctx->s_compute);
+    if (rc) return rc;
+    t.stop(2);
+    rc = t.finish();
+    if (rc) return rc;
+    return sx_check_status(ctx, "sx_score_alignments");
+}
+
+extern "C" int sx_read_max_dev(sx_ctx* ctx, const sx_align_batch* d, const double* lnp_dev, double* max_lnp_dev, uint32_t* max_aln_dev)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    if (!d || !lnp_dev || !max_lnp_dev || !max_aln_dev) return sx_fail(ctx, SX_ERR_ARG, "sx_read_max_dev: NULL argument");
+    if (d->n_reads == 0) return SX_OK;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    sx_kernel_timer t(ctx);
+    k1_read_max_kernel<<<(d->n_reads + 255) / 256, 256, 0, ctx->s_compute>>>(d->alns, d->n_alns, d->n_reads, lnp_dev, max_lnp_dev, max_aln_dev);
+    SX_CUDA(ctx, cudaGetLastError());
+    t.stop(1);
+    return t.finish();
+}
+
+// Host-buffer entry: the batch is cut into chunks of whole regions; chunk k+1's H2D copies overlap chunk k's kernel and chunk
+// k-1's D2H (three streams, events).  Device pools keep the HOST offsets (a chunk is copied to the same byte offsets it has on
+// the host), so nothing is re-based.
+extern "C" int sx_score_alignments(sx_ctx* ctx, const sx_align_batch* b, double* lnp_out)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    if (!b || !lnp_out) return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments: NULL argument");
+    if (b->n_regions == 0 || b->n_alns == 0) return SX_OK;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t smem = 0;
+    int rc = validate_host_batch(ctx, b, &smem);
+    if (rc) return rc;
+
+    sx_align_batch d = *b;
+    void* p = nullptr;
+    const size_t reg_bytes = (size_t)(b->n_regions + 1) * sizeof(sx_region);
+    const size_t aln_bytes = (size_t)(b->n_alns + 1) * sizeof(sx_aln);
+    const size_t seg_bytes = (size_t)b->n_segs * sizeof(sx_aln_seg) + SX_POOL_SLACK;
+#define SX_POOL(slot, field, type, bytes)            \
+    if ((rc = sx_ensure(ctx, slot, (bytes), &p))) return rc; \
+    d.field = static_cast<type>(p);
+    SX_POOL(0, regions, const sx_region*, reg_bytes)
+    SX_POOL(1, read_len, const uint16_t*, (size_t)b->n_reads * 2 + 16)
+    SX_POOL(2, seq4, const uint8_t*, b->seq4_bytes + SX_POOL_SLACK)
+    SX_POOL(3, qual, const uint8_t*, b->qual_bytes + SX_POOL_SLACK)
+    SX_POOL(4, ref, const char*, b->ref_bytes + SX_POOL_SLACK)
+    SX_POOL(5, alns, const sx_aln*, aln_bytes)
+    SX_POOL(6, segs, const sx_aln_seg*, seg_bytes)
+    SX_POOL(7, ins, const char*, b->ins_bytes + SX_POOL_SLACK)
+#undef SX_POOL
+    double* d_out = nullptr;
+    if ((rc = sx_ensure(ctx, 8, (size_t)b->n_alns * sizeof(double), reinterpret_cast<void**>(&d_out)))) return rc;
+
+    int chunks = ctx->params.pipeline_chunks;
+    if (chunks <= 0) chunks = b->n_regions >= 4096 ? 8 : 1;
+    chunks = std::max(1, std::min<int>(chunks, (int)b->n_regions));
+    while (ctx->ev_pool.size() < (size_t)chunks * 2)
+    {
+        cudaEvent_t ev;
+        SX_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->ev_pool.push_back(ev);
+    }
+    cudaEvent_t t0, t1;
+    t0 = ctx->ev_a;
+    t1 = ctx->ev_b;
+    SX_CUDA(ctx, cudaEventRecord(t0, ctx->s_h2d));
+    // the small tables go first, whole
+    SX_CUDA(ctx, cudaMemcpyAsync(const_cast<sx_region*>(d.regions), b->regions, reg_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+    SX_CUDA(ctx, cudaMemcpyAsync(const_cast<uint16_t*>(d.read_len), b->read_len, (size_t)b->n_reads * 2, cudaMemcpyHostToDevice, ctx->s_h2d));
+    SX_CUDA(ctx, cudaMemcpyAsync(const_cast<char*>(d.ref), b->ref, b->ref_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+    for (int c = 0; c < chunks; ++c)
+    {
+        const uint32_t ra = (uint32_t)((uint64_t)b->n_regions * c / chunks);
+        const uint32_t rb = (uint32_t)((uint64_t)b->n_regions * (c + 1) / chunks);
+        const sx_region& A = b->regions[ra];
+        const sx_region& B = b->regions[rb];
+        auto cp = [&](const void* hbase, const void* dbase, size_t lo, size_t hi) -> cudaError_t {
+            if (hi <= lo) return cudaSuccess;
+            return cudaMemcpyAsync((char*)const_cast<void*>(dbase) + lo, (const char*)hbase + lo, hi - lo, cudaMemcpyHostToDevice, ctx->s_h2d);
+        };
+        SX_CUDA(ctx, cp(b->seq4, d.seq4, A.seq_off, B.seq_off));
+        SX_CUDA(ctx, cp(b->qual, d.qual, A.qual_off, B.qual_off));
+        SX_CUDA(ctx, cp(b->alns, d.alns, (size_t)A.aln_begin * sizeof(sx_aln), (size_t)(B.aln_begin + 1) * sizeof(sx_aln)));
+        SX_CUDA(ctx, cp(b->segs, d.segs, (size_t)A.seg_begin * sizeof(sx_aln_seg), (size_t)B.seg_begin * sizeof(sx_aln_seg)));
+        SX_CUDA(ctx, cp(b->ins, d.ins, A.ins_begin, B.ins_begin));
+        SX_CUDA(ctx, cudaEventRecord(ctx->ev_pool[2 * c], ctx->s_h2d));
+        SX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_compute, ctx->ev_pool[2 * c], 0));
+        if ((rc = sx_k1_launch(ctx, &d, ra, rb, d_out, smem, ctx->s_compute))) return rc;
+        SX_CUDA(ctx, cudaEventRecord(ctx->ev_pool[2 * c + 1], ctx->s_compute));
+        SX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_pool[2 * c + 1], 0));
+        if (B.aln_begin > A.aln_begin)
+            SX_CUDA(ctx, cudaMemcpyAsync(lnp_out + A.aln_begin, d_out + A.aln_begin, (size_t)(B.aln_begin - A.aln_begin) * sizeof(double), cudaMemcpyDeviceToHost,
+                                         ctx->s_d2h));
+    }
+    SX_CUDA(ctx, cudaEventRecord(t1, ctx->s_d2h));
+    SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_d2h));
+    SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t0, t1);
+    ctx->timing.kernel_ms = ms; // whole pipelined call (copies + kernels), see sx_timing
+    ctx->timing.launches = chunks;
+    ctx->total_launches += chunks;
+    return sx_check_status(ctx, "sx_score_alignments");
+}

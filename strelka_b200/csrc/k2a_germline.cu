@@ -1,0 +1,521 @@
+// k2a_germline.cu -- K2a site_gl_germline: per-site diploid genotype likelihoods, PLs and posteriors from a pileup.
+//
+// One warp per site.  Fuses, in the reference's order (paths relative to /root/reference/src/c++/lib/):
+//   CleanPileupFilter              starling_common/PileupCleaner.cpp:30-64
+//   adjust_joint_eprob             blt_common/adjust_joint_eprob.cpp:60-243    (dependent error probabilities)
+//   get_diploid_gt_lhood x3        blt_common/position_snp_call_pprob_digt.cpp:326-385 (all / fwd-specific / rev-specific)
+//   position_snp_call_pprob_digt   :471-539  (PLs, calculate_result_set for genomic and polymorphic priors, strand bias)
+//
+// Parity contract.  The likelihoods are float sums taken in pileup order; the integer PLs are rounded from them, so every
+// float operation is reproduced in the reference's order and rounding:
+//   * the 10 genotypes x {all, fwd, rev} accumulate in 30 lanes, each lane adding its terms call by call;
+//   * std::log(float) / std::pow(float,float) are the glibc-FMA-variant mirrors of sx_libm_mirror.h;
+//   * std::sort's permutation of each (strand x base) group is reproduced by sx_stdsort_mirror.h (one lane per group);
+//   * q-only terms come from host tables (sx_context.cu).
+// The posterior normalisation runs in double with CUDA's exp/log10 (<= 1 ulp from glibc's): ref_pprob is a tolerance field, and
+// an integer Q derived from it can only differ if the probability sits within ~1e-15 (relative) of a rounding boundary.
+#include "sx_device_util.cuh"
+#include "sx_internal.h"
+#include "sx_libm_mirror.h"
+#include "sx_stdsort_mirror.h"
+
+#include <algorithm>
+
+namespace
+{
+constexpr int K2_WARPS = 4;
+constexpr int K2_CAP_SMEM = 256;   // cleaned calls per site handled in shared memory
+constexpr int K2_CAP_BIG = 8192;   // cleaned calls per site handled through the global scratch
+constexpr unsigned FULL = 0xffffffffu;
+
+struct germ_tables // the slice of sx_tables this kernel reads, staged in shared memory
+{
+    float eprob[SX_MAX_QSCORE + 1], val1[SX_MAX_QSCORE + 1], val2[SX_MAX_QSCORE + 1], weight[SX_MAX_QSCORE + 1], depmin[SX_MAX_QSCORE + 1];
+    float lnprior[2][5][2][10];
+};
+
+struct QKey // sort_icall_by_eprob's view: quality of call index i
+{
+    const uint16_t* calls;
+    __device__ __forceinline__ uint32_t operator[](uint32_t i) const { return calls[i] & 63u; }
+};
+
+__device__ __forceinline__ float dependent_eprob(float eprob, float vexp) // get_dependent_eprob, adjust_joint_eprob.cpp:60-70
+{
+    const float val = sx_powf(eprob, vexp);
+    const float frac = f_div(f_sub(1.0f, val), f_sub(1.0f, eprob));
+    const float x = f_add(f_mul(frac, val), f_mul(f_sub(1.0f, frac), 0.75f));
+    return (eprob < x) ? x : eprob; // std::max(eprob, x)
+}
+
+// expect2(obs, gt) for obs 0..3 packed 2 bits each  (blt_util/digt.hh:119-140)
+__device__ __forceinline__ uint32_t expect2_pack(uint32_t gt)
+{
+    if (gt < 4) return 2u << (2 * gt);
+    const uint32_t a = (gt < 7) ? 0u : (gt < 9) ? 1u : 2u;
+    const uint32_t b = (gt < 7) ? gt - 3u : (gt < 9) ? gt - 5u : 3u;
+    return (1u << (2 * a)) | (1u << (2 * b));
+}
+
+struct rs_out
+{
+    double ref_pprob;
+    uint32_t max_gt;
+    int snp_qphred, max_gt_qphred;
+};
+
+// calculate_result_set (position_snp_call_pprob_digt.cpp:412-433) + normalizeLogDistro/prob_comp (blt_util/prob_util.hh:179-237).
+// lanes 0..9 hold lhood[gt]; all lanes return the same result.
+__device__ __forceinline__ rs_out result_set(float lh, const float* lnprior, uint32_t ref_gt, uint32_t lane)
+{
+    const double pp = (lane < 10) ? static_cast<double>(f_add(lh, lnprior[lane])) : 0.0;
+    // first maximum, strict '>' scan
+    double mx = shfl_d(pp, 0);
+    uint32_t max_gt = 0;
+#pragma unroll
+    for (int gt = 1; gt < 10; ++gt)
+    {
+        const double v = shfl_d(pp, gt);
+        if (v > mx)
+        {
+            mx = v;
+            max_gt = gt;
+        }
+    }
+    const double e = (lane < 10) ? exp(d_sub(pp, mx)) : 0.0;
+    double sum = 0.0;
+#pragma unroll
+    for (int gt = 0; gt < 10; ++gt) sum = d_add(sum, shfl_d(e, gt));
+    sum = d_div(1.0, sum);
+    const double p = d_mul(e, sum);
+    double comp = 0.0;
+#pragma unroll
+    for (int gt = 0; gt < 10; ++gt)
+    {
+        const double v = shfl_d(p, gt);
+        if (gt != (int)max_gt) comp = d_add(comp, v);
+    }
+    rs_out o;
+    o.max_gt = max_gt;
+    o.ref_pprob = shfl_d(p, ref_gt);
+    o.snp_qphred = error_prob_to_qphred_d(o.ref_pprob);
+    o.max_gt_qphred = error_prob_to_qphred_d(comp);
+    return o;
+}
+
+__global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline_kernel(const uint32_t* __restrict__ site_off, const uint16_t* __restrict__ calls_g,
+                                                                     const char* __restrict__ ref_base, const uint8_t* __restrict__ ploidy,
+                                                                     uint32_t n_sites, int is_always_test, const sx_tables* __restrict__ tables,
+                                                                     sx_digt_result* __restrict__ out, uint32_t* __restrict__ de_off,
+                                                                     float* __restrict__ de_out, unsigned char* __restrict__ scratch, int* __restrict__ status)
+{
+    __shared__ germ_tables T;
+    __shared__ uint16_t s_calls[K2_WARPS][K2_CAP_SMEM];
+    __shared__ float s_val[K2_WARPS][K2_CAP_SMEM];
+    __shared__ uint16_t s_ord[K2_WARPS][K2_CAP_SMEM];
+    __shared__ uint32_t s_gstart[K2_WARPS][9];
+    for (int i = threadIdx.x; i <= SX_MAX_QSCORE; i += blockDim.x)
+    {
+        T.eprob[i] = tables->g_eprob[i];
+        T.val1[i] = tables->g_val1[i];
+        T.val2[i] = tables->g_val2[i];
+        T.weight[i] = tables->g_weight[i];
+        T.depmin[i] = tables->g_depmin[i];
+    }
+    for (int i = threadIdx.x; i < 200; i += blockDim.x) (&T.lnprior[0][0][0][0])[i] = (&tables->g_lnprior[0][0][0][0])[i];
+    __syncthreads();
+    const float log_one_third = tables->g_log_one_third;
+    const float ln10f = tables->g_ln10f;
+    const float min_vexp = tables->g_min_vexp;
+    const double ssd_no = tables->g_ssd_no_mismatch, ssd_one = tables->g_ssd_one_mismatch;
+    const bool is_dep = tables->g_is_dependent_eprob != 0;
+    const bool is_limit_vexp = tables->g_is_min_vexp != 0;
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t gwarp = blockIdx.x * K2_WARPS + warp, nwarps = gridDim.x * K2_WARPS;
+
+    for (uint32_t site = gwarp; site < n_sites; site += nwarps)
+    {
+        const uint32_t c0 = site_off[site], c1 = site_off[site + 1];
+        const uint32_t n_raw = c1 - c0;
+        uint16_t* w_calls = s_calls[warp];
+        float* w_val = s_val[warp];
+        uint16_t* w_ord = s_ord[warp];
+        uint32_t cap = K2_CAP_SMEM;
+        if (n_raw > K2_CAP_SMEM)
+        {
+            if (scratch == nullptr || n_raw > K2_CAP_BIG)
+            {
+                if (lane == 0) atomicOr(status, 16);
+                continue;
+            }
+            unsigned char* base = scratch + (size_t)gwarp * (K2_CAP_BIG * 8);
+            w_calls = reinterpret_cast<uint16_t*>(base);
+            w_ord = reinterpret_cast<uint16_t*>(base + K2_CAP_BIG * 2);
+            w_val = reinterpret_cast<float*>(base + K2_CAP_BIG * 4);
+            cap = K2_CAP_BIG;
+        }
+        const char rb = ref_base[site];
+        const uint32_t ref_gt = rb == 'A' ? 0u : rb == 'C' ? 1u : rb == 'G' ? 2u : rb == 'T' ? 3u : 4u;
+
+        // ---- CleanPileupFilter: keep calls with is_call_filter == 0, order preserved
+        uint32_t n = 0;
+        bool nonref = false;
+        for (uint32_t b = 0; b < n_raw; b += 32)
+        {
+            const uint32_t i = b + lane;
+            const uint32_t c = i < n_raw ? calls_g[c0 + i] : 0x1000u;
+            const bool keep = !((c >> 12) & 1u);
+            const uint32_t m = __ballot_sync(FULL, keep);
+            if (keep)
+            {
+                w_calls[n + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(c);
+                if (((c >> 6) & 15u) != ref_gt) nonref = true;
+            }
+            n += __popc(m);
+        }
+        nonref = __any_sync(FULL, nonref);
+        __syncwarp();
+
+        // ---- dependent error probabilities
+        for (uint32_t i = lane; i < n; i += 32) w_val[i] = T.eprob[w_calls[i] & 63u];
+        if (is_dep)
+        {
+            // group = is_fwd + 2*base_id, calls with q < 3 excluded; stable partition into w_ord
+            uint32_t start = 0;
+            for (uint32_t g = 0; g < 8; ++g)
+            {
+                if (lane == 0) s_gstart[warp][g] = start;
+                for (uint32_t b = 0; b < n; b += 32)
+                {
+                    const uint32_t i = b + lane;
+                    bool in = false;
+                    if (i < n)
+                    {
+                        const uint32_t c = w_calls[i];
+                        in = ((c & 63u) >= 3u) && ((((c >> 10) & 1u) + 2u * ((c >> 6) & 15u)) == g);
+                    }
+                    const uint32_t m = __ballot_sync(FULL, in);
+                    if (in) w_ord[start + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(i);
+                    start += __popc(m);
+                }
+            }
+            if (lane == 0) s_gstart[warp][8] = start;
+            __syncwarp();
+            if (lane < 8)
+            {
+                const uint32_t g0 = s_gstart[warp][lane], sz = s_gstart[warp][lane + 1] - g0;
+                if (sz)
+                {
+                    uint16_t* ic = w_ord + g0;
+                    float num = 0.f, den = 0.f; // adjust_icalls_eprob :112-127, in pileup order (before the sort)
+                    for (uint32_t k = 0; k < sz; ++k)
+                    {
+                        const uint32_t c = w_calls[ic[k]];
+                        const float weight = T.weight[c & 63u];
+                        den = f_add(den, weight);
+                        if ((c >> 11) & 1u) num = f_add(num, weight);
+                    }
+                    float mismatch_frac = 0.f;
+                    if (static_cast<double>(den) > 0.) mismatch_frac = f_div(num, den);
+                    // (1-mismatch_frac)*opt.bsnp_ssd_no_mismatch + mismatch_frac*opt.bsnp_ssd_one_mismatch : float*double, summed in double, narrowed
+                    const float vexp_frac = static_cast<float>(d_add(d_mul(static_cast<double>(f_sub(1.0f, mismatch_frac)), ssd_no), d_mul(static_cast<double>(mismatch_frac), ssd_one)));
+                    const QKey key{w_calls};
+                    sx_stdsort_desc(ic, sz, key);
+                    float vexp = 1.0f;
+                    bool is_min_vexp = false;
+                    const float step = f_sub(1.0f, vexp_frac);
+                    for (uint32_t k = 0; k < sz; ++k)
+                    {
+                        const uint32_t idx = ic[k];
+                        const uint32_t q = w_calls[idx] & 63u;
+                        if (!is_min_vexp)
+                        {
+                            w_val[idx] = dependent_eprob(T.eprob[q], vexp);
+                            const float next_vexp = f_mul(vexp, step);
+                            if (is_limit_vexp)
+                            {
+                                is_min_vexp = (next_vexp <= min_vexp);
+                                vexp = (min_vexp < next_vexp) ? next_vexp : min_vexp; // std::max(min_vexp, next_vexp)
+                            }
+                            else
+                            {
+                                vexp = next_vexp;
+                            }
+                        }
+                        else
+                        {
+                            w_val[idx] = T.depmin[q]; // dependent_prob_cache: get_dependent_eprob(q, min_vexp)
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (de_out != nullptr)
+        {
+            const uint32_t o = de_off[site];
+            for (uint32_t i = lane; i < n; i += 32) de_out[o + i] = w_val[i];
+            __syncwarp();
+            if (out == nullptr) continue;
+        }
+
+        sx_digt_result* res = out + site;
+        // diploid_genotype::reset() values for the early returns
+        const bool computed = (ref_gt < 4u) && (is_always_test || nonref);
+        if (!computed)
+        {
+            uint32_t* w = reinterpret_cast<uint32_t*>(res);
+            for (uint32_t i = lane; i < sizeof(sx_digt_result) / 4; i += 32) w[i] = 0u;
+            __syncwarp();
+            if (lane == 0)
+            {
+                res->ref_gt = (ref_gt < 4u) ? ref_gt : 0u;
+                res->n_used_calls = n;
+            }
+            continue;
+        }
+
+        // ---- val[0] = std::log(eprob) + log_one_third for every call (position_snp_call_pprob_digt.cpp:352)
+        for (uint32_t i = lane; i < n; i += 32) w_val[i] = f_add(sx_logf(w_val[i]), log_one_third);
+        __syncwarp();
+
+        // ---- get_diploid_gt_lhood: lanes 0-9 all calls, 10-19 fwd-strand-specific, 20-29 rev-strand-specific
+        const uint32_t pass = lane / 10u, gt = lane - pass * 10u;
+        const uint32_t e2_gt = expect2_pack(gt < 10u ? gt : 0u), e2_ref = expect2_pack(ref_gt);
+        float lh = 0.f;
+        if (lane < 30)
+        {
+            for (uint32_t i = 0; i < n; ++i)
+            {
+                const uint32_t c = w_calls[i];
+                const uint32_t q = c & 63u, obs = (c >> 6) & 3u, fwd = (c >> 10) & 1u;
+                const bool force_ref = (pass != 0u) && ((pass == 1u) != (fwd != 0u));
+                const uint32_t k = ((force_ref ? e2_ref : e2_gt) >> (2u * obs)) & 3u;
+                const float v = (k == 0u) ? w_val[i] : (k == 1u) ? T.val1[q] : T.val2[q];
+                lh = f_add(lh, v);
+            }
+        }
+
+        // ---- phredLoghood
+        const bool haploid = ploidy != nullptr && ploidy[site] == 1;
+        const uint32_t gtcount = haploid ? 4u : 10u;
+        float lmax = __shfl_sync(FULL, lh, 0);
+        for (uint32_t g = 1; g < gtcount; ++g)
+        {
+            const float v = __shfl_sync(FULL, lh, g);
+            if (v > lmax) lmax = v;
+        }
+        uint32_t pl = 0;
+        if (lane < gtcount) pl = static_cast<uint32_t>(ln_error_prob_to_qphred_f(f_sub(lh, lmax), ln10f));
+
+        // ---- posteriors
+        const float* pri = T.lnprior[haploid ? 1 : 0][ref_gt][0];
+        const rs_out genome = result_set(lh, pri, ref_gt, lane);
+        const rs_out poly = result_set(lh, pri + 10, ref_gt, lane);
+
+        // ---- strand bias (is_snp: genome.snp_qphred != 0)
+        double strand_bias = 0.0;
+        {
+            const uint32_t tgt = genome.max_gt;
+            const float lf = __shfl_sync(FULL, lh, 10 + tgt), lr = __shfl_sync(FULL, lh, 20 + tgt), l0 = __shfl_sync(FULL, lh, tgt);
+            if (genome.snp_qphred != 0) strand_bias = static_cast<double>(f_sub((lf < lr) ? lr : lf, l0)); // std::max(lf, lr) - lhood[tgt]
+        }
+
+        if (lane < 10)
+        {
+            res->lhood[lane] = lh;
+            res->phredLoghood[lane] = pl;
+        }
+        if (lane == 0)
+        {
+            res->genome.ref_pprob = genome.ref_pprob;
+            res->genome.max_gt = genome.max_gt;
+            res->genome.snp_qphred = genome.snp_qphred;
+            res->genome.max_gt_qphred = genome.max_gt_qphred;
+            res->genome.pad = 0;
+            res->poly.ref_pprob = poly.ref_pprob;
+            res->poly.max_gt = poly.max_gt;
+            res->poly.snp_qphred = poly.snp_qphred;
+            res->poly.max_gt_qphred = poly.max_gt_qphred;
+            res->poly.pad = 0;
+            res->strand_bias = strand_bias;
+            res->ref_gt = ref_gt;
+            res->is_computed = 1;
+            res->n_used_calls = n;
+            res->pad = 0;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void k2_max_site_kernel(const uint32_t* __restrict__ site_off, uint32_t n_sites, uint32_t* __restrict__ out)
+{
+    uint32_t m = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_sites; i += gridDim.x * blockDim.x) m = max(m, site_off[i + 1] - site_off[i]);
+    for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(FULL, m, d));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// cleaned-call count per site (for sx_dependent_eprob's CSR offsets)
+__global__ void k2_clean_count_kernel(const uint32_t* __restrict__ site_off, const uint16_t* __restrict__ calls, uint32_t n_sites, uint32_t* __restrict__ cnt)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sites) return;
+    uint32_t n = 0;
+    for (uint32_t i = site_off[s]; i < site_off[s + 1]; ++i) n += !((calls[i] >> 12) & 1u);
+    cnt[s] = n;
+}
+
+int germline_run(sx_ctx* ctx, const sx_pileup_batch* d, int is_always_test, sx_digt_result* out_dev, uint32_t* de_off_dev, float* de_dev, uint32_t max_site)
+{
+    unsigned char* scratch = nullptr;
+    const int grid = static_cast<int>(std::min<uint32_t>((d->n_sites + K2_WARPS - 1) / K2_WARPS, (uint32_t)ctx->sm_count * 8));
+    if (max_site > K2_CAP_BIG)
+        return sx_fail(ctx, SX_ERR_UNSUPPORTED, "sx_site_gl_germline: a site holds %u calls; the kernel handles at most %d per site", max_site, K2_CAP_BIG);
+    if (max_site > K2_CAP_SMEM)
+    {
+        int rc = sx_ensure(ctx, 19, (size_t)grid * K2_WARPS * K2_CAP_BIG * 8, reinterpret_cast<void**>(&scratch));
+        if (rc) return rc;
+    }
+    k2a_germline_kernel<<<grid, K2_WARPS * 32, 0, ctx->s_compute>>>(d->site_off, d->calls, d->ref_base, d->ploidy, d->n_sites, is_always_test, ctx->d_tables, out_dev,
+                                                                   de_off_dev, de_dev, scratch, ctx->d_status);
+    SX_CUDA(ctx, cudaGetLastError());
+    return SX_OK;
+}
+
+int max_site_dev(sx_ctx* ctx, const uint32_t* site_off_dev, uint32_t n_sites, uint32_t* out)
+{
+    uint32_t* d = nullptr;
+    int rc = sx_ensure(ctx, 20, sizeof(uint32_t), reinterpret_cast<void**>(&d));
+    if (rc) return rc;
+    SX_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(uint32_t), ctx->s_compute));
+    k2_max_site_kernel<<<std::min<uint32_t>((n_sites + 255) / 256, 1184), 256, 0, ctx->s_compute>>>(site_off_dev, n_sites, d);
+    SX_CUDA(ctx, cudaMemcpyAsync(out, d, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_compute));
+    SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    return SX_OK;
+}
+} // namespace
+
+int sx_k2_max_site_dev(sx_ctx* ctx, const uint32_t* site_off_dev, uint32_t n_sites, uint32_t* out) { return max_site_dev(ctx, site_off_dev, n_sites, out); }
+
+extern "C" int sx_site_gl_germline_dev(sx_ctx* ctx, const sx_pileup_batch* d, int is_always_test, sx_digt_result* out_dev)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    if (!d || !out_dev || !d->site_off || !d->calls || !d->ref_base) return sx_fail(ctx, SX_ERR_ARG, "sx_site_gl_germline_dev: NULL argument");
+    if (d->n_sites == 0) return SX_OK;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    sx_kernel_timer t(ctx);
+    uint32_t max_site = 0;
+    int rc = max_site_dev(ctx, d->site_off, d->n_sites, &max_site);
+    if (rc) return rc;
+    rc = germline_run(ctx, d, is_always_test, out_dev, nullptr, nullptr, max_site);
+    if (rc) return rc;
+    t.stop(2);
+    rc = t.finish();
+    if (rc) return rc;
+    return sx_check_status(ctx, "sx_site_gl_germline");
+}
+
+// upload a host pileup batch into ctx arenas (slots base..base+5); returns the device view
+int sx_upload_pileup(sx_ctx* ctx, const sx_pileup_batch* b, int slot_base, sx_pileup_batch* d, uint32_t* max_site, cudaStream_t st)
+{
+    if (!b->site_off || !b->calls || !b->ref_base) return sx_fail(ctx, SX_ERR_ARG, "pileup batch: NULL array");
+    *d = *b;
+    void* p = nullptr;
+    int rc;
+    const uint32_t n_calls = b->site_off[b->n_sites];
+    uint32_t m = 0;
+    for (uint32_t s = 0; s < b->n_sites; ++s)
+    {
+        if (b->site_off[s + 1] < b->site_off[s]) return sx_fail(ctx, SX_ERR_ARG, "pileup batch: site_off not monotone at site %u", s);
+        m = std::max(m, b->site_off[s + 1] - b->site_off[s]);
+    }
+    *max_site = m;
+#define SX_UP(slot, field, type, bytes)                                                                      \
+    if ((rc = sx_ensure(ctx, slot_base + slot, (bytes) + 16, &p))) return rc;                                  \
+    SX_CUDA(ctx, cudaMemcpyAsync(p, b->field, (bytes), cudaMemcpyHostToDevice, st));                          \
+    d->field = static_cast<type>(p);
+    SX_UP(0, site_off, const uint32_t*, (size_t)(b->n_sites + 1) * 4)
+    SX_UP(1, calls, const uint16_t*, (size_t)n_calls * 2)
+    SX_UP(2, ref_base, const char*, (size_t)b->n_sites)
+    if (b->ploidy)
+    {
+        SX_UP(3, ploidy, const uint8_t*, (size_t)b->n_sites)
+    }
+    if (b->t2_off)
+    {
+        if (!b->t2_calls) return sx_fail(ctx, SX_ERR_ARG, "pileup batch: t2_off without t2_calls");
+        const uint32_t n2 = b->t2_off[b->n_sites];
+        SX_UP(4, t2_off, const uint32_t*, (size_t)(b->n_sites + 1) * 4)
+        SX_UP(5, t2_calls, const uint16_t*, (size_t)n2 * 2)
+        uint32_t m2 = 0;
+        for (uint32_t s = 0; s < b->n_sites; ++s) m2 = std::max(m2, b->site_off[s + 1] - b->site_off[s] + b->t2_off[s + 1] - b->t2_off[s]);
+        *max_site = std::max(*max_site, m2);
+    }
+#undef SX_UP
+    return SX_OK;
+}
+
+extern "C" int sx_site_gl_germline(sx_ctx* ctx, const sx_pileup_batch* b, int is_always_test, sx_digt_result* out_host)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    if (!b || !out_host) return sx_fail(ctx, SX_ERR_ARG, "sx_site_gl_germline: NULL argument");
+    if (b->n_sites == 0) return SX_OK;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    sx_pileup_batch d;
+    uint32_t max_site = 0;
+    SX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->s_compute));
+    int rc = sx_upload_pileup(ctx, b, 9, &d, &max_site, ctx->s_compute);
+    if (rc) return rc;
+    sx_digt_result* d_out = nullptr;
+    if ((rc = sx_ensure(ctx, 15, (size_t)b->n_sites * sizeof(sx_digt_result), reinterpret_cast<void**>(&d_out)))) return rc;
+    if ((rc = germline_run(ctx, &d, is_always_test, d_out, nullptr, nullptr, max_site))) return rc;
+    SX_CUDA(ctx, cudaMemcpyAsync(out_host, d_out, (size_t)b->n_sites * sizeof(sx_digt_result), cudaMemcpyDeviceToHost, ctx->s_compute));
+    SX_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->s_compute));
+    SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+    ctx->timing.kernel_ms = ms;
+    ctx->timing.launches = 1;
+    ctx->total_launches += 1;
+    return sx_check_status(ctx, "sx_site_gl_germline");
+}
+
+extern "C" int sx_dependent_eprob(sx_ctx* ctx, const sx_pileup_batch* b, uint32_t* out_off_host, float* de_host)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    if (!b || !out_off_host || !de_host) return sx_fail(ctx, SX_ERR_ARG, "sx_dependent_eprob: NULL argument");
+    if (b->n_sites == 0)
+    {
+        out_off_host[0] = 0;
+        return SX_OK;
+    }
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    // offsets of the cleaned calls (host side: the filter bit is in the input)
+    uint32_t off = 0;
+    for (uint32_t s = 0; s < b->n_sites; ++s)
+    {
+        out_off_host[s] = off;
+        for (uint32_t i = b->site_off[s]; i < b->site_off[s + 1]; ++i) off += !((b->calls[i] >> 12) & 1u);
+    }
+    out_off_host[b->n_sites] = off;
+    sx_pileup_batch d;
+    uint32_t max_site = 0;
+    int rc = sx_upload_pileup(ctx, b, 9, &d, &max_site, ctx->s_compute);
+    if (rc) return rc;
+    uint32_t* d_off = nullptr;
+    float* d_de = nullptr;
+    if ((rc = sx_ensure(ctx, 16, (size_t)(b->n_sites + 1) * 4, reinterpret_cast<void**>(&d_off)))) return rc;
+    if ((rc = sx_ensure(ctx, 17, (size_t)off * 4 + 16, reinterpret_cast<void**>(&d_de)))) return rc;
+    SX_CUDA(ctx, cudaMemcpyAsync(d_off, out_off_host, (size_t)(b->n_sites + 1) * 4, cudaMemcpyHostToDevice, ctx->s_compute));
+    if ((rc = germline_run(ctx, &d, 1, nullptr, d_off, d_de, max_site))) return rc;
+    SX_CUDA(ctx, cudaMemcpyAsync(de_host, d_de, (size_t)off * 4, cudaMemcpyDeviceToHost, ctx->s_compute));
+    SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    ctx->timing.launches = 1;
+    ctx->total_launches += 1;
+    return sx_check_status(ctx, "sx_dependent_eprob");
+}

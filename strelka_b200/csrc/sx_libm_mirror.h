@@ -20,12 +20,8 @@
 #include <stdint.h>
 
 #if defined(__CUDACC__)
-#define SX_HD __host__ __device__ __forceinline__
-#else
-#define SX_HD static inline
-#endif
-
-#if defined(__CUDA_ARCH__)
+// device build: __device__-only functions, tables in constant memory, explicit rounding intrinsics
+#define SX_HD __device__ __forceinline__
 #define SX_FMA(a, b, c) __fma_rn((a), (b), (c))
 #define SX_DMUL(a, b) __dmul_rn((a), (b))
 #define SX_DADD(a, b) __dadd_rn((a), (b))
@@ -33,9 +29,11 @@
 #define SX_U2F(x) __uint_as_float(x)
 #define SX_D2U(x) ((uint64_t)__double_as_longlong(x))
 #define SX_U2D(x) __longlong_as_double((long long)(x))
-#define SX_MIRROR_CONST __constant__
+#define SX_MIRROR_CONST static __constant__
 #else
+// host build (oracle test exports only): compile with -ffp-contract=off so that only SX_FMA fuses
 #include <string.h>
+#define SX_HD static inline
 #define SX_FMA(a, b, c) __builtin_fma((a), (b), (c))
 #define SX_DMUL(a, b) ((a) * (b))
 #define SX_DADD(a, b) ((a) + (b))

@@ -17,7 +17,7 @@
 
 #ifndef SX_HD
 #if defined(__CUDACC__)
-#define SX_HD __host__ __device__ __forceinline__
+#define SX_HD __device__ __forceinline__
 #else
 #define SX_HD static inline
 #endif
@@ -25,7 +25,7 @@
 
 #define SX_SORT_COMP(a, b) (key[(a)] > key[(b)]) /* sort_icall_by_eprob::operator() */
 
-template <typename IdxT, typename KeyT> SX_HD void sx_sort_unguarded_linear_insert(IdxT* v, int last, const KeyT* key)
+template <typename IdxT, typename KeyT> SX_HD void sx_sort_unguarded_linear_insert(IdxT* v, int last, const KeyT& key)
 {
     const IdxT val = v[last];
     int next = last - 1;
@@ -38,7 +38,7 @@ template <typename IdxT, typename KeyT> SX_HD void sx_sort_unguarded_linear_inse
     v[last] = val;
 }
 
-template <typename IdxT, typename KeyT> SX_HD void sx_sort_insertion(IdxT* v, int first, int last, const KeyT* key)
+template <typename IdxT, typename KeyT> SX_HD void sx_sort_insertion(IdxT* v, int first, int last, const KeyT& key)
 {
     if (first == last) return;
     for (int i = first + 1; i != last; ++i)
@@ -56,7 +56,7 @@ template <typename IdxT, typename KeyT> SX_HD void sx_sort_insertion(IdxT* v, in
     }
 }
 
-template <typename IdxT, typename KeyT> SX_HD void sx_sort_push_heap(IdxT* v, int first, int holeIndex, int topIndex, IdxT value, const KeyT* key)
+template <typename IdxT, typename KeyT> SX_HD void sx_sort_push_heap(IdxT* v, int first, int holeIndex, int topIndex, IdxT value, const KeyT& key)
 {
     int parent = (holeIndex - 1) / 2;
     while (holeIndex > topIndex && SX_SORT_COMP(v[first + parent], value))
@@ -68,7 +68,7 @@ template <typename IdxT, typename KeyT> SX_HD void sx_sort_push_heap(IdxT* v, in
     v[first + holeIndex] = value;
 }
 
-template <typename IdxT, typename KeyT> SX_HD void sx_sort_adjust_heap(IdxT* v, int first, int holeIndex, int len, IdxT value, const KeyT* key)
+template <typename IdxT, typename KeyT> SX_HD void sx_sort_adjust_heap(IdxT* v, int first, int holeIndex, int len, IdxT value, const KeyT& key)
 {
     const int topIndex = holeIndex;
     int secondChild = holeIndex;
@@ -89,7 +89,7 @@ template <typename IdxT, typename KeyT> SX_HD void sx_sort_adjust_heap(IdxT* v, 
 }
 
 // std::__partial_sort(first, last, last): __heap_select degenerates to make_heap, then sort_heap
-template <typename IdxT, typename KeyT> SX_HD void sx_sort_heapsort(IdxT* v, int first, int last, const KeyT* key)
+template <typename IdxT, typename KeyT> SX_HD void sx_sort_heapsort(IdxT* v, int first, int last, const KeyT& key)
 {
     const int len = last - first;
     if (len >= 2)
@@ -112,7 +112,7 @@ template <typename IdxT, typename KeyT> SX_HD void sx_sort_heapsort(IdxT* v, int
     }
 }
 
-template <typename IdxT, typename KeyT> SX_HD void sx_stdsort_desc(IdxT* v, const uint32_t n_, const KeyT* key)
+template <typename IdxT, typename KeyT> SX_HD void sx_stdsort_desc(IdxT* v, const uint32_t n_, const KeyT& key)
 {
     const int n = (int)n_;
     if (n == 0) return;

@@ -1,0 +1,99 @@
+"""CPU: the oracle against the reference's committed golden vectors, and the libm / std::sort mirrors against the live
+libm / libstdc++ (the mirrors are what the DEVICE code executes; the oracle itself calls the real functions)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+import reflib
+import specgen
+from strelka_b200 import _abi as A
+from strelka_b200 import batch as B
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_oracle_global_aligner_goldens():
+    gold = json.load(open(os.path.join(HERE, "golden", "global_aligner_goldens.json")))
+    assert len(gold["cases"]) == 22
+    for case in gold["cases"]:
+        sc = A.SxGaScores(*[int(x) for x in case["scores"]])
+        gb = B.GaBatch([case["query"]], [case["ref"]], max_ops=64)
+        res, cig = reflib.ox_global_align(sc, gb)
+        assert B.cigar_string(cig[0, : res["n_ops"][0]]) == case["cigar"], case["name"]
+        assert int(res["beginPos"][0]) == case["beginPos"], case["name"]
+        if "score" in case:
+            assert int(res["score"][0]) == case["score"], case["name"]
+
+
+def test_oracle_score_fixture():
+    """Frozen outputs of the reference's scoreCandidateAlignment (tests/golden/make_fixtures.py)."""
+    fx = np.load(os.path.join(HERE, "golden", "k1_fixture.npz"), allow_pickle=False)
+    rng = np.random.default_rng(int(fx["seed"]))
+    regions = [specgen.random_region(rng, n_reads=int(rng.integers(1, 8))) for _ in range(int(fx["n_regions"]))]
+    batch = B.build_align_batch(regions)
+    got = reflib.ox_score(batch)
+    assert np.array_equal(got.view(np.uint64), fx["lnp_bits"])
+
+
+def test_oracle_site_fixtures():
+    fx = np.load(os.path.join(HERE, "golden", "k2_fixture.npz"), allow_pickle=False)
+    rng = np.random.default_rng(int(fx["seed"]))
+    pb = specgen.random_pileups(rng, int(fx["n_sites"]), depth=30.0)
+    got = reflib.ox_germline(A.default_params(), pb, True)
+    assert np.array_equal(got["phredLoghood"], fx["germ_pl"])
+    assert np.array_equal(got["lhood"].view(np.uint32), fx["germ_lhood_bits"])
+    assert np.array_equal(got["genome"]["snp_qphred"], fx["germ_snp_q"])
+    assert np.array_equal(got["genome"]["max_gt"], fx["germ_max_gt"])
+    npb = specgen.random_pileups(rng, int(fx["n_sites"]), depth=30.0, alt_frac_choices=(0.0, 0.0, 0.0, 0.0, 0.02, 0.5))
+    tpb0 = specgen.random_pileups(rng, int(fx["n_sites"]), depth=60.0, alt_frac_choices=(0.0, 0.0, 0.05, 0.1, 0.2, 0.4))
+    tpb = B.PileupBatch(tpb0.site_off, tpb0.calls, npb.ref_base)
+    s = reflib.ox_somatic(A.default_params(), npb, tpb)
+    assert np.array_equal(s["is_computed"], fx["som_computed"])
+    assert np.array_equal(s["qphred"], fx["som_qss"])
+    assert np.array_equal(s["from_ntype_qphred"], fx["som_qss_nt"])
+    assert np.array_equal(s["ntype"], fx["som_ntype"])
+
+
+def test_logf_mirror_matches_libm():
+    lib = reflib.oracle()
+    libm = C.CDLL("libm.so.6")
+    libm.logf.restype = C.c_float
+    libm.logf.argtypes = [C.c_float]
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.integers(0x00800000, 0x7F800000, 200000, dtype=np.int64).astype(np.uint32).view(np.float32),
+                         (10.0 ** (-np.arange(0, 71) / 10.0)).astype(np.float32), rng.random(100000, dtype=np.float32) + np.float32(1e-7)])
+    for x in xs[:: max(1, len(xs) // 60000)]:
+        a = np.float32(libm.logf(float(x)))
+        b = np.float32(lib.ox_logf_restated(float(x)))
+        assert a.view(np.uint32) == b.view(np.uint32), x
+
+
+def test_powf_mirror_matches_libm():
+    lib = reflib.oracle()
+    libm = C.CDLL("libm.so.6")
+    libm.powf.restype = C.c_float
+    libm.powf.argtypes = [C.c_float, C.c_float]
+    rng = np.random.default_rng(1)
+    for q in range(3, 71):
+        e = np.float32(10.0 ** (-q / 10.0))
+        for y in np.concatenate([rng.uniform(0.2, 1.0, 400).astype(np.float32), np.float32([1.0, 0.25, 0.65, 0.4225])]):
+            a = np.float32(libm.powf(float(e), float(y)))
+            b = np.float32(lib.ox_powf_restated(float(e), float(y)))
+            assert a.view(np.uint32) == b.view(np.uint32), (q, y)
+
+
+def test_stdsort_mirror_matches_libstdcxx():
+    lib = reflib.oracle()
+    rng = np.random.default_rng(2)
+    for it in range(4000):
+        n = int(rng.integers(0, 200)) if it % 10 else int(rng.integers(200, 3000))
+        key = rng.integers(0, int(rng.integers(1, 8)), n).astype(np.uint8)
+        if it % 7 == 0:
+            key.sort()
+        a = np.arange(n, dtype=np.uint32)
+        b = np.arange(n, dtype=np.uint32)
+        lib.ox_sort_restated(a.ctypes.data, n, key.ctypes.data)
+        lib.ox_sort_std(b.ctypes.data, n, key.ctypes.data)
+        assert np.array_equal(a, b)

@@ -1,0 +1,227 @@
+"""GPU parity: the CUDA path (through the C ABI) against oracle/liboracle.so on the same seeded inputs.
+Bit-exact for every integer field and for the float/double likelihood sums the reference accumulates sequentially."""
+import numpy as np
+import pytest
+
+import reflib
+import specgen
+from strelka_b200 import _abi as A
+from strelka_b200 import batch as B
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from strelka_b200.api import Context
+
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint64 if a.dtype == np.float64 else np.uint32)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_k1_score_alignments_random_regions(ctx, seed):
+    rng = np.random.default_rng(1000 + seed)
+    regions = [specgen.random_region(rng, n_reads=int(rng.integers(1, 12))) for _ in range(40)]
+    regions += [specgen.simple_region(rng, n_reads=int(rng.integers(5, 40))) for _ in range(10)]
+    batch = B.build_align_batch(regions)
+    want = reflib.ox_score(batch)
+    got = ctx.score_alignments(batch)
+    assert np.array_equal(_bits(got), _bits(want))
+    t = ctx.timing()
+    assert t.launches >= 1
+
+
+def test_k1_device_resident_and_read_max(ctx):
+    from strelka_b200.api import DevAlignBatch, DeviceArray
+
+    rng = np.random.default_rng(5)
+    regions = [specgen.simple_region(rng, n_reads=30) for _ in range(300)]
+    batch = B.build_align_batch(regions)
+    want = reflib.ox_score(batch)
+    db = DevAlignBatch(ctx, batch)
+    ctx.score_alignments_dev(db)
+    got = db.out.download(np.float64, batch.n_alns)
+    assert np.array_equal(_bits(got), _bits(want))
+    mx = DeviceArray(ctx, batch.n_reads * 8)
+    ma = DeviceArray(ctx, batch.n_reads * 4)
+    ctx.read_max_dev(db, mx, ma)
+    mlnp = mx.download(np.float64, batch.n_reads)
+    maln = ma.download(np.uint32, batch.n_reads)
+    reads = batch.alns["read"][:-1]
+    for r in range(0, batch.n_reads, 97):
+        idx = np.nonzero(reads == r)[0]
+        assert mlnp[r] == want[idx].max()
+        assert maln[r] == idx[np.argmax(want[idx])]
+
+
+def test_k1_edge_cases(ctx):
+    rng = np.random.default_rng(9)
+    # a region without alignments, a region with one 1-base read, alignments far outside the held reference window
+    r_empty = B.RegionSpec("ACGT" * 10, 100, [(B.codes_of("ACGT"), np.full(4, 30, np.uint8))], [])
+    r_one = B.RegionSpec("ACGT" * 10, 100, [(B.codes_of("A"), np.array([40], np.uint8))], [B.CandidateAlignmentSpec(0, 100, [("M", 1)])])
+    r_out = B.RegionSpec(
+        "ACGTACGTAC", 100, [(B.codes_of("ACGTACGTACGT"), np.full(12, 37, np.uint8))],
+        [B.CandidateAlignmentSpec(0, 95, [("M", 12)]), B.CandidateAlignmentSpec(0, 105, [("M", 12)]), B.CandidateAlignmentSpec(0, 5000, [("M", 12)]),
+         B.CandidateAlignmentSpec(0, 100, [("S", 12)]), B.CandidateAlignmentSpec(0, 100, [("H", 5), ("S", 3), ("M", 9)])],
+    )
+    batch = B.build_align_batch([r_empty, r_one, r_out, specgen.random_region(rng)])
+    want = reflib.ox_score(batch)
+    got = ctx.score_alignments(batch)
+    assert np.array_equal(_bits(got), _bits(want))
+    # empty batch is a no-op
+    empty = B.build_align_batch([])
+    assert ctx.score_alignments(empty).size == 0
+
+
+def test_k1_rejects_bad_input(ctx):
+    from strelka_b200.api import SxError
+
+    rng = np.random.default_rng(3)
+    batch = B.build_align_batch([specgen.simple_region(rng, n_reads=4)])
+    batch.qual[3] = 99  # qphred_cache::qscore_check throws above 70
+    with pytest.raises(SxError) as e:
+        ctx.score_alignments(batch)
+    assert e.value.code == A.SX_ERR_RANGE
+    batch = B.build_align_batch([specgen.simple_region(rng, n_reads=4), specgen.simple_region(rng, n_reads=4)])
+    batch.regions["qual_off"][1] += 1
+    with pytest.raises(SxError) as e:
+        ctx.score_alignments(batch)
+    assert e.value.code == A.SX_ERR_ALIGNMENT
+
+
+def _ga_scores(match, mismatch, open_, extend, off_edge, ins_del=0, allow_edge_ins=False, require_edge_del=False):
+    return A.SxGaScores(match, mismatch, open_, extend, off_edge, ins_del, int(allow_edge_ins), int(require_edge_del))
+
+
+@pytest.mark.parametrize("flags", [(False, False), (True, False), (False, True), (True, True)])
+def test_k3_global_align_random(ctx, flags):
+    rng = np.random.default_rng(77)
+    qs, rs = specgen.random_ga_problems(rng, 400, n_frac=0.01)
+    qs += ["A", "ACGT", "A" * 300, specgen.rand_seq(rng, 257)]
+    rs += ["A", "T", "A" * 280, specgen.rand_seq(rng, 300)]
+    gb = B.GaBatch(qs, rs, max_ops=700)
+    for sc in (_ga_scores(1, -4, -5, -1, -100, -5, *flags), _ga_scores(2, -4, -5, -1, -1, 0, *flags)):
+        o_res, o_cig = reflib.ox_global_align(sc, gb)
+        g_res, g_cig = ctx.global_align(sc, gb)
+        assert np.array_equal(o_res, g_res)
+        assert np.array_equal(o_cig, g_cig)
+
+
+def test_k3_reference_unit_test_goldens(ctx):
+    import json
+    import os
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "global_aligner_goldens.json")))
+    for case in gold["cases"]:
+        sc = _ga_scores(*case["scores"])
+        gb = B.GaBatch([case["query"]], [case["ref"]], max_ops=64)
+        res, cig = ctx.global_align(sc, gb)
+        assert B.cigar_string(cig[0, : res["n_ops"][0]]) == case["cigar"], case["name"]
+        assert int(res["beginPos"][0]) == case["beginPos"], case["name"]
+        if "score" in case:
+            assert int(res["score"][0]) == case["score"], case["name"]
+
+
+@pytest.mark.parametrize("seed,depth", [(0, 8.0), (1, 30.0), (2, 60.0), (3, 150.0)])
+@pytest.mark.parametrize("always", [True, False])
+def test_k2a_site_gl_germline(ctx, seed, depth, always):
+    rng = np.random.default_rng(2000 + seed)
+    pb = specgen.random_pileups(rng, 2000, depth=depth)
+    p = A.default_params()
+    want = reflib.ox_germline(p, pb, always)
+    got = ctx.site_gl_germline(pb, always)
+    for f in ("ref_gt", "is_computed", "n_used_calls", "phredLoghood"):
+        assert np.array_equal(want[f], got[f]), f
+    assert np.array_equal(_bits(want["lhood"]), _bits(got["lhood"]))
+    assert np.array_equal(_bits(want["strand_bias"]), _bits(got["strand_bias"]))
+    for rs in ("genome", "poly"):
+        for f in ("max_gt", "snp_qphred", "max_gt_qphred"):
+            assert np.array_equal(want[rs][f], got[rs][f]), (rs, f)
+        np.testing.assert_allclose(got[rs]["ref_pprob"], want[rs]["ref_pprob"], rtol=1e-12, atol=1e-300)
+    o_off, o_de = reflib.ox_dependent_eprob(p, pb)
+    g_off, g_de = ctx.dependent_eprob(pb)
+    assert np.array_equal(o_off, g_off)
+    assert np.array_equal(_bits(o_de), _bits(g_de))
+
+
+def test_k2a_deep_and_empty_sites(ctx):
+    rng = np.random.default_rng(31)
+    deep = specgen.random_pileups(rng, 40, depth=900.0, max_depth=3000)  # beyond the shared-memory tile: global scratch path
+    p = A.default_params()
+    want = reflib.ox_germline(p, deep, True)
+    got = ctx.site_gl_germline(deep, True)
+    assert np.array_equal(want["phredLoghood"], got["phredLoghood"])
+    assert np.array_equal(_bits(want["lhood"]), _bits(got["lhood"]))
+    empty = B.PileupBatch.from_sites([[], [], [int(B.pack_call(30, 1, 1))]], "ANC")
+    want = reflib.ox_germline(p, empty, True)
+    got = ctx.site_gl_germline(empty, True)
+    assert want.tobytes() == got.tobytes()
+
+
+def test_k2a_haploid_and_no_dependency(ctx):
+    from strelka_b200.api import Context
+
+    rng = np.random.default_rng(8)
+    pb0 = specgen.random_pileups(rng, 1000, depth=25.0)
+    pl = rng.integers(1, 3, pb0.n_sites).astype(np.uint8)
+    pb = B.PileupBatch(pb0.site_off, pb0.calls, pb0.ref_base, pl)
+    want = reflib.ox_germline(A.default_params(), pb, True)
+    got = ctx.site_gl_germline(pb, True)
+    assert np.array_equal(want["phredLoghood"], got["phredLoghood"])
+    assert np.array_equal(_bits(want["lhood"]), _bits(got["lhood"]))
+    p2 = A.SxParams(0.001, 0.0, 0.0, 0, 1, 0.0, 0.0, 1e-4, 5e-10, 0.0, 0.15, 0, 0)
+    c2 = Context(0, p2)
+    want = reflib.ox_germline(p2, pb, True)
+    got = c2.site_gl_germline(pb, True)
+    c2.close()
+    assert np.array_equal(want["phredLoghood"], got["phredLoghood"])
+    assert np.array_equal(_bits(want["lhood"]), _bits(got["lhood"]))
+
+
+@pytest.mark.parametrize("seed", range(3))
+@pytest.mark.parametrize("tier2", [False, True])
+def test_k2b_site_gl_somatic(ctx, seed, tier2):
+    rng = np.random.default_rng(3000 + seed)
+    n = 2000
+    npb = specgen.random_pileups(rng, n, depth=30.0, with_tier2=tier2, alt_frac_choices=(0.0, 0.0, 0.0, 0.0, 0.02, 0.5))
+    tpb0 = specgen.random_pileups(rng, n, depth=60.0, with_tier2=tier2, alt_frac_choices=(0.0, 0.0, 0.05, 0.1, 0.2, 0.4))
+    tpb = B.PileupBatch(tpb0.site_off, tpb0.calls, npb.ref_base, None, tpb0.t2_off, tpb0.t2_calls)
+    forced = (rng.random(n) < 0.2).astype(np.uint8)
+    p = A.default_params()
+    want = reflib.ox_somatic(p, npb, tpb, forced)
+    got = ctx.site_gl_somatic(npb, tpb, forced)
+    assert np.array_equal(want["is_computed"], got["is_computed"])
+    m = want["is_computed"] == 1
+    assert m.sum() > 50
+    for f in ("ref_gt", "snv_tier", "snv_from_ntype_tier", "ntype", "max_gt", "qphred", "from_ntype_qphred", "normal_alt_id", "tumor_alt_id"):
+        assert np.array_equal(want[f][m], got[f][m]), f
+    # the 21 grid likelihoods are float sums of table values: bit-exact
+    assert np.array_equal(_bits(want["normal_lhood"][m][:, :21]), _bits(got["normal_lhood"][m][:, :21]))
+    assert np.array_equal(_bits(want["tumor_lhood"][m][:, :21]), _bits(got["tumor_lhood"][m][:, :21]))
+    # strand states end in a float log-sum through glibc expf/log1pf: tolerance fields (north_star: 1e-4 relative)
+    np.testing.assert_allclose(got["tumor_lhood"][m][:, 21:30], want["tumor_lhood"][m][:, 21:30], rtol=1e-5)
+    np.testing.assert_allclose(got["strandBias"][m], want["strandBias"][m], rtol=1e-4, atol=1e-4)
+
+
+def test_libm_mirrors_on_device(ctx):
+    """de (powf mirror) and lhood (logf mirror) bit-equality above already exercise the mirrors; this adds a dense sweep of
+    dependency exponents by driving single-group pileups with controlled neighbour-mismatch fractions."""
+    rng = np.random.default_rng(123)
+    sites = []
+    for _ in range(3000):
+        n = int(rng.integers(1, 40))
+        q = rng.integers(3, 64, n)
+        nbr = rng.random(n) < rng.random()
+        sites.append(list(B.pack_call(q, 0, 1, nbr, 0, 0)))
+    pb = B.PileupBatch.from_sites(sites, "A" * len(sites))
+    p = A.default_params()
+    o_off, o_de = reflib.ox_dependent_eprob(p, pb)
+    g_off, g_de = ctx.dependent_eprob(pb)
+    assert np.array_equal(_bits(o_de), _bits(g_de))
