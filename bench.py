@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of Strelka2's per-locus scoring on synthetic BASELINE.json workloads.
+
+One "step" = one pass of the hot path over one batch of candidate loci:
+    K1  score_alignments   every read x every candidate haplotype path of the locus      (+ per-read max epilogue)
+    K2a site_gl_germline   the locus's pileup column -> genotype likelihoods, PLs, posteriors
+    K3  global_align       haplotype-vs-reference DP for the loci that sit in an active region (50 %, 3 haplotypes each)
+At N GPUs the loci shard across ranks with no data-path collective; each step ends with ONE NCCL gather of the per-locus
+call records to rank 0 (weak scaling: per-GPU work is fixed).
+
+    python bench.py [--gpus N --steps K --warmup W]            our arm (CUDA, sm_100a)
+    python bench.py --impl reference [...]                      the CPU arm: the path's CPU implementation on the host cores
+
+Prints ONE JSON line (see the contract in the task statement): value = candidate loci / s with inputs resident in HBM,
+e2e = the same through the C-ABI with pinned HOST buffers (H2D + kernels + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from strelka_b200 import _abi as A  # noqa: E402
+from strelka_b200 import batch as B  # noqa: E402
+
+CONFIGS = {
+    # name: (n_loci, depth, read_len, n_haps, description)
+    "cfg2": (1_000_000, 30, 150, 4, "synthetic 30x germline pileup, 150 bp reads, 1M candidate loci, 4 haplotypes/locus"),
+    "cfg5": (10_000, 300, 150, 32, "300x high-depth amplicon, 32 haplotypes/locus"),
+    "tiny": (20_000, 30, 150, 4, "cfg2 shape at 20k loci (plumbing)"),
+}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# synthetic workload (tools/libsx_synth.so)
+# ----------------------------------------------------------------------------------------------------------------------
+class SynthSizes(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_regions", "n_reads", "n_alns", "n_segs", "seq4_bytes", "qual_bytes", "ref_bytes", "ins_bytes", "cells")]
+
+
+def load_synth():
+    p = os.path.join(ROOT, "tools", "libsx_synth.so")
+    if not os.path.exists(p):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tools")])
+    lib = C.CDLL(p)
+    lib.synth_pileups.restype = C.c_uint64
+    lib.synth_ga.restype = C.c_uint64
+    return lib
+
+
+class HostAlloc:
+    """numpy arrays over pinned host memory (sx_host_alloc) when a CUDA runtime is usable, else plain numpy."""
+
+    def __init__(self, lib, pinned: bool):
+        self.lib, self.pinned, self.ptrs = lib, pinned, []
+
+    def array(self, nbytes: int, dtype) -> np.ndarray:
+        dt = np.dtype(dtype)
+        n = max(1, (nbytes + dt.itemsize - 1) // dt.itemsize)
+        if self.pinned:
+            p = self.lib.sx_host_alloc(n * dt.itemsize)
+            if p:
+                self.ptrs.append(p)
+                buf = (C.c_char * (n * dt.itemsize)).from_address(p)
+                return np.frombuffer(buf, dtype=dt, count=n)
+        return np.zeros(n, dtype=dt)
+
+    def free(self):
+        for p in self.ptrs:
+            self.lib.sx_host_free(p)
+        self.ptrs = []
+
+
+def make_workload(synth, alloc: HostAlloc, n_loci: int, depth: int, read_len: int, n_haps: int, seed: int, threads: int):
+    regions = alloc.array((n_loci + 1) * A.REGION_DT.itemsize, A.REGION_DT)
+    sz = SynthSizes()
+    rc = synth.synth_k1_plan(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, C.c_void_p(regions.ctypes.data), C.byref(sz))
+    assert rc == 0, rc
+    S = A.SX_POOL_SLACK
+    read_lens = alloc.array(sz.n_reads * 2 + 16, np.uint16)
+    seq4 = alloc.array(sz.seq4_bytes + S, np.uint8)
+    qual = alloc.array(sz.qual_bytes + S, np.uint8)
+    ref = alloc.array(sz.ref_bytes + S, np.uint8)
+    alns = alloc.array((sz.n_alns + 1) * A.ALN_DT.itemsize, A.ALN_DT)
+    segs = alloc.array((sz.n_segs + 16) * A.ALN_SEG_DT.itemsize, A.ALN_SEG_DT)
+    ins = alloc.array(sz.ins_bytes + S, np.uint8)
+    rc = synth.synth_k1_fill(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, C.c_void_p(regions.ctypes.data), C.c_void_p(read_lens.ctypes.data),
+                             C.c_void_p(seq4.ctypes.data), C.c_void_p(qual.ctypes.data), C.c_void_p(ref.ctypes.data), C.c_void_p(alns.ctypes.data),
+                             C.c_void_p(segs.ctypes.data), C.c_void_p(ins.ctypes.data))
+    assert rc == 0, rc
+    used = {"seq4": int(sz.seq4_bytes), "qual": int(sz.qual_bytes), "ref": int(sz.ref_bytes), "ins": int(sz.ins_bytes)}
+    ab = B.AlignBatch(regions, read_lens[: sz.n_reads], seq4, qual, ref, alns[: sz.n_alns + 1], segs, ins, used)
+    # K2a: one pileup column per locus
+    site_off = alloc.array((n_loci + 1) * 4, np.uint32)
+    n_calls = synth.synth_pileups(n_loci, C.c_double(float(depth)), 0, C.c_uint64(seed), threads, C.c_void_p(site_off.ctypes.data), None, None)
+    calls = alloc.array(n_calls * 2 + 16, np.uint16)
+    ref_base = alloc.array(n_loci, np.uint8)
+    synth.synth_pileups(n_loci, C.c_double(float(depth)), 0, C.c_uint64(seed), threads, C.c_void_p(site_off.ctypes.data), C.c_void_p(calls.ctypes.data),
+                        C.c_void_p(ref_base.ctypes.data))
+    pb = B.PileupBatch.__new__(B.PileupBatch)
+    pb.site_off, pb.calls, pb.ref_base, pb.ploidy, pb.t2_off, pb.t2_calls, pb.n_sites = site_off[: n_loci + 1], calls, ref_base[:n_loci], None, None, None, n_loci
+    pb.c = A.SxPileupBatch(n_loci, A.ptr(pb.site_off), A.ptr(pb.calls), None, None, A.ptr(pb.ref_base), None)
+    # K3: 3 haplotypes for half of the loci
+    n_ga = (n_loci // 2) * 3
+    q_off = alloc.array((n_ga + 1) * 4, np.uint32)
+    r_off = alloc.array((n_ga + 1) * 4, np.uint32)
+    tot = synth.synth_ga(n_ga, C.c_uint64(seed), threads, C.c_void_p(q_off.ctypes.data), C.c_void_p(r_off.ctypes.data), None, None)
+    qb, rb = tot & 0xFFFFFFFF, tot >> 32
+    query = alloc.array(qb + 16, np.uint8)
+    gref = alloc.array(rb + 16, np.uint8)
+    synth.synth_ga(n_ga, C.c_uint64(seed), threads, C.c_void_p(q_off.ctypes.data), C.c_void_p(r_off.ctypes.data), C.c_void_p(query.ctypes.data), C.c_void_p(gref.ctypes.data))
+    gb = B.GaBatch.__new__(B.GaBatch)
+    gb.n, gb.query, gb.ref, gb.query_off, gb.ref_off, gb.max_ops = n_ga, query, gref, q_off[: n_ga + 1], r_off[: n_ga + 1], 24
+    gb.c = A.SxGaBatch(n_ga, A.ptr(query), A.ptr(gref), A.ptr(gb.query_off), A.ptr(gb.ref_off), gb.max_ops)
+    return ab, pb, gb
+
+
+def workload_cells(ab: B.AlignBatch, gb: B.GaBatch) -> int:
+    return ab.cells() + gb.cells()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.samples, self.stop_flag, self.thread = gpu_index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    f = [x.strip() for x in line.split(",")]
+                    self.samples.append((float(f[1]), float(f[2]), f[3:]))
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(s[0] for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i, v in enumerate(s[2]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": reasons}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle / reference on the host cores)
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_pass(ab: B.AlignBatch, pb: B.PileupBatch, gb: B.GaBatch, n_sample_loci: int, threads: int):
+    """One pass of the hot path on the first n_sample_loci loci with `threads` host threads (ctypes releases the GIL).
+    Uses oracle/liboracle.so (kind "port"): plain scalar C++ of the reference algorithms, same arithmetic, none of the
+    reference's container overhead -- a conservative (fast) CPU baseline."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import reflib
+
+    ox = reflib.oracle()
+    n = min(n_sample_loci, ab.n_regions)
+    lnp = np.zeros(ab.n_alns, np.float64)
+    gout = np.zeros(n, A.DIGT_RESULT_DT)
+    n_ga = min(gb.n, (n // 2) * 3)
+    gres = np.zeros(max(1, n_ga), A.GA_RESULT_DT)
+    gcig = np.zeros((max(1, n_ga), gb.max_ops), np.uint32)
+    sc = A.SxGaScores(1, -4, -5, -1, -100, -5, 1, 1)
+    params = A.default_params()
+
+    def work(t):
+        a, b = n * t // threads, n * (t + 1) // threads
+        ox.ox_score_alignments_range(C.byref(ab.c), a, b, lnp.ctypes.data)
+        ox.ox_site_gl_germline_range(C.byref(params), C.byref(pb.c), 1, a, b, gout.ctypes.data)
+        ga, gbb = n_ga * t // threads, n_ga * (t + 1) // threads
+        if gbb > ga:  # offsets are absolute into the pools, so a sub-batch is just a shifted view of the offset arrays
+            sub = A.SxGaBatch(gbb - ga, gb.c.query, gb.c.ref, gb.query_off.ctypes.data + 4 * ga, gb.ref_off.ctypes.data + 4 * ga, gb.max_ops)
+            ox.ox_global_align(C.byref(sc), C.byref(sub), gres.ctypes.data + 16 * ga, gcig.ctypes.data + 4 * gb.max_ops * ga)
+
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return n, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
+    ap.add_argument("--loci", type=int, default=0, help="override the number of candidate loci per GPU")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-loci", type=int, default=0)
+    args = ap.parse_args()
+    assert args.warmup >= 0 and args.steps >= 1
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_loci, depth, read_len, n_haps, desc = CONFIGS[args.config]
+    if args.loci:
+        n_loci = args.loci
+    ncpu = os.cpu_count() or 8
+    threads = max(1, ncpu // max(1, world))
+    synth = load_synth()
+
+    # ------------------------------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        lib = None
+        alloc = HostAlloc(lib, False)
+        sample = args.cpu_sample_loci or min(n_loci, max(2000, 600 * ncpu))
+        ab, pb, gb = make_workload(synth, alloc, sample, depth, read_len, n_haps, args.seed, ncpu)
+        for _ in range(args.warmup):
+            cpu_pass(ab, pb, gb, sample, ncpu)
+        t_tot, n_tot = 0.0, 0
+        for _ in range(args.steps):
+            n, dt = cpu_pass(ab, pb, gb, sample, ncpu)
+            t_tot += dt
+            n_tot += n
+        value = n_tot / t_tot
+        cells = workload_cells(ab, gb)
+        line = {
+            "impl": "reference", "metric": "candidate_loci_per_sec", "value": value, "unit": "loci/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {desc}", "loci_per_step": sample, "depth": depth, "read_len": read_len, "haplotypes": n_haps,
+                       "note": "bounded sample of the workload; throughput is per locus"},
+            "gcups": cells * args.steps / t_tot / 1e9,
+            "cpu_baseline": {"value": value, "unit": "loci/s", "cores": ncpu, "kind": "port", "sample": f"{sample} loci x {args.steps} passes, {ncpu} host threads, oracle/liboracle.so"},
+            "e2e": {"value": value, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+
+    from strelka_b200.api import Context, DevAlignBatch, DevGaBatch, DeviceArray, DevPileupBatch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; strelka_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = Context(local_rank)
+    lib = ctx.lib
+    alloc = HostAlloc(lib, True)
+    t_gen = time.perf_counter()
+    ab, pb, gb = make_workload(synth, alloc, n_loci, depth, read_len, n_haps, args.seed + 1000 * rank, threads)
+    t_gen = time.perf_counter() - t_gen
+    cells_k1, cells_k3 = ab.cells(), gb.cells()
+    sc = ctx.active_region_scores()
+
+    # inputs resident in HBM before the timed region
+    dab = DevAlignBatch(ctx, ab)
+    dpb = DevPileupBatch(ctx, pb)
+    dgb = DevGaBatch(ctx, gb)
+    d_gl = DeviceArray(ctx, pb.n_sites * A.DIGT_RESULT_DT.itemsize)
+    d_max = DeviceArray(ctx, ab.n_reads * 8)
+    d_maxa = DeviceArray(ctx, ab.n_reads * 4)
+    rec_bytes = pb.n_sites * A.DIGT_RESULT_DT.itemsize
+    d_all = DeviceArray(ctx, rec_bytes * world) if (world > 1 and rank == 0) else None
+    if world > 1:
+        idbuf = torch.zeros(A.SX_NCCL_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            raw = (C.c_ubyte * A.SX_NCCL_ID_BYTES)()
+            ctx._chk(lib.sx_comm_get_unique_id(raw))
+            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+        idbuf = idbuf.cuda()
+        dist.broadcast(idbuf, 0)
+        raw = (C.c_ubyte * A.SX_NCCL_ID_BYTES)(*idbuf.cpu().tolist())
+        ctx._chk(lib.sx_comm_init(ctx.h, raw, rank, world))
+
+    k1_ms = []
+    parts = {"k1_score": 0.0, "k1_read_max": 0.0, "k2a_germline": 0.0, "k3_global_align": 0.0}
+
+    def step_resident():
+        ctx.score_alignments_dev(dab)
+        k1_ms.append(ctx.timing().kernel_ms)
+        parts["k1_score"] += ctx.timing().kernel_ms
+        ctx.read_max_dev(dab, d_max, d_maxa)
+        parts["k1_read_max"] += ctx.timing().kernel_ms
+        ctx.site_gl_germline_dev(dpb, d_gl, True)
+        parts["k2a_germline"] += ctx.timing().kernel_ms
+        ctx.global_align_dev(sc, dgb)
+        parts["k3_global_align"] += ctx.timing().kernel_ms
+        if world > 1:
+            ctx._chk(lib.sx_gather_records(ctx.h, d_gl.ptr, rec_bytes, d_all.ptr if d_all else None, 0))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    launches0 = ctx.total_launches()
+    k1_ms.clear()
+    for k in parts:
+        parts[k] = 0.0
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_resident()
+    barrier()
+    dt = time.perf_counter() - t0
+    launches = ctx.total_launches() - launches0
+    k1_avg_ms = float(np.mean(k1_ms))
+
+    # end to end: pinned host buffers through the C ABI, H2D + kernels + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        lnp_host = alloc.array(ab.n_alns * 8, np.float64)
+        gl_host = alloc.array(pb.n_sites * A.DIGT_RESULT_DT.itemsize, A.DIGT_RESULT_DT)
+        ga_res = alloc.array(gb.n * A.GA_RESULT_DT.itemsize, A.GA_RESULT_DT)
+        ga_cig = alloc.array(gb.n * gb.max_ops * 4, np.uint32)
+
+        def step_e2e():
+            ctx.score_alignments(ab, lnp_host)
+            ctx.site_gl_germline(pb, True, gl_host)
+            ctx._chk(lib.sx_global_align(ctx.h, C.byref(sc), C.byref(gb.c), ga_res.ctypes.data, ga_cig.ctypes.data))
+
+        for _ in range(min(2, args.warmup)):
+            step_e2e()
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        dt_e2e = time.perf_counter() - t1
+        h2d = ab.algorithmic_bytes() - ab.n_alns * 8 + pb.n_calls * 2 + pb.n_sites * 5 + int(gb.query_off[-1]) + int(gb.ref_off[-1]) + (gb.n + 1) * 8
+        d2h = ab.n_alns * 8 + pb.n_sites * A.DIGT_RESULT_DT.itemsize + gb.n * (16 + gb.max_ops * 4)
+        e2e = (dt_e2e, h2d, d2h)
+    clk = clocks.stop() if rank == 0 else None
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([dt, e2e[0] if e2e else 0.0, k1_avg_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt, dt_e2e_max, k1_avg_ms = tt.tolist()
+        if e2e:
+            e2e = (dt_e2e_max, e2e[1], e2e[2])
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        total_loci = n_loci * world
+        value = total_loci * args.steps / dt
+        alg_bytes = ab.algorithmic_bytes()
+        achieved = alg_bytes / (k1_avg_ms * 1e-3) / 1e9
+        line = {
+            "metric": "candidate_loci_per_sec", "value": value, "unit": "loci/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {desc}", "loci_per_gpu": n_loci, "depth": depth, "read_len": read_len, "haplotypes": n_haps,
+                       "parallelism": f"region-shard x{world}, one NCCL gather of call records per step" if world > 1 else "single GPU",
+                       "l2": "inputs (%.1f GB per GPU) far exceed the 126 MB L2; no flush needed" % (alg_bytes / 1e9), "gen_seconds": round(t_gen, 1)},
+            "gcups": (cells_k1 + cells_k3) * world * args.steps / dt / 1e9,
+            "k1_gcups_kernel_only": cells_k1 / (k1_avg_ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "k1_score_kernel", "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k1_avg_ms, "peak_source": peak_src},
+            "gpu_launches": launches,
+            "kernel_ms_per_step": {k: v / args.steps for k, v in parts.items()},
+            "clocks": clk,
+        }
+        if e2e:
+            line["e2e"] = {"value": total_loci * args.steps / e2e[0], "unit": "loci/s", "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2]),
+                           "ms_per_step": 1e3 * e2e[0] / args.steps}
+        # reported CPU baseline: bounded sample of the same workload on the host cores
+        if world == 1:
+            sample = args.cpu_sample_loci or min(n_loci, max(2000, 600 * ncpu))
+            n, t_cpu = cpu_pass(ab, pb, gb, sample, ncpu)
+            line["cpu_baseline"] = {"value": n / t_cpu, "unit": "loci/s", "cores": ncpu, "kind": "port",
+                                    "sample": f"first {n} loci of the workload, one pass, {ncpu} host threads, oracle/liboracle.so"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

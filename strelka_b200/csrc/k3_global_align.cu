@@ -411,6 +411,7 @@ extern "C" int sx_global_align(sx_ctx* ctx, const sx_ga_scores* sc, const sx_ga_
     uint32_t* d_cig = nullptr;
     if ((rc = sx_ensure(ctx, 13, (size_t)b->n * sizeof(sx_ga_result), reinterpret_cast<void**>(&d_res)))) return rc;
     if ((rc = sx_ensure(ctx, 14, (size_t)b->n * b->max_ops * 4 + 16, reinterpret_cast<void**>(&d_cig)))) return rc;
+    SX_CUDA(ctx, cudaMemsetAsync(d_cig, 0, (size_t)b->n * b->max_ops * 4, ctx->s_compute)); // unused cigar slots read as 0
     if ((rc = k3_run(ctx, sc, &d, d_res, d_cig, need))) return rc;
     SX_CUDA(ctx, cudaMemcpyAsync(res_host, d_res, (size_t)b->n * sizeof(sx_ga_result), cudaMemcpyDeviceToHost, ctx->s_compute));
     SX_CUDA(ctx, cudaMemcpyAsync(cigar_host, d_cig, (size_t)b->n * b->max_ops * 4, cudaMemcpyDeviceToHost, ctx->s_compute));

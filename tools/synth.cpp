@@ -1,0 +1,408 @@
+// tools/synth.cpp -- BENCH/TEST TOOLING (not part of the product ABI): seeded, multi-threaded generator of the synthetic
+// workloads of BASELINE.json, written straight into the flattened batch layout of include/strelka_b200.h.
+//
+//   cfg2  "synthetic 30x germline pileup, 150 bp reads, 1M candidate loci, 4 haplotypes/locus":
+//         per locus one region = a 416-base reference window, `depth` reads of `read_len` bases sampled from the locus's diploid
+//         genotype over {ref, 3 alt indel alleles} with phred-distributed base errors, each read scored against all 4 haplotype
+//         paths (K1); one germline pileup column (K2a); for half of the loci 3 haplotype-vs-reference DP problems (K3).
+//   cfg3  somatic 60x/30x pileups (K2b).
+//   cfg5  300x depth, 32 haplotypes/locus.
+// Qualities are i.i.d. {Q11: 3 %, Q25: 7 %, Q37: 90 %}; alt alleles are insertions/deletions of length
+// Geom(0.4) capped at 20.  Every locus has its own counter-based RNG stream, so output is independent of the thread count.
+#include "strelka_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace
+{
+struct rng_t // splitmix64 stream per (seed, locus)
+{
+    uint64_t s;
+    explicit rng_t(uint64_t seed, uint64_t stream) : s(seed * 0x9E3779B97F4A7C15ull + stream * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull) { next(); }
+    inline uint64_t next()
+    {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    inline uint32_t below(uint32_t n) { return (uint32_t)(((next() >> 32) * (uint64_t)n) >> 32); }
+    inline double unit() { return (next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+
+const char BASES[4] = {'A', 'C', 'G', 'T'};
+inline uint8_t code_of(char c) { return c == 'A' ? 1 : c == 'C' ? 2 : c == 'G' ? 4 : c == 'T' ? 8 : 15; }
+inline uint32_t pad16(uint64_t x) { return (uint32_t)((x + 15) & ~15ull); }
+
+struct allele
+{
+    bool is_ins;
+    uint32_t len;
+    char seq[32];
+};
+
+struct k1_cfg
+{
+    uint32_t n_loci, depth, read_len, n_haps, ref_len;
+    uint64_t seed;
+};
+
+inline uint32_t geom_len(rng_t& r)
+{
+    uint32_t n = 1;
+    while (n < 20 && r.unit() > 0.4) ++n;
+    return n;
+}
+
+// everything that depends only on the locus: alleles, window
+struct locus_desc
+{
+    allele alt[31];
+    uint32_t n_alt;
+};
+
+inline void make_locus(const k1_cfg& c, uint32_t l, rng_t& r, locus_desc& d, char* ref /*ref_len*/)
+{
+    for (uint32_t i = 0; i < c.ref_len; ++i) ref[i] = BASES[r.below(4)];
+    d.n_alt = c.n_haps - 1;
+    for (uint32_t a = 0; a < d.n_alt; ++a)
+    {
+        d.alt[a].is_ins = r.below(2) != 0;
+        d.alt[a].len = geom_len(r);
+        for (uint32_t i = 0; i < d.alt[a].len; ++i) d.alt[a].seq[i] = BASES[r.below(4)];
+    }
+}
+
+// per-region sizes are a pure function of the config except for the insert pool (sum over reads and insertion alleles of the
+// observed insert length); pass 1 computes it
+struct region_sizes
+{
+    uint32_t ins_bytes;
+};
+
+inline uint32_t pick_qual(rng_t& r)
+{
+    const double u = r.unit();
+    return u < 0.03 ? 11u : u < 0.10 ? 25u : 37u;
+}
+
+const double QERR[3] = {0.07943282347242814, 0.0031622776601683794, 0.00019952623149688788}; // 10^-1.1, 10^-2.5, 10^-3.7
+
+void gen_region(const k1_cfg& c, uint32_t l, bool fill, region_sizes& sz, const sx_region* reg, uint16_t* read_len, uint8_t* seq4, uint8_t* qual, char* ref_pool,
+                sx_aln* alns, sx_aln_seg* segs, char* ins)
+{
+    rng_t r(c.seed, l);                      // structure stream: window, alleles, genotype, read placement
+    rng_t rb(c.seed ^ 0x5DEECE66Dull, l);    // base-level stream: qualities and sequencing errors (skipped by the sizing pass)
+    locus_desc d;
+    std::vector<char> refv(c.ref_len);
+    make_locus(c, l, r, d, refv.data());
+    const int32_t ref_begin = 1000 + (int32_t)(l % 2000000u) * 1000;
+    const uint32_t locus = c.ref_len / 2; // window-relative
+    if (fill) memcpy(ref_pool + reg->ref_off, refv.data(), c.ref_len);
+    // genotype: two haplotype indices
+    const uint32_t g0 = r.below(c.n_haps), g1 = r.below(3) ? r.below(c.n_haps) : g0;
+    uint32_t ins_off = fill ? reg->ins_begin : 0;
+    uint32_t ins_used = 0;
+    const uint32_t segs_per_read = 1 + 3 * d.n_alt;
+    const uint32_t packed = (c.read_len + 1) / 2;
+    std::vector<char> rd(c.read_len);
+    for (uint32_t k = 0; k < c.depth; ++k)
+    {
+        const uint32_t left = 10 + r.below(c.read_len - 20);     // read bases before the locus
+        const uint32_t start = locus - left;                      // window-relative start
+        const uint32_t h = r.below(2) ? g0 : g1;
+        // source sequence
+        if (fill)
+        {
+            uint32_t n = 0;
+            for (uint32_t i = 0; i < left; ++i) rd[n++] = refv[start + i];
+            uint32_t rp = locus;
+            if (h > 0)
+            {
+                const allele& a = d.alt[h - 1];
+                if (a.is_ins)
+                    for (uint32_t i = 0; i < a.len && n < c.read_len; ++i) rd[n++] = a.seq[i];
+                else
+                    rp += a.len;
+            }
+            while (n < c.read_len) rd[n++] = refv[rp++];
+        }
+        const uint32_t ridx = k;
+        if (fill)
+        {
+            read_len[reg->read_begin + ridx] = (uint16_t)c.read_len;
+            uint8_t* sq = seq4 + reg->seq_off + (uint64_t)ridx * packed;
+            uint8_t* ql = qual + reg->qual_off + (uint64_t)ridx * c.read_len;
+            memset(sq, 0, packed);
+            for (uint32_t i = 0; i < c.read_len; ++i)
+            {
+                const uint32_t q = pick_qual(rb);
+                char b = rd[i];
+                if (rb.unit() < QERR[q == 11 ? 0 : q == 25 ? 1 : 2]) b = BASES[rb.below(4)];
+                ql[i] = (uint8_t)q;
+                sq[i >> 1] |= code_of(b) << ((~i & 1) << 2);
+            }
+        }
+        // alignments: one per haplotype
+        uint32_t sbase = fill ? reg->seg_begin + ridx * segs_per_read : 0;
+        for (uint32_t hh = 0; hh < c.n_haps; ++hh)
+        {
+            const uint32_t aidx = ridx * c.n_haps + hh;
+            if (fill)
+            {
+                sx_aln& A = alns[reg->aln_begin + aidx];
+                A.read = reg->read_begin + ridx;
+                A.ref_pos = ref_begin + (int32_t)start;
+                A.seg_off = sbase;
+                A.ins_off = ins_off;
+            }
+            if (hh == 0)
+            {
+                if (fill) segs[sbase] = sx_aln_seg{(uint16_t)c.read_len, SX_SEG_MATCH, 0};
+                sbase += 1;
+            }
+            else
+            {
+                const allele& a = d.alt[hh - 1];
+                if (a.is_ins)
+                {
+                    const uint32_t n = std::min(a.len, c.read_len - left);
+                    if (fill)
+                    {
+                        segs[sbase + 0] = sx_aln_seg{(uint16_t)left, SX_SEG_MATCH, 0};
+                        segs[sbase + 1] = sx_aln_seg{(uint16_t)n, SX_SEG_INSERT, 0};
+                        segs[sbase + 2] = sx_aln_seg{(uint16_t)(c.read_len - left - n), SX_SEG_MATCH, 0};
+                        memcpy(ins + ins_off, a.seq, n);
+                    }
+                    ins_off += n;
+                    ins_used += n;
+                }
+                else
+                {
+                    if (fill)
+                    {
+                        segs[sbase + 0] = sx_aln_seg{(uint16_t)left, SX_SEG_MATCH, 0};
+                        segs[sbase + 1] = sx_aln_seg{(uint16_t)a.len, SX_SEG_REFSKIP, 0};
+                        segs[sbase + 2] = sx_aln_seg{(uint16_t)(c.read_len - left), SX_SEG_MATCH, 0};
+                    }
+                }
+                sbase += 3;
+            }
+        }
+    }
+    sz.ins_bytes = ins_used;
+}
+
+template <typename F> void parallel_for(uint32_t n, int threads, F f)
+{
+    threads = std::max(1, threads);
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t)
+        th.emplace_back([=] {
+            const uint32_t a = (uint32_t)((uint64_t)n * t / threads), b = (uint32_t)((uint64_t)n * (t + 1) / threads);
+            for (uint32_t i = a; i < b; ++i) f(i);
+        });
+    for (auto& x : th) x.join();
+}
+} // namespace
+
+extern "C" {
+
+struct synth_k1_sizes
+{
+    uint64_t n_regions, n_reads, n_alns, n_segs, seq4_bytes, qual_bytes, ref_bytes, ins_bytes, cells;
+};
+
+// pass 1: region table (needs the per-region insert bytes) + totals.  regions must hold n_loci+1 entries.
+int synth_k1_plan(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n_haps, uint64_t seed, int threads, sx_region* regions, synth_k1_sizes* out)
+{
+    if (n_haps < 1 || n_haps > 32 || read_len < 40 || read_len > 1000) return -1;
+    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed};
+    std::vector<uint32_t> ins(n_loci);
+    parallel_for(n_loci, threads, [&](uint32_t l) {
+        region_sizes sz;
+        gen_region(c, l, false, sz, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        ins[l] = sz.ins_bytes;
+    });
+    const uint32_t packed = (read_len + 1) / 2;
+    const uint32_t segs_per_region = (depth * (1 + 3 * (n_haps - 1)) + 3u) & ~3u;
+    uint64_t seq = 0, qual = 0, ref = 0, insb = 0, seg = 0;
+    for (uint32_t l = 0; l <= n_loci; ++l)
+    {
+        sx_region& R = regions[l];
+        R.seq_off = seq;
+        R.qual_off = qual;
+        R.ref_off = ref;
+        R.read_begin = l * depth;
+        R.aln_begin = l * depth * n_haps;
+        R.seg_begin = (uint32_t)seg;
+        R.ins_begin = (uint32_t)insb;
+        R.ref_begin = 1000 + (int32_t)(l % 2000000u) * 1000;
+        R.ref_len = l < n_loci ? c.ref_len : 0;
+        if (l == n_loci) break;
+        seq += pad16((uint64_t)depth * packed);
+        qual += pad16((uint64_t)depth * read_len);
+        ref += pad16(c.ref_len);
+        insb += pad16(ins[l]);
+        seg += segs_per_region;
+    }
+    if (seg > 0xffffffffull || insb > 0xffffffffull) return -2;
+    out->n_regions = n_loci;
+    out->n_reads = (uint64_t)n_loci * depth;
+    out->n_alns = (uint64_t)n_loci * depth * n_haps;
+    out->n_segs = seg;
+    out->seq4_bytes = seq;
+    out->qual_bytes = qual;
+    out->ref_bytes = ref;
+    out->ins_bytes = insb;
+    out->cells = (uint64_t)n_loci * depth * n_haps * read_len; // upper bound; exact count via sx_align_batch_cells
+    return 0;
+}
+
+// pass 2: fill caller-allocated pools (sizes from synth_k1_plan, plus SX_POOL_SLACK; alns has n_alns+1 entries, segs n_segs+16)
+int synth_k1_fill(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n_haps, uint64_t seed, int threads, const sx_region* regions,
+                  uint16_t* read_lens, uint8_t* seq4, uint8_t* qual, char* ref, sx_aln* alns, sx_aln_seg* segs, char* ins)
+{
+    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed};
+    const uint32_t n_segs = regions[n_loci].seg_begin;
+    for (uint32_t i = 0; i < n_segs + 16; ++i) segs[i] = sx_aln_seg{0, SX_SEG_HARDCLIP, 0};
+    parallel_for(n_loci, threads, [&](uint32_t l) {
+        region_sizes sz;
+        gen_region(c, l, true, sz, &regions[l], read_lens, seq4, qual, ref, alns, segs, ins);
+    });
+    sx_aln& S = alns[(uint64_t)n_loci * depth * n_haps];
+    S.read = n_loci * depth;
+    S.ref_pos = 0;
+    S.seg_off = n_segs;
+    S.ins_off = regions[n_loci].ins_begin;
+    return 0;
+}
+
+// pileup columns: Poisson-ish depth (binomial approximation via sum of uniforms is avoided: exact inverse-CDF Poisson), a
+// site is hom-ref (80 %), het (13 %) or hom-alt (7 %) for germline; for the tumour sample `vaf` gives the alt fraction.
+static uint32_t poisson(rng_t& r, double mean)
+{
+    // Knuth for small means, normal approximation above 60
+    if (mean > 60)
+    {
+        double u = 0;
+        for (int i = 0; i < 12; ++i) u += r.unit();
+        const double v = mean + (u - 6.0) * std::sqrt(mean);
+        return v < 0 ? 0u : (uint32_t)(v + 0.5);
+    }
+    const double L = std::exp(-mean);
+    uint32_t k = 0;
+    double p = 1.0;
+    do
+    {
+        ++k;
+        p *= r.unit();
+    } while (p > L);
+    return k - 1;
+}
+
+// mode 0: germline site; mode 1: somatic normal; mode 2: somatic tumour.  site_off must hold n_sites+1 entries; pass calls=NULL to size.
+uint64_t synth_pileups(uint32_t n_sites, double depth, int mode, uint64_t seed, int threads, uint32_t* site_off, uint16_t* calls, char* ref_base)
+{
+    std::vector<uint32_t> cnt(n_sites);
+    parallel_for(n_sites, threads, [&](uint32_t s) {
+        rng_t r(seed ^ 0xABCDEFull, s);
+        cnt[s] = poisson(r, depth);
+    });
+    uint64_t off = 0;
+    for (uint32_t s = 0; s < n_sites; ++s)
+    {
+        site_off[s] = (uint32_t)off;
+        off += cnt[s];
+    }
+    site_off[n_sites] = (uint32_t)off;
+    if (!calls) return off;
+    parallel_for(n_sites, threads, [&](uint32_t s) {
+        rng_t r(seed ^ 0xABCDEFull, s);
+        const uint32_t n = poisson(r, depth);
+        rng_t g(seed ^ 0x13579Bull, s); // genotype stream shared by the normal/tumour samples of a site
+        const uint32_t ref_id = g.below(4), alt_id = (ref_id + 1 + g.below(3)) & 3;
+        const double u = g.unit();
+        double af;
+        if (mode == 0) af = u < 0.80 ? 0.0 : u < 0.93 ? 0.5 : 1.0;
+        else if (mode == 1) af = u < 0.97 ? 0.0 : 0.5;                       // normal: mostly hom-ref, some germline hets
+        else
+        {
+            const double v = g.unit();
+            af = u < 0.97 ? (v < 0.6 ? 0.0 : v < 0.7 ? 0.05 : v < 0.8 ? 0.1 : v < 0.9 ? 0.2 : 0.4) : 0.5; // tumour: somatic VAF mix on hom-ref normals
+        }
+        ref_base[s] = BASES[ref_id];
+        uint16_t* c = calls + site_off[s];
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            const uint32_t q = pick_qual(r);
+            uint32_t b = (r.unit() < af) ? alt_id : ref_id;
+            if (r.unit() < QERR[q == 11 ? 0 : q == 25 ? 1 : 2]) b = r.below(4);
+            const uint32_t fwd = r.below(2), nbr = r.unit() < 0.05, filt = r.unit() < 0.03;
+            c[i] = SX_CALL(q, b, fwd, nbr, filt, 0);
+        }
+    });
+    return off;
+}
+
+// haplotype-vs-reference DP problems: reference segment of 30..100 bases, query = segment with 1..3 edits (SNV / short indel)
+uint64_t synth_ga(uint32_t n, uint64_t seed, int threads, uint32_t* q_off, uint32_t* r_off, char* query, char* ref)
+{
+    std::vector<uint32_t> ql(n), rl(n);
+    auto gen = [&](uint32_t i, char* q, char* rf, uint32_t& Q, uint32_t& R) {
+        rng_t r(seed ^ 0x777ull, i);
+        R = 30 + r.below(71);
+        char rb[128], qb[192];
+        for (uint32_t k = 0; k < R; ++k) rb[k] = BASES[r.below(4)];
+        uint32_t n_q = 0;
+        const uint32_t n_ed = 1 + r.below(3);
+        uint32_t ed_pos[3], ed_kind[3], ed_len[3];
+        for (uint32_t e = 0; e < n_ed; ++e)
+        {
+            ed_pos[e] = 5 + r.below(R - 10);
+            ed_kind[e] = r.below(3);
+            ed_len[e] = 1 + r.below(8);
+        }
+        for (uint32_t k = 0; k < R; ++k)
+        {
+            bool skip = false;
+            for (uint32_t e = 0; e < n_ed; ++e)
+            {
+                if (ed_pos[e] == k)
+                {
+                    if (ed_kind[e] == 0) { qb[n_q++] = BASES[r.below(4)]; skip = true; }
+                    else if (ed_kind[e] == 1) { for (uint32_t z = 0; z < ed_len[e] && n_q < 180; ++z) qb[n_q++] = BASES[r.below(4)]; }
+                }
+                if (ed_kind[e] == 2 && k >= ed_pos[e] && k < ed_pos[e] + ed_len[e]) skip = true;
+            }
+            if (!skip && n_q < 190) qb[n_q++] = rb[k];
+        }
+        if (n_q == 0) qb[n_q++] = 'A';
+        Q = n_q;
+        if (q) memcpy(q, qb, Q);
+        if (rf) memcpy(rf, rb, R);
+    };
+    parallel_for(n, threads, [&](uint32_t i) { gen(i, nullptr, nullptr, ql[i], rl[i]); });
+    uint64_t qo = 0, ro = 0;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        q_off[i] = (uint32_t)qo;
+        r_off[i] = (uint32_t)ro;
+        qo += ql[i];
+        ro += rl[i];
+    }
+    q_off[n] = (uint32_t)qo;
+    r_off[n] = (uint32_t)ro;
+    if (!query) return qo | (ro << 32);
+    parallel_for(n, threads, [&](uint32_t i) {
+        uint32_t Q, R;
+        gen(i, query + q_off[i], ref + r_off[i], Q, R);
+    });
+    return qo | (ro << 32);
+}
+}
