@@ -406,3 +406,143 @@ extern "C" int ref_site_gl_somatic(const sx_params* p, const sx_pileup_batch* no
 // small numerics probes (blt_util/logSumUtil.hh) used to pin the float log-sum in the strand-state likelihood
 extern "C" float ref_getLogSum_float(float a, float b) { return getLogSum(a, b); }
 extern "C" double ref_getLogSum_double(double a, double b) { return getLogSum(a, b); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// scoreCandidateAlignment over regions [r0, r1) of a FLATTENED batch (bench.py --impl reference).
+// The reference objects (IndelBuffer, CandidateAlignment, read_segment) are rebuilt from the flattened description -- the inverse of
+// the host-side flattening -- and only the scoreCandidateAlignment calls themselves are timed (score_seconds), so the reported CPU
+// number is the reference's own scoring loop (starling_read_align.cpp:1564-1571), not this shim's object construction.
+// Supported segment kinds: MATCH, INSERT (internal, leading/trailing edge, or followed by a REFSKIP = swap), REFSKIP (as DELETE),
+// SOFTCLIP, HARDCLIP; zero-length segments are dropped.
+// ---------------------------------------------------------------------------------------------------------------
+#include <chrono>
+
+extern "C" int ref_score_flat_batch(const sx_align_batch* b, uint32_t r0, uint32_t r1, double* out_lnp, double* score_seconds, char* err, int errlen)
+{
+    try
+    {
+        harness_options opt;
+        opt.is_candidate_indel_signal_test = false;
+        starling_base_deriv_options dopt(opt);
+        double secs(0);
+        for (uint32_t ri = r0; ri < r1; ++ri)
+        {
+            const sx_region& reg(b->regions[ri]);
+            const sx_region& nxt(b->regions[ri + 1]);
+            reference_contig_segment ref;
+            ref.seq() = std::string(b->ref + reg.ref_off, reg.ref_len);
+            ref.set_offset(reg.ref_begin);
+            IndelBuffer indelBuffer(opt, dopt, ref);
+            depth_buffer db, db2;
+            indelBuffer.registerSample(db, db2, false);
+            indelBuffer.finalizeSamples();
+
+            std::vector<std::unique_ptr<bam_record>> bams;
+            std::vector<std::unique_ptr<starling_read>> sreads;
+            uint64_t so(reg.seq_off), qo(reg.qual_off);
+            for (uint32_t r = reg.read_begin; r < nxt.read_begin; ++r)
+            {
+                const int len(b->read_len[r]);
+                std::unique_ptr<bam_record> br(new bam_record);
+                br->set_qname("R");
+                const std::string dummy(len, 'A');
+                br->set_readqual(dummy.c_str(), b->qual + qo);
+                std::memcpy(bam_get_seq(br->get_data()), b->seq4 + so, (len + 1) / 2);
+                alignment al;
+                al.pos = 0;
+                al.path.push_back(ALIGNPATH::path_segment(ALIGNPATH::MATCH, len));
+                br->get_data()->core.pos = al.pos;
+                edit_bam_cigar(al.path, *(br->get_data()));
+                sreads.emplace_back(new starling_read(*br, al, MAPLEVEL::UNKNOWN, r));
+                bams.push_back(std::move(br));
+                so += (len + 1) / 2;
+                qo += len;
+            }
+            std::vector<CandidateAlignment> cals(nxt.aln_begin - reg.aln_begin);
+            for (uint32_t a = reg.aln_begin; a < nxt.aln_begin; ++a)
+            {
+                const sx_aln& A(b->alns[a]);
+                CandidateAlignment& cal(cals[a - reg.aln_begin]);
+                cal.al.pos = A.ref_pos;
+                cal.al.is_fwd_strand = true;
+                indel_set_t iset;
+                pos_t ref_head(A.ref_pos);
+                const char* ins(b->ins + A.ins_off);
+                bool seenMatch(false);
+                const uint32_t s1(b->alns[a + 1].seg_off);
+                // last MATCH segment, to tell trailing-edge insertions
+                int lastMatch(-1);
+                for (uint32_t s = A.seg_off; s < s1; ++s)
+                    if (b->segs[s].kind == SX_SEG_MATCH && b->segs[s].len) lastMatch = (int)s;
+                for (uint32_t s = A.seg_off; s < s1; ++s)
+                {
+                    const sx_aln_seg& sg(b->segs[s]);
+                    if (sg.len == 0) continue;
+                    const bool cand(!(sg.flags & SX_SEGF_NONCANDIDATE));
+                    auto observe = [&](const IndelKey& k, const bool isCand) {
+                        IndelObservation obs;
+                        obs.key = k;
+                        obs.data.id = 1 + a;
+                        obs.data.iat = isCand ? INDEL_ALIGN_TYPE::GENOME_TIER1_READ : INDEL_ALIGN_TYPE::GENOME_SUBMAP_READ;
+                        indelBuffer.addIndelObservation(0, obs);
+                    };
+                    if (sg.kind == SX_SEG_MATCH)
+                    {
+                        cal.al.path.push_back(ALIGNPATH::path_segment(ALIGNPATH::MATCH, sg.len));
+                        ref_head += sg.len;
+                        seenMatch = true;
+                    }
+                    else if (sg.kind == SX_SEG_INSERT)
+                    {
+                        const std::string seq(ins, ins + sg.len);
+                        ins += sg.len;
+                        unsigned del(0);
+                        if (s + 1 < s1 && b->segs[s + 1].kind == SX_SEG_REFSKIP && b->segs[s + 1].len && seenMatch && (int)s < lastMatch) del = b->segs[s + 1].len;
+                        const IndelKey k(ref_head, INDEL::INDEL, del, seq.c_str());
+                        observe(k, cand && del == 0);
+                        cal.al.path.push_back(ALIGNPATH::path_segment(ALIGNPATH::INSERT, sg.len));
+                        if (!seenMatch) cal.leading_indel_key = k;
+                        else if ((int)s > lastMatch) cal.trailing_indel_key = k;
+                        else iset.insert(k);
+                        if (del)
+                        {
+                            cal.al.path.push_back(ALIGNPATH::path_segment(ALIGNPATH::DELETE, del));
+                            ref_head += del;
+                            ++s;
+                        }
+                    }
+                    else if (sg.kind == SX_SEG_REFSKIP)
+                    {
+                        const IndelKey k(ref_head, INDEL::INDEL, sg.len, "");
+                        observe(k, cand);
+                        iset.insert(k);
+                        cal.al.path.push_back(ALIGNPATH::path_segment(ALIGNPATH::DELETE, sg.len));
+                        ref_head += sg.len;
+                    }
+                    else if (sg.kind == SX_SEG_SOFTCLIP) cal.al.path.push_back(ALIGNPATH::path_segment(ALIGNPATH::SOFT_CLIP, sg.len));
+                    else if (sg.kind == SX_SEG_HARDCLIP) cal.al.path.push_back(ALIGNPATH::path_segment(ALIGNPATH::HARD_CLIP, sg.len));
+                }
+                cal.setIndels(iset);
+            }
+            const auto t0(std::chrono::steady_clock::now());
+            for (uint32_t a = reg.aln_begin; a < nxt.aln_begin; ++a)
+            {
+                const read_segment& rseg(sreads[b->alns[a].read - reg.read_begin]->get_full_segment());
+                out_lnp[a] = scoreCandidateAlignment(opt, indelBuffer, rseg, cals[a - reg.aln_begin], ref);
+            }
+            secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        }
+        if (score_seconds) *score_seconds = secs;
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        set_err(err, errlen, e.what());
+        return 1;
+    }
+    catch (...)
+    {
+        set_err(err, errlen, "unknown exception");
+        return 2;
+    }
+}

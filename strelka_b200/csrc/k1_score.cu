@@ -21,6 +21,7 @@ namespace
 {
 constexpr int K1_THREADS = 128;
 constexpr int K1_TAB_BYTES = SX_K1_ROWS * 16;
+constexpr int K1_CHUNK = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -58,7 +59,7 @@ __host__ __device__ __forceinline__ uint32_t pad16(uint32_t x) { return (x + 15u
 
 struct k1_layout
 {
-    uint32_t tab, alns, segs, ref, ins, seq, qual, rlen, boff, soff, ent, total;
+    uint32_t tab, alns, segs, ref, ins, seq, qual, rlen, boff, soff, eoff, desc, ent, total;
     uint32_t n_reads, n_alns, seg_bytes, ref_bytes, ins_bytes, seq_bytes, qual_bytes;
 };
 
@@ -93,8 +94,13 @@ __host__ __device__ __forceinline__ k1_layout k1_make_layout(const sx_region& r0
     o += pad16((L.n_reads + 1) * 4u);
     L.soff = o;
     o += pad16((L.n_reads + 1) * 4u);
+    L.eoff = 0;
+    L.desc = o;
+    o += 64;
     L.ent = o;
-    o += L.qual_bytes * 2u;
+    // entries: 2 bytes per base, every read padded to an even count; + slack: the uniform chunk loop may load (and discard) up to
+    // K1_CHUNK-1 entries past a read
+    o += pad16((L.qual_bytes + L.n_reads) * 2u) + 32u;
     L.total = o;
     return L;
 }
@@ -136,7 +142,17 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
     uint16_t* rlen_s = reinterpret_cast<uint16_t*>(smem + L.rlen);
     uint32_t* boff_s = reinterpret_cast<uint32_t*>(smem + L.boff);
     uint32_t* soff_s = reinterpret_cast<uint32_t*>(smem + L.soff);
+    uint32_t* desc_s = reinterpret_cast<uint32_t*>(smem + L.desc);
     uint16_t* ent_s = reinterpret_cast<uint16_t*>(smem + L.ent);
+    if (threadIdx.x < 16)
+    {
+        const uint32_t code = threadIdx.x;
+        uint32_t d;
+        if (code == 15u) d = (SX_K1_ROW_ZERO << 4);                                   // BAM_BASE::ANY: skipped (adds +0.0), q ignored
+        else if (code == 0u) d = (SX_K1_ROW_EQ << 4) | 0xffff0000u;                   // BAM_BASE::REF: always "is_ref"
+        else d = ((code == 1u || code == 2u || code == 4u || code == 8u) ? code : 0u) | 0xffff0000u; // other nibbles match nothing
+        desc_s[code] = d;
+    }
 
     if (threadIdx.x == 0)
     {
@@ -196,33 +212,32 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
         if (threadIdx.x == 0) atomicOr(status, 2);
         return;
     }
-    // expand each read once: entry = (table row << 4) | one-hot base
+    // expand each read once: entry = (table row << 4) | one-hot base.  One packed byte (two bases) per lane and iteration; the
+    // per-nibble part of the entry comes from a 16-entry descriptor table: low half = (row base << 4) | one-hot nibble, high half =
+    // mask applied to (q << 4)  (0 for 'N': the zero row ignores q).
     {
         const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        bool bad_q = false;
+        uint32_t qmax = 0; // largest quality seen on a non-N base: the reference only looks at those (score.cpp:125-126,158-159)
         for (uint32_t r = warp; r < L.n_reads; r += K1_THREADS / 32)
         {
             const uint32_t len = rlen_s[r];
             const uint8_t* sq = seq_s + soff_s[r];
             const uint8_t* ql = qual_s + boff_s[r];
-            uint16_t* en = ent_s + boff_s[r];
-            for (uint32_t i = lane; i < len; i += 32)
+            uint32_t* en2 = reinterpret_cast<uint32_t*>(ent_s) + soff_s[r]; // every read is padded to an even entry count: entry offset = 2*soff
+            const uint32_t npair = (len + 1) >> 1;
+            for (uint32_t p = lane; p < npair; p += 32)
             {
-                const uint32_t code = (sq[i >> 1] >> ((~i & 1u) << 2)) & 15u; // bam_seq::get_code, high nibble first
-                uint32_t q = ql[i];
-                if (q > SX_MAX_QSCORE)
-                {
-                    if (code != 15u) bad_q = true; // the reference only looks at the quality of non-N bases (score.cpp:125-126,158-159)
-                    q = SX_MAX_QSCORE;
-                }
-                uint32_t row, nib;
-                if (code == 15u) { row = SX_K1_ROW_ZERO; nib = 0; }            // BAM_BASE::ANY: skipped (adds +0.0)
-                else if (code == 0u) { row = SX_K1_ROW_EQ + q; nib = 0; }      // BAM_BASE::REF: always "is_ref"
-                else { row = q; nib = (code == 1u || code == 2u || code == 4u || code == 8u) ? code : 0u; }
-                en[i] = static_cast<uint16_t>((row << 4) | nib);
+                const uint32_t byte = sq[p];
+                const uint32_t d0 = desc_s[byte >> 4], d1 = desc_s[byte & 15u]; // bam_seq::get_code: high nibble first
+                const uint32_t q0 = ql[2 * p], q1 = (2 * p + 1 < len) ? ql[2 * p + 1] : 0u;
+                qmax = max(qmax, (d0 >> 16) ? q0 : 0u);
+                qmax = max(qmax, (d1 >> 16) ? q1 : 0u);
+                const uint32_t e0 = (d0 & 0xffffu) + ((min(q0, (uint32_t)SX_MAX_QSCORE) << 4) & (d0 >> 16));
+                const uint32_t e1 = (d1 & 0xffffu) + ((min(q1, (uint32_t)SX_MAX_QSCORE) << 4) & (d1 >> 16));
+                en2[p] = e0 | (e1 << 16);
             }
         }
-        if (bad_q) atomicOr(status, 1);
+        if (qmax > SX_MAX_QSCORE) atomicOr(status, 1);
         for (uint32_t i = threadIdx.x; i < L.ref_bytes; i += K1_THREADS) ref_s[i] = onehot_of_char(ref_s[i]);
         for (uint32_t i = threadIdx.x; i < L.ins_bytes; i += K1_THREADS) ins_s[i] = onehot_of_char(ins_s[i]);
     }
@@ -242,7 +257,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
             atomicOr(status, 2);
             continue;
         }
-        const uint16_t* ent = ent_s + boff_s[rl];
+        const uint16_t* ent = ent_s + 2u * soff_s[rl];
         int read_left = static_cast<int>(boff_s[rl + 1] - boff_s[rl]);
         int refp = static_cast<int>(h.y) - r0.ref_begin;
         const uint8_t* insp = ins_s + (h.w - r0.ins_begin);
@@ -324,37 +339,23 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
                 }
             }
             if (done) break;
-            if (rem >= 8)
+            // One uniform chunk of K1_CHUNK read bases.  Lanes whose segment ends inside the chunk substitute the all-zero table row
+            // for the surplus steps (x + 0.0 == x exactly for every x this sum can hold), so all lanes run the same straight-line
+            // code and a warp diverges only in the short segment fetch above.  Surplus loads stay inside the CTA's shared memory
+            // (the entry array carries slack; ref/ins/seq areas follow each other).
             {
+                const int n = rem < K1_CHUNK ? rem : K1_CHUNK;
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
+                for (int k = 0; k < K1_CHUNK; ++k)
                 {
-                    const uint32_t e = ent[k];
+                    const uint32_t e = (k < n) ? static_cast<uint32_t>(ent[k]) : static_cast<uint32_t>(SX_K1_ROW_ZERO << 4);
                     const uint32_t c = cp[k];
                     const uint32_t off = (e & 0xfff0u) + ((e & c) ? 8u : 0u);
                     lnp = __dadd_rn(lnp, *reinterpret_cast<const double*>(tabb + off));
                 }
-                ent += 8;
-                cp += 8;
-                rem -= 8;
-            }
-            else
-            {
-                const int n = rem;
-#pragma unroll
-                for (int k = 0; k < 7; ++k)
-                {
-                    if (k < n)
-                    {
-                        const uint32_t e = ent[k];
-                        const uint32_t c = cp[k];
-                        const uint32_t off = (e & 0xfff0u) + ((e & c) ? 8u : 0u);
-                        lnp = __dadd_rn(lnp, *reinterpret_cast<const double*>(tabb + off));
-                    }
-                }
                 ent += n;
                 cp += n;
-                rem = 0;
+                rem -= n;
             }
         }
         lnp_out[r0.aln_begin + a] = lnp;
@@ -545,7 +546,12 @@ extern "C" int sx_score_alignments(sx_ctx* ctx, const sx_align_batch* b, double*
     if ((rc = sx_ensure(ctx, 8, (size_t)b->n_alns * sizeof(double), reinterpret_cast<void**>(&d_out)))) return rc;
 
     int chunks = ctx->params.pipeline_chunks;
-    if (chunks <= 0) chunks = b->n_regions >= 4096 ? 8 : 1;
+    if (chunks <= 0)
+    {
+        // ~128 MB of input per chunk: small enough that the first kernel starts early, large enough to keep copies at link rate
+        const uint64_t in_bytes = b->seq4_bytes + b->qual_bytes + aln_bytes + seg_bytes + b->ins_bytes;
+        chunks = static_cast<int>(std::min<uint64_t>(64, std::max<uint64_t>(1, in_bytes >> 27)));
+    }
     chunks = std::max(1, std::min<int>(chunks, (int)b->n_regions));
     while (ctx->ev_pool.size() < (size_t)chunks * 2)
     {

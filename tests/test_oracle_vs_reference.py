@@ -91,3 +91,31 @@ def test_site_gl_somatic(seed, tier2):
     for f in ("ref_gt", "snv_tier", "snv_from_ntype_tier", "ntype", "max_gt", "qphred", "from_ntype_qphred", "normal_alt_id", "tumor_alt_id"):
         assert np.array_equal(want[f][m], got[f][m]), f
     assert np.array_equal(want["strandBias"][m].view(np.uint32), got["strandBias"][m].view(np.uint32))
+
+
+def test_flat_batch_reference_scorer_matches_oracle_on_bench_workload():
+    """bench.py --impl reference scores the synthetic workload with the reference's own scoreCandidateAlignment, rebuilt from the
+    flattened batch; it must agree bit for bit with the oracle on that batch (so both arms of the bench compute the same thing)."""
+    import ctypes as C
+    import sys, os
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    synth = bench.load_synth()
+    ab, pb, gb = bench.make_workload(synth, bench.HostAlloc(None, False), 300, 30, 150, 4, 7, 4)
+    want = reflib.ox_score(ab)
+    got = np.zeros(ab.n_alns, np.float64)
+    secs = C.c_double(0)
+    err = C.create_string_buffer(512)
+    rc = reflib.ref().ref_score_flat_batch(C.byref(ab.c), C.c_uint32(0), C.c_uint32(ab.n_regions), C.c_void_p(got.ctypes.data), C.byref(secs), err, 512)
+    assert rc == 0, err.value
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    assert secs.value > 0
+    # the other two kernels' inputs from the same generator
+    p = A.default_params()
+    assert reflib.ref_germline(p, pb, True).tobytes() == reflib.ox_germline(p, pb, True).tobytes()
+    sc = A.SxGaScores(1, -4, -5, -1, -100, -5, 1, 1)
+    r1, c1 = reflib.ref_global_align(sc, gb)
+    r2, c2 = reflib.ox_global_align(sc, gb)
+    assert np.array_equal(r1, r2) and np.array_equal(c1, c2)
