@@ -1,0 +1,85 @@
+"""CPU, gloo, world_size 2: the N>1 host logic -- shard the loci, compute per rank, gather fixed-size call records to rank 0 --
+reproduces the single-process result.  The per-rank compute stand-in here is the CPU oracle (tests may use it); on GPUs the same
+sharding feeds sx_site_gl_germline and the gather is sx_gather_records over NCCL (bench.py --gpus N)."""
+import os
+import socket
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_sites, out_path):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    import reflib
+    import specgen
+    from strelka_b200 import _abi as A
+    from strelka_b200 import batch as B
+    from strelka_b200.shard import shard_range
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(99)  # every rank sees the same full input and takes its shard
+    pb = specgen.random_pileups(rng, n_sites, depth=20.0)
+    a, b = shard_range(n_sites, rank, world)
+    sub = B.PileupBatch(pb.site_off[a:b + 1] - pb.site_off[a], pb.calls[pb.site_off[a]:pb.site_off[b]], pb.ref_base[a:b])
+    rec = reflib.ox_germline(A.default_params(), sub, True)
+    local = torch.from_numpy(rec.view(np.uint8).reshape(b - a, -1).copy())
+    # equal-count shards pad to the largest block so that one fixed-size gather suffices
+    cap = (n_sites + world - 1) // world
+    buf = torch.zeros((cap, local.shape[1]), dtype=torch.uint8)
+    buf[: b - a] = local
+    gathered = [torch.zeros_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, gathered, dst=0)
+    if rank == 0:
+        parts = []
+        for r in range(world):
+            ra, rb = shard_range(n_sites, r, world)
+            parts.append(gathered[r][: rb - ra].numpy())
+        allrec = np.concatenate(parts).reshape(-1).view(A.DIGT_RESULT_DT)
+        np.save(out_path, allrec)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_compute_and_gather_matches_single_process(tmp_path):
+    import torch.multiprocessing as mp
+
+    sys.path.insert(0, HERE)
+    import reflib
+    import specgen
+    from strelka_b200 import _abi as A
+
+    n_sites, world = 501, 2
+    out = str(tmp_path / "gathered.npy")
+    mp.spawn(_worker, args=(world, _free_port(), n_sites, out), nprocs=world, join=True)
+    got = np.load(out)
+    rng = np.random.default_rng(99)
+    pb = specgen.random_pileups(rng, n_sites, depth=20.0)
+    want = reflib.ox_germline(A.default_params(), pb, True)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_shard_ranges_cover_and_balance():
+    from strelka_b200.shard import gathered_offsets, shard_ranges
+
+    for n in (0, 1, 7, 1000, 1_000_003):
+        for w in (1, 2, 4, 8):
+            rs = shard_ranges(n, w)
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in rs]
+            assert max(sizes) - min(sizes) <= 1
+            assert gathered_offsets(sizes)[-1] + sizes[-1] == n
