@@ -1,0 +1,474 @@
+// strelka_b200.hh -- C++ host side above the C ABI (include/strelka_b200.h).
+//
+// The reference is C++, so this is the layer a reference developer programs against: the same nouns and argument meaning as the
+// reference's own interface for this path (paths relative to /root/reference/src/c++/lib/), batch-oriented where the reference is
+// per-object, and free of reference headers so it builds stand-alone:
+//
+//   sx::path_segment / sx::path_t         ALIGNPATH::path_segment, path_t                 blt_util/align_path.hh:171
+//   sx::IndelKey                          IndelKey{pos,type,deletionLength,insertSequence} starling_common/IndelKey.hh:39-193
+//   sx::CandidateAlignment                CandidateAlignment{al, indels, leading/trailing} starling_common/CandidateAlignment.hh:36-83
+//   sx::ReadAlignBatch::scoreCandidateAlignments   the loop at starling_read_align.cpp:1564-1571 over scoreCandidateAlignment
+//   sx::AlignmentScores<int>, sx::GlobalAligner<int>::align, sx::AlignmentResult<int>   alignment/{AlignmentScores,GlobalAligner}.hh
+//   sx::Context                           RAII sx_ctx; failures throw sx::Exception (the reference throws blt_exception)
+//
+// Header-only; link with -lstrelka_b200.
+#pragma once
+
+#include "strelka_b200.h"
+
+#include <cstring>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace sx
+{
+typedef int32_t pos_t;
+
+struct Exception : public std::runtime_error
+{
+    Exception(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+    int code;
+};
+
+class Context
+{
+public:
+    explicit Context(int cudaDevice = 0, const sx_params* params = nullptr)
+    {
+        sx_params p;
+        if (params) p = *params;
+        else sx_default_params(&p);
+        const int rc(sx_create(cudaDevice, &p, &_ctx));
+        if (rc != SX_OK) throw Exception(rc, sx_last_error(nullptr));
+    }
+    ~Context() { sx_destroy(_ctx); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    sx_ctx* get() const { return _ctx; }
+    void check(int rc) const
+    {
+        if (rc != SX_OK) throw Exception(rc, sx_last_error(_ctx));
+    }
+
+private:
+    sx_ctx* _ctx = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// alignment paths and indel keys
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace ALIGNPATH
+{
+enum align_t { NONE, MATCH, INSERT, DELETE, SKIP, SOFT_CLIP, HARD_CLIP, PAD, SEQ_MATCH, SEQ_MISMATCH }; // blt_util/align_path.hh:41-55
+}
+struct path_segment
+{
+    path_segment(ALIGNPATH::align_t t = ALIGNPATH::NONE, unsigned l = 0) : type(t), length(l) {}
+    ALIGNPATH::align_t type;
+    unsigned length;
+};
+typedef std::vector<path_segment> path_t;
+
+inline ALIGNPATH::align_t cigar_code_to_segment_type(char c)
+{
+    using namespace ALIGNPATH;
+    switch (c)
+    {
+    case 'M': return MATCH;
+    case 'I': return INSERT;
+    case 'D': return DELETE;
+    case 'N': return SKIP;
+    case 'S': return SOFT_CLIP;
+    case 'H': return HARD_CLIP;
+    case 'P': return PAD;
+    case '=': return SEQ_MATCH;
+    case 'X': return SEQ_MISMATCH;
+    default: return NONE;
+    }
+}
+inline void cigar_to_apath(const char* cigar, path_t& apath)
+{
+    apath.clear();
+    unsigned n(0);
+    for (const char* p(cigar); *p; ++p)
+    {
+        if (*p >= '0' && *p <= '9') n = n * 10 + (*p - '0');
+        else
+        {
+            apath.push_back(path_segment(cigar_code_to_segment_type(*p), n));
+            n = 0;
+        }
+    }
+}
+inline std::string apath_to_cigar(const path_t& apath)
+{
+    static const char* codes = "?MIDNSHP=X";
+    std::string s;
+    for (const path_segment& ps : apath) s += std::to_string(ps.length) + codes[ps.type];
+    return s;
+}
+
+namespace INDEL
+{
+enum index_t { NONE, INDEL, MISMATCH, BP_LEFT, BP_RIGHT }; // starling_common/indel_core.hh:57-66
+}
+struct IndelKey
+{
+    IndelKey(pos_t p = 0, INDEL::index_t t = INDEL::NONE, unsigned l = 0, const char* is = "") : pos(p), type(t), deletionLength(l), insertSequence(is) {}
+    unsigned insert_length() const { return insertSequence.size(); }
+    unsigned delete_length() const { return deletionLength; }
+    bool isMismatch() const { return type == INDEL::MISMATCH; }
+    pos_t pos;
+    INDEL::index_t type;
+    unsigned deletionLength;
+    std::string insertSequence;
+};
+
+struct alignment
+{
+    path_t path;
+    pos_t pos = 0;
+    bool is_fwd_strand = true;
+};
+
+struct CandidateAlignment
+{
+    alignment al;
+    std::vector<IndelKey> indels; ///< getIndels(), ordered by position like indel_set_t
+    IndelKey leading_indel_key;
+    IndelKey trailing_indel_key;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// K1: batch of regions / reads / candidate alignments -> ln P(read | path)
+// ---------------------------------------------------------------------------------------------------------------------------
+class ReadAlignBatch
+{
+public:
+    /// isCandidate(key): what IndelBuffer::isCandidateIndel would answer (starling_read_align_score.cpp:473-475);
+    /// insertSeqOf(key): getInsertSeq (score.cpp:229-256) -- the key's own sequence unless it is a breakpoint
+    typedef std::function<bool(const IndelKey&)> candidate_fn;
+
+    void beginRegion(const std::string& ref, pos_t refBegin)
+    {
+        closeRegion();
+        pad();
+        sx_region r;
+        std::memset(&r, 0, sizeof(r));
+        r.seq_off = _seq4.size();
+        r.qual_off = _qual.size();
+        r.ref_off = _ref.size();
+        r.read_begin = _readLen.size();
+        r.aln_begin = _alns.size();
+        r.seg_begin = _segs.size();
+        r.ins_begin = _ins.size();
+        r.ref_begin = refBegin;
+        r.ref_len = ref.size();
+        _regions.push_back(r);
+        _ref.insert(_ref.end(), ref.begin(), ref.end());
+        _open = true;
+    }
+
+    /// read given as BAM 4-bit codes (bam_seq::get_code) and qualities; returns the read's index in the batch
+    unsigned addRead(const uint8_t* codes, const uint8_t* qual, unsigned len)
+    {
+        require(_open, "addRead outside a region");
+        _readLen.push_back(len);
+        for (unsigned i(0); i < len; i += 2) _seq4.push_back(static_cast<uint8_t>(((codes[i] & 15) << 4) | ((i + 1 < len) ? (codes[i + 1] & 15) : 0)));
+        _qual.insert(_qual.end(), qual, qual + len);
+        return _readLen.size() - 1;
+    }
+    unsigned addRead(const std::string& bases, const uint8_t* qual)
+    {
+        std::vector<uint8_t> codes(bases.size());
+        for (size_t i(0); i < bases.size(); ++i) codes[i] = get_bam_seq_code(bases[i]);
+        return addRead(codes.data(), qual, bases.size());
+    }
+
+    /// flattening of one CandidateAlignment: the segment walk of scoreCandidateAlignment (score.cpp:289-499) with every host-side
+    /// lookup resolved (getMatchingIndelKey :172-224, leading-edge insert tail :334-338/:394-398, candidacy :473-475)
+    void addCandidateAlignment(unsigned readIndex, const CandidateAlignment& cal, const candidate_fn& isCandidate)
+    {
+        using namespace ALIGNPATH;
+        require(_open, "addCandidateAlignment outside a region");
+        require(_alns.empty() || _alns.back().read <= readIndex, "alignments must be added in read order");
+        const path_t& path(cal.al.path);
+        const unsigned aps(path.size());
+        std::pair<unsigned, unsigned> ends(aps, aps); // get_match_edge_segments, blt_util/align_path.cpp:736-752
+        {
+            bool isFirst(false);
+            for (unsigned i(0); i < aps; ++i)
+                if (isAlignMatch(path[i].type))
+                {
+                    if (!isFirst) ends.first = i;
+                    isFirst = true;
+                    ends.second = i;
+                }
+        }
+        sx_aln a{readIndex, cal.al.pos, static_cast<uint32_t>(_segs.size()), static_cast<uint32_t>(_ins.size())};
+        pos_t ref_head_pos(cal.al.pos);
+        unsigned path_index(0);
+        while (path_index < aps)
+        {
+            const path_segment& ps(path[path_index]);
+            unsigned n_seg(1);
+            // is_segment_swap_start, blt_util/align_path.cpp:868-895
+            unsigned j(path_index), insLen(0), delLen(0);
+            for (; j < aps && (path[j].type == INSERT || path[j].type == DELETE); ++j) (path[j].type == INSERT ? insLen : delLen) += path[j].length;
+            const bool isSwap(insLen && delLen);
+            if (isSwap || ps.type == SEQ_MISMATCH)
+            {
+                unsigned del, ins;
+                if (ps.type == SEQ_MISMATCH) del = ins = ps.length;
+                else
+                {
+                    del = delLen;
+                    ins = insLen;
+                    n_seg = j - path_index;
+                }
+                const IndelKey& k(matchingKey(cal, ref_head_pos, del, ins, ends, path_index));
+                pushInsert(k, ps.length, ins, path_index < ends.first, isCandidate(k) ? 0 : SX_SEGF_NONCANDIDATE);
+                pushSeg(del, SX_SEG_REFSKIP, 0);
+                ref_head_pos += del;
+            }
+            else if (isAlignMatch(ps.type))
+            {
+                pushSeg(ps.length, SX_SEG_MATCH, 0);
+                ref_head_pos += ps.length;
+            }
+            else if (ps.type == INSERT)
+            {
+                const IndelKey& k(matchingKey(cal, ref_head_pos, 0, ps.length, ends, path_index));
+                pushInsert(k, ps.length, ps.length, path_index < ends.first, isCandidate(k) ? 0 : SX_SEGF_NONCANDIDATE);
+            }
+            else if (ps.type == DELETE)
+            {
+                const IndelKey& k(matchingKey(cal, ref_head_pos, ps.length, 0, ends, path_index));
+                pushSeg(ps.length, SX_SEG_REFSKIP, isCandidate(k) ? 0 : SX_SEGF_NONCANDIDATE);
+                ref_head_pos += ps.length;
+            }
+            else if (ps.type == SKIP)
+            {
+                pushSeg(ps.length, SX_SEG_REFSKIP, 0);
+                ref_head_pos += ps.length;
+            }
+            else if (ps.type == SOFT_CLIP) pushSeg(ps.length, SX_SEG_SOFTCLIP, 0);
+            else if (ps.type == HARD_CLIP) pushSeg(ps.length, SX_SEG_HARDCLIP, 0);
+            else throw Exception(SX_ERR_ARG, "Can't handle cigar code"); // score.cpp:461-466
+            path_index += n_seg;
+        }
+        _alns.push_back(a);
+    }
+
+    /// the loop of starling_read_align.cpp:1564-1571 for every alignment in the batch
+    void scoreCandidateAlignments(const Context& ctx, std::vector<double>& candAlignmentScores)
+    {
+        const sx_align_batch b(view());
+        candAlignmentScores.assign(b.n_alns, 0.);
+        ctx.check(sx_score_alignments(ctx.get(), &b, candAlignmentScores.data()));
+    }
+
+    /// closes the batch (sentinels, slack) and returns the ABI view; valid until the next mutation
+    sx_align_batch view()
+    {
+        closeRegion();
+        pad();
+        _regionsOut = _regions;
+        sx_region s;
+        std::memset(&s, 0, sizeof(s));
+        s.seq_off = _seq4.size();
+        s.qual_off = _qual.size();
+        s.ref_off = _ref.size();
+        s.read_begin = _readLen.size();
+        s.aln_begin = _alns.size();
+        s.seg_begin = _segs.size();
+        s.ins_begin = _ins.size();
+        _regionsOut.push_back(s);
+        _alnsOut = _alns;
+        _alnsOut.push_back(sx_aln{static_cast<uint32_t>(_readLen.size()), 0, static_cast<uint32_t>(_segs.size()), static_cast<uint32_t>(_ins.size())});
+        _seq4Out = _seq4;
+        _qualOut = _qual;
+        _refOut = _ref;
+        _insOut = _ins;
+        _segsOut = _segs;
+        _seq4Out.resize(_seq4.size() + SX_POOL_SLACK);
+        _qualOut.resize(_qual.size() + SX_POOL_SLACK);
+        _refOut.resize(_ref.size() + SX_POOL_SLACK);
+        _insOut.resize(_ins.size() + SX_POOL_SLACK);
+        _segsOut.resize(_segs.size() + 16, sx_aln_seg{0, SX_SEG_HARDCLIP, 0});
+        sx_align_batch b;
+        std::memset(&b, 0, sizeof(b));
+        b.n_regions = _regions.size();
+        b.n_reads = _readLen.size();
+        b.n_alns = _alns.size();
+        b.n_segs = _segs.size();
+        b.regions = _regionsOut.data();
+        b.read_len = _readLen.data();
+        b.seq4 = _seq4Out.data();
+        b.qual = _qualOut.data();
+        b.ref = _refOut.data();
+        b.alns = _alnsOut.data();
+        b.segs = _segsOut.data();
+        b.ins = _insOut.data();
+        b.seq4_bytes = _seq4.size();
+        b.qual_bytes = _qual.size();
+        b.ref_bytes = _ref.size();
+        b.ins_bytes = _ins.size();
+        return b;
+    }
+
+    static uint8_t get_bam_seq_code(char c) // htsapi/bam_seq.hh:98-118
+    {
+        switch (c)
+        {
+        case '=': return 0;
+        case 'A': return 1;
+        case 'C': return 2;
+        case 'G': return 4;
+        case 'T': return 8;
+        default: return 15;
+        }
+    }
+
+private:
+    static bool isAlignMatch(ALIGNPATH::align_t t) { return t == ALIGNPATH::MATCH || t == ALIGNPATH::SEQ_MATCH || t == ALIGNPATH::SEQ_MISMATCH; }
+    static void require(bool ok, const char* msg)
+    {
+        if (!ok) throw Exception(SX_ERR_ARG, msg);
+    }
+    void closeRegion() { _open = false; }
+    void pad()
+    {
+        // staging rule of include/strelka_b200.h: every region slice starts 16-byte aligned; pad segments are no-op hard clips
+        while (_seq4.size() & 15) _seq4.push_back(0);
+        while (_qual.size() & 15) _qual.push_back(0);
+        while (_ref.size() & 15) _ref.push_back(0);
+        while (_ins.size() & 15) _ins.push_back(0);
+        while (_segs.size() & 3) _segs.push_back(sx_aln_seg{0, SX_SEG_HARDCLIP, 0});
+    }
+    void pushSeg(unsigned len, uint8_t kind, uint8_t flags) { _segs.push_back(sx_aln_seg{static_cast<uint16_t>(len), kind, flags}); }
+    void pushInsert(const IndelKey& k, unsigned firstSegLen, unsigned insertLength, bool isLeadingEdge, uint8_t flags)
+    {
+        const std::string& seq(k.insertSequence);
+        int head(0);
+        if (isLeadingEdge) head = static_cast<int>(seq.size()) - static_cast<int>(firstSegLen);
+        for (unsigned i(0); i < insertLength; ++i)
+        {
+            const int p(head + static_cast<int>(i));
+            _ins.push_back((p >= 0 && p < static_cast<int>(seq.size())) ? seq[p] : 'N'); // string_bam_seq::get_char out of range
+        }
+        pushSeg(insertLength, SX_SEG_INSERT, flags);
+    }
+    static const IndelKey& matchingKey(const CandidateAlignment& cal, pos_t ref_head_pos, unsigned del, unsigned ins, const std::pair<unsigned, unsigned>& ends,
+                                       unsigned path_index)
+    {
+        if (path_index < ends.first) return cal.leading_indel_key;
+        if (path_index > ends.second) return cal.trailing_indel_key;
+        for (const IndelKey& k : cal.indels)
+            if (k.pos == ref_head_pos && (k.type == INDEL::INDEL || k.isMismatch()) && k.delete_length() == del && k.insert_length() == ins) return k;
+        throw Exception(SX_ERR_ARG, "candidate alignment does not contain the indel its path implies"); // assert(isFound), score.cpp:222
+    }
+
+    bool _open = false;
+    std::vector<sx_region> _regions, _regionsOut;
+    std::vector<uint16_t> _readLen;
+    std::vector<uint8_t> _seq4, _qual, _seq4Out, _qualOut;
+    std::vector<char> _ref, _ins, _refOut, _insOut;
+    std::vector<sx_aln> _alns, _alnsOut;
+    std::vector<sx_aln_seg> _segs, _segsOut;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// K3: GlobalAligner
+// ---------------------------------------------------------------------------------------------------------------------------
+template <typename ScoreType> struct AlignmentScores // alignment/AlignmentScores.hh:24-53
+{
+    AlignmentScores(ScoreType initMatch, ScoreType initMismatch, ScoreType initOpen, ScoreType initExtend, ScoreType initOffEdge, ScoreType initInsertDelete = 0,
+                    bool initIsAllowEdgeInsertion = false, bool initIsRequireEdgeDeletion = false)
+        : match(initMatch), mismatch(initMismatch), open(initOpen), extend(initExtend), offEdge(initOffEdge), insertDelete(initInsertDelete),
+          isAllowEdgeInsertion(initIsAllowEdgeInsertion), isRequireEdgeDeletion(initIsRequireEdgeDeletion)
+    {
+    }
+    const ScoreType match, mismatch, open, extend, offEdge, insertDelete;
+    const bool isAllowEdgeInsertion, isRequireEdgeDeletion;
+};
+
+struct Alignment // alignment/Alignment.hh:30-52
+{
+    pos_t beginPos = 0;
+    path_t apath;
+};
+template <typename ScoreType> struct AlignmentResult // alignment/SingleRefAlignerShared.hh:33-50
+{
+    ScoreType score = 0;
+    Alignment align;
+};
+
+template <typename ScoreType> class GlobalAligner
+{
+public:
+    GlobalAligner(const Context& ctx, const AlignmentScores<ScoreType>& scores) : _ctx(ctx)
+    {
+        _sc.match = scores.match;
+        _sc.mismatch = scores.mismatch;
+        _sc.open = scores.open;
+        _sc.extend = scores.extend;
+        _sc.offEdge = scores.offEdge;
+        _sc.insertDelete = scores.insertDelete;
+        _sc.isAllowEdgeInsertion = scores.isAllowEdgeInsertion;
+        _sc.isRequireEdgeDeletion = scores.isRequireEdgeDeletion;
+    }
+
+    /// GlobalAligner<ScoreType>::align(queryBegin, queryEnd, refBegin, refEnd, result)  alignment/GlobalAlignerImpl.hh:36
+    template <typename SymIter> void align(SymIter queryBegin, SymIter queryEnd, SymIter refBegin, SymIter refEnd, AlignmentResult<ScoreType>& result) const
+    {
+        std::vector<std::pair<std::string, std::string>> one(1, std::make_pair(std::string(queryBegin, queryEnd), std::string(refBegin, refEnd)));
+        std::vector<AlignmentResult<ScoreType>> res;
+        alignBatch(one, res);
+        result = res[0];
+    }
+
+    /// all (haplotype, reference segment) pairs of an active region in one launch
+    void alignBatch(const std::vector<std::pair<std::string, std::string>>& queryRef, std::vector<AlignmentResult<ScoreType>>& results) const
+    {
+        const uint32_t n(queryRef.size());
+        std::string q, r;
+        std::vector<uint32_t> qo(n + 1, 0), ro(n + 1, 0);
+        uint32_t maxOps(8);
+        for (uint32_t i(0); i < n; ++i)
+        {
+            q += queryRef[i].first;
+            r += queryRef[i].second;
+            qo[i + 1] = q.size();
+            ro[i + 1] = r.size();
+            maxOps = std::max<uint32_t>(maxOps, queryRef[i].first.size() + queryRef[i].second.size() + 2);
+        }
+        q.resize(q.size() + 16);
+        r.resize(r.size() + 16);
+        sx_ga_batch b{n, q.data(), r.data(), qo.data(), ro.data(), maxOps};
+        std::vector<sx_ga_result> res(n);
+        std::vector<uint32_t> cig(static_cast<size_t>(n) * maxOps);
+        _ctx.check(sx_global_align(_ctx.get(), &_sc, &b, res.data(), cig.data()));
+        results.assign(n, AlignmentResult<ScoreType>());
+        for (uint32_t i(0); i < n; ++i)
+        {
+            if (res[i].status != 0) throw Exception(SX_ERR_ARG, "sx_global_align: problem too large for the kernel's shared-memory tile");
+            results[i].score = static_cast<ScoreType>(res[i].score);
+            results[i].align.beginPos = res[i].beginPos;
+            for (uint32_t k(0); k < res[i].n_ops; ++k)
+            {
+                const uint32_t op(cig[static_cast<size_t>(i) * maxOps + k]);
+                results[i].align.apath.push_back(path_segment(cigar_code_to_segment_type("MIDNSHP=X"[op & 15]), op >> 4));
+            }
+        }
+    }
+
+private:
+    const Context& _ctx;
+    sx_ga_scores _sc;
+};
+
+} // namespace sx

@@ -225,3 +225,20 @@ def test_libm_mirrors_on_device(ctx):
     o_off, o_de = reflib.ox_dependent_eprob(p, pb)
     g_off, g_de = ctx.dependent_eprob(pb)
     assert np.array_equal(_bits(o_de), _bits(g_de))
+
+
+def test_cpp_host_mirror(tmp_path):
+    """The C++ host mirror (strelka_b200/host/strelka_b200.hh, the layer a reference developer programs against): the reference's
+    22 GlobalAligner goldens and reference-frozen scoreCandidateAlignment values, through sx::GlobalAligner<int>::align and
+    sx::ReadAlignBatch::scoreCandidateAlignments."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_host_mirror")
+    lib = os.path.join(root, "strelka_b200", "csrc")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "strelka_b200", "host"),
+                           os.path.join(root, "tests", "cpp", "test_host_mirror.cpp"), "-o", exe, "-L" + lib, "-lstrelka_b200", "-Wl,-rpath," + lib])
+    out = subprocess.run([exe, os.path.join(root, "tests", "golden")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "0 failures" in out.stdout
