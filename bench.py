@@ -421,6 +421,14 @@ def main():
         value = total_loci * args.steps / dt
         alg_bytes = ab.algorithmic_bytes()
         achieved = alg_bytes / (k1_avg_ms * 1e-3) / 1e9
+        traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch from the committed ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if args.config in tj and n_loci == CONFIGS[args.config][0]:
+                t = tj[args.config]["k1_score_kernel"]
+                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+        except Exception:
+            pass
         line = {
             "metric": "candidate_loci_per_sec", "value": value, "unit": "loci/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -429,7 +437,7 @@ def main():
                        "l2": "inputs (%.1f GB per GPU) far exceed the 126 MB L2; no flush needed" % (alg_bytes / 1e9), "gen_seconds": round(t_gen, 1)},
             "gcups": (cells_k1 + cells_k3) * world * args.steps / dt / 1e9,
             "k1_gcups_kernel_only": cells_k1 / (k1_avg_ms * 1e-3) / 1e9,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k1_score_kernel", "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k1_avg_ms, "peak_source": peak_src},
             "gpu_launches": launches,
             "kernel_ms_per_step": {k: v / args.steps for k, v in parts.items()},

@@ -67,7 +67,10 @@ typedef struct sx_params {
     double ssnv_contam_tolerance;                    /* 0.15 */
     /* runtime knobs (not reference options) */
     int32_t pipeline_chunks;   /* host-buffer entry points split a batch into this many H2D/compute/D2H chunks; 0 = auto */
-    int32_t reserved;
+    /* indel genotype model (starling_base_options, starling_common/starling_base_shared.hh:108,177,245) */
+    int32_t min_read_bp_flank;             /* 5 */
+    double randomBaseMatchProb;            /* 0.25 */
+    double readConfidentSupportThreshold;  /* 0.51 */
 } sx_params;
 
 void sx_default_params(sx_params* p);
@@ -295,6 +298,45 @@ int sx_site_gl_somatic(sx_ctx* ctx, const sx_pileup_batch* normal_host, const sx
                        const uint8_t* is_forced_output_host, sx_ssnv_result* out_host /*[n_sites]*/);
 int sx_site_gl_somatic_dev(sx_ctx* ctx, const sx_pileup_batch* normal_dev, const sx_pileup_batch* tumor_dev,
                            const uint8_t* is_forced_output_dev, sx_ssnv_result* out_dev);
+
+/* ==========================================================================================
+ * K5  indel_gl
+ *   replaces the per-read loop of getVariantAlleleGroupGenotypeLhoodsForSample
+ *   starling_common/AlleleGroupGenotype.cpp:184-258 (updateGenotypeLogLhoodFromAlleleLogLhood :34-111,
+ *   updateSupportingReadStats :122-152), with integrateOutMappingStatus
+ *   (starling_common/readMappingAdjustmentUtil.hh:46-56) and get_het_observed_allele_ratio
+ *   (starling_common/starling_indel_call_pprob_digt.cpp:40-71), called from
+ *   applications/starling/starling_pos_processor.cpp:1335 (updateIndelLocusWithSampleInfo).
+ *
+ * Per locus: an orthogonal allele group of A non-reference indel alleles (1 <= A <= SX_INDEL_MAX_ALLELES) and,
+ * per supporting read in readId order, the allele log-likelihoods the host takes out of the ReadPathScores maps
+ * (getAlleleLogLhoodFromRead, OrthogonalVariantAlleleCandidateGroupUtil.cpp:132-196: index 0 = reference).
+ * ======================================================================================== */
+#define SX_INDEL_MAX_ALLELES 4
+#define SX_INDEL_MAX_GT 15 /* (A+1)(A+2)/2 at A = 4 */
+
+typedef struct sx_indel_batch {
+    uint32_t n_loci;
+    const uint32_t* read_off;       /* [n_loci+1] offsets into the per-read arrays */
+    const uint32_t* lnp_off;        /* [n_loci+1] offsets into allele_lnp; a locus holds n_reads*(A+1) floats, read-major */
+    const uint32_t* allele_off;     /* [n_loci+1] offsets into the per-allele arrays (A = allele_off[l+1]-allele_off[l]) */
+    const uint8_t* ploidy;          /* [n_loci] callerPloidy 1 or 2 */
+    const uint16_t* allele_del_len; /* per non-ref allele: IndelKey::delete_length() */
+    const uint16_t* allele_ins_len; /* per non-ref allele: IndelKey::insert_length() */
+    const float* allele_lnp;        /* ReadPathScores::score_t values: [read][0] = ref path, [read][1+a] = allele a */
+    const uint16_t* read_length;    /* per read: ReadPathScores::read_length */
+    const uint16_t* non_ambig;      /* per read: ReadPathScores::nonAmbiguousBasesInRead */
+    const uint8_t* is_fwd;          /* per read: ReadPathScores::is_fwd_strand */
+} sx_indel_batch;
+
+typedef struct sx_indel_result {
+    double gt_lhood[SX_INDEL_MAX_GT];                 /* genotypeLogLhood, VcfGenotypeUtil::getGenotypeIndex order (htsapi/vcf_util.hh:373-390) */
+    uint16_t support[2][SX_INDEL_MAX_ALLELES + 2];    /* LocusSupportingReadStats: [rev=0|fwd=1][ref, alt1.., last = nonConfidentCount] */
+    uint32_t n_gt;
+} sx_indel_result;
+
+int sx_indel_gl(sx_ctx* ctx, const sx_indel_batch* batch_host, sx_indel_result* out_host /*[n_loci]*/);
+int sx_indel_gl_dev(sx_ctx* ctx, const sx_indel_batch* batch_dev, sx_indel_result* out_dev);
 
 /* ==========================================================================================
  * Multi-GPU: regions shard across ranks with no data-path collective; one gather of fixed-size

@@ -546,3 +546,85 @@ extern "C" int ref_score_flat_batch(const sx_align_batch* b, uint32_t r0, uint32
         return 2;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// indel genotype likelihoods: getVariantAlleleGroupGenotypeLhoodsForSample (starling_common/AlleleGroupGenotype.cpp:184)
+// The allele group is rebuilt in an IndelBuffer; every read gets a ReadPathScores entry under every allele whose `ref` is the
+// read's reference-path score and whose `indel` is that allele's score, which is what getAlleleLogLhoodFromRead turns back into
+// the flat per-read vector {ref, alt1, ...} the batch carries.
+// ---------------------------------------------------------------------------------------------------------------
+#include "starling_common/AlleleGroupGenotype.hh"
+#include "starling_common/OrthogonalVariantAlleleCandidateGroup.hh"
+
+extern "C" int ref_indel_gl(const sx_params* p, const sx_indel_batch* b, sx_indel_result* out, char* err, int errlen)
+{
+    try
+    {
+        harness_options opt;
+        opt.is_candidate_indel_signal_test = false;
+        opt.randomBaseMatchProb = p->randomBaseMatchProb;
+        opt.default_min_read_bp_flank = p->min_read_bp_flank;
+        {
+            char buf[64];
+            snprintf(buf, sizeof(buf), "%.17g", p->readConfidentSupportThreshold);
+            opt.readConfidentSupportThreshold.update(buf);
+        }
+        starling_base_deriv_options dopt(opt);
+        starling_sample_options sample_opt(opt);
+        for (uint32_t l = 0; l < b->n_loci; ++l)
+        {
+            sx_indel_result& o(out[l]);
+            std::memset(&o, 0, sizeof(o));
+            const unsigned A(b->allele_off[l + 1] - b->allele_off[l]);
+            reference_contig_segment ref;
+            ref.seq() = std::string(2000, 'A');
+            IndelBuffer indelBuffer(opt, dopt, ref);
+            depth_buffer db, db2;
+            indelBuffer.registerSample(db, db2, false);
+            indelBuffer.finalizeSamples();
+            std::vector<IndelKey> keys;
+            for (unsigned a = 0; a < A; ++a)
+            {
+                const unsigned dl(b->allele_del_len[b->allele_off[l] + a]), il(b->allele_ins_len[b->allele_off[l] + a]);
+                // distinct keys: vary the insert sequence per allele index so equal-length alleles do not collide
+                std::string ins(il, "ACGT"[a & 3]);
+                keys.emplace_back(500 + (int)a, INDEL::INDEL, dl, ins.c_str());
+                IndelObservation obs;
+                obs.key = keys.back();
+                obs.data.id = 1;
+                obs.data.iat = INDEL_ALIGN_TYPE::GENOME_TIER1_READ;
+                indelBuffer.addIndelObservation(0, obs);
+            }
+            const uint32_t r0(b->read_off[l]), r1(b->read_off[l + 1]);
+            OrthogonalVariantAlleleCandidateGroup group, contrast;
+            for (unsigned a = 0; a < A; ++a)
+            {
+                IndelBuffer::iterator it(indelBuffer.getIndelIter(keys[a]));
+                IndelSampleData& isd(getIndelData(it).getSampleData(0));
+                for (uint32_t r = r0; r < r1; ++r)
+                {
+                    const float* lnp(b->allele_lnp + b->lnp_off[l] + (size_t)(r - r0) * (A + 1));
+                    isd.read_path_lnp[r - r0] = ReadPathScores(lnp[0], lnp[1 + a], b->non_ambig[r], b->read_length[r], true, b->is_fwd[r] != 0, 0, 0);
+                }
+                group.addVariantAllele(indelBuffer.getIndelIter(keys[a]));
+            }
+            std::vector<double> gl;
+            LocusSupportingReadStats stats;
+            getVariantAlleleGroupGenotypeLhoodsForSample(opt, dopt, sample_opt, b->ploidy[l], 0, group, contrast, gl, stats);
+            o.n_gt = gl.size();
+            for (size_t g = 0; g < gl.size() && g < SX_INDEL_MAX_GT; ++g) o.gt_lhood[g] = gl[g];
+            for (int s = 0; s < 2; ++s)
+            {
+                const SupportingReadCountGroup& c(stats.getCounts(s == 1));
+                for (unsigned a = 0; a <= A; ++a) o.support[s][a] = c.confidentAlleleCount(a);
+                o.support[s][SX_INDEL_MAX_ALLELES + 1] = c.nonConfidentCount;
+            }
+        }
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        set_err(err, errlen, e.what());
+        return 1;
+    }
+}

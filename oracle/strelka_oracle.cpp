@@ -1342,3 +1342,129 @@ extern "C" void ox_sort_std(uint32_t* idx, uint32_t n, const uint8_t* key_by_idx
 {
     std::sort(idx, idx + n, [key_by_idx](const uint32_t& a, const uint32_t& b) { return key_by_idx[a] > key_by_idx[b]; });
 }
+
+// ------------------------------------------------------------------------------------------------
+// a12  indel genotype likelihoods
+//   getVariantAlleleGroupGenotypeLhoodsForSample       starling_common/AlleleGroupGenotype.cpp:184-258
+//   updateGenotypeLogLhoodFromAlleleLogLhood           :34-111
+//   updateSupportingReadStats                          :122-152
+//   integrateOutMappingStatus                          starling_common/readMappingAdjustmentUtil.hh:28-56
+//   get_het_observed_allele_ratio                      starling_common/starling_indel_call_pprob_digt.cpp:40-71
+//   getLogSum<double>                                  blt_util/logSumUtil.hh:33-41
+// ------------------------------------------------------------------------------------------------
+namespace
+{
+double getLogSumD(double x1, double x2)
+{
+    if (x1 < x2) std::swap(x1, x2);
+    return x1 + log1p_switch(std::exp(x2 - x1));
+}
+
+void get_het_observed_allele_ratio(const unsigned read_length, const unsigned min_overlap, const unsigned del_len, const unsigned ins_len,
+                                   const double het_allele_ratio, double& log_ref_prob, double& log_indel_prob)
+{
+    const unsigned base_expect((read_length + 1) < (2 * min_overlap) ? 0 : (read_length + 1) - (2 * min_overlap));
+    const double ref_path_expect(base_expect + std::min(del_len, base_expect));
+    const double indel_path_expect(base_expect + std::min(ins_len, base_expect));
+    const double ref_path_term((1 - het_allele_ratio) * ref_path_expect);
+    const double indel_path_term(het_allele_ratio * indel_path_expect);
+    const double total_path_term(ref_path_term + indel_path_term);
+    if (total_path_term > 0)
+    {
+        const double indel_prob(indel_path_term / total_path_term);
+        log_ref_prob = std::log(1. - indel_prob);
+        log_indel_prob = std::log(indel_prob);
+    }
+}
+} // namespace
+
+extern "C" int ox_indel_gl(const sx_params* p, const sx_indel_batch* b, sx_indel_result* out)
+{
+    const double randomBaseMatchLogProb(std::log(p->randomBaseMatchProb));  // starling_base_shared.cpp:44
+    const double correctMappingLogPrior(std::log(1.7e-10));                 // :66
+    const unsigned min_read_bp_flank(p->min_read_bp_flank);
+    const double readSupportThreshold(p->readConfidentSupportThreshold);
+    auto integrateOutMappingStatus = [&](const uint16_t nonAmbiguousBasesInRead, const double correctMappingLogLikelihood) {
+        return getLogSumD((correctMappingLogLikelihood + correctMappingLogPrior), randomBaseMatchLogProb * nonAmbiguousBasesInRead);
+    };
+    for (uint32_t l = 0; l < b->n_loci; ++l)
+    {
+        sx_indel_result& o(out[l]);
+        std::memset(&o, 0, sizeof(o));
+        const unsigned nonRefAlleleCount(b->allele_off[l + 1] - b->allele_off[l]);
+        const unsigned fullAlleleCount(nonRefAlleleCount + 1);
+        if (nonRefAlleleCount < 1 || nonRefAlleleCount > SX_INDEL_MAX_ALLELES) return SX_ERR_ARG;
+        const unsigned callerPloidy(b->ploidy[l]);
+        if (callerPloidy != 1 && callerPloidy != 2) return SX_ERR_ARG;
+        const unsigned genotypeCount(callerPloidy == 1 ? fullAlleleCount : (fullAlleleCount * (fullAlleleCount + 1)) / 2);
+        o.n_gt = genotypeCount;
+        const uint16_t* del(b->allele_del_len + b->allele_off[l]);
+        const uint16_t* ins(b->allele_ins_len + b->allele_off[l]);
+        const uint32_t r0(b->read_off[l]), r1(b->read_off[l + 1]);
+        for (uint32_t r = r0; r < r1; ++r)
+        {
+            const float* lnp(b->allele_lnp + b->lnp_off[l] + (size_t)(r - r0) * fullAlleleCount);
+            std::vector<double> alleleLogLhood(fullAlleleCount);
+            for (unsigned a(0); a < fullAlleleCount; ++a) alleleLogLhood[a] = lnp[a];
+            const unsigned read_length(b->read_length[r]);
+            const uint16_t nonAmbig(b->non_ambig[r]);
+            if (callerPloidy == 1)
+            {
+                for (unsigned allele0Index(0); allele0Index < fullAlleleCount; ++allele0Index)
+                    o.gt_lhood[allele0Index] += integrateOutMappingStatus(nonAmbig, alleleLogLhood[allele0Index]);
+            }
+            else
+            {
+                for (unsigned allele1Index(0); allele1Index < fullAlleleCount; ++allele1Index)
+                {
+                    for (unsigned allele0Index(0); allele0Index <= allele1Index; ++allele0Index)
+                    {
+                        const bool isHet(allele0Index != allele1Index);
+                        const unsigned genotypeIndex(allele0Index + (allele1Index * (allele1Index + 1) / 2));
+                        double rawLogLhood(0);
+                        if (isHet)
+                        {
+                            static const double hetAlleleRatio(0.5);
+                            static const double loghalf(std::log(0.5));
+                            double logHetAllele0Prior(loghalf);
+                            double logHetAllele1Prior(loghalf);
+                            get_het_observed_allele_ratio(read_length, min_read_bp_flank, del[allele1Index - 1], ins[allele1Index - 1], hetAlleleRatio, logHetAllele0Prior,
+                                                          logHetAllele1Prior);
+                            if (allele0Index > 0)
+                            {
+                                double logRefPrior(loghalf);
+                                logHetAllele0Prior = loghalf;
+                                get_het_observed_allele_ratio(read_length, min_read_bp_flank, del[allele0Index - 1], ins[allele0Index - 1], hetAlleleRatio, logRefPrior,
+                                                              logHetAllele0Prior);
+                                const double normalizeHetRatio(getLogSumD(logHetAllele0Prior, logHetAllele1Prior));
+                                logHetAllele0Prior -= normalizeHetRatio;
+                                logHetAllele1Prior -= normalizeHetRatio;
+                            }
+                            rawLogLhood = getLogSumD(alleleLogLhood[allele0Index] + logHetAllele0Prior, alleleLogLhood[allele1Index] + logHetAllele1Prior);
+                        }
+                        else
+                        {
+                            rawLogLhood = alleleLogLhood[allele0Index];
+                        }
+                        o.gt_lhood[genotypeIndex] += integrateOutMappingStatus(nonAmbig, rawLogLhood);
+                    }
+                }
+            }
+            // updateSupportingReadStats
+            for (double& alleleHood : alleleLogLhood) alleleHood = integrateOutMappingStatus(nonAmbig, alleleHood);
+            unsigned maxIndex(0);
+            normalizeLogDistro(alleleLogLhood.begin(), alleleLogLhood.end(), maxIndex);
+            bool isConfidentAlleleFound(false);
+            const unsigned strand(b->is_fwd[r] ? 1 : 0);
+            for (unsigned alleleIndex(0); alleleIndex < fullAlleleCount; ++alleleIndex)
+            {
+                if (alleleLogLhood[alleleIndex] < readSupportThreshold) continue;
+                o.support[strand][alleleIndex]++;
+                isConfidentAlleleFound = true;
+                break;
+            }
+            if (!isConfidentAlleleFound) o.support[strand][SX_INDEL_MAX_ALLELES + 1]++;
+        }
+    }
+    return SX_OK;
+}

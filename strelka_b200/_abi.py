@@ -35,13 +35,15 @@ class SxParams(C.Structure):
         ("shared_site_error_strand_bias_fraction", C.c_double),
         ("ssnv_contam_tolerance", C.c_double),
         ("pipeline_chunks", C.c_int32),
-        ("reserved", C.c_int32),
+        ("min_read_bp_flank", C.c_int32),
+        ("randomBaseMatchProb", C.c_double),
+        ("readConfidentSupportThreshold", C.c_double),
     ]
 
 
 def default_params() -> SxParams:
     """Reference defaults: starling_options (starling_shared.hh:34-39) + configureStrelkaSomaticWorkflow.py.ini."""
-    return SxParams(0.001, 0.35, 0.6, 1, 1, 0.25, 0.0, 1e-4, 5e-10, 0.0, 0.15, 0, 0)
+    return SxParams(0.001, 0.35, 0.6, 1, 1, 0.25, 0.0, 1e-4, 5e-10, 0.0, 0.15, 0, 5, 0.25, 0.51)
 
 
 # numpy mirrors of the POD arrays (layout == C structs; checked against sizeof in tests/test_abi.py)
@@ -84,6 +86,14 @@ SSNV_RESULT_DT = np.dtype(
         ("pad", "<u4"),
     ]
 )
+
+
+INDEL_RESULT_DT = np.dtype([("gt_lhood", "<f8", (15,)), ("support", "<u2", (2, 6)), ("n_gt", "<u4"), ("pad", "<u4")])
+
+
+class SxIndelBatch(C.Structure):
+    _fields_ = [("n_loci", C.c_uint32)] + [(n, C.c_void_p) for n in (
+        "read_off", "lnp_off", "allele_off", "ploidy", "allele_del_len", "allele_ins_len", "allele_lnp", "read_length", "non_ambig", "is_fwd")]
 
 
 class SxAlignBatch(C.Structure):
@@ -165,6 +175,8 @@ SYMBOLS = [
     ("sx_dependent_eprob", C.c_int, [_P, C.POINTER(SxPileupBatch), _P, _P]),
     ("sx_site_gl_somatic", C.c_int, [_P, C.POINTER(SxPileupBatch), C.POINTER(SxPileupBatch), _P, _P]),
     ("sx_site_gl_somatic_dev", C.c_int, [_P, C.POINTER(SxPileupBatch), C.POINTER(SxPileupBatch), _P, _P]),
+    ("sx_indel_gl", C.c_int, [_P, C.POINTER(SxIndelBatch), _P]),
+    ("sx_indel_gl_dev", C.c_int, [_P, C.POINTER(SxIndelBatch), _P]),
     ("sx_comm_get_unique_id", C.c_int, [_P]),
     ("sx_comm_init", C.c_int, [_P, _P, C.c_int, C.c_int]),
     ("sx_gather_records", C.c_int, [_P, _P, C.c_size_t, _P, C.c_int]),

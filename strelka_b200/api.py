@@ -189,3 +189,13 @@ class Context:
 
     def site_gl_somatic_dev(self, dn: DevPileupBatch, dt: DevPileupBatch, forced: Optional[DeviceArray], out: DeviceArray) -> None:
         self._chk(self.lib.sx_site_gl_somatic_dev(self.h, C.byref(dn.c), C.byref(dt.c), forced.ptr if forced else None, out.ptr))
+
+
+def _indel_gl(self, ib: "B.IndelBatch", out=None) -> np.ndarray:
+    if out is None:
+        out = np.zeros(ib.n_loci, A.INDEL_RESULT_DT)
+    self._chk(self.lib.sx_indel_gl(self.h, C.byref(ib.c), out.ctypes.data))
+    return out
+
+
+Context.indel_gl = _indel_gl  # K5

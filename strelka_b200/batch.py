@@ -329,3 +329,39 @@ class GaBatch:
 
 def cigar_string(ops: np.ndarray) -> str:
     return "".join(f"{int(o) >> 4}{'MIDNSHP=X'[int(o) & 15]}" for o in ops)
+
+
+class IndelBatch:
+    """sx_indel_batch: per locus an orthogonal allele group (A non-ref indel alleles) and, per supporting read, the flat allele
+    log-likelihood vector {ref, alt1..altA} (ReadPathScores floats), read_length, nonAmbiguousBasesInRead, strand."""
+
+    def __init__(self, loci):
+        """loci: list of dicts {ploidy, alleles: [(del_len, ins_len)], reads: [(lnp[A+1], read_length, non_ambig, is_fwd)]}"""
+        n = len(loci)
+        self.n_loci = n
+        self.read_off = np.zeros(n + 1, np.uint32)
+        self.lnp_off = np.zeros(n + 1, np.uint32)
+        self.allele_off = np.zeros(n + 1, np.uint32)
+        self.ploidy = np.array([l["ploidy"] for l in loci], np.uint8)
+        dl, il, lnp, rl, na, fw = [], [], [], [], [], []
+        for i, l in enumerate(loci):
+            A_ = len(l["alleles"])
+            self.read_off[i + 1] = self.read_off[i] + len(l["reads"])
+            self.lnp_off[i + 1] = self.lnp_off[i] + len(l["reads"]) * (A_ + 1)
+            self.allele_off[i + 1] = self.allele_off[i] + A_
+            for d, ins in l["alleles"]:
+                dl.append(d)
+                il.append(ins)
+            for v, rlen, nonamb, fwd in l["reads"]:
+                assert len(v) == A_ + 1
+                lnp.extend(v)
+                rl.append(rlen)
+                na.append(nonamb)
+                fw.append(fwd)
+        pad = lambda a, dt: np.array(a if len(a) else [0], dtype=dt)
+        self.allele_del_len, self.allele_ins_len = pad(dl, np.uint16), pad(il, np.uint16)
+        self.allele_lnp, self.read_length, self.non_ambig, self.is_fwd = pad(lnp, np.float32), pad(rl, np.uint16), pad(na, np.uint16), pad(fw, np.uint8)
+        if self.ploidy.size == 0:
+            self.ploidy = np.zeros(1, np.uint8)
+        self.c = A.SxIndelBatch(n, A.ptr(self.read_off), A.ptr(self.lnp_off), A.ptr(self.allele_off), A.ptr(self.ploidy), A.ptr(self.allele_del_len),
+                                A.ptr(self.allele_ins_len), A.ptr(self.allele_lnp), A.ptr(self.read_length), A.ptr(self.non_ambig), A.ptr(self.is_fwd))

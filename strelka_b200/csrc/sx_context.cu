@@ -23,7 +23,8 @@ static_assert(sizeof(sx_aln_seg) == 4 && sizeof(sx_aln) == 16 && sizeof(sx_regio
 static_assert(sizeof(sx_ga_result) == 16 && sizeof(sx_ga_scores) == 32, "K3 POD layout");
 static_assert(sizeof(sx_digt_result_set) == 24 && sizeof(sx_digt_result) == 152, "K2a POD layout");
 static_assert(sizeof(sx_ssnv_result) == 288, "K2b POD layout");
-static_assert(sizeof(sx_params) == 88, "sx_params layout");
+static_assert(sizeof(sx_params) == 104, "sx_params layout");
+static_assert(sizeof(sx_indel_result) == 152, "K5 POD layout");
 
 static thread_local std::string g_create_err;
 
@@ -49,6 +50,9 @@ extern "C" void sx_default_params(sx_params* p)
     p->shared_site_error_strand_bias_fraction = 0.0;
     p->ssnv_contam_tolerance = 0.15;
     p->pipeline_chunks = 0;
+    p->min_read_bp_flank = 5;              // starling_common/starling_base_shared.hh:108
+    p->randomBaseMatchProb = 0.25;         // :177
+    p->readConfidentSupportThreshold = 0.51; // :245
 }
 
 extern "C" void sx_ga_active_region_scores(sx_ga_scores* s)
@@ -232,6 +236,14 @@ void build_tables(const sx_params& p, sx_tables& t)
         t.g_is_dependent_eprob = (p.is_bsnp_diploid && (p.bsnp_ssd_no_mismatch > 0. || p.bsnp_ssd_one_mismatch > 0)) ? 1 : 0; // blt_shared.hh:76-81
         t.g_is_min_vexp = p.is_min_vexp ? 1 : 0;
         fill_priors(static_cast<blt_float_t>(p.bsnp_diploid_theta), t.g_lnprior);
+    }
+    // indel genotype model: starling_base_shared.cpp:44,66 ; AlleleGroupGenotype.cpp:76-77
+    {
+        t.i_randomBaseMatchLogProb = std::log(p.randomBaseMatchProb);
+        t.i_correctMappingLogPrior = std::log(1.7e-10);
+        t.i_loghalf = std::log(0.5);
+        t.i_readSupportThreshold = p.readConfidentSupportThreshold;
+        t.i_min_flank = p.min_read_bp_flank;
     }
     // somatic: position_somatic_snv_strand_grid_lhood_cached.cpp ; position_somatic_snv_strand_grid.cpp:42-55 ; qscore_calculator.cpp:33-60
     {
@@ -466,6 +478,8 @@ int sx_check_status(sx_ctx* ctx, const char* what)
         if (st & 2) return sx_fail(ctx, SX_ERR_ARG, "%s: a region does not fit the shared-memory tile the kernel was launched with", what);
         if (st & 4) return sx_fail(ctx, SX_ERR_ARG, "%s: unknown segment kind", what);
         if (st & 8) return sx_fail(ctx, SX_ERR_ARG, "%s: alignment path consumes more read bases than the read holds", what);
+        if (st & 16) return sx_fail(ctx, SX_ERR_UNSUPPORTED, "%s: a site holds more calls than the kernel handles", what);
+        if (st & 32) return sx_fail(ctx, SX_ERR_ARG, "%s: allele count outside 1..%d or ploidy outside {1,2}", what, SX_INDEL_MAX_ALLELES);
         return sx_fail(ctx, SX_ERR_ARG, "%s: device status %d", what, st);
     }
     return SX_OK;

@@ -58,6 +58,9 @@ struct sx_tables
     uint32_t s_n_terms[6];
     float s_geno_prior[6]; // germlineGenotypeLogPrior[ngt] + (tgt==0 ? lnmatch : lnmismatch), float add
     float pad2_[2];
+    // indel genotype model
+    double i_randomBaseMatchLogProb, i_correctMappingLogPrior, i_loghalf, i_readSupportThreshold;
+    int32_t i_min_flank, i_pad;
 };
 
 int sx_upload_pileup(sx_ctx* ctx, const sx_pileup_batch* b, int slot_base, sx_pileup_batch* d, uint32_t* max_site, cudaStream_t st);

@@ -182,3 +182,21 @@ def ref_somatic(params: A.SxParams, npb: B.PileupBatch, tpb: B.PileupBatch, forc
     if rc != 0:
         raise RuntimeError(err.value.decode(errors="replace"))
     return out
+
+
+def ox_indel_gl(params: A.SxParams, ib: B.IndelBatch) -> np.ndarray:
+    out = np.zeros(ib.n_loci, A.INDEL_RESULT_DT)
+    lib = oracle()
+    lib.ox_indel_gl.argtypes = [C.POINTER(A.SxParams), C.POINTER(A.SxIndelBatch), _P]
+    rc = lib.ox_indel_gl(C.byref(params), C.byref(ib.c), A.ptr(out))
+    assert rc == 0, rc
+    return out
+
+
+def ref_indel_gl(params: A.SxParams, ib: B.IndelBatch) -> np.ndarray:
+    out = np.zeros(ib.n_loci, A.INDEL_RESULT_DT)
+    err = _err()
+    rc = ref().ref_indel_gl(C.byref(params), C.byref(ib.c), _P(A.ptr(out)), err, 1024)
+    if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    return out

@@ -295,3 +295,31 @@ def random_ga_problems(rng: np.random.Generator, n: int, qlen=(5, 120), rlen=(5,
         qs.append(q)
         rs.append(r)
     return qs, rs
+
+
+def random_indel_loci(rng: np.random.Generator, n_loci: int, depth=(5, 60)):
+    """Orthogonal allele groups with 1..4 non-ref indel alleles; per read a ref-path score and one score per allele, shaped like
+    the max-path scores score_indels leaves in ReadPathScores (a read supports one allele strongly, the rest weakly)."""
+    loci = []
+    for _ in range(n_loci):
+        A_ = int(rng.choice([1, 1, 1, 2, 2, 3, 4]))
+        alleles = []
+        for _a in range(A_):
+            if rng.random() < 0.5:
+                alleles.append((int(min(49, rng.geometric(0.3))), 0))
+            elif rng.random() < 0.8:
+                alleles.append((0, int(min(49, rng.geometric(0.3)))))
+            else:
+                alleles.append((int(rng.integers(1, 10)), int(rng.integers(1, 10))))
+        n = int(rng.integers(depth[0], depth[1]))
+        reads = []
+        for _r in range(n):
+            rl = int(rng.choice([75, 100, 150, 151, 8]))
+            supp = int(rng.integers(0, A_ + 1))
+            v = rng.normal(-60.0, 15.0, A_ + 1)
+            v[supp] = rng.normal(-8.0, 4.0)
+            if rng.random() < 0.1:
+                v[:] = v[supp]  # uninformative read
+            reads.append(([float(np.float32(min(x, -0.01))) for x in v], rl, int(rng.integers(max(1, rl - 10), rl + 1)), int(rng.random() < 0.5)))
+        loci.append({"ploidy": int(rng.choice([2, 2, 2, 1])), "alleles": alleles, "reads": reads})
+    return loci

@@ -29,7 +29,8 @@ def test_pod_layouts():
     assert A.GA_RESULT_DT.itemsize == 16 and C.sizeof(A.SxGaScores) == 32
     assert A.DIGT_RS_DT.itemsize == 24 and A.DIGT_RESULT_DT.itemsize == 152
     assert A.SSNV_RESULT_DT.itemsize == 288
-    assert C.sizeof(A.SxParams) == 88
+    assert C.sizeof(A.SxParams) == 104
+    assert A.INDEL_RESULT_DT.itemsize == 152
     p = A.SxParams()
     A.load().sx_default_params(C.byref(p))
     d = A.default_params()

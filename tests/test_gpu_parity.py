@@ -242,3 +242,16 @@ def test_cpp_host_mirror(tmp_path):
     out = subprocess.run([exe, os.path.join(root, "tests", "golden")], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "0 failures" in out.stdout
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_k5_indel_gl(ctx, seed):
+    rng = np.random.default_rng(5000 + seed)
+    ib = B.IndelBatch(specgen.random_indel_loci(rng, 1500))
+    p = A.default_params()
+    want = reflib.ox_indel_gl(p, ib)
+    got = ctx.indel_gl(ib)
+    assert np.array_equal(want["n_gt"], got["n_gt"])
+    assert np.array_equal(want["support"], got["support"])
+    # double log-sum-exp through CUDA's exp/log/log1p: agreement far inside the 1e-4 the north star asks of likelihoods
+    np.testing.assert_allclose(got["gt_lhood"], want["gt_lhood"], rtol=1e-10, atol=1e-9)

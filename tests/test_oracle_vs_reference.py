@@ -119,3 +119,15 @@ def test_flat_batch_reference_scorer_matches_oracle_on_bench_workload():
     r1, c1 = reflib.ref_global_align(sc, gb)
     r2, c2 = reflib.ox_global_align(sc, gb)
     assert np.array_equal(r1, r2) and np.array_equal(c1, c2)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_indel_genotype_likelihoods(seed):
+    rng = np.random.default_rng(400 + seed)
+    ib = B.IndelBatch(specgen.random_indel_loci(rng, 150))
+    p = A.default_params()
+    want = reflib.ref_indel_gl(p, ib)
+    got = reflib.ox_indel_gl(p, ib)
+    assert np.array_equal(want["n_gt"], got["n_gt"])
+    assert np.array_equal(want["support"], got["support"])
+    assert np.array_equal(want["gt_lhood"].view(np.uint64), got["gt_lhood"].view(np.uint64))
