@@ -81,10 +81,10 @@ class HostAlloc:
         self.ptrs = []
 
 
-def make_workload(synth, alloc: HostAlloc, n_loci: int, depth: int, read_len: int, n_haps: int, seed: int, threads: int):
+def make_workload(synth, alloc: HostAlloc, n_loci: int, depth: int, read_len: int, n_haps: int, seed: int, threads: int, qual_bits: int = 4):
     regions = alloc.array((n_loci + 1) * A.REGION_DT.itemsize, A.REGION_DT)
     sz = SynthSizes()
-    rc = synth.synth_k1_plan(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, C.c_void_p(regions.ctypes.data), C.byref(sz))
+    rc = synth.synth_k1_plan(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, qual_bits, C.c_void_p(regions.ctypes.data), C.byref(sz))
     assert rc == 0, rc
     S = A.SX_POOL_SLACK
     read_lens = alloc.array(sz.n_reads * 2 + 16, np.uint16)
@@ -94,12 +94,12 @@ def make_workload(synth, alloc: HostAlloc, n_loci: int, depth: int, read_len: in
     alns = alloc.array((sz.n_alns + 1) * A.ALN_DT.itemsize, A.ALN_DT)
     segs = alloc.array((sz.n_segs + 16) * A.ALN_SEG_DT.itemsize, A.ALN_SEG_DT)
     ins = alloc.array(sz.ins_bytes + S, np.uint8)
-    rc = synth.synth_k1_fill(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, C.c_void_p(regions.ctypes.data), C.c_void_p(read_lens.ctypes.data),
+    rc = synth.synth_k1_fill(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, qual_bits, C.c_void_p(regions.ctypes.data), C.c_void_p(read_lens.ctypes.data),
                              C.c_void_p(seq4.ctypes.data), C.c_void_p(qual.ctypes.data), C.c_void_p(ref.ctypes.data), C.c_void_p(alns.ctypes.data),
                              C.c_void_p(segs.ctypes.data), C.c_void_p(ins.ctypes.data))
     assert rc == 0, rc
     used = {"seq4": int(sz.seq4_bytes), "qual": int(sz.qual_bytes), "ref": int(sz.ref_bytes), "ins": int(sz.ins_bytes)}
-    ab = B.AlignBatch(regions, read_lens[: sz.n_reads], seq4, qual, ref, alns[: sz.n_alns + 1], segs, ins, used)
+    ab = B.AlignBatch(regions, read_lens[: sz.n_reads], seq4, qual, ref, alns[: sz.n_alns + 1], segs, ins, used, qual_bits, [11, 25, 37] if qual_bits == 4 else None)
     # K2a: one pileup column per locus
     site_off = alloc.array((n_loci + 1) * 4, np.uint32)
     n_calls = synth.synth_pileups(n_loci, C.c_double(float(depth)), 0, C.c_uint64(seed), threads, C.c_void_p(site_off.ctypes.data), None, None)

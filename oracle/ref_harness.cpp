@@ -446,7 +446,13 @@ extern "C" int ref_score_flat_batch(const sx_align_batch* b, uint32_t r0, uint32
                 std::unique_ptr<bam_record> br(new bam_record);
                 br->set_qname("R");
                 const std::string dummy(len, 'A');
-                br->set_readqual(dummy.c_str(), b->qual + qo);
+                if (b->qual_bits == 4)
+                {
+                    std::vector<uint8_t> q8(len);
+                    for (int i = 0; i < len; ++i) q8[i] = b->qual_dict[((b->qual + qo)[i >> 1] >> ((~i & 1) << 2)) & 0xf];
+                    br->set_readqual(dummy.c_str(), q8.data());
+                }
+                else br->set_readqual(dummy.c_str(), b->qual + qo);
                 std::memcpy(bam_get_seq(br->get_data()), b->seq4 + so, (len + 1) / 2);
                 alignment al;
                 al.pos = 0;
@@ -456,7 +462,7 @@ extern "C" int ref_score_flat_batch(const sx_align_batch* b, uint32_t r0, uint32
                 sreads.emplace_back(new starling_read(*br, al, MAPLEVEL::UNKNOWN, r));
                 bams.push_back(std::move(br));
                 so += (len + 1) / 2;
-                qo += len;
+                qo += (b->qual_bits == 4) ? (len + 1) / 2 : len;
             }
             std::vector<CandidateAlignment> cals(nxt.aln_begin - reg.aln_begin);
             for (uint32_t a = reg.aln_begin; a < nxt.aln_begin; ++a)

@@ -98,7 +98,7 @@ extern "C" int ox_score_alignments_range(const sx_align_batch* b, uint32_t r0, u
                 seqOff.push_back(so);
                 qualOff.push_back(qo);
                 so += (b->read_len[r] + 1) / 2;
-                qo += b->read_len[r];
+                qo += (b->qual_bits == 4) ? (b->read_len[r] + 1) / 2 : b->read_len[r];
             }
         }
         for (uint32_t a = reg.aln_begin; a < nxt.aln_begin; ++a)
@@ -123,7 +123,8 @@ extern "C" int ox_score_alignments_range(const sx_align_batch* b, uint32_t r0, u
                         const unsigned readPos(read_offset + i);
                         const uint8_t sbase((seq[readPos >> 1] >> ((~readPos & 1) << 2)) & 0xf); // bam_seq::get_code
                         if (sbase == 15) continue; // BAM_BASE::ANY
-                        const uint8_t qscore(qual[readPos]);
+                        // qualities: one byte per base, or (qual_bits == 4) dictionary-coded nibbles, high nibble first
+                        const uint8_t qscore((b->qual_bits == 4) ? b->qual_dict[(qual[readPos >> 1] >> ((~readPos & 1) << 2)) & 0xf] : qual[readPos]);
                         bool is_ref(sbase == 0); // BAM_BASE::REF
                         if (!is_ref)
                         {

@@ -114,6 +114,9 @@ class SxAlignBatch(C.Structure):
         ("qual_bytes", C.c_uint64),
         ("ref_bytes", C.c_uint64),
         ("ins_bytes", C.c_uint64),
+        ("qual_bits", C.c_uint32),
+        ("qual_dict", C.c_uint8 * 16),
+        ("reserved_", C.c_uint32),
     ]
 
 

@@ -170,8 +170,10 @@ def _pad16(n: int) -> int:
 class AlignBatch:
     """Owns the numpy pools of one sx_align_batch and exposes the ctypes struct (``.c``)."""
 
-    def __init__(self, regions, read_len, seq4, qual, ref, alns, segs, ins, used):
+    def __init__(self, regions, read_len, seq4, qual, ref, alns, segs, ins, used, qual_bits=8, qual_dict=None):
         self.regions, self.read_len, self.seq4, self.qual, self.ref = regions, read_len, seq4, qual, ref
+        self.qual_bits = qual_bits
+        self.qual_dict = (C.c_uint8 * 16)(*([int(x) for x in qual_dict] + [0] * (16 - len(qual_dict)))) if qual_dict is not None else (C.c_uint8 * 16)()
         self.alns, self.segs, self.ins = alns, segs, ins
         self.n_regions = len(regions) - 1
         self.n_reads = len(read_len)
@@ -181,7 +183,7 @@ class AlignBatch:
         self.c = A.SxAlignBatch(
             self.n_regions, self.n_reads, self.n_alns, self.n_segs,
             A.ptr(regions), A.ptr(read_len), A.ptr(seq4), A.ptr(qual), A.ptr(ref), A.ptr(alns), A.ptr(segs), A.ptr(ins),
-            used["seq4"], used["qual"], used["ref"], used["ins"],
+            used["seq4"], used["qual"], used["ref"], used["ins"], qual_bits, self.qual_dict, 0,
         )
 
     def cells(self) -> int:
@@ -199,7 +201,14 @@ class AlignBatch:
         )
 
 
-def build_align_batch(regions: Sequence[RegionSpec]) -> AlignBatch:
+def build_align_batch(regions: Sequence[RegionSpec], qual_bits: int = 8) -> AlignBatch:
+    """qual_bits=4 sends qualities dictionary-coded, two per byte (needs <= 16 distinct values in the batch)."""
+    qdict = None
+    if qual_bits == 4:
+        vals = sorted({int(x) for r in regions for _, q in r.reads for x in np.asarray(q).tolist()})
+        assert len(vals) <= 16, "4-bit quality coding needs at most 16 distinct quality values"
+        qdict = vals
+        qcode = {v: i for i, v in enumerate(vals)}
     reg = np.zeros(len(regions) + 1, dtype=A.REGION_DT)
     read_len: List[int] = []
     seq4 = bytearray()
@@ -224,7 +233,13 @@ def build_align_batch(regions: Sequence[RegionSpec]) -> AlignBatch:
             if n & 1:
                 c = np.concatenate([c, np.zeros(1, np.uint8)])
             seq4.extend(((c[0::2] << 4) | c[1::2]).astype(np.uint8).tobytes())
-            qual.extend(np.asarray(q, dtype=np.uint8).tobytes())
+            if qual_bits == 4:
+                qc = np.array([qcode[int(x)] for x in np.asarray(q).tolist()], dtype=np.uint8)
+                if n & 1:
+                    qc = np.concatenate([qc, np.zeros(1, np.uint8)])
+                qual.extend(((qc[0::2] << 4) | qc[1::2]).astype(np.uint8).tobytes())
+            else:
+                qual.extend(np.asarray(q, dtype=np.uint8).tobytes())
         order = sorted(range(len(r.alns)), key=lambda k: r.alns[k].read)
         assert order == list(range(len(r.alns))), "alignments of a region must be sorted by read"
         for cal in r.alns:
@@ -255,6 +270,8 @@ def build_align_batch(regions: Sequence[RegionSpec]) -> AlignBatch:
         seg_arr,
         np.frombuffer(bytes(ins) + slack, dtype=np.uint8).copy(),
         used,
+        qual_bits,
+        qdict,
     )
 
 

@@ -16,6 +16,7 @@
 #include "sx_internal.h"
 
 #include <algorithm>
+#include <cstring>
 
 namespace
 {
@@ -96,11 +97,11 @@ __host__ __device__ __forceinline__ k1_layout k1_make_layout(const sx_region& r0
     o += pad16((L.n_reads + 1) * 4u);
     L.eoff = 0;
     L.desc = o;
-    o += 64;
+    o += 64 + 16; // 16 nibble descriptors + the 16-entry quality dictionary
     L.ent = o;
     // entries: 2 bytes per base, every read padded to an even count; + slack: the uniform chunk loop may load (and discard) up to
     // K1_CHUNK-1 entries past a read
-    o += pad16((L.qual_bytes + L.n_reads) * 2u) + 32u;
+    o += L.seq_bytes * 4u + 32u;
     L.total = o;
     return L;
 }
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
                                                               const char* __restrict__ ref, const sx_aln* __restrict__ alns,
                                                               const sx_aln_seg* __restrict__ segs, const char* __restrict__ ins,
                                                               const sx_tables* __restrict__ tables, uint32_t region_begin, double* __restrict__ lnp_out,
-                                                              int* __restrict__ status, uint32_t smem_bytes)
+                                                              int* __restrict__ status, uint32_t smem_bytes, uint32_t qual_bits, uint4 qual_dict)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t ri = region_begin + blockIdx.x;
@@ -144,6 +145,14 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
     uint32_t* soff_s = reinterpret_cast<uint32_t*>(smem + L.soff);
     uint32_t* desc_s = reinterpret_cast<uint32_t*>(smem + L.desc);
     uint16_t* ent_s = reinterpret_cast<uint16_t*>(smem + L.ent);
+    // quality dictionary of the 4-bit wire format lives in the descriptor block's tail (16 bytes after the 16 descriptors)
+    uint8_t* qd_s = reinterpret_cast<uint8_t*>(desc_s + 16);
+    if (threadIdx.x < 16)
+    {
+        const uint32_t w = threadIdx.x >> 2, sh = (threadIdx.x & 3u) * 8u;
+        const uint32_t word = w == 0 ? qual_dict.x : w == 1 ? qual_dict.y : w == 2 ? qual_dict.z : qual_dict.w;
+        qd_s[threadIdx.x] = static_cast<uint8_t>(word >> sh);
+    }
     if (threadIdx.x < 16)
     {
         const uint32_t code = threadIdx.x;
@@ -207,7 +216,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
     }
     mbar_wait(bar, 0);
     __syncthreads();
-    if (boff_s[L.n_reads] > L.qual_bytes || soff_s[L.n_reads] > L.seq_bytes)
+    if ((qual_bits == 4 ? soff_s[L.n_reads] : boff_s[L.n_reads]) > L.qual_bytes || soff_s[L.n_reads] > L.seq_bytes)
     {
         if (threadIdx.x == 0) atomicOr(status, 2);
         return;
@@ -222,14 +231,25 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
         {
             const uint32_t len = rlen_s[r];
             const uint8_t* sq = seq_s + soff_s[r];
-            const uint8_t* ql = qual_s + boff_s[r];
+            const uint8_t* ql = qual_s + (qual_bits == 4 ? soff_s[r] : boff_s[r]);
             uint32_t* en2 = reinterpret_cast<uint32_t*>(ent_s) + soff_s[r]; // every read is padded to an even entry count: entry offset = 2*soff
             const uint32_t npair = (len + 1) >> 1;
             for (uint32_t p = lane; p < npair; p += 32)
             {
                 const uint32_t byte = sq[p];
                 const uint32_t d0 = desc_s[byte >> 4], d1 = desc_s[byte & 15u]; // bam_seq::get_code: high nibble first
-                const uint32_t q0 = ql[2 * p], q1 = (2 * p + 1 < len) ? ql[2 * p + 1] : 0u;
+                uint32_t q0, q1;
+                if (qual_bits == 4)
+                {
+                    const uint32_t qb = ql[p]; // both qualities of the pair in one byte, high nibble first
+                    q0 = qd_s[qb >> 4];
+                    q1 = (2 * p + 1 < len) ? qd_s[qb & 15u] : 0u;
+                }
+                else
+                {
+                    q0 = ql[2 * p];
+                    q1 = (2 * p + 1 < len) ? ql[2 * p + 1] : 0u;
+                }
                 qmax = max(qmax, (d0 >> 16) ? q0 : 0u);
                 qmax = max(qmax, (d1 >> 16) ? q1 : 0u);
                 const uint32_t e0 = (d0 & 0xffffu) + ((min(q0, (uint32_t)SX_MAX_QSCORE) << 4) & (d0 >> 16));
@@ -436,8 +456,10 @@ int sx_k1_launch(sx_ctx* ctx, const sx_align_batch* d, uint32_t region_begin, ui
         SX_CUDA(ctx, cudaFuncSetAttribute(k1_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
         attr_set = ctx->smem_optin;
     }
+    uint4 qd;
+    memcpy(&qd, d->qual_dict, 16);
     k1_score_kernel<<<region_end - region_begin, K1_THREADS, smem_bytes, st>>>(d->regions, d->read_len, d->seq4, d->qual, d->ref, d->alns, d->segs, d->ins,
-                                                                              ctx->d_tables, region_begin, lnp_dev, ctx->d_status, static_cast<uint32_t>(smem_bytes));
+                                                                              ctx->d_tables, region_begin, lnp_dev, ctx->d_status, static_cast<uint32_t>(smem_bytes), d->qual_bits == 4 ? 4u : 8u, qd);
     SX_CUDA(ctx, cudaGetLastError());
     return SX_OK;
 }

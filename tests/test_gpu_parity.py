@@ -255,3 +255,18 @@ def test_k5_indel_gl(ctx, seed):
     assert np.array_equal(want["support"], got["support"])
     # double log-sum-exp through CUDA's exp/log/log1p: agreement far inside the 1e-4 the north star asks of likelihoods
     np.testing.assert_allclose(got["gt_lhood"], want["gt_lhood"], rtol=1e-10, atol=1e-9)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_k1_four_bit_quality_wire_format(ctx, seed):
+    """qual_bits=4 (dictionary-coded qualities, two per byte) is lossless: same doubles as the 8-bit format and as the oracle."""
+    rng = np.random.default_rng(7000 + seed)
+    regions = [specgen.random_region(rng, n_reads=int(rng.integers(1, 12))) for _ in range(30)]
+    regions += [specgen.simple_region(rng, n_reads=int(rng.integers(5, 40))) for _ in range(10)]
+    b8 = B.build_align_batch(regions, qual_bits=8)
+    b4 = B.build_align_batch(regions, qual_bits=4)
+    assert b4.used["qual"] < b8.used["qual"]
+    want = reflib.ox_score(b8)
+    assert np.array_equal(_bits(reflib.ox_score(b4)), _bits(want))
+    assert np.array_equal(_bits(ctx.score_alignments(b4)), _bits(want))
+    assert np.array_equal(_bits(ctx.score_alignments(b8)), _bits(want))

@@ -50,6 +50,7 @@ struct k1_cfg
 {
     uint32_t n_loci, depth, read_len, n_haps, ref_len;
     uint64_t seed;
+    uint32_t qual_bits; // 8: one byte per base; 4: dictionary-coded nibbles (dictionary {11, 25, 37})
 };
 
 inline uint32_t geom_len(rng_t& r)
@@ -137,14 +138,16 @@ void gen_region(const k1_cfg& c, uint32_t l, bool fill, region_sizes& sz, const 
         {
             read_len[reg->read_begin + ridx] = (uint16_t)c.read_len;
             uint8_t* sq = seq4 + reg->seq_off + (uint64_t)ridx * packed;
-            uint8_t* ql = qual + reg->qual_off + (uint64_t)ridx * c.read_len;
+            uint8_t* ql = qual + reg->qual_off + (uint64_t)ridx * (c.qual_bits == 4 ? packed : c.read_len);
             memset(sq, 0, packed);
+            if (c.qual_bits == 4) memset(ql, 0, packed);
             for (uint32_t i = 0; i < c.read_len; ++i)
             {
                 const uint32_t q = pick_qual(rb);
                 char b = rd[i];
                 if (rb.unit() < QERR[q == 11 ? 0 : q == 25 ? 1 : 2]) b = BASES[rb.below(4)];
-                ql[i] = (uint8_t)q;
+                if (c.qual_bits == 4) ql[i >> 1] |= (q == 11 ? 0 : q == 25 ? 1 : 2) << ((~i & 1) << 2);
+                else ql[i] = (uint8_t)q;
                 sq[i >> 1] |= code_of(b) << ((~i & 1) << 2);
             }
         }
@@ -219,10 +222,11 @@ struct synth_k1_sizes
 };
 
 // pass 1: region table (needs the per-region insert bytes) + totals.  regions must hold n_loci+1 entries.
-int synth_k1_plan(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n_haps, uint64_t seed, int threads, sx_region* regions, synth_k1_sizes* out)
+int synth_k1_plan(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n_haps, uint64_t seed, int threads, uint32_t qual_bits, sx_region* regions,
+                  synth_k1_sizes* out)
 {
     if (n_haps < 1 || n_haps > 32 || read_len < 40 || read_len > 1000) return -1;
-    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed};
+    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed, qual_bits};
     std::vector<uint32_t> ins(n_loci);
     parallel_for(n_loci, threads, [&](uint32_t l) {
         region_sizes sz;
@@ -246,7 +250,7 @@ int synth_k1_plan(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n
         R.ref_len = l < n_loci ? c.ref_len : 0;
         if (l == n_loci) break;
         seq += pad16((uint64_t)depth * packed);
-        qual += pad16((uint64_t)depth * read_len);
+        qual += pad16((uint64_t)depth * (qual_bits == 4 ? packed : read_len));
         ref += pad16(c.ref_len);
         insb += pad16(ins[l]);
         seg += segs_per_region;
@@ -265,10 +269,10 @@ int synth_k1_plan(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n
 }
 
 // pass 2: fill caller-allocated pools (sizes from synth_k1_plan, plus SX_POOL_SLACK; alns has n_alns+1 entries, segs n_segs+16)
-int synth_k1_fill(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n_haps, uint64_t seed, int threads, const sx_region* regions,
+int synth_k1_fill(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n_haps, uint64_t seed, int threads, uint32_t qual_bits, const sx_region* regions,
                   uint16_t* read_lens, uint8_t* seq4, uint8_t* qual, char* ref, sx_aln* alns, sx_aln_seg* segs, char* ins)
 {
-    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed};
+    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed, qual_bits};
     const uint32_t n_segs = regions[n_loci].seg_begin;
     for (uint32_t i = 0; i < n_segs + 16; ++i) segs[i] = sx_aln_seg{0, SX_SEG_HARDCLIP, 0};
     parallel_for(n_loci, threads, [&](uint32_t l) {
