@@ -36,7 +36,7 @@ from strelka_b200 import batch as B  # noqa: E402
 CONFIGS = {
     # name: (n_loci, depth, read_len, n_haps, description)
     "cfg2": (1_000_000, 30, 150, 4, "synthetic 30x germline pileup, 150 bp reads, 1M candidate loci, 4 haplotypes/locus"),
-    "cfg5": (10_000, 300, 150, 32, "300x high-depth amplicon, 32 haplotypes/locus"),
+    "cfg5": (10_000, 300, 150, 32, "300x high-depth amplicon, 32 haplotypes/locus (regions of 32 reads)"),
     "tiny": (20_000, 30, 150, 4, "cfg2 shape at 20k loci (plumbing)"),
 }
 
@@ -81,10 +81,12 @@ class HostAlloc:
         self.ptrs = []
 
 
-def make_workload(synth, alloc: HostAlloc, n_loci: int, depth: int, read_len: int, n_haps: int, seed: int, threads: int, qual_bits: int = 4):
-    regions = alloc.array((n_loci + 1) * A.REGION_DT.itemsize, A.REGION_DT)
+def make_workload(synth, alloc: HostAlloc, n_loci: int, depth: int, read_len: int, n_haps: int, seed: int, threads: int, qual_bits: int = 4, reads_per_region: int = 0):
+    rpr = min(reads_per_region, depth) if reads_per_region else depth
+    n_regions = n_loci * ((depth + rpr - 1) // rpr)  # a locus deeper than rpr reads is cut into regions sharing its reference window
+    regions = alloc.array((n_regions + 1) * A.REGION_DT.itemsize, A.REGION_DT)
     sz = SynthSizes()
-    rc = synth.synth_k1_plan(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, qual_bits, C.c_void_p(regions.ctypes.data), C.byref(sz))
+    rc = synth.synth_k1_plan(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, qual_bits, reads_per_region, C.c_void_p(regions.ctypes.data), C.byref(sz))
     assert rc == 0, rc
     S = A.SX_POOL_SLACK
     read_lens = alloc.array(sz.n_reads * 2 + 16, np.uint16)
@@ -94,12 +96,12 @@ def make_workload(synth, alloc: HostAlloc, n_loci: int, depth: int, read_len: in
     alns = alloc.array((sz.n_alns + 1) * A.ALN_DT.itemsize, A.ALN_DT)
     segs = alloc.array((sz.n_segs + 16) * A.ALN_SEG_DT.itemsize, A.ALN_SEG_DT)
     ins = alloc.array(sz.ins_bytes + S, np.uint8)
-    rc = synth.synth_k1_fill(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, qual_bits, C.c_void_p(regions.ctypes.data), C.c_void_p(read_lens.ctypes.data),
+    rc = synth.synth_k1_fill(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, qual_bits, reads_per_region, C.c_void_p(regions.ctypes.data), C.c_void_p(read_lens.ctypes.data),
                              C.c_void_p(seq4.ctypes.data), C.c_void_p(qual.ctypes.data), C.c_void_p(ref.ctypes.data), C.c_void_p(alns.ctypes.data),
                              C.c_void_p(segs.ctypes.data), C.c_void_p(ins.ctypes.data))
     assert rc == 0, rc
     used = {"seq4": int(sz.seq4_bytes), "qual": int(sz.qual_bytes), "ref": int(sz.ref_bytes), "ins": int(sz.ins_bytes)}
-    ab = B.AlignBatch(regions, read_lens[: sz.n_reads], seq4, qual, ref, alns[: sz.n_alns + 1], segs, ins, used, qual_bits, [11, 25, 37] if qual_bits == 4 else None)
+    ab = B.AlignBatch(regions[: n_regions + 1], read_lens[: sz.n_reads], seq4, qual, ref, alns[: sz.n_alns + 1], segs, ins, used, qual_bits, [11, 25, 37] if qual_bits == 4 else None)
     # K2a: one pileup column per locus
     site_off = alloc.array((n_loci + 1) * 4, np.uint32)
     n_calls = synth.synth_pileups(n_loci, C.c_double(float(depth)), 0, C.c_uint64(seed), threads, C.c_void_p(site_off.ctypes.data), None, None)
@@ -175,7 +177,8 @@ def cpu_pass(ab: B.AlignBatch, pb: B.PileupBatch, gb: B.GaBatch, n_sample_loci: 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import reflib
 
-    n = min(n_sample_loci, ab.n_regions)
+    rpl = max(1, ab.n_regions // max(1, pb.n_sites))  # regions per locus (deep loci are cut into several regions)
+    n = min(n_sample_loci, pb.n_sites)
     lnp = np.zeros(ab.n_alns, np.float64)
     gout = np.zeros(n, A.DIGT_RESULT_DT)
     n_ga = min(gb.n, (n // 2) * 3)
@@ -196,7 +199,7 @@ def cpu_pass(ab: B.AlignBatch, pb: B.PileupBatch, gb: B.GaBatch, n_sample_loci: 
             a, b = n * t // threads, n * (t + 1) // threads
             secs = C.c_double(0.0)
             err = C.create_string_buffer(512)
-            rc = rf.ref_score_flat_batch(C.byref(ab.c), C.c_uint32(a), C.c_uint32(b), _P(lnp.ctypes.data), C.byref(secs), err, 512)
+            rc = rf.ref_score_flat_batch(C.byref(ab.c), C.c_uint32(a * rpl), C.c_uint32(b * rpl), _P(lnp.ctypes.data), C.byref(secs), err, 512)
             assert rc == 0, err.value
             t1 = time.perf_counter()
             if b > a:
@@ -215,7 +218,7 @@ def cpu_pass(ab: B.AlignBatch, pb: B.PileupBatch, gb: B.GaBatch, n_sample_loci: 
         def work(t):
             t1 = time.perf_counter()
             a, b = n * t // threads, n * (t + 1) // threads
-            ox.ox_score_alignments_range(C.byref(ab.c), a, b, lnp.ctypes.data)
+            ox.ox_score_alignments_range(C.byref(ab.c), a * rpl, b * rpl, lnp.ctypes.data)
             ox.ox_site_gl_germline_range(C.byref(params), C.byref(pb.c), 1, a, b, gout.ctypes.data)
             ga, gbb = n_ga * t // threads, n_ga * (t + 1) // threads
             if gbb > ga:
@@ -250,6 +253,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_loci, depth, read_len, n_haps, desc = CONFIGS[args.config]
+    rpr = 32 if depth > 64 else 0
     if args.loci:
         n_loci = args.loci
     ncpu = os.cpu_count() or 8
@@ -263,7 +267,7 @@ def main():
         lib = None
         alloc = HostAlloc(lib, False)
         sample = args.cpu_sample_loci or min(n_loci, max(2000, 600 * ncpu))
-        ab, pb, gb = make_workload(synth, alloc, sample, depth, read_len, n_haps, args.seed, ncpu)
+        ab, pb, gb = make_workload(synth, alloc, sample, depth, read_len, n_haps, args.seed, ncpu, 4, rpr)
         for _ in range(args.warmup):
             cpu_pass(ab, pb, gb, sample, ncpu)
         t_tot, n_tot = 0.0, 0
@@ -302,7 +306,7 @@ def main():
     lib = ctx.lib
     alloc = HostAlloc(lib, True)
     t_gen = time.perf_counter()
-    ab, pb, gb = make_workload(synth, alloc, n_loci, depth, read_len, n_haps, args.seed + 1000 * rank, threads)
+    ab, pb, gb = make_workload(synth, alloc, n_loci, depth, read_len, n_haps, args.seed + 1000 * rank, threads, 4, rpr)
     t_gen = time.perf_counter() - t_gen
     cells_k1, cells_k3 = ab.cells(), gb.cells()
     sc = ctx.active_region_scores()

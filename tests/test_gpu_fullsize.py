@@ -154,3 +154,32 @@ def test_cfg3_somatic_full_size(ctx):
         assert np.array_equal(g[f][mm], want[f][mm]), f
     assert np.array_equal(g["normal_lhood"][mm][:, :21].view(np.uint32), want["normal_lhood"][mm][:, :21].view(np.uint32))
     assert np.array_equal(g["tumor_lhood"][mm][:, :21].view(np.uint32), want["tumor_lhood"][mm][:, :21].view(np.uint32))
+
+
+def test_cfg5_high_depth_amplicon(ctx):
+    """BASELINE.json configs[4]: 300x depth, 32 haplotype paths per read, 10k loci (1.44e10 cell updates).  Loci are cut into
+    regions of 32 reads that share the reference window; pileup columns of ~300 calls take K2a's global-scratch path."""
+    import bench
+
+    synth = bench.load_synth()
+    alloc = bench.HostAlloc(ctx.lib, True)
+    n_loci = int(os.environ.get("SX_FULLSIZE_CFG5_LOCI", "10000"))
+    ab, pb, gb = bench.make_workload(synth, alloc, n_loci, 300, 150, 32, 21, os.cpu_count() or 8, 4, 32)
+    assert ab.n_regions == n_loci * 10 and ab.n_alns == n_loci * 300 * 32
+    got = ctx.score_alignments(ab)
+    rng = np.random.default_rng(4)
+    want = np.zeros(ab.n_alns, np.float64)
+    ox = reflib.oracle()
+    for r in rng.integers(0, ab.n_regions, 60):
+        ox.ox_score_alignments_range(C.byref(ab.c), C.c_uint32(int(r)), C.c_uint32(int(r) + 1), want.ctypes.data)
+        a0, a1 = int(ab.regions["aln_begin"][r]), int(ab.regions["aln_begin"][r + 1])
+        assert np.array_equal(got[a0:a1].view(np.uint64), want[a0:a1].view(np.uint64)), r
+    gl = ctx.site_gl_germline(pb, True)
+    idx = np.sort(rng.choice(pb.n_sites, 300, replace=False))
+    sub_off = np.zeros(len(idx) + 1, np.uint32)
+    sub_off[1:] = np.cumsum(pb.site_off[idx + 1] - pb.site_off[idx])
+    sub = B.PileupBatch(sub_off, np.concatenate([pb.calls[pb.site_off[i]:pb.site_off[i + 1]] for i in idx]), pb.ref_base[idx])
+    w = reflib.ox_germline(A.default_params(), sub, True)
+    assert np.array_equal(gl[idx]["phredLoghood"], w["phredLoghood"])
+    assert np.array_equal(gl[idx]["lhood"].view(np.uint32), w["lhood"].view(np.uint32))
+    alloc.free()

@@ -51,6 +51,7 @@ struct k1_cfg
     uint32_t n_loci, depth, read_len, n_haps, ref_len;
     uint64_t seed;
     uint32_t qual_bits; // 8: one byte per base; 4: dictionary-coded nibbles (dictionary {11, 25, 37})
+    uint32_t rpr;       // reads per region: a locus deeper than this is cut into several regions sharing the reference window
 };
 
 inline uint32_t geom_len(rng_t& r)
@@ -94,11 +95,13 @@ inline uint32_t pick_qual(rng_t& r)
 
 const double QERR[3] = {0.07943282347242814, 0.0031622776601683794, 0.00019952623149688788}; // 10^-1.1, 10^-2.5, 10^-3.7
 
-void gen_region(const k1_cfg& c, uint32_t l, bool fill, region_sizes& sz, const sx_region* reg, uint16_t* read_len, uint8_t* seq4, uint8_t* qual, char* ref_pool,
+void gen_region(const k1_cfg& c, uint32_t rg, bool fill, region_sizes& sz, const sx_region* reg, uint16_t* read_len, uint8_t* seq4, uint8_t* qual, char* ref_pool,
                 sx_aln* alns, sx_aln_seg* segs, char* ins)
 {
-    rng_t r(c.seed, l);                      // structure stream: window, alleles, genotype, read placement
-    rng_t rb(c.seed ^ 0x5DEECE66Dull, l);    // base-level stream: qualities and sequencing errors (skipped by the sizing pass)
+    const uint32_t chunks = (c.depth + c.rpr - 1) / c.rpr;
+    const uint32_t l = rg / chunks, chunk = rg % chunks;
+    const uint32_t k_begin = chunk * c.rpr, k_end = std::min(c.depth, k_begin + c.rpr);
+    rng_t r(c.seed, l);                      // structure stream of the locus: window, alleles, genotype, read placement
     locus_desc d;
     std::vector<char> refv(c.ref_len);
     make_locus(c, l, r, d, refv.data());
@@ -112,8 +115,14 @@ void gen_region(const k1_cfg& c, uint32_t l, bool fill, region_sizes& sz, const 
     const uint32_t segs_per_read = 1 + 3 * d.n_alt;
     const uint32_t packed = (c.read_len + 1) / 2;
     std::vector<char> rd(c.read_len);
-    for (uint32_t k = 0; k < c.depth; ++k)
+    for (uint32_t k = 0; k < k_begin; ++k) // reads of earlier regions of this locus: consume their structure draws
     {
+        r.below(c.read_len - 20);
+        r.below(2);
+    }
+    for (uint32_t k = k_begin; k < k_end; ++k)
+    {
+        rng_t rb(c.seed ^ 0x5DEECE66Dull, (uint64_t)l * c.depth + k); // base-level stream of this read: qualities and sequencing errors
         const uint32_t left = 10 + r.below(c.read_len - 20);     // read bases before the locus
         const uint32_t start = locus - left;                      // window-relative start
         const uint32_t h = r.below(2) ? g0 : g1;
@@ -133,7 +142,7 @@ void gen_region(const k1_cfg& c, uint32_t l, bool fill, region_sizes& sz, const 
             }
             while (n < c.read_len) rd[n++] = refv[rp++];
         }
-        const uint32_t ridx = k;
+        const uint32_t ridx = k - k_begin;
         if (fill)
         {
             read_len[reg->read_begin + ridx] = (uint16_t)c.read_len;
@@ -222,41 +231,46 @@ struct synth_k1_sizes
 };
 
 // pass 1: region table (needs the per-region insert bytes) + totals.  regions must hold n_loci+1 entries.
-int synth_k1_plan(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n_haps, uint64_t seed, int threads, uint32_t qual_bits, sx_region* regions,
-                  synth_k1_sizes* out)
+int synth_k1_plan(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n_haps, uint64_t seed, int threads, uint32_t qual_bits, uint32_t reads_per_region,
+                  sx_region* regions, synth_k1_sizes* out)
 {
     if (n_haps < 1 || n_haps > 32 || read_len < 40 || read_len > 1000) return -1;
-    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed, qual_bits};
-    std::vector<uint32_t> ins(n_loci);
-    parallel_for(n_loci, threads, [&](uint32_t l) {
+    const uint32_t rpr = reads_per_region ? std::min(reads_per_region, depth) : depth;
+    const uint32_t chunks = (depth + rpr - 1) / rpr;
+    const uint32_t n_regions = n_loci * chunks;
+    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed, qual_bits, rpr};
+    std::vector<uint32_t> ins(n_regions);
+    parallel_for(n_regions, threads, [&](uint32_t rg) {
         region_sizes sz;
-        gen_region(c, l, false, sz, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-        ins[l] = sz.ins_bytes;
+        gen_region(c, rg, false, sz, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        ins[rg] = sz.ins_bytes;
     });
     const uint32_t packed = (read_len + 1) / 2;
-    const uint32_t segs_per_region = (depth * (1 + 3 * (n_haps - 1)) + 3u) & ~3u;
-    uint64_t seq = 0, qual = 0, ref = 0, insb = 0, seg = 0;
-    for (uint32_t l = 0; l <= n_loci; ++l)
+    uint64_t seq = 0, qual = 0, ref = 0, insb = 0, seg = 0, reads = 0;
+    for (uint32_t rg = 0; rg <= n_regions; ++rg)
     {
-        sx_region& R = regions[l];
+        sx_region& R = regions[rg];
+        const uint32_t l = rg / chunks, chunk = rg % chunks;
+        const uint32_t nr = rg < n_regions ? std::min(depth, (chunk + 1) * rpr) - chunk * rpr : 0;
         R.seq_off = seq;
         R.qual_off = qual;
         R.ref_off = ref;
-        R.read_begin = l * depth;
-        R.aln_begin = l * depth * n_haps;
+        R.read_begin = (uint32_t)reads;
+        R.aln_begin = (uint32_t)(reads * n_haps);
         R.seg_begin = (uint32_t)seg;
         R.ins_begin = (uint32_t)insb;
         R.ref_begin = 1000 + (int32_t)(l % 2000000u) * 1000;
-        R.ref_len = l < n_loci ? c.ref_len : 0;
-        if (l == n_loci) break;
-        seq += pad16((uint64_t)depth * packed);
-        qual += pad16((uint64_t)depth * (qual_bits == 4 ? packed : read_len));
+        R.ref_len = rg < n_regions ? c.ref_len : 0;
+        if (rg == n_regions) break;
+        reads += nr;
+        seq += pad16((uint64_t)nr * packed);
+        qual += pad16((uint64_t)nr * (qual_bits == 4 ? packed : read_len));
         ref += pad16(c.ref_len);
-        insb += pad16(ins[l]);
-        seg += segs_per_region;
+        insb += pad16(ins[rg]);
+        seg += ((uint64_t)nr * (1 + 3 * (n_haps - 1)) + 3u) & ~3ull;
     }
     if (seg > 0xffffffffull || insb > 0xffffffffull) return -2;
-    out->n_regions = n_loci;
+    out->n_regions = n_regions;
     out->n_reads = (uint64_t)n_loci * depth;
     out->n_alns = (uint64_t)n_loci * depth * n_haps;
     out->n_segs = seg;
@@ -269,21 +283,24 @@ int synth_k1_plan(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n
 }
 
 // pass 2: fill caller-allocated pools (sizes from synth_k1_plan, plus SX_POOL_SLACK; alns has n_alns+1 entries, segs n_segs+16)
-int synth_k1_fill(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n_haps, uint64_t seed, int threads, uint32_t qual_bits, const sx_region* regions,
+int synth_k1_fill(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n_haps, uint64_t seed, int threads, uint32_t qual_bits, uint32_t reads_per_region,
+                  const sx_region* regions,
                   uint16_t* read_lens, uint8_t* seq4, uint8_t* qual, char* ref, sx_aln* alns, sx_aln_seg* segs, char* ins)
 {
-    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed, qual_bits};
-    const uint32_t n_segs = regions[n_loci].seg_begin;
+    const uint32_t rpr = reads_per_region ? std::min(reads_per_region, depth) : depth;
+    const uint32_t n_regions = n_loci * ((depth + rpr - 1) / rpr);
+    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed, qual_bits, rpr};
+    const uint32_t n_segs = regions[n_regions].seg_begin;
     for (uint32_t i = 0; i < n_segs + 16; ++i) segs[i] = sx_aln_seg{0, SX_SEG_HARDCLIP, 0};
-    parallel_for(n_loci, threads, [&](uint32_t l) {
+    parallel_for(n_regions, threads, [&](uint32_t rg) {
         region_sizes sz;
-        gen_region(c, l, true, sz, &regions[l], read_lens, seq4, qual, ref, alns, segs, ins);
+        gen_region(c, rg, true, sz, &regions[rg], read_lens, seq4, qual, ref, alns, segs, ins);
     });
     sx_aln& S = alns[(uint64_t)n_loci * depth * n_haps];
     S.read = n_loci * depth;
     S.ref_pos = 0;
     S.seg_off = n_segs;
-    S.ins_off = regions[n_loci].ins_begin;
+    S.ins_off = regions[n_regions].ins_begin;
     return 0;
 }
 
