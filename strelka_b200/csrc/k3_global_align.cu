@@ -13,6 +13,7 @@
 // The traceback is a pointer chase (one lane); the '='/'X' expansion and run-length encoding of the path is done by the whole
 // warp with ballot/popc scans.  Scores are int32 and max3 keeps the reference's first-argument-wins tie rule
 // (alignment/AlignerBase.hh:71-92), so score, beginPos and CIGAR are bit-exact.
+#include "k3_common.cuh"
 #include "sx_internal.h"
 
 #include <algorithm>
@@ -20,62 +21,8 @@
 
 namespace
 {
-constexpr unsigned FULL = 0xffffffffu;
-constexpr int BAD = -10000; // badVal, GlobalAlignerImpl.hh:58
+using namespace k3;
 constexpr int K3_WARPS = 4;
-enum { ST_MATCH = 0, ST_DELETE = 1, ST_INSERT = 2 };
-enum { CIG_M = 0, CIG_I = 1, CIG_D = 2, CIG_S = 4, CIG_EQ = 7, CIG_X = 8 };
-
-__device__ __forceinline__ uint32_t max3(int& mx, int v0, int v1, int v2)
-{
-    mx = v0;
-    uint32_t p = 0;
-    if (v1 > v0)
-    {
-        mx = v1;
-        p = 1;
-    }
-    if (v2 > mx)
-    {
-        mx = v2;
-        p = 2;
-    }
-    return p;
-}
-
-struct bt_state // BackTrace<int>, alignment/AlignerUtil.hh:47-80
-{
-    int max;
-    int state;
-    uint32_t queryBegin, refBegin;
-    bool isInit;
-};
-__device__ __forceinline__ void update_bt(bt_state& b, int v, uint32_t refIndex, uint32_t queryIndex, int state)
-{
-    if (!b.isInit || v > b.max)
-    {
-        b.max = v;
-        b.refBegin = refIndex;
-        b.queryBegin = queryIndex;
-        b.isInit = true;
-        b.state = state;
-    }
-}
-
-__host__ __device__ __forceinline__ uint32_t pad16u(uint32_t x) { return (x + 15u) & ~15u; }
-
-// per-warp shared-memory slot for a (Q, R) problem
-__host__ __device__ __forceinline__ uint32_t k3_slot_bytes(uint32_t Q, uint32_t R)
-{
-    const uint32_t T = (Q + 31) / 32;
-    uint32_t o = 0;
-    o += pad16u((Q + 1) * (R + 1)); // pointer matrix
-    o += 3u * 32u * T * 4u;         // final-column score strips (and the working strips of the long-query fallback)
-    o += pad16u(Q + 8);             // query
-    o += pad16u(R + 8);             // ref
-    o += pad16u(Q + R + 8);         // traceback steps
-    return o;
-}
 
 struct problem_smem
 {
@@ -102,20 +49,6 @@ __device__ __forceinline__ problem_smem carve(unsigned char* base, uint32_t Q, u
     o += pad16u(R + 8);
     p.steps = base + o;
     return p;
-}
-
-// scores of DP row 0 at matrix column c >= 1 (GlobalAlignerImpl.hh:104-126) and of the initial column at DP row `row` (:69-88)
-__device__ __forceinline__ void row0_scores(const sx_ga_scores& sc, int c, int& m, int& d, int& i)
-{
-    m = sc.isRequireEdgeDeletion ? BAD : 0;
-    d = sc.isRequireEdgeDeletion ? sc.open + c * sc.extend : BAD;
-    i = BAD;
-}
-__device__ __forceinline__ void col0_scores(const sx_ga_scores& sc, int row, int& m, int& d, int& i)
-{
-    m = row * sc.offEdge;
-    d = BAD;
-    i = sc.isAllowEdgeInsertion ? sc.open + row * sc.extend : BAD;
 }
 
 // The wavefront.  STRIP_IN_REGS: T_ rows per lane in registers (T_ == T); otherwise T_ is ignored and the strip lives in shared memory.
@@ -334,14 +267,16 @@ __device__ __forceinline__ void dp_wavefront(const sx_ga_scores& sc, const probl
 __global__ void __launch_bounds__(K3_WARPS * 32) k3_global_align_kernel(const char* __restrict__ query_pool, const char* __restrict__ ref_pool,
                                                                         const uint32_t* __restrict__ query_off, const uint32_t* __restrict__ ref_off, uint32_t n,
                                                                         uint32_t max_ops, sx_ga_scores sc, sx_ga_result* __restrict__ res,
-                                                                        uint32_t* __restrict__ cigar, uint32_t slot_bytes)
+                                                                        uint32_t* __restrict__ cigar, uint32_t slot_bytes, const uint32_t* __restrict__ order)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nwarps = blockDim.x >> 5;
     unsigned char* slot = smem + (size_t)warp * slot_bytes;
-    for (uint32_t prob = blockIdx.x * nwarps + warp; prob < n; prob += gridDim.x * nwarps)
+    // `order`: the list of problem indices this launch owns (n entries)
+    for (uint32_t k = blockIdx.x * nwarps + warp; k < n; k += gridDim.x * nwarps)
     {
+        const uint32_t prob = order[k];
         const uint32_t Q = query_off[prob + 1] - query_off[prob];
         const uint32_t R = ref_off[prob + 1] - ref_off[prob];
         if (Q == 0 || R == 0 || k3_slot_bytes(Q, R) > slot_bytes)
@@ -548,27 +483,27 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_global_align_kernel(const ch
     }
 }
 
-__global__ void k3_smem_need_kernel(const uint32_t* __restrict__ query_off, const uint32_t* __restrict__ ref_off, uint32_t n, uint32_t* __restrict__ out)
+int k3_run(sx_ctx* ctx, const sx_ga_scores* sc, const sx_ga_batch* d, sx_ga_result* res_dev, uint32_t* cigar_dev)
 {
-    uint32_t m = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        m = max(m, k3_slot_bytes(query_off[i + 1] - query_off[i], ref_off[i + 1] - ref_off[i]));
-    for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(FULL, m, d));
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
-}
-
-int k3_run(sx_ctx* ctx, const sx_ga_scores* sc, const sx_ga_batch* d, sx_ga_result* res_dev, uint32_t* cigar_dev, uint32_t need)
-{
-    // one slot per warp; problems that do not fit a slot report status 2
-    size_t slot = (need + 15u) & ~size_t(15);
-    int warps = K3_WARPS;
-    while (warps > 1 && slot * warps > ctx->smem_optin) warps >>= 1; // large matrices: fewer warps per CTA
-    slot = std::min(slot, ctx->smem_optin & ~size_t(15));
-    const size_t smem = slot * warps;
-    if (smem > 48 * 1024) SX_CUDA(ctx, cudaFuncSetAttribute(k3_global_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
-    const int grid = static_cast<int>(std::min<uint32_t>((d->n + warps - 1) / warps, (uint32_t)ctx->sm_count * 16));
-    k3_global_align_kernel<<<grid, warps * 32, smem, ctx->s_compute>>>(d->query, d->ref, d->query_off, d->ref_off, d->n, d->max_ops, *sc, res_dev, cigar_dev, (uint32_t)slot);
-    SX_CUDA(ctx, cudaGetLastError());
+    // small matrices (the common case: haplotypes of an active region) run in 8-lane groups; what is left comes back as a list
+    const uint32_t* large = nullptr;
+    uint32_t n_large = 0, need = 0;
+    int rc = sx_k3_group_run(ctx, sc, d, res_dev, cigar_dev, &large, &n_large, &need);
+    if (rc) return rc;
+    if (n_large)
+    {
+        // one warp per matrix, one shared-memory slot per warp; problems that do not fit a slot report status 2
+        size_t slot = (need + 15u) & ~size_t(15);
+        int warps = K3_WARPS;
+        while (warps > 1 && slot * warps > ctx->smem_optin) warps >>= 1; // very large matrices: fewer warps per CTA
+        slot = std::min(slot, ctx->smem_optin & ~size_t(15));
+        const size_t smem = slot * warps;
+        if (smem > 48 * 1024) SX_CUDA(ctx, cudaFuncSetAttribute(k3_global_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+        const int grid = static_cast<int>(std::min<uint32_t>((n_large + warps - 1) / warps, (uint32_t)ctx->sm_count * 16));
+        k3_global_align_kernel<<<grid, warps * 32, smem, ctx->s_compute>>>(d->query, d->ref, d->query_off, d->ref_off, n_large, d->max_ops, *sc, res_dev, cigar_dev, (uint32_t)slot,
+                                                                         large);
+        SX_CUDA(ctx, cudaGetLastError());
+    }
     return SX_OK;
 }
 } // namespace
@@ -581,16 +516,9 @@ extern "C" int sx_global_align_dev(sx_ctx* ctx, const sx_ga_scores* sc, const sx
     if (d->n == 0) return SX_OK;
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
     sx_kernel_timer t(ctx);
-    uint32_t* dneed = nullptr;
-    int rc = sx_ensure(ctx, 20, sizeof(uint32_t), reinterpret_cast<void**>(&dneed));
+    int rc = k3_run(ctx, sc, d, res_dev, cigar_dev);
     if (rc) return rc;
-    SX_CUDA(ctx, cudaMemsetAsync(dneed, 0, 4, ctx->s_compute));
-    k3_smem_need_kernel<<<std::min<uint32_t>((d->n + 255) / 256, 1184), 256, 0, ctx->s_compute>>>(d->query_off, d->ref_off, d->n, dneed);
-    uint32_t need = 0;
-    SX_CUDA(ctx, cudaMemcpyAsync(&need, dneed, 4, cudaMemcpyDeviceToHost, ctx->s_compute));
-    SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
-    if ((rc = k3_run(ctx, sc, d, res_dev, cigar_dev, need))) return rc;
-    t.stop(2);
+    t.stop(4);
     return t.finish();
 }
 
@@ -601,12 +529,10 @@ extern "C" int sx_global_align(sx_ctx* ctx, const sx_ga_scores* sc, const sx_ga_
     if (!sc || !b || !res_host || !cigar_host || !b->query_off || !b->ref_off) return sx_fail(ctx, SX_ERR_ARG, "sx_global_align: NULL argument");
     if (b->n == 0) return SX_OK;
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
-    uint32_t need = 0;
     for (uint32_t i = 0; i < b->n; ++i)
     {
         const uint32_t Q = b->query_off[i + 1] - b->query_off[i], R = b->ref_off[i + 1] - b->ref_off[i];
         if (Q == 0 || R == 0) return sx_fail(ctx, SX_ERR_ARG, "sx_global_align: empty query or reference in problem %u (asserted at GlobalAlignerImpl.hh:47-48)", i);
-        need = std::max(need, k3_slot_bytes(Q, R));
     }
     SX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->s_compute));
     sx_ga_batch d = *b;
@@ -627,7 +553,7 @@ extern "C" int sx_global_align(sx_ctx* ctx, const sx_ga_scores* sc, const sx_ga_
     if ((rc = sx_ensure(ctx, 13, (size_t)b->n * sizeof(sx_ga_result), reinterpret_cast<void**>(&d_res)))) return rc;
     if ((rc = sx_ensure(ctx, 14, (size_t)b->n * b->max_ops * 4 + 16, reinterpret_cast<void**>(&d_cig)))) return rc;
     SX_CUDA(ctx, cudaMemsetAsync(d_cig, 0, (size_t)b->n * b->max_ops * 4, ctx->s_compute)); // unused cigar slots read as 0
-    if ((rc = k3_run(ctx, sc, &d, d_res, d_cig, need))) return rc;
+    if ((rc = k3_run(ctx, sc, &d, d_res, d_cig))) return rc;
     SX_CUDA(ctx, cudaMemcpyAsync(res_host, d_res, (size_t)b->n * sizeof(sx_ga_result), cudaMemcpyDeviceToHost, ctx->s_compute));
     SX_CUDA(ctx, cudaMemcpyAsync(cigar_host, d_cig, (size_t)b->n * b->max_ops * 4, cudaMemcpyDeviceToHost, ctx->s_compute));
     SX_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->s_compute));
