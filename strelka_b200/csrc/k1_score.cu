@@ -56,6 +56,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  : "memory");
 }
 
+// 8-byte shared-memory load from a shared-window address
+__device__ __forceinline__ double lds_f64(uint32_t saddr)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
+    return v;
+}
+
 __host__ __device__ __forceinline__ uint32_t pad16(uint32_t x) { return (x + 15u) & ~15u; }
 
 struct k1_layout
@@ -145,6 +153,12 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
     uint32_t* soff_s = reinterpret_cast<uint32_t*>(smem + L.soff);
     uint32_t* desc_s = reinterpret_cast<uint32_t*>(smem + L.desc);
     uint16_t* ent_s = reinterpret_cast<uint16_t*>(smem + L.ent);
+    const uint32_t tab_saddr = smem_u32(tab); // shared-window address of the term table
+    if (tab_saddr + K1_TAB_BYTES > 0xfff0u || (tab_saddr & 15u))
+    {
+        if (threadIdx.x == 0) atomicOr(status, 2);
+        return;
+    }
     // quality dictionary of the 4-bit wire format lives in the descriptor block's tail (16 bytes after the 16 descriptors)
     uint8_t* qd_s = reinterpret_cast<uint8_t*>(desc_s + 16);
     if (threadIdx.x < 16)
@@ -160,7 +174,9 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
         if (code == 15u) d = (SX_K1_ROW_ZERO << 4);                                   // BAM_BASE::ANY: skipped (adds +0.0), q ignored
         else if (code == 0u) d = (SX_K1_ROW_EQ << 4) | 0xffff0000u;                   // BAM_BASE::REF: always "is_ref"
         else d = ((code == 1u || code == 2u || code == 4u || code == 8u) ? code : 0u) | 0xffff0000u; // other nibbles match nothing
-        desc_s[code] = d;
+        // entries carry the ABSOLUTE shared-memory address of their table row (16-byte aligned, < 64 KB), so the scoring loop
+        // forms the load address with one LOP3 and no add
+        desc_s[code] = d + tab_saddr;
     }
 
     if (threadIdx.x == 0)
@@ -265,7 +281,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
 
     const double softclip = tables->k1_softclip;
     const double noncand = tables->k1_noncand;
-    const unsigned char* tabb = reinterpret_cast<const unsigned char*>(tab);
+    const uint32_t zero_entry = (SX_K1_ROW_ZERO << 4) + tab_saddr; // the all-zero table row: adds +0.0
     const int ref_len = static_cast<int>(r0.ref_len);
 
     for (uint32_t a = threadIdx.x; a < L.n_alns; a += K1_THREADS)
@@ -331,8 +347,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
                             const uint32_t e = ent[i];
                             const int p = refp + i;
                             const uint32_t c = (p >= 0 && p < ref_len) ? ref_s[p] : 0u;
-                            const uint32_t off = (e & 0xfff0u) + ((e & c) ? 8u : 0u);
-                            lnp = __dadd_rn(lnp, *reinterpret_cast<const double*>(tabb + off));
+                            lnp = __dadd_rn(lnp, lds_f64((e & 0xfff0u) | ((e & c) ? 8u : 0u)));
                         }
                         ent += len;
                     }
@@ -368,10 +383,9 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
 #pragma unroll
                 for (int k = 0; k < K1_CHUNK; ++k)
                 {
-                    const uint32_t e = (k < n) ? static_cast<uint32_t>(ent[k]) : static_cast<uint32_t>(SX_K1_ROW_ZERO << 4);
+                    const uint32_t e = (k < n) ? static_cast<uint32_t>(ent[k]) : zero_entry;
                     const uint32_t c = cp[k];
-                    const uint32_t off = (e & 0xfff0u) + ((e & c) ? 8u : 0u);
-                    lnp = __dadd_rn(lnp, *reinterpret_cast<const double*>(tabb + off));
+                    lnp = __dadd_rn(lnp, lds_f64((e & 0xfff0u) | ((e & c) ? 8u : 0u)));
                 }
                 ent += n;
                 cp += n;
