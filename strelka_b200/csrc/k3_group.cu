@@ -86,6 +86,8 @@ template <int T> __host__ __device__ constexpr uint32_t kg_warp_smem(uint32_t ma
     return 3u * T * 32u * 4u + 4u * (((T * KG_G + 15u) & ~15u) + ((max_r + 15u) & ~15u) + ((T * KG_G + max_r + 15u) & ~15u));
 }
 
+__device__ __forceinline__ int key_of(int score, int state) { return 4 * score + (3 - state); }
+
 template <int T>
 __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __restrict__ query_pool, const char* __restrict__ ref_pool,
                                                                  const uint32_t* __restrict__ query_off, const uint32_t* __restrict__ ref_off,
@@ -111,8 +113,12 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
     const int s_match = sc.match, s_mismatch = sc.mismatch, s_open = sc.open, s_extend = sc.extend, s_insdel = sc.insertDelete;
     const bool req_del = sc.isRequireEdgeDeletion != 0, allow_ins = sc.isAllowEdgeInsertion != 0;
     const int row0M = req_del ? BAD : 0;
-    const uint32_t ptr_c0 = ST_MATCH | (ST_MATCH << 2) | ((allow_ins ? ST_INSERT : ST_MATCH) << 4);
-    const uint32_t ptr_r0 = ST_MATCH | ((req_del ? ST_DELETE : ST_MATCH) << 2) | (ST_MATCH << 4);
+    // initial-column / initial-row back pointers, in the stored tag encoding (tag = 3 - state)
+    const uint32_t ptr_c0 = (3u - ST_MATCH) | ((3u - ST_MATCH) << 2) | ((3u - (allow_ins ? ST_INSERT : ST_MATCH)) << 4);
+    const uint32_t ptr_r0 = (3u - ST_MATCH) | ((3u - (req_del ? ST_DELETE : ST_MATCH)) << 2) | ((3u - ST_MATCH) << 4);
+    const int o4 = 4 * s_open, e4 = 4 * s_extend, id4 = 4 * s_insdel;
+    const int ma4t = 4 * s_match + 3, mi4t = 4 * s_mismatch + 3, e4tD = e4 + 2, e4tI = e4 + 1;
+    const int kRow0M = key_of(row0M, ST_MATCH), kBadD = key_of(BAD, ST_DELETE), kBadI = key_of(BAD, ST_INSERT), kDel0 = key_of(s_open, ST_DELETE);
     const bool is_lane0 = gl == 0;
     const uint32_t row0 = gl * T; // query index of this lane's first row
 
@@ -132,17 +138,28 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
             for (uint32_t i = gl; i < R; i += KG_G) rs[i] = rg[i];
         }
         __syncwarp();
+        // Scores live in registers as KEYS: 4*score + tag, tag = 3 - state (match 3, delete 2, insert 1).  A plain integer max of keys is
+        // then exactly AlignerBase::max3's "largest value, first argument wins ties", the low two bits of the winner say which
+        // argument won, and the three-way maxima become single VIMNMX3 / VIADDMNMX instructions.  (|score| <= ~1e4 + 383*|penalty|,
+        // far from overflow.)
         int rM[T], rD[T], rI[T];
         char qc[T];
 #pragma unroll
         for (int r = 0; r < T; ++r)
         {
             const uint32_t qi = row0 + r;
-            col0_scores(sc, (int)qi + 1, rM[r], rD[r], rI[r]);
+            int m, dd, ii;
+            col0_scores(sc, (int)qi + 1, m, dd, ii);
+            rM[r] = key_of(m, ST_MATCH);
+            rD[r] = key_of(dd, ST_DELETE);
+            rI[r] = key_of(ii, ST_INSERT);
             qc[r] = qi < Q ? qs[qi] : 0;
         }
         int c0M, c0D, c0I; // initial column at the DP row above this strip
         col0_scores(sc, (int)row0, c0M, c0D, c0I);
+        c0M = key_of(c0M, ST_MATCH);
+        c0D = key_of(c0D, ST_DELETE);
+        c0I = key_of(c0I, ST_INSERT);
         const uint32_t r_last = have ? (Q - 1) - last_lane * T : 0; // strip-relative index of DP row Q in the group's last lane
         // warp-uniform step count: the longest wavefront of the four groups
         uint32_t n_steps = have ? R + last_lane : 0;
@@ -161,26 +178,32 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
             {
                 const char rc = rs[j];
                 const bool j0 = j == 0;
-                int upM = is_lane0 ? row0M : recvM;
-                int upD = is_lane0 ? (req_del ? s_open + (j + 1) * s_extend : BAD) : recvD;
-                int upI = is_lane0 ? BAD : recvI;
-                int dgM = j0 ? c0M : (is_lane0 ? row0M : prevRecvM);
-                int dgD = j0 ? c0D : (is_lane0 ? (req_del ? s_open + j * s_extend : BAD) : prevRecvD);
-                int dgI = j0 ? c0I : (is_lane0 ? BAD : prevRecvI);
+                int upM = is_lane0 ? kRow0M : recvM;
+                int upD = is_lane0 ? (req_del ? kDel0 + (j + 1) * e4 : kBadD) : recvD;
+                int upI = is_lane0 ? kBadI : recvI;
+                int dgM = j0 ? c0M : (is_lane0 ? kRow0M : prevRecvM);
+                int dgD = j0 ? c0D : (is_lane0 ? (req_del ? kDel0 + j * e4 : kBadD) : prevRecvD);
+                int dgI = j0 ? c0I : (is_lane0 ? kBadI : prevRecvI);
                 int mQ = 0;
 #pragma unroll
                 for (int r = 0; r < T; ++r)
                 {
                     const int lfM = rM[r], lfD = rD[r], lfI = rI[r];
-                    int m, d, ins;
-                    const uint32_t pm = max3(m, dgM, dgD, dgI);
-                    m += (qc[r] == rc) ? s_match : s_mismatch;
-                    const uint32_t pd = max3(d, lfM + s_open, lfD, lfI + s_insdel);
-                    d = j0 ? BAD : d + s_extend;
-                    const uint32_t pi = max3(ins, upM + s_open, BAD, upI);
-                    ins += s_extend;
-                    if (r == 0) ins = (row0 == 0) ? BAD : ins; // queryIndex 0
-                    if (row0 + r < Q) pstep[r * 32] = static_cast<unsigned char>(pm | (pd << 2) | (pi << 4));
+                    // match: max3(diag M, diag D, diag I) + match/mismatch
+                    const int km = __vimax3_s32(dgM, dgD, dgI);
+                    const int tm = km & 3;
+                    const int m = km - tm + ((qc[r] == rc) ? ma4t : mi4t);
+                    // delete: max3(left M + open, left D, left I + insertDelete) + extend
+                    const int kd = __viaddmax_s32(lfM, o4, __viaddmax_s32(lfI, id4, lfD));
+                    const int td = kd & 3;
+                    const int d = j0 ? kBadD : kd - td + e4tD;
+                    // insert: max3(up M + open, badVal, up I) + extend
+                    const int ki = __viaddmax_s32(upM, o4, max(kBadD, upI));
+                    const int ti = ki & 3;
+                    int ins = ki - ti + e4tI;
+                    if (r == 0) ins = (row0 == 0) ? kBadI : ins; // queryIndex 0
+                    // back pointers are stored as the raw tags (state = 3 - tag), decoded by the traceback
+                    if (row0 + r < Q) pstep[r * 32] = static_cast<unsigned char>(tm + 4 * td + 16 * ti);
                     dgM = lfM;
                     dgD = lfD;
                     dgI = lfI;
@@ -195,7 +218,7 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
                 sendM = upM;
                 sendD = upD;
                 sendI = upI;
-                if (gl == last_lane && !req_del) update_bt(colbt, mQ, j + 1, Q, ST_MATCH); // :170-175
+                if (gl == last_lane && !req_del) update_bt(colbt, mQ >> 2, j + 1, Q, ST_MATCH); // :170-175
             }
             prevRecvM = recvM;
             prevRecvD = recvD;
@@ -206,9 +229,9 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
 #pragma unroll
         for (int r = 0; r < T; ++r)
         {
-            sM[r * 32 + lane] = rM[r];
-            sD[r * 32 + lane] = rD[r];
-            sI[r * 32 + lane] = rI[r];
+            sM[r * 32 + lane] = rM[r] >> 2; // key -> score (arithmetic shift = floor, exact for negative scores too)
+            sD[r * 32 + lane] = rD[r] >> 2;
+            sI[r * 32 + lane] = rI[r] >> 2;
         }
         __syncwarp();
         // ---- backtrace start selection (:178-209)
@@ -278,7 +301,7 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
                 qb -= dq;
                 rb -= dr;
                 steps[nsteps++] = static_cast<uint8_t>(state);
-                state = (pv >> (2 * state)) & 3;
+                state = 3 - static_cast<int>((pv >> (2 * state)) & 3u);
             }
             uint32_t* cg = cigar + static_cast<size_t>(prob) * max_ops;
             uint32_t n_ops = 0;
