@@ -36,14 +36,15 @@ struct kg_info
     uint32_t large_need; // shared-memory slot of the largest "large" problem
 };
 
-__device__ __forceinline__ uint32_t kg_bucket(uint32_t Q, uint32_t R)
+__device__ __forceinline__ uint32_t kg_bucket(uint32_t Q, uint32_t R, uint32_t max_q)
 {
-    if (Q == 0 || R == 0 || Q > KG_MAX_Q || R > KG_MAX_R) return KG_BUCKETS - 1;
+    if (Q == 0 || R == 0 || Q > max_q || R > KG_MAX_R) return KG_BUCKETS - 1;
     const uint32_t T = (Q + KG_G - 1) / KG_G;
     return (T - 1) * KG_RCLASSES + min((uint32_t)KG_RCLASSES - 1, R >> 6);
 }
 
-__global__ void kg_classify_kernel(const uint32_t* __restrict__ query_off, const uint32_t* __restrict__ ref_off, uint32_t n, kg_info* __restrict__ info)
+__global__ void kg_classify_kernel(const uint32_t* __restrict__ query_off, const uint32_t* __restrict__ ref_off, uint32_t n, kg_info* __restrict__ info,
+                                   uint32_t max_q)
 {
     __shared__ uint32_t h[KG_BUCKETS];
     __shared__ uint32_t mr[16];
@@ -55,7 +56,7 @@ __global__ void kg_classify_kernel(const uint32_t* __restrict__ query_off, const
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
         const uint32_t Q = query_off[i + 1] - query_off[i], R = ref_off[i + 1] - ref_off[i];
-        const uint32_t b = kg_bucket(Q, R);
+        const uint32_t b = kg_bucket(Q, R, max_q);
         atomicAdd(&h[b], 1u);
         if (b == KG_BUCKETS - 1)
         {
@@ -71,11 +72,11 @@ __global__ void kg_classify_kernel(const uint32_t* __restrict__ query_off, const
 }
 
 __global__ void kg_scatter_kernel(const uint32_t* __restrict__ query_off, const uint32_t* __restrict__ ref_off, uint32_t n, uint32_t* __restrict__ cursor,
-                                  uint32_t* __restrict__ order)
+                                  uint32_t* __restrict__ order, uint32_t max_q)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
-        const uint32_t b = kg_bucket(query_off[i + 1] - query_off[i], ref_off[i + 1] - ref_off[i]);
+        const uint32_t b = kg_bucket(query_off[i + 1] - query_off[i], ref_off[i + 1] - ref_off[i], max_q);
         order[atomicAdd(&cursor[b], 1u)] = i;
     }
 }
@@ -86,7 +87,17 @@ template <int T> __host__ __device__ constexpr uint32_t kg_warp_smem(uint32_t ma
     return 3u * T * 32u * 4u + 4u * (((T * KG_G + 15u) & ~15u) + ((max_r + 15u) & ~15u) + ((T * KG_G + max_r + 15u) & ~15u));
 }
 
-__device__ __forceinline__ int key_of(int score, int state) { return 4 * score + (3 - state); }
+// Score keys: 64*score + tag, tag = 21 * (3 - state) = the 2-bit code (3 - state) replicated into three 2-bit fields (match 0b111111,
+// delete 0b101010, insert 0b010101).  See the comment in kg_align_kernel.
+constexpr int KG_KEY_SHIFT = 6;
+__device__ __forceinline__ int key_of(int score, int state) { return score * (1 << KG_KEY_SHIFT) + 21 * (3 - state); }
+// keeps a loop-invariant constant in its register: without it the compiler folds "cond ? 64*a+63 : 64*b+63" back into per-cell
+// multiply-adds on the raw parameters
+__device__ __forceinline__ int opaque(int x)
+{
+    asm volatile("" : "+r"(x));
+    return x;
+}
 
 template <int T>
 __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __restrict__ query_pool, const char* __restrict__ ref_pool,
@@ -116,9 +127,10 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
     // initial-column / initial-row back pointers, in the stored tag encoding (tag = 3 - state)
     const uint32_t ptr_c0 = (3u - ST_MATCH) | ((3u - ST_MATCH) << 2) | ((3u - (allow_ins ? ST_INSERT : ST_MATCH)) << 4);
     const uint32_t ptr_r0 = (3u - ST_MATCH) | ((3u - (req_del ? ST_DELETE : ST_MATCH)) << 2) | ((3u - ST_MATCH) << 4);
-    const int o4 = 4 * s_open, e4 = 4 * s_extend, id4 = 4 * s_insdel;
-    const int ma4t = 4 * s_match + 3, mi4t = 4 * s_mismatch + 3, e4tD = e4 + 2, e4tI = e4 + 1;
-    const int kRow0M = key_of(row0M, ST_MATCH), kBadD = key_of(BAD, ST_DELETE), kBadI = key_of(BAD, ST_INSERT), kDel0 = key_of(s_open, ST_DELETE);
+    const int o4 = opaque(s_open * 64), e4 = s_extend * 64, id4 = opaque(s_insdel * 64);
+    // addends that also re-tag a winner whose tag bits were cleared
+    const int ma4t = opaque(s_match * 64 + 63), mi4t = opaque(s_mismatch * 64 + 63), e4tD = opaque(e4 + 42), e4tI = opaque(e4 + 21);
+    const int kRow0M = key_of(row0M, ST_MATCH), kBadD = opaque(key_of(BAD, ST_DELETE)), kBadI = key_of(BAD, ST_INSERT), kDel0 = key_of(s_open, ST_DELETE);
     const bool is_lane0 = gl == 0;
     const uint32_t row0 = gl * T; // query index of this lane's first row
 
@@ -138,10 +150,12 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
             for (uint32_t i = gl; i < R; i += KG_G) rs[i] = rg[i];
         }
         __syncwarp();
-        // Scores live in registers as KEYS: 4*score + tag, tag = 3 - state (match 3, delete 2, insert 1).  A plain integer max of keys is
-        // then exactly AlignerBase::max3's "largest value, first argument wins ties", the low two bits of the winner say which
-        // argument won, and the three-way maxima become single VIMNMX3 / VIADDMNMX instructions.  (|score| <= ~1e4 + 383*|penalty|,
-        // far from overflow.)
+        // Scores live in registers as KEYS: 64*score + tag (key_of).  The three arguments of every max3 of the recurrence are (a match
+        // value, a delete value, an insert value) in that order, so a plain integer max of keys is exactly AlignerBase::max3's "largest
+        // value, first argument wins ties", the tag of the winner says which argument won, and the three-way maxima become single
+        // VIMNMX3 / VIADDMNMX instructions.  The tag is replicated in three 2-bit fields so the back-pointer byte of a cell is two
+        // bit-selects of the three winners (no shifts).  sx_k3_group_run keeps batches whose penalties could overflow 64*score out of
+        // this kernel.
         int rM[T], rD[T], rI[T];
         char qc[T];
 #pragma unroll
@@ -191,19 +205,17 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
                     const int lfM = rM[r], lfD = rD[r], lfI = rI[r];
                     // match: max3(diag M, diag D, diag I) + match/mismatch
                     const int km = __vimax3_s32(dgM, dgD, dgI);
-                    const int tm = km & 3;
-                    const int m = km - tm + ((qc[r] == rc) ? ma4t : mi4t);
+                    const int m = (km & ~63) + ((qc[r] == rc) ? ma4t : mi4t);
                     // delete: max3(left M + open, left D, left I + insertDelete) + extend
                     const int kd = __viaddmax_s32(lfM, o4, __viaddmax_s32(lfI, id4, lfD));
-                    const int td = kd & 3;
-                    const int d = j0 ? kBadD : kd - td + e4tD;
+                    const int d = (kd & ~63) + e4tD; // (column 0: overwritten with badVal below)
                     // insert: max3(up M + open, badVal, up I) + extend
                     const int ki = __viaddmax_s32(upM, o4, max(kBadD, upI));
-                    const int ti = ki & 3;
-                    int ins = ki - ti + e4tI;
+                    int ins = (ki & ~63) + e4tI;
                     if (r == 0) ins = (row0 == 0) ? kBadI : ins; // queryIndex 0
-                    // back pointers are stored as the raw tags (state = 3 - tag), decoded by the traceback
-                    if (row0 + r < Q) pstep[r * 32] = static_cast<unsigned char>(tm + 4 * td + 16 * ti);
+                    // back pointers: bits 0-1 from the match winner, 2-3 from the delete winner, 4-5 from the insert winner (raw tags,
+                    // state = 3 - tag, decoded by the traceback; bits 6-7 are don't-care).  Rows past Q store too: the slot covers them.
+                    pstep[r * 32] = static_cast<unsigned char>((km & 3) | (((kd & 0xf) | (ki & ~0xf)) & ~3));
                     dgM = lfM;
                     dgD = lfD;
                     dgI = lfI;
@@ -215,10 +227,16 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
                     rI[r] = ins;
                     if ((uint32_t)r == r_last) mQ = m;
                 }
+                if (j0) // delete state of the first column is badVal (once per lane per matrix)
+                {
+#pragma unroll
+                    for (int r = 0; r < T; ++r) rD[r] = kBadD;
+                    upD = kBadD;
+                }
                 sendM = upM;
                 sendD = upD;
                 sendI = upI;
-                if (gl == last_lane && !req_del) update_bt(colbt, mQ >> 2, j + 1, Q, ST_MATCH); // :170-175
+                if (gl == last_lane && !req_del) update_bt(colbt, mQ >> KG_KEY_SHIFT, j + 1, Q, ST_MATCH); // :170-175
             }
             prevRecvM = recvM;
             prevRecvD = recvD;
@@ -229,9 +247,9 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
 #pragma unroll
         for (int r = 0; r < T; ++r)
         {
-            sM[r * 32 + lane] = rM[r] >> 2; // key -> score (arithmetic shift = floor, exact for negative scores too)
-            sD[r * 32 + lane] = rD[r] >> 2;
-            sI[r * 32 + lane] = rI[r] >> 2;
+            sM[r * 32 + lane] = rM[r] >> KG_KEY_SHIFT; // key -> score (arithmetic shift = floor, exact for negative scores too)
+            sD[r * 32 + lane] = rD[r] >> KG_KEY_SHIFT;
+            sI[r * 32 + lane] = rI[r] >> KG_KEY_SHIFT;
         }
         __syncwarp();
         // ---- backtrace start selection (:178-209)
@@ -397,7 +415,10 @@ int sx_k3_group_run(sx_ctx* ctx, const sx_ga_scores* sc, const sx_ga_batch* d, s
     if ((rc = sx_ensure(ctx, 22, sizeof(uint32_t) * (size_t)d->n, reinterpret_cast<void**>(&d_order)))) return rc;
     SX_CUDA(ctx, cudaMemsetAsync(d_info, 0, sizeof(kg_info), ctx->s_compute));
     const int cgrid = static_cast<int>(std::min<uint32_t>((d->n + 255) / 256, 1184));
-    kg_classify_kernel<<<cgrid, 256, 0, ctx->s_compute>>>(d->query_off, d->ref_off, d->n, d_info);
+    // the group kernel keeps 64*score in 32 bits: penalties that could overflow it send the whole batch to the warp kernel
+    const auto big = [](int v) { return v > 4096 || v < -4096; };
+    const uint32_t max_q = (big(sc->match) || big(sc->mismatch) || big(sc->open) || big(sc->extend) || big(sc->offEdge) || big(sc->insertDelete)) ? 0u : KG_MAX_Q;
+    kg_classify_kernel<<<cgrid, 256, 0, ctx->s_compute>>>(d->query_off, d->ref_off, d->n, d_info, max_q);
     kg_info info;
     SX_CUDA(ctx, cudaMemcpyAsync(&info, d_info, sizeof(info), cudaMemcpyDeviceToHost, ctx->s_compute));
     SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
@@ -410,7 +431,7 @@ int sx_k3_group_run(sx_ctx* ctx, const sx_ga_scores* sc, const sx_ga_batch* d, s
     }
     begin[KG_BUCKETS] = acc;
     SX_CUDA(ctx, cudaMemcpyAsync(d_cursor, cursor, sizeof(cursor), cudaMemcpyHostToDevice, ctx->s_compute));
-    kg_scatter_kernel<<<cgrid, 256, 0, ctx->s_compute>>>(d->query_off, d->ref_off, d->n, d_cursor, d_order);
+    kg_scatter_kernel<<<cgrid, 256, 0, ctx->s_compute>>>(d->query_off, d->ref_off, d->n, d_cursor, d_order, max_q);
     SX_CUDA(ctx, cudaGetLastError());
 #define KG_CASE(TT)                                                                                                                           \
     {                                                                                                                                         \
