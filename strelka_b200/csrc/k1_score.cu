@@ -14,6 +14,7 @@
 // (cp.async.bulk ... mbarrier::complete_tx) issued by one thread; each read is then expanded ONCE into a 16-bit
 // (table-row | one-hot base) entry that all of its H alignments share, so HBM sees every read byte exactly once.
 #include "sx_internal.h"
+#include "k1q_layout.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
     {
         const uint32_t w = threadIdx.x >> 2, sh = (threadIdx.x & 3u) * 8u;
         const uint32_t word = w == 0 ? qual_dict.x : w == 1 ? qual_dict.y : w == 2 ? qual_dict.z : qual_dict.w;
-        qd_s[threadIdx.x] = static_cast<uint8_t>(word >> sh);
+        qd_s[threadIdx.x] = threadIdx.x == 15 ? 255 : static_cast<uint8_t>(word >> sh); // code 15 is reserved: reads as "quality out of range"
     }
     if (threadIdx.x < 16)
     {
@@ -397,16 +398,26 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
 }
 
 // max shared-memory footprint over regions [begin, end) (device-resident batches: the region table is not on the host)
+// out[0]: general kernel, out[1]: fast path (k1_score4.cu)
 __global__ void k1_smem_need_kernel(const sx_region* __restrict__ regions, uint32_t begin, uint32_t end, uint32_t* __restrict__ out)
 {
-    uint32_t m = 0;
+    uint32_t m = 0, mq = 0;
     for (uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x)
     {
-        const k1_layout L = k1_make_layout(regions[i], regions[i + 1]);
-        m = max(m, L.total);
+        const sx_region a = regions[i], b = regions[i + 1];
+        m = max(m, k1_make_layout(a, b).total);
+        mq = max(mq, k1q::make_layout(a, b).total);
     }
-    for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+    for (int d = 16; d; d >>= 1)
+    {
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+        mq = max(mq, __shfl_xor_sync(0xffffffffu, mq, d));
+    }
+    if ((threadIdx.x & 31) == 0 && m)
+    {
+        atomicMax(out, m);
+        atomicMax(out + 1, mq);
+    }
 }
 
 // per-read max over its alignments (first max in batch order), one thread per read; alignments are sorted by read
@@ -438,16 +449,16 @@ __global__ void k1_read_max_kernel(const sx_aln* __restrict__ alns, uint32_t n_a
     max_aln[r] = besta;
 }
 
-int k1_smem_need_dev(sx_ctx* ctx, const sx_region* regions_dev, uint32_t begin, uint32_t end, uint32_t* need)
+int k1_smem_need_dev(sx_ctx* ctx, const sx_region* regions_dev, uint32_t begin, uint32_t end, uint32_t need[2])
 {
     uint32_t* d = nullptr;
-    int rc = sx_ensure(ctx, 20, sizeof(uint32_t), reinterpret_cast<void**>(&d));
+    int rc = sx_ensure(ctx, 20, 2 * sizeof(uint32_t), reinterpret_cast<void**>(&d));
     if (rc) return rc;
-    SX_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(uint32_t), ctx->s_compute));
+    SX_CUDA(ctx, cudaMemsetAsync(d, 0, 2 * sizeof(uint32_t), ctx->s_compute));
     const uint32_t n = end - begin;
     const int blocks = static_cast<int>(std::min<uint32_t>((n + 255) / 256, 1184));
     k1_smem_need_kernel<<<blocks, 256, 0, ctx->s_compute>>>(regions_dev, begin, end, d);
-    SX_CUDA(ctx, cudaMemcpyAsync(need, d, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_compute));
+    SX_CUDA(ctx, cudaMemcpyAsync(need, d, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_compute));
     SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
     return SX_OK;
 }
@@ -458,9 +469,11 @@ size_t sx_k1_region_smem(const sx_region* r0, const sx_region* r1, const sx_aln*
     return k1_make_layout(*r0, *r1).total;
 }
 
-int sx_k1_launch(sx_ctx* ctx, const sx_align_batch* d, uint32_t region_begin, uint32_t region_end, double* lnp_dev, size_t smem_bytes, cudaStream_t st)
+// smem_bytes: largest region footprint of the general kernel; smem_fast: of the 4-bit fast path (0: not computed)
+int sx_k1_launch(sx_ctx* ctx, const sx_align_batch* d, uint32_t region_begin, uint32_t region_end, double* lnp_dev, size_t smem_bytes, size_t smem_fast, cudaStream_t st)
 {
     if (region_end <= region_begin) return SX_OK;
+    if (d->qual_bits == 4 && smem_fast && smem_fast <= k1q::KQ_MAX_SMEM) return sx_k1q_launch(ctx, d, region_begin, region_end, lnp_dev, smem_fast, st);
     if (smem_bytes > ctx->smem_optin)
         return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments: a region needs %zu bytes of shared memory (limit %zu); split it into smaller regions", smem_bytes,
                        ctx->smem_optin);
@@ -489,10 +502,10 @@ extern "C" uint64_t sx_align_batch_cells(const sx_align_batch* b)
     return n;
 }
 
-static int validate_host_batch(sx_ctx* ctx, const sx_align_batch* b, size_t* max_smem)
+static int validate_host_batch(sx_ctx* ctx, const sx_align_batch* b, size_t* max_smem, size_t* max_smem_fast)
 {
     if (!b || !b->regions || !b->alns || (b->n_reads && !b->read_len)) return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments: NULL batch array");
-    size_t m = 0;
+    size_t m = 0, mq = 0;
     for (uint32_t i = 0; i < b->n_regions; ++i)
     {
         const sx_region& r = b->regions[i];
@@ -504,6 +517,7 @@ static int validate_host_batch(sx_ctx* ctx, const sx_align_batch* b, size_t* max
             n.qual_off < r.qual_off)
             return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments: region table is not monotone at region %u", i);
         m = std::max(m, sx_k1_region_smem(&r, &n, b->alns));
+        mq = std::max<size_t>(mq, k1q::make_layout(r, n).total);
     }
     if (b->n_regions)
     {
@@ -511,6 +525,7 @@ static int validate_host_batch(sx_ctx* ctx, const sx_align_batch* b, size_t* max
         if (e.read_begin != b->n_reads || e.aln_begin != b->n_alns) return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments: sentinel region does not close the batch");
     }
     *max_smem = m;
+    *max_smem_fast = mq;
     return SX_OK;
 }
 
@@ -522,10 +537,10 @@ extern "C" int sx_score_alignments_dev(sx_ctx* ctx, const sx_align_batch* d, dou
     if (d->n_regions == 0) return SX_OK;
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
     sx_kernel_timer t(ctx);
-    uint32_t need = 0;
-    int rc = k1_smem_need_dev(ctx, d->regions, 0, d->n_regions, &need);
+    uint32_t need[2] = {0, 0};
+    int rc = k1_smem_need_dev(ctx, d->regions, 0, d->n_regions, need);
     if (rc) return rc;
-    rc = sx_k1_launch(ctx, d, 0, d->n_regions, lnp_out_dev, need, ctx->s_compute);
+    rc = sx_k1_launch(ctx, d, 0, d->n_regions, lnp_out_dev, need[0], need[1], ctx->s_compute);
     if (rc) return rc;
     t.stop(2);
     rc = t.finish();
@@ -557,8 +572,8 @@ extern "C" int sx_score_alignments(sx_ctx* ctx, const sx_align_batch* b, double*
     if (!b || !lnp_out) return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments: NULL argument");
     if (b->n_regions == 0 || b->n_alns == 0) return SX_OK;
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
-    size_t smem = 0;
-    int rc = validate_host_batch(ctx, b, &smem);
+    size_t smem = 0, smem_fast = 0;
+    int rc = validate_host_batch(ctx, b, &smem, &smem_fast);
     if (rc) return rc;
 
     sx_align_batch d = *b;
@@ -620,7 +635,7 @@ extern "C" int sx_score_alignments(sx_ctx* ctx, const sx_align_batch* b, double*
         SX_CUDA(ctx, cp(b->ins, d.ins, A.ins_begin, B.ins_begin));
         SX_CUDA(ctx, cudaEventRecord(ctx->ev_pool[2 * c], ctx->s_h2d));
         SX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_compute, ctx->ev_pool[2 * c], 0));
-        if ((rc = sx_k1_launch(ctx, &d, ra, rb, d_out, smem, ctx->s_compute))) return rc;
+        if ((rc = sx_k1_launch(ctx, &d, ra, rb, d_out, smem, smem_fast, ctx->s_compute))) return rc;
         SX_CUDA(ctx, cudaEventRecord(ctx->ev_pool[2 * c + 1], ctx->s_compute));
         SX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_pool[2 * c + 1], 0));
         if (B.aln_begin > A.aln_begin)
