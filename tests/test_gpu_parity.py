@@ -96,6 +96,46 @@ def test_k1_rejects_bad_input(ctx):
     assert e.value.code == A.SX_ERR_ALIGNMENT
 
 
+def test_k1_four_bit_rejects_bad_quality_codes(ctx):
+    """4-bit wire format: a dictionary quality above 70 used on a real base, and the reserved code 15, are range errors; the same
+    quality on an N base is ignored, as the reference ignores it (score.cpp:125-126)."""
+    from strelka_b200.api import SxError
+
+    rng = np.random.default_rng(31)
+    region = specgen.simple_region(rng, n_reads=6)
+    batch = B.build_align_batch([region], qual_bits=4)
+    want = ctx.score_alignments(batch)
+    free = int(np.max(np.asarray(batch.qual[: batch.used["qual"]]) >> 4)) + 1  # first unused dictionary code
+    assert free < 15
+    # base 0 of read 0: quality code in the high nibble of byte 0
+    keep = batch.qual[0]
+    batch.c.qual_dict[free] = 99
+    batch.qual[0] = (free << 4) | (keep & 15)
+    with pytest.raises(SxError) as e:
+        ctx.score_alignments(batch)
+    assert e.value.code == A.SX_ERR_RANGE
+    batch.qual[0] = (15 << 4) | (keep & 15)
+    with pytest.raises(SxError) as e:
+        ctx.score_alignments(batch)
+    assert e.value.code == A.SX_ERR_RANGE
+    # ... but not when that base is an N: the read nibble 15 is skipped before its quality is looked at
+    batch.qual[0] = (free << 4) | (keep & 15)
+    seq0 = batch.seq4[0]
+    batch.seq4[0] = (15 << 4) | (seq0 & 15)
+    got = ctx.score_alignments(batch)
+    assert got.shape == want.shape and np.all(np.isfinite(got))
+
+
+def test_k1_four_bit_large_region_uses_general_kernel(ctx):
+    """A region too large for the byte-entry kernel's 16-bit shared addresses is scored by the general kernel: same doubles."""
+    rng = np.random.default_rng(32)
+    regions = [specgen.simple_region(rng, n_reads=330), specgen.simple_region(rng, n_reads=5)]
+    b4 = B.build_align_batch(regions, qual_bits=4)
+    b8 = B.build_align_batch(regions, qual_bits=8)
+    want = reflib.ox_score(b8)
+    assert np.array_equal(_bits(ctx.score_alignments(b4)), _bits(want))
+
+
 def _ga_scores(match, mismatch, open_, extend, off_edge, ins_del=0, allow_edge_ins=False, require_edge_del=False):
     return A.SxGaScores(match, mismatch, open_, extend, off_edge, ins_del, int(allow_edge_ins), int(require_edge_del))
 
