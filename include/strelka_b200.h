@@ -163,11 +163,10 @@ typedef struct sx_align_batch {
     const sx_aln_seg* segs;    /* [n_segs] */
     const char* ins;           /* ASCII inserted bases */
     uint64_t seq4_bytes, qual_bytes, ref_bytes, ins_bytes; /* used bytes of each pool (without slack) */
-    /* Quality wire format.  qual_bits 0 or 8: `qual` holds one byte per base.  qual_bits 4: a batch whose reads use at most 15
+    /* Quality wire format.  qual_bits 0 or 8: `qual` holds one byte per base.  qual_bits 4: a batch whose reads use at most 16
      * distinct quality values (binned Illumina qualities do) may send them dictionary-coded, two per byte, high nibble first,
-     * each read starting on a byte boundary exactly like seq4; nibble v (0..14) stands for quality qual_dict[v]; nibble 15 is
-     * reserved (SX_ERR_RANGE on a non-N base).  Lossless; it cuts the host->device bytes of a 150 bp read from 225 to 150 and
-     * selects the byte-entry scoring kernel (k1_score4.cu). */
+     * each read starting on a byte boundary exactly like seq4; nibble v stands for quality qual_dict[v].  Lossless; it cuts the
+     * host->device bytes of a 150 bp read from 225 to 150 and selects the byte-entry scoring kernel (k1_score4.cu). */
     uint32_t qual_bits;
     uint8_t qual_dict[16];
     uint32_t reserved_;

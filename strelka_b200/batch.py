@@ -202,11 +202,11 @@ class AlignBatch:
 
 
 def build_align_batch(regions: Sequence[RegionSpec], qual_bits: int = 8) -> AlignBatch:
-    """qual_bits=4 sends qualities dictionary-coded, two per byte (needs <= 15 distinct values in the batch; code 15 is reserved)."""
+    """qual_bits=4 sends qualities dictionary-coded, two per byte (needs <= 16 distinct values in the batch)."""
     qdict = None
     if qual_bits == 4:
         vals = sorted({int(x) for r in regions for _, q in r.reads for x in np.asarray(q).tolist()})
-        assert len(vals) <= 15, "4-bit quality coding needs at most 15 distinct quality values (code 15 is reserved)"
+        assert len(vals) <= 16, "4-bit quality coding needs at most 16 distinct quality values"
         qdict = vals
         qcode = {v: i for i, v in enumerate(vals)}
     reg = np.zeros(len(regions) + 1, dtype=A.REGION_DT)

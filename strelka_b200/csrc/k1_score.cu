@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
     {
         const uint32_t w = threadIdx.x >> 2, sh = (threadIdx.x & 3u) * 8u;
         const uint32_t word = w == 0 ? qual_dict.x : w == 1 ? qual_dict.y : w == 2 ? qual_dict.z : qual_dict.w;
-        qd_s[threadIdx.x] = threadIdx.x == 15 ? 255 : static_cast<uint8_t>(word >> sh); // code 15 is reserved: reads as "quality out of range"
+        qd_s[threadIdx.x] = static_cast<uint8_t>(word >> sh);
     }
     if (threadIdx.x < 16)
     {

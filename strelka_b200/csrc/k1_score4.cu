@@ -4,17 +4,18 @@
 // alignment) path, terms added in read order with __dadd_rn, addends from the host-built table), re-organised around what the ncu
 // profile of that kernel showed: it was bound by issue slots and shared-memory wavefronts, not by HBM, and only 40 % of its
 // instructions were the per-cell work.  Here
-//   * a read base is ONE byte: (row code << 3) | base code.  Row codes index a 32-row table built per CTA from the quality
-//     dictionary: 0..14 = dictionary quality (match, mismatch) terms, 16..30 = the same qualities for a '=' read base (match term in
-//     both columns), 31 = the all-zero row of an 'N' read base.  Base codes: A C G T = 0..3, any other read base 4, any other
-//     reference base 5 -- so "mismatch" is (entry ^ reference) & 7 != 0.  Dictionary code 15 is reserved.
+//   * a read base is ONE byte: quality code << 4 | page << 2 | base (A C G T = 0..3).  The byte is, up to two masks, the address of
+//     its term in a 1 KB table built per CTA from the quality dictionary: tab[page][quality code][mismatch], page 0 = ordinary base
+//     (match, mismatch), 1 = '=' read base (match, match), 2 = 'N' read base (0, 0), 3 = any other read base (mismatch, mismatch).
+//     Reference bases are 0..3 or 4 ("matches nothing"), so "mismatch" is ((entry & 3) ^ reference) != 0.  Rows are 16 bytes, so the
+//     (match, mismatch) terms of different qualities lie in different banks.
 //   * reads are expanded by one linear pass over the region's packed bytes (4 packed bytes -> 8 entries per lane and iteration,
 //     through a 256-entry (nibble, quality code) table), not read by read;
 //   * each alignment's segments are turned into 8-byte run records by a converged pre-pass, so the divergent part of the scoring loop
 //     is a 10-instruction record fetch;
 //   * the scoring loop handles 8 cells per iteration with SIMD-in-a-register byte arithmetic: 3+3 aligned 32-bit shared loads and
-//     PRMT funnels fetch the 8 entries and 8 reference codes, five logic ops per 4 cells produce the table addresses (including the
-//     substitution of the zero row for the cells past a run's end), and a cell is PRMT + LDS.64 + DADD.
+//     PRMT funnels fetch the 8 entries and 8 reference codes, six logic ops per 4 cells produce the table addresses (including the
+//     substitution of the zero page for the cells past a run's end), and a cell is PRMT + LDS.64 + DADD.
 // Regions that do not fit the 16-bit shared-window addresses used here (KQ_MAX_SMEM) are scored by the general kernel.
 #include "k1q_layout.cuh"
 
@@ -24,8 +25,9 @@ namespace
 {
 using namespace k1q;
 
-constexpr uint32_t ROW_EQ = 16, ROW_ZERO = 31;
-constexpr uint32_t BASE_OTHER = 4, REF_OTHER = 5, BASE_BAD = 7;
+constexpr uint32_t PAGE_BASE = 0, PAGE_EQ = 1, PAGE_ZERO = 2, PAGE_NOMATCH = 3;
+constexpr uint32_t REF_OTHER = 4;
+constexpr uint32_t ENTRY_BAD = (PAGE_ZERO << 2) | 3u; // low nibble of an entry whose quality is out of range (scores as zero; flagged)
 enum { REC_RUN = 0, REC_SOFT = 1, REC_OOW = 2, REC_END = 3 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -72,10 +74,10 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
-__device__ __forceinline__ uint4 lds_u128(uint32_t a)
+__device__ __forceinline__ uint2 lds_u64(uint32_t a)
 {
-    uint4 v;
-    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
 }
 __device__ __forceinline__ double lds_f64(uint32_t a)
@@ -121,17 +123,17 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
     const layout L = make_layout(r0, r1);
     if (L.n_alns == 0) return;
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t tab_saddr = (sbase + L.tab + 511u) & ~511u; // 512-aligned in the shared window: a cell's address is two PRMT'd bytes
-    if (L.total > smem_bytes || sbase + L.total > 0xffffu || tab_saddr + 512u > 0x7f00u || L.n_segs > 0xffffu)
+    const uint32_t tab_saddr = (sbase + L.tab + 1023u) & ~1023u; // 1 KB-aligned in the shared window: a cell's address is two PRMT'd bytes
+    if (L.total > smem_bytes || sbase + L.total > 0xffffu || tab_saddr + 1024u > 0x7f00u || L.n_segs > 0xffffu)
     {
         if (threadIdx.x == 0) atomicOr(status, 2);
         return;
     }
     const uint32_t tid = threadIdx.x;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    uint4* lut = reinterpret_cast<uint4*>(smem + L.lut);
+    uint2* lut = reinterpret_cast<uint2*>(smem + L.lut);
     uint8_t* e8 = smem + L.e8;
-    double* tabM = reinterpret_cast<double*>(smem + (tab_saddr - sbase)); // [32] match column; mismatch column 256 bytes later
+    double* tab = reinterpret_cast<double*>(smem + (tab_saddr - sbase)); // [4 pages][16 quality codes][match, mismatch]
     const uint4* alns_s = reinterpret_cast<const uint4*>(smem + L.alns);
     const uint32_t* segs_s = reinterpret_cast<const uint32_t*>(smem + L.segs);
     uint8_t* ref_s = smem + L.ref;
@@ -140,40 +142,31 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
     uint32_t* soff_s = reinterpret_cast<uint32_t*>(smem + L.soff);
 
     // ---- per-CTA tables (independent of the TMA data)
-    if (tid < 32)
+    if (tid < 64)
     {
-        double m = 0.0, x = 0.0;
-        if (tid < 15)
-        {
-            const uint32_t q = min(dict_at(qual_dict, tid), (uint32_t)SX_MAX_QSCORE);
-            x = tables->k1_tab[2 * q + 0];
-            m = tables->k1_tab[2 * q + 1];
-        }
-        else if (tid >= ROW_EQ && tid < ROW_ZERO)
-        {
-            const uint32_t q = min(dict_at(qual_dict, tid - ROW_EQ), (uint32_t)SX_MAX_QSCORE);
-            x = m = tables->k1_tab[2 * (SX_K1_ROW_EQ + q) + 1];
-        }
-        tabM[tid] = m;
-        tabM[32 + tid] = x;
+        const uint32_t page = tid >> 4, q = min(dict_at(qual_dict, tid & 15u), (uint32_t)SX_MAX_QSCORE);
+        const double x = tables->k1_tab[2 * q + 0], m = tables->k1_tab[2 * q + 1]; // (mismatch, match) terms of quality q
+        tab[2 * tid + 0] = page == PAGE_ZERO ? 0.0 : page == PAGE_NOMATCH ? x : m;
+        tab[2 * tid + 1] = page == PAGE_ZERO ? 0.0 : page == PAGE_EQ ? m : x;
     }
     for (uint32_t idx = tid; idx < 256; idx += KQ_THREADS)
     {
         // (read nibble << 4 | quality code) -> entry.  bam_seq::get_code nibbles: 0 '=', 1 A, 2 C, 4 G, 8 T, 15 N, others IUPAC.
         const uint32_t nib = idx >> 4, qc = idx & 15u;
         uint32_t e;
-        if (nib == 15u) e = (ROW_ZERO << 3) | BASE_OTHER;                                            // skipped: adds +0.0, quality ignored
-        else if (qc == 15u || dict_at(qual_dict, qc) > SX_MAX_QSCORE) e = (ROW_ZERO << 3) | BASE_BAD; // qphred_cache::qscore_check would throw
-        else if (nib == 0u) e = ((ROW_EQ + qc) << 3) | BASE_OTHER;                                   // always "is_ref"
-        else e = (qc << 3) | (nib == 1u ? 0u : nib == 2u ? 1u : nib == 4u ? 2u : nib == 8u ? 3u : BASE_OTHER);
-        e8[idx] = static_cast<uint8_t>(e);
+        if (nib == 15u) e = PAGE_ZERO << 2;                                          // skipped: adds +0.0, quality ignored
+        else if (dict_at(qual_dict, qc) > SX_MAX_QSCORE) e = ENTRY_BAD;              // qphred_cache::qscore_check would throw
+        else if (nib == 0u) e = PAGE_EQ << 2;                                        // always "is_ref"
+        else if (nib == 1u || nib == 2u || nib == 4u || nib == 8u) e = (PAGE_BASE << 2) | (nib == 1u ? 0u : nib == 2u ? 1u : nib == 4u ? 2u : 3u);
+        else e = PAGE_NOMATCH << 2;                                                  // IUPAC codes match nothing
+        e8[idx] = static_cast<uint8_t>((qc << 4) | e);
     }
     if (tid < 9)
     {
-        // masks of the first n cells of a chunk: bytes of 0xf8 (row-code field) and of 0x01
+        // page-field masks of the first n cells of a chunk (0x03 in the bytes of cells 0..n-1)
         const uint32_t nlo = min(tid, 4u), nhi = tid > 4u ? tid - 4u : 0u;
-        const uint32_t lo = nlo ? (0x01010101u >> (32u - 8u * nlo)) : 0u, hi = nhi ? (0x01010101u >> (32u - 8u * nhi)) : 0u;
-        lut[tid] = make_uint4(lo * 0xf8u, hi * 0xf8u, lo, hi);
+        const uint32_t lo = nlo ? (0x03030303u >> (32u - 8u * nlo)) : 0u, hi = nhi ? (0x03030303u >> (32u - 8u * nhi)) : 0u;
+        lut[tid] = make_uint2(lo, hi);
     }
 
     if (tid == 0)
@@ -237,10 +230,11 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
             const uint32_t a6 = lds_u8(e8_s + (hi >> 24)), a7 = lds_u8(e8_s + (lo >> 24));
             const uint32_t w0 = a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
             const uint32_t w1 = a4 | (a5 << 8) | (a6 << 16) | (a7 << 24);
-            acc |= (w0 & (w0 >> 1)) | (w1 & (w1 >> 1)); // base code 7 = bits 1 and 2 set
+            // ENTRY_BAD: low nibble 1011
+            acc |= (w0 & (w0 >> 1) & ~(w0 >> 2) & (w0 >> 3)) | (w1 & (w1 >> 1) & ~(w1 >> 2) & (w1 >> 3));
             ent64[w] = make_uint2(w0, w1);
         }
-        if (acc & 0x02020202u) atomicOr(status, 1);
+        if (acc & 0x01010101u) atomicOr(status, 1);
         uint32_t* ref32 = reinterpret_cast<uint32_t*>(ref_s);
         for (uint32_t i = tid; i < L.ref_bytes / 4; i += KQ_THREADS)
         {
@@ -256,7 +250,8 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
     const double noncand = tables->k1_noncand;
     const int ref_len = static_cast<int>(r0.ref_len);
     const uint32_t ent_s0 = sbase + L.ent, ref_s0 = sbase + L.ref, ins_s0 = sbase + L.ins, recs_s0 = sbase + L.recs, lut_s0 = sbase + L.lut;
-    const uint32_t hrep = (tab_saddr >> 8) * 0x01010101u; // high address byte of the table, in every byte lane (bit 0 and bit 7 clear)
+    // high address byte of a masked cell, in every byte lane: table page 2 (all zeros).  Bits 0-1 of tab_saddr >> 8 are clear, bit 7 too.
+    const uint32_t k2 = ((tab_saddr >> 8) | PAGE_ZERO) * 0x01010101u;
 
     for (uint32_t a = tid; a < L.n_alns; a += KQ_THREADS)
     {
@@ -366,7 +361,7 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
                         const uint32_t e = lds_u8(ea + i);
                         const int p = p0 + static_cast<int>(i);
                         const uint32_t c = (p >= 0 && p < ref_len) ? ref_s[p] : REF_OTHER;
-                        lnp = __dadd_rn(lnp, lds_f64(tab_saddr + (e & 0xf8u) + (((e ^ c) & 7u) ? 256u : 0u)));
+                        lnp = __dadd_rn(lnp, lds_f64(tab_saddr + ((e >> 2) & 3u) * 256u + (e & 0xf0u) + (((e & 3u) ^ c) ? 8u : 0u)));
                     }
                 }
                 else
@@ -376,20 +371,24 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
                 }
             }
             if (done) break;
-            // One chunk of 8 cells.  Cells past the end of the run get the zero row (x + 0.0 == x exactly for every x this sum can hold)
-            // through the byte masks of lut[n]; surplus loads stay inside the CTA's shared memory.
+            // One chunk of 8 cells.  Cells past the end of the run are sent to the all-zero table page through the byte masks of lut[n]
+            // (x + 0.0 == x exactly for every x this sum can hold); surplus loads stay inside the CTA's shared memory, and whatever they
+            // return only picks a row inside that page.
             {
                 const uint32_t n = min(rem, 8u);
-                const uint4 mk = lds_u128(lut_s0 + n * 16u);
+                const uint2 mk = lds_u64(lut_s0 + n * 8u);
                 const uint32_t ea = ent & ~3u, ca = cp & ~3u;
                 const uint32_t w0 = lds_u32(ea), w1 = lds_u32(ea + 4), w2 = lds_u32(ea + 8);
                 const uint32_t v0 = lds_u32(ca), v1 = lds_u32(ca + 4), v2 = lds_u32(ca + 8);
                 const uint32_t e0 = prmt(w0, w1, sel_e), e1 = prmt(w1, w2, sel_e);
                 const uint32_t c0 = prmt(v0, v1, sel_c), c1 = prmt(v1, v2, sel_c);
-                // per byte: low address byte = row code * 8 (zero row past the run), high address byte = table page | mismatch
-                const uint32_t a0 = (e0 & mk.x) | (0xf8f8f8f8u & ~mk.x), a1 = (e1 & mk.y) | (0xf8f8f8f8u & ~mk.y);
-                const uint32_t x0 = (((((e0 ^ c0) & 0x07070707u) + 0x07070707u) >> 3) & mk.z) | hrep;
-                const uint32_t x1 = (((((e1 ^ c1) & 0x07070707u) + 0x07070707u) >> 3) & mk.w) | hrep;
+                // per byte: low address byte = quality code * 16 + mismatch * 8, high address byte = table base | page
+                // ((e & 3) ^ c is 0..7 in a live cell, so + 7 sets bit 3 iff it is non-zero; a surplus byte may carry, but only upwards,
+                // into other surplus bytes)
+                const uint32_t a0 = (e0 & 0xf0f0f0f0u) | ((((e0 & 0x03030303u) ^ c0) + 0x07070707u) & 0x08080808u);
+                const uint32_t a1 = (e1 & 0xf0f0f0f0u) | ((((e1 & 0x03030303u) ^ c1) + 0x07070707u) & 0x08080808u);
+                const uint32_t x0 = ((e0 >> 2) & mk.x) | (k2 & ~mk.x);
+                const uint32_t x1 = ((e1 >> 2) & mk.y) | (k2 & ~mk.y);
                 // selector: byte 0 = a[k], byte 1 = x[k], bytes 2-3 = sign of x[k] replicated (= 0)
                 lnp = __dadd_rn(lnp, lds_f64(prmt(a0, x0, 0xcc40u)));
                 lnp = __dadd_rn(lnp, lds_f64(prmt(a0, x0, 0xdd51u)));

@@ -9,8 +9,8 @@ constexpr uint32_t KQ_THREADS = 128;
 // records and entries carry 16-bit shared-window addresses, and the term table must sit below 0x7f00 (see the kernel): regions that
 // need more than this go to the general kernel (k1_score.cu)
 constexpr uint32_t KQ_MAX_SMEM = 60u * 1024u;
-constexpr uint32_t KQ_LUT_BYTES = 9 * 16;
-constexpr uint32_t KQ_TAB_RESERVE = 1024; // 2 x 32 doubles, placed on a 512-byte boundary of the shared window inside this reserve
+constexpr uint32_t KQ_LUT_BYTES = 80; // 9 x 8
+constexpr uint32_t KQ_TAB_RESERVE = 2048; // 4 pages x 16 rows x 2 doubles, placed on a 1 KB boundary of the shared window inside this reserve
 
 __host__ __device__ __forceinline__ uint32_t pad16(uint32_t x) { return (x + 15u) & ~15u; }
 
