@@ -36,7 +36,7 @@ from strelka_b200 import batch as B  # noqa: E402
 CONFIGS = {
     # name: (n_loci, depth, read_len, n_haps, description)
     "cfg2": (1_000_000, 30, 150, 4, "synthetic 30x germline pileup, 150 bp reads, 1M candidate loci, 4 haplotypes/locus"),
-    "cfg5": (10_000, 300, 150, 32, "300x high-depth amplicon, 32 haplotypes/locus (regions of 32 reads)"),
+    "cfg5": (10_000, 300, 150, 32, "300x high-depth amplicon, 32 haplotypes/locus (regions of 16 reads)"),
     "tiny": (20_000, 30, 150, 4, "cfg2 shape at 20k loci (plumbing)"),
 }
 
@@ -253,7 +253,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_loci, depth, read_len, n_haps, desc = CONFIGS[args.config]
-    rpr = 32 if depth > 64 else 0
+    rpr = 16 if depth > 64 else 0  # deep loci are cut into regions small enough for the K1 fast path's 60 KB of shared memory
     if args.loci:
         n_loci = args.loci
     ncpu = os.cpu_count() or 8
@@ -429,7 +429,7 @@ def main():
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
             if args.config in tj and n_loci == CONFIGS[args.config][0]:
-                t = tj[args.config]["k1_score_kernel"]
+                t = tj[args.config]["k1q_score_kernel"]
                 traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
         except Exception:
             pass
@@ -442,7 +442,7 @@ def main():
             "gcups": (cells_k1 + cells_k3) * world * args.steps / dt / 1e9,
             "k1_gcups_kernel_only": cells_k1 / (k1_avg_ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "k1_score_kernel", "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k1_avg_ms, "peak_source": peak_src},
+                         "kernel": "k1q_score_kernel (K1 fast path, k1_score4.cu)" if ab.qual_bits == 4 else "k1_score_kernel","algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k1_avg_ms, "peak_source": peak_src},
             "gpu_launches": launches,
             "kernel_ms_per_step": {k: v / args.steps for k, v in parts.items()},
             "clocks": clk,
