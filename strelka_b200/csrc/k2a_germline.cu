@@ -349,6 +349,265 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline_kernel(const uint3
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Batched variant for batches whose sites all fit the shared-memory cap (the common case: depth <= 256).
+//
+// ncu on the kernel above: the per-group phase of adjust_joint_eprob (weight sums in pileup order, the std::sort mirror, the
+// dependency-exponent chain) is serial per (strand, base) group and ran on 8 lanes of which ~1.5 had work -- 40 % of the kernel's
+// instructions at 1-2 active lanes.  Here a warp takes FOUR sites at a time: the warp-parallel phases (filter, grouping, logf,
+// likelihood accumulation, posteriors) run site after site exactly as above, and the serial phase runs once for the 32
+// (site, group) pairs, one per lane.  Arithmetic and orders are unchanged.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int K2_BATCH = 4;
+
+__global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline4_kernel(const uint32_t* __restrict__ site_off, const uint16_t* __restrict__ calls_g,
+                                                                      const char* __restrict__ ref_base, const uint8_t* __restrict__ ploidy,
+                                                                      uint32_t n_sites, int is_always_test, const sx_tables* __restrict__ tables,
+                                                                      sx_digt_result* __restrict__ out, uint32_t* __restrict__ de_off,
+                                                                      float* __restrict__ de_out, int* __restrict__ status)
+{
+    __shared__ germ_tables T;
+    __shared__ uint16_t s_calls[K2_WARPS][K2_BATCH][K2_CAP_SMEM];
+    __shared__ float s_val[K2_WARPS][K2_BATCH][K2_CAP_SMEM];
+    __shared__ uint16_t s_ord[K2_WARPS][K2_BATCH][K2_CAP_SMEM];
+    __shared__ uint32_t s_gstart[K2_WARPS][K2_BATCH][9];
+    __shared__ uint32_t s_n[K2_WARPS][K2_BATCH];
+    for (int i = threadIdx.x; i <= SX_MAX_QSCORE; i += blockDim.x)
+    {
+        T.eprob[i] = tables->g_eprob[i];
+        T.val1[i] = tables->g_val1[i];
+        T.val2[i] = tables->g_val2[i];
+        T.weight[i] = tables->g_weight[i];
+        T.depmin[i] = tables->g_depmin[i];
+    }
+    for (int i = threadIdx.x; i < 200; i += blockDim.x) (&T.lnprior[0][0][0][0])[i] = (&tables->g_lnprior[0][0][0][0])[i];
+    __syncthreads();
+    const float log_one_third = tables->g_log_one_third;
+    const float ln10f = tables->g_ln10f;
+    const float min_vexp = tables->g_min_vexp;
+    const double ssd_no = tables->g_ssd_no_mismatch, ssd_one = tables->g_ssd_one_mismatch;
+    const bool is_dep = tables->g_is_dependent_eprob != 0;
+    const bool is_limit_vexp = tables->g_is_min_vexp != 0;
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t gwarp = blockIdx.x * K2_WARPS + warp, nwarps = gridDim.x * K2_WARPS;
+
+    for (uint32_t base = gwarp * K2_BATCH; base < n_sites; base += nwarps * K2_BATCH)
+    {
+        const uint32_t nb = min((uint32_t)K2_BATCH, n_sites - base);
+        // ---- phase A, site by site: CleanPileupFilter, initial eprobs, grouping
+        uint32_t nonref_mask = 0;
+        for (uint32_t s = 0; s < K2_BATCH; ++s)
+        {
+            uint16_t* w_calls = s_calls[warp][s];
+            float* w_val = s_val[warp][s];
+            uint16_t* w_ord = s_ord[warp][s];
+            uint32_t n = 0;
+            bool nonref = false;
+            if (s < nb)
+            {
+                const uint32_t site = base + s;
+                const uint32_t c0 = site_off[site], c1 = site_off[site + 1];
+                uint32_t n_raw = c1 - c0;
+                if (n_raw > K2_CAP_SMEM) // the host only launches this kernel when every site fits
+                {
+                    if (lane == 0) atomicOr(status, 16);
+                    n_raw = 0;
+                }
+                const char rb = ref_base[site];
+                const uint32_t ref_gt = rb == 'A' ? 0u : rb == 'C' ? 1u : rb == 'G' ? 2u : rb == 'T' ? 3u : 4u;
+                for (uint32_t b = 0; b < n_raw; b += 32)
+                {
+                    const uint32_t i = b + lane;
+                    const uint32_t c = i < n_raw ? calls_g[c0 + i] : 0x1000u;
+                    const bool keep = !((c >> 12) & 1u);
+                    const uint32_t m = __ballot_sync(FULL, keep);
+                    if (keep)
+                    {
+                        w_calls[n + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(c);
+                        if (((c >> 6) & 15u) != ref_gt) nonref = true;
+                    }
+                    n += __popc(m);
+                }
+                nonref = __any_sync(FULL, nonref);
+                __syncwarp();
+                for (uint32_t i = lane; i < n; i += 32) w_val[i] = T.eprob[w_calls[i] & 63u];
+            }
+            if (nonref) nonref_mask |= 1u << s;
+            if (lane == 0) s_n[warp][s] = n;
+            if (is_dep)
+            {
+                // group = is_fwd + 2*base_id, calls with q < 3 excluded; stable partition into w_ord
+                uint32_t start = 0;
+                for (uint32_t g = 0; g < 8; ++g)
+                {
+                    if (lane == 0) s_gstart[warp][s][g] = start;
+                    for (uint32_t b = 0; b < n; b += 32)
+                    {
+                        const uint32_t i = b + lane;
+                        bool in = false;
+                        if (i < n)
+                        {
+                            const uint32_t c = w_calls[i];
+                            in = ((c & 63u) >= 3u) && ((((c >> 10) & 1u) + 2u * ((c >> 6) & 15u)) == g);
+                        }
+                        const uint32_t m = __ballot_sync(FULL, in);
+                        if (in) w_ord[start + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(i);
+                        start += __popc(m);
+                    }
+                }
+                if (lane == 0) s_gstart[warp][s][8] = start;
+            }
+        }
+        __syncwarp();
+        // ---- phase B: one (site, group) pair per lane -- adjust_icalls_eprob (adjust_joint_eprob.cpp:100-180)
+        if (is_dep)
+        {
+            const uint32_t s = lane >> 3, g = lane & 7u;
+            const uint16_t* w_calls = s_calls[warp][s];
+            float* w_val = s_val[warp][s];
+            const uint32_t g0 = s_gstart[warp][s][g], sz = s_gstart[warp][s][g + 1] - g0;
+            if (sz)
+            {
+                uint16_t* ic = s_ord[warp][s] + g0;
+                float num = 0.f, den = 0.f; // :112-127, in pileup order (before the sort)
+                for (uint32_t k = 0; k < sz; ++k)
+                {
+                    const uint32_t c = w_calls[ic[k]];
+                    const float weight = T.weight[c & 63u];
+                    den = f_add(den, weight);
+                    if ((c >> 11) & 1u) num = f_add(num, weight);
+                }
+                float mismatch_frac = 0.f;
+                if (static_cast<double>(den) > 0.) mismatch_frac = f_div(num, den);
+                const float vexp_frac = static_cast<float>(d_add(d_mul(static_cast<double>(f_sub(1.0f, mismatch_frac)), ssd_no), d_mul(static_cast<double>(mismatch_frac), ssd_one)));
+                const QKey key{w_calls};
+                sx_stdsort_desc(ic, sz, key);
+                float vexp = 1.0f;
+                bool is_min_vexp = false;
+                const float step = f_sub(1.0f, vexp_frac);
+                for (uint32_t k = 0; k < sz; ++k)
+                {
+                    const uint32_t idx = ic[k];
+                    const uint32_t q = w_calls[idx] & 63u;
+                    if (!is_min_vexp)
+                    {
+                        w_val[idx] = dependent_eprob(T.eprob[q], vexp);
+                        const float next_vexp = f_mul(vexp, step);
+                        if (is_limit_vexp)
+                        {
+                            is_min_vexp = (next_vexp <= min_vexp);
+                            vexp = (min_vexp < next_vexp) ? next_vexp : min_vexp; // std::max(min_vexp, next_vexp)
+                        }
+                        else
+                        {
+                            vexp = next_vexp;
+                        }
+                    }
+                    else
+                    {
+                        w_val[idx] = T.depmin[q];
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---- phase C, site by site: likelihoods and posteriors
+        for (uint32_t s = 0; s < nb; ++s)
+        {
+            const uint32_t site = base + s;
+            const uint16_t* w_calls = s_calls[warp][s];
+            float* w_val = s_val[warp][s];
+            const uint32_t n = s_n[warp][s];
+            const bool nonref = (nonref_mask >> s) & 1u;
+            const char rb = ref_base[site];
+            const uint32_t ref_gt = rb == 'A' ? 0u : rb == 'C' ? 1u : rb == 'G' ? 2u : rb == 'T' ? 3u : 4u;
+            if (de_out != nullptr)
+            {
+                const uint32_t o = de_off[site];
+                for (uint32_t i = lane; i < n; i += 32) de_out[o + i] = w_val[i];
+                __syncwarp();
+                if (out == nullptr) continue;
+            }
+            sx_digt_result* res = out + site;
+            const bool computed = (ref_gt < 4u) && (is_always_test || nonref);
+            if (!computed)
+            {
+                uint32_t* w = reinterpret_cast<uint32_t*>(res);
+                for (uint32_t i = lane; i < sizeof(sx_digt_result) / 4; i += 32) w[i] = 0u;
+                __syncwarp();
+                if (lane == 0)
+                {
+                    res->ref_gt = (ref_gt < 4u) ? ref_gt : 0u;
+                    res->n_used_calls = n;
+                }
+                continue;
+            }
+            for (uint32_t i = lane; i < n; i += 32) w_val[i] = f_add(sx_logf(w_val[i]), log_one_third);
+            __syncwarp();
+            const uint32_t pass = lane / 10u, gt = lane - pass * 10u;
+            const uint32_t e2_gt = expect2_pack(gt < 10u ? gt : 0u), e2_ref = expect2_pack(ref_gt);
+            float lh = 0.f;
+            if (lane < 30)
+            {
+                for (uint32_t i = 0; i < n; ++i)
+                {
+                    const uint32_t c = w_calls[i];
+                    const uint32_t q = c & 63u, obs = (c >> 6) & 3u, fwd = (c >> 10) & 1u;
+                    const bool force_ref = (pass != 0u) && ((pass == 1u) != (fwd != 0u));
+                    const uint32_t k = ((force_ref ? e2_ref : e2_gt) >> (2u * obs)) & 3u;
+                    const float v = (k == 0u) ? w_val[i] : (k == 1u) ? T.val1[q] : T.val2[q];
+                    lh = f_add(lh, v);
+                }
+            }
+            const bool haploid = ploidy != nullptr && ploidy[site] == 1;
+            const uint32_t gtcount = haploid ? 4u : 10u;
+            float lmax = __shfl_sync(FULL, lh, 0);
+            for (uint32_t g = 1; g < gtcount; ++g)
+            {
+                const float v = __shfl_sync(FULL, lh, g);
+                if (v > lmax) lmax = v;
+            }
+            uint32_t pl = 0;
+            if (lane < gtcount) pl = static_cast<uint32_t>(ln_error_prob_to_qphred_f(f_sub(lh, lmax), ln10f));
+            const float* pri = T.lnprior[haploid ? 1 : 0][ref_gt][0];
+            const rs_out genome = result_set(lh, pri, ref_gt, lane);
+            const rs_out poly = result_set(lh, pri + 10, ref_gt, lane);
+            double strand_bias = 0.0;
+            {
+                const uint32_t tgt = genome.max_gt;
+                const float lf = __shfl_sync(FULL, lh, 10 + tgt), lr = __shfl_sync(FULL, lh, 20 + tgt), l0 = __shfl_sync(FULL, lh, tgt);
+                if (genome.snp_qphred != 0) strand_bias = static_cast<double>(f_sub((lf < lr) ? lr : lf, l0));
+            }
+            if (lane < 10)
+            {
+                res->lhood[lane] = lh;
+                res->phredLoghood[lane] = pl;
+            }
+            if (lane == 0)
+            {
+                res->genome.ref_pprob = genome.ref_pprob;
+                res->genome.max_gt = genome.max_gt;
+                res->genome.snp_qphred = genome.snp_qphred;
+                res->genome.max_gt_qphred = genome.max_gt_qphred;
+                res->genome.pad = 0;
+                res->poly.ref_pprob = poly.ref_pprob;
+                res->poly.max_gt = poly.max_gt;
+                res->poly.snp_qphred = poly.snp_qphred;
+                res->poly.max_gt_qphred = poly.max_gt_qphred;
+                res->poly.pad = 0;
+                res->strand_bias = strand_bias;
+                res->ref_gt = ref_gt;
+                res->is_computed = 1;
+                res->n_used_calls = n;
+                res->pad = 0;
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void k2_max_site_kernel(const uint32_t* __restrict__ site_off, uint32_t n_sites, uint32_t* __restrict__ out)
 {
     uint32_t m = 0;
@@ -373,7 +632,16 @@ int germline_run(sx_ctx* ctx, const sx_pileup_batch* d, int is_always_test, sx_d
     const int grid = static_cast<int>(std::min<uint32_t>((d->n_sites + K2_WARPS - 1) / K2_WARPS, (uint32_t)ctx->sm_count * 8));
     if (max_site > K2_CAP_BIG)
         return sx_fail(ctx, SX_ERR_UNSUPPORTED, "sx_site_gl_germline: a site holds %u calls; the kernel handles at most %d per site", max_site, K2_CAP_BIG);
-    if (max_site > K2_CAP_SMEM)
+    if (max_site <= K2_CAP_SMEM)
+    {
+        // every site fits the shared-memory cap: four sites per warp (35 KB of static shared memory per CTA -> 6 CTAs per SM)
+        const uint32_t per_cta = K2_WARPS * K2_BATCH;
+        const int grid4 = static_cast<int>(std::min<uint32_t>((d->n_sites + per_cta - 1) / per_cta, (uint32_t)ctx->sm_count * 6));
+        k2a_germline4_kernel<<<grid4, K2_WARPS * 32, 0, ctx->s_compute>>>(d->site_off, d->calls, d->ref_base, d->ploidy, d->n_sites, is_always_test, ctx->d_tables, out_dev,
+                                                                         de_off_dev, de_dev, ctx->d_status);
+        SX_CUDA(ctx, cudaGetLastError());
+        return SX_OK;
+    }
     {
         int rc = sx_ensure(ctx, 19, (size_t)grid * K2_WARPS * K2_CAP_BIG * 8, reinterpret_cast<void**>(&scratch));
         if (rc) return rc;
