@@ -34,6 +34,7 @@ struct kg_info
     uint32_t hist[KG_BUCKETS];
     uint32_t max_r[16];  // per T class
     uint32_t large_need; // shared-memory slot of the largest "large" problem
+    uint32_t work[16];   // per T class: next quad to hand out (kg_align_kernel)
 };
 
 __device__ __forceinline__ uint32_t kg_bucket(uint32_t Q, uint32_t R, uint32_t max_q)
@@ -81,10 +82,13 @@ __global__ void kg_scatter_kernel(const uint32_t* __restrict__ query_off, const 
     }
 }
 
-// per-warp shared memory: final-column score strips [3][T][32] ints, then per group: query (T*8), reference (max_r), steps (T*8 + max_r)
+constexpr int KG_B = 8; // quads whose DP a warp finishes before it traces back their 4 * KG_B matrices, one per lane
+constexpr uint32_t KG_SAVE_WORDS = 6; // per-matrix state kept from the DP to the traceback
+
+// per-warp shared memory: final-column score strips [3][T][32] ints, per group: query (T*8), reference (max_r); the saved start states
 template <int T> __host__ __device__ constexpr uint32_t kg_warp_smem(uint32_t max_r)
 {
-    return 3u * T * 32u * 4u + 4u * (((T * KG_G + 15u) & ~15u) + ((max_r + 15u) & ~15u) + ((T * KG_G + max_r + 15u) & ~15u));
+    return 3u * T * 32u * 4u + 4u * (((T * KG_G + 15u) & ~15u) + ((max_r + 15u) & ~15u)) + KG_SAVE_WORDS * 32u * 4u;
 }
 
 // Score keys: 64*score + tag, tag = 21 * (3 - state) = the 2-bit code (3 - state) replicated into three 2-bit fields (match 0b111111,
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
                                                                  const uint32_t* __restrict__ query_off, const uint32_t* __restrict__ ref_off,
                                                                  const uint32_t* __restrict__ order, uint32_t n, uint32_t max_ops, sx_ga_scores sc,
                                                                  sx_ga_result* __restrict__ res, uint32_t* __restrict__ cigar, uint32_t max_r,
-                                                                 unsigned char* __restrict__ scratch, size_t scratch_slot)
+                                                                 unsigned char* __restrict__ scratch, size_t scratch_slot, uint32_t* __restrict__ work)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -113,13 +117,14 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
     int* sM = reinterpret_cast<int*>(wsm);
     int* sD = sM + T * 32;
     int* sI = sD + T * 32;
-    const uint32_t qpad = (T * KG_G + 15u) & ~15u, rpad = (max_r + 15u) & ~15u, spad = (T * KG_G + max_r + 15u) & ~15u;
-    unsigned char* gsm = wsm + 3u * T * 32u * 4u + grp * (qpad + rpad + spad);
+    const uint32_t qpad = (T * KG_G + 15u) & ~15u, rpad = (max_r + 15u) & ~15u;
+    unsigned char* gsm = wsm + 3u * T * 32u * 4u + grp * (qpad + rpad);
     char* qs = reinterpret_cast<char*>(gsm);
     char* rs = qs + qpad;
-    uint8_t* steps = reinterpret_cast<uint8_t*>(rs + rpad);
-    const uint32_t gwarp = blockIdx.x * KG_WARPS + warp, n_gwarps = gridDim.x * KG_WARPS;
-    unsigned char* ptr = scratch + (size_t)gwarp * scratch_slot;
+    // start states of the warp's pending matrices (slot = quad-in-batch * 4 + group): prob, Q, queryBegin, refBegin, state, score
+    uint32_t* sv = reinterpret_cast<uint32_t*>(wsm + 3u * T * 32u * 4u + 4u * (qpad + rpad));
+    const uint32_t gwarp = blockIdx.x * KG_WARPS + warp;
+    unsigned char* const wscratch = scratch + (size_t)gwarp * scratch_slot * KG_B;
 
     const int s_match = sc.match, s_mismatch = sc.mismatch, s_open = sc.open, s_extend = sc.extend, s_insdel = sc.insertDelete;
     const bool req_del = sc.isRequireEdgeDeletion != 0, allow_ins = sc.isAllowEdgeInsertion != 0;
@@ -135,8 +140,18 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
     const uint32_t row0 = gl * T; // query index of this lane's first row
 
     const uint32_t n_quads = (n + 3) / 4;
-    for (uint32_t quad = gwarp; quad < n_quads; quad += n_gwarps)
+    // Quads are handed out one at a time through an atomic counter (so the tail of a launch is one quad, not one batch); a warp runs
+    // the DP of up to KG_B quads, keeping their back pointers in KG_B scratch slots, and then traces all of them back at once.
+    uint32_t n_pending = 0;
+    for (;;)
     {
+        uint32_t quad = 0;
+        if (lane == 0) quad = atomicAdd(work, 1u);
+        quad = __shfl_sync(FULL, quad, 0);
+        const bool got = quad < n_quads;
+        if (got)
+        {
+        unsigned char* ptr = wscratch + (size_t)n_pending * scratch_slot;
         const uint32_t k = quad * 4 + grp;
         const bool have = k < n;
         const uint32_t prob = have ? order[k] : 0;
@@ -299,93 +314,117 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
             }
             update_bt(bt, best, R, besti, ST_MATCH);
         }
-        // ---- traceback + emission: lane 0 of each group
-        if (have && is_lane0)
+        // ---- keep the start state for the batched traceback
+        if (is_lane0)
         {
-            uint32_t nsteps = 0, qb = bt.queryBegin, rb = bt.refBegin;
-            const uint32_t trailing_clip = (qb < Q) ? (Q - qb) : 0;
-            int state = bt.state;
-            while (true)
-            {
-                uint32_t pv;
-                if (qb == 0 || rb == 0) pv = (rb == 0) ? ptr_c0 : ptr_r0;
-                else
-                {
-                    const uint32_t row = qb - 1, ln = row / T, r = row - ln * T, t = (rb - 1) + ln;
-                    pv = ptr[(static_cast<size_t>(t) * T + r) * 32 + gbase + ln];
-                }
-                const uint32_t dq = state != ST_DELETE, dr = state != ST_INSERT;
-                if ((dq && qb == 0) || (dr && rb == 0)) break;
-                qb -= dq;
-                rb -= dr;
-                steps[nsteps++] = static_cast<uint8_t>(state);
-                state = 3 - static_cast<int>((pv >> (2 * state)) & 3u);
-            }
-            uint32_t* cg = cigar + static_cast<size_t>(prob) * max_ops;
-            uint32_t n_ops = 0;
-            if (qb)
-            {
-                if (n_ops < max_ops) cg[n_ops] = (qb << 4) | CIG_S;
-                ++n_ops;
-            }
-            uint32_t qi = qb, rix = rb;
-            int cur_type = -1;
-            uint32_t cur_len = 0;
-            for (uint32_t f = nsteps; f-- > 0;)
-            {
-                const int st = steps[f];
-                int type;
-                if (st == ST_MATCH)
-                {
-                    const char a = qs[qi], c = rs[rix];
-                    type = (a == c && a != 'N' && c != 'N') ? CIG_EQ : CIG_X;
-                    ++qi;
-                    ++rix;
-                }
-                else if (st == ST_DELETE)
-                {
-                    type = CIG_D;
-                    ++rix;
-                }
-                else
-                {
-                    type = CIG_I;
-                    ++qi;
-                }
-                if (type == cur_type) ++cur_len;
-                else
-                {
-                    if (cur_type >= 0)
-                    {
-                        if (n_ops < max_ops) cg[n_ops] = (cur_len << 4) | static_cast<uint32_t>(cur_type);
-                        ++n_ops;
-                    }
-                    cur_type = type;
-                    cur_len = 1;
-                }
-            }
-            if (cur_type >= 0)
-            {
-                if (n_ops < max_ops) cg[n_ops] = (cur_len << 4) | static_cast<uint32_t>(cur_type);
-                ++n_ops;
-            }
-            if (trailing_clip)
-            {
-                if (n_ops < max_ops) cg[n_ops] = (trailing_clip << 4) | CIG_S;
-                ++n_ops;
-            }
-            res[prob].score = bt.max;
-            res[prob].beginPos = static_cast<int>(rb);
-            res[prob].n_ops = n_ops;
-            res[prob].status = n_ops > max_ops ? 1u : 0u;
+            uint32_t* s = sv + (n_pending * 4 + grp) * KG_SAVE_WORDS;
+            s[0] = have ? prob : 0xffffffffu;
+            s[1] = Q;
+            s[2] = bt.queryBegin;
+            s[3] = bt.refBegin;
+            s[4] = static_cast<uint32_t>(bt.state);
+            s[5] = static_cast<uint32_t>(bt.max);
         }
+        ++n_pending;
         __syncwarp();
+        } // got
+        if (n_pending == KG_B || (!got && n_pending))
+        {
+            __syncwarp();
+            // ---- traceback + emission: one matrix per lane (4 * n_pending of them).  The path is walked from its end, so the CIGAR is
+            // produced last operation first, into a ring over the caller's max_ops slots, and put in order at the end; the ring keeps
+            // exactly what the forward emission keeps on overflow (the first max_ops operations).
+            const uint32_t* s = sv + lane * KG_SAVE_WORDS;
+            const uint32_t prob = lane < n_pending * 4 ? s[0] : 0xffffffffu;
+            if (prob != 0xffffffffu)
+            {
+                const unsigned char* pm = wscratch + (size_t)(lane >> 2) * scratch_slot;
+                const uint32_t gbase = (lane & 3u) * KG_G;
+                const uint32_t Q = s[1];
+                uint32_t qb = s[2], rb = s[3];
+                int state = static_cast<int>(s[4]);
+                const char* qg = query_pool + query_off[prob];
+                const char* rg = ref_pool + ref_off[prob];
+                uint32_t* cg = cigar + static_cast<size_t>(prob) * max_ops;
+                uint32_t n_ops = 0, wpos = 0;
+                auto push = [&](uint32_t type, uint32_t len) {
+                    if (max_ops)
+                    {
+                        cg[wpos] = (len << 4) | type;
+                        if (++wpos == max_ops) wpos = 0;
+                    }
+                    ++n_ops;
+                };
+                if (qb < Q) push(CIG_S, Q - qb); // trailing soft clip
+                int cur_type = -1;
+                uint32_t cur_len = 0;
+                while (true)
+                {
+                    uint32_t pv;
+                    if (qb == 0 || rb == 0) pv = (rb == 0) ? ptr_c0 : ptr_r0;
+                    else
+                    {
+                        const uint32_t row = qb - 1, ln = row / T, r = row - ln * T, t = (rb - 1) + ln;
+                        pv = pm[(static_cast<size_t>(t) * T + r) * 32 + gbase + ln];
+                    }
+                    const uint32_t dq = state != ST_DELETE, dr = state != ST_INSERT;
+                    if ((dq && qb == 0) || (dr && rb == 0)) break;
+                    qb -= dq;
+                    rb -= dr;
+                    int type;
+                    if (state == ST_MATCH)
+                    {
+                        const char a = __ldg(qg + qb), c = __ldg(rg + rb);
+                        type = (a == c && a != 'N' && c != 'N') ? CIG_EQ : CIG_X;
+                    }
+                    else type = (state == ST_DELETE) ? CIG_D : CIG_I;
+                    if (type == cur_type) ++cur_len;
+                    else
+                    {
+                        if (cur_type >= 0) push(static_cast<uint32_t>(cur_type), cur_len);
+                        cur_type = type;
+                        cur_len = 1;
+                    }
+                    state = 3 - static_cast<int>((pv >> (2 * state)) & 3u);
+                }
+                if (cur_type >= 0) push(static_cast<uint32_t>(cur_type), cur_len);
+                if (qb) push(CIG_S, qb); // leading soft clip
+                // ring -> forward order
+                auto reverse = [&](uint32_t lo, uint32_t hi) { // [lo, hi)
+                    while (lo + 1 < hi)
+                    {
+                        --hi;
+                        const uint32_t tmp = cg[lo];
+                        cg[lo] = cg[hi];
+                        cg[hi] = tmp;
+                        ++lo;
+                    }
+                };
+                if (n_ops <= max_ops) reverse(0, n_ops);
+                else
+                {
+                    // slot of the forward-first operation is p = (n_ops - 1) mod max_ops; forward[f] = ring[(p - f) mod max_ops]
+                    const uint32_t p = (wpos + max_ops - 1) % max_ops, sh = max_ops - 1 - p;
+                    reverse(0, max_ops);
+                    reverse(0, sh);
+                    reverse(sh, max_ops);
+                    reverse(0, max_ops);
+                }
+                res[prob].score = static_cast<int>(s[5]);
+                res[prob].beginPos = static_cast<int>(rb);
+                res[prob].n_ops = n_ops;
+                res[prob].status = n_ops > max_ops ? 1u : 0u;
+            }
+            __syncwarp();
+            n_pending = 0;
+        }
+        if (!got) break;
     }
 }
 
 template <int T>
 int kg_launch(sx_ctx* ctx, const sx_ga_scores* sc, const sx_ga_batch* d, sx_ga_result* res_dev, uint32_t* cigar_dev, const uint32_t* order, uint32_t n, uint32_t max_r,
-              int scratch_slot_id)
+              int scratch_slot_id, uint32_t* work_dev)
 {
     if (n == 0) return SX_OK;
     const size_t smem = (size_t)kg_warp_smem<T>(max_r) * KG_WARPS;
@@ -393,11 +432,11 @@ int kg_launch(sx_ctx* ctx, const sx_ga_scores* sc, const sx_ga_batch* d, sx_ga_r
     const uint32_t quads = (n + 3) / 4;
     const int grid = static_cast<int>(std::min<uint32_t>((quads + KG_WARPS - 1) / KG_WARPS, (uint32_t)ctx->sm_count * 4));
     unsigned char* scratch = nullptr;
-    int rc = sx_ensure(ctx, scratch_slot_id, slot * (size_t)grid * KG_WARPS, reinterpret_cast<void**>(&scratch));
+    int rc = sx_ensure(ctx, scratch_slot_id, slot * KG_B * (size_t)grid * KG_WARPS, reinterpret_cast<void**>(&scratch));
     if (rc) return rc;
     if (smem > 48 * 1024) SX_CUDA(ctx, cudaFuncSetAttribute(kg_align_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
     kg_align_kernel<T><<<grid, KG_WARPS * 32, smem, ctx->s_compute>>>(d->query, d->ref, d->query_off, d->ref_off, order, n, d->max_ops, *sc, res_dev, cigar_dev, max_r, scratch,
-                                                                     slot);
+                                                                     slot, work_dev);
     SX_CUDA(ctx, cudaGetLastError());
     return SX_OK;
 }
@@ -436,7 +475,7 @@ int sx_k3_group_run(sx_ctx* ctx, const sx_ga_scores* sc, const sx_ga_batch* d, s
 #define KG_CASE(TT)                                                                                                                           \
     {                                                                                                                                         \
         const uint32_t b0 = begin[(TT - 1) * KG_RCLASSES], b1 = begin[TT * KG_RCLASSES];                                                       \
-        if ((rc = kg_launch<TT>(ctx, sc, d, res_dev, cigar_dev, d_order + b0, b1 - b0, info.max_r[TT - 1], 23))) return rc;                     \
+        if ((rc = kg_launch<TT>(ctx, sc, d, res_dev, cigar_dev, d_order + b0, b1 - b0, info.max_r[TT - 1], 23, &d_info->work[TT - 1]))) return rc; \
     }
     // one launch per strip height; launches on one stream reuse the same scratch arena (sized for the largest so far by sx_ensure,
     // which only ever grows between launches after a stream-ordered free would be unsafe -- so size it once for the worst class)
@@ -445,7 +484,7 @@ int sx_k3_group_run(sx_ctx* ctx, const sx_ga_scores* sc, const sx_ga_batch* d, s
         for (int t = 1; t <= 16; ++t)
             if (begin[t * KG_RCLASSES] > begin[(t - 1) * KG_RCLASSES]) worst = std::max(worst, ((size_t)(info.max_r[t - 1] + KG_G) * t * 32 + 255) & ~size_t(255));
         void* p = nullptr;
-        if (worst && (rc = sx_ensure(ctx, 23, worst * (size_t)ctx->sm_count * 4 * KG_WARPS, &p))) return rc;
+        if (worst && (rc = sx_ensure(ctx, 23, worst * KG_B * (size_t)ctx->sm_count * 4 * KG_WARPS, &p))) return rc;
     }
     KG_CASE(1) KG_CASE(2) KG_CASE(3) KG_CASE(4) KG_CASE(5) KG_CASE(6) KG_CASE(7) KG_CASE(8)
     KG_CASE(9) KG_CASE(10) KG_CASE(11) KG_CASE(12) KG_CASE(13) KG_CASE(14) KG_CASE(15) KG_CASE(16)
