@@ -150,6 +150,23 @@ def test_k3_global_align_random(ctx, flags):
         assert np.array_equal(o_cig, g_cig)
 
 
+@pytest.mark.parametrize("max_ops", [1, 2, 3, 5])
+def test_k3_cigar_overflow_keeps_the_first_ops(ctx, max_ops):
+    """More CIGAR operations than the caller's max_ops: status 1, n_ops = the true count, and the first max_ops operations are
+    stored (both kernels: the group kernel builds the CIGAR backwards in a ring and must un-rotate it)."""
+    rng = np.random.default_rng(78)
+    qs, rs = specgen.random_ga_problems(rng, 300, n_frac=0.01)
+    qs += ["A" * 300, specgen.rand_seq(rng, 257)]
+    rs += ["A" * 280, specgen.rand_seq(rng, 300)]
+    gb = B.GaBatch(qs, rs, max_ops=max_ops)
+    sc = _ga_scores(1, -4, -5, -1, -100, -5, True, False)
+    o_res, o_cig = reflib.ox_global_align(sc, gb)
+    g_res, g_cig = ctx.global_align(sc, gb)
+    assert (o_res["status"] == 1).any() and (o_res["status"] == 0).any() or max_ops == 1
+    assert np.array_equal(o_res, g_res)
+    assert np.array_equal(o_cig, g_cig)
+
+
 def test_k3_reference_unit_test_goldens(ctx):
     import json
     import os
