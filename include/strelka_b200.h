@@ -135,6 +135,21 @@ typedef struct sx_aln {
     uint32_t ins_off; /* byte offset of this alignment's inserted bases in the insert pool */
 } sx_aln;
 
+/* Compact wire formats (sx_align_batch.format bits).  The scoring entry points are PCIe-bound from host buffers, so bytes are
+ * throughput: a batch may send its alignment headers and segments in half the space.  Semantics are identical; the builder falls
+ * back to the wide structs when a field would not fit. */
+#define SX_FMT_ALN8 0x1u /* `alns` points to sx_aln8[n_alns + 1] */
+#define SX_FMT_SEG2 0x2u /* `segs` points to sx_aln_seg2[n_segs]; every region's seg_begin is a multiple of 8 */
+
+typedef struct sx_aln8 {  /* every field relative to the alignment's region; an alignment's segments end at the next alignment's */
+    uint16_t read;        /* seg_off, the last alignment's at the region's last segment                                          */
+    int16_t ref_pos;      /* ref_pos - region.ref_begin */
+    uint16_t seg_off;     /* seg_off - region.seg_begin */
+    uint16_t ins_off;     /* ins_off - region.ins_begin */
+} sx_aln8;
+
+typedef uint16_t sx_aln_seg2; /* len (bits 0-11, <= 4095) | kind << 12 (3 bits) | flags << 15 */
+
 typedef struct sx_region {
     uint64_t seq_off;    /* byte offset in seq4 pool of the region's first read (multiple of 16) */
     uint64_t qual_off;   /* byte offset in qual pool (multiple of 16) */
@@ -166,10 +181,13 @@ typedef struct sx_align_batch {
     /* Quality wire format.  qual_bits 0 or 8: `qual` holds one byte per base.  qual_bits 4: a batch whose reads use at most 16
      * distinct quality values (binned Illumina qualities do) may send them dictionary-coded, two per byte, high nibble first,
      * each read starting on a byte boundary exactly like seq4; nibble v stands for quality qual_dict[v].  Lossless; it cuts the
-     * host->device bytes of a 150 bp read from 225 to 150 and selects the byte-entry scoring kernel (k1_score4.cu). */
+     * host->device bytes of a 150 bp read from 225 to 150 and selects the byte-entry scoring kernel (k1_score4.cu).
+     * qual_bits 2: at most 4 distinct values (NovaSeq-style binning): one 2-bit code per NIBBLE POSITION of the region's seq4
+     * slice, pad nibbles included -- the code of the nibble at position p (counted from the region's seq_off, two per byte) is
+     * bits 7-2*(p&3) .. 6-2*(p&3) of byte region.qual_off + p/4; a region's quality slice is half its seq4 slice. */
     uint32_t qual_bits;
     uint8_t qual_dict[16];
-    uint32_t reserved_;
+    uint32_t format; /* SX_FMT_* bits; 0 = sx_aln / sx_aln_seg */
 } sx_align_batch;
 
 /* lnp_out[n_alns] <- ln P(read | alignment path); bit-identical to the reference's double. */

@@ -12,6 +12,7 @@
 // bench.py may use as the "reference" CPU baseline.  Never shipped, never on the product path.
 
 #include "../include/strelka_b200.h"
+#include "flat_batch_normalize.h"
 
 #include "alignment/GlobalAligner.hh"
 #include "applications/strelka/position_somatic_snv_strand_grid.hh"
@@ -421,6 +422,8 @@ extern "C" int ref_score_flat_batch(const sx_align_batch* b, uint32_t r0, uint32
 {
     try
     {
+        sx_norm_batch wide; // compact wire formats are widened first (same values, wider fields)
+        b = sx_normalize_range(b, r0, r1, wide);
         harness_options opt;
         opt.is_candidate_indel_signal_test = false;
         starling_base_deriv_options dopt(opt);

@@ -9,6 +9,7 @@
 // x86-64 SSE2, src/cmake/cxxConfigure.cmake:438): see oracle/Makefile.
 
 #include "strelka_oracle.h"
+#include "flat_batch_normalize.h"
 
 #include "../strelka_b200/csrc/sx_libm_mirror.h" // only for the ox_*_restated test exports below
 
@@ -80,6 +81,8 @@ inline uint8_t bam_code_of_char(const char c) // htsapi/bam_seq.hh:98-118
 
 extern "C" int ox_score_alignments_range(const sx_align_batch* b, uint32_t r0, uint32_t r1, double* lnp_out)
 {
+    sx_norm_batch wide; // compact wire formats are widened first (same values, wider fields)
+    b = sx_normalize_range(b, r0, r1, wide);
     static const double lnthird(-std::log(3.));                           // score.cpp:118,152
     static const double unalignedBasecallLogLikelihood(std::log(0.25));   // score.cpp:453
     static const double nonCandidateIndelPenalty(std::log(1e-5));         // score.cpp:483

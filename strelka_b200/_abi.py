@@ -49,6 +49,8 @@ def default_params() -> SxParams:
 # numpy mirrors of the POD arrays (layout == C structs; checked against sizeof in tests/test_abi.py)
 ALN_SEG_DT = np.dtype([("len", "<u2"), ("kind", "u1"), ("flags", "u1")])
 ALN_DT = np.dtype([("read", "<u4"), ("ref_pos", "<i4"), ("seg_off", "<u4"), ("ins_off", "<u4")])
+ALN8_DT = np.dtype([("read", "<u2"), ("ref_pos", "<i2"), ("seg_off", "<u2"), ("ins_off", "<u2")])  # sx_aln8 (SX_FMT_ALN8)
+SX_FMT_ALN8, SX_FMT_SEG2 = 1, 2
 REGION_DT = np.dtype(
     [("seq_off", "<u8"), ("qual_off", "<u8"), ("ref_off", "<u8"), ("read_begin", "<u4"), ("aln_begin", "<u4"), ("seg_begin", "<u4"), ("ins_begin", "<u4"),
      ("ref_begin", "<i4"), ("ref_len", "<u4")]
@@ -116,7 +118,7 @@ class SxAlignBatch(C.Structure):
         ("ins_bytes", C.c_uint64),
         ("qual_bits", C.c_uint32),
         ("qual_dict", C.c_uint8 * 16),
-        ("reserved_", C.c_uint32),
+        ("format", C.c_uint32),
     ]
 
 

@@ -170,46 +170,55 @@ def _pad16(n: int) -> int:
 class AlignBatch:
     """Owns the numpy pools of one sx_align_batch and exposes the ctypes struct (``.c``)."""
 
-    def __init__(self, regions, read_len, seq4, qual, ref, alns, segs, ins, used, qual_bits=8, qual_dict=None):
+    def __init__(self, regions, read_len, seq4, qual, ref, alns, segs, ins, used, qual_bits=8, qual_dict=None, fmt=0, n_segs=None, n_alns=None):
         self.regions, self.read_len, self.seq4, self.qual, self.ref = regions, read_len, seq4, qual, ref
         self.qual_bits = qual_bits
+        self.fmt = fmt
         self.qual_dict = (C.c_uint8 * 16)(*([int(x) for x in qual_dict] + [0] * (16 - len(qual_dict)))) if qual_dict is not None else (C.c_uint8 * 16)()
         self.alns, self.segs, self.ins = alns, segs, ins
         self.n_regions = len(regions) - 1
         self.n_reads = len(read_len)
-        self.n_alns = len(alns) - 1
-        self.n_segs = int(alns["seg_off"][-1])
+        self.n_alns = len(alns) - 1 if n_alns is None else int(n_alns)
+        self.n_segs = int(alns["seg_off"][-1]) if n_segs is None else int(n_segs)
         self.used = used
         self.c = A.SxAlignBatch(
             self.n_regions, self.n_reads, self.n_alns, self.n_segs,
             A.ptr(regions), A.ptr(read_len), A.ptr(seq4), A.ptr(qual), A.ptr(ref), A.ptr(alns), A.ptr(segs), A.ptr(ins),
-            used["seq4"], used["qual"], used["ref"], used["ins"], qual_bits, self.qual_dict, 0,
+            used["seq4"], used["qual"], used["ref"], used["ins"], qual_bits, self.qual_dict, fmt,
         )
 
     def cells(self) -> int:
         """SURVEY 8a cell-update count: read bases in MATCH/INSERT segments over all alignments."""
         s = self.segs[: self.n_segs]
-        m = (s["kind"] == A.SX_SEG_MATCH) | (s["kind"] == A.SX_SEG_INSERT)
-        return int(s["len"][m].astype(np.int64).sum())
+        if self.fmt & A.SX_FMT_SEG2:
+            kind, ln = (s >> 12) & 7, s & 0xFFF
+        else:
+            kind, ln = s["kind"], s["len"]
+        m = (kind == A.SX_SEG_MATCH) | (kind == A.SX_SEG_INSERT)
+        return int(ln[m].astype(np.int64).sum())
 
     def algorithmic_bytes(self) -> int:
         """SURVEY 8d K1 bytes: each read once (packed bases + quals), headers, segments, inserted bases, ref windows, 8 B out/aln."""
         return int(
             self.used["seq4"] + self.used["qual"] + self.used["ref"] + self.used["ins"]
-            + self.n_alns * (A.ALN_DT.itemsize + 8) + self.n_segs * A.ALN_SEG_DT.itemsize
+            + self.n_alns * (self.alns.dtype.itemsize + 8) + self.n_segs * self.segs.dtype.itemsize
             + self.n_reads * 2 + self.n_regions * A.REGION_DT.itemsize
         )
 
 
-def build_align_batch(regions: Sequence[RegionSpec], qual_bits: int = 8) -> AlignBatch:
-    """qual_bits=4 sends qualities dictionary-coded, two per byte (needs <= 16 distinct values in the batch)."""
+def build_align_batch(regions: Sequence[RegionSpec], qual_bits: int = 8, compact: bool = False) -> AlignBatch:
+    """qual_bits=4 sends qualities dictionary-coded, two per byte (needs <= 16 distinct values in the batch); qual_bits=2 one
+    2-bit code per nibble position of the seq4 stream (<= 4 distinct values).  compact=True sends alignment headers and segments in
+    the 8-byte / 2-byte wire formats (SX_FMT_ALN8 | SX_FMT_SEG2)."""
     qdict = None
-    if qual_bits == 4:
+    if qual_bits in (2, 4):
         vals = sorted({int(x) for r in regions for _, q in r.reads for x in np.asarray(q).tolist()})
-        assert len(vals) <= 16, "4-bit quality coding needs at most 16 distinct quality values"
+        assert len(vals) <= (1 << qual_bits), "%d-bit quality coding needs at most %d distinct quality values" % (qual_bits, 1 << qual_bits)
         qdict = vals
         qcode = {v: i for i, v in enumerate(vals)}
+    seg_align = 8 if compact else 4
     reg = np.zeros(len(regions) + 1, dtype=A.REGION_DT)
+    q2_codes: List[int] = []
     read_len: List[int] = []
     seq4 = bytearray()
     qual = bytearray()
@@ -220,8 +229,12 @@ def build_align_batch(regions: Sequence[RegionSpec], qual_bits: int = 8) -> Alig
     for ri, r in enumerate(regions):
         for pool in (seq4, qual, ref, ins):
             pool.extend(b"\0" * (_pad16(len(pool)) - len(pool)))
-        while len(segs) % 4:
+        while len(segs) % seg_align:
             segs.append((0, A.SX_SEG_HARDCLIP, 0))  # no-op pad, absorbed by the previous region's last alignment
+        if qual_bits == 2:
+            qual.extend(_pack2(q2_codes))
+            qual.extend(b"\0" * (_pad16(len(qual)) - len(qual)))
+            q2_codes = []
         reg[ri] = (len(seq4), len(qual), len(ref), len(read_len), len(alns), len(segs), len(ins), r.ref_begin, len(r.ref))
         ref.extend(r.ref.encode())
         rbase = len(read_len)
@@ -238,6 +251,10 @@ def build_align_batch(regions: Sequence[RegionSpec], qual_bits: int = 8) -> Alig
                 if n & 1:
                     qc = np.concatenate([qc, np.zeros(1, np.uint8)])
                 qual.extend(((qc[0::2] << 4) | qc[1::2]).astype(np.uint8).tobytes())
+            elif qual_bits == 2:
+                q2_codes.extend(qcode[int(x)] for x in np.asarray(q).tolist())
+                if n & 1:
+                    q2_codes.append(0)  # the pad nibble of an odd-length read has a (don't-care) code too
             else:
                 qual.extend(np.asarray(q, dtype=np.uint8).tobytes())
         order = sorted(range(len(r.alns)), key=lambda k: r.alns[k].read)
@@ -247,9 +264,11 @@ def build_align_batch(regions: Sequence[RegionSpec], qual_bits: int = 8) -> Alig
             alns.append((rbase + cal.read, cal.pos, len(segs), len(ins)))
             segs.extend(s)
             ins.extend(ib)
+    if qual_bits == 2:
+        qual.extend(_pack2(q2_codes))
     for pool in (seq4, qual, ref, ins):
         pool.extend(b"\0" * (_pad16(len(pool)) - len(pool)))
-    while len(segs) % 4:
+    while len(segs) % seg_align:
         segs.append((0, A.SX_SEG_HARDCLIP, 0))
     used = {"seq4": len(seq4), "qual": len(qual), "ref": len(ref), "ins": len(ins)}
     reg[len(regions)] = (len(seq4), len(qual), len(ref), len(read_len), len(alns), len(segs), len(ins), 0, 0)
@@ -260,6 +279,27 @@ def build_align_batch(regions: Sequence[RegionSpec], qual_bits: int = 8) -> Alig
     if segs:
         seg_arr[: len(segs)] = np.array(segs, dtype=A.ALN_SEG_DT)
     seg_arr["kind"][len(segs):] = A.SX_SEG_HARDCLIP
+    fmt = 0
+    n_segs = len(segs)
+    if compact:
+        # region of every alignment, then every field relative to it
+        ri_of = np.searchsorted(reg["aln_begin"][1:], np.arange(len(alns) - 1), side="right")
+        a8 = np.zeros(len(alns) + 2, dtype=A.ALN8_DT)  # + 16 bytes of slack: the kernels load the slice from a 16-byte boundary
+        rel = {
+            "read": aln_arr["read"][:-1].astype(np.int64) - reg["read_begin"][ri_of],
+            "ref_pos": aln_arr["ref_pos"][:-1].astype(np.int64) - reg["ref_begin"][ri_of],
+            "seg_off": aln_arr["seg_off"][:-1].astype(np.int64) - reg["seg_begin"][ri_of],
+            "ins_off": aln_arr["ins_off"][:-1].astype(np.int64) - reg["ins_begin"][ri_of],
+        }
+        fits = all(int(v.min(initial=0)) >= (-32768 if k == "ref_pos" else 0) and int(v.max(initial=0)) <= (32767 if k == "ref_pos" else 65535) for k, v in rel.items())
+        if fits:
+            for k, v in rel.items():
+                a8[k][: len(alns) - 1] = v
+            aln_arr = a8
+            fmt |= A.SX_FMT_ALN8
+        if int(seg_arr["len"].max(initial=0)) <= 4095:
+            seg_arr = (seg_arr["len"].astype(np.uint16) | (seg_arr["kind"].astype(np.uint16) << 12) | (seg_arr["flags"].astype(np.uint16) << 15)).astype(np.uint16)
+            fmt |= A.SX_FMT_SEG2
     return AlignBatch(
         reg,
         np.array(read_len, dtype=np.uint16),
@@ -272,7 +312,16 @@ def build_align_batch(regions: Sequence[RegionSpec], qual_bits: int = 8) -> Alig
         used,
         qual_bits,
         qdict,
+        fmt,
+        n_segs,
+        len(alns) - 1,
     )
+
+
+def _pack2(codes) -> bytes:
+    """2-bit codes -> bytes, first code in the two high bits."""
+    c = np.asarray(list(codes) + [0] * (-len(codes) % 4), dtype=np.uint8).reshape(-1, 4)
+    return ((c[:, 0] << 6) | (c[:, 1] << 4) | (c[:, 2] << 2) | c[:, 3]).astype(np.uint8).tobytes()
 
 
 # ------------------------------------------------------------------------------------------------------------------

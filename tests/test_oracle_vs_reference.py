@@ -122,6 +122,34 @@ def test_flat_batch_reference_scorer_matches_oracle_on_bench_workload():
 
 
 @pytest.mark.parametrize("seed", range(3))
+def test_compact_wire_formats_are_lossless(seed):
+    """sx_aln8 / sx_aln_seg2 / 2-bit qualities carry the same batch: the oracle and the reference's own scorer return the same doubles
+    on the compact batch as on the wide one (full and partial region ranges)."""
+    import ctypes as C
+
+    rng = np.random.default_rng(900 + seed)
+    regions = [specgen.random_region(rng, n_reads=int(rng.integers(1, 10))) for _ in range(25)]
+    for r in regions:  # <= 4 distinct qualities so that the 2-bit format applies
+        r.reads = [(codes, np.array([11, 25, 37, 2], np.uint8)[np.asarray(q) % 4]) for codes, q in r.reads]
+    regions += [specgen.simple_region(rng, n_reads=int(rng.integers(3, 30))) for _ in range(10)]
+    wide = B.build_align_batch(regions)
+    want = reflib.ox_score(wide)
+    for qb, compact in ((8, True), (4, True), (2, False), (2, True)):
+        cb = B.build_align_batch(regions, qual_bits=qb, compact=compact)
+        assert cb.fmt == (3 if compact else 0)
+        assert cb.cells() == wide.cells()
+        assert np.array_equal(reflib.ox_score(cb).view(np.uint64), want.view(np.uint64)), (qb, compact)
+        got = np.zeros(cb.n_alns, np.float64)
+        secs = C.c_double(0)
+        err = C.create_string_buffer(512)
+        lo, hi = 26, cb.n_regions - 1  # a partial range of the cfg2-shaped regions (the flat-batch shim rebuilds only those shapes)
+        rc = reflib.ref().ref_score_flat_batch(C.byref(cb.c), C.c_uint32(lo), C.c_uint32(hi), C.c_void_p(got.ctypes.data), C.byref(secs), err, 512)
+        assert rc == 0, err.value
+        a0, a1 = int(cb.regions["aln_begin"][lo]), int(cb.regions["aln_begin"][hi])
+        assert np.array_equal(got[a0:a1].view(np.uint64), want[a0:a1].view(np.uint64)), (qb, compact)
+
+
+@pytest.mark.parametrize("seed", range(3))
 def test_indel_genotype_likelihoods(seed):
     rng = np.random.default_rng(400 + seed)
     ib = B.IndelBatch(specgen.random_indel_loci(rng, 150))
