@@ -64,7 +64,7 @@ class DevAlignBatch:
             hb.n_regions, hb.n_reads, hb.n_alns, hb.n_segs,
             self.bufs["regions"].ptr, self.bufs["read_len"].ptr, self.bufs["seq4"].ptr, self.bufs["qual"].ptr, self.bufs["ref"].ptr,
             self.bufs["alns"].ptr, self.bufs["segs"].ptr, self.bufs["ins"].ptr,
-            hb.used["seq4"], hb.used["qual"], hb.used["ref"], hb.used["ins"], hb.qual_bits, hb.qual_dict, 0,
+            hb.used["seq4"], hb.used["qual"], hb.used["ref"], hb.used["ins"], hb.qual_bits, hb.qual_dict, hb.fmt,
         )
         self.out = DeviceArray(ctx, hb.n_alns * 8)
 

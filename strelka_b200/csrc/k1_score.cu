@@ -73,12 +73,12 @@ struct k1_layout
     uint32_t n_reads, n_alns, seg_bytes, ref_bytes, ins_bytes, seq_bytes, qual_bytes;
 };
 
-__host__ __device__ __forceinline__ k1_layout k1_make_layout(const sx_region& r0, const sx_region& r1)
+__host__ __device__ __forceinline__ k1_layout k1_make_layout(const sx_region& r0, const sx_region& r1, uint32_t fmt)
 {
     k1_layout L;
     L.n_reads = r1.read_begin - r0.read_begin;
     L.n_alns = r1.aln_begin - r0.aln_begin;
-    L.seg_bytes = pad16((r1.seg_begin - r0.seg_begin) * 4u);
+    L.seg_bytes = pad16((r1.seg_begin - r0.seg_begin) * ((fmt & SX_FMT_SEG2) ? 2u : 4u));
     L.ref_bytes = pad16(r0.ref_len);
     L.ins_bytes = pad16(r1.ins_begin - r0.ins_begin);
     L.seq_bytes = pad16(static_cast<uint32_t>(r1.seq_off - r0.seq_off));
@@ -87,7 +87,7 @@ __host__ __device__ __forceinline__ k1_layout k1_make_layout(const sx_region& r0
     L.tab = o;
     o += K1_TAB_BYTES;
     L.alns = o;
-    o += (L.n_alns + 1) * 16u;
+    o += k1q::aln_slice_bytes(r0.aln_begin, L.n_alns, fmt);
     L.segs = o;
     o += L.seg_bytes;
     L.ref = o;
@@ -128,13 +128,13 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
                                                               const char* __restrict__ ref, const sx_aln* __restrict__ alns,
                                                               const sx_aln_seg* __restrict__ segs, const char* __restrict__ ins,
                                                               const sx_tables* __restrict__ tables, uint32_t region_begin, double* __restrict__ lnp_out,
-                                                              int* __restrict__ status, uint32_t smem_bytes, uint32_t qual_bits, uint4 qual_dict)
+                                                              int* __restrict__ status, uint32_t smem_bytes, uint32_t qual_bits, uint4 qual_dict, uint32_t fmt)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t ri = region_begin + blockIdx.x;
     const sx_region r0 = regions[ri];
     const sx_region r1 = regions[ri + 1];
-    const k1_layout L = k1_make_layout(r0, r1);
+    const k1_layout L = k1_make_layout(r0, r1, fmt);
     if (L.n_alns == 0) return;
     if (L.total > smem_bytes)
     {
@@ -143,8 +143,33 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
     }
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     const double* tab = reinterpret_cast<const double*>(smem + L.tab);
-    const uint4* alns_s = reinterpret_cast<const uint4*>(smem + L.alns);
-    const uint32_t* segs_s = reinterpret_cast<const uint32_t*>(smem + L.segs);
+    // alignment headers and segments, read through accessors that hide the wire format (sx_aln / sx_aln8, sx_aln_seg / sx_aln_seg2)
+    const bool aln8 = fmt & SX_FMT_ALN8, seg2 = fmt & SX_FMT_SEG2;
+    const uint32_t aln_skew = aln8 ? (r0.aln_begin & 1u) : 0u; // the sx_aln8 slice is staged from a 16-byte boundary
+    const uint32_t n_segs_region = r1.seg_begin - r0.seg_begin;
+    const unsigned char* alns_raw = smem + L.alns;
+    const unsigned char* segs_raw = smem + L.segs;
+    auto aln_at = [&](uint32_t a) -> uint4 { // region-relative: x read, y first reference position, z first segment, w first inserted base
+        if (aln8)
+        {
+            const uint2 v = reinterpret_cast<const uint2*>(alns_raw)[a + aln_skew];
+            return make_uint4(v.x & 0xffffu, static_cast<uint32_t>(static_cast<int32_t>(v.x) >> 16), v.y & 0xffffu, v.y >> 16);
+        }
+        const uint4 h = reinterpret_cast<const uint4*>(alns_raw)[a];
+        return make_uint4(h.x - r0.read_begin, h.y - static_cast<uint32_t>(r0.ref_begin), h.z - r0.seg_begin, h.w - r0.ins_begin);
+    };
+    auto seg_end_of = [&](uint32_t a) -> uint32_t {
+        if (aln8) return a + 1 < L.n_alns ? aln_at(a + 1).z : n_segs_region;
+        return reinterpret_cast<const uint4*>(alns_raw)[a + 1].z - r0.seg_begin;
+    };
+    auto seg_at = [&](uint32_t s) -> uint32_t { // len | kind << 16 | flags << 24
+        if (seg2)
+        {
+            const uint32_t v = reinterpret_cast<const uint16_t*>(segs_raw)[s];
+            return (v & 0xfffu) | (((v >> 12) & 7u) << 16) | ((v >> 15) << 24);
+        }
+        return reinterpret_cast<const uint32_t*>(segs_raw)[s];
+    };
     uint8_t* ref_s = smem + L.ref;
     uint8_t* ins_s = smem + L.ins;
     const uint8_t* seq_s = smem + L.seq;
@@ -184,11 +209,12 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
     {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t tx = K1_TAB_BYTES + (L.n_alns + 1) * 16u + L.seg_bytes + L.ref_bytes + L.ins_bytes + L.seq_bytes + L.qual_bytes;
+        const uint32_t aln_bytes = k1q::aln_slice_bytes(r0.aln_begin, L.n_alns, fmt);
+        const uint32_t tx = K1_TAB_BYTES + aln_bytes + L.seg_bytes + L.ref_bytes + L.ins_bytes + L.seq_bytes + L.qual_bytes;
         mbar_expect_tx(bar, tx);
         tma_bulk_g2s(smem + L.tab, tables->k1_tab, K1_TAB_BYTES, bar);
-        tma_bulk_g2s(smem + L.alns, alns + r0.aln_begin, (L.n_alns + 1) * 16u, bar);
-        if (L.seg_bytes) tma_bulk_g2s(smem + L.segs, segs + r0.seg_begin, L.seg_bytes, bar);
+        tma_bulk_g2s(smem + L.alns, reinterpret_cast<const unsigned char*>(alns) + (aln8 ? (size_t)(r0.aln_begin & ~1u) * 8u : (size_t)r0.aln_begin * 16u), aln_bytes, bar);
+        if (L.seg_bytes) tma_bulk_g2s(smem + L.segs, reinterpret_cast<const unsigned char*>(segs) + (size_t)r0.seg_begin * (seg2 ? 2u : 4u), L.seg_bytes, bar);
         if (L.ref_bytes) tma_bulk_g2s(smem + L.ref, ref + r0.ref_off, L.ref_bytes, bar);
         if (L.ins_bytes) tma_bulk_g2s(smem + L.ins, ins + r0.ins_begin, L.ins_bytes, bar);
         if (L.seq_bytes) tma_bulk_g2s(smem + L.seq, seq4 + r0.seq_off, L.seq_bytes, bar);
@@ -233,7 +259,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
     }
     mbar_wait(bar, 0);
     __syncthreads();
-    if ((qual_bits == 4 ? soff_s[L.n_reads] : boff_s[L.n_reads]) > L.qual_bytes || soff_s[L.n_reads] > L.seq_bytes)
+    if ((qual_bits == 2 ? (soff_s[L.n_reads] + 1) / 2 : qual_bits == 4 ? soff_s[L.n_reads] : boff_s[L.n_reads]) > L.qual_bytes || soff_s[L.n_reads] > L.seq_bytes)
     {
         if (threadIdx.x == 0) atomicOr(status, 2);
         return;
@@ -262,6 +288,13 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
                     q0 = qd_s[qb >> 4];
                     q1 = (2 * p + 1 < len) ? qd_s[qb & 15u] : 0u;
                 }
+                else if (qual_bits == 2)
+                {
+                    // one 2-bit code per nibble position of the region's seq4 slice: packed byte b = soff + p holds positions 2b, 2b+1
+                    const uint32_t b = soff_s[r] + p, qb = qual_s[b >> 1] >> ((~b & 1u) << 2);
+                    q0 = qd_s[(qb >> 2) & 3u];
+                    q1 = (2 * p + 1 < len) ? qd_s[qb & 3u] : 0u;
+                }
                 else
                 {
                     q0 = ql[2 * p];
@@ -287,8 +320,8 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
 
     for (uint32_t a = threadIdx.x; a < L.n_alns; a += K1_THREADS)
     {
-        const uint4 h = alns_s[a];
-        const uint32_t rl = h.x - r0.read_begin;
+        const uint4 h = aln_at(a);
+        const uint32_t rl = h.x;
         if (rl >= L.n_reads)
         {
             atomicOr(status, 2);
@@ -296,10 +329,10 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
         }
         const uint16_t* ent = ent_s + 2u * soff_s[rl];
         int read_left = static_cast<int>(boff_s[rl + 1] - boff_s[rl]);
-        int refp = static_cast<int>(h.y) - r0.ref_begin;
-        const uint8_t* insp = ins_s + (h.w - r0.ins_begin);
-        uint32_t s = h.z - r0.seg_begin;
-        const uint32_t s_end = alns_s[a + 1].z - r0.seg_begin;
+        int refp = static_cast<int>(h.y);
+        const uint8_t* insp = ins_s + h.w;
+        uint32_t s = h.z;
+        const uint32_t s_end = seg_end_of(a);
         double lnp = 0.0;
         int rem = 0;
         bool pend = false;
@@ -319,7 +352,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
                     done = true;
                     break;
                 }
-                const uint32_t seg = segs_s[s++];
+                const uint32_t seg = seg_at(s++);
                 const int len = static_cast<int>(seg & 0xffffu);
                 const uint32_t kind = (seg >> 16) & 0xffu;
                 pend = (seg >> 24) & SX_SEGF_NONCANDIDATE;
@@ -399,14 +432,14 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
 
 // max shared-memory footprint over regions [begin, end) (device-resident batches: the region table is not on the host)
 // out[0]: general kernel, out[1]: fast path (k1_score4.cu)
-__global__ void k1_smem_need_kernel(const sx_region* __restrict__ regions, uint32_t begin, uint32_t end, uint32_t* __restrict__ out)
+__global__ void k1_smem_need_kernel(const sx_region* __restrict__ regions, uint32_t begin, uint32_t end, uint32_t* __restrict__ out, uint32_t fmt)
 {
     uint32_t m = 0, mq = 0;
     for (uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x)
     {
         const sx_region a = regions[i], b = regions[i + 1];
-        m = max(m, k1_make_layout(a, b).total);
-        mq = max(mq, k1q::make_layout(a, b).total);
+        m = max(m, k1_make_layout(a, b, fmt).total);
+        mq = max(mq, k1q::make_layout(a, b, fmt).total);
     }
     for (int d = 16; d; d >>= 1)
     {
@@ -421,6 +454,42 @@ __global__ void k1_smem_need_kernel(const sx_region* __restrict__ regions, uint3
 }
 
 // per-read max over its alignments (first max in batch order), one thread per read; alignments are sorted by read
+// the same for sx_aln8 headers (read indices relative to the region): find the read's region, then its alignments inside the region
+__global__ void k1_read_max8_kernel(const sx_region* __restrict__ regions, uint32_t n_regions, const sx_aln8* __restrict__ alns, uint32_t n_reads,
+                                    const double* __restrict__ lnp, double* __restrict__ max_lnp, uint32_t* __restrict__ max_aln)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    uint32_t lo = 0, hi = n_regions; // last region with read_begin <= r (regions without reads share a read_begin: take the last)
+    while (lo + 1 < hi)
+    {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (regions[mid].read_begin <= r) lo = mid;
+        else hi = mid;
+    }
+    const uint32_t a0 = regions[lo].aln_begin, a1 = regions[lo + 1].aln_begin, rel = r - regions[lo].read_begin;
+    uint32_t l2 = a0, h2 = a1;
+    while (l2 < h2)
+    {
+        const uint32_t mid = (l2 + h2) >> 1;
+        if (alns[mid].read < rel) l2 = mid + 1;
+        else h2 = mid;
+    }
+    double best = 0;
+    uint32_t besta = 0xffffffffu;
+    for (uint32_t a = l2; a < a1 && alns[a].read == rel; ++a)
+    {
+        const double v = lnp[a];
+        if (besta == 0xffffffffu || v > best)
+        {
+            best = v;
+            besta = a;
+        }
+    }
+    max_lnp[r] = best;
+    max_aln[r] = besta;
+}
+
 __global__ void k1_read_max_kernel(const sx_aln* __restrict__ alns, uint32_t n_alns, uint32_t n_reads, const double* __restrict__ lnp,
                                    double* __restrict__ max_lnp, uint32_t* __restrict__ max_aln)
 {
@@ -449,7 +518,7 @@ __global__ void k1_read_max_kernel(const sx_aln* __restrict__ alns, uint32_t n_a
     max_aln[r] = besta;
 }
 
-int k1_smem_need_dev(sx_ctx* ctx, const sx_region* regions_dev, uint32_t begin, uint32_t end, uint32_t need[2])
+int k1_smem_need_dev(sx_ctx* ctx, const sx_region* regions_dev, uint32_t begin, uint32_t end, uint32_t need[2], uint32_t fmt)
 {
     uint32_t* d = nullptr;
     int rc = sx_ensure(ctx, 20, 2 * sizeof(uint32_t), reinterpret_cast<void**>(&d));
@@ -457,7 +526,7 @@ int k1_smem_need_dev(sx_ctx* ctx, const sx_region* regions_dev, uint32_t begin, 
     SX_CUDA(ctx, cudaMemsetAsync(d, 0, 2 * sizeof(uint32_t), ctx->s_compute));
     const uint32_t n = end - begin;
     const int blocks = static_cast<int>(std::min<uint32_t>((n + 255) / 256, 1184));
-    k1_smem_need_kernel<<<blocks, 256, 0, ctx->s_compute>>>(regions_dev, begin, end, d);
+    k1_smem_need_kernel<<<blocks, 256, 0, ctx->s_compute>>>(regions_dev, begin, end, d, fmt);
     SX_CUDA(ctx, cudaMemcpyAsync(need, d, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_compute));
     SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
     return SX_OK;
@@ -466,14 +535,14 @@ int k1_smem_need_dev(sx_ctx* ctx, const sx_region* regions_dev, uint32_t begin, 
 
 size_t sx_k1_region_smem(const sx_region* r0, const sx_region* r1, const sx_aln*)
 {
-    return k1_make_layout(*r0, *r1).total;
+    return k1_make_layout(*r0, *r1, 0).total;
 }
 
 // smem_bytes: largest region footprint of the general kernel; smem_fast: of the 4-bit fast path (0: not computed)
 int sx_k1_launch(sx_ctx* ctx, const sx_align_batch* d, uint32_t region_begin, uint32_t region_end, double* lnp_dev, size_t smem_bytes, size_t smem_fast, cudaStream_t st)
 {
     if (region_end <= region_begin) return SX_OK;
-    if (d->qual_bits == 4 && smem_fast && smem_fast <= k1q::KQ_MAX_SMEM) return sx_k1q_launch(ctx, d, region_begin, region_end, lnp_dev, smem_fast, st);
+    if ((d->qual_bits == 4 || d->qual_bits == 2) && smem_fast && smem_fast <= k1q::KQ_MAX_SMEM) return sx_k1q_launch(ctx, d, region_begin, region_end, lnp_dev, smem_fast, st);
     if (smem_bytes > ctx->smem_optin)
         return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments: a region needs %zu bytes of shared memory (limit %zu); split it into smaller regions", smem_bytes,
                        ctx->smem_optin);
@@ -486,7 +555,7 @@ int sx_k1_launch(sx_ctx* ctx, const sx_align_batch* d, uint32_t region_begin, ui
     uint4 qd;
     memcpy(&qd, d->qual_dict, 16);
     k1_score_kernel<<<region_end - region_begin, K1_THREADS, smem_bytes, st>>>(d->regions, d->read_len, d->seq4, d->qual, d->ref, d->alns, d->segs, d->ins,
-                                                                              ctx->d_tables, region_begin, lnp_dev, ctx->d_status, static_cast<uint32_t>(smem_bytes), d->qual_bits == 4 ? 4u : 8u, qd);
+                                                                              ctx->d_tables, region_begin, lnp_dev, ctx->d_status, static_cast<uint32_t>(smem_bytes), d->qual_bits == 4 ? 4u : d->qual_bits == 2 ? 2u : 8u, qd, d->format);
     SX_CUDA(ctx, cudaGetLastError());
     return SX_OK;
 }
@@ -498,7 +567,21 @@ extern "C" uint64_t sx_align_batch_cells(const sx_align_batch* b)
 {
     uint64_t n = 0;
     for (uint32_t i = 0; i < b->n_segs; ++i)
-        if (b->segs[i].kind == SX_SEG_MATCH || b->segs[i].kind == SX_SEG_INSERT) n += b->segs[i].len;
+    {
+        uint32_t kind, len;
+        if (b->format & SX_FMT_SEG2)
+        {
+            const uint32_t v = reinterpret_cast<const sx_aln_seg2*>(b->segs)[i];
+            kind = (v >> 12) & 7u;
+            len = v & 0xfffu;
+        }
+        else
+        {
+            kind = b->segs[i].kind;
+            len = b->segs[i].len;
+        }
+        if (kind == SX_SEG_MATCH || kind == SX_SEG_INSERT) n += len;
+    }
     return n;
 }
 
@@ -510,14 +593,14 @@ static int validate_host_batch(sx_ctx* ctx, const sx_align_batch* b, size_t* max
     {
         const sx_region& r = b->regions[i];
         const sx_region& n = b->regions[i + 1];
-        if ((r.seq_off | r.qual_off | r.ref_off | r.ins_begin) & 15u || (r.seg_begin & 3u))
+        if ((r.seq_off | r.qual_off | r.ref_off | r.ins_begin) & 15u || (r.seg_begin & ((b->format & SX_FMT_SEG2) ? 7u : 3u)))
             return sx_fail(ctx, SX_ERR_ALIGNMENT, "sx_score_alignments: region %u violates the 16-byte staging rule (seq_off %llu qual_off %llu ref_off %llu ins_begin %u seg_begin %u)", i,
                            (unsigned long long)r.seq_off, (unsigned long long)r.qual_off, (unsigned long long)r.ref_off, r.ins_begin, r.seg_begin);
         if (n.read_begin < r.read_begin || n.aln_begin < r.aln_begin || n.seg_begin < r.seg_begin || n.ins_begin < r.ins_begin || n.seq_off < r.seq_off ||
             n.qual_off < r.qual_off)
             return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments: region table is not monotone at region %u", i);
-        m = std::max(m, sx_k1_region_smem(&r, &n, b->alns));
-        mq = std::max<size_t>(mq, k1q::make_layout(r, n).total);
+        m = std::max<size_t>(m, k1_make_layout(r, n, b->format).total);
+        mq = std::max<size_t>(mq, k1q::make_layout(r, n, b->format).total);
     }
     if (b->n_regions)
     {
@@ -538,7 +621,7 @@ extern "C" int sx_score_alignments_dev(sx_ctx* ctx, const sx_align_batch* d, dou
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
     sx_kernel_timer t(ctx);
     uint32_t need[2] = {0, 0};
-    int rc = k1_smem_need_dev(ctx, d->regions, 0, d->n_regions, need);
+    int rc = k1_smem_need_dev(ctx, d->regions, 0, d->n_regions, need, d->format);
     if (rc) return rc;
     rc = sx_k1_launch(ctx, d, 0, d->n_regions, lnp_out_dev, need[0], need[1], ctx->s_compute);
     if (rc) return rc;
@@ -556,7 +639,11 @@ extern "C" int sx_read_max_dev(sx_ctx* ctx, const sx_align_batch* d, const doubl
     if (d->n_reads == 0) return SX_OK;
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
     sx_kernel_timer t(ctx);
-    k1_read_max_kernel<<<(d->n_reads + 255) / 256, 256, 0, ctx->s_compute>>>(d->alns, d->n_alns, d->n_reads, lnp_dev, max_lnp_dev, max_aln_dev);
+    if (d->format & SX_FMT_ALN8)
+        k1_read_max8_kernel<<<(d->n_reads + 255) / 256, 256, 0, ctx->s_compute>>>(d->regions, d->n_regions, reinterpret_cast<const sx_aln8*>(d->alns), d->n_reads, lnp_dev,
+                                                                                  max_lnp_dev, max_aln_dev);
+    else
+        k1_read_max_kernel<<<(d->n_reads + 255) / 256, 256, 0, ctx->s_compute>>>(d->alns, d->n_alns, d->n_reads, lnp_dev, max_lnp_dev, max_aln_dev);
     SX_CUDA(ctx, cudaGetLastError());
     t.stop(1);
     return t.finish();
@@ -579,8 +666,9 @@ extern "C" int sx_score_alignments(sx_ctx* ctx, const sx_align_batch* b, double*
     sx_align_batch d = *b;
     void* p = nullptr;
     const size_t reg_bytes = (size_t)(b->n_regions + 1) * sizeof(sx_region);
-    const size_t aln_bytes = (size_t)(b->n_alns + 1) * sizeof(sx_aln);
-    const size_t seg_bytes = (size_t)b->n_segs * sizeof(sx_aln_seg) + SX_POOL_SLACK;
+    const size_t aln_sz = (b->format & SX_FMT_ALN8) ? sizeof(sx_aln8) : sizeof(sx_aln), seg_sz = (b->format & SX_FMT_SEG2) ? sizeof(sx_aln_seg2) : sizeof(sx_aln_seg);
+    const size_t aln_bytes = (size_t)(b->n_alns + 1) * aln_sz + 16; // + slack: an sx_aln8 slice is staged from a 16-byte boundary
+    const size_t seg_bytes = (size_t)b->n_segs * seg_sz + SX_POOL_SLACK;
 #define SX_POOL(slot, field, type, bytes)            \
     if ((rc = sx_ensure(ctx, slot, (bytes), &p))) return rc; \
     d.field = static_cast<type>(p);
@@ -630,8 +718,8 @@ extern "C" int sx_score_alignments(sx_ctx* ctx, const sx_align_batch* b, double*
         };
         SX_CUDA(ctx, cp(b->seq4, d.seq4, A.seq_off, B.seq_off));
         SX_CUDA(ctx, cp(b->qual, d.qual, A.qual_off, B.qual_off));
-        SX_CUDA(ctx, cp(b->alns, d.alns, (size_t)A.aln_begin * sizeof(sx_aln), (size_t)(B.aln_begin + 1) * sizeof(sx_aln)));
-        SX_CUDA(ctx, cp(b->segs, d.segs, (size_t)A.seg_begin * sizeof(sx_aln_seg), (size_t)B.seg_begin * sizeof(sx_aln_seg)));
+        SX_CUDA(ctx, cp(b->alns, d.alns, (size_t)A.aln_begin * aln_sz, (size_t)(B.aln_begin + 1) * aln_sz));
+        SX_CUDA(ctx, cp(b->segs, d.segs, (size_t)A.seg_begin * seg_sz, (size_t)B.seg_begin * seg_sz));
         SX_CUDA(ctx, cp(b->ins, d.ins, A.ins_begin, B.ins_begin));
         SX_CUDA(ctx, cudaEventRecord(ctx->ev_pool[2 * c], ctx->s_h2d));
         SX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_compute, ctx->ev_pool[2 * c], 0));

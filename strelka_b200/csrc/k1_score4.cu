@@ -114,13 +114,13 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
                                                                const char* __restrict__ ref, const sx_aln* __restrict__ alns,
                                                                const sx_aln_seg* __restrict__ segs, const char* __restrict__ ins,
                                                                const sx_tables* __restrict__ tables, uint32_t region_begin, double* __restrict__ lnp_out,
-                                                               int* __restrict__ status, uint32_t smem_bytes, uint4 qual_dict)
+                                                               int* __restrict__ status, uint32_t smem_bytes, uint4 qual_dict, uint32_t fmt, uint32_t qual_bits)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t ri = region_begin + blockIdx.x;
     const sx_region r0 = regions[ri];
     const sx_region r1 = regions[ri + 1];
-    const layout L = make_layout(r0, r1);
+    const layout L = make_layout(r0, r1, fmt);
     if (L.n_alns == 0) return;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t tab_saddr = (sbase + L.tab + 1023u) & ~1023u; // 1 KB-aligned in the shared window: a cell's address is two PRMT'd bytes
@@ -134,8 +134,35 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
     uint2* lut = reinterpret_cast<uint2*>(smem + L.lut);
     uint8_t* e8 = smem + L.e8;
     double* tab = reinterpret_cast<double*>(smem + (tab_saddr - sbase)); // [4 pages][16 quality codes][match, mismatch]
-    const uint4* alns_s = reinterpret_cast<const uint4*>(smem + L.alns);
-    const uint32_t* segs_s = reinterpret_cast<const uint32_t*>(smem + L.segs);
+    // alignment headers and segments, read through accessors that hide the wire format (sx_aln / sx_aln8, sx_aln_seg / sx_aln_seg2)
+    const bool aln8 = fmt & SX_FMT_ALN8, seg2 = fmt & SX_FMT_SEG2;
+    const uint32_t aln_skew = aln8 ? (r0.aln_begin & 1u) : 0u; // the sx_aln8 slice is staged from a 16-byte boundary
+    const unsigned char* alns_raw = smem + L.alns;
+    const unsigned char* segs_raw = smem + L.segs;
+    // region-relative header of alignment a: x read, y first reference position, z first segment, w first inserted base
+    auto aln_at = [&](uint32_t a) -> uint4 {
+        if (aln8)
+        {
+            const uint2 v = reinterpret_cast<const uint2*>(alns_raw)[a + aln_skew];
+            return make_uint4(v.x & 0xffffu, static_cast<uint32_t>(static_cast<int32_t>(v.x) >> 16), v.y & 0xffffu, v.y >> 16);
+        }
+        const uint4 h = reinterpret_cast<const uint4*>(alns_raw)[a];
+        return make_uint4(h.x - r0.read_begin, h.y - static_cast<uint32_t>(r0.ref_begin), h.z - r0.seg_begin, h.w - r0.ins_begin);
+    };
+    // end of alignment a's segment list
+    auto seg_end_of = [&](uint32_t a) -> uint32_t {
+        if (aln8) return a + 1 < L.n_alns ? aln_at(a + 1).z : L.n_segs;
+        return reinterpret_cast<const uint4*>(alns_raw)[a + 1].z - r0.seg_begin;
+    };
+    // segment s as len | kind << 16 | flags << 24
+    auto seg_at = [&](uint32_t s) -> uint32_t {
+        if (seg2)
+        {
+            const uint32_t v = reinterpret_cast<const uint16_t*>(segs_raw)[s];
+            return (v & 0xfffu) | (((v >> 12) & 7u) << 16) | ((v >> 15) << 24);
+        }
+        return reinterpret_cast<const uint32_t*>(segs_raw)[s];
+    };
     uint8_t* ref_s = smem + L.ref;
     uint8_t* ins_s = smem + L.ins;
     uint16_t* rlen_s = reinterpret_cast<uint16_t*>(smem + L.rlen);
@@ -173,10 +200,13 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
     {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t tx = (L.n_alns + 1) * 16u + L.seg_bytes + L.ref_bytes + L.ins_bytes + L.seq_bytes + L.qual_bytes;
+        const uint32_t aln_bytes = aln_slice_bytes(r0.aln_begin, L.n_alns, fmt);
+        const uint32_t tx = aln_bytes + L.seg_bytes + L.ref_bytes + L.ins_bytes + L.seq_bytes + L.qual_bytes;
         mbar_expect_tx(bar, tx);
-        tma_bulk_g2s(smem + L.alns, alns + r0.aln_begin, (L.n_alns + 1) * 16u, bar);
-        if (L.seg_bytes) tma_bulk_g2s(smem + L.segs, segs + r0.seg_begin, L.seg_bytes, bar);
+        const unsigned char* aln_src = reinterpret_cast<const unsigned char*>(alns) + (aln8 ? (size_t)(r0.aln_begin & ~1u) * 8u : (size_t)r0.aln_begin * 16u);
+        const unsigned char* seg_src = reinterpret_cast<const unsigned char*>(segs) + (size_t)r0.seg_begin * (seg2 ? 2u : 4u);
+        tma_bulk_g2s(smem + L.alns, aln_src, aln_bytes, bar);
+        if (L.seg_bytes) tma_bulk_g2s(smem + L.segs, seg_src, L.seg_bytes, bar);
         if (L.ref_bytes) tma_bulk_g2s(smem + L.ref, ref + r0.ref_off, L.ref_bytes, bar);
         if (L.ins_bytes) tma_bulk_g2s(smem + L.ins, ins + r0.ins_begin, L.ins_bytes, bar);
         if (L.seq_bytes) tma_bulk_g2s(smem + L.seq, seq4 + r0.seq_off, L.seq_bytes, bar);
@@ -206,7 +236,7 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
     }
     mbar_wait(bar, 0);
     __syncthreads();
-    if (soff_s[L.n_reads] > L.seq_bytes || soff_s[L.n_reads] > L.qual_bytes)
+    if (soff_s[L.n_reads] > L.seq_bytes || (qual_bits == 2 ? (soff_s[L.n_reads] + 1) / 2 : soff_s[L.n_reads]) > L.qual_bytes)
     {
         if (tid == 0) atomicOr(status, 2);
         return;
@@ -221,7 +251,18 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
         uint32_t acc = 0;
         for (uint32_t w = tid; w < nw; w += KQ_THREADS)
         {
-            const uint32_t s = seq32[w], q = qual32[w];
+            const uint32_t s = seq32[w];
+            uint32_t q;
+            if (qual_bits == 2)
+            {
+                // 16 bits = the 2-bit codes of this word's 8 nibbles, first nibble in the two high bits of the first byte; spread them
+                // to the nibble layout of the 4-bit format (byte k: code of base 2k in the high nibble, of base 2k+1 in the low one)
+                const uint32_t h = reinterpret_cast<const uint16_t*>(qual32)[w];
+                const uint32_t b0 = h & 0xffu, b1 = h >> 8;
+                q = (((b0 >> 2) & 0x30u) | ((b0 >> 4) & 0x03u)) | ((((b0 << 2) & 0x30u) | (b0 & 0x03u)) << 8) |
+                    ((((b1 >> 2) & 0x30u) | ((b1 >> 4) & 0x03u)) << 16) | ((((b1 << 2) & 0x30u) | (b1 & 0x03u)) << 24);
+            }
+            else q = qual32[w];
             const uint32_t hi = (s & 0xf0f0f0f0u) | ((q >> 4) & 0x0f0f0f0fu); // table indices of the four first bases of the packed bytes
             const uint32_t lo = ((s << 4) & 0xf0f0f0f0u) | (q & 0x0f0f0f0fu); // ... and of the four second bases
             const uint32_t a0 = lds_u8(e8_s + (hi & 0xffu)), a1 = lds_u8(e8_s + (lo & 0xffu));
@@ -255,9 +296,9 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
 
     for (uint32_t a = tid; a < L.n_alns; a += KQ_THREADS)
     {
-        const uint4 h = alns_s[a];
-        const uint32_t rl = h.x - r0.read_begin;
-        const uint32_t seg0 = h.z - r0.seg_begin, seg1 = alns_s[a + 1].z - r0.seg_begin;
+        const uint4 h = aln_at(a);
+        const uint32_t rl = h.x;
+        const uint32_t seg0 = h.z, seg1 = seg_end_of(a);
         if (rl >= L.n_reads || seg1 > L.n_segs || seg0 > seg1)
         {
             atomicOr(status, 2);
@@ -270,12 +311,12 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
         {
             uint32_t ent = ent_s0 + 2u * soff_s[rl];
             int read_left = rlen_s[rl];
-            int refp = static_cast<int>(h.y) - r0.ref_begin;
-            uint32_t insp = ins_s0 + (h.w - r0.ins_begin);
+            int refp = static_cast<int>(h.y);
+            uint32_t insp = ins_s0 + h.w;
             uint32_t rp = rec0, pre = 0;
             for (uint32_t s = seg0; s < seg1; ++s)
             {
-                const uint32_t seg = segs_s[s];
+                const uint32_t seg = seg_at(s);
                 const int len = static_cast<int>(seg & 0xffffu);
                 const uint32_t kind = (seg >> 16) & 0xffu;
                 if (kind == SX_SEG_MATCH || kind == SX_SEG_INSERT || kind == SX_SEG_SOFTCLIP)
@@ -349,10 +390,10 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
                 else if (type == REC_OOW)
                 {
                     // part of the segment lies outside the held reference window: those positions read as 'N'.  Rare: plain loop.
-                    int p0 = static_cast<int>(h.y) - r0.ref_begin;
+                    int p0 = static_cast<int>(h.y);
                     for (uint32_t ss = seg0; ss < (rec.x >> 16); ++ss)
                     {
-                        const uint32_t sg = segs_s[ss], k = (sg >> 16) & 0xffu;
+                        const uint32_t sg = seg_at(ss), k = (sg >> 16) & 0xffu;
                         if (k == SX_SEG_MATCH || k == SX_SEG_REFSKIP) p0 += static_cast<int>(sg & 0xffffu);
                     }
                     const uint32_t ea = rec.x & 0xffffu, len = rec.y & 0xffffu;
@@ -416,7 +457,7 @@ int sx_k1q_launch(sx_ctx* ctx, const sx_align_batch* d, uint32_t region_begin, u
     uint4 qd;
     memcpy(&qd, d->qual_dict, 16);
     k1q_score_kernel<<<region_end - region_begin, k1q::KQ_THREADS, smem_bytes, st>>>(d->regions, d->read_len, d->seq4, d->qual, d->ref, d->alns, d->segs, d->ins,
-                                                                                    ctx->d_tables, region_begin, lnp_dev, ctx->d_status, static_cast<uint32_t>(smem_bytes), qd);
+                                                                                    ctx->d_tables, region_begin, lnp_dev, ctx->d_status, static_cast<uint32_t>(smem_bytes), qd, d->format, d->qual_bits);
     SX_CUDA(ctx, cudaGetLastError());
     return SX_OK;
 }

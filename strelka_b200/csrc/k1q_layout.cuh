@@ -20,13 +20,20 @@ struct layout
     uint32_t n_reads, n_alns, n_segs, seg_bytes, ref_bytes, ins_bytes, seq_bytes, qual_bytes;
 };
 
-__host__ __device__ __forceinline__ layout make_layout(const sx_region& r0, const sx_region& r1)
+// bytes of the alignment-header slice as the kernels stage it: wide headers are 16 bytes each (+ the next one, which closes the last
+// segment list); sx_aln8 headers are copied from the 16-byte boundary at or below the region's first header
+__host__ __device__ __forceinline__ uint32_t aln_slice_bytes(uint32_t aln_begin, uint32_t n_alns, uint32_t fmt)
+{
+    return (fmt & SX_FMT_ALN8) ? pad16((n_alns + (aln_begin & 1u)) * 8u) : (n_alns + 1) * 16u;
+}
+
+__host__ __device__ __forceinline__ layout make_layout(const sx_region& r0, const sx_region& r1, uint32_t fmt)
 {
     layout L;
     L.n_reads = r1.read_begin - r0.read_begin;
     L.n_alns = r1.aln_begin - r0.aln_begin;
     L.n_segs = r1.seg_begin - r0.seg_begin;
-    L.seg_bytes = pad16(L.n_segs * 4u);
+    L.seg_bytes = pad16(L.n_segs * ((fmt & SX_FMT_SEG2) ? 2u : 4u));
     L.ref_bytes = pad16(r0.ref_len);
     L.ins_bytes = pad16(r1.ins_begin - r0.ins_begin);
     L.seq_bytes = pad16(static_cast<uint32_t>(r1.seq_off - r0.seq_off));
@@ -39,7 +46,7 @@ __host__ __device__ __forceinline__ layout make_layout(const sx_region& r0, cons
     L.tab = o;
     o += KQ_TAB_RESERVE;
     L.alns = o;
-    o += (L.n_alns + 1) * 16u;
+    o += aln_slice_bytes(r0.aln_begin, L.n_alns, fmt);
     L.segs = o;
     o += L.seg_bytes;
     L.recs = o; // one 8-byte record per segment + one END per alignment

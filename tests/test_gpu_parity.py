@@ -61,6 +61,58 @@ def test_k1_device_resident_and_read_max(ctx):
         assert maln[r] == idx[np.argmax(want[idx])]
 
 
+@pytest.mark.parametrize("qb,compact", [(8, True), (4, True), (2, False), (2, True)])
+def test_k1_compact_wire_formats(ctx, qb, compact):
+    """sx_aln8 / sx_aln_seg2 / 2-bit qualities: same doubles as the wide batch through the host entry (chunked copies), the device
+    entry, and the per-read max epilogue; both kernels (a region too large for the fast path is in the batch)."""
+    from strelka_b200.api import DevAlignBatch, DeviceArray
+
+    rng = np.random.default_rng(41)
+    regions = [specgen.random_region(rng, n_reads=int(rng.integers(1, 10))) for _ in range(40)]
+    r_out = B.RegionSpec(
+        "ACGTACGTAC", 100, [(B.codes_of("ACGTACGTACGT"), np.full(12, 37, np.uint8))],
+        [B.CandidateAlignmentSpec(0, 95, [("M", 12)]), B.CandidateAlignmentSpec(0, 105, [("M", 12)]), B.CandidateAlignmentSpec(0, 5000, [("M", 12)]),
+         B.CandidateAlignmentSpec(0, 100, [("S", 12)]), B.CandidateAlignmentSpec(0, 100, [("H", 5), ("S", 3), ("M", 9)])],
+    )
+    regions.append(r_out)
+    regions.append(B.RegionSpec("ACGT" * 10, 100, [(B.codes_of("ACGT"), np.full(4, 37, np.uint8))], []))  # no alignments
+    for r in regions:  # <= 4 distinct qualities so that the 2-bit format applies
+        r.reads = [(codes, np.array([11, 25, 37, 2], np.uint8)[np.asarray(q) % 4]) for codes, q in r.reads]
+    regions += [specgen.simple_region(rng, n_reads=int(rng.integers(3, 40))) for _ in range(30)]
+    small = list(regions)
+    for with_large in (False, True):
+        regs = small + ([specgen.simple_region(rng, n_reads=330)] if with_large else [])
+        wide = B.build_align_batch(regs)
+        want = reflib.ox_score(wide)
+        cb = B.build_align_batch(regs, qual_bits=qb, compact=compact)
+        assert cb.fmt == (3 if compact else 0)
+        assert np.array_equal(_bits(ctx.score_alignments(cb)), _bits(want))
+        if not with_large:
+            # the chunk-pipelined host entry with chunk borders at arbitrary (odd) alignment indices
+            from strelka_b200.api import Context
+
+            p = A.default_params()
+            p.pipeline_chunks = 7
+            c7 = Context(0, p)
+            assert np.array_equal(_bits(c7.score_alignments(cb)), _bits(want))
+            c7.close()
+        db = DevAlignBatch(ctx, cb)
+        ctx.score_alignments_dev(db)
+        assert np.array_equal(_bits(db.out.download(np.float64, cb.n_alns)), _bits(want))
+        mx = DeviceArray(ctx, cb.n_reads * 8)
+        ma = DeviceArray(ctx, cb.n_reads * 4)
+        ctx.read_max_dev(db, mx, ma)
+        mlnp = mx.download(np.float64, cb.n_reads)
+        maln = ma.download(np.uint32, cb.n_reads)
+        reads = wide.alns["read"][:-1]
+        for r in range(0, cb.n_reads, 7):
+            idx = np.nonzero(reads == r)[0]
+            if idx.size == 0:
+                assert maln[r] == 0xFFFFFFFF
+            else:
+                assert mlnp[r] == want[idx].max() and maln[r] == idx[np.argmax(want[idx])]
+
+
 def test_k1_edge_cases(ctx):
     rng = np.random.default_rng(9)
     # a region without alignments, a region with one 1-base read, alignments far outside the held reference window
