@@ -81,27 +81,33 @@ class HostAlloc:
         self.ptrs = []
 
 
-def make_workload(synth, alloc: HostAlloc, n_loci: int, depth: int, read_len: int, n_haps: int, seed: int, threads: int, qual_bits: int = 4, reads_per_region: int = 0):
+def make_workload(synth, alloc: HostAlloc, n_loci: int, depth: int, read_len: int, n_haps: int, seed: int, threads: int, qual_bits: int = 2, reads_per_region: int = 0,
+                  fmt: int = A.SX_FMT_ALN8 | A.SX_FMT_SEG2):
+    """The K1/K2a/K3 inputs of n_loci candidate loci.  Defaults = the most compact wire formats of include/strelka_b200.h (2-bit
+    quality codes, 8-byte alignment headers, 2-byte segments): the host entry points are PCIe-bound, so bytes are throughput."""
     rpr = min(reads_per_region, depth) if reads_per_region else depth
     n_regions = n_loci * ((depth + rpr - 1) // rpr)  # a locus deeper than rpr reads is cut into regions sharing its reference window
     regions = alloc.array((n_regions + 1) * A.REGION_DT.itemsize, A.REGION_DT)
     sz = SynthSizes()
-    rc = synth.synth_k1_plan(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, qual_bits, reads_per_region, C.c_void_p(regions.ctypes.data), C.byref(sz))
+    rc = synth.synth_k1_plan(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, qual_bits, reads_per_region, fmt, C.c_void_p(regions.ctypes.data), C.byref(sz))
     assert rc == 0, rc
     S = A.SX_POOL_SLACK
+    aln_dt = A.ALN8_DT if fmt & A.SX_FMT_ALN8 else A.ALN_DT
+    seg_dt = np.dtype(np.uint16) if fmt & A.SX_FMT_SEG2 else A.ALN_SEG_DT
     read_lens = alloc.array(sz.n_reads * 2 + 16, np.uint16)
     seq4 = alloc.array(sz.seq4_bytes + S, np.uint8)
     qual = alloc.array(sz.qual_bytes + S, np.uint8)
     ref = alloc.array(sz.ref_bytes + S, np.uint8)
-    alns = alloc.array((sz.n_alns + 1) * A.ALN_DT.itemsize, A.ALN_DT)
-    segs = alloc.array((sz.n_segs + 16) * A.ALN_SEG_DT.itemsize, A.ALN_SEG_DT)
+    alns = alloc.array((sz.n_alns + 3) * aln_dt.itemsize, aln_dt)  # + slack: an sx_aln8 slice is staged from a 16-byte boundary
+    segs = alloc.array((sz.n_segs + 16) * seg_dt.itemsize, seg_dt)
     ins = alloc.array(sz.ins_bytes + S, np.uint8)
-    rc = synth.synth_k1_fill(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, qual_bits, reads_per_region, C.c_void_p(regions.ctypes.data), C.c_void_p(read_lens.ctypes.data),
-                             C.c_void_p(seq4.ctypes.data), C.c_void_p(qual.ctypes.data), C.c_void_p(ref.ctypes.data), C.c_void_p(alns.ctypes.data),
-                             C.c_void_p(segs.ctypes.data), C.c_void_p(ins.ctypes.data))
+    rc = synth.synth_k1_fill(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, qual_bits, reads_per_region, fmt, C.c_void_p(regions.ctypes.data),
+                             C.c_void_p(read_lens.ctypes.data), C.c_void_p(seq4.ctypes.data), C.c_void_p(qual.ctypes.data), C.c_void_p(ref.ctypes.data),
+                             C.c_void_p(alns.ctypes.data), C.c_void_p(segs.ctypes.data), C.c_void_p(ins.ctypes.data))
     assert rc == 0, rc
     used = {"seq4": int(sz.seq4_bytes), "qual": int(sz.qual_bytes), "ref": int(sz.ref_bytes), "ins": int(sz.ins_bytes)}
-    ab = B.AlignBatch(regions[: n_regions + 1], read_lens[: sz.n_reads], seq4, qual, ref, alns[: sz.n_alns + 1], segs, ins, used, qual_bits, [11, 25, 37] if qual_bits == 4 else None)
+    ab = B.AlignBatch(regions[: n_regions + 1], read_lens[: sz.n_reads], seq4, qual, ref, alns[: sz.n_alns + 3], segs, ins, used, qual_bits,
+                      [11, 25, 37] if qual_bits in (2, 4) else None, fmt, int(sz.n_segs), int(sz.n_alns))
     # K2a: one pileup column per locus
     site_off = alloc.array((n_loci + 1) * 4, np.uint32)
     n_calls = synth.synth_pileups(n_loci, C.c_double(float(depth)), 0, C.c_uint64(seed), threads, C.c_void_p(site_off.ctypes.data), None, None)
@@ -442,7 +448,7 @@ def main():
             "gcups": (cells_k1 + cells_k3) * world * args.steps / dt / 1e9,
             "k1_gcups_kernel_only": cells_k1 / (k1_avg_ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "k1q_score_kernel (K1 fast path, k1_score4.cu)" if ab.qual_bits == 4 else "k1_score_kernel","algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k1_avg_ms, "peak_source": peak_src},
+                         "kernel": "k1q_score_kernel (K1 fast path, k1_score4.cu)" if ab.qual_bits in (2, 4) else "k1_score_kernel","algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k1_avg_ms, "peak_source": peak_src},
             "gpu_launches": launches,
             "kernel_ms_per_step": {k: v / args.steps for k, v in parts.items()},
             "clocks": clk,

@@ -50,9 +50,42 @@ struct k1_cfg
 {
     uint32_t n_loci, depth, read_len, n_haps, ref_len;
     uint64_t seed;
-    uint32_t qual_bits; // 8: one byte per base; 4: dictionary-coded nibbles (dictionary {11, 25, 37})
+    uint32_t qual_bits; // 8: one byte per base; 4: dictionary-coded nibbles; 2: 2-bit codes per seq4 nibble position (dictionary {11, 25, 37})
     uint32_t rpr;       // reads per region: a locus deeper than this is cut into several regions sharing the reference window
+    uint32_t fmt;       // SX_FMT_ALN8 | SX_FMT_SEG2: write the compact alignment-header / segment wire formats
 };
+
+inline uint64_t qual_slice_bytes(const k1_cfg& c, uint32_t n_reads_region)
+{
+    const uint64_t packed = (c.read_len + 1) / 2;
+    return c.qual_bits == 2 ? (n_reads_region * packed + 1) / 2 : c.qual_bits == 4 ? n_reads_region * packed : (uint64_t)n_reads_region * c.read_len;
+}
+
+inline void put_aln(const k1_cfg& c, void* alns, const sx_region* reg, uint32_t aidx, uint32_t ridx, uint32_t start, uint32_t seg_abs, uint32_t ins_abs)
+{
+    if (c.fmt & SX_FMT_ALN8)
+    {
+        sx_aln8& A = static_cast<sx_aln8*>(alns)[reg->aln_begin + aidx];
+        A.read = (uint16_t)ridx;
+        A.ref_pos = (int16_t)start;
+        A.seg_off = (uint16_t)(seg_abs - reg->seg_begin);
+        A.ins_off = (uint16_t)(ins_abs - reg->ins_begin);
+    }
+    else
+    {
+        sx_aln& A = static_cast<sx_aln*>(alns)[reg->aln_begin + aidx];
+        A.read = reg->read_begin + ridx;
+        A.ref_pos = reg->ref_begin + (int32_t)start;
+        A.seg_off = seg_abs;
+        A.ins_off = ins_abs;
+    }
+}
+
+inline void put_seg(const k1_cfg& c, void* segs, uint32_t s, uint32_t len, uint32_t kind)
+{
+    if (c.fmt & SX_FMT_SEG2) static_cast<sx_aln_seg2*>(segs)[s] = (sx_aln_seg2)(len | (kind << 12));
+    else static_cast<sx_aln_seg*>(segs)[s] = sx_aln_seg{(uint16_t)len, (uint8_t)kind, 0};
+}
 
 inline uint32_t geom_len(rng_t& r)
 {
@@ -96,7 +129,7 @@ inline uint32_t pick_qual(rng_t& r)
 const double QERR[3] = {0.07943282347242814, 0.0031622776601683794, 0.00019952623149688788}; // 10^-1.1, 10^-2.5, 10^-3.7
 
 void gen_region(const k1_cfg& c, uint32_t rg, bool fill, region_sizes& sz, const sx_region* reg, uint16_t* read_len, uint8_t* seq4, uint8_t* qual, char* ref_pool,
-                sx_aln* alns, sx_aln_seg* segs, char* ins)
+                void* alns, void* segs, char* ins)
 {
     const uint32_t chunks = (c.depth + c.rpr - 1) / c.rpr;
     const uint32_t l = rg / chunks, chunk = rg % chunks;
@@ -115,6 +148,7 @@ void gen_region(const k1_cfg& c, uint32_t rg, bool fill, region_sizes& sz, const
     const uint32_t segs_per_read = 1 + 3 * d.n_alt;
     const uint32_t packed = (c.read_len + 1) / 2;
     std::vector<char> rd(c.read_len);
+    if (fill && c.qual_bits == 2) memset(qual + reg->qual_off, 0, qual_slice_bytes(c, k_end - k_begin));
     for (uint32_t k = 0; k < k_begin; ++k) // reads of earlier regions of this locus: consume their structure draws
     {
         r.below(c.read_len - 20);
@@ -147,7 +181,7 @@ void gen_region(const k1_cfg& c, uint32_t rg, bool fill, region_sizes& sz, const
         {
             read_len[reg->read_begin + ridx] = (uint16_t)c.read_len;
             uint8_t* sq = seq4 + reg->seq_off + (uint64_t)ridx * packed;
-            uint8_t* ql = qual + reg->qual_off + (uint64_t)ridx * (c.qual_bits == 4 ? packed : c.read_len);
+            uint8_t* ql = qual + reg->qual_off + (c.qual_bits == 2 ? 0 : (uint64_t)ridx * (c.qual_bits == 4 ? packed : c.read_len));
             memset(sq, 0, packed);
             if (c.qual_bits == 4) memset(ql, 0, packed);
             for (uint32_t i = 0; i < c.read_len; ++i)
@@ -155,7 +189,13 @@ void gen_region(const k1_cfg& c, uint32_t rg, bool fill, region_sizes& sz, const
                 const uint32_t q = pick_qual(rb);
                 char b = rd[i];
                 if (rb.unit() < QERR[q == 11 ? 0 : q == 25 ? 1 : 2]) b = BASES[rb.below(4)];
-                if (c.qual_bits == 4) ql[i >> 1] |= (q == 11 ? 0 : q == 25 ? 1 : 2) << ((~i & 1) << 2);
+                const uint32_t qcode = q == 11 ? 0 : q == 25 ? 1 : 2;
+                if (c.qual_bits == 2)
+                {
+                    const uint64_t pos = (uint64_t)ridx * packed * 2 + i; // nibble position in the region's seq4 slice
+                    ql[pos >> 2] |= qcode << (6 - 2 * (pos & 3));
+                }
+                else if (c.qual_bits == 4) ql[i >> 1] |= qcode << ((~i & 1) << 2);
                 else ql[i] = (uint8_t)q;
                 sq[i >> 1] |= code_of(b) << ((~i & 1) << 2);
             }
@@ -165,17 +205,10 @@ void gen_region(const k1_cfg& c, uint32_t rg, bool fill, region_sizes& sz, const
         for (uint32_t hh = 0; hh < c.n_haps; ++hh)
         {
             const uint32_t aidx = ridx * c.n_haps + hh;
-            if (fill)
-            {
-                sx_aln& A = alns[reg->aln_begin + aidx];
-                A.read = reg->read_begin + ridx;
-                A.ref_pos = ref_begin + (int32_t)start;
-                A.seg_off = sbase;
-                A.ins_off = ins_off;
-            }
+            if (fill) put_aln(c, alns, reg, aidx, ridx, start, sbase, ins_off);
             if (hh == 0)
             {
-                if (fill) segs[sbase] = sx_aln_seg{(uint16_t)c.read_len, SX_SEG_MATCH, 0};
+                if (fill) put_seg(c, segs, sbase, c.read_len, SX_SEG_MATCH);
                 sbase += 1;
             }
             else
@@ -186,9 +219,9 @@ void gen_region(const k1_cfg& c, uint32_t rg, bool fill, region_sizes& sz, const
                     const uint32_t n = std::min(a.len, c.read_len - left);
                     if (fill)
                     {
-                        segs[sbase + 0] = sx_aln_seg{(uint16_t)left, SX_SEG_MATCH, 0};
-                        segs[sbase + 1] = sx_aln_seg{(uint16_t)n, SX_SEG_INSERT, 0};
-                        segs[sbase + 2] = sx_aln_seg{(uint16_t)(c.read_len - left - n), SX_SEG_MATCH, 0};
+                        put_seg(c, segs, sbase + 0, left, SX_SEG_MATCH);
+                        put_seg(c, segs, sbase + 1, n, SX_SEG_INSERT);
+                        put_seg(c, segs, sbase + 2, c.read_len - left - n, SX_SEG_MATCH);
                         memcpy(ins + ins_off, a.seq, n);
                     }
                     ins_off += n;
@@ -198,9 +231,9 @@ void gen_region(const k1_cfg& c, uint32_t rg, bool fill, region_sizes& sz, const
                 {
                     if (fill)
                     {
-                        segs[sbase + 0] = sx_aln_seg{(uint16_t)left, SX_SEG_MATCH, 0};
-                        segs[sbase + 1] = sx_aln_seg{(uint16_t)a.len, SX_SEG_REFSKIP, 0};
-                        segs[sbase + 2] = sx_aln_seg{(uint16_t)(c.read_len - left), SX_SEG_MATCH, 0};
+                        put_seg(c, segs, sbase + 0, left, SX_SEG_MATCH);
+                        put_seg(c, segs, sbase + 1, a.len, SX_SEG_REFSKIP);
+                        put_seg(c, segs, sbase + 2, c.read_len - left, SX_SEG_MATCH);
                     }
                 }
                 sbase += 3;
@@ -232,13 +265,13 @@ struct synth_k1_sizes
 
 // pass 1: region table (needs the per-region insert bytes) + totals.  regions must hold n_loci+1 entries.
 int synth_k1_plan(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n_haps, uint64_t seed, int threads, uint32_t qual_bits, uint32_t reads_per_region,
-                  sx_region* regions, synth_k1_sizes* out)
+                  uint32_t fmt, sx_region* regions, synth_k1_sizes* out)
 {
     if (n_haps < 1 || n_haps > 32 || read_len < 40 || read_len > 1000) return -1;
     const uint32_t rpr = reads_per_region ? std::min(reads_per_region, depth) : depth;
     const uint32_t chunks = (depth + rpr - 1) / rpr;
     const uint32_t n_regions = n_loci * chunks;
-    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed, qual_bits, rpr};
+    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed, qual_bits, rpr, fmt};
     std::vector<uint32_t> ins(n_regions);
     parallel_for(n_regions, threads, [&](uint32_t rg) {
         region_sizes sz;
@@ -264,10 +297,10 @@ int synth_k1_plan(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n
         if (rg == n_regions) break;
         reads += nr;
         seq += pad16((uint64_t)nr * packed);
-        qual += pad16((uint64_t)nr * (qual_bits == 4 ? packed : read_len));
+        qual += pad16(qual_slice_bytes(c, nr));
         ref += pad16(c.ref_len);
         insb += pad16(ins[rg]);
-        seg += ((uint64_t)nr * (1 + 3 * (n_haps - 1)) + 3u) & ~3ull;
+        seg += (fmt & SX_FMT_SEG2) ? (((uint64_t)nr * (1 + 3 * (n_haps - 1)) + 7u) & ~7ull) : (((uint64_t)nr * (1 + 3 * (n_haps - 1)) + 3u) & ~3ull);
     }
     if (seg > 0xffffffffull || insb > 0xffffffffull) return -2;
     out->n_regions = n_regions;
@@ -284,19 +317,24 @@ int synth_k1_plan(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n
 
 // pass 2: fill caller-allocated pools (sizes from synth_k1_plan, plus SX_POOL_SLACK; alns has n_alns+1 entries, segs n_segs+16)
 int synth_k1_fill(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n_haps, uint64_t seed, int threads, uint32_t qual_bits, uint32_t reads_per_region,
-                  const sx_region* regions,
-                  uint16_t* read_lens, uint8_t* seq4, uint8_t* qual, char* ref, sx_aln* alns, sx_aln_seg* segs, char* ins)
+                  uint32_t fmt, const sx_region* regions,
+                  uint16_t* read_lens, uint8_t* seq4, uint8_t* qual, char* ref, void* alns, void* segs, char* ins)
 {
     const uint32_t rpr = reads_per_region ? std::min(reads_per_region, depth) : depth;
     const uint32_t n_regions = n_loci * ((depth + rpr - 1) / rpr);
-    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed, qual_bits, rpr};
+    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed, qual_bits, rpr, fmt};
     const uint32_t n_segs = regions[n_regions].seg_begin;
-    for (uint32_t i = 0; i < n_segs + 16; ++i) segs[i] = sx_aln_seg{0, SX_SEG_HARDCLIP, 0};
+    for (uint32_t i = 0; i < n_segs + 16; ++i) put_seg(c, segs, i, 0, SX_SEG_HARDCLIP);
     parallel_for(n_regions, threads, [&](uint32_t rg) {
         region_sizes sz;
         gen_region(c, rg, true, sz, &regions[rg], read_lens, seq4, qual, ref, alns, segs, ins);
     });
-    sx_aln& S = alns[(uint64_t)n_loci * depth * n_haps];
+    if (fmt & SX_FMT_ALN8)
+    {
+        static_cast<sx_aln8*>(alns)[(uint64_t)n_loci * depth * n_haps] = sx_aln8{0, 0, 0, 0}; // unused sentinel
+        return 0;
+    }
+    sx_aln& S = static_cast<sx_aln*>(alns)[(uint64_t)n_loci * depth * n_haps];
     S.read = n_loci * depth;
     S.ref_pos = 0;
     S.seg_off = n_segs;
