@@ -273,7 +273,7 @@ def main():
         lib = None
         alloc = HostAlloc(lib, False)
         sample = args.cpu_sample_loci or min(n_loci, max(2000, 600 * ncpu))
-        ab, pb, gb = make_workload(synth, alloc, sample, depth, read_len, n_haps, args.seed, ncpu, 4, rpr)
+        ab, pb, gb = make_workload(synth, alloc, sample, depth, read_len, n_haps, args.seed, ncpu, 2, rpr)
         for _ in range(args.warmup):
             cpu_pass(ab, pb, gb, sample, ncpu)
         t_tot, n_tot = 0.0, 0
@@ -312,7 +312,7 @@ def main():
     lib = ctx.lib
     alloc = HostAlloc(lib, True)
     t_gen = time.perf_counter()
-    ab, pb, gb = make_workload(synth, alloc, n_loci, depth, read_len, n_haps, args.seed + 1000 * rank, threads, 4, rpr)
+    ab, pb, gb = make_workload(synth, alloc, n_loci, depth, read_len, n_haps, args.seed + 1000 * rank, threads, 2, rpr)
     t_gen = time.perf_counter() - t_gen
     cells_k1, cells_k3 = ab.cells(), gb.cells()
     sc = ctx.active_region_scores()
