@@ -317,8 +317,12 @@ public:
         b.qual_bytes = _qual.size();
         b.ref_bytes = _ref.size();
         b.ins_bytes = _ins.size();
+        if (_compact) compactView(b);
         return b;
     }
+
+    /// false: always send the wide structs and one quality byte per base (default: the most compact formats that fit)
+    void setCompactWireFormats(bool on) { _compact = on; }
 
     static uint8_t get_bam_seq_code(char c) // htsapi/bam_seq.hh:98-118
     {
@@ -347,7 +351,7 @@ private:
         while (_qual.size() & 15) _qual.push_back(0);
         while (_ref.size() & 15) _ref.push_back(0);
         while (_ins.size() & 15) _ins.push_back(0);
-        while (_segs.size() & 3) _segs.push_back(sx_aln_seg{0, SX_SEG_HARDCLIP, 0});
+        while (_segs.size() & 7) _segs.push_back(sx_aln_seg{0, SX_SEG_HARDCLIP, 0}); // 8: also valid for the 2-byte segment format
     }
     void pushSeg(unsigned len, uint8_t kind, uint8_t flags) { _segs.push_back(sx_aln_seg{static_cast<uint16_t>(len), kind, flags}); }
     void pushInsert(const IndelKey& k, unsigned firstSegLen, unsigned insertLength, bool isLeadingEdge, uint8_t flags)
@@ -372,7 +376,107 @@ private:
         throw Exception(SX_ERR_ARG, "candidate alignment does not contain the indel its path implies"); // assert(isFound), score.cpp:222
     }
 
+    /// Compact wire formats (include/strelka_b200.h: sx_aln8, sx_aln_seg2, 4-/2-bit quality codes).  Lossless; each is used only
+    /// when every value of the batch fits it.  The host entry points are PCIe-bound, so bytes are throughput.
+    void compactView(sx_align_batch& b)
+    {
+        // ---- qualities: dictionary of the distinct values
+        bool seen[256] = {false};
+        for (size_t ri(0); ri < _regions.size(); ++ri)
+        {
+            size_t qo(_regions[ri].qual_off);
+            const size_t r1(ri + 1 < _regions.size() ? _regions[ri + 1].read_begin : _readLen.size());
+            for (size_t r(_regions[ri].read_begin); r < r1; ++r)
+                for (unsigned i(0); i < _readLen[r]; ++i) seen[_qual[qo++]] = true;
+        }
+        unsigned nq(0);
+        uint8_t code[256] = {0};
+        for (unsigned q(0); q < 256; ++q)
+            if (seen[q])
+            {
+                if (nq < 16) b.qual_dict[nq] = static_cast<uint8_t>(q);
+                code[q] = static_cast<uint8_t>(nq++);
+            }
+        const unsigned qbits(nq <= 4 ? 2 : nq <= 16 ? 4 : 8);
+        if (qbits != 8)
+        {
+            _qualOut.clear();
+            for (size_t ri(0); ri < _regions.size(); ++ri)
+            {
+                while (_qualOut.size() & 15) _qualOut.push_back(0);
+                size_t qo(_regions[ri].qual_off);
+                _regionsOut[ri].qual_off = _qualOut.size();
+                const size_t r1(ri + 1 < _regions.size() ? _regions[ri + 1].read_begin : _readLen.size());
+                std::vector<uint8_t> codes; // one code per nibble position of the region's seq4 slice
+                for (size_t r(_regions[ri].read_begin); r < r1; ++r)
+                {
+                    const unsigned len(_readLen[r]);
+                    for (unsigned i(0); i < len; ++i) codes.push_back(code[_qual[qo++]]);
+                    if (len & 1) codes.push_back(0);
+                }
+                if (qbits == 4)
+                    for (size_t i(0); i < codes.size(); i += 2) _qualOut.push_back(static_cast<uint8_t>((codes[i] << 4) | codes[i + 1]));
+                else
+                {
+                    while (codes.size() & 3) codes.push_back(0);
+                    for (size_t i(0); i < codes.size(); i += 4)
+                        _qualOut.push_back(static_cast<uint8_t>((codes[i] << 6) | (codes[i + 1] << 4) | (codes[i + 2] << 2) | codes[i + 3]));
+                }
+            }
+            while (_qualOut.size() & 15) _qualOut.push_back(0);
+            _regionsOut.back().qual_off = _qualOut.size();
+            b.qual_bytes = _qualOut.size();
+            _qualOut.resize(_qualOut.size() + SX_POOL_SLACK);
+            b.qual = _qualOut.data();
+            b.qual_bits = qbits;
+        }
+        else std::memset(b.qual_dict, 0, sizeof(b.qual_dict));
+        // ---- alignment headers: region-relative 16-bit fields
+        bool fits(true);
+        for (size_t ri(0); ri < _regions.size() && fits; ++ri)
+        {
+            const sx_region& reg(_regions[ri]);
+            const size_t a1(ri + 1 < _regions.size() ? _regions[ri + 1].aln_begin : _alns.size());
+            for (size_t a(reg.aln_begin); a < a1; ++a)
+            {
+                const int64_t rp(static_cast<int64_t>(_alns[a].ref_pos) - reg.ref_begin);
+                if (_alns[a].read - reg.read_begin > 65535u || rp < -32768 || rp > 32767 || _alns[a].seg_off - reg.seg_begin > 65535u || _alns[a].ins_off - reg.ins_begin > 65535u)
+                {
+                    fits = false;
+                    break;
+                }
+            }
+        }
+        if (fits)
+        {
+            _alns8Out.assign(_alns.size() + 3, sx_aln8{0, 0, 0, 0}); // + slack: the kernels stage a slice from a 16-byte boundary
+            for (size_t ri(0); ri < _regions.size(); ++ri)
+            {
+                const sx_region& reg(_regions[ri]);
+                const size_t a1(ri + 1 < _regions.size() ? _regions[ri + 1].aln_begin : _alns.size());
+                for (size_t a(reg.aln_begin); a < a1; ++a)
+                    _alns8Out[a] = sx_aln8{static_cast<uint16_t>(_alns[a].read - reg.read_begin), static_cast<int16_t>(_alns[a].ref_pos - reg.ref_begin),
+                                           static_cast<uint16_t>(_alns[a].seg_off - reg.seg_begin), static_cast<uint16_t>(_alns[a].ins_off - reg.ins_begin)};
+            }
+            b.alns = reinterpret_cast<const sx_aln*>(_alns8Out.data());
+            b.format |= SX_FMT_ALN8;
+        }
+        // ---- segments: 12-bit lengths
+        fits = true;
+        for (const sx_aln_seg& sg : _segs) fits = fits && sg.len <= 4095;
+        if (fits)
+        {
+            _segs2Out.assign(_segs.size() + 16, static_cast<sx_aln_seg2>(SX_SEG_HARDCLIP << 12));
+            for (size_t i(0); i < _segs.size(); ++i) _segs2Out[i] = static_cast<sx_aln_seg2>(_segs[i].len | (_segs[i].kind << 12) | ((_segs[i].flags & 1) << 15));
+            b.segs = reinterpret_cast<const sx_aln_seg*>(_segs2Out.data());
+            b.format |= SX_FMT_SEG2;
+        }
+    }
+
     bool _open = false;
+    bool _compact = true;
+    std::vector<sx_aln8> _alns8Out;
+    std::vector<sx_aln_seg2> _segs2Out;
     std::vector<sx_region> _regions, _regionsOut;
     std::vector<uint16_t> _readLen;
     std::vector<uint8_t> _seq4, _qual, _seq4Out, _qualOut;

@@ -109,8 +109,21 @@ int main(int argc, char** argv)
                     want.push_back(strtoull(f[7].c_str(), nullptr, 16));
                 }
             }
-            std::vector<double> got;
-            batch.scoreCandidateAlignments(ctx, got);
+            std::vector<double> got, gotWide;
+            batch.scoreCandidateAlignments(ctx, got); // default: the most compact wire formats that fit
+            if (!(batch.view().format & SX_FMT_SEG2))
+            {
+                ++failures;
+                std::cerr << "FAIL k1: the batch was expected to fit the compact segment format\n";
+            }
+            batch.setCompactWireFormats(false);
+            batch.scoreCandidateAlignments(ctx, gotWide);
+            ++checks;
+            if (batch.view().format != 0 || gotWide.size() != got.size() || std::memcmp(gotWide.data(), got.data(), got.size() * sizeof(double)) != 0)
+            {
+                ++failures;
+                std::cerr << "FAIL k1: wide and compact wire formats disagree\n";
+            }
             if (got.size() != want.size())
             {
                 ++failures;
