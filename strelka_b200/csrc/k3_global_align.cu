@@ -5,8 +5,11 @@
 //          apath_add_seqmatch          (blt_util/align_path_impl.hh:36-86)
 // as called from ActiveRegionProcessor::discoverIndelsAndMismatches (starling_common/ActiveRegionProcessor.cpp:591).
 //
+// This file holds the entry points and the kernel for LARGE matrices (Q > 128 or R > 255, and batches whose penalties do not fit
+// the key encoding of k3_group.cu, which takes everything else first -- see sx_k3_group_run).
+//
 // One warp per DP matrix.  Lane l owns the strip of T = ceil(Q/32) consecutive query rows and keeps the three state scores
-// of its rows IN REGISTERS (T is a template parameter up to 8, i.e. Q <= 256; longer queries fall back to a shared-memory
+// of its rows IN REGISTERS (T is a template parameter up to 4, i.e. Q <= 128; longer queries fall back to a shared-memory
 // strip).  The warp sweeps the matrix as an anti-diagonal wavefront: lane l is at reference column t-l at step t, and the
 // scores of the row above / the diagonal cross strips through three __shfl_up per step.  The 3 x 2-bit back pointers of every
 // cell go to a (Q+1) x (R+1) byte matrix in shared memory, so HBM sees only the Q+R input bytes and the result.

@@ -138,8 +138,7 @@ void gen_region(const k1_cfg& c, uint32_t rg, bool fill, region_sizes& sz, const
     locus_desc d;
     std::vector<char> refv(c.ref_len);
     make_locus(c, l, r, d, refv.data());
-    const int32_t ref_begin = 1000 + (int32_t)(l % 2000000u) * 1000;
-    const uint32_t locus = c.ref_len / 2; // window-relative
+    const uint32_t locus = c.ref_len / 2; // window-relative (the window's contig coordinate is reg->ref_begin, set by synth_k1_plan)
     if (fill) memcpy(ref_pool + reg->ref_off, refv.data(), c.ref_len);
     // genotype: two haplotype indices
     const uint32_t g0 = r.below(c.n_haps), g1 = r.below(3) ? r.below(c.n_haps) : g0;
