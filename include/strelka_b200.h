@@ -140,6 +140,15 @@ typedef struct sx_aln {
  * back to the wide structs when a field would not fit. */
 #define SX_FMT_ALN8 0x1u /* `alns` points to sx_aln8[n_alns + 1] */
 #define SX_FMT_SEG2 0x2u /* `segs` points to sx_aln_seg2[n_segs]; every region's seg_begin is a multiple of 8 */
+/* SX_FMT_BASEQ: base and quality in ONE nibble per base.  The seq4 pool keeps its layout (reads back to back, byte-aligned, high
+ * nibble first) but a nibble is (base << 2) | quality code, base A C G T = 0..3, quality code an index into qual_dict[0..3]
+ * (qual_bits must be 2, every dictionary quality <= 70); the qual pool is not read.  The few bases that are not A/C/G/T are listed
+ * per region in `exc` (their nibble still carries the quality code).  Halves the read bytes again: 75 bytes per 150 bp read. */
+#define SX_FMT_BASEQ 0x4u
+/* SX_FMT_REF4: the ref pool holds BAM 4-bit codes, two bases per byte, high nibble first (anything that is not A/C/G/T as 15);
+ * region.ref_off is the byte offset of the window's first packed byte (multiple of 16), ref_len stays in bases. */
+#define SX_FMT_REF4 0x8u
+#define SX_EXC(pos, bam_code) ((uint32_t)(pos) | ((uint32_t)(bam_code) << 24)) /* exception: nibble position in the region's seq4 slice (< 2^24), bam_seq code */
 
 typedef struct sx_aln8 {  /* every field relative to the alignment's region; an alignment's segments end at the next alignment's */
     uint16_t read;        /* seg_off, the last alignment's at the region's last segment                                          */
@@ -188,6 +197,9 @@ typedef struct sx_align_batch {
     uint32_t qual_bits;
     uint8_t qual_dict[16];
     uint32_t format; /* SX_FMT_* bits; 0 = sx_aln / sx_aln_seg */
+    /* SX_FMT_BASEQ only: exceptions of region i are exc[exc_off[i] .. exc_off[i+1]), SX_EXC words in any order */
+    const uint32_t* exc_off; /* [n_regions + 1] */
+    const uint32_t* exc;
 } sx_align_batch;
 
 /* lnp_out[n_alns] <- ln P(read | alignment path); bit-identical to the reference's double. */

@@ -50,7 +50,7 @@ def default_params() -> SxParams:
 ALN_SEG_DT = np.dtype([("len", "<u2"), ("kind", "u1"), ("flags", "u1")])
 ALN_DT = np.dtype([("read", "<u4"), ("ref_pos", "<i4"), ("seg_off", "<u4"), ("ins_off", "<u4")])
 ALN8_DT = np.dtype([("read", "<u2"), ("ref_pos", "<i2"), ("seg_off", "<u2"), ("ins_off", "<u2")])  # sx_aln8 (SX_FMT_ALN8)
-SX_FMT_ALN8, SX_FMT_SEG2 = 1, 2
+SX_FMT_ALN8, SX_FMT_SEG2, SX_FMT_BASEQ, SX_FMT_REF4 = 1, 2, 4, 8
 REGION_DT = np.dtype(
     [("seq_off", "<u8"), ("qual_off", "<u8"), ("ref_off", "<u8"), ("read_begin", "<u4"), ("aln_begin", "<u4"), ("seg_begin", "<u4"), ("ins_begin", "<u4"),
      ("ref_begin", "<i4"), ("ref_len", "<u4")]
@@ -119,6 +119,8 @@ class SxAlignBatch(C.Structure):
         ("qual_bits", C.c_uint32),
         ("qual_dict", C.c_uint8 * 16),
         ("format", C.c_uint32),
+        ("exc_off", C.c_void_p),
+        ("exc", C.c_void_p),
     ]
 
 

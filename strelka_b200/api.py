@@ -57,14 +57,17 @@ class DevAlignBatch:
     def __init__(self, ctx: "Context", hb: B.AlignBatch):
         self.host = hb
         self.bufs = {}
-        for name in ("regions", "read_len", "seq4", "qual", "ref", "alns", "segs", "ins"):
+        for name in ("regions", "read_len", "seq4", "qual", "ref", "alns", "segs", "ins", "exc_off", "exc"):
             arr = getattr(hb, name)
+            if arr is None:  # exception arrays exist only in the SX_FMT_BASEQ format
+                continue
             self.bufs[name] = DeviceArray(ctx, arr.nbytes + 64).upload(arr)
         self.c = A.SxAlignBatch(
             hb.n_regions, hb.n_reads, hb.n_alns, hb.n_segs,
             self.bufs["regions"].ptr, self.bufs["read_len"].ptr, self.bufs["seq4"].ptr, self.bufs["qual"].ptr, self.bufs["ref"].ptr,
             self.bufs["alns"].ptr, self.bufs["segs"].ptr, self.bufs["ins"].ptr,
             hb.used["seq4"], hb.used["qual"], hb.used["ref"], hb.used["ins"], hb.qual_bits, hb.qual_dict, hb.fmt,
+            self.bufs["exc_off"].ptr if "exc_off" in self.bufs else None, self.bufs["exc"].ptr if "exc" in self.bufs else None,
         )
         self.out = DeviceArray(ctx, hb.n_alns * 8)
 

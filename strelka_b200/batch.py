@@ -170,10 +170,11 @@ def _pad16(n: int) -> int:
 class AlignBatch:
     """Owns the numpy pools of one sx_align_batch and exposes the ctypes struct (``.c``)."""
 
-    def __init__(self, regions, read_len, seq4, qual, ref, alns, segs, ins, used, qual_bits=8, qual_dict=None, fmt=0, n_segs=None, n_alns=None):
+    def __init__(self, regions, read_len, seq4, qual, ref, alns, segs, ins, used, qual_bits=8, qual_dict=None, fmt=0, n_segs=None, n_alns=None, exc_off=None, exc=None):
         self.regions, self.read_len, self.seq4, self.qual, self.ref = regions, read_len, seq4, qual, ref
         self.qual_bits = qual_bits
         self.fmt = fmt
+        self.exc_off, self.exc = exc_off, exc
         self.qual_dict = (C.c_uint8 * 16)(*([int(x) for x in qual_dict] + [0] * (16 - len(qual_dict)))) if qual_dict is not None else (C.c_uint8 * 16)()
         self.alns, self.segs, self.ins = alns, segs, ins
         self.n_regions = len(regions) - 1
@@ -185,6 +186,7 @@ class AlignBatch:
             self.n_regions, self.n_reads, self.n_alns, self.n_segs,
             A.ptr(regions), A.ptr(read_len), A.ptr(seq4), A.ptr(qual), A.ptr(ref), A.ptr(alns), A.ptr(segs), A.ptr(ins),
             used["seq4"], used["qual"], used["ref"], used["ins"], qual_bits, self.qual_dict, fmt,
+            A.ptr(exc_off) if exc_off is not None else None, A.ptr(exc) if exc is not None else None,
         )
 
     def cells(self) -> int:
@@ -200,7 +202,7 @@ class AlignBatch:
     def algorithmic_bytes(self) -> int:
         """SURVEY 8d K1 bytes: each read once (packed bases + quals), headers, segments, inserted bases, ref windows, 8 B out/aln."""
         return int(
-            self.used["seq4"] + self.used["qual"] + self.used["ref"] + self.used["ins"]
+            self.used["seq4"] + self.used["qual"] + self.used["ref"] + self.used["ins"] + (0 if self.exc_off is None else 4 * (self.n_regions + int(self.exc_off[-1])))
             + self.n_alns * (self.alns.dtype.itemsize + 8) + self.n_segs * self.segs.dtype.itemsize
             + self.n_reads * 2 + self.n_regions * A.REGION_DT.itemsize
         )
@@ -217,6 +219,10 @@ def build_align_batch(regions: Sequence[RegionSpec], qual_bits: int = 8, compact
         qdict = vals
         qcode = {v: i for i, v in enumerate(vals)}
     seg_align = 8 if compact else 4
+    # base and quality in one nibble (SX_FMT_BASEQ): needs the 2-bit dictionary and no quality the reference would reject
+    baseq = bool(compact and qual_bits == 2 and (not qdict or max(qdict) <= 70))
+    exc: List[int] = []
+    exc_off: List[int] = []
     reg = np.zeros(len(regions) + 1, dtype=A.REGION_DT)
     q2_codes: List[int] = []
     read_len: List[int] = []
@@ -231,10 +237,12 @@ def build_align_batch(regions: Sequence[RegionSpec], qual_bits: int = 8, compact
             pool.extend(b"\0" * (_pad16(len(pool)) - len(pool)))
         while len(segs) % seg_align:
             segs.append((0, A.SX_SEG_HARDCLIP, 0))  # no-op pad, absorbed by the previous region's last alignment
-        if qual_bits == 2:
+        if qual_bits == 2 and not baseq:
             qual.extend(_pack2(q2_codes))
             qual.extend(b"\0" * (_pad16(len(qual)) - len(qual)))
             q2_codes = []
+        exc_off.append(len(exc))
+        region_seq0 = len(seq4)
         reg[ri] = (len(seq4), len(qual), len(ref), len(read_len), len(alns), len(segs), len(ins), r.ref_begin, len(r.ref))
         ref.extend(r.ref.encode())
         rbase = len(read_len)
@@ -243,10 +251,19 @@ def build_align_batch(regions: Sequence[RegionSpec], qual_bits: int = 8, compact
             assert len(q) == n
             read_len.append(n)
             c = np.asarray(codes, dtype=np.uint8)
+            if baseq:
+                qc = np.array([qcode[int(x)] for x in np.asarray(q).tolist()], dtype=np.uint8)
+                base = np.select([c == 1, c == 2, c == 4, c == 8], [0, 1, 2, 3], default=255).astype(np.uint8)
+                pos0 = 2 * (len(seq4) - region_seq0)
+                for i in np.nonzero(base == 255)[0].tolist():
+                    exc.append(int(pos0 + i) | (int(c[i]) << 24))  # SX_EXC
+                c = (np.where(base == 255, 0, base).astype(np.uint8) << 2) | qc
             if n & 1:
                 c = np.concatenate([c, np.zeros(1, np.uint8)])
             seq4.extend(((c[0::2] << 4) | c[1::2]).astype(np.uint8).tobytes())
-            if qual_bits == 4:
+            if baseq:
+                pass
+            elif qual_bits == 4:
                 qc = np.array([qcode[int(x)] for x in np.asarray(q).tolist()], dtype=np.uint8)
                 if n & 1:
                     qc = np.concatenate([qc, np.zeros(1, np.uint8)])
@@ -264,8 +281,9 @@ def build_align_batch(regions: Sequence[RegionSpec], qual_bits: int = 8, compact
             alns.append((rbase + cal.read, cal.pos, len(segs), len(ins)))
             segs.extend(s)
             ins.extend(ib)
-    if qual_bits == 2:
+    if qual_bits == 2 and not baseq:
         qual.extend(_pack2(q2_codes))
+    exc_off.append(len(exc))
     for pool in (seq4, qual, ref, ins):
         pool.extend(b"\0" * (_pad16(len(pool)) - len(pool)))
     while len(segs) % seg_align:
@@ -300,6 +318,27 @@ def build_align_batch(regions: Sequence[RegionSpec], qual_bits: int = 8, compact
         if int(seg_arr["len"].max(initial=0)) <= 4095:
             seg_arr = (seg_arr["len"].astype(np.uint16) | (seg_arr["kind"].astype(np.uint16) << 12) | (seg_arr["flags"].astype(np.uint16) << 15)).astype(np.uint16)
             fmt |= A.SX_FMT_SEG2
+        if baseq:
+            fmt |= A.SX_FMT_BASEQ
+        # reference windows as BAM 4-bit codes (SX_FMT_REF4): repack window by window at new 16-byte aligned offsets
+        code_of_char = np.full(256, 15, np.uint8)
+        for ch, cd in zip(b"ACGT", (1, 2, 4, 8)):
+            code_of_char[ch] = cd
+        ref_arr = np.frombuffer(bytes(ref), dtype=np.uint8)
+        ref4 = bytearray()
+        for ri in range(len(regions)):
+            ref4.extend(b"\0" * (_pad16(len(ref4)) - len(ref4)))
+            o, n_ref = int(reg["ref_off"][ri]), int(reg["ref_len"][ri])
+            reg["ref_off"][ri] = len(ref4)
+            cw = code_of_char[ref_arr[o: o + n_ref]]
+            if n_ref & 1:
+                cw = np.concatenate([cw, np.zeros(1, np.uint8)])
+            ref4.extend(((cw[0::2] << 4) | cw[1::2]).astype(np.uint8).tobytes())
+        ref4.extend(b"\0" * (_pad16(len(ref4)) - len(ref4)))
+        reg["ref_off"][len(regions)] = len(ref4)
+        ref = ref4
+        used["ref"] = len(ref4)
+        fmt |= A.SX_FMT_REF4
     return AlignBatch(
         reg,
         np.array(read_len, dtype=np.uint16),
@@ -315,6 +354,8 @@ def build_align_batch(regions: Sequence[RegionSpec], qual_bits: int = 8, compact
         fmt,
         n_segs,
         len(alns) - 1,
+        np.array(exc_off, dtype=np.uint32) if baseq else None,
+        np.array(exc + [0], dtype=np.uint32) if baseq else None,
     )
 
 

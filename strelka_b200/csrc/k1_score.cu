@@ -69,8 +69,8 @@ __host__ __device__ __forceinline__ uint32_t pad16(uint32_t x) { return (x + 15u
 
 struct k1_layout
 {
-    uint32_t tab, alns, segs, ref, ins, seq, qual, rlen, boff, soff, eoff, desc, ent, total;
-    uint32_t n_reads, n_alns, seg_bytes, ref_bytes, ins_bytes, seq_bytes, qual_bytes;
+    uint32_t tab, alns, segs, ref, refp, ins, seq, qual, rlen, boff, soff, eoff, desc, ent, total;
+    uint32_t n_reads, n_alns, seg_bytes, ref_bytes, refp_bytes, ins_bytes, seq_bytes, qual_bytes;
 };
 
 __host__ __device__ __forceinline__ k1_layout k1_make_layout(const sx_region& r0, const sx_region& r1, uint32_t fmt)
@@ -82,7 +82,8 @@ __host__ __device__ __forceinline__ k1_layout k1_make_layout(const sx_region& r0
     L.ref_bytes = pad16(r0.ref_len);
     L.ins_bytes = pad16(r1.ins_begin - r0.ins_begin);
     L.seq_bytes = pad16(static_cast<uint32_t>(r1.seq_off - r0.seq_off));
-    L.qual_bytes = pad16(static_cast<uint32_t>(r1.qual_off - r0.qual_off));
+    L.qual_bytes = (fmt & SX_FMT_BASEQ) ? 0u : pad16(static_cast<uint32_t>(r1.qual_off - r0.qual_off));
+    L.refp_bytes = (fmt & SX_FMT_REF4) ? pad16((r0.ref_len + 1u) / 2u) : 0u;
     uint32_t o = 16; // mbarrier
     L.tab = o;
     o += K1_TAB_BYTES;
@@ -92,6 +93,8 @@ __host__ __device__ __forceinline__ k1_layout k1_make_layout(const sx_region& r0
     o += L.seg_bytes;
     L.ref = o;
     o += L.ref_bytes;
+    L.refp = o;
+    o += L.refp_bytes;
     L.ins = o;
     o += L.ins_bytes;
     L.seq = o;
@@ -128,7 +131,8 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
                                                               const char* __restrict__ ref, const sx_aln* __restrict__ alns,
                                                               const sx_aln_seg* __restrict__ segs, const char* __restrict__ ins,
                                                               const sx_tables* __restrict__ tables, uint32_t region_begin, double* __restrict__ lnp_out,
-                                                              int* __restrict__ status, uint32_t smem_bytes, uint32_t qual_bits, uint4 qual_dict, uint32_t fmt)
+                                                              int* __restrict__ status, uint32_t smem_bytes, uint32_t qual_bits, uint4 qual_dict, uint32_t fmt,
+                                                              const uint32_t* __restrict__ exc_off, const uint32_t* __restrict__ exc)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t ri = region_begin + blockIdx.x;
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     const double* tab = reinterpret_cast<const double*>(smem + L.tab);
     // alignment headers and segments, read through accessors that hide the wire format (sx_aln / sx_aln8, sx_aln_seg / sx_aln_seg2)
-    const bool aln8 = fmt & SX_FMT_ALN8, seg2 = fmt & SX_FMT_SEG2;
+    const bool aln8 = fmt & SX_FMT_ALN8, seg2 = fmt & SX_FMT_SEG2, baseq = fmt & SX_FMT_BASEQ, ref4 = fmt & SX_FMT_REF4;
     const uint32_t aln_skew = aln8 ? (r0.aln_begin & 1u) : 0u; // the sx_aln8 slice is staged from a 16-byte boundary
     const uint32_t n_segs_region = r1.seg_begin - r0.seg_begin;
     const unsigned char* alns_raw = smem + L.alns;
@@ -210,12 +214,13 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t aln_bytes = k1q::aln_slice_bytes(r0.aln_begin, L.n_alns, fmt);
-        const uint32_t tx = K1_TAB_BYTES + aln_bytes + L.seg_bytes + L.ref_bytes + L.ins_bytes + L.seq_bytes + L.qual_bytes;
+        const uint32_t ref_tx = ref4 ? L.refp_bytes : L.ref_bytes;
+        const uint32_t tx = K1_TAB_BYTES + aln_bytes + L.seg_bytes + ref_tx + L.ins_bytes + L.seq_bytes + L.qual_bytes;
         mbar_expect_tx(bar, tx);
         tma_bulk_g2s(smem + L.tab, tables->k1_tab, K1_TAB_BYTES, bar);
         tma_bulk_g2s(smem + L.alns, reinterpret_cast<const unsigned char*>(alns) + (aln8 ? (size_t)(r0.aln_begin & ~1u) * 8u : (size_t)r0.aln_begin * 16u), aln_bytes, bar);
         if (L.seg_bytes) tma_bulk_g2s(smem + L.segs, reinterpret_cast<const unsigned char*>(segs) + (size_t)r0.seg_begin * (seg2 ? 2u : 4u), L.seg_bytes, bar);
-        if (L.ref_bytes) tma_bulk_g2s(smem + L.ref, ref + r0.ref_off, L.ref_bytes, bar);
+        if (ref_tx) tma_bulk_g2s(smem + (ref4 ? L.refp : L.ref), ref + r0.ref_off, ref_tx, bar);
         if (L.ins_bytes) tma_bulk_g2s(smem + L.ins, ins + r0.ins_begin, L.ins_bytes, bar);
         if (L.seq_bytes) tma_bulk_g2s(smem + L.seq, seq4 + r0.seq_off, L.seq_bytes, bar);
         if (L.qual_bytes) tma_bulk_g2s(smem + L.qual, qual + r0.qual_off, L.qual_bytes, bar);
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
     }
     mbar_wait(bar, 0);
     __syncthreads();
-    if ((qual_bits == 2 ? (soff_s[L.n_reads] + 1) / 2 : qual_bits == 4 ? soff_s[L.n_reads] : boff_s[L.n_reads]) > L.qual_bytes || soff_s[L.n_reads] > L.seq_bytes)
+    if ((!baseq && (qual_bits == 2 ? (soff_s[L.n_reads] + 1) / 2 : qual_bits == 4 ? soff_s[L.n_reads] : boff_s[L.n_reads]) > L.qual_bytes) || soff_s[L.n_reads] > L.seq_bytes)
     {
         if (threadIdx.x == 0) atomicOr(status, 2);
         return;
@@ -280,9 +285,15 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
             for (uint32_t p = lane; p < npair; p += 32)
             {
                 const uint32_t byte = sq[p];
-                const uint32_t d0 = desc_s[byte >> 4], d1 = desc_s[byte & 15u]; // bam_seq::get_code: high nibble first
+                // bam_seq::get_code nibbles, high nibble first; SX_FMT_BASEQ nibbles are (base << 2) | quality code
+                const uint32_t d0 = desc_s[baseq ? (1u << (byte >> 6)) : (byte >> 4)], d1 = desc_s[baseq ? (1u << ((byte >> 2) & 3u)) : (byte & 15u)];
                 uint32_t q0, q1;
-                if (qual_bits == 4)
+                if (baseq)
+                {
+                    q0 = qd_s[(byte >> 4) & 3u];
+                    q1 = (2 * p + 1 < len) ? qd_s[byte & 3u] : 0u;
+                }
+                else if (qual_bits == 4)
                 {
                     const uint32_t qb = ql[p]; // both qualities of the pair in one byte, high nibble first
                     q0 = qd_s[qb >> 4];
@@ -308,6 +319,32 @@ __global__ void __launch_bounds__(K1_THREADS) k1_score_kernel(const sx_region* _
             }
         }
         if (qmax > SX_MAX_QSCORE) atomicOr(status, 1);
+        if (baseq && exc_off[ri + 1] > exc_off[ri])
+        {
+            // the bases that are not A/C/G/T: rebuild their entries from the real code (the nibble kept the quality code)
+            __syncthreads();
+            for (uint32_t i = exc_off[ri] + threadIdx.x; i < exc_off[ri + 1]; i += K1_THREADS)
+            {
+                const uint32_t v = exc[i], pos = v & 0xffffffu, d = desc_s[(v >> 24) & 15u];
+                if (pos >= 2u * soff_s[L.n_reads])
+                {
+                    atomicOr(status, 2);
+                    continue;
+                }
+                const uint32_t q = qd_s[(seq_s[pos >> 1] >> ((~pos & 1u) << 2)) & 3u];
+                ent_s[pos] = static_cast<uint16_t>((d & 0xffffu) + ((min(q, (uint32_t)SX_MAX_QSCORE) << 4) & (d >> 16)));
+            }
+        }
+        if (ref4)
+        {
+            const uint8_t* rp = smem + L.refp; // packed BAM codes -> one-hot codes, two per packed byte
+            for (uint32_t i = threadIdx.x; i < L.ref_bytes; i += K1_THREADS)
+            {
+                const uint32_t b = (i >> 1) < L.refp_bytes ? rp[i >> 1] : 0xffu, c = (i & 1u) ? (b & 15u) : (b >> 4);
+                ref_s[i] = static_cast<uint8_t>((c == 1u || c == 2u || c == 4u || c == 8u) ? c : 0u);
+            }
+        }
+        else
         for (uint32_t i = threadIdx.x; i < L.ref_bytes; i += K1_THREADS) ref_s[i] = onehot_of_char(ref_s[i]);
         for (uint32_t i = threadIdx.x; i < L.ins_bytes; i += K1_THREADS) ins_s[i] = onehot_of_char(ins_s[i]);
     }
@@ -555,7 +592,7 @@ int sx_k1_launch(sx_ctx* ctx, const sx_align_batch* d, uint32_t region_begin, ui
     uint4 qd;
     memcpy(&qd, d->qual_dict, 16);
     k1_score_kernel<<<region_end - region_begin, K1_THREADS, smem_bytes, st>>>(d->regions, d->read_len, d->seq4, d->qual, d->ref, d->alns, d->segs, d->ins,
-                                                                              ctx->d_tables, region_begin, lnp_dev, ctx->d_status, static_cast<uint32_t>(smem_bytes), d->qual_bits == 4 ? 4u : d->qual_bits == 2 ? 2u : 8u, qd, d->format);
+                                                                              ctx->d_tables, region_begin, lnp_dev, ctx->d_status, static_cast<uint32_t>(smem_bytes), d->qual_bits == 4 ? 4u : d->qual_bits == 2 ? 2u : 8u, qd, d->format, d->exc_off, d->exc);
     SX_CUDA(ctx, cudaGetLastError());
     return SX_OK;
 }
@@ -588,12 +625,20 @@ extern "C" uint64_t sx_align_batch_cells(const sx_align_batch* b)
 static int validate_host_batch(sx_ctx* ctx, const sx_align_batch* b, size_t* max_smem, size_t* max_smem_fast)
 {
     if (!b || !b->regions || !b->alns || (b->n_reads && !b->read_len)) return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments: NULL batch array");
+    if (b->format & SX_FMT_BASEQ)
+    {
+        if (b->qual_bits != 2 || !b->exc_off || (b->exc_off[b->n_regions] && !b->exc))
+            return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments: SX_FMT_BASEQ needs qual_bits == 2 and the exception arrays");
+        for (int i = 0; i < 4; ++i)
+            if (b->qual_dict[i] > SX_MAX_QSCORE)
+                return sx_fail(ctx, SX_ERR_RANGE, "sx_score_alignments: SX_FMT_BASEQ dictionary quality %d above %d (send such batches with a quality pool)", b->qual_dict[i], SX_MAX_QSCORE);
+    }
     size_t m = 0, mq = 0;
     for (uint32_t i = 0; i < b->n_regions; ++i)
     {
         const sx_region& r = b->regions[i];
         const sx_region& n = b->regions[i + 1];
-        if ((r.seq_off | r.qual_off | r.ref_off | r.ins_begin) & 15u || (r.seg_begin & ((b->format & SX_FMT_SEG2) ? 7u : 3u)))
+        if ((r.seq_off | ((b->format & SX_FMT_BASEQ) ? 0u : r.qual_off) | r.ref_off | r.ins_begin) & 15u || (r.seg_begin & ((b->format & SX_FMT_SEG2) ? 7u : 3u)))
             return sx_fail(ctx, SX_ERR_ALIGNMENT, "sx_score_alignments: region %u violates the 16-byte staging rule (seq_off %llu qual_off %llu ref_off %llu ins_begin %u seg_begin %u)", i,
                            (unsigned long long)r.seq_off, (unsigned long long)r.qual_off, (unsigned long long)r.ref_off, r.ins_begin, r.seg_begin);
         if (n.read_begin < r.read_begin || n.aln_begin < r.aln_begin || n.seg_begin < r.seg_begin || n.ins_begin < r.ins_begin || n.seq_off < r.seq_off ||
@@ -680,6 +725,11 @@ extern "C" int sx_score_alignments(sx_ctx* ctx, const sx_align_batch* b, double*
     SX_POOL(5, alns, const sx_aln*, aln_bytes)
     SX_POOL(6, segs, const sx_aln_seg*, seg_bytes)
     SX_POOL(7, ins, const char*, b->ins_bytes + SX_POOL_SLACK)
+    if (b->format & SX_FMT_BASEQ)
+    {
+        SX_POOL(24, exc_off, const uint32_t*, (size_t)(b->n_regions + 1) * 4)
+        SX_POOL(25, exc, const uint32_t*, (size_t)b->exc_off[b->n_regions] * 4 + 16)
+    }
 #undef SX_POOL
     double* d_out = nullptr;
     if ((rc = sx_ensure(ctx, 8, (size_t)b->n_alns * sizeof(double), reinterpret_cast<void**>(&d_out)))) return rc;
@@ -706,6 +756,12 @@ extern "C" int sx_score_alignments(sx_ctx* ctx, const sx_align_batch* b, double*
     SX_CUDA(ctx, cudaMemcpyAsync(const_cast<sx_region*>(d.regions), b->regions, reg_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
     SX_CUDA(ctx, cudaMemcpyAsync(const_cast<uint16_t*>(d.read_len), b->read_len, (size_t)b->n_reads * 2, cudaMemcpyHostToDevice, ctx->s_h2d));
     SX_CUDA(ctx, cudaMemcpyAsync(const_cast<char*>(d.ref), b->ref, b->ref_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+    if (b->format & SX_FMT_BASEQ)
+    {
+        SX_CUDA(ctx, cudaMemcpyAsync(const_cast<uint32_t*>(d.exc_off), b->exc_off, (size_t)(b->n_regions + 1) * 4, cudaMemcpyHostToDevice, ctx->s_h2d));
+        if (b->exc_off[b->n_regions])
+            SX_CUDA(ctx, cudaMemcpyAsync(const_cast<uint32_t*>(d.exc), b->exc, (size_t)b->exc_off[b->n_regions] * 4, cudaMemcpyHostToDevice, ctx->s_h2d));
+    }
     for (int c = 0; c < chunks; ++c)
     {
         const uint32_t ra = (uint32_t)((uint64_t)b->n_regions * c / chunks);
@@ -717,7 +773,7 @@ extern "C" int sx_score_alignments(sx_ctx* ctx, const sx_align_batch* b, double*
             return cudaMemcpyAsync((char*)const_cast<void*>(dbase) + lo, (const char*)hbase + lo, hi - lo, cudaMemcpyHostToDevice, ctx->s_h2d);
         };
         SX_CUDA(ctx, cp(b->seq4, d.seq4, A.seq_off, B.seq_off));
-        SX_CUDA(ctx, cp(b->qual, d.qual, A.qual_off, B.qual_off));
+        if (!(b->format & SX_FMT_BASEQ)) SX_CUDA(ctx, cp(b->qual, d.qual, A.qual_off, B.qual_off));
         SX_CUDA(ctx, cp(b->alns, d.alns, (size_t)A.aln_begin * aln_sz, (size_t)(B.aln_begin + 1) * aln_sz));
         SX_CUDA(ctx, cp(b->segs, d.segs, (size_t)A.seg_begin * seg_sz, (size_t)B.seg_begin * seg_sz));
         SX_CUDA(ctx, cp(b->ins, d.ins, A.ins_begin, B.ins_begin));

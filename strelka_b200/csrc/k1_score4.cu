@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
                                                                const char* __restrict__ ref, const sx_aln* __restrict__ alns,
                                                                const sx_aln_seg* __restrict__ segs, const char* __restrict__ ins,
                                                                const sx_tables* __restrict__ tables, uint32_t region_begin, double* __restrict__ lnp_out,
-                                                               int* __restrict__ status, uint32_t smem_bytes, uint4 qual_dict, uint32_t fmt, uint32_t qual_bits)
+                                                               int* __restrict__ status, uint32_t smem_bytes, uint4 qual_dict, uint32_t fmt, uint32_t qual_bits,
+                                                               const uint32_t* __restrict__ exc_off, const uint32_t* __restrict__ exc)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t ri = region_begin + blockIdx.x;
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
     uint8_t* e8 = smem + L.e8;
     double* tab = reinterpret_cast<double*>(smem + (tab_saddr - sbase)); // [4 pages][16 quality codes][match, mismatch]
     // alignment headers and segments, read through accessors that hide the wire format (sx_aln / sx_aln8, sx_aln_seg / sx_aln_seg2)
-    const bool aln8 = fmt & SX_FMT_ALN8, seg2 = fmt & SX_FMT_SEG2;
+    const bool aln8 = fmt & SX_FMT_ALN8, seg2 = fmt & SX_FMT_SEG2, baseq = fmt & SX_FMT_BASEQ, ref4 = fmt & SX_FMT_REF4;
     const uint32_t aln_skew = aln8 ? (r0.aln_begin & 1u) : 0u; // the sx_aln8 slice is staged from a 16-byte boundary
     const unsigned char* alns_raw = smem + L.alns;
     const unsigned char* segs_raw = smem + L.segs;
@@ -201,13 +202,14 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t aln_bytes = aln_slice_bytes(r0.aln_begin, L.n_alns, fmt);
-        const uint32_t tx = aln_bytes + L.seg_bytes + L.ref_bytes + L.ins_bytes + L.seq_bytes + L.qual_bytes;
+        const uint32_t ref_tx = ref4 ? L.refp_bytes : L.ref_bytes;
+        const uint32_t tx = aln_bytes + L.seg_bytes + ref_tx + L.ins_bytes + L.seq_bytes + L.qual_bytes;
         mbar_expect_tx(bar, tx);
         const unsigned char* aln_src = reinterpret_cast<const unsigned char*>(alns) + (aln8 ? (size_t)(r0.aln_begin & ~1u) * 8u : (size_t)r0.aln_begin * 16u);
         const unsigned char* seg_src = reinterpret_cast<const unsigned char*>(segs) + (size_t)r0.seg_begin * (seg2 ? 2u : 4u);
         tma_bulk_g2s(smem + L.alns, aln_src, aln_bytes, bar);
         if (L.seg_bytes) tma_bulk_g2s(smem + L.segs, seg_src, L.seg_bytes, bar);
-        if (L.ref_bytes) tma_bulk_g2s(smem + L.ref, ref + r0.ref_off, L.ref_bytes, bar);
+        if (ref_tx) tma_bulk_g2s(smem + (ref4 ? L.refp : L.ref), ref + r0.ref_off, ref_tx, bar);
         if (L.ins_bytes) tma_bulk_g2s(smem + L.ins, ins + r0.ins_begin, L.ins_bytes, bar);
         if (L.seq_bytes) tma_bulk_g2s(smem + L.seq, seq4 + r0.seq_off, L.seq_bytes, bar);
         if (L.qual_bytes) tma_bulk_g2s(smem + L.qual, qual4 + r0.qual_off, L.qual_bytes, bar);
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
     }
     mbar_wait(bar, 0);
     __syncthreads();
-    if (soff_s[L.n_reads] > L.seq_bytes || (qual_bits == 2 ? (soff_s[L.n_reads] + 1) / 2 : soff_s[L.n_reads]) > L.qual_bytes)
+    if (soff_s[L.n_reads] > L.seq_bytes || (!baseq && (qual_bits == 2 ? (soff_s[L.n_reads] + 1) / 2 : soff_s[L.n_reads]) > L.qual_bytes))
     {
         if (tid == 0) atomicOr(status, 2);
         return;
@@ -249,6 +251,38 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
         const uint32_t e8_s = sbase + L.e8;
         const uint32_t nw = (soff_s[L.n_reads] + 3u) >> 2;
         uint32_t acc = 0;
+        if (baseq)
+        {
+            // one nibble per base, (base << 2) | quality code: the entry (code << 4 | page 0 << 2 | base) is a bit shuffle, no lookup;
+            // the host guarantees every dictionary quality <= 70 in this format
+            for (uint32_t w = tid; w < nw; w += KQ_THREADS)
+            {
+                const uint32_t s = seq32[w];
+                const uint32_t h = (s >> 4) & 0x0f0f0f0fu, l = s & 0x0f0f0f0fu;  // first / second bases of the four packed bytes
+                const uint32_t eh = ((h & 0x03030303u) << 4) | ((h >> 2) & 0x03030303u);
+                const uint32_t el = ((l & 0x03030303u) << 4) | ((l >> 2) & 0x03030303u);
+                ent64[w] = make_uint2(prmt(eh, el, 0x5140u), prmt(eh, el, 0x7362u)); // interleave back into read order
+            }
+            // the bases that are not A/C/G/T: 'N' -> zero page, '=' -> always-match page, IUPAC -> never-match page (quality code kept)
+            const uint32_t x0 = exc_off[ri], x1 = exc_off[ri + 1];
+            if (x1 > x0)
+            {
+                __syncthreads();
+                uint8_t* ent8 = smem + L.ent;
+                for (uint32_t i = x0 + tid; i < x1; i += KQ_THREADS)
+                {
+                    const uint32_t v = exc[i], pos = v & 0xffffffu, code = v >> 24;
+                    if (pos >= 2u * soff_s[L.n_reads])
+                    {
+                        atomicOr(status, 2);
+                        continue;
+                    }
+                    const uint32_t page = code == 15u ? PAGE_ZERO : code == 0u ? PAGE_EQ : PAGE_NOMATCH;
+                    ent8[pos] = static_cast<uint8_t>((ent8[pos] & 0xf0u) | (page << 2));
+                }
+            }
+        }
+        else
         for (uint32_t w = tid; w < nw; w += KQ_THREADS)
         {
             const uint32_t s = seq32[w];
@@ -277,6 +311,21 @@ __global__ void __launch_bounds__(KQ_THREADS) k1q_score_kernel(const sx_region* 
         }
         if (acc & 0x01010101u) atomicOr(status, 1);
         uint32_t* ref32 = reinterpret_cast<uint32_t*>(ref_s);
+        if (ref4)
+        {
+            // packed BAM codes -> one reference code per byte (two per packed byte, high nibble first)
+            const uint8_t* rp = smem + L.refp;
+            uint16_t* ref16 = reinterpret_cast<uint16_t*>(ref_s);
+            for (uint32_t i = tid; i < L.ref_bytes / 2; i += KQ_THREADS)
+            {
+                const uint32_t b = i < L.refp_bytes ? rp[i] : 0xffu;
+                const uint32_t hi = b >> 4, lo = b & 15u;
+                const uint32_t ch = hi == 1u ? 0u : hi == 2u ? 1u : hi == 4u ? 2u : hi == 8u ? 3u : REF_OTHER;
+                const uint32_t cl = lo == 1u ? 0u : lo == 2u ? 1u : lo == 4u ? 2u : lo == 8u ? 3u : REF_OTHER;
+                ref16[i] = static_cast<uint16_t>(ch | (cl << 8));
+            }
+        }
+        else
         for (uint32_t i = tid; i < L.ref_bytes / 4; i += KQ_THREADS)
         {
             const uint32_t v = ref32[i];
@@ -457,7 +506,7 @@ int sx_k1q_launch(sx_ctx* ctx, const sx_align_batch* d, uint32_t region_begin, u
     uint4 qd;
     memcpy(&qd, d->qual_dict, 16);
     k1q_score_kernel<<<region_end - region_begin, k1q::KQ_THREADS, smem_bytes, st>>>(d->regions, d->read_len, d->seq4, d->qual, d->ref, d->alns, d->segs, d->ins,
-                                                                                    ctx->d_tables, region_begin, lnp_dev, ctx->d_status, static_cast<uint32_t>(smem_bytes), qd, d->format, d->qual_bits);
+                                                                                    ctx->d_tables, region_begin, lnp_dev, ctx->d_status, static_cast<uint32_t>(smem_bytes), qd, d->format, d->qual_bits, d->exc_off, d->exc);
     SX_CUDA(ctx, cudaGetLastError());
     return SX_OK;
 }

@@ -16,8 +16,8 @@ __host__ __device__ __forceinline__ uint32_t pad16(uint32_t x) { return (x + 15u
 
 struct layout
 {
-    uint32_t lut, e8, tab, alns, segs, recs, ref, ins, seq, qual, rlen, soff, ent, total;
-    uint32_t n_reads, n_alns, n_segs, seg_bytes, ref_bytes, ins_bytes, seq_bytes, qual_bytes;
+    uint32_t lut, e8, tab, alns, segs, recs, ref, refp, ins, seq, qual, rlen, soff, ent, total;
+    uint32_t n_reads, n_alns, n_segs, seg_bytes, ref_bytes, refp_bytes, ins_bytes, seq_bytes, qual_bytes;
 };
 
 // bytes of the alignment-header slice as the kernels stage it: wide headers are 16 bytes each (+ the next one, which closes the last
@@ -37,7 +37,8 @@ __host__ __device__ __forceinline__ layout make_layout(const sx_region& r0, cons
     L.ref_bytes = pad16(r0.ref_len);
     L.ins_bytes = pad16(r1.ins_begin - r0.ins_begin);
     L.seq_bytes = pad16(static_cast<uint32_t>(r1.seq_off - r0.seq_off));
-    L.qual_bytes = pad16(static_cast<uint32_t>(r1.qual_off - r0.qual_off));
+    L.qual_bytes = (fmt & SX_FMT_BASEQ) ? 0u : pad16(static_cast<uint32_t>(r1.qual_off - r0.qual_off)); // BASEQ: qualities ride in the base nibbles
+    L.refp_bytes = (fmt & SX_FMT_REF4) ? pad16((r0.ref_len + 1u) / 2u) : 0u;                         // REF4: packed window, unpacked into `ref`
     uint32_t o = 16; // mbarrier
     L.lut = o;
     o += KQ_LUT_BYTES;
@@ -53,6 +54,8 @@ __host__ __device__ __forceinline__ layout make_layout(const sx_region& r0, cons
     o += pad16((L.n_segs + L.n_alns) * 8u);
     L.ref = o;
     o += L.ref_bytes;
+    L.refp = o;
+    o += L.refp_bytes;
     L.ins = o;
     o += L.ins_bytes;
     L.seq = o;

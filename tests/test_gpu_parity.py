@@ -85,7 +85,7 @@ def test_k1_compact_wire_formats(ctx, qb, compact):
         wide = B.build_align_batch(regs)
         want = reflib.ox_score(wide)
         cb = B.build_align_batch(regs, qual_bits=qb, compact=compact)
-        assert cb.fmt == (3 if compact else 0)
+        assert cb.fmt == (0 if not compact else 15 if qb == 2 else 11)  # ALN8 | SEG2 | REF4 (| BASEQ with the 2-bit dictionary)
         assert np.array_equal(_bits(ctx.score_alignments(cb)), _bits(want))
         if not with_large:
             # the chunk-pipelined host entry with chunk borders at arbitrary (odd) alignment indices

@@ -136,7 +136,7 @@ def test_compact_wire_formats_are_lossless(seed):
     want = reflib.ox_score(wide)
     for qb, compact in ((8, True), (4, True), (2, False), (2, True)):
         cb = B.build_align_batch(regions, qual_bits=qb, compact=compact)
-        assert cb.fmt == (3 if compact else 0)
+        assert cb.fmt == (0 if not compact else 15 if qb == 2 else 11)  # ALN8 | SEG2 | REF4 (| BASEQ with the 2-bit dictionary)
         assert cb.cells() == wide.cells()
         assert np.array_equal(reflib.ox_score(cb).view(np.uint64), want.view(np.uint64)), (qb, compact)
         got = np.zeros(cb.n_alns, np.float64)
