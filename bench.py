@@ -82,9 +82,12 @@ class HostAlloc:
 
 
 def make_workload(synth, alloc: HostAlloc, n_loci: int, depth: int, read_len: int, n_haps: int, seed: int, threads: int, qual_bits: int = 2, reads_per_region: int = 0,
-                  fmt: int = A.SX_FMT_ALN8 | A.SX_FMT_SEG2):
-    """The K1/K2a/K3 inputs of n_loci candidate loci.  Defaults = the most compact wire formats of include/strelka_b200.h (2-bit
-    quality codes, 8-byte alignment headers, 2-byte segments): the host entry points are PCIe-bound, so bytes are throughput."""
+                  fmt: int = A.SX_FMT_ALN8 | A.SX_FMT_SEG2 | A.SX_FMT_BASEQ | A.SX_FMT_REF4):
+    """The K1/K2a/K3 inputs of n_loci candidate loci.  Defaults = the most compact wire formats of include/strelka_b200.h (base and
+    2-bit quality code in one nibble, 8-byte alignment headers, 2-byte segments, packed reference windows): the host entry points
+    are PCIe-bound, so bytes are throughput."""
+    if qual_bits != 2:
+        fmt &= ~A.SX_FMT_BASEQ
     rpr = min(reads_per_region, depth) if reads_per_region else depth
     n_regions = n_loci * ((depth + rpr - 1) // rpr)  # a locus deeper than rpr reads is cut into regions sharing its reference window
     regions = alloc.array((n_regions + 1) * A.REGION_DT.itemsize, A.REGION_DT)
@@ -106,8 +109,14 @@ def make_workload(synth, alloc: HostAlloc, n_loci: int, depth: int, read_len: in
                              C.c_void_p(alns.ctypes.data), C.c_void_p(segs.ctypes.data), C.c_void_p(ins.ctypes.data))
     assert rc == 0, rc
     used = {"seq4": int(sz.seq4_bytes), "qual": int(sz.qual_bytes), "ref": int(sz.ref_bytes), "ins": int(sz.ins_bytes)}
+    exc_off = exc = None
+    if fmt & A.SX_FMT_BASEQ:  # the generator emits A/C/G/T only: an empty exception list
+        exc_off, exc = alloc.array((n_regions + 1) * 4, np.uint32), alloc.array(16, np.uint32)
+        exc_off[:] = 0
+        exc[:] = 0
     ab = B.AlignBatch(regions[: n_regions + 1], read_lens[: sz.n_reads], seq4, qual, ref, alns[: sz.n_alns + 3], segs, ins, used, qual_bits,
-                      [11, 25, 37] if qual_bits in (2, 4) else None, fmt, int(sz.n_segs), int(sz.n_alns))
+                      [11, 25, 37] if qual_bits in (2, 4) else None, fmt, int(sz.n_segs), int(sz.n_alns),
+                      exc_off, exc)
     # K2a: one pileup column per locus
     site_off = alloc.array((n_loci + 1) * 4, np.uint32)
     n_calls = synth.synth_pileups(n_loci, C.c_double(float(depth)), 0, C.c_uint64(seed), threads, C.c_void_p(site_off.ctypes.data), None, None)

@@ -398,7 +398,47 @@ private:
                 code[q] = static_cast<uint8_t>(nq++);
             }
         const unsigned qbits(nq <= 4 ? 2 : nq <= 16 ? 4 : 8);
-        if (qbits != 8)
+        bool allCallable(true); // SX_FMT_BASEQ needs every quality <= 70 (a larger one must reach the kernel's range check)
+        for (unsigned q(71); q < 256; ++q) allCallable = allCallable && !seen[q];
+        if (qbits == 2 && allCallable)
+        {
+            // base and quality code in one nibble; the bases that are not A/C/G/T go to the exception list
+            _excOff.assign(_regions.size() + 1, 0);
+            _exc.clear();
+            for (size_t ri(0); ri < _regions.size(); ++ri)
+            {
+                _excOff[ri] = static_cast<uint32_t>(_exc.size());
+                size_t qo(_regions[ri].qual_off), so(_regions[ri].seq_off);
+                const size_t r1(ri + 1 < _regions.size() ? _regions[ri + 1].read_begin : _readLen.size());
+                for (size_t r(_regions[ri].read_begin); r < r1; ++r)
+                {
+                    const unsigned len(_readLen[r]);
+                    for (unsigned i(0); i < len; ++i)
+                    {
+                        uint8_t& byte(_seq4Out[so + (i >> 1)]);
+                        const unsigned sh((~i & 1) << 2), bam((byte >> sh) & 15), qc(code[_qual[qo++]]);
+                        unsigned base(0);
+                        if (bam == 1) base = 0;
+                        else if (bam == 2) base = 1;
+                        else if (bam == 4) base = 2;
+                        else if (bam == 8) base = 3;
+                        else _exc.push_back(SX_EXC(2 * (so - _regions[ri].seq_off) + i, bam));
+                        byte = static_cast<uint8_t>((byte & ~(15u << sh)) | (((base << 2) | qc) << sh));
+                    }
+                    so += (len + 1) / 2;
+                }
+                _regionsOut[ri].qual_off = 0;
+            }
+            _excOff[_regions.size()] = static_cast<uint32_t>(_exc.size());
+            _exc.push_back(0);
+            _regionsOut.back().qual_off = 0;
+            b.qual_bytes = 0;
+            b.qual_bits = 2;
+            b.exc_off = _excOff.data();
+            b.exc = _exc.data();
+            b.format |= SX_FMT_BASEQ;
+        }
+        else if (qbits != 8)
         {
             _qualOut.clear();
             for (size_t ri(0); ri < _regions.size(); ++ri)
@@ -461,6 +501,26 @@ private:
             b.alns = reinterpret_cast<const sx_aln*>(_alns8Out.data());
             b.format |= SX_FMT_ALN8;
         }
+        // ---- reference windows as BAM 4-bit codes
+        {
+            std::vector<char> packed;
+            for (size_t ri(0); ri < _regions.size(); ++ri)
+            {
+                while (packed.size() & 15) packed.push_back(0);
+                const size_t o(_regions[ri].ref_off), n(_regions[ri].ref_len);
+                _regionsOut[ri].ref_off = packed.size();
+                for (size_t i(0); i < n; i += 2)
+                    packed.push_back(static_cast<char>((get_bam_seq_code(_ref[o + i] == '=' ? 'N' : _ref[o + i]) << 4) |
+                                                       (i + 1 < n ? get_bam_seq_code(_ref[o + i + 1] == '=' ? 'N' : _ref[o + i + 1]) : 0)));
+            }
+            while (packed.size() & 15) packed.push_back(0);
+            _regionsOut.back().ref_off = packed.size();
+            b.ref_bytes = packed.size();
+            packed.resize(packed.size() + SX_POOL_SLACK);
+            _refOut.swap(packed);
+            b.ref = _refOut.data();
+            b.format |= SX_FMT_REF4;
+        }
         // ---- segments: 12-bit lengths
         fits = true;
         for (const sx_aln_seg& sg : _segs) fits = fits && sg.len <= 4095;
@@ -476,6 +536,7 @@ private:
     bool _open = false;
     bool _compact = true;
     std::vector<sx_aln8> _alns8Out;
+    std::vector<uint32_t> _excOff, _exc;
     std::vector<sx_aln_seg2> _segs2Out;
     std::vector<sx_region> _regions, _regionsOut;
     std::vector<uint16_t> _readLen;

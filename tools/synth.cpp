@@ -139,7 +139,16 @@ void gen_region(const k1_cfg& c, uint32_t rg, bool fill, region_sizes& sz, const
     std::vector<char> refv(c.ref_len);
     make_locus(c, l, r, d, refv.data());
     const uint32_t locus = c.ref_len / 2; // window-relative (the window's contig coordinate is reg->ref_begin, set by synth_k1_plan)
-    if (fill) memcpy(ref_pool + reg->ref_off, refv.data(), c.ref_len);
+    if (fill)
+    {
+        if (c.fmt & SX_FMT_REF4) // BAM 4-bit codes, two bases per byte, high nibble first
+        {
+            uint8_t* rp = reinterpret_cast<uint8_t*>(ref_pool) + reg->ref_off;
+            memset(rp, 0, (c.ref_len + 1) / 2);
+            for (uint32_t i = 0; i < c.ref_len; ++i) rp[i >> 1] |= code_of(refv[i]) << ((~i & 1) << 2);
+        }
+        else memcpy(ref_pool + reg->ref_off, refv.data(), c.ref_len);
+    }
     // genotype: two haplotype indices
     const uint32_t g0 = r.below(c.n_haps), g1 = r.below(3) ? r.below(c.n_haps) : g0;
     uint32_t ins_off = fill ? reg->ins_begin : 0;
@@ -147,7 +156,7 @@ void gen_region(const k1_cfg& c, uint32_t rg, bool fill, region_sizes& sz, const
     const uint32_t segs_per_read = 1 + 3 * d.n_alt;
     const uint32_t packed = (c.read_len + 1) / 2;
     std::vector<char> rd(c.read_len);
-    if (fill && c.qual_bits == 2) memset(qual + reg->qual_off, 0, qual_slice_bytes(c, k_end - k_begin));
+    if (fill && c.qual_bits == 2 && !(c.fmt & SX_FMT_BASEQ)) memset(qual + reg->qual_off, 0, qual_slice_bytes(c, k_end - k_begin));
     for (uint32_t k = 0; k < k_begin; ++k) // reads of earlier regions of this locus: consume their structure draws
     {
         r.below(c.read_len - 20);
@@ -189,14 +198,19 @@ void gen_region(const k1_cfg& c, uint32_t rg, bool fill, region_sizes& sz, const
                 char b = rd[i];
                 if (rb.unit() < QERR[q == 11 ? 0 : q == 25 ? 1 : 2]) b = BASES[rb.below(4)];
                 const uint32_t qcode = q == 11 ? 0 : q == 25 ? 1 : 2;
-                if (c.qual_bits == 2)
+                if (c.fmt & SX_FMT_BASEQ)
+                {
+                    // the quality code rides in the base nibble (below); no quality pool
+                }
+                else if (c.qual_bits == 2)
                 {
                     const uint64_t pos = (uint64_t)ridx * packed * 2 + i; // nibble position in the region's seq4 slice
                     ql[pos >> 2] |= qcode << (6 - 2 * (pos & 3));
                 }
                 else if (c.qual_bits == 4) ql[i >> 1] |= qcode << ((~i & 1) << 2);
                 else ql[i] = (uint8_t)q;
-                sq[i >> 1] |= code_of(b) << ((~i & 1) << 2);
+                if (c.fmt & SX_FMT_BASEQ) sq[i >> 1] |= (((b == 'A' ? 0u : b == 'C' ? 1u : b == 'G' ? 2u : 3u) << 2) | qcode) << ((~i & 1) << 2);
+                else sq[i >> 1] |= code_of(b) << ((~i & 1) << 2);
             }
         }
         // alignments: one per haplotype
@@ -296,8 +310,8 @@ int synth_k1_plan(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n
         if (rg == n_regions) break;
         reads += nr;
         seq += pad16((uint64_t)nr * packed);
-        qual += pad16(qual_slice_bytes(c, nr));
-        ref += pad16(c.ref_len);
+        qual += (fmt & SX_FMT_BASEQ) ? 0 : pad16(qual_slice_bytes(c, nr));
+        ref += pad16((fmt & SX_FMT_REF4) ? (c.ref_len + 1) / 2 : c.ref_len);
         insb += pad16(ins[rg]);
         seg += (fmt & SX_FMT_SEG2) ? (((uint64_t)nr * (1 + 3 * (n_haps - 1)) + 7u) & ~7ull) : (((uint64_t)nr * (1 + 3 * (n_haps - 1)) + 3u) & ~3ull);
     }
