@@ -422,6 +422,9 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_align_kernel(const char* __r
     }
 }
 
+// upper bound on resident CTAs per SM used for the grid and for the scratch sizing (strips of 10+ rows need > 100 registers)
+inline int kg_max_ctas_per_sm(int T) { return T >= 10 ? 4 : 8; }
+
 template <int T>
 int kg_launch(sx_ctx* ctx, const sx_ga_scores* sc, const sx_ga_batch* d, sx_ga_result* res_dev, uint32_t* cigar_dev, const uint32_t* order, uint32_t n, uint32_t max_r,
               int scratch_slot_id, uint32_t* work_dev)
@@ -430,11 +433,15 @@ int kg_launch(sx_ctx* ctx, const sx_ga_scores* sc, const sx_ga_batch* d, sx_ga_r
     const size_t smem = (size_t)kg_warp_smem<T>(max_r) * KG_WARPS;
     const size_t slot = (((size_t)(max_r + KG_G) * T * 32) + 255) & ~size_t(255);
     const uint32_t quads = (n + 3) / 4;
-    const int grid = static_cast<int>(std::min<uint32_t>((quads + KG_WARPS - 1) / KG_WARPS, (uint32_t)ctx->sm_count * 4));
+    if (smem > 48 * 1024) SX_CUDA(ctx, cudaFuncSetAttribute(kg_align_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+    // persistent grid: as many CTAs per SM as the instantiation's registers / shared memory allow (4 for the tall strips, more below)
+    int occ = 4;
+    SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kg_align_kernel<T>, KG_WARPS * 32, smem));
+    occ = std::max(1, std::min(occ, kg_max_ctas_per_sm(T)));
+    const int grid = static_cast<int>(std::min<uint32_t>((quads + KG_WARPS - 1) / KG_WARPS, (uint32_t)(ctx->sm_count * occ)));
     unsigned char* scratch = nullptr;
     int rc = sx_ensure(ctx, scratch_slot_id, slot * KG_B * (size_t)grid * KG_WARPS, reinterpret_cast<void**>(&scratch));
     if (rc) return rc;
-    if (smem > 48 * 1024) SX_CUDA(ctx, cudaFuncSetAttribute(kg_align_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
     kg_align_kernel<T><<<grid, KG_WARPS * 32, smem, ctx->s_compute>>>(d->query, d->ref, d->query_off, d->ref_off, order, n, d->max_ops, *sc, res_dev, cigar_dev, max_r, scratch,
                                                                      slot, work_dev);
     SX_CUDA(ctx, cudaGetLastError());
@@ -482,9 +489,10 @@ int sx_k3_group_run(sx_ctx* ctx, const sx_ga_scores* sc, const sx_ga_batch* d, s
     {
         size_t worst = 0;
         for (int t = 1; t <= 16; ++t)
-            if (begin[t * KG_RCLASSES] > begin[(t - 1) * KG_RCLASSES]) worst = std::max(worst, ((size_t)(info.max_r[t - 1] + KG_G) * t * 32 + 255) & ~size_t(255));
+            if (begin[t * KG_RCLASSES] > begin[(t - 1) * KG_RCLASSES])
+                worst = std::max(worst, (((size_t)(info.max_r[t - 1] + KG_G) * t * 32 + 255) & ~size_t(255)) * kg_max_ctas_per_sm(t));
         void* p = nullptr;
-        if (worst && (rc = sx_ensure(ctx, 23, worst * KG_B * (size_t)ctx->sm_count * 4 * KG_WARPS, &p))) return rc;
+        if (worst && (rc = sx_ensure(ctx, 23, worst * KG_B * (size_t)ctx->sm_count * KG_WARPS, &p))) return rc;
     }
     KG_CASE(1) KG_CASE(2) KG_CASE(3) KG_CASE(4) KG_CASE(5) KG_CASE(6) KG_CASE(7) KG_CASE(8)
     KG_CASE(9) KG_CASE(10) KG_CASE(11) KG_CASE(12) KG_CASE(13) KG_CASE(14) KG_CASE(15) KG_CASE(16)
