@@ -364,12 +364,15 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline4_kernel(const uint
                                                                       const char* __restrict__ ref_base, const uint8_t* __restrict__ ploidy,
                                                                       uint32_t n_sites, int is_always_test, const sx_tables* __restrict__ tables,
                                                                       sx_digt_result* __restrict__ out, uint32_t* __restrict__ de_off,
-                                                                      float* __restrict__ de_out, int* __restrict__ status)
+                                                                      float* __restrict__ de_out, int* __restrict__ status, uint32_t cap)
 {
     __shared__ germ_tables T;
-    __shared__ uint16_t s_calls[K2_WARPS][K2_BATCH][K2_CAP_SMEM];
-    __shared__ float s_val[K2_WARPS][K2_BATCH][K2_CAP_SMEM];
-    __shared__ uint16_t s_ord[K2_WARPS][K2_BATCH][K2_CAP_SMEM];
+    // per (warp, site slot): `cap` cleaned calls (uint16), their values (float), the per-group order (uint16).  cap = the batch's
+    // deepest site rounded up to 32: shallow batches leave room for more resident CTAs.
+    extern __shared__ __align__(16) unsigned char k2_dyn[];
+    float* const s_val_all = reinterpret_cast<float*>(k2_dyn);
+    uint16_t* const s_calls_all = reinterpret_cast<uint16_t*>(k2_dyn + (size_t)K2_WARPS * K2_BATCH * cap * 4);
+    uint16_t* const s_ord_all = s_calls_all + (size_t)K2_WARPS * K2_BATCH * cap;
     __shared__ uint32_t s_gstart[K2_WARPS][K2_BATCH][9];
     __shared__ uint32_t s_n[K2_WARPS][K2_BATCH];
     for (int i = threadIdx.x; i <= SX_MAX_QSCORE; i += blockDim.x)
@@ -399,9 +402,9 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline4_kernel(const uint
         uint32_t nonref_mask = 0;
         for (uint32_t s = 0; s < K2_BATCH; ++s)
         {
-            uint16_t* w_calls = s_calls[warp][s];
-            float* w_val = s_val[warp][s];
-            uint16_t* w_ord = s_ord[warp][s];
+            uint16_t* w_calls = s_calls_all + (warp * K2_BATCH + s) * cap;
+            float* w_val = s_val_all + (warp * K2_BATCH + s) * cap;
+            uint16_t* w_ord = s_ord_all + (warp * K2_BATCH + s) * cap;
             uint32_t n = 0;
             bool nonref = false;
             if (s < nb)
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline4_kernel(const uint
                 const uint32_t site = base + s;
                 const uint32_t c0 = site_off[site], c1 = site_off[site + 1];
                 uint32_t n_raw = c1 - c0;
-                if (n_raw > K2_CAP_SMEM) // the host only launches this kernel when every site fits
+                if (n_raw > cap) // the host sizes cap from the deepest site
                 {
                     if (lane == 0) atomicOr(status, 16);
                     n_raw = 0;
@@ -464,12 +467,12 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline4_kernel(const uint
         if (is_dep)
         {
             const uint32_t s = lane >> 3, g = lane & 7u;
-            const uint16_t* w_calls = s_calls[warp][s];
-            float* w_val = s_val[warp][s];
+            const uint16_t* w_calls = s_calls_all + (warp * K2_BATCH + s) * cap;
+            float* w_val = s_val_all + (warp * K2_BATCH + s) * cap;
             const uint32_t g0 = s_gstart[warp][s][g], sz = s_gstart[warp][s][g + 1] - g0;
             if (sz)
             {
-                uint16_t* ic = s_ord[warp][s] + g0;
+                uint16_t* ic = s_ord_all + (warp * K2_BATCH + s) * cap + g0;
                 float num = 0.f, den = 0.f; // :112-127, in pileup order (before the sort)
                 for (uint32_t k = 0; k < sz; ++k)
                 {
@@ -516,8 +519,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline4_kernel(const uint
         for (uint32_t s = 0; s < nb; ++s)
         {
             const uint32_t site = base + s;
-            const uint16_t* w_calls = s_calls[warp][s];
-            float* w_val = s_val[warp][s];
+            const uint16_t* w_calls = s_calls_all + (warp * K2_BATCH + s) * cap;
+            float* w_val = s_val_all + (warp * K2_BATCH + s) * cap;
             const uint32_t n = s_n[warp][s];
             const bool nonref = (nonref_mask >> s) & 1u;
             const char rb = ref_base[site];
@@ -634,11 +637,15 @@ int germline_run(sx_ctx* ctx, const sx_pileup_batch* d, int is_always_test, sx_d
         return sx_fail(ctx, SX_ERR_UNSUPPORTED, "sx_site_gl_germline: a site holds %u calls; the kernel handles at most %d per site", max_site, K2_CAP_BIG);
     if (max_site <= K2_CAP_SMEM)
     {
-        // every site fits the shared-memory cap: four sites per warp (35 KB of static shared memory per CTA -> 6 CTAs per SM)
+        // every site fits the shared-memory cap: four sites per warp, 8 bytes of shared memory per call slot
         const uint32_t per_cta = K2_WARPS * K2_BATCH;
-        const int grid4 = static_cast<int>(std::min<uint32_t>((d->n_sites + per_cta - 1) / per_cta, (uint32_t)ctx->sm_count * 6));
-        k2a_germline4_kernel<<<grid4, K2_WARPS * 32, 0, ctx->s_compute>>>(d->site_off, d->calls, d->ref_base, d->ploidy, d->n_sites, is_always_test, ctx->d_tables, out_dev,
-                                                                         de_off_dev, de_dev, ctx->d_status);
+        const uint32_t cap = std::max<uint32_t>(32, (max_site + 31) & ~31u);
+        const size_t smem = (size_t)per_cta * cap * 8;
+        int occ = 6;
+        SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2a_germline4_kernel, K2_WARPS * 32, smem));
+        const int grid4 = static_cast<int>(std::min<uint32_t>((d->n_sites + per_cta - 1) / per_cta, (uint32_t)(ctx->sm_count * std::max(1, occ))));
+        k2a_germline4_kernel<<<grid4, K2_WARPS * 32, smem, ctx->s_compute>>>(d->site_off, d->calls, d->ref_base, d->ploidy, d->n_sites, is_always_test, ctx->d_tables,
+                                                                            out_dev, de_off_dev, de_dev, ctx->d_status, cap);
         SX_CUDA(ctx, cudaGetLastError());
         return SX_OK;
     }
