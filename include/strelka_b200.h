@@ -376,6 +376,81 @@ int sx_indel_gl(sx_ctx* ctx, const sx_indel_batch* batch_host, sx_indel_result* 
 int sx_indel_gl_dev(sx_ctx* ctx, const sx_indel_batch* batch_dev, sx_indel_result* out_dev);
 
 /* ==========================================================================================
+ * K4  pileup_reads   (the producer of K2's input)
+ *   replaces  starling_pos_processor_base::pileup_read_segment
+ *   (starling_common/starling_pos_processor_base.cpp:1127-1421) called for every read buffered at a position
+ *   (pileup_pos_reads :1096-1123), with create_mismatch_filter_map (starling_read_util.cpp:120-217),
+ *   getReadAmbiguousEndLength (htsapi/bam_seq_read_util.cpp:29-54) and qphred_to_mapped_qphred (blt_util/qscore.hh:117).
+ *
+ * Input: the reads of one contig segment with their BEST alignment (the host keeps the decisions that need its containers:
+ * realigned vs input alignment, is_any_nonovermax, the largest-indel-span check), in the order the reference piles them up
+ * (ascending alignment position, buffer order within a position).  Output: for every position of the report range the
+ * column of base_call words in exactly that order -- the tier1 buffer (`calls`) and the tier2 buffer (`t2_calls`) of
+ * pos_basecall_buffer::insert_pos_basecall -- i.e. an sx_pileup_batch ready for K2, plus the spanning-deletion and
+ * sub-mapped read counts of each position.  Not produced: MAPQ tallies and the EVS feature accumulators (out of scope).
+ * ======================================================================================== */
+enum { SX_SEG_DELETE = 5, SX_SEG_SKIP = 6 }; /* K4 paths keep DELETE and SKIP apart: only a DELETE is a spanning deletion */
+
+#define SX_PRF_FWD 0x01u        /* best_al.is_fwd_strand */
+#define SX_PRF_TIER1 0x02u      /* rseg.is_tier1_mapping() */
+#define SX_PRF_TIER1OR2 0x04u   /* rseg.is_tier1or2_mapping(); clear = sub-mapped read */
+#define SX_PRF_PIN_FIRST 0x08u  /* rseg.get_segment_edge_pin().first  (an exon borders the leading edge) */
+#define SX_PRF_PIN_SECOND 0x10u /* ... .second */
+
+typedef struct sx_pileup_read {
+    uint32_t seq_off;  /* byte offset of the read's first packed byte in seq4 (reads start on byte boundaries) */
+    uint32_t qual_off; /* byte offset of its first quality (one byte per base) */
+    uint32_t seg_off;  /* first segment of its alignment path in `segs`; the path ends at the next read's seg_off */
+    int32_t pos;       /* best_al.pos */
+    uint16_t len;      /* rseg.read_size() */
+    uint8_t mapq;
+    uint8_t flags;     /* SX_PRF_* */
+} sx_pileup_read;
+
+typedef struct sx_pileup_opts { /* blt_options / starling_base_options fields read by the pileup */
+    int32_t isBasecallQualAdjustedForMapq;         /* 1 */
+    int32_t minBasecallErrorPhredProb;             /* 17 */
+    uint32_t mismatchDensityFilterFlankSize;       /* 0 = filter off (blt_shared.hh:116-119) */
+    uint32_t mismatchDensityFilterMaxMismatchCount;
+    int32_t useTier2Evidence;                      /* 0 */
+    int32_t tier2MismatchDensityFilterMaxMismatchCount; /* 10 */
+    uint32_t minDistanceFromReadEdge;              /* 0 */
+    uint32_t reserved_;
+} sx_pileup_opts;
+
+typedef struct sx_pileup_reads_batch {
+    uint32_t n_reads;
+    uint32_t n_segs;
+    const sx_pileup_read* reads; /* [n_reads + 1]; sorted by pos; the sentinel carries the end offsets */
+    const uint8_t* seq4;         /* BAM 4-bit packed bases */
+    const uint8_t* qual;
+    const sx_aln_seg* segs;      /* kinds MATCH, INSERT, DELETE, SKIP, SOFTCLIP, HARDCLIP */
+    const char* ref;             /* reference_contig_segment: ASCII, ref[i] is contig position ref_begin + i; 'N' outside */
+    int32_t ref_begin;
+    uint32_t ref_len;
+    int32_t report_begin, report_end; /* _reportRange, half open; output site i is position report_begin + i */
+    const uint32_t* cand_snv;    /* sorted keys ((pos - report_begin) << 2) | base id: CandidateSnvBuffer::isCandidateSnvAnySample */
+    uint32_t n_cand_snv;
+    uint32_t max_ref_span;       /* >= the reference span of every read's alignment; the kernel tiles the range by windows >= this */
+    sx_pileup_opts opts;
+} sx_pileup_reads_batch;
+
+typedef struct sx_pileup_columns { /* caller-allocated; n_sites = report_end - report_begin */
+    uint32_t* site_off;   /* [n_sites + 1] */
+    uint16_t* calls;      /* [calls_capacity]   tier1 buffer, base_call words (blt_common/snp_pos_info.hh:109-118) */
+    uint32_t* t2_off;     /* [n_sites + 1] */
+    uint16_t* t2_calls;   /* [t2_capacity]      tier2 buffer */
+    uint32_t* n_spandel;  /* [n_sites] insert_pos_spandel_count */
+    uint32_t* n_submapped; /* [n_sites] insert_pos_submap_count */
+    uint64_t calls_capacity, t2_capacity; /* in words; the total read bases of the batch always suffices for each */
+} sx_pileup_columns;
+
+void sx_default_pileup_opts(sx_pileup_opts* o);
+/* SX_ERR_NOMEM if a capacity is too small (site_off / t2_off are still filled, so the caller can size and retry) */
+int sx_pileup_reads(sx_ctx* ctx, const sx_pileup_reads_batch* batch_host, sx_pileup_columns* out_host);
+int sx_pileup_reads_dev(sx_ctx* ctx, const sx_pileup_reads_batch* batch_dev, sx_pileup_columns* out_dev);
+
+/* ==========================================================================================
  * Multi-GPU: regions shard across ranks with no data-path collective; one gather of fixed-size
  * call records at the end (the in-memory analogue of concatIndexVcf,
  * src/python/lib/strelkaSharedWorkflow.py:126-136).  The NCCL communicator is created from an

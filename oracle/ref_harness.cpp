@@ -637,3 +637,133 @@ extern "C" int ref_indel_gl(const sx_params* p, const sx_indel_batch* b, sx_inde
         return 1;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// starling_pos_processor_base::pileup_read_segment (starling_pos_processor_base.cpp:1127-1421) driven for every read of a
+// flattened sx_pileup_reads_batch, on a real (minimal) pos processor; the per-position buffers are then read back.
+// pileup_read_segment is private: it is reached through the explicit-instantiation idiom (no source is modified, no macro
+// redefines keywords).
+// ---------------------------------------------------------------------------------------------------------------
+#include "appstats/RunStatsManager.hh"
+#include "starling_common/starling_pos_processor_base.hh"
+#include "starling_common/starling_streams_base.hh"
+
+namespace
+{
+struct HarnessPosProcessor : public starling_pos_processor_base
+{
+    using starling_pos_processor_base::starling_pos_processor_base;
+    void process_pos_variants_impl(const pos_t, const bool) override {}
+    void resetRegionForTest(const std::string& chrom, const known_pos_range2& range) { resetRegionBase(chrom, range); }
+    CandidateSnvBuffer& snvBuffer() { return getCandidateSnvBuffer(); }
+};
+
+template <typename Tag, typename Tag::type M> struct MemberPtrOf
+{
+    friend typename Tag::type memberPtr(Tag) { return M; }
+};
+struct PileupReadSegmentTag
+{
+    typedef void (starling_pos_processor_base::*type)(const read_segment&, const unsigned);
+    friend type memberPtr(PileupReadSegmentTag);
+};
+template struct MemberPtrOf<PileupReadSegmentTag, &starling_pos_processor_base::pileup_read_segment>;
+} // namespace
+
+extern "C" int ref_pileup_reads(const sx_pileup_reads_batch* b, uint32_t* site_off, uint16_t* calls, uint64_t calls_cap, uint32_t* t2_off, uint16_t* t2_calls,
+                                uint64_t t2_cap, uint32_t* n_spandel, uint32_t* n_submapped, char* err, int errlen)
+{
+    try
+    {
+        harness_options opt;
+        opt.is_candidate_indel_signal_test = false;
+        opt.isBasecallQualAdjustedForMapq = (b->opts.isBasecallQualAdjustedForMapq != 0);
+        opt.minBasecallErrorPhredProb = b->opts.minBasecallErrorPhredProb;
+        opt.mismatchDensityFilterFlankSize = b->opts.mismatchDensityFilterFlankSize;
+        opt.mismatchDensityFilterMaxMismatchCount = b->opts.mismatchDensityFilterMaxMismatchCount;
+        opt.useTier2Evidence = (b->opts.useTier2Evidence != 0);
+        opt.tier2.mismatchDensityFilterMaxMismatchCount = b->opts.tier2MismatchDensityFilterMaxMismatchCount;
+        opt.minDistanceFromReadEdge = b->opts.minDistanceFromReadEdge;
+        starling_base_deriv_options dopt(opt);
+        reference_contig_segment ref;
+        ref.seq() = std::string(b->ref, b->ref_len);
+        ref.set_offset(b->ref_begin);
+        starling_streams_base streams(1);
+        RunStatsManager stats("");
+        HarnessPosProcessor proc(opt, dopt, ref, streams, 1, stats);
+        proc.resetRegionForTest("chrT", known_pos_range2(b->report_begin, b->report_end));
+        for (uint32_t i = 0; i < b->n_cand_snv; ++i)
+        {
+            static const char BASE[4] = {'A', 'C', 'G', 'T'};
+            proc.snvBuffer().addCandidateSnv(0, b->report_begin + static_cast<pos_t>(b->cand_snv[i] >> 2), BASE[b->cand_snv[i] & 3], 1, 0.5f);
+        }
+        const auto pileup(memberPtr(PileupReadSegmentTag()));
+        std::vector<std::unique_ptr<bam_record>> bams;
+        std::vector<std::unique_ptr<starling_read>> sreads;
+        for (uint32_t r = 0; r < b->n_reads; ++r)
+        {
+            const sx_pileup_read& rd(b->reads[r]);
+            const int len(rd.len);
+            std::unique_ptr<bam_record> br(new bam_record);
+            br->set_qname("R");
+            const std::string dummy(len, 'A');
+            br->set_readqual(dummy.c_str(), b->qual + rd.qual_off);
+            std::memcpy(bam_get_seq(br->get_data()), b->seq4 + rd.seq_off, (len + 1) / 2);
+            alignment al;
+            al.pos = rd.pos;
+            al.is_fwd_strand = (rd.flags & SX_PRF_FWD) != 0;
+            for (uint32_t s = rd.seg_off; s < b->reads[r + 1].seg_off; ++s)
+            {
+                const sx_aln_seg& sg(b->segs[s]);
+                ALIGNPATH::align_t t(ALIGNPATH::NONE);
+                switch (sg.kind)
+                {
+                case SX_SEG_MATCH: t = ALIGNPATH::MATCH; break;
+                case SX_SEG_INSERT: t = ALIGNPATH::INSERT; break;
+                case SX_SEG_DELETE: t = ALIGNPATH::DELETE; break;
+                case SX_SEG_SKIP: t = ALIGNPATH::SKIP; break;
+                case SX_SEG_SOFTCLIP: t = ALIGNPATH::SOFT_CLIP; break;
+                case SX_SEG_HARDCLIP: t = ALIGNPATH::HARD_CLIP; break;
+                default: throw blt_exception("ref_pileup_reads: unknown segment kind");
+                }
+                al.path.push_back(ALIGNPATH::path_segment(t, sg.len));
+            }
+            br->get_data()->core.pos = al.pos;
+            br->get_data()->core.qual = rd.mapq;
+            edit_bam_cigar(al.path, *(br->get_data()));
+            const MAPLEVEL::index_t lev((rd.flags & SX_PRF_TIER1) ? MAPLEVEL::TIER1_MAPPED : (rd.flags & SX_PRF_TIER1OR2) ? MAPLEVEL::TIER2_MAPPED : MAPLEVEL::SUB_MAPPED);
+            sreads.emplace_back(new starling_read(*br, al, lev, r));
+            bams.push_back(std::move(br));
+            (proc.*pileup)(sreads.back()->get_full_segment(), 0);
+        }
+        const pos_basecall_buffer& buf(proc.sample(0).basecallBuffer);
+        const uint32_t n_sites(static_cast<uint32_t>(b->report_end - b->report_begin));
+        uint64_t n1(0), n2(0);
+        for (uint32_t i = 0; i < n_sites; ++i)
+        {
+            const snp_pos_info& pi(buf.get_pos(b->report_begin + static_cast<pos_t>(i)));
+            site_off[i] = static_cast<uint32_t>(n1);
+            t2_off[i] = static_cast<uint32_t>(n2);
+            for (const base_call& bc : pi.calls)
+            {
+                if (n1 >= calls_cap) throw blt_exception("ref_pileup_reads: calls capacity");
+                std::memcpy(&calls[n1++], &bc, 2);
+            }
+            for (const base_call& bc : pi.tier2_calls)
+            {
+                if (n2 >= t2_cap) throw blt_exception("ref_pileup_reads: tier2 capacity");
+                std::memcpy(&t2_calls[n2++], &bc, 2);
+            }
+            n_spandel[i] = pi.spanningDeletionReadCount;
+            n_submapped[i] = pi.submappedReadCount;
+        }
+        site_off[n_sites] = static_cast<uint32_t>(n1);
+        t2_off[n_sites] = static_cast<uint32_t>(n2);
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        set_err(err, errlen, e.what());
+        return 1;
+    }
+}

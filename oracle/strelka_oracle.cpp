@@ -1472,3 +1472,310 @@ extern "C" int ox_indel_gl(const sx_params* p, const sx_indel_batch* b, sx_indel
     }
     return SX_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// f1  pileup_read_segment  starling_common/starling_pos_processor_base.cpp:1127-1421
+//     create_mismatch_filter_map  starling_common/starling_read_util.cpp:52-217 (ddata + the map)
+//     getReadAmbiguousEndLength   htsapi/bam_seq_read_util.cpp:29-54
+//     qphred_cache::mappedq       blt_util/qscore_cache.cpp:39-48, blt_util/qscore.hh:107-113
+// Per-position columns are std::vector push_backs in read order (pos_basecall_buffer.hh:118-130).
+// ------------------------------------------------------------------------------------------------
+namespace
+{
+struct mapped_q_table
+{
+    mapped_q_table()
+    {
+        for (int i(0); i <= 70; ++i)
+            for (int j(0); j <= 90; ++j)
+            {
+                const double be(std::pow(10., -static_cast<double>(i) / 10.)); // phred_to_error_prob
+                const double me(std::pow(10., -static_cast<double>(j) / 10.));
+                q[j][i] = static_cast<uint8_t>(error_prob_to_qphred(((1. - me) * be) + (me * 0.75)));
+            }
+    }
+    uint8_t q[91][71];
+};
+
+inline char char_of_bam_code(const uint8_t c) // bam_seq::get_char, htsapi/bam_seq.hh:60-80
+{
+    switch (c)
+    {
+    case 0: return '=';
+    case 1: return 'A';
+    case 2: return 'C';
+    case 4: return 'G';
+    case 8: return 'T';
+    default: return 'N';
+    }
+}
+inline bool is_match_kind(const uint8_t k) { return k == SX_SEG_MATCH; }
+} // namespace
+
+static int pileup_reads_impl(const sx_pileup_reads_batch* b, std::vector<uint16_t>* tier1 /*[n_sites]*/, std::vector<uint16_t>* tier2, uint32_t* n_spandel,
+                            uint32_t* n_submapped)
+{
+    static const mapped_q_table mq;
+    const sx_pileup_opts& opt(b->opts);
+    const int64_t n_sites(static_cast<int64_t>(b->report_end) - b->report_begin);
+    for (int64_t i = 0; i < n_sites; ++i)
+    {
+        tier1[i].clear();
+        tier2[i].clear();
+        n_spandel[i] = 0;
+        n_submapped[i] = 0;
+    }
+    auto ref_char = [&](const int64_t pos) -> char { // reference_contig_segment::get_base
+        const int64_t i(pos - b->ref_begin);
+        return (i >= 0 && i < static_cast<int64_t>(b->ref_len)) ? b->ref[i] : 'N';
+    };
+    auto is_cand_snv = [&](const int64_t pos, const char readChar) -> bool {
+        const int id(readChar == 'A' ? 0 : readChar == 'C' ? 1 : readChar == 'G' ? 2 : readChar == 'T' ? 3 : 4);
+        if (id == 4) return false;
+        const int64_t rel(pos - b->report_begin);
+        if (rel < 0 || rel >= (static_cast<int64_t>(1) << 30)) return false;
+        const uint32_t key((static_cast<uint32_t>(rel) << 2) | id);
+        return std::binary_search(b->cand_snv, b->cand_snv + b->n_cand_snv, key);
+    };
+    struct rmi_t
+    {
+        int delta;
+        bool is_mismatch, mismatch_filter_map, tier2_mismatch_filter_map;
+        int mismatch_count, mismatch_count_ns;
+    };
+    std::vector<rmi_t> rmi;
+    for (uint32_t r = 0; r < b->n_reads; ++r)
+    {
+        const sx_pileup_read& rd(b->reads[r]);
+        const unsigned read_size(rd.len);
+        const uint8_t* seq(b->seq4 + rd.seq_off);
+        const uint8_t* qual(b->qual + rd.qual_off);
+        const sx_aln_seg* path(b->segs + rd.seg_off);
+        const unsigned as(b->reads[r + 1].seg_off - rd.seg_off);
+        const bool is_fwd(rd.flags & SX_PRF_FWD);
+        auto code_at = [&](const unsigned i) -> uint8_t { return (seq[i >> 1] >> ((~i & 1) << 2)) & 0xf; };
+
+        static const uint8_t min_adjust_mapq(5);
+        const uint8_t mapq(rd.mapq);
+        const uint8_t adjustedMapq(std::max(min_adjust_mapq, mapq));
+        const bool is_mapq_adjust(opt.isBasecallQualAdjustedForMapq && (adjustedMapq <= 80));
+        unsigned read_ref_mapped_size(0);
+        for (unsigned i(0); i < as; ++i)
+            if (path[i].kind == SX_SEG_MATCH || path[i].kind == SX_SEG_DELETE || path[i].kind == SX_SEG_SKIP) read_ref_mapped_size += path[i].len;
+        // exact begin and end report range filters (:1189-1194)
+        if (rd.pos >= b->report_end) continue;
+        if (static_cast<int64_t>(rd.pos) + read_ref_mapped_size <= b->report_begin) continue;
+
+        unsigned ambig(0); // getReadAmbiguousEndLength
+        if (is_fwd)
+        {
+            unsigned read_end(read_size);
+            while ((read_end > 0) && (char_of_bam_code(code_at(read_end - 1)) == 'N')) read_end--;
+            ambig = read_size - read_end;
+        }
+        else
+        {
+            while ((ambig < read_size) && (char_of_bam_code(code_at(ambig)) == 'N')) ambig++;
+        }
+        unsigned read_begin(0), read_end(read_size);
+        if (ambig > 0)
+        {
+            if (is_fwd) read_end -= ambig;
+            else read_begin += ambig;
+        }
+        if (opt.minDistanceFromReadEdge > 0)
+        {
+            read_begin += opt.minDistanceFromReadEdge;
+            if (opt.minDistanceFromReadEdge <= read_end) read_end -= opt.minDistanceFromReadEdge;
+            else read_end = 0;
+            if (read_end <= read_begin) continue;
+        }
+        bool is_neighbor_mismatch(false);
+        const bool is_submapped(!(rd.flags & SX_PRF_TIER1OR2));
+        const bool is_tier1(rd.flags & SX_PRF_TIER1);
+        const bool isDensity(opt.mismatchDensityFilterFlankSize > 0);
+
+        // get_match_edge_segments
+        std::pair<unsigned, unsigned> ends(as, as);
+        {
+            bool isFirst(false);
+            for (unsigned i(0); i < as; ++i)
+                if (is_match_kind(path[i].kind))
+                {
+                    if (!isFirst) ends.first = i;
+                    isFirst = true;
+                    ends.second = i;
+                }
+        }
+        if ((!is_submapped) && isDensity)
+        {
+            // create_mismatch_filter_map
+            rmi.assign(read_size + 1, rmi_t{0, false, false, false, 0, 0});
+            const unsigned fs(opt.mismatchDensityFilterFlankSize), fs2(fs * 2);
+            const unsigned delta_size(std::max(1 + fs2, read_size) - fs2);
+            auto inc = [&](const unsigned start_pos, const unsigned length) {
+                rmi[std::max(fs2, start_pos) - fs2].delta += 1;
+                if ((start_pos + length) < delta_size) rmi[start_pos + length].delta -= 1;
+            };
+            int64_t ref_head_pos(rd.pos);
+            unsigned read_head_pos(0);
+            for (unsigned i(0); i < as; ++i)
+            {
+                const sx_aln_seg& ps(path[i]);
+                const bool is_edge_segment((i < ends.first) || (i > ends.second));
+                if (ps.kind == SX_SEG_INSERT)
+                {
+                    if (!is_edge_segment) inc(read_head_pos, ps.len);
+                    read_head_pos += ps.len;
+                }
+                else if (ps.kind == SX_SEG_DELETE)
+                {
+                    if (!is_edge_segment) inc(read_head_pos, 0);
+                    ref_head_pos += ps.len;
+                }
+                else if (is_match_kind(ps.kind))
+                {
+                    for (unsigned j(0); j < ps.len; ++j)
+                    {
+                        const unsigned read_pos(read_head_pos + j);
+                        if ((read_pos < read_begin) || (read_pos >= read_end)) continue;
+                        const int64_t ref_pos(ref_head_pos + j);
+                        const char readChar(char_of_bam_code(code_at(read_pos)));
+                        if (readChar != ref_char(ref_pos))
+                        {
+                            if (!is_cand_snv(ref_pos, readChar))
+                            {
+                                rmi[read_pos].is_mismatch = true;
+                                inc(read_pos, 1);
+                            }
+                        }
+                    }
+                    read_head_pos += ps.len;
+                    ref_head_pos += ps.len;
+                }
+                else if (ps.kind == SX_SEG_SOFTCLIP) read_head_pos += ps.len;
+                else if (ps.kind == SX_SEG_HARDCLIP) {}
+                else if (ps.kind == SX_SEG_SKIP) return SX_ERR_ARG; // "Can't handle cigar code" (the map has no SKIP branch)
+                else return SX_ERR_ARG;
+            }
+            for (unsigned i(1); i < delta_size; ++i) rmi[i].delta += rmi[i - 1].delta; // ddata::total
+            const int max_pass(static_cast<int>(opt.mismatchDensityFilterMaxMismatchCount));
+            std::vector<int> del(read_size);
+            for (unsigned i(0); i < read_size; ++i) del[i] = rmi[std::min(delta_size - 1, std::max(fs, i) - fs)].delta;
+            for (unsigned i(0); i < read_size; ++i)
+            {
+                rmi[i].mismatch_count = del[i];
+                rmi[i].mismatch_count_ns = del[i] - rmi[i].is_mismatch;
+                rmi[i].mismatch_filter_map = (max_pass < del[i]);
+            }
+            if (opt.useTier2Evidence)
+            {
+                const int max_pass2(opt.tier2MismatchDensityFilterMaxMismatchCount);
+                for (unsigned i(0); i < read_size; ++i) rmi[i].tier2_mismatch_filter_map = (max_pass2 < rmi[i].mismatch_count);
+            }
+        }
+
+        int64_t ref_head_pos(rd.pos);
+        unsigned read_head_pos(0);
+        for (unsigned i(0); i < as; ++i)
+        {
+            const sx_aln_seg& ps(path[i]);
+            if (is_match_kind(ps.kind))
+            {
+                for (unsigned j(0); j < ps.len; ++j)
+                {
+                    const unsigned read_pos(read_head_pos + j);
+                    if ((read_pos < read_begin) || (read_pos >= read_end)) continue;
+                    const int64_t ref_pos(ref_head_pos + j);
+                    if (ref_pos < b->report_begin || ref_pos >= b->report_end) continue; // is_pos_reportable
+                    const uint8_t call_code(code_at(read_pos));
+                    uint8_t call_id; // bam_seq_code_to_id with ref = ANY
+                    switch (call_code)
+                    {
+                    case 1: call_id = 0; break;
+                    case 2: call_id = 1; break;
+                    case 4: call_id = 2; break;
+                    case 8: call_id = 3; break;
+                    case 0:
+                    case 15: call_id = 4; break;
+                    default: return SX_ERR_ARG; // base_error
+                    }
+                    uint8_t qscore(qual[read_pos]);
+                    if (is_mapq_adjust)
+                    {
+                        if (qscore > 70) return SX_ERR_RANGE; // qscore_check in get_mapped_qscore_imp
+                        qscore = mq.q[std::min<int>(adjustedMapq, 90)][qscore];
+                    }
+                    bool current_call_filter(true), is_tier_specific_filter(false);
+                    if (!is_submapped)
+                    {
+                        bool is_call_filter((call_code == 15) || (qscore < opt.minBasecallErrorPhredProb));
+                        bool is_tier2_call_filter(is_call_filter);
+                        if ((!is_call_filter) && isDensity)
+                        {
+                            is_call_filter = rmi[read_pos].mismatch_filter_map;
+                            if (opt.useTier2Evidence) is_tier2_call_filter = rmi[read_pos].tier2_mismatch_filter_map;
+                            else is_tier2_call_filter = is_call_filter;
+                        }
+                        current_call_filter = (is_tier1 ? is_call_filter : is_tier2_call_filter);
+                        is_tier_specific_filter = (is_tier1 && is_call_filter && (!is_tier2_call_filter));
+                        if (isDensity) is_neighbor_mismatch = (rmi[read_pos].mismatch_count_ns > 0);
+                    }
+                    const int64_t site(ref_pos - b->report_begin);
+                    if (is_submapped)
+                    {
+                        n_submapped[site]++;
+                        continue;
+                    }
+                    // base_call ctor (snp_pos_info.hh:51-79): the quality is clipped to 6 bits (63) BEFORE its qscore_check, which
+                    // therefore cannot fire
+                    const uint16_t bc(static_cast<uint16_t>((std::min<unsigned>(qscore, 63u)) | (call_id << 6) | ((is_fwd ? 1u : 0u) << 10) |
+                                                            ((is_neighbor_mismatch ? 1u : 0u) << 11) | ((current_call_filter ? 1u : 0u) << 12) |
+                                                            ((is_tier_specific_filter ? 1u : 0u) << 13)));
+                    (is_tier1 ? tier1 : tier2)[site].push_back(bc);
+                }
+            }
+            else if (ps.kind == SX_SEG_DELETE)
+            {
+                const bool is_edge_deletion((i < ends.first) || (i > ends.second));
+                const bool is_pinned_deletion(((i < ends.first) && (rd.flags & SX_PRF_PIN_FIRST)) || ((i > ends.second) && (rd.flags & SX_PRF_PIN_SECOND)));
+                if ((!is_edge_deletion) || is_pinned_deletion)
+                {
+                    for (unsigned j(0); j < ps.len; ++j)
+                    {
+                        const int64_t ref_pos(ref_head_pos + j);
+                        if (ref_pos < b->report_begin || ref_pos >= b->report_end) continue;
+                        const int64_t site(ref_pos - b->report_begin);
+                        if (is_submapped) n_submapped[site]++;
+                        else n_spandel[site]++;
+                    }
+                }
+            }
+            if (ps.kind == SX_SEG_MATCH || ps.kind == SX_SEG_INSERT || ps.kind == SX_SEG_SOFTCLIP) read_head_pos += ps.len; // is_segment_type_read_length
+            if (ps.kind == SX_SEG_MATCH || ps.kind == SX_SEG_DELETE || ps.kind == SX_SEG_SKIP) ref_head_pos += ps.len;      // is_segment_type_ref_length
+        }
+    }
+    return SX_OK;
+}
+
+// flat C interface: CSR columns into caller buffers (SX_ERR_NOMEM if a capacity is too small)
+extern "C" int ox_pileup_reads(const sx_pileup_reads_batch* b, uint32_t* site_off, uint16_t* calls, uint64_t calls_cap, uint32_t* t2_off, uint16_t* t2_calls,
+                               uint64_t t2_cap, uint32_t* n_spandel, uint32_t* n_submapped)
+{
+    const size_t n_sites(static_cast<size_t>(static_cast<int64_t>(b->report_end) - b->report_begin));
+    std::vector<std::vector<uint16_t>> t1(n_sites), t2(n_sites);
+    const int rc(pileup_reads_impl(b, t1.data(), t2.data(), n_spandel, n_submapped));
+    if (rc) return rc;
+    uint64_t n1(0), n2(0);
+    for (size_t i = 0; i < n_sites; ++i)
+    {
+        site_off[i] = static_cast<uint32_t>(n1);
+        t2_off[i] = static_cast<uint32_t>(n2);
+        if (n1 + t1[i].size() > calls_cap || n2 + t2[i].size() > t2_cap) return SX_ERR_NOMEM;
+        for (const uint16_t c : t1[i]) calls[n1++] = c;
+        for (const uint16_t c : t2[i]) t2_calls[n2++] = c;
+    }
+    site_off[n_sites] = static_cast<uint32_t>(n1);
+    t2_off[n_sites] = static_cast<uint32_t>(n2);
+    return SX_OK;
+}

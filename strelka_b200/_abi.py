@@ -124,6 +124,63 @@ class SxAlignBatch(C.Structure):
     ]
 
 
+# K4 pileup_reads
+SX_SEG_DELETE, SX_SEG_SKIP = 5, 6
+SX_PRF_FWD, SX_PRF_TIER1, SX_PRF_TIER1OR2, SX_PRF_PIN_FIRST, SX_PRF_PIN_SECOND = 1, 2, 4, 8, 16
+PILEUP_READ_DT = np.dtype([("seq_off", "<u4"), ("qual_off", "<u4"), ("seg_off", "<u4"), ("pos", "<i4"), ("len", "<u2"), ("mapq", "u1"), ("flags", "u1")])
+
+
+class SxPileupOpts(C.Structure):
+    _fields_ = [
+        ("isBasecallQualAdjustedForMapq", C.c_int32),
+        ("minBasecallErrorPhredProb", C.c_int32),
+        ("mismatchDensityFilterFlankSize", C.c_uint32),
+        ("mismatchDensityFilterMaxMismatchCount", C.c_uint32),
+        ("useTier2Evidence", C.c_int32),
+        ("tier2MismatchDensityFilterMaxMismatchCount", C.c_int32),
+        ("minDistanceFromReadEdge", C.c_uint32),
+        ("reserved_", C.c_uint32),
+    ]
+
+
+class SxPileupReadsBatch(C.Structure):
+    _fields_ = [
+        ("n_reads", C.c_uint32),
+        ("n_segs", C.c_uint32),
+        ("reads", C.c_void_p),
+        ("seq4", C.c_void_p),
+        ("qual", C.c_void_p),
+        ("segs", C.c_void_p),
+        ("ref", C.c_void_p),
+        ("ref_begin", C.c_int32),
+        ("ref_len", C.c_uint32),
+        ("report_begin", C.c_int32),
+        ("report_end", C.c_int32),
+        ("cand_snv", C.c_void_p),
+        ("n_cand_snv", C.c_uint32),
+        ("max_ref_span", C.c_uint32),
+        ("opts", SxPileupOpts),
+    ]
+
+
+class SxPileupColumns(C.Structure):
+    _fields_ = [
+        ("site_off", C.c_void_p),
+        ("calls", C.c_void_p),
+        ("t2_off", C.c_void_p),
+        ("t2_calls", C.c_void_p),
+        ("n_spandel", C.c_void_p),
+        ("n_submapped", C.c_void_p),
+        ("calls_capacity", C.c_uint64),
+        ("t2_capacity", C.c_uint64),
+    ]
+
+
+def default_pileup_opts() -> SxPileupOpts:
+    """blt_options / starling_base_options defaults + the germline workflow's mismatch density filter (flank 20, max 2)."""
+    return SxPileupOpts(1, 17, 20, 2, 0, 10, 0, 0)
+
+
 class SxGaScores(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("match", "mismatch", "open", "extend", "offEdge", "insertDelete", "isAllowEdgeInsertion", "isRequireEdgeDeletion")]
 
@@ -184,6 +241,9 @@ SYMBOLS = [
     ("sx_site_gl_somatic_dev", C.c_int, [_P, C.POINTER(SxPileupBatch), C.POINTER(SxPileupBatch), _P, _P]),
     ("sx_indel_gl", C.c_int, [_P, C.POINTER(SxIndelBatch), _P]),
     ("sx_indel_gl_dev", C.c_int, [_P, C.POINTER(SxIndelBatch), _P]),
+    ("sx_default_pileup_opts", None, [C.POINTER(SxPileupOpts)]),
+    ("sx_pileup_reads", C.c_int, [_P, C.POINTER(SxPileupReadsBatch), C.POINTER(SxPileupColumns)]),
+    ("sx_pileup_reads_dev", C.c_int, [_P, C.POINTER(SxPileupReadsBatch), C.POINTER(SxPileupColumns)]),
     ("sx_comm_get_unique_id", C.c_int, [_P]),
     ("sx_comm_init", C.c_int, [_P, _P, C.c_int, C.c_int]),
     ("sx_gather_records", C.c_int, [_P, _P, C.c_size_t, _P, C.c_int]),

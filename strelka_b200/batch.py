@@ -472,3 +472,70 @@ class IndelBatch:
             self.ploidy = np.zeros(1, np.uint8)
         self.c = A.SxIndelBatch(n, A.ptr(self.read_off), A.ptr(self.lnp_off), A.ptr(self.allele_off), A.ptr(self.ploidy), A.ptr(self.allele_del_len),
                                 A.ptr(self.allele_ins_len), A.ptr(self.allele_lnp), A.ptr(self.read_length), A.ptr(self.non_ambig), A.ptr(self.is_fwd))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K4 pileup_reads
+# ------------------------------------------------------------------------------------------------------------------
+_PILEUP_KIND = {"M": A.SX_SEG_MATCH, "I": A.SX_SEG_INSERT, "D": A.SX_SEG_DELETE, "N": A.SX_SEG_SKIP, "S": A.SX_SEG_SOFTCLIP, "H": A.SX_SEG_HARDCLIP}
+
+
+class PileupReadSpec:
+    """One read with its best alignment, as pileup_read_segment sees it."""
+
+    def __init__(self, codes, quals, pos, path, fwd=True, mapq=60, tier=1, pins=(False, False)):
+        self.codes, self.quals, self.pos, self.path, self.fwd, self.mapq, self.tier, self.pins = codes, quals, pos, path, fwd, mapq, tier, pins
+
+
+class PileupReadsBatch:
+    """Owns the pools of one sx_pileup_reads_batch (reads must be given in pile-up order: ascending position)."""
+
+    def __init__(self, reads: Sequence[PileupReadSpec], ref: str, ref_begin: int, report_begin: int, report_end: int, cand_snv=(), opts=None):
+        self.n_reads = len(reads)
+        hdr = np.zeros(len(reads) + 1, dtype=A.PILEUP_READ_DT)
+        seq4, qual, segs = bytearray(), bytearray(), []
+        span = 1
+        for i, r in enumerate(reads):
+            n = len(r.codes)
+            assert len(r.quals) == n
+            flags = (A.SX_PRF_FWD if r.fwd else 0) | (A.SX_PRF_TIER1 if r.tier == 1 else 0) | (A.SX_PRF_TIER1OR2 if r.tier in (1, 2) else 0)
+            flags |= (A.SX_PRF_PIN_FIRST if r.pins[0] else 0) | (A.SX_PRF_PIN_SECOND if r.pins[1] else 0)
+            hdr[i] = (len(seq4), len(qual), len(segs), r.pos, n, r.mapq, flags)
+            c = np.asarray(r.codes, dtype=np.uint8)
+            if n & 1:
+                c = np.concatenate([c, np.zeros(1, np.uint8)])
+            seq4.extend(((c[0::2] << 4) | c[1::2]).astype(np.uint8).tobytes())
+            qual.extend(np.asarray(r.quals, dtype=np.uint8).tobytes())
+            segs.extend((ln, _PILEUP_KIND[k], 0) for k, ln in r.path)
+            span = max(span, sum(ln for k, ln in r.path if k in "MDN"))
+        hdr[len(reads)] = (len(seq4), len(qual), len(segs), 0, 0, 0, 0)
+        self.reads = hdr
+        self.total_bases = int(hdr["len"].astype(np.int64).sum())
+        self.seq4 = np.frombuffer(bytes(seq4) + b"\0" * 64, dtype=np.uint8).copy()
+        self.qual = np.frombuffer(bytes(qual) + b"\0" * 64, dtype=np.uint8).copy()
+        self.segs = np.zeros(len(segs) + 16, dtype=A.ALN_SEG_DT)
+        if segs:
+            self.segs[: len(segs)] = np.array(segs, dtype=A.ALN_SEG_DT)
+        self.ref = np.frombuffer(ref.encode() + b"\0" * 64, dtype=np.uint8).copy()
+        keys = sorted(((p - report_begin) << 2) | b for p, b in cand_snv if report_begin <= p < report_end)
+        self.cand_snv = np.array(keys + [0], dtype=np.uint32)
+        self.n_sites = report_end - report_begin
+        self.opts = opts or A.default_pileup_opts()
+        self.c = A.SxPileupReadsBatch(
+            len(reads), len(segs), A.ptr(self.reads), A.ptr(self.seq4), A.ptr(self.qual), A.ptr(self.segs), A.ptr(self.ref), ref_begin, len(ref),
+            report_begin, report_end, A.ptr(self.cand_snv), len(keys), span, self.opts,
+        )
+
+
+class PileupColumns:
+    """Host buffers for sx_pileup_columns sized for a batch (capacity = total read bases, always enough)."""
+
+    def __init__(self, pb: PileupReadsBatch):
+        n, cap = pb.n_sites, pb.total_bases + 16
+        self.site_off, self.t2_off = np.zeros(n + 1, np.uint32), np.zeros(n + 1, np.uint32)
+        self.calls, self.t2_calls = np.zeros(cap, np.uint16), np.zeros(cap, np.uint16)
+        self.n_spandel, self.n_submapped = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        self.c = A.SxPileupColumns(A.ptr(self.site_off), A.ptr(self.calls), A.ptr(self.t2_off), A.ptr(self.t2_calls), A.ptr(self.n_spandel), A.ptr(self.n_submapped), cap, cap)
+
+    def trimmed(self):
+        return (self.site_off, self.calls[: int(self.site_off[-1])], self.t2_off, self.t2_calls[: int(self.t2_off[-1])], self.n_spandel, self.n_submapped)

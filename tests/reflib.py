@@ -200,3 +200,26 @@ def ref_indel_gl(params: A.SxParams, ib: B.IndelBatch) -> np.ndarray:
     if rc != 0:
         raise RuntimeError(err.value.decode(errors="replace"))
     return out
+
+
+def ox_pileup_reads(pb: "B.PileupReadsBatch"):
+    out = B.PileupColumns(pb)
+    lib = oracle()
+    lib.ox_pileup_reads.argtypes = [C.POINTER(A.SxPileupReadsBatch), _P, _P, C.c_uint64, _P, _P, C.c_uint64, _P, _P]
+    rc = lib.ox_pileup_reads(C.byref(pb.c), A.ptr(out.site_off), A.ptr(out.calls), out.calls.size, A.ptr(out.t2_off), A.ptr(out.t2_calls), out.t2_calls.size,
+                             A.ptr(out.n_spandel), A.ptr(out.n_submapped))
+    assert rc == 0, rc
+    return out.trimmed()
+
+
+def ref_pileup_reads(pb: "B.PileupReadsBatch"):
+    """The reference's own starling_pos_processor_base::pileup_read_segment, driven read by read (oracle/ref_harness.cpp)."""
+    out = B.PileupColumns(pb)
+    err = _err()
+    fn = ref().ref_pileup_reads
+    fn.argtypes = [C.POINTER(A.SxPileupReadsBatch), _P, _P, C.c_uint64, _P, _P, C.c_uint64, _P, _P, C.c_char_p, C.c_int]
+    rc = fn(C.byref(pb.c), A.ptr(out.site_off), A.ptr(out.calls), out.calls.size, A.ptr(out.t2_off), A.ptr(out.t2_calls), out.t2_calls.size,
+            A.ptr(out.n_spandel), A.ptr(out.n_submapped), err, 1024)
+    if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    return out.trimmed()

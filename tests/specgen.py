@@ -323,3 +323,97 @@ def random_indel_loci(rng: np.random.Generator, n_loci: int, depth=(5, 60)):
             reads.append(([float(np.float32(min(x, -0.01))) for x in v], rl, int(rng.integers(max(1, rl - 10), rl + 1)), int(rng.random() < 0.5)))
         loci.append({"ploidy": int(rng.choice([2, 2, 2, 1])), "alleles": alleles, "reads": reads})
     return loci
+
+
+def random_pileup_reads(rng: np.random.Generator, n_reads: int = 200, ref_len: int = 1200, ref_begin: int = 5000, read_len=(40, 151), n_frac: float = 0.02,
+                        snv_rate: float = 0.01, allow_skip: bool = False):
+    """Reads piled over one contig segment, in pile-up order: plain matches, internal and edge insertions / deletions, soft and hard
+    clips, N runs at either end, mismatches (some of them registered as candidate SNVs), all three mapping tiers, both strands,
+    low mapping qualities (the mapq adjustment), reads hanging off the report range."""
+    ref = rand_seq(rng, ref_len)
+    alt = {}  # position -> alt base of a "true" SNV (registered as candidate for about half of them)
+    for p in rng.choice(ref_len, size=max(1, int(snv_rate * ref_len)), replace=False).tolist():
+        alt[p] = BASES[(BASES.index(ref[p]) + 1 + int(rng.integers(0, 3))) % 4]
+    cand = [(ref_begin + p, BASES.index(b)) for p, b in alt.items() if rng.random() < 0.5]
+    reads = []
+    starts = np.sort(rng.integers(-60, ref_len - 20, size=n_reads))
+    for s0 in starts.tolist():
+        L = int(rng.integers(read_len[0], read_len[1]))
+        path, bases = [], []
+        remaining, rp = L, s0
+        if rng.random() < 0.1:
+            path.append(("H", int(rng.integers(1, 6))))
+        if rng.random() < 0.15 and remaining > 30:
+            n = int(rng.integers(1, 9))
+            path.append(("S", n))
+            bases += list(rand_seq(rng, n))
+            remaining -= n
+        if rng.random() < 0.08 and remaining > 30:  # leading-edge insertion
+            n = int(rng.integers(1, 5))
+            path.append(("I", n))
+            bases += list(rand_seq(rng, n))
+            remaining -= n
+        if rng.random() < 0.05:  # leading-edge deletion
+            n = int(rng.integers(1, 5))
+            path.append(("D", n))
+            rp += n
+        tail_clip = int(rng.integers(1, 9)) if (rng.random() < 0.15 and remaining > 30) else 0
+        remaining -= tail_clip
+        n_ev = int(rng.choice([0, 0, 0, 1, 1, 2]))
+        while remaining > 0:
+            m = remaining if n_ev == 0 else int(rng.integers(1, max(2, remaining - 2 * n_ev)))
+            path.append(("M", m))
+            for k in range(m):
+                q = rp + k
+                b = ref[q] if 0 <= q < ref_len else "A"
+                if q in alt and rng.random() < 0.5:
+                    b = alt[q]
+                elif rng.random() < 0.02:
+                    b = BASES[int(rng.integers(0, 4))]
+                bases.append(b)
+            rp += m
+            remaining -= m
+            if remaining <= 0 or n_ev == 0:
+                continue
+            n_ev -= 1
+            u = rng.random()
+            if u < 0.4:
+                n = int(min(remaining - 1, rng.integers(1, 6))) if remaining > 1 else 0
+                if n > 0:
+                    path.append(("I", n))
+                    bases += list(rand_seq(rng, n))
+                    remaining -= n
+            elif u < 0.9 or not allow_skip:
+                n = int(rng.integers(1, 8))
+                path.append(("D", n))
+                rp += n
+            else:
+                n = int(rng.integers(20, 60))
+                path.append(("N", n))
+                rp += n
+        if rng.random() < 0.04:  # trailing-edge deletion
+            path.append(("D", int(rng.integers(1, 4))))
+        if tail_clip:
+            path.append(("S", tail_clip))
+            bases += list(rand_seq(rng, tail_clip))
+        # merge adjacent equal kinds (a path never repeats a kind back to back)
+        merged = []
+        for k, n in path:
+            if merged and merged[-1][0] == k:
+                merged[-1] = (k, merged[-1][1] + n)
+            else:
+                merged.append((k, n))
+        bases = np.array(bases)
+        assert len(bases) == L
+        codes = np.array([CODE_OF[b] for b in bases], np.uint8)
+        if rng.random() < n_frac * 5:  # N run at an end (ambiguous end trimming), N inside
+            n = int(rng.integers(1, 6))
+            if rng.random() < 0.5:
+                codes[:n] = 15
+            else:
+                codes[-n:] = 15
+        codes[rng.random(L) < n_frac * 0.2] = 15
+        quals = rng.choice(QUALS, size=L, p=QUAL_P).astype(np.uint8)
+        tier = int(rng.choice([1, 1, 1, 1, 2, 0]))
+        reads.append(B.PileupReadSpec(codes, quals, ref_begin + s0, merged, fwd=bool(rng.random() < 0.5), mapq=int(rng.choice([0, 3, 12, 30, 60, 60, 60, 255])), tier=tier))
+    return reads, ref, ref_begin, cand

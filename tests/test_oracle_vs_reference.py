@@ -159,3 +159,26 @@ def test_indel_genotype_likelihoods(seed):
     assert np.array_equal(want["n_gt"], got["n_gt"])
     assert np.array_equal(want["support"], got["support"])
     assert np.array_equal(want["gt_lhood"].view(np.uint64), got["gt_lhood"].view(np.uint64))
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("mode", ["germline", "somatic", "nofilter", "edge"])
+def test_pileup_reads_columns_match_the_reference(seed, mode):
+    """f1: the restated pileup loop (oracle) against starling_pos_processor_base::pileup_read_segment itself, driven read by read on
+    a real pos processor: every position's tier1 / tier2 base_call column in order, spanning-deletion and sub-mapped counts."""
+    rng = np.random.default_rng(4000 + seed)
+    reads, ref, ref_begin, cand = specgen.random_pileup_reads(rng, n_reads=250)
+    opts = A.default_pileup_opts()
+    if mode == "somatic":
+        opts = A.SxPileupOpts(1, 0, 20, 3, 1, 10, 0, 0)
+    elif mode == "nofilter":
+        opts = A.SxPileupOpts(0, 17, 0, 0, 0, 10, 0, 0)
+    elif mode == "edge":
+        opts = A.SxPileupOpts(1, 17, 3, 1, 1, 2, 5, 0)
+    lo, hi = ref_begin + 100, ref_begin + len(ref) - 150  # reads hang off both ends of the report range
+    pb = B.PileupReadsBatch(reads, ref, ref_begin, lo, hi, cand, opts)
+    want = reflib.ref_pileup_reads(pb)
+    got = reflib.ox_pileup_reads(pb)
+    assert int(want[0][-1]) > 1000 and int(want[4].sum()) > 0 and int(want[5].sum()) > 0
+    for w, g, name in zip(want, got, ("site_off", "calls", "t2_off", "t2_calls", "n_spandel", "n_submapped")):
+        assert np.array_equal(w, g), name
