@@ -202,3 +202,13 @@ def _indel_gl(self, ib: "B.IndelBatch", out=None) -> np.ndarray:
 
 
 Context.indel_gl = _indel_gl  # K5
+
+
+def _pileup_reads(self, pb: B.PileupReadsBatch):
+    """K4: per-position base_call columns of a read batch (host buffers in, host columns out)."""
+    out = B.PileupColumns(pb)
+    self._chk(self.lib.sx_pileup_reads(self.h, C.byref(pb.c), C.byref(out.c)))
+    return out.trimmed()
+
+
+Context.pileup_reads = _pileup_reads

@@ -1,0 +1,690 @@
+// k4_pileup.cu -- K4 pileup_reads: per-position base_call columns from reads with their best alignment.
+//
+// Replaces starling_pos_processor_base::pileup_read_segment (/root/reference/src/c++/lib/starling_common/
+// starling_pos_processor_base.cpp:1127-1421) with create_mismatch_filter_map (starling_read_util.cpp:52-217),
+// getReadAmbiguousEndLength (htsapi/bam_seq_read_util.cpp:29-54) and the mapq adjustment (blt_util/qscore_cache.cpp:44-47).
+//
+// What has to be preserved is ORDER: a position's column is a std::vector the reference push_backs into read after read, and K2's
+// float sums run over that order.  Reads arrive sorted by position, so the output range is cut into windows of W >= the longest
+// alignment span: a read starting in window c can only reach windows c and c+1.  Three passes:
+//   1. k4_count_kernel (thread per read): every covered interval is two atomics on difference arrays (tier1 / tier2 column sizes,
+//      the part of each that spills into the next window, spanning deletions, sub-mapped bases).  Integer, order-free.
+//   2. scans (k4_scan_*): difference arrays -> counts, counts -> CSR offsets.
+//   3. k4_fill_kernel (one WARP per window): walks its reads in order; per read the 32 lanes compute the mismatch-density map
+//      (shared-memory delta array + warp scan) and every base's base_call word, and place it at
+//      site_off[s] + (calls already placed at s).  The running per-site counters live in shared memory for the 2W sites the window's
+//      reads can touch and start, for the window's own sites, at the number of calls spilling in from window c-1 -- whose reads all
+//      precede this window's reads.
+// Everything is integer/byte work; the only table is qphred_cache::mappedq, built on the host (sx_context.cu).
+#include "sx_internal.h"
+
+#include <algorithm>
+
+namespace
+{
+constexpr int K4_WARPS = 4;
+constexpr uint32_t K4_MAX_W = 2048;    // window size limit (shared memory: 16 bytes per window site and warp)
+constexpr uint32_t K4_MAX_READ = 1024; // read length limit (delta + mismatch arrays)
+constexpr uint32_t K4_MAX_SEGS = 64;   // path segments per read
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int ST_ORDER = 64, ST_BASE = 128, ST_LIMIT = 256, ST_QUAL = 1, ST_KIND = 4;
+
+struct k4_args
+{
+    const sx_pileup_read* reads;
+    const uint8_t* seq4;
+    const uint8_t* qual;
+    const sx_aln_seg* segs;
+    const char* ref;
+    const uint32_t* cand_snv;
+    uint32_t n_reads, n_cand_snv, ref_len;
+    int32_t ref_begin, report_begin, report_end;
+    int32_t origin; // position of window 0's first site (= report_begin - W)
+    uint32_t W, n_windows, n_sites;
+    sx_pileup_opts opt;
+};
+
+__device__ __forceinline__ uint32_t code_at(const uint8_t* seq, uint32_t i) { return (seq[i >> 1] >> ((~i & 1u) << 2)) & 15u; }
+__device__ __forceinline__ bool kind_ref(uint32_t k) { return k == SX_SEG_MATCH || k == SX_SEG_DELETE || k == SX_SEG_SKIP; }
+__device__ __forceinline__ bool kind_read(uint32_t k) { return k == SX_SEG_MATCH || k == SX_SEG_INSERT || k == SX_SEG_SOFTCLIP; }
+
+__device__ __forceinline__ int64_t i64max(int64_t a, int64_t b) { return a > b ? a : b; }
+__device__ __forceinline__ int64_t i64min(int64_t a, int64_t b) { return a < b ? a : b; }
+
+// +1 over sites [a, b) of a difference array with n entries
+__device__ __forceinline__ void diff_add(int* d, int64_t a, int64_t b, uint32_t n)
+{
+    if (a >= b) return;
+    atomicAdd(&d[a], 1);
+    if (b < static_cast<int64_t>(n)) atomicAdd(&d[b], -1);
+}
+
+// the per-read preamble of pileup_read_segment (:1175-1233): false = the read contributes nothing
+struct read_window
+{
+    uint32_t read_begin, read_end, ref_span;
+};
+template <typename CodeFn> __device__ __forceinline__ bool read_preamble(const k4_args& A, const sx_pileup_read& rd, uint32_t ref_span, CodeFn code, read_window& w)
+{
+    if (rd.pos >= A.report_end) return false;
+    if (static_cast<int64_t>(rd.pos) + ref_span <= A.report_begin) return false;
+    const uint32_t read_size = rd.len;
+    uint32_t ambig = 0; // getReadAmbiguousEndLength: the run of 'N' (code 15) at the 3' end of the read as sequenced
+    if (rd.flags & SX_PRF_FWD)
+    {
+        uint32_t e = read_size;
+        while (e > 0 && code(e - 1) == 15u) --e;
+        ambig = read_size - e;
+    }
+    else
+    {
+        while (ambig < read_size && code(ambig) == 15u) ++ambig;
+    }
+    w.read_begin = 0;
+    w.read_end = read_size;
+    if (ambig > 0)
+    {
+        if (rd.flags & SX_PRF_FWD) w.read_end -= ambig;
+        else w.read_begin += ambig;
+    }
+    if (A.opt.minDistanceFromReadEdge > 0)
+    {
+        w.read_begin += A.opt.minDistanceFromReadEdge;
+        if (A.opt.minDistanceFromReadEdge <= w.read_end) w.read_end -= A.opt.minDistanceFromReadEdge;
+        else w.read_end = 0;
+        if (w.read_end <= w.read_begin) return false;
+    }
+    w.ref_span = ref_span;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pass 1: column sizes as difference arrays
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void k4_count_kernel(k4_args A, int* __restrict__ d1, int* __restrict__ d2, int* __restrict__ s1, int* __restrict__ s2, int* __restrict__ dsd,
+                                int* __restrict__ dsm, int* __restrict__ status)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= A.n_reads) return;
+    const sx_pileup_read rd = A.reads[r];
+    if (r > 0 && A.reads[r - 1].pos > rd.pos) atomicOr(status, ST_ORDER);
+    const sx_aln_seg* path = A.segs + rd.seg_off;
+    const uint32_t as = A.reads[r + 1].seg_off - rd.seg_off;
+    if (rd.len > K4_MAX_READ || as > K4_MAX_SEGS)
+    {
+        atomicOr(status, ST_LIMIT);
+        return;
+    }
+    uint32_t ref_span = 0, first = as, last = as;
+    for (uint32_t i = 0; i < as; ++i)
+    {
+        const uint32_t k = path[i].kind;
+        if (kind_ref(k)) ref_span += path[i].len;
+        if (k == SX_SEG_MATCH)
+        {
+            if (first == as) first = i;
+            last = i;
+        }
+        if (k > SX_SEG_SKIP) atomicOr(status, ST_KIND);
+    }
+    const uint8_t* seq = A.seq4 + rd.seq_off;
+    read_window w;
+    if (!read_preamble(A, rd, ref_span, [&](uint32_t i) { return code_at(seq, i); }, w)) return;
+    if (ref_span > A.W || rd.pos < A.origin)
+    {
+        atomicOr(status, ST_ORDER);
+        return;
+    }
+    const bool submapped = !(rd.flags & SX_PRF_TIER1OR2), tier1 = rd.flags & SX_PRF_TIER1;
+    const uint32_t c = static_cast<uint32_t>(rd.pos - A.origin) / A.W;
+    const int64_t next_win_site = static_cast<int64_t>(A.origin) + static_cast<int64_t>(c + 1) * A.W - A.report_begin; // first site of window c+1
+    int64_t ref_head = rd.pos;
+    uint32_t read_head = 0;
+    for (uint32_t i = 0; i < as; ++i)
+    {
+        const uint32_t k = path[i].kind, len = path[i].len;
+        if (k == SX_SEG_MATCH)
+        {
+            const uint32_t rb = max(read_head, w.read_begin), re = min(read_head + len, w.read_end);
+            if (rb < re)
+            {
+                const int64_t p0 = ref_head + (rb - read_head), p1 = p0 + (re - rb);
+                const int64_t a = i64max(p0, A.report_begin) - A.report_begin, b = i64min(p1, A.report_end) - A.report_begin;
+                if (submapped) diff_add(dsm, a, b, A.n_sites);
+                else
+                {
+                    diff_add(tier1 ? d1 : d2, a, b, A.n_sites + 1);
+                    diff_add(tier1 ? s1 : s2, i64max(a, next_win_site), b, A.n_sites);
+                }
+            }
+        }
+        else if (k == SX_SEG_DELETE)
+        {
+            const bool edge = (i < first) || (i > last);
+            const bool pinned = ((i < first) && (rd.flags & SX_PRF_PIN_FIRST)) || ((i > last) && (rd.flags & SX_PRF_PIN_SECOND));
+            if (!edge || pinned)
+            {
+                const int64_t a = i64max(ref_head, A.report_begin) - A.report_begin, b = i64min(ref_head + len, A.report_end) - A.report_begin;
+                diff_add(submapped ? dsm : dsd, a, b, A.n_sites);
+            }
+        }
+        if (kind_read(k)) read_head += len;
+        if (kind_ref(k)) ref_head += len;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pass 2: in-place scans of up to 8 int arrays at once (blockIdx.y picks the array).  Three kernels: tile sums, the scan of the tile
+// sums (one CTA per array), tiles again with their offsets.  exclusive[k] selects the flavour.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t SCAN_TILE = 4096, SCAN_THREADS = 256;
+struct scan_job
+{
+    int* data[8];
+    uint32_t n[8];
+    int exclusive[8];
+};
+
+__device__ __forceinline__ int block_scan_incl(int v, int* warp_sums) // inclusive scan across SCAN_THREADS threads
+{
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const int y = __shfl_up_sync(FULL, v, d);
+        if (lane >= (uint32_t)d) v += y;
+    }
+    if (lane == 31) warp_sums[wid] = v;
+    __syncthreads();
+    if (wid == 0)
+    {
+        int s = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const int y = __shfl_up_sync(FULL, s, d);
+            if (lane >= (uint32_t)d) s += y;
+        }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    if (wid > 0) v += warp_sums[wid - 1];
+    return v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k4_scan_tile_sums(scan_job J, int* __restrict__ tile_sums, uint32_t tiles_per_array)
+{
+    const uint32_t k = blockIdx.y, tile = blockIdx.x;
+    const uint32_t base = tile * SCAN_TILE;
+    if (base >= J.n[k]) return;
+    int s = 0;
+    for (uint32_t i = base + threadIdx.x; i < min(base + SCAN_TILE, J.n[k]); i += SCAN_THREADS) s += J.data[k][i];
+    __shared__ int ws[SCAN_THREADS / 32];
+    const int incl = block_scan_incl(s, ws);
+    if (threadIdx.x == SCAN_THREADS - 1) tile_sums[k * tiles_per_array + tile] = incl;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k4_scan_of_sums(scan_job J, int* __restrict__ tile_sums, uint32_t tiles_per_array)
+{
+    const uint32_t k = blockIdx.x;
+    const uint32_t nt = (J.n[k] + SCAN_TILE - 1) / SCAN_TILE;
+    __shared__ int ws[SCAN_THREADS / 32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t b = 0; b < nt; b += SCAN_THREADS)
+    {
+        const uint32_t i = b + threadIdx.x;
+        const int v = i < nt ? tile_sums[k * tiles_per_array + i] : 0;
+        const int incl = block_scan_incl(v, ws);
+        const int carry = carry_s;
+        if (i < nt) tile_sums[k * tiles_per_array + i] = carry + incl - v; // exclusive prefix of the tile sums
+        __syncthreads();
+        if (threadIdx.x == SCAN_THREADS - 1) carry_s = carry + incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k4_scan_tiles(scan_job J, const int* __restrict__ tile_sums, uint32_t tiles_per_array)
+{
+    const uint32_t k = blockIdx.y, tile = blockIdx.x;
+    const uint32_t base = tile * SCAN_TILE, n = J.n[k];
+    if (base >= n) return;
+    __shared__ int ws[SCAN_THREADS / 32];
+    int carry = tile_sums[k * tiles_per_array + tile];
+    constexpr uint32_t PER = SCAN_TILE / SCAN_THREADS; // consecutive elements per thread
+    int v[PER];
+    int s = 0;
+    const uint32_t i0 = base + threadIdx.x * PER;
+#pragma unroll
+    for (uint32_t e = 0; e < PER; ++e)
+    {
+        v[e] = (i0 + e) < n ? J.data[k][i0 + e] : 0;
+        s += v[e];
+    }
+    const int incl = block_scan_incl(s, ws);
+    int run = carry + incl - s;
+#pragma unroll
+    for (uint32_t e = 0; e < PER; ++e)
+    {
+        const int out = J.exclusive[k] ? run : run + v[e];
+        run += v[e];
+        if ((i0 + e) < n) J.data[k][i0 + e] = out;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pass 3: one warp per window, reads in order
+// ---------------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t k4_warp_smem(uint32_t W)
+{
+    // run1[2W], run2[2W] (uint32), delta[K4_MAX_READ + 1] (int), mism[K4_MAX_READ] (uint8), segment table 3 x K4_MAX_SEGS uint32
+    return 2u * 2u * W * 4u + (K4_MAX_READ + 4u) * 4u + K4_MAX_READ + 3u * K4_MAX_SEGS * 4u;
+}
+
+__device__ __forceinline__ uint32_t lower_bound_pos(const sx_pileup_read* reads, uint32_t n, int64_t pos)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi)
+    {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (reads[mid].pos < pos) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const uint32_t* __restrict__ site_off, const uint32_t* __restrict__ t2_off,
+                                                               const int* __restrict__ spill1, const int* __restrict__ spill2, uint16_t* __restrict__ calls,
+                                                               uint16_t* __restrict__ t2_calls, const sx_tables* __restrict__ tables, int* __restrict__ status)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t c = blockIdx.x * K4_WARPS + warp;
+    if (c >= A.n_windows) return;
+    unsigned char* wsm = smem + (size_t)warp * k4_warp_smem(A.W);
+    uint32_t* run1 = reinterpret_cast<uint32_t*>(wsm);
+    uint32_t* run2 = run1 + 2 * A.W;
+    int* delta = reinterpret_cast<int*>(run2 + 2 * A.W);
+    uint8_t* mism = reinterpret_cast<uint8_t*>(delta + K4_MAX_READ + 4);
+    uint32_t* seg_kl = reinterpret_cast<uint32_t*>(mism + K4_MAX_READ); // kind << 16 | len
+    uint32_t* seg_rd = seg_kl + K4_MAX_SEGS;                            // read offset of the segment
+    uint32_t* seg_rf = seg_rd + K4_MAX_SEGS;                            // reference offset (relative to the alignment position)
+
+    const int64_t win_pos0 = static_cast<int64_t>(A.origin) + static_cast<int64_t>(c) * A.W;
+    const int64_t site0 = win_pos0 - A.report_begin; // site index of local index 0 (negative in window 0)
+    uint32_t lo = 0, hi = 0;
+    if (lane == 0)
+    {
+        lo = lower_bound_pos(A.reads, A.n_reads, win_pos0);
+        hi = lower_bound_pos(A.reads, A.n_reads, win_pos0 + A.W);
+    }
+    lo = __shfl_sync(FULL, lo, 0);
+    hi = __shfl_sync(FULL, hi, 0);
+    if (lo == hi) return;
+    // calls already placed at a site when this window's first read arrives: those of window c-1's reads (own sites only)
+    for (uint32_t li = lane; li < 2 * A.W; li += 32)
+    {
+        const int64_t s = site0 + li;
+        const bool own = li < A.W && s >= 0 && s < static_cast<int64_t>(A.n_sites);
+        run1[li] = own ? static_cast<uint32_t>(spill1[s]) : 0u;
+        run2[li] = own ? static_cast<uint32_t>(spill2[s]) : 0u;
+    }
+    __syncwarp();
+    const bool isDensity = A.opt.mismatchDensityFilterFlankSize > 0;
+    const uint32_t fs = A.opt.mismatchDensityFilterFlankSize, fs2 = fs * 2;
+
+    for (uint32_t r = lo; r < hi; ++r)
+    {
+        const sx_pileup_read rd = A.reads[r];
+        if (!(rd.flags & SX_PRF_TIER1OR2)) continue; // sub-mapped reads only count (pass 1)
+        const uint32_t as = A.reads[r + 1].seg_off - rd.seg_off;
+        if (rd.len > K4_MAX_READ || as > K4_MAX_SEGS) continue; // flagged by pass 1
+        const sx_aln_seg* path = A.segs + rd.seg_off;
+        const uint8_t* seq = A.seq4 + rd.seq_off;
+        const uint8_t* ql = A.qual + rd.qual_off;
+        const uint32_t read_size = rd.len;
+        // segment table (lane 0; paths are a handful of segments)
+        uint32_t ref_span = 0, first = as, last = as;
+        if (lane == 0)
+        {
+            uint32_t rh = 0, fh = 0;
+            for (uint32_t i = 0; i < as; ++i)
+            {
+                const uint32_t k = path[i].kind, len = path[i].len;
+                seg_kl[i] = (k << 16) | len;
+                seg_rd[i] = rh;
+                seg_rf[i] = fh;
+                if (k == SX_SEG_MATCH)
+                {
+                    if (first == as) first = i;
+                    last = i;
+                }
+                if (kind_read(k)) rh += len;
+                if (kind_ref(k)) fh += len;
+            }
+            ref_span = fh;
+        }
+        ref_span = __shfl_sync(FULL, ref_span, 0);
+        first = __shfl_sync(FULL, first, 0);
+        last = __shfl_sync(FULL, last, 0);
+        __syncwarp();
+        read_window w;
+        if (!read_preamble(A, rd, ref_span, [&](uint32_t i) { return code_at(seq, i); }, w)) continue; // uniform across the warp
+        if (ref_span > A.W) continue;                                                                     // flagged by pass 1
+        const bool tier1 = rd.flags & SX_PRF_TIER1, fwd = rd.flags & SX_PRF_FWD;
+        const uint32_t adjustedMapq = max(5u, (uint32_t)rd.mapq);
+        const bool is_mapq_adjust = A.opt.isBasecallQualAdjustedForMapq && adjustedMapq <= 80u;
+        const uint32_t delta_size = max(1u + fs2, read_size) - fs2;
+
+        // segment of read position p (MATCH segments only matter): linear search in the small table
+        auto match_ref_pos = [&](uint32_t p, int64_t& ref_pos) -> bool {
+            for (uint32_t i = 0; i < as; ++i)
+            {
+                const uint32_t kl = seg_kl[i];
+                if ((kl >> 16) != SX_SEG_MATCH) continue;
+                const uint32_t b = seg_rd[i];
+                if (p >= b && p < b + (kl & 0xffffu))
+                {
+                    ref_pos = static_cast<int64_t>(rd.pos) + seg_rf[i] + (p - b);
+                    return true;
+                }
+            }
+            return false;
+        };
+
+        if (isDensity)
+        {
+            // create_mismatch_filter_map: ddata deltas, then their running sum
+            for (uint32_t i = lane; i < delta_size; i += 32) delta[i] = 0;
+            for (uint32_t i = lane; i < read_size; i += 32) mism[i] = 0;
+            __syncwarp();
+            auto inc = [&](uint32_t start_pos, uint32_t length) {
+                atomicAdd(&delta[max(fs2, start_pos) - fs2], 1);
+                if (start_pos + length < delta_size) atomicAdd(&delta[start_pos + length], -1);
+            };
+            for (uint32_t i = lane; i < as; i += 32)
+            {
+                const uint32_t k = seg_kl[i] >> 16, len = seg_kl[i] & 0xffffu;
+                const bool edge = (i < first) || (i > last);
+                if (k == SX_SEG_INSERT && !edge) inc(seg_rd[i], len);
+                else if (k == SX_SEG_DELETE && !edge) inc(seg_rd[i], 0);
+                else if (k == SX_SEG_SKIP) atomicOr(status, ST_KIND); // "Can't handle cigar code" in create_mismatch_filter_map
+            }
+            for (uint32_t p = lane; p < read_size; p += 32)
+            {
+                int64_t ref_pos;
+                if (p < w.read_begin || p >= w.read_end || !match_ref_pos(p, ref_pos)) continue;
+                const uint32_t code = code_at(seq, p);
+                const char readChar = code == 1u ? 'A' : code == 2u ? 'C' : code == 4u ? 'G' : code == 8u ? 'T' : code == 0u ? '=' : 'N';
+                const int64_t ri = ref_pos - A.ref_begin;
+                const char refChar = (ri >= 0 && ri < static_cast<int64_t>(A.ref_len)) ? A.ref[ri] : 'N';
+                if (readChar == refChar) continue;
+                // CandidateSnvBuffer::isCandidateSnvAnySample: a registered (position, base) is not counted as a mismatch
+                bool cand = false;
+                const int id = code == 1u ? 0 : code == 2u ? 1 : code == 4u ? 2 : code == 8u ? 3 : 4;
+                const int64_t rel = ref_pos - A.report_begin;
+                if (id < 4 && rel >= 0 && rel < (static_cast<int64_t>(1) << 30))
+                {
+                    const uint32_t key = (static_cast<uint32_t>(rel) << 2) | static_cast<uint32_t>(id);
+                    uint32_t l2 = 0, h2 = A.n_cand_snv;
+                    while (l2 < h2)
+                    {
+                        const uint32_t mid = (l2 + h2) >> 1;
+                        if (A.cand_snv[mid] < key) l2 = mid + 1;
+                        else h2 = mid;
+                    }
+                    cand = l2 < A.n_cand_snv && A.cand_snv[l2] == key;
+                }
+                if (!cand)
+                {
+                    mism[p] = 1;
+                    inc(p, 1);
+                }
+            }
+            __syncwarp();
+            int carry = 0; // ddata::total
+            for (uint32_t b = 0; b < delta_size; b += 32)
+            {
+                const uint32_t i = b + lane;
+                int v = i < delta_size ? delta[i] : 0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1)
+                {
+                    const int y = __shfl_up_sync(FULL, v, d);
+                    if (lane >= (uint32_t)d) v += y;
+                }
+                v += carry;
+                if (i < delta_size) delta[i] = v;
+                carry = __shfl_sync(FULL, v, 31);
+            }
+            __syncwarp();
+        }
+
+        const int max_pass = static_cast<int>(A.opt.mismatchDensityFilterMaxMismatchCount), max_pass2 = A.opt.tier2MismatchDensityFilterMaxMismatchCount;
+        for (uint32_t p = lane; p < read_size; p += 32)
+        {
+            int64_t ref_pos;
+            if (p < w.read_begin || p >= w.read_end || !match_ref_pos(p, ref_pos)) continue;
+            if (ref_pos < A.report_begin || ref_pos >= A.report_end) continue; // is_pos_reportable
+            const uint32_t call_code = code_at(seq, p);
+            uint32_t call_id;
+            if (call_code == 1u) call_id = 0;
+            else if (call_code == 2u) call_id = 1;
+            else if (call_code == 4u) call_id = 2;
+            else if (call_code == 8u) call_id = 3;
+            else if (call_code == 0u || call_code == 15u) call_id = 4;
+            else
+            {
+                atomicOr(status, ST_BASE);
+                continue;
+            }
+            uint32_t qscore = ql[p];
+            if (is_mapq_adjust)
+            {
+                if (qscore > SX_MAX_QSCORE)
+                {
+                    atomicOr(status, ST_QUAL);
+                    continue;
+                }
+                qscore = tables->mappedq[adjustedMapq][qscore];
+            }
+            bool is_call_filter = (call_code == 15u) || (static_cast<int>(qscore) < A.opt.minBasecallErrorPhredProb);
+            bool is_tier2_call_filter = is_call_filter, is_neighbor_mismatch = false;
+            if (isDensity)
+            {
+                const int del = delta[min(delta_size - 1, max(fs, p) - fs)]; // ddata::get
+                if (!is_call_filter)
+                {
+                    is_call_filter = max_pass < del;
+                    is_tier2_call_filter = A.opt.useTier2Evidence ? (max_pass2 < del) : is_call_filter;
+                }
+                is_neighbor_mismatch = (del - static_cast<int>(mism[p])) > 0;
+            }
+            const bool current_call_filter = tier1 ? is_call_filter : is_tier2_call_filter;
+            const bool is_tier_specific_filter = tier1 && is_call_filter && !is_tier2_call_filter;
+            const uint16_t bc = static_cast<uint16_t>(min(qscore, 63u) | (call_id << 6) | ((fwd ? 1u : 0u) << 10) | ((is_neighbor_mismatch ? 1u : 0u) << 11) |
+                                                      ((current_call_filter ? 1u : 0u) << 12) | ((is_tier_specific_filter ? 1u : 0u) << 13));
+            const int64_t s = ref_pos - A.report_begin;
+            const uint32_t li = static_cast<uint32_t>(s - site0); // < 2W: the read starts in this window and spans <= W
+            if (tier1) calls[site_off[s] + run1[li]++] = bc;
+            else t2_calls[t2_off[s] + run2[li]++] = bc;
+        }
+        __syncwarp();
+    }
+}
+
+int upload(sx_ctx* ctx, int slot, const void* src, size_t bytes, const void** dst, cudaStream_t st)
+{
+    void* p = nullptr;
+    int rc = sx_ensure(ctx, slot, bytes + 64, &p);
+    if (rc) return rc;
+    if (bytes) SX_CUDA(ctx, cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, st));
+    *dst = p;
+    return SX_OK;
+}
+} // namespace
+
+extern "C" void sx_default_pileup_opts(sx_pileup_opts* o)
+{
+    o->isBasecallQualAdjustedForMapq = 1;         // starling_common/starling_base_shared.hh:225
+    o->minBasecallErrorPhredProb = 17;            // blt_common/blt_shared.hh:107
+    o->mismatchDensityFilterFlankSize = 20;       // applications/starling/starling_shared.hh:37
+    o->mismatchDensityFilterMaxMismatchCount = 2; // :36
+    o->useTier2Evidence = 0;                      // starling_base_shared.hh:227
+    o->tier2MismatchDensityFilterMaxMismatchCount = 10; // starling_common/Tier2Options.hh:37
+    o->minDistanceFromReadEdge = 0;               // starling_base_shared.hh:252
+    o->reserved_ = 0;
+}
+
+// all pointers (batch arrays and output columns) are device pointers
+extern "C" int sx_pileup_reads_dev(sx_ctx* ctx, const sx_pileup_reads_batch* d, sx_pileup_columns* out)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    if (!d || !out || !out->site_off || !out->t2_off || !out->n_spandel || !out->n_submapped || !out->calls || !out->t2_calls)
+        return sx_fail(ctx, SX_ERR_ARG, "sx_pileup_reads_dev: NULL argument");
+    if (d->report_end < d->report_begin) return sx_fail(ctx, SX_ERR_ARG, "sx_pileup_reads_dev: empty report range");
+    const uint32_t n_sites = static_cast<uint32_t>(d->report_end - d->report_begin);
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->s_compute;
+    const uint32_t W = std::max<uint32_t>(256, (d->max_ref_span + 31u) & ~31u);
+    if (W > K4_MAX_W)
+        return sx_fail(ctx, SX_ERR_UNSUPPORTED, "sx_pileup_reads: max_ref_span %u exceeds the %u positions a window can hold (spliced alignments are not accelerated)",
+                       d->max_ref_span, K4_MAX_W);
+    k4_args A;
+    A.reads = d->reads;
+    A.seq4 = d->seq4;
+    A.qual = d->qual;
+    A.segs = d->segs;
+    A.ref = d->ref;
+    A.cand_snv = d->cand_snv;
+    A.n_reads = d->n_reads;
+    A.n_cand_snv = d->n_cand_snv;
+    A.ref_len = d->ref_len;
+    A.ref_begin = d->ref_begin;
+    A.report_begin = d->report_begin;
+    A.report_end = d->report_end;
+    A.origin = d->report_begin - static_cast<int32_t>(W);
+    A.W = W;
+    A.n_windows = static_cast<uint32_t>((static_cast<int64_t>(d->report_end) - A.origin + W - 1) / W);
+    A.n_sites = n_sites;
+    A.opt = d->opts;
+
+    sx_kernel_timer t(ctx);
+    // working arrays: the two offset arrays and the two count arrays are scanned in place in the caller's buffers
+    int* d1 = reinterpret_cast<int*>(out->site_off);
+    int* d2 = reinterpret_cast<int*>(out->t2_off);
+    int* dsd = reinterpret_cast<int*>(out->n_spandel);
+    int* dsm = reinterpret_cast<int*>(out->n_submapped);
+    int *s1 = nullptr, *s2 = nullptr, *tile_sums = nullptr;
+    int rc;
+    const uint32_t tiles = (n_sites + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    if ((rc = sx_ensure(ctx, 26, (size_t)(n_sites + 1) * 8 + 64, reinterpret_cast<void**>(&s1)))) return rc;
+    s2 = s1 + (n_sites + 1);
+    if ((rc = sx_ensure(ctx, 27, (size_t)tiles * 8 * sizeof(int) + 64, reinterpret_cast<void**>(&tile_sums)))) return rc;
+    SX_CUDA(ctx, cudaMemsetAsync(d1, 0, (size_t)(n_sites + 1) * 4, st));
+    SX_CUDA(ctx, cudaMemsetAsync(d2, 0, (size_t)(n_sites + 1) * 4, st));
+    SX_CUDA(ctx, cudaMemsetAsync(dsd, 0, (size_t)n_sites * 4, st));
+    SX_CUDA(ctx, cudaMemsetAsync(dsm, 0, (size_t)n_sites * 4, st));
+    SX_CUDA(ctx, cudaMemsetAsync(s1, 0, (size_t)(n_sites + 1) * 8, st));
+    unsigned launches = 0;
+    if (d->n_reads)
+    {
+        k4_count_kernel<<<(d->n_reads + 127) / 128, 128, 0, st>>>(A, d1, d2, s1, s2, dsd, dsm, ctx->d_status);
+        SX_CUDA(ctx, cudaGetLastError());
+        ++launches;
+    }
+    auto run_scans = [&](const scan_job& J, int n_arrays) -> int {
+        const dim3 grid(tiles, n_arrays);
+        k4_scan_tile_sums<<<grid, SCAN_THREADS, 0, st>>>(J, tile_sums, tiles);
+        k4_scan_of_sums<<<n_arrays, SCAN_THREADS, 0, st>>>(J, tile_sums, tiles);
+        k4_scan_tiles<<<grid, SCAN_THREADS, 0, st>>>(J, tile_sums, tiles);
+        SX_CUDA(ctx, cudaGetLastError());
+        launches += 3;
+        return SX_OK;
+    };
+    {
+        scan_job J{}; // differences -> counts
+        int* arr[6] = {d1, d2, s1, s2, dsd, dsm};
+        const uint32_t n[6] = {n_sites + 1, n_sites + 1, n_sites, n_sites, n_sites, n_sites};
+        for (int k = 0; k < 6; ++k)
+        {
+            J.data[k] = arr[k];
+            J.n[k] = n[k];
+            J.exclusive[k] = 0;
+        }
+        if ((rc = run_scans(J, 6))) return rc;
+        scan_job K{}; // counts -> CSR offsets
+        K.data[0] = d1;
+        K.data[1] = d2;
+        K.n[0] = K.n[1] = n_sites + 1;
+        K.exclusive[0] = K.exclusive[1] = 1;
+        if ((rc = run_scans(K, 2))) return rc;
+    }
+    uint32_t totals[2] = {0, 0};
+    SX_CUDA(ctx, cudaMemcpyAsync(&totals[0], out->site_off + n_sites, 4, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaMemcpyAsync(&totals[1], out->t2_off + n_sites, 4, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    if (totals[0] > out->calls_capacity || totals[1] > out->t2_capacity)
+        return sx_fail(ctx, SX_ERR_NOMEM, "sx_pileup_reads: the columns hold %u + %u calls, capacities are %llu + %llu", totals[0], totals[1],
+                       (unsigned long long)out->calls_capacity, (unsigned long long)out->t2_capacity);
+    if (d->n_reads)
+    {
+        const size_t smem = (size_t)k4_warp_smem(W) * K4_WARPS;
+        if (smem > 48 * 1024) SX_CUDA(ctx, cudaFuncSetAttribute(k4_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+        k4_fill_kernel<<<(A.n_windows + K4_WARPS - 1) / K4_WARPS, K4_WARPS * 32, smem, st>>>(A, out->site_off, out->t2_off, s1, s2, out->calls, out->t2_calls, ctx->d_tables,
+                                                                                         ctx->d_status);
+        SX_CUDA(ctx, cudaGetLastError());
+        ++launches;
+    }
+    t.stop(launches);
+    rc = t.finish();
+    if (rc) return rc;
+    return sx_check_status(ctx, "sx_pileup_reads");
+}
+
+extern "C" int sx_pileup_reads(sx_ctx* ctx, const sx_pileup_reads_batch* b, sx_pileup_columns* out)
+{
+    if (!ctx) return SX_ERR_ARG;
+    if (!b || !out || !b->reads || !out->site_off || !out->t2_off || !out->n_spandel || !out->n_submapped)
+        return sx_fail(ctx, SX_ERR_ARG, "sx_pileup_reads: NULL argument");
+    if (b->report_end < b->report_begin) return sx_fail(ctx, SX_ERR_ARG, "sx_pileup_reads: empty report range");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->s_compute;
+    const uint32_t n_sites = static_cast<uint32_t>(b->report_end - b->report_begin);
+    sx_pileup_reads_batch d = *b;
+    int rc;
+    const sx_pileup_read& end = b->reads[b->n_reads];
+    if ((rc = upload(ctx, 0, b->reads, (size_t)(b->n_reads + 1) * sizeof(sx_pileup_read), reinterpret_cast<const void**>(&d.reads), st))) return rc;
+    if ((rc = upload(ctx, 1, b->seq4, end.seq_off, reinterpret_cast<const void**>(&d.seq4), st))) return rc;
+    if ((rc = upload(ctx, 2, b->qual, end.qual_off, reinterpret_cast<const void**>(&d.qual), st))) return rc;
+    if ((rc = upload(ctx, 3, b->segs, (size_t)b->n_segs * sizeof(sx_aln_seg), reinterpret_cast<const void**>(&d.segs), st))) return rc;
+    if ((rc = upload(ctx, 4, b->ref, b->ref_len, reinterpret_cast<const void**>(&d.ref), st))) return rc;
+    if ((rc = upload(ctx, 5, b->cand_snv, (size_t)b->n_cand_snv * 4, reinterpret_cast<const void**>(&d.cand_snv), st))) return rc;
+    sx_pileup_columns dc = *out;
+    void* p = nullptr;
+    if ((rc = sx_ensure(ctx, 6, (size_t)(n_sites + 1) * 4 * 4 + 64, &p))) return rc;
+    dc.site_off = static_cast<uint32_t*>(p);
+    dc.t2_off = dc.site_off + (n_sites + 1);
+    dc.n_spandel = dc.t2_off + (n_sites + 1);
+    dc.n_submapped = dc.n_spandel + (n_sites + 1);
+    if ((rc = sx_ensure(ctx, 7, (size_t)out->calls_capacity * 2 + 64, &p))) return rc;
+    dc.calls = static_cast<uint16_t*>(p);
+    if ((rc = sx_ensure(ctx, 8, (size_t)out->t2_capacity * 2 + 64, &p))) return rc;
+    dc.t2_calls = static_cast<uint16_t*>(p);
+    rc = sx_pileup_reads_dev(ctx, &d, &dc);
+    if (rc && rc != SX_ERR_NOMEM) return rc;
+    // offsets and counts are valid even when a capacity was too small (the caller can size and retry)
+    SX_CUDA(ctx, cudaMemcpyAsync(out->site_off, dc.site_off, (size_t)(n_sites + 1) * 4, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaMemcpyAsync(out->t2_off, dc.t2_off, (size_t)(n_sites + 1) * 4, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaMemcpyAsync(out->n_spandel, dc.n_spandel, (size_t)n_sites * 4, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaMemcpyAsync(out->n_submapped, dc.n_submapped, (size_t)n_sites * 4, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    if (rc) return rc;
+    const uint32_t n1 = out->site_off[n_sites], n2 = out->t2_off[n_sites];
+    if (n1) SX_CUDA(ctx, cudaMemcpyAsync(out->calls, dc.calls, (size_t)n1 * 2, cudaMemcpyDeviceToHost, st));
+    if (n2) SX_CUDA(ctx, cudaMemcpyAsync(out->t2_calls, dc.t2_calls, (size_t)n2 * 2, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    return SX_OK;
+}

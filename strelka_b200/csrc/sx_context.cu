@@ -211,6 +211,18 @@ void build_tables(const sx_params& p, sx_tables& t)
         t.k1_softclip = std::log(0.25);
         t.k1_noncand = std::log(1e-5);
     }
+    // K4: mappedq[j][i] = error_prob_to_qphred(phred_to_mapped_error_prob(i, j))  (qscore_cache.cpp:44-47, qscore.hh:40-63,107-113)
+    {
+        static const double minlog10(static_cast<double>(std::numeric_limits<double>::min_exponent10));
+        for (int i(0); i <= SX_MAX_QSCORE; ++i)
+            for (int j(0); j <= 90; ++j)
+            {
+                const double be(std::pow(10., -static_cast<double>(i) / 10.));
+                const double me(std::pow(10., -static_cast<double>(j) / 10.));
+                const double prob(((1. - me) * be) + (me * 0.75));
+                t.mappedq[j][i] = static_cast<uint8_t>(static_cast<int>(std::floor(-10. * std::max(minlog10, std::log10(prob)) + 0.5)));
+            }
+    }
     // germline: position_snp_call_pprob_digt.cpp:40-43,343-355 ; adjust_joint_eprob.cpp:112-121
     {
         const blt_float_t one_third(1. / 3.);
@@ -480,6 +492,9 @@ int sx_check_status(sx_ctx* ctx, const char* what)
         if (st & 8) return sx_fail(ctx, SX_ERR_ARG, "%s: alignment path consumes more read bases than the read holds", what);
         if (st & 16) return sx_fail(ctx, SX_ERR_UNSUPPORTED, "%s: a site holds more calls than the kernel handles", what);
         if (st & 32) return sx_fail(ctx, SX_ERR_ARG, "%s: allele count outside 1..%d or ploidy outside {1,2}", what, SX_INDEL_MAX_ALLELES);
+        if (st & 64) return sx_fail(ctx, SX_ERR_ARG, "%s: reads are not in position order, or an alignment spans more reference than max_ref_span", what);
+        if (st & 128) return sx_fail(ctx, SX_ERR_ARG, "%s: unknown base code (bam_seq_code_to_id would throw)", what);
+        if (st & 256) return sx_fail(ctx, SX_ERR_UNSUPPORTED, "%s: a read is longer, or has more path segments, than the kernel handles", what);
         return sx_fail(ctx, SX_ERR_ARG, "%s: device status %d", what, st);
     }
     return SX_OK;

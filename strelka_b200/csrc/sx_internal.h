@@ -31,6 +31,8 @@ struct sx_tables
     double k1_tab[SX_K1_ROWS * 2];  // [row][0] mismatch term q2lne+ln(1/3), [row][1] match term q2lncompe
     double k1_softclip;             // ln(0.25)
     double k1_noncand;              // ln(1e-5)
+    // K4: qphred_cache::mappedq[mapq 0..90][basecall q 0..70] (blt_util/qscore_cache.cpp:44-47)
+    uint8_t mappedq[91][SX_MAX_QSCORE + 1];
     // germline site model
     float g_eprob[SX_MAX_QSCORE + 1];     // (float) q2p
     float g_val1[SX_MAX_QSCORE + 1];      // (float)( log(ceprob + (1-ceprob)/3) + ln 1/2 )

@@ -375,3 +375,56 @@ def test_k1_four_bit_quality_wire_format(ctx, seed):
     assert np.array_equal(_bits(reflib.ox_score(b4)), _bits(want))
     assert np.array_equal(_bits(ctx.score_alignments(b4)), _bits(want))
     assert np.array_equal(_bits(ctx.score_alignments(b8)), _bits(want))
+
+
+@pytest.mark.parametrize("mode", ["germline", "somatic", "nofilter", "edge"])
+@pytest.mark.parametrize("seed", range(3))
+def test_k4_pileup_reads(ctx, seed, mode):
+    """K4: the per-position tier1/tier2 base_call columns, in pile-up order, and the spanning-deletion / sub-mapped counts,
+    against the oracle (itself pinned to the reference's pileup_read_segment)."""
+    rng = np.random.default_rng(6000 + seed)
+    reads, ref, ref_begin, cand = specgen.random_pileup_reads(rng, n_reads=int(rng.integers(300, 1500)), ref_len=int(rng.integers(700, 4000)))
+    opts = A.default_pileup_opts()
+    if mode == "somatic":
+        opts = A.SxPileupOpts(1, 0, 20, 3, 1, 10, 0, 0)
+    elif mode == "nofilter":
+        opts = A.SxPileupOpts(0, 17, 0, 0, 0, 10, 0, 0)
+    elif mode == "edge":
+        opts = A.SxPileupOpts(1, 17, 3, 1, 1, 2, 5, 0)
+    lo, hi = ref_begin + 100, ref_begin + len(ref) - 150
+    pb = B.PileupReadsBatch(reads, ref, ref_begin, lo, hi, cand, opts)
+    want = reflib.ox_pileup_reads(pb)
+    got = ctx.pileup_reads(pb)
+    assert int(want[0][-1]) > 1000
+    for w, g, name in zip(want, got, ("site_off", "calls", "t2_off", "t2_calls", "n_spandel", "n_submapped")):
+        assert np.array_equal(w, g), name
+
+
+def test_k4_pileup_feeds_k2(ctx):
+    """The columns K4 produces are an sx_pileup_batch: K2a on them == K2a on the oracle's columns."""
+    rng = np.random.default_rng(6100)
+    reads, ref, ref_begin, cand = specgen.random_pileup_reads(rng, n_reads=1200, ref_len=2500, n_frac=0.0)
+    lo, hi = ref_begin + 50, ref_begin + len(ref) - 50
+    pb = B.PileupReadsBatch(reads, ref, ref_begin, lo, hi, cand)
+    site_off, calls, t2_off, t2_calls, _, _ = ctx.pileup_reads(pb)
+    ref_base = np.frombuffer(ref[lo - ref_begin: hi - ref_begin].encode(), dtype=np.uint8).copy()
+    k2 = B.PileupBatch(site_off.copy(), np.concatenate([calls, np.zeros(16, np.uint16)]), ref_base, None)
+    o = reflib.ox_pileup_reads(pb)
+    k2o = B.PileupBatch(o[0].copy(), np.concatenate([o[1], np.zeros(16, np.uint16)]), ref_base, None)
+    p = A.default_params()
+    got, want = ctx.site_gl_germline(k2, True), reflib.ox_germline(p, k2o, True)
+    for f in ("ref_gt", "is_computed", "n_used_calls", "phredLoghood"):
+        assert np.array_equal(want[f], got[f]), f
+    assert np.array_equal(_bits(want["lhood"]), _bits(got["lhood"]))
+
+
+def test_k4_rejects_unsorted_reads(ctx):
+    from strelka_b200.api import SxError
+
+    rng = np.random.default_rng(6200)
+    reads, ref, ref_begin, cand = specgen.random_pileup_reads(rng, n_reads=50, ref_len=800)
+    reads[10], reads[40] = reads[40], reads[10]
+    pb = B.PileupReadsBatch(reads, ref, ref_begin, ref_begin, ref_begin + len(ref), cand)
+    with pytest.raises(SxError) as e:
+        ctx.pileup_reads(pb)
+    assert e.value.code == A.SX_ERR_ARG
