@@ -142,6 +142,108 @@ def make_workload(synth, alloc: HostAlloc, n_loci: int, depth: int, read_len: in
     return ab, pb, gb
 
 
+def make_pileup_reads_workload(n_sites: int, depth: int, read_len: int, seed: int):
+    """K4 input: reads over one contig segment in pile-up order (vectorised numpy): 90 % plain matches, 5 % with a 3-base deletion,
+    5 % with a 3-base insertion, 0.5 % base errors, qualities {11, 25, 37}, both strands, tier1 mapping."""
+    rng = np.random.default_rng(seed)
+    L = read_len
+    n_reads = n_sites * depth // L
+    ref_len = n_sites + 2 * L + 16
+    ref_id = rng.integers(0, 4, ref_len, dtype=np.uint8)
+    starts = np.sort(rng.integers(0, n_sites + L - 8, n_reads)).astype(np.int64)  # window-relative; report range starts at L
+    shape = rng.random(n_reads)
+    is_del, is_ins = shape < 0.05, (shape >= 0.05) & (shape < 0.10)
+    cut = rng.integers(20, L - 20, n_reads)
+    j = np.arange(L, dtype=np.int64)[None, :]
+    # reference offset of read base j: deletions skip 3 reference bases after `cut`, insertions hold the reference for 3 read bases
+    roff = j + np.where(is_del[:, None] & (j >= cut[:, None]), 3, 0) - np.where(is_ins[:, None], np.clip(j - cut[:, None], 0, 3), 0)
+    base = ref_id[np.minimum(starts[:, None] + roff, ref_len - 1)]
+    err = rng.random((n_reads, L)) < 0.005
+    base = np.where(err, rng.integers(0, 4, (n_reads, L), dtype=np.uint8), base).astype(np.uint8)
+    code = (1 << base).astype(np.uint8)
+    if L & 1:
+        code = np.concatenate([code, np.zeros((n_reads, 1), np.uint8)], axis=1)
+    seq4 = ((code[:, 0::2] << 4) | code[:, 1::2]).astype(np.uint8).reshape(-1)
+    qual = rng.choice(np.array([11, 25, 37], np.uint8), size=(n_reads, L), p=[0.03, 0.07, 0.90]).reshape(-1)
+    n_seg = np.where(is_del | is_ins, 3, 1)
+    seg_off = np.concatenate([[0], np.cumsum(n_seg)]).astype(np.uint32)
+    segs = np.zeros(int(seg_off[-1]) + 16, dtype=A.ALN_SEG_DT)
+    plain = ~(is_del | is_ins)
+    segs["len"][seg_off[:-1][plain]] = L
+    for mask, kind, tail in ((is_del, A.SX_SEG_DELETE, 0), (is_ins, A.SX_SEG_INSERT, 3)):
+        o = seg_off[:-1][mask]
+        segs["len"][o], segs["len"][o + 1], segs["len"][o + 2] = cut[mask], 3, L - cut[mask] - tail
+        segs["kind"][o + 1] = kind
+    hdr = np.zeros(n_reads + 1, dtype=A.PILEUP_READ_DT)
+    packed = (L + 1) // 2
+    hdr["seq_off"][:-1] = np.arange(n_reads, dtype=np.uint64) * packed
+    hdr["qual_off"][:-1] = np.arange(n_reads, dtype=np.uint64) * L
+    hdr["seg_off"] = seg_off
+    hdr["pos"][:-1] = starts
+    hdr["len"][:-1] = L
+    hdr["mapq"][:-1] = 60
+    hdr["flags"][:-1] = (A.SX_PRF_TIER1 | A.SX_PRF_TIER1OR2) | (rng.random(n_reads) < 0.5).astype(np.uint8)
+    hdr[n_reads] = (n_reads * packed, n_reads * L, seg_off[-1], 0, 0, 0, 0)
+    ref = np.frombuffer(b"ACGT", dtype=np.uint8)[ref_id]
+    return {"reads": hdr, "seq4": np.concatenate([seq4, np.zeros(64, np.uint8)]), "qual": np.concatenate([qual, np.zeros(64, np.uint8)]), "segs": segs,
+            "ref": np.concatenate([ref, np.zeros(64, np.uint8)]), "ref_len": ref_len, "n_reads": n_reads, "n_segs": int(seg_off[-1]),
+            "report_begin": L, "report_end": L + n_sites, "max_ref_span": L + 3, "bases": n_reads * L}
+
+
+def k4_pileup_leg(ctx, peak_gbs: float, n_sites: int = 2_000_000, depth: int = 30, read_len: int = 150, reps: int = 5, cpu_reads: int = 20000):
+    """SURVEY 8f1 measured beside the headline step (not part of `value`): K4 pileup_reads, inputs and outputs resident in HBM;
+    the reference's own pileup_read_segment on one host thread over the first `cpu_reads` reads as the CPU figure."""
+    from strelka_b200.api import DeviceArray
+
+    w = make_pileup_reads_workload(n_sites, depth, read_len, 12345)
+    dev = {k: DeviceArray(ctx, w[k].nbytes + 64).upload(w[k]) for k in ("reads", "seq4", "qual", "segs", "ref")}
+    opts = A.default_pileup_opts()
+    bc = A.SxPileupReadsBatch(w["n_reads"], w["n_segs"], dev["reads"].ptr, dev["seq4"].ptr, dev["qual"].ptr, dev["segs"].ptr, dev["ref"].ptr, 0, w["ref_len"],
+                              w["report_begin"], w["report_end"], None, 0, w["max_ref_span"], opts)
+    cap = w["bases"] + 16
+    out = {"site_off": DeviceArray(ctx, (n_sites + 1) * 4), "t2_off": DeviceArray(ctx, (n_sites + 1) * 4), "n_spandel": DeviceArray(ctx, n_sites * 4),
+           "n_submapped": DeviceArray(ctx, n_sites * 4), "calls": DeviceArray(ctx, cap * 2), "t2_calls": DeviceArray(ctx, 64)}
+    cols = A.SxPileupColumns(out["site_off"].ptr, out["calls"].ptr, out["t2_off"].ptr, out["t2_calls"].ptr, out["n_spandel"].ptr, out["n_submapped"].ptr, cap, 16)
+    ms = []
+    for i in range(reps + 2):
+        ctx._chk(ctx.lib.sx_pileup_reads_dev(ctx.h, C.byref(bc), C.byref(cols)))
+        if i >= 2:
+            ms.append(ctx.timing().kernel_ms)
+    n_calls = int(out["site_off"].download(np.uint32, n_sites + 1)[-1])
+    t = float(np.mean(ms)) * 1e-3
+    # algorithmic bytes: every read byte once (packed bases + qualities + header + segments), every call once, the per-site arrays
+    alg = w["bases"] * 1.5 + w["n_reads"] * 20 + w["n_segs"] * 4 + n_calls * 2 + n_sites * 16 + w["ref_len"]
+    leg = {"what": f"K4 pileup_reads: {n_sites} positions at {depth}x, {read_len} bp reads, resident in HBM", "bases_per_s": w["bases"] / t, "ms": 1e3 * t,
+           "calls": n_calls, "roofline": {"bound": "hbm", "achieved": alg / t / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": alg / t / 1e9 / peak_gbs,
+                                          "algorithmic_bytes": int(alg)}}
+    # CPU figure: the reference's member function on a prefix of the reads (one thread: the pos processor is not thread safe)
+    p = os.path.join(ROOT, "oracle", "_ref", "libstrelka_ref.so")
+    if os.path.exists(p):
+        rf = C.CDLL(p)
+        m = min(cpu_reads, w["n_reads"])
+        hdr = w["reads"][: m + 1].copy()
+        hdr[m] = (m * ((read_len + 1) // 2), m * read_len, hdr["seg_off"][m], 0, 0, 0, 0)
+        hi = int(hdr["pos"][m - 1]) + read_len + 8
+        hb = A.SxPileupReadsBatch(m, int(hdr["seg_off"][m]), A.ptr(hdr), A.ptr(w["seq4"]), A.ptr(w["qual"]), A.ptr(w["segs"]), A.ptr(w["ref"]), 0, w["ref_len"],
+                                  w["report_begin"], min(hi, w["report_end"]), None, 0, w["max_ref_span"], opts)
+        ns = hb.report_end - hb.report_begin
+        so, t2o = np.zeros(ns + 1, np.uint32), np.zeros(ns + 1, np.uint32)
+        cl, t2c = np.zeros(m * read_len + 16, np.uint16), np.zeros(16, np.uint16)
+        sd, sm = np.zeros(ns, np.uint32), np.zeros(ns, np.uint32)
+        err = C.create_string_buffer(512)
+        fn = rf.ref_pileup_reads
+        fn.argtypes = [C.POINTER(A.SxPileupReadsBatch), C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        t0 = time.perf_counter()
+        rc = fn(C.byref(hb), A.ptr(so), A.ptr(cl), cl.size, A.ptr(t2o), A.ptr(t2c), t2c.size, A.ptr(sd), A.ptr(sm), err, 512)
+        dt_cpu = time.perf_counter() - t0
+        if rc == 0:
+            leg["cpu_reference"] = {"bases_per_s": m * read_len / dt_cpu, "cores": 1,
+                                    "sample": f"first {m} reads through starling_pos_processor_base::pileup_read_segment (incl. the shim's read construction)"}
+    for d in list(dev.values()) + list(out.values()):
+        d.free()
+    return leg
+
+
 def workload_cells(ab: B.AlignBatch, gb: B.GaBatch) -> int:
     return ab.cells() + gb.cells()
 
@@ -260,6 +362,7 @@ def main():
     ap.add_argument("--loci", type=int, default=0, help="override the number of candidate loci per GPU")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pileup", action="store_true", help="skip the K4 pileup_reads leg (SURVEY 8f1) measured beside the headline step")
     ap.add_argument("--cpu-sample-loci", type=int, default=0)
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
@@ -472,6 +575,8 @@ def main():
             line["cpu_baseline"] = {"value": n / t_cpu, "unit": "loci/s", "cores": ncpu, "kind": kind,
                                     "sample": f"first {n} loci of the workload, one pass, {ncpu} host threads, "
                                               + ("oracle/_ref/libstrelka_ref.so (the reference's own functions)" if kind == "reference" else "oracle/liboracle.so")}
+            if not args.no_pileup and args.config != "tiny":
+                line["k4_pileup"] = k4_pileup_leg(ctx, peak)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

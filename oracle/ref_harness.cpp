@@ -747,12 +747,14 @@ extern "C" int ref_pileup_reads(const sx_pileup_reads_batch* b, uint32_t* site_o
             for (const base_call& bc : pi.calls)
             {
                 if (n1 >= calls_cap) throw blt_exception("ref_pileup_reads: calls capacity");
-                std::memcpy(&calls[n1++], &bc, 2);
+                std::memcpy(&calls[n1], &bc, 2);
+                calls[n1++] &= 0x3fffu; // the bit-field struct has 14 used bits; the two padding bits are indeterminate
             }
             for (const base_call& bc : pi.tier2_calls)
             {
                 if (n2 >= t2_cap) throw blt_exception("ref_pileup_reads: tier2 capacity");
-                std::memcpy(&t2_calls[n2++], &bc, 2);
+                std::memcpy(&t2_calls[n2], &bc, 2);
+                t2_calls[n2++] &= 0x3fffu;
             }
             n_spandel[i] = pi.spanningDeletionReadCount;
             n_submapped[i] = pi.submappedReadCount;

@@ -182,3 +182,25 @@ def test_pileup_reads_columns_match_the_reference(seed, mode):
     assert int(want[0][-1]) > 1000 and int(want[4].sum()) > 0 and int(want[5].sum()) > 0
     for w, g, name in zip(want, got, ("site_off", "calls", "t2_off", "t2_calls", "n_spandel", "n_submapped")):
         assert np.array_equal(w, g), name
+
+
+def test_pileup_bench_workload_matches_the_reference():
+    """The K4 leg of bench.py: the oracle and the reference's pileup_read_segment agree on the synthetic read set it times."""
+    import ctypes as C
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    w = bench.make_pileup_reads_workload(8000, 30, 150, 3)
+    hb = A.SxPileupReadsBatch(w["n_reads"], w["n_segs"], A.ptr(w["reads"]), A.ptr(w["seq4"]), A.ptr(w["qual"]), A.ptr(w["segs"]), A.ptr(w["ref"]), 0, w["ref_len"],
+                              w["report_begin"], w["report_end"], None, 0, w["max_ref_span"], A.default_pileup_opts())
+
+    class _PB:  # the two fields the reflib wrappers need beside the ABI struct
+        c, n_sites, total_bases = hb, w["report_end"] - w["report_begin"], w["bases"]
+
+    want, got = reflib.ref_pileup_reads(_PB), reflib.ox_pileup_reads(_PB)
+    assert int(want[0][-1]) > 0.9 * w["bases"] * 8000 / (8000 + 150) and int(want[4].sum()) > 0
+    for a, b, name in zip(want, got, ("site_off", "calls", "t2_off", "t2_calls", "n_spandel", "n_submapped")):
+        assert np.array_equal(a, b), name
