@@ -199,7 +199,7 @@ def k4_pileup_leg(ctx, peak_gbs: float, n_sites: int = 2_000_000, depth: int = 3
     dev = {k: DeviceArray(ctx, w[k].nbytes + 64).upload(w[k]) for k in ("reads", "seq4", "qual", "segs", "ref")}
     opts = A.default_pileup_opts()
     bc = A.SxPileupReadsBatch(w["n_reads"], w["n_segs"], dev["reads"].ptr, dev["seq4"].ptr, dev["qual"].ptr, dev["segs"].ptr, dev["ref"].ptr, 0, w["ref_len"],
-                              w["report_begin"], w["report_end"], None, 0, w["max_ref_span"], opts)
+                              w["report_begin"], w["report_end"], None, 0, w["max_ref_span"], read_len, 0, opts)
     cap = w["bases"] + 16
     out = {"site_off": DeviceArray(ctx, (n_sites + 1) * 4), "t2_off": DeviceArray(ctx, (n_sites + 1) * 4), "n_spandel": DeviceArray(ctx, n_sites * 4),
            "n_submapped": DeviceArray(ctx, n_sites * 4), "calls": DeviceArray(ctx, cap * 2), "t2_calls": DeviceArray(ctx, 64)}
@@ -225,7 +225,7 @@ def k4_pileup_leg(ctx, peak_gbs: float, n_sites: int = 2_000_000, depth: int = 3
         hdr[m] = (m * ((read_len + 1) // 2), m * read_len, hdr["seg_off"][m], 0, 0, 0, 0)
         hi = int(hdr["pos"][m - 1]) + read_len + 8
         hb = A.SxPileupReadsBatch(m, int(hdr["seg_off"][m]), A.ptr(hdr), A.ptr(w["seq4"]), A.ptr(w["qual"]), A.ptr(w["segs"]), A.ptr(w["ref"]), 0, w["ref_len"],
-                                  w["report_begin"], min(hi, w["report_end"]), None, 0, w["max_ref_span"], opts)
+                                  w["report_begin"], min(hi, w["report_end"]), None, 0, w["max_ref_span"], read_len, 0, opts)
         ns = hb.report_end - hb.report_begin
         so, t2o = np.zeros(ns + 1, np.uint32), np.zeros(ns + 1, np.uint32)
         cl, t2c = np.zeros(m * read_len + 16, np.uint16), np.zeros(16, np.uint16)

@@ -432,6 +432,8 @@ typedef struct sx_pileup_reads_batch {
     const uint32_t* cand_snv;    /* sorted keys ((pos - report_begin) << 2) | base id: CandidateSnvBuffer::isCandidateSnvAnySample */
     uint32_t n_cand_snv;
     uint32_t max_ref_span;       /* >= the reference span of every read's alignment; the kernel tiles the range by windows >= this */
+    uint32_t max_read_len;       /* >= every read's length (0 = unknown: the kernel's limit of 1024 is assumed) */
+    uint32_t reserved_;
     sx_pileup_opts opts;
 } sx_pileup_reads_batch;
 

@@ -159,6 +159,8 @@ class SxPileupReadsBatch(C.Structure):
         ("cand_snv", C.c_void_p),
         ("n_cand_snv", C.c_uint32),
         ("max_ref_span", C.c_uint32),
+        ("max_read_len", C.c_uint32),
+        ("reserved_", C.c_uint32),
         ("opts", SxPileupOpts),
     ]
 

@@ -523,7 +523,7 @@ class PileupReadsBatch:
         self.opts = opts or A.default_pileup_opts()
         self.c = A.SxPileupReadsBatch(
             len(reads), len(segs), A.ptr(self.reads), A.ptr(self.seq4), A.ptr(self.qual), A.ptr(self.segs), A.ptr(self.ref), ref_begin, len(ref),
-            report_begin, report_end, A.ptr(self.cand_snv), len(keys), span, self.opts,
+            report_begin, report_end, A.ptr(self.cand_snv), len(keys), span, int(hdr["len"].max(initial=1)), 0, self.opts,
         )
 
 

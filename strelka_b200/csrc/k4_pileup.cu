@@ -41,12 +41,23 @@ struct k4_args
     int32_t ref_begin, report_begin, report_end;
     int32_t origin; // position of window 0's first site (= report_begin - W)
     uint32_t W, n_windows, n_sites;
+    uint32_t Lcap; // read-length capacity of the per-warp arrays (the batch's longest read, rounded up)
     sx_pileup_opts opt;
 };
 
 __device__ __forceinline__ uint32_t code_at(const uint8_t* seq, uint32_t i) { return (seq[i >> 1] >> ((~i & 1u) << 2)) & 15u; }
 __device__ __forceinline__ bool kind_ref(uint32_t k) { return k == SX_SEG_MATCH || k == SX_SEG_DELETE || k == SX_SEG_SKIP; }
 __device__ __forceinline__ bool kind_read(uint32_t k) { return k == SX_SEG_MATCH || k == SX_SEG_INSERT || k == SX_SEG_SOFTCLIP; }
+
+// bam_seq code -> base_call id (0..3 ACGT, 4 for '=' / 'N', 5 = bam_seq_code_to_id would throw) and -> bam_seq::get_char, as nibble /
+// byte look-ups in 64-bit literals: a branch per base value makes the compiler duplicate the whole loop body per branch
+__device__ __forceinline__ uint32_t id_of_code(uint32_t c) { return static_cast<uint32_t>(0x4555555355525104ull >> (4u * c)) & 15u; }
+__device__ __forceinline__ char char_of_code(uint32_t c)
+{
+    // codes 0..7: '=', 'A', 'C', 'N', 'G', 'N', 'N', 'N'; codes 8..15: 'T', 'N' x 7
+    const unsigned long long lut = c < 8u ? 0x4e4e4e474e43413dull : 0x4e4e4e4e4e4e4e54ull;
+    return static_cast<char>((lut >> (8u * (c & 7u))) & 0xffu);
+}
 
 __device__ __forceinline__ int64_t i64max(int64_t a, int64_t b) { return a > b ? a : b; }
 __device__ __forceinline__ int64_t i64min(int64_t a, int64_t b) { return a < b ? a : b; }
@@ -110,7 +121,7 @@ __global__ void k4_count_kernel(k4_args A, int* __restrict__ d1, int* __restrict
     if (r > 0 && A.reads[r - 1].pos > rd.pos) atomicOr(status, ST_ORDER);
     const sx_aln_seg* path = A.segs + rd.seg_off;
     const uint32_t as = A.reads[r + 1].seg_off - rd.seg_off;
-    if (rd.len > K4_MAX_READ || as > K4_MAX_SEGS)
+    if (rd.len > A.Lcap || as > K4_MAX_SEGS)
     {
         atomicOr(status, ST_LIMIT);
         return;
@@ -276,10 +287,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k4_scan_tiles(scan_job J, const 
 // ---------------------------------------------------------------------------------------------------------------------
 // pass 3: one warp per window, reads in order
 // ---------------------------------------------------------------------------------------------------------------------
-__host__ __device__ inline uint32_t k4_warp_smem(uint32_t W)
+__host__ __device__ inline uint32_t k4_warp_smem(uint32_t W, uint32_t Lcap)
 {
-    // run1[2W], run2[2W] (uint32), delta[K4_MAX_READ + 1] (int), mism[K4_MAX_READ] (uint8), segment table 3 x K4_MAX_SEGS uint32
-    return 2u * 2u * W * 4u + (K4_MAX_READ + 4u) * 4u + K4_MAX_READ + 3u * K4_MAX_SEGS * 4u;
+    // run1[2W], run2[2W] (uint32), delta[Lcap + 4] (int), mism[Lcap] (uint8), segment table 3 x K4_MAX_SEGS uint32; Lcap % 16 == 0
+    return 2u * 2u * W * 4u + (Lcap + 4u) * 4u + Lcap + 3u * K4_MAX_SEGS * 4u;
 }
 
 __device__ __forceinline__ uint32_t lower_bound_pos(const sx_pileup_read* reads, uint32_t n, int64_t pos)
@@ -302,12 +313,12 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t c = blockIdx.x * K4_WARPS + warp;
     if (c >= A.n_windows) return;
-    unsigned char* wsm = smem + (size_t)warp * k4_warp_smem(A.W);
+    unsigned char* wsm = smem + (size_t)warp * k4_warp_smem(A.W, A.Lcap);
     uint32_t* run1 = reinterpret_cast<uint32_t*>(wsm);
     uint32_t* run2 = run1 + 2 * A.W;
     int* delta = reinterpret_cast<int*>(run2 + 2 * A.W);
-    uint8_t* mism = reinterpret_cast<uint8_t*>(delta + K4_MAX_READ + 4);
-    uint32_t* seg_kl = reinterpret_cast<uint32_t*>(mism + K4_MAX_READ); // kind << 16 | len
+    uint8_t* mism = reinterpret_cast<uint8_t*>(delta + A.Lcap + 4);
+    uint32_t* seg_kl = reinterpret_cast<uint32_t*>(mism + A.Lcap); // kind << 16 | len
     uint32_t* seg_rd = seg_kl + K4_MAX_SEGS;                            // read offset of the segment
     uint32_t* seg_rf = seg_rd + K4_MAX_SEGS;                            // reference offset (relative to the alignment position)
 
@@ -322,13 +333,14 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
     lo = __shfl_sync(FULL, lo, 0);
     hi = __shfl_sync(FULL, hi, 0);
     if (lo == hi) return;
-    // calls already placed at a site when this window's first read arrives: those of window c-1's reads (own sites only)
+    // write cursor of every site this window's reads can reach: the start of its column + (own sites only) the calls of window c-1's
+    // reads, which all precede this window's reads
     for (uint32_t li = lane; li < 2 * A.W; li += 32)
     {
         const int64_t s = site0 + li;
-        const bool own = li < A.W && s >= 0 && s < static_cast<int64_t>(A.n_sites);
-        run1[li] = own ? static_cast<uint32_t>(spill1[s]) : 0u;
-        run2[li] = own ? static_cast<uint32_t>(spill2[s]) : 0u;
+        const bool in = s >= 0 && s < static_cast<int64_t>(A.n_sites), own = in && li < A.W;
+        run1[li] = in ? site_off[s] + (own ? static_cast<uint32_t>(spill1[s]) : 0u) : 0u;
+        run2[li] = in ? t2_off[s] + (own ? static_cast<uint32_t>(spill2[s]) : 0u) : 0u;
     }
     __syncwarp();
     const bool isDensity = A.opt.mismatchDensityFilterFlankSize > 0;
@@ -339,7 +351,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
         const sx_pileup_read rd = A.reads[r];
         if (!(rd.flags & SX_PRF_TIER1OR2)) continue; // sub-mapped reads only count (pass 1)
         const uint32_t as = A.reads[r + 1].seg_off - rd.seg_off;
-        if (rd.len > K4_MAX_READ || as > K4_MAX_SEGS) continue; // flagged by pass 1
+        if (rd.len > A.Lcap || as > K4_MAX_SEGS) continue; // flagged by pass 1
         const sx_aln_seg* path = A.segs + rd.seg_off;
         const uint8_t* seq = A.seq4 + rd.seq_off;
         const uint8_t* ql = A.qual + rd.qual_off;
@@ -416,13 +428,13 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
                 int64_t ref_pos;
                 if (p < w.read_begin || p >= w.read_end || !match_ref_pos(p, ref_pos)) continue;
                 const uint32_t code = code_at(seq, p);
-                const char readChar = code == 1u ? 'A' : code == 2u ? 'C' : code == 4u ? 'G' : code == 8u ? 'T' : code == 0u ? '=' : 'N';
+                const char readChar = char_of_code(code);
                 const int64_t ri = ref_pos - A.ref_begin;
                 const char refChar = (ri >= 0 && ri < static_cast<int64_t>(A.ref_len)) ? A.ref[ri] : 'N';
                 if (readChar == refChar) continue;
                 // CandidateSnvBuffer::isCandidateSnvAnySample: a registered (position, base) is not counted as a mismatch
                 bool cand = false;
-                const int id = code == 1u ? 0 : code == 2u ? 1 : code == 4u ? 2 : code == 8u ? 3 : 4;
+                const int id = static_cast<int>(id_of_code(code));
                 const int64_t rel = ref_pos - A.report_begin;
                 if (id < 4 && rel >= 0 && rel < (static_cast<int64_t>(1) << 30))
                 {
@@ -468,13 +480,8 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
             if (p < w.read_begin || p >= w.read_end || !match_ref_pos(p, ref_pos)) continue;
             if (ref_pos < A.report_begin || ref_pos >= A.report_end) continue; // is_pos_reportable
             const uint32_t call_code = code_at(seq, p);
-            uint32_t call_id;
-            if (call_code == 1u) call_id = 0;
-            else if (call_code == 2u) call_id = 1;
-            else if (call_code == 4u) call_id = 2;
-            else if (call_code == 8u) call_id = 3;
-            else if (call_code == 0u || call_code == 15u) call_id = 4;
-            else
+            const uint32_t call_id = id_of_code(call_code);
+            if (call_id > 4u)
             {
                 atomicOr(status, ST_BASE);
                 continue;
@@ -507,8 +514,8 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
                                                       ((current_call_filter ? 1u : 0u) << 12) | ((is_tier_specific_filter ? 1u : 0u) << 13));
             const int64_t s = ref_pos - A.report_begin;
             const uint32_t li = static_cast<uint32_t>(s - site0); // < 2W: the read starts in this window and spans <= W
-            if (tier1) calls[site_off[s] + run1[li]++] = bc;
-            else t2_calls[t2_off[s] + run2[li]++] = bc;
+            if (tier1) calls[run1[li]++] = bc;
+            else t2_calls[run2[li]++] = bc;
         }
         __syncwarp();
     }
@@ -548,7 +555,8 @@ extern "C" int sx_pileup_reads_dev(sx_ctx* ctx, const sx_pileup_reads_batch* d, 
     const uint32_t n_sites = static_cast<uint32_t>(d->report_end - d->report_begin);
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->s_compute;
-    const uint32_t W = std::max<uint32_t>(256, (d->max_ref_span + 31u) & ~31u);
+    const uint32_t W = std::max<uint32_t>(64, (d->max_ref_span + 31u) & ~31u);
+    const uint32_t Lcap = std::max<uint32_t>(64, (std::min<uint32_t>(d->max_read_len ? d->max_read_len : K4_MAX_READ, K4_MAX_READ) + 15u) & ~15u);
     if (W > K4_MAX_W)
         return sx_fail(ctx, SX_ERR_UNSUPPORTED, "sx_pileup_reads: max_ref_span %u exceeds the %u positions a window can hold (spliced alignments are not accelerated)",
                        d->max_ref_span, K4_MAX_W);
@@ -567,6 +575,7 @@ extern "C" int sx_pileup_reads_dev(sx_ctx* ctx, const sx_pileup_reads_batch* d, 
     A.report_end = d->report_end;
     A.origin = d->report_begin - static_cast<int32_t>(W);
     A.W = W;
+    A.Lcap = Lcap;
     A.n_windows = static_cast<uint32_t>((static_cast<int64_t>(d->report_end) - A.origin + W - 1) / W);
     A.n_sites = n_sites;
     A.opt = d->opts;
@@ -631,7 +640,7 @@ extern "C" int sx_pileup_reads_dev(sx_ctx* ctx, const sx_pileup_reads_batch* d, 
                        (unsigned long long)out->calls_capacity, (unsigned long long)out->t2_capacity);
     if (d->n_reads)
     {
-        const size_t smem = (size_t)k4_warp_smem(W) * K4_WARPS;
+        const size_t smem = (size_t)k4_warp_smem(W, Lcap) * K4_WARPS;
         if (smem > 48 * 1024) SX_CUDA(ctx, cudaFuncSetAttribute(k4_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
         k4_fill_kernel<<<(A.n_windows + K4_WARPS - 1) / K4_WARPS, K4_WARPS * 32, smem, st>>>(A, out->site_off, out->t2_off, s1, s2, out->calls, out->t2_calls, ctx->d_tables,
                                                                                          ctx->d_status);

@@ -195,7 +195,7 @@ def test_pileup_bench_workload_matches_the_reference():
 
     w = bench.make_pileup_reads_workload(8000, 30, 150, 3)
     hb = A.SxPileupReadsBatch(w["n_reads"], w["n_segs"], A.ptr(w["reads"]), A.ptr(w["seq4"]), A.ptr(w["qual"]), A.ptr(w["segs"]), A.ptr(w["ref"]), 0, w["ref_len"],
-                              w["report_begin"], w["report_end"], None, 0, w["max_ref_span"], A.default_pileup_opts())
+                              w["report_begin"], w["report_end"], None, 0, w["max_ref_span"], 150, 0, A.default_pileup_opts())
 
     class _PB:  # the two fields the reflib wrappers need beside the ABI struct
         c, n_sites, total_bases = hb, w["report_end"] - w["report_begin"], w["bases"]
