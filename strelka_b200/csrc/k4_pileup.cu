@@ -289,8 +289,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k4_scan_tiles(scan_job J, const 
 // ---------------------------------------------------------------------------------------------------------------------
 __host__ __device__ inline uint32_t k4_warp_smem(uint32_t W, uint32_t Lcap)
 {
-    // run1[2W], run2[2W] (uint32), delta[Lcap + 4] (int), mism[Lcap] (uint8), segment table 3 x K4_MAX_SEGS uint32; Lcap % 16 == 0
-    return 2u * 2u * W * 4u + (Lcap + 4u) * 4u + Lcap + 3u * K4_MAX_SEGS * 4u;
+    // run1[2W], run2[2W] (uint32), delta[Lcap + 4] (int), mism[Lcap] (uint8), segment table 3 x K4_MAX_SEGS uint32, and the staged
+    // read: packed bases [Lcap/2 + 16], qualities [Lcap], reference bases under the alignment [W + 16], mappedq row [80]; Lcap % 16 == 0
+    return 2u * 2u * W * 4u + (Lcap + 4u) * 4u + Lcap + 3u * K4_MAX_SEGS * 4u + (Lcap / 2u + 16u) + Lcap + (W + 16u) + 80u;
 }
 
 __device__ __forceinline__ uint32_t lower_bound_pos(const sx_pileup_read* reads, uint32_t n, int64_t pos)
@@ -321,6 +322,11 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
     uint32_t* seg_kl = reinterpret_cast<uint32_t*>(mism + A.Lcap); // kind << 16 | len
     uint32_t* seg_rd = seg_kl + K4_MAX_SEGS;                            // read offset of the segment
     uint32_t* seg_rf = seg_rd + K4_MAX_SEGS;                            // reference offset (relative to the alignment position)
+    uint8_t* seq = reinterpret_cast<uint8_t*>(seg_rf + K4_MAX_SEGS);    // the current read, staged once per read by coalesced loads
+    uint8_t* ql = seq + (A.Lcap / 2u + 16u);
+    char* refb = reinterpret_cast<char*>(ql + A.Lcap);                  // refb[i] = reference base at rd.pos + i ('N' outside the segment)
+    uint8_t* mqrow = reinterpret_cast<uint8_t*>(refb + (A.W + 16u));    // mappedq[adjustedMapq][*]
+    uint32_t mqrow_of = 0xffffffffu;
 
     const int64_t win_pos0 = static_cast<int64_t>(A.origin) + static_cast<int64_t>(c) * A.W;
     const int64_t site0 = win_pos0 - A.report_begin; // site index of local index 0 (negative in window 0)
@@ -353,8 +359,6 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
         const uint32_t as = A.reads[r + 1].seg_off - rd.seg_off;
         if (rd.len > A.Lcap || as > K4_MAX_SEGS) continue; // flagged by pass 1
         const sx_aln_seg* path = A.segs + rd.seg_off;
-        const uint8_t* seq = A.seq4 + rd.seq_off;
-        const uint8_t* ql = A.qual + rd.qual_off;
         const uint32_t read_size = rd.len;
         // segment table (lane 0; paths are a handful of segments)
         uint32_t ref_span = 0, first = as, last = as;
@@ -381,29 +385,37 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
         first = __shfl_sync(FULL, first, 0);
         last = __shfl_sync(FULL, last, 0);
         __syncwarp();
+        if (ref_span > A.W) continue; // flagged by pass 1
+        if (rd.pos >= A.report_end || static_cast<int64_t>(rd.pos) + ref_span <= A.report_begin) continue; // (the preamble's range test, before staging)
+        const uint32_t adjustedMapq = max(5u, (uint32_t)rd.mapq);
+        {
+            // stage the read: every later access is shared memory
+            const uint8_t* gs = A.seq4 + rd.seq_off;
+            const uint8_t* gq = A.qual + rd.qual_off;
+            for (uint32_t i = lane; i < (read_size + 1) / 2; i += 32) seq[i] = gs[i];
+            for (uint32_t i = lane; i < read_size; i += 32) ql[i] = gq[i];
+            for (uint32_t i = lane; i < ref_span; i += 32)
+            {
+                const int64_t ri = static_cast<int64_t>(rd.pos) + i - A.ref_begin;
+                refb[i] = (ri >= 0 && ri < static_cast<int64_t>(A.ref_len)) ? A.ref[ri] : 'N';
+            }
+            if (mqrow_of != adjustedMapq)
+            {
+                for (uint32_t i = lane; i <= SX_MAX_QSCORE; i += 32) mqrow[i] = tables->mappedq[min(adjustedMapq, 90u)][i];
+                mqrow_of = adjustedMapq;
+            }
+        }
+        __syncwarp();
         read_window w;
         if (!read_preamble(A, rd, ref_span, [&](uint32_t i) { return code_at(seq, i); }, w)) continue; // uniform across the warp
-        if (ref_span > A.W) continue;                                                                     // flagged by pass 1
         const bool tier1 = rd.flags & SX_PRF_TIER1, fwd = rd.flags & SX_PRF_FWD;
-        const uint32_t adjustedMapq = max(5u, (uint32_t)rd.mapq);
         const bool is_mapq_adjust = A.opt.isBasecallQualAdjustedForMapq && adjustedMapq <= 80u;
         const uint32_t delta_size = max(1u + fs2, read_size) - fs2;
 
-        // segment of read position p (MATCH segments only matter): linear search in the small table
-        auto match_ref_pos = [&](uint32_t p, int64_t& ref_pos) -> bool {
-            for (uint32_t i = 0; i < as; ++i)
-            {
-                const uint32_t kl = seg_kl[i];
-                if ((kl >> 16) != SX_SEG_MATCH) continue;
-                const uint32_t b = seg_rd[i];
-                if (p >= b && p < b + (kl & 0xffffu))
-                {
-                    ref_pos = static_cast<int64_t>(rd.pos) + seg_rf[i] + (p - b);
-                    return true;
-                }
-            }
-            return false;
-        };
+        // Both per-base passes walk the MATCH segments (a warp-uniform loop) and stride the lanes over each segment's trimmed bases:
+        // no per-base segment search, and positions stay 32-bit offsets from the alignment start.
+        const int32_t pos_rel = static_cast<int32_t>(static_cast<int64_t>(rd.pos) - A.report_begin); // site index of the alignment start
+        const int32_t site0_32 = static_cast<int32_t>(site0);
 
         if (isDensity)
         {
@@ -423,20 +435,22 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
                 else if (k == SX_SEG_DELETE && !edge) inc(seg_rd[i], 0);
                 else if (k == SX_SEG_SKIP) atomicOr(status, ST_KIND); // "Can't handle cigar code" in create_mismatch_filter_map
             }
-            for (uint32_t p = lane; p < read_size; p += 32)
+            for (uint32_t si = 0; si < as; ++si)
             {
-                int64_t ref_pos;
-                if (p < w.read_begin || p >= w.read_end || !match_ref_pos(p, ref_pos)) continue;
+                const uint32_t kl = seg_kl[si];
+                if ((kl >> 16) != SX_SEG_MATCH) continue;
+                const uint32_t sb = seg_rd[si], sf = seg_rf[si];
+                const uint32_t p_lo = max(sb, w.read_begin), p_hi = min(sb + (kl & 0xffffu), w.read_end);
+            for (uint32_t p = p_lo + lane; p < p_hi; p += 32)
+            {
+                const uint32_t roff = sf + (p - sb); // reference offset from the alignment start
                 const uint32_t code = code_at(seq, p);
-                const char readChar = char_of_code(code);
-                const int64_t ri = ref_pos - A.ref_begin;
-                const char refChar = (ri >= 0 && ri < static_cast<int64_t>(A.ref_len)) ? A.ref[ri] : 'N';
-                if (readChar == refChar) continue;
+                if (char_of_code(code) == refb[roff]) continue;
                 // CandidateSnvBuffer::isCandidateSnvAnySample: a registered (position, base) is not counted as a mismatch
                 bool cand = false;
                 const int id = static_cast<int>(id_of_code(code));
-                const int64_t rel = ref_pos - A.report_begin;
-                if (id < 4 && rel >= 0 && rel < (static_cast<int64_t>(1) << 30))
+                const int32_t rel = pos_rel + static_cast<int32_t>(roff);
+                if (id < 4 && rel >= 0 && rel < (1 << 30))
                 {
                     const uint32_t key = (static_cast<uint32_t>(rel) << 2) | static_cast<uint32_t>(id);
                     uint32_t l2 = 0, h2 = A.n_cand_snv;
@@ -453,6 +467,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
                     mism[p] = 1;
                     inc(p, 1);
                 }
+            }
             }
             __syncwarp();
             int carry = 0; // ddata::total
@@ -474,11 +489,16 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
         }
 
         const int max_pass = static_cast<int>(A.opt.mismatchDensityFilterMaxMismatchCount), max_pass2 = A.opt.tier2MismatchDensityFilterMaxMismatchCount;
-        for (uint32_t p = lane; p < read_size; p += 32)
+        for (uint32_t si = 0; si < as; ++si)
         {
-            int64_t ref_pos;
-            if (p < w.read_begin || p >= w.read_end || !match_ref_pos(p, ref_pos)) continue;
-            if (ref_pos < A.report_begin || ref_pos >= A.report_end) continue; // is_pos_reportable
+            const uint32_t kl = seg_kl[si];
+            if ((kl >> 16) != SX_SEG_MATCH) continue;
+            const uint32_t sb = seg_rd[si], sf = seg_rf[si];
+            const uint32_t p_lo = max(sb, w.read_begin), p_hi = min(sb + (kl & 0xffffu), w.read_end);
+        for (uint32_t p = p_lo + lane; p < p_hi; p += 32)
+        {
+            const int32_t s = pos_rel + static_cast<int32_t>(sf + (p - sb)); // site index
+            if (s < 0 || s >= static_cast<int32_t>(A.n_sites)) continue;       // is_pos_reportable
             const uint32_t call_code = code_at(seq, p);
             const uint32_t call_id = id_of_code(call_code);
             if (call_id > 4u)
@@ -494,7 +514,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
                     atomicOr(status, ST_QUAL);
                     continue;
                 }
-                qscore = tables->mappedq[adjustedMapq][qscore];
+                qscore = mqrow[qscore];
             }
             bool is_call_filter = (call_code == 15u) || (static_cast<int>(qscore) < A.opt.minBasecallErrorPhredProb);
             bool is_tier2_call_filter = is_call_filter, is_neighbor_mismatch = false;
@@ -512,10 +532,10 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
             const bool is_tier_specific_filter = tier1 && is_call_filter && !is_tier2_call_filter;
             const uint16_t bc = static_cast<uint16_t>(min(qscore, 63u) | (call_id << 6) | ((fwd ? 1u : 0u) << 10) | ((is_neighbor_mismatch ? 1u : 0u) << 11) |
                                                       ((current_call_filter ? 1u : 0u) << 12) | ((is_tier_specific_filter ? 1u : 0u) << 13));
-            const int64_t s = ref_pos - A.report_begin;
-            const uint32_t li = static_cast<uint32_t>(s - site0); // < 2W: the read starts in this window and spans <= W
+            const uint32_t li = static_cast<uint32_t>(s - site0_32); // < 2W: the read starts in this window and spans <= W
             if (tier1) calls[run1[li]++] = bc;
             else t2_calls[run2[li]++] = bc;
+        }
         }
         __syncwarp();
     }
