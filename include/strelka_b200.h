@@ -453,6 +453,105 @@ int sx_pileup_reads(sx_ctx* ctx, const sx_pileup_reads_batch* batch_host, sx_pil
 int sx_pileup_reads_dev(sx_ctx* ctx, const sx_pileup_reads_batch* batch_dev, sx_pileup_columns* out_dev);
 
 /* ==========================================================================================
+ * K6  score_indels   (the consumer of K1's scores)
+ *   replaces, per read segment that is a tier1 or tier2 mapping,
+ *     the arg-max epilogue of scoreCandidateAlignments   starling_common/starling_read_align.cpp:1573-1593
+ *       (ties by isFirstCandidateAlignmentPreferred :1352-1377, getExtraPathInfo :1295-1320, getCandidateIndelCount :1324-1336)
+ *     score_indels                                        starling_common/starling_read_align_score_indels.cpp:454-1079
+ *       with late_indel_normalization_filter :281-450, is_equiv_candidate :247-276, is_first_indel_dominant :285-300,
+ *       get_alignment_indel_bp_overlap :131-234, which_interfering_indel :100-118, is_indel_conflict (indel_util.cpp:29-45),
+ *       IndelBuffer::rangeIterator (IndelBuffer.cpp:76-91), get_soft_clip_alignment_range (alignment_util.cpp:45-55),
+ *       getLowestFwdReadPosForRefRange (alignment_util.cpp:272-302), ReadPathScores::insertAlt (IndelData.cpp:42-68)
+ *   called from scoreCandidateAlignmentsAndIndels (starling_read_align.cpp:1750-1812).
+ *
+ * Input: K1's scores where K1 left them (device, one double per candidate alignment) plus the small integer description the
+ * reference's containers hold: per region the IndelBuffer entries of its window in IndelKey order, per alignment its path and the
+ * keys of its indels.  Output: what score_indels writes into the IndelBuffer -- one record per (read, evaluated indel): the
+ * ReadPathScores entry (read_path_lnp[readId]) or the suboverlap mark -- in IndelKey order per read.
+ * The std::map / std::set bookkeeping of the reference becomes per-read maxima over its alignments.
+ * ======================================================================================== */
+#define SX_INDEL_TYPE_INDEL 0u    /* INDEL::INDEL */
+#define SX_INDEL_TYPE_MISMATCH 1u /* INDEL::MISMATCH (never evaluated, never "interfering", conflicts without the +1 margin) */
+#define SX_IKF_CANDIDATE 0x1u     /* indelBuffer.isCandidateIndel(key) */
+
+typedef struct sx_indel_key { /* one IndelBuffer entry; a region's entries are in IndelKey order (IndelKey.hh:53-76) */
+    int32_t pos;
+    uint16_t del_len;          /* IndelKey::delete_length() */
+    uint16_t ins_len;          /* IndelKey::insert_length() */
+    uint32_t ins_id;           /* within a region: equal insert sequences <=> equal ins_id (0 = empty) */
+    uint8_t type;              /* SX_INDEL_TYPE_* ; breakends are not supported (SX_ERR_UNSUPPORTED) */
+    uint8_t flags;             /* SX_IKF_* */
+    uint16_t pad;
+    double ref_to_indel_lnp;   /* getSampleData(sample).getErrorRates().refToIndelErrorProb.getLogValue() */
+    double indel_to_ref_lnp;   /* ... indelToRefErrorProb.getLogValue() */
+} sx_indel_key;
+
+#define SX_SIF_FWD 0x01u        /* cal.al.is_fwd_strand (the same for every candidate alignment of a read) */
+#define SX_SIF_TIER1 0x02u      /* rseg.is_tier1_mapping(); clear = tier2 (reads that are neither are not sent) */
+#define SX_SIF_INCOMPLETE 0x04u /* is_incomplete_search (starling_read_align.cpp:2100) */
+
+typedef struct sx_score_indels_opts {
+    uint32_t max_indel_size;         /* opt.maxIndelSize, 49 */
+    uint32_t upstream_oligo_size;    /* 0 */
+    int32_t min_read_bp_flank;       /* sample_opt.min_read_bp_flank, 5 */
+    int32_t is_smoothed_alignments;  /* 1 */
+    double smoothed_lnp_range;       /* std::log(10.) */
+} sx_score_indels_opts;
+
+typedef struct sx_score_indels_batch {
+    uint32_t n_regions, n_reads, n_alns, n_keys;
+    const uint32_t* region_read_off; /* [n_regions + 1] the reads of a region */
+    const uint32_t* region_key_off;  /* [n_regions + 1] its IndelBuffer window: every entry a rangeIterator() over any of its
+                                        alignments can visit, at most 65535 per region */
+    const sx_indel_key* keys;        /* [n_keys] */
+    const uint32_t* aln_off;         /* [n_reads + 1] read r owns scores lnp[aln_off[r] .. aln_off[r+1]) -- K1's alignment order,
+                                        which is the iteration order of std::set<CandidateAlignment> */
+    const int32_t* aln_pos;          /* [n_alns] cal.al.pos */
+    const uint32_t* aln_seg_off;     /* [n_alns + 1] */
+    const sx_aln_seg* segs;          /* cal.al.path: MATCH (also SEQ_MATCH / SEQ_MISMATCH), INSERT, SX_SEG_DELETE, SOFTCLIP, HARDCLIP;
+                                        flags unused; SX_SEG_SKIP is outside score_indels' domain (its assert, :176) */
+    const uint32_t* aln_key_off;     /* [n_alns + 1] */
+    const uint16_t* aln_keys;        /* cal.getIndels(): indices into the region's window, ascending */
+    const uint16_t* read_len;        /* [n_reads] rseg.read_size() */
+    const uint16_t* non_ambig;       /* [n_reads] bases of the segment that are not 'N' (:866-875) */
+    const uint16_t* full_len;        /* [n_reads] rseg.full_read_size();   NULL: == read_len  */
+    const uint16_t* full_off;        /* [n_reads] rseg.full_read_offset(); NULL: 0            */
+    const uint8_t* read_flags;       /* [n_reads] SX_SIF_* */
+    const uint32_t* rec_off;         /* [n_reads + 1] output slots of each read; a read never needs more than the number of
+                                        window entries with pos in [min soft-clip begin - max_indel_size, max soft-clip end) */
+    sx_score_indels_opts opts;
+} sx_score_indels_batch;
+
+#define SX_RIS_SCORED 0x1u        /* read_path_lnp[readId] = ReadPathScores(...) (:1069) */
+#define SX_RIS_SUBOVERLAP 0x2u    /* suboverlap_tier{1,2}_read_ids.insert(readId) (:640-648); the tier is the read's */
+
+typedef struct sx_read_indel_score { /* 32 bytes */
+    uint16_t key;            /* index into the region's window */
+    uint8_t flags;           /* SX_RIS_* */
+    uint8_t n_alt;           /* ReadPathScores::alt_indel.size(), <= 2 */
+    int16_t read_pos;        /* ReadPathScores::read_pos */
+    int16_t dist_from_edge;  /* ReadPathScores::distanceFromClosestReadEdge */
+    float ref_lnp;           /* ReadPathScores::ref   */
+    float indel_lnp;         /* ReadPathScores::indel */
+    uint16_t alt_key[2];     /* alt_indel[i].first, as window index */
+    float alt_lnp[2];        /* alt_indel[i].second */
+    uint32_t pad;
+} sx_read_indel_score;
+
+typedef struct sx_score_indels_out { /* caller-allocated */
+    sx_read_indel_score* recs; /* [rec_off[n_reads]]; read r's records are recs[rec_off[r] .. rec_off[r] + n_rec[r]) */
+    uint32_t* n_rec;           /* [n_reads] */
+    uint32_t* max_aln;         /* [n_reads] maxCandAlignmentPtr after scoreCandidateAlignments (:1593), as alignment index */
+    uint32_t* eval_aln;        /* [n_reads] ... after late_indel_normalization_filter (:430-449): the alignment score_indels evaluates */
+} sx_score_indels_out;
+
+void sx_default_score_indels_opts(sx_score_indels_opts* o);
+/* lnp: the K1 scores, [n_alns].  Host variant copies everything; the _dev variant takes device pointers inside *batch_dev,
+ * lnp_dev (typically the buffer sx_score_alignments_dev just wrote) and *out_dev. */
+int sx_score_indels(sx_ctx* ctx, const sx_score_indels_batch* batch_host, const double* lnp_host, sx_score_indels_out* out_host);
+int sx_score_indels_dev(sx_ctx* ctx, const sx_score_indels_batch* batch_dev, const double* lnp_dev, sx_score_indels_out* out_dev);
+
+/* ==========================================================================================
  * Multi-GPU: regions shard across ranks with no data-path collective; one gather of fixed-size
  * call records at the end (the in-memory analogue of concatIndexVcf,
  * src/python/lib/strelkaSharedWorkflow.py:126-136).  The NCCL communicator is created from an

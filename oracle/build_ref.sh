@@ -96,7 +96,8 @@ ar rcs libboost.a obj/boost_1_58_0_subset_*.o
 
 # 5. the harness .so --------------------------------------------------------------------------
 g++ $CXXFLAGS $INC -include limits -I"$REF/src/c++/lib/starling_common" -c "$HERE/ref_harness.cpp" -o obj/ref_harness.o
-g++ -shared -o "$OUT/libstrelka_ref.so" obj/ref_harness.o \
+g++ $CXXFLAGS $INC -include limits -I"$REF/src/c++/lib/starling_common" -c "$HERE/ref_harness_score_indels.cpp" -o obj/ref_harness_score_indels.o
+g++ -shared -o "$OUT/libstrelka_ref.so" obj/ref_harness.o obj/ref_harness_score_indels.o \
     -Wl,--start-group libapp_strelka.a libreftest.a libcommon.a -Wl,--end-group libboost.a \
     htslib-1.7-6-g6d2bfb7/libhts.a -lz -lpthread
 echo "built $OUT/libstrelka_ref.so"

@@ -38,6 +38,11 @@ int ox_site_gl_somatic(const sx_params* p, const sx_pileup_batch* normal, const 
 int ox_site_gl_somatic_range(const sx_params* p, const sx_pileup_batch* normal, const sx_pileup_batch* tumor,
                              const uint8_t* is_forced_output, uint32_t s0, uint32_t s1, sx_ssnv_result* out);
 
+/* f2: the arg-max epilogue of scoreCandidateAlignments (starling_read_align.cpp:1573-1593) + score_indels
+ * (starling_read_align_score_indels.cpp:454-1079); oracle/score_indels_oracle.cpp */
+void ox_default_score_indels_opts(sx_score_indels_opts* o);
+int ox_score_indels(const sx_score_indels_batch* b, const double* lnp, sx_read_indel_score* recs, uint32_t* n_rec, uint32_t* max_aln, uint32_t* eval_aln);
+
 /* restatements of the host-libm single-precision routines the device mirrors (glibc 2.39 x86_64 FMA ifunc variants),
  * exported so tests can compare them with the real logf/powf exhaustively */
 float ox_logf_restated(float x);

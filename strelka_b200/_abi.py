@@ -183,6 +183,40 @@ def default_pileup_opts() -> SxPileupOpts:
     return SxPileupOpts(1, 17, 20, 2, 0, 10, 0, 0)
 
 
+# K6 score_indels
+SX_INDEL_TYPE_INDEL, SX_INDEL_TYPE_MISMATCH = 0, 1
+SX_IKF_CANDIDATE = 1
+SX_SIF_FWD, SX_SIF_TIER1, SX_SIF_INCOMPLETE = 1, 2, 4
+SX_RIS_SCORED, SX_RIS_SUBOVERLAP = 1, 2
+INDEL_KEY_DT = np.dtype([("pos", "<i4"), ("del_len", "<u2"), ("ins_len", "<u2"), ("ins_id", "<u4"), ("type", "u1"), ("flags", "u1"), ("pad", "<u2"),
+                         ("ref_to_indel_lnp", "<f8"), ("indel_to_ref_lnp", "<f8")])
+READ_INDEL_SCORE_DT = np.dtype([("key", "<u2"), ("flags", "u1"), ("n_alt", "u1"), ("read_pos", "<i2"), ("dist_from_edge", "<i2"), ("ref_lnp", "<f4"),
+                                ("indel_lnp", "<f4"), ("alt_key", "<u2", (2,)), ("alt_lnp", "<f4", (2,)), ("pad", "<u4")])
+assert INDEL_KEY_DT.itemsize == 32 and READ_INDEL_SCORE_DT.itemsize == 32
+
+
+class SxScoreIndelsOpts(C.Structure):
+    _fields_ = [("max_indel_size", C.c_uint32), ("upstream_oligo_size", C.c_uint32), ("min_read_bp_flank", C.c_int32), ("is_smoothed_alignments", C.c_int32),
+                ("smoothed_lnp_range", C.c_double)]
+
+
+class SxScoreIndelsBatch(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("n_regions", "n_reads", "n_alns", "n_keys")] + [(n, C.c_void_p) for n in (
+        "region_read_off", "region_key_off", "keys", "aln_off", "aln_pos", "aln_seg_off", "segs", "aln_key_off", "aln_keys", "read_len", "non_ambig",
+        "full_len", "full_off", "read_flags", "rec_off")] + [("opts", SxScoreIndelsOpts)]
+
+
+class SxScoreIndelsOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("recs", "n_rec", "max_aln", "eval_aln")]
+
+
+def default_score_indels_opts() -> SxScoreIndelsOpts:
+    """starling_base_options defaults (starling_base_shared.hh:108,124,170-171,206)."""
+    import math
+
+    return SxScoreIndelsOpts(49, 0, 5, 1, math.log(10.0))
+
+
 class SxGaScores(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("match", "mismatch", "open", "extend", "offEdge", "insertDelete", "isAllowEdgeInsertion", "isRequireEdgeDeletion")]
 
@@ -241,6 +275,9 @@ SYMBOLS = [
     ("sx_dependent_eprob", C.c_int, [_P, C.POINTER(SxPileupBatch), _P, _P]),
     ("sx_site_gl_somatic", C.c_int, [_P, C.POINTER(SxPileupBatch), C.POINTER(SxPileupBatch), _P, _P]),
     ("sx_site_gl_somatic_dev", C.c_int, [_P, C.POINTER(SxPileupBatch), C.POINTER(SxPileupBatch), _P, _P]),
+    ("sx_default_score_indels_opts", None, [C.POINTER(SxScoreIndelsOpts)]),
+    ("sx_score_indels", C.c_int, [_P, C.POINTER(SxScoreIndelsBatch), _P, C.POINTER(SxScoreIndelsOut)]),
+    ("sx_score_indels_dev", C.c_int, [_P, C.POINTER(SxScoreIndelsBatch), _P, C.POINTER(SxScoreIndelsOut)]),
     ("sx_indel_gl", C.c_int, [_P, C.POINTER(SxIndelBatch), _P]),
     ("sx_indel_gl_dev", C.c_int, [_P, C.POINTER(SxIndelBatch), _P]),
     ("sx_default_pileup_opts", None, [C.POINTER(SxPileupOpts)]),

@@ -539,3 +539,109 @@ class PileupColumns:
 
     def trimmed(self):
         return (self.site_off, self.calls[: int(self.site_off[-1])], self.t2_off, self.t2_calls[: int(self.t2_off[-1])], self.n_spandel, self.n_submapped)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# K6 score_indels
+# ---------------------------------------------------------------------------------------------------------------------------
+class WindowKeySpec:
+    """One IndelBuffer entry of a region's window (IndelKey + the per-sample facts score_indels reads)."""
+
+    def __init__(self, pos, del_len=0, ins="", mismatch=False, candidate=True, ref_to_indel_lnp=-11.5, indel_to_ref_lnp=-11.5):
+        self.pos, self.del_len, self.ins, self.mismatch, self.candidate = pos, del_len, ins, mismatch, candidate
+        self.ref_to_indel_lnp, self.indel_to_ref_lnp = ref_to_indel_lnp, indel_to_ref_lnp
+
+    def order(self):
+        """IndelKey::operator< (IndelKey.hh:53-76): pos, type, insert length, delete length, insert sequence."""
+        return (self.pos, 2 if self.mismatch else 1, len(self.ins), self.del_len, self.ins)
+
+
+class ScoredReadSpec:
+    """A read segment with its candidate alignments: alns = [(pos, [(kind, len)...], [window index...])] in std::set order."""
+
+    def __init__(self, length, alns, fwd=True, tier1=True, non_ambig=None, incomplete=False):
+        self.length, self.alns, self.fwd, self.tier1, self.incomplete = length, alns, fwd, tier1, incomplete
+        self.non_ambig = length if non_ambig is None else non_ambig
+
+
+class ScoreIndelsBatch:
+    """Owns the arrays of one sx_score_indels_batch.  regions = [(window keys in IndelKey order, reads)]."""
+
+    def __init__(self, regions, opts=None):
+        keys, ins_pool, ins_off = [], bytearray(), [0]
+        region_read_off, region_key_off = [0], [0]
+        aln_off, aln_pos, aln_seg_off, segs, aln_key_off, aln_keys = [0], [], [0], [], [0], []
+        read_len, non_ambig, read_flags, rec_off = [], [], [], [0]
+        for win, reads in regions:
+            assert len(win) <= 65535
+            assert all(win[i].order() < win[i + 1].order() for i in range(len(win) - 1)), "window must be in IndelKey order"
+            intern = {"": 0}
+            for k in win:
+                iid = intern.setdefault(k.ins, len(intern))
+                keys.append((k.pos, k.del_len, len(k.ins), iid, A.SX_INDEL_TYPE_MISMATCH if k.mismatch else A.SX_INDEL_TYPE_INDEL,
+                             A.SX_IKF_CANDIDATE if k.candidate else 0, 0, k.ref_to_indel_lnp, k.indel_to_ref_lnp))
+                ins_pool.extend(k.ins.encode())
+                ins_off.append(len(ins_pool))
+            for r in reads:
+                for pos, path, kidx in r.alns:
+                    aln_pos.append(pos)
+                    segs.extend((ln, _PILEUP_KIND[k], 0) for k, ln in path)
+                    aln_seg_off.append(len(segs))
+                    assert list(kidx) == sorted(set(kidx)) and all(0 <= i < len(win) for i in kidx)
+                    aln_keys.extend(kidx)
+                    aln_key_off.append(len(aln_keys))
+                aln_off.append(len(aln_pos))
+                read_len.append(r.length)
+                non_ambig.append(r.non_ambig)
+                read_flags.append((A.SX_SIF_FWD if r.fwd else 0) | (A.SX_SIF_TIER1 if r.tier1 else 0) | (A.SX_SIF_INCOMPLETE if r.incomplete else 0))
+                rec_off.append(rec_off[-1] + len(win))
+            region_read_off.append(len(read_len))
+            region_key_off.append(len(keys))
+        u32 = lambda x: np.array(x, dtype=np.uint32)  # noqa: E731  (every list starts with its leading 0)
+        self.n_regions, self.n_reads, self.n_alns, self.n_keys = len(regions), len(read_len), len(aln_pos), len(keys)
+        self.region_read_off, self.region_key_off = u32(region_read_off), u32(region_key_off)
+        self.keys = np.zeros(len(keys) + 1, dtype=A.INDEL_KEY_DT)
+        if keys:
+            self.keys[: len(keys)] = np.array(keys, dtype=A.INDEL_KEY_DT)
+        self.aln_off, self.aln_seg_off, self.aln_key_off, self.rec_off = u32(aln_off), u32(aln_seg_off), u32(aln_key_off), u32(rec_off)
+        self.aln_pos = np.array(aln_pos + [0], dtype=np.int32)
+        self.segs = np.zeros(len(segs) + 16, dtype=A.ALN_SEG_DT)
+        if segs:
+            self.segs[: len(segs)] = np.array(segs, dtype=A.ALN_SEG_DT)
+        self.aln_keys = np.array(aln_keys + [0], dtype=np.uint16)
+        self.read_len = np.array(read_len + [0], dtype=np.uint16)
+        self.non_ambig = np.array(non_ambig + [0], dtype=np.uint16)
+        self.read_flags = np.array(read_flags + [0], dtype=np.uint8)
+        self.n_segs, self.n_aln_keys, self.n_rec_slots = len(segs), len(aln_keys), rec_off[-1]
+        # test-only: the insert sequences behind ins_id (the reference harness rebuilds IndelKeys from them)
+        self.ins_pool = np.frombuffer(bytes(ins_pool) + b"\0", dtype=np.uint8).copy()
+        self.ins_off = u32(ins_off)
+        self.opts = opts or A.default_score_indels_opts()
+        self.c = A.SxScoreIndelsBatch(
+            self.n_regions, self.n_reads, self.n_alns, self.n_keys, A.ptr(self.region_read_off), A.ptr(self.region_key_off), A.ptr(self.keys),
+            A.ptr(self.aln_off), A.ptr(self.aln_pos), A.ptr(self.aln_seg_off), A.ptr(self.segs), A.ptr(self.aln_key_off), A.ptr(self.aln_keys),
+            A.ptr(self.read_len), A.ptr(self.non_ambig), None, None, A.ptr(self.read_flags), A.ptr(self.rec_off), self.opts,
+        )
+
+    def algorithmic_bytes(self) -> int:
+        """bytes one pass must move: every input array once + the scores + one record slot header per read."""
+        return (self.n_keys * 32 + self.n_alns * (8 + 4 + 4 + 4) + self.n_segs * 4 + self.n_aln_keys * 2 + self.n_reads * (4 + 2 + 2 + 1 + 4 + 12))
+
+
+class ScoreIndelsOut:
+    """Host buffers for sx_score_indels_out."""
+
+    def __init__(self, sb: ScoreIndelsBatch):
+        self.recs = np.zeros(sb.n_rec_slots + 1, dtype=A.READ_INDEL_SCORE_DT)
+        self.n_rec = np.zeros(sb.n_reads + 1, np.uint32)
+        self.max_aln = np.zeros(sb.n_reads + 1, np.uint32)
+        self.eval_aln = np.zeros(sb.n_reads + 1, np.uint32)
+        self.c = A.SxScoreIndelsOut(A.ptr(self.recs), A.ptr(self.n_rec), A.ptr(self.max_aln), A.ptr(self.eval_aln))
+        self._sb = sb
+
+    def compact(self):
+        """(per-read record lists concatenated, n_rec, max_aln, eval_aln) with the unused slots dropped."""
+        sb = self._sb
+        parts = [self.recs[int(sb.rec_off[r]) : int(sb.rec_off[r]) + int(self.n_rec[r])] for r in range(sb.n_reads)]
+        recs = np.concatenate(parts) if parts else self.recs[:0]
+        return recs, self.n_rec[: sb.n_reads].copy(), self.max_aln[: sb.n_reads].copy(), self.eval_aln[: sb.n_reads].copy()

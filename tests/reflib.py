@@ -223,3 +223,38 @@ def ref_pileup_reads(pb: "B.PileupReadsBatch"):
     if rc != 0:
         raise RuntimeError(err.value.decode(errors="replace"))
     return out.trimmed()
+
+
+def ox_score_indels(sb: "B.ScoreIndelsBatch", lnp: np.ndarray):
+    out = B.ScoreIndelsOut(sb)
+    lib = oracle()
+    lib.ox_score_indels.argtypes = [C.POINTER(A.SxScoreIndelsBatch), _P, _P, _P, _P, _P]
+    rc = lib.ox_score_indels(C.byref(sb.c), A.ptr(lnp), A.ptr(out.recs), A.ptr(out.n_rec), A.ptr(out.max_aln), A.ptr(out.eval_aln))
+    assert rc == 0, rc
+    return out.compact()
+
+
+def ref_candidate_alignment_order(sb: "B.ScoreIndelsBatch") -> np.ndarray:
+    """Iteration order of the reference's std::set<CandidateAlignment> over each read's alignments (as alignment indices)."""
+    perm = np.zeros(sb.n_alns + 1, np.uint32)
+    err = _err()
+    fn = ref().ref_candidate_alignment_order
+    fn.argtypes = [C.POINTER(A.SxScoreIndelsBatch), _P, _P, _P, C.c_char_p, C.c_int]
+    rc = fn(C.byref(sb.c), A.ptr(sb.ins_pool), A.ptr(sb.ins_off), A.ptr(perm), err, 1024)
+    if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    return perm[: sb.n_alns]
+
+
+def ref_score_indels(sb: "B.ScoreIndelsBatch", lnp: np.ndarray):
+    """The reference's own score_indels on rebuilt IndelBuffer / read_segment / CandidateAlignment objects
+    (oracle/ref_harness_score_indels.cpp); returns (records, n_rec, max_aln)."""
+    out = B.ScoreIndelsOut(sb)
+    err = _err()
+    fn = ref().ref_score_indels
+    fn.argtypes = [C.POINTER(A.SxScoreIndelsBatch), _P, _P, _P, _P, _P, _P, C.c_char_p, C.c_int]
+    rc = fn(C.byref(sb.c), A.ptr(lnp), A.ptr(sb.ins_pool), A.ptr(sb.ins_off), A.ptr(out.recs), A.ptr(out.n_rec), A.ptr(out.max_aln), err, 1024)
+    if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    recs, n_rec, max_aln, _ = out.compact()
+    return recs, n_rec, max_aln

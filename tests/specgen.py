@@ -417,3 +417,110 @@ def random_pileup_reads(rng: np.random.Generator, n_reads: int = 200, ref_len: i
         tier = int(rng.choice([1, 1, 1, 1, 2, 0]))
         reads.append(B.PileupReadSpec(codes, quals, ref_begin + s0, merged, fwd=bool(rng.random() < 0.5), mapq=int(rng.choice([0, 3, 12, 30, 60, 60, 60, 255])), tier=tier))
     return reads, ref, ref_begin, cand
+
+
+_PATH_ENUM = {"M": 1, "I": 2, "D": 3, "N": 4, "S": 5, "H": 6}  # ALIGNPATH::align_t (blt_util/align_path.hh:36-48)
+
+
+def _alignment_order_key(aln, fwd):
+    """CandidateAlignment::operator< (CandidateAlignment.hh:37-47): alignment (pos, strand, path size, segments), then the indel set."""
+    pos, path, kidx = aln
+    return (pos, int(fwd), len(path), [(_PATH_ENUM[k], ln) for k, ln in path], list(kidx))
+
+
+def random_score_indels_regions(rng: np.random.Generator, n_regions: int = 8, reads_per_region=(1, 6), alns_per_read=(1, 7), tie_rate: float = 0.5):
+    """Regions for K6: per region a window of IndelBuffer entries (deletions, insertions, swaps, a few mismatch entries; candidates
+    and non-candidates; shifted copies of the same deletion / insertion so that late_indel_normalization_filter finds equivalent
+    alignments) and reads whose candidate alignments carry consistent paths over subsets of the window.  Returns (regions, lnp)."""
+    regions, lnp = [], []
+    for _ in range(n_regions):
+        base = int(rng.integers(1000, 100000))
+        # ---- window
+        specs = {}
+        n_keys = int(rng.integers(1, 8))
+        while len(specs) < n_keys:
+            pos = base + int(rng.integers(20, 140))
+            t = rng.random()
+            if t < 0.45:
+                k = B.WindowKeySpec(pos, del_len=int(rng.integers(1, 12)))
+            elif t < 0.8:
+                k = B.WindowKeySpec(pos, ins=rand_seq(rng, int(rng.integers(1, 5))))
+            elif t < 0.92:
+                k = B.WindowKeySpec(pos, del_len=int(rng.integers(1, 5)), ins=rand_seq(rng, int(rng.integers(1, 4))))
+            else:
+                k = B.WindowKeySpec(pos, del_len=1, ins=rand_seq(rng, 1), mismatch=True)
+            specs[k.order()] = k
+            if not k.mismatch and rng.random() < 0.35:  # the same event one or two bases over: an "equivalent" indel
+                k2 = B.WindowKeySpec(pos + int(rng.integers(1, 3)), del_len=k.del_len, ins=k.ins)
+                specs[k2.order()] = k2
+        win = [specs[o] for o in sorted(specs)]
+        for k in win:
+            k.candidate = bool(rng.random() < 0.8)
+            k.ref_to_indel_lnp = float(np.log(rng.choice([1e-4, 5e-5, 2e-5, 1e-3]) * (1 + 0.01 * rng.integers(0, 3))))
+            k.indel_to_ref_lnp = float(np.log(rng.choice([1e-4, 5e-5, 2e-5, 1e-3]) * (1 + 0.01 * rng.integers(0, 3))))
+        # ---- reads
+        reads = []
+        for _r in range(int(rng.integers(reads_per_region[0], reads_per_region[1] + 1))):
+            L = int(rng.integers(30, 151))
+            fwd = bool(rng.random() < 0.5)
+            start0 = base + int(rng.integers(-40, 120))
+            alns = {}
+            for _a in range(int(rng.integers(alns_per_read[0], alns_per_read[1] + 1))):
+                start = start0 + int(rng.integers(-3, 4)) * int(rng.random() < 0.3)
+                lead_clip = int(rng.integers(1, 8)) if rng.random() < 0.15 else 0
+                trail_clip = int(rng.integers(1, 8)) if rng.random() < 0.15 else 0
+                lead_ins = int(rng.integers(1, 6)) if rng.random() < 0.08 else 0
+                path, kidx = [], []
+                if rng.random() < 0.05:
+                    path.append(("H", int(rng.integers(1, 5))))
+                if lead_clip:
+                    path.append(("S", lead_clip))
+                remaining = L - lead_clip - trail_clip
+                if lead_ins and lead_ins < remaining - 2:
+                    path.append(("I", lead_ins))
+                    remaining -= lead_ins
+                ref_head = start
+                take_p = rng.choice([0.0, 0.3, 0.6, 0.9])
+                for i, k in enumerate(win):
+                    if k.mismatch:
+                        if ref_head <= k.pos and rng.random() < 0.3:
+                            kidx.append(i)  # no trace in the path (a SEQ_MISMATCH block is sent as MATCH)
+                        continue
+                    if k.pos <= ref_head or rng.random() >= take_p:
+                        continue
+                    m = k.pos - ref_head
+                    if m + len(k.ins) >= remaining - 1:
+                        break
+                    path.append(("M", m))
+                    remaining -= m
+                    if k.ins:
+                        path.append(("I", len(k.ins)))
+                        remaining -= len(k.ins)
+                    if k.del_len:
+                        path.append(("D", k.del_len))
+                    ref_head = k.pos + k.del_len
+                    kidx.append(i)
+                if remaining <= 0:
+                    continue
+                trail_ins = int(rng.integers(1, 6)) if (rng.random() < 0.08 and remaining > 8) else 0
+                path.append(("M", remaining - trail_ins))
+                if trail_ins:
+                    path.append(("I", trail_ins))
+                if trail_clip:
+                    path.append(("S", trail_clip))
+                # merge adjacent equal kinds (M after M when a key was skipped cannot happen, but keep paths canonical)
+                aln = (start, tuple(path), tuple(sorted(kidx)))
+                alns[(start, tuple(path), tuple(sorted(kidx)))] = aln
+            ordered = sorted(alns.values(), key=lambda a: _alignment_order_key(a, fwd))
+            if not ordered:
+                continue
+            reads.append(B.ScoredReadSpec(L, [(a[0], list(a[1]), list(a[2])) for a in ordered], fwd=fwd, tier1=bool(rng.random() < 0.7),
+                                          non_ambig=L - int(rng.integers(0, 3)), incomplete=bool(rng.random() < 0.2)))
+            top = -float(rng.integers(8, 40))
+            for _a in ordered:
+                if rng.random() < tie_rate:
+                    lnp.append(top - float(rng.choice([0.0, 0.0, 0.5, 2.0, 2.5])))
+                else:
+                    lnp.append(top - float(rng.random() * 12))
+        regions.append((win, reads))
+    return regions, np.array(lnp + [0.0], dtype=np.float64)
