@@ -244,6 +244,92 @@ def k4_pileup_leg(ctx, peak_gbs: float, n_sites: int = 2_000_000, depth: int = 3
     return leg
 
 
+class SynthK6Sizes(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_regions", "n_reads", "n_alns", "n_keys", "n_segs", "n_aln_keys", "n_slots")]
+
+
+def make_score_indels_workload(synth, n_loci: int, depth: int, read_len: int, n_haps: int, seed: int, threads: int, reads_per_region: int = 0) -> B.ScoreIndelsBatch:
+    """The K6 view of the SAME loci make_workload() builds for K1 (same seed -> same reads, alleles and alignment order, so K1's
+    lnp[a] is the score of K6's alignment a): per region the window of distinct alt alleles, per alignment its path and indel."""
+    rpr = min(reads_per_region, depth) if reads_per_region else depth
+    n_regions = n_loci * ((depth + rpr - 1) // rpr)
+    counts = np.zeros(3 * n_regions + 3, np.uint32)
+    sz = SynthK6Sizes()
+    rc = synth.synth_k6_plan(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, reads_per_region, C.c_void_p(counts.ctypes.data), C.byref(sz))
+    assert rc == 0, rc
+    a = {
+        "region_read_off": np.zeros(n_regions + 1, np.uint32), "region_key_off": np.zeros(n_regions + 1, np.uint32),
+        "keys": np.zeros(sz.n_keys + 1, A.INDEL_KEY_DT), "aln_off": np.zeros(sz.n_reads + 1, np.uint32), "aln_pos": np.zeros(sz.n_alns + 1, np.int32),
+        "aln_seg_off": np.zeros(sz.n_alns + 1, np.uint32), "segs": np.zeros(sz.n_segs + 16, A.ALN_SEG_DT), "aln_key_off": np.zeros(sz.n_alns + 1, np.uint32),
+        "aln_keys": np.zeros(sz.n_aln_keys + 8, np.uint16), "read_len": np.zeros(sz.n_reads + 8, np.uint16), "non_ambig": np.zeros(sz.n_reads + 8, np.uint16),
+        "read_flags": np.zeros(sz.n_reads + 8, np.uint8), "rec_off": np.zeros(sz.n_reads + 1, np.uint32),
+    }
+    order = ("region_read_off", "region_key_off", "keys", "aln_off", "aln_pos", "aln_seg_off", "segs", "aln_key_off", "aln_keys", "read_len", "non_ambig",
+             "read_flags", "rec_off")
+    key_ins = np.zeros(32 * (sz.n_keys + 1), np.uint8)  # the insert sequences (test / reference-harness side information)
+    rc = synth.synth_k6_fill(n_loci, depth, read_len, n_haps, C.c_uint64(seed), threads, reads_per_region, C.c_void_p(counts.ctypes.data),
+                             *[C.c_void_p(a[k].ctypes.data) for k in order], C.c_void_p(key_ins.ctypes.data))
+    assert rc == 0, rc
+    sb = B.ScoreIndelsBatch.from_arrays(a)
+    lens = sb.keys["ins_len"][: sb.n_keys].astype(np.int64)
+    sb.ins_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    rows = key_ins[: 32 * sb.n_keys].reshape(-1, 32)
+    sb.ins_pool = np.concatenate([rows[np.arange(32)[None, :] < lens[:, None]], np.zeros(1, np.uint8)]).astype(np.uint8)
+    return sb
+
+
+def k6_score_indels_leg(ctx, synth, peak_gbs: float, n_loci: int, depth: int, read_len: int, n_haps: int, seed: int, threads: int, rpr: int, lnp_dev=None,
+                        reps: int = 5, cpu_regions: int = 3000):
+    """SURVEY 8f2 measured beside the headline step (not part of `value`): K6 score_indels on the step's own loci, reading the
+    scores K1 left in HBM (`lnp_dev` = DevAlignBatch.out after a K1 pass); inputs and records resident.  CPU figure: the reference's
+    own score_indels on one host thread over the first `cpu_regions` regions."""
+    from strelka_b200.api import DevScoreIndelsBatch, DeviceArray
+
+    sb = make_score_indels_workload(synth, n_loci, depth, read_len, n_haps, seed, threads, rpr)
+    own = None
+    if lnp_dev is None:  # stand-alone run (tools/k6_leg.py): synthetic scores with the structure K1 gives (one haplotype fits, the rest do not)
+        rng = np.random.default_rng(1)
+        lnp = -(rng.integers(0, 4, sb.n_alns + 1) * 30.0 + rng.random(sb.n_alns + 1))
+        own = lnp_dev = DeviceArray(ctx, lnp.nbytes).upload(lnp)
+    dsb = DevScoreIndelsBatch(ctx, sb)
+    ms = []
+    for i in range(reps + 2):
+        ctx.score_indels_dev(dsb, lnp_dev)
+        if i >= 2:
+            ms.append(ctx.timing().kernel_ms)
+    n_rec = dsb.n_rec.download(np.uint32, sb.n_reads)
+    t = float(np.mean(ms)) * 1e-3
+    n_records = int(n_rec.sum())
+    alg = sb.algorithmic_bytes() + n_records * 32
+    leg = {"what": f"K6 score_indels on the step's {n_loci} loci ({sb.n_reads} reads, {sb.n_alns} alignments), scores read where K1 wrote them", "ms": 1e3 * t,
+           "reads_per_s": sb.n_reads / t, "loci_per_s": n_loci / t, "records": n_records,
+           "roofline": {"bound": "hbm", "achieved": alg / t / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": alg / t / 1e9 / peak_gbs, "algorithmic_bytes": int(alg)}}
+    p = os.path.join(ROOT, "oracle", "_ref", "libstrelka_ref.so")
+    if os.path.exists(p) and hasattr(C.CDLL(p), "ref_score_indels_ex"):
+        rf = C.CDLL(p)
+        m = min(cpu_regions, sb.n_regions)
+        n_reads_m, n_alns_m = int(sb.region_read_off[m]), int(sb.aln_off[int(sb.region_read_off[m])])
+        sub = A.SxScoreIndelsBatch(m, n_reads_m, n_alns_m, int(sb.region_key_off[m]), *[getattr(sb.c, f) for f, _ in A.SxScoreIndelsBatch._fields_[4:-1]], sb.opts)
+        lnp_h = lnp_dev.download(np.float64, n_alns_m + 1)
+        pool, ins_off = sb.ins_pool, sb.ins_off
+        recs = np.zeros(int(sb.rec_off[n_reads_m]) + 1, A.READ_INDEL_SCORE_DT)
+        nr, ma = np.zeros(n_reads_m + 1, np.uint32), np.zeros(n_reads_m + 1, np.uint32)
+        err = C.create_string_buffer(512)
+        fn = rf.ref_score_indels_ex  # allow_unordered: one alignment per haplotype in haplotype order -> the harness builds the std::set
+        fn.argtypes = [C.POINTER(A.SxScoreIndelsBatch)] + [C.c_void_p] * 6 + [C.c_int, C.c_char_p, C.c_int]
+        t0 = time.perf_counter()
+        rc = fn(C.byref(sub), A.ptr(lnp_h), A.ptr(pool), A.ptr(ins_off), A.ptr(recs), A.ptr(nr), A.ptr(ma), 1, err, 512)
+        dt_cpu = time.perf_counter() - t0
+        if rc == 0:
+            leg["cpu_reference"] = {"reads_per_s": n_reads_m / dt_cpu, "cores": 1,
+                                    "sample": f"first {m} regions ({n_reads_m} reads) through the reference's score_indels (incl. the shim's object construction)"}
+        else:
+            leg["cpu_reference"] = {"error": err.value.decode(errors="replace")}
+    for d in list(dsb.bufs.values()) + [dsb.recs, dsb.n_rec, dsb.max_aln, dsb.eval_aln] + ([own] if own else []):
+        d.free()
+    return leg
+
+
 def workload_cells(ab: B.AlignBatch, gb: B.GaBatch) -> int:
     return ab.cells() + gb.cells()
 
@@ -577,6 +663,8 @@ def main():
                                               + ("oracle/_ref/libstrelka_ref.so (the reference's own functions)" if kind == "reference" else "oracle/liboracle.so")}
             if not args.no_pileup and args.config != "tiny":
                 line["k4_pileup"] = k4_pileup_leg(ctx, peak)
+                ctx.score_alignments_dev(dab)  # the scores K6 consumes: K1's own output buffer, never copied out
+                line["k6_score_indels"] = k6_score_indels_leg(ctx, synth, peak, n_loci, depth, read_len, n_haps, args.seed + 1000 * rank, threads, rpr, dab.out)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -133,8 +133,20 @@ extern "C" int ref_candidate_alignment_order(const sx_score_indels_batch* b, con
     }
 }
 
+// allow_unordered = 0: the flat alignment order must be the std::set's (tests).  1: the alignments of a read are put into set order
+// here and exact duplicates are dropped, as the reference's container would (bench.py: the synthetic K1 workload lists one
+// alignment per haplotype in haplotype order); max_aln still reports the flat index.
+extern "C" int ref_score_indels_ex(const sx_score_indels_batch* b, const double* lnp, const char* ins_pool, const uint32_t* ins_off, sx_read_indel_score* recs,
+                                   uint32_t* n_rec, uint32_t* max_aln, int allow_unordered, char* err, int errlen);
+
 extern "C" int ref_score_indels(const sx_score_indels_batch* b, const double* lnp, const char* ins_pool, const uint32_t* ins_off, sx_read_indel_score* recs,
                                 uint32_t* n_rec, uint32_t* max_aln, char* err, int errlen)
+{
+    return ref_score_indels_ex(b, lnp, ins_pool, ins_off, recs, n_rec, max_aln, 0, err, errlen);
+}
+
+extern "C" int ref_score_indels_ex(const sx_score_indels_batch* b, const double* lnp, const char* ins_pool, const uint32_t* ins_off, sx_read_indel_score* recs,
+                                   uint32_t* n_rec, uint32_t* max_aln, int allow_unordered, char* err, int errlen)
 {
     try
     {
@@ -227,16 +239,35 @@ extern "C" int ref_score_indels(const sx_score_indels_batch* b, const double* ln
 
                 std::set<CandidateAlignment> cals;
                 std::vector<double> scores;
-                for (uint32_t a = a0; a < a1; ++a)
+                std::vector<uint32_t> flatIndex;
+                if (allow_unordered)
                 {
-                    CandidateAlignment cal;
-                    cal_of(b, a, fwd, winKeys, cal);
-                    const auto ins(cals.insert(cal));
-                    if (!ins.second) throw blt_exception("ref_score_indels: duplicate candidate alignment");
-                    // the flat order must already be the set's order: a new element must land at the end
-                    if (std::next(ins.first) != cals.end()) throw blt_exception("ref_score_indels: alignments are not in std::set<CandidateAlignment> order");
-                    scores.push_back(lnp[a]);
+                    std::map<CandidateAlignment, uint32_t> first;
+                    for (uint32_t a = a0; a < a1; ++a)
+                    {
+                        CandidateAlignment cal;
+                        cal_of(b, a, fwd, winKeys, cal);
+                        first.insert(std::make_pair(cal, a));
+                    }
+                    for (const auto& kv : first)
+                    {
+                        cals.insert(cals.end(), kv.first);
+                        scores.push_back(lnp[kv.second]);
+                        flatIndex.push_back(kv.second);
+                    }
                 }
+                else
+                    for (uint32_t a = a0; a < a1; ++a)
+                    {
+                        CandidateAlignment cal;
+                        cal_of(b, a, fwd, winKeys, cal);
+                        const auto ins(cals.insert(cal));
+                        if (!ins.second) throw blt_exception("ref_score_indels: duplicate candidate alignment");
+                        // the flat order must already be the set's order: a new element must land at the end
+                        if (std::next(ins.first) != cals.end()) throw blt_exception("ref_score_indels: alignments are not in std::set<CandidateAlignment> order");
+                        scores.push_back(lnp[a]);
+                        flatIndex.push_back(a);
+                    }
 
                 // starling_read_align.cpp:1573-1593 with the reference's own tie-break
                 double maxScore(0);
@@ -255,7 +286,7 @@ extern "C" int ref_score_indels(const sx_score_indels_batch* b, const double* ln
                     maxPtr = &ical;
                     maxIndex = thisIndex;
                 }
-                max_aln[r] = a0 + maxIndex;
+                max_aln[r] = flatIndex[maxIndex];
 
                 score_indels(opt, dopt, sample_opt, rseg, indelBuffer, 0, cals, (b->read_flags[r] & SX_SIF_INCOMPLETE) != 0, scores, maxScore, maxPtr);
 

@@ -212,3 +212,49 @@ def _pileup_reads(self, pb: B.PileupReadsBatch):
 
 
 Context.pileup_reads = _pileup_reads
+
+
+class DevScoreIndelsBatch:
+    """sx_score_indels_batch whose arrays live in HBM, with device output buffers; `lnp` is usually DevAlignBatch.out."""
+
+    _ARRAYS = ("region_read_off", "region_key_off", "keys", "aln_off", "aln_pos", "aln_seg_off", "segs", "aln_key_off", "aln_keys", "read_len", "non_ambig",
+               "read_flags", "rec_off")
+
+    def __init__(self, ctx: "Context", hb: B.ScoreIndelsBatch):
+        self.host = hb
+        self.bufs = {n: DeviceArray(ctx, getattr(hb, n).nbytes + 64).upload(getattr(hb, n)) for n in self._ARRAYS}
+        p = {n: self.bufs[n].ptr for n in self._ARRAYS}
+        self.c = A.SxScoreIndelsBatch(
+            hb.n_regions, hb.n_reads, hb.n_alns, hb.n_keys, p["region_read_off"], p["region_key_off"], p["keys"], p["aln_off"], p["aln_pos"], p["aln_seg_off"],
+            p["segs"], p["aln_key_off"], p["aln_keys"], p["read_len"], p["non_ambig"], None, None, p["read_flags"], p["rec_off"], hb.opts,
+        )
+        self.recs = DeviceArray(ctx, (hb.n_rec_slots + 1) * A.READ_INDEL_SCORE_DT.itemsize)
+        self.n_rec, self.max_aln, self.eval_aln = (DeviceArray(ctx, (hb.n_reads + 1) * 4) for _ in range(3))
+        self.out = A.SxScoreIndelsOut(self.recs.ptr, self.n_rec.ptr, self.max_aln.ptr, self.eval_aln.ptr)
+
+    def download(self):
+        hb = self.host
+        out = B.ScoreIndelsOut(hb)
+        out.recs[:] = self.recs.download(A.READ_INDEL_SCORE_DT, hb.n_rec_slots + 1)
+        out.n_rec[:] = self.n_rec.download(np.uint32, hb.n_reads + 1)
+        out.max_aln[:] = self.max_aln.download(np.uint32, hb.n_reads + 1)
+        out.eval_aln[:] = self.eval_aln.download(np.uint32, hb.n_reads + 1)
+        return out.compact()
+
+
+def _score_indels(self, sb: B.ScoreIndelsBatch, lnp: np.ndarray):
+    """K6: the arg-max epilogue of scoreCandidateAlignments + score_indels (host buffers in, host records out).
+    Returns (records in key order per read, n_rec[n_reads], max_aln[n_reads], eval_aln[n_reads])."""
+    lnp = np.ascontiguousarray(lnp, dtype=np.float64)
+    assert lnp.size >= sb.n_alns
+    out = B.ScoreIndelsOut(sb)
+    self._chk(self.lib.sx_score_indels(self.h, C.byref(sb.c), lnp.ctypes.data, C.byref(out.c)))
+    return out.compact()
+
+
+def _score_indels_dev(self, db: DevScoreIndelsBatch, lnp_dev: DeviceArray) -> None:
+    self._chk(self.lib.sx_score_indels_dev(self.h, C.byref(db.c), lnp_dev.ptr, C.byref(db.out)))
+
+
+Context.score_indels = _score_indels  # K6
+Context.score_indels_dev = _score_indels_dev

@@ -623,6 +623,24 @@ class ScoreIndelsBatch:
             A.ptr(self.read_len), A.ptr(self.non_ambig), None, None, A.ptr(self.read_flags), A.ptr(self.rec_off), self.opts,
         )
 
+    @classmethod
+    def from_arrays(cls, arrays: dict, opts=None) -> "ScoreIndelsBatch":
+        """Wrap ready-made flat arrays (tools/synth.cpp synth_k6_fill): keys are the sx_score_indels_batch field names."""
+        self = cls.__new__(cls)
+        for k, v in arrays.items():
+            setattr(self, k, v)
+        self.n_regions, self.n_reads = len(self.region_read_off) - 1, len(self.aln_off) - 1
+        self.n_alns, self.n_keys = int(self.aln_off[-1]), int(self.region_key_off[-1])
+        self.n_segs, self.n_aln_keys, self.n_rec_slots = int(self.aln_seg_off[self.n_alns]), int(self.aln_key_off[self.n_alns]), int(self.rec_off[-1])
+        self.ins_pool = self.ins_off = None
+        self.opts = opts or A.default_score_indels_opts()
+        self.c = A.SxScoreIndelsBatch(
+            self.n_regions, self.n_reads, self.n_alns, self.n_keys, A.ptr(self.region_read_off), A.ptr(self.region_key_off), A.ptr(self.keys),
+            A.ptr(self.aln_off), A.ptr(self.aln_pos), A.ptr(self.aln_seg_off), A.ptr(self.segs), A.ptr(self.aln_key_off), A.ptr(self.aln_keys),
+            A.ptr(self.read_len), A.ptr(self.non_ambig), None, None, A.ptr(self.read_flags), A.ptr(self.rec_off), self.opts,
+        )
+        return self
+
     def algorithmic_bytes(self) -> int:
         """bytes one pass must move: every input array once + the scores + one record slot header per read."""
         return (self.n_keys * 32 + self.n_alns * (8 + 4 + 4 + 4) + self.n_segs * 4 + self.n_aln_keys * 2 + self.n_reads * (4 + 2 + 2 + 1 + 4 + 12))
@@ -645,3 +663,32 @@ class ScoreIndelsOut:
         parts = [self.recs[int(sb.rec_off[r]) : int(sb.rec_off[r]) + int(self.n_rec[r])] for r in range(sb.n_reads)]
         recs = np.concatenate(parts) if parts else self.recs[:0]
         return recs, self.n_rec[: sb.n_reads].copy(), self.max_aln[: sb.n_reads].copy(), self.eval_aln[: sb.n_reads].copy()
+
+
+def score_indels_batch_from_regions(regions: Sequence[RegionSpec], fwd=True, ref_to_indel_lnp=-9.903487552536127, indel_to_ref_lnp=-9.903487552536127,
+                                    opts=None) -> ScoreIndelsBatch:
+    """The K6 view of the regions a K1 batch was built from (same alignment order, so K1's lnp[a] is K6's score of alignment a):
+    per region the window = the distinct IndelKeys of its alignments' indel sets (edge keys are not part of cal.getIndels()) in
+    IndelKey order; '=' / 'X' path segments are sent as MATCH.  Every alignment of a region must belong to consecutive reads."""
+    out = []
+    for rg in regions:
+        keyspecs = {}
+        for cal in rg.alns:
+            for i, k in enumerate(cal.indels):
+                if i in (cal.leading, cal.trailing):
+                    continue
+                w = WindowKeySpec(k.pos, k.delete_length, k.insert_seq, k.type == INDEL_MISMATCH, k.is_candidate, ref_to_indel_lnp, indel_to_ref_lnp)
+                keyspecs.setdefault(w.order(), w)
+        order = sorted(keyspecs)
+        index_of = {o: i for i, o in enumerate(order)}
+        reads = [ScoredReadSpec(len(codes), [], fwd=fwd, non_ambig=int((np.asarray(codes) != 15).sum())) for codes, _q in rg.reads]
+        last = -1
+        for cal in rg.alns:
+            assert cal.read >= last, "alignments must be grouped by read"
+            last = cal.read
+            kidx = sorted({index_of[WindowKeySpec(k.pos, k.delete_length, k.insert_seq, k.type == INDEL_MISMATCH).order()]
+                           for i, k in enumerate(cal.indels) if i not in (cal.leading, cal.trailing)})
+            path = [("M" if t in _ALIGN_MATCH else t, ln) for t, ln in cal.path]
+            reads[cal.read].alns.append((cal.pos, path, kidx))
+        out.append(([keyspecs[o] for o in order], reads))
+    return ScoreIndelsBatch(out, opts)

@@ -1,0 +1,250 @@
+// k6_score_indels.cu -- K6: the arg-max epilogue of scoreCandidateAlignments and score_indels, one read per thread.
+//
+// Replaces (include/strelka_b200.h, "K6 score_indels")
+//   starling_common/starling_read_align.cpp:1573-1593            arg-max with isFirstCandidateAlignmentPreferred
+//   starling_common/starling_read_align_score_indels.cpp:454-1079 score_indels
+// and consumes K1's scores where K1 wrote them (device memory).
+//
+// Shape of the work: per read a handful of alignments x a handful of indels of integer bookkeeping and a few fp64 adds and
+// compares -- no reuse between reads and nothing GEMM-like.  One thread owns one read (grid-stride over reads, the grid a multiple
+// of the SM count); its per-read state (k6_scratch: sort order, filter flags, per-indel maxima) lives in one arena laid out
+// element-major across threads, so that the threads of a warp touching "their" element i hit consecutive addresses.  The batch
+// arrays are read once through the read-only path; the output is one 32-byte record per (read, evaluated indel).
+// The per-read body is k6_core.cuh.
+
+#include "k6_core.cuh"
+#include "sx_internal.h"
+
+#include <algorithm>
+
+namespace
+{
+constexpr int K6_THREADS = 128;
+constexpr int K6_ST_SHIFT = 9; // K6_ST_* bits are reported as ctx status bits 512, 1024, ...
+
+__global__ void k6_max_kernel(const uint32_t* __restrict__ aln_off, const uint32_t* __restrict__ rec_off, const uint32_t n_reads, uint32_t* __restrict__ out)
+{
+    uint32_t mA(0), mS(0);
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x)
+    {
+        mA = max(mA, aln_off[r + 1] - aln_off[r]);
+        mS = max(mS, rec_off[r + 1] - rec_off[r]);
+    }
+    mA = __reduce_max_sync(0xffffffffu, mA);
+    mS = __reduce_max_sync(0xffffffffu, mS);
+    if ((threadIdx.x & 31) == 0)
+    {
+        atomicMax(out, mA);
+        atomicMax(out + 1, mS);
+    }
+}
+
+__global__ void __launch_bounds__(K6_THREADS) k6_score_kernel(const k6_view v, const k6_scratch S0, int* __restrict__ status)
+{
+    const uint32_t t(blockIdx.x * blockDim.x + threadIdx.x), T(gridDim.x * blockDim.x);
+    k6_scratch S(S0); // this thread's columns of the element-major arena
+    S.ord.p += t;
+    S.smooth.p += t;
+    S.filt.p += t;
+    S.ev.p += t;
+    S.present.p += t;
+    S.absent.p += t;
+    S.has.p += t;
+    S.alt.p += t;
+    S.pair.p += t;
+    uint32_t st(0);
+    for (uint32_t r = t; r < v.b.n_reads; r += T)
+    {
+        // region of read r: last region whose first read is <= r and which is not empty at r
+        uint32_t lo(0), hi(v.b.n_regions);
+        while (hi - lo > 1)
+        {
+            const uint32_t mid((lo + hi) >> 1);
+            if (v.b.region_read_off[mid] <= r) lo = mid;
+            else hi = mid;
+        }
+        st |= k6_score_read(v, lo, r, S);
+    }
+    if (st) atomicOr(status, (int)(st << K6_ST_SHIFT));
+}
+
+struct k6_layout
+{
+    size_t off[9];
+    size_t bytes;
+};
+
+// element-major arena for T threads: array a occupies count_a * T elements
+k6_layout k6_plan(const uint32_t maxA, const uint32_t maxE, const size_t T)
+{
+    const size_t count[9] = {maxA, maxA, maxA, maxE, maxE, maxE, maxE, (size_t)maxE * maxE, (size_t)maxE * maxE};
+    const size_t elem[9] = {4, 8, 1, 2, 8, 8, 1, 8, 1};
+    k6_layout L;
+    size_t o(0);
+    for (int i = 0; i < 9; ++i)
+    {
+        o = (o + 255) & ~(size_t)255;
+        L.off[i] = o;
+        o += count[i] * elem[i] * T;
+    }
+    L.bytes = o;
+    return L;
+}
+
+int k6_run(sx_ctx* ctx, const sx_score_indels_batch* d, const double* lnp_dev, const sx_score_indels_out* out_dev, unsigned* launches)
+{
+    cudaStream_t st(ctx->s_compute);
+    // sizes of the per-read scratch: the deepest read of the batch decides
+    uint32_t* d_max(nullptr);
+    int rc;
+    if ((rc = sx_ensure(ctx, 29, 8, reinterpret_cast<void**>(&d_max)))) return rc;
+    SX_CUDA(ctx, cudaMemsetAsync(d_max, 0, 8, st));
+    const int grid0(std::max(1, std::min<int>((int)((d->n_reads + 255) / 256), ctx->sm_count * 8)));
+    k6_max_kernel<<<grid0, 256, 0, st>>>(d->aln_off, d->rec_off, d->n_reads, d_max);
+    SX_CUDA(ctx, cudaGetLastError());
+    uint32_t h_max[2] = {0, 0};
+    SX_CUDA(ctx, cudaMemcpyAsync(h_max, d_max, 8, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t maxA(std::max(1u, h_max[0])), maxE(std::max(1u, std::min(K6_MAX_EVAL, h_max[1])));
+
+    // threads: one per read up to a few resident CTAs per SM; fewer when a deep batch would make the arena too large
+    size_t T(std::min<size_t>(((size_t)d->n_reads + K6_THREADS - 1) / K6_THREADS, (size_t)ctx->sm_count * 8) * K6_THREADS);
+    const size_t arena_cap((size_t)1 << 30);
+    while (T > K6_THREADS && k6_plan(maxA, maxE, T).bytes > arena_cap) T = ((T / 2 + K6_THREADS - 1) / K6_THREADS) * K6_THREADS;
+    const k6_layout L(k6_plan(maxA, maxE, T));
+    char* arena(nullptr);
+    if ((rc = sx_ensure(ctx, 28, L.bytes, reinterpret_cast<void**>(&arena)))) return rc;
+    k6_scratch S;
+    S.ord = {reinterpret_cast<uint32_t*>(arena + L.off[0]), T};
+    S.smooth = {reinterpret_cast<double*>(arena + L.off[1]), T};
+    S.filt = {reinterpret_cast<uint8_t*>(arena + L.off[2]), T};
+    S.ev = {reinterpret_cast<uint16_t*>(arena + L.off[3]), T};
+    S.present = {reinterpret_cast<double*>(arena + L.off[4]), T};
+    S.absent = {reinterpret_cast<double*>(arena + L.off[5]), T};
+    S.has = {reinterpret_cast<uint8_t*>(arena + L.off[6]), T};
+    S.alt = {reinterpret_cast<double*>(arena + L.off[7]), T};
+    S.pair = {reinterpret_cast<uint8_t*>(arena + L.off[8]), T};
+    S.maxA = maxA;
+    S.maxE = maxE;
+    k6_view v;
+    v.b = *d;
+    v.lnp = lnp_dev;
+    v.recs = out_dev->recs;
+    v.n_rec = out_dev->n_rec;
+    v.max_aln = out_dev->max_aln;
+    v.eval_aln = out_dev->eval_aln;
+    k6_score_kernel<<<(unsigned)(T / K6_THREADS), K6_THREADS, 0, st>>>(v, S, ctx->d_status);
+    SX_CUDA(ctx, cudaGetLastError());
+    *launches = 2;
+    return SX_OK;
+}
+
+int k6_check_args(sx_ctx* ctx, const sx_score_indels_batch* b, const double* lnp, const sx_score_indels_out* out, const char* what)
+{
+    if (!b || !out) return sx_fail(ctx, SX_ERR_ARG, "%s: NULL argument", what);
+    if (b->n_reads == 0) return SX_OK;
+    if (!lnp || !b->region_read_off || !b->region_key_off || !b->aln_off || !b->aln_pos || !b->aln_seg_off || !b->aln_key_off || !b->read_len || !b->non_ambig ||
+        !b->read_flags || !b->rec_off || !out->recs || !out->n_rec || !out->max_aln || !out->eval_aln)
+        return sx_fail(ctx, SX_ERR_ARG, "%s: NULL array", what);
+    if ((b->n_keys && !b->keys) || b->n_regions == 0) return sx_fail(ctx, SX_ERR_ARG, "%s: reads without a region / keys without a table", what);
+    if (b->opts.min_read_bp_flank < 0) return sx_fail(ctx, SX_ERR_ARG, "%s: negative min_read_bp_flank", what);
+    return SX_OK;
+}
+} // namespace
+
+extern "C" void sx_default_score_indels_opts(sx_score_indels_opts* o)
+{
+    if (!o) return;
+    o->max_indel_size = 49;                       // starling_base_shared.hh:124
+    o->upstream_oligo_size = 0;                   // :206
+    o->min_read_bp_flank = 5;                     // :108 default_min_read_bp_flank
+    o->is_smoothed_alignments = 1;                // :170
+    o->smoothed_lnp_range = 2.302585092994046;    // :171 std::log(10.)
+}
+
+extern "C" int sx_score_indels_dev(sx_ctx* ctx, const sx_score_indels_batch* d, const double* lnp_dev, sx_score_indels_out* out_dev)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    int rc;
+    if ((rc = k6_check_args(ctx, d, lnp_dev, out_dev, "sx_score_indels_dev"))) return rc;
+    if (d->n_reads == 0) return SX_OK;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    sx_kernel_timer t(ctx);
+    unsigned launches(0);
+    if ((rc = k6_run(ctx, d, lnp_dev, out_dev, &launches))) return rc;
+    t.stop(launches);
+    if ((rc = t.finish())) return rc;
+    return sx_check_status(ctx, "sx_score_indels");
+}
+
+extern "C" int sx_score_indels(sx_ctx* ctx, const sx_score_indels_batch* b, const double* lnp_host, sx_score_indels_out* out_host)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    int rc;
+    if ((rc = k6_check_args(ctx, b, lnp_host, out_host, "sx_score_indels"))) return rc;
+    if (b->n_reads == 0) return SX_OK;
+    // host-side consistency of the offsets the uploads are sized from
+    if (b->region_read_off[b->n_regions] != b->n_reads || b->region_key_off[b->n_regions] != b->n_keys || b->aln_off[b->n_reads] != b->n_alns)
+        return sx_fail(ctx, SX_ERR_ARG, "sx_score_indels: offset arrays do not end at n_reads / n_keys / n_alns");
+    for (uint32_t g = 0; g < b->n_regions; ++g)
+        if (b->region_key_off[g + 1] - b->region_key_off[g] > 65535u) return sx_fail(ctx, SX_ERR_RANGE, "sx_score_indels: more than 65535 window entries in a region");
+    for (uint32_t k = 0; k < b->n_keys; ++k)
+        if (b->keys[k].type > SX_INDEL_TYPE_MISMATCH) return sx_fail(ctx, SX_ERR_UNSUPPORTED, "sx_score_indels: breakend entries are not supported");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st(ctx->s_compute);
+    SX_CUDA(ctx, cudaEventRecord(ctx->ev_a, st));
+    sx_score_indels_batch d(*b);
+    void* p(nullptr);
+    const size_t n_segs(b->aln_seg_off[b->n_alns]), n_akeys(b->aln_key_off[b->n_alns]), n_slots(b->rec_off[b->n_reads]);
+#define SX_UP(slot, field, type, bytes)                                                     \
+    if ((rc = sx_ensure(ctx, slot, (size_t)(bytes) + 16, &p))) return rc;                    \
+    if (bytes) SX_CUDA(ctx, cudaMemcpyAsync(p, b->field, (bytes), cudaMemcpyHostToDevice, st)); \
+    d.field = static_cast<type>(p);
+    SX_UP(0, region_read_off, const uint32_t*, (size_t)(b->n_regions + 1) * 4)
+    SX_UP(1, region_key_off, const uint32_t*, (size_t)(b->n_regions + 1) * 4)
+    SX_UP(2, keys, const sx_indel_key*, (size_t)b->n_keys * sizeof(sx_indel_key))
+    SX_UP(3, aln_off, const uint32_t*, (size_t)(b->n_reads + 1) * 4)
+    SX_UP(4, aln_pos, const int32_t*, (size_t)b->n_alns * 4)
+    SX_UP(5, aln_seg_off, const uint32_t*, (size_t)(b->n_alns + 1) * 4)
+    SX_UP(6, segs, const sx_aln_seg*, n_segs * sizeof(sx_aln_seg))
+    SX_UP(7, aln_key_off, const uint32_t*, (size_t)(b->n_alns + 1) * 4)
+    SX_UP(8, aln_keys, const uint16_t*, n_akeys * 2)
+    SX_UP(9, read_len, const uint16_t*, (size_t)b->n_reads * 2)
+    SX_UP(10, non_ambig, const uint16_t*, (size_t)b->n_reads * 2)
+    SX_UP(11, read_flags, const uint8_t*, (size_t)b->n_reads)
+    SX_UP(12, rec_off, const uint32_t*, (size_t)(b->n_reads + 1) * 4)
+    if (b->full_len)
+    {
+        SX_UP(13, full_len, const uint16_t*, (size_t)b->n_reads * 2)
+    }
+    if (b->full_off)
+    {
+        SX_UP(14, full_off, const uint16_t*, (size_t)b->n_reads * 2)
+    }
+#undef SX_UP
+    double* d_lnp(nullptr);
+    if ((rc = sx_ensure(ctx, 15, (size_t)b->n_alns * 8 + 16, reinterpret_cast<void**>(&d_lnp)))) return rc;
+    SX_CUDA(ctx, cudaMemcpyAsync(d_lnp, lnp_host, (size_t)b->n_alns * 8, cudaMemcpyHostToDevice, st));
+    sx_score_indels_out o;
+    if ((rc = sx_ensure(ctx, 16, (n_slots + 1) * sizeof(sx_read_indel_score), reinterpret_cast<void**>(&o.recs)))) return rc;
+    if ((rc = sx_ensure(ctx, 17, (size_t)b->n_reads * 4, reinterpret_cast<void**>(&o.n_rec)))) return rc;
+    if ((rc = sx_ensure(ctx, 18, (size_t)b->n_reads * 4, reinterpret_cast<void**>(&o.max_aln)))) return rc;
+    if ((rc = sx_ensure(ctx, 19, (size_t)b->n_reads * 4, reinterpret_cast<void**>(&o.eval_aln)))) return rc;
+    SX_CUDA(ctx, cudaMemsetAsync(o.recs, 0, (n_slots + 1) * sizeof(sx_read_indel_score), st)); // unused slots read back as zeros
+    unsigned launches(0);
+    if ((rc = k6_run(ctx, &d, d_lnp, &o, &launches))) return rc;
+    SX_CUDA(ctx, cudaMemcpyAsync(out_host->recs, o.recs, n_slots * sizeof(sx_read_indel_score), cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaMemcpyAsync(out_host->n_rec, o.n_rec, (size_t)b->n_reads * 4, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaMemcpyAsync(out_host->max_aln, o.max_aln, (size_t)b->n_reads * 4, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaMemcpyAsync(out_host->eval_aln, o.eval_aln, (size_t)b->n_reads * 4, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaEventRecord(ctx->ev_b, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms(0);
+    cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+    ctx->timing.kernel_ms = ms;
+    ctx->timing.launches = launches;
+    ctx->total_launches += launches;
+    return sx_check_status(ctx, "sx_score_indels");
+}

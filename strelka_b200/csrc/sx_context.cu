@@ -495,6 +495,11 @@ int sx_check_status(sx_ctx* ctx, const char* what)
         if (st & 64) return sx_fail(ctx, SX_ERR_ARG, "%s: reads are not in position order, or an alignment spans more reference than max_ref_span", what);
         if (st & 128) return sx_fail(ctx, SX_ERR_ARG, "%s: unknown base code (bam_seq_code_to_id would throw)", what);
         if (st & 256) return sx_fail(ctx, SX_ERR_UNSUPPORTED, "%s: a read is longer, or has more path segments, than the kernel handles", what);
+        if (st & 512) return sx_fail(ctx, SX_ERR_UNSUPPORTED, "%s: a path segment kind outside score_indels' domain (SKIP / REFSKIP / unknown)", what);
+        if (st & 1024) return sx_fail(ctx, SX_ERR_ARG, "%s: a read has more alignments than the scratch was sized for", what);
+        if (st & 2048) return sx_fail(ctx, SX_ERR_UNSUPPORTED, "%s: a read evaluates more than 64 indels", what);
+        if (st & 4096) return sx_fail(ctx, SX_ERR_NOMEM, "%s: rec_off leaves too few record slots for a read", what);
+        if (st & 8192) return sx_fail(ctx, SX_ERR_ARG, "%s: an alignment key index outside its region's window, or an unsupported key type", what);
         return sx_fail(ctx, SX_ERR_ARG, "%s: device status %d", what, st);
     }
     return SX_OK;

@@ -213,7 +213,7 @@ def simple_region(rng: np.random.Generator, n_reads: int = 30, n_haps: int = 4, 
         s = s.ljust(read_len, "A")
         q = rng.choice(np.array([11, 25, 37], np.uint8), size=read_len, p=[0.03, 0.07, 0.90])
         bases = np.array(list(s))
-        err = rng.random(read_len) < 10.0 ** (-q / 10.0)
+        err = rng.random(read_len) < 10.0 ** (-q.astype(np.float64) / 10.0)  # (uint8 would wrap under the minus sign)
         bases[err] = np.array(list(BASES))[rng.integers(0, 4, int(err.sum()))]
         reads.append((np.array([CODE_OF[b] for b in bases], np.uint8), q.astype(np.uint8)))
         for hh in haps:
@@ -524,3 +524,24 @@ def random_score_indels_regions(rng: np.random.Generator, n_regions: int = 8, re
                     lnp.append(top - float(rng.random() * 12))
         regions.append((win, reads))
     return regions, np.array(lnp + [0.0], dtype=np.float64)
+
+
+SCORE_INDELS_GOLDEN_CASES = 8
+
+
+def score_indels_case(case: int):
+    """The seeded K6 batch number `case` (tests/golden/score_indels_ref.npz holds the reference's output for cases 0..7; the
+    option set cycles through oligo anchors, smoothing off, small maxIndelSize / large flank)."""
+    from strelka_b200 import _abi as A
+
+    rng = np.random.default_rng(1000 + case)
+    regions, lnp = random_score_indels_regions(rng, 8, tie_rate=float(rng.choice([0.2, 0.5, 0.9])))
+    opts = A.default_score_indels_opts()
+    if case % 4 == 1:
+        opts.upstream_oligo_size = int(rng.integers(1, 12))
+    if case % 4 == 2:
+        opts.is_smoothed_alignments = 0
+    if case % 4 == 3:
+        opts.max_indel_size = int(rng.integers(1, 20))
+        opts.min_read_bp_flank = int(rng.integers(1, 40))
+    return B.ScoreIndelsBatch(regions, opts), lnp

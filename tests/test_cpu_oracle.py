@@ -97,3 +97,42 @@ def test_stdsort_mirror_matches_libstdcxx():
         lib.ox_sort_restated(a.ctypes.data, n, key.ctypes.data)
         lib.ox_sort_std(b.ctypes.data, n, key.ctypes.data)
         assert np.array_equal(a, b)
+
+
+def test_score_indels_oracle_against_reference_golden():
+    """tests/golden/score_indels_ref.npz = the reference's own score_indels output (made by make_score_indels_golden.py)."""
+    gold = np.load(os.path.join(HERE, "golden", "score_indels_ref.npz"))
+    total = 0
+    for case in range(specgen.SCORE_INDELS_GOLDEN_CASES):
+        sb, lnp = specgen.score_indels_case(case)
+        recs, n_rec, max_aln, _ = reflib.ox_score_indels(sb, lnp)
+        assert np.array_equal(n_rec, gold[f"n_rec{case}"]) and np.array_equal(max_aln, gold[f"max_aln{case}"])
+        assert recs.tobytes() == gold[f"recs{case}"].tobytes()
+        total += len(recs)
+    assert total > 200
+
+
+def test_k6_device_body_on_the_host(tmp_path):
+    """strelka_b200/csrc/k6_core.cuh is __host__ __device__: the exact per-read body the kernel runs, compiled with g++
+    (tests/cpp/k6_core_host.cpp) and run read by read on the CPU, against the oracle -- the logic of the CUDA path is checked in the
+    GPU-less container too.  (A test harness only: libstrelka_b200.so has no host execution path.)"""
+    import subprocess
+
+    root = os.path.dirname(HERE)
+    so = str(tmp_path / "libk6core.so")
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "strelka_b200", "csrc"),
+                           os.path.join(HERE, "cpp", "k6_core_host.cpp"), "-o", so])
+    lib = C.CDLL(so)
+    lib.k6core_run.argtypes = [C.POINTER(A.SxScoreIndelsBatch)] + [C.c_void_p] * 6
+    total = 0
+    for case in range(60):
+        sb, lnp = specgen.score_indels_case(case)
+        want = reflib.ox_score_indels(sb, lnp)
+        out = B.ScoreIndelsOut(sb)
+        st = np.zeros(1, np.uint32)
+        lib.k6core_run(C.byref(sb.c), A.ptr(lnp), A.ptr(out.recs), A.ptr(out.n_rec), A.ptr(out.max_aln), A.ptr(out.eval_aln), A.ptr(st))
+        assert st[0] == 0
+        for w, g in zip(want, out.compact()):
+            assert w.tobytes() == g.tobytes()
+        total += len(want[0])
+    assert total > 1500

@@ -428,3 +428,85 @@ def test_k4_rejects_unsorted_reads(ctx):
     with pytest.raises(SxError) as e:
         ctx.pileup_reads(pb)
     assert e.value.code == A.SX_ERR_ARG
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# K6 score_indels
+# ----------------------------------------------------------------------------------------------------------------------------
+def _same_k6(want, got):
+    for w, g in zip(want, got):
+        assert w.dtype == g.dtype and w.shape == g.shape
+        assert w.tobytes() == g.tobytes()
+
+
+@pytest.mark.parametrize("case", range(16))
+def test_k6_score_indels(ctx, case):
+    """Records (ReadPathScores incl. alternate alleles, suboverlap marks), the arg-max and the evaluated alignment, byte for byte
+    against the oracle; cases 0..7 also against what the REFERENCE's score_indels wrote (tests/golden/score_indels_ref.npz)."""
+    import os
+
+    sb, lnp = specgen.score_indels_case(case)
+    got = ctx.score_indels(sb, lnp)
+    _same_k6(reflib.ox_score_indels(sb, lnp), got)
+    if case < specgen.SCORE_INDELS_GOLDEN_CASES:
+        gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "score_indels_ref.npz"))
+        assert got[0].tobytes() == gold[f"recs{case}"].tobytes()
+        assert np.array_equal(got[1], gold[f"n_rec{case}"]) and np.array_equal(got[2], gold[f"max_aln{case}"])
+    assert ctx.timing().launches == 2
+
+
+def test_k6_large_batch_with_deep_reads(ctx):
+    """Thousands of regions (grid-stride over reads, every thread's scratch column in use) and reads with up to 60 candidate
+    alignments (the per-batch scratch sizing)."""
+    rng = np.random.default_rng(606)
+    regions, lnp = specgen.random_score_indels_regions(rng, 3000, reads_per_region=(1, 8), alns_per_read=(1, 8))
+    deep, lnp_deep = specgen.random_score_indels_regions(rng, 40, reads_per_region=(1, 4), alns_per_read=(20, 60), tie_rate=0.8)
+    sb = B.ScoreIndelsBatch(regions + deep)
+    lnp = np.concatenate([lnp[:-1], lnp_deep])
+    assert lnp.size == sb.n_alns + 1 and sb.n_reads > 8000
+    want = reflib.ox_score_indels(sb, lnp)
+    _same_k6(want, ctx.score_indels(sb, lnp))
+    assert int((want[0]["flags"] & A.SX_RIS_SCORED).sum()) > 5000 and int((want[2] != want[3]).sum()) > 50
+
+
+def test_k6_consumes_k1_scores_on_device(ctx):
+    """K1 -> K6 without the scores leaving HBM: sx_score_alignments_dev writes lnp, sx_score_indels_dev reads that buffer."""
+    from strelka_b200.api import DevAlignBatch, DevScoreIndelsBatch
+
+    rng = np.random.default_rng(607)
+    regions = [specgen.simple_region(rng, n_reads=int(rng.integers(5, 40))) for _ in range(200)]
+    ab = B.build_align_batch(regions, qual_bits=2, compact=True)
+    sb = B.score_indels_batch_from_regions(regions)
+    assert ab.n_alns == sb.n_alns
+    dab, dsb = DevAlignBatch(ctx, ab), DevScoreIndelsBatch(ctx, sb)
+    ctx.score_alignments_dev(dab)
+    ctx.score_indels_dev(dsb, dab.out)
+    want = reflib.ox_score_indels(sb, np.concatenate([reflib.ox_score(B.build_align_batch(regions)), [0.0]]))
+    _same_k6(want, dsb.download())
+    assert int((want[0]["flags"] & A.SX_RIS_SCORED).sum()) > 5000 and int((want[0]["n_alt"] > 0).sum()) > 1000
+
+
+def test_k6_rejects_what_the_reference_asserts_on(ctx):
+    from strelka_b200.api import SxError
+
+    sb, lnp = specgen.score_indels_case(0)
+    kind0 = int(sb.segs["kind"][0])
+    sb.segs["kind"][0] = A.SX_SEG_SKIP  # score_indels' get_alignment_indel_bp_overlap asserts on SKIP (:176)
+    with pytest.raises(SxError) as e:
+        ctx.score_indels(sb, lnp)
+    assert e.value.code == A.SX_ERR_UNSUPPORTED
+    sb.segs["kind"][0] = kind0
+    keep = sb.rec_off.copy()
+    sb.rec_off[:] = 0  # no output slots at all
+    with pytest.raises(SxError) as e:
+        ctx.score_indels(sb, lnp)
+    assert e.value.code == A.SX_ERR_NOMEM
+    sb.rec_off[:] = keep
+    k0 = int(sb.aln_keys[0]) if sb.n_aln_keys else 0
+    if sb.n_aln_keys:
+        sb.aln_keys[0] = 60000  # outside the region's window
+        with pytest.raises(SxError) as e:
+            ctx.score_indels(sb, lnp)
+        assert e.value.code == A.SX_ERR_ARG
+        sb.aln_keys[0] = k0
+    _same_k6(reflib.ox_score_indels(sb, lnp), ctx.score_indels(sb, lnp))  # the context is usable again

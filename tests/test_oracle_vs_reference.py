@@ -204,3 +204,52 @@ def test_pileup_bench_workload_matches_the_reference():
     assert int(want[0][-1]) > 0.9 * w["bases"] * 8000 / (8000 + 150) and int(want[4].sum()) > 0
     for a, b, name in zip(want, got, ("site_off", "calls", "t2_off", "t2_calls", "n_spandel", "n_submapped")):
         assert np.array_equal(a, b), name
+
+
+@pytest.mark.parametrize("case", range(40))
+def test_score_indels_matches_the_reference(case):
+    """K6 oracle vs the reference's own score_indels (and its isFirstCandidateAlignmentPreferred tie-break) on rebuilt IndelBuffer /
+    read_segment / std::set<CandidateAlignment> objects: records (ReadPathScores incl. alternate alleles, suboverlap marks) byte for
+    byte, and the chosen maximum alignment.  Option sets cycle through oligo anchors, smoothing off, small maxIndelSize / large flank."""
+    sb, lnp = specgen.score_indels_case(case)
+    # the generator's Python restatement of CandidateAlignment::operator< must agree with the reference's std::set
+    assert np.array_equal(reflib.ref_candidate_alignment_order(sb), np.arange(sb.n_alns))
+    o_recs, o_n, o_max, _ = reflib.ox_score_indels(sb, lnp)
+    r_recs, r_n, r_max = reflib.ref_score_indels(sb, lnp)
+    assert np.array_equal(o_n, r_n)
+    assert np.array_equal(o_max, r_max)
+    assert o_recs.tobytes() == r_recs.tobytes()
+
+
+def test_score_indels_on_k1_scores_matches_the_reference():
+    """K1 oracle scores of haplotype-shaped loci fed to K6: oracle vs reference (real score ties between equivalent alignments)."""
+    rng = np.random.default_rng(77)
+    regions = [specgen.simple_region(rng, n_reads=12) for _ in range(12)]
+    # the reference keeps a std::set: drop duplicate alignments of a read (two identical haplotypes) and order them its way
+    for rg in regions:
+        seen, keep = set(), []
+        for cal in rg.alns:
+            key = (cal.read, cal.pos, tuple(cal.path), tuple((k.pos, k.delete_length, k.insert_seq) for k in cal.indels))
+            if key not in seen and cal.trailing < 0 and cal.leading < 0:
+                seen.add(key)
+                keep.append(cal)
+        rg.alns = keep
+    sb = B.score_indels_batch_from_regions(regions)
+    perm = reflib.ref_candidate_alignment_order(sb)
+    ab = B.build_align_batch(regions)
+    assert ab.n_alns == sb.n_alns
+    lnp = reflib.ox_score(ab)
+    # reorder each read's alignments (and their scores) into std::set order
+    flat = [a for rg in regions for a in rg.alns]
+    by_region, pos = [], 0
+    for rg in regions:
+        n = len(rg.alns)
+        rg.alns = [flat[int(i)] for i in perm[pos : pos + n]]
+        pos += n
+    sb = B.score_indels_batch_from_regions(regions)
+    lnp = np.concatenate([lnp[perm], [0.0]])
+    assert np.array_equal(reflib.ref_candidate_alignment_order(sb), np.arange(sb.n_alns))
+    o_recs, o_n, o_max, _ = reflib.ox_score_indels(sb, lnp)
+    r_recs, r_n, r_max = reflib.ref_score_indels(sb, lnp)
+    assert np.array_equal(o_n, r_n) and np.array_equal(o_max, r_max) and o_recs.tobytes() == r_recs.tobytes()
+    assert int((o_recs["flags"] & A.SX_RIS_SCORED).sum()) > 100

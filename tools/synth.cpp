@@ -355,6 +355,240 @@ int synth_k1_fill(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// K6 view of the same cfg2/cfg5 workload: per region the IndelBuffer window = the distinct alt alleles of its locus (IndelKey
+// order), per read the same n_haps candidate alignments as the K1 batch (same RNG draws, same order), each with its path in K4
+// kinds and the window index of its indel.  An insertion that runs off the read end is an edge insertion: not in the indel set.
+// ---------------------------------------------------------------------------------------------------------------------------
+struct synth_k6_sizes
+{
+    uint64_t n_regions, n_reads, n_alns, n_keys, n_segs, n_aln_keys, n_slots;
+};
+// the insert sequences behind ins_id are also available (tests / the reference harness rebuild IndelKeys from them): key_ins[32 * key]
+
+namespace
+{
+struct k6_counts
+{
+    uint32_t keys, segs, akeys;
+};
+
+struct k6_out
+{
+    uint32_t *region_read_off, *region_key_off, *aln_off, *aln_seg_off, *aln_key_off, *rec_off;
+    sx_indel_key* keys;
+    int32_t* aln_pos;
+    sx_aln_seg* segs;
+    uint16_t *aln_keys, *read_len, *non_ambig;
+    uint8_t* read_flags;
+    char* key_ins; // optional: 32 bytes per key, the insert sequence (zero padded)
+};
+
+void gen_region_k6(const k1_cfg& c, uint32_t rg, bool fill, k6_counts& cnt, const k6_counts* base /*prefix of this region*/, const k6_out* o)
+{
+    const uint32_t chunks = (c.depth + c.rpr - 1) / c.rpr;
+    const uint32_t l = rg / chunks, chunk = rg % chunks;
+    const uint32_t k_begin = chunk * c.rpr, k_end = std::min(c.depth, k_begin + c.rpr);
+    rng_t r(c.seed, l);
+    locus_desc d;
+    std::vector<char> refv(c.ref_len);
+    make_locus(c, l, r, d, refv.data());
+    const uint32_t locus = c.ref_len / 2;
+    const int32_t ref_begin = 1000 + (int32_t)(l % 2000000u) * 1000;
+    r.below(c.n_haps); // g0
+    if (r.below(3)) r.below(c.n_haps); // g1
+    // window: distinct alleles in IndelKey order (same pos and type: insert length, delete length, insert sequence)
+    uint32_t order[31], n_win = 0, win_of[31];
+    auto less = [&](uint32_t x, uint32_t y) {
+        const allele &a = d.alt[x], &b = d.alt[y];
+        const uint32_t ai = a.is_ins ? a.len : 0, bi = b.is_ins ? b.len : 0, ad = a.is_ins ? 0 : a.len, bd = b.is_ins ? 0 : b.len;
+        if (ai != bi) return ai < bi;
+        if (ad != bd) return ad < bd;
+        return a.is_ins && memcmp(a.seq, b.seq, a.len) < 0;
+    };
+    for (uint32_t a = 0; a < d.n_alt; ++a) order[a] = a;
+    std::sort(order, order + d.n_alt, less);
+    for (uint32_t i = 0; i < d.n_alt; ++i)
+    {
+        if (i > 0 && !less(order[i - 1], order[i])) win_of[order[i]] = n_win - 1; // equal to its predecessor
+        else win_of[order[i]] = n_win++;
+    }
+    cnt.keys = n_win;
+    const uint32_t first_read = l * c.depth + k_begin; // == region's read_begin in the K1 batch
+    if (fill)
+    {
+        o->region_read_off[rg] = first_read;
+        o->region_key_off[rg] = base->keys;
+        uint32_t w = 0;
+        for (uint32_t i = 0; i < d.n_alt; ++i)
+        {
+            if (win_of[order[i]] != w) continue;
+            const allele& a = d.alt[order[i]];
+            sx_indel_key& k = o->keys[base->keys + w];
+            memset(&k, 0, sizeof(k));
+            k.pos = ref_begin + (int32_t)locus;
+            k.del_len = a.is_ins ? 0 : (uint16_t)a.len;
+            k.ins_len = a.is_ins ? (uint16_t)a.len : 0;
+            k.ins_id = a.is_ins ? w + 1 : 0;
+            k.type = SX_INDEL_TYPE_INDEL;
+            k.flags = SX_IKF_CANDIDATE;
+            k.ref_to_indel_lnp = -9.903487552536127; // ln 5e-5
+            k.indel_to_ref_lnp = -9.903487552536127;
+            if (o->key_ins)
+            {
+                memset(o->key_ins + 32ull * (base->keys + w), 0, 32);
+                if (a.is_ins) memcpy(o->key_ins + 32ull * (base->keys + w), a.seq, a.len);
+            }
+            ++w;
+        }
+    }
+    for (uint32_t k = 0; k < k_begin; ++k)
+    {
+        r.below(c.read_len - 20);
+        r.below(2);
+    }
+    uint32_t segs = 0, akeys = 0;
+    for (uint32_t k = k_begin; k < k_end; ++k)
+    {
+        const uint32_t left = 10 + r.below(c.read_len - 20);
+        const uint32_t start = locus - left;
+        r.below(2);
+        const uint32_t read = first_read + (k - k_begin);
+        if (fill)
+        {
+            o->aln_off[read] = read * c.n_haps;
+            o->read_len[read] = (uint16_t)c.read_len;
+            o->non_ambig[read] = (uint16_t)c.read_len;
+            o->read_flags[read] = SX_SIF_FWD | SX_SIF_TIER1;
+            o->rec_off[read] = 0; // per-read slot counts first; prefix-summed by synth_k6_fill
+        }
+        for (uint32_t hh = 0; hh < c.n_haps; ++hh)
+        {
+            const uint32_t a_idx = read * c.n_haps + hh;
+            sx_aln_seg* sg = fill ? o->segs + base->segs + segs : nullptr;
+            if (fill)
+            {
+                o->aln_pos[a_idx] = ref_begin + (int32_t)start;
+                o->aln_seg_off[a_idx] = base->segs + segs;
+                o->aln_key_off[a_idx] = base->akeys + akeys;
+            }
+            if (hh == 0)
+            {
+                if (fill) sg[0] = sx_aln_seg{(uint16_t)c.read_len, SX_SEG_MATCH, 0};
+                segs += 1;
+                continue;
+            }
+            const allele& a = d.alt[hh - 1];
+            bool in_set = true;
+            if (a.is_ins)
+            {
+                const uint32_t n = std::min(a.len, c.read_len - left), rest = c.read_len - left - n;
+                if (fill)
+                {
+                    sg[0] = sx_aln_seg{(uint16_t)left, SX_SEG_MATCH, 0};
+                    sg[1] = sx_aln_seg{(uint16_t)n, SX_SEG_INSERT, 0};
+                    if (rest) sg[2] = sx_aln_seg{(uint16_t)rest, SX_SEG_MATCH, 0};
+                }
+                segs += rest ? 3 : 2;
+                in_set = rest != 0;
+            }
+            else
+            {
+                if (fill)
+                {
+                    sg[0] = sx_aln_seg{(uint16_t)left, SX_SEG_MATCH, 0};
+                    sg[1] = sx_aln_seg{(uint16_t)a.len, SX_SEG_DELETE, 0};
+                    sg[2] = sx_aln_seg{(uint16_t)(c.read_len - left), SX_SEG_MATCH, 0};
+                }
+                segs += 3;
+            }
+            if (in_set)
+            {
+                if (fill) o->aln_keys[base->akeys + akeys] = (uint16_t)win_of[hh - 1];
+                akeys += 1;
+            }
+        }
+    }
+    cnt.segs = segs;
+    cnt.akeys = akeys;
+}
+} // namespace
+
+// pass 1: per-region counts (counts[3 * n_regions]: keys, segs, alignment keys) and totals
+int synth_k6_plan(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n_haps, uint64_t seed, int threads, uint32_t reads_per_region, uint32_t* counts,
+                  synth_k6_sizes* out)
+{
+    if (n_haps < 1 || n_haps > 32 || read_len < 40 || read_len > 1000) return -1;
+    const uint32_t rpr = reads_per_region ? std::min(reads_per_region, depth) : depth;
+    const uint32_t n_regions = n_loci * ((depth + rpr - 1) / rpr);
+    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed, 8, rpr, 0};
+    parallel_for(n_regions, threads, [&](uint32_t rg) {
+        k6_counts cnt;
+        gen_region_k6(c, rg, false, cnt, nullptr, nullptr);
+        counts[3 * rg] = cnt.keys;
+        counts[3 * rg + 1] = cnt.segs;
+        counts[3 * rg + 2] = cnt.akeys;
+    });
+    memset(out, 0, sizeof(*out));
+    out->n_regions = n_regions;
+    out->n_reads = (uint64_t)n_loci * depth;
+    out->n_alns = out->n_reads * n_haps;
+    const uint32_t chunks = (depth + rpr - 1) / rpr;
+    for (uint32_t rg = 0; rg < n_regions; ++rg)
+    {
+        const uint32_t chunk = rg % chunks, nr = std::min(depth, (chunk + 1) * rpr) - chunk * rpr;
+        out->n_keys += counts[3 * rg];
+        out->n_segs += counts[3 * rg + 1];
+        out->n_aln_keys += counts[3 * rg + 2];
+        out->n_slots += (uint64_t)nr * counts[3 * rg];
+    }
+    return 0;
+}
+
+// pass 2: fill caller-allocated arrays ([n+1] offset arrays, keys[n_keys], segs[n_segs], aln_keys[n_aln_keys], per-read arrays)
+int synth_k6_fill(uint32_t n_loci, uint32_t depth, uint32_t read_len, uint32_t n_haps, uint64_t seed, int threads, uint32_t reads_per_region, const uint32_t* counts,
+                  uint32_t* region_read_off, uint32_t* region_key_off, sx_indel_key* keys, uint32_t* aln_off, int32_t* aln_pos, uint32_t* aln_seg_off, sx_aln_seg* segs,
+                  uint32_t* aln_key_off, uint16_t* aln_keys, uint16_t* read_lens, uint16_t* non_ambig, uint8_t* read_flags, uint32_t* rec_off, char* key_ins /*optional, 32 bytes per key*/)
+{
+    const uint32_t rpr = reads_per_region ? std::min(reads_per_region, depth) : depth;
+    const uint32_t chunks = (depth + rpr - 1) / rpr;
+    const uint32_t n_regions = n_loci * chunks;
+    k1_cfg c{n_loci, depth, read_len, n_haps, 416, seed, 8, rpr, 0};
+    std::vector<k6_counts> base(n_regions + 1);
+    k6_counts run{0, 0, 0};
+    for (uint32_t rg = 0; rg < n_regions; ++rg)
+    {
+        base[rg] = run;
+        run.keys += counts[3 * rg];
+        run.segs += counts[3 * rg + 1];
+        run.akeys += counts[3 * rg + 2];
+    }
+    base[n_regions] = run;
+    k6_out o{region_read_off, region_key_off, aln_off, aln_seg_off, aln_key_off, rec_off, keys, aln_pos, segs, aln_keys, read_lens, non_ambig, read_flags, key_ins};
+    parallel_for(n_regions, threads, [&](uint32_t rg) {
+        k6_counts cnt;
+        gen_region_k6(c, rg, true, cnt, &base[rg], &o);
+    });
+    const uint64_t n_reads = (uint64_t)n_loci * depth, n_alns = n_reads * n_haps;
+    region_read_off[n_regions] = (uint32_t)n_reads;
+    region_key_off[n_regions] = run.keys;
+    aln_off[n_reads] = (uint32_t)n_alns;
+    aln_seg_off[n_alns] = run.segs;
+    aln_key_off[n_alns] = run.akeys;
+    uint64_t slots = 0; // a read may evaluate every entry of its region's window
+    for (uint32_t rg = 0; rg < n_regions; ++rg)
+    {
+        const uint32_t chunk = rg % chunks, nr = std::min(depth, (chunk + 1) * rpr) - chunk * rpr;
+        for (uint32_t i = 0; i < nr; ++i)
+        {
+            rec_off[region_read_off[rg] + i] = (uint32_t)slots;
+            slots += counts[3 * rg];
+        }
+    }
+    rec_off[n_reads] = (uint32_t)slots;
+    return slots > 0xffffffffull ? -2 : 0;
+}
+
 // pileup columns: Poisson-ish depth (binomial approximation via sum of uniforms is avoided: exact inverse-CDF Poisson), a
 // site is hom-ref (80 %), het (13 %) or hom-alt (7 %) for germline; for the tumour sample `vaf` gives the alt fraction.
 static uint32_t poisson(rng_t& r, double mean)
