@@ -6,11 +6,12 @@
 // and consumes K1's scores where K1 wrote them (device memory).
 //
 // Shape of the work: per read a handful of alignments x a handful of indels of integer bookkeeping and a few fp64 adds and
-// compares -- no reuse between reads and nothing GEMM-like.  One thread owns one read (grid-stride over reads, the grid a multiple
-// of the SM count); its per-read state (k6_scratch: sort order, filter flags, per-indel maxima) lives in one arena laid out
-// element-major across threads, so that the threads of a warp touching "their" element i hit consecutive addresses.  The batch
-// arrays are read once through the read-only path; the output is one 32-byte record per (read, evaluated indel).
-// The per-read body is k6_core.cuh.
+// compares -- no reuse between reads and nothing GEMM-like; the algorithmic floor is reading every input once.  A thread block
+// takes 128 consecutive reads per iteration (persistent grid: resident blocks x SM count): the reads own contiguous slices of every
+// CSR array, which the block copies into shared memory with coalesced loads (k6_stage); then one thread runs one read on a view
+// rebased into that copy, so the body's many small dependent loads are shared-memory accesses.  Per-read state (sort order,
+// filter flags, per-indel maxima) is local memory for ordinary reads (<= 8 alignments, <= 4 output slots) and a column of an
+// element-major global arena for deep ones.  Output: one 32-byte record per (read, evaluated indel).  The body is k6_core.cuh.
 
 #include "k6_core.cuh"
 #include "sx_internal.h"
@@ -22,27 +23,42 @@ namespace
 constexpr int K6_THREADS = 128;
 constexpr int K6_ST_SHIFT = 9; // K6_ST_* bits are reported as ctx status bits 512, 1024, ...
 
-__global__ void k6_max_kernel(const uint32_t* __restrict__ aln_off, const uint32_t* __restrict__ rec_off, const uint32_t n_reads, uint32_t* __restrict__ out)
+// sizes the launch needs: out[0] = max alignments of a read, out[1] = max output slots of a read, out[2] / out[3] = largest staging
+// footprint (k6_plan_block().bytes) of a 128-read / 32-read block
+__global__ void k6_max_kernel(const sx_score_indels_batch b, uint32_t* __restrict__ out)
 {
-    uint32_t mA(0), mS(0);
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x)
+    uint32_t mA(0), mS(0), m128(0), m32(0);
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < b.n_reads; r += gridDim.x * blockDim.x)
     {
-        mA = max(mA, aln_off[r + 1] - aln_off[r]);
-        mS = max(mS, rec_off[r + 1] - rec_off[r]);
+        mA = max(mA, b.aln_off[r + 1] - b.aln_off[r]);
+        mS = max(mS, b.rec_off[r + 1] - b.rec_off[r]);
+        if ((r & 31) == 0)
+        {
+            m32 = max(m32, k6_plan_block(b, r, min(b.n_reads, r + 32)).bytes);
+            if ((r & 127) == 0) m128 = max(m128, k6_plan_block(b, r, min(b.n_reads, r + 128)).bytes);
+        }
     }
     mA = __reduce_max_sync(0xffffffffu, mA);
     mS = __reduce_max_sync(0xffffffffu, mS);
+    m128 = __reduce_max_sync(0xffffffffu, m128);
+    m32 = __reduce_max_sync(0xffffffffu, m32);
     if ((threadIdx.x & 31) == 0)
     {
         atomicMax(out, mA);
         atomicMax(out + 1, mS);
+        atomicMax(out + 2, m128);
+        atomicMax(out + 3, m32);
     }
 }
 
-__global__ void __launch_bounds__(K6_THREADS) k6_score_kernel(const k6_view v, const k6_scratch S0, int* __restrict__ status)
+extern __shared__ __align__(16) unsigned char k6_smem[];
+
+// one block = blockDim.x consecutive reads per iteration: stage their slices, one read per thread
+__global__ void __launch_bounds__(K6_THREADS) k6_score_kernel(const k6_view v, const k6_scratch S0, const uint32_t smem_cap, int* __restrict__ status)
 {
-    const uint32_t t(blockIdx.x * blockDim.x + threadIdx.x), T(gridDim.x * blockDim.x);
-    k6_scratch S(S0); // this thread's columns of the element-major arena
+    __shared__ k6_block_plan plan;
+    const uint32_t t(blockIdx.x * blockDim.x + threadIdx.x);
+    k6_scratch S(S0); // this thread's columns of the element-major arena (reads too deep for the local-memory scratch)
     S.ord.p += t;
     S.smooth.p += t;
     S.filt.p += t;
@@ -53,17 +69,23 @@ __global__ void __launch_bounds__(K6_THREADS) k6_score_kernel(const k6_view v, c
     S.alt.p += t;
     S.pair.p += t;
     uint32_t st(0);
-    for (uint32_t r = t; r < v.b.n_reads; r += T)
+    const uint32_t n_chunks((v.b.n_reads + blockDim.x - 1) / blockDim.x);
+    for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x)
     {
-        // region of read r: last region whose first read is <= r and which is not empty at r
-        uint32_t lo(0), hi(v.b.n_regions);
-        while (hi - lo > 1)
+        const uint32_t r0(chunk * blockDim.x), r1(min(v.b.n_reads, r0 + blockDim.x));
+        if (threadIdx.x == 0) plan = k6_plan_block(v.b, r0, r1);
+        __syncthreads();
+        const k6_block_plan p(plan);
+        k6_view lv(v);
+        if (p.bytes <= smem_cap)
         {
-            const uint32_t mid((lo + hi) >> 1);
-            if (v.b.region_read_off[mid] <= r) lo = mid;
-            else hi = mid;
+            k6_stage(v, p, k6_smem, threadIdx.x, blockDim.x);
+            __syncthreads();
+            lv = k6_rebased(v, p, k6_smem);
         }
-        st |= k6_score_read(v, lo, r, S);
+        const uint32_t r(r0 + threadIdx.x);
+        if (r < r1) st |= k6_score_read_in_block(lv, p, r, S);
+        __syncthreads(); // the next iteration overwrites plan and the staged slices
     }
     if (st) atomicOr(status, (int)(st << K6_ST_SHIFT));
 }
@@ -94,23 +116,32 @@ k6_layout k6_plan(const uint32_t maxA, const uint32_t maxE, const size_t T)
 int k6_run(sx_ctx* ctx, const sx_score_indels_batch* d, const double* lnp_dev, const sx_score_indels_out* out_dev, unsigned* launches)
 {
     cudaStream_t st(ctx->s_compute);
-    // sizes of the per-read scratch: the deepest read of the batch decides
+    // sizes of the launch: the deepest read of the batch decides the scratch, the largest block footprint the shared memory
     uint32_t* d_max(nullptr);
     int rc;
-    if ((rc = sx_ensure(ctx, 29, 8, reinterpret_cast<void**>(&d_max)))) return rc;
-    SX_CUDA(ctx, cudaMemsetAsync(d_max, 0, 8, st));
+    if ((rc = sx_ensure(ctx, 29, 16, reinterpret_cast<void**>(&d_max)))) return rc;
+    SX_CUDA(ctx, cudaMemsetAsync(d_max, 0, 16, st));
     const int grid0(std::max(1, std::min<int>((int)((d->n_reads + 255) / 256), ctx->sm_count * 8)));
-    k6_max_kernel<<<grid0, 256, 0, st>>>(d->aln_off, d->rec_off, d->n_reads, d_max);
+    k6_max_kernel<<<grid0, 256, 0, st>>>(*d, d_max);
     SX_CUDA(ctx, cudaGetLastError());
-    uint32_t h_max[2] = {0, 0};
-    SX_CUDA(ctx, cudaMemcpyAsync(h_max, d_max, 8, cudaMemcpyDeviceToHost, st));
+    uint32_t h_max[4] = {0, 0, 0, 0};
+    SX_CUDA(ctx, cudaMemcpyAsync(h_max, d_max, 16, cudaMemcpyDeviceToHost, st));
     SX_CUDA(ctx, cudaStreamSynchronize(st));
     const uint32_t maxA(std::max(1u, h_max[0])), maxE(std::max(1u, std::min(K6_MAX_EVAL, h_max[1])));
+    // 128 reads per block when their slices fit a modest tile (several blocks per SM), else 32 reads per block; a block whose
+    // slices still do not fit runs on the global arrays
+    const uint32_t smem_limit(48u * 1024u);
+    const int threads(h_max[2] <= smem_limit ? K6_THREADS : 32);
+    const uint32_t smem_bytes(std::min(smem_limit, threads == K6_THREADS ? h_max[2] : h_max[3]));
+    int per_sm(1);
+    SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k6_score_kernel, threads, smem_bytes));
+    per_sm = std::max(1, per_sm);
 
-    // threads: one per read up to a few resident CTAs per SM; fewer when a deep batch would make the arena too large
-    size_t T(std::min<size_t>(((size_t)d->n_reads + K6_THREADS - 1) / K6_THREADS, (size_t)ctx->sm_count * 8) * K6_THREADS);
+    // threads: one per read, up to the resident blocks of every SM; fewer when a deep batch would make the arena too large
+    const size_t n_chunks(((size_t)d->n_reads + threads - 1) / threads);
+    size_t T(std::min<size_t>(n_chunks, (size_t)ctx->sm_count * per_sm) * threads);
     const size_t arena_cap((size_t)1 << 30);
-    while (T > K6_THREADS && k6_plan(maxA, maxE, T).bytes > arena_cap) T = ((T / 2 + K6_THREADS - 1) / K6_THREADS) * K6_THREADS;
+    while (T > (size_t)threads && k6_plan(maxA, maxE, T).bytes > arena_cap) T = ((T / 2 + threads - 1) / threads) * threads;
     const k6_layout L(k6_plan(maxA, maxE, T));
     char* arena(nullptr);
     if ((rc = sx_ensure(ctx, 28, L.bytes, reinterpret_cast<void**>(&arena)))) return rc;
@@ -133,7 +164,7 @@ int k6_run(sx_ctx* ctx, const sx_score_indels_batch* d, const double* lnp_dev, c
     v.n_rec = out_dev->n_rec;
     v.max_aln = out_dev->max_aln;
     v.eval_aln = out_dev->eval_aln;
-    k6_score_kernel<<<(unsigned)(T / K6_THREADS), K6_THREADS, 0, st>>>(v, S, ctx->d_status);
+    k6_score_kernel<<<(unsigned)(T / threads), threads, smem_bytes, st>>>(v, S, smem_bytes, ctx->d_status);
     SX_CUDA(ctx, cudaGetLastError());
     *launches = 2;
     return SX_OK;

@@ -7,8 +7,9 @@
 #include <vector>
 
 extern "C" int k6core_run(const sx_score_indels_batch* b, const double* lnp, sx_read_indel_score* recs, uint32_t* n_rec, uint32_t* max_aln, uint32_t* eval_aln,
-                          uint32_t* status_out)
+                          uint32_t* status_out, uint32_t block_reads, uint32_t smem_cap, uint32_t* staged_blocks)
 {
+    *staged_blocks = 0;
     uint32_t maxA(1), maxE(1);
     for (uint32_t r = 0; r < b->n_reads; ++r)
     {
@@ -39,8 +40,31 @@ extern "C" int k6core_run(const sx_score_indels_batch* b, const double* lnp, sx_
     v.max_aln = max_aln;
     v.eval_aln = eval_aln;
     uint32_t status(0);
-    for (uint32_t region = 0; region < b->n_regions; ++region)
-        for (uint32_t r = b->region_read_off[region]; r < b->region_read_off[region + 1]; ++r) status |= k6_score_read(v, region, r, S);
+    if (block_reads == 0) // the plain body, read by read
+    {
+        for (uint32_t region = 0; region < b->n_regions; ++region)
+            for (uint32_t r = b->region_read_off[region]; r < b->region_read_off[region + 1]; ++r) status |= k6_score_read(v, region, r, S);
+    }
+    else // what a thread block does: plan, stage the block's slices ("threads" t = 0..nt-1 in turn), run the body on the rebased view
+    {
+        std::vector<uint64_t> smem;
+        for (uint32_t r0 = 0; r0 < b->n_reads; r0 += block_reads)
+        {
+            const uint32_t r1(std::min(b->n_reads, r0 + block_reads));
+            const k6_block_plan p(k6_plan_block(v.b, r0, r1));
+            const bool staged(p.bytes <= smem_cap);
+            k6_view lv(v);
+            if (staged)
+            {
+                smem.assign(p.bytes / 8 + 2, 0xdeadbeefdeadbeefull);
+                unsigned char* sm(reinterpret_cast<unsigned char*>(smem.data()));
+                for (uint32_t t = 0; t < block_reads; ++t) k6_stage(v, p, sm, t, block_reads);
+                lv = k6_rebased(v, p, sm);
+                ++*staged_blocks;
+            }
+            for (uint32_t r = r0; r < r1; ++r) status |= k6_score_read_in_block(lv, p, r, S);
+        }
+    }
     *status_out = status;
     return 0;
 }

@@ -123,16 +123,21 @@ def test_k6_device_body_on_the_host(tmp_path):
     subprocess.check_call(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "strelka_b200", "csrc"),
                            os.path.join(HERE, "cpp", "k6_core_host.cpp"), "-o", so])
     lib = C.CDLL(so)
-    lib.k6core_run.argtypes = [C.POINTER(A.SxScoreIndelsBatch)] + [C.c_void_p] * 6
-    total = 0
+    lib.k6core_run.argtypes = [C.POINTER(A.SxScoreIndelsBatch)] + [C.c_void_p] * 6 + [C.c_uint32, C.c_uint32, C.c_void_p]
+    total = staged_total = 0
     for case in range(60):
         sb, lnp = specgen.score_indels_case(case)
         want = reflib.ox_score_indels(sb, lnp)
-        out = B.ScoreIndelsOut(sb)
-        st = np.zeros(1, np.uint32)
-        lib.k6core_run(C.byref(sb.c), A.ptr(lnp), A.ptr(out.recs), A.ptr(out.n_rec), A.ptr(out.max_aln), A.ptr(out.eval_aln), A.ptr(st))
-        assert st[0] == 0
-        for w, g in zip(want, out.compact()):
-            assert w.tobytes() == g.tobytes()
+        # 0: the plain per-read body; otherwise what a thread block of that many reads does (plan, stage its slices into "shared
+        # memory", run the body on the rebased view; blocks whose slices exceed the capacity run on the global view)
+        for block_reads, cap in ((0, 0), (128, 49152), (32, 49152), (7, 4096), (3, 700), (128, 0)):
+            out = B.ScoreIndelsOut(sb)
+            st, staged = np.zeros(1, np.uint32), np.zeros(1, np.uint32)
+            lib.k6core_run(C.byref(sb.c), A.ptr(lnp), A.ptr(out.recs), A.ptr(out.n_rec), A.ptr(out.max_aln), A.ptr(out.eval_aln), A.ptr(st), block_reads, cap,
+                           A.ptr(staged))
+            assert st[0] == 0
+            for w, g in zip(want, out.compact()):
+                assert w.tobytes() == g.tobytes()
+            staged_total += int(staged[0])
         total += len(want[0])
-    assert total > 1500
+    assert total > 1500 and staged_total > 300
