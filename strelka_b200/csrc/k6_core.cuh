@@ -39,16 +39,19 @@ template <class T> struct k6_strided
     K6_HD T& operator[](const size_t i) const { return p[i * stride]; }
 };
 
+// The three kinds of maxima are kept as FLOATS: the reference keeps doubles and converts the winner to ReadPathScores::score_t
+// (float) at the very end; rounding to nearest is monotone, so max_i (float)x_i == (float) max_i x_i -- same bits, half the state.
 struct k6_scratch
 {
     k6_strided<uint32_t> ord;   // [maxA] alignments, best score first
-    k6_strided<double> smooth;  // [maxA]
+    k6_strided<double> smooth;  // [maxA] (compared in double against the smoothing range)
     k6_strided<uint8_t> filt;   // [maxA]
     k6_strided<uint16_t> ev;    // [maxE] evaluated window indices, ascending
-    k6_strided<double> present; // [maxE] best score, indel present   (iks key (e,(true ,e)))
-    k6_strided<double> absent;  // [maxE] best score, indel absent    (iks key (e,(false,e)))
+    k6_strided<uint16_t> slot;  // [maxE] output slot reserved for ev[i]
+    k6_strided<float> present;  // [maxE] best score, indel present   (iks key (e,(true ,e)))
+    k6_strided<float> absent;   // [maxE] best score, indel absent    (iks key (e,(false,e)))
     k6_strided<uint8_t> has;    // [maxE] bit0: present set, bit1: absent set
-    k6_strided<double> alt;     // [maxE*maxE] row e, column o: best score with alternate o present  (iks key (e,(true,o)))
+    k6_strided<float> alt;      // [maxE*maxE] row e, column o: best score with alternate o present  (iks key (e,(true,o)))
     k6_strided<uint8_t> pair;   // [maxE*maxE] bit0: e and o conflict (orthogonalIndelMap), bit1: alt set
     uint32_t maxA, maxE;
 };
@@ -57,13 +60,13 @@ struct k6_scratch
 // L1-cached write-back, the strided arena is an L2 round trip per access)
 template <int MA, int ME> struct k6_local_scratch
 {
-    uint32_t ord[MA];
     double smooth[MA];
+    float present[ME], absent[ME];
+    float alt[ME * ME];
+    uint16_t ev[ME], slot[ME];
+    uint8_t ord[MA]; // MA <= 255
     uint8_t filt[MA];
-    uint16_t ev[ME];
-    double present[ME], absent[ME];
     uint8_t has[ME];
-    double alt[ME * ME];
     uint8_t pair[ME * ME];
     static constexpr uint32_t maxA = MA, maxE = ME;
 };
@@ -261,10 +264,11 @@ K6_HD int32_t k6_lowest_fwd_read_pos(const k6_aln& al, const bool fwd, const int
     return fwd ? readOffset : readLength - (readOffset + 1);
 }
 
-K6_HD void k6_tick(double& slot, uint8_t& flags, const uint8_t bit, const double lnp)
+K6_HD void k6_tick(float& slot, uint8_t& flags, const uint8_t bit, const double lnp)
 {
-    if ((flags & bit) && slot >= lnp) return; // updateIndelScoringInfo, score_indels.cpp:60-75
-    slot = lnp;
+    const float f((float)lnp); // see k6_scratch: the maximum of the rounded values is the rounded maximum
+    if ((flags & bit) && slot >= f) return; // updateIndelScoringInfo, score_indels.cpp:60-75
+    slot = f;
     flags |= bit;
 }
 
@@ -437,12 +441,16 @@ template <class SC> K6_HD uint32_t k6_score_read(const k6_view& v, const uint32_
             sx_read_indel_score rec = {};
             rec.key = (uint16_t)k;
             rec.flags = sub ? SX_RIS_SUBOVERLAP : 0;
-            out[n_out++] = rec;
-            if (sub) continue;
-            if (E >= S.maxE) return K6_ST_LIMIT_E;
-            S.ev[E] = (uint16_t)k;
-            S.has[E] = 0;
-            ++E;
+            out[n_out] = rec;
+            if (!sub)
+            {
+                if (E >= S.maxE) return K6_ST_LIMIT_E;
+                S.ev[E] = (uint16_t)k;
+                S.slot[E] = (uint16_t)n_out;
+                S.has[E] = 0;
+                ++E;
+            }
+            ++n_out;
         }
     }
 
@@ -508,19 +516,26 @@ template <class SC> K6_HD uint32_t k6_score_read(const k6_view& v, const uint32_
     const unsigned read_length(b.read_len[r]);
     const unsigned fullReadLength(b.full_len ? b.full_len[r] : read_length);
     const unsigned fullReadOffset(b.full_off ? b.full_off[r] : 0);
-    uint32_t slot(0);
+    uint32_t n_dead(0);
     for (uint32_t ei = 0; ei < E; ++ei)
     {
         const uint32_t e(S.ev[ei]);
-        while (out[slot].key != e || out[slot].flags != 0) ++slot; // its placeholder (both lists ascend)
-        double indelScore(maxScore);
+        float indelScore((float)maxScore);
         if (!k6_contains(maxAl, e))
         {
-            if (!(S.has[ei] & 1)) continue;
+            if (!(S.has[ei] & 1))
+            {
+                ++n_dead;
+                continue;
+            }
             indelScore = S.present[ei];
         }
-        if (!(S.has[ei] & 2)) continue;
-        const double refScore(S.absent[ei]);
+        if (!(S.has[ei] & 2))
+        {
+            ++n_dead;
+            continue;
+        }
+        const float refScore(S.absent[ei]);
         const sx_indel_key ek(win[e]);
         const int32_t right_pos(ek.pos + (int32_t)ek.del_len);
         const int32_t readPos(k6_lowest_fwd_read_pos(maxAl, fwd, ek.pos - 1, right_pos + 1));
@@ -535,8 +550,8 @@ template <class SC> K6_HD uint32_t k6_score_read(const k6_view& v, const uint32_
         sx_read_indel_score rec = {};
         rec.key = (uint16_t)e;
         rec.flags = SX_RIS_SCORED;
-        rec.ref_lnp = (float)refScore;
-        rec.indel_lnp = (float)indelScore;
+        rec.ref_lnp = refScore;
+        rec.indel_lnp = indelScore;
         rec.read_pos = (int16_t)readPos;
         rec.dist_from_edge = (int16_t)dist;
         // ReadPathScores::insertAlt, IndelData.cpp:42-68, over orthogonalIndelMap[e] in key order
@@ -545,7 +560,7 @@ template <class SC> K6_HD uint32_t k6_score_read(const k6_view& v, const uint32_
         {
             const unsigned pr(S.pair[ei * S.maxE + oj]);
             if ((pr & 3) != 3) continue;
-            const float a((float)S.alt[ei * S.maxE + oj]);
+            const float a(S.alt[ei * S.maxE + oj]);
             if (n_alt < 2)
             {
                 rec.alt_key[n_alt] = S.ev[oj];
@@ -570,15 +585,19 @@ template <class SC> K6_HD uint32_t k6_score_read(const k6_view& v, const uint32_
             }
         }
         rec.n_alt = (uint8_t)n_alt;
-        out[slot] = rec;
+        out[S.slot[ei]] = rec;
     }
-    // drop the placeholders step (3) skipped
-    uint32_t w(0);
-    for (uint32_t i = 0; i < n_out; ++i)
+    // drop the placeholders step (3) skipped (rare: an indel no surviving alignment carries, or none without it)
+    uint32_t w(n_out);
+    if (n_dead)
     {
-        if (out[i].flags == 0) continue;
-        if (w != i) out[w] = out[i];
-        ++w;
+        w = 0;
+        for (uint32_t i = 0; i < n_out; ++i)
+        {
+            if (out[i].flags == 0) continue;
+            if (w != i) out[w] = out[i];
+            ++w;
+        }
     }
     v.n_rec[r] = w;
     return 0;

@@ -28,15 +28,17 @@ constexpr int K6_ST_SHIFT = 9; // K6_ST_* bits are reported as ctx status bits 5
 __global__ void k6_max_kernel(const sx_score_indels_batch b, uint32_t* __restrict__ out)
 {
     uint32_t mA(0), mS(0), m128(0), m32(0);
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < b.n_reads; r += gridDim.x * blockDim.x)
+    const uint32_t tid(blockIdx.x * blockDim.x + threadIdx.x), nthr(gridDim.x * blockDim.x);
+    for (uint32_t r = tid; r < b.n_reads; r += nthr)
     {
         mA = max(mA, b.aln_off[r + 1] - b.aln_off[r]);
         mS = max(mS, b.rec_off[r + 1] - b.rec_off[r]);
-        if ((r & 31) == 0)
-        {
-            m32 = max(m32, k6_plan_block(b, r, min(b.n_reads, r + 32)).bytes);
-            if ((r & 127) == 0) m128 = max(m128, k6_plan_block(b, r, min(b.n_reads, r + 128)).bytes);
-        }
+    }
+    for (uint32_t c = tid; c < (b.n_reads + 31) / 32; c += nthr) // one thread per 32-read block (and per 128-read block)
+    {
+        const uint32_t r(c * 32);
+        m32 = max(m32, k6_plan_block(b, r, min(b.n_reads, r + 32)).bytes);
+        if ((c & 3) == 0) m128 = max(m128, k6_plan_block(b, r, min(b.n_reads, r + 128)).bytes);
     }
     mA = __reduce_max_sync(0xffffffffu, mA);
     mS = __reduce_max_sync(0xffffffffu, mS);
@@ -63,6 +65,7 @@ __global__ void __launch_bounds__(K6_THREADS) k6_score_kernel(const k6_view v, c
     S.smooth.p += t;
     S.filt.p += t;
     S.ev.p += t;
+    S.slot.p += t;
     S.present.p += t;
     S.absent.p += t;
     S.has.p += t;
@@ -92,18 +95,18 @@ __global__ void __launch_bounds__(K6_THREADS) k6_score_kernel(const k6_view v, c
 
 struct k6_layout
 {
-    size_t off[9];
+    size_t off[10];
     size_t bytes;
 };
 
 // element-major arena for T threads: array a occupies count_a * T elements
 k6_layout k6_plan(const uint32_t maxA, const uint32_t maxE, const size_t T)
 {
-    const size_t count[9] = {maxA, maxA, maxA, maxE, maxE, maxE, maxE, (size_t)maxE * maxE, (size_t)maxE * maxE};
-    const size_t elem[9] = {4, 8, 1, 2, 8, 8, 1, 8, 1};
+    const size_t count[10] = {maxA, maxA, maxA, maxE, maxE, maxE, maxE, (size_t)maxE * maxE, (size_t)maxE * maxE, maxE};
+    const size_t elem[10] = {4, 8, 1, 2, 4, 4, 1, 4, 1, 2};
     k6_layout L;
     size_t o(0);
-    for (int i = 0; i < 9; ++i)
+    for (int i = 0; i < 10; ++i)
     {
         o = (o + 255) & ~(size_t)255;
         L.off[i] = o;
@@ -150,11 +153,12 @@ int k6_run(sx_ctx* ctx, const sx_score_indels_batch* d, const double* lnp_dev, c
     S.smooth = {reinterpret_cast<double*>(arena + L.off[1]), T};
     S.filt = {reinterpret_cast<uint8_t*>(arena + L.off[2]), T};
     S.ev = {reinterpret_cast<uint16_t*>(arena + L.off[3]), T};
-    S.present = {reinterpret_cast<double*>(arena + L.off[4]), T};
-    S.absent = {reinterpret_cast<double*>(arena + L.off[5]), T};
+    S.present = {reinterpret_cast<float*>(arena + L.off[4]), T};
+    S.absent = {reinterpret_cast<float*>(arena + L.off[5]), T};
     S.has = {reinterpret_cast<uint8_t*>(arena + L.off[6]), T};
-    S.alt = {reinterpret_cast<double*>(arena + L.off[7]), T};
+    S.alt = {reinterpret_cast<float*>(arena + L.off[7]), T};
     S.pair = {reinterpret_cast<uint8_t*>(arena + L.off[8]), T};
+    S.slot = {reinterpret_cast<uint16_t*>(arena + L.off[9]), T};
     S.maxA = maxA;
     S.maxE = maxE;
     k6_view v;

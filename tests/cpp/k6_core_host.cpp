@@ -17,7 +17,9 @@ extern "C" int k6core_run(const sx_score_indels_batch* b, const double* lnp, sx_
         maxE = std::max(maxE, std::min<uint32_t>(K6_MAX_EVAL, b->rec_off[r + 1] - b->rec_off[r]));
     }
     std::vector<uint32_t> ord(maxA);
-    std::vector<double> smooth(maxA), present(maxE), absent(maxE), alt((size_t)maxE * maxE);
+    std::vector<double> smooth(maxA);
+    std::vector<float> present(maxE), absent(maxE), alt((size_t)maxE * maxE);
+    std::vector<uint16_t> slot(maxE);
     std::vector<uint8_t> filt(maxA), has(maxE), pair((size_t)maxE * maxE);
     std::vector<uint16_t> ev(maxE);
     k6_scratch S;
@@ -25,6 +27,7 @@ extern "C" int k6core_run(const sx_score_indels_batch* b, const double* lnp, sx_
     S.smooth = {smooth.data(), 1};
     S.filt = {filt.data(), 1};
     S.ev = {ev.data(), 1};
+    S.slot = {slot.data(), 1};
     S.present = {present.data(), 1};
     S.absent = {absent.data(), 1};
     S.has = {has.data(), 1};
