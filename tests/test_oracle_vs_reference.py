@@ -253,3 +253,39 @@ def test_score_indels_on_k1_scores_matches_the_reference():
     r_recs, r_n, r_max = reflib.ref_score_indels(sb, lnp)
     assert np.array_equal(o_n, r_n) and np.array_equal(o_max, r_max) and o_recs.tobytes() == r_recs.tobytes()
     assert int((o_recs["flags"] & A.SX_RIS_SCORED).sum()) > 100
+
+
+def test_score_indels_bench_workload_matches_the_reference():
+    """The K6 leg of bench.py: its synthetic batch describes the same alignments as the K1 batch of the same loci (so K1's lnp[a] is
+    K6's score of alignment a), and on K1's scores the oracle and the reference's score_indels produce the same records.  The
+    synthetic workload lists one alignment per haplotype in haplotype order; the harness puts them into the reference's std::set
+    (ordering them, dropping exact duplicates), which does not change any record."""
+    import ctypes as C
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    class _Alloc:
+        def array(self, nbytes, dt):
+            return np.zeros(nbytes // np.dtype(dt).itemsize + 1, dt)
+
+    synth = bench.load_synth()
+    for n_loci, depth, n_haps, rpr in ((400, 30, 4, 0), (12, 300, 32, 16)):  # cfg2- and cfg5-shaped
+        sb = bench.make_score_indels_workload(synth, n_loci, depth, 150, n_haps, 5, 4, rpr)
+        ab, _pb, _gb = bench.make_workload(synth, _Alloc(), n_loci, depth, 150, n_haps, 5, 4, 8, rpr, 0)
+        assert sb.n_alns == ab.n_alns and sb.n_reads == ab.n_reads and sb.n_regions == ab.n_regions
+        assert np.array_equal(ab.alns["ref_pos"][: ab.n_alns], sb.aln_pos[: sb.n_alns])
+        assert np.array_equal(ab.regions["read_begin"][: ab.n_regions + 1], sb.region_read_off)
+        lnp = np.concatenate([reflib.ox_score(ab), [0.0]])
+        o_recs, o_n, _o_max, _ = reflib.ox_score_indels(sb, lnp)
+        out = B.ScoreIndelsOut(sb)
+        err = C.create_string_buffer(512)
+        fn = reflib.ref().ref_score_indels_ex
+        fn.argtypes = [C.POINTER(A.SxScoreIndelsBatch)] + [C.c_void_p] * 6 + [C.c_int, C.c_char_p, C.c_int]
+        rc = fn(C.byref(sb.c), A.ptr(lnp), A.ptr(sb.ins_pool), A.ptr(sb.ins_off), A.ptr(out.recs), A.ptr(out.n_rec), A.ptr(out.max_aln), 1, err, 512)
+        assert rc == 0, err.value
+        r_recs, r_n, _r_max, _ = out.compact()
+        assert np.array_equal(o_n, r_n) and o_recs.tobytes() == r_recs.tobytes()
+        assert int((o_recs["flags"] & A.SX_RIS_SCORED).sum()) > 0.5 * sb.n_reads
