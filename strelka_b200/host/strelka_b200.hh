@@ -8,6 +8,8 @@
 //   sx::IndelKey                          IndelKey{pos,type,deletionLength,insertSequence} starling_common/IndelKey.hh:39-193
 //   sx::CandidateAlignment                CandidateAlignment{al, indels, leading/trailing} starling_common/CandidateAlignment.hh:36-83
 //   sx::ReadAlignBatch::scoreCandidateAlignments   the loop at starling_read_align.cpp:1564-1571 over scoreCandidateAlignment
+//   sx::IndelScoreBatch::scoreIndels      score_indels (starling_read_align_score_indels.cpp:454) + the arg-max of scoreCandidateAlignments
+//   sx::ReadPathScores                    ReadPathScores                                   starling_common/IndelData.hh:64-116
 //   sx::AlignmentScores<int>, sx::GlobalAligner<int>::align, sx::AlignmentResult<int>   alignment/{AlignmentScores,GlobalAligner}.hh
 //   sx::Context                           RAII sx_ctx; failures throw sx::Exception (the reference throws blt_exception)
 //
@@ -16,6 +18,7 @@
 
 #include "strelka_b200.h"
 
+#include <algorithm>
 #include <cstring>
 #include <functional>
 #include <stdexcept>
@@ -121,6 +124,16 @@ struct IndelKey
     unsigned insert_length() const { return insertSequence.size(); }
     unsigned delete_length() const { return deletionLength; }
     bool isMismatch() const { return type == INDEL::MISMATCH; }
+    bool operator<(const IndelKey& rhs) const // IndelKey.hh:53-76
+    {
+        if (pos != rhs.pos) return pos < rhs.pos;
+        if (type != rhs.type) return type < rhs.type;
+        if (type == INDEL::NONE || type == INDEL::BP_LEFT || type == INDEL::BP_RIGHT) return false;
+        if (insert_length() != rhs.insert_length()) return insert_length() < rhs.insert_length();
+        if (delete_length() != rhs.delete_length()) return delete_length() < rhs.delete_length();
+        return insertSequence < rhs.insertSequence;
+    }
+    bool operator==(const IndelKey& rhs) const { return pos == rhs.pos && type == rhs.type && deletionLength == rhs.deletionLength && insertSequence == rhs.insertSequence; }
     pos_t pos;
     INDEL::index_t type;
     unsigned deletionLength;
@@ -544,6 +557,222 @@ private:
     std::vector<char> _ref, _ins, _refOut, _insOut;
     std::vector<sx_aln> _alns, _alnsOut;
     std::vector<sx_aln_seg> _segs, _segsOut;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// K6: score_indels over a batch of reads (starling_read_align_score_indels.cpp:454-1079 + starling_read_align.cpp:1573-1593)
+// ---------------------------------------------------------------------------------------------------------------------------
+struct IndelBufferEntry ///< what score_indels reads of one IndelBuffer entry
+{
+    IndelKey key;
+    bool isCandidate = true;            ///< indelBuffer.isCandidateIndel(key)
+    double refToIndelLogProb = 0;       ///< getErrorRates().refToIndelErrorProb.getLogValue()
+    double indelToRefLogProb = 0;       ///< getErrorRates().indelToRefErrorProb.getLogValue()
+};
+
+struct ReadPathScores ///< starling_common/IndelData.hh:64-116
+{
+    float ref = 0, indel = 0;
+    uint16_t nonAmbiguousBasesInRead = 0, read_length = 0;
+    bool is_tier1_read = true, is_fwd_strand = true;
+    int16_t read_pos = 0, distanceFromClosestReadEdge = 0;
+    std::vector<std::pair<IndelKey, float>> alt_indel;
+};
+
+class IndelScoreBatch
+{
+public:
+    struct Result
+    {
+        unsigned read;        ///< index returned by addRead
+        IndelKey key;         ///< the evaluated indel
+        bool isSuboverlap;    ///< true: only suboverlap_tier{1,2}_read_ids.insert(read); false: read_path_lnp[read] = scores
+        ReadPathScores scores;
+    };
+
+    /// window: every IndelBuffer entry a rangeIterator() over any alignment of the region's reads can visit, in IndelKey order
+    void beginRegion(const std::vector<IndelBufferEntry>& window)
+    {
+        closeRegion();
+        for (size_t i(1); i < window.size(); ++i) require(window[i - 1].key < window[i].key, "window is not in IndelKey order");
+        require(window.size() <= 65535, "more than 65535 window entries");
+        _regionKeyOff.push_back(_keys.size());
+        _regionReadOff.push_back(_readLen.size());
+        std::vector<std::string> interned(1, "");
+        for (const IndelBufferEntry& e : window)
+        {
+            require(e.key.type == INDEL::INDEL || e.key.type == INDEL::MISMATCH, "breakend entries are not supported");
+            sx_indel_key k;
+            std::memset(&k, 0, sizeof(k));
+            k.pos = e.key.pos;
+            k.del_len = e.key.delete_length();
+            k.ins_len = e.key.insert_length();
+            size_t id(0);
+            for (; id < interned.size(); ++id)
+                if (interned[id] == e.key.insertSequence) break;
+            if (id == interned.size()) interned.push_back(e.key.insertSequence);
+            k.ins_id = id;
+            k.type = e.key.isMismatch() ? SX_INDEL_TYPE_MISMATCH : SX_INDEL_TYPE_INDEL;
+            k.flags = e.isCandidate ? SX_IKF_CANDIDATE : 0;
+            k.ref_to_indel_lnp = e.refToIndelLogProb;
+            k.indel_to_ref_lnp = e.indelToRefLogProb;
+            _keys.push_back(k);
+            _keyObjects.push_back(e.key);
+        }
+        _open = true;
+    }
+
+    /// a tier1 or tier2 read segment (rseg.read_size(), its non-'N' base count, strand of its candidate alignments, tier, incomplete search)
+    unsigned addRead(unsigned readSize, unsigned nonAmbiguousBases, bool isFwdStrand, bool isTier1, bool isIncompleteSearch = false)
+    {
+        require(_open, "addRead outside a region");
+        _alnOff.push_back(_alnPos.size());
+        _recOff.push_back(_slots);
+        _slots += _keys.size() - _regionKeyOff.back();
+        _readLen.push_back(readSize);
+        _nonAmbig.push_back(nonAmbiguousBases);
+        _readFlags.push_back((isFwdStrand ? SX_SIF_FWD : 0) | (isTier1 ? SX_SIF_TIER1 : 0) | (isIncompleteSearch ? SX_SIF_INCOMPLETE : 0));
+        return _readLen.size() - 1;
+    }
+
+    /// the next candidate alignment of the last added read, in std::set<CandidateAlignment> order (== the order their scores come in)
+    void addCandidateAlignment(const CandidateAlignment& cal)
+    {
+        using namespace ALIGNPATH;
+        require(_open && !_readLen.empty() && _regionReadOff.back() < _readLen.size(), "addCandidateAlignment before addRead");
+        _alnPos.push_back(cal.al.pos);
+        _alnSegOff.push_back(_segs.size());
+        _alnKeyOff.push_back(_alnKeys.size());
+        for (const path_segment& ps : cal.al.path)
+        {
+            uint8_t kind(0);
+            switch (ps.type)
+            {
+            case MATCH: case SEQ_MATCH: case SEQ_MISMATCH: kind = SX_SEG_MATCH; break;
+            case INSERT: kind = SX_SEG_INSERT; break;
+            case DELETE: kind = SX_SEG_DELETE; break;
+            case SOFT_CLIP: kind = SX_SEG_SOFTCLIP; break;
+            case HARD_CLIP: kind = SX_SEG_HARDCLIP; break;
+            default: throw Exception(SX_ERR_UNSUPPORTED, "score_indels: segment type outside its domain (get_alignment_indel_bp_overlap asserts)");
+            }
+            require(ps.length <= 65535, "path segment longer than 65535");
+            _segs.push_back(sx_aln_seg{static_cast<uint16_t>(ps.length), kind, 0});
+        }
+        const size_t k0(_regionKeyOff.back());
+        std::vector<uint16_t> idx;
+        for (const IndelKey& key : cal.indels)
+        {
+            size_t lo(k0), hi(_keyObjects.size()); // binary search in the region's window
+            while (lo < hi)
+            {
+                const size_t mid((lo + hi) / 2);
+                if (_keyObjects[mid] < key) lo = mid + 1;
+                else hi = mid;
+            }
+            require(lo < _keyObjects.size() && _keyObjects[lo] == key, "an alignment's indel is not in the region's window");
+            idx.push_back(lo - k0);
+        }
+        std::sort(idx.begin(), idx.end());
+        _alnKeys.insert(_alnKeys.end(), idx.begin(), idx.end());
+    }
+
+    size_t alignmentCount() const { return _alnPos.size(); }
+
+    /// candAlignmentScores[alignmentCount()]: the K1 scores in the order the alignments were added.
+    /// maxAlignment[read] = maxCandAlignmentPtr of scoreCandidateAlignments as an alignment index (UINT32_MAX: read without alignments)
+    void scoreIndels(const Context& ctx, const std::vector<double>& candAlignmentScores, const sx_score_indels_opts* opts, std::vector<Result>& results,
+                     std::vector<uint32_t>& maxAlignment)
+    {
+        closeRegion();
+        require(candAlignmentScores.size() == _alnPos.size(), "one score per candidate alignment");
+        results.clear();
+        const size_t nReads(_readLen.size());
+        maxAlignment.assign(nReads, UINT32_MAX);
+        if (nReads == 0) return;
+        std::vector<uint32_t> alnOff(_alnOff), recOff(_recOff), alnSegOff(_alnSegOff), alnKeyOff(_alnKeyOff), regionReadOff(_regionReadOff), regionKeyOff(_regionKeyOff);
+        alnOff.push_back(_alnPos.size());
+        recOff.push_back(_slots);
+        alnSegOff.push_back(_segs.size());
+        alnKeyOff.push_back(_alnKeys.size());
+        regionReadOff.push_back(nReads);
+        regionKeyOff.push_back(_keys.size());
+        std::vector<sx_indel_key> keys(_keys);
+        keys.resize(keys.size() + 1);
+        std::vector<sx_aln_seg> segs(_segs);
+        segs.resize(segs.size() + 4);
+        std::vector<uint16_t> alnKeys(_alnKeys);
+        alnKeys.resize(alnKeys.size() + 4);
+        std::vector<int32_t> alnPos(_alnPos);
+        alnPos.push_back(0);
+        std::vector<double> lnp(candAlignmentScores);
+        lnp.push_back(0);
+        sx_score_indels_batch b;
+        std::memset(&b, 0, sizeof(b));
+        b.n_regions = regionReadOff.size() - 1;
+        b.n_reads = nReads;
+        b.n_alns = _alnPos.size();
+        b.n_keys = _keys.size();
+        b.region_read_off = regionReadOff.data();
+        b.region_key_off = regionKeyOff.data();
+        b.keys = keys.data();
+        b.aln_off = alnOff.data();
+        b.aln_pos = alnPos.data();
+        b.aln_seg_off = alnSegOff.data();
+        b.segs = segs.data();
+        b.aln_key_off = alnKeyOff.data();
+        b.aln_keys = alnKeys.data();
+        b.read_len = _readLen.data();
+        b.non_ambig = _nonAmbig.data();
+        b.read_flags = _readFlags.data();
+        b.rec_off = recOff.data();
+        if (opts) b.opts = *opts;
+        else sx_default_score_indels_opts(&b.opts);
+        std::vector<sx_read_indel_score> recs(_slots + 1);
+        std::vector<uint32_t> nRec(nReads), evalAln(nReads);
+        sx_score_indels_out out{recs.data(), nRec.data(), maxAlignment.data(), evalAln.data()};
+        ctx.check(sx_score_indels(ctx.get(), &b, lnp.data(), &out));
+        for (size_t g(0); g + 1 < regionReadOff.size(); ++g)
+            for (size_t r(regionReadOff[g]); r < regionReadOff[g + 1]; ++r)
+                for (uint32_t j(0); j < nRec[r]; ++j)
+                {
+                    const sx_read_indel_score& q(recs[recOff[r] + j]);
+                    Result res;
+                    res.read = r;
+                    res.key = _keyObjects[regionKeyOff[g] + q.key];
+                    res.isSuboverlap = (q.flags & SX_RIS_SUBOVERLAP) != 0;
+                    if (q.flags & SX_RIS_SCORED)
+                    {
+                        ReadPathScores& s(res.scores);
+                        s.ref = q.ref_lnp;
+                        s.indel = q.indel_lnp;
+                        s.nonAmbiguousBasesInRead = _nonAmbig[r];
+                        s.read_length = _readLen[r];
+                        s.is_tier1_read = (_readFlags[r] & SX_SIF_TIER1) != 0;
+                        s.is_fwd_strand = (_readFlags[r] & SX_SIF_FWD) != 0;
+                        s.read_pos = q.read_pos;
+                        s.distanceFromClosestReadEdge = q.dist_from_edge;
+                        for (unsigned i(0); i < q.n_alt; ++i) s.alt_indel.push_back(std::make_pair(_keyObjects[regionKeyOff[g] + q.alt_key[i]], q.alt_lnp[i]));
+                    }
+                    results.push_back(res);
+                }
+    }
+
+private:
+    static void require(bool ok, const char* what)
+    {
+        if (!ok) throw Exception(SX_ERR_ARG, std::string("IndelScoreBatch: ") + what);
+    }
+    void closeRegion() { _open = false; }
+
+    bool _open = false;
+    uint32_t _slots = 0;
+    std::vector<uint32_t> _regionReadOff, _regionKeyOff, _alnOff, _alnSegOff, _alnKeyOff, _recOff;
+    std::vector<sx_indel_key> _keys;
+    std::vector<IndelKey> _keyObjects;
+    std::vector<int32_t> _alnPos;
+    std::vector<sx_aln_seg> _segs;
+    std::vector<uint16_t> _alnKeys, _readLen, _nonAmbig;
+    std::vector<uint8_t> _readFlags;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------------

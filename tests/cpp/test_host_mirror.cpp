@@ -143,6 +143,76 @@ int main(int argc, char** argv)
                 }
             }
         }
+        // ---- K6: score_indels through sx::IndelScoreBatch; expected values = the reference's own score_indels on this case
+        //      (tests/test_oracle_vs_reference.py pins the oracle, the oracle produced these numbers, the reference harness agreed)
+        {
+            const double r2i(-9.903487552536127); // ln 5e-5
+            std::vector<sx::IndelBufferEntry> window(2);
+            window[0].key = sx::IndelKey(1050, sx::INDEL::INDEL, 3, "");
+            window[1].key = sx::IndelKey(1052, sx::INDEL::INDEL, 0, "AC");
+            for (auto& e : window) e.refToIndelLogProb = e.indelToRefLogProb = r2i;
+            sx::IndelScoreBatch ib;
+            ib.beginRegion(window);
+            auto cal = [](sx::pos_t pos, const char* cigar, std::vector<sx::IndelKey> keys) {
+                sx::CandidateAlignment c;
+                c.al.pos = pos;
+                sx::cigar_to_apath(cigar, c.al.path);
+                c.indels = keys;
+                return c;
+            };
+            ib.addRead(100, 99, true, true);
+            ib.addCandidateAlignment(cal(1000, "100M", {}));
+            ib.addCandidateAlignment(cal(1000, "50M3D50M", {window[0].key}));
+            ib.addCandidateAlignment(cal(1000, "52M2I46M", {window[1].key}));
+            ib.addRead(60, 60, false, false);
+            ib.addCandidateAlignment(cal(1047, "60M", {}));
+            ib.addCandidateAlignment(cal(1047, "3M3D57M", {window[0].key}));
+            std::vector<sx::IndelScoreBatch::Result> res;
+            std::vector<uint32_t> maxAln;
+            ib.scoreIndels(ctx, {-20.0, -3.0, -25.0, -4.0, -4.5}, nullptr, res, maxAln);
+            auto bitsOf = [](float f) {
+                uint32_t u;
+                std::memcpy(&u, &f, 4);
+                return u;
+            };
+            ++checks;
+            bool ok(res.size() == 3 && maxAln.size() == 2 && maxAln[0] == 1 && maxAln[1] == 3);
+            if (ok)
+            {
+                const sx::ReadPathScores &a(res[0].scores), &b(res[1].scores);
+                ok = ok && res[0].read == 0 && res[0].key == window[0].key && !res[0].isSuboverlap && bitsOf(a.ref) == 3243144367u && a.indel == -3.0f &&
+                     a.read_pos == 49 && a.distanceFromClosestReadEdge == 49 && a.alt_indel.size() == 1 && a.alt_indel[0].first == window[1].key &&
+                     a.alt_indel[0].second == -25.0f && a.nonAmbiguousBasesInRead == 99 && a.read_length == 100 && a.is_tier1_read && a.is_fwd_strand;
+                ok = ok && res[1].read == 0 && res[1].key == window[1].key && !res[1].isSuboverlap && bitsOf(b.ref) == 3243144367u && bitsOf(b.indel) == 3243144367u &&
+                     b.read_pos == -1 && b.distanceFromClosestReadEdge == 100 && b.alt_indel.size() == 1 && b.alt_indel[0].first == window[0].key &&
+                     b.alt_indel[0].second == -3.0f;
+                ok = ok && res[2].read == 1 && res[2].key == window[0].key && res[2].isSuboverlap;
+            }
+            if (!ok)
+            {
+                ++failures;
+                std::cerr << "FAIL k6: IndelScoreBatch::scoreIndels differs from the reference's score_indels on the known-answer case (" << res.size() << " results)\n";
+            }
+            // a SKIP segment is outside score_indels' domain: the builder refuses it like the reference's assert
+            bool threw(false);
+            try
+            {
+                sx::IndelScoreBatch bad;
+                bad.beginRegion(window);
+                bad.addRead(100, 100, true, true);
+                bad.addCandidateAlignment(cal(1000, "50M10N50M", {}));
+            }
+            catch (const sx::Exception& e)
+            {
+                threw = (e.code == SX_ERR_UNSUPPORTED);
+            }
+            ++checks;
+            if (!threw)
+            {
+                ++failures;
+                std::cerr << "FAIL k6: a SKIP segment did not raise SX_ERR_UNSUPPORTED\n";
+            }
+        }
         // ---- error behaviour: a failing call throws, like the reference's blt_exception
         {
             sx::ReadAlignBatch bad;
