@@ -552,6 +552,107 @@ int sx_score_indels(sx_ctx* ctx, const sx_score_indels_batch* batch_host, const 
 int sx_score_indels_dev(sx_ctx* ctx, const sx_score_indels_batch* batch_dev, const double* lnp_dev, sx_score_indels_out* out_dev);
 
 /* ==========================================================================================
+ * K7  enumerate_alignments   (the producer of K1's and K6's input)
+ *   replaces  getCandidateAlignments           starling_common/starling_read_align.cpp:1816-1994
+ *   with      candidate_alignment_search       :857-1277  (the recursive toggle search)
+ *             make_start_pos_alignment         :393-584,  get_end_pin_start_pos :593-719
+ *             add_indels_in_range              :322-375,  sort_remove_only_indels_last :724-749
+ *             addKeysToCandidateAlignment      :786-804,  HaplotypeStatus / getCurIndelHaplotypeIds :56-179, :807-849
+ *   and the container semantics around them: std::set<CandidateAlignment> (CandidateAlignment.hh:38-49,
+ *   alignment.hh:73-91, align_path.hh:184-196), IndelBuffer::rangeIterator (IndelBuffer.cpp:76-91),
+ *   is_range_{intersect,adjacent}_indel_breakpoints (indel_util.cpp:49-76), is_indel_conflict (:29-45),
+ *   starling_align_limit::get_max_toggle (starling_align_limit.hh:41-52).
+ *
+ * Input, per region (the reads buffered around one realignment window): the IndelBuffer window in IndelKey order (the
+ * sx_indel_key table K6 reads, plus what the search consults of IndelData: SX_IKF_NOT_DISCOVERED / SX_IKF_FORCED_OUTPUT and the
+ * optional sx_key_hap rows); per read the NORMALIZED input alignment realignAndScoreRead hands to getCandidateAlignments
+ * (:2034-2045: edge indels matchified, soft clips matchified), the window entries that alignment already contains
+ * (getAlignmentIndels(..., includeMismatches = true), CandidateAlignment.cpp:58-173, mapped to window indices by the host, which
+ * holds the read bases and the reference) and the non-candidate entries this read is an observation of (is_usable_indel :271-287).
+ * Output, per read: the std::set<CandidateAlignment> in ITS iteration order -- which is K1's and K6's alignment order -- as CSR
+ * arrays shaped like sx_score_indels_batch's (aln_pos / path segments / cal.getIndels() as window indices) + the leading / trailing
+ * edge keys + the warn flags that make is_incomplete_search.
+ *
+ * Path segments carry the reference's own ALIGNPATH::align_t values (SX_AP_*, blt_util/align_path.hh:36-48) because the set's
+ * order compares them numerically.
+ * ======================================================================================== */
+enum { SX_AP_MATCH = 1, SX_AP_INSERT = 2, SX_AP_DELETE = 3, SX_AP_SKIP = 4, SX_AP_SOFT_CLIP = 5, SX_AP_HARD_CLIP = 6, SX_AP_PAD = 7, SX_AP_SEQ_MATCH = 8, SX_AP_SEQ_MISMATCH = 9 };
+
+#define SX_IKF_NOT_DISCOVERED 0x2u /* IndelData::status.notDiscoveredFromReads */
+#define SX_IKF_FORCED_OUTPUT 0x4u  /* IndelData::isForcedOutput */
+#define SX_ENUM_MAX_SAMPLES 4
+#define SX_NO_KEY 0xFFFFu          /* leading_indel_key / trailing_indel_key of type INDEL::NONE */
+
+typedef struct sx_key_hap { /* the active-region phasing data of one window entry (IndelData.hh) */
+    int32_t active_region_id;                  /* IndelData::activeRegionId, < 0 = none */
+    int8_t haplotype_id[SX_ENUM_MAX_SAMPLES];  /* IndelSampleData::haplotypeId per sample (0, 1, 2, 3) */
+    uint8_t bypass_mask;                       /* bit s: IndelSampleData::isHaplotypingBypassed of sample s */
+    uint8_t pad[3];
+} sx_key_hap;
+
+#define SX_ENUM_ST_ORIGIN_SKIP 0x01u /* mca_warnings::origin_skip  (:1243)                                      */
+#define SX_ENUM_ST_MAX_TOGGLE 0x02u  /* mca_warnings::max_toggle_depth (:975, :1145); either => is_incomplete_search (:2104) */
+#define SX_ENUM_ST_EXCEPTION 0x04u   /* the reference throws blt_exception for this read (:450, :486, :539, :654, :678, :703, :1875);
+                                        no alignments are returned for it */
+#define SX_ENUM_ST_LIMIT 0x08u       /* more indels / alignments / segments than this build's per-read scratch holds; no alignments are
+                                        returned and the caller runs the read through its own getCandidateAlignments */
+
+typedef struct sx_enum_opts {
+    uint32_t max_indel_size;             /* opt.maxIndelSize, 49 (rangeIterator) */
+    int32_t max_read_indel_toggle;       /* opt.max_read_indel_toggle, 5 (starling_base_shared.hh:139) */
+    double max_candidate_indel_density;  /* 0.15 (:145) */
+    uint32_t n_max_toggle;               /* starling_align_limit::_max_toggle.size() */
+    uint8_t max_toggle[100];             /* ... its values for opt.max_realignment_candidates = 5000 (starling_align_limit.cpp:64-88);
+                                            indices >= n_max_toggle mean 1 */
+    int32_t is_haplotyping_enabled;      /* opt.isHaplotypingEnabled */
+    uint32_t n_samples;                  /* opt.getSampleCount(), <= SX_ENUM_MAX_SAMPLES */
+    uint32_t sample_id;                  /* the sample the reads belong to */
+    uint32_t max_alns_per_read;          /* scratch capacity per read, 0 = 64; reads that need more get SX_ENUM_ST_LIMIT */
+} sx_enum_opts;
+
+typedef struct sx_enum_batch {
+    uint32_t n_regions, n_reads, n_keys;
+    const uint32_t* region_read_off;   /* [n_regions + 1] */
+    const uint32_t* region_key_off;    /* [n_regions + 1] the IndelBuffer window of a region, IndelKey order, <= 65535 entries */
+    const sx_indel_key* keys;          /* [n_keys] (the error-rate fields are not read) */
+    const sx_key_hap* key_hap;         /* [n_keys] or NULL: no entry lies in an active region */
+    const int32_t* realign_begin;      /* [n_regions] realign_buffer_range (starling_pos_processor_base.cpp:735) */
+    const int32_t* realign_end;        /* [n_regions] */
+    const int32_t* in_pos;             /* [n_reads] normalizedInputAlignment.pos (>= 0, :2047) */
+    const uint32_t* in_seg_off;        /* [n_reads + 1] */
+    const sx_aln_seg* in_segs;         /* normalizedInputAlignment.path, kind = SX_AP_* */
+    const uint32_t* in_key_off;        /* [n_reads + 1] */
+    const uint16_t* in_keys;           /* window indices of getAlignmentIndels(cal, ref, rseg, maxIndelSize, true), ascending; mismatches
+                                          that are not window entries are dropped (:1869), as the reference does */
+    const uint32_t* use_key_off;       /* [n_reads + 1] */
+    const uint16_t* use_keys;          /* window indices of the entries whose tier1/tier2/submap/noise read-id sets hold this read */
+    const uint16_t* in_lead_key;       /* [n_reads] leading_indel_key of getCandidateAlignment (:1481-1522) as window index, or SX_NO_KEY */
+    const uint16_t* in_trail_key;      /* [n_reads] trailing_indel_key */
+    const uint16_t* read_len;          /* [n_reads] rseg.read_size() */
+    sx_enum_opts opts;
+} sx_enum_batch;
+
+typedef struct sx_enum_out { /* caller-allocated, capacities stated */
+    uint32_t cap_alns, cap_segs, cap_keys;
+    uint32_t* totals;        /* [3] alignments, segments, keys the batch produces (written even when a capacity is too small) */
+    uint32_t* aln_off;       /* [n_reads + 1] */
+    uint8_t* status;         /* [n_reads] SX_ENUM_ST_* */
+    int32_t* aln_pos;        /* [cap_alns] */
+    uint32_t* aln_seg_off;   /* [cap_alns + 1] */
+    sx_aln_seg* segs;        /* [cap_segs] kind = SX_AP_* */
+    uint32_t* aln_key_off;   /* [cap_alns + 1] */
+    uint16_t* aln_keys;      /* [cap_keys] cal.getIndels() as ascending window indices */
+    uint16_t* aln_lead_key;  /* [cap_alns] */
+    uint16_t* aln_trail_key; /* [cap_alns] */
+} sx_enum_out;
+
+#define SX_ERR_CAPACITY (-8) /* an sx_enum_out capacity is too small: totals[] says what the batch needs */
+
+void sx_default_enum_opts(sx_enum_opts* o);
+int sx_enumerate_alignments(sx_ctx* ctx, const sx_enum_batch* batch_host, sx_enum_out* out_host);
+int sx_enumerate_alignments_dev(sx_ctx* ctx, const sx_enum_batch* batch_dev, sx_enum_out* out_dev /* device pointers; totals too */);
+
+/* ==========================================================================================
  * Multi-GPU: regions shard across ranks with no data-path collective; one gather of fixed-size
  * call records at the end (the in-memory analogue of concatIndexVcf,
  * src/python/lib/strelkaSharedWorkflow.py:126-136).  The NCCL communicator is created from an

@@ -346,3 +346,5 @@ extern "C" int ref_score_indels_ex(const sx_score_indels_batch* b, const double*
         return 2;
     }
 }
+
+#include "ref_harness_enumerate.inc" // K7: the reference getCandidateAlignments (same translation unit: the function is file-static)

@@ -217,6 +217,41 @@ def default_score_indels_opts() -> SxScoreIndelsOpts:
     return SxScoreIndelsOpts(49, 0, 5, 1, math.log(10.0))
 
 
+# K7 enumerate_alignments
+SX_AP_MATCH, SX_AP_INSERT, SX_AP_DELETE, SX_AP_SKIP, SX_AP_SOFT_CLIP, SX_AP_HARD_CLIP, SX_AP_PAD, SX_AP_SEQ_MATCH, SX_AP_SEQ_MISMATCH = 1, 2, 3, 4, 5, 6, 7, 8, 9
+SX_IKF_NOT_DISCOVERED, SX_IKF_FORCED_OUTPUT = 2, 4
+SX_ENUM_MAX_SAMPLES = 4
+SX_NO_KEY = 0xFFFF
+SX_ENUM_ST_ORIGIN_SKIP, SX_ENUM_ST_MAX_TOGGLE, SX_ENUM_ST_EXCEPTION, SX_ENUM_ST_LIMIT = 1, 2, 4, 8
+SX_ERR_CAPACITY = -8
+KEY_HAP_DT = np.dtype([("active_region_id", "<i4"), ("haplotype_id", "i1", (4,)), ("bypass_mask", "u1"), ("pad", "u1", (3,))])
+assert KEY_HAP_DT.itemsize == 12
+
+
+class SxEnumOpts(C.Structure):
+    _fields_ = [("max_indel_size", C.c_uint32), ("max_read_indel_toggle", C.c_int32), ("max_candidate_indel_density", C.c_double), ("n_max_toggle", C.c_uint32),
+                ("max_toggle", C.c_uint8 * 100), ("is_haplotyping_enabled", C.c_int32), ("n_samples", C.c_uint32), ("sample_id", C.c_uint32),
+                ("max_alns_per_read", C.c_uint32)]
+
+
+class SxEnumBatch(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("n_regions", "n_reads", "n_keys")] + [(n, C.c_void_p) for n in (
+        "region_read_off", "region_key_off", "keys", "key_hap", "realign_begin", "realign_end", "in_pos", "in_seg_off", "in_segs", "in_key_off", "in_keys",
+        "use_key_off", "use_keys", "in_lead_key", "in_trail_key", "read_len")] + [("opts", SxEnumOpts)]
+
+
+class SxEnumOut(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("cap_alns", "cap_segs", "cap_keys")] + [(n, C.c_void_p) for n in (
+        "totals", "aln_off", "status", "aln_pos", "aln_seg_off", "segs", "aln_key_off", "aln_keys", "aln_lead_key", "aln_trail_key")]
+
+
+def default_enum_opts() -> SxEnumOpts:
+    """starling_base_options defaults (starling_base_shared.hh:124,139,145,160) through the library's own sx_default_enum_opts."""
+    o = SxEnumOpts()
+    load().sx_default_enum_opts(C.byref(o))
+    return o
+
+
 class SxGaScores(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("match", "mismatch", "open", "extend", "offEdge", "insertDelete", "isAllowEdgeInsertion", "isRequireEdgeDeletion")]
 
@@ -278,6 +313,9 @@ SYMBOLS = [
     ("sx_default_score_indels_opts", None, [C.POINTER(SxScoreIndelsOpts)]),
     ("sx_score_indels", C.c_int, [_P, C.POINTER(SxScoreIndelsBatch), _P, C.POINTER(SxScoreIndelsOut)]),
     ("sx_score_indels_dev", C.c_int, [_P, C.POINTER(SxScoreIndelsBatch), _P, C.POINTER(SxScoreIndelsOut)]),
+    ("sx_default_enum_opts", None, [C.POINTER(SxEnumOpts)]),
+    ("sx_enumerate_alignments", C.c_int, [_P, C.POINTER(SxEnumBatch), C.POINTER(SxEnumOut)]),
+    ("sx_enumerate_alignments_dev", C.c_int, [_P, C.POINTER(SxEnumBatch), C.POINTER(SxEnumOut)]),
     ("sx_indel_gl", C.c_int, [_P, C.POINTER(SxIndelBatch), _P]),
     ("sx_indel_gl_dev", C.c_int, [_P, C.POINTER(SxIndelBatch), _P]),
     ("sx_default_pileup_opts", None, [C.POINTER(SxPileupOpts)]),

@@ -258,3 +258,47 @@ def _score_indels_dev(self, db: DevScoreIndelsBatch, lnp_dev: DeviceArray) -> No
 
 Context.score_indels = _score_indels  # K6
 Context.score_indels_dev = _score_indels_dev
+
+
+class DevEnumBatch:
+    """An sx_enum_batch and its sx_enum_out resident in device memory (for sx_enumerate_alignments_dev)."""
+
+    _ARRAYS = ("region_read_off", "region_key_off", "keys", "key_hap", "realign_begin", "realign_end", "in_pos", "in_seg_off", "in_segs", "in_key_off", "in_keys",
+               "use_key_off", "use_keys", "in_lead_key", "in_trail_key", "read_len")
+
+    def __init__(self, ctx: "Context", hb: B.EnumBatch, cap_alns=None, cap_segs=None, cap_keys=None):
+        self.host = hb
+        self.bufs = {n: DeviceArray(ctx, getattr(hb, n).nbytes + 64).upload(getattr(hb, n)) for n in self._ARRAYS}
+        p = {n: self.bufs[n].ptr for n in self._ARRAYS}
+        self.c = A.SxEnumBatch(hb.n_regions, hb.n_reads, hb.n_keys, p["region_read_off"], p["region_key_off"], p["keys"], p["key_hap"] if hb.has_hap else None,
+                               p["realign_begin"], p["realign_end"], p["in_pos"], p["in_seg_off"], p["in_segs"], p["in_key_off"], p["in_keys"], p["use_key_off"],
+                               p["use_keys"], p["in_lead_key"], p["in_trail_key"], p["read_len"], hb.opts)
+        self.shape = B.EnumOut(hb, cap_alns, cap_segs, cap_keys)  # host twin: sizes and the download target
+        s = self.shape
+        self.obufs = {n: DeviceArray(ctx, getattr(s, n).nbytes + 64) for n in ("totals", "aln_off", "status", "aln_pos", "aln_seg_off", "segs", "aln_key_off",
+                                                                               "aln_keys", "aln_lead_key", "aln_trail_key")}
+        o = {n: b.ptr for n, b in self.obufs.items()}
+        self.out = A.SxEnumOut(s.cap_alns, s.cap_segs, s.cap_keys, o["totals"], o["aln_off"], o["status"], o["aln_pos"], o["aln_seg_off"], o["segs"], o["aln_key_off"],
+                               o["aln_keys"], o["aln_lead_key"], o["aln_trail_key"])
+
+    def download(self) -> B.EnumOut:
+        s = self.shape
+        for n, buf in self.obufs.items():
+            a = getattr(s, n)
+            a[...] = buf.download(a.dtype, a.size)
+        return s
+
+
+def _enumerate_alignments(self, eb: B.EnumBatch, cap_alns=None, cap_segs=None, cap_keys=None) -> B.EnumOut:
+    """K7: the candidate alignments of every read (getCandidateAlignments), host buffers in, host CSR out."""
+    out = B.EnumOut(eb, cap_alns, cap_segs, cap_keys)
+    self._chk(self.lib.sx_enumerate_alignments(self.h, C.byref(eb.c), C.byref(out.c)))
+    return out
+
+
+def _enumerate_alignments_dev(self, db: DevEnumBatch) -> None:
+    self._chk(self.lib.sx_enumerate_alignments_dev(self.h, C.byref(db.c), C.byref(db.out)))
+
+
+Context.enumerate_alignments = _enumerate_alignments  # K7
+Context.enumerate_alignments_dev = _enumerate_alignments_dev

@@ -692,3 +692,216 @@ def score_indels_batch_from_regions(regions: Sequence[RegionSpec], fwd=True, ref
             reads[cal.read].alns.append((cal.pos, path, kidx))
         out.append(([keyspecs[o] for o in order], reads))
     return ScoreIndelsBatch(out, opts)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# K7 enumerate_alignments
+# ------------------------------------------------------------------------------------------------------------------------------
+_AP_OF = {"M": A.SX_AP_MATCH, "I": A.SX_AP_INSERT, "D": A.SX_AP_DELETE, "N": A.SX_AP_SKIP, "S": A.SX_AP_SOFT_CLIP, "H": A.SX_AP_HARD_CLIP, "=": A.SX_AP_SEQ_MATCH,
+          "X": A.SX_AP_SEQ_MISMATCH}
+AP_CHAR = {v: k for k, v in _AP_OF.items()}
+
+
+class EnumKeySpec(WindowKeySpec):
+    """A window entry with what the alignment search reads of its IndelData (IndelData.hh:270-273,374,382,387)."""
+
+    def __init__(self, pos, del_len=0, ins="", mismatch=False, candidate=True, not_discovered=False, forced=False, active_region=-1, hap_ids=(0, 0, 0, 0), bypass=0):
+        super().__init__(pos, del_len, ins, mismatch, candidate)
+        self.not_discovered, self.forced, self.active_region, self.hap_ids, self.bypass = not_discovered, forced, active_region, tuple(hap_ids), bypass
+
+
+class EnumReadSpec:
+    """One read of a K7 batch: bases (ASCII), the normalized input alignment (pos, [(cigar char, len)...]) and the window indices of
+    the non-candidate entries the read is an observation of."""
+
+    def __init__(self, seq, pos, path, use_keys=()):
+        self.seq, self.pos, self.path, self.use_keys = seq, pos, list(path), sorted(set(use_keys))
+
+
+_COMPLEMENT_FREE_CODES = {"A": 1, "C": 2, "G": 4, "T": 8}
+
+
+def alignment_indels(read: EnumReadSpec, ref: str, ref_begin: int, win: Sequence[WindowKeySpec], max_indel_size: int = 49):
+    """Host side of K7's input: getAlignmentIndels(cal, ref, rseg, maxIndelSize, includeMismatches=true) (CandidateAlignment.cpp:58-173)
+    and the edge keys of getCandidateAlignment (starling_read_align.cpp:1481-1522), as window indices.  Returns (in_keys, lead, trail).
+    Raises KeyError for an indel of the alignment that is not a window entry (the reference throws, starling_read_align.cpp:1875)."""
+    index_of = {k.order(): i for i, k in enumerate(win)}
+    path = read.path
+    match_idx = [i for i, (t, _l) in enumerate(path) if t in "M=X"]
+    first, last = (match_idx[0], match_idx[-1]) if match_idx else (len(path), len(path))
+    keys, lead, trail = set(), A.SX_NO_KEY, A.SX_NO_KEY
+    read_off, ref_pos = 0, read.pos
+    i = 0
+    while i < len(path):
+        t, ln = path[i]
+        edge = i < first or i > last
+        # a swap = a run of adjacent insert / delete segments (align_path.hh swap_info)
+        j = i
+        ins_len = del_len = 0
+        if t in "ID" and not edge:
+            while j < len(path) and path[j][0] in "ID" and not (j > last):
+                if path[j][0] == "I":
+                    ins_len += path[j][1]
+                else:
+                    del_len += path[j][1]
+                j += 1
+        if edge:
+            if t in "ID":
+                k = WindowKeySpec(ref_pos, ln if t == "D" else 0, read.seq[read_off : read_off + ln] if t == "I" else "")
+                w = index_of[k.order()]
+                keys.add(w)
+                if i < first:
+                    lead = w
+                else:
+                    trail = w
+            j = i + 1
+        elif t in "ID":
+            if max(ins_len, del_len) > max_indel_size:
+                raise NotImplementedError("breakend keys are not part of this build")
+            k = WindowKeySpec(ref_pos, del_len, read.seq[read_off : read_off + ins_len])
+            keys.add(index_of[k.order()])
+        else:
+            j = i + 1
+            if t in "M=X":
+                for b in range(ln):
+                    base = read.seq[read_off + b]
+                    if base not in "ACGT":  # BAM_BASE::REF ('=') and ANY ('N') are skipped; other IUPAC codes never equal the reference
+                        if base in "=N":
+                            continue
+                    rp = ref_pos + b
+                    rb = ref[rp - ref_begin] if 0 <= rp - ref_begin < len(ref) else "N"
+                    if base == rb:
+                        continue
+                    w = index_of.get(WindowKeySpec(rp, 1, base, mismatch=True).order())
+                    if w is not None:  # a mismatch that is no window entry is dropped (starling_read_align.cpp:1869)
+                        keys.add(w)
+        for s in range(i, j):
+            st, sl = path[s]
+            if st in "MIS=X":
+                read_off += sl
+            if st in "MDN=X":
+                ref_pos += sl
+        i = j
+    return sorted(keys), lead, trail
+
+
+class EnumBatch:
+    """Owns the arrays of one sx_enum_batch.  regions = [(ref, ref_begin, (realign_begin, realign_end), window keys in IndelKey order, reads)]."""
+
+    def __init__(self, regions, opts=None):
+        self.opts = opts or A.default_enum_opts()
+        keys, hap, ins_pool, ins_off = [], [], bytearray(), [0]
+        region_read_off, region_key_off, rb, re_ = [0], [0], [], []
+        in_pos, in_seg_off, in_segs, in_key_off, in_keys, use_key_off, use_keys, lead, trail, read_len = [], [0], [], [0], [], [0], [], [], [], []
+        ref_pool, ref_off, ref_begin, read_pool, read_off = bytearray(), [0], [], bytearray(), [0]
+        any_hap = False
+        for ref, rbeg, (ra, rz), win, reads in regions:
+            assert all(win[i].order() < win[i + 1].order() for i in range(len(win) - 1)), "window must be in IndelKey order"
+            intern = {"": 0}
+            for k in win:
+                iid = intern.setdefault(k.ins, len(intern))
+                flags = (A.SX_IKF_CANDIDATE if k.candidate else 0) | (A.SX_IKF_NOT_DISCOVERED if getattr(k, "not_discovered", False) else 0) | (
+                    A.SX_IKF_FORCED_OUTPUT if getattr(k, "forced", False) else 0)
+                keys.append((k.pos, k.del_len, len(k.ins), iid, A.SX_INDEL_TYPE_MISMATCH if k.mismatch else A.SX_INDEL_TYPE_INDEL, flags, 0, 0.0, 0.0))
+                ar = getattr(k, "active_region", -1)
+                any_hap = any_hap or ar >= 0
+                hap.append((ar, tuple(getattr(k, "hap_ids", (0, 0, 0, 0))), getattr(k, "bypass", 0), (0, 0, 0)))
+                ins_pool.extend(k.ins.encode())
+                ins_off.append(len(ins_pool))
+            for r in reads:
+                ik, ld, tr = alignment_indels(r, ref, rbeg, win, self.opts.max_indel_size)
+                in_pos.append(r.pos)
+                in_segs.extend((ln, _AP_OF[t], 0) for t, ln in r.path)
+                in_seg_off.append(len(in_segs))
+                in_keys.extend(ik)
+                in_key_off.append(len(in_keys))
+                use_keys.extend(r.use_keys)
+                use_key_off.append(len(use_keys))
+                lead.append(ld)
+                trail.append(tr)
+                read_len.append(len(r.seq))
+                read_pool.extend(r.seq.encode())
+                read_off.append(len(read_pool))
+            region_read_off.append(len(read_len))
+            region_key_off.append(len(keys))
+            rb.append(ra)
+            re_.append(rz)
+            ref_pool.extend(ref.encode())
+            ref_off.append(len(ref_pool))
+            ref_begin.append(rbeg)
+        u32 = lambda x: np.array(x, dtype=np.uint32)  # noqa: E731
+        u16 = lambda x: np.array(list(x) + [0], dtype=np.uint16)  # noqa: E731
+        self.n_regions, self.n_reads, self.n_keys = len(regions), len(read_len), len(keys)
+        self.region_read_off, self.region_key_off = u32(region_read_off), u32(region_key_off)
+        self.keys = np.zeros(len(keys) + 1, dtype=A.INDEL_KEY_DT)
+        if keys:
+            self.keys[: len(keys)] = np.array(keys, dtype=A.INDEL_KEY_DT)
+        self.key_hap = np.zeros(len(keys) + 1, dtype=A.KEY_HAP_DT)
+        if hap:
+            self.key_hap[: len(hap)] = np.array(hap, dtype=A.KEY_HAP_DT)
+        self.has_hap = any_hap
+        self.realign_begin, self.realign_end = np.array(rb + [0], np.int32), np.array(re_ + [0], np.int32)
+        self.in_pos = np.array(in_pos + [0], np.int32)
+        self.in_seg_off, self.in_key_off, self.use_key_off = u32(in_seg_off), u32(in_key_off), u32(use_key_off)
+        self.in_segs = np.zeros(len(in_segs) + 4, dtype=A.ALN_SEG_DT)
+        if in_segs:
+            self.in_segs[: len(in_segs)] = np.array(in_segs, dtype=A.ALN_SEG_DT)
+        self.in_keys, self.use_keys, self.in_lead_key, self.in_trail_key, self.read_len = u16(in_keys), u16(use_keys), u16(lead), u16(trail), u16(read_len)
+        # test-only: what the reference harness needs to rebuild the reference's objects
+        self.ins_pool = np.frombuffer(bytes(ins_pool) + b"\0", dtype=np.uint8).copy()
+        self.ins_off = u32(ins_off)
+        self.ref_pool = np.frombuffer(bytes(ref_pool) + b"\0", dtype=np.uint8).copy()
+        self.ref_off, self.ref_begin = u32(ref_off), np.array(ref_begin + [0], np.int32)
+        self.read_pool = np.frombuffer(bytes(read_pool) + b"\0", dtype=np.uint8).copy()
+        self.read_off = u32(read_off)
+        self.c = A.SxEnumBatch(
+            self.n_regions, self.n_reads, self.n_keys, A.ptr(self.region_read_off), A.ptr(self.region_key_off), A.ptr(self.keys),
+            A.ptr(self.key_hap) if any_hap else None, A.ptr(self.realign_begin), A.ptr(self.realign_end), A.ptr(self.in_pos), A.ptr(self.in_seg_off),
+            A.ptr(self.in_segs), A.ptr(self.in_key_off), A.ptr(self.in_keys), A.ptr(self.use_key_off), A.ptr(self.use_keys), A.ptr(self.in_lead_key),
+            A.ptr(self.in_trail_key), A.ptr(self.read_len), self.opts,
+        )
+
+    def algorithmic_bytes(self, n_alns: int, n_segs: int, n_keys: int) -> int:
+        """bytes one enumeration must move: every input array once + the CSR it writes."""
+        n_in_segs, n_in_keys, n_use = int(self.in_seg_off[-1]), int(self.in_key_off[-1]), int(self.use_key_off[-1])
+        inp = self.n_keys * (32 + (12 if self.has_hap else 0)) + self.n_regions * 16 + self.n_reads * (4 + 4 + 4 + 4 + 2 + 2 + 2) + n_in_segs * 4 + (n_in_keys + n_use) * 2
+        out = self.n_reads * (4 + 1) + n_alns * (4 + 4 + 4 + 2 + 2) + n_segs * 4 + n_keys * 2
+        return inp + out
+
+
+class EnumOut:
+    """Host buffers for sx_enum_out."""
+
+    def __init__(self, eb: EnumBatch, cap_alns=None, cap_segs=None, cap_keys=None):
+        self.cap_alns = cap_alns if cap_alns is not None else max(64, eb.n_reads * 64)
+        self.cap_segs = cap_segs if cap_segs is not None else self.cap_alns * 8
+        self.cap_keys = cap_keys if cap_keys is not None else self.cap_alns * 6
+        self.totals = np.zeros(4, np.uint32)
+        self.aln_off = np.zeros(eb.n_reads + 1, np.uint32)
+        self.status = np.zeros(eb.n_reads + 1, np.uint8)
+        self.aln_pos = np.zeros(self.cap_alns + 1, np.int32)
+        self.aln_seg_off = np.zeros(self.cap_alns + 2, np.uint32)
+        self.segs = np.zeros(self.cap_segs + 1, dtype=A.ALN_SEG_DT)
+        self.aln_key_off = np.zeros(self.cap_alns + 2, np.uint32)
+        self.aln_keys = np.zeros(self.cap_keys + 1, np.uint16)
+        self.aln_lead_key = np.zeros(self.cap_alns + 1, np.uint16)
+        self.aln_trail_key = np.zeros(self.cap_alns + 1, np.uint16)
+        self.c = A.SxEnumOut(self.cap_alns, self.cap_segs, self.cap_keys, A.ptr(self.totals), A.ptr(self.aln_off), A.ptr(self.status), A.ptr(self.aln_pos),
+                             A.ptr(self.aln_seg_off), A.ptr(self.segs), A.ptr(self.aln_key_off), A.ptr(self.aln_keys), A.ptr(self.aln_lead_key),
+                             A.ptr(self.aln_trail_key))
+        self._n_reads = eb.n_reads
+
+    def trimmed(self):
+        """(aln_off, status, aln_pos, aln_seg_off, segs, aln_key_off, aln_keys, lead, trail) cut to the produced sizes."""
+        nA, nS, nK = (int(x) for x in self.totals[:3])
+        return (self.aln_off[: self._n_reads + 1].copy(), self.status[: self._n_reads].copy(), self.aln_pos[:nA].copy(), self.aln_seg_off[: nA + 1].copy(),
+                self.segs[:nS].copy(), self.aln_key_off[: nA + 1].copy(), self.aln_keys[:nK].copy(), self.aln_lead_key[:nA].copy(), self.aln_trail_key[:nA].copy())
+
+    def alignments_of(self, r: int):
+        """read r's candidate alignments as [(pos, cigar string, [keys], lead, trail)] (debugging aid)."""
+        out = []
+        for a in range(int(self.aln_off[r]), int(self.aln_off[r + 1])):
+            cig = "".join(f"{int(s['len'])}{AP_CHAR[int(s['kind'])]}" for s in self.segs[int(self.aln_seg_off[a]) : int(self.aln_seg_off[a + 1])])
+            out.append((int(self.aln_pos[a]), cig, [int(k) for k in self.aln_keys[int(self.aln_key_off[a]) : int(self.aln_key_off[a + 1])]],
+                        int(self.aln_lead_key[a]), int(self.aln_trail_key[a])))
+        return out

@@ -1,0 +1,409 @@
+// k7_enumerate.cu -- K7: candidate-alignment enumeration, one read per thread.
+//
+// Replaces (include/strelka_b200.h, "K7 enumerate_alignments")
+//   starling_common/starling_read_align.cpp:1816-1994  getCandidateAlignments
+//   starling_common/starling_read_align.cpp:857-1277   candidate_alignment_search (+ the helpers listed in the header)
+// and produces the alignment lists K1 scores and K6 evaluates, in the order both expect (std::set<CandidateAlignment>).
+//
+// Shape of the work: per read an irregular depth-first search over a handful of indels (typically 2-6, capped at 64), integer
+// only, with a variable-size result.  There is no reuse between reads and nothing GEMM-like; the algorithmic floor is reading the
+// window and the input alignment once and writing the alignments once.  The reference's by-value containers become an explicit
+// frame stack with position-indexed bit masks (k7_core.cuh), so a read's whole working set is a fixed-size block of a per-thread
+// arena.  The result size is unknown until the search has run, and the output must be a dense CSR in read order (it IS the next
+// kernels' input), so the search runs twice with a scan in between:
+//   k7_count_kernel : search -> per read (alignments, segments, keys) + status
+//   scan            : three exclusive prefix sums over reads (one block per 2048 reads + a single-block pass over the block sums)
+//   k7_write_kernel : search again (deterministic) -> the set, in its order, at the read's offsets
+// Searching twice costs less than a second arena large enough to keep every read's set between the passes, and keeps the output
+// independent of scheduling.  Persistent grid: resident blocks x SM count, a thread strides over reads.
+
+#include "k7_core.cuh"
+#include "sx_internal.h"
+
+#include <algorithm>
+
+namespace
+{
+constexpr int K7_THREADS = 64;
+constexpr int K7_ST_SHIFT = 14; // device status bit 16384: an output capacity is too small (reported as SX_ERR_CAPACITY by the host)
+constexpr int K7_SCAN_THREADS = 256;
+constexpr int K7_SCAN_ITEMS = 8; // reads per thread of the scan kernels
+
+struct k7_counts // per read, then (after the scan) its exclusive offsets
+{
+    uint32_t* aln;
+    uint32_t* seg;
+    uint32_t* key;
+};
+
+__global__ void __launch_bounds__(K7_THREADS) k7_count_kernel(const k7_view v, unsigned char* __restrict__ arena, const size_t per_thread, const uint32_t maxA,
+                                                              const uint32_t* __restrict__ read_region, uint8_t* __restrict__ status, const k7_counts c)
+{
+    const uint32_t t(blockIdx.x * blockDim.x + threadIdx.x), nthr(gridDim.x * blockDim.x);
+    k7_scratch S(k7_scratch_at(arena + (size_t)t * per_thread, maxA));
+    for (uint32_t r = t; r < v.b.n_reads; r += nthr)
+    {
+        const uint32_t st(k7_enumerate_read(v, read_region[r], r, S));
+        uint32_t na, ns, nk;
+        k7_count(S, st, na, ns, nk);
+        status[r] = (uint8_t)st;
+        c.aln[r] = na;
+        c.seg[r] = ns;
+        c.key[r] = nk;
+    }
+}
+
+// region of every read (reads of a region are consecutive): one thread per region fills its reads' entries
+__global__ void k7_read_region_kernel(const uint32_t n_regions, const uint32_t* __restrict__ region_read_off, uint32_t* __restrict__ read_region)
+{
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_regions; g += gridDim.x * blockDim.x)
+        for (uint32_t r = region_read_off[g]; r < region_read_off[g + 1]; ++r) read_region[r] = g;
+}
+
+// exclusive scan of three arrays at once, tile = K7_SCAN_THREADS * K7_SCAN_ITEMS reads per block.
+// phase 0: in-tile exclusive scan in place, tile totals to sums[3][n_tiles]; phase 1 (one block): exclusive scan of the tile totals in
+// place, grand totals to totals[3]; phase 2: add the tile offset.
+__global__ void __launch_bounds__(K7_SCAN_THREADS) k7_scan_tiles(const uint32_t n, uint32_t* a0, uint32_t* a1, uint32_t* a2, uint32_t* sums, const uint32_t n_tiles)
+{
+    __shared__ uint32_t warp_sum[3][K7_SCAN_THREADS / 32];
+    uint32_t* arr[3] = {a0, a1, a2};
+    const uint32_t base(blockIdx.x * K7_SCAN_THREADS * K7_SCAN_ITEMS + threadIdx.x * K7_SCAN_ITEMS);
+    const uint32_t lane(threadIdx.x & 31), warp(threadIdx.x >> 5);
+    for (int q = 0; q < 3; ++q)
+    {
+        uint32_t vals[K7_SCAN_ITEMS];
+        uint32_t sum(0);
+        for (int i = 0; i < K7_SCAN_ITEMS; ++i)
+        {
+            vals[i] = (base + i < n) ? arr[q][base + i] : 0u;
+            sum += vals[i];
+        }
+        uint32_t incl(sum);
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t y(__shfl_up_sync(0xffffffffu, incl, d));
+            if ((int)lane >= d) incl += y;
+        }
+        if (lane == 31) warp_sum[q][warp] = incl;
+        __syncthreads();
+        uint32_t warp_off(0);
+        for (uint32_t w = 0; w < warp; ++w) warp_off += warp_sum[q][w];
+        uint32_t run(warp_off + incl - sum);
+        for (int i = 0; i < K7_SCAN_ITEMS; ++i)
+        {
+            if (base + i < n) arr[q][base + i] = run;
+            run += vals[i];
+        }
+        if (threadIdx.x == K7_SCAN_THREADS - 1) sums[(size_t)q * n_tiles + blockIdx.x] = run;
+    }
+}
+
+__global__ void __launch_bounds__(K7_SCAN_THREADS) k7_scan_sums(uint32_t* sums, const uint32_t n_tiles, uint32_t* __restrict__ totals)
+{
+    // a single block walks the tile totals in chunks of blockDim.x, carrying the running sum
+    __shared__ uint32_t warp_sum[K7_SCAN_THREADS / 32];
+    __shared__ uint32_t carry;
+    const uint32_t lane(threadIdx.x & 31), warp(threadIdx.x >> 5);
+    for (int q = 0; q < 3; ++q)
+    {
+        uint32_t* s(sums + (size_t)q * n_tiles);
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        for (uint32_t b0 = 0; b0 < n_tiles; b0 += K7_SCAN_THREADS)
+        {
+            const uint32_t i(b0 + threadIdx.x);
+            const uint32_t x(i < n_tiles ? s[i] : 0u);
+            uint32_t incl(x);
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const uint32_t y(__shfl_up_sync(0xffffffffu, incl, d));
+                if ((int)lane >= d) incl += y;
+            }
+            if (lane == 31) warp_sum[warp] = incl;
+            __syncthreads();
+            uint32_t warp_off(0);
+            for (uint32_t w = 0; w < warp; ++w) warp_off += warp_sum[w];
+            const uint32_t c(carry);
+            if (i < n_tiles) s[i] = c + warp_off + incl - x;
+            __syncthreads();
+            if (threadIdx.x == K7_SCAN_THREADS - 1) carry = c + warp_off + incl;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) totals[q] = carry;
+        __syncthreads();
+    }
+}
+
+// phase 2 of the scan + the batch-wide closing entries; flags the capacity overflow
+__global__ void __launch_bounds__(K7_SCAN_THREADS) k7_scan_finish(const uint32_t n, const k7_counts c, const uint32_t* __restrict__ sums, const uint32_t n_tiles,
+                                                                  const uint32_t* __restrict__ totals, const sx_enum_out o, int* __restrict__ status)
+{
+    const uint32_t tile(blockIdx.x);
+    const uint32_t base(tile * K7_SCAN_THREADS * K7_SCAN_ITEMS + threadIdx.x * K7_SCAN_ITEMS);
+    const uint32_t oa(sums[tile]), os(sums[(size_t)n_tiles + tile]), ok(sums[(size_t)2 * n_tiles + tile]);
+    for (int i = 0; i < K7_SCAN_ITEMS; ++i)
+        if (base + i < n)
+        {
+            const uint32_t a(c.aln[base + i] + oa);
+            c.aln[base + i] = a;
+            c.seg[base + i] += os;
+            c.key[base + i] += ok;
+            o.aln_off[base + i] = a;
+        }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        o.aln_off[n] = totals[0];
+        o.totals[0] = totals[0];
+        o.totals[1] = totals[1];
+        o.totals[2] = totals[2];
+        if (totals[0] > o.cap_alns || totals[1] > o.cap_segs || totals[2] > o.cap_keys) atomicOr(status, 1 << K7_ST_SHIFT);
+        else
+        {
+            o.aln_seg_off[totals[0]] = totals[1];
+            o.aln_key_off[totals[0]] = totals[2];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(K7_THREADS) k7_write_kernel(const k7_view v, unsigned char* __restrict__ arena, const size_t per_thread, const uint32_t maxA,
+                                                              const uint32_t* __restrict__ read_region, const uint8_t* __restrict__ status, const k7_counts c,
+                                                              const sx_enum_out o, const uint32_t* __restrict__ totals)
+{
+    if (totals[0] > o.cap_alns || totals[1] > o.cap_segs || totals[2] > o.cap_keys) return; // reported by k7_scan_finish
+    const uint32_t t(blockIdx.x * blockDim.x + threadIdx.x), nthr(gridDim.x * blockDim.x);
+    k7_scratch S(k7_scratch_at(arena + (size_t)t * per_thread, maxA));
+    for (uint32_t r = t; r < v.b.n_reads; r += nthr)
+    {
+        if (status[r] & (SX_ENUM_ST_EXCEPTION | SX_ENUM_ST_LIMIT)) continue;
+        const uint32_t na((r + 1 < v.b.n_reads ? c.aln[r + 1] : totals[0]) - c.aln[r]);
+        if (na == 0) continue;
+        k7_enumerate_read(v, read_region[r], r, S);
+        k7_write(S, o, c.aln[r], c.seg[r], c.key[r]);
+    }
+}
+
+// the reference's table: starling_align_limit (starling_align_limit.cpp:53-88).  Every quantity is an integer far below 2^24 until
+// the running sum passes max_alignments, so the float arithmetic of the reference is exact there and doubles reproduce it.
+unsigned k7_max_candidate_alignment_toggle(const unsigned n_indel, const unsigned max_alignments)
+{
+    const double max(max_alignments);
+    double sum(1.);
+    for (unsigned i = 0; i < n_indel; ++i)
+    {
+        const unsigned k(i + 1);
+        double binom(1.);
+        for (unsigned j = 1; j <= k; ++j) binom = binom * (double)(n_indel - k + j) / (double)j; // exact: each partial product is an integer
+        sum += std::ldexp(1., (int)k) * std::floor(binom + 0.5);
+        if (sum > max) return i;
+    }
+    return n_indel;
+}
+
+int k7_run(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsigned* launches)
+{
+    cudaStream_t st(ctx->s_compute);
+    const uint32_t n(d->n_reads);
+    const uint32_t maxA(d->opts.max_alns_per_read ? std::min<uint32_t>(d->opts.max_alns_per_read, 65535u) : 64u);
+    const size_t per_thread((k7_scratch_bytes(maxA) + 255) & ~(size_t)255);
+    int per_sm(1);
+    SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k7_count_kernel, K7_THREADS, 0));
+    per_sm = std::max(1, per_sm);
+    size_t blocks(std::min<size_t>(((size_t)n + K7_THREADS - 1) / K7_THREADS, (size_t)ctx->sm_count * per_sm));
+    const size_t arena_cap((size_t)4 << 30);
+    while (blocks > 1 && blocks * K7_THREADS * per_thread > arena_cap) blocks = (blocks + 1) / 2;
+    int rc;
+    unsigned char* arena(nullptr);
+    if ((rc = sx_ensure(ctx, 40, blocks * K7_THREADS * per_thread, reinterpret_cast<void**>(&arena)))) return rc;
+    uint32_t* read_region(nullptr);
+    if ((rc = sx_ensure(ctx, 41, (size_t)n * 4 + 16, reinterpret_cast<void**>(&read_region)))) return rc;
+    k7_counts c;
+    if ((rc = sx_ensure(ctx, 42, (size_t)n * 4 + 16, reinterpret_cast<void**>(&c.aln)))) return rc;
+    if ((rc = sx_ensure(ctx, 43, (size_t)n * 4 + 16, reinterpret_cast<void**>(&c.seg)))) return rc;
+    if ((rc = sx_ensure(ctx, 44, (size_t)n * 4 + 16, reinterpret_cast<void**>(&c.key)))) return rc;
+    const uint32_t tile(K7_SCAN_THREADS * K7_SCAN_ITEMS), n_tiles((n + tile - 1) / tile);
+    uint32_t* sums(nullptr);
+    if ((rc = sx_ensure(ctx, 45, ((size_t)3 * n_tiles + 4) * 4, reinterpret_cast<void**>(&sums)))) return rc;
+    uint32_t* totals(sums + (size_t)3 * n_tiles);
+
+    k7_view v;
+    v.b = *d;
+    const int g0(std::max(1, std::min<int>((int)((d->n_regions + 127) / 128), ctx->sm_count * 8)));
+    k7_read_region_kernel<<<g0, 128, 0, st>>>(d->n_regions, d->region_read_off, read_region);
+    SX_CUDA(ctx, cudaGetLastError());
+    k7_count_kernel<<<(unsigned)blocks, K7_THREADS, 0, st>>>(v, arena, per_thread, maxA, read_region, o->status, c);
+    SX_CUDA(ctx, cudaGetLastError());
+    k7_scan_tiles<<<n_tiles, K7_SCAN_THREADS, 0, st>>>(n, c.aln, c.seg, c.key, sums, n_tiles);
+    SX_CUDA(ctx, cudaGetLastError());
+    k7_scan_sums<<<1, K7_SCAN_THREADS, 0, st>>>(sums, n_tiles, totals);
+    SX_CUDA(ctx, cudaGetLastError());
+    k7_scan_finish<<<n_tiles, K7_SCAN_THREADS, 0, st>>>(n, c, sums, n_tiles, totals, *o, ctx->d_status);
+    SX_CUDA(ctx, cudaGetLastError());
+    k7_write_kernel<<<(unsigned)blocks, K7_THREADS, 0, st>>>(v, arena, per_thread, maxA, read_region, o->status, c, *o, totals);
+    SX_CUDA(ctx, cudaGetLastError());
+    *launches = 6;
+    return SX_OK;
+}
+
+int k7_check_args(sx_ctx* ctx, const sx_enum_batch* b, const sx_enum_out* o, const char* what)
+{
+    if (!b || !o) return sx_fail(ctx, SX_ERR_ARG, "%s: NULL argument", what);
+    if (!o->totals || !o->aln_off) return sx_fail(ctx, SX_ERR_ARG, "%s: NULL output array", what);
+    if (b->n_reads == 0) return SX_OK;
+    if (!b->region_read_off || !b->region_key_off || !b->realign_begin || !b->realign_end || !b->in_pos || !b->in_seg_off || !b->in_segs || !b->in_key_off ||
+        !b->use_key_off || !b->in_lead_key || !b->in_trail_key || !b->read_len || !o->status || !o->aln_pos || !o->aln_seg_off || !o->segs || !o->aln_key_off ||
+        !o->aln_keys || !o->aln_lead_key || !o->aln_trail_key)
+        return sx_fail(ctx, SX_ERR_ARG, "%s: NULL array", what);
+    if ((b->n_keys && !b->keys) || b->n_regions == 0) return sx_fail(ctx, SX_ERR_ARG, "%s: reads without a region / keys without a table", what);
+    if (b->opts.n_samples == 0 || b->opts.n_samples > SX_ENUM_MAX_SAMPLES || b->opts.sample_id >= b->opts.n_samples)
+        return sx_fail(ctx, SX_ERR_ARG, "%s: n_samples outside 1..%d or sample_id outside the samples", what, SX_ENUM_MAX_SAMPLES);
+    if (b->opts.n_max_toggle > 100) return sx_fail(ctx, SX_ERR_ARG, "%s: n_max_toggle above 100", what);
+    if (b->opts.max_read_indel_toggle < 0 || b->opts.max_read_indel_toggle > 127) return sx_fail(ctx, SX_ERR_RANGE, "%s: max_read_indel_toggle outside 0..127", what);
+    return SX_OK;
+}
+
+int k7_finish(sx_ctx* ctx, const char* what, const uint32_t* totals_host)
+{
+    int st(0);
+    SX_CUDA(ctx, cudaMemcpyAsync(&st, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_compute));
+    SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    if (st & (1 << K7_ST_SHIFT))
+    {
+        cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->s_compute);
+        if (totals_host)
+            return sx_fail(ctx, SX_ERR_CAPACITY, "%s: output capacity too small: the batch produces %u alignments, %u segments, %u keys", what, totals_host[0],
+                           totals_host[1], totals_host[2]);
+        return sx_fail(ctx, SX_ERR_CAPACITY, "%s: output capacity too small (totals[] holds the needed sizes)", what);
+    }
+    return sx_check_status(ctx, what);
+}
+} // namespace
+
+extern "C" void sx_default_enum_opts(sx_enum_opts* o)
+{
+    if (!o) return;
+    o->max_indel_size = 49;                 // starling_base_shared.hh:124
+    o->max_read_indel_toggle = 5;           // :139
+    o->max_candidate_indel_density = 0.15;  // :145
+    // starling_align_limit(opt.max_realignment_candidates = 5000), starling_align_limit.cpp:77-88
+    o->n_max_toggle = 0;
+    for (unsigned i = 0; i < 100; ++i)
+    {
+        const unsigned mt(k7_max_candidate_alignment_toggle(i, 5000));
+        if (i > 1 && mt < 2) break;
+        o->max_toggle[o->n_max_toggle++] = (uint8_t)mt;
+    }
+    for (unsigned i = o->n_max_toggle; i < 100; ++i) o->max_toggle[i] = 1;
+    o->is_haplotyping_enabled = 0;          // starling_base_shared.hh:99 (the germline workflow switches it on)
+    o->n_samples = 1;
+    o->sample_id = 0;
+    o->max_alns_per_read = 64;
+}
+
+extern "C" int sx_enumerate_alignments_dev(sx_ctx* ctx, const sx_enum_batch* d, sx_enum_out* out_dev)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    int rc;
+    if ((rc = k7_check_args(ctx, d, out_dev, "sx_enumerate_alignments_dev"))) return rc;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (d->n_reads == 0)
+    {
+        SX_CUDA(ctx, cudaMemsetAsync(out_dev->totals, 0, 12, ctx->s_compute));
+        SX_CUDA(ctx, cudaMemsetAsync(out_dev->aln_off, 0, 4, ctx->s_compute));
+        SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+        return SX_OK;
+    }
+    sx_kernel_timer t(ctx);
+    unsigned launches(0);
+    if ((rc = k7_run(ctx, d, out_dev, &launches))) return rc;
+    t.stop(launches);
+    if ((rc = t.finish())) return rc;
+    return k7_finish(ctx, "sx_enumerate_alignments", nullptr);
+}
+
+extern "C" int sx_enumerate_alignments(sx_ctx* ctx, const sx_enum_batch* b, sx_enum_out* out_host)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    int rc;
+    if ((rc = k7_check_args(ctx, b, out_host, "sx_enumerate_alignments"))) return rc;
+    if (b->n_reads == 0)
+    {
+        out_host->totals[0] = out_host->totals[1] = out_host->totals[2] = 0;
+        out_host->aln_off[0] = 0;
+        return SX_OK;
+    }
+    if (b->region_read_off[b->n_regions] != b->n_reads || b->region_key_off[b->n_regions] != b->n_keys)
+        return sx_fail(ctx, SX_ERR_ARG, "sx_enumerate_alignments: offset arrays do not end at n_reads / n_keys");
+    for (uint32_t g = 0; g < b->n_regions; ++g)
+        if (b->region_key_off[g + 1] - b->region_key_off[g] > 65535u) return sx_fail(ctx, SX_ERR_RANGE, "sx_enumerate_alignments: more than 65535 window entries in a region");
+    for (uint32_t k = 0; k < b->n_keys; ++k)
+        if (b->keys[k].type > SX_INDEL_TYPE_MISMATCH) return sx_fail(ctx, SX_ERR_UNSUPPORTED, "sx_enumerate_alignments: breakend entries are not supported");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st(ctx->s_compute);
+    SX_CUDA(ctx, cudaEventRecord(ctx->ev_a, st));
+    sx_enum_batch d(*b);
+    void* p(nullptr);
+    const size_t n_segs(b->in_seg_off[b->n_reads]), n_ikeys(b->in_key_off[b->n_reads]), n_ukeys(b->use_key_off[b->n_reads]);
+#define SX_UP(slot, field, type, bytes)                                                        \
+    if ((rc = sx_ensure(ctx, slot, (size_t)(bytes) + 16, &p))) return rc;                       \
+    if (bytes) SX_CUDA(ctx, cudaMemcpyAsync(p, b->field, (bytes), cudaMemcpyHostToDevice, st)); \
+    d.field = static_cast<type>(p);
+    SX_UP(0, region_read_off, const uint32_t*, (size_t)(b->n_regions + 1) * 4)
+    SX_UP(1, region_key_off, const uint32_t*, (size_t)(b->n_regions + 1) * 4)
+    SX_UP(2, keys, const sx_indel_key*, (size_t)b->n_keys * sizeof(sx_indel_key))
+    if (b->key_hap)
+    {
+        SX_UP(3, key_hap, const sx_key_hap*, (size_t)b->n_keys * sizeof(sx_key_hap))
+    }
+    SX_UP(4, realign_begin, const int32_t*, (size_t)b->n_regions * 4)
+    SX_UP(5, realign_end, const int32_t*, (size_t)b->n_regions * 4)
+    SX_UP(6, in_pos, const int32_t*, (size_t)b->n_reads * 4)
+    SX_UP(7, in_seg_off, const uint32_t*, (size_t)(b->n_reads + 1) * 4)
+    SX_UP(8, in_segs, const sx_aln_seg*, n_segs * sizeof(sx_aln_seg))
+    SX_UP(9, in_key_off, const uint32_t*, (size_t)(b->n_reads + 1) * 4)
+    SX_UP(10, in_keys, const uint16_t*, n_ikeys * 2)
+    SX_UP(11, use_key_off, const uint32_t*, (size_t)(b->n_reads + 1) * 4)
+    SX_UP(12, use_keys, const uint16_t*, n_ukeys * 2)
+    SX_UP(13, in_lead_key, const uint16_t*, (size_t)b->n_reads * 2)
+    SX_UP(14, in_trail_key, const uint16_t*, (size_t)b->n_reads * 2)
+    SX_UP(15, read_len, const uint16_t*, (size_t)b->n_reads * 2)
+#undef SX_UP
+    sx_enum_out o(*out_host);
+    if ((rc = sx_ensure(ctx, 16, 16, reinterpret_cast<void**>(&o.totals)))) return rc;
+    if ((rc = sx_ensure(ctx, 17, (size_t)(b->n_reads + 1) * 4, reinterpret_cast<void**>(&o.aln_off)))) return rc;
+    if ((rc = sx_ensure(ctx, 18, (size_t)b->n_reads + 16, reinterpret_cast<void**>(&o.status)))) return rc;
+    if ((rc = sx_ensure(ctx, 19, (size_t)o.cap_alns * 4 + 16, reinterpret_cast<void**>(&o.aln_pos)))) return rc;
+    if ((rc = sx_ensure(ctx, 20, ((size_t)o.cap_alns + 1) * 4 + 16, reinterpret_cast<void**>(&o.aln_seg_off)))) return rc;
+    if ((rc = sx_ensure(ctx, 21, (size_t)o.cap_segs * sizeof(sx_aln_seg) + 16, reinterpret_cast<void**>(&o.segs)))) return rc;
+    if ((rc = sx_ensure(ctx, 22, ((size_t)o.cap_alns + 1) * 4 + 16, reinterpret_cast<void**>(&o.aln_key_off)))) return rc;
+    if ((rc = sx_ensure(ctx, 23, (size_t)o.cap_keys * 2 + 16, reinterpret_cast<void**>(&o.aln_keys)))) return rc;
+    if ((rc = sx_ensure(ctx, 24, (size_t)o.cap_alns * 2 + 16, reinterpret_cast<void**>(&o.aln_lead_key)))) return rc;
+    if ((rc = sx_ensure(ctx, 25, (size_t)o.cap_alns * 2 + 16, reinterpret_cast<void**>(&o.aln_trail_key)))) return rc;
+    unsigned launches(0);
+    if ((rc = k7_run(ctx, &d, &o, &launches))) return rc;
+    // the totals decide how much comes back
+    SX_CUDA(ctx, cudaMemcpyAsync(out_host->totals, o.totals, 12, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaMemcpyAsync(out_host->aln_off, o.aln_off, (size_t)(b->n_reads + 1) * 4, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaMemcpyAsync(out_host->status, o.status, (size_t)b->n_reads, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t nA(out_host->totals[0]), nS(out_host->totals[1]), nK(out_host->totals[2]);
+    if (nA <= o.cap_alns && nS <= o.cap_segs && nK <= o.cap_keys)
+    {
+        SX_CUDA(ctx, cudaMemcpyAsync(out_host->aln_pos, o.aln_pos, (size_t)nA * 4, cudaMemcpyDeviceToHost, st));
+        SX_CUDA(ctx, cudaMemcpyAsync(out_host->aln_seg_off, o.aln_seg_off, ((size_t)nA + 1) * 4, cudaMemcpyDeviceToHost, st));
+        SX_CUDA(ctx, cudaMemcpyAsync(out_host->segs, o.segs, (size_t)nS * sizeof(sx_aln_seg), cudaMemcpyDeviceToHost, st));
+        SX_CUDA(ctx, cudaMemcpyAsync(out_host->aln_key_off, o.aln_key_off, ((size_t)nA + 1) * 4, cudaMemcpyDeviceToHost, st));
+        SX_CUDA(ctx, cudaMemcpyAsync(out_host->aln_keys, o.aln_keys, (size_t)nK * 2, cudaMemcpyDeviceToHost, st));
+        SX_CUDA(ctx, cudaMemcpyAsync(out_host->aln_lead_key, o.aln_lead_key, (size_t)nA * 2, cudaMemcpyDeviceToHost, st));
+        SX_CUDA(ctx, cudaMemcpyAsync(out_host->aln_trail_key, o.aln_trail_key, (size_t)nA * 2, cudaMemcpyDeviceToHost, st));
+    }
+    SX_CUDA(ctx, cudaEventRecord(ctx->ev_b, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms(0);
+    cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+    ctx->timing.kernel_ms = ms;
+    ctx->timing.launches = launches;
+    ctx->total_launches += launches;
+    return k7_finish(ctx, "sx_enumerate_alignments", out_host->totals);
+}

@@ -89,7 +89,7 @@ struct sx_ctx
     std::string err;
     sx_timing timing{};
     uint64_t total_launches = 0;
-    sx_buf buf[32];          // grow-only device arenas, one per logical pool
+    sx_buf buf[64];          // grow-only device arenas, one per logical pool (K7 uses 40..45)
     void* nccl = nullptr;    // ncclComm_t
     void* nccl_lib = nullptr;
     int rank = 0, world = 1;

@@ -258,3 +258,49 @@ def ref_score_indels(sb: "B.ScoreIndelsBatch", lnp: np.ndarray):
         raise RuntimeError(err.value.decode(errors="replace"))
     recs, n_rec, max_aln, _ = out.compact()
     return recs, n_rec, max_aln
+
+
+def ref_max_toggle_table(max_alignment_count: int) -> np.ndarray:
+    """starling_align_limit(max_alignment_count).get_max_toggle(i), i < 100, from the reference."""
+    out = np.zeros(100, np.uint8)
+    fn = ref().ref_max_toggle_table
+    fn.argtypes = [C.c_uint, _P]
+    fn(max_alignment_count, A.ptr(out))
+    return out
+
+
+def ref_enumerate_alignments(eb: "B.EnumBatch", cap_alns=None) -> "B.EnumOut":
+    """The reference's own getCandidateAlignments on rebuilt IndelBuffer / read_segment objects (oracle/ref_harness_enumerate.inc)."""
+    out = B.EnumOut(eb, cap_alns)
+    err = _err()
+    fn = ref().ref_enumerate_alignments
+    fn.argtypes = [C.POINTER(A.SxEnumBatch), _P, _P, _P, _P, _P, _P, _P, C.POINTER(A.SxEnumOut), C.c_char_p, C.c_int]
+    rc = fn(C.byref(eb.c), A.ptr(eb.ins_pool), A.ptr(eb.ins_off), A.ptr(eb.ref_pool), A.ptr(eb.ref_off), A.ptr(eb.ref_begin), A.ptr(eb.read_pool), A.ptr(eb.read_off),
+            C.byref(out.c), err, 1024)
+    if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    return out
+
+
+_k7core = None
+
+
+def k7core_enumerate(eb: "B.EnumBatch", max_alns: int = 0, cap_alns=None, cap_segs=None, cap_keys=None):
+    """strelka_b200/csrc/k7_core.cuh compiled for the host (tests/cpp/k7_core_host.cpp): the device body run read by read on the CPU.
+    Returns (rc, EnumOut)."""
+    global _k7core
+    if _k7core is None:
+        import tempfile
+
+        so = os.path.join(tempfile.mkdtemp(prefix="k7core"), "libk7core.so")
+        subprocess.check_call(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "strelka_b200", "csrc"),
+                               os.path.join(ROOT, "tests", "cpp", "k7_core_host.cpp"), "-o", so])
+        _k7core = C.CDLL(so)
+        _k7core.k7core_run.argtypes = [C.POINTER(A.SxEnumBatch), C.POINTER(A.SxEnumOut), C.c_uint32]
+        _k7core.k7core_make_start_pos.argtypes = [_P, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32, _P, _P, _P, _P, _P]
+        _k7core.k7core_end_pin_start_pos.argtypes = [_P, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _P, _P]
+    if eb is None:
+        return _k7core
+    out = B.EnumOut(eb, cap_alns, cap_segs, cap_keys)
+    rc = _k7core.k7core_run(C.byref(eb.c), C.byref(out.c), max_alns)
+    return rc, out

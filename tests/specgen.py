@@ -5,6 +5,7 @@ from typing import List, Tuple
 
 import numpy as np
 
+from strelka_b200 import _abi as A
 from strelka_b200 import batch as B
 
 BASES = "ACGT"
@@ -545,3 +546,149 @@ def score_indels_case(case: int):
         opts.max_indel_size = int(rng.integers(1, 20))
         opts.min_read_bp_flank = int(rng.integers(1, 40))
     return B.ScoreIndelsBatch(regions, opts), lnp
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# K7 enumerate_alignments: regions with a reference, an IndelBuffer window and reads whose input alignments use some of its entries
+# ------------------------------------------------------------------------------------------------------------------------------
+def _keys_conflict(a, b) -> bool:
+    """is_indel_conflict (indel_util.cpp:29-45)."""
+    margin = 0 if (a.mismatch or b.mismatch) else 1
+    return (b.pos + b.del_len + margin > a.pos) and (b.pos < a.pos + a.del_len + margin)
+
+
+def random_enum_region(rng: np.random.Generator, n_reads: int = 6, ref_len: int = 420, ref_begin: int = 1000, n_keys=(1, 8), read_len=(30, 120), hap: bool = False,
+                       n_samples: int = 1, cluster: bool = False, clip_rate: float = 0.1):
+    ref = rand_seq(rng, ref_len)
+    keys = {}
+    centre = ref_begin + int(rng.integers(120, ref_len - 120))
+    for _ in range(int(rng.integers(n_keys[0], n_keys[1] + 1))):
+        pos = int(centre + rng.integers(-25, 26)) if cluster else ref_begin + int(rng.integers(70, ref_len - 90))
+        u = rng.random()
+        common = dict(candidate=bool(rng.random() < 0.8), not_discovered=bool(rng.random() < 0.12))
+        if hap:
+            common.update(active_region=int(rng.choice([-1, 0, 0, 1])), hap_ids=tuple(int(x) for x in rng.integers(0, 4, 4)), bypass=int(rng.integers(0, 4)) if rng.random() < 0.3 else 0,
+                          forced=bool(rng.random() < 0.1))
+        if u < 0.33:
+            k = B.EnumKeySpec(pos, int(rng.integers(1, 13)), "", **common)
+        elif u < 0.66:
+            k = B.EnumKeySpec(pos, 0, rand_seq(rng, int(rng.integers(1, 11))), **common)
+        elif u < 0.78:
+            d = int(rng.integers(1, 7))
+            k = B.EnumKeySpec(pos, d, rand_seq(rng, d if rng.random() < 0.4 else int(rng.integers(1, 7))), **common)
+        else:
+            rb = ref[pos - ref_begin]
+            base = str(rng.choice([c for c in "ACGT" if c != rb]))
+            if hap and common["active_region"] < 0:
+                common["active_region"] = 0
+            k = B.EnumKeySpec(pos, 1, base, mismatch=True, **common)
+        keys.setdefault(k.order(), k)
+    win = [keys[o] for o in sorted(keys)]
+    mm_at = {k.pos: k for k in win if k.mismatch}
+    reads = []
+    for _ in range(n_reads):
+        rl = int(rng.integers(read_len[0], read_len[1] + 1))
+        u = rng.random()
+        anchor = win[int(rng.integers(0, len(win)))]
+        if u < 0.25:
+            start = anchor.pos - int(rng.integers(1, 12))
+        elif u < 0.5:
+            start = anchor.pos - rl + int(rng.integers(-3, 10))
+        else:
+            start = anchor.pos - int(rng.integers(0, rl))
+        start = max(ref_begin + 20, min(start, ref_begin + ref_len - rl - 40))
+        # the indels the mapper's alignment already contains: a non-conflicting subset, spaced so that each is flanked by matches
+        chosen = []
+        for k in win:
+            if k.mismatch or rng.random() > 0.35:
+                continue
+            if any(_keys_conflict(k, c) for c in chosen):
+                continue
+            chosen.append(k)
+        path, seq, ref_pos, remaining = [], [], start, rl
+        used = []
+
+        def match(n):
+            nonlocal ref_pos
+            for _i in range(n):
+                rb = ref[ref_pos - ref_begin]
+                mk = mm_at.get(ref_pos)
+                v = rng.random()
+                if mk is not None and v < 0.5:
+                    seq.append(mk.ins)
+                elif v < 0.03:
+                    seq.append(str(rng.choice(list("ACGT"))))
+                elif v < 0.04:
+                    seq.append("N")
+                else:
+                    seq.append(rb)
+                ref_pos += 1
+
+        for k in chosen:
+            m = k.pos - ref_pos
+            if m < 1 or m + len(k.ins) + 1 > remaining:
+                continue
+            match(m)
+            path.append(("M", m))
+            remaining -= m
+            if k.del_len:
+                path.append(("D", k.del_len))
+                ref_pos += k.del_len
+            if k.ins:
+                path.append(("I", len(k.ins)))
+                seq.append(k.ins)
+                remaining -= len(k.ins)
+            used.append(k)
+        match(remaining)
+        if path and path[-1][0] == "M":
+            path[-1] = ("M", path[-1][1] + remaining)
+        else:
+            path.append(("M", remaining))
+        seq = "".join(seq)
+        assert len(seq) == rl
+        if rng.random() < clip_rate:  # hard clips (not part of read_size()).  Soft clips never reach getCandidateAlignments: its caller
+            # matchifies them first (starling_read_align.cpp:2037-2043), and the reference asserts (:466) on some soft-clipped inputs
+            if rng.random() < 0.6:
+                path.insert(0, ("H", int(rng.integers(1, 20))))
+            if rng.random() < 0.6:
+                path.append(("H", int(rng.integers(1, 20))))
+        index_of = {k.order(): i for i, k in enumerate(win)}
+        use = [index_of[k.order()] for k in used if not k.candidate and rng.random() > 0.03]
+        use += [i for i, k in enumerate(win) if not k.candidate and rng.random() < 0.3]
+        reads.append(B.EnumReadSpec(seq, start, path, use))
+    if rng.random() < 0.15 and reads:
+        r = reads[int(rng.integers(0, len(reads)))]
+        span = sum(ln for t, ln in r.path if t in "MD=X")
+        realign = (r.pos - int(rng.integers(0, 15)), r.pos + span + int(rng.integers(0, 15)))
+    else:
+        realign = (ref_begin + 5, ref_begin + ref_len - 5)
+    return ref, ref_begin, realign, win, reads
+
+
+def enum_case(case: int, n_regions: int = 6):
+    """Seeded K7 batches: plain windows, clustered (conflicting) windows, phased active-region windows with two samples, dense windows
+    (the density and max-toggle limits), tight toggle budgets."""
+    rng = np.random.default_rng(7000 + case)
+    mode = case % 6
+    opts = A.default_enum_opts()
+    kw = {}
+    if mode == 1:
+        kw = dict(cluster=True, n_keys=(2, 9))
+    elif mode == 2:
+        kw = dict(hap=True, cluster=bool(case & 8), n_keys=(2, 8))
+        opts.is_haplotyping_enabled = 1
+        opts.n_samples = 2
+        opts.sample_id = (case // 6) % 2
+    elif mode == 3:
+        kw = dict(cluster=True, n_keys=(8, 16), read_len=(30, 60))
+    elif mode == 4:
+        opts.max_read_indel_toggle = int(rng.integers(0, 4))
+        kw = dict(cluster=bool(case & 8))
+    elif mode == 5:
+        kw = dict(hap=True, n_keys=(1, 6), clip_rate=0.4)
+        opts.is_haplotyping_enabled = int(case & 8 != 0)
+    regions = [random_enum_region(rng, n_reads=int(rng.integers(1, 7)), **kw) for _ in range(n_regions)]
+    return B.EnumBatch(regions, opts)
+
+
+ENUM_GOLDEN_CASES = 12

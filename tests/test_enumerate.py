@@ -1,0 +1,159 @@
+"""K7 enumerate_alignments without a GPU: the device body (strelka_b200/csrc/k7_core.cuh, __host__
+__device__) compiled for the host and run the way the kernels run it, against
+  * the known-answer vectors of the reference's own unit test (starling_common/test/starling_read_align_test.cpp),
+  * the reference's getCandidateAlignments itself (oracle/_ref/libstrelka_ref.so) on seeded batches, when it is built here,
+  * the frozen outputs of the same function (tests/golden/enumerate_ref.npz).
+The GPU parity tests (tests/test_gpu_enumerate.py) run the CUDA kernels against the same checkers."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import reflib
+import specgen
+from strelka_b200 import _abi as A
+from strelka_b200 import batch as B
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+needs_ref = pytest.mark.skipif(not reflib.have_ref(), reason="oracle/_ref/libstrelka_ref.so not built (needs /root/reference)")
+GOLD_NAMES = ("aln_off", "status", "aln_pos", "aln_seg_off", "segs", "aln_key_off", "aln_keys", "lead", "trail")
+
+
+def _keys(specs):
+    specs = sorted(specs, key=lambda k: k.order())
+    arr = np.zeros(len(specs) + 1, dtype=A.INDEL_KEY_DT)
+    for i, k in enumerate(specs):
+        arr[i] = (k.pos, k.del_len, len(k.ins), 1 if k.ins else 0, A.SX_INDEL_TYPE_INDEL, A.SX_IKF_CANDIDATE, 0, 0.0, 0.0)
+    return specs, arr
+
+
+def _cigar(segs, n):
+    return "".join(f"{int(s['len'])}{B.AP_CHAR[int(s['kind'])]}" for s in segs[:n])
+
+
+def test_reference_unit_test_vectors():
+    """test_make_start_pos_alignment and test_end_pin_start_pos of the reference's starling_read_align_test.cpp, through the device
+    functions k7_make_start_pos / k7_end_pin_start_pos."""
+    gold = json.load(open(os.path.join(HERE, "golden", "read_align_unit_goldens.json")))
+    lib = reflib.k7core_enumerate(None)
+    fixed = B.WindowKeySpec(**gold["fixed_key"])
+    n_start = n_end = 0
+    for case in gold["make_start_pos_alignment"]:
+        specs, win = _keys([fixed, B.WindowKeySpec(**case["key"])])
+        me = [i for i, k in enumerate(specs) if k is not fixed][0]
+        pos, lead, trail, n_seg = np.zeros(1, np.int32), np.zeros(1, np.uint16), np.zeros(1, np.uint16), np.zeros(1, np.uint32)
+        segs = np.zeros(40, dtype=A.ALN_SEG_DT)
+        rc = lib.k7core_make_start_pos(A.ptr(win), 2, gold["ref_start"], case["read_start"], gold["read_length"], A.ptr(pos), A.ptr(lead), A.ptr(trail), A.ptr(segs),
+                                       A.ptr(n_seg))
+        assert rc == 0
+        assert _cigar(segs, int(n_seg[0])) == case["path"], case
+        if "pos" in case:
+            assert int(pos[0]) == case["pos"]
+        for side, got in (("leading", int(lead[0])), ("trailing", int(trail[0]))):
+            if side in case:
+                assert got == (me if case[side] else A.SX_NO_KEY), (case, side, got)
+        n_start += 1
+    for case in gold["get_end_pin_start_pos"]:
+        _specs, win = _keys([fixed, B.WindowKeySpec(**case["key"])])
+        ref_start, read_start = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        rc = lib.k7core_end_pin_start_pos(A.ptr(win), 2, gold["read_length"], gold["ref_end"], case["read_end"], A.ptr(ref_start), A.ptr(read_start))
+        if case.get("throws"):
+            assert rc == A.SX_ENUM_ST_EXCEPTION
+        else:
+            assert rc == 0 and (int(ref_start[0]), int(read_start[0])) == (case["ref_start"], case["read_start"]), case
+        n_end += 1
+    assert n_start == 12 and n_end == 15
+
+
+def test_goldens_are_the_reference_unit_test():
+    """the committed JSON still is what tests/golden/make_read_align_goldens.py extracts (only checkable where the reference is)."""
+    src = "/root/reference/src/c++/lib/starling_common/test/starling_read_align_test.cpp"
+    if not os.path.exists(src):
+        pytest.skip("no /root/reference here")
+    text = open(src).read()
+    gold = json.load(open(os.path.join(HERE, "golden", "read_align_unit_goldens.json")))
+    assert len(re.findall(r"path_compare\(\"", text)) == len(gold["make_start_pos_alignment"])
+    for case in gold["make_start_pos_alignment"]:
+        assert f'path_compare("{case["path"]}"' in text
+
+
+def _same(a: B.EnumOut, b: B.EnumOut):
+    for x, y in zip(a.trimmed(), b.trimmed()):
+        assert x.tobytes() == y.tobytes()
+
+
+@needs_ref
+def test_max_toggle_table_is_the_references():
+    """sx_default_enum_opts computes starling_align_limit's table itself (k7_enumerate.cu); the reference's for 5000 candidates."""
+    o = A.default_enum_opts()
+    want = reflib.ref_max_toggle_table(5000)
+    got = np.array([o.max_toggle[i] if i < o.n_max_toggle else 1 for i in range(100)], np.uint8)
+    assert np.array_equal(want, got) and o.n_max_toggle < 100
+
+
+@needs_ref
+def test_device_body_against_the_reference():
+    """every alignment, in std::set order, with its keys, edge keys and the warn / exception status: identical to the reference's
+    getCandidateAlignments on 48 seeded batches (plain, clustered, phased two-sample, dense, tight toggle budgets, hard clips)."""
+    total, statuses = 0, set()
+    for case in range(48):
+        eb = specgen.enum_case(case)
+        want = reflib.ref_enumerate_alignments(eb, cap_alns=eb.n_reads * 6000 + 64)
+        rc, got = reflib.k7core_enumerate(eb, max_alns=6000, cap_alns=eb.n_reads * 6000 + 64)
+        assert rc == 0
+        _same(want, got)
+        total += int(want.totals[0])
+        statuses |= set(int(s) for s in want.status[: eb.n_reads])
+    assert total > 15000
+    assert {0, A.SX_ENUM_ST_MAX_TOGGLE, A.SX_ENUM_ST_EXCEPTION} <= statuses
+
+
+def test_device_body_against_the_frozen_reference_output():
+    gold = np.load(os.path.join(HERE, "golden", "enumerate_ref.npz"))
+    total = 0
+    for case in range(specgen.ENUM_GOLDEN_CASES):
+        eb = specgen.enum_case(case)
+        rc, got = reflib.k7core_enumerate(eb, max_alns=6000, cap_alns=eb.n_reads * 6000 + 64)
+        assert rc == 0
+        for name, arr in zip(GOLD_NAMES, got.trimmed()):
+            assert arr.tobytes() == gold[f"{name}{case}"].tobytes(), (case, name)
+        total += int(got.totals[0])
+    assert total > 3000
+
+
+def test_limits_and_capacity():
+    """a read that needs more alignment slots than max_alns_per_read is flagged SX_ENUM_ST_LIMIT and contributes nothing (the other
+    reads are unaffected); output arrays that are too small make the call fail with the needed sizes in totals[]."""
+    eb = specgen.enum_case(3)
+    rc, full = reflib.k7core_enumerate(eb, max_alns=6000, cap_alns=eb.n_reads * 6000 + 64)
+    assert rc == 0
+    n = np.diff(full.aln_off[: eb.n_reads + 1].astype(np.int64))
+    cut = int(np.sort(n)[len(n) // 2])
+    assert 0 < cut < n.max()
+    rc, lim = reflib.k7core_enumerate(eb, max_alns=cut, cap_alns=eb.n_reads * 6000 + 64)
+    assert rc == 0
+    for r in range(eb.n_reads):
+        if n[r] > cut:
+            assert lim.status[r] & A.SX_ENUM_ST_LIMIT and lim.aln_off[r + 1] == lim.aln_off[r]
+        else:
+            assert lim.status[r] == full.status[r] and lim.alignments_of(r) == full.alignments_of(r)
+    rc, small = reflib.k7core_enumerate(eb, max_alns=6000, cap_alns=int(full.totals[0]) - 1, cap_segs=1 << 20, cap_keys=1 << 20)
+    assert rc == A.SX_ERR_CAPACITY and list(small.totals[:3]) == list(full.totals[:3])
+
+
+def test_host_builder_restates_getAlignmentIndels():
+    """batch.alignment_indels (the host side of K7's input): indels, swaps, edge keys and window mismatches of an input alignment."""
+    ref, rb = "ACGTACGTACGTACGTACGTACGTACGTACGT", 100
+    win = sorted([B.WindowKeySpec(104, 2, ""), B.WindowKeySpec(110, 0, "GG"), B.WindowKeySpec(116, 1, "TT"), B.WindowKeySpec(102, 1, "A", mismatch=True),
+                  B.WindowKeySpec(121, 1, "T", mismatch=True)], key=lambda k: k.order())
+    idx = {k.order(): i for i, k in enumerate(win)}
+    #        100..103 M4 | D2 (104,105) | 106..109 M4 | I2 GG | 110..115 M6 | D1 (116) I2 TT swap | 117..122 M6
+    seq = "ACAT" + "GTAC" + "GG" + "GTACGT" + "TT" + "CGTACG"
+    r = B.EnumReadSpec(seq, 100, [("M", 4), ("D", 2), ("M", 4), ("I", 2), ("M", 6), ("D", 1), ("I", 2), ("M", 6)])
+    keys, lead, trail = B.alignment_indels(r, ref, rb, win)
+    want = sorted([idx[(104, 1, 0, 2, "")], idx[(110, 1, 2, 0, "GG")], idx[(116, 1, 2, 1, "TT")], idx[(102, 2, 1, 1, "A")]])
+    assert keys == want and lead == A.SX_NO_KEY and trail == A.SX_NO_KEY
+    with pytest.raises(KeyError):  # an indel of the alignment that the window does not hold: the reference throws (:1875)
+        B.alignment_indels(B.EnumReadSpec("ACGTAAACGT", 100, [("M", 4), ("I", 2), ("M", 4)]), ref, rb, win)

@@ -1,0 +1,95 @@
+"""GPU parity of K7 enumerate_alignments: the CUDA kernels through the C ABI (host-buffer entry and
+device-resident entry) against the CPU oracle (oracle/enumerate_oracle.cpp), the frozen output of the reference's own
+getCandidateAlignments (tests/golden/enumerate_ref.npz) and, where oracle/_ref/libstrelka_ref.so travelled, the reference itself.
+Every field is an integer: bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import reflib
+import specgen
+from strelka_b200 import _abi as A
+from strelka_b200 import batch as B
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD_NAMES = ("aln_off", "status", "aln_pos", "aln_seg_off", "segs", "aln_key_off", "aln_keys", "lead", "trail")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from strelka_b200.api import Context
+
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _same(want: B.EnumOut, got: B.EnumOut):
+    for name, x, y in zip(GOLD_NAMES, want.trimmed(), got.trimmed()):
+        assert x.tobytes() == y.tobytes(), name
+
+
+def _big_opts(opts):
+    opts.max_alns_per_read = 6000
+    return opts
+
+
+@pytest.mark.parametrize("case", range(24))
+def test_k7_enumerate_alignments(ctx, case):
+    eb = specgen.enum_case(case)
+    _big_opts(eb.opts)
+    eb.c.opts = eb.opts
+    cap = eb.n_reads * 6000 + 64
+    got = ctx.enumerate_alignments(eb, cap_alns=cap)
+    assert ctx.timing().launches == 6
+    _same(reflib.ox_enumerate_alignments(eb, cap_alns=cap), got)
+    if case < specgen.ENUM_GOLDEN_CASES:
+        gold = np.load(os.path.join(HERE, "golden", "enumerate_ref.npz"))
+        for name, arr in zip(GOLD_NAMES, got.trimmed()):
+            assert arr.tobytes() == gold[f"{name}{case}"].tobytes(), name
+    if reflib.have_ref():
+        _same(reflib.ref_enumerate_alignments(eb, cap_alns=cap), got)
+
+
+def test_k7_device_resident_many_regions(ctx):
+    """a batch large enough that every thread of the persistent grid strides over several reads and the scan runs over many tiles;
+    default per-read capacity (64 alignments): deeper reads come back flagged SX_ENUM_ST_LIMIT exactly as the oracle flags them."""
+    from strelka_b200.api import DevEnumBatch
+
+    rng = np.random.default_rng(77)
+    regions = [specgen.random_enum_region(rng, n_reads=int(rng.integers(1, 9)), cluster=bool(i % 3 == 0), n_keys=(1, 6)) for i in range(6000)]
+    eb = B.EnumBatch(regions)
+    want = reflib.ox_enumerate_alignments(eb, cap_alns=eb.n_reads * 64 + 64)
+    db = DevEnumBatch(ctx, eb, cap_alns=eb.n_reads * 64 + 64)
+    ctx.enumerate_alignments_dev(db)
+    got = db.download()
+    _same(want, got)
+    st = want.status[: eb.n_reads]
+    assert int(want.totals[0]) > 100000 and (st & A.SX_ENUM_ST_LIMIT).any() and (st == 0).sum() > eb.n_reads // 2
+
+
+def test_k7_capacity_error_reports_the_needed_sizes(ctx):
+    from strelka_b200.api import SxError
+
+    eb = specgen.enum_case(1)
+    full = ctx.enumerate_alignments(eb)
+    with pytest.raises(SxError) as e:
+        ctx.enumerate_alignments(eb, cap_alns=int(full.totals[0]) - 1)
+    assert e.value.code == A.SX_ERR_CAPACITY and str(int(full.totals[0])) in str(e.value)
+    again = ctx.enumerate_alignments(eb)  # the context is usable afterwards
+    _same(full, again)
+
+
+def test_k7_feeds_k6(ctx):
+    """the enumerator's output IS K6's alignment description: same order (std::set<CandidateAlignment>), same key lists.  Score the
+    enumerated alignments of a batch with synthetic scores and run score_indels on them: records identical to the oracle's."""
+    eb = specgen.enum_case(0)
+    out = ctx.enumerate_alignments(eb)
+    sb = specgen.score_indels_batch_from_enumeration(eb, out)
+    rng = np.random.default_rng(3)
+    lnp = np.concatenate([-rng.random(sb.n_alns) * 30.0, [0.0]])
+    got = ctx.score_indels(sb, lnp)
+    for a, b in zip(reflib.ox_score_indels(sb, lnp), got):
+        assert a.tobytes() == b.tobytes()
