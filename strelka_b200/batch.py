@@ -874,8 +874,8 @@ class EnumOut:
 
     def __init__(self, eb: EnumBatch, cap_alns=None, cap_segs=None, cap_keys=None):
         self.cap_alns = cap_alns if cap_alns is not None else max(64, eb.n_reads * 64)
-        self.cap_segs = cap_segs if cap_segs is not None else self.cap_alns * 8
-        self.cap_keys = cap_keys if cap_keys is not None else self.cap_alns * 6
+        self.cap_segs = cap_segs if cap_segs is not None else self.cap_alns * 16
+        self.cap_keys = cap_keys if cap_keys is not None else self.cap_alns * 8
         self.totals = np.zeros(4, np.uint32)
         self.aln_off = np.zeros(eb.n_reads + 1, np.uint32)
         self.status = np.zeros(eb.n_reads + 1, np.uint8)

@@ -862,8 +862,18 @@ struct k7_view
     sx_enum_batch b;
 };
 
-// getCandidateAlignments, :1816-1994, for read r of `region`: fills S (the set), returns the read's status bits
-K7_HDN uint32_t k7_enumerate_read(const k7_view& v, const uint32_t region, const uint32_t r, k7_scratch& S)
+K7_HDN uint32_t k7_enumerate_read_raw(const k7_view& v, const uint32_t region, const uint32_t r, k7_scratch& S);
+
+// getCandidateAlignments, :1816-1994, for read r of `region`: fills S (the set), returns the read's status bits.  A read that failed
+// (SX_ENUM_ST_EXCEPTION / SX_ENUM_ST_LIMIT) reports that bit alone: the warnings collected before the failure are meaningless.
+K7_HD uint32_t k7_enumerate_read(const k7_view& v, const uint32_t region, const uint32_t r, k7_scratch& S)
+{
+    const uint32_t st(k7_enumerate_read_raw(v, region, r, S));
+    const uint32_t fail(st & (SX_ENUM_ST_EXCEPTION | SX_ENUM_ST_LIMIT));
+    return fail ? fail : st;
+}
+
+K7_HDN uint32_t k7_enumerate_read_raw(const k7_view& v, const uint32_t region, const uint32_t r, k7_scratch& S)
 {
     const sx_enum_batch& b(v.b);
     S.n = 0;

@@ -304,3 +304,14 @@ def k7core_enumerate(eb: "B.EnumBatch", max_alns: int = 0, cap_alns=None, cap_se
     out = B.EnumOut(eb, cap_alns, cap_segs, cap_keys)
     rc = _k7core.k7core_run(C.byref(eb.c), C.byref(out.c), max_alns)
     return rc, out
+
+
+def ox_enumerate_alignments(eb: "B.EnumBatch", cap_alns=None, cap_segs=None, cap_keys=None, limits: bool = True) -> "B.EnumOut":
+    """oracle/enumerate_oracle.cpp: the CPU restatement of getCandidateAlignments; limits=True applies the device build's per-read
+    capacities (SX_ENUM_ST_LIMIT), False is the reference's unlimited behaviour."""
+    out = B.EnumOut(eb, cap_alns, cap_segs, cap_keys)
+    lib = oracle()
+    lib.ox_enumerate_alignments.argtypes = [C.POINTER(A.SxEnumBatch), C.POINTER(A.SxEnumOut), C.c_int]
+    out.rc = lib.ox_enumerate_alignments(C.byref(eb.c), C.byref(out.c), 1 if limits else 0)
+    assert out.rc in (0, A.SX_ERR_CAPACITY), out.rc
+    return out

@@ -692,3 +692,24 @@ def enum_case(case: int, n_regions: int = 6):
 
 
 ENUM_GOLDEN_CASES = 12
+
+
+def score_indels_batch_from_enumeration(eb: "B.EnumBatch", out: "B.EnumOut", ref_to_indel_lnp=-9.9, indel_to_ref_lnp=-9.9) -> "B.ScoreIndelsBatch":
+    """K7's output as K6's input: the same alignments in the same (std::set) order with the same key lists; only the segment kinds
+    are relabelled ('=' / 'X' are MATCH for score_indels, DELETE keeps its own kind) and the per-read fields K6 needs are added."""
+    kind = np.zeros(16, np.uint8)
+    kind[[A.SX_AP_MATCH, A.SX_AP_SEQ_MATCH, A.SX_AP_SEQ_MISMATCH]] = A.SX_SEG_MATCH
+    kind[A.SX_AP_INSERT], kind[A.SX_AP_DELETE], kind[A.SX_AP_SOFT_CLIP], kind[A.SX_AP_HARD_CLIP] = A.SX_SEG_INSERT, 5, A.SX_SEG_SOFTCLIP, A.SX_SEG_HARDCLIP
+    aln_off, _st, aln_pos, aln_seg_off, segs, aln_key_off, aln_keys, _lead, _trail = out.trimmed()
+    segs2 = np.zeros(len(segs) + 16, dtype=A.ALN_SEG_DT)
+    segs2["len"][: len(segs)] = segs["len"]
+    segs2["kind"][: len(segs)] = kind[segs["kind"]]
+    keys = eb.keys.copy()
+    keys["ref_to_indel_lnp"], keys["indel_to_ref_lnp"] = ref_to_indel_lnp, indel_to_ref_lnp
+    n_win = np.diff(eb.region_key_off.astype(np.int64))
+    read_region = np.repeat(np.arange(eb.n_regions), np.diff(eb.region_read_off.astype(np.int64)))
+    rec_off = np.concatenate([[0], np.cumsum(n_win[read_region])]).astype(np.uint32)
+    arrays = dict(region_read_off=eb.region_read_off, region_key_off=eb.region_key_off, keys=keys, aln_off=aln_off, aln_pos=np.concatenate([aln_pos, [0]]).astype(np.int32),
+                  aln_seg_off=aln_seg_off, segs=segs2, aln_key_off=aln_key_off, aln_keys=np.concatenate([aln_keys, [0]]).astype(np.uint16), read_len=eb.read_len,
+                  non_ambig=eb.read_len.copy(), read_flags=np.full(eb.n_reads + 1, A.SX_SIF_FWD | A.SX_SIF_TIER1, np.uint8), rec_off=rec_off)
+    return B.ScoreIndelsBatch.from_arrays(arrays)

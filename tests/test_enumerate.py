@@ -123,6 +123,28 @@ def test_device_body_against_the_frozen_reference_output():
     assert total > 3000
 
 
+def test_device_body_against_the_oracle_with_the_device_limits():
+    """default per-read capacity (64 alignments, 64 indels, 32 segments, 24 keys): the oracle applies the same limits at the same
+    points of the search, so SX_ENUM_ST_LIMIT lands on the same reads and everything else is identical (this is the comparison the
+    GPU tests make); the oracle itself is pinned against the reference in tests/test_oracle_vs_reference.py and here on the goldens."""
+    gold = np.load(os.path.join(HERE, "golden", "enumerate_ref.npz"))
+    total = limited = 0
+    for case in range(150):
+        eb = specgen.enum_case(case)
+        cap = eb.n_reads * 64 + 64
+        want = reflib.ox_enumerate_alignments(eb, cap_alns=cap)
+        rc, got = reflib.k7core_enumerate(eb, cap_alns=cap)
+        assert rc == 0 and want.rc == 0
+        _same(want, got)
+        total += int(want.totals[0])
+        limited += int((want.status[: eb.n_reads] & A.SX_ENUM_ST_LIMIT != 0).sum())
+        if case < specgen.ENUM_GOLDEN_CASES:
+            free = reflib.ox_enumerate_alignments(eb, cap_alns=eb.n_reads * 6000 + 64, limits=False)
+            for name, arr in zip(GOLD_NAMES, free.trimmed()):
+                assert arr.tobytes() == gold[f"{name}{case}"].tobytes(), (case, name)
+    assert total > 20000 and limited > 50
+
+
 def test_limits_and_capacity():
     """a read that needs more alignment slots than max_alns_per_read is flagged SX_ENUM_ST_LIMIT and contributes nothing (the other
     reads are unaffected); output arrays that are too small make the call fail with the needed sizes in totals[]."""

@@ -289,3 +289,24 @@ def test_score_indels_bench_workload_matches_the_reference():
         r_recs, r_n, _r_max, _ = out.compact()
         assert np.array_equal(o_n, r_n) and o_recs.tobytes() == r_recs.tobytes()
         assert int((o_recs["flags"] & A.SX_RIS_SCORED).sum()) > 0.5 * sb.n_reads
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# K7 enumerate_alignments: oracle/enumerate_oracle.cpp against the reference's getCandidateAlignments (oracle/ref_harness_enumerate.inc)
+# ------------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("chunk", range(12))
+def test_enumerate_alignments_matches_the_reference(chunk):
+    """every candidate alignment in std::set order -- position, path, indel keys, leading / trailing edge keys -- and the per-read
+    status (warn flags, blt_exception): 25 seeded batches per chunk (plain / clustered / phased two-sample / dense / tight toggle
+    budget / hard-clipped windows)."""
+    total = 0
+    for case in range(25 * chunk, 25 * (chunk + 1)):
+        eb = specgen.enum_case(case)
+        cap = eb.n_reads * 6000 + 64
+        want = reflib.ref_enumerate_alignments(eb, cap_alns=cap)
+        got = reflib.ox_enumerate_alignments(eb, cap_alns=cap, limits=False)
+        assert got.rc == 0
+        for x, y in zip(want.trimmed(), got.trimmed()):
+            assert x.tobytes() == y.tobytes(), case
+        total += int(want.totals[0])
+    assert total > 4000
