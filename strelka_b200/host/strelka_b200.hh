@@ -776,6 +776,307 @@ private:
 };
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// K7: getCandidateAlignments over a batch of reads (starling_read_align.cpp:1816-1994 + candidate_alignment_search :857-1277)
+// ---------------------------------------------------------------------------------------------------------------------------
+struct IndelSearchEntry ///< what the alignment search reads of one IndelBuffer entry (IndelData.hh:270-273,374,382,387)
+{
+    IndelKey key;
+    bool isCandidate = true;             ///< indelBuffer.isCandidateIndel(key, data)
+    bool notDiscoveredFromReads = false; ///< data.status.notDiscoveredFromReads
+    bool isForcedOutput = false;         ///< data.isForcedOutput
+    int activeRegionId = -1;             ///< data.activeRegionId
+    int8_t haplotypeId[SX_ENUM_MAX_SAMPLES] = {0, 0, 0, 0};             ///< data.getSampleData(s).haplotypeId
+    bool isHaplotypingBypassed[SX_ENUM_MAX_SAMPLES] = {false, false, false, false};
+};
+
+class AlignmentSearchBatch
+{
+public:
+    struct ReadResult
+    {
+        std::vector<CandidateAlignment> alignments; ///< the std::set<CandidateAlignment>, in its iteration order
+        bool originSkip = false, maxToggleDepth = false; ///< mca_warnings; either one = is_incomplete_search (:2104)
+        bool threw = false;      ///< the reference throws blt_exception for this read
+        bool overLimit = false;  ///< outside this build's per-read capacity: run the reference's own getCandidateAlignments on it
+    };
+
+    /// window: every IndelBuffer entry a rangeIterator() over any candidate alignment of the region's reads can visit, IndelKey order;
+    /// ref / refBegin: the reference bases getAlignmentIndels compares read bases with (reference_contig_segment: 'N' outside)
+    void beginRegion(const std::vector<IndelSearchEntry>& window, const std::string& ref, pos_t refBegin, pos_t realignBegin, pos_t realignEnd)
+    {
+        for (size_t i(1); i < window.size(); ++i) require(window[i - 1].key < window[i].key, "window is not in IndelKey order");
+        require(window.size() < 65535, "more than 65534 window entries");
+        _regionKeyOff.push_back(_keys.size());
+        _regionReadOff.push_back(_readLen.size());
+        _realignBegin.push_back(realignBegin);
+        _realignEnd.push_back(realignEnd);
+        _ref = ref;
+        _refBegin = refBegin;
+        for (const IndelSearchEntry& e : window)
+        {
+            require(e.key.type == INDEL::INDEL || e.key.type == INDEL::MISMATCH, "breakend entries are not supported");
+            sx_indel_key k;
+            std::memset(&k, 0, sizeof(k));
+            k.pos = e.key.pos;
+            k.del_len = e.key.delete_length();
+            k.ins_len = e.key.insert_length();
+            k.type = e.key.isMismatch() ? SX_INDEL_TYPE_MISMATCH : SX_INDEL_TYPE_INDEL;
+            k.flags = (e.isCandidate ? SX_IKF_CANDIDATE : 0) | (e.notDiscoveredFromReads ? SX_IKF_NOT_DISCOVERED : 0) | (e.isForcedOutput ? SX_IKF_FORCED_OUTPUT : 0);
+            _keys.push_back(k);
+            sx_key_hap h;
+            std::memset(&h, 0, sizeof(h));
+            h.active_region_id = e.activeRegionId;
+            for (unsigned s(0); s < SX_ENUM_MAX_SAMPLES; ++s)
+            {
+                h.haplotype_id[s] = e.haplotypeId[s];
+                if (e.isHaplotypingBypassed[s]) h.bypass_mask |= (1u << s);
+            }
+            _hap.push_back(h);
+            _anyHap = _anyHap || e.activeRegionId >= 0;
+            _keyObjects.push_back(e.key);
+        }
+        _open = true;
+    }
+
+    /// one read segment: its bases (ASCII), the NORMALIZED input alignment realignAndScoreRead passes on (:2034-2045) and the
+    /// window entries whose tier1 / tier2 / submap / noise read-id sets hold this read (is_usable_indel :271-287).
+    /// Throws what the reference throws when the alignment holds an indel the window lacks (:1875).
+    unsigned addRead(const std::string& readBases, const alignment& normalizedInputAlignment, const std::vector<IndelKey>& observedKeys, unsigned maxIndelSize = 49)
+    {
+        using namespace ALIGNPATH;
+        require(_open, "addRead outside a region");
+        const path_t& path(normalizedInputAlignment.path);
+        _inPos.push_back(normalizedInputAlignment.pos);
+        _inSegOff.push_back(_inSegs.size());
+        _inKeyOff.push_back(_inKeys.size());
+        _useKeyOff.push_back(_useKeys.size());
+        for (const path_segment& ps : path)
+        {
+            require(ps.length <= 65535 && ps.type != NONE, "bad path segment");
+            _inSegs.push_back(sx_aln_seg{static_cast<uint16_t>(ps.length), static_cast<uint8_t>(ps.type), 0});
+        }
+        // getAlignmentIndels(cal, ref, rseg, maxIndelSize, includeMismatches = true), CandidateAlignment.cpp:58-173, and the edge keys
+        // of getCandidateAlignment, starling_read_align.cpp:1481-1522
+        size_t first(path.size()), last(path.size());
+        for (size_t i(0); i < path.size(); ++i)
+            if (path[i].type == MATCH || path[i].type == SEQ_MATCH || path[i].type == SEQ_MISMATCH)
+            {
+                if (first == path.size()) first = i;
+                last = i;
+            }
+        std::vector<uint16_t> keys;
+        uint16_t lead(SX_NO_KEY), trail(SX_NO_KEY);
+        unsigned readOff(0);
+        pos_t refPos(normalizedInputAlignment.pos);
+        for (size_t i(0); i < path.size();)
+        {
+            const path_segment& ps(path[i]);
+            const bool edge(i < first || i > last);
+            size_t j(i + 1);
+            if (edge)
+            {
+                if (ps.type == INSERT || ps.type == DELETE)
+                {
+                    const IndelKey k(refPos, INDEL::INDEL, ps.type == DELETE ? ps.length : 0, ps.type == INSERT ? readBases.substr(readOff, ps.length).c_str() : "");
+                    const uint16_t w(indexOf(k, true));
+                    keys.push_back(w);
+                    (i < first ? lead : trail) = w;
+                }
+            }
+            else if (ps.type == INSERT || ps.type == DELETE)
+            {
+                unsigned insLen(0), delLen(0);
+                for (j = i; j < path.size() && j <= last && (path[j].type == INSERT || path[j].type == DELETE); ++j)
+                    (path[j].type == INSERT ? insLen : delLen) += path[j].length;
+                if (std::max(insLen, delLen) > maxIndelSize) throw Exception(SX_ERR_UNSUPPORTED, "AlignmentSearchBatch: indel above maxIndelSize (breakend keys are not supported)");
+                keys.push_back(indexOf(IndelKey(refPos, INDEL::INDEL, delLen, readBases.substr(readOff, insLen).c_str()), true));
+            }
+            else if (ps.type == MATCH || ps.type == SEQ_MATCH || ps.type == SEQ_MISMATCH)
+            {
+                for (unsigned b(0); b < ps.length; ++b)
+                {
+                    const char base(readBases[readOff + b]);
+                    if (base == '=' || base == 'N') continue; // BAM_BASE::REF, BAM_BASE::ANY
+                    const pos_t rp(refPos + static_cast<pos_t>(b));
+                    const char refBase((rp >= _refBegin && rp < _refBegin + static_cast<pos_t>(_ref.size())) ? _ref[rp - _refBegin] : 'N');
+                    if (base == refBase) continue;
+                    const char ins[2] = {base, 0};
+                    const uint16_t w(indexOf(IndelKey(rp, INDEL::MISMATCH, 1, ins), false));
+                    if (w != SX_NO_KEY) keys.push_back(w); // a mismatch that is no window entry is dropped (:1869)
+                }
+            }
+            for (size_t s(i); s < j; ++s)
+            {
+                const ALIGNPATH::align_t t(path[s].type);
+                if (t == MATCH || t == INSERT || t == SOFT_CLIP || t == SEQ_MATCH || t == SEQ_MISMATCH) readOff += path[s].length;
+                if (t == MATCH || t == DELETE || t == SKIP || t == SEQ_MATCH || t == SEQ_MISMATCH) refPos += path[s].length;
+            }
+            i = j;
+        }
+        std::sort(keys.begin(), keys.end());
+        keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+        _inKeys.insert(_inKeys.end(), keys.begin(), keys.end());
+        std::vector<uint16_t> use;
+        for (const IndelKey& k : observedKeys)
+        {
+            const uint16_t w(indexOf(k, false));
+            if (w != SX_NO_KEY) use.push_back(w);
+        }
+        std::sort(use.begin(), use.end());
+        use.erase(std::unique(use.begin(), use.end()), use.end());
+        _useKeys.insert(_useKeys.end(), use.begin(), use.end());
+        _lead.push_back(lead);
+        _trail.push_back(trail);
+        _readLen.push_back(readBases.size());
+        _fwd.push_back(normalizedInputAlignment.is_fwd_strand);
+        return _readLen.size() - 1;
+    }
+
+    /// results[read]: what getCandidateAlignments would have put into cal_set (and the warn flags)
+    void enumerate(const Context& ctx, const sx_enum_opts* opts, std::vector<ReadResult>& results)
+    {
+        _open = false;
+        const size_t nReads(_readLen.size());
+        results.assign(nReads, ReadResult());
+        if (nReads == 0) return;
+        std::vector<uint32_t> regionReadOff(_regionReadOff), regionKeyOff(_regionKeyOff), inSegOff(_inSegOff), inKeyOff(_inKeyOff), useKeyOff(_useKeyOff);
+        regionReadOff.push_back(nReads);
+        regionKeyOff.push_back(_keys.size());
+        inSegOff.push_back(_inSegs.size());
+        inKeyOff.push_back(_inKeys.size());
+        useKeyOff.push_back(_useKeys.size());
+        std::vector<sx_indel_key> keys(_keys);
+        keys.resize(keys.size() + 1);
+        std::vector<sx_key_hap> hap(_hap);
+        hap.resize(hap.size() + 1);
+        std::vector<sx_aln_seg> inSegs(_inSegs);
+        inSegs.resize(inSegs.size() + 4);
+        std::vector<uint16_t> inKeys(_inKeys), useKeys(_useKeys);
+        inKeys.resize(inKeys.size() + 4);
+        useKeys.resize(useKeys.size() + 4);
+        sx_enum_batch b;
+        std::memset(&b, 0, sizeof(b));
+        b.n_regions = regionReadOff.size() - 1;
+        b.n_reads = nReads;
+        b.n_keys = _keys.size();
+        b.region_read_off = regionReadOff.data();
+        b.region_key_off = regionKeyOff.data();
+        b.keys = keys.data();
+        b.key_hap = _anyHap ? hap.data() : nullptr;
+        b.realign_begin = _realignBegin.data();
+        b.realign_end = _realignEnd.data();
+        b.in_pos = _inPos.data();
+        b.in_seg_off = inSegOff.data();
+        b.in_segs = inSegs.data();
+        b.in_key_off = inKeyOff.data();
+        b.in_keys = inKeys.data();
+        b.use_key_off = useKeyOff.data();
+        b.use_keys = useKeys.data();
+        b.in_lead_key = _lead.data();
+        b.in_trail_key = _trail.data();
+        b.read_len = _readLen.data();
+        if (opts) b.opts = *opts;
+        else sx_default_enum_opts(&b.opts);
+        const uint32_t perRead(b.opts.max_alns_per_read ? b.opts.max_alns_per_read : 64u);
+        sx_enum_out o;
+        std::memset(&o, 0, sizeof(o));
+        uint32_t totals[3] = {0, 0, 0};
+        std::vector<uint32_t> alnOff(nReads + 1), alnSegOff, alnKeyOff;
+        std::vector<uint8_t> status(nReads);
+        std::vector<int32_t> alnPos;
+        std::vector<sx_aln_seg> segs;
+        std::vector<uint16_t> alnKeys, alnLead, alnTrail;
+        // first guess: a few alignments per read; on SX_ERR_CAPACITY the library says what is needed
+        o.cap_alns = std::min<uint64_t>(nReads * std::min<uint32_t>(perRead, 16u), 0x7fffffffu);
+        o.cap_segs = o.cap_alns * 8;
+        o.cap_keys = o.cap_alns * 4;
+        for (int attempt(0); attempt < 2; ++attempt)
+        {
+            alnPos.resize(o.cap_alns + 1);
+            alnSegOff.resize(o.cap_alns + 2);
+            alnKeyOff.resize(o.cap_alns + 2);
+            segs.resize(o.cap_segs + 1);
+            alnKeys.resize(o.cap_keys + 1);
+            alnLead.resize(o.cap_alns + 1);
+            alnTrail.resize(o.cap_alns + 1);
+            o.totals = totals;
+            o.aln_off = alnOff.data();
+            o.status = status.data();
+            o.aln_pos = alnPos.data();
+            o.aln_seg_off = alnSegOff.data();
+            o.segs = segs.data();
+            o.aln_key_off = alnKeyOff.data();
+            o.aln_keys = alnKeys.data();
+            o.aln_lead_key = alnLead.data();
+            o.aln_trail_key = alnTrail.data();
+            const int rc(sx_enumerate_alignments(ctx.get(), &b, &o));
+            if (rc == SX_ERR_CAPACITY && attempt == 0)
+            {
+                o.cap_alns = totals[0];
+                o.cap_segs = totals[1];
+                o.cap_keys = totals[2];
+                continue;
+            }
+            ctx.check(rc);
+            break;
+        }
+        for (size_t g(0); g + 1 < regionReadOff.size(); ++g)
+            for (size_t r(regionReadOff[g]); r < regionReadOff[g + 1]; ++r)
+            {
+                ReadResult& res(results[r]);
+                res.originSkip = (status[r] & SX_ENUM_ST_ORIGIN_SKIP) != 0;
+                res.maxToggleDepth = (status[r] & SX_ENUM_ST_MAX_TOGGLE) != 0;
+                res.threw = (status[r] & SX_ENUM_ST_EXCEPTION) != 0;
+                res.overLimit = (status[r] & SX_ENUM_ST_LIMIT) != 0;
+                for (uint32_t a(alnOff[r]); a < alnOff[r + 1]; ++a)
+                {
+                    CandidateAlignment cal;
+                    cal.al.pos = alnPos[a];
+                    cal.al.is_fwd_strand = _fwd[r];
+                    for (uint32_t s(alnSegOff[a]); s < alnSegOff[a + 1]; ++s) cal.al.path.push_back(path_segment(static_cast<ALIGNPATH::align_t>(segs[s].kind), segs[s].len));
+                    for (uint32_t k(alnKeyOff[a]); k < alnKeyOff[a + 1]; ++k) cal.indels.push_back(_keyObjects[regionKeyOff[g] + alnKeys[k]]);
+                    if (alnLead[a] != SX_NO_KEY) cal.leading_indel_key = _keyObjects[regionKeyOff[g] + alnLead[a]];
+                    if (alnTrail[a] != SX_NO_KEY) cal.trailing_indel_key = _keyObjects[regionKeyOff[g] + alnTrail[a]];
+                    res.alignments.push_back(cal);
+                }
+            }
+    }
+
+private:
+    static void require(bool ok, const char* what)
+    {
+        if (!ok) throw Exception(SX_ERR_ARG, std::string("AlignmentSearchBatch: ") + what);
+    }
+    /// window index of `key` in the open region; absent: SX_NO_KEY, or (must = true) the reference's exception
+    uint16_t indexOf(const IndelKey& key, bool must) const
+    {
+        size_t lo(_regionKeyOff.back()), hi(_keyObjects.size());
+        const size_t k0(lo);
+        while (lo < hi)
+        {
+            const size_t mid((lo + hi) / 2);
+            if (_keyObjects[mid] < key) lo = mid + 1;
+            else hi = mid;
+        }
+        if (lo < _keyObjects.size() && _keyObjects[lo] == key) return static_cast<uint16_t>(lo - k0);
+        if (must) throw Exception(SX_ERR_ARG, "Exemplar alignment contains indel not found in the overlap indel set"); // starling_read_align.cpp:1875
+        return SX_NO_KEY;
+    }
+
+    bool _open = false, _anyHap = false;
+    std::string _ref;
+    pos_t _refBegin = 0;
+    std::vector<uint32_t> _regionReadOff, _regionKeyOff, _inSegOff, _inKeyOff, _useKeyOff;
+    std::vector<int32_t> _realignBegin, _realignEnd, _inPos;
+    std::vector<sx_indel_key> _keys;
+    std::vector<sx_key_hap> _hap;
+    std::vector<IndelKey> _keyObjects;
+    std::vector<sx_aln_seg> _inSegs;
+    std::vector<uint16_t> _inKeys, _useKeys, _lead, _trail, _readLen;
+    std::vector<bool> _fwd;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
 // K3: GlobalAligner
 // ---------------------------------------------------------------------------------------------------------------------------
 template <typename ScoreType> struct AlignmentScores // alignment/AlignmentScores.hh:24-53

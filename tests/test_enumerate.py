@@ -179,3 +179,19 @@ def test_host_builder_restates_getAlignmentIndels():
     assert keys == want and lead == A.SX_NO_KEY and trail == A.SX_NO_KEY
     with pytest.raises(KeyError):  # an indel of the alignment that the window does not hold: the reference throws (:1875)
         B.alignment_indels(B.EnumReadSpec("ACGTAAACGT", 100, [("M", 4), ("I", 2), ("M", 4)]), ref, rb, win)
+
+
+def test_cpp_host_mirror_builder_on_the_cpu(tmp_path):
+    """sx::AlignmentSearchBatch (strelka_b200/host/strelka_b200.hh): reference-shaped objects in, CandidateAlignments out, against
+    the candidate alignments the reference returned (tests/golden/k7_cases.tsv).  Without a GPU the library call in the middle is
+    answered by the device body compiled for the host (tests/cpp/test_k7_mirror_cpu.cpp); tests/test_gpu_parity.py::
+    test_cpp_host_mirror runs the same check through libstrelka_b200.so."""
+    import subprocess
+
+    root = os.path.dirname(HERE)
+    exe = str(tmp_path / "test_k7_mirror_cpu")
+    lib = os.path.join(root, "strelka_b200", "csrc")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "strelka_b200", "host"), "-I" + lib,
+                           os.path.join(HERE, "cpp", "test_k7_mirror_cpu.cpp"), "-o", exe, "-L" + lib, "-lstrelka_b200", "-Wl,-rpath," + lib])
+    out = subprocess.run([exe, os.path.join(HERE, "golden")], capture_output=True, text=True)
+    assert out.returncode == 0 and "0 failures" in out.stdout, out.stdout + out.stderr
