@@ -330,6 +330,120 @@ def k6_score_indels_leg(ctx, synth, peak_gbs: float, n_loci: int, depth: int, re
     return leg
 
 
+def make_enum_workload(n_loci: int, depth: int, read_len: int, seed: int) -> B.EnumBatch:
+    """The K7 view of cfg2-shaped loci: per candidate locus a window of three candidate alleles around the locus centre (a deletion
+    and an insertion at the same position and a second deletion one base on: overlapping alleles, as alternatives at one locus are),
+    `depth` reads that cover it, each with the mapper's plain `read_len`M alignment -- the enumerator finds the alignments that carry
+    the alleles.  Built with numpy (no per-read Python)."""
+    rng = np.random.default_rng(seed)
+    span = 1000
+    ref_begin = (np.arange(n_loci, dtype=np.int64) * span + 1000).astype(np.int32)
+    centre = ref_begin + 400
+    geo = lambda n: np.minimum(rng.geometric(0.4, n), 20).astype(np.uint16)  # noqa: E731  (SURVEY 8d: indel lengths Geom(0.4) capped at 20)
+    d0, i1, d2 = geo(n_loci), geo(n_loci), geo(n_loci)
+    keys = np.zeros(3 * n_loci + 1, dtype=A.INDEL_KEY_DT)
+    k = keys[: 3 * n_loci].reshape(n_loci, 3)
+    k["pos"][:, 0], k["pos"][:, 1], k["pos"][:, 2] = centre, centre, centre + 1
+    k["del_len"][:, 0], k["del_len"][:, 2] = d0, d2
+    k["ins_len"][:, 1] = i1
+    k["ins_id"][:, 1] = 1
+    k["type"], k["flags"] = A.SX_INDEL_TYPE_INDEL, A.SX_IKF_CANDIDATE
+    n_reads = n_loci * depth
+    start = (np.repeat(centre, depth) - rng.integers(10, read_len - 10, n_reads)).astype(np.int32)
+    eb = B.EnumBatch.__new__(B.EnumBatch)
+    eb.opts = A.default_enum_opts()
+    eb.n_regions, eb.n_reads, eb.n_keys = n_loci, n_reads, 3 * n_loci
+    u32 = lambda a: np.ascontiguousarray(a, dtype=np.uint32)  # noqa: E731
+    eb.region_read_off, eb.region_key_off = u32(np.arange(n_loci + 1, dtype=np.int64) * depth), u32(np.arange(n_loci + 1, dtype=np.int64) * 3)
+    eb.keys, eb.key_hap, eb.has_hap = keys, np.zeros(1, dtype=A.KEY_HAP_DT), False
+    eb.realign_begin, eb.realign_end = ref_begin.copy(), (ref_begin + span - 100).astype(np.int32)
+    eb.in_pos = np.concatenate([start, [0]]).astype(np.int32)
+    eb.in_seg_off = u32(np.arange(n_reads + 1, dtype=np.int64))
+    eb.in_segs = np.zeros(n_reads + 4, dtype=A.ALN_SEG_DT)
+    eb.in_segs["len"][:n_reads], eb.in_segs["kind"][:n_reads] = read_len, A.SX_AP_MATCH
+    eb.in_key_off = eb.use_key_off = np.zeros(n_reads + 1, np.uint32)
+    eb.in_keys = eb.use_keys = np.zeros(4, np.uint16)
+    eb.in_lead_key = eb.in_trail_key = np.full(n_reads + 1, A.SX_NO_KEY, np.uint16)
+    eb.read_len = np.full(n_reads + 1, read_len, np.uint16)
+    # what the reference harness needs to rebuild its objects: all-'A' reference and reads (no mismatch entries in these windows, so
+    # the bases never matter), insert sequences of 'C'
+    eb.ins_off = np.zeros(3 * n_loci + 1, np.uint32)
+    eb.ins_off[1:] = np.cumsum(keys["ins_len"][: 3 * n_loci])
+    eb.ins_pool = np.full(int(eb.ins_off[-1]) + 1, ord("C"), np.uint8)
+    eb.ref_pool = np.full(n_loci * span + 1, ord("A"), np.uint8)
+    eb.ref_off, eb.ref_begin = u32(np.arange(n_loci + 1, dtype=np.int64) * span), np.concatenate([ref_begin, [0]]).astype(np.int32)
+    eb.read_pool = np.full(n_reads * read_len + 1, ord("A"), np.uint8)
+    eb.read_off = u32(np.arange(n_reads + 1, dtype=np.int64) * read_len)
+    eb.c = A.SxEnumBatch(eb.n_regions, eb.n_reads, eb.n_keys, A.ptr(eb.region_read_off), A.ptr(eb.region_key_off), A.ptr(eb.keys), None, A.ptr(eb.realign_begin),
+                         A.ptr(eb.realign_end), A.ptr(eb.in_pos), A.ptr(eb.in_seg_off), A.ptr(eb.in_segs), A.ptr(eb.in_key_off), A.ptr(eb.in_keys), A.ptr(eb.use_key_off),
+                         A.ptr(eb.use_keys), A.ptr(eb.in_lead_key), A.ptr(eb.in_trail_key), A.ptr(eb.read_len), eb.opts)
+    return eb
+
+
+def enum_subbatch(eb: B.EnumBatch, m: int) -> A.SxEnumBatch:
+    """the first m regions of eb as an sx_enum_batch (the CSR arrays are prefixes)."""
+    return A.SxEnumBatch(m, int(eb.region_read_off[m]), int(eb.region_key_off[m]), *[getattr(eb.c, f) for f, _ in A.SxEnumBatch._fields_[3:-1]], eb.opts)
+
+
+def k7_enumerate_leg(ctx, peak_gbs: float, n_loci: int = 200_000, depth: int = 30, read_len: int = 150, seed: int = 7, reps: int = 3, cpu_regions: int = 400):
+    """SURVEY 8a row a3 / 8f3 measured beside the headline step (not part of `value`): K7 enumerate_alignments on cfg2-shaped loci,
+    inputs and the CSR it writes resident in HBM.  CPU figure: the reference's own getCandidateAlignments on one host thread over the
+    first `cpu_regions` regions (the oracle port where the reference library is absent)."""
+    from strelka_b200.api import DevEnumBatch
+
+    eb = make_enum_workload(n_loci, depth, read_len, seed)
+    db = DevEnumBatch(ctx, eb, cap_alns=eb.n_reads * 16, cap_segs=eb.n_reads * 64, cap_keys=eb.n_reads * 32)
+    ms = []
+    for i in range(reps + 1):
+        ctx.enumerate_alignments_dev(db)
+        if i >= 1:
+            ms.append(ctx.timing().kernel_ms)
+    totals = db.obufs["totals"].download(np.uint32, 4)
+    status = db.obufs["status"].download(np.uint8, eb.n_reads)
+    nA, nS, nK = (int(x) for x in totals[:3])
+    t = float(np.mean(ms)) * 1e-3
+    alg = eb.algorithmic_bytes(nA, nS, nK)
+    leg = {"what": f"K7 enumerate_alignments: {n_loci} cfg2-shaped loci ({eb.n_reads} reads, 3 overlapping candidate alleles each) -> {nA} candidate alignments, resident in HBM",
+           "ms": 1e3 * t, "reads_per_s": eb.n_reads / t, "loci_per_s": n_loci / t, "alignments_per_s": nA / t, "alignments": nA,
+           "reads_flagged": {"max_toggle": int((status & A.SX_ENUM_ST_MAX_TOGGLE != 0).sum()), "exception": int((status & A.SX_ENUM_ST_EXCEPTION != 0).sum()),
+                             "limit": int((status & A.SX_ENUM_ST_LIMIT != 0).sum())},
+           "roofline": {"bound": "hbm", "achieved": alg / t / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": alg / t / 1e9 / peak_gbs, "algorithmic_bytes": int(alg)}}
+    # parity spot check inside the leg: the first regions against the CPU checker, alignment by alignment
+    m = min(cpu_regions, eb.n_regions)
+    sub = enum_subbatch(eb, m)
+    n_reads_m = int(eb.region_read_off[m])
+    host = B.EnumOut(eb, cap_alns=n_reads_m * 64 + 64)
+    p = os.path.join(ROOT, "oracle", "_ref", "libstrelka_ref.so")
+    err = C.create_string_buffer(512)
+    kind = "port"
+    t0 = time.perf_counter()
+    if os.path.exists(p) and hasattr(C.CDLL(p), "ref_enumerate_alignments"):
+        fn = C.CDLL(p).ref_enumerate_alignments
+        fn.argtypes = [C.POINTER(A.SxEnumBatch)] + [C.c_void_p] * 7 + [C.POINTER(A.SxEnumOut), C.c_char_p, C.c_int]
+        rc = fn(C.byref(sub), A.ptr(eb.ins_pool), A.ptr(eb.ins_off), A.ptr(eb.ref_pool), A.ptr(eb.ref_off), A.ptr(eb.ref_begin), A.ptr(eb.read_pool), A.ptr(eb.read_off),
+                C.byref(host.c), err, 512)
+        kind = "reference"
+    else:
+        ox = C.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+        ox.ox_enumerate_alignments.argtypes = [C.POINTER(A.SxEnumBatch), C.POINTER(A.SxEnumOut), C.c_int]
+        rc = ox.ox_enumerate_alignments(C.byref(sub), C.byref(host.c), 0)
+    dt_cpu = time.perf_counter() - t0
+    if rc == 0:
+        n_m = int(host.totals[0])
+        got_off = db.obufs["aln_off"].download(np.uint32, n_reads_m + 1)
+        got_pos = db.obufs["aln_pos"].download(np.int32, n_m)
+        same = bool(np.array_equal(got_off, host.aln_off[: n_reads_m + 1]) and np.array_equal(got_pos, host.aln_pos[:n_m]))
+        leg["cpu_reference"] = {"reads_per_s": n_reads_m / dt_cpu, "cores": 1, "kind": kind, "matches_gpu": same,
+                                "sample": f"first {m} regions ({n_reads_m} reads, {n_m} alignments) through "
+                                          + ("the reference's getCandidateAlignments (incl. the shim's object construction)" if kind == "reference"
+                                             else "oracle/enumerate_oracle.cpp")}
+    else:
+        leg["cpu_reference"] = {"error": err.value.decode(errors="replace") or f"rc {rc}"}
+    for d in list(db.bufs.values()) + list(db.obufs.values()):
+        d.free()
+    return leg
+
+
 def workload_cells(ab: B.AlignBatch, gb: B.GaBatch) -> int:
     return ab.cells() + gb.cells()
 
@@ -665,6 +779,10 @@ def main():
                 line["k4_pileup"] = k4_pileup_leg(ctx, peak)
                 ctx.score_alignments_dev(dab)  # the scores K6 consumes: K1's own output buffer, never copied out
                 line["k6_score_indels"] = k6_score_indels_leg(ctx, synth, peak, n_loci, depth, read_len, n_haps, args.seed + 1000 * rank, threads, rpr, dab.out)
+                try:  # the youngest leg must never take the headline line down with it
+                    line["k7_enumerate"] = k7_enumerate_leg(ctx, peak, depth=min(depth, 30), read_len=read_len)
+                except Exception as e:  # noqa: BLE001
+                    line["k7_enumerate"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

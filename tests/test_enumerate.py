@@ -195,3 +195,26 @@ def test_cpp_host_mirror_builder_on_the_cpu(tmp_path):
                            os.path.join(HERE, "cpp", "test_k7_mirror_cpu.cpp"), "-o", exe, "-L" + lib, "-lstrelka_b200", "-Wl,-rpath," + lib])
     out = subprocess.run([exe, os.path.join(HERE, "golden")], capture_output=True, text=True)
     assert out.returncode == 0 and "0 failures" in out.stdout, out.stdout + out.stderr
+
+
+def test_bench_workload_of_the_k7_leg():
+    """bench.py's k7_enumerate leg: its numpy-built cfg2-shaped workload is a valid K7 batch, the device body and the oracle agree on
+    it, and (where the reference library is built) both agree with the reference's getCandidateAlignments -- which is also how the
+    leg itself spot-checks the GPU result."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(HERE))
+    import bench
+
+    eb = bench.make_enum_workload(300, 30, 150, 7)
+    cap = eb.n_reads * 64 + 64
+    want = reflib.ox_enumerate_alignments(eb, cap_alns=cap)
+    rc, got = reflib.k7core_enumerate(eb, cap_alns=cap)
+    assert rc == 0 and want.rc == 0
+    _same(want, got)
+    assert int(want.totals[0]) > 5 * eb.n_reads and not want.status[: eb.n_reads].any()
+    assert eb.algorithmic_bytes(*[int(x) for x in want.totals[:3]]) > 200 * eb.n_reads
+    if reflib.have_ref():
+        _same(reflib.ref_enumerate_alignments(eb, cap_alns=cap), want)
+        sub = bench.enum_subbatch(eb, 100)
+        assert sub.n_regions == 100 and sub.n_reads == 3000 and sub.n_keys == 300
