@@ -556,8 +556,8 @@ int sx_score_indels_dev(sx_ctx* ctx, const sx_score_indels_batch* batch_dev, con
  *   replaces  getCandidateAlignments           starling_common/starling_read_align.cpp:1816-1994
  *   with      candidate_alignment_search       :857-1277  (the recursive toggle search)
  *             make_start_pos_alignment         :393-584,  get_end_pin_start_pos :593-719
- *             add_indels_in_range              :322-375,  sort_remove_only_indels_last :724-749
- *             addKeysToCandidateAlignment      :786-804,  HaplotypeStatus / getCurIndelHaplotypeIds :56-179, :807-849
+ *             add_indels_in_range              :311-375,  sort_remove_only_indels_last :724-749
+ *             addKeysToCandidateAlignment      :789-804,  HaplotypeStatus / getCurIndelHaplotypeIds :56-179, :811-849
  *   and the container semantics around them: std::set<CandidateAlignment> (CandidateAlignment.hh:38-49,
  *   alignment.hh:73-91, align_path.hh:184-196), IndelBuffer::rangeIterator (IndelBuffer.cpp:76-91),
  *   is_range_{intersect,adjacent}_indel_breakpoints (indel_util.cpp:49-76), is_indel_conflict (:29-45),
@@ -566,9 +566,9 @@ int sx_score_indels_dev(sx_ctx* ctx, const sx_score_indels_batch* batch_dev, con
  * Input, per region (the reads buffered around one realignment window): the IndelBuffer window in IndelKey order (the
  * sx_indel_key table K6 reads, plus what the search consults of IndelData: SX_IKF_NOT_DISCOVERED / SX_IKF_FORCED_OUTPUT and the
  * optional sx_key_hap rows); per read the NORMALIZED input alignment realignAndScoreRead hands to getCandidateAlignments
- * (:2034-2045: edge indels matchified, soft clips matchified), the window entries that alignment already contains
+ * (:2049-2057: edge indels matchified, soft clips matchified), the window entries that alignment already contains
  * (getAlignmentIndels(..., includeMismatches = true), CandidateAlignment.cpp:58-173, mapped to window indices by the host, which
- * holds the read bases and the reference) and the non-candidate entries this read is an observation of (is_usable_indel :271-287).
+ * holds the read bases and the reference) and the non-candidate entries this read is an observation of (is_usable_indel :289-305).
  * Output, per read: the std::set<CandidateAlignment> in ITS iteration order -- which is K1's and K6's alignment order -- as CSR
  * arrays shaped like sx_score_indels_batch's (aln_pos / path segments / cal.getIndels() as window indices) + the leading / trailing
  * edge keys + the warn flags that make is_incomplete_search.
@@ -590,9 +590,9 @@ typedef struct sx_key_hap { /* the active-region phasing data of one window entr
     uint8_t pad[3];
 } sx_key_hap;
 
-#define SX_ENUM_ST_ORIGIN_SKIP 0x01u /* mca_warnings::origin_skip  (:1243)                                      */
-#define SX_ENUM_ST_MAX_TOGGLE 0x02u  /* mca_warnings::max_toggle_depth (:975, :1145); either => is_incomplete_search (:2104) */
-#define SX_ENUM_ST_EXCEPTION 0x04u   /* the reference throws blt_exception for this read (:450, :486, :539, :654, :678, :703, :1875);
+#define SX_ENUM_ST_ORIGIN_SKIP 0x01u /* mca_warnings::origin_skip  (:1248)                                      */
+#define SX_ENUM_ST_MAX_TOGGLE 0x02u  /* mca_warnings::max_toggle_depth (:971, :1135); either => is_incomplete_search (:2100) */
+#define SX_ENUM_ST_EXCEPTION 0x04u   /* the reference throws blt_exception for this read (:446, :493, :572, :658, :676, :709, :1872);
                                         no alignments are returned for it */
 #define SX_ENUM_ST_LIMIT 0x08u       /* more indels / alignments / segments than this build's per-read scratch holds; no alignments are
                                         returned and the caller runs the read through its own getCandidateAlignments */
@@ -618,12 +618,12 @@ typedef struct sx_enum_batch {
     const sx_key_hap* key_hap;         /* [n_keys] or NULL: no entry lies in an active region */
     const int32_t* realign_begin;      /* [n_regions] realign_buffer_range (starling_pos_processor_base.cpp:735) */
     const int32_t* realign_end;        /* [n_regions] */
-    const int32_t* in_pos;             /* [n_reads] normalizedInputAlignment.pos (>= 0, :2047) */
+    const int32_t* in_pos;             /* [n_reads] normalizedInputAlignment.pos (>= 0, :2062) */
     const uint32_t* in_seg_off;        /* [n_reads + 1] */
     const sx_aln_seg* in_segs;         /* normalizedInputAlignment.path, kind = SX_AP_* */
     const uint32_t* in_key_off;        /* [n_reads + 1] */
     const uint16_t* in_keys;           /* window indices of getAlignmentIndels(cal, ref, rseg, maxIndelSize, true), ascending; mismatches
-                                          that are not window entries are dropped (:1869), as the reference does */
+                                          that are not window entries are dropped (:1865), as the reference does */
     const uint32_t* use_key_off;       /* [n_reads + 1] */
     const uint16_t* use_keys;          /* window indices of the entries whose tier1/tier2/submap/noise read-id sets hold this read */
     const uint16_t* in_lead_key;       /* [n_reads] leading_indel_key of getCandidateAlignment (:1481-1522) as window index, or SX_NO_KEY */

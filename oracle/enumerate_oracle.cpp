@@ -3,8 +3,8 @@
 //   getCandidateAlignments          starling_common/starling_read_align.cpp:1816-1994
 //   candidate_alignment_search      :857-1277
 //   make_start_pos_alignment        :393-584      get_end_pin_start_pos   :593-719
-//   add_indels_in_range             :322-375      sort_remove_only_indels_last :724-749
-//   addKeysToCandidateAlignment     :786-804      getCurIndelHaplotypeIds :807-849
+//   add_indels_in_range             :311-375      sort_remove_only_indels_last :724-749
+//   addKeysToCandidateAlignment     :789-804      getCurIndelHaplotypeIds :811-849
 //   HaplotypeStatus                 :56-179
 // Unlike the device body (strelka_b200/csrc/k7_core.cuh: explicit frame stack, bit masks, sorted index array) this restatement
 // keeps the reference's own shape -- a recursion whose arguments are ordered containers passed by value, results collected in a
@@ -169,7 +169,7 @@ bool bpAdjacent(int b, int e, const sx_indel_key& k)
     return rightPos(k) != k.pos && closedAdjacent(b, e, rightPos(k));
 }
 
-// :322-375 over IndelBuffer::rangeIterator (IndelBuffer.cpp:76-91)
+// :311-375 over IndelBuffer::rangeIterator (IndelBuffer.cpp:76-91)
 void addIndelsInRange(const Ctx& C, int b, int e, StatusMap& status, std::vector<Key>& order)
 {
     unsigned k(0);
@@ -444,7 +444,7 @@ void search(const Ctx& C, unsigned read_length, std::set<Cal>& out, Warn& warn, 
     }
     const bool curUndiscovered((cur.flags & SX_IKF_NOT_DISCOVERED) != 0);
     std::vector<int> ids(nSamples, 0);
-    if (inAr) // :807-849
+    if (inAr) // :811-849
         for (unsigned s = 0; s < nSamples; ++s)
         {
             int id(C.hap[curKey].haplotype_id[s]);

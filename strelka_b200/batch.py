@@ -724,7 +724,7 @@ _COMPLEMENT_FREE_CODES = {"A": 1, "C": 2, "G": 4, "T": 8}
 def alignment_indels(read: EnumReadSpec, ref: str, ref_begin: int, win: Sequence[WindowKeySpec], max_indel_size: int = 49):
     """Host side of K7's input: getAlignmentIndels(cal, ref, rseg, maxIndelSize, includeMismatches=true) (CandidateAlignment.cpp:58-173)
     and the edge keys of getCandidateAlignment (starling_read_align.cpp:1481-1522), as window indices.  Returns (in_keys, lead, trail).
-    Raises KeyError for an indel of the alignment that is not a window entry (the reference throws, starling_read_align.cpp:1875)."""
+    Raises KeyError for an indel of the alignment that is not a window entry (the reference throws, starling_read_align.cpp:1866-1872)."""
     index_of = {k.order(): i for i, k in enumerate(win)}
     path = read.path
     match_idx = [i for i, (t, _l) in enumerate(path) if t in "M=X"]
@@ -773,7 +773,7 @@ def alignment_indels(read: EnumReadSpec, ref: str, ref_begin: int, win: Sequence
                     if base == rb:
                         continue
                     w = index_of.get(WindowKeySpec(rp, 1, base, mismatch=True).order())
-                    if w is not None:  # a mismatch that is no window entry is dropped (starling_read_align.cpp:1869)
+                    if w is not None:  # a mismatch that is no window entry is dropped (starling_read_align.cpp:1865)
                         keys.add(w)
         for s in range(i, j):
             st, sl = path[s]

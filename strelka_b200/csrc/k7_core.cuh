@@ -4,8 +4,8 @@
 // (starling_common/starling_read_align.cpp:857-878: indel_status_map, haplotypeStatusMap, indel_order, read_range, cal) and
 // collects the results in a std::set<CandidateAlignment>.  Read closely, the containers are append-only along a search path:
 //   * indel_order and indel_status_map always hold the same keys (every insertion into one is an insertion into the other:
-//     add_indels_in_range :359-367, getCandidateAlignments :1899-1910); sort_remove_only_indels_last only permutes the entries
-//     appended in the same call (:910, `current_depth` = the size before the call), so once a key has a position in indel_order it
+//     add_indels_in_range :359-367, getCandidateAlignments :1895-1908); sort_remove_only_indels_last only permutes the entries
+//     appended in the same call (:920, `current_depth` = the size before the call), so once a key has a position in indel_order it
 //     keeps it for the whole subtree.  Hence ONE shared order[] array used as a stack (a child appends, the parent truncates) and
 //     per-frame 64-bit masks indexed by that position for is_present / is_remove_only.
 //   * the IndelBuffer window of the region is in IndelKey order, so "iterate the map" = ascending window index and IndelKey
@@ -117,7 +117,7 @@ struct k7_read // what the search reads of one read and its region
     const uint16_t* use_keys;
     uint32_t n_use;
     int32_t realign_begin, realign_end;
-    uint32_t read_length; // cal_read_length (:1939-1960)
+    uint32_t read_length; // cal_read_length (:1933-1953)
     uint32_t hc_lead, hc_trail, sc_lead, sc_trail;
     const sx_enum_opts* opt;
 };
@@ -261,9 +261,9 @@ K7_HDN uint32_t k7_make_start_pos(const sx_indel_key* win, const int32_t ref_sta
         const bool first(cal.n_seg == 0);
         if (is_leading_read && first)
         {
-            if (ik.pos != ref_start) return SX_ENUM_ST_EXCEPTION;                 // :450 "Anomalous condition for indel candidate"
-            if (ik.ins_len == 0) return SX_ENUM_ST_EXCEPTION;                     // assert :473 (breakends are not sent)
-            if ((int32_t)ik.ins_len < read_start) return SX_ENUM_ST_EXCEPTION;    // assert :478
+            if (ik.pos != ref_start) return SX_ENUM_ST_EXCEPTION;                 // :440-458 "Anomalous condition for indel candidate"
+            if (ik.ins_len == 0) return SX_ENUM_ST_EXCEPTION;                     // assert :461 (breakends are not sent)
+            if ((int32_t)ik.ins_len < read_start) return SX_ENUM_ST_EXCEPTION;    // assert :466
             if (!k7_push_seg(cal, SX_AP_INSERT, (uint32_t)read_start)) return SX_ENUM_ST_LIMIT;
             if (ik.del_len > 0)
             {
@@ -274,14 +274,14 @@ K7_HDN uint32_t k7_make_start_pos(const sx_indel_key* win, const int32_t ref_sta
             prev_mismatch = mismatch;
             continue;
         }
-        if (first && read_start != 0) return SX_ENUM_ST_EXCEPTION; // assert :493
+        if (first && read_start != 0) return SX_ENUM_ST_EXCEPTION; // assert :480
         const bool is_edge_delete(k7_prim_del(ik) && ik.pos == ref_start);
         const int32_t matchSegmentSize(ik.pos - ref_head);
         const int32_t minMatchSegmentSize((prev_mismatch || mismatch) ? 0 : 1);
-        if (matchSegmentSize < minMatchSegmentSize && !is_edge_delete) return SX_ENUM_ST_EXCEPTION; // :504
-        if (ik.pos < ref_head) return SX_ENUM_ST_EXCEPTION;                                         // assert :507
+        if (matchSegmentSize < minMatchSegmentSize && !is_edge_delete) return SX_ENUM_ST_EXCEPTION; // :487-493
+        if (ik.pos < ref_head) return SX_ENUM_ST_EXCEPTION;                                         // assert :495
         const uint32_t match_segment((uint32_t)matchSegmentSize);
-        if (!(first || match_segment > 0 || mismatch || prev_mismatch)) return SX_ENUM_ST_EXCEPTION; // assert :510
+        if (!(first || match_segment > 0 || mismatch || prev_mismatch)) return SX_ENUM_ST_EXCEPTION; // assert :498
         if (((uint32_t)read_head + match_segment > read_length) || (((uint32_t)read_head + match_segment == read_length) && !k7_prim_del(ik))) break;
         if (match_segment > 0)
         {
@@ -321,7 +321,7 @@ K7_HDN uint32_t k7_make_start_pos(const sx_indel_key* win, const int32_t ref_sta
                 else if (read_head == (int32_t)read_length) cal.trail = w;
             }
         }
-        else return SX_ENUM_ST_EXCEPTION; // :572 "Unexpected indel state"
+        else return SX_ENUM_ST_EXCEPTION; // :568-572 "Unexpected indel state"
         prev_mismatch = mismatch;
     }
     if (read_head > (int32_t)read_length) return SX_ENUM_ST_EXCEPTION; // assert :577
@@ -354,16 +354,16 @@ K7_HDN uint32_t k7_end_pin_start_pos(const sx_indel_key* win, const uint16_t* in
         const bool is_trailing_indel(!mismatch && k7_right(ik) == ref_end);
         if (is_trailing_indel)
         {
-            if (!(is_first && ref_start == ref_end)) return SX_ENUM_ST_EXCEPTION; // assert :637
-            if (ik.ins_len > 0 && ik.ins_len < read_length - (uint32_t)read_end) return SX_ENUM_ST_EXCEPTION; // assert :645
+            if (!(is_first && ref_start == ref_end)) return SX_ENUM_ST_EXCEPTION; // assert :636
+            if (ik.ins_len > 0 && ik.ins_len < read_length - (uint32_t)read_end) return SX_ENUM_ST_EXCEPTION; // assert :644
             ref_start -= (int32_t)ik.del_len;
         }
         else
         {
-            if (is_first && read_end != (int32_t)read_length) return SX_ENUM_ST_EXCEPTION; // :654 "Unexpected realignment state"
+            if (is_first && read_end != (int32_t)read_length) return SX_ENUM_ST_EXCEPTION; // :652-658 "Unexpected realignment state"
             const int32_t matchSegmentSize(ref_start - k7_right(ik));
             const int32_t minMatchSegmentSize((prev_mismatch || mismatch) ? 0 : 1);
-            if (matchSegmentSize < minMatchSegmentSize) return SX_ENUM_ST_EXCEPTION; // :678 "Unexpected indel position"
+            if (matchSegmentSize < minMatchSegmentSize) return SX_ENUM_ST_EXCEPTION; // :670-676 "Unexpected indel position"
             const uint32_t match_segment((uint32_t)(matchSegmentSize < read_start ? matchSegmentSize : read_start));
             ref_start -= (int32_t)match_segment;
             read_start -= (int32_t)match_segment;
@@ -383,12 +383,12 @@ K7_HDN uint32_t k7_end_pin_start_pos(const sx_indel_key* win, const uint16_t* in
                     read_start -= (int32_t)ik.ins_len;
                 }
             }
-            else return SX_ENUM_ST_EXCEPTION; // :703
+            else return SX_ENUM_ST_EXCEPTION; // :705-709
         }
         is_first = false;
         prev_mismatch = mismatch;
     }
-    if (read_start < 0) return SX_ENUM_ST_EXCEPTION; // assert :715
+    if (read_start < 0) return SX_ENUM_ST_EXCEPTION; // assert :716
     ref_start -= read_start;
     read_start = 0;
     return 0;
@@ -430,12 +430,12 @@ K7_HD bool k7_add_key(k7_cal& c, const uint16_t w) // std::set<IndelKey>::insert
     return true;
 }
 
-// recursion terminus (:922-928) + the two post-passes of getCandidateAlignments (:1962-1993): keys, clips back on, range filter,
+// recursion terminus (:924-931) + the two post-passes of getCandidateAlignments (:1966-1993): keys, clips back on, range filter,
 // cal_set.insert
 K7_HDN uint32_t k7_emit(const k7_read& R, k7_scratch& S, const k7_frame& f)
 {
     k7_cal& c(S.slots[S.n]); // slots has maxA + 1 entries: the candidate is built in place and kept only if it is new
-    // addKeysToCandidateAlignment, :786-804
+    // addKeysToCandidateAlignment, :789-804
     const int32_t sb(f.cal.pos), se(f.cal.pos + (int32_t)k7_ref_length(f.cal));
     c.n_keys = 0;
     for (uint32_t i = 0; i < f.n; ++i)
@@ -478,7 +478,7 @@ K7_HDN uint32_t k7_emit(const k7_read& R, k7_scratch& S, const k7_frame& f)
     return 0;
 }
 
-K7_HD bool k7_usable(const k7_read& R, const uint16_t w) // is_usable_indel, :271-287
+K7_HD bool k7_usable(const k7_read& R, const uint16_t w) // is_usable_indel, :289-305
 {
     if (R.win[w].flags & SX_IKF_CANDIDATE) return true;
     for (uint32_t i = 0; i < R.n_use; ++i)
@@ -486,7 +486,7 @@ K7_HD bool k7_usable(const k7_read& R, const uint16_t w) // is_usable_indel, :27
     return false;
 }
 
-// add_indels_in_range, :322-375, appending to order[0..n); new entries are never present.  0 or a status bit
+// add_indels_in_range, :311-375, appending to order[0..n); new entries are never present.  0 or a status bit
 K7_HDN uint32_t k7_add_indels_in_range(const k7_read& R, uint16_t* order, uint32_t& n, uint64_t& remove_only, const int32_t b, const int32_t e)
 {
     // IndelBuffer::rangeIterator(b, e), IndelBuffer.cpp:76-91
@@ -631,7 +631,7 @@ K7_HDN uint32_t k7_search(const k7_read& R, k7_scratch& S, const uint64_t inorig
         k7_frame& f(S.frames[sp]);
         if (f.stage == 0)
         {
-            // ---- new indel overlaps, :888-912
+            // ---- new indel overlaps, :888-922
             bool is_new_indels(f.itd == 0);
             uint32_t n(f.n);
             {
@@ -661,7 +661,7 @@ K7_HDN uint32_t k7_search(const k7_read& R, k7_scratch& S, const uint64_t inorig
                 if (is_new_indels) k7_sort_remove_only_last(S.order, start_size, n, f.present, f.remove_only, nullptr);
                 f.n = (uint16_t)n;
             }
-            // ---- recursion terminus, :915-921
+            // ---- recursion terminus, :924-931
             if (f.depth == n)
             {
                 const uint32_t st(k7_emit(R, S, f));
@@ -669,7 +669,7 @@ K7_HDN uint32_t k7_search(const k7_read& R, k7_scratch& S, const uint64_t inorig
                 --sp;
                 continue;
             }
-            // ---- toggle limits, :923-966
+            // ---- toggle limits, :933-974
             if (is_new_indels)
             {
                 const double max_indels(R.read_length * opt.max_candidate_indel_density);
@@ -732,7 +732,7 @@ K7_HDN uint32_t k7_search(const k7_read& R, k7_scratch& S, const uint64_t inorig
         {
             for (arSlot = 0; arSlot < f.n_hap; ++arSlot)
                 if (f.hap[arSlot].id == curAr) break;
-            // getCurIndelHaplotypeIds, :807-849
+            // getCurIndelHaplotypeIds, :811-849
             const bool inOriginal((inorig >> f.depth) & 1);
             for (uint32_t s = 0; s < n_samples; ++s)
             {
@@ -930,7 +930,7 @@ K7_HDN uint32_t k7_enumerate_read_raw(const k7_view& v, const uint32_t region, c
         if (at == n)
         {
             if (mismatch) continue;
-            return SX_ENUM_ST_EXCEPTION; // :1875 "Exemplar alignment contains indel not found in the overlap indel set"
+            return SX_ENUM_ST_EXCEPTION; // :1866-1872 "Exemplar alignment contains indel not found in the overlap indel set"
         }
         if (mismatch) recompute = true;
         present |= (uint64_t)1 << at;
@@ -944,8 +944,8 @@ K7_HDN uint32_t k7_enumerate_read_raw(const k7_view& v, const uint32_t region, c
         if (st) return st;
         k7_copy_path(f.cal, tmp);
     }
-    // indel_order: present entries first, each group in key order (:1897-1910) -- add_indels_in_range appended in key order --
-    // then the non-present remove-only entries last (:1913)
+    // indel_order: present entries first, each group in key order (:1895-1908) -- add_indels_in_range appended in key order --
+    // then the non-present remove-only entries last (:1911)
     {
         uint16_t tmp[K7_MAX_INDELS];
         uint64_t p2(0), r2(0), o2(0);
@@ -967,7 +967,7 @@ K7_HDN uint32_t k7_enumerate_read_raw(const k7_view& v, const uint32_t region, c
         inorig = o2;
         k7_sort_remove_only_last(S.order, 0, n, present, remove_only, &inorig);
     }
-    // clips come off for the search and go back on afterwards, :1939-1960 (apath_clip_clipper, align_path.cpp:464-510)
+    // clips come off for the search and go back on afterwards, :1933-1953 (apath_clip_clipper, align_path.cpp:464-510)
     uint32_t cal_read_length(read_length);
     {
         const uint32_t ns(f.cal.n_seg);
@@ -985,12 +985,12 @@ K7_HDN uint32_t k7_enumerate_read_raw(const k7_view& v, const uint32_t region, c
                 else
                 {
                     is_lead = false;
-                    if (R.hc_trail || R.sc_trail) return SX_ENUM_ST_EXCEPTION; // asserts :504-505
+                    if (R.hc_trail || R.sc_trail) return SX_ENUM_ST_EXCEPTION; // asserts align_path.cpp:504-505
                     f.cal.seg[m++] = sg;
                 }
             }
             f.cal.n_seg = m;
-            if (cal_read_length < R.sc_lead + R.sc_trail) return SX_ENUM_ST_EXCEPTION; // assert :1957
+            if (cal_read_length < R.sc_lead + R.sc_trail) return SX_ENUM_ST_EXCEPTION; // assert :1950
             cal_read_length -= R.sc_lead + R.sc_trail;
         }
     }

@@ -795,7 +795,7 @@ public:
     struct ReadResult
     {
         std::vector<CandidateAlignment> alignments; ///< the std::set<CandidateAlignment>, in its iteration order
-        bool originSkip = false, maxToggleDepth = false; ///< mca_warnings; either one = is_incomplete_search (:2104)
+        bool originSkip = false, maxToggleDepth = false; ///< mca_warnings; either one = is_incomplete_search (:2100)
         bool threw = false;      ///< the reference throws blt_exception for this read
         bool overLimit = false;  ///< outside this build's per-read capacity: run the reference's own getCandidateAlignments on it
     };
@@ -838,9 +838,9 @@ public:
         _open = true;
     }
 
-    /// one read segment: its bases (ASCII), the NORMALIZED input alignment realignAndScoreRead passes on (:2034-2045) and the
-    /// window entries whose tier1 / tier2 / submap / noise read-id sets hold this read (is_usable_indel :271-287).
-    /// Throws what the reference throws when the alignment holds an indel the window lacks (:1875).
+    /// one read segment: its bases (ASCII), the NORMALIZED input alignment realignAndScoreRead passes on (:2049-2057) and the
+    /// window entries whose tier1 / tier2 / submap / noise read-id sets hold this read (is_usable_indel :289-305).
+    /// Throws what the reference throws when the alignment holds an indel the window lacks (:1866-1872).
     unsigned addRead(const std::string& readBases, const alignment& normalizedInputAlignment, const std::vector<IndelKey>& observedKeys, unsigned maxIndelSize = 49)
     {
         using namespace ALIGNPATH;
@@ -902,7 +902,7 @@ public:
                     if (base == refBase) continue;
                     const char ins[2] = {base, 0};
                     const uint16_t w(indexOf(IndelKey(rp, INDEL::MISMATCH, 1, ins), false));
-                    if (w != SX_NO_KEY) keys.push_back(w); // a mismatch that is no window entry is dropped (:1869)
+                    if (w != SX_NO_KEY) keys.push_back(w); // a mismatch that is no window entry is dropped (:1865)
                 }
             }
             for (size_t s(i); s < j; ++s)
@@ -1059,7 +1059,7 @@ private:
             else hi = mid;
         }
         if (lo < _keyObjects.size() && _keyObjects[lo] == key) return static_cast<uint16_t>(lo - k0);
-        if (must) throw Exception(SX_ERR_ARG, "Exemplar alignment contains indel not found in the overlap indel set"); // starling_read_align.cpp:1875
+        if (must) throw Exception(SX_ERR_ARG, "Exemplar alignment contains indel not found in the overlap indel set"); // starling_read_align.cpp:1866-1872
         return SX_NO_KEY;
     }
 

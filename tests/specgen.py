@@ -647,7 +647,7 @@ def random_enum_region(rng: np.random.Generator, n_reads: int = 6, ref_len: int 
         seq = "".join(seq)
         assert len(seq) == rl
         if rng.random() < clip_rate:  # hard clips (not part of read_size()).  Soft clips never reach getCandidateAlignments: its caller
-            # matchifies them first (starling_read_align.cpp:2037-2043), and the reference asserts (:466) on some soft-clipped inputs
+            # matchifies them first (starling_read_align.cpp:2051-2057), and the reference asserts (:466) on some soft-clipped inputs
             if rng.random() < 0.6:
                 path.insert(0, ("H", int(rng.integers(1, 20))))
             if rng.random() < 0.6:

@@ -177,7 +177,7 @@ def test_host_builder_restates_getAlignmentIndels():
     keys, lead, trail = B.alignment_indels(r, ref, rb, win)
     want = sorted([idx[(104, 1, 0, 2, "")], idx[(110, 1, 2, 0, "GG")], idx[(116, 1, 2, 1, "TT")], idx[(102, 2, 1, 1, "A")]])
     assert keys == want and lead == A.SX_NO_KEY and trail == A.SX_NO_KEY
-    with pytest.raises(KeyError):  # an indel of the alignment that the window does not hold: the reference throws (:1875)
+    with pytest.raises(KeyError):  # an indel of the alignment that the window does not hold: the reference throws (:1866-1872)
         B.alignment_indels(B.EnumReadSpec("ACGTAAACGT", 100, [("M", 4), ("I", 2), ("M", 4)]), ref, rb, win)
 
 
