@@ -653,6 +653,40 @@ int sx_enumerate_alignments(sx_ctx* ctx, const sx_enum_batch* batch_host, sx_enu
 int sx_enumerate_alignments_dev(sx_ctx* ctx, const sx_enum_batch* batch_dev, sx_enum_out* out_dev /* device pointers; totals too */);
 
 /* ==========================================================================================
+ * K7b  link_alignments   (K7's output -> K1's alignment description; keeps the chain K7 -> K1 -> K6 in device memory)
+ *   replaces the per-alignment host work in front of K1: the segment walk of scoreCandidateAlignment
+ *   (starling_common/starling_read_align_score.cpp:289-499) with every container look-up resolved --
+ *   getMatchingIndelKey :177-224 (which key of cal.getIndels(), or which edge key, a path gap stands for), the insert
+ *   sequence each inserted segment is scored against incl. the leading-edge tail rule :334-338 / :394-398, and
+ *   IndelBuffer::isCandidateIndel :473-475 (SX_SEGF_NONCANDIDATE) -- i.e. what sx::ReadAlignBatch::addCandidateAlignment
+ *   does for host-built batches.
+ *
+ * Input: the sx_enum_batch K7 read (window keys; reads of a region are consecutive), K7's sx_enum_out and the insert
+ * sequences of the window entries.  Output: the alignment part of an sx_align_batch -- alns[] (read = the K7 read
+ * index, so the caller's read pools must list the reads in K7's order), segs[] (sx_aln_seg; '=' as MATCH, 'X' and swaps
+ * as INSERT + REFSKIP), ins[] -- laid out under K1's staging rule (every region's first segment index a multiple of 8
+ * with no-op HARDCLIP pads, its first insert byte a multiple of 16), and aln_begin / seg_begin / ins_begin of regions[]
+ * (the caller fills the read / quality / reference fields of the same records).  Alignment order is preserved, so
+ * lnp[a] of K1 is the score of K7's alignment a and of K6's alignment a.
+ * ======================================================================================== */
+typedef struct sx_link_out { /* caller-allocated */
+    uint32_t cap_segs, cap_ins;
+    uint32_t* totals;     /* [2] segments and insert-pool bytes produced (written even when a capacity is too small) */
+    sx_region* regions;   /* [n_regions + 1] in/out, incl. the sentinel */
+    sx_aln* alns;         /* [n_alns + 1] n_alns = the enumeration's totals[0] */
+    sx_aln_seg* segs;     /* [cap_segs]; leave 16 entries beyond totals[0] for K1's slack (filled with no-op segments where they fit) */
+    char* ins;            /* [cap_ins + SX_POOL_SLACK] */
+} sx_link_out;
+
+/* key_ins_off[n_keys + 1] / key_ins: the insert sequence of window entry k is key_ins[key_ins_off[k] .. key_ins_off[k+1]).
+ * n_alns: the enumeration's totals[0] (host value).  SX_ERR_CAPACITY: totals[] says what is needed.  A path whose gap matches no
+ * key of its alignment (the reference's assert(isFound), :222) fails the call with SX_ERR_ARG. */
+int sx_link_alignments(sx_ctx* ctx, const sx_enum_batch* batch_host, const sx_enum_out* enum_host, uint32_t n_alns, const uint32_t* key_ins_off_host,
+                       const char* key_ins_host, sx_link_out* out_host);
+int sx_link_alignments_dev(sx_ctx* ctx, const sx_enum_batch* batch_dev, const sx_enum_out* enum_dev, uint32_t n_alns, const uint32_t* key_ins_off_dev,
+                           const char* key_ins_dev, sx_link_out* out_dev);
+
+/* ==========================================================================================
  * Multi-GPU: regions shard across ranks with no data-path collective; one gather of fixed-size
  * call records at the end (the in-memory analogue of concatIndexVcf,
  * src/python/lib/strelkaSharedWorkflow.py:126-136).  The NCCL communicator is created from an

@@ -179,12 +179,12 @@ extern "C" int ref_score_alignments(const char* ref_seq, int ref_len, int ref_of
             for (int i = aln_indel_off[a]; i < aln_indel_off[a + 1]; ++i)
             {
                 const int li(i - aln_indel_off[a]);
-                if (li == aln_leading[a])
-                    cal.leading_indel_key = keys[i];
-                else if (li == aln_trailing[a])
-                    cal.trailing_indel_key = keys[i];
-                else
-                    iset.insert(keys[i]);
+                if (li == aln_leading[a]) cal.leading_indel_key = keys[i];
+                if (li == aln_trailing[a]) cal.trailing_indel_key = keys[i];
+                // cal.getIndels() holds the edge keys too (addKeysToCandidateAlignment, starling_read_align.cpp:801-802) -- and
+                // getMatchingIndelKey may need them for an INTERIOR gap: make_start_pos_alignment labels a deletion that follows a
+                // mismatch segment without a match in between as leading_indel_key (:552-555)
+                iset.insert(keys[i]);
             }
             cal.setIndels(iset);
             const read_segment& rseg(sreads[aln_read[a]]->get_full_segment());

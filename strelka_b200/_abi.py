@@ -245,6 +245,10 @@ class SxEnumOut(C.Structure):
         "totals", "aln_off", "status", "aln_pos", "aln_seg_off", "segs", "aln_key_off", "aln_keys", "aln_lead_key", "aln_trail_key")]
 
 
+class SxLinkOut(C.Structure):
+    _fields_ = [("cap_segs", C.c_uint32), ("cap_ins", C.c_uint32)] + [(n, C.c_void_p) for n in ("totals", "regions", "alns", "segs", "ins")]
+
+
 def default_enum_opts() -> SxEnumOpts:
     """starling_base_options defaults (starling_base_shared.hh:124,139,145,160) through the library's own sx_default_enum_opts."""
     o = SxEnumOpts()
@@ -316,6 +320,8 @@ SYMBOLS = [
     ("sx_default_enum_opts", None, [C.POINTER(SxEnumOpts)]),
     ("sx_enumerate_alignments", C.c_int, [_P, C.POINTER(SxEnumBatch), C.POINTER(SxEnumOut)]),
     ("sx_enumerate_alignments_dev", C.c_int, [_P, C.POINTER(SxEnumBatch), C.POINTER(SxEnumOut)]),
+    ("sx_link_alignments", C.c_int, [_P, C.POINTER(SxEnumBatch), C.POINTER(SxEnumOut), C.c_uint32, _P, _P, C.POINTER(SxLinkOut)]),
+    ("sx_link_alignments_dev", C.c_int, [_P, C.POINTER(SxEnumBatch), C.POINTER(SxEnumOut), C.c_uint32, _P, _P, C.POINTER(SxLinkOut)]),
     ("sx_indel_gl", C.c_int, [_P, C.POINTER(SxIndelBatch), _P]),
     ("sx_indel_gl_dev", C.c_int, [_P, C.POINTER(SxIndelBatch), _P]),
     ("sx_default_pileup_opts", None, [C.POINTER(SxPileupOpts)]),

@@ -101,9 +101,7 @@ def flatten_alignment(cal: CandidateAlignmentSpec) -> Tuple[List[Tuple[int, int,
             if cal.trailing < 0:
                 raise ValueError("trailing edge indel without trailing_indel_key")
             return cal.indels[cal.trailing]
-        for k, key in enumerate(cal.indels):
-            if k in (cal.leading, cal.trailing):
-                continue
+        for key in cal.indels:  # every key of cal.getIndels(), the edge keys included (score.cpp:203-218)
             if key.pos == ref_head_pos and key.type in (INDEL_INDEL, INDEL_MISMATCH) and key.delete_length == dl and len(key.insert_seq) == il:
                 return key
         raise ValueError(f"no indel key matches path segment {path_index} at ref pos {ref_head_pos} (del {dl}, ins {il})")
@@ -905,3 +903,58 @@ class EnumOut:
             out.append((int(self.aln_pos[a]), cig, [int(k) for k in self.aln_keys[int(self.aln_key_off[a]) : int(self.aln_key_off[a + 1])]],
                         int(self.aln_lead_key[a]), int(self.aln_trail_key[a])))
         return out
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# K7b link_alignments: K7's output -> the alignment part of K1's batch
+# ------------------------------------------------------------------------------------------------------------------------------
+class LinkOut:
+    """Host buffers for sx_link_out.  `regions` = the region records of the K1 batch the alignments will join (a copy is taken: the
+    call fills aln_begin / seg_begin / ins_begin)."""
+
+    def __init__(self, regions: np.ndarray, n_alns: int, cap_segs: int, cap_ins: int):
+        self.cap_segs, self.cap_ins, self.n_alns = int(cap_segs), int(cap_ins), int(n_alns)
+        self.totals = np.zeros(2, np.uint32)
+        self.regions = regions.copy()
+        self.alns = np.zeros(n_alns + 1, dtype=A.ALN_DT)
+        self.segs = np.zeros(self.cap_segs + 16, dtype=A.ALN_SEG_DT)
+        self.segs["kind"][:] = A.SX_SEG_HARDCLIP
+        self.ins = np.zeros(self.cap_ins + A.SX_POOL_SLACK + 16, np.uint8)
+        self.c = A.SxLinkOut(self.cap_segs, self.cap_ins, A.ptr(self.totals), A.ptr(self.regions), A.ptr(self.alns), A.ptr(self.segs), A.ptr(self.ins))
+
+    def align_batch(self, reads_of: "AlignBatch") -> "AlignBatch":
+        """the K1 batch made of `reads_of`'s read / quality / reference pools and the linked alignments."""
+        used = dict(reads_of.used)
+        used["ins"] = int(self.totals[1])
+        assert reads_of.fmt == 0 and reads_of.qual_bits in (0, 8), "the linked alignment arrays are in the wide formats"
+        return AlignBatch(self.regions, reads_of.read_len, reads_of.seq4, reads_of.qual, reads_of.ref, self.alns, self.segs, self.ins, used, qual_bits=reads_of.qual_bits,
+                          n_segs=int(self.totals[0]), n_alns=self.n_alns)
+
+
+def regions_from_enumeration(eb: EnumBatch, out: "EnumOut", quals_of=None) -> List[RegionSpec]:
+    """The enumerated alignments as reference-shaped objects (RegionSpec / CandidateAlignmentSpec with IndelKeySpecs): what the host
+    path (build_align_batch, the reference harness ref_score_region) consumes.  quals_of(read index, length) -> qualities."""
+    regions = []
+    for g in range(eb.n_regions):
+        k0 = int(eb.region_key_off[g])
+        ref = bytes(eb.ref_pool[int(eb.ref_off[g]) : int(eb.ref_off[g + 1])]).decode()
+        reads, alns = [], []
+        r0, r1 = int(eb.region_read_off[g]), int(eb.region_read_off[g + 1])
+        for r in range(r0, r1):
+            seq = bytes(eb.read_pool[int(eb.read_off[r]) : int(eb.read_off[r + 1])]).decode()
+            q = quals_of(r, len(seq)) if quals_of else np.full(len(seq), 30, np.uint8)
+            reads.append((codes_of(seq), np.asarray(q, np.uint8)))
+            for a in range(int(out.aln_off[r]), int(out.aln_off[r + 1])):
+                kidx = [int(x) for x in out.aln_keys[int(out.aln_key_off[a]) : int(out.aln_key_off[a + 1])]]
+                keys = []
+                for w in kidx:
+                    k = eb.keys[k0 + w]
+                    ins = bytes(eb.ins_pool[int(eb.ins_off[k0 + w]) : int(eb.ins_off[k0 + w + 1])]).decode()
+                    keys.append(IndelKeySpec(int(k["pos"]), INDEL_MISMATCH if int(k["type"]) == A.SX_INDEL_TYPE_MISMATCH else INDEL_INDEL, int(k["del_len"]), ins,
+                                             bool(int(k["flags"]) & A.SX_IKF_CANDIDATE)))
+                lead, trail = int(out.aln_lead_key[a]), int(out.aln_trail_key[a])
+                path = [(AP_CHAR[int(s["kind"])], int(s["len"])) for s in out.segs[int(out.aln_seg_off[a]) : int(out.aln_seg_off[a + 1])]]
+                alns.append(CandidateAlignmentSpec(r - r0, int(out.aln_pos[a]), path, keys, kidx.index(lead) if lead != A.SX_NO_KEY else -1,
+                                                   kidx.index(trail) if trail != A.SX_NO_KEY else -1))
+        regions.append(RegionSpec(ref, int(eb.ref_begin[g]), reads, alns))
+    return regions

@@ -19,6 +19,7 @@
 
 #include "k7_core.cuh"
 #include "sx_internal.h"
+#include "sx_scan3.cuh"
 
 #include <algorithm>
 
@@ -26,8 +27,6 @@ namespace
 {
 constexpr int K7_THREADS = 64;
 constexpr int K7_ST_SHIFT = 14; // device status bit 16384: an output capacity is too small (reported as SX_ERR_CAPACITY by the host)
-constexpr int K7_SCAN_THREADS = 256;
-constexpr int K7_SCAN_ITEMS = 8; // reads per thread of the scan kernels
 
 struct k7_counts // per read, then (after the scan) its exclusive offsets
 {
@@ -58,80 +57,6 @@ __global__ void k7_read_region_kernel(const uint32_t n_regions, const uint32_t* 
 {
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_regions; g += gridDim.x * blockDim.x)
         for (uint32_t r = region_read_off[g]; r < region_read_off[g + 1]; ++r) read_region[r] = g;
-}
-
-// exclusive scan of three arrays at once, tile = K7_SCAN_THREADS * K7_SCAN_ITEMS reads per block.
-// phase 0: in-tile exclusive scan in place, tile totals to sums[3][n_tiles]; phase 1 (one block): exclusive scan of the tile totals in
-// place, grand totals to totals[3]; phase 2: add the tile offset.
-__global__ void __launch_bounds__(K7_SCAN_THREADS) k7_scan_tiles(const uint32_t n, uint32_t* a0, uint32_t* a1, uint32_t* a2, uint32_t* sums, const uint32_t n_tiles)
-{
-    __shared__ uint32_t warp_sum[3][K7_SCAN_THREADS / 32];
-    uint32_t* arr[3] = {a0, a1, a2};
-    const uint32_t base(blockIdx.x * K7_SCAN_THREADS * K7_SCAN_ITEMS + threadIdx.x * K7_SCAN_ITEMS);
-    const uint32_t lane(threadIdx.x & 31), warp(threadIdx.x >> 5);
-    for (int q = 0; q < 3; ++q)
-    {
-        uint32_t vals[K7_SCAN_ITEMS];
-        uint32_t sum(0);
-        for (int i = 0; i < K7_SCAN_ITEMS; ++i)
-        {
-            vals[i] = (base + i < n) ? arr[q][base + i] : 0u;
-            sum += vals[i];
-        }
-        uint32_t incl(sum);
-        for (int d = 1; d < 32; d <<= 1)
-        {
-            const uint32_t y(__shfl_up_sync(0xffffffffu, incl, d));
-            if ((int)lane >= d) incl += y;
-        }
-        if (lane == 31) warp_sum[q][warp] = incl;
-        __syncthreads();
-        uint32_t warp_off(0);
-        for (uint32_t w = 0; w < warp; ++w) warp_off += warp_sum[q][w];
-        uint32_t run(warp_off + incl - sum);
-        for (int i = 0; i < K7_SCAN_ITEMS; ++i)
-        {
-            if (base + i < n) arr[q][base + i] = run;
-            run += vals[i];
-        }
-        if (threadIdx.x == K7_SCAN_THREADS - 1) sums[(size_t)q * n_tiles + blockIdx.x] = run;
-    }
-}
-
-__global__ void __launch_bounds__(K7_SCAN_THREADS) k7_scan_sums(uint32_t* sums, const uint32_t n_tiles, uint32_t* __restrict__ totals)
-{
-    // a single block walks the tile totals in chunks of blockDim.x, carrying the running sum
-    __shared__ uint32_t warp_sum[K7_SCAN_THREADS / 32];
-    __shared__ uint32_t carry;
-    const uint32_t lane(threadIdx.x & 31), warp(threadIdx.x >> 5);
-    for (int q = 0; q < 3; ++q)
-    {
-        uint32_t* s(sums + (size_t)q * n_tiles);
-        if (threadIdx.x == 0) carry = 0;
-        __syncthreads();
-        for (uint32_t b0 = 0; b0 < n_tiles; b0 += K7_SCAN_THREADS)
-        {
-            const uint32_t i(b0 + threadIdx.x);
-            const uint32_t x(i < n_tiles ? s[i] : 0u);
-            uint32_t incl(x);
-            for (int d = 1; d < 32; d <<= 1)
-            {
-                const uint32_t y(__shfl_up_sync(0xffffffffu, incl, d));
-                if ((int)lane >= d) incl += y;
-            }
-            if (lane == 31) warp_sum[warp] = incl;
-            __syncthreads();
-            uint32_t warp_off(0);
-            for (uint32_t w = 0; w < warp; ++w) warp_off += warp_sum[w];
-            const uint32_t c(carry);
-            if (i < n_tiles) s[i] = c + warp_off + incl - x;
-            __syncthreads();
-            if (threadIdx.x == K7_SCAN_THREADS - 1) carry = c + warp_off + incl;
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) totals[q] = carry;
-        __syncthreads();
-    }
 }
 
 // phase 2 of the scan + the batch-wide closing entries; flags the capacity overflow

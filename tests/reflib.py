@@ -315,3 +315,24 @@ def ox_enumerate_alignments(eb: "B.EnumBatch", cap_alns=None, cap_segs=None, cap
     out.rc = lib.ox_enumerate_alignments(C.byref(eb.c), C.byref(out.c), 1 if limits else 0)
     assert out.rc in (0, A.SX_ERR_CAPACITY), out.rc
     return out
+
+
+_k8core = None
+
+
+def k8core_link(eb: "B.EnumBatch", out: "B.EnumOut", regions: np.ndarray, cap_segs=None, cap_ins=None):
+    """strelka_b200/csrc/k8_core.cuh compiled for the host (tests/cpp/k8_core_host.cpp): K7b's device body on the CPU.  (rc, LinkOut)"""
+    global _k8core
+    if _k8core is None:
+        import tempfile
+
+        so = os.path.join(tempfile.mkdtemp(prefix="k8core"), "libk8core.so")
+        subprocess.check_call(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "strelka_b200", "csrc"),
+                               os.path.join(ROOT, "tests", "cpp", "k8_core_host.cpp"), "-o", so])
+        _k8core = C.CDLL(so)
+        _k8core.k8core_run.argtypes = [C.POINTER(A.SxEnumBatch), C.POINTER(A.SxEnumOut), C.c_uint32, _P, _P, C.POINTER(A.SxLinkOut)]
+    n_alns = int(out.totals[0])
+    lo = B.LinkOut(regions, n_alns, cap_segs if cap_segs is not None else 2 * int(out.totals[1]) + 8 * eb.n_regions + 64,
+                   cap_ins if cap_ins is not None else 64 * n_alns + 16 * eb.n_regions + 64)
+    rc = _k8core.k8core_run(C.byref(eb.c), C.byref(out.c), n_alns, A.ptr(eb.ins_off), A.ptr(eb.ins_pool), C.byref(lo.c))
+    return rc, lo

@@ -575,6 +575,7 @@ def random_enum_region(rng: np.random.Generator, n_reads: int = 6, ref_len: int 
             k = B.EnumKeySpec(pos, 0, rand_seq(rng, int(rng.integers(1, 11))), **common)
         elif u < 0.78:
             d = int(rng.integers(1, 7))
+            common["candidate"] = False  # a complex allele is never a candidate (IndelBuffer.cpp:119-128, :218: doNotGenotype)
             k = B.EnumKeySpec(pos, d, rand_seq(rng, d if rng.random() < 0.4 else int(rng.integers(1, 7))), **common)
         else:
             rb = ref[pos - ref_begin]

@@ -218,3 +218,67 @@ def test_bench_workload_of_the_k7_leg():
         _same(reflib.ref_enumerate_alignments(eb, cap_alns=cap), want)
         sub = bench.enum_subbatch(eb, 100)
         assert sub.n_regions == 100 and sub.n_reads == 3000 and sub.n_keys == 300
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# K7b link_alignments: K7's output -> K1's alignment description
+# ------------------------------------------------------------------------------------------------------------------------------
+def _link_case(case):
+    eb = specgen.enum_case(case)
+    out = reflib.ox_enumerate_alignments(eb, cap_alns=eb.n_reads * 64 + 64)
+    rng = np.random.default_rng(case)
+    regions = B.regions_from_enumeration(eb, out, lambda r, n: rng.choice([11, 25, 37], n).astype(np.uint8))
+    return eb, out, regions, B.build_align_batch(regions)
+
+
+def _same_alignment_description(want: B.AlignBatch, got: B.AlignBatch):
+    """per alignment: header, segments (no-op pads aside) and insert bytes."""
+    assert want.n_alns == got.n_alns
+    pad = lambda s: s[~((s["kind"] == A.SX_SEG_HARDCLIP) & (s["len"] == 0))]  # noqa: E731
+    for i in range(want.n_alns):
+        ws = pad(want.segs[int(want.alns["seg_off"][i]) : int(want.alns["seg_off"][i + 1])])
+        gs = pad(got.segs[int(got.alns["seg_off"][i]) : int(got.alns["seg_off"][i + 1])])
+        n_ins = int(ws["len"][ws["kind"] == A.SX_SEG_INSERT].sum())
+        wi = bytes(want.ins[int(want.alns["ins_off"][i]) : int(want.alns["ins_off"][i]) + n_ins])
+        gi = bytes(got.ins[int(got.alns["ins_off"][i]) : int(got.alns["ins_off"][i]) + n_ins])
+        assert ws.tobytes() == gs.tobytes() and wi == gi, i
+        assert want.alns["read"][i] == got.alns["read"][i] and want.alns["ref_pos"][i] == got.alns["ref_pos"][i]
+    # K1's staging rule: every region's first segment index a multiple of 8, its first insert byte a multiple of 16
+    assert not (got.regions["seg_begin"] % 8).any() and not (got.regions["ins_begin"] % 16).any()
+    assert np.array_equal(got.regions["aln_begin"], want.regions["aln_begin"])
+
+
+def test_link_device_body_against_the_host_flattening_and_the_reference():
+    """K7b's device body (k8_core.cuh compiled for the host, run like the kernels of k8_link.cu) on K7's output: the K1 alignment
+    description it writes equals what the host flattening (batch.flatten_alignment = the segment walk of scoreCandidateAlignment)
+    writes for the same alignments; scoring both with the K1 oracle gives identical doubles, and -- where the reference library is
+    built -- the reference's own scoreCandidateAlignment on the CandidateAlignment objects gives the same bits: enumerator -> link ->
+    scorer is one pinned chain."""
+    n = 0
+    for case in range(36):
+        eb, out, regions, want = _link_case(case)
+        rc, lo = reflib.k8core_link(eb, out, want.regions)
+        assert rc == 0
+        got = lo.align_batch(want)
+        _same_alignment_description(want, got)
+        s_got = reflib.ox_score(got)
+        assert np.array_equal(s_got.view(np.uint64), reflib.ox_score(want).view(np.uint64))
+        if reflib.have_ref():
+            s_ref = np.concatenate([reflib.ref_score_region(r) for r in regions])
+            assert np.array_equal(s_ref.view(np.uint64), s_got.view(np.uint64)), case
+        n += got.n_alns
+    assert n > 5000
+
+
+def test_link_capacity_and_bad_key():
+    eb, out, regions, want = _link_case(1)
+    rc, full = reflib.k8core_link(eb, out, want.regions)
+    assert rc == 0
+    rc, small = reflib.k8core_link(eb, out, want.regions, cap_segs=int(full.totals[0]) - 1)
+    assert rc == A.SX_ERR_CAPACITY and list(small.totals) == list(full.totals)
+    # a path gap that matches no key of its alignment (here: every window deletion made one base longer than the paths say): the
+    # reference's assert(isFound) (score.cpp:222) -> an error status, not garbage
+    assert (out.segs[: int(out.totals[1])]["kind"] == A.SX_AP_DELETE).any()
+    eb.keys["del_len"][eb.keys["del_len"] > 0] += 1
+    rc, _ = reflib.k8core_link(eb, out, want.regions)
+    assert rc == -1

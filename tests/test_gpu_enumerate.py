@@ -93,3 +93,52 @@ def test_k7_feeds_k6(ctx):
     got = ctx.score_indels(sb, lnp)
     for a, b in zip(reflib.ox_score_indels(sb, lnp), got):
         assert a.tobytes() == b.tobytes()
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# K7b link_alignments, and the chain K7 -> K7b -> K1 -> K6 through the C ABI
+# ------------------------------------------------------------------------------------------------------------------------------
+def _pad(s):
+    return s[~((s["kind"] == A.SX_SEG_HARDCLIP) & (s["len"] == 0))]
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_k7b_link_alignments_and_the_chain(ctx, case):
+    """enumerate on the GPU, link on the GPU, score the linked batch on the GPU: the alignment description equals the host
+    flattening of the same alignments, and K1's scores of it equal the oracle's scores of the host-built batch bit for bit."""
+    eb = specgen.enum_case(case)
+    out = ctx.enumerate_alignments(eb)
+    _same(reflib.ox_enumerate_alignments(eb), out)
+    rng = np.random.default_rng(case)
+    regions = B.regions_from_enumeration(eb, out, lambda r, n: rng.choice([11, 25, 37], n).astype(np.uint8))
+    want = B.build_align_batch(regions)
+    lo = ctx.link_alignments(eb, out, want.regions)
+    assert ctx.timing().launches == 9
+    got = lo.align_batch(want)
+    assert got.n_alns == want.n_alns and not (got.regions["seg_begin"] % 8).any() and not (got.regions["ins_begin"] % 16).any()
+    for i in range(want.n_alns):
+        ws = _pad(want.segs[int(want.alns["seg_off"][i]) : int(want.alns["seg_off"][i + 1])])
+        gs = _pad(got.segs[int(got.alns["seg_off"][i]) : int(got.alns["seg_off"][i + 1])])
+        n_ins = int(ws["len"][ws["kind"] == A.SX_SEG_INSERT].sum())
+        assert ws.tobytes() == gs.tobytes(), i
+        assert bytes(want.ins[int(want.alns["ins_off"][i]) : int(want.alns["ins_off"][i]) + n_ins]) == bytes(got.ins[int(got.alns["ins_off"][i]) : int(got.alns["ins_off"][i]) + n_ins])
+    lnp = ctx.score_alignments(got)
+    assert np.array_equal(lnp.view(np.uint64), reflib.ox_score(want).view(np.uint64))
+    # ... and K6 on those scores, in the enumerator's order
+    sb = specgen.score_indels_batch_from_enumeration(eb, out)
+    lnp1 = np.concatenate([lnp, [0.0]])
+    for a, b in zip(reflib.ox_score_indels(sb, lnp1), ctx.score_indels(sb, lnp1)):
+        assert a.tobytes() == b.tobytes()
+
+
+def test_k7b_capacity_error(ctx):
+    from strelka_b200.api import SxError
+
+    eb = specgen.enum_case(1)
+    out = ctx.enumerate_alignments(eb)
+    regions = B.regions_from_enumeration(eb, out)
+    want = B.build_align_batch(regions)
+    full = ctx.link_alignments(eb, out, want.regions)
+    with pytest.raises(SxError) as e:
+        ctx.link_alignments(eb, out, want.regions, cap_segs=int(full.totals[0]) - 1)
+    assert e.value.code == A.SX_ERR_CAPACITY
