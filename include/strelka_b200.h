@@ -676,6 +676,8 @@ typedef struct sx_link_out { /* caller-allocated */
     sx_aln* alns;         /* [n_alns + 1] n_alns = the enumeration's totals[0] */
     sx_aln_seg* segs;     /* [cap_segs]; leave 16 entries beyond totals[0] for K1's slack (filled with no-op segments where they fit) */
     char* ins;            /* [cap_ins + SX_POOL_SLACK] */
+    sx_aln_seg* k6_segs;  /* NULL, or [the enumeration's totals[1]]: K7's segments with K6's kinds (MATCH for '=' / 'X', SX_SEG_DELETE,
+                             SX_SEG_SKIP, ...), index for index -- with K7's other arrays this is sx_score_indels_batch's alignment part */
 } sx_link_out;
 
 /* key_ins_off[n_keys + 1] / key_ins: the insert sequence of window entry k is key_ins[key_ins_off[k] .. key_ins_off[k+1]).

@@ -246,7 +246,7 @@ class SxEnumOut(C.Structure):
 
 
 class SxLinkOut(C.Structure):
-    _fields_ = [("cap_segs", C.c_uint32), ("cap_ins", C.c_uint32)] + [(n, C.c_void_p) for n in ("totals", "regions", "alns", "segs", "ins")]
+    _fields_ = [("cap_segs", C.c_uint32), ("cap_ins", C.c_uint32)] + [(n, C.c_void_p) for n in ("totals", "regions", "alns", "segs", "ins", "k6_segs")]
 
 
 def default_enum_opts() -> SxEnumOpts:

@@ -308,7 +308,7 @@ def _link_alignments(self, eb: B.EnumBatch, out: B.EnumOut, regions: np.ndarray,
     """K7b: K7's alignments as the alignment part of a K1 batch (host buffers).  `regions`: the K1 batch's region records."""
     n_alns = int(out.totals[0])
     lo = B.LinkOut(regions, n_alns, cap_segs if cap_segs is not None else 2 * int(out.totals[1]) + 8 * eb.n_regions + 64,
-                   cap_ins if cap_ins is not None else 64 * n_alns + 16 * eb.n_regions + 64)
+                   cap_ins if cap_ins is not None else 64 * n_alns + 16 * eb.n_regions + 64, n_enum_segs=int(out.totals[1]))
     self._chk(self.lib.sx_link_alignments(self.h, C.byref(eb.c), C.byref(out.c), n_alns, A.ptr(eb.ins_off), A.ptr(eb.ins_pool), C.byref(lo.c)))
     return lo
 

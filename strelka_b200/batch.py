@@ -912,7 +912,7 @@ class LinkOut:
     """Host buffers for sx_link_out.  `regions` = the region records of the K1 batch the alignments will join (a copy is taken: the
     call fills aln_begin / seg_begin / ins_begin)."""
 
-    def __init__(self, regions: np.ndarray, n_alns: int, cap_segs: int, cap_ins: int):
+    def __init__(self, regions: np.ndarray, n_alns: int, cap_segs: int, cap_ins: int, n_enum_segs: int = 0):
         self.cap_segs, self.cap_ins, self.n_alns = int(cap_segs), int(cap_ins), int(n_alns)
         self.totals = np.zeros(2, np.uint32)
         self.regions = regions.copy()
@@ -920,7 +920,9 @@ class LinkOut:
         self.segs = np.zeros(self.cap_segs + 16, dtype=A.ALN_SEG_DT)
         self.segs["kind"][:] = A.SX_SEG_HARDCLIP
         self.ins = np.zeros(self.cap_ins + A.SX_POOL_SLACK + 16, np.uint8)
-        self.c = A.SxLinkOut(self.cap_segs, self.cap_ins, A.ptr(self.totals), A.ptr(self.regions), A.ptr(self.alns), A.ptr(self.segs), A.ptr(self.ins))
+        self.k6_segs = np.zeros(n_enum_segs + 16, dtype=A.ALN_SEG_DT) if n_enum_segs else None  # K7's segments with K6's kinds
+        self.c = A.SxLinkOut(self.cap_segs, self.cap_ins, A.ptr(self.totals), A.ptr(self.regions), A.ptr(self.alns), A.ptr(self.segs), A.ptr(self.ins),
+                             A.ptr(self.k6_segs) if n_enum_segs else None)
 
     def align_batch(self, reads_of: "AlignBatch") -> "AlignBatch":
         """the K1 batch made of `reads_of`'s read / quality / reference pools and the linked alignments."""

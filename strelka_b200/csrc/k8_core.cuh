@@ -33,6 +33,22 @@ struct k8_view
     const char* key_ins;
 };
 
+// K7's path segment kinds (ALIGNPATH::align_t) as sx_score_indels_batch wants them
+K8_HD uint8_t k8_k6_kind(const unsigned t)
+{
+    switch (t)
+    {
+    case SX_AP_MATCH:
+    case SX_AP_SEQ_MATCH:
+    case SX_AP_SEQ_MISMATCH: return SX_SEG_MATCH;
+    case SX_AP_INSERT: return SX_SEG_INSERT;
+    case SX_AP_DELETE: return SX_SEG_DELETE;
+    case SX_AP_SKIP: return SX_SEG_SKIP;
+    case SX_AP_SOFT_CLIP: return SX_SEG_SOFTCLIP;
+    default: return SX_SEG_HARDCLIP;
+    }
+}
+
 K8_HD bool k8_align_match(const unsigned t) { return t == SX_AP_MATCH || t == SX_AP_SEQ_MATCH || t == SX_AP_SEQ_MISMATCH; }
 
 // Walks alignment a (of a read of `region`).  With segs == nullptr it only counts; otherwise it writes the K1 segments to segs[] and

@@ -113,6 +113,8 @@ __global__ void k8_write_kernel(const k8_view v, const uint32_t n_alns, const ui
         o.alns[a] = sx_aln{r, v.e.aln_pos[a], s, b};
         uint32_t ns, ni;
         k8_walk(v, g, a, ns, ni, o.segs + s, o.ins + b);
+        if (o.k6_segs)
+            for (uint32_t q = v.e.aln_seg_off[a]; q < v.e.aln_seg_off[a + 1]; ++q) o.k6_segs[q] = sx_aln_seg{v.e.segs[q].len, k8_k6_kind(v.e.segs[q].kind), 0};
     }
 }
 
@@ -273,6 +275,10 @@ extern "C" int sx_link_alignments(sx_ctx* ctx, const sx_enum_batch* b, const sx_
     if ((rc = sx_ensure(ctx, 15, ((size_t)n_alns + 1) * sizeof(sx_aln) + 16, reinterpret_cast<void**>(&o.alns)))) return rc;
     if ((rc = sx_ensure(ctx, 16, (size_t)o.cap_segs * sizeof(sx_aln_seg) + 16, reinterpret_cast<void**>(&o.segs)))) return rc;
     if ((rc = sx_ensure(ctx, 17, (size_t)o.cap_ins + SX_POOL_SLACK + 16, reinterpret_cast<void**>(&o.ins)))) return rc;
+    if (out_host->k6_segs)
+    {
+        if ((rc = sx_ensure(ctx, 18, n_segs * sizeof(sx_aln_seg) + 16, reinterpret_cast<void**>(&o.k6_segs)))) return rc;
+    }
     unsigned launches(0);
     if ((rc = k8_run(ctx, &d, &de, n_alns, d_key_ins_off, d_key_ins, &o, &launches))) return rc;
     SX_CUDA(ctx, cudaMemcpyAsync(out_host->totals, o.totals, 8, cudaMemcpyDeviceToHost, st));
@@ -284,6 +290,7 @@ extern "C" int sx_link_alignments(sx_ctx* ctx, const sx_enum_batch* b, const sx_
         SX_CUDA(ctx, cudaMemcpyAsync(out_host->alns, o.alns, ((size_t)n_alns + 1) * sizeof(sx_aln), cudaMemcpyDeviceToHost, st));
         SX_CUDA(ctx, cudaMemcpyAsync(out_host->segs, o.segs, (size_t)nS * sizeof(sx_aln_seg), cudaMemcpyDeviceToHost, st));
         SX_CUDA(ctx, cudaMemcpyAsync(out_host->ins, o.ins, (size_t)nI, cudaMemcpyDeviceToHost, st));
+        if (out_host->k6_segs) SX_CUDA(ctx, cudaMemcpyAsync(out_host->k6_segs, o.k6_segs, n_segs * sizeof(sx_aln_seg), cudaMemcpyDeviceToHost, st));
     }
     SX_CUDA(ctx, cudaEventRecord(ctx->ev_b, st));
     SX_CUDA(ctx, cudaStreamSynchronize(st));

@@ -58,6 +58,8 @@ extern "C" int k8core_run(const sx_enum_batch* b, const sx_enum_out* e, uint32_t
         o->alns[a] = sx_aln{r, e->aln_pos[a], s, i};
         uint32_t ns, ni;
         k8_walk(v, g, a, ns, ni, o->segs + s, o->ins + i);
+        if (o->k6_segs)
+            for (uint32_t q = e->aln_seg_off[a]; q < e->aln_seg_off[a + 1]; ++q) o->k6_segs[q] = sx_aln_seg{e->segs[q].len, k8_k6_kind(e->segs[q].kind), 0};
     }
     for (uint32_t g = 0; g < b->n_regions; ++g) // k8_pad_kernel
     {

@@ -333,6 +333,6 @@ def k8core_link(eb: "B.EnumBatch", out: "B.EnumOut", regions: np.ndarray, cap_se
         _k8core.k8core_run.argtypes = [C.POINTER(A.SxEnumBatch), C.POINTER(A.SxEnumOut), C.c_uint32, _P, _P, C.POINTER(A.SxLinkOut)]
     n_alns = int(out.totals[0])
     lo = B.LinkOut(regions, n_alns, cap_segs if cap_segs is not None else 2 * int(out.totals[1]) + 8 * eb.n_regions + 64,
-                   cap_ins if cap_ins is not None else 64 * n_alns + 16 * eb.n_regions + 64)
+                   cap_ins if cap_ins is not None else 64 * n_alns + 16 * eb.n_regions + 64, n_enum_segs=int(out.totals[1]))
     rc = _k8core.k8core_run(C.byref(eb.c), C.byref(out.c), n_alns, A.ptr(eb.ins_off), A.ptr(eb.ins_pool), C.byref(lo.c))
     return rc, lo

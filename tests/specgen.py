@@ -695,7 +695,7 @@ def enum_case(case: int, n_regions: int = 6):
 ENUM_GOLDEN_CASES = 12
 
 
-def score_indels_batch_from_enumeration(eb: "B.EnumBatch", out: "B.EnumOut", ref_to_indel_lnp=-9.9, indel_to_ref_lnp=-9.9) -> "B.ScoreIndelsBatch":
+def score_indels_batch_from_enumeration(eb: "B.EnumBatch", out: "B.EnumOut", ref_to_indel_lnp=-9.9, indel_to_ref_lnp=-9.9, k6_segs=None) -> "B.ScoreIndelsBatch":
     """K7's output as K6's input: the same alignments in the same (std::set) order with the same key lists; only the segment kinds
     are relabelled ('=' / 'X' are MATCH for score_indels, DELETE keeps its own kind) and the per-read fields K6 needs are added."""
     kind = np.zeros(16, np.uint8)
@@ -705,6 +705,8 @@ def score_indels_batch_from_enumeration(eb: "B.EnumBatch", out: "B.EnumOut", ref
     segs2 = np.zeros(len(segs) + 16, dtype=A.ALN_SEG_DT)
     segs2["len"][: len(segs)] = segs["len"]
     segs2["kind"][: len(segs)] = kind[segs["kind"]]
+    if k6_segs is not None:  # the relabelled copy K7b wrote (sx_link_out.k6_segs): must be this array
+        assert k6_segs[: len(segs)].tobytes() == segs2[: len(segs)].tobytes()
     keys = eb.keys.copy()
     keys["ref_to_indel_lnp"], keys["indel_to_ref_lnp"] = ref_to_indel_lnp, indel_to_ref_lnp
     n_win = np.diff(eb.region_key_off.astype(np.int64))

@@ -261,6 +261,7 @@ def test_link_device_body_against_the_host_flattening_and_the_reference():
         assert rc == 0
         got = lo.align_batch(want)
         _same_alignment_description(want, got)
+        specgen.score_indels_batch_from_enumeration(eb, out, k6_segs=lo.k6_segs)  # asserts the K6-kind copy of K7's segments
         s_got = reflib.ox_score(got)
         assert np.array_equal(s_got.view(np.uint64), reflib.ox_score(want).view(np.uint64))
         if reflib.have_ref():

@@ -125,7 +125,7 @@ def test_k7b_link_alignments_and_the_chain(ctx, case):
     lnp = ctx.score_alignments(got)
     assert np.array_equal(lnp.view(np.uint64), reflib.ox_score(want).view(np.uint64))
     # ... and K6 on those scores, in the enumerator's order
-    sb = specgen.score_indels_batch_from_enumeration(eb, out)
+    sb = specgen.score_indels_batch_from_enumeration(eb, out, k6_segs=lo.k6_segs)
     lnp1 = np.concatenate([lnp, [0.0]])
     for a, b in zip(reflib.ox_score_indels(sb, lnp1), ctx.score_indels(sb, lnp1)):
         assert a.tobytes() == b.tobytes()
