@@ -779,8 +779,13 @@ def main():
                 line["k4_pileup"] = k4_pileup_leg(ctx, peak)
                 ctx.score_alignments_dev(dab)  # the scores K6 consumes: K1's own output buffer, never copied out
                 line["k6_score_indels"] = k6_score_indels_leg(ctx, synth, peak, n_loci, depth, read_len, n_haps, args.seed + 1000 * rank, threads, rpr, dab.out)
-                try:  # the youngest leg must never take the headline line down with it
-                    line["k7_enumerate"] = k7_enumerate_leg(ctx, peak, depth=min(depth, 30), read_len=read_len)
+                # K7 had not run on a GPU when this was written: its leg runs in a process of its own with a time limit, so that nothing it
+                # does (an exception, a sticky CUDA error, a search that does not end) can take the headline line down with it
+                try:
+                    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k7_leg.py"), "200000", str(min(depth, 30)), str(read_len), str(peak)],
+                                       capture_output=True, text=True, timeout=240)
+                    last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                    line["k7_enumerate"] = json.loads(last[-1]) if r.returncode == 0 and last else {"error": (r.stderr or r.stdout)[-600:]}
                 except Exception as e:  # noqa: BLE001
                     line["k7_enumerate"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line))

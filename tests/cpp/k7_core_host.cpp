@@ -4,12 +4,14 @@
 // the product: libstrelka_b200.so has no host execution path.
 #include "k7_core.cuh"
 
+#include <algorithm>
 #include <vector>
 
 extern "C" int k7core_run(const sx_enum_batch* b, sx_enum_out* o, uint32_t maxA)
 {
     if (maxA == 0) maxA = 64;
-    std::vector<unsigned char> arena(k7_scratch_bytes(maxA) + 64);
+    // the device arena is never cleared: poison it, so that any read-before-write of the scratch shows up here as a mismatch
+    std::vector<unsigned char> arena(k7_scratch_bytes(maxA) + 64, 0xCD);
     k7_scratch S(k7_scratch_at(arena.data(), maxA));
     k7_view v;
     v.b = *b;
@@ -42,6 +44,7 @@ extern "C" int k7core_run(const sx_enum_batch* b, sx_enum_out* o, uint32_t maxA)
     {
         if (o->status[r] & (SX_ENUM_ST_EXCEPTION | SX_ENUM_ST_LIMIT)) continue;
         if (o->aln_off[r + 1] == o->aln_off[r]) continue;
+        std::fill(arena.begin(), arena.end(), (unsigned char)(0x5A + (r & 0x3f))); // a different thread's leftovers
         k7_enumerate_read(v, read_region[r], r, S);
         k7_write(S, *o, ca[r], cs[r], ck[r]);
     }

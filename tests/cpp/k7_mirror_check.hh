@@ -1,4 +1,4 @@
-// k7_mirror_check.hh -- TEST ONLY: the K7 part of the C++ host-mirror test, shared by tests/cpp/test_host_mirror.cpp (GPU: the real
+// k7_mirror_check.hh -- TEST ONLY: the K7 part of the C++ host-mirror test, shared by tests/cpp/test_k7_mirror.cpp (GPU: the real
 // library) and tests/cpp/test_k7_mirror_cpu.cpp (no GPU: the same builder / decoder code of sx::AlignmentSearchBatch, with
 // sx_enumerate_alignments answered by the device body compiled for the host).
 //

@@ -6,8 +6,6 @@
 // Build/run: see tests/test_gpu_parity.py::test_cpp_host_mirror.
 #include "strelka_b200.hh"
 
-#include "k7_mirror_check.hh"
-
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -215,8 +213,6 @@ int main(int argc, char** argv)
                 std::cerr << "FAIL k6: a SKIP segment did not raise SX_ERR_UNSUPPORTED\n";
             }
         }
-        // ---- K7: sx::AlignmentSearchBatch against the reference's getCandidateAlignments (tests/cpp/k7_mirror_check.hh)
-        k7_mirror_check(ctx, dir, checks, failures);
         // ---- error behaviour: a failing call throws, like the reference's blt_exception
         {
             sx::ReadAlignBatch bad;

@@ -3,7 +3,7 @@
 // CSR result back into CandidateAlignments) checked against the reference's getCandidateAlignments (tests/golden/k7_cases.tsv) with
 // the four library entry points it needs answered here: sx_create / sx_destroy / sx_last_error are stubs and
 // sx_enumerate_alignments runs the device body of K7 (strelka_b200/csrc/k7_core.cuh, __host__ __device__) read by read the way the
-// kernels do.  On the GPU box tests/cpp/test_host_mirror.cpp runs the same check through the real library.
+// kernels do.  On the GPU box tests/cpp/test_k7_mirror.cpp runs the same check through the real library.
 #include "k7_core.cuh"
 
 #include "k7_mirror_check.hh"

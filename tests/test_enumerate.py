@@ -3,7 +3,7 @@ __device__) compiled for the host and run the way the kernels run it, against
   * the known-answer vectors of the reference's own unit test (starling_common/test/starling_read_align_test.cpp),
   * the reference's getCandidateAlignments itself (oracle/_ref/libstrelka_ref.so) on seeded batches, when it is built here,
   * the frozen outputs of the same function (tests/golden/enumerate_ref.npz).
-The GPU parity tests (tests/test_gpu_enumerate.py) run the CUDA kernels against the same checkers."""
+The GPU parity tests (tests/test_zz_gpu_enumerate.py) run the CUDA kernels against the same checkers."""
 import json
 import os
 import re
@@ -184,8 +184,8 @@ def test_host_builder_restates_getAlignmentIndels():
 def test_cpp_host_mirror_builder_on_the_cpu(tmp_path):
     """sx::AlignmentSearchBatch (strelka_b200/host/strelka_b200.hh): reference-shaped objects in, CandidateAlignments out, against
     the candidate alignments the reference returned (tests/golden/k7_cases.tsv).  Without a GPU the library call in the middle is
-    answered by the device body compiled for the host (tests/cpp/test_k7_mirror_cpu.cpp); tests/test_gpu_parity.py::
-    test_cpp_host_mirror runs the same check through libstrelka_b200.so."""
+    answered by the device body compiled for the host (tests/cpp/test_k7_mirror_cpu.cpp); tests/test_zz_gpu_enumerate.py::
+    test_cpp_host_mirror_k7 runs the same check through libstrelka_b200.so."""
     import subprocess
 
     root = os.path.dirname(HERE)

@@ -12,7 +12,10 @@ import specgen
 from strelka_b200 import _abi as A
 from strelka_b200 import batch as B
 
-pytestmark = pytest.mark.gpu
+# This file sorts after every other test file on purpose: K7 / K7b had not run on a GPU when this was written (the round's GPU
+# minutes were spent), so under `pytest -x` a first-run failure here must not mask the parity tests of the measured kernels; the
+# timeout (pytest-timeout, thread method: the process is ended even if a kernel never returns) bounds a runaway search.
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD_NAMES = ("aln_off", "status", "aln_pos", "aln_seg_off", "segs", "aln_key_off", "aln_keys", "lead", "trail")
 
@@ -59,7 +62,7 @@ def test_k7_device_resident_many_regions(ctx):
     from strelka_b200.api import DevEnumBatch
 
     rng = np.random.default_rng(77)
-    regions = [specgen.random_enum_region(rng, n_reads=int(rng.integers(1, 9)), cluster=bool(i % 3 == 0), n_keys=(1, 6)) for i in range(6000)]
+    regions = [specgen.random_enum_region(rng, n_reads=int(rng.integers(1, 9)), cluster=bool(i % 3 == 0), n_keys=(1, 6)) for i in range(3000)]
     eb = B.EnumBatch(regions)
     want = reflib.ox_enumerate_alignments(eb, cap_alns=eb.n_reads * 64 + 64)
     db = DevEnumBatch(ctx, eb, cap_alns=eb.n_reads * 64 + 64)
@@ -67,7 +70,7 @@ def test_k7_device_resident_many_regions(ctx):
     got = db.download()
     _same(want, got)
     st = want.status[: eb.n_reads]
-    assert int(want.totals[0]) > 100000 and (st & A.SX_ENUM_ST_LIMIT).any() and (st == 0).sum() > eb.n_reads // 2
+    assert int(want.totals[0]) > 50000 and (st & A.SX_ENUM_ST_LIMIT).any() and (st == 0).sum() > eb.n_reads // 2
 
 
 def test_k7_capacity_error_reports_the_needed_sizes(ctx):
@@ -142,3 +145,17 @@ def test_k7b_capacity_error(ctx):
     with pytest.raises(SxError) as e:
         ctx.link_alignments(eb, out, want.regions, cap_segs=int(full.totals[0]) - 1)
     assert e.value.code == A.SX_ERR_CAPACITY
+
+
+def test_cpp_host_mirror_k7(tmp_path):
+    """sx::AlignmentSearchBatch (the C++ layer a reference developer programs against) through libstrelka_b200.so against the
+    reference's getCandidateAlignments results frozen in tests/golden/k7_cases.tsv."""
+    import subprocess
+
+    root = os.path.dirname(HERE)
+    exe = str(tmp_path / "test_k7_mirror")
+    lib = os.path.join(root, "strelka_b200", "csrc")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "strelka_b200", "host"),
+                           os.path.join(HERE, "cpp", "test_k7_mirror.cpp"), "-o", exe, "-L" + lib, "-lstrelka_b200", "-Wl,-rpath," + lib])
+    out = subprocess.run([exe, os.path.join(HERE, "golden")], capture_output=True, text=True)
+    assert out.returncode == 0 and "0 failures" in out.stdout, out.stdout + out.stderr
