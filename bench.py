@@ -385,13 +385,17 @@ def enum_subbatch(eb: B.EnumBatch, m: int) -> A.SxEnumBatch:
     return A.SxEnumBatch(m, int(eb.region_read_off[m]), int(eb.region_key_off[m]), *[getattr(eb.c, f) for f, _ in A.SxEnumBatch._fields_[3:-1]], eb.opts)
 
 
-def k7_enumerate_leg(ctx, peak_gbs: float, n_loci: int = 200_000, depth: int = 30, read_len: int = 150, seed: int = 7, reps: int = 3, cpu_regions: int = 400):
+def k7_enumerate_leg(ctx, peak_gbs: float, n_loci: int = 200_000, depth: int = 30, read_len: int = 150, seed: int = 7, reps: int = 3, cpu_regions: int = 400,
+                     fast: bool = False):
     """SURVEY 8a row a3 / 8f3 measured beside the headline step (not part of `value`): K7 enumerate_alignments on cfg2-shaped loci,
     inputs and the CSR it writes resident in HBM.  CPU figure: the reference's own getCandidateAlignments on one host thread over the
     first `cpu_regions` regions (the oracle port where the reference library is absent)."""
     from strelka_b200.api import DevEnumBatch
 
     eb = make_enum_workload(n_loci, depth, read_len, seed)
+    if fast:  # the second launch plan (include/strelka_b200.h SX_ENUM_F_FAST)
+        eb.opts.flags = A.SX_ENUM_F_FAST
+        eb.c.opts = eb.opts
     db = DevEnumBatch(ctx, eb, cap_alns=eb.n_reads * 16, cap_segs=eb.n_reads * 64, cap_keys=eb.n_reads * 32)
     ms = []
     for i in range(reps + 1):
@@ -403,7 +407,8 @@ def k7_enumerate_leg(ctx, peak_gbs: float, n_loci: int = 200_000, depth: int = 3
     nA, nS, nK = (int(x) for x in totals[:3])
     t = float(np.mean(ms)) * 1e-3
     alg = eb.algorithmic_bytes(nA, nS, nK)
-    leg = {"what": f"K7 enumerate_alignments: {n_loci} cfg2-shaped loci ({eb.n_reads} reads, 3 overlapping candidate alleles each) -> {nA} candidate alignments, resident in HBM",
+    leg = {"plan": "SX_ENUM_F_FAST (local-memory tier + arena tier, one search, log + gather)" if fast else "original (arena scratch, count / scan / write)",
+           "what": f"K7 enumerate_alignments: {n_loci} cfg2-shaped loci ({eb.n_reads} reads, 3 overlapping candidate alleles each) -> {nA} candidate alignments, resident in HBM",
            "ms": 1e3 * t, "reads_per_s": eb.n_reads / t, "loci_per_s": n_loci / t, "alignments_per_s": nA / t, "alignments": nA,
            "reads_flagged": {"max_toggle": int((status & A.SX_ENUM_ST_MAX_TOGGLE != 0).sum()), "exception": int((status & A.SX_ENUM_ST_EXCEPTION != 0).sum()),
                              "limit": int((status & A.SX_ENUM_ST_LIMIT != 0).sum())},
@@ -781,13 +786,14 @@ def main():
                 line["k6_score_indels"] = k6_score_indels_leg(ctx, synth, peak, n_loci, depth, read_len, n_haps, args.seed + 1000 * rank, threads, rpr, dab.out)
                 # K7 had not run on a GPU when this was written: its leg runs in a process of its own with a time limit, so that nothing it
                 # does (an exception, a sticky CUDA error, a search that does not end) can take the headline line down with it
-                try:
-                    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k7_leg.py"), "200000", str(min(depth, 30)), str(read_len), str(peak)],
-                                       capture_output=True, text=True, timeout=240)
-                    last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-                    line["k7_enumerate"] = json.loads(last[-1]) if r.returncode == 0 and last else {"error": (r.stderr or r.stdout)[-600:]}
-                except Exception as e:  # noqa: BLE001
-                    line["k7_enumerate"] = {"error": f"{type(e).__name__}: {e}"}
+                for key, plan in (("k7_enumerate", "original"), ("k7_enumerate_fast", "fast")):  # the second plan has never run on a GPU
+                    try:
+                        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k7_leg.py"), "200000", str(min(depth, 30)), str(read_len), str(peak), plan],
+                                           capture_output=True, text=True, timeout=240)
+                        last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                        line[key] = json.loads(last[-1]) if r.returncode == 0 and last else {"error": (r.stderr or r.stdout)[-600:]}
+                    except Exception as e:  # noqa: BLE001
+                        line[key] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -608,7 +608,14 @@ typedef struct sx_enum_opts {
     uint32_t n_samples;                  /* opt.getSampleCount(), <= SX_ENUM_MAX_SAMPLES */
     uint32_t sample_id;                  /* the sample the reads belong to */
     uint32_t max_alns_per_read;          /* scratch capacity per read, 0 = 64; reads that need more get SX_ENUM_ST_LIMIT */
+    uint32_t flags;                      /* SX_ENUM_F_* */
 } sx_enum_opts;
+
+/* SX_ENUM_F_FAST: the second-generation launch plan (same results): ordinary reads (<= 11 nested toggles, <= 16 alignments) search in
+ * per-lane-interleaved local memory, the others in the global arena; every read is searched ONCE, its alignments appended to a log
+ * and gathered into read order after the scan.  Written from the first ncu capture of the original plan (profiles/r1_k7_count.summary.txt:
+ * 93 % long-scoreboard stalls on the per-thread arena, the search run twice); off by default until it has been timed on a B200. */
+#define SX_ENUM_F_FAST 0x1u
 
 typedef struct sx_enum_batch {
     uint32_t n_regions, n_reads, n_keys;

@@ -224,6 +224,7 @@ SX_ENUM_MAX_SAMPLES = 4
 SX_NO_KEY = 0xFFFF
 SX_ENUM_ST_ORIGIN_SKIP, SX_ENUM_ST_MAX_TOGGLE, SX_ENUM_ST_EXCEPTION, SX_ENUM_ST_LIMIT = 1, 2, 4, 8
 SX_ERR_CAPACITY = -8
+SX_ENUM_F_FAST = 1
 KEY_HAP_DT = np.dtype([("active_region_id", "<i4"), ("haplotype_id", "i1", (4,)), ("bypass_mask", "u1"), ("pad", "u1", (3,))])
 assert KEY_HAP_DT.itemsize == 12
 
@@ -231,7 +232,7 @@ assert KEY_HAP_DT.itemsize == 12
 class SxEnumOpts(C.Structure):
     _fields_ = [("max_indel_size", C.c_uint32), ("max_read_indel_toggle", C.c_int32), ("max_candidate_indel_density", C.c_double), ("n_max_toggle", C.c_uint32),
                 ("max_toggle", C.c_uint8 * 100), ("is_haplotyping_enabled", C.c_int32), ("n_samples", C.c_uint32), ("sample_id", C.c_uint32),
-                ("max_alns_per_read", C.c_uint32)]
+                ("max_alns_per_read", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class SxEnumBatch(C.Structure):

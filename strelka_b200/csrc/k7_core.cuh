@@ -73,38 +73,44 @@ struct k7_frame // the by-value arguments of one candidate_alignment_search call
     k7_path cal;
 };
 
+#define K7_ST_RETRY 0x80u // internal: the small (local-memory) scratch of the fast path is full; the read goes to the arena tier
+
 struct k7_scratch // one thread's working memory (contiguous per thread)
 {
     uint16_t* order;  // [K7_MAX_INDELS] window indices, the shared indel_order stack
-    k7_frame* frames; // [K7_MAX_INDELS + 1]
+    k7_frame* frames; // [maxF]
     k7_cal* slots;    // [maxA + 1]
     uint16_t* idx;    // [maxA] slots in std::set order
     uint32_t maxA;
+    uint32_t maxF;    // frames available (K7_MAX_INDELS + 1 = as deep as a search can get)
+    uint32_t full;    // status when a frame or an alignment slot is missing: SX_ENUM_ST_LIMIT, or K7_ST_RETRY for the small tier
     uint32_t n;       // alignments in the set
 };
 
-K7_HD size_t k7_scratch_bytes(const uint32_t maxA)
+K7_HD size_t k7_scratch_bytes(const uint32_t maxA, const uint32_t maxF = K7_MAX_INDELS + 1)
 {
     size_t b(0);
     b += ((size_t)K7_MAX_INDELS * 2 + 15) & ~(size_t)15;
-    b += (sizeof(k7_frame) * (K7_MAX_INDELS + 1) + 15) & ~(size_t)15;
+    b += (sizeof(k7_frame) * maxF + 15) & ~(size_t)15;
     b += (sizeof(k7_cal) * ((size_t)maxA + 1) + 15) & ~(size_t)15;
     b += ((size_t)maxA * 2 + 15) & ~(size_t)15;
     return b;
 }
 
-K7_HD k7_scratch k7_scratch_at(unsigned char* base, const uint32_t maxA)
+K7_HD k7_scratch k7_scratch_at(unsigned char* base, const uint32_t maxA, const uint32_t maxF = K7_MAX_INDELS + 1, const uint32_t full = SX_ENUM_ST_LIMIT)
 {
     k7_scratch S;
     size_t o(0);
     S.frames = reinterpret_cast<k7_frame*>(base + o);
-    o += (sizeof(k7_frame) * (K7_MAX_INDELS + 1) + 15) & ~(size_t)15;
+    o += (sizeof(k7_frame) * maxF + 15) & ~(size_t)15;
     S.slots = reinterpret_cast<k7_cal*>(base + o);
     o += (sizeof(k7_cal) * ((size_t)maxA + 1) + 15) & ~(size_t)15;
     S.order = reinterpret_cast<uint16_t*>(base + o);
     o += ((size_t)K7_MAX_INDELS * 2 + 15) & ~(size_t)15;
     S.idx = reinterpret_cast<uint16_t*>(base + o);
     S.maxA = maxA;
+    S.maxF = maxF;
+    S.full = full;
     S.n = 0;
     return S;
 }
@@ -471,7 +477,7 @@ K7_HDN uint32_t k7_emit(const k7_read& R, k7_scratch& S, const k7_frame& f)
         if (cmp < 0) lo = mid + 1;
         else hi = mid;
     }
-    if (S.n >= S.maxA) return SX_ENUM_ST_LIMIT;
+    if (S.n >= S.maxA) return S.full;
     for (uint32_t i = S.n; i > lo; --i) S.idx[i] = S.idx[i - 1];
     S.idx[lo] = (uint16_t)S.n;
     S.n++;
@@ -748,6 +754,7 @@ K7_HDN uint32_t k7_search(const k7_read& R, k7_scratch& S, const uint64_t inorig
             }
         }
 
+        if ((uint32_t)sp + 1 >= S.maxF) return status | S.full; // no frame left for a child call (only the small tier can get here)
         if (f.stage == 0)
         {
             // ---- alignment 1: unchanged, :1043-1096
@@ -869,6 +876,7 @@ K7_HDN uint32_t k7_enumerate_read_raw(const k7_view& v, const uint32_t region, c
 K7_HD uint32_t k7_enumerate_read(const k7_view& v, const uint32_t region, const uint32_t r, k7_scratch& S)
 {
     const uint32_t st(k7_enumerate_read_raw(v, region, r, S));
+    if (st & K7_ST_RETRY) return K7_ST_RETRY;
     const uint32_t fail(st & (SX_ENUM_ST_EXCEPTION | SX_ENUM_ST_LIMIT));
     return fail ? fail : st;
 }
@@ -1014,7 +1022,7 @@ K7_HDN uint32_t k7_enumerate_read_raw(const k7_view& v, const uint32_t region, c
 K7_HD void k7_count(const k7_scratch& S, const uint32_t status, uint32_t& n_aln, uint32_t& n_seg, uint32_t& n_key)
 {
     n_aln = n_seg = n_key = 0;
-    if (status & (SX_ENUM_ST_EXCEPTION | SX_ENUM_ST_LIMIT)) return;
+    if (status & (SX_ENUM_ST_EXCEPTION | SX_ENUM_ST_LIMIT | K7_ST_RETRY)) return;
     n_aln = S.n;
     for (uint32_t i = 0; i < S.n; ++i)
     {
@@ -1040,5 +1048,56 @@ K7_HD void k7_write(const k7_scratch& S, const sx_enum_out& o, const uint32_t a0
         for (uint32_t j = 0; j < c.n_keys; ++j) o.aln_keys[k0 + j] = c.keys[j];
         s0 += c.p.n_seg;
         k0 += c.n_keys;
+    }
+}
+
+// ---- the fast path's result log: a read's set as one blob of 32-bit words, in set order:
+//   per alignment  [pos] [lead | trail << 16] [n_seg | n_keys << 8] [segs: n_seg words] [keys: ceil(n_keys / 2) words]
+K7_HD uint32_t k7_blob_words(const k7_scratch& S)
+{
+    uint32_t w(0);
+    for (uint32_t i = 0; i < S.n; ++i) w += 3u + S.slots[i].p.n_seg + (S.slots[i].n_keys + 1u) / 2u;
+    return w;
+}
+
+K7_HD void k7_blob_write(const k7_scratch& S, uint32_t* dst)
+{
+    for (uint32_t i = 0; i < S.n; ++i)
+    {
+        const k7_cal& c(S.slots[S.idx[i]]);
+        *dst++ = (uint32_t)c.p.pos;
+        *dst++ = (uint32_t)c.p.lead | ((uint32_t)c.p.trail << 16);
+        *dst++ = c.p.n_seg | (c.n_keys << 8);
+        for (uint32_t j = 0; j < c.p.n_seg; ++j) *dst++ = (uint32_t)c.p.seg[j].len | ((uint32_t)c.p.seg[j].kind << 16) | ((uint32_t)c.p.seg[j].flags << 24);
+        for (uint32_t j = 0; j < c.n_keys; j += 2) *dst++ = (uint32_t)c.keys[j] | ((j + 1 < c.n_keys ? (uint32_t)c.keys[j + 1] : 0u) << 16);
+    }
+}
+
+// blob -> the read's place in the CSR output (what k7_write does from the scratch)
+K7_HD void k7_blob_gather(const uint32_t* src, const uint32_t n_aln, const sx_enum_out& o, const uint32_t a0, uint32_t s0, uint32_t k0)
+{
+    for (uint32_t i = 0; i < n_aln; ++i)
+    {
+        const uint32_t a(a0 + i);
+        o.aln_pos[a] = (int32_t)src[0];
+        o.aln_lead_key[a] = (uint16_t)(src[1] & 0xFFFFu);
+        o.aln_trail_key[a] = (uint16_t)(src[1] >> 16);
+        const uint32_t ns(src[2] & 0xFFu), nk(src[2] >> 8);
+        src += 3;
+        o.aln_seg_off[a] = s0;
+        o.aln_key_off[a] = k0;
+        for (uint32_t j = 0; j < ns; ++j)
+        {
+            const uint32_t w(*src++);
+            o.segs[s0 + j] = sx_aln_seg{(uint16_t)(w & 0xFFFFu), (uint8_t)((w >> 16) & 0xFFu), (uint8_t)(w >> 24)};
+        }
+        for (uint32_t j = 0; j < nk; j += 2)
+        {
+            const uint32_t w(*src++);
+            o.aln_keys[k0 + j] = (uint16_t)(w & 0xFFFFu);
+            if (j + 1 < nk) o.aln_keys[k0 + j + 1] = (uint16_t)(w >> 16);
+        }
+        s0 += ns;
+        k0 += nk;
     }
 }

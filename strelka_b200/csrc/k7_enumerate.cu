@@ -107,6 +107,95 @@ __global__ void __launch_bounds__(K7_THREADS) k7_write_kernel(const k7_view v, u
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// SX_ENUM_F_FAST: one search per read.  Tier 1 keeps the scratch in LOCAL memory (the hardware interleaves it per lane, so a converged
+// warp touches one line where the arena touches 32 sectors) sized for ordinary reads; a read that needs more frames or slots is
+// marked and searched again by tier 2 in the global arena.  Either tier appends the read's alignments to a log (bump allocator) and
+// records where; after the scan k7_gather_kernel copies every blob to its place in read order -- the output is independent of
+// which thread got which piece of the log.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t K7_LOCAL_ALNS = 16, K7_LOCAL_FRAMES = 12;
+constexpr uint32_t K7_LOCAL_BYTES = 6400; // >= k7_scratch_bytes(K7_LOCAL_ALNS, K7_LOCAL_FRAMES); checked in k7_run_fast
+
+struct k7_log
+{
+    uint32_t* words;             // the log
+    unsigned long long* cursor;  // next free word
+    uint32_t cap;                // words available
+    uint32_t* blob_off;          // [n_reads] where a read's blob starts (UINT32_MAX: it did not fit -- then the output does not either)
+};
+
+__device__ __forceinline__ void k7_log_append(const k7_log& L, const k7_scratch& S, const uint32_t r)
+{
+    const uint32_t w(k7_blob_words(S));
+    uint32_t off(UINT32_MAX);
+    if (w)
+    {
+        const unsigned long long at(atomicAdd(L.cursor, (unsigned long long)w));
+        if (at + w <= (unsigned long long)L.cap)
+        {
+            off = (uint32_t)at;
+            k7_blob_write(S, L.words + off);
+        }
+    }
+    L.blob_off[r] = off;
+}
+
+__global__ void __launch_bounds__(K7_THREADS) k7_search_local_kernel(const k7_view v, const uint32_t* __restrict__ read_region, uint8_t* __restrict__ status,
+                                                                     uint8_t* __restrict__ tier, const k7_counts c, const k7_log L)
+{
+    __align__(16) unsigned char local[K7_LOCAL_BYTES];
+    k7_scratch S(k7_scratch_at(local, K7_LOCAL_ALNS, K7_LOCAL_FRAMES, K7_ST_RETRY));
+    const uint32_t t(blockIdx.x * blockDim.x + threadIdx.x), nthr(gridDim.x * blockDim.x);
+    for (uint32_t r = t; r < v.b.n_reads; r += nthr)
+    {
+        const uint32_t st(k7_enumerate_read(v, read_region[r], r, S));
+        const bool retry((st & K7_ST_RETRY) != 0);
+        tier[r] = retry ? 1 : 0;
+        uint32_t na(0), ns(0), nk(0);
+        if (!retry)
+        {
+            k7_count(S, st, na, ns, nk);
+            status[r] = (uint8_t)st;
+            if (na) k7_log_append(L, S, r);
+        }
+        c.aln[r] = na;
+        c.seg[r] = ns;
+        c.key[r] = nk;
+    }
+}
+
+__global__ void __launch_bounds__(K7_THREADS) k7_search_arena_kernel(const k7_view v, unsigned char* __restrict__ arena, const size_t per_thread, const uint32_t maxA,
+                                                                     const uint32_t* __restrict__ read_region, uint8_t* __restrict__ status,
+                                                                     const uint8_t* __restrict__ tier, const k7_counts c, const k7_log L)
+{
+    const uint32_t t(blockIdx.x * blockDim.x + threadIdx.x), nthr(gridDim.x * blockDim.x);
+    k7_scratch S(k7_scratch_at(arena + (size_t)t * per_thread, maxA));
+    for (uint32_t r = t; r < v.b.n_reads; r += nthr)
+    {
+        if (!tier[r]) continue;
+        const uint32_t st(k7_enumerate_read(v, read_region[r], r, S));
+        uint32_t na, ns, nk;
+        k7_count(S, st, na, ns, nk);
+        status[r] = (uint8_t)st;
+        if (na) k7_log_append(L, S, r);
+        c.aln[r] = na;
+        c.seg[r] = ns;
+        c.key[r] = nk;
+    }
+}
+
+__global__ void k7_gather_kernel(const uint32_t n_reads, const k7_counts c, const k7_log L, const sx_enum_out o, const uint32_t* __restrict__ totals)
+{
+    if (totals[0] > o.cap_alns || totals[1] > o.cap_segs || totals[2] > o.cap_keys) return; // reported by k7_scan_finish
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x)
+    {
+        const uint32_t na((r + 1 < n_reads ? c.aln[r + 1] : totals[0]) - c.aln[r]);
+        if (na == 0 || L.blob_off[r] == UINT32_MAX) continue;
+        k7_blob_gather(L.words + L.blob_off[r], na, o, c.aln[r], c.seg[r], c.key[r]);
+    }
+}
+
 // the reference's table: starling_align_limit (starling_align_limit.cpp:53-88).  Every quantity is an integer far below 2^24 until
 // the running sum passes max_alignments, so the float arithmetic of the reference is exact there and doubles reproduce it.
 unsigned k7_max_candidate_alignment_toggle(const unsigned n_indel, const unsigned max_alignments)
@@ -169,6 +258,71 @@ int k7_run(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsigned* 
     return SX_OK;
 }
 
+int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsigned* launches)
+{
+    static_assert(K7_LOCAL_ALNS < 256 && K7_LOCAL_FRAMES <= K7_MAX_INDELS + 1, "local tier sizes");
+    if (k7_scratch_bytes(K7_LOCAL_ALNS, K7_LOCAL_FRAMES) > K7_LOCAL_BYTES) return sx_fail(ctx, SX_ERR_ARG, "k7: local scratch smaller than its contents");
+    cudaStream_t st(ctx->s_compute);
+    const uint32_t n(d->n_reads);
+    const uint32_t maxA(d->opts.max_alns_per_read ? std::min<uint32_t>(d->opts.max_alns_per_read, 65535u) : 64u);
+    const size_t per_thread((k7_scratch_bytes(maxA) + 255) & ~(size_t)255);
+    int per_sm(1), per_sm_local(1);
+    SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k7_search_arena_kernel, K7_THREADS, 0));
+    SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_local, k7_search_local_kernel, K7_THREADS, 0));
+    per_sm = std::max(1, per_sm);
+    per_sm_local = std::max(1, per_sm_local);
+    const size_t n_blocks(((size_t)n + K7_THREADS - 1) / K7_THREADS);
+    const size_t blocks_local(std::min<size_t>(n_blocks, (size_t)ctx->sm_count * per_sm_local));
+    // the arena tier sees few reads: a quarter of the device is plenty and keeps the arena small enough for the L2
+    size_t blocks(std::min<size_t>(n_blocks, std::max<size_t>(1, (size_t)ctx->sm_count * per_sm / 4)));
+    const size_t arena_cap((size_t)1 << 30);
+    while (blocks > 1 && blocks * K7_THREADS * per_thread > arena_cap) blocks = (blocks + 1) / 2;
+    int rc;
+    unsigned char* arena(nullptr);
+    if ((rc = sx_ensure(ctx, 40, blocks * K7_THREADS * per_thread, reinterpret_cast<void**>(&arena)))) return rc;
+    uint32_t* read_region(nullptr);
+    if ((rc = sx_ensure(ctx, 41, (size_t)n * 4 + 16, reinterpret_cast<void**>(&read_region)))) return rc;
+    k7_counts c;
+    if ((rc = sx_ensure(ctx, 42, (size_t)n * 4 + 16, reinterpret_cast<void**>(&c.aln)))) return rc;
+    if ((rc = sx_ensure(ctx, 43, (size_t)n * 4 + 16, reinterpret_cast<void**>(&c.seg)))) return rc;
+    if ((rc = sx_ensure(ctx, 44, (size_t)n * 4 + 16, reinterpret_cast<void**>(&c.key)))) return rc;
+    const uint32_t tile(K7_SCAN_THREADS * K7_SCAN_ITEMS), n_tiles((n + tile - 1) / tile);
+    uint32_t* sums(nullptr);
+    if ((rc = sx_ensure(ctx, 45, ((size_t)3 * n_tiles + 4) * 4, reinterpret_cast<void**>(&sums)))) return rc;
+    uint32_t* totals(sums + (size_t)3 * n_tiles);
+    // the log holds whatever the output arrays can hold: 3 words + segments + ceil(keys / 2) words per alignment
+    const unsigned long long want_words((unsigned long long)o->cap_alns * 4ull + o->cap_segs + (o->cap_keys + 1ull) / 2ull + 16ull);
+    k7_log L;
+    L.cap = (uint32_t)std::min<unsigned long long>(want_words, 0xFFFFFFF0ull);
+    uint8_t* tier(nullptr);
+    if ((rc = sx_ensure(ctx, 54, (size_t)L.cap * 4 + 16, reinterpret_cast<void**>(&L.words)))) return rc;
+    if ((rc = sx_ensure(ctx, 55, (size_t)n * 4 + 16, reinterpret_cast<void**>(&L.blob_off)))) return rc;
+    if ((rc = sx_ensure(ctx, 56, 16, reinterpret_cast<void**>(&L.cursor)))) return rc;
+    if ((rc = sx_ensure(ctx, 57, (size_t)n + 16, reinterpret_cast<void**>(&tier)))) return rc;
+    SX_CUDA(ctx, cudaMemsetAsync(L.cursor, 0, 16, st));
+
+    k7_view v;
+    v.b = *d;
+    const int g0(std::max(1, std::min<int>((int)((d->n_regions + 127) / 128), ctx->sm_count * 8)));
+    k7_read_region_kernel<<<g0, 128, 0, st>>>(d->n_regions, d->region_read_off, read_region);
+    SX_CUDA(ctx, cudaGetLastError());
+    k7_search_local_kernel<<<(unsigned)blocks_local, K7_THREADS, 0, st>>>(v, read_region, o->status, tier, c, L);
+    SX_CUDA(ctx, cudaGetLastError());
+    k7_search_arena_kernel<<<(unsigned)blocks, K7_THREADS, 0, st>>>(v, arena, per_thread, maxA, read_region, o->status, tier, c, L);
+    SX_CUDA(ctx, cudaGetLastError());
+    k7_scan_tiles<<<n_tiles, K7_SCAN_THREADS, 0, st>>>(n, c.aln, c.seg, c.key, sums, n_tiles);
+    SX_CUDA(ctx, cudaGetLastError());
+    k7_scan_sums<<<1, K7_SCAN_THREADS, 0, st>>>(sums, n_tiles, totals);
+    SX_CUDA(ctx, cudaGetLastError());
+    k7_scan_finish<<<n_tiles, K7_SCAN_THREADS, 0, st>>>(n, c, sums, n_tiles, totals, *o, ctx->d_status);
+    SX_CUDA(ctx, cudaGetLastError());
+    const int g1(std::max(1, std::min<int>((int)((n + 127) / 128), ctx->sm_count * 16)));
+    k7_gather_kernel<<<g1, 128, 0, st>>>(n, c, L, *o, totals);
+    SX_CUDA(ctx, cudaGetLastError());
+    *launches = 7;
+    return SX_OK;
+}
+
 int k7_check_args(sx_ctx* ctx, const sx_enum_batch* b, const sx_enum_out* o, const char* what)
 {
     if (!b || !o) return sx_fail(ctx, SX_ERR_ARG, "%s: NULL argument", what);
@@ -222,6 +376,7 @@ extern "C" void sx_default_enum_opts(sx_enum_opts* o)
     o->n_samples = 1;
     o->sample_id = 0;
     o->max_alns_per_read = 64;
+    o->flags = 0; // SX_ENUM_F_FAST: see include/strelka_b200.h
 }
 
 extern "C" int sx_enumerate_alignments_dev(sx_ctx* ctx, const sx_enum_batch* d, sx_enum_out* out_dev)
@@ -240,7 +395,7 @@ extern "C" int sx_enumerate_alignments_dev(sx_ctx* ctx, const sx_enum_batch* d, 
     }
     sx_kernel_timer t(ctx);
     unsigned launches(0);
-    if ((rc = k7_run(ctx, d, out_dev, &launches))) return rc;
+    if ((rc = (d->opts.flags & SX_ENUM_F_FAST) ? k7_run_fast(ctx, d, out_dev, &launches) : k7_run(ctx, d, out_dev, &launches))) return rc;
     t.stop(launches);
     if ((rc = t.finish())) return rc;
     return k7_finish(ctx, "sx_enumerate_alignments", nullptr);
@@ -306,7 +461,7 @@ extern "C" int sx_enumerate_alignments(sx_ctx* ctx, const sx_enum_batch* b, sx_e
     if ((rc = sx_ensure(ctx, 24, (size_t)o.cap_alns * 2 + 16, reinterpret_cast<void**>(&o.aln_lead_key)))) return rc;
     if ((rc = sx_ensure(ctx, 25, (size_t)o.cap_alns * 2 + 16, reinterpret_cast<void**>(&o.aln_trail_key)))) return rc;
     unsigned launches(0);
-    if ((rc = k7_run(ctx, &d, &o, &launches))) return rc;
+    if ((rc = (d.opts.flags & SX_ENUM_F_FAST) ? k7_run_fast(ctx, &d, &o, &launches) : k7_run(ctx, &d, &o, &launches))) return rc;
     // the totals decide how much comes back
     SX_CUDA(ctx, cudaMemcpyAsync(out_host->totals, o.totals, 12, cudaMemcpyDeviceToHost, st));
     SX_CUDA(ctx, cudaMemcpyAsync(out_host->aln_off, o.aln_off, (size_t)(b->n_reads + 1) * 4, cudaMemcpyDeviceToHost, st));

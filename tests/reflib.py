@@ -285,7 +285,7 @@ def ref_enumerate_alignments(eb: "B.EnumBatch", cap_alns=None) -> "B.EnumOut":
 _k7core = None
 
 
-def k7core_enumerate(eb: "B.EnumBatch", max_alns: int = 0, cap_alns=None, cap_segs=None, cap_keys=None):
+def k7core_enumerate(eb: "B.EnumBatch", max_alns: int = 0, cap_alns=None, cap_segs=None, cap_keys=None, fast: bool = False):
     """strelka_b200/csrc/k7_core.cuh compiled for the host (tests/cpp/k7_core_host.cpp): the device body run read by read on the CPU.
     Returns (rc, EnumOut)."""
     global _k7core
@@ -297,11 +297,17 @@ def k7core_enumerate(eb: "B.EnumBatch", max_alns: int = 0, cap_alns=None, cap_se
                                os.path.join(ROOT, "tests", "cpp", "k7_core_host.cpp"), "-o", so])
         _k7core = C.CDLL(so)
         _k7core.k7core_run.argtypes = [C.POINTER(A.SxEnumBatch), C.POINTER(A.SxEnumOut), C.c_uint32]
+        _k7core.k7core_run_fast.argtypes = [C.POINTER(A.SxEnumBatch), C.POINTER(A.SxEnumOut), C.c_uint32, _P]
         _k7core.k7core_make_start_pos.argtypes = [_P, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32, _P, _P, _P, _P, _P]
         _k7core.k7core_end_pin_start_pos.argtypes = [_P, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _P, _P]
     if eb is None:
         return _k7core
     out = B.EnumOut(eb, cap_alns, cap_segs, cap_keys)
+    if fast:  # the SX_ENUM_F_FAST launch plan (two scratch tiers, one search, log + gather)
+        retried = np.zeros(1, np.uint32)
+        rc = _k7core.k7core_run_fast(C.byref(eb.c), C.byref(out.c), max_alns, A.ptr(retried))
+        out.n_retried = int(retried[0])
+        return rc, out
     rc = _k7core.k7core_run(C.byref(eb.c), C.byref(out.c), max_alns)
     return rc, out
 

@@ -283,3 +283,22 @@ def test_link_capacity_and_bad_key():
     eb.keys["del_len"][eb.keys["del_len"] > 0] += 1
     rc, _ = reflib.k8core_link(eb, out, want.regions)
     assert rc == -1
+
+
+def test_fast_launch_plan_on_the_cpu():
+    """SX_ENUM_F_FAST as the kernels run it (tests/cpp/k7_core_host.cpp::k7core_run_fast): the small scratch tier with K7_ST_RETRY, the
+    arena tier for the marked reads, ONE search per read, blobs appended to a log in reverse read order, scan, gather -- identical to
+    the oracle, whichever tier served a read."""
+    total = retried = 0
+    for case in range(60):
+        eb = specgen.enum_case(case)
+        cap = eb.n_reads * 64 + 64
+        want = reflib.ox_enumerate_alignments(eb, cap_alns=cap)
+        rc, got = reflib.k7core_enumerate(eb, cap_alns=cap, fast=True)
+        assert rc == 0
+        _same(want, got)
+        total += int(want.totals[0])
+        retried += got.n_retried
+    assert total > 8000 and retried > 100  # both tiers did real work
+    rc, small = reflib.k7core_enumerate(specgen.enum_case(3), cap_alns=5, fast=True)
+    assert rc == A.SX_ERR_CAPACITY

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs only the K7 enumerate_alignments leg of bench.py (bench.py starts it as a process of its own; also the ncu target):
-python tools/k7_leg.py [n_loci [depth [read_len [hbm_peak_gbs]]]]"""
+python tools/k7_leg.py [n_loci [depth [read_len [hbm_peak_gbs [original|fast]]]]]"""
 import json
 import os
 import sys
@@ -11,4 +11,4 @@ from strelka_b200.api import Context  # noqa: E402
 
 ctx = Context(0)
 arg = lambda i, d, t: t(sys.argv[i]) if len(sys.argv) > i else d  # noqa: E731
-print(json.dumps(bench.k7_enumerate_leg(ctx, arg(4, 6572.2, float), n_loci=arg(1, 200_000, int), depth=arg(2, 30, int), read_len=arg(3, 150, int))))
+print(json.dumps(bench.k7_enumerate_leg(ctx, arg(4, 6572.2, float), n_loci=arg(1, 200_000, int), depth=arg(2, 30, int), read_len=arg(3, 150, int), fast=arg(5, "original", str) == "fast")))
