@@ -630,7 +630,9 @@ typedef struct sx_enum_batch {
     const sx_aln_seg* in_segs;         /* normalizedInputAlignment.path, kind = SX_AP_* */
     const uint32_t* in_key_off;        /* [n_reads + 1] */
     const uint16_t* in_keys;           /* window indices of getAlignmentIndels(cal, ref, rseg, maxIndelSize, true), ascending; mismatches
-                                          that are not window entries are dropped (:1865), as the reference does */
+                                          that are not window entries are dropped (:1865), as the reference does; SX_NO_KEY = an indel of
+                                          the alignment that is no window entry: the read gets SX_ENUM_ST_EXCEPTION (:1866-1872).  K7a
+                                          (sx_alignment_indels) computes this array and the two below on the device */
     const uint32_t* use_key_off;       /* [n_reads + 1] */
     const uint16_t* use_keys;          /* window indices of the entries whose tier1/tier2/submap/noise read-id sets hold this read */
     const uint16_t* in_lead_key;       /* [n_reads] leading_indel_key of getCandidateAlignment (:1481-1522) as window index, or SX_NO_KEY */
@@ -658,6 +660,36 @@ typedef struct sx_enum_out { /* caller-allocated, capacities stated */
 void sx_default_enum_opts(sx_enum_opts* o);
 int sx_enumerate_alignments(sx_ctx* ctx, const sx_enum_batch* batch_host, sx_enum_out* out_host);
 int sx_enumerate_alignments_dev(sx_ctx* ctx, const sx_enum_batch* batch_dev, sx_enum_out* out_dev /* device pointers; totals too */);
+
+/* ==========================================================================================
+ * K7a  alignment_indels   (the first step of getCandidateAlignments: which window entries the input alignment already contains)
+ *   replaces  getCandidateAlignment              starling_common/starling_read_align.cpp:1481-1522 (the edge keys)
+ *             getAlignmentIndels(cal, ref, rseg, opt.maxIndelSize, includeMismatches = true)
+ *                                                starling_common/CandidateAlignment.cpp:58-173, called at starling_read_align.cpp:1857
+ *   i.e. the per-BASE host loop in front of K7: every aligned read base is compared with the reference (a mismatch that is a
+ *   window entry is a key of the alignment), every insert / delete / swap of the path is looked up by position, lengths and
+ *   inserted bases.
+ *
+ * Input: the sx_enum_batch being prepared (window, region offsets, in_pos / in_segs / read_len), the read bases and reference
+ * windows where K1 keeps them (the wide formats: seq4 = BAM 4-bit codes, reads of a region back to back from regions[g].seq_off,
+ * each read starting on a byte boundary; ref = ASCII from regions[g].ref_off, positions outside read as 'N') and the insert
+ * sequences of the window entries.  Output: the batch's own in_key_off / in_keys / in_lead_key / in_trail_key arrays.  An indel of
+ * the alignment that is no window entry is written as SX_NO_KEY: K7 then answers the read as the reference does (blt_exception,
+ * :1866-1872 -> SX_ENUM_ST_EXCEPTION); a mismatch that is no window entry is dropped (:1865).
+ * ======================================================================================== */
+typedef struct sx_prep_out { /* caller-allocated */
+    uint32_t cap_keys;
+    uint32_t* totals;        /* [1] keys produced (written even when cap_keys is too small: SX_ERR_CAPACITY) */
+    uint32_t* in_key_off;    /* [n_reads + 1] */
+    uint16_t* in_keys;       /* [cap_keys] ascending per read */
+    uint16_t* in_lead_key;   /* [n_reads] */
+    uint16_t* in_trail_key;  /* [n_reads] */
+} sx_prep_out;
+
+int sx_alignment_indels(sx_ctx* ctx, const sx_enum_batch* batch_host, const sx_region* regions_host /*[n_regions + 1]*/, const uint8_t* seq4_host, const char* ref_host,
+                        const uint32_t* key_ins_off_host, const char* key_ins_host, sx_prep_out* out_host);
+int sx_alignment_indels_dev(sx_ctx* ctx, const sx_enum_batch* batch_dev, const sx_region* regions_dev, const uint8_t* seq4_dev, const char* ref_dev,
+                            const uint32_t* key_ins_off_dev, const char* key_ins_dev, sx_prep_out* out_dev);
 
 /* ==========================================================================================
  * K7b  link_alignments   (K7's output -> K1's alignment description; keeps the chain K7 -> K1 -> K6 in device memory)

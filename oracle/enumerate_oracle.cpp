@@ -526,6 +526,7 @@ void candidateAlignments(const Ctx& C, const sx_enum_batch& b, unsigned r, Warn&
         bool recompute(false);
         for (unsigned i = b.in_key_off[r]; i < b.in_key_off[r + 1]; ++i)
         {
+            if (b.in_keys[i] == SX_NO_KEY) throw Thrown(); // an indel of the alignment that is no window entry (:1866-1872)
             const Key w(b.in_keys[i]);
             const bool mm(isMismatch(C.win[w]));
             auto it(status.find(w));

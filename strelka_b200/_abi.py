@@ -250,6 +250,10 @@ class SxLinkOut(C.Structure):
     _fields_ = [("cap_segs", C.c_uint32), ("cap_ins", C.c_uint32)] + [(n, C.c_void_p) for n in ("totals", "regions", "alns", "segs", "ins", "k6_segs")]
 
 
+class SxPrepOut(C.Structure):
+    _fields_ = [("cap_keys", C.c_uint32)] + [(n, C.c_void_p) for n in ("totals", "in_key_off", "in_keys", "in_lead_key", "in_trail_key")]
+
+
 def default_enum_opts() -> SxEnumOpts:
     """starling_base_options defaults (starling_base_shared.hh:124,139,145,160) through the library's own sx_default_enum_opts."""
     o = SxEnumOpts()
@@ -321,6 +325,8 @@ SYMBOLS = [
     ("sx_default_enum_opts", None, [C.POINTER(SxEnumOpts)]),
     ("sx_enumerate_alignments", C.c_int, [_P, C.POINTER(SxEnumBatch), C.POINTER(SxEnumOut)]),
     ("sx_enumerate_alignments_dev", C.c_int, [_P, C.POINTER(SxEnumBatch), C.POINTER(SxEnumOut)]),
+    ("sx_alignment_indels", C.c_int, [_P, C.POINTER(SxEnumBatch), _P, _P, _P, _P, _P, C.POINTER(SxPrepOut)]),
+    ("sx_alignment_indels_dev", C.c_int, [_P, C.POINTER(SxEnumBatch), _P, _P, _P, _P, _P, C.POINTER(SxPrepOut)]),
     ("sx_link_alignments", C.c_int, [_P, C.POINTER(SxEnumBatch), C.POINTER(SxEnumOut), C.c_uint32, _P, _P, C.POINTER(SxLinkOut)]),
     ("sx_link_alignments_dev", C.c_int, [_P, C.POINTER(SxEnumBatch), C.POINTER(SxEnumOut), C.c_uint32, _P, _P, C.POINTER(SxLinkOut)]),
     ("sx_indel_gl", C.c_int, [_P, C.POINTER(SxIndelBatch), _P]),

@@ -314,3 +314,15 @@ def _link_alignments(self, eb: B.EnumBatch, out: B.EnumOut, regions: np.ndarray,
 
 
 Context.link_alignments = _link_alignments  # K7b
+
+
+def _alignment_indels(self, eb: B.EnumBatch, pools: B.AlignBatch, cap_keys=None) -> B.PrepOut:
+    """K7a: the window entries every read's input alignment already contains (host buffers).  `pools`: the K1 batch holding the reads
+    and reference windows (B.read_pools_of)."""
+    po = B.PrepOut(eb, cap_keys)
+    self._chk(self.lib.sx_alignment_indels(self.h, C.byref(eb.c), A.ptr(pools.regions), A.ptr(pools.seq4), A.ptr(pools.ref), A.ptr(eb.ins_off), A.ptr(eb.ins_pool),
+                                           C.byref(po.c)))
+    return po
+
+
+Context.alignment_indels = _alignment_indels  # K7a

@@ -719,74 +719,84 @@ class EnumReadSpec:
 _COMPLEMENT_FREE_CODES = {"A": 1, "C": 2, "G": 4, "T": 8}
 
 
-def alignment_indels(read: EnumReadSpec, ref: str, ref_begin: int, win: Sequence[WindowKeySpec], max_indel_size: int = 49):
-    """Host side of K7's input: getAlignmentIndels(cal, ref, rseg, maxIndelSize, includeMismatches=true) (CandidateAlignment.cpp:58-173)
-    and the edge keys of getCandidateAlignment (starling_read_align.cpp:1481-1522), as window indices.  Returns (in_keys, lead, trail).
-    Raises KeyError for an indel of the alignment that is not a window entry (the reference throws, starling_read_align.cpp:1866-1872)."""
+def alignment_indels(read: EnumReadSpec, ref: str, ref_begin: int, win: Sequence[WindowKeySpec], max_indel_size: int = 49, strict: bool = True):
+    """Host side of K7's input (what K7a, sx_alignment_indels, computes on the device): getAlignmentIndels(cal, ref, rseg, maxIndelSize,
+    includeMismatches=true) (CandidateAlignment.cpp:58-173) and the edge keys of getCandidateAlignment (starling_read_align.cpp:1481-1522),
+    as window indices.  Returns (in_keys, lead, trail).  An indel of the alignment that is not a window entry: KeyError (the reference
+    throws, starling_read_align.cpp:1866-1872), or with strict=False the index SX_NO_KEY, which makes K7 answer SX_ENUM_ST_EXCEPTION."""
     index_of = {k.order(): i for i, k in enumerate(win)}
+
+    def find(k):
+        w = index_of.get(k.order())
+        if w is None:
+            if strict:
+                raise KeyError(k.order())
+            return A.SX_NO_KEY
+        return w
+
     path = read.path
     match_idx = [i for i, (t, _l) in enumerate(path) if t in "M=X"]
     first, last = (match_idx[0], match_idx[-1]) if match_idx else (len(path), len(path))
-    keys, lead, trail = set(), A.SX_NO_KEY, A.SX_NO_KEY
+    keys, lead, trail, has_lead, has_trail = set(), A.SX_NO_KEY, A.SX_NO_KEY, False, False
     read_off, ref_pos = 0, read.pos
     i = 0
     while i < len(path):
         t, ln = path[i]
         edge = i < first or i > last
-        # a swap = a run of adjacent insert / delete segments (align_path.hh swap_info)
-        j = i
-        ins_len = del_len = 0
-        if t in "ID" and not edge:
-            while j < len(path) and path[j][0] in "ID" and not (j > last):
-                if path[j][0] == "I":
-                    ins_len += path[j][1]
-                else:
-                    del_len += path[j][1]
-                j += 1
+        # a swap = a run of adjacent insert / delete segments holding BOTH kinds (is_segment_swap_start, align_path.cpp:868-895)
+        j, ins_len, del_len = i, 0, 0
+        while j < len(path) and path[j][0] in "ID":
+            if path[j][0] == "I":
+                ins_len += path[j][1]
+            else:
+                del_len += path[j][1]
+            j += 1
+        swap = ins_len > 0 and del_len > 0
+        step = 1
         if edge:
-            if t in "ID":
-                k = WindowKeySpec(ref_pos, ln if t == "D" else 0, read.seq[read_off : read_off + ln] if t == "I" else "")
-                w = index_of[k.order()]
-                keys.add(w)
+            if t in "ID":  # getCandidateAlignment sets the edge key for every edge indel segment, the last one wins; it is inserted once
+                w = find(WindowKeySpec(ref_pos, ln if t == "D" else 0, read.seq[read_off : read_off + ln] if t == "I" else ""))
                 if i < first:
-                    lead = w
+                    lead, has_lead = w, True
                 else:
-                    trail = w
-            j = i + 1
+                    trail, has_trail = w, True
+        elif swap:
+            step = j - i
+            keys.add(find(WindowKeySpec(ref_pos, del_len, read.seq[read_off : read_off + ins_len])) if max(ins_len, del_len) <= max_indel_size else A.SX_NO_KEY)
         elif t in "ID":
-            if max(ins_len, del_len) > max_indel_size:
-                raise NotImplementedError("breakend keys are not part of this build")
-            k = WindowKeySpec(ref_pos, del_len, read.seq[read_off : read_off + ins_len])
-            keys.add(index_of[k.order()])
-        else:
-            j = i + 1
-            if t in "M=X":
-                for b in range(ln):
-                    base = read.seq[read_off + b]
-                    if base not in "ACGT":  # BAM_BASE::REF ('=') and ANY ('N') are skipped; other IUPAC codes never equal the reference
-                        if base in "=N":
-                            continue
-                    rp = ref_pos + b
-                    rb = ref[rp - ref_begin] if 0 <= rp - ref_begin < len(ref) else "N"
-                    if base == rb:
-                        continue
-                    w = index_of.get(WindowKeySpec(rp, 1, base, mismatch=True).order())
-                    if w is not None:  # a mismatch that is no window entry is dropped (starling_read_align.cpp:1865)
-                        keys.add(w)
-        for s in range(i, j):
+            keys.add(find(WindowKeySpec(ref_pos, ln if t == "D" else 0, read.seq[read_off : read_off + ln] if t == "I" else "")) if ln <= max_indel_size else A.SX_NO_KEY)
+        elif t in "M=X":
+            for b in range(ln):
+                base = read.seq[read_off + b]
+                if base in "=N":  # BAM_BASE::REF and ANY are skipped; every other IUPAC code reads back as 'N' and never equals the reference code
+                    continue
+                if base not in "ACGT":
+                    base = "N"
+                rp = ref_pos + b
+                rb = ref[rp - ref_begin] if 0 <= rp - ref_begin < len(ref) else "N"
+                if base == rb:
+                    continue
+                w = index_of.get(WindowKeySpec(rp, 1, base, mismatch=True).order())
+                if w is not None:  # a mismatch that is no window entry is dropped (starling_read_align.cpp:1865)
+                    keys.add(w)
+        for s in range(i, i + step):
             st, sl = path[s]
             if st in "MIS=X":
                 read_off += sl
             if st in "MDN=X":
                 ref_pos += sl
-        i = j
+        i += step
+    if has_lead:
+        keys.add(lead)
+    if has_trail:
+        keys.add(trail)
     return sorted(keys), lead, trail
 
 
 class EnumBatch:
     """Owns the arrays of one sx_enum_batch.  regions = [(ref, ref_begin, (realign_begin, realign_end), window keys in IndelKey order, reads)]."""
 
-    def __init__(self, regions, opts=None):
+    def __init__(self, regions, opts=None, strict=True):
         self.opts = opts or A.default_enum_opts()
         keys, hap, ins_pool, ins_off = [], [], bytearray(), [0]
         region_read_off, region_key_off, rb, re_ = [0], [0], [], []
@@ -807,7 +817,7 @@ class EnumBatch:
                 ins_pool.extend(k.ins.encode())
                 ins_off.append(len(ins_pool))
             for r in reads:
-                ik, ld, tr = alignment_indels(r, ref, rbeg, win, self.opts.max_indel_size)
+                ik, ld, tr = alignment_indels(r, ref, rbeg, win, self.opts.max_indel_size, strict)
                 in_pos.append(r.pos)
                 in_segs.extend((ln, _AP_OF[t], 0) for t, ln in r.path)
                 in_seg_off.append(len(in_segs))
@@ -960,3 +970,33 @@ def regions_from_enumeration(eb: EnumBatch, out: "EnumOut", quals_of=None) -> Li
                                                    kidx.index(trail) if trail != A.SX_NO_KEY else -1))
         regions.append(RegionSpec(ref, int(eb.ref_begin[g]), reads, alns))
     return regions
+
+
+class PrepOut:
+    """Host buffers for sx_prep_out (K7a)."""
+
+    def __init__(self, eb: EnumBatch, cap_keys=None):
+        self.cap_keys = cap_keys if cap_keys is not None else 8 * eb.n_reads + 64
+        self.totals = np.zeros(2, np.uint32)
+        self.in_key_off = np.zeros(eb.n_reads + 1, np.uint32)
+        self.in_keys = np.zeros(self.cap_keys + 1, np.uint16)
+        self.in_lead_key = np.zeros(eb.n_reads + 1, np.uint16)
+        self.in_trail_key = np.zeros(eb.n_reads + 1, np.uint16)
+        self.c = A.SxPrepOut(self.cap_keys, A.ptr(self.totals), A.ptr(self.in_key_off), A.ptr(self.in_keys), A.ptr(self.in_lead_key), A.ptr(self.in_trail_key))
+        self._n = eb.n_reads
+
+    def trimmed(self):
+        return self.in_key_off[: self._n + 1].copy(), self.in_keys[: int(self.totals[0])].copy(), self.in_lead_key[: self._n].copy(), self.in_trail_key[: self._n].copy()
+
+
+def read_pools_of(eb: EnumBatch) -> AlignBatch:
+    """The reads and reference windows of an EnumBatch where K1 keeps them (an AlignBatch without alignments): K7a's other input."""
+    regions = []
+    for g in range(eb.n_regions):
+        ref = bytes(eb.ref_pool[int(eb.ref_off[g]) : int(eb.ref_off[g + 1])]).decode()
+        reads = []
+        for r in range(int(eb.region_read_off[g]), int(eb.region_read_off[g + 1])):
+            seq = bytes(eb.read_pool[int(eb.read_off[r]) : int(eb.read_off[r + 1])]).decode()
+            reads.append((codes_of(seq), np.full(len(seq), 30, np.uint8)))
+        regions.append(RegionSpec(ref, int(eb.ref_begin[g]), reads, []))
+    return build_align_batch(regions)

@@ -926,6 +926,7 @@ K7_HDN uint32_t k7_enumerate_read_raw(const k7_view& v, const uint32_t region, c
     for (uint32_t i = b.in_key_off[r]; i < b.in_key_off[r + 1]; ++i)
     {
         const uint16_t w(b.in_keys[i]);
+        if (w == SX_NO_KEY) return SX_ENUM_ST_EXCEPTION; // an indel of the alignment that the window does not hold: what :1866-1872 throws for
         if (w >= R.n_win) return SX_ENUM_ST_LIMIT;
         uint32_t at(n);
         for (uint32_t j = 0; j < n; ++j)

@@ -1,0 +1,233 @@
+// k7a_prepare.cu -- K7a alignment_indels: the keys an input alignment already contains, on the device.
+//
+// Replaces (include/strelka_b200.h, "K7a alignment_indels") the first step of getCandidateAlignments
+// (starling_common/starling_read_align.cpp:1853-1858): getCandidateAlignment :1481-1522 + getAlignmentIndels
+// (CandidateAlignment.cpp:58-173) -- the per-base host loop in front of K7.  Per-read body: k7a_core.cuh.
+//
+// Shape of the work: one pass over every aligned read base (a nibble load + a reference byte load + a compare; a binary search of the
+// window only at a mismatch) -- HBM-bound at ~1.5 bytes per base, all of it data K1 reads anyway.  One read per thread; the CSR
+// output needs the usual count -> scan -> write, and the body is cheap enough to run twice.
+
+#include "k7a_core.cuh"
+#include "sx_internal.h"
+#include "sx_scan3.cuh"
+
+#include <algorithm>
+
+namespace
+{
+constexpr int K7A_CAP_BIT = 1 << 18;
+
+// byte offset of every read's first packed base: reads of a region are back to back from its seq_off, each on a byte boundary
+__global__ void k7a_read_offsets_kernel(const k7a_view v, unsigned long long* __restrict__ read_byte, uint32_t* __restrict__ read_region)
+{
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < v.b.n_regions; g += gridDim.x * blockDim.x)
+    {
+        unsigned long long at(v.regions[g].seq_off);
+        for (uint32_t r = v.b.region_read_off[g]; r < v.b.region_read_off[g + 1]; ++r)
+        {
+            read_byte[r] = at;
+            read_region[r] = g;
+            at += (v.b.read_len[r] + 1u) / 2u;
+        }
+    }
+}
+
+__global__ void k7a_count_kernel(const k7a_view v, const unsigned long long* __restrict__ read_byte, const uint32_t* __restrict__ read_region, uint32_t* __restrict__ cnt,
+                                 uint32_t* __restrict__ zero1, uint32_t* __restrict__ zero2, const sx_prep_out o)
+{
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < v.b.n_reads; r += gridDim.x * blockDim.x)
+    {
+        uint16_t keys[K7A_MAX_KEYS], lead, trail;
+        cnt[r] = k7a_read(v, read_region[r], r, read_byte[r], keys, lead, trail);
+        zero1[r] = zero2[r] = 0;
+        o.in_lead_key[r] = lead;
+        o.in_trail_key[r] = trail;
+    }
+}
+
+__global__ void __launch_bounds__(K7_SCAN_THREADS) k7a_finish_kernel(const uint32_t n, uint32_t* __restrict__ cnt, const uint32_t* __restrict__ sums, const uint32_t* __restrict__ totals,
+                                                                    const sx_prep_out o, int* __restrict__ status)
+{
+    const uint32_t tile(blockIdx.x), base(tile * K7_SCAN_THREADS * K7_SCAN_ITEMS + threadIdx.x * K7_SCAN_ITEMS);
+    const uint32_t off(sums[tile]);
+    for (int i = 0; i < K7_SCAN_ITEMS; ++i)
+        if (base + i < n)
+        {
+            const uint32_t x(cnt[base + i] + off);
+            cnt[base + i] = x;
+            o.in_key_off[base + i] = x;
+        }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        o.in_key_off[n] = totals[0];
+        o.totals[0] = totals[0];
+        if (totals[0] > o.cap_keys) atomicOr(status, K7A_CAP_BIT);
+    }
+}
+
+__global__ void k7a_write_kernel(const k7a_view v, const unsigned long long* __restrict__ read_byte, const uint32_t* __restrict__ read_region, const uint32_t* __restrict__ off,
+                                 const uint32_t* __restrict__ totals, const sx_prep_out o)
+{
+    if (totals[0] > o.cap_keys) return;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < v.b.n_reads; r += gridDim.x * blockDim.x)
+    {
+        uint16_t keys[K7A_MAX_KEYS], lead, trail;
+        const uint32_t n(k7a_read(v, read_region[r], r, read_byte[r], keys, lead, trail));
+        for (uint32_t i = 0; i < n; ++i) o.in_keys[off[r] + i] = keys[i];
+    }
+}
+
+int k7a_run(sx_ctx* ctx, const k7a_view& v, const sx_prep_out* o, unsigned* launches)
+{
+    cudaStream_t st(ctx->s_compute);
+    const uint32_t n(v.b.n_reads);
+    int rc;
+    unsigned long long* read_byte(nullptr);
+    uint32_t *read_region(nullptr), *cnt(nullptr), *z1(nullptr), *z2(nullptr), *sums(nullptr);
+    if ((rc = sx_ensure(ctx, 58, (size_t)n * 8 + 16, reinterpret_cast<void**>(&read_byte)))) return rc;
+    if ((rc = sx_ensure(ctx, 59, (size_t)n * 4 + 16, reinterpret_cast<void**>(&read_region)))) return rc;
+    if ((rc = sx_ensure(ctx, 60, (size_t)n * 4 + 16, reinterpret_cast<void**>(&cnt)))) return rc;
+    if ((rc = sx_ensure(ctx, 61, (size_t)n * 4 + 16, reinterpret_cast<void**>(&z1)))) return rc;
+    if ((rc = sx_ensure(ctx, 62, (size_t)n * 4 + 16, reinterpret_cast<void**>(&z2)))) return rc;
+    const uint32_t tile(K7_SCAN_THREADS * K7_SCAN_ITEMS), n_tiles((n + tile - 1) / tile);
+    if ((rc = sx_ensure(ctx, 63, ((size_t)3 * n_tiles + 4) * 4, reinterpret_cast<void**>(&sums)))) return rc;
+    uint32_t* totals(sums + (size_t)3 * n_tiles);
+    const int cap(ctx->sm_count * 16);
+    const auto grid = [cap](const uint32_t m) { return (unsigned)std::max(1, std::min<int>((int)((m + 127) / 128), cap)); };
+    k7a_read_offsets_kernel<<<grid(v.b.n_regions), 128, 0, st>>>(v, read_byte, read_region);
+    SX_CUDA(ctx, cudaGetLastError());
+    k7a_count_kernel<<<grid(n), 128, 0, st>>>(v, read_byte, read_region, cnt, z1, z2, *o);
+    SX_CUDA(ctx, cudaGetLastError());
+    k7_scan_tiles<<<n_tiles, K7_SCAN_THREADS, 0, st>>>(n, cnt, z1, z2, sums, n_tiles);
+    SX_CUDA(ctx, cudaGetLastError());
+    k7_scan_sums<<<1, K7_SCAN_THREADS, 0, st>>>(sums, n_tiles, totals);
+    SX_CUDA(ctx, cudaGetLastError());
+    k7a_finish_kernel<<<n_tiles, K7_SCAN_THREADS, 0, st>>>(n, cnt, sums, totals, *o, ctx->d_status);
+    SX_CUDA(ctx, cudaGetLastError());
+    k7a_write_kernel<<<grid(n), 128, 0, st>>>(v, read_byte, read_region, cnt, totals, *o);
+    SX_CUDA(ctx, cudaGetLastError());
+    *launches = 6;
+    return SX_OK;
+}
+
+int k7a_finish(sx_ctx* ctx, const char* what, const uint32_t* totals_host)
+{
+    int st(0);
+    SX_CUDA(ctx, cudaMemcpyAsync(&st, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_compute));
+    SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    if (st & K7A_CAP_BIT)
+    {
+        cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->s_compute);
+        if (totals_host) return sx_fail(ctx, SX_ERR_CAPACITY, "%s: cap_keys too small: %u keys needed", what, totals_host[0]);
+        return sx_fail(ctx, SX_ERR_CAPACITY, "%s: cap_keys too small (totals[0] holds the needed size)", what);
+    }
+    return sx_check_status(ctx, what);
+}
+
+int k7a_check_args(sx_ctx* ctx, const sx_enum_batch* b, const sx_region* regions, const uint8_t* seq4, const char* ref, const uint32_t* key_ins_off, const char* key_ins,
+                   const sx_prep_out* o, const char* what)
+{
+    if (!b || !o || !regions || !seq4 || !ref) return sx_fail(ctx, SX_ERR_ARG, "%s: NULL argument", what);
+    if (!o->totals || !o->in_key_off) return sx_fail(ctx, SX_ERR_ARG, "%s: NULL output array", what);
+    if (b->n_reads == 0) return SX_OK;
+    if (!b->region_read_off || !b->region_key_off || !b->in_pos || !b->in_seg_off || !b->in_segs || !b->read_len || (b->n_keys && (!b->keys || !key_ins_off || !key_ins)) ||
+        !o->in_keys || !o->in_lead_key || !o->in_trail_key)
+        return sx_fail(ctx, SX_ERR_ARG, "%s: NULL array", what);
+    if (b->n_regions == 0) return sx_fail(ctx, SX_ERR_ARG, "%s: reads without a region", what);
+    return SX_OK;
+}
+} // namespace
+
+extern "C" int sx_alignment_indels_dev(sx_ctx* ctx, const sx_enum_batch* d, const sx_region* regions, const uint8_t* seq4, const char* ref, const uint32_t* key_ins_off,
+                                       const char* key_ins, sx_prep_out* out_dev)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    int rc;
+    if ((rc = k7a_check_args(ctx, d, regions, seq4, ref, key_ins_off, key_ins, out_dev, "sx_alignment_indels_dev"))) return rc;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (d->n_reads == 0)
+    {
+        SX_CUDA(ctx, cudaMemsetAsync(out_dev->totals, 0, 4, ctx->s_compute));
+        SX_CUDA(ctx, cudaMemsetAsync(out_dev->in_key_off, 0, 4, ctx->s_compute));
+        SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+        return SX_OK;
+    }
+    k7a_view v;
+    v.b = *d;
+    v.regions = regions;
+    v.seq4 = seq4;
+    v.ref = ref;
+    v.key_ins_off = key_ins_off;
+    v.key_ins = key_ins;
+    sx_kernel_timer t(ctx);
+    unsigned launches(0);
+    if ((rc = k7a_run(ctx, v, out_dev, &launches))) return rc;
+    t.stop(launches);
+    if ((rc = t.finish())) return rc;
+    return k7a_finish(ctx, "sx_alignment_indels", nullptr);
+}
+
+extern "C" int sx_alignment_indels(sx_ctx* ctx, const sx_enum_batch* b, const sx_region* regions, const uint8_t* seq4, const char* ref, const uint32_t* key_ins_off,
+                                   const char* key_ins, sx_prep_out* out_host)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    int rc;
+    if ((rc = k7a_check_args(ctx, b, regions, seq4, ref, key_ins_off, key_ins, out_host, "sx_alignment_indels"))) return rc;
+    if (b->n_reads == 0)
+    {
+        out_host->totals[0] = 0;
+        out_host->in_key_off[0] = 0;
+        return SX_OK;
+    }
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st(ctx->s_compute);
+    SX_CUDA(ctx, cudaEventRecord(ctx->ev_a, st));
+    k7a_view v;
+    v.b = *b;
+    void* p(nullptr);
+    const size_t n_segs(b->in_seg_off[b->n_reads]);
+    const sx_region& end(regions[b->n_regions]); // the sentinel carries the pool sizes
+#define SX_UPX(slot, dst, src, type, bytes)                                                \
+    if ((rc = sx_ensure(ctx, slot, (size_t)(bytes) + 16, &p))) return rc;                   \
+    if (bytes) SX_CUDA(ctx, cudaMemcpyAsync(p, (src), (bytes), cudaMemcpyHostToDevice, st)); \
+    dst = static_cast<type>(p);
+    SX_UPX(0, v.b.region_read_off, b->region_read_off, const uint32_t*, (size_t)(b->n_regions + 1) * 4)
+    SX_UPX(1, v.b.region_key_off, b->region_key_off, const uint32_t*, (size_t)(b->n_regions + 1) * 4)
+    SX_UPX(2, v.b.keys, b->keys, const sx_indel_key*, (size_t)b->n_keys * sizeof(sx_indel_key))
+    SX_UPX(3, v.b.in_pos, b->in_pos, const int32_t*, (size_t)b->n_reads * 4)
+    SX_UPX(4, v.b.in_seg_off, b->in_seg_off, const uint32_t*, (size_t)(b->n_reads + 1) * 4)
+    SX_UPX(5, v.b.in_segs, b->in_segs, const sx_aln_seg*, n_segs * sizeof(sx_aln_seg))
+    SX_UPX(6, v.b.read_len, b->read_len, const uint16_t*, (size_t)b->n_reads * 2)
+    SX_UPX(7, v.regions, regions, const sx_region*, ((size_t)b->n_regions + 1) * sizeof(sx_region))
+    SX_UPX(8, v.seq4, seq4, const uint8_t*, (size_t)end.seq_off + SX_POOL_SLACK)
+    SX_UPX(9, v.ref, ref, const char*, (size_t)end.ref_off + SX_POOL_SLACK)
+    const size_t ins_bytes(b->n_keys ? key_ins_off[b->n_keys] : 0);
+    SX_UPX(10, v.key_ins_off, key_ins_off, const uint32_t*, b->n_keys ? ((size_t)b->n_keys + 1) * 4 : 0)
+    SX_UPX(11, v.key_ins, key_ins, const char*, ins_bytes)
+#undef SX_UPX
+    sx_prep_out o(*out_host);
+    if ((rc = sx_ensure(ctx, 12, 16, reinterpret_cast<void**>(&o.totals)))) return rc;
+    if ((rc = sx_ensure(ctx, 13, (size_t)(b->n_reads + 1) * 4 + 16, reinterpret_cast<void**>(&o.in_key_off)))) return rc;
+    if ((rc = sx_ensure(ctx, 14, (size_t)o.cap_keys * 2 + 16, reinterpret_cast<void**>(&o.in_keys)))) return rc;
+    if ((rc = sx_ensure(ctx, 15, (size_t)b->n_reads * 2 + 16, reinterpret_cast<void**>(&o.in_lead_key)))) return rc;
+    if ((rc = sx_ensure(ctx, 16, (size_t)b->n_reads * 2 + 16, reinterpret_cast<void**>(&o.in_trail_key)))) return rc;
+    unsigned launches(0);
+    if ((rc = k7a_run(ctx, v, &o, &launches))) return rc;
+    SX_CUDA(ctx, cudaMemcpyAsync(out_host->totals, o.totals, 4, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaMemcpyAsync(out_host->in_key_off, o.in_key_off, (size_t)(b->n_reads + 1) * 4, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaMemcpyAsync(out_host->in_lead_key, o.in_lead_key, (size_t)b->n_reads * 2, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaMemcpyAsync(out_host->in_trail_key, o.in_trail_key, (size_t)b->n_reads * 2, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    if (out_host->totals[0] <= o.cap_keys) SX_CUDA(ctx, cudaMemcpyAsync(out_host->in_keys, o.in_keys, (size_t)out_host->totals[0] * 2, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaEventRecord(ctx->ev_b, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms(0);
+    cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+    ctx->timing.kernel_ms = ms;
+    ctx->timing.launches = launches;
+    ctx->total_launches += launches;
+    return k7a_finish(ctx, "sx_alignment_indels", out_host->totals);
+}

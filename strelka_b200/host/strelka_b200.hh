@@ -866,37 +866,55 @@ public:
             }
         std::vector<uint16_t> keys;
         uint16_t lead(SX_NO_KEY), trail(SX_NO_KEY);
+        bool hasLead(false), hasTrail(false);
         unsigned readOff(0);
         pos_t refPos(normalizedInputAlignment.pos);
         for (size_t i(0); i < path.size();)
         {
             const path_segment& ps(path[i]);
             const bool edge(i < first || i > last);
-            size_t j(i + 1);
+            // a swap = a run of adjacent insert / delete segments holding BOTH kinds (is_segment_swap_start, align_path.cpp:868-895)
+            size_t j(i);
+            unsigned insLen(0), delLen(0);
+            for (; j < path.size() && (path[j].type == INSERT || path[j].type == DELETE); ++j) (path[j].type == INSERT ? insLen : delLen) += path[j].length;
+            const bool isSwap(insLen && delLen);
+            size_t step(1);
             if (edge)
             {
-                if (ps.type == INSERT || ps.type == DELETE)
+                if (ps.type == INSERT || ps.type == DELETE) // the edge key is set anew for every edge indel segment (:1495-1518); it is inserted once
                 {
                     const IndelKey k(refPos, INDEL::INDEL, ps.type == DELETE ? ps.length : 0, ps.type == INSERT ? readBases.substr(readOff, ps.length).c_str() : "");
                     const uint16_t w(indexOf(k, true));
-                    keys.push_back(w);
-                    (i < first ? lead : trail) = w;
+                    if (i < first)
+                    {
+                        lead = w;
+                        hasLead = true;
+                    }
+                    else
+                    {
+                        trail = w;
+                        hasTrail = true;
+                    }
                 }
+            }
+            else if (isSwap)
+            {
+                step = j - i;
+                if (std::max(insLen, delLen) > maxIndelSize) throw Exception(SX_ERR_UNSUPPORTED, "AlignmentSearchBatch: indel above maxIndelSize (breakend keys are not supported)");
+                keys.push_back(indexOf(IndelKey(refPos, INDEL::INDEL, delLen, readBases.substr(readOff, insLen).c_str()), true));
             }
             else if (ps.type == INSERT || ps.type == DELETE)
             {
-                unsigned insLen(0), delLen(0);
-                for (j = i; j < path.size() && j <= last && (path[j].type == INSERT || path[j].type == DELETE); ++j)
-                    (path[j].type == INSERT ? insLen : delLen) += path[j].length;
-                if (std::max(insLen, delLen) > maxIndelSize) throw Exception(SX_ERR_UNSUPPORTED, "AlignmentSearchBatch: indel above maxIndelSize (breakend keys are not supported)");
-                keys.push_back(indexOf(IndelKey(refPos, INDEL::INDEL, delLen, readBases.substr(readOff, insLen).c_str()), true));
+                if (ps.length > maxIndelSize) throw Exception(SX_ERR_UNSUPPORTED, "AlignmentSearchBatch: indel above maxIndelSize (breakend keys are not supported)");
+                keys.push_back(indexOf(IndelKey(refPos, INDEL::INDEL, ps.type == DELETE ? ps.length : 0, ps.type == INSERT ? readBases.substr(readOff, ps.length).c_str() : ""), true));
             }
             else if (ps.type == MATCH || ps.type == SEQ_MATCH || ps.type == SEQ_MISMATCH)
             {
                 for (unsigned b(0); b < ps.length; ++b)
                 {
-                    const char base(readBases[readOff + b]);
+                    char base(readBases[readOff + b]);
                     if (base == '=' || base == 'N') continue; // BAM_BASE::REF, BAM_BASE::ANY
+                    if (base != 'A' && base != 'C' && base != 'G' && base != 'T') base = 'N'; // every other code reads back as 'N' and never equals the reference code
                     const pos_t rp(refPos + static_cast<pos_t>(b));
                     const char refBase((rp >= _refBegin && rp < _refBegin + static_cast<pos_t>(_ref.size())) ? _ref[rp - _refBegin] : 'N');
                     if (base == refBase) continue;
@@ -905,14 +923,16 @@ public:
                     if (w != SX_NO_KEY) keys.push_back(w); // a mismatch that is no window entry is dropped (:1865)
                 }
             }
-            for (size_t s(i); s < j; ++s)
+            for (size_t s(i); s < i + step; ++s)
             {
                 const ALIGNPATH::align_t t(path[s].type);
                 if (t == MATCH || t == INSERT || t == SOFT_CLIP || t == SEQ_MATCH || t == SEQ_MISMATCH) readOff += path[s].length;
                 if (t == MATCH || t == DELETE || t == SKIP || t == SEQ_MATCH || t == SEQ_MISMATCH) refPos += path[s].length;
             }
-            i = j;
+            i += step;
         }
+        if (hasLead) keys.push_back(lead);
+        if (hasTrail) keys.push_back(trail);
         std::sort(keys.begin(), keys.end());
         keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
         _inKeys.insert(_inKeys.end(), keys.begin(), keys.end());

@@ -342,3 +342,37 @@ def k8core_link(eb: "B.EnumBatch", out: "B.EnumOut", regions: np.ndarray, cap_se
                    cap_ins if cap_ins is not None else 64 * n_alns + 16 * eb.n_regions + 64, n_enum_segs=int(out.totals[1]))
     rc = _k8core.k8core_run(C.byref(eb.c), C.byref(out.c), n_alns, A.ptr(eb.ins_off), A.ptr(eb.ins_pool), C.byref(lo.c))
     return rc, lo
+
+
+def ref_alignment_indels(eb: "B.EnumBatch"):
+    """The reference's getCandidateAlignment + getAlignmentIndels(includeMismatches) for every read, as window indices
+    (oracle/ref_harness_enumerate.inc): (in_key_off, in_keys, lead, trail)."""
+    po = B.PrepOut(eb, 64 * eb.n_reads + 64)
+    err = _err()
+    fn = ref().ref_alignment_indels
+    fn.argtypes = [C.POINTER(A.SxEnumBatch), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint32, _P, _P, C.c_char_p, C.c_int]
+    rc = fn(C.byref(eb.c), A.ptr(eb.ins_pool), A.ptr(eb.ins_off), A.ptr(eb.ref_pool), A.ptr(eb.ref_off), A.ptr(eb.ref_begin), A.ptr(eb.read_pool), A.ptr(eb.read_off),
+            A.ptr(po.in_key_off), A.ptr(po.in_keys), po.cap_keys, A.ptr(po.in_lead_key), A.ptr(po.in_trail_key), err, 1024)
+    if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    po.totals[0] = po.in_key_off[eb.n_reads]
+    return po
+
+
+_k7acore = None
+
+
+def k7acore_prepare(eb: "B.EnumBatch", pools: "B.AlignBatch", cap_keys=None):
+    """strelka_b200/csrc/k7a_core.cuh compiled for the host (tests/cpp/k7a_core_host.cpp): K7a's device body on the CPU.  (rc, PrepOut)"""
+    global _k7acore
+    if _k7acore is None:
+        import tempfile
+
+        so = os.path.join(tempfile.mkdtemp(prefix="k7acore"), "libk7acore.so")
+        subprocess.check_call(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "strelka_b200", "csrc"),
+                               os.path.join(ROOT, "tests", "cpp", "k7a_core_host.cpp"), "-o", so])
+        _k7acore = C.CDLL(so)
+        _k7acore.k7acore_run.argtypes = [C.POINTER(A.SxEnumBatch), _P, _P, _P, _P, _P, C.POINTER(A.SxPrepOut)]
+    po = B.PrepOut(eb, cap_keys)
+    rc = _k7acore.k7acore_run(C.byref(eb.c), A.ptr(pools.regions), A.ptr(pools.seq4), A.ptr(pools.ref), A.ptr(eb.ins_off), A.ptr(eb.ins_pool), C.byref(po.c))
+    return rc, po

@@ -716,3 +716,75 @@ def score_indels_batch_from_enumeration(eb: "B.EnumBatch", out: "B.EnumOut", ref
                   aln_seg_off=aln_seg_off, segs=segs2, aln_key_off=aln_key_off, aln_keys=np.concatenate([aln_keys, [0]]).astype(np.uint16), read_len=eb.read_len,
                   non_ambig=eb.read_len.copy(), read_flags=np.full(eb.n_reads + 1, A.SX_SIF_FWD | A.SX_SIF_TIER1, np.uint8), rec_off=rec_off)
     return B.ScoreIndelsBatch.from_arrays(arrays)
+
+
+def enum_edge_case(case: int, n_regions: int = 5):
+    """K7a / K7 inputs outside the tidy ones enum_case makes: input alignments with leading / trailing edge insertions and deletions
+    (RNA-style pinned edges), indels that are no window entries (private indels: SX_NO_KEY, the reference throws), adjacent
+    insert + delete runs in both orders, read bases '=' and non-ACGT letters."""
+    rng = np.random.default_rng(9000 + case)
+    regions = []
+    for _ in range(n_regions):
+        ref, ref_begin, realign, win, reads = random_enum_region(rng, n_reads=int(rng.integers(2, 7)), cluster=bool(case & 1), n_keys=(2, 8), clip_rate=0.2)
+        extra = {}
+        out_reads = []
+        for r in reads:
+            path, seq, pos = list(r.path), r.seq, r.pos
+            body = [i for i, (t, _l) in enumerate(path) if t != "H"]
+            u = rng.random()
+            if u < 0.3 and path[body[0]][0] == "M" and path[body[0]][1] > 8:  # leading edge insertion (+ sometimes a deletion behind it)
+                n = int(rng.integers(1, 5))
+                i0 = body[0]
+                path[i0] = ("M", path[i0][1] - n)
+                ins = [("I", n)]  # (an insertion + deletion at the leading edge makes the reference assert, starling_read_align.cpp:461)
+                path[i0:i0] = ins
+                pos += n  # the first n read bases are inserted: the match now starts n reference bases further on
+                if rng.random() < 0.7:  # make the edge key(s) window entries
+                    rp = pos
+                    for t, ln in ins:
+                        k = B.EnumKeySpec(rp, ln if t == "D" else 0, seq[:n] if t == "I" else "", candidate=bool(rng.random() < 0.5))
+                        extra.setdefault(k.order(), k)
+                        rp += ln if t == "D" else 0
+            elif u < 0.55 and path[body[-1]][0] == "M" and path[body[-1]][1] > 8:  # trailing edge insertion / deletion
+                i1 = body[-1]
+                if rng.random() < 0.5:
+                    n = int(rng.integers(1, 5))
+                    path[i1] = ("M", path[i1][1] - n)
+                    path.insert(i1 + 1, ("I", n))
+                    end = pos + sum(ln for t, ln in path if t in "MD=X")
+                    if rng.random() < 0.7:
+                        k = B.EnumKeySpec(end, 0, seq[len(seq) - n:], candidate=True)
+                        extra.setdefault(k.order(), k)
+                else:
+                    d = int(rng.integers(1, 6))
+                    end = pos + sum(ln for t, ln in path if t in "MD=X")
+                    path.insert(i1 + 1, ("D", d))
+                    if rng.random() < 0.7:
+                        k = B.EnumKeySpec(end, d, "", candidate=True)
+                        extra.setdefault(k.order(), k)
+            elif u < 0.75:  # a private indel in the middle of the first long match: not a window entry
+                for i, (t, ln) in enumerate(path):
+                    if t == "M" and ln > 20:
+                        a = int(rng.integers(5, ln - 5))
+                        if rng.random() < 0.5:
+                            path[i:i + 1] = [("M", a), ("D", int(rng.integers(1, 4))), ("M", ln - a)]
+                        else:
+                            n = int(rng.integers(1, 4))
+                            path[i:i + 1] = [("M", a), ("I", n), ("D", int(rng.integers(1, 4))), ("M", ln - a - n)] if rng.random() < 0.5 else [("M", a), ("I", n), ("M", ln - a - n)]
+                        break
+            if rng.random() < 0.3:  # '=' and IUPAC letters among the read bases
+                s = list(seq)
+                for _i in range(3):
+                    s[int(rng.integers(0, len(s)))] = str(rng.choice(list("=NRYM")))
+                seq = "".join(s)
+            out_reads.append(B.EnumReadSpec(seq, pos, path, r.use_keys))
+        keys = {k.order(): k for k in win}
+        # the read-specific `use_keys` were window indices of the old window: recompute them by key
+        old_order = [k.order() for k in win]
+        keys.update({o: k for o, k in extra.items() if o not in keys})
+        new_win = [keys[o] for o in sorted(keys)]
+        index_of = {k.order(): i for i, k in enumerate(new_win)}
+        for r in out_reads:
+            r.use_keys = sorted({index_of[old_order[w]] for w in r.use_keys} | {i for i, k in enumerate(new_win) if not k.candidate and rng.random() < 0.5})
+        regions.append((ref, ref_begin, realign, new_win, out_reads))
+    return B.EnumBatch(regions, strict=False)

@@ -302,3 +302,42 @@ def test_fast_launch_plan_on_the_cpu():
     assert total > 8000 and retried > 100  # both tiers did real work
     rc, small = reflib.k7core_enumerate(specgen.enum_case(3), cap_alns=5, fast=True)
     assert rc == A.SX_ERR_CAPACITY
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# K7a alignment_indels: which window entries an input alignment already contains (getAlignmentIndels + the edge keys)
+# ------------------------------------------------------------------------------------------------------------------------------
+def _prep_inputs(eb):
+    return (eb.in_key_off[: eb.n_reads + 1], eb.in_keys[: int(eb.in_key_off[eb.n_reads])], eb.in_lead_key[: eb.n_reads], eb.in_trail_key[: eb.n_reads])
+
+
+def test_alignment_indels_device_body_host_builder_and_reference_agree():
+    """K7a's device body (k7a_core.cuh compiled for the host, on K1's packed read / reference pools), the host builder
+    (batch.alignment_indels) and -- where the reference library is built -- the reference's own getCandidateAlignment +
+    getAlignmentIndels(includeMismatches) (oracle/ref_harness_enumerate.inc): the same keys, edge keys and SX_NO_KEY marks on tidy
+    inputs and on the awkward ones (edge insertions / deletions, private indels, insert+delete runs, '=' and IUPAC bases); and K7 on
+    those inputs is the reference's getCandidateAlignments, blt_exception included."""
+    n_keys = n_nokey = n_edge = n_exc = 0
+    for case in range(40):
+        eb = specgen.enum_edge_case(case) if case % 2 else specgen.enum_case(case)
+        rc, got = reflib.k7acore_prepare(eb, B.read_pools_of(eb))
+        assert rc == 0
+        for x, y in zip(got.trimmed(), _prep_inputs(eb)):
+            assert np.array_equal(x, y), case
+        if reflib.have_ref():
+            for x, y in zip(got.trimmed(), reflib.ref_alignment_indels(eb).trimmed()):
+                assert np.array_equal(x, y), case
+            cap = eb.n_reads * 6000 + 64
+            want = reflib.ref_enumerate_alignments(eb, cap_alns=cap)
+            rc, en = reflib.k7core_enumerate(eb, max_alns=6000, cap_alns=cap)
+            assert rc == 0
+            _same(want, en)
+            n_exc += int((want.status[: eb.n_reads] & A.SX_ENUM_ST_EXCEPTION != 0).sum())
+        keys = got.trimmed()[1]
+        n_keys += len(keys)
+        n_nokey += int((keys == A.SX_NO_KEY).sum())
+        n_edge += int((got.in_lead_key[: eb.n_reads] != A.SX_NO_KEY).sum() + (got.in_trail_key[: eb.n_reads] != A.SX_NO_KEY).sum())
+    assert n_keys > 800 and n_nokey > 100 and n_edge > 50
+    assert n_exc > 100 or not reflib.have_ref()
+    rc, small = reflib.k7acore_prepare(eb, B.read_pools_of(eb), cap_keys=1)
+    assert rc == A.SX_ERR_CAPACITY and small.totals[0] == got.totals[0]

@@ -159,3 +159,21 @@ def test_cpp_host_mirror_k7(tmp_path):
                            os.path.join(HERE, "cpp", "test_k7_mirror.cpp"), "-o", exe, "-L" + lib, "-lstrelka_b200", "-Wl,-rpath," + lib])
     out = subprocess.run([exe, os.path.join(HERE, "golden")], capture_output=True, text=True)
     assert out.returncode == 0 and "0 failures" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("case", range(16))
+def test_k7a_alignment_indels(ctx, case):
+    """K7a on the GPU: the keys of every input alignment from K1's packed read / reference pools == the host builder's (which is
+    pinned against the reference's getAlignmentIndels in tests/test_enumerate.py), tidy and awkward inputs; then K7 on the device-made
+    arrays == the oracle."""
+    eb = specgen.enum_edge_case(case) if case % 2 else specgen.enum_case(case)
+    po = ctx.alignment_indels(eb, B.read_pools_of(eb))
+    assert ctx.timing().launches == 6
+    n = eb.n_reads
+    want = (eb.in_key_off[: n + 1], eb.in_keys[: int(eb.in_key_off[n])], eb.in_lead_key[:n], eb.in_trail_key[:n])
+    for x, y in zip(po.trimmed(), want):
+        assert np.array_equal(x, y)
+    # swap the device-made arrays in and enumerate
+    eb.in_key_off, eb.in_keys, eb.in_lead_key, eb.in_trail_key = po.in_key_off, po.in_keys, po.in_lead_key, po.in_trail_key
+    eb.c.in_key_off, eb.c.in_keys, eb.c.in_lead_key, eb.c.in_trail_key = A.ptr(po.in_key_off), A.ptr(po.in_keys), A.ptr(po.in_lead_key), A.ptr(po.in_trail_key)
+    _same(reflib.ox_enumerate_alignments(eb), ctx.enumerate_alignments(eb))
