@@ -449,6 +449,77 @@ def k7_enumerate_leg(ctx, peak_gbs: float, n_loci: int = 200_000, depth: int = 3
     return leg
 
 
+def make_enum_read_pools(eb: B.EnumBatch, depth: int, read_len: int, seed: int) -> B.AlignBatch:
+    """The reads, qualities and reference windows of make_enum_workload's loci where K1 keeps them (wide formats), built with numpy:
+    all-'A' reads on an all-'A' reference (the workload's windows hold no mismatch entries), qualities from the cfg2 dictionary."""
+    rng = np.random.default_rng(seed + 1)
+    n_loci, n_reads = eb.n_regions, eb.n_reads
+    span = int(eb.ref_off[1] - eb.ref_off[0])
+    pad16 = lambda x: (x + 15) & ~15  # noqa: E731
+    seq_stride, qual_stride, ref_stride = pad16(depth * ((read_len + 1) // 2)), pad16(depth * read_len), pad16(span)
+    reg = np.zeros(n_loci + 1, dtype=A.REGION_DT)
+    g = np.arange(n_loci + 1, dtype=np.int64)
+    reg["seq_off"], reg["qual_off"], reg["ref_off"], reg["read_begin"] = g * seq_stride, g * qual_stride, g * ref_stride, g * depth
+    reg["ref_begin"][:n_loci], reg["ref_len"][:n_loci] = eb.ref_begin[:n_loci], span
+    seq4 = np.full(n_loci * seq_stride + A.SX_POOL_SLACK, 0x11, np.uint8)
+    qual = np.zeros(n_loci * qual_stride + A.SX_POOL_SLACK, np.uint8)
+    q = rng.choice(np.array([11, 25, 37], np.uint8), size=(n_loci, depth * read_len), p=[0.03, 0.07, 0.90])
+    qual[: n_loci * qual_stride].reshape(n_loci, qual_stride)[:, : depth * read_len] = q
+    ref = np.full(n_loci * ref_stride + A.SX_POOL_SLACK, ord("A"), np.uint8)
+    alns = np.zeros(1, dtype=A.ALN_DT)
+    alns[0] = (n_reads, 0, 0, 0)
+    segs = np.zeros(16, dtype=A.ALN_SEG_DT)
+    segs["kind"] = A.SX_SEG_HARDCLIP
+    used = {"seq4": n_loci * seq_stride, "qual": n_loci * qual_stride, "ref": n_loci * ref_stride, "ins": 0}
+    return B.AlignBatch(reg, eb.read_len[:n_reads].copy(), seq4, qual, ref, alns, segs, np.zeros(A.SX_POOL_SLACK, np.uint8), used, qual_bits=8, n_segs=0, n_alns=0)
+
+
+def realign_chain_leg(ctx, peak_gbs: float, n_loci: int = 100_000, depth: int = 30, read_len: int = 150, seed: int = 7, reps: int = 2, fast: bool = False,
+                      check_loci: int = 60):
+    """The device-resident chain of realignAndScoreRead measured beside the headline step (not part of `value`): K7a -> K7 -> K7b -> K1 ->
+    K6 on cfg2-shaped loci, every intermediate in HBM (strelka_b200.api.DevRealignChain).  A small instance of the same chain is first
+    compared, array by array, with the chain run step by step through the CPU oracles."""
+    from strelka_b200.api import DevRealignChain
+
+    leg = {"plan": "K7 SX_ENUM_F_FAST" if fast else "K7 original"}
+    try:  # parity of a small instance (the oracles and the host flattening are Python-speed)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from test_chain_plumbing import check_chain
+
+        small = make_enum_workload(check_loci, depth, read_len, seed + 100)
+        if fast:
+            small.opts.flags = A.SX_ENUM_F_FAST
+            small.c.opts = small.opts
+        sp = B.read_pools_of(small)
+        ch = DevRealignChain(ctx, small, sp, cap_alns_per_read=64)
+        ch.run()
+        n_alns, n_recs = check_chain(ch, small)
+        ch.free()
+        leg["parity"] = f"{check_loci} loci ({n_alns} alignments, {n_recs} score_indels records): identical to the oracle chain"
+    except AssertionError as e:
+        leg["parity"] = f"MISMATCH on the {check_loci}-locus instance: {e}"
+    eb = make_enum_workload(n_loci, depth, read_len, seed)
+    if fast:
+        eb.opts.flags = A.SX_ENUM_F_FAST
+        eb.c.opts = eb.opts
+    pools = make_enum_read_pools(eb, depth, read_len, seed)
+    chain = DevRealignChain(ctx, eb, pools, cap_alns_per_read=16)
+    acc = {}
+    for i in range(reps + 1):
+        ms = chain.run()
+        if i >= 1:
+            for k, v in ms.items():
+                acc[k] = acc.get(k, 0.0) + v / reps
+    total = sum(acc.values())
+    nA = chain.totals[0]
+    n_rec = int(chain.n_rec.download(np.uint32, eb.n_reads).sum())
+    leg.update({"what": f"realignAndScoreRead chain K7a -> K7 -> K7b -> K1 -> K6 on {n_loci} cfg2-shaped loci ({eb.n_reads} reads -> {nA} candidate alignments -> "
+                        f"{n_rec} score_indels records), device-resident", "kernel_ms": acc, "ms": total, "loci_per_s": n_loci / max(total * 1e-3, 1e-12),
+                "reads_per_s": eb.n_reads / max(total * 1e-3, 1e-12), "alignments": nA})
+    chain.free()
+    return leg
+
+
 def workload_cells(ab: B.AlignBatch, gb: B.GaBatch) -> int:
     return ab.cells() + gb.cells()
 
@@ -786,10 +857,11 @@ def main():
                 line["k6_score_indels"] = k6_score_indels_leg(ctx, synth, peak, n_loci, depth, read_len, n_haps, args.seed + 1000 * rank, threads, rpr, dab.out)
                 # K7 had not run on a GPU when this was written: its leg runs in a process of its own with a time limit, so that nothing it
                 # does (an exception, a sticky CUDA error, a search that does not end) can take the headline line down with it
-                for key, plan in (("k7_enumerate", "original"), ("k7_enumerate_fast", "fast")):  # the second plan has never run on a GPU
+                for key, tool, plan in (("k7_enumerate", "k7_leg.py", "original"), ("k7_enumerate_fast", "k7_leg.py", "fast"),  # the second plan, K7a and the
+                                        ("realign_chain", "chain_leg.py", "original"), ("realign_chain_fast", "chain_leg.py", "fast")):  # chain have never run on a GPU
                     try:
-                        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k7_leg.py"), "200000", str(min(depth, 30)), str(read_len), str(peak), plan],
-                                           capture_output=True, text=True, timeout=240)
+                        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), "200000" if tool == "k7_leg.py" else "100000", str(min(depth, 30)),
+                                            str(read_len), str(peak), plan], capture_output=True, text=True, timeout=240)
                         last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
                         line[key] = json.loads(last[-1]) if r.returncode == 0 and last else {"error": (r.stderr or r.stdout)[-600:]}
                     except Exception as e:  # noqa: BLE001

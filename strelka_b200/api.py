@@ -326,3 +326,91 @@ def _alignment_indels(self, eb: B.EnumBatch, pools: B.AlignBatch, cap_keys=None)
 
 
 Context.alignment_indels = _alignment_indels  # K7a
+
+
+class DevRealignChain:
+    """The device-resident chain of realignAndScoreRead for a batch of reads: K7a (keys of the input alignments) -> K7 (candidate
+    alignments) -> K7b (K1's alignment arrays) -> K1 (scores) -> K6 (score_indels), every intermediate staying in HBM; what crosses to the
+    host between the steps is the three + two totals that size the next buffers.  `pools`: the K1 batch holding the reads, qualities
+    and reference windows in K7's read order (B.read_pools_of or a real one); its region records receive the alignment offsets."""
+
+    def __init__(self, ctx: "Context", eb: B.EnumBatch, pools: B.AlignBatch, cap_alns_per_read: int = 16, read_flags=None, rec_off=None):
+        assert pools.fmt == 0 and pools.qual_bits in (0, 8) and pools.n_reads == eb.n_reads
+        self.ctx, self.eb = ctx, eb
+        self.enum = DevEnumBatch(ctx, eb, cap_alns=eb.n_reads * cap_alns_per_read + 64, cap_segs=eb.n_reads * cap_alns_per_read * 4 + 64,
+                                 cap_keys=eb.n_reads * cap_alns_per_read * 2 + 64)
+        self.pools = DevAlignBatch(ctx, pools)
+        self.key_ins_off = DeviceArray(ctx, eb.ins_off.nbytes + 64).upload(eb.ins_off)
+        self.key_ins = DeviceArray(ctx, eb.ins_pool.nbytes + 64).upload(eb.ins_pool)
+        n = eb.n_reads
+        self.cap_in_keys = 8 * n + 64
+        self.prep = {"totals": DeviceArray(ctx, 16), "in_key_off": DeviceArray(ctx, (n + 1) * 4 + 16), "in_keys": DeviceArray(ctx, self.cap_in_keys * 2 + 16),
+                     "in_lead_key": DeviceArray(ctx, n * 2 + 16), "in_trail_key": DeviceArray(ctx, n * 2 + 16)}
+        p = self.prep
+        self.prep_out = A.SxPrepOut(self.cap_in_keys, p["totals"].ptr, p["in_key_off"].ptr, p["in_keys"].ptr, p["in_lead_key"].ptr, p["in_trail_key"].ptr)
+        # K7 reads what K7a writes
+        c = self.enum.c
+        c.in_key_off, c.in_keys, c.in_lead_key, c.in_trail_key = p["in_key_off"].ptr, p["in_keys"].ptr, p["in_lead_key"].ptr, p["in_trail_key"].ptr
+        # K6's per-read inputs
+        flags = read_flags if read_flags is not None else np.full(n + 1, A.SX_SIF_FWD | A.SX_SIF_TIER1, np.uint8)
+        if rec_off is None:
+            n_win = np.diff(eb.region_key_off.astype(np.int64))
+            rec_off = np.concatenate([[0], np.cumsum(np.repeat(n_win, np.diff(eb.region_read_off.astype(np.int64))))]).astype(np.uint32)
+        self.rec_off_host = rec_off
+        self.read_flags = DeviceArray(ctx, flags.nbytes + 16).upload(flags)
+        self.rec_off = DeviceArray(ctx, rec_off.nbytes + 16).upload(rec_off)
+        self.n_slots = int(rec_off[-1])
+        self.recs = DeviceArray(ctx, (self.n_slots + 1) * A.READ_INDEL_SCORE_DT.itemsize)
+        self.n_rec, self.max_aln, self.eval_aln = (DeviceArray(ctx, (n + 1) * 4) for _ in range(3))
+        self.link = self.lnp = None
+        self.ms = {}
+
+    def run(self):
+        ctx, eb, e = self.ctx, self.eb, self.enum
+        pc = self.pools.c
+        ctx._chk(ctx.lib.sx_alignment_indels_dev(ctx.h, C.byref(e.c), pc.regions, pc.seq4, pc.ref, self.key_ins_off.ptr, self.key_ins.ptr, C.byref(self.prep_out)))
+        self.ms["k7a_alignment_indels"] = ctx.timing().kernel_ms
+        ctx.enumerate_alignments_dev(e)
+        self.ms["k7_enumerate"] = ctx.timing().kernel_ms
+        nA, nS, nK = (int(x) for x in e.obufs["totals"].download(np.uint32, 3))
+        self.totals = (nA, nS, nK)
+        if self.link is None or self.link["n_alns"] < nA or self.link["n_enum_segs"] < nS:  # sized by what the enumeration produced
+            max_ins = max(1, int(eb.keys["ins_len"].max(initial=0)))
+            cap_segs, cap_ins = 2 * nS + 8 * eb.n_regions + 64, nS * max_ins + 16 * eb.n_regions + 64
+            self.link = {"n_alns": nA, "n_enum_segs": nS, "cap_segs": cap_segs, "cap_ins": cap_ins, "totals": DeviceArray(ctx, 16),
+                         "alns": DeviceArray(ctx, (nA + 1) * A.ALN_DT.itemsize + 16), "segs": DeviceArray(ctx, (cap_segs + 16) * 4 + 16),
+                         "ins": DeviceArray(ctx, cap_ins + A.SX_POOL_SLACK + 16), "k6_segs": DeviceArray(ctx, (nS + 16) * 4 + 16)}
+            self.lnp = DeviceArray(ctx, (nA + 1) * 8 + 16)
+        L = self.link
+        lo = A.SxLinkOut(L["cap_segs"], L["cap_ins"], L["totals"].ptr, pc.regions, L["alns"].ptr, L["segs"].ptr, L["ins"].ptr, L["k6_segs"].ptr)
+        ctx._chk(ctx.lib.sx_link_alignments_dev(ctx.h, C.byref(e.c), C.byref(e.out), nA, self.key_ins_off.ptr, self.key_ins.ptr, C.byref(lo)))
+        self.ms["k7b_link"] = ctx.timing().kernel_ms
+        n_k1_segs, ins_bytes = (int(x) for x in L["totals"].download(np.uint32, 2))
+        self.k1_totals = (n_k1_segs, ins_bytes)
+        k1 = A.SxAlignBatch(eb.n_regions, eb.n_reads, nA, n_k1_segs, pc.regions, pc.read_len, pc.seq4, pc.qual, pc.ref, L["alns"].ptr, L["segs"].ptr, L["ins"].ptr,
+                            pc.seq4_bytes, pc.qual_bytes, pc.ref_bytes, ins_bytes, pc.qual_bits, pc.qual_dict, 0, None, None)
+        ctx._chk(ctx.lib.sx_score_alignments_dev(ctx.h, C.byref(k1), self.lnp.ptr))
+        self.ms["k1_score_alignments"] = ctx.timing().kernel_ms
+        o = e.obufs
+        b = e.bufs
+        k6 = A.SxScoreIndelsBatch(eb.n_regions, eb.n_reads, nA, eb.n_keys, b["region_read_off"].ptr, b["region_key_off"].ptr, b["keys"].ptr, o["aln_off"].ptr,
+                                  o["aln_pos"].ptr, o["aln_seg_off"].ptr, L["k6_segs"].ptr, o["aln_key_off"].ptr, o["aln_keys"].ptr, b["read_len"].ptr, b["read_len"].ptr,
+                                  None, None, self.read_flags.ptr, self.rec_off.ptr, A.default_score_indels_opts())
+        out = A.SxScoreIndelsOut(self.recs.ptr, self.n_rec.ptr, self.max_aln.ptr, self.eval_aln.ptr)
+        ctx._chk(ctx.lib.sx_score_indels_dev(ctx.h, C.byref(k6), self.lnp.ptr, C.byref(out)))
+        self.ms["k6_score_indels"] = ctx.timing().kernel_ms
+        return dict(self.ms)
+
+    def download(self):
+        """(EnumOut, lnp[n_alns], n_rec[n_reads], max_aln[n_reads], records of read r = recs[rec_off[r] : rec_off[r] + n_rec[r]])"""
+        n = self.eb.n_reads
+        return (self.enum.download(), self.lnp.download(np.float64, self.totals[0]), self.n_rec.download(np.uint32, n), self.max_aln.download(np.uint32, n),
+                self.recs.download(A.READ_INDEL_SCORE_DT, self.n_slots))
+
+    def free(self):
+        bufs = list(self.enum.bufs.values()) + list(self.enum.obufs.values()) + list(self.pools.bufs.values()) + list(self.prep.values())
+        bufs += [self.key_ins_off, self.key_ins, self.read_flags, self.rec_off, self.recs, self.n_rec, self.max_aln, self.eval_aln, self.pools.out]
+        if self.link:
+            bufs += [v for v in self.link.values() if isinstance(v, DeviceArray)] + [self.lnp]
+        for d in bufs:
+            d.free()

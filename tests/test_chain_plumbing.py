@@ -1,0 +1,76 @@
+"""The device-resident realignment chain (strelka_b200.api.DevRealignChain: K7a -> K7 -> K7b -> K1 -> K6 with every intermediate in
+"device" memory) dry-run on the CPU: tests/mockctx.py answers each `*_dev` entry point with the host-compiled body of that kernel (or
+the oracle), so that the plumbing -- struct fields, buffer sizes, which totals size what -- is checked without a GPU.  The same chain on
+a B200 against the same expectation: tests/test_zz_gpu_enumerate.py::test_device_resident_chain."""
+import numpy as np
+import pytest
+
+import reflib
+import specgen
+from strelka_b200 import _abi as A
+from strelka_b200 import batch as B
+
+
+def expected_chain(eb):
+    """the chain on the CPU, step by step through the oracles (enumerate -> host flattening -> K1 oracle -> K6 oracle)."""
+    out = reflib.ox_enumerate_alignments(eb, cap_alns=eb.n_reads * 64 + 64)
+    regions = B.regions_from_enumeration(eb, out)
+    lnp = reflib.ox_score(B.build_align_batch(regions))
+    sb = specgen.score_indels_batch_from_enumeration(eb, out, ref_to_indel_lnp=0.0, indel_to_ref_lnp=0.0)
+    recs, n_rec, max_aln, _ev = reflib.ox_score_indels(sb, np.concatenate([lnp, [0.0]]))
+    return out, lnp, recs, n_rec, max_aln
+
+
+def check_chain(chain, eb):
+    out, lnp, recs, n_rec, max_aln = expected_chain(eb)
+    g_out, g_lnp, g_n_rec, g_max_aln, g_recs = chain.download()
+    for x, y in zip(out.trimmed(), g_out.trimmed()):
+        assert x.tobytes() == y.tobytes()
+    assert np.array_equal(lnp.view(np.uint64), g_lnp.view(np.uint64))
+    assert np.array_equal(n_rec, g_n_rec) and np.array_equal(max_aln, g_max_aln)
+    parts = [g_recs[int(chain.rec_off_host[r]) : int(chain.rec_off_host[r]) + int(g_n_rec[r])] for r in range(eb.n_reads)]
+    got = np.concatenate(parts) if parts else g_recs[:0]
+    assert got.tobytes() == recs.tobytes()
+    return len(lnp), len(recs)
+
+
+@pytest.mark.parametrize("case", [0, 1, 3, 5, 7])
+def test_device_resident_chain_plumbing_on_the_cpu(case):
+    from mockctx import MockContext
+    from strelka_b200.api import DevRealignChain
+
+    eb = specgen.enum_edge_case(case) if case % 2 else specgen.enum_case(case)
+    pools = B.read_pools_of(eb)
+    chain = DevRealignChain(MockContext(eb, pools), eb, pools, cap_alns_per_read=64)
+    ms = chain.run()
+    assert set(ms) == {"k7a_alignment_indels", "k7_enumerate", "k7b_link", "k1_score_alignments", "k6_score_indels"}
+    n_alns, n_recs = check_chain(chain, eb)
+    assert n_alns > 50
+    chain.run()  # a second pass over the same buffers
+    check_chain(chain, eb)
+
+
+def test_bench_chain_leg_on_the_mock():
+    """bench.py's realign_chain leg (its numpy-built read pools included) through the mock context: the leg's own parity check passes
+    and the K1 pools it builds obey K1's staging rule."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from mockctx import MockContext
+
+    eb = bench.make_enum_workload(40, 30, 150, 7)
+    pools = bench.make_enum_read_pools(eb, 30, 150, 7)
+    assert not (pools.regions["seq_off"] % 16).any() and not (pools.regions["qual_off"] % 16).any() and not (pools.regions["ref_off"] % 16).any()
+    leg = bench.realign_chain_leg(MockContext(eb, pools), 6572.2, n_loci=40, reps=1, check_loci=8)
+    assert "identical to the oracle chain" in leg["parity"], leg
+    assert leg["alignments"] > 40 * 30 * 5 and set(leg["kernel_ms"]) == {"k7a_alignment_indels", "k7_enumerate", "k7b_link", "k1_score_alignments", "k6_score_indels"}
+    # the numpy-built pools are what read_pools_of builds from the same workload (up to the qualities)
+    ref = B.read_pools_of(eb)
+    assert np.array_equal(pools.regions["read_begin"], ref.regions["read_begin"]) and np.array_equal(pools.regions["ref_begin"][:40], ref.regions["ref_begin"][:40])
+    stride = int(ref.regions["seq_off"][1])
+    used = 30 * 75  # 30 reads of 150 bases, two per byte; the rest of a region's slice is padding
+    assert np.array_equal(pools.seq4[: 40 * stride].reshape(40, stride)[:, :used], ref.seq4[: 40 * stride].reshape(40, stride)[:, :used])
+    rstride = int(ref.regions["ref_off"][1])
+    assert np.array_equal(pools.ref[: 40 * rstride].reshape(40, rstride)[:, :1000], ref.ref[: 40 * rstride].reshape(40, rstride)[:, :1000])

@@ -177,3 +177,20 @@ def test_k7a_alignment_indels(ctx, case):
     eb.in_key_off, eb.in_keys, eb.in_lead_key, eb.in_trail_key = po.in_key_off, po.in_keys, po.in_lead_key, po.in_trail_key
     eb.c.in_key_off, eb.c.in_keys, eb.c.in_lead_key, eb.c.in_trail_key = A.ptr(po.in_key_off), A.ptr(po.in_keys), A.ptr(po.in_lead_key), A.ptr(po.in_trail_key)
     _same(reflib.ox_enumerate_alignments(eb), ctx.enumerate_alignments(eb))
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3, 5, 7])
+def test_device_resident_chain(ctx, case):
+    """K7a -> K7 -> K7b -> K1 -> K6 with every intermediate in HBM (strelka_b200.api.DevRealignChain) against the chain run step by step
+    through the CPU oracles: alignments, scores (bit for bit), score_indels records (byte for byte).  The same check on the CPU with a
+    mock context: tests/test_chain_plumbing.py."""
+    from strelka_b200.api import DevRealignChain
+    from test_chain_plumbing import check_chain
+
+    eb = specgen.enum_edge_case(case) if case % 2 else specgen.enum_case(case)
+    chain = DevRealignChain(ctx, eb, B.read_pools_of(eb), cap_alns_per_read=64)
+    chain.run()
+    check_chain(chain, eb)
+    chain.run()
+    check_chain(chain, eb)
+    chain.free()
