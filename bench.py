@@ -463,8 +463,10 @@ def make_enum_read_pools(eb: B.EnumBatch, depth: int, read_len: int, seed: int) 
     reg["ref_begin"][:n_loci], reg["ref_len"][:n_loci] = eb.ref_begin[:n_loci], span
     seq4 = np.full(n_loci * seq_stride + A.SX_POOL_SLACK, 0x11, np.uint8)
     qual = np.zeros(n_loci * qual_stride + A.SX_POOL_SLACK, np.uint8)
-    q = rng.choice(np.array([11, 25, 37], np.uint8), size=(n_loci, depth * read_len), p=[0.03, 0.07, 0.90])
-    qual[: n_loci * qual_stride].reshape(n_loci, qual_stride)[:, : depth * read_len] = q
+    block = rng.choice(np.array([11, 25, 37], np.uint8), size=(min(n_loci, 512), depth * read_len), p=[0.03, 0.07, 0.90])  # tiled: values, not entropy, matter here
+    qv = qual[: n_loci * qual_stride].reshape(n_loci, qual_stride)
+    for g0 in range(0, n_loci, block.shape[0]):
+        qv[g0 : g0 + block.shape[0], : depth * read_len] = block[: min(block.shape[0], n_loci - g0)]
     ref = np.full(n_loci * ref_stride + A.SX_POOL_SLACK, ord("A"), np.uint8)
     alns = np.zeros(1, dtype=A.ALN_DT)
     alns[0] = (n_reads, 0, 0, 0)
