@@ -41,6 +41,7 @@ struct k7_path // CandidateAlignment minus its indel set
     int32_t pos;
     uint16_t lead, trail; // window index or SX_NO_KEY
     uint32_t n_seg;
+    uint32_t ref_len;     // apath_ref_length of seg[0..n_seg), kept up to date by k7_push_seg (the search asks for it at every call)
     sx_aln_seg seg[K7_MAX_SEGS]; // kind = SX_AP_*
 };
 
@@ -68,6 +69,7 @@ struct k7_frame // the by-value arguments of one candidate_alignment_search call
     uint8_t stage;                 // 0 entry, 1 after the unchanged branch, 2 after the start pin, 3 done
     int8_t mt;                     // max_read_indel_toggle
     uint8_t is_on;                 // isCurIndelOn at entry
+    uint8_t cal_at;                // the frame whose `cal` is this call's alignment: a call that leaves the indel as it is shares its caller's
     uint32_t n_hap;
     k7_hap hap[K7_MAX_HAP];
     k7_path cal;
@@ -163,13 +165,14 @@ K7_HD bool k7_seg_read_len(const unsigned t) { return t == SX_AP_MATCH || t == S
 K7_HD bool k7_seg_ref_len(const unsigned t) { return t == SX_AP_MATCH || t == SX_AP_DELETE || t == SX_AP_SKIP || t == SX_AP_SEQ_MATCH || t == SX_AP_SEQ_MISMATCH; }
 K7_HD bool k7_seg_unaligned_edge(const unsigned t) { return t == SX_AP_INSERT || t == SX_AP_HARD_CLIP || t == SX_AP_SOFT_CLIP; }
 
-K7_HD uint32_t k7_ref_length(const k7_path& p) // apath_ref_length, align_path.cpp:160-169
+K7_HD uint32_t k7_ref_length_of(const k7_path& p) // apath_ref_length, align_path.cpp:160-169
 {
     uint32_t v(0);
     for (uint32_t i = 0; i < p.n_seg; ++i)
         if (k7_seg_ref_len(p.seg[i].kind)) v += p.seg[i].len;
     return v;
 }
+K7_HD uint32_t k7_ref_length(const k7_path& p) { return p.ref_len; }
 
 K7_HD uint32_t k7_unaligned_prefix(const k7_path& p) // align_path.cpp:192-201
 {
@@ -222,6 +225,7 @@ K7_HD bool k7_push_seg(k7_path& p, const unsigned kind, const uint32_t len)
     p.seg[p.n_seg].len = (uint16_t)len;
     p.seg[p.n_seg].flags = 0;
     p.n_seg++;
+    if (k7_seg_ref_len(kind)) p.ref_len += len;
     return true;
 }
 
@@ -250,6 +254,7 @@ K7_HDN uint32_t k7_make_start_pos(const sx_indel_key* win, const int32_t ref_sta
     cal.pos = ref_start;
     cal.lead = cal.trail = SX_NO_KEY;
     cal.n_seg = 0;
+    cal.ref_len = 0;
     int32_t ref_head(ref_start), read_head(read_start);
     bool prev_mismatch(false);
     for (uint32_t ii = 0; ii < n_indels; ++ii)
@@ -438,11 +443,11 @@ K7_HD bool k7_add_key(k7_cal& c, const uint16_t w) // std::set<IndelKey>::insert
 
 // recursion terminus (:924-931) + the two post-passes of getCandidateAlignments (:1966-1993): keys, clips back on, range filter,
 // cal_set.insert
-K7_HDN uint32_t k7_emit(const k7_read& R, k7_scratch& S, const k7_frame& f)
+K7_HDN uint32_t k7_emit(const k7_read& R, k7_scratch& S, const k7_frame& f, const k7_path& fcal)
 {
     k7_cal& c(S.slots[S.n]); // slots has maxA + 1 entries: the candidate is built in place and kept only if it is new
     // addKeysToCandidateAlignment, :789-804
-    const int32_t sb(f.cal.pos), se(f.cal.pos + (int32_t)k7_ref_length(f.cal));
+    const int32_t sb(fcal.pos), se(fcal.pos + (int32_t)k7_ref_length(fcal));
     c.n_keys = 0;
     for (uint32_t i = 0; i < f.n; ++i)
     {
@@ -451,17 +456,18 @@ K7_HDN uint32_t k7_emit(const k7_read& R, k7_scratch& S, const k7_frame& f)
         if (!k7_bp_intersect(sb, se, R.win[w])) continue;
         if (!k7_add_key(c, w)) return SX_ENUM_ST_LIMIT;
     }
-    if (f.cal.lead != SX_NO_KEY && !k7_add_key(c, f.cal.lead)) return SX_ENUM_ST_LIMIT;
-    if (f.cal.trail != SX_NO_KEY && !k7_add_key(c, f.cal.trail)) return SX_ENUM_ST_LIMIT;
+    if (fcal.lead != SX_NO_KEY && !k7_add_key(c, fcal.lead)) return SX_ENUM_ST_LIMIT;
+    if (fcal.trail != SX_NO_KEY && !k7_add_key(c, fcal.trail)) return SX_ENUM_ST_LIMIT;
     // apath_clip_adder, align_path.cpp:515-549
-    c.p.pos = f.cal.pos;
-    c.p.lead = f.cal.lead;
-    c.p.trail = f.cal.trail;
+    c.p.pos = fcal.pos;
+    c.p.lead = fcal.lead;
+    c.p.trail = fcal.trail;
     c.p.n_seg = 0;
+    c.p.ref_len = 0;
     bool ok(true);
     if (R.hc_lead) ok = ok && k7_push_seg(c.p, SX_AP_HARD_CLIP, R.hc_lead);
     if (R.sc_lead) ok = ok && k7_push_seg(c.p, SX_AP_SOFT_CLIP, R.sc_lead);
-    for (uint32_t i = 0; i < f.cal.n_seg; ++i) ok = ok && k7_push_seg(c.p, f.cal.seg[i].kind, f.cal.seg[i].len);
+    for (uint32_t i = 0; i < fcal.n_seg; ++i) ok = ok && k7_push_seg(c.p, fcal.seg[i].kind, fcal.seg[i].len);
     if (R.sc_trail) ok = ok && k7_push_seg(c.p, SX_AP_SOFT_CLIP, R.sc_trail);
     if (R.hc_trail) ok = ok && k7_push_seg(c.p, SX_AP_HARD_CLIP, R.hc_trail);
     if (!ok) return SX_ENUM_ST_LIMIT;
@@ -605,6 +611,7 @@ K7_HD void k7_copy_path(k7_path& d, const k7_path& s)
     d.lead = s.lead;
     d.trail = s.trail;
     d.n_seg = s.n_seg;
+    d.ref_len = s.ref_len;
     for (uint32_t i = 0; i < s.n_seg; ++i) d.seg[i] = s.seg[i];
 }
 
@@ -635,6 +642,7 @@ K7_HDN uint32_t k7_search(const k7_read& R, k7_scratch& S, const uint64_t inorig
     while (sp >= 0)
     {
         k7_frame& f(S.frames[sp]);
+        const k7_path& cal(S.frames[f.cal_at].cal);
         if (f.stage == 0)
         {
             // ---- new indel overlaps, :888-922
@@ -643,7 +651,7 @@ K7_HDN uint32_t k7_search(const k7_read& R, k7_scratch& S, const uint64_t inorig
             {
                 const uint32_t start_size(n);
                 int32_t pb, pe;
-                k7_soft_clip_range(f.cal, pb, pe);
+                k7_soft_clip_range(cal, pb, pe);
                 if (!(pb >= R.realign_begin && pe <= R.realign_end))
                 {
                     --sp;
@@ -670,7 +678,7 @@ K7_HDN uint32_t k7_search(const k7_read& R, k7_scratch& S, const uint64_t inorig
             // ---- recursion terminus, :924-931
             if (f.depth == n)
             {
-                const uint32_t st(k7_emit(R, S, f));
+                const uint32_t st(k7_emit(R, S, f, cal));
                 if (st) return status | st;
                 --sp;
                 continue;
@@ -768,7 +776,7 @@ K7_HDN uint32_t k7_search(const k7_read& R, k7_scratch& S, const uint64_t inorig
             if (!valid && f.ttd == 0) valid = true;
             if (valid)
             {
-                k7_copy_path(c.cal, f.cal);
+                c.cal_at = f.cal_at; // the same alignment: nothing to copy
                 ++sp;
                 continue;
             }
@@ -804,22 +812,23 @@ K7_HDN uint32_t k7_search(const k7_read& R, k7_scratch& S, const uint64_t inorig
             if (isOn) f.present &= ~((uint64_t)1 << f.depth);
             else f.present |= ((uint64_t)1 << f.depth);
             // ---- alignment 2: start pin, :1170-1219
-            const int32_t ref_start(f.cal.pos);
+            const int32_t ref_start(cal.pos);
             bool start_pin_valid(true);
             if (!curMismatch)
             {
                 const bool delete_span(cur.pos <= ref_start && ref_start < k7_right(cur));
-                const bool indel_span(isOn && curW == f.cal.lead);
+                const bool indel_span(isOn && curW == cal.lead);
                 start_pin_valid = !(delete_span || indel_span);
             }
             if (start_pin_valid)
             {
                 uint16_t cur_indels[K7_MAX_INDELS];
                 const uint32_t n_cur(k7_present_sorted(S.order, n, f.present, cur_indels));
-                const int32_t read_start((int32_t)k7_unaligned_prefix(f.cal));
+                const int32_t read_start((int32_t)k7_unaligned_prefix(cal));
                 const uint32_t st(k7_make_start_pos(R.win, ref_start, read_start, R.read_length, cur_indels, n_cur, c.cal));
                 if (st) return status | st;
                 k7_push_child(c, f, f.itd + inc, f.ttd + 1u);
+                c.cal_at = (uint8_t)(sp + 1);
                 if (!conflicting && inAr) k7_update_hap(c.hap[arSlot], ids, !isOn, n_samples);
                 ++sp;
                 continue;
@@ -834,14 +843,14 @@ K7_HDN uint32_t k7_search(const k7_read& R, k7_scratch& S, const uint64_t inorig
                 --sp;
                 continue;
             }
-            const int32_t ref_end(f.cal.pos + (int32_t)k7_ref_length(f.cal));
+            const int32_t ref_end(cal.pos + (int32_t)k7_ref_length(cal));
             const bool delete_span(cur.pos <= ref_end - 1 && ref_end - 1 < k7_right(cur));
-            const bool indel_span(isOn && curW == f.cal.trail);
+            const bool indel_span(isOn && curW == cal.trail);
             if (!(delete_span || indel_span))
             {
                 uint16_t cur_indels[K7_MAX_INDELS];
                 const uint32_t n_cur(k7_present_sorted(S.order, n, f.present, cur_indels));
-                const int32_t read_end((int32_t)R.read_length - (int32_t)k7_unaligned_suffix(f.cal));
+                const int32_t read_end((int32_t)R.read_length - (int32_t)k7_unaligned_suffix(cal));
                 int32_t ref_start(0), read_start(0);
                 uint32_t st(k7_end_pin_start_pos(R.win, cur_indels, n_cur, R.read_length, ref_end, read_end, ref_start, read_start));
                 if (st) return status | st;
@@ -853,6 +862,7 @@ K7_HDN uint32_t k7_search(const k7_read& R, k7_scratch& S, const uint64_t inorig
                     if (st) return status | st;
                     const uint32_t inc(1);
                     k7_push_child(c, f, f.itd + inc, f.ttd + 1u);
+                    c.cal_at = (uint8_t)(sp + 1);
                     if (!conflicting && inAr) k7_update_hap(c.hap[arSlot], ids, !isOn, n_samples);
                     ++sp;
                     continue;
@@ -909,6 +919,7 @@ K7_HDN uint32_t k7_enumerate_read_raw(const k7_view& v, const uint32_t region, c
         f.cal.trail = b.in_trail_key[r];
         f.cal.n_seg = ns;
         for (uint32_t i = 0; i < ns; ++i) f.cal.seg[i] = b.in_segs[s0 + i];
+        f.cal.ref_len = k7_ref_length_of(f.cal);
     }
     // indel set of the exemplar, :1843-1845
     int32_t eb, ee;
@@ -998,7 +1009,7 @@ K7_HDN uint32_t k7_enumerate_read_raw(const k7_view& v, const uint32_t region, c
                     f.cal.seg[m++] = sg;
                 }
             }
-            f.cal.n_seg = m;
+            f.cal.n_seg = m; // (clips carry no reference length: ref_len stands)
             if (cal_read_length < R.sc_lead + R.sc_trail) return SX_ENUM_ST_EXCEPTION; // assert :1950
             cal_read_length -= R.sc_lead + R.sc_trail;
         }
@@ -1015,6 +1026,7 @@ K7_HDN uint32_t k7_enumerate_read_raw(const k7_view& v, const uint32_t region, c
     f.stage = 0;
     f.mt = (int8_t)b.opts.max_read_indel_toggle;
     f.is_on = 0;
+    f.cal_at = 0;
     f.n_hap = 0;
     return k7_search(R, S, inorig);
 }
