@@ -728,6 +728,58 @@ int sx_link_alignments_dev(sx_ctx* ctx, const sx_enum_batch* batch_dev, const sx
                            const char* key_ins_dev, sx_link_out* out_dev);
 
 /* ==========================================================================================
+ * K9  choose_realignment   (second half: from the scores to rseg.realignment -- the alignment the pileup uses)
+ *   replaces the tail of scoreCandidateAlignments   starling_common/starling_read_align.cpp:1573-1741:
+ *     the arg-max with isFirstCandidateAlignmentPreferred :1573-1593 (:1352-1377), the smooth pool :1659-1683 (every alignment within
+ *     smoothed_lnp_range of the maximum, and among them the preferred one), finishRealignment :1411-1450 with
+ *     getClippedAlignmentFromTopAlignmentPool (starling_read_align_clipper.cpp:340-424: read positions on which the alignments of the
+ *     pool disagree are soft-clipped off the ends of the chosen one; soft_clip_alignment :255-338).
+ *   Not covered: reads with an exon edge pin (rseg.get_segment_edge_pin(), RNA: :1600-1657) and the retain-optimal-soft-clipping test
+ *   (:1700-1737, switched on by the RNA workflow only) -- such reads are reported SX_REALIGN_ST_UNSUPPORTED and stay with the caller.
+ *
+ * Input: the candidate alignments in K7's output arrays (reference path kinds, set order) with K1's scores, the window (candidacy
+ * counts of the preference rule), per read its length.  Output, per read: the realignment as (pos, path segments) -- exactly what K4
+ * takes as a read's best alignment -- in a CSR whose slots are reserved from the longest path of the read (+2 for the clips).
+ * ======================================================================================== */
+#define SX_REALIGN_ST_REALIGNED 0x01u   /* rseg.is_realigned = true, realignment written */
+#define SX_REALIGN_ST_UNSUPPORTED 0x02u /* pinned read: left to the caller */
+#define SX_REALIGN_ST_LIMIT 0x04u       /* read longer than this build's 1024 bases */
+#define SX_REALIGN_ST_BADPATH 0x08u     /* "Can't handle cigar code" / a path that does not cover the read (the reference would throw / assert) */
+
+typedef struct sx_realign_batch {
+    uint32_t n_regions, n_reads, n_alns;
+    const uint32_t* region_read_off;  /* [n_regions + 1] */
+    const uint32_t* region_key_off;   /* [n_regions + 1] */
+    const sx_indel_key* keys;         /* window entries (flags: SX_IKF_CANDIDATE) */
+    const uint32_t* aln_off;          /* [n_reads + 1]  -- K7's output arrays from here on */
+    const int32_t* aln_pos;
+    const uint32_t* aln_seg_off;      /* [n_alns + 1] */
+    const sx_aln_seg* segs;           /* kind = SX_AP_* */
+    const uint32_t* aln_key_off;      /* [n_alns + 1] */
+    const uint16_t* aln_keys;
+    const uint16_t* read_len;         /* [n_reads] */
+    const uint8_t* pin_flags;         /* [n_reads] or NULL: nonzero = the read has an edge pin */
+    int32_t is_smoothed_alignments;   /* opt.is_smoothed_alignments, 1 */
+    int32_t k4_kinds;                 /* 0: output kinds are SX_AP_* (the reference's path); 1: K4's segment kinds (SX_SEG_*, '=' / 'X' as MATCH) */
+    double smoothed_lnp_range;        /* std::log(10.) */
+} sx_realign_batch;
+
+typedef struct sx_realign_out { /* caller-allocated */
+    uint32_t cap_segs;
+    uint32_t* totals;        /* [1] segment slots reserved (written even when cap_segs is too small: SX_ERR_CAPACITY) */
+    uint32_t* seg_off;       /* [n_reads + 1] read r's slots are segs[seg_off[r] .. seg_off[r+1]); the first n_seg[r] hold the path, the rest are
+                                zero-length HARD_CLIP pads */
+    int32_t* pos;            /* [n_reads] realignment.pos */
+    uint16_t* n_seg;         /* [n_reads] */
+    uint8_t* status;         /* [n_reads] SX_REALIGN_ST_* (0: a read without candidate alignments) */
+    uint32_t* best_aln;      /* [n_reads] smooth_cal_ptr as alignment index (UINT32_MAX: none) */
+    sx_aln_seg* segs;        /* [cap_segs] */
+} sx_realign_out;
+
+int sx_choose_realignment(sx_ctx* ctx, const sx_realign_batch* batch_host, const double* lnp_host, sx_realign_out* out_host);
+int sx_choose_realignment_dev(sx_ctx* ctx, const sx_realign_batch* batch_dev, const double* lnp_dev, sx_realign_out* out_dev);
+
+/* ==========================================================================================
  * Multi-GPU: regions shard across ranks with no data-path collective; one gather of fixed-size
  * call records at the end (the in-memory analogue of concatIndexVcf,
  * src/python/lib/strelkaSharedWorkflow.py:126-136).  The NCCL communicator is created from an

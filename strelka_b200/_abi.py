@@ -254,6 +254,19 @@ class SxPrepOut(C.Structure):
     _fields_ = [("cap_keys", C.c_uint32)] + [(n, C.c_void_p) for n in ("totals", "in_key_off", "in_keys", "in_lead_key", "in_trail_key")]
 
 
+SX_REALIGN_ST_REALIGNED, SX_REALIGN_ST_UNSUPPORTED, SX_REALIGN_ST_LIMIT, SX_REALIGN_ST_BADPATH = 1, 2, 4, 8
+
+
+class SxRealignBatch(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("n_regions", "n_reads", "n_alns")] + [(n, C.c_void_p) for n in (
+        "region_read_off", "region_key_off", "keys", "aln_off", "aln_pos", "aln_seg_off", "segs", "aln_key_off", "aln_keys", "read_len", "pin_flags")] + [
+        ("is_smoothed_alignments", C.c_int32), ("k4_kinds", C.c_int32), ("smoothed_lnp_range", C.c_double)]
+
+
+class SxRealignOut(C.Structure):
+    _fields_ = [("cap_segs", C.c_uint32)] + [(n, C.c_void_p) for n in ("totals", "seg_off", "pos", "n_seg", "status", "best_aln", "segs")]
+
+
 def default_enum_opts() -> SxEnumOpts:
     """starling_base_options defaults (starling_base_shared.hh:124,139,145,160) through the library's own sx_default_enum_opts."""
     o = SxEnumOpts()
@@ -327,6 +340,8 @@ SYMBOLS = [
     ("sx_enumerate_alignments_dev", C.c_int, [_P, C.POINTER(SxEnumBatch), C.POINTER(SxEnumOut)]),
     ("sx_alignment_indels", C.c_int, [_P, C.POINTER(SxEnumBatch), _P, _P, _P, _P, _P, C.POINTER(SxPrepOut)]),
     ("sx_alignment_indels_dev", C.c_int, [_P, C.POINTER(SxEnumBatch), _P, _P, _P, _P, _P, C.POINTER(SxPrepOut)]),
+    ("sx_choose_realignment", C.c_int, [_P, C.POINTER(SxRealignBatch), _P, C.POINTER(SxRealignOut)]),
+    ("sx_choose_realignment_dev", C.c_int, [_P, C.POINTER(SxRealignBatch), _P, C.POINTER(SxRealignOut)]),
     ("sx_link_alignments", C.c_int, [_P, C.POINTER(SxEnumBatch), C.POINTER(SxEnumOut), C.c_uint32, _P, _P, C.POINTER(SxLinkOut)]),
     ("sx_link_alignments_dev", C.c_int, [_P, C.POINTER(SxEnumBatch), C.POINTER(SxEnumOut), C.c_uint32, _P, _P, C.POINTER(SxLinkOut)]),
     ("sx_indel_gl", C.c_int, [_P, C.POINTER(SxIndelBatch), _P]),

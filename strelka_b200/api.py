@@ -414,3 +414,14 @@ class DevRealignChain:
             bufs += [v for v in self.link.values() if isinstance(v, DeviceArray)] + [self.lnp]
         for d in bufs:
             d.free()
+
+
+def _choose_realignment(self, rb: B.RealignBatch, lnp: np.ndarray, cap_segs=None) -> B.RealignOut:
+    """K9: rseg.realignment of every read from its candidate alignments and their scores (host buffers)."""
+    lnp = np.ascontiguousarray(lnp, dtype=np.float64)
+    ro = B.RealignOut(rb, cap_segs)
+    self._chk(self.lib.sx_choose_realignment(self.h, C.byref(rb.c), lnp.ctypes.data, C.byref(ro.c)))
+    return ro
+
+
+Context.choose_realignment = _choose_realignment  # K9

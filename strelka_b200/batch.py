@@ -1000,3 +1000,43 @@ def read_pools_of(eb: EnumBatch) -> AlignBatch:
             reads.append((codes_of(seq), np.full(len(seq), 30, np.uint8)))
         regions.append(RegionSpec(ref, int(eb.ref_begin[g]), reads, []))
     return build_align_batch(regions)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# K9 choose_realignment
+# ------------------------------------------------------------------------------------------------------------------------------
+class RealignBatch:
+    """sx_realign_batch over K7's output (host arrays): the candidate alignments of EnumBatch `eb` as enumerated into `out`."""
+
+    def __init__(self, eb: EnumBatch, out: "EnumOut", is_smoothed=True, smoothed_lnp_range=2.302585092994046, k4_kinds=False, pin_flags=None):
+        self.eb, self.enum_out = eb, out
+        self.n_alns = int(out.totals[0])
+        self.pin_flags = pin_flags
+        self.c = A.SxRealignBatch(eb.n_regions, eb.n_reads, self.n_alns, A.ptr(eb.region_read_off), A.ptr(eb.region_key_off), A.ptr(eb.keys), A.ptr(out.aln_off),
+                                  A.ptr(out.aln_pos), A.ptr(out.aln_seg_off), A.ptr(out.segs), A.ptr(out.aln_key_off), A.ptr(out.aln_keys), A.ptr(eb.read_len),
+                                  A.ptr(pin_flags) if pin_flags is not None else None, 1 if is_smoothed else 0, 1 if k4_kinds else 0, smoothed_lnp_range)
+
+
+class RealignOut:
+    """Host buffers for sx_realign_out."""
+
+    def __init__(self, rb: RealignBatch, cap_segs=None):
+        n = rb.eb.n_reads
+        self.cap_segs = cap_segs if cap_segs is not None else int(rb.enum_out.totals[1]) + 2 * n + 64
+        self.totals = np.zeros(2, np.uint32)
+        self.seg_off = np.zeros(n + 1, np.uint32)
+        self.pos = np.zeros(n + 1, np.int32)
+        self.n_seg = np.zeros(n + 1, np.uint16)
+        self.status = np.zeros(n + 1, np.uint8)
+        self.best_aln = np.zeros(n + 1, np.uint32)
+        self.segs = np.zeros(self.cap_segs + 1, dtype=A.ALN_SEG_DT)
+        self.c = A.SxRealignOut(self.cap_segs, A.ptr(self.totals), A.ptr(self.seg_off), A.ptr(self.pos), A.ptr(self.n_seg), A.ptr(self.status), A.ptr(self.best_aln),
+                                A.ptr(self.segs))
+        self._n = n
+
+    def realignment_of(self, r: int):
+        """(pos, cigar string) of read r, or None when it was not realigned."""
+        if not (int(self.status[r]) & A.SX_REALIGN_ST_REALIGNED):
+            return None
+        s0 = int(self.seg_off[r])
+        return int(self.pos[r]), "".join(f"{int(s['len'])}{AP_CHAR[int(s['kind'])]}" for s in self.segs[s0 : s0 + int(self.n_seg[r])])

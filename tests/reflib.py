@@ -376,3 +376,47 @@ def k7acore_prepare(eb: "B.EnumBatch", pools: "B.AlignBatch", cap_keys=None):
     po = B.PrepOut(eb, cap_keys)
     rc = _k7acore.k7acore_run(C.byref(eb.c), A.ptr(pools.regions), A.ptr(pools.seq4), A.ptr(pools.ref), A.ptr(eb.ins_off), A.ptr(eb.ins_pool), C.byref(po.c))
     return rc, po
+
+
+def ref_choose_realignment(eb: "B.EnumBatch", out: "B.EnumOut", quals: np.ndarray, is_smoothed=True, smoothed_range=2.302585092994046, max_segs=48):
+    """The reference's own scoreCandidateAlignments on rebuilt objects (oracle/ref_harness_enumerate.inc): (lnp[n_alns], realignment per
+    read as (pos, cigar) or None)."""
+    n, nA = eb.n_reads, int(out.totals[0])
+    lnp = np.zeros(nA + 1, np.float64)
+    pos, nseg, real = np.zeros(n + 1, np.int32), np.zeros(n + 1, np.uint16), np.zeros(n + 1, np.uint8)
+    segs = np.zeros((n + 1) * max_segs, dtype=A.ALN_SEG_DT)
+    err = _err()
+    fn = ref().ref_choose_realignment
+    fn.argtypes = [C.POINTER(A.SxEnumBatch), C.POINTER(A.SxEnumOut)] + [_P] * 8 + [C.c_int, C.c_double] + [_P] * 4 + [C.c_uint32, _P, C.c_char_p, C.c_int]
+    rc = fn(C.byref(eb.c), C.byref(out.c), A.ptr(eb.ins_pool), A.ptr(eb.ins_off), A.ptr(eb.ref_pool), A.ptr(eb.ref_off), A.ptr(eb.ref_begin), A.ptr(eb.read_pool),
+            A.ptr(eb.read_off), A.ptr(quals), 1 if is_smoothed else 0, smoothed_range, A.ptr(lnp), A.ptr(pos), A.ptr(nseg), A.ptr(segs), max_segs, A.ptr(real), err, 1024)
+    if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    res = []
+    for r in range(n):
+        if not real[r]:
+            res.append(None)
+            continue
+        row = segs[r * max_segs : r * max_segs + int(nseg[r])]
+        res.append((int(pos[r]), "".join(f"{int(s['len'])}{B.AP_CHAR[int(s['kind'])]}" for s in row)))
+    return lnp[:nA], res
+
+
+_k9core = None
+
+
+def k9core_choose(rb: "B.RealignBatch", lnp: np.ndarray, cap_segs=None):
+    """strelka_b200/csrc/k9_core.cuh compiled for the host (tests/cpp/k9_core_host.cpp).  (rc, RealignOut)"""
+    global _k9core
+    if _k9core is None:
+        import tempfile
+
+        so = os.path.join(tempfile.mkdtemp(prefix="k9core"), "libk9core.so")
+        subprocess.check_call(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "strelka_b200", "csrc"),
+                               os.path.join(ROOT, "tests", "cpp", "k9_core_host.cpp"), "-o", so])
+        _k9core = C.CDLL(so)
+        _k9core.k9core_run.argtypes = [C.POINTER(A.SxRealignBatch), _P, C.POINTER(A.SxRealignOut)]
+    lnp = np.ascontiguousarray(lnp, dtype=np.float64)
+    ro = B.RealignOut(rb, cap_segs)
+    rc = _k9core.k9core_run(C.byref(rb.c), A.ptr(lnp), C.byref(ro.c))
+    return rc, ro

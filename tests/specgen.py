@@ -788,3 +788,18 @@ def enum_edge_case(case: int, n_regions: int = 5):
             r.use_keys = sorted({index_of[old_order[w]] for w in r.use_keys} | {i for i, k in enumerate(new_win) if not k.candidate and rng.random() < 0.5})
         regions.append((ref, ref_begin, realign, new_win, out_reads))
     return B.EnumBatch(regions, strict=False)
+
+
+# K9 choose_realignment: the batches whose reference results are frozen in tests/golden/realign_ref.npz
+REALIGN_GOLDEN_CASES = [("enum", c) for c in range(10)] + [("edge", c) for c in (1, 3, 5, 7)]
+REALIGN_MODES = {"ln10": (True, 2.302585092994046), "off": (False, 2.3), "wide": (True, 25.0), "all": (True, 400.0)}
+
+
+def realign_case_batch(name: str, case: int):
+    return enum_edge_case(case) if name == "edge" else enum_case(case)
+
+
+def realign_quals(eb, case: int) -> np.ndarray:
+    """one quality per read base of the batch (the K1 read pools of the realignment tests use the same values)."""
+    rng = np.random.default_rng(4242 + case)
+    return rng.choice(np.array([11, 25, 37], np.uint8), int(eb.read_off[eb.n_reads]) + 1)

@@ -341,3 +341,62 @@ def test_alignment_indels_device_body_host_builder_and_reference_agree():
     assert n_exc > 100 or not reflib.have_ref()
     rc, small = reflib.k7acore_prepare(eb, B.read_pools_of(eb), cap_keys=1)
     assert rc == A.SX_ERR_CAPACITY and small.totals[0] == got.totals[0]
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# K9 choose_realignment: from the scores to rseg.realignment (the tail of scoreCandidateAlignments)
+# ------------------------------------------------------------------------------------------------------------------------------
+def _realign_expect(gold, name, case, tag, n_reads):
+    pos, cig = gold[f"pos_{name}{case}_{tag}"], gold[f"cigar_{name}{case}_{tag}"]
+    return [(int(pos[r]), str(cig[r])) if str(cig[r]) else None for r in range(n_reads)]
+
+
+def test_choose_realignment_device_body_against_the_frozen_reference_output():
+    """K9's device body (k9_core.cuh compiled for the host, poisoned per-thread map) fed with the REFERENCE's scores: the realignment of
+    every read -- chosen alignment, soft-clipped ends where the smooth pool disagrees -- equals what the reference's
+    scoreCandidateAlignments wrote into rseg.realignment (tests/golden/realign_ref.npz), for the default smoothing range, smoothing off and
+    two wide ranges that put many alignments into the pool."""
+    gold = np.load(os.path.join(HERE, "golden", "realign_ref.npz"))
+    n = clipped = 0
+    for name, case in specgen.REALIGN_GOLDEN_CASES:
+        eb = specgen.realign_case_batch(name, case)
+        out = reflib.ox_enumerate_alignments(eb, cap_alns=eb.n_reads * 64 + 64)
+        for tag, (smooth, rng_) in specgen.REALIGN_MODES.items():
+            lnp = gold[f"lnp_{name}{case}_{tag}"]
+            rb = B.RealignBatch(eb, out, is_smoothed=smooth, smoothed_lnp_range=rng_)
+            rc, got = reflib.k9core_choose(rb, np.concatenate([lnp, [0.0]]))
+            assert rc == 0
+            want = _realign_expect(gold, name, case, tag, eb.n_reads)
+            for r in range(eb.n_reads):
+                g = got.realignment_of(r)
+                assert g == want[r], (name, case, tag, r)
+                n += 1
+                clipped += bool(g and "S" in g[1])
+    assert n > 1000 and clipped > 50
+
+
+@needs_ref
+def test_choose_realignment_device_body_against_the_reference():
+    """... and against the reference itself on further batches; its scores are also what the K1 oracle computes for the linked batch."""
+    n = 0
+    for case in range(20, 50):
+        eb = specgen.enum_case(case)
+        out = reflib.ox_enumerate_alignments(eb, cap_alns=eb.n_reads * 64 + 64)
+        quals = specgen.realign_quals(eb, case)
+        for smooth, rng_ in ((True, 2.302585092994046), (True, 60.0)):
+            lnp, want = reflib.ref_choose_realignment(eb, out, quals, is_smoothed=smooth, smoothed_range=rng_)
+            rc, got = reflib.k9core_choose(B.RealignBatch(eb, out, is_smoothed=smooth, smoothed_lnp_range=rng_), np.concatenate([lnp, [0.0]]))
+            assert rc == 0
+            for r in range(eb.n_reads):
+                assert got.realignment_of(r) == want[r], (case, r)
+                n += 1
+        if case % 10 == 0:  # the reference's scores == the K1 oracle's on the batch K7b links
+            regions = B.regions_from_enumeration(eb, out, lambda r, k: quals[int(eb.read_off[r]) : int(eb.read_off[r]) + k])
+            assert np.array_equal(reflib.ox_score(B.build_align_batch(regions)).view(np.uint64), lnp.view(np.uint64))
+    assert n > 1000
+    # K4's segment kinds on request; capacity error
+    rb = B.RealignBatch(eb, out, k4_kinds=True)
+    rc, k4 = reflib.k9core_choose(rb, np.concatenate([lnp, [0.0]]))
+    assert rc == 0 and set(np.unique(k4.segs["kind"][: int(k4.totals[0])])) <= {0, 1, 3, 4, 5, 6}
+    rc, small = reflib.k9core_choose(rb, np.concatenate([lnp, [0.0]]), cap_segs=3)
+    assert rc == A.SX_ERR_CAPACITY and small.totals[0] == k4.totals[0]

@@ -194,3 +194,22 @@ def test_device_resident_chain(ctx, case):
     chain.run()
     check_chain(chain, eb)
     chain.free()
+
+
+@pytest.mark.parametrize("which", range(len(specgen.REALIGN_GOLDEN_CASES)))
+def test_k9_choose_realignment(ctx, which):
+    """K9 on the GPU with the REFERENCE's scores: rseg.realignment of every read as the reference's scoreCandidateAlignments wrote it
+    (tests/golden/realign_ref.npz): default smoothing range, smoothing off, two wide ranges."""
+    name, case = specgen.REALIGN_GOLDEN_CASES[which]
+    gold = np.load(os.path.join(HERE, "golden", "realign_ref.npz"))
+    eb = specgen.realign_case_batch(name, case)
+    out = ctx.enumerate_alignments(eb)
+    for tag, (smooth, rng_) in specgen.REALIGN_MODES.items():
+        lnp = gold[f"lnp_{name}{case}_{tag}"]
+        assert len(lnp) == int(out.totals[0])
+        got = ctx.choose_realignment(B.RealignBatch(eb, out, is_smoothed=smooth, smoothed_lnp_range=rng_), np.concatenate([lnp, [0.0]]))
+        assert ctx.timing().launches == 5
+        pos, cig = gold[f"pos_{name}{case}_{tag}"], gold[f"cigar_{name}{case}_{tag}"]
+        for r in range(eb.n_reads):
+            want = (int(pos[r]), str(cig[r])) if str(cig[r]) else None
+            assert got.realignment_of(r) == want, (tag, r)
