@@ -515,7 +515,7 @@ def realign_chain_leg(ctx, peak_gbs: float, n_loci: int = 100_000, depth: int = 
     total = sum(acc.values())
     nA = chain.totals[0]
     n_rec = int(chain.n_rec.download(np.uint32, eb.n_reads).sum())
-    leg.update({"what": f"realignAndScoreRead chain K7a -> K7 -> K7b -> K1 -> K6 on {n_loci} cfg2-shaped loci ({eb.n_reads} reads -> {nA} candidate alignments -> "
+    leg.update({"what": f"realignAndScoreRead chain K7a -> K7 -> K7b -> K1 -> K6 + K9 on {n_loci} cfg2-shaped loci ({eb.n_reads} reads -> {nA} candidate alignments -> "
                         f"{n_rec} score_indels records), device-resident", "kernel_ms": acc, "ms": total, "loci_per_s": n_loci / max(total * 1e-3, 1e-12),
                 "reads_per_s": eb.n_reads / max(total * 1e-3, 1e-12), "alignments": nA})
     chain.free()

@@ -363,6 +363,7 @@ class DevRealignChain:
         self.recs = DeviceArray(ctx, (self.n_slots + 1) * A.READ_INDEL_SCORE_DT.itemsize)
         self.n_rec, self.max_aln, self.eval_aln = (DeviceArray(ctx, (n + 1) * 4) for _ in range(3))
         self.link = self.lnp = None
+        self.realign = None
         self.ms = {}
 
     def run(self):
@@ -399,7 +400,27 @@ class DevRealignChain:
         out = A.SxScoreIndelsOut(self.recs.ptr, self.n_rec.ptr, self.max_aln.ptr, self.eval_aln.ptr)
         ctx._chk(ctx.lib.sx_score_indels_dev(ctx.h, C.byref(k6), self.lnp.ptr, C.byref(out)))
         self.ms["k6_score_indels"] = ctx.timing().kernel_ms
+        # K9: rseg.realignment of every read, in K4's segment kinds
+        n = eb.n_reads
+        cap = nS + 2 * n + 64
+        if self.realign is None or self.realign["cap"] < cap:
+            self.realign = {"cap": cap, "totals": DeviceArray(ctx, 16), "seg_off": DeviceArray(ctx, (n + 1) * 4 + 16), "pos": DeviceArray(ctx, n * 4 + 16),
+                            "n_seg": DeviceArray(ctx, n * 2 + 16), "status": DeviceArray(ctx, n + 16), "best_aln": DeviceArray(ctx, n * 4 + 16),
+                            "segs": DeviceArray(ctx, cap * 4 + 16)}
+        R = self.realign
+        rb = A.SxRealignBatch(eb.n_regions, n, nA, b["region_read_off"].ptr, b["region_key_off"].ptr, b["keys"].ptr, o["aln_off"].ptr, o["aln_pos"].ptr,
+                              o["aln_seg_off"].ptr, o["segs"].ptr, o["aln_key_off"].ptr, o["aln_keys"].ptr, b["read_len"].ptr, None, 1, 1, 2.302585092994046)
+        ro = A.SxRealignOut(R["cap"], R["totals"].ptr, R["seg_off"].ptr, R["pos"].ptr, R["n_seg"].ptr, R["status"].ptr, R["best_aln"].ptr, R["segs"].ptr)
+        ctx._chk(ctx.lib.sx_choose_realignment_dev(ctx.h, C.byref(rb), self.lnp.ptr, C.byref(ro)))
+        self.ms["k9_choose_realignment"] = ctx.timing().kernel_ms
         return dict(self.ms)
+
+    def download_realignments(self):
+        """(pos[n_reads], n_seg[n_reads], status[n_reads], seg_off[n_reads + 1], segs in K4's kinds)"""
+        n, R = self.eb.n_reads, self.realign
+        seg_off = R["seg_off"].download(np.uint32, n + 1)
+        return (R["pos"].download(np.int32, n), R["n_seg"].download(np.uint16, n), R["status"].download(np.uint8, n), seg_off,
+                R["segs"].download(A.ALN_SEG_DT, int(seg_off[n])))
 
     def download(self):
         """(EnumOut, lnp[n_alns], n_rec[n_reads], max_aln[n_reads], records of read r = recs[rec_off[r] : rec_off[r] + n_rec[r]])"""
@@ -412,6 +433,8 @@ class DevRealignChain:
         bufs += [self.key_ins_off, self.key_ins, self.read_flags, self.rec_off, self.recs, self.n_rec, self.max_aln, self.eval_aln, self.pools.out]
         if self.link:
             bufs += [v for v in self.link.values() if isinstance(v, DeviceArray)] + [self.lnp]
+        if self.realign:
+            bufs += [v for v in self.realign.values() if isinstance(v, DeviceArray)]
         for d in bufs:
             d.free()
 

@@ -9,6 +9,7 @@ import numpy as np
 import reflib
 from strelka_b200 import _abi as A
 from strelka_b200 import api
+from strelka_b200 import batch as B
 
 
 class _Timing:
@@ -62,12 +63,17 @@ class _MockLib:
         return lib.ox_score_indels(batch, lnp, o.recs, o.n_rec, o.max_aln, o.eval_aln)
 
 
+    def sx_choose_realignment_dev(self, h, batch, lnp, out):
+        return reflib._k9core.k9core_run(batch, lnp, out)
+
+
 class MockContext:
     def __init__(self, eb, pools):
         # load the host-compiled bodies the mock forwards to
         reflib.k7acore_prepare(eb, pools)
         out = reflib.ox_enumerate_alignments(eb)
         reflib.k8core_link(eb, out, pools.regions)
+        reflib.k9core_choose(B.RealignBatch(eb, out), np.zeros(int(out.totals[0]) + 1))
         self.lib = _MockLib()
         self.h = 1
 

@@ -1,4 +1,4 @@
-"""The device-resident realignment chain (strelka_b200.api.DevRealignChain: K7a -> K7 -> K7b -> K1 -> K6 with every intermediate in
+"""The device-resident realignment chain (strelka_b200.api.DevRealignChain: K7a -> K7 -> K7b -> K1 -> K6 + K9 with every intermediate in
 "device" memory) dry-run on the CPU: tests/mockctx.py answers each `*_dev` entry point with the host-compiled body of that kernel (or
 the oracle), so that the plumbing -- struct fields, buffer sizes, which totals size what -- is checked without a GPU.  The same chain on
 a B200 against the same expectation: tests/test_zz_gpu_enumerate.py::test_device_resident_chain."""
@@ -31,6 +31,21 @@ def check_chain(chain, eb):
     parts = [g_recs[int(chain.rec_off_host[r]) : int(chain.rec_off_host[r]) + int(g_n_rec[r])] for r in range(eb.n_reads)]
     got = np.concatenate(parts) if parts else g_recs[:0]
     assert got.tobytes() == recs.tobytes()
+    # K9: the realignments, in K4's segment kinds -- against the reference itself where its library is built (the frozen reference
+    # outputs cover the GPU box: tests/test_zz_gpu_enumerate.py::test_k9_choose_realignment)
+    pos, n_seg, status, seg_off, segs = chain.download_realignments()
+    assert int(seg_off[-1]) <= chain.realign["cap"] and set(np.unique(segs["kind"])) <= {0, 1, 3, 4, 5, 6}
+    if reflib.have_ref():
+        quals = np.full(int(eb.read_off[eb.n_reads]) + 1, 30, np.uint8)  # what B.read_pools_of gives every base
+        ref_lnp, want = reflib.ref_choose_realignment(eb, out, quals)
+        assert np.array_equal(ref_lnp.view(np.uint64), g_lnp.view(np.uint64))
+        k4_char = {0: "M", 1: "I", 3: "S", 4: "H", 5: "D", 6: "N"}
+        for r in range(eb.n_reads):
+            if want[r] is None:
+                assert not (int(status[r]) & A.SX_REALIGN_ST_REALIGNED)
+                continue
+            cig = "".join(f"{int(s['len'])}{k4_char[int(s['kind'])]}" for s in segs[int(seg_off[r]) : int(seg_off[r]) + int(n_seg[r])])
+            assert (int(pos[r]), cig) == (want[r][0], want[r][1].replace("=", "M").replace("X", "M")), r
     return len(lnp), len(recs)
 
 
@@ -43,7 +58,7 @@ def test_device_resident_chain_plumbing_on_the_cpu(case):
     pools = B.read_pools_of(eb)
     chain = DevRealignChain(MockContext(eb, pools), eb, pools, cap_alns_per_read=64)
     ms = chain.run()
-    assert set(ms) == {"k7a_alignment_indels", "k7_enumerate", "k7b_link", "k1_score_alignments", "k6_score_indels"}
+    assert set(ms) == {"k7a_alignment_indels", "k7_enumerate", "k7b_link", "k1_score_alignments", "k6_score_indels", "k9_choose_realignment"}
     n_alns, n_recs = check_chain(chain, eb)
     assert n_alns > 50
     chain.run()  # a second pass over the same buffers
@@ -65,7 +80,7 @@ def test_bench_chain_leg_on_the_mock():
     assert not (pools.regions["seq_off"] % 16).any() and not (pools.regions["qual_off"] % 16).any() and not (pools.regions["ref_off"] % 16).any()
     leg = bench.realign_chain_leg(MockContext(eb, pools), 6572.2, n_loci=40, reps=1, check_loci=8)
     assert "identical to the oracle chain" in leg["parity"], leg
-    assert leg["alignments"] > 40 * 30 * 5 and set(leg["kernel_ms"]) == {"k7a_alignment_indels", "k7_enumerate", "k7b_link", "k1_score_alignments", "k6_score_indels"}
+    assert leg["alignments"] > 40 * 30 * 5 and set(leg["kernel_ms"]) == {"k7a_alignment_indels", "k7_enumerate", "k7b_link", "k1_score_alignments", "k6_score_indels", "k9_choose_realignment"}
     # the numpy-built pools are what read_pools_of builds from the same workload (up to the qualities)
     ref = B.read_pools_of(eb)
     assert np.array_equal(pools.regions["read_begin"], ref.regions["read_begin"]) and np.array_equal(pools.regions["ref_begin"][:40], ref.regions["ref_begin"][:40])

@@ -181,7 +181,7 @@ def test_k7a_alignment_indels(ctx, case):
 
 @pytest.mark.parametrize("case", [0, 1, 2, 3, 5, 7])
 def test_device_resident_chain(ctx, case):
-    """K7a -> K7 -> K7b -> K1 -> K6 with every intermediate in HBM (strelka_b200.api.DevRealignChain) against the chain run step by step
+    """K7a -> K7 -> K7b -> K1 -> K6 + K9 with every intermediate in HBM (strelka_b200.api.DevRealignChain) against the chain run step by step
     through the CPU oracles: alignments, scores (bit for bit), score_indels records (byte for byte).  The same check on the CPU with a
     mock context: tests/test_chain_plumbing.py."""
     from strelka_b200.api import DevRealignChain
