@@ -83,3 +83,55 @@ def test_shard_ranges_cover_and_balance():
             sizes = [b - a for a, b in rs]
             assert max(sizes) - min(sizes) <= 1
             assert gathered_offsets(sizes)[-1] + sizes[-1] == n
+
+
+def _enum_regions(seed, n_regions):
+    import specgen
+
+    rng = np.random.default_rng(seed)
+    return [specgen.random_enum_region(rng, n_reads=int(rng.integers(1, 6)), cluster=bool(i % 2), n_keys=(1, 6)) for i in range(n_regions)]
+
+
+def _enum_worker(rank, world, port, n_regions, out_path):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    import reflib
+    from strelka_b200 import batch as B
+    from strelka_b200.shard import shard_range
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    regions = _enum_regions(123, n_regions)  # every rank sees the same loci and takes its shard: regions are independent
+    a, b = shard_range(n_regions, rank, world)
+    eb = B.EnumBatch(regions[a:b])
+    out = reflib.ox_enumerate_alignments(eb, cap_alns=eb.n_reads * 64 + 64)  # the per-rank stand-in for sx_enumerate_alignments
+    # what a rank contributes to the job-wide tally: reads, alignments, segments, keys, a checksum of the alignment positions
+    local = torch.tensor([eb.n_reads, int(out.totals[0]), int(out.totals[1]), int(out.totals[2]), int(out.aln_pos[: int(out.totals[0])].astype(np.int64).sum())],
+                         dtype=torch.int64)
+    gathered = [torch.zeros_like(local) for _ in range(world)] if rank == 0 else None
+    dist.gather(local, gathered, dst=0)
+    if rank == 0:
+        np.save(out_path, torch.stack(gathered).numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_enumeration_shards_by_region(tmp_path):
+    """K7 (and with it the whole realignment chain) shards like everything else: regions are independent, each rank enumerates its
+    contiguous block, no data-path collective; the gathered per-rank tallies add up to the single-process result."""
+    import torch.multiprocessing as mp
+
+    sys.path.insert(0, HERE)
+    import reflib
+    from strelka_b200 import batch as B
+
+    n_regions, world = 41, 2
+    out = str(tmp_path / "enum_tally.npy")
+    mp.spawn(_enum_worker, args=(world, _free_port(), n_regions, out), nprocs=world, join=True)
+    got = np.load(out).sum(axis=0)
+    eb = B.EnumBatch(_enum_regions(123, n_regions))
+    whole = reflib.ox_enumerate_alignments(eb, cap_alns=eb.n_reads * 64 + 64)
+    want = [eb.n_reads, int(whole.totals[0]), int(whole.totals[1]), int(whole.totals[2]), int(whole.aln_pos[: int(whole.totals[0])].astype(np.int64).sum())]
+    assert list(got) == want and want[1] > 300
