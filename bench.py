@@ -449,31 +449,41 @@ def k7_enumerate_leg(ctx, peak_gbs: float, n_loci: int = 200_000, depth: int = 3
     return leg
 
 
-def make_enum_read_pools(eb: B.EnumBatch, depth: int, read_len: int, seed: int) -> B.AlignBatch:
-    """The reads, qualities and reference windows of make_enum_workload's loci where K1 keeps them (wide formats), built with numpy:
-    all-'A' reads on an all-'A' reference (the workload's windows hold no mismatch entries), qualities from the cfg2 dictionary."""
+def make_enum_read_pools(eb: B.EnumBatch, depth: int, read_len: int, seed: int, qual_bits: int = 4) -> B.AlignBatch:
+    """The reads, qualities and reference windows of make_enum_workload's loci where K1 keeps them, built with numpy: all-'A' reads on an
+    all-'A' reference (the workload's windows hold no mismatch entries), qualities from the cfg2 dictionary {11, 25, 37} -- dictionary-coded
+    two per byte (qual_bits 4: K1's byte-entry kernel) or one byte per base (qual_bits 8).  Bases and reference stay in the wide formats K7a reads."""
     rng = np.random.default_rng(seed + 1)
     n_loci, n_reads = eb.n_regions, eb.n_reads
     span = int(eb.ref_off[1] - eb.ref_off[0])
     pad16 = lambda x: (x + 15) & ~15  # noqa: E731
-    seq_stride, qual_stride, ref_stride = pad16(depth * ((read_len + 1) // 2)), pad16(depth * read_len), pad16(span)
+    read_bytes = (read_len + 1) // 2
+    per_read_q = read_bytes if qual_bits == 4 else read_len
+    seq_stride, qual_stride, ref_stride = pad16(depth * read_bytes), pad16(depth * per_read_q), pad16(span)
     reg = np.zeros(n_loci + 1, dtype=A.REGION_DT)
     g = np.arange(n_loci + 1, dtype=np.int64)
     reg["seq_off"], reg["qual_off"], reg["ref_off"], reg["read_begin"] = g * seq_stride, g * qual_stride, g * ref_stride, g * depth
     reg["ref_begin"][:n_loci], reg["ref_len"][:n_loci] = eb.ref_begin[:n_loci], span
     seq4 = np.full(n_loci * seq_stride + A.SX_POOL_SLACK, 0x11, np.uint8)
     qual = np.zeros(n_loci * qual_stride + A.SX_POOL_SLACK, np.uint8)
-    block = rng.choice(np.array([11, 25, 37], np.uint8), size=(min(n_loci, 512), depth * read_len), p=[0.03, 0.07, 0.90])  # tiled: values, not entropy, matter here
+    dictionary = np.array([11, 25, 37], np.uint8)
+    codes = rng.choice(np.arange(3, dtype=np.uint8), size=(min(n_loci, 512), depth, read_len), p=[0.03, 0.07, 0.90])  # tiled: values, not entropy, matter here
+    if qual_bits == 4:  # two codes per byte, high nibble first, every read on a byte boundary -- laid out like seq4
+        c = np.concatenate([codes, np.zeros((codes.shape[0], depth, read_len & 1), np.uint8)], axis=2)
+        block = ((c[:, :, 0::2] << 4) | c[:, :, 1::2]).reshape(codes.shape[0], depth * read_bytes)
+    else:
+        block = dictionary[codes].reshape(codes.shape[0], depth * read_len)
     qv = qual[: n_loci * qual_stride].reshape(n_loci, qual_stride)
     for g0 in range(0, n_loci, block.shape[0]):
-        qv[g0 : g0 + block.shape[0], : depth * read_len] = block[: min(block.shape[0], n_loci - g0)]
+        qv[g0 : g0 + block.shape[0], : block.shape[1]] = block[: min(block.shape[0], n_loci - g0)]
     ref = np.full(n_loci * ref_stride + A.SX_POOL_SLACK, ord("A"), np.uint8)
     alns = np.zeros(1, dtype=A.ALN_DT)
     alns[0] = (n_reads, 0, 0, 0)
     segs = np.zeros(16, dtype=A.ALN_SEG_DT)
     segs["kind"] = A.SX_SEG_HARDCLIP
     used = {"seq4": n_loci * seq_stride, "qual": n_loci * qual_stride, "ref": n_loci * ref_stride, "ins": 0}
-    return B.AlignBatch(reg, eb.read_len[:n_reads].copy(), seq4, qual, ref, alns, segs, np.zeros(A.SX_POOL_SLACK, np.uint8), used, qual_bits=8, n_segs=0, n_alns=0)
+    return B.AlignBatch(reg, eb.read_len[:n_reads].copy(), seq4, qual, ref, alns, segs, np.zeros(A.SX_POOL_SLACK, np.uint8), used, qual_bits=qual_bits,
+                        qual_dict=[11, 25, 37] if qual_bits == 4 else None, n_segs=0, n_alns=0)
 
 
 def realign_chain_leg(ctx, peak_gbs: float, n_loci: int = 100_000, depth: int = 30, read_len: int = 150, seed: int = 7, reps: int = 2, fast: bool = False,

@@ -335,7 +335,8 @@ class DevRealignChain:
     and reference windows in K7's read order (B.read_pools_of or a real one); its region records receive the alignment offsets."""
 
     def __init__(self, ctx: "Context", eb: B.EnumBatch, pools: B.AlignBatch, cap_alns_per_read: int = 16, read_flags=None, rec_off=None):
-        assert pools.fmt == 0 and pools.qual_bits in (0, 8) and pools.n_reads == eb.n_reads
+        # bases / reference in the wide formats (K7a reads them); qualities may be dictionary-coded (qual_bits 4 selects K1's byte-entry kernel)
+        assert pools.fmt == 0 and pools.qual_bits in (0, 4, 8) and pools.n_reads == eb.n_reads
         self.ctx, self.eb = ctx, eb
         self.enum = DevEnumBatch(ctx, eb, cap_alns=eb.n_reads * cap_alns_per_read + 64, cap_segs=eb.n_reads * cap_alns_per_read * 4 + 64,
                                  cap_keys=eb.n_reads * cap_alns_per_read * 2 + 64)

@@ -89,3 +89,25 @@ def test_bench_chain_leg_on_the_mock():
     assert np.array_equal(pools.seq4[: 40 * stride].reshape(40, stride)[:, :used], ref.seq4[: 40 * stride].reshape(40, stride)[:, :used])
     rstride = int(ref.regions["ref_off"][1])
     assert np.array_equal(pools.ref[: 40 * rstride].reshape(40, rstride)[:, :1000], ref.ref[: 40 * rstride].reshape(40, rstride)[:, :1000])
+
+
+def test_bench_pools_quality_packing():
+    """the chain leg's numpy-built K1 pools with dictionary-coded qualities (qual_bits 4) describe the same reads as the one-byte-per-base
+    pools: the K1 oracle scores the linked alignments identically on both."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from mockctx import MockContext
+    from strelka_b200.api import DevRealignChain
+
+    eb = bench.make_enum_workload(12, 30, 150, 11)
+    lnp = {}
+    for bits in (4, 8):
+        pools = bench.make_enum_read_pools(eb, 30, 150, 11, qual_bits=bits)
+        chain = DevRealignChain(MockContext(eb, pools), eb, pools, cap_alns_per_read=16)
+        chain.run()
+        lnp[bits] = chain.download()[1]
+    assert len(lnp[4]) > 12 * 30 * 5 and np.array_equal(lnp[4].view(np.uint64), lnp[8].view(np.uint64))
+    assert len(np.unique(lnp[4])) > 50  # three quality values really vary the scores
