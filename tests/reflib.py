@@ -420,3 +420,13 @@ def k9core_choose(rb: "B.RealignBatch", lnp: np.ndarray, cap_segs=None):
     ro = B.RealignOut(rb, cap_segs)
     rc = _k9core.k9core_run(C.byref(rb.c), A.ptr(lnp), C.byref(ro.c))
     return rc, ro
+
+
+def ox_choose_realignment(rb: "B.RealignBatch", lnp: np.ndarray, cap_segs=None) -> "B.RealignOut":
+    """oracle/realign_oracle.cpp: the CPU restatement of the tail of scoreCandidateAlignments + finishRealignment + the pool clipper."""
+    lnp = np.ascontiguousarray(lnp, dtype=np.float64)
+    ro = B.RealignOut(rb, cap_segs)
+    lib = oracle()
+    lib.ox_choose_realignment.argtypes = [C.POINTER(A.SxRealignBatch), _P, C.POINTER(A.SxRealignOut)]
+    ro.rc = lib.ox_choose_realignment(C.byref(rb.c), A.ptr(lnp), C.byref(ro.c))
+    return ro

@@ -35,6 +35,11 @@ def check_chain(chain, eb):
     # outputs cover the GPU box: tests/test_zz_gpu_enumerate.py::test_k9_choose_realignment)
     pos, n_seg, status, seg_off, segs = chain.download_realignments()
     assert int(seg_off[-1]) <= chain.realign["cap"] and set(np.unique(segs["kind"])) <= {0, 1, 3, 4, 5, 6}
+    # ... and against the travelling oracle everywhere
+    rb = B.RealignBatch(eb, out, k4_kinds=True)
+    ox = reflib.ox_choose_realignment(rb, np.concatenate([lnp, [0.0]]))
+    assert np.array_equal(ox.pos[: eb.n_reads], pos) and np.array_equal(ox.n_seg[: eb.n_reads], n_seg) and np.array_equal(ox.status[: eb.n_reads], status)
+    assert np.array_equal(ox.seg_off[: eb.n_reads + 1], seg_off) and ox.segs[: int(seg_off[-1])].tobytes() == segs.tobytes()
     if reflib.have_ref():
         quals = np.full(int(eb.read_off[eb.n_reads]) + 1, 30, np.uint8)  # what B.read_pools_of gives every base
         ref_lnp, want = reflib.ref_choose_realignment(eb, out, quals)

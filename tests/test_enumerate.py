@@ -400,3 +400,25 @@ def test_choose_realignment_device_body_against_the_reference():
     assert rc == 0 and set(np.unique(k4.segs["kind"][: int(k4.totals[0])])) <= {0, 1, 3, 4, 5, 6}
     rc, small = reflib.k9core_choose(rb, np.concatenate([lnp, [0.0]]), cap_segs=3)
     assert rc == A.SX_ERR_CAPACITY and small.totals[0] == k4.totals[0]
+
+
+def test_choose_realignment_device_body_against_the_oracle():
+    """every output array of K9's device body == oracle/realign_oracle.cpp's (the comparison the GPU tests make), on scores with many
+    exact ties (a coarse grid) as well as on distinct ones; both segment-kind conventions."""
+    n = 0
+    for case in range(30):
+        eb = specgen.enum_edge_case(case) if case % 3 == 0 else specgen.enum_case(case)
+        out = reflib.ox_enumerate_alignments(eb, cap_alns=eb.n_reads * 64 + 64)
+        rng = np.random.default_rng(case)
+        nA = int(out.totals[0])
+        for lnp in (-rng.random(nA + 1) * 40.0, -rng.integers(0, 4, nA + 1) * 2.0):
+            for k4 in (False, True):
+                rb = B.RealignBatch(eb, out, k4_kinds=k4)
+                want = reflib.ox_choose_realignment(rb, lnp)
+                rc, got = reflib.k9core_choose(rb, lnp)
+                assert rc == 0 and want.rc == 0
+                for nm in ("seg_off", "pos", "n_seg", "status", "best_aln"):
+                    assert np.array_equal(getattr(want, nm)[: eb.n_reads], getattr(got, nm)[: eb.n_reads]), (case, nm)
+                assert want.segs[: int(want.totals[0])].tobytes() == got.segs[: int(got.totals[0])].tobytes()
+                n += eb.n_reads
+    assert n > 2000

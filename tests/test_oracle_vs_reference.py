@@ -310,3 +310,24 @@ def test_enumerate_alignments_matches_the_reference(chunk):
             assert x.tobytes() == y.tobytes(), case
         total += int(want.totals[0])
     assert total > 4000
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_choose_realignment_matches_the_reference(chunk):
+    """oracle/realign_oracle.cpp (K9's checker) against the reference's own scoreCandidateAlignments: rseg.realignment of every read, for
+    the default smoothing range, smoothing off and two wide ranges; tidy and awkward batches."""
+    n = clipped = 0
+    for case in range(20 * chunk, 20 * (chunk + 1)):
+        eb = specgen.enum_edge_case(case) if case % 3 == 0 else specgen.enum_case(case)
+        out = reflib.ox_enumerate_alignments(eb, cap_alns=eb.n_reads * 64 + 64)
+        quals = specgen.realign_quals(eb, case)
+        for smooth, rng_ in ((True, 2.302585092994046), (False, 1.0), (True, 30.0), (True, 500.0)):
+            lnp, want = reflib.ref_choose_realignment(eb, out, quals, is_smoothed=smooth, smoothed_range=rng_)
+            ox = reflib.ox_choose_realignment(B.RealignBatch(eb, out, is_smoothed=smooth, smoothed_lnp_range=rng_), np.concatenate([lnp, [0.0]]))
+            assert ox.rc == 0
+            for r in range(eb.n_reads):
+                g = ox.realignment_of(r)
+                assert g == want[r], (case, r)
+                n += 1
+                clipped += bool(g and "S" in g[1])
+    assert n > 1000 and clipped > 20

@@ -213,3 +213,19 @@ def test_k9_choose_realignment(ctx, which):
         for r in range(eb.n_reads):
             want = (int(pos[r]), str(cig[r])) if str(cig[r]) else None
             assert got.realignment_of(r) == want, (tag, r)
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_k9_choose_realignment_against_the_oracle(ctx, case):
+    """K9 on the GPU == oracle/realign_oracle.cpp, every output array, on scores with many exact ties and on distinct ones."""
+    eb = specgen.enum_edge_case(case) if case % 3 == 0 else specgen.enum_case(case)
+    out = ctx.enumerate_alignments(eb)
+    rng = np.random.default_rng(case)
+    nA = int(out.totals[0])
+    for lnp in (-rng.random(nA + 1) * 40.0, -rng.integers(0, 4, nA + 1) * 2.0):
+        for k4 in (False, True):
+            rb = B.RealignBatch(eb, out, k4_kinds=k4)
+            want, got = reflib.ox_choose_realignment(rb, lnp), ctx.choose_realignment(rb, lnp)
+            for nm in ("seg_off", "pos", "n_seg", "status", "best_aln"):
+                assert np.array_equal(getattr(want, nm)[: eb.n_reads], getattr(got, nm)[: eb.n_reads]), nm
+            assert want.segs[: int(want.totals[0])].tobytes() == got.segs[: int(got.totals[0])].tobytes()
