@@ -36,10 +36,10 @@ struct k7_counts // per read, then (after the scan) its exclusive offsets
 };
 
 __global__ void __launch_bounds__(K7_THREADS) k7_count_kernel(const k7_view v, unsigned char* __restrict__ arena, const size_t per_thread, const uint32_t maxA,
-                                                              const uint32_t* __restrict__ read_region, uint8_t* __restrict__ status, const k7_counts c)
+                                                              const uint32_t maxF, const uint32_t* __restrict__ read_region, uint8_t* __restrict__ status, const k7_counts c)
 {
     const uint32_t t(blockIdx.x * blockDim.x + threadIdx.x), nthr(gridDim.x * blockDim.x);
-    k7_scratch S(k7_scratch_at(arena + (size_t)t * per_thread, maxA));
+    k7_scratch S(k7_scratch_at(arena + (size_t)t * per_thread, maxA, maxF));
     for (uint32_t r = t; r < v.b.n_reads; r += nthr)
     {
         const uint32_t st(k7_enumerate_read(v, read_region[r], r, S));
@@ -52,11 +52,34 @@ __global__ void __launch_bounds__(K7_THREADS) k7_count_kernel(const k7_view v, u
     }
 }
 
-// region of every read (reads of a region are consecutive): one thread per region fills its reads' entries
-__global__ void k7_read_region_kernel(const uint32_t n_regions, const uint32_t* __restrict__ region_read_off, uint32_t* __restrict__ read_region)
+// region of every read (reads of a region are consecutive): one thread per region fills its reads' entries; and the largest window of
+// the batch -- a search can hold at most as many indels as its region's window has entries, so that many + 1 frames always suffice
+__global__ void k7_read_region_kernel(const uint32_t n_regions, const uint32_t* __restrict__ region_read_off, const uint32_t* __restrict__ region_key_off,
+                                      uint32_t* __restrict__ read_region, uint32_t* __restrict__ max_window)
 {
+    uint32_t m(0);
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_regions; g += gridDim.x * blockDim.x)
+    {
         for (uint32_t r = region_read_off[g]; r < region_read_off[g + 1]; ++r) read_region[r] = g;
+        m = max(m, region_key_off[g + 1] - region_key_off[g]);
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(max_window, m);
+}
+
+// frames a search of this batch can need (see k7_read_region_kernel): one host round trip of 4 bytes sizes the arena
+int k7_frames_needed(sx_ctx* ctx, const sx_enum_batch* d, uint32_t* read_region, uint32_t* max_window_dev, uint32_t* frames)
+{
+    cudaStream_t st(ctx->s_compute);
+    SX_CUDA(ctx, cudaMemsetAsync(max_window_dev, 0, 4, st));
+    const int g0(std::max(1, std::min<int>((int)((d->n_regions + 127) / 128), ctx->sm_count * 8)));
+    k7_read_region_kernel<<<g0, 128, 0, st>>>(d->n_regions, d->region_read_off, d->region_key_off, read_region, max_window_dev);
+    SX_CUDA(ctx, cudaGetLastError());
+    uint32_t h(0);
+    SX_CUDA(ctx, cudaMemcpyAsync(&h, max_window_dev, 4, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    *frames = std::min<uint32_t>(K7_MAX_INDELS, h) + 1u;
+    return SX_OK;
 }
 
 // phase 2 of the scan + the batch-wide closing entries; flags the capacity overflow
@@ -91,12 +114,12 @@ __global__ void __launch_bounds__(K7_SCAN_THREADS) k7_scan_finish(const uint32_t
 }
 
 __global__ void __launch_bounds__(K7_THREADS) k7_write_kernel(const k7_view v, unsigned char* __restrict__ arena, const size_t per_thread, const uint32_t maxA,
-                                                              const uint32_t* __restrict__ read_region, const uint8_t* __restrict__ status, const k7_counts c,
-                                                              const sx_enum_out o, const uint32_t* __restrict__ totals)
+                                                              const uint32_t maxF, const uint32_t* __restrict__ read_region, const uint8_t* __restrict__ status,
+                                                              const k7_counts c, const sx_enum_out o, const uint32_t* __restrict__ totals)
 {
     if (totals[0] > o.cap_alns || totals[1] > o.cap_segs || totals[2] > o.cap_keys) return; // reported by k7_scan_finish
     const uint32_t t(blockIdx.x * blockDim.x + threadIdx.x), nthr(gridDim.x * blockDim.x);
-    k7_scratch S(k7_scratch_at(arena + (size_t)t * per_thread, maxA));
+    k7_scratch S(k7_scratch_at(arena + (size_t)t * per_thread, maxA, maxF));
     for (uint32_t r = t; r < v.b.n_reads; r += nthr)
     {
         if (status[r] & (SX_ENUM_ST_EXCEPTION | SX_ENUM_ST_LIMIT)) continue;
@@ -166,11 +189,11 @@ __global__ void __launch_bounds__(K7_THREADS) k7_search_local_kernel(const k7_vi
 }
 
 __global__ void __launch_bounds__(K7_THREADS) k7_search_arena_kernel(const k7_view v, unsigned char* __restrict__ arena, const size_t per_thread, const uint32_t maxA,
-                                                                     const uint32_t* __restrict__ read_region, uint8_t* __restrict__ status,
+                                                                     const uint32_t maxF, const uint32_t* __restrict__ read_region, uint8_t* __restrict__ status,
                                                                      const uint8_t* __restrict__ tier, const k7_counts c, const k7_log L)
 {
     const uint32_t t(blockIdx.x * blockDim.x + threadIdx.x), nthr(gridDim.x * blockDim.x);
-    k7_scratch S(k7_scratch_at(arena + (size_t)t * per_thread, maxA));
+    k7_scratch S(k7_scratch_at(arena + (size_t)t * per_thread, maxA, maxF));
     for (uint32_t r = t; r < v.b.n_reads; r += nthr)
     {
         if (!tier[r]) continue;
@@ -218,18 +241,20 @@ int k7_run(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsigned* 
     cudaStream_t st(ctx->s_compute);
     const uint32_t n(d->n_reads);
     const uint32_t maxA(d->opts.max_alns_per_read ? std::min<uint32_t>(d->opts.max_alns_per_read, 65535u) : 64u);
-    const size_t per_thread((k7_scratch_bytes(maxA) + 255) & ~(size_t)255);
+    int rc;
+    uint32_t* read_region(nullptr);
+    if ((rc = sx_ensure(ctx, 41, (size_t)n * 4 + 32, reinterpret_cast<void**>(&read_region)))) return rc;
+    uint32_t maxF(K7_MAX_INDELS + 1);
+    if ((rc = k7_frames_needed(ctx, d, read_region, read_region + n + 1, &maxF))) return rc; // (also fills read_region)
+    const size_t per_thread((k7_scratch_bytes(maxA, maxF) + 255) & ~(size_t)255);
     int per_sm(1);
     SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k7_count_kernel, K7_THREADS, 0));
     per_sm = std::max(1, per_sm);
     size_t blocks(std::min<size_t>(((size_t)n + K7_THREADS - 1) / K7_THREADS, (size_t)ctx->sm_count * per_sm));
     const size_t arena_cap((size_t)4 << 30);
     while (blocks > 1 && blocks * K7_THREADS * per_thread > arena_cap) blocks = (blocks + 1) / 2;
-    int rc;
     unsigned char* arena(nullptr);
     if ((rc = sx_ensure(ctx, 40, blocks * K7_THREADS * per_thread, reinterpret_cast<void**>(&arena)))) return rc;
-    uint32_t* read_region(nullptr);
-    if ((rc = sx_ensure(ctx, 41, (size_t)n * 4 + 16, reinterpret_cast<void**>(&read_region)))) return rc;
     k7_counts c;
     if ((rc = sx_ensure(ctx, 42, (size_t)n * 4 + 16, reinterpret_cast<void**>(&c.aln)))) return rc;
     if ((rc = sx_ensure(ctx, 43, (size_t)n * 4 + 16, reinterpret_cast<void**>(&c.seg)))) return rc;
@@ -241,10 +266,7 @@ int k7_run(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsigned* 
 
     k7_view v;
     v.b = *d;
-    const int g0(std::max(1, std::min<int>((int)((d->n_regions + 127) / 128), ctx->sm_count * 8)));
-    k7_read_region_kernel<<<g0, 128, 0, st>>>(d->n_regions, d->region_read_off, read_region);
-    SX_CUDA(ctx, cudaGetLastError());
-    k7_count_kernel<<<(unsigned)blocks, K7_THREADS, 0, st>>>(v, arena, per_thread, maxA, read_region, o->status, c);
+    k7_count_kernel<<<(unsigned)blocks, K7_THREADS, 0, st>>>(v, arena, per_thread, maxA, maxF, read_region, o->status, c);
     SX_CUDA(ctx, cudaGetLastError());
     k7_scan_tiles<<<n_tiles, K7_SCAN_THREADS, 0, st>>>(n, c.aln, c.seg, c.key, sums, n_tiles);
     SX_CUDA(ctx, cudaGetLastError());
@@ -252,7 +274,7 @@ int k7_run(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsigned* 
     SX_CUDA(ctx, cudaGetLastError());
     k7_scan_finish<<<n_tiles, K7_SCAN_THREADS, 0, st>>>(n, c, sums, n_tiles, totals, *o, ctx->d_status);
     SX_CUDA(ctx, cudaGetLastError());
-    k7_write_kernel<<<(unsigned)blocks, K7_THREADS, 0, st>>>(v, arena, per_thread, maxA, read_region, o->status, c, *o, totals);
+    k7_write_kernel<<<(unsigned)blocks, K7_THREADS, 0, st>>>(v, arena, per_thread, maxA, maxF, read_region, o->status, c, *o, totals);
     SX_CUDA(ctx, cudaGetLastError());
     *launches = 6;
     return SX_OK;
@@ -265,7 +287,12 @@ int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsig
     cudaStream_t st(ctx->s_compute);
     const uint32_t n(d->n_reads);
     const uint32_t maxA(d->opts.max_alns_per_read ? std::min<uint32_t>(d->opts.max_alns_per_read, 65535u) : 64u);
-    const size_t per_thread((k7_scratch_bytes(maxA) + 255) & ~(size_t)255);
+    int rc;
+    uint32_t* read_region(nullptr);
+    if ((rc = sx_ensure(ctx, 41, (size_t)n * 4 + 32, reinterpret_cast<void**>(&read_region)))) return rc;
+    uint32_t maxF(K7_MAX_INDELS + 1);
+    if ((rc = k7_frames_needed(ctx, d, read_region, read_region + n + 1, &maxF))) return rc; // (also fills read_region)
+    const size_t per_thread((k7_scratch_bytes(maxA, maxF) + 255) & ~(size_t)255);
     int per_sm(1), per_sm_local(1);
     SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k7_search_arena_kernel, K7_THREADS, 0));
     SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_local, k7_search_local_kernel, K7_THREADS, 0));
@@ -277,11 +304,8 @@ int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsig
     size_t blocks(std::min<size_t>(n_blocks, std::max<size_t>(1, (size_t)ctx->sm_count * per_sm / 4)));
     const size_t arena_cap((size_t)1 << 30);
     while (blocks > 1 && blocks * K7_THREADS * per_thread > arena_cap) blocks = (blocks + 1) / 2;
-    int rc;
     unsigned char* arena(nullptr);
     if ((rc = sx_ensure(ctx, 40, blocks * K7_THREADS * per_thread, reinterpret_cast<void**>(&arena)))) return rc;
-    uint32_t* read_region(nullptr);
-    if ((rc = sx_ensure(ctx, 41, (size_t)n * 4 + 16, reinterpret_cast<void**>(&read_region)))) return rc;
     k7_counts c;
     if ((rc = sx_ensure(ctx, 42, (size_t)n * 4 + 16, reinterpret_cast<void**>(&c.aln)))) return rc;
     if ((rc = sx_ensure(ctx, 43, (size_t)n * 4 + 16, reinterpret_cast<void**>(&c.seg)))) return rc;
@@ -303,12 +327,9 @@ int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsig
 
     k7_view v;
     v.b = *d;
-    const int g0(std::max(1, std::min<int>((int)((d->n_regions + 127) / 128), ctx->sm_count * 8)));
-    k7_read_region_kernel<<<g0, 128, 0, st>>>(d->n_regions, d->region_read_off, read_region);
-    SX_CUDA(ctx, cudaGetLastError());
     k7_search_local_kernel<<<(unsigned)blocks_local, K7_THREADS, 0, st>>>(v, read_region, o->status, tier, c, L);
     SX_CUDA(ctx, cudaGetLastError());
-    k7_search_arena_kernel<<<(unsigned)blocks, K7_THREADS, 0, st>>>(v, arena, per_thread, maxA, read_region, o->status, tier, c, L);
+    k7_search_arena_kernel<<<(unsigned)blocks, K7_THREADS, 0, st>>>(v, arena, per_thread, maxA, maxF, read_region, o->status, tier, c, L);
     SX_CUDA(ctx, cudaGetLastError());
     k7_scan_tiles<<<n_tiles, K7_SCAN_THREADS, 0, st>>>(n, c.aln, c.seg, c.key, sums, n_tiles);
     SX_CUDA(ctx, cudaGetLastError());

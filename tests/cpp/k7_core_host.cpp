@@ -7,12 +7,22 @@
 #include <algorithm>
 #include <vector>
 
+
+// what k7_frames_needed (k7_enumerate.cu) computes on the device: a search holds at most as many indels as its region's window has entries
+static uint32_t frames_needed(const sx_enum_batch* b)
+{
+    uint32_t m(0);
+    for (uint32_t g = 0; g < b->n_regions; ++g) m = std::max(m, b->region_key_off[g + 1] - b->region_key_off[g]);
+    return std::min<uint32_t>(K7_MAX_INDELS, m) + 1u;
+}
+
 extern "C" int k7core_run(const sx_enum_batch* b, sx_enum_out* o, uint32_t maxA)
 {
     if (maxA == 0) maxA = 64;
     // the device arena is never cleared: poison it, so that any read-before-write of the scratch shows up here as a mismatch
-    std::vector<unsigned char> arena(k7_scratch_bytes(maxA) + 64, 0xCD);
-    k7_scratch S(k7_scratch_at(arena.data(), maxA));
+    const uint32_t maxF(frames_needed(b));
+    std::vector<unsigned char> arena(k7_scratch_bytes(maxA, maxF) + 64, 0xCD);
+    k7_scratch S(k7_scratch_at(arena.data(), maxA, maxF));
     k7_view v;
     v.b = *b;
     std::vector<uint32_t> read_region(b->n_reads), ca(b->n_reads + 1), cs(b->n_reads + 1), ck(b->n_reads + 1);
@@ -84,7 +94,8 @@ extern "C" int k7core_run_fast(const sx_enum_batch* b, sx_enum_out* o, uint32_t 
 {
     if (maxA == 0) maxA = 64;
     const uint32_t LA(16), LF(12);
-    std::vector<unsigned char> small(k7_scratch_bytes(LA, LF) + 64, 0xCD), arena(k7_scratch_bytes(maxA) + 64, 0xCD);
+    const uint32_t maxF(frames_needed(b));
+    std::vector<unsigned char> small(k7_scratch_bytes(LA, LF) + 64, 0xCD), arena(k7_scratch_bytes(maxA, maxF) + 64, 0xCD);
     k7_view v;
     v.b = *b;
     const uint32_t n(b->n_reads);
@@ -100,7 +111,7 @@ extern "C" int k7core_run_fast(const sx_enum_batch* b, sx_enum_out* o, uint32_t 
             const uint32_t r(n - 1 - rr);
             if (pass == 1 && !tier[r]) continue;
             std::fill(small.begin(), small.end(), (unsigned char)(0x3C + (r & 0x1f)));
-            k7_scratch S(pass == 0 ? k7_scratch_at(small.data(), LA, LF, K7_ST_RETRY) : k7_scratch_at(arena.data(), maxA));
+            k7_scratch S(pass == 0 ? k7_scratch_at(small.data(), LA, LF, K7_ST_RETRY) : k7_scratch_at(arena.data(), maxA, maxF));
             const uint32_t st(k7_enumerate_read(v, read_region[r], r, S));
             if (pass == 0 && (st & K7_ST_RETRY))
             {
