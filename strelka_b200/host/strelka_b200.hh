@@ -1040,6 +1040,15 @@ public:
             ctx.check(rc);
             break;
         }
+        // keep the enumeration as the library wrote it: chooseRealignments() (K9) reads the same arrays
+        _eRegionReadOff = regionReadOff;
+        _eRegionKeyOff = regionKeyOff;
+        _eAlnOff = alnOff;
+        _eAlnPos.assign(alnPos.begin(), alnPos.begin() + totals[0]);
+        _eAlnSegOff.assign(alnSegOff.begin(), alnSegOff.begin() + totals[0] + 1);
+        _eSegs.assign(segs.begin(), segs.begin() + totals[1]);
+        _eAlnKeyOff.assign(alnKeyOff.begin(), alnKeyOff.begin() + totals[0] + 1);
+        _eAlnKeys.assign(alnKeys.begin(), alnKeys.begin() + totals[2]);
         for (size_t g(0); g + 1 < regionReadOff.size(); ++g)
             for (size_t r(regionReadOff[g]); r < regionReadOff[g + 1]; ++r)
             {
@@ -1060,6 +1069,81 @@ public:
                     res.alignments.push_back(cal);
                 }
             }
+    }
+
+    struct Realignment ///< what scoreCandidateAlignments leaves in the read segment (:1739-1740)
+    {
+        bool is_realigned = false;
+        alignment realignment;
+        uint32_t bestAlignment = UINT32_MAX; ///< smooth_cal_ptr as an index into the read's alignments of enumerate()
+        bool unsupported = false;            ///< pinned read / malformed path: stays with the caller
+    };
+
+    /// K9, after enumerate(): candAlignmentScores = the K1 scores of every alignment in result order (read by read, alignment by
+    /// alignment).  The tail of scoreCandidateAlignments (:1573-1741) for unpinned reads: smooth pool, preferred alignment,
+    /// finishRealignment with the pool clipper.
+    void chooseRealignments(const Context& ctx, const std::vector<double>& candAlignmentScores, bool isSmoothedAlignments, double smoothedLnpRange,
+                            std::vector<Realignment>& out)
+    {
+        const size_t nReads(_readLen.size()), nAlns(_eAlnPos.size());
+        require(candAlignmentScores.size() == nAlns, "one score per enumerated alignment");
+        out.assign(nReads, Realignment());
+        if (nReads == 0) return;
+        std::vector<sx_indel_key> keys(_keys);
+        keys.resize(keys.size() + 1);
+        std::vector<int32_t> alnPos(_eAlnPos);
+        alnPos.push_back(0);
+        std::vector<sx_aln_seg> segs(_eSegs);
+        segs.resize(segs.size() + 4);
+        std::vector<uint16_t> alnKeys(_eAlnKeys);
+        alnKeys.resize(alnKeys.size() + 4);
+        std::vector<double> lnp(candAlignmentScores);
+        lnp.push_back(0);
+        sx_realign_batch b;
+        std::memset(&b, 0, sizeof(b));
+        b.n_regions = _eRegionReadOff.size() - 1;
+        b.n_reads = nReads;
+        b.n_alns = nAlns;
+        b.region_read_off = _eRegionReadOff.data();
+        b.region_key_off = _eRegionKeyOff.data();
+        b.keys = keys.data();
+        b.aln_off = _eAlnOff.data();
+        b.aln_pos = alnPos.data();
+        b.aln_seg_off = _eAlnSegOff.data();
+        b.segs = segs.data();
+        b.aln_key_off = _eAlnKeyOff.data();
+        b.aln_keys = alnKeys.data();
+        b.read_len = _readLen.data();
+        b.is_smoothed_alignments = isSmoothedAlignments ? 1 : 0;
+        b.smoothed_lnp_range = smoothedLnpRange;
+        sx_realign_out o;
+        std::memset(&o, 0, sizeof(o));
+        uint32_t total(0);
+        std::vector<uint32_t> segOff(nReads + 1), best(nReads);
+        std::vector<int32_t> pos(nReads);
+        std::vector<uint16_t> nSeg(nReads);
+        std::vector<uint8_t> status(nReads);
+        o.cap_segs = _eSegs.size() + 2 * nReads + 64;
+        std::vector<sx_aln_seg> outSegs(o.cap_segs + 1);
+        o.totals = &total;
+        o.seg_off = segOff.data();
+        o.pos = pos.data();
+        o.n_seg = nSeg.data();
+        o.status = status.data();
+        o.best_aln = best.data();
+        o.segs = outSegs.data();
+        ctx.check(sx_choose_realignment(ctx.get(), &b, lnp.data(), &o));
+        for (size_t r(0); r < nReads; ++r)
+        {
+            Realignment& res(out[r]);
+            res.unsupported = (status[r] & (SX_REALIGN_ST_UNSUPPORTED | SX_REALIGN_ST_LIMIT | SX_REALIGN_ST_BADPATH)) != 0;
+            if (!(status[r] & SX_REALIGN_ST_REALIGNED)) continue;
+            res.is_realigned = true;
+            res.realignment.pos = pos[r];
+            res.realignment.is_fwd_strand = _fwd[r];
+            for (uint32_t i(0); i < nSeg[r]; ++i) res.realignment.path.push_back(path_segment(static_cast<ALIGNPATH::align_t>(outSegs[segOff[r] + i].kind), outSegs[segOff[r] + i].len));
+            res.bestAlignment = best[r] - _eAlnOff[r];
+        }
     }
 
 private:
@@ -1094,6 +1178,11 @@ private:
     std::vector<sx_aln_seg> _inSegs;
     std::vector<uint16_t> _inKeys, _useKeys, _lead, _trail, _readLen;
     std::vector<bool> _fwd;
+    // the last enumeration, as the library wrote it
+    std::vector<uint32_t> _eRegionReadOff, _eRegionKeyOff, _eAlnOff, _eAlnSegOff, _eAlnKeyOff;
+    std::vector<int32_t> _eAlnPos;
+    std::vector<sx_aln_seg> _eSegs;
+    std::vector<uint16_t> _eAlnKeys;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@
 #include "strelka_b200.hh"
 
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <sstream>
@@ -32,6 +33,7 @@ inline void k7_mirror_check(const sx::Context& ctx, const std::string& dir, int&
     {
         int status;
         std::vector<std::vector<std::string>> alns;
+        std::string realignPos, realignCigar; // the reference's rseg.realignment ("" = not realigned)
     };
     sx::AlignmentSearchBatch batch;
     std::vector<Want> want;
@@ -49,6 +51,22 @@ inline void k7_mirror_check(const sx::Context& ctx, const std::string& dir, int&
     auto flush = [&]() {
         std::vector<sx::AlignmentSearchBatch::ReadResult> res;
         batch.enumerate(ctx, &opts, res);
+        // K9 through the mirror: the reference's own scores (frozen as bit patterns) -> the reference's realignments
+        std::vector<double> scores;
+        bool scorable(true);
+        for (size_t r(0); r < res.size(); ++r)
+        {
+            if (res[r].alignments.size() != want[r].alns.size()) scorable = false;
+            for (const std::vector<std::string>& w : want[r].alns)
+            {
+                const unsigned long long bits(std::strtoull(w[6].c_str(), nullptr, 16));
+                double d;
+                std::memcpy(&d, &bits, 8);
+                scores.push_back(d);
+            }
+        }
+        std::vector<sx::AlignmentSearchBatch::Realignment> realn;
+        if (scorable) batch.chooseRealignments(ctx, scores, true, 2.302585092994046, realn);
         for (size_t r(0); r < res.size(); ++r)
         {
             ++checks;
@@ -66,6 +84,18 @@ inline void k7_mirror_check(const sx::Context& ctx, const std::string& dir, int&
                 const std::string trail(cal.trailing_indel_key.type == sx::INDEL::NONE ? "65535" : keyString(cal.trailing_indel_key, windowOfRead[r]));
                 ok = cal.al.pos == atoi(w[1].c_str()) && sx::apath_to_cigar(cal.al.path) == w[2] && keys == w[3] && lead == w[4] && trail == w[5];
                 ++k7alns;
+            }
+            if (ok && scorable)
+            {
+                ++checks;
+                const bool wantRealigned(!want[r].realignCigar.empty());
+                if (realn[r].is_realigned != wantRealigned ||
+                    (wantRealigned && (realn[r].realignment.pos != atoi(want[r].realignPos.c_str()) || sx::apath_to_cigar(realn[r].realignment.path) != want[r].realignCigar)))
+                {
+                    ++failures;
+                    std::cerr << "FAIL k9 read " << r << ": realignment " << realn[r].realignment.pos << " " << sx::apath_to_cigar(realn[r].realignment.path) << ", want "
+                              << want[r].realignPos << " " << want[r].realignCigar << "\n";
+                }
             }
             if (!ok)
             {
@@ -127,10 +157,15 @@ inline void k7_mirror_check(const sx::Context& ctx, const std::string& dir, int&
             if (f[4] != "-")
                 for (const std::string& i : k7_split(f[4], ';')) observed.push_back(winKeys[atoi(i.c_str())]);
             batch.addRead(f[1], al, observed);
-            want.push_back(Want{atoi(f[5].c_str()), {}});
+            want.push_back(Want{atoi(f[5].c_str()), {}, "", ""});
             windowOfRead.push_back(winKeys);
         }
         else if (f[0] == "ALN") want.back().alns.push_back(f);
+        else if (f[0] == "REALIGN")
+        {
+            want.back().realignPos = f[1];
+            want.back().realignCigar = f[2];
+        }
         else if (f[0] == "END") flush();
     }
     if (k7checks < 100 || k7alns < 1000)

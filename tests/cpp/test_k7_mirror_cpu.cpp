@@ -5,6 +5,7 @@
 // sx_enumerate_alignments runs the device body of K7 (strelka_b200/csrc/k7_core.cuh, __host__ __device__) read by read the way the
 // kernels do.  On the GPU box tests/cpp/test_k7_mirror.cpp runs the same check through the real library.
 #include "k7_core.cuh"
+#include "k9_core.cuh"
 
 #include "k7_mirror_check.hh"
 
@@ -56,6 +57,39 @@ extern "C" int sx_enumerate_alignments(sx_ctx*, const sx_enum_batch* b, sx_enum_
         if (o->aln_off[r + 1] == o->aln_off[r]) continue;
         k7_enumerate_read(v, region[r], r, S);
         k7_write(S, *o, ca[r], cs[r], ck[r]);
+    }
+    return SX_OK;
+}
+
+extern "C" int sx_choose_realignment(sx_ctx*, const sx_realign_batch* b, const double* lnp, sx_realign_out* o)
+{
+    k9_view v;
+    v.b = *b;
+    v.lnp = lnp;
+    std::vector<uint32_t> region(b->n_reads);
+    for (uint32_t g = 0; g < b->n_regions; ++g)
+        for (uint32_t r = b->region_read_off[g]; r < b->region_read_off[g + 1]; ++r) region[r] = g;
+    uint32_t total(0);
+    for (uint32_t r = 0; r < b->n_reads; ++r)
+    {
+        o->seg_off[r] = total;
+        total += k9_slots(*b, r);
+    }
+    o->seg_off[b->n_reads] = total;
+    o->totals[0] = total;
+    if (total > o->cap_segs) return SX_ERR_CAPACITY;
+    std::vector<uint8_t> type(K9_MAX_READ);
+    std::vector<int32_t> pos(K9_MAX_READ);
+    k9_scratch S = {type.data(), pos.data()};
+    for (uint32_t r = 0; r < b->n_reads; ++r)
+    {
+        int32_t p;
+        uint16_t ns;
+        uint32_t best;
+        o->status[r] = (uint8_t)k9_read(v, region[r], r, S, o->segs + o->seg_off[r], o->seg_off[r + 1] - o->seg_off[r], p, ns, best);
+        o->pos[r] = p;
+        o->n_seg[r] = ns;
+        o->best_aln[r] = best;
     }
     return SX_OK;
 }

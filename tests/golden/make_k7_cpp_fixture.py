@@ -19,6 +19,10 @@ with open(os.path.join(HERE, "k7_cases.tsv"), "w") as f:
     for case in CASES:
         eb = specgen.enum_case(case)
         ref = reflib.ref_enumerate_alignments(eb, cap_alns=eb.n_reads * 6000 + 64)
+        # K9: the reference's own scores (qualities 30 everywhere) and the realignment it chooses, default smoothing
+        import numpy as np
+
+        lnp, realn = reflib.ref_choose_realignment(eb, ref, np.full(int(eb.read_off[eb.n_reads]) + 1, 30, np.uint8))
         o = eb.opts
         f.write(f"BATCH\t{o.n_samples}\t{o.sample_id}\t{o.is_haplotyping_enabled}\t{o.max_read_indel_toggle}\n")
         for g in range(eb.n_regions):
@@ -35,8 +39,11 @@ with open(os.path.join(HERE, "k7_cases.tsv"), "w") as f:
                 cig = "".join(f"{int(s['len'])}{B.AP_CHAR[int(s['kind'])]}" for s in eb.in_segs[int(eb.in_seg_off[r]) : int(eb.in_seg_off[r + 1])])
                 use = ";".join(str(int(x)) for x in eb.use_keys[int(eb.use_key_off[r]) : int(eb.use_key_off[r + 1])]) or "-"
                 f.write(f"READ\t{seq}\t{int(eb.in_pos[r])}\t{cig}\t{use}\t{int(ref.status[r])}\n")
-                for pos, cigar, keys, lead, trail in ref.alignments_of(r):
-                    f.write(f"ALN\t{pos}\t{cigar}\t{';'.join(map(str, keys)) or '-'}\t{lead}\t{trail}\n")
+                for i, (pos, cigar, keys, lead, trail) in enumerate(ref.alignments_of(r)):
+                    score = np.float64(lnp[int(ref.aln_off[r]) + i]).view(np.uint64)
+                    f.write(f"ALN\t{pos}\t{cigar}\t{';'.join(map(str, keys)) or '-'}\t{lead}\t{trail}\t{int(score):016x}\n")
                     n_alns += 1
+                if realn[r] is not None:
+                    f.write(f"REALIGN\t{realn[r][0]}\t{realn[r][1]}\n")
         f.write("END\n")
 print("k7_cases.tsv:", len(CASES), "batches,", n_alns, "alignments")
