@@ -692,6 +692,45 @@ int sx_alignment_indels_dev(sx_ctx* ctx, const sx_enum_batch* batch_dev, const s
                             const uint32_t* key_ins_off_dev, const char* key_ins_dev, sx_prep_out* out_dev);
 
 /* ==========================================================================================
+ * K7g  realign_gates   (the front of realignAndScoreRead, starling_common/starling_read_align.cpp:2045-2062: which reads go into the
+ *   search at all, and with which input alignment)
+ *   replaces  alignment::is_realignable / is_overmax        starling_common/alignment.cpp:34-50
+ *             check_for_candidate_indel_overlap             starling_read_align.cpp:222-283 (get_alignment_zone, alignment_util.cpp:76-85)
+ *             normalizeInputAlignmentIndels                 :2000-2021 (matchify_edge_indels = remove_edge_deletions + matchify_edge_insertions,
+ *                                                           alignment_util.cpp:89-198; is_edge_readref_len_segment, align_path.cpp:827-846)
+ *             matchify_edge_soft_clip                       alignment_util.cpp:203-207 (:2051-2057), the negative-start test :2062
+ * Input: the mapper's alignment of every read (pos + path, SX_AP_* kinds) in the CSR the K7 batch will use, the window, the realignment
+ * range.  Output: gate[r] and -- for the reads that pass -- the normalized alignment written into the same CSR slots (a normalized path
+ * is never longer than the original; unused slots become zero-length HARD_CLIP segments, which the search strips like any clip).
+ * ======================================================================================== */
+#define SX_GATE_REALIGN 0x01u      /* the read goes on to getCandidateAlignments */
+#define SX_GATE_SOFT_CLIPPED 0x02u /* isSoftClippedInputAlignment (:2051): the caller's retain-optimal-soft-clipping test wants to know */
+
+typedef struct sx_gate_batch {
+    uint32_t n_regions, n_reads;
+    const uint32_t* region_read_off;  /* [n_regions + 1] */
+    const uint32_t* region_key_off;   /* [n_regions + 1] */
+    const sx_indel_key* keys;         /* window entries (pos, lengths, type, SX_IKF_CANDIDATE) */
+    const int32_t* realign_begin;     /* [n_regions] */
+    const int32_t* realign_end;
+    const int32_t* raw_pos;           /* [n_reads] rseg.getInputAlignment().pos */
+    const uint32_t* seg_off;          /* [n_reads + 1] */
+    const sx_aln_seg* raw_segs;       /* rseg.getInputAlignment().path */
+    const uint16_t* read_len;         /* [n_reads] rseg.read_size() */
+    const uint8_t* pin_flags;         /* [n_reads] or NULL: bit 0 / 1 = rseg.get_segment_edge_pin().first / .second */
+    uint32_t max_indel_size;          /* opt.maxIndelSize */
+} sx_gate_batch;
+
+typedef struct sx_gate_out { /* caller-allocated */
+    uint8_t* gate;        /* [n_reads] SX_GATE_* */
+    int32_t* in_pos;      /* [n_reads] normalizedInputAlignment.pos */
+    sx_aln_seg* in_segs;  /* [seg_off[n_reads]] normalizedInputAlignment.path in the slots of the raw one */
+} sx_gate_out;
+
+int sx_realign_gates(sx_ctx* ctx, const sx_gate_batch* batch_host, sx_gate_out* out_host);
+int sx_realign_gates_dev(sx_ctx* ctx, const sx_gate_batch* batch_dev, sx_gate_out* out_dev);
+
+/* ==========================================================================================
  * K7b  link_alignments   (K7's output -> K1's alignment description; keeps the chain K7 -> K1 -> K6 in device memory)
  *   replaces the per-alignment host work in front of K1: the segment walk of scoreCandidateAlignment
  *   (starling_common/starling_read_align_score.cpp:289-499) with every container look-up resolved --

@@ -267,6 +267,19 @@ class SxRealignOut(C.Structure):
     _fields_ = [("cap_segs", C.c_uint32)] + [(n, C.c_void_p) for n in ("totals", "seg_off", "pos", "n_seg", "status", "best_aln", "segs")]
 
 
+SX_GATE_REALIGN, SX_GATE_SOFT_CLIPPED = 1, 2
+
+
+class SxGateBatch(C.Structure):
+    _fields_ = [("n_regions", C.c_uint32), ("n_reads", C.c_uint32)] + [(n, C.c_void_p) for n in (
+        "region_read_off", "region_key_off", "keys", "realign_begin", "realign_end", "raw_pos", "seg_off", "raw_segs", "read_len", "pin_flags")] + [
+        ("max_indel_size", C.c_uint32)]
+
+
+class SxGateOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("gate", "in_pos", "in_segs")]
+
+
 def default_enum_opts() -> SxEnumOpts:
     """starling_base_options defaults (starling_base_shared.hh:124,139,145,160) through the library's own sx_default_enum_opts."""
     o = SxEnumOpts()
@@ -342,6 +355,8 @@ SYMBOLS = [
     ("sx_alignment_indels_dev", C.c_int, [_P, C.POINTER(SxEnumBatch), _P, _P, _P, _P, _P, C.POINTER(SxPrepOut)]),
     ("sx_choose_realignment", C.c_int, [_P, C.POINTER(SxRealignBatch), _P, C.POINTER(SxRealignOut)]),
     ("sx_choose_realignment_dev", C.c_int, [_P, C.POINTER(SxRealignBatch), _P, C.POINTER(SxRealignOut)]),
+    ("sx_realign_gates", C.c_int, [_P, C.POINTER(SxGateBatch), C.POINTER(SxGateOut)]),
+    ("sx_realign_gates_dev", C.c_int, [_P, C.POINTER(SxGateBatch), C.POINTER(SxGateOut)]),
     ("sx_link_alignments", C.c_int, [_P, C.POINTER(SxEnumBatch), C.POINTER(SxEnumOut), C.c_uint32, _P, _P, C.POINTER(SxLinkOut)]),
     ("sx_link_alignments_dev", C.c_int, [_P, C.POINTER(SxEnumBatch), C.POINTER(SxEnumOut), C.c_uint32, _P, _P, C.POINTER(SxLinkOut)]),
     ("sx_indel_gl", C.c_int, [_P, C.POINTER(SxIndelBatch), _P]),

@@ -449,3 +449,13 @@ def _choose_realignment(self, rb: B.RealignBatch, lnp: np.ndarray, cap_segs=None
 
 
 Context.choose_realignment = _choose_realignment  # K9
+
+
+def _realign_gates(self, gb: B.GateBatch) -> B.GateOut:
+    """K7g: which reads go into the alignment search and with which (normalized) input alignment (host buffers)."""
+    go = B.GateOut(gb)
+    self._chk(self.lib.sx_realign_gates(self.h, C.byref(gb.c), C.byref(go.c)))
+    return go
+
+
+Context.realign_gates = _realign_gates  # K7g

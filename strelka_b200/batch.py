@@ -1040,3 +1040,47 @@ class RealignOut:
             return None
         s0 = int(self.seg_off[r])
         return int(self.pos[r]), "".join(f"{int(s['len'])}{AP_CHAR[int(s['kind'])]}" for s in self.segs[s0 : s0 + int(self.n_seg[r])])
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# K7g realign_gates
+# ------------------------------------------------------------------------------------------------------------------------------
+class GateBatch:
+    """sx_gate_batch: the mapper's alignments of an EnumBatch's reads (raw = [(pos, [(cigar char, len)...])] per read, batch order) with the
+    batch's window and realignment ranges."""
+
+    def __init__(self, eb: EnumBatch, raw, max_indel_size=49, pin_flags=None):
+        assert len(raw) == eb.n_reads
+        self.eb = eb
+        segs, seg_off, pos = [], [0], []
+        for p, path in raw:
+            pos.append(p)
+            segs.extend((ln, _AP_OF[t], 0) for t, ln in path)
+            seg_off.append(len(segs))
+        self.raw_pos = np.array(pos + [0], np.int32)
+        self.seg_off = np.array(seg_off, np.uint32)
+        self.raw_segs = np.zeros(len(segs) + 4, dtype=A.ALN_SEG_DT)
+        if segs:
+            self.raw_segs[: len(segs)] = np.array(segs, dtype=A.ALN_SEG_DT)
+        self.n_segs = len(segs)
+        self.pin_flags = pin_flags
+        self.c = A.SxGateBatch(eb.n_regions, eb.n_reads, A.ptr(eb.region_read_off), A.ptr(eb.region_key_off), A.ptr(eb.keys), A.ptr(eb.realign_begin),
+                               A.ptr(eb.realign_end), A.ptr(self.raw_pos), A.ptr(self.seg_off), A.ptr(self.raw_segs), A.ptr(eb.read_len),
+                               A.ptr(pin_flags) if pin_flags is not None else None, max_indel_size)
+
+
+class GateOut:
+    def __init__(self, gb: GateBatch):
+        n = gb.eb.n_reads
+        self.gate = np.zeros(n + 1, np.uint8)
+        self.in_pos = np.zeros(n + 1, np.int32)
+        self.in_segs = np.zeros(gb.n_segs + 4, dtype=A.ALN_SEG_DT)
+        self.c = A.SxGateOut(A.ptr(self.gate), A.ptr(self.in_pos), A.ptr(self.in_segs))
+        self._gb = gb
+
+    def alignment_of(self, r: int):
+        """(pos, cigar) of the normalized alignment (pads dropped), or None when the read does not go into the search."""
+        if not (int(self.gate[r]) & A.SX_GATE_REALIGN):
+            return None
+        s0, s1 = int(self._gb.seg_off[r]), int(self._gb.seg_off[r + 1])
+        return int(self.in_pos[r]), "".join(f"{int(s['len'])}{AP_CHAR[int(s['kind'])]}" for s in self.in_segs[s0:s1] if not (int(s["kind"]) == A.SX_AP_HARD_CLIP and int(s["len"]) == 0))

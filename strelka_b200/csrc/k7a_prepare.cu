@@ -78,6 +78,25 @@ __global__ void k7a_write_kernel(const k7a_view v, const unsigned long long* __r
     }
 }
 
+__global__ void k7g_gates_kernel(const sx_gate_batch b, const sx_gate_out o, uint32_t* __restrict__ read_region)
+{
+    // reads of a region are consecutive: a thread finds its read's region by a binary search of region_read_off
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < b.n_reads; r += gridDim.x * blockDim.x)
+    {
+        uint32_t lo(0), hi(b.n_regions);
+        while (lo + 1 < hi)
+        {
+            const uint32_t mid((lo + hi) / 2);
+            if (b.region_read_off[mid] <= r) lo = mid;
+            else hi = mid;
+        }
+        int32_t pos;
+        o.gate[r] = (uint8_t)k7g_read(b, lo, r, pos, o.in_segs + b.seg_off[r]);
+        o.in_pos[r] = pos;
+    }
+    (void)read_region;
+}
+
 int k7a_run(sx_ctx* ctx, const k7a_view& v, const sx_prep_out* o, unsigned* launches)
 {
     cudaStream_t st(ctx->s_compute);
@@ -138,6 +157,88 @@ int k7a_check_args(sx_ctx* ctx, const sx_enum_batch* b, const sx_region* regions
     return SX_OK;
 }
 } // namespace
+
+namespace
+{
+int k7g_check_args(sx_ctx* ctx, const sx_gate_batch* b, const sx_gate_out* o, const char* what)
+{
+    if (!b || !o) return sx_fail(ctx, SX_ERR_ARG, "%s: NULL argument", what);
+    if (b->n_reads == 0) return SX_OK;
+    if (!b->region_read_off || !b->region_key_off || !b->realign_begin || !b->realign_end || !b->raw_pos || !b->seg_off || !b->raw_segs || !b->read_len || !o->gate ||
+        !o->in_pos || !o->in_segs)
+        return sx_fail(ctx, SX_ERR_ARG, "%s: NULL array", what);
+    if (b->n_regions == 0) return sx_fail(ctx, SX_ERR_ARG, "%s: reads without a region", what);
+    return SX_OK;
+}
+} // namespace
+
+extern "C" int sx_realign_gates_dev(sx_ctx* ctx, const sx_gate_batch* d, sx_gate_out* out_dev)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    int rc;
+    if ((rc = k7g_check_args(ctx, d, out_dev, "sx_realign_gates_dev"))) return rc;
+    if (d->n_reads == 0) return SX_OK;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    sx_kernel_timer t(ctx);
+    const unsigned grid((unsigned)std::max(1, std::min<int>((int)((d->n_reads + 127) / 128), ctx->sm_count * 16)));
+    k7g_gates_kernel<<<grid, 128, 0, ctx->s_compute>>>(*d, *out_dev, nullptr);
+    SX_CUDA(ctx, cudaGetLastError());
+    t.stop(1);
+    if ((rc = t.finish())) return rc;
+    return sx_check_status(ctx, "sx_realign_gates");
+}
+
+extern "C" int sx_realign_gates(sx_ctx* ctx, const sx_gate_batch* b, sx_gate_out* out_host)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    int rc;
+    if ((rc = k7g_check_args(ctx, b, out_host, "sx_realign_gates"))) return rc;
+    if (b->n_reads == 0) return SX_OK;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st(ctx->s_compute);
+    SX_CUDA(ctx, cudaEventRecord(ctx->ev_a, st));
+    sx_gate_batch d(*b);
+    void* p(nullptr);
+    const size_t n_segs(b->seg_off[b->n_reads]), n_win(b->region_key_off[b->n_regions]);
+#define SX_UPX(slot, dst, src, type, bytes)                                                \
+    if ((rc = sx_ensure(ctx, slot, (size_t)(bytes) + 16, &p))) return rc;                   \
+    if (bytes) SX_CUDA(ctx, cudaMemcpyAsync(p, (src), (bytes), cudaMemcpyHostToDevice, st)); \
+    dst = static_cast<type>(p);
+    SX_UPX(0, d.region_read_off, b->region_read_off, const uint32_t*, (size_t)(b->n_regions + 1) * 4)
+    SX_UPX(1, d.region_key_off, b->region_key_off, const uint32_t*, (size_t)(b->n_regions + 1) * 4)
+    SX_UPX(2, d.keys, b->keys, const sx_indel_key*, n_win * sizeof(sx_indel_key))
+    SX_UPX(3, d.realign_begin, b->realign_begin, const int32_t*, (size_t)b->n_regions * 4)
+    SX_UPX(4, d.realign_end, b->realign_end, const int32_t*, (size_t)b->n_regions * 4)
+    SX_UPX(5, d.raw_pos, b->raw_pos, const int32_t*, (size_t)b->n_reads * 4)
+    SX_UPX(6, d.seg_off, b->seg_off, const uint32_t*, (size_t)(b->n_reads + 1) * 4)
+    SX_UPX(7, d.raw_segs, b->raw_segs, const sx_aln_seg*, n_segs * sizeof(sx_aln_seg))
+    SX_UPX(8, d.read_len, b->read_len, const uint16_t*, (size_t)b->n_reads * 2)
+    if (b->pin_flags)
+    {
+        SX_UPX(9, d.pin_flags, b->pin_flags, const uint8_t*, (size_t)b->n_reads)
+    }
+#undef SX_UPX
+    sx_gate_out o;
+    if ((rc = sx_ensure(ctx, 10, (size_t)b->n_reads + 16, reinterpret_cast<void**>(&o.gate)))) return rc;
+    if ((rc = sx_ensure(ctx, 11, (size_t)b->n_reads * 4 + 16, reinterpret_cast<void**>(&o.in_pos)))) return rc;
+    if ((rc = sx_ensure(ctx, 12, n_segs * sizeof(sx_aln_seg) + 16, reinterpret_cast<void**>(&o.in_segs)))) return rc;
+    const unsigned grid((unsigned)std::max(1, std::min<int>((int)((b->n_reads + 127) / 128), ctx->sm_count * 16)));
+    k7g_gates_kernel<<<grid, 128, 0, st>>>(d, o, nullptr);
+    SX_CUDA(ctx, cudaGetLastError());
+    SX_CUDA(ctx, cudaMemcpyAsync(out_host->gate, o.gate, (size_t)b->n_reads, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaMemcpyAsync(out_host->in_pos, o.in_pos, (size_t)b->n_reads * 4, cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaMemcpyAsync(out_host->in_segs, o.in_segs, n_segs * sizeof(sx_aln_seg), cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaEventRecord(ctx->ev_b, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms(0);
+    cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+    ctx->timing.kernel_ms = ms;
+    ctx->timing.launches = 1;
+    ctx->total_launches += 1;
+    return sx_check_status(ctx, "sx_realign_gates");
+}
 
 extern "C" int sx_alignment_indels_dev(sx_ctx* ctx, const sx_enum_batch* d, const sx_region* regions, const uint8_t* seq4, const char* ref, const uint32_t* key_ins_off,
                                        const char* key_ins, sx_prep_out* out_dev)

@@ -50,3 +50,16 @@ extern "C" int k7acore_run(const sx_enum_batch* b, const sx_region* regions, con
     }
     return 0;
 }
+
+// K7g realign_gates: the per-read body run read by read (one kernel, no scan)
+extern "C" int k7gcore_run(const sx_gate_batch* b, sx_gate_out* o)
+{
+    for (uint32_t g = 0; g < b->n_regions; ++g)
+        for (uint32_t r = b->region_read_off[g]; r < b->region_read_off[g + 1]; ++r)
+        {
+            int32_t pos;
+            o->gate[r] = (uint8_t)k7g_read(*b, g, r, pos, o->in_segs + b->seg_off[r]);
+            o->in_pos[r] = pos;
+        }
+    return 0;
+}

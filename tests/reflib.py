@@ -430,3 +430,35 @@ def ox_choose_realignment(rb: "B.RealignBatch", lnp: np.ndarray, cap_segs=None) 
     lib.ox_choose_realignment.argtypes = [C.POINTER(A.SxRealignBatch), _P, C.POINTER(A.SxRealignOut)]
     ro.rc = lib.ox_choose_realignment(C.byref(rb.c), A.ptr(lnp), C.byref(ro.c))
     return ro
+
+
+def ref_realign_gates(gb: "B.GateBatch", max_segs=64):
+    """The reference's own is_realignable / check_for_candidate_indel_overlap / normalizeInputAlignmentIndels / matchify_edge_soft_clip per read
+    (oracle/ref_harness_enumerate.inc): (gate[n_reads], [(pos, cigar) or None])."""
+    eb = gb.eb
+    n = eb.n_reads
+    gate, pos, nseg = np.zeros(n + 1, np.uint8), np.zeros(n + 1, np.int32), np.zeros(n + 1, np.uint16)
+    segs = np.zeros((n + 1) * max_segs, dtype=A.ALN_SEG_DT)
+    err = _err()
+    fn = ref().ref_realign_gates
+    fn.argtypes = [C.POINTER(A.SxGateBatch)] + [_P] * 8 + [C.c_uint32, C.c_char_p, C.c_int]
+    rc = fn(C.byref(gb.c), A.ptr(eb.ins_pool), A.ptr(eb.ins_off), A.ptr(eb.read_pool), A.ptr(eb.read_off), A.ptr(gate), A.ptr(pos), A.ptr(nseg), A.ptr(segs), max_segs, err, 1024)
+    if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    res = []
+    for r in range(n):
+        if not (int(gate[r]) & A.SX_GATE_REALIGN):
+            res.append(None)
+            continue
+        row = segs[r * max_segs : r * max_segs + int(nseg[r])]
+        res.append((int(pos[r]), "".join(f"{int(s['len'])}{B.AP_CHAR[int(s['kind'])]}" for s in row)))
+    return gate[:n], res
+
+
+def k7gcore_gates(gb: "B.GateBatch"):
+    """k7g_read (strelka_b200/csrc/k7a_core.cuh) compiled for the host."""
+    k7acore_prepare(gb.eb, B.read_pools_of(gb.eb)) if _k7acore is None else None
+    _k7acore.k7gcore_run.argtypes = [C.POINTER(A.SxGateBatch), C.POINTER(A.SxGateOut)]
+    go = B.GateOut(gb)
+    rc = _k7acore.k7gcore_run(C.byref(gb.c), C.byref(go.c))
+    return rc, go

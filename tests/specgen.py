@@ -803,3 +803,40 @@ def realign_quals(eb, case: int) -> np.ndarray:
     """one quality per read base of the batch (the K1 read pools of the realignment tests use the same values)."""
     rng = np.random.default_rng(4242 + case)
     return rng.choice(np.array([11, 25, 37], np.uint8), int(eb.read_off[eb.n_reads]) + 1)
+
+
+def raw_alignments_for(eb, case: int):
+    """Mapper-style alignments for the reads of an EnumBatch: its normalized input alignments made raw again -- soft clips cut out of the
+    first / last match, edge insertions and deletions kept, sometimes an over-long deletion (not realignable) -- so that every gate of
+    realignAndScoreRead has something to decide."""
+    rng = np.random.default_rng(31000 + case)
+    raw = []
+    for r in range(eb.n_reads):
+        path = [(B.AP_CHAR[int(s["kind"])], int(s["len"])) for s in eb.in_segs[int(eb.in_seg_off[r]) : int(eb.in_seg_off[r + 1])]]
+        pos = int(eb.in_pos[r])
+        body = [i for i, (t, _l) in enumerate(path) if t != "H"]
+        u = rng.random()
+        if u < 0.35 and path[body[0]][0] == "M" and path[body[0]][1] > 6:  # leading soft clip
+            n = int(rng.integers(1, 5))
+            i0 = body[0]
+            path[i0] = ("M", path[i0][1] - n)
+            path.insert(i0, ("S", n))
+            pos += n
+        if rng.random() < 0.35:
+            body = [i for i, (t, _l) in enumerate(path) if t != "H"]
+            i1 = body[-1]
+            if path[i1][0] == "M" and path[i1][1] > 6:  # trailing soft clip
+                n = int(rng.integers(1, 5))
+                path[i1] = ("M", path[i1][1] - n)
+                path.insert(i1 + 1, ("S", n))
+        if rng.random() < 0.05:  # an interior deletion longer than maxIndelSize
+            for i, (t, ln) in enumerate(path):
+                if t == "M" and ln > 20 and 0 < i < len(path) - 1 or (t == "M" and ln > 20 and len(path) == 1):
+                    a = ln // 2
+                    path[i:i + 1] = [("M", a), ("D", 60), ("M", ln - a)]
+                    break
+        raw.append((pos, path))
+    return raw
+
+
+GATES_GOLDEN_CASES = 12

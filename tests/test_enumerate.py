@@ -422,3 +422,62 @@ def test_choose_realignment_device_body_against_the_oracle():
                 assert want.segs[: int(want.totals[0])].tobytes() == got.segs[: int(got.totals[0])].tobytes()
                 n += eb.n_reads
     assert n > 2000
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# K7g realign_gates: the front of realignAndScoreRead
+# ------------------------------------------------------------------------------------------------------------------------------
+def test_realign_gates_device_body_against_the_reference():
+    """k7g_read (k7a_core.cuh compiled for the host) against the reference's own is_realignable / check_for_candidate_indel_overlap /
+    normalizeInputAlignmentIndels / matchify_edge_soft_clip on mapper-style alignments (soft clips, edge insertions and deletions,
+    over-long deletions, reads outside the realignment range or away from every candidate): the same reads pass, with the same
+    normalized alignment."""
+    if not reflib.have_ref():
+        pytest.skip("oracle/_ref/libstrelka_ref.so not built (needs /root/reference)")
+    n = 0
+    seen = set()
+    for case in range(40):
+        eb = specgen.enum_edge_case(case) if case % 2 else specgen.enum_case(case)
+        gb = B.GateBatch(eb, specgen.raw_alignments_for(eb, case))
+        gate, want = reflib.ref_realign_gates(gb)
+        rc, got = reflib.k7gcore_gates(gb)
+        assert rc == 0
+        for r in range(eb.n_reads):
+            assert int(got.gate[r]) == int(gate[r]) and got.alignment_of(r) == want[r], (case, r)
+            seen.add(int(gate[r]))
+            n += 1
+    assert n > 700 and seen >= {0, A.SX_GATE_REALIGN, A.SX_GATE_REALIGN | A.SX_GATE_SOFT_CLIPPED}
+
+
+def test_search_ignores_zero_length_hard_clip_pads():
+    """K7g writes a normalized path into the slots of the raw one and fills the rest with zero-length HARD_CLIP segments; K7a and K7 must
+    not see them: the enumeration of a batch with padded input paths == that of the clean batch (device body and oracle)."""
+    for case in (0, 1, 2, 5):
+        rng = np.random.default_rng(case)
+        regions = [specgen.random_enum_region(rng, n_reads=5, cluster=bool(case & 1), n_keys=(2, 7), hap=(case == 2)) for _ in range(4)]
+        clean = B.EnumBatch(regions)
+        padded = B.EnumBatch([(ref, rb, rr, win, [B.EnumReadSpec(r.seq, r.pos, list(r.path) + [("H", 0)] * int(rng.integers(1, 3)), r.use_keys) for r in reads])
+                              for ref, rb, rr, win, reads in regions])
+        assert np.array_equal(clean.in_keys, padded.in_keys)
+        cap = clean.n_reads * 64 + 64
+        want = reflib.ox_enumerate_alignments(clean, cap_alns=cap)
+        _same(want, reflib.ox_enumerate_alignments(padded, cap_alns=cap))
+        rc, got = reflib.k7core_enumerate(padded, cap_alns=cap)
+        assert rc == 0
+        _same(want, got)
+        rc, prep = reflib.k7acore_prepare(padded, B.read_pools_of(padded))
+        assert rc == 0 and np.array_equal(prep.trimmed()[1], padded.in_keys[: int(padded.in_key_off[padded.n_reads])])
+
+
+def test_realign_gates_device_body_against_the_frozen_reference_output():
+    gold = np.load(os.path.join(HERE, "golden", "gates_ref.npz"))
+    n = 0
+    for case in range(specgen.GATES_GOLDEN_CASES):
+        eb = specgen.enum_edge_case(case) if case % 2 else specgen.enum_case(case)
+        rc, got = reflib.k7gcore_gates(B.GateBatch(eb, specgen.raw_alignments_for(eb, case)))
+        assert rc == 0 and np.array_equal(got.gate[: eb.n_reads], gold[f"gate{case}"])
+        for r in range(eb.n_reads):
+            want = (int(gold[f"pos{case}"][r]), str(gold[f"cigar{case}"][r])) if int(gold[f"gate{case}"][r]) & A.SX_GATE_REALIGN else None
+            assert got.alignment_of(r) == want, (case, r)
+            n += 1
+    assert n > 200

@@ -229,3 +229,21 @@ def test_k9_choose_realignment_against_the_oracle(ctx, case):
             for nm in ("seg_off", "pos", "n_seg", "status", "best_aln"):
                 assert np.array_equal(getattr(want, nm)[: eb.n_reads], getattr(got, nm)[: eb.n_reads]), nm
             assert want.segs[: int(want.totals[0])].tobytes() == got.segs[: int(got.totals[0])].tobytes()
+
+
+@pytest.mark.parametrize("case", range(10))
+def test_k7g_realign_gates(ctx, case):
+    """K7g on the GPU == its host-compiled body (which tests/test_enumerate.py pins against the reference's own gate functions), and
+    where the reference library travelled, == the reference."""
+    eb = specgen.enum_edge_case(case) if case % 2 else specgen.enum_case(case)
+    gb = B.GateBatch(eb, specgen.raw_alignments_for(eb, case))
+    got = ctx.realign_gates(gb)
+    assert ctx.timing().launches == 1
+    rc, want = reflib.k7gcore_gates(gb)
+    assert np.array_equal(got.gate[: eb.n_reads], want.gate[: eb.n_reads]) and np.array_equal(got.in_pos[: eb.n_reads], want.in_pos[: eb.n_reads])
+    assert got.in_segs[: gb.n_segs].tobytes() == want.in_segs[: gb.n_segs].tobytes()
+    gold = np.load(os.path.join(HERE, "golden", "gates_ref.npz"))  # the reference's own answers, frozen
+    assert np.array_equal(got.gate[: eb.n_reads], gold[f"gate{case}"])
+    for r in range(eb.n_reads):
+        ref = (int(gold[f"pos{case}"][r]), str(gold[f"cigar{case}"][r])) if int(gold[f"gate{case}"][r]) & A.SX_GATE_REALIGN else None
+        assert got.alignment_of(r) == ref, r
