@@ -376,7 +376,7 @@ def make_enum_workload(n_loci: int, depth: int, read_len: int, seed: int) -> B.E
     eb.read_off = u32(np.arange(n_reads + 1, dtype=np.int64) * read_len)
     eb.c = A.SxEnumBatch(eb.n_regions, eb.n_reads, eb.n_keys, A.ptr(eb.region_read_off), A.ptr(eb.region_key_off), A.ptr(eb.keys), None, A.ptr(eb.realign_begin),
                          A.ptr(eb.realign_end), A.ptr(eb.in_pos), A.ptr(eb.in_seg_off), A.ptr(eb.in_segs), A.ptr(eb.in_key_off), A.ptr(eb.in_keys), A.ptr(eb.use_key_off),
-                         A.ptr(eb.use_keys), A.ptr(eb.in_lead_key), A.ptr(eb.in_trail_key), A.ptr(eb.read_len), eb.opts)
+                         A.ptr(eb.use_keys), A.ptr(eb.in_lead_key), A.ptr(eb.in_trail_key), A.ptr(eb.read_len), None, eb.opts)
     return eb
 
 

@@ -638,6 +638,8 @@ typedef struct sx_enum_batch {
     const uint16_t* in_lead_key;       /* [n_reads] leading_indel_key of getCandidateAlignment (:1481-1522) as window index, or SX_NO_KEY */
     const uint16_t* in_trail_key;      /* [n_reads] trailing_indel_key */
     const uint16_t* read_len;          /* [n_reads] rseg.read_size() */
+    const uint8_t* gate;               /* [n_reads] or NULL: K7g's output; a read whose SX_GATE_REALIGN bit is clear is answered with no alignments
+                                          and status 0 (realignAndScoreRead returned before the search), by K7a with no keys */
     sx_enum_opts opts;
 } sx_enum_batch;
 

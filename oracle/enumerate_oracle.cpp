@@ -622,7 +622,7 @@ extern "C" int ox_enumerate_alignments(const sx_enum_batch* b, sx_enum_out* o, i
                 unsigned status(0);
                 try
                 {
-                    candidateAlignments(C, *b, r, warn, cals);
+                    if (!b->gate || (b->gate[r] & SX_GATE_REALIGN)) candidateAlignments(C, *b, r, warn, cals);
                 }
                 catch (const Thrown&)
                 {

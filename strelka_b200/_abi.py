@@ -238,7 +238,7 @@ class SxEnumOpts(C.Structure):
 class SxEnumBatch(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("n_regions", "n_reads", "n_keys")] + [(n, C.c_void_p) for n in (
         "region_read_off", "region_key_off", "keys", "key_hap", "realign_begin", "realign_end", "in_pos", "in_seg_off", "in_segs", "in_key_off", "in_keys",
-        "use_key_off", "use_keys", "in_lead_key", "in_trail_key", "read_len")] + [("opts", SxEnumOpts)]
+        "use_key_off", "use_keys", "in_lead_key", "in_trail_key", "read_len", "gate")] + [("opts", SxEnumOpts)]
 
 
 class SxEnumOut(C.Structure):

@@ -272,7 +272,7 @@ class DevEnumBatch:
         p = {n: self.bufs[n].ptr for n in self._ARRAYS}
         self.c = A.SxEnumBatch(hb.n_regions, hb.n_reads, hb.n_keys, p["region_read_off"], p["region_key_off"], p["keys"], p["key_hap"] if hb.has_hap else None,
                                p["realign_begin"], p["realign_end"], p["in_pos"], p["in_seg_off"], p["in_segs"], p["in_key_off"], p["in_keys"], p["use_key_off"],
-                               p["use_keys"], p["in_lead_key"], p["in_trail_key"], p["read_len"], hb.opts)
+                               p["use_keys"], p["in_lead_key"], p["in_trail_key"], p["read_len"], None, hb.opts)
         self.shape = B.EnumOut(hb, cap_alns, cap_segs, cap_keys)  # host twin: sizes and the download target
         s = self.shape
         self.obufs = {n: DeviceArray(ctx, getattr(s, n).nbytes + 64) for n in ("totals", "aln_off", "status", "aln_pos", "aln_seg_off", "segs", "aln_key_off",

@@ -866,8 +866,13 @@ class EnumBatch:
             self.n_regions, self.n_reads, self.n_keys, A.ptr(self.region_read_off), A.ptr(self.region_key_off), A.ptr(self.keys),
             A.ptr(self.key_hap) if any_hap else None, A.ptr(self.realign_begin), A.ptr(self.realign_end), A.ptr(self.in_pos), A.ptr(self.in_seg_off),
             A.ptr(self.in_segs), A.ptr(self.in_key_off), A.ptr(self.in_keys), A.ptr(self.use_key_off), A.ptr(self.use_keys), A.ptr(self.in_lead_key),
-            A.ptr(self.in_trail_key), A.ptr(self.read_len), self.opts,
+            A.ptr(self.in_trail_key), A.ptr(self.read_len), None, self.opts,
         )
+
+    def set_gate(self, gate: Optional[np.ndarray]):
+        """K7g's per-read gate bytes (or None): reads whose SX_GATE_REALIGN bit is clear get no alignments."""
+        self.gate = None if gate is None else np.ascontiguousarray(gate, dtype=np.uint8)
+        self.c.gate = A.ptr(self.gate)
 
     def algorithmic_bytes(self, n_alns: int, n_segs: int, n_keys: int) -> int:
         """bytes one enumeration must move: every input array once + the CSR it writes."""

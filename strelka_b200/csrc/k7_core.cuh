@@ -895,6 +895,7 @@ K7_HDN uint32_t k7_enumerate_read_raw(const k7_view& v, const uint32_t region, c
 {
     const sx_enum_batch& b(v.b);
     S.n = 0;
+    if (b.gate && !(b.gate[r] & SX_GATE_REALIGN)) return 0; // realignAndScoreRead returned before the search (K7g)
     k7_read R;
     const uint32_t k0(b.region_key_off[region]);
     R.win = b.keys + k0;

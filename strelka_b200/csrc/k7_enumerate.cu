@@ -469,6 +469,10 @@ extern "C" int sx_enumerate_alignments(sx_ctx* ctx, const sx_enum_batch* b, sx_e
     SX_UP(13, in_lead_key, const uint16_t*, (size_t)b->n_reads * 2)
     SX_UP(14, in_trail_key, const uint16_t*, (size_t)b->n_reads * 2)
     SX_UP(15, read_len, const uint16_t*, (size_t)b->n_reads * 2)
+    if (b->gate)
+    {
+        SX_UP(26, gate, const uint8_t*, (size_t)b->n_reads)
+    }
 #undef SX_UP
     sx_enum_out o(*out_host);
     if ((rc = sx_ensure(ctx, 16, 16, reinterpret_cast<void**>(&o.totals)))) return rc;

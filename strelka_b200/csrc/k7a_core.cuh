@@ -102,6 +102,7 @@ K7A_HD uint32_t k7a_read(const k7a_view& v, const uint32_t region, const uint32_
     uint32_t n(0), ro(0);
     int32_t ref_pos(v.b.in_pos[r]);
     lead = trail = SX_NO_KEY;
+    if (v.b.gate && !(v.b.gate[r] & SX_GATE_REALIGN)) return 0; // the read does not go into the search (K7g)
     bool hasLead(false), hasTrail(false);
     uint32_t i(0);
     while (i < aps)

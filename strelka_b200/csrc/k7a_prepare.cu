@@ -302,6 +302,10 @@ extern "C" int sx_alignment_indels(sx_ctx* ctx, const sx_enum_batch* b, const sx
     SX_UPX(4, v.b.in_seg_off, b->in_seg_off, const uint32_t*, (size_t)(b->n_reads + 1) * 4)
     SX_UPX(5, v.b.in_segs, b->in_segs, const sx_aln_seg*, n_segs * sizeof(sx_aln_seg))
     SX_UPX(6, v.b.read_len, b->read_len, const uint16_t*, (size_t)b->n_reads * 2)
+    if (b->gate)
+    {
+        SX_UPX(17, v.b.gate, b->gate, const uint8_t*, (size_t)b->n_reads)
+    }
     SX_UPX(7, v.regions, regions, const sx_region*, ((size_t)b->n_regions + 1) * sizeof(sx_region))
     SX_UPX(8, v.seq4, seq4, const uint8_t*, (size_t)end.seq_off + SX_POOL_SLACK)
     SX_UPX(9, v.ref, ref, const char*, (size_t)end.ref_off + SX_POOL_SLACK)

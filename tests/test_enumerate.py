@@ -481,3 +481,33 @@ def test_realign_gates_device_body_against_the_frozen_reference_output():
             assert got.alignment_of(r) == want, (case, r)
             n += 1
     assert n > 200
+
+
+def test_gated_out_reads_get_no_alignments():
+    """sx_enum_batch.gate (K7g's output): a read whose SX_GATE_REALIGN bit is clear contributes no keys (K7a) and no alignments (K7, status 0);
+    every other read is unaffected -- device bodies, both launch plans, and the oracle."""
+    eb = specgen.enum_case(1)
+    cap = eb.n_reads * 64 + 64
+    full = reflib.ox_enumerate_alignments(eb, cap_alns=cap)
+    rng = np.random.default_rng(5)
+    gate = (rng.random(eb.n_reads + 1) < 0.6).astype(np.uint8) * A.SX_GATE_REALIGN | (rng.random(eb.n_reads + 1) < 0.3).astype(np.uint8) * A.SX_GATE_SOFT_CLIPPED
+    eb.set_gate(gate)
+    want = reflib.ox_enumerate_alignments(eb, cap_alns=cap)
+    for fast in (False, True):
+        rc, got = reflib.k7core_enumerate(eb, cap_alns=cap, fast=fast)
+        assert rc == 0
+        _same(want, got)
+    off = 0
+    for r in range(eb.n_reads):
+        if gate[r] & A.SX_GATE_REALIGN:
+            assert want.alignments_of(r) == full.alignments_of(r) and want.status[r] == full.status[r]
+        else:
+            assert want.aln_off[r + 1] == want.aln_off[r] and want.status[r] == 0
+            off += 1
+    assert 0 < off < eb.n_reads
+    rc, prep = reflib.k7acore_prepare(eb, B.read_pools_of(eb))
+    assert rc == 0
+    for r in range(eb.n_reads):
+        n = int(prep.in_key_off[r + 1]) - int(prep.in_key_off[r])
+        assert n == (int(eb.in_key_off[r + 1]) - int(eb.in_key_off[r]) if gate[r] & A.SX_GATE_REALIGN else 0)
+    eb.set_gate(None)

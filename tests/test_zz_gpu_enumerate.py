@@ -247,3 +247,14 @@ def test_k7g_realign_gates(ctx, case):
     for r in range(eb.n_reads):
         ref = (int(gold[f"pos{case}"][r]), str(gold[f"cigar{case}"][r])) if int(gold[f"gate{case}"][r]) & A.SX_GATE_REALIGN else None
         assert got.alignment_of(r) == ref, r
+
+
+def test_k7_honours_the_gate_array(ctx):
+    """a read K7g gated out is answered with no alignments / no keys by the kernels exactly as by the oracle."""
+    eb = specgen.enum_case(1)
+    rng = np.random.default_rng(5)
+    eb.set_gate((rng.random(eb.n_reads + 1) < 0.6).astype(np.uint8) * A.SX_GATE_REALIGN)
+    _same(reflib.ox_enumerate_alignments(eb), ctx.enumerate_alignments(eb))
+    eb.opts.flags = A.SX_ENUM_F_FAST
+    eb.c.opts = eb.opts
+    _same(reflib.ox_enumerate_alignments(eb), ctx.enumerate_alignments(eb))
