@@ -334,7 +334,7 @@ class DevRealignChain:
     host between the steps is the three + two totals that size the next buffers.  `pools`: the K1 batch holding the reads, qualities
     and reference windows in K7's read order (B.read_pools_of or a real one); its region records receive the alignment offsets."""
 
-    def __init__(self, ctx: "Context", eb: B.EnumBatch, pools: B.AlignBatch, cap_alns_per_read: int = 16, read_flags=None, rec_off=None):
+    def __init__(self, ctx: "Context", eb: B.EnumBatch, pools: B.AlignBatch, cap_alns_per_read: int = 16, read_flags=None, rec_off=None, raw: "B.GateBatch" = None):
         # bases / reference in the wide formats (K7a reads them); qualities may be dictionary-coded (qual_bits 4 selects K1's byte-entry kernel)
         assert pools.fmt == 0 and pools.qual_bits in (0, 4, 8) and pools.n_reads == eb.n_reads
         self.ctx, self.eb = ctx, eb
@@ -366,10 +366,27 @@ class DevRealignChain:
         self.link = self.lnp = None
         self.realign = None
         self.ms = {}
+        # optional first step K7g: the mapper's alignments (`raw`, a B.GateBatch over the same reads) -> gate + normalized input alignment,
+        # written where K7a / K7 read them; eb's own in_pos / in_segs / in_seg_off are then not used
+        self.gates = None
+        if raw is not None:
+            assert raw.eb is eb
+            g = {"raw_pos": DeviceArray(ctx, raw.raw_pos.nbytes + 16).upload(raw.raw_pos), "seg_off": DeviceArray(ctx, raw.seg_off.nbytes + 16).upload(raw.seg_off),
+                 "raw_segs": DeviceArray(ctx, raw.raw_segs.nbytes + 16).upload(raw.raw_segs), "gate": DeviceArray(ctx, n + 16), "in_pos": DeviceArray(ctx, n * 4 + 16),
+                 "in_segs": DeviceArray(ctx, raw.raw_segs.nbytes + 16)}
+            b0 = self.enum.bufs
+            self.gate_batch = A.SxGateBatch(eb.n_regions, n, b0["region_read_off"].ptr, b0["region_key_off"].ptr, b0["keys"].ptr, b0["realign_begin"].ptr,
+                                            b0["realign_end"].ptr, g["raw_pos"].ptr, g["seg_off"].ptr, g["raw_segs"].ptr, b0["read_len"].ptr, None, eb.opts.max_indel_size)
+            self.gate_out = A.SxGateOut(g["gate"].ptr, g["in_pos"].ptr, g["in_segs"].ptr)
+            c.in_pos, c.in_seg_off, c.in_segs, c.gate = g["in_pos"].ptr, g["seg_off"].ptr, g["in_segs"].ptr, g["gate"].ptr
+            self.gates = g
 
     def run(self):
         ctx, eb, e = self.ctx, self.eb, self.enum
         pc = self.pools.c
+        if self.gates is not None:
+            ctx._chk(ctx.lib.sx_realign_gates_dev(ctx.h, C.byref(self.gate_batch), C.byref(self.gate_out)))
+            self.ms["k7g_realign_gates"] = ctx.timing().kernel_ms
         ctx._chk(ctx.lib.sx_alignment_indels_dev(ctx.h, C.byref(e.c), pc.regions, pc.seq4, pc.ref, self.key_ins_off.ptr, self.key_ins.ptr, C.byref(self.prep_out)))
         self.ms["k7a_alignment_indels"] = ctx.timing().kernel_ms
         ctx.enumerate_alignments_dev(e)
@@ -436,6 +453,8 @@ class DevRealignChain:
             bufs += [v for v in self.link.values() if isinstance(v, DeviceArray)] + [self.lnp]
         if self.realign:
             bufs += [v for v in self.realign.values() if isinstance(v, DeviceArray)]
+        if self.gates:
+            bufs += list(self.gates.values())
         for d in bufs:
             d.free()
 

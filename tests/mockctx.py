@@ -63,6 +63,9 @@ class _MockLib:
         return lib.ox_score_indels(batch, lnp, o.recs, o.n_rec, o.max_aln, o.eval_aln)
 
 
+    def sx_realign_gates_dev(self, h, batch, out):
+        return reflib._k7acore.k7gcore_run(batch, out)
+
     def sx_choose_realignment_dev(self, h, batch, lnp, out):
         return reflib._k9core.k9core_run(batch, lnp, out)
 
@@ -74,6 +77,7 @@ class MockContext:
         out = reflib.ox_enumerate_alignments(eb)
         reflib.k8core_link(eb, out, pools.regions)
         reflib.k9core_choose(B.RealignBatch(eb, out), np.zeros(int(out.totals[0]) + 1))
+        reflib._k7acore.k7gcore_run.argtypes = [C.POINTER(A.SxGateBatch), C.POINTER(A.SxGateOut)]
         self.lib = _MockLib()
         self.h = 1
 

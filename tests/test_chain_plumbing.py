@@ -116,3 +116,50 @@ def test_bench_pools_quality_packing():
         lnp[bits] = chain.download()[1]
     assert len(lnp[4]) > 12 * 30 * 5 and np.array_equal(lnp[4].view(np.uint64), lnp[8].view(np.uint64))
     assert len(np.unique(lnp[4])) > 50  # three quality values really vary the scores
+
+
+def normalized_batch(eb, gb, gate_out):
+    """the EnumBatch a host shim would build after the gates: the same reads with their NORMALIZED input alignment (pads dropped) and the
+    gate bytes set -- built through the ordinary host builder, so in_keys come from batch.alignment_indels."""
+    regions = []
+    for g in range(eb.n_regions):
+        k0, k1 = int(eb.region_key_off[g]), int(eb.region_key_off[g + 1])
+        win = []
+        for k in range(k0, k1):
+            key, hap = eb.keys[k], eb.key_hap[k]
+            ins = bytes(eb.ins_pool[int(eb.ins_off[k]) : int(eb.ins_off[k + 1])]).decode()
+            fl = int(key["flags"])
+            win.append(B.EnumKeySpec(int(key["pos"]), int(key["del_len"]), ins, mismatch=int(key["type"]) == A.SX_INDEL_TYPE_MISMATCH, candidate=bool(fl & 1),
+                                     not_discovered=bool(fl & 2), forced=bool(fl & 4), active_region=int(hap["active_region_id"]),
+                                     hap_ids=tuple(int(x) for x in hap["haplotype_id"]), bypass=int(hap["bypass_mask"])))
+        reads = []
+        for r in range(int(eb.region_read_off[g]), int(eb.region_read_off[g + 1])):
+            seq = bytes(eb.read_pool[int(eb.read_off[r]) : int(eb.read_off[r + 1])]).decode()
+            al = gate_out.alignment_of(r)
+            if al is None:  # gated out: any valid alignment will do, the gate byte keeps the read out of the search
+                al = (int(eb.in_pos[r]), "".join(f"{int(s['len'])}{B.AP_CHAR[int(s['kind'])]}" for s in eb.in_segs[int(eb.in_seg_off[r]) : int(eb.in_seg_off[r + 1])]))
+            use = [int(x) for x in eb.use_keys[int(eb.use_key_off[r]) : int(eb.use_key_off[r + 1])]]
+            reads.append(B.EnumReadSpec(seq, al[0], B.parse_cigar(al[1]), use))
+        ref = bytes(eb.ref_pool[int(eb.ref_off[g]) : int(eb.ref_off[g + 1])]).decode()
+        regions.append((ref, int(eb.ref_begin[g]), (int(eb.realign_begin[g]), int(eb.realign_end[g])), win, reads))
+    nb = B.EnumBatch(regions, eb.opts, strict=False)
+    nb.set_gate(gate_out.gate[: eb.n_reads + 1].copy())
+    return nb
+
+
+@pytest.mark.parametrize("case", [0, 1, 3, 4])
+def test_chain_from_the_mappers_alignments_on_the_cpu(case):
+    """the chain with K7g in front (mapper alignments in): identical to the chain run on the batch a host shim would build from the
+    gates' answers with the ordinary host builder."""
+    from mockctx import MockContext
+    from strelka_b200.api import DevRealignChain
+
+    eb = specgen.enum_edge_case(case) if case % 2 else specgen.enum_case(case)
+    gb = B.GateBatch(eb, specgen.raw_alignments_for(eb, case))
+    pools = B.read_pools_of(eb)
+    chain = DevRealignChain(MockContext(eb, pools), eb, pools, cap_alns_per_read=64, raw=gb)
+    ms = chain.run()
+    assert "k7g_realign_gates" in ms
+    rc, gates = reflib.k7gcore_gates(gb)
+    assert rc == 0 and 0 < int((gates.gate[: eb.n_reads] & A.SX_GATE_REALIGN != 0).sum())
+    check_chain(chain, normalized_batch(eb, gb, gates))

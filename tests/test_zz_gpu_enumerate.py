@@ -258,3 +258,19 @@ def test_k7_honours_the_gate_array(ctx):
     eb.opts.flags = A.SX_ENUM_F_FAST
     eb.c.opts = eb.opts
     _same(reflib.ox_enumerate_alignments(eb), ctx.enumerate_alignments(eb))
+
+
+@pytest.mark.parametrize("case", [0, 1, 3, 4])
+def test_device_resident_chain_from_the_mappers_alignments(ctx, case):
+    """K7g -> K7a -> K7 -> K7b -> K1 -> K6 + K9 on device-resident data, the mapper's alignments in: identical to the chain run through the
+    oracles on the batch a host shim would build from the gates' answers (tests/test_chain_plumbing.py does the same on a mock context)."""
+    from strelka_b200.api import DevRealignChain
+    from test_chain_plumbing import check_chain, normalized_batch
+
+    eb = specgen.enum_edge_case(case) if case % 2 else specgen.enum_case(case)
+    gb = B.GateBatch(eb, specgen.raw_alignments_for(eb, case))
+    chain = DevRealignChain(ctx, eb, B.read_pools_of(eb), cap_alns_per_read=64, raw=gb)
+    chain.run()
+    gates = ctx.realign_gates(gb)
+    check_chain(chain, normalized_batch(eb, gb, gates))
+    chain.free()
