@@ -566,9 +566,11 @@ int sx_score_indels_dev(sx_ctx* ctx, const sx_score_indels_batch* batch_dev, con
  * Input, per region (the reads buffered around one realignment window): the IndelBuffer window in IndelKey order (the
  * sx_indel_key table K6 reads, plus what the search consults of IndelData: SX_IKF_NOT_DISCOVERED / SX_IKF_FORCED_OUTPUT and the
  * optional sx_key_hap rows); per read the NORMALIZED input alignment realignAndScoreRead hands to getCandidateAlignments
- * (:2049-2057: edge indels matchified, soft clips matchified), the window entries that alignment already contains
- * (getAlignmentIndels(..., includeMismatches = true), CandidateAlignment.cpp:58-173, mapped to window indices by the host, which
- * holds the read bases and the reference) and the non-candidate entries this read is an observation of (is_usable_indel :289-305).
+ * (:2049-2057: edge indels matchified, soft clips matchified -- by the host, or by K7g sx_realign_gates from the mapper's alignment),
+ * the window entries that alignment already contains (getAlignmentIndels(..., includeMismatches = true), CandidateAlignment.cpp:58-173,
+ * as window indices -- by the host, or by K7a sx_alignment_indels from the read bases and the reference where K1 keeps them) and the
+ * non-candidate entries this read is an observation of (is_usable_indel :289-305).  The chain K7g -> K7a -> K7 -> K7b -> K1 -> K6 / K9 is
+ * realignAndScoreRead for a batch of reads with every intermediate in device memory.
  * Output, per read: the std::set<CandidateAlignment> in ITS iteration order -- which is K1's and K6's alignment order -- as CSR
  * arrays shaped like sx_score_indels_batch's (aln_pos / path segments / cal.getIndels() as window indices) + the leading / trailing
  * edge keys + the warn flags that make is_incomplete_search.
