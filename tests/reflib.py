@@ -455,6 +455,30 @@ def ref_realign_gates(gb: "B.GateBatch", max_segs=64):
     return gate[:n], res
 
 
+def ref_realign_and_score_read(gb: "B.GateBatch", quals: np.ndarray, retain_soft=False, is_smoothed=True, smoothed_range=2.302585092994046, max_segs=64):
+    """The reference's whole realignAndScoreRead per read (oracle/ref_harness_enumerate.inc), mapper alignments in: (status[n_reads] --
+    0 not realigned, 1 realigned, 2 the reference threw --, [(pos, cigar) or None])."""
+    eb = gb.eb
+    n = eb.n_reads
+    status, pos, nseg = np.zeros(n + 1, np.uint8), np.zeros(n + 1, np.int32), np.zeros(n + 1, np.uint16)
+    segs = np.zeros((n + 1) * max_segs, dtype=A.ALN_SEG_DT)
+    err = _err()
+    fn = ref().ref_realign_and_score_read
+    fn.argtypes = [C.POINTER(A.SxGateBatch)] + [_P] * 8 + [C.c_int, C.c_int, C.c_double] + [_P] * 4 + [C.c_uint32, C.c_char_p, C.c_int]
+    rc = fn(C.byref(gb.c), A.ptr(eb.ins_pool), A.ptr(eb.ins_off), A.ptr(eb.ref_pool), A.ptr(eb.ref_off), A.ptr(eb.ref_begin), A.ptr(eb.read_pool), A.ptr(eb.read_off),
+            A.ptr(quals), 1 if retain_soft else 0, 1 if is_smoothed else 0, smoothed_range, A.ptr(status), A.ptr(pos), A.ptr(nseg), A.ptr(segs), max_segs, err, 1024)
+    if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    res = []
+    for r in range(n):
+        if status[r] != 1:
+            res.append(None)
+            continue
+        row = segs[r * max_segs : r * max_segs + int(nseg[r])]
+        res.append((int(pos[r]), "".join(f"{int(s['len'])}{B.AP_CHAR[int(s['kind'])]}" for s in row)))
+    return status[:n], res
+
+
 def k7gcore_gates(gb: "B.GateBatch"):
     """k7g_read (strelka_b200/csrc/k7a_core.cuh) compiled for the host."""
     k7acore_prepare(gb.eb, B.read_pools_of(gb.eb)) if _k7acore is None else None

@@ -163,3 +163,46 @@ def test_chain_from_the_mappers_alignments_on_the_cpu(case):
     rc, gates = reflib.k7gcore_gates(gb)
     assert rc == 0 and 0 < int((gates.gate[: eb.n_reads] & A.SX_GATE_REALIGN != 0).sum())
     check_chain(chain, normalized_batch(eb, gb, gates))
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("case", range(10))
+def test_chain_against_the_references_realignAndScoreRead(case):
+    """end to end: the chain K7g -> K7a -> K7 -> K7b -> K1 -> K9 from the mapper's alignments against the reference's own
+    realignAndScoreRead (starling_read_align.cpp:2026-2127) run per read on rebuilt objects -- is_realigned and rseg.realignment."""
+    from mockctx import MockContext
+    from strelka_b200.api import DevRealignChain
+
+    eb = specgen.enum_edge_case(case) if case % 2 else specgen.enum_case(case)
+    gb = B.GateBatch(eb, specgen.raw_alignments_for(eb, 100 + case))
+    pools = B.read_pools_of(eb)
+    chain = DevRealignChain(MockContext(eb, pools), eb, pools, cap_alns_per_read=64, raw=gb)
+    chain.run()
+    pos, n_seg, status, seg_off, segs = chain.download_realignments()
+    enum_status = chain.download()[0].status
+    quals = np.full(int(eb.read_off[eb.n_reads]) + 1, 30, np.uint8)
+    ref_status, want = reflib.ref_realign_and_score_read(gb, quals)
+    k4_char = {0: "M", 1: "I", 3: "S", 4: "H", 5: "D", 6: "N"}
+    n_real = n_limit = n_h_gap = 0
+    for r in range(eb.n_reads):
+        if ref_status[r] == 2:
+            continue  # the reference threw (generator corner); the chain's answer is not defined by it
+        if int(enum_status[r]) & A.SX_ENUM_ST_LIMIT:
+            n_limit += 1  # more alignments than this test's per-read capacity (the reference's own limit is 5000): reported, nothing produced
+            assert not (int(status[r]) & A.SX_REALIGN_ST_REALIGNED)
+            continue
+        if want[r] is None:
+            assert not (int(status[r]) & A.SX_REALIGN_ST_REALIGNED), (r, int(status[r]))
+            continue
+        n_real += 1
+        assert int(status[r]) & A.SX_REALIGN_ST_REALIGNED, (r, int(status[r]), want[r])
+        cig = "".join(f"{int(s['len'])}{k4_char[int(s['kind'])]}" for s in segs[int(seg_off[r]) : int(seg_off[r]) + int(n_seg[r])])
+        # KNOWN GAP (DESIGN.md, "what the end-to-end check found"): for a hard-clipped read the reference's rseg.realignment carries the
+        # hard clips ("3H111M4S11H"), the chain's does not ("111M4S"); position and every other segment agree.  Compared modulo H here.
+        import re
+
+        strip_h = lambda c: re.sub(r"\d+H", "", c)  # noqa: E731
+        want_cig = want[r][1].replace("=", "M").replace("X", "M")
+        assert (int(pos[r]), strip_h(cig)) == (want[r][0], strip_h(want_cig)), (r, cig, want_cig)
+        n_h_gap += cig != want_cig
+    assert n_real > 0 and int((ref_status == 2).sum()) <= eb.n_reads // 2, (n_real, int((ref_status == 2).sum()), n_limit, n_h_gap)
