@@ -831,9 +831,18 @@ int sx_choose_realignment_dev(sx_ctx* ctx, const sx_realign_batch* batch_dev, co
 #define SX_NCCL_ID_BYTES 128
 int sx_comm_get_unique_id(void* id_out /*[SX_NCCL_ID_BYTES]*/);
 int sx_comm_init(sx_ctx* ctx, const void* id, int rank, int world_size);
-/* every rank contributes `bytes` from local_dev; rank `root` receives world_size*bytes in all_dev (ncclGather
- * semantics via grouped send/recv); blocks until complete */
+/* every rank contributes the SAME `bytes` from local_dev; rank `root` (0 <= root < world_size) receives world_size*bytes in all_dev
+ * (non-NULL on the root; ncclGather semantics via grouped send/recv); blocks until complete.  Ranks whose blocks differ in size
+ * (n % world_size != 0 under strelka_b200/shard.py's shard_range) use sx_gatherv_records. */
 int sx_gather_records(sx_ctx* ctx, const void* local_dev, size_t bytes, void* all_dev, int root);
+/* the same exchange enqueued on the context's communication stream behind the work already on its compute stream: returns at once, so
+ * the next step's kernels overlap rank 0's receives; sx_comm_wait blocks until the last enqueued gather has completed. */
+int sx_gather_records_async(sx_ctx* ctx, const void* local_dev, size_t bytes, void* all_dev, int root);
+int sx_comm_wait(sx_ctx* ctx);
+/* variable block sizes: the per-rank byte counts are exchanged first, rank p's block lands at offsets_out[p] (= the exclusive prefix
+ * sum of the counts; offsets_out[world_size] = total; written on the root, may be NULL).  SX_ERR_CAPACITY on EVERY rank (no rank is
+ * left waiting) when the total exceeds all_capacity.  Blocking. */
+int sx_gatherv_records(sx_ctx* ctx, const void* local_dev, size_t bytes, void* all_dev, size_t all_capacity, uint64_t* offsets_out, int root);
 
 /* ------------------------------------------------------------------------------------------
  * Instrumentation: device time (ms, CUDA events on the launching stream) and launch count of

@@ -367,6 +367,9 @@ SYMBOLS = [
     ("sx_comm_get_unique_id", C.c_int, [_P]),
     ("sx_comm_init", C.c_int, [_P, _P, C.c_int, C.c_int]),
     ("sx_gather_records", C.c_int, [_P, _P, C.c_size_t, _P, C.c_int]),
+    ("sx_gather_records_async", C.c_int, [_P, _P, C.c_size_t, _P, C.c_int]),
+    ("sx_comm_wait", C.c_int, [_P]),
+    ("sx_gatherv_records", C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, _P, C.c_int]),
     ("sx_last_timing", C.c_int, [_P, C.POINTER(SxTiming)]),
     ("sx_total_launches", C.c_uint64, [_P]),
 ]

@@ -583,12 +583,9 @@ int sx_k1_launch(sx_ctx* ctx, const sx_align_batch* d, uint32_t region_begin, ui
     if (smem_bytes > ctx->smem_optin)
         return sx_fail(ctx, SX_ERR_ARG, "sx_score_alignments: a region needs %zu bytes of shared memory (limit %zu); split it into smaller regions", smem_bytes,
                        ctx->smem_optin);
-    static thread_local size_t attr_set = 0;
-    if (smem_bytes > 48 * 1024 && smem_bytes > attr_set)
-    {
+    // the opt-in is a property of (function, device), so it is set per launch like the other kernels' (cheap: a driver-side attribute write)
+    if (smem_bytes > 48 * 1024)
         SX_CUDA(ctx, cudaFuncSetAttribute(k1_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
-        attr_set = ctx->smem_optin;
-    }
     uint4 qd;
     memcpy(&qd, d->qual_dict, 16);
     k1_score_kernel<<<region_end - region_begin, K1_THREADS, smem_bytes, st>>>(d->regions, d->read_len, d->seq4, d->qual, d->ref, d->alns, d->segs, d->ins,

@@ -411,7 +411,7 @@ extern "C" int sx_create(int cuda_device, const sx_params* p, sx_ctx** out)
     ctx->params = *p;
     auto bail = [&](const char* what, cudaError_t ce) {
         g_create_err = std::string("sx_create: ") + what + ": " + cudaGetErrorString(ce);
-        delete ctx;
+        sx_destroy(ctx); // releases whatever was created so far (streams, events, tables)
         return SX_ERR_CUDA;
     };
     if ((e = cudaSetDevice(cuda_device)) != cudaSuccess) return bail("cudaSetDevice", e);
@@ -420,7 +420,7 @@ extern "C" int sx_create(int cuda_device, const sx_params* p, sx_ctx** out)
     if (prop.major < 10)
     {
         g_create_err = "sx_create: this library is built for sm_100a (B200) only";
-        delete ctx;
+        sx_destroy(ctx);
         return SX_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
@@ -444,6 +444,7 @@ extern "C" void sx_destroy(sx_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    sx_comm_release(ctx);
     for (auto& b : ctx->buf)
         if (b.p) cudaFree(b.p);
     if (ctx->d_tables) cudaFree(ctx->d_tables);

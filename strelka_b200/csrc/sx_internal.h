@@ -93,7 +93,12 @@ struct sx_ctx
     void* nccl = nullptr;    // ncclComm_t
     void* nccl_lib = nullptr;
     int rank = 0, world = 1;
+    cudaStream_t s_comm = nullptr;   // the gather's own stream (created by sx_comm_init)
+    cudaEvent_t ev_comm = nullptr;   // compute -> comm ordering
+    std::vector<unsigned long long> comm_counts; // per-rank byte counts of the last gather (root: receive offsets)
+    void* d_comm_counts = nullptr;
 };
+void sx_comm_release(sx_ctx* ctx); // sx_comm.cu: ncclCommDestroy + the comm stream (no-op without a communicator)
 
 int sx_fail(sx_ctx* ctx, int code, const char* fmt, ...);
 #define SX_CUDA(ctx, call)                                                                                        \
