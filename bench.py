@@ -393,9 +393,8 @@ def k7_enumerate_leg(ctx, peak_gbs: float, n_loci: int = 200_000, depth: int = 3
     from strelka_b200.api import DevEnumBatch
 
     eb = make_enum_workload(n_loci, depth, read_len, seed)
-    if fast:  # the second launch plan (include/strelka_b200.h SX_ENUM_F_FAST)
-        eb.opts.flags = A.SX_ENUM_F_FAST
-        eb.c.opts = eb.opts
+    eb.opts.flags = A.SX_ENUM_F_FAST if fast else 0  # (the fast plan is sx_default_enum_opts' default)
+    eb.c.opts = eb.opts
     db = DevEnumBatch(ctx, eb, cap_alns=eb.n_reads * 16, cap_segs=eb.n_reads * 64, cap_keys=eb.n_reads * 32)
     ms = []
     for i in range(reps + 1):
@@ -499,9 +498,8 @@ def realign_chain_leg(ctx, peak_gbs: float, n_loci: int = 100_000, depth: int = 
         from test_chain_plumbing import check_chain
 
         small = make_enum_workload(check_loci, depth, read_len, seed + 100)
-        if fast:
-            small.opts.flags = A.SX_ENUM_F_FAST
-            small.c.opts = small.opts
+        small.opts.flags = A.SX_ENUM_F_FAST if fast else 0
+        small.c.opts = small.opts
         sp = B.read_pools_of(small)
         ch = DevRealignChain(ctx, small, sp, cap_alns_per_read=64)
         ch.run()
@@ -511,9 +509,8 @@ def realign_chain_leg(ctx, peak_gbs: float, n_loci: int = 100_000, depth: int = 
     except AssertionError as e:
         leg["parity"] = f"MISMATCH on the {check_loci}-locus instance: {e}"
     eb = make_enum_workload(n_loci, depth, read_len, seed)
-    if fast:
-        eb.opts.flags = A.SX_ENUM_F_FAST
-        eb.c.opts = eb.opts
+    eb.opts.flags = A.SX_ENUM_F_FAST if fast else 0
+    eb.c.opts = eb.opts
     pools = make_enum_read_pools(eb, depth, read_len, seed)
     chain = DevRealignChain(ctx, eb, pools, cap_alns_per_read=16)
     acc = {}

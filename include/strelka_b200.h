@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SX_ABI_VERSION 1
+#define SX_ABI_VERSION 2
 
 enum {
     SX_OK = 0,
@@ -383,8 +383,8 @@ int sx_indel_gl_dev(sx_ctx* ctx, const sx_indel_batch* batch_dev, sx_indel_resul
  *   getReadAmbiguousEndLength (htsapi/bam_seq_read_util.cpp:29-54) and qphred_to_mapped_qphred (blt_util/qscore.hh:117).
  *
  * Input: the reads of one contig segment with their BEST alignment (the host keeps the decisions that need its containers:
- * realigned vs input alignment, is_any_nonovermax, the largest-indel-span check), in the order the reference piles them up
- * (ascending alignment position, buffer order within a position).  Output: for every position of the report range the
+ * is_any_nonovermax, the largest-indel-span check; realigned vs input alignment is K9's output when it is given the mapper's alignments),
+ * in the order the reference piles them up (read-buffer order: see buffer_pos below).  Output: for every position of the report range the
  * column of base_call words in exactly that order -- the tier1 buffer (`calls`) and the tier2 buffer (`t2_calls`) of
  * pos_basecall_buffer::insert_pos_basecall -- i.e. an sx_pileup_batch ready for K2, plus the spanning-deletion and
  * sub-mapped read counts of each position.  Not produced: MAPQ tallies and the EVS feature accumulators (out of scope).
@@ -435,6 +435,16 @@ typedef struct sx_pileup_reads_batch {
     uint32_t max_read_len;       /* >= every read's length (0 = unknown: the kernel's limit of 1024 is assumed) */
     uint32_t reserved_;
     sx_pileup_opts opts;
+    /* The order key.  The reference piles reads up in read-buffer order -- rseg.buffer_pos = the MAPPER's alignment position minus its
+     * unaligned prefix (starling_read_buffer.cpp:68-78, starling_read_util.cpp:30-35), read index within a position -- while a read
+     * contributes through its best alignment, whose start a realignment may have moved.  buffer_pos[n_reads] (ascending; NULL: the
+     * reads are ordered by reads[].pos itself) carries that key; max_pos_shift >= |reads[r].pos - buffer_pos[r]| for every read. */
+    const int32_t* buffer_pos;
+    uint32_t max_pos_shift;
+    /* qual_bits 0 / 8: one byte per base.  4: dictionary-coded, two per byte, high nibble first, every read on a byte boundary (the
+     * layout of seq4 and of sx_align_batch.qual with qual_bits 4); reads[].qual_off is then the offset of the read's first packed byte. */
+    uint32_t qual_bits;
+    uint8_t qual_dict[16];
 } sx_pileup_reads_batch;
 
 typedef struct sx_pileup_columns { /* caller-allocated; n_sites = report_end - report_begin */
@@ -613,10 +623,10 @@ typedef struct sx_enum_opts {
     uint32_t flags;                      /* SX_ENUM_F_* */
 } sx_enum_opts;
 
-/* SX_ENUM_F_FAST: the second-generation launch plan (same results): ordinary reads (<= 11 nested toggles, <= 16 alignments) search in
- * per-lane-interleaved local memory, the others in the global arena; every read is searched ONCE, its alignments appended to a log
- * and gathered into read order after the scan.  Written from the first ncu capture of the original plan (profiles/r1_k7_count.summary.txt:
- * 93 % long-scoreboard stalls on the per-thread arena, the search run twice); off by default until it has been timed on a B200. */
+/* SX_ENUM_F_FAST (the default of sx_default_enum_opts): ordinary reads (<= 11 nested toggles, <= 16 alignments) search in per-lane-interleaved
+ * local memory, the others in a global arena; every read is searched ONCE, its alignments appended to a log and gathered into read order
+ * after the scan.  flags = 0 selects the first launch plan (per-thread arena, count / scan / write: the search runs twice) -- same results,
+ * 6x slower on cfg2-shaped loci (BENCH_r01: 80.9 vs 13.2 ms per 100k loci); kept as a cross-check of the fast plan. */
 #define SX_ENUM_F_FAST 0x1u
 
 typedef struct sx_enum_batch {
@@ -805,6 +815,13 @@ typedef struct sx_realign_batch {
     int32_t is_smoothed_alignments;   /* opt.is_smoothed_alignments, 1 */
     int32_t k4_kinds;                 /* 0: output kinds are SX_AP_* (the reference's path); 1: K4's segment kinds (SX_SEG_*, '=' / 'X' as MATCH) */
     double smoothed_lnp_range;        /* std::log(10.) */
+    /* Optional (all three NULL or all three set): rseg.getInputAlignment() of every read, SX_AP_* kinds.  With them the output is
+     * read_segment::getBestAlignment() (starling_read_segment.hh:134-138) of EVERY read -- the realignment where one was chosen, the
+     * mapper's alignment otherwise (status without SX_REALIGN_ST_REALIGNED) -- i.e. K4's input for the whole batch; a read's slots
+     * are then reserved from max(longest candidate path + 2, its input path). */
+    const int32_t* raw_pos;           /* [n_reads] */
+    const uint32_t* raw_seg_off;      /* [n_reads + 1] */
+    const sx_aln_seg* raw_segs;
 } sx_realign_batch;
 
 typedef struct sx_realign_out { /* caller-allocated */

@@ -219,7 +219,9 @@ extern "C" int ox_choose_realignment(const sx_realign_batch* b, const double* ln
         o->seg_off[r] = total;
         uint32_t longest(0);
         for (uint32_t a = b->aln_off[r]; a < b->aln_off[r + 1]; ++a) longest = std::max(longest, b->aln_seg_off[a + 1] - b->aln_seg_off[a]);
-        total += longest ? longest + 2 : 0;
+        uint32_t need(longest ? longest + 2 : 0);
+        if (b->raw_seg_off) need = std::max(need, b->raw_seg_off[r + 1] - b->raw_seg_off[r]);
+        total += need;
     }
     o->seg_off[b->n_reads] = total;
     o->totals[0] = total;
@@ -233,6 +235,13 @@ extern "C" int ox_choose_realignment(const sx_realign_batch* b, const double* ln
             o->n_seg[r] = 0;
             o->status[r] = 0;
             o->best_aln[r] = UINT32_MAX;
+            if (b->raw_seg_off) // getBestAlignment of a read that keeps the mapper's alignment (starling_read_segment.hh:134-138); overwritten below by a realignment
+            {
+                const uint32_t q0(b->raw_seg_off[r]), nq(b->raw_seg_off[r + 1] - q0);
+                for (uint32_t i = 0; i < nq; ++i) o->segs[s0 + i] = sx_aln_seg{b->raw_segs[q0 + i].len, outKind(*b, b->raw_segs[q0 + i].kind), 0};
+                o->pos[r] = b->raw_pos[r];
+                o->n_seg[r] = (uint16_t)nq;
+            }
             const uint32_t a0(b->aln_off[r]), a1(b->aln_off[r + 1]);
             if (a0 == a1) continue;
             if (b->pin_flags && b->pin_flags[r])
@@ -287,6 +296,7 @@ extern "C" int ox_choose_realignment(const sx_realign_batch* b, const double* ln
                 if (realignment.path.size() > s1 - s0) throw BadPath();
                 for (size_t i = 0; i < realignment.path.size(); ++i)
                     o->segs[s0 + i] = sx_aln_seg{(uint16_t)realignment.path[i].length, outKind(*b, realignment.path[i].type), 0};
+                for (uint32_t i = s0 + (uint32_t)realignment.path.size(); i < s1; ++i) o->segs[i] = sx_aln_seg{0, outKind(*b, SX_AP_HARD_CLIP), 0};
                 o->pos[r] = realignment.pos;
                 o->n_seg[r] = (uint16_t)realignment.path.size();
                 o->status[r] = SX_REALIGN_ST_REALIGNED;

@@ -707,7 +707,14 @@ extern "C" int ref_pileup_reads(const sx_pileup_reads_batch* b, uint32_t* site_o
             std::unique_ptr<bam_record> br(new bam_record);
             br->set_qname("R");
             const std::string dummy(len, 'A');
-            br->set_readqual(dummy.c_str(), b->qual + rd.qual_off);
+            if (b->qual_bits == 4) // dictionary-coded qualities, two per byte: widened for the reference's bam_record
+            {
+                std::vector<uint8_t> wide(len);
+                for (int i = 0; i < len; ++i) wide[i] = b->qual_dict[(b->qual[rd.qual_off + (i >> 1)] >> ((~i & 1) << 2)) & 15];
+                br->set_readqual(dummy.c_str(), wide.data());
+            }
+            else
+                br->set_readqual(dummy.c_str(), b->qual + rd.qual_off);
             std::memcpy(bam_get_seq(br->get_data()), b->seq4 + rd.seq_off, (len + 1) / 2);
             alignment al;
             al.pos = rd.pos;

@@ -21,6 +21,7 @@
 #include "starling_common/starling_read_align_score_indels.hh"
 #include "test/starling_base_options_test.hh"
 
+#include <chrono>
 #include <cstring>
 #include <iterator>
 #include <map>

@@ -1700,7 +1700,7 @@ static int pileup_reads_impl(const sx_pileup_reads_batch* b, std::vector<uint16_
                     case 15: call_id = 4; break;
                     default: return SX_ERR_ARG; // base_error
                     }
-                    uint8_t qscore(qual[read_pos]);
+                    uint8_t qscore(b->qual_bits == 4 ? b->qual_dict[(qual[read_pos >> 1] >> ((~read_pos & 1) << 2)) & 15] : qual[read_pos]);
                     if (is_mapq_adjust)
                     {
                         if (qscore > 70) return SX_ERR_RANGE; // qscore_check in get_mapped_qscore_imp

@@ -162,6 +162,10 @@ class SxPileupReadsBatch(C.Structure):
         ("max_read_len", C.c_uint32),
         ("reserved_", C.c_uint32),
         ("opts", SxPileupOpts),
+        ("buffer_pos", C.c_void_p),
+        ("max_pos_shift", C.c_uint32),
+        ("qual_bits", C.c_uint32),
+        ("qual_dict", C.c_uint8 * 16),
     ]
 
 
@@ -260,7 +264,8 @@ SX_REALIGN_ST_REALIGNED, SX_REALIGN_ST_UNSUPPORTED, SX_REALIGN_ST_LIMIT, SX_REAL
 class SxRealignBatch(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("n_regions", "n_reads", "n_alns")] + [(n, C.c_void_p) for n in (
         "region_read_off", "region_key_off", "keys", "aln_off", "aln_pos", "aln_seg_off", "segs", "aln_key_off", "aln_keys", "read_len", "pin_flags")] + [
-        ("is_smoothed_alignments", C.c_int32), ("k4_kinds", C.c_int32), ("smoothed_lnp_range", C.c_double)]
+        ("is_smoothed_alignments", C.c_int32), ("k4_kinds", C.c_int32), ("smoothed_lnp_range", C.c_double),
+        ("raw_pos", C.c_void_p), ("raw_seg_off", C.c_void_p), ("raw_segs", C.c_void_p)]
 
 
 class SxRealignOut(C.Structure):

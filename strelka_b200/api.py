@@ -369,6 +369,7 @@ class DevRealignChain:
         # optional first step K7g: the mapper's alignments (`raw`, a B.GateBatch over the same reads) -> gate + normalized input alignment,
         # written where K7a / K7 read them; eb's own in_pos / in_segs / in_seg_off are then not used
         self.gates = None
+        self.raw_host = raw
         if raw is not None:
             assert raw.eb is eb
             g = {"raw_pos": DeviceArray(ctx, raw.raw_pos.nbytes + 16).upload(raw.raw_pos), "seg_off": DeviceArray(ctx, raw.seg_off.nbytes + 16).upload(raw.seg_off),
@@ -420,7 +421,8 @@ class DevRealignChain:
         self.ms["k6_score_indels"] = ctx.timing().kernel_ms
         # K9: rseg.realignment of every read, in K4's segment kinds
         n = eb.n_reads
-        cap = nS + 2 * n + 64
+        n_raw = int(self.raw_host.seg_off[n]) if self.gates is not None else 0
+        cap = nS + 2 * n + n_raw + 64
         if self.realign is None or self.realign["cap"] < cap:
             self.realign = {"cap": cap, "totals": DeviceArray(ctx, 16), "seg_off": DeviceArray(ctx, (n + 1) * 4 + 16), "pos": DeviceArray(ctx, n * 4 + 16),
                             "n_seg": DeviceArray(ctx, n * 2 + 16), "status": DeviceArray(ctx, n + 16), "best_aln": DeviceArray(ctx, n * 4 + 16),
@@ -428,6 +430,8 @@ class DevRealignChain:
         R = self.realign
         rb = A.SxRealignBatch(eb.n_regions, n, nA, b["region_read_off"].ptr, b["region_key_off"].ptr, b["keys"].ptr, o["aln_off"].ptr, o["aln_pos"].ptr,
                               o["aln_seg_off"].ptr, o["segs"].ptr, o["aln_key_off"].ptr, o["aln_keys"].ptr, b["read_len"].ptr, None, 1, 1, 2.302585092994046)
+        if self.gates is not None:  # the mapper's alignments are at hand: K9's output is then getBestAlignment() of every read (K4's input)
+            rb.raw_pos, rb.raw_seg_off, rb.raw_segs = self.gates["raw_pos"].ptr, self.gates["seg_off"].ptr, self.gates["raw_segs"].ptr
         ro = A.SxRealignOut(R["cap"], R["totals"].ptr, R["seg_off"].ptr, R["pos"].ptr, R["n_seg"].ptr, R["status"].ptr, R["best_aln"].ptr, R["segs"].ptr)
         ctx._chk(ctx.lib.sx_choose_realignment_dev(ctx.h, C.byref(rb), self.lnp.ptr, C.byref(ro)))
         self.ms["k9_choose_realignment"] = ctx.timing().kernel_ms

@@ -1013,13 +1013,16 @@ def read_pools_of(eb: EnumBatch) -> AlignBatch:
 class RealignBatch:
     """sx_realign_batch over K7's output (host arrays): the candidate alignments of EnumBatch `eb` as enumerated into `out`."""
 
-    def __init__(self, eb: EnumBatch, out: "EnumOut", is_smoothed=True, smoothed_lnp_range=2.302585092994046, k4_kinds=False, pin_flags=None):
+    def __init__(self, eb: EnumBatch, out: "EnumOut", is_smoothed=True, smoothed_lnp_range=2.302585092994046, k4_kinds=False, pin_flags=None, raw: "GateBatch" = None):
         self.eb, self.enum_out = eb, out
         self.n_alns = int(out.totals[0])
         self.pin_flags = pin_flags
+        self.raw = raw  # the mapper's alignments: with them the output is getBestAlignment() of every read
         self.c = A.SxRealignBatch(eb.n_regions, eb.n_reads, self.n_alns, A.ptr(eb.region_read_off), A.ptr(eb.region_key_off), A.ptr(eb.keys), A.ptr(out.aln_off),
                                   A.ptr(out.aln_pos), A.ptr(out.aln_seg_off), A.ptr(out.segs), A.ptr(out.aln_key_off), A.ptr(out.aln_keys), A.ptr(eb.read_len),
                                   A.ptr(pin_flags) if pin_flags is not None else None, 1 if is_smoothed else 0, 1 if k4_kinds else 0, smoothed_lnp_range)
+        if raw is not None:
+            self.c.raw_pos, self.c.raw_seg_off, self.c.raw_segs = A.ptr(raw.raw_pos), A.ptr(raw.seg_off), A.ptr(raw.raw_segs)
 
 
 class RealignOut:
@@ -1027,7 +1030,8 @@ class RealignOut:
 
     def __init__(self, rb: RealignBatch, cap_segs=None):
         n = rb.eb.n_reads
-        self.cap_segs = cap_segs if cap_segs is not None else int(rb.enum_out.totals[1]) + 2 * n + 64
+        n_raw = int(rb.raw.seg_off[n]) if getattr(rb, "raw", None) is not None else 0
+        self.cap_segs = cap_segs if cap_segs is not None else int(rb.enum_out.totals[1]) + 2 * n + n_raw + 64
         self.totals = np.zeros(2, np.uint32)
         self.seg_off = np.zeros(n + 1, np.uint32)
         self.pos = np.zeros(n + 1, np.int32)

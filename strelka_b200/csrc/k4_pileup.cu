@@ -5,20 +5,28 @@
 // getReadAmbiguousEndLength (htsapi/bam_seq_read_util.cpp:29-54) and the mapq adjustment (blt_util/qscore_cache.cpp:44-47).
 //
 // What has to be preserved is ORDER: a position's column is a std::vector the reference push_backs into read after read, and K2's
-// float sums run over that order.  Reads arrive sorted by position, so the output range is cut into windows of W >= the longest
-// alignment span: a read starting in window c can only reach windows c and c+1.  Three passes:
+// float sums run over that order.  The reference piles reads up in READ-BUFFER order: by rseg.buffer_pos -- the position of the
+// MAPPER's alignment minus its unaligned prefix (starling_read_buffer.cpp:68-78, get_alignment_buffer_pos starling_read_util.cpp:30-35;
+// the re-buffering after realignment is compiled out, starling_pos_processor_base.cpp:1034-1070) --, read index within a position,
+// while each read contributes through its BEST alignment, whose start a realignment may have moved by up to D = max_pos_shift.  So
+// reads arrive sorted by buffer position and the output range is cut into windows of W >= the longest alignment span + D: a read
+// buffered in window c can only reach the sites of windows c-1 (its last D), c and c+1.  Three passes:
 //   1. k4_count_kernel (thread per read): every covered interval is two atomics on difference arrays (tier1 / tier2 column sizes,
-//      the part of each that spills into the next window, spanning deletions, sub-mapped bases).  Integer, order-free.
+//      the part of each that spills forward into the next window and back into the previous one, spanning deletions, sub-mapped
+//      bases).  Integer, order-free.
 //   2. scans (k4_scan_*): difference arrays -> counts, counts -> CSR offsets.
 //   3. k4_fill_kernel (one WARP per window): walks its reads in order; per read the 32 lanes compute the mismatch-density map
 //      (shared-memory delta array + warp scan) and every base's base_call word, and place it at
-//      site_off[s] + (calls already placed at s).  The running per-site counters live in shared memory for the 2W sites the window's
-//      reads can touch and start, for the window's own sites, at the number of calls spilling in from window c-1 -- whose reads all
-//      precede this window's reads.
+//      site_off[s] + (calls already placed at s).  The running per-site counters live in shared memory for the 3W sites the window's
+//      reads can touch.  A column holds, in this order, the calls of window c-1's reads (forward spill), of window c's own reads and of
+//      window c+1's reads (back spill): all reads of an earlier window precede all reads of a later one.  So the cursors start at
+//      site_off[s] + spill[s] for the window's own sites, at site_off[s] for the next window's sites and at site_off[s+1] - back[s]
+//      for the previous window's.
 // Everything is integer/byte work; the only table is qphred_cache::mappedq, built on the host (sx_context.cu).
 #include "sx_internal.h"
 
 #include <algorithm>
+#include <cstring>
 
 namespace
 {
@@ -32,6 +40,9 @@ constexpr int ST_ORDER = 64, ST_BASE = 128, ST_LIMIT = 256, ST_QUAL = 1, ST_KIND
 struct k4_args
 {
     const sx_pileup_read* reads;
+    const int32_t* bpos; // buffer positions (NULL: reads[].pos)
+    uint32_t qual_bits;  // 4: dictionary-coded qualities, two per byte
+    uint8_t qual_dict[16];
     const uint8_t* seq4;
     const uint8_t* qual;
     const sx_aln_seg* segs;
@@ -58,6 +69,8 @@ __device__ __forceinline__ char char_of_code(uint32_t c)
     const unsigned long long lut = c < 8u ? 0x4e4e4e474e43413dull : 0x4e4e4e4e4e4e4e54ull;
     return static_cast<char>((lut >> (8u * (c & 7u))) & 0xffu);
 }
+
+__device__ __forceinline__ int32_t bpos_of(const k4_args& A, uint32_t r) { return A.bpos ? A.bpos[r] : A.reads[r].pos; }
 
 __device__ __forceinline__ int64_t i64max(int64_t a, int64_t b) { return a > b ? a : b; }
 __device__ __forceinline__ int64_t i64min(int64_t a, int64_t b) { return a < b ? a : b; }
@@ -112,13 +125,14 @@ template <typename CodeFn> __device__ __forceinline__ bool read_preamble(const k
 // ---------------------------------------------------------------------------------------------------------------------
 // pass 1: column sizes as difference arrays
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void k4_count_kernel(k4_args A, int* __restrict__ d1, int* __restrict__ d2, int* __restrict__ s1, int* __restrict__ s2, int* __restrict__ dsd,
-                                int* __restrict__ dsm, int* __restrict__ status)
+__global__ void k4_count_kernel(k4_args A, int* __restrict__ d1, int* __restrict__ d2, int* __restrict__ s1, int* __restrict__ s2, int* __restrict__ b1,
+                                int* __restrict__ b2, int* __restrict__ dsd, int* __restrict__ dsm, int* __restrict__ status)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= A.n_reads) return;
     const sx_pileup_read rd = A.reads[r];
-    if (r > 0 && A.reads[r - 1].pos > rd.pos) atomicOr(status, ST_ORDER);
+    const int32_t bp = bpos_of(A, r);
+    if (r > 0 && bpos_of(A, r - 1) > bp) atomicOr(status, ST_ORDER);
     const sx_aln_seg* path = A.segs + rd.seg_off;
     const uint32_t as = A.reads[r + 1].seg_off - rd.seg_off;
     if (rd.len > A.Lcap || as > K4_MAX_SEGS)
@@ -141,14 +155,22 @@ __global__ void k4_count_kernel(k4_args A, int* __restrict__ d1, int* __restrict
     const uint8_t* seq = A.seq4 + rd.seq_off;
     read_window w;
     if (!read_preamble(A, rd, ref_span, [&](uint32_t i) { return code_at(seq, i); }, w)) return;
-    if (ref_span > A.W || rd.pos < A.origin)
+    if (ref_span > A.W || bp < A.origin)
     {
         atomicOr(status, ST_ORDER);
         return;
     }
     const bool submapped = !(rd.flags & SX_PRF_TIER1OR2), tier1 = rd.flags & SX_PRF_TIER1;
-    const uint32_t c = static_cast<uint32_t>(rd.pos - A.origin) / A.W;
-    const int64_t next_win_site = static_cast<int64_t>(A.origin) + static_cast<int64_t>(c + 1) * A.W - A.report_begin; // first site of window c+1
+    const uint32_t c = static_cast<uint32_t>(bp - A.origin) / A.W;
+    const int64_t this_win_pos = static_cast<int64_t>(A.origin) + static_cast<int64_t>(c) * A.W;
+    const int64_t this_win_site = this_win_pos - A.report_begin;       // first site of window c (negative in window 0)
+    const int64_t next_win_site = this_win_site + A.W;                 // first site of window c+1
+    // the best alignment must stay within the three windows the fill pass holds cursors for (guaranteed by W >= span + max_pos_shift)
+    if (static_cast<int64_t>(rd.pos) < this_win_pos - A.W || static_cast<int64_t>(rd.pos) + ref_span > this_win_pos + 2 * static_cast<int64_t>(A.W))
+    {
+        atomicOr(status, ST_ORDER);
+        return;
+    }
     int64_t ref_head = rd.pos;
     uint32_t read_head = 0;
     for (uint32_t i = 0; i < as; ++i)
@@ -166,6 +188,7 @@ __global__ void k4_count_kernel(k4_args A, int* __restrict__ d1, int* __restrict
                 {
                     diff_add(tier1 ? d1 : d2, a, b, A.n_sites + 1);
                     diff_add(tier1 ? s1 : s2, i64max(a, next_win_site), b, A.n_sites);
+                    diff_add(tier1 ? b1 : b2, a, i64min(b, this_win_site), A.n_sites);
                 }
             }
         }
@@ -289,25 +312,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) k4_scan_tiles(scan_job J, const 
 // ---------------------------------------------------------------------------------------------------------------------
 __host__ __device__ inline uint32_t k4_warp_smem(uint32_t W, uint32_t Lcap)
 {
-    // run1[2W], run2[2W] (uint32), delta[Lcap + 4] (int), mism[Lcap] (uint8), segment table 3 x K4_MAX_SEGS uint32, and the staged
+    // run1[3W], run2[3W] (uint32), delta[Lcap + 4] (int), mism[Lcap] (uint8), segment table 3 x K4_MAX_SEGS uint32, and the staged
     // read: packed bases [Lcap/2 + 16], qualities [Lcap], reference bases under the alignment [W + 16], mappedq row [80]; Lcap % 16 == 0
-    return 2u * 2u * W * 4u + (Lcap + 4u) * 4u + Lcap + 3u * K4_MAX_SEGS * 4u + (Lcap / 2u + 16u) + Lcap + (W + 16u) + 80u;
+    return 2u * 3u * W * 4u + (Lcap + 4u) * 4u + Lcap + 3u * K4_MAX_SEGS * 4u + (Lcap / 2u + 16u) + Lcap + (W + 16u) + 80u;
 }
 
-__device__ __forceinline__ uint32_t lower_bound_pos(const sx_pileup_read* reads, uint32_t n, int64_t pos)
+__device__ __forceinline__ uint32_t lower_bound_pos(const k4_args& A, int64_t pos)
 {
-    uint32_t lo = 0, hi = n;
+    uint32_t lo = 0, hi = A.n_reads;
     while (lo < hi)
     {
         const uint32_t mid = (lo + hi) >> 1;
-        if (reads[mid].pos < pos) lo = mid + 1;
+        if (bpos_of(A, mid) < pos) lo = mid + 1;
         else hi = mid;
     }
     return lo;
 }
 
 __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const uint32_t* __restrict__ site_off, const uint32_t* __restrict__ t2_off,
-                                                               const int* __restrict__ spill1, const int* __restrict__ spill2, uint16_t* __restrict__ calls,
+                                                               const int* __restrict__ spill1, const int* __restrict__ spill2, const int* __restrict__ back1,
+                                                               const int* __restrict__ back2, uint16_t* __restrict__ calls,
                                                                uint16_t* __restrict__ t2_calls, const sx_tables* __restrict__ tables, int* __restrict__ status)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -316,8 +340,8 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
     if (c >= A.n_windows) return;
     unsigned char* wsm = smem + (size_t)warp * k4_warp_smem(A.W, A.Lcap);
     uint32_t* run1 = reinterpret_cast<uint32_t*>(wsm);
-    uint32_t* run2 = run1 + 2 * A.W;
-    int* delta = reinterpret_cast<int*>(run2 + 2 * A.W);
+    uint32_t* run2 = run1 + 3 * A.W;
+    int* delta = reinterpret_cast<int*>(run2 + 3 * A.W);
     uint8_t* mism = reinterpret_cast<uint8_t*>(delta + A.Lcap + 4);
     uint32_t* seg_kl = reinterpret_cast<uint32_t*>(mism + A.Lcap); // kind << 16 | len
     uint32_t* seg_rd = seg_kl + K4_MAX_SEGS;                            // read offset of the segment
@@ -329,24 +353,43 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
     uint32_t mqrow_of = 0xffffffffu;
 
     const int64_t win_pos0 = static_cast<int64_t>(A.origin) + static_cast<int64_t>(c) * A.W;
-    const int64_t site0 = win_pos0 - A.report_begin; // site index of local index 0 (negative in window 0)
+    const int64_t site0 = win_pos0 - A.W - A.report_begin; // site index of local index 0: the first site of window c-1 (may be negative)
     uint32_t lo = 0, hi = 0;
     if (lane == 0)
     {
-        lo = lower_bound_pos(A.reads, A.n_reads, win_pos0);
-        hi = lower_bound_pos(A.reads, A.n_reads, win_pos0 + A.W);
+        lo = lower_bound_pos(A, win_pos0);
+        hi = lower_bound_pos(A, win_pos0 + A.W);
     }
     lo = __shfl_sync(FULL, lo, 0);
     hi = __shfl_sync(FULL, hi, 0);
     if (lo == hi) return;
     // write cursor of every site this window's reads can reach: the start of its column + (own sites only) the calls of window c-1's
     // reads, which all precede this window's reads
-    for (uint32_t li = lane; li < 2 * A.W; li += 32)
+    for (uint32_t li = lane; li < 3 * A.W; li += 32)
     {
         const int64_t s = site0 + li;
-        const bool in = s >= 0 && s < static_cast<int64_t>(A.n_sites), own = in && li < A.W;
-        run1[li] = in ? site_off[s] + (own ? static_cast<uint32_t>(spill1[s]) : 0u) : 0u;
-        run2[li] = in ? t2_off[s] + (own ? static_cast<uint32_t>(spill2[s]) : 0u) : 0u;
+        const bool in = s >= 0 && s < static_cast<int64_t>(A.n_sites);
+        uint32_t c1 = 0, c2 = 0;
+        if (in)
+        {
+            if (li < A.W) // the previous window's sites: after its spill-in and its own reads' calls = before the back spill, which is ours
+            {
+                c1 = site_off[s + 1] - static_cast<uint32_t>(back1[s]);
+                c2 = t2_off[s + 1] - static_cast<uint32_t>(back2[s]);
+            }
+            else if (li < 2 * A.W) // our own sites: after the calls spilling in from window c-1, whose reads all precede ours
+            {
+                c1 = site_off[s] + static_cast<uint32_t>(spill1[s]);
+                c2 = t2_off[s] + static_cast<uint32_t>(spill2[s]);
+            }
+            else // the next window's sites: we are first
+            {
+                c1 = site_off[s];
+                c2 = t2_off[s];
+            }
+        }
+        run1[li] = c1;
+        run2[li] = c2;
     }
     __syncwarp();
     const bool isDensity = A.opt.mismatchDensityFilterFlankSize > 0;
@@ -393,7 +436,10 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
             const uint8_t* gs = A.seq4 + rd.seq_off;
             const uint8_t* gq = A.qual + rd.qual_off;
             for (uint32_t i = lane; i < (read_size + 1) / 2; i += 32) seq[i] = gs[i];
-            for (uint32_t i = lane; i < read_size; i += 32) ql[i] = gq[i];
+            if (A.qual_bits == 4)
+                for (uint32_t i = lane; i < read_size; i += 32) ql[i] = A.qual_dict[(gq[i >> 1] >> ((~i & 1u) << 2)) & 15u];
+            else
+                for (uint32_t i = lane; i < read_size; i += 32) ql[i] = gq[i];
             for (uint32_t i = lane; i < ref_span; i += 32)
             {
                 const int64_t ri = static_cast<int64_t>(rd.pos) + i - A.ref_begin;
@@ -532,7 +578,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
             const bool is_tier_specific_filter = tier1 && is_call_filter && !is_tier2_call_filter;
             const uint16_t bc = static_cast<uint16_t>(min(qscore, 63u) | (call_id << 6) | ((fwd ? 1u : 0u) << 10) | ((is_neighbor_mismatch ? 1u : 0u) << 11) |
                                                       ((current_call_filter ? 1u : 0u) << 12) | ((is_tier_specific_filter ? 1u : 0u) << 13));
-            const uint32_t li = static_cast<uint32_t>(s - site0_32); // < 2W: the read starts in this window and spans <= W
+            const uint32_t li = static_cast<uint32_t>(s - site0_32); // < 3W: the read is buffered in this window, its alignment within D of that, D + span <= W
             if (tier1) calls[run1[li]++] = bc;
             else t2_calls[run2[li]++] = bc;
         }
@@ -575,13 +621,18 @@ extern "C" int sx_pileup_reads_dev(sx_ctx* ctx, const sx_pileup_reads_batch* d, 
     const uint32_t n_sites = static_cast<uint32_t>(d->report_end - d->report_begin);
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->s_compute;
-    const uint32_t W = std::max<uint32_t>(64, (d->max_ref_span + 31u) & ~31u);
+    if (d->qual_bits != 0 && d->qual_bits != 8 && d->qual_bits != 4) return sx_fail(ctx, SX_ERR_ARG, "sx_pileup_reads: qual_bits must be 0, 8 or 4");
+    const uint32_t shift = d->buffer_pos ? d->max_pos_shift : 0u;
+    const uint32_t W = std::max<uint32_t>(64, (d->max_ref_span + shift + 31u) & ~31u);
     const uint32_t Lcap = std::max<uint32_t>(64, (std::min<uint32_t>(d->max_read_len ? d->max_read_len : K4_MAX_READ, K4_MAX_READ) + 15u) & ~15u);
     if (W > K4_MAX_W)
         return sx_fail(ctx, SX_ERR_UNSUPPORTED, "sx_pileup_reads: max_ref_span %u exceeds the %u positions a window can hold (spliced alignments are not accelerated)",
                        d->max_ref_span, K4_MAX_W);
     k4_args A;
     A.reads = d->reads;
+    A.bpos = d->buffer_pos;
+    A.qual_bits = d->qual_bits;
+    memcpy(A.qual_dict, d->qual_dict, 16);
     A.seq4 = d->seq4;
     A.qual = d->qual;
     A.segs = d->segs;
@@ -606,21 +657,24 @@ extern "C" int sx_pileup_reads_dev(sx_ctx* ctx, const sx_pileup_reads_batch* d, 
     int* d2 = reinterpret_cast<int*>(out->t2_off);
     int* dsd = reinterpret_cast<int*>(out->n_spandel);
     int* dsm = reinterpret_cast<int*>(out->n_submapped);
-    int *s1 = nullptr, *s2 = nullptr, *tile_sums = nullptr;
+    int *s1 = nullptr, *s2 = nullptr, *b1 = nullptr, *b2 = nullptr, *tile_sums = nullptr;
     int rc;
     const uint32_t tiles = (n_sites + 1 + SCAN_TILE - 1) / SCAN_TILE;
     if ((rc = sx_ensure(ctx, 26, (size_t)(n_sites + 1) * 8 + 64, reinterpret_cast<void**>(&s1)))) return rc;
     s2 = s1 + (n_sites + 1);
+    if ((rc = sx_ensure(ctx, 28, (size_t)(n_sites + 1) * 8 + 64, reinterpret_cast<void**>(&b1)))) return rc;
+    b2 = b1 + (n_sites + 1);
     if ((rc = sx_ensure(ctx, 27, (size_t)tiles * 8 * sizeof(int) + 64, reinterpret_cast<void**>(&tile_sums)))) return rc;
     SX_CUDA(ctx, cudaMemsetAsync(d1, 0, (size_t)(n_sites + 1) * 4, st));
     SX_CUDA(ctx, cudaMemsetAsync(d2, 0, (size_t)(n_sites + 1) * 4, st));
     SX_CUDA(ctx, cudaMemsetAsync(dsd, 0, (size_t)n_sites * 4, st));
     SX_CUDA(ctx, cudaMemsetAsync(dsm, 0, (size_t)n_sites * 4, st));
     SX_CUDA(ctx, cudaMemsetAsync(s1, 0, (size_t)(n_sites + 1) * 8, st));
+    SX_CUDA(ctx, cudaMemsetAsync(b1, 0, (size_t)(n_sites + 1) * 8, st));
     unsigned launches = 0;
     if (d->n_reads)
     {
-        k4_count_kernel<<<(d->n_reads + 127) / 128, 128, 0, st>>>(A, d1, d2, s1, s2, dsd, dsm, ctx->d_status);
+        k4_count_kernel<<<(d->n_reads + 127) / 128, 128, 0, st>>>(A, d1, d2, s1, s2, b1, b2, dsd, dsm, ctx->d_status);
         SX_CUDA(ctx, cudaGetLastError());
         ++launches;
     }
@@ -635,15 +689,15 @@ extern "C" int sx_pileup_reads_dev(sx_ctx* ctx, const sx_pileup_reads_batch* d, 
     };
     {
         scan_job J{}; // differences -> counts
-        int* arr[6] = {d1, d2, s1, s2, dsd, dsm};
-        const uint32_t n[6] = {n_sites + 1, n_sites + 1, n_sites, n_sites, n_sites, n_sites};
-        for (int k = 0; k < 6; ++k)
+        int* arr[8] = {d1, d2, s1, s2, dsd, dsm, b1, b2};
+        const uint32_t n[8] = {n_sites + 1, n_sites + 1, n_sites, n_sites, n_sites, n_sites, n_sites, n_sites};
+        for (int k = 0; k < 8; ++k)
         {
             J.data[k] = arr[k];
             J.n[k] = n[k];
             J.exclusive[k] = 0;
         }
-        if ((rc = run_scans(J, 6))) return rc;
+        if ((rc = run_scans(J, 8))) return rc;
         scan_job K{}; // counts -> CSR offsets
         K.data[0] = d1;
         K.data[1] = d2;
@@ -662,7 +716,7 @@ extern "C" int sx_pileup_reads_dev(sx_ctx* ctx, const sx_pileup_reads_batch* d, 
     {
         const size_t smem = (size_t)k4_warp_smem(W, Lcap) * K4_WARPS;
         if (smem > 48 * 1024) SX_CUDA(ctx, cudaFuncSetAttribute(k4_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
-        k4_fill_kernel<<<(A.n_windows + K4_WARPS - 1) / K4_WARPS, K4_WARPS * 32, smem, st>>>(A, out->site_off, out->t2_off, s1, s2, out->calls, out->t2_calls, ctx->d_tables,
+        k4_fill_kernel<<<(A.n_windows + K4_WARPS - 1) / K4_WARPS, K4_WARPS * 32, smem, st>>>(A, out->site_off, out->t2_off, s1, s2, b1, b2, out->calls, out->t2_calls, ctx->d_tables,
                                                                                          ctx->d_status);
         SX_CUDA(ctx, cudaGetLastError());
         ++launches;
@@ -691,6 +745,7 @@ extern "C" int sx_pileup_reads(sx_ctx* ctx, const sx_pileup_reads_batch* b, sx_p
     if ((rc = upload(ctx, 3, b->segs, (size_t)b->n_segs * sizeof(sx_aln_seg), reinterpret_cast<const void**>(&d.segs), st))) return rc;
     if ((rc = upload(ctx, 4, b->ref, b->ref_len, reinterpret_cast<const void**>(&d.ref), st))) return rc;
     if ((rc = upload(ctx, 5, b->cand_snv, (size_t)b->n_cand_snv * 4, reinterpret_cast<const void**>(&d.cand_snv), st))) return rc;
+    if (b->buffer_pos && (rc = upload(ctx, 9, b->buffer_pos, (size_t)b->n_reads * 4, reinterpret_cast<const void**>(&d.buffer_pos), st))) return rc;
     sx_pileup_columns dc = *out;
     void* p = nullptr;
     if ((rc = sx_ensure(ctx, 6, (size_t)(n_sites + 1) * 4 * 4 + 64, &p))) return rc;

@@ -90,7 +90,13 @@ K9_HD uint32_t k9_slots(const sx_realign_batch& b, const uint32_t r)
         const uint32_t n(b.aln_seg_off[a + 1] - b.aln_seg_off[a]);
         m = n > m ? n : m;
     }
-    return m ? m + 2 : 0;
+    m = m ? m + 2 : 0;
+    if (b.raw_seg_off)
+    {
+        const uint32_t nr(b.raw_seg_off[r + 1] - b.raw_seg_off[r]);
+        m = nr > m ? nr : m;
+    }
+    return m;
 }
 
 K9_HD uint8_t k9_out_kind(const sx_realign_batch& b, const unsigned t)
@@ -298,4 +304,21 @@ K9_HD uint32_t k9_read(const k9_view& v, const uint32_t region, const uint32_t r
     out_pos = pos;
     out_n = (uint16_t)w.n;
     return SX_REALIGN_ST_REALIGNED;
+}
+
+// a read without a realignment: its slots become no-op pads or, when the batch carries the mapper's alignments, that alignment
+// (read_segment::getBestAlignment, starling_read_segment.hh:134-138)
+K9_HD void k9_fallback(const sx_realign_batch& b, const uint32_t r, sx_aln_seg* slots, const uint32_t cap, int32_t& out_pos, uint16_t& out_n)
+{
+    uint32_t n(0);
+    if (b.raw_seg_off)
+    {
+        const uint32_t s0(b.raw_seg_off[r]);
+        n = b.raw_seg_off[r + 1] - s0;
+        n = n < cap ? n : cap;
+        for (uint32_t i = 0; i < n; ++i) slots[i] = sx_aln_seg{b.raw_segs[s0 + i].len, k9_out_kind(b, b.raw_segs[s0 + i].kind), 0};
+        out_pos = b.raw_pos[r];
+        out_n = (uint16_t)n;
+    }
+    for (uint32_t i = n; i < cap; ++i) slots[i] = sx_aln_seg{0, k9_out_kind(b, SX_AP_HARD_CLIP), 0};
 }

@@ -65,8 +65,7 @@ __global__ void __launch_bounds__(128) k9_choose_kernel(const k9_view v, const u
         uint16_t ns;
         uint32_t best;
         const uint32_t st(k9_read(v, read_region[r], r, S, o.segs + s0, s1 - s0, p, ns, best));
-        if (!(st & SX_REALIGN_ST_REALIGNED))
-            for (uint32_t i = s0; i < s1; ++i) o.segs[i] = sx_aln_seg{0, k9_out_kind(v.b, SX_AP_HARD_CLIP), 0};
+        if (!(st & SX_REALIGN_ST_REALIGNED)) k9_fallback(v.b, r, o.segs + s0, s1 - s0, p, ns);
         o.pos[r] = p;
         o.n_seg[r] = ns;
         o.status[r] = (uint8_t)st;

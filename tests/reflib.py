@@ -455,18 +455,27 @@ def ref_realign_gates(gb: "B.GateBatch", max_segs=64):
     return gate[:n], res
 
 
-def ref_realign_and_score_read(gb: "B.GateBatch", quals: np.ndarray, retain_soft=False, is_smoothed=True, smoothed_range=2.302585092994046, max_segs=64):
+def ref_realign_and_score_read(gb: "B.GateBatch", quals: np.ndarray, retain_soft=False, is_smoothed=True, smoothed_range=2.302585092994046, max_segs=64,
+                               full_window=True, read_flags=None, rec_off=None):
     """The reference's whole realignAndScoreRead per read (oracle/ref_harness_enumerate.inc), mapper alignments in: (status[n_reads] --
-    0 not realigned, 1 realigned, 2 the reference threw --, [(pos, cigar) or None])."""
+    0 not realigned, 1 realigned, 2 the reference threw --, [(pos, cigar) or None]).  full_window: the IndelBuffer is rebuilt with everything
+    the batch says about its window (observation sets from use_keys, notDiscoveredFromReads, forced output, phasing rows, search options), as
+    ref_enumerate_alignments does -- what the chain sees; False: candidacy only (the harness of round 1).  rec_off: also return what
+    score_indels left in the indel buffer, (recs, n_rec) with read r's records at recs[rec_off[r] : rec_off[r] + n_rec[r]]."""
     eb = gb.eb
     n = eb.n_reads
     status, pos, nseg = np.zeros(n + 1, np.uint8), np.zeros(n + 1, np.int32), np.zeros(n + 1, np.uint16)
     segs = np.zeros((n + 1) * max_segs, dtype=A.ALN_SEG_DT)
     err = _err()
-    fn = ref().ref_realign_and_score_read
-    fn.argtypes = [C.POINTER(A.SxGateBatch)] + [_P] * 8 + [C.c_int, C.c_int, C.c_double] + [_P] * 4 + [C.c_uint32, C.c_char_p, C.c_int]
-    rc = fn(C.byref(gb.c), A.ptr(eb.ins_pool), A.ptr(eb.ins_off), A.ptr(eb.ref_pool), A.ptr(eb.ref_off), A.ptr(eb.ref_begin), A.ptr(eb.read_pool), A.ptr(eb.read_off),
-            A.ptr(quals), 1 if retain_soft else 0, 1 if is_smoothed else 0, smoothed_range, A.ptr(status), A.ptr(pos), A.ptr(nseg), A.ptr(segs), max_segs, err, 1024)
+    fn = ref().ref_realign_and_score_read_ex
+    fn.argtypes = [C.POINTER(A.SxGateBatch), C.POINTER(A.SxEnumBatch)] + [_P] * 9 + [C.c_int, C.c_int, C.c_double] + [_P] * 4 + [C.c_uint32] + [_P] * 4 + [C.c_char_p, C.c_int]
+    recs = n_rec = None
+    if rec_off is not None:
+        recs, n_rec = np.zeros(int(rec_off[n]) + 1, A.READ_INDEL_SCORE_DT), np.zeros(n + 1, np.uint32)
+    secs = C.c_double(0.0)
+    rc = fn(C.byref(gb.c), C.byref(eb.c) if full_window else None, A.ptr(eb.ins_pool), A.ptr(eb.ins_off), A.ptr(eb.ref_pool), A.ptr(eb.ref_off), A.ptr(eb.ref_begin),
+            A.ptr(eb.read_pool), A.ptr(eb.read_off), A.ptr(quals), A.ptr(read_flags), 1 if retain_soft else 0, 1 if is_smoothed else 0, smoothed_range, A.ptr(status),
+            A.ptr(pos), A.ptr(nseg), A.ptr(segs), max_segs, A.ptr(rec_off), A.ptr(recs), A.ptr(n_rec), C.addressof(secs), err, 1024)
     if rc != 0:
         raise RuntimeError(err.value.decode(errors="replace"))
     res = []
@@ -476,6 +485,8 @@ def ref_realign_and_score_read(gb: "B.GateBatch", quals: np.ndarray, retain_soft
             continue
         row = segs[r * max_segs : r * max_segs + int(nseg[r])]
         res.append((int(pos[r]), "".join(f"{int(s['len'])}{B.AP_CHAR[int(s['kind'])]}" for s in row)))
+    if rec_off is not None:
+        return status[:n], res, recs, n_rec[:n]
     return status[:n], res
 
 

@@ -21,7 +21,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == bound, declared ^ bound
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.sx_abi_version() == 1
+    assert lib.sx_abi_version() == 2
 
 
 def test_pod_layouts():
