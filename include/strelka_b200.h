@@ -396,6 +396,9 @@ enum { SX_SEG_DELETE = 5, SX_SEG_SKIP = 6 }; /* K4 paths keep DELETE and SKIP ap
 #define SX_PRF_TIER1OR2 0x04u   /* rseg.is_tier1or2_mapping(); clear = sub-mapped read */
 #define SX_PRF_PIN_FIRST 0x08u  /* rseg.get_segment_edge_pin().first  (an exon borders the leading edge) */
 #define SX_PRF_PIN_SECOND 0x10u /* ... .second */
+#define SX_PRF_SKIP 0x20u       /* buffered (it keeps its place in the order) but not piled up: a read that was not realigned and has no alignment
+                                   with indels the caller handles (! is_any_nonovermax, :1147), or whose realignment left the stage buffer
+                                   (is_invalid_realignment, :1171) */
 
 typedef struct sx_pileup_read {
     uint32_t seq_off;  /* byte offset of the read's first packed byte in seq4 (reads start on byte boundaries) */
@@ -838,6 +841,98 @@ typedef struct sx_realign_out { /* caller-allocated */
 
 int sx_choose_realignment(sx_ctx* ctx, const sx_realign_batch* batch_host, const double* lnp_host, sx_realign_out* out_host);
 int sx_choose_realignment_dev(sx_ctx* ctx, const sx_realign_batch* batch_dev, const double* lnp_dev, sx_realign_out* out_dev);
+
+/* ==========================================================================================
+ * process_window   (the READ_BUFFER and POST_ALIGN stages of starling_pos_processor_base::process_pos for a window of positions, with
+ *   every intermediate in device memory)
+ *   replaces  align_pos                         starling_common/starling_pos_processor_base.cpp:732-773
+ *                                               (realignAndScoreRead, starling_read_align.cpp:2025-2127, per buffered read segment that is a
+ *                                               tier1 / tier2 mapping)
+ *             pileup_pos_reads                  :1107-1123 (pileup_read_segment :1127-1421 per read, in read-buffer order, each read through
+ *                                               read_segment::getBestAlignment, starling_read_segment.hh:134-138)
+ *             computeSampleDiploidSiteGenotype  applications/starling/starling_pos_processor.cpp:254-267 per position (optional)
+ *   as the chain  K7g -> K7a -> K7 -> K7b -> K1 -> K6 + K9 -> K4 -> K2a  on ONE description of the window: the reads in read-buffer order
+ *   with the MAPPER's alignments, bases and qualities, the IndelBuffer entries around them, the reference.
+ *
+ * Input (device pointers; the struct itself is host): the union of what the chain's stages read --
+ *   regions of reads (the reads buffered around one realignment window share its IndelBuffer entries: sx_enum_batch's region arrays),
+ *   per read the mapper's alignment (SX_AP_* kinds), length, SX_PRF_* flags, MAPQ and the non-candidate entries it is an observation of,
+ *   the read / quality / reference pools where K1 keeps them (wide base and reference formats; qualities one byte per base or 4-bit
+ *   dictionary codes): `regions[g]` carries seq_off / qual_off / read_begin / ref_off / ref_begin / ref_len of region g (its alignment
+ *   fields are filled by the link step: the array is in/out), and `ref` is ONE contig segment -- ref[i] is contig position ref_begin + i,
+ *   so regions[g].ref_off == regions[g].ref_begin - ref_begin (a multiple of 16) --, which is also the reference the pile-up reads.
+ * Output: per read the gate / search / realignment status and its best alignment (pos + path in K4's kinds), score_indels' records,
+ *   the pile-up columns of [report_begin, report_end) and -- with do_site_gl -- one sx_digt_result per position.
+ *   Any output pointer may be NULL: the result then stays in the context's own buffers (the next stage still reads it).
+ * Reads the search leaves to the caller are reported, never silently dropped: SX_ENUM_ST_EXCEPTION (the reference throws), SX_ENUM_ST_LIMIT
+ *   (more than 64 indels / 32 segments / 24 keys in one search; the alignment count itself is bounded like the reference's, by
+ *   enum_opts.max_alns_per_read = 5000), SX_REALIGN_ST_UNSUPPORTED (exon edge pins).  Such reads are piled up with the mapper's alignment.
+ * ======================================================================================== */
+typedef struct sx_window_batch {
+    uint32_t n_regions, n_reads, n_keys;
+    const uint32_t* region_read_off;   /* [n_regions + 1] */
+    const uint32_t* region_key_off;    /* [n_regions + 1] */
+    const sx_indel_key* keys;          /* [n_keys] incl. the error-rate fields score_indels reads */
+    const sx_key_hap* key_hap;         /* [n_keys] or NULL */
+    const uint32_t* key_ins_off;       /* [n_keys + 1] */
+    const char* key_ins;
+    const int32_t* realign_begin;      /* [n_regions] */
+    const int32_t* realign_end;
+    const int32_t* raw_pos;            /* [n_reads] rseg.getInputAlignment().pos; the reads are in READ-BUFFER order (ascending
+                                          get_alignment_buffer_pos, read index within a position) */
+    const uint32_t* raw_seg_off;       /* [n_reads + 1] */
+    const sx_aln_seg* raw_segs;        /* SX_AP_* kinds */
+    const uint16_t* read_len;          /* [n_reads] */
+    const uint8_t* read_flags;         /* [n_reads] SX_PRF_* */
+    const uint8_t* mapq;               /* [n_reads] */
+    const uint32_t* use_key_off;       /* [n_reads + 1] */
+    const uint16_t* use_keys;
+    const uint32_t* rec_off;           /* [n_reads + 1] score_indels' output slots per read (sx_score_indels_batch.rec_off) */
+    sx_region* regions;                /* [n_regions + 1] in/out */
+    const uint8_t* seq4;
+    const uint8_t* qual;
+    const char* ref;
+    uint64_t seq4_bytes, qual_bytes, ref_bytes;
+    uint32_t qual_bits;                /* 0 / 8, or 4 with qual_dict */
+    uint8_t qual_dict[16];
+    int32_t ref_begin;                 /* contig position of ref[0] */
+    int32_t report_begin, report_end;  /* the positions piled up (and genotyped) */
+    const uint32_t* cand_snv;          /* sx_pileup_reads_batch.cand_snv, or NULL */
+    uint32_t n_cand_snv;
+    uint32_t max_read_len;             /* >= every read_len (0: 1024) */
+    int32_t do_site_gl;                /* run K2a on the columns */
+    int32_t is_always_test;            /* K2a's is_always_test (the germline caller genotypes every site: 1) */
+    sx_enum_opts enum_opts;
+    sx_score_indels_opts score_opts;
+    sx_pileup_opts pileup_opts;
+} sx_window_batch;
+
+#define SX_WIN_TOTALS 8 /* alignments, their segments, their keys, K1 segments, insert-pool bytes, best-alignment slots, tier1 calls, tier2 calls */
+
+typedef struct sx_window_out { /* device pointers, each may be NULL (capacities count only for non-NULL arrays) */
+    uint8_t* gate;               /* [n_reads] SX_GATE_* (sub-mapped reads: 0, align_pos :746) */
+    uint8_t* enum_status;        /* [n_reads] SX_ENUM_ST_* */
+    uint8_t* realign_status;     /* [n_reads] SX_REALIGN_ST_* */
+    int32_t* best_pos;           /* [n_reads] getBestAlignment().pos */
+    uint32_t* best_seg_off;      /* [n_reads + 1] */
+    uint16_t* best_n_seg;        /* [n_reads] */
+    sx_aln_seg* best_segs;       /* [cap_best_segs] K4's kinds */
+    uint32_t cap_best_segs;
+    sx_read_indel_score* recs;   /* [rec_off[n_reads]] */
+    uint32_t* n_rec;             /* [n_reads] */
+    sx_pileup_columns cols;      /* each array NULL or caller-allocated with the stated capacities */
+    sx_digt_result* site_gl;     /* [report_end - report_begin] */
+    uint32_t* totals;            /* [SX_WIN_TOTALS] */
+} sx_window_out;
+
+enum { SX_WIN_ST_PREP = 0, SX_WIN_ST_GATES, SX_WIN_ST_KEYS, SX_WIN_ST_ENUMERATE, SX_WIN_ST_LINK, SX_WIN_ST_SCORE, SX_WIN_ST_SCORE_INDELS, SX_WIN_ST_CHOOSE,
+       SX_WIN_ST_PILEUP, SX_WIN_ST_SITE_GL, SX_WIN_N_STAGES };
+
+void sx_default_window_opts(sx_window_batch* b); /* fills enum_opts (max_alns_per_read = 5000), score_opts, pileup_opts, is_always_test = 1 */
+/* SX_ERR_CAPACITY: a caller-provided output array is too small (totals_host, if given, says what the window produced). */
+int sx_process_window_dev(sx_ctx* ctx, const sx_window_batch* batch_dev, sx_window_out* out_dev, uint32_t* totals_host /* [SX_WIN_TOTALS] or NULL */);
+/* device time of each stage of the most recent sx_process_window_dev on ctx (CUDA events on the compute stream), ms[SX_WIN_N_STAGES] */
+int sx_last_window_timing(const sx_ctx* ctx, float* ms);
 
 /* ==========================================================================================
  * Multi-GPU: regions shard across ranks with no data-path collective; one gather of fixed-size

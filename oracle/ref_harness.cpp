@@ -703,6 +703,7 @@ extern "C" int ref_pileup_reads(const sx_pileup_reads_batch* b, uint32_t* site_o
         for (uint32_t r = 0; r < b->n_reads; ++r)
         {
             const sx_pileup_read& rd(b->reads[r]);
+            if (rd.flags & SX_PRF_SKIP) continue;
             const int len(rd.len);
             std::unique_ptr<bam_record> br(new bam_record);
             br->set_qname("R");
@@ -722,6 +723,7 @@ extern "C" int ref_pileup_reads(const sx_pileup_reads_batch* b, uint32_t* site_o
             for (uint32_t s = rd.seg_off; s < b->reads[r + 1].seg_off; ++s)
             {
                 const sx_aln_seg& sg(b->segs[s]);
+                if (sg.len == 0 && sg.kind == SX_SEG_HARDCLIP) continue; // a pad of K9's slot layout: not a segment of the path
                 ALIGNPATH::align_t t(ALIGNPATH::NONE);
                 switch (sg.kind)
                 {

@@ -1547,6 +1547,7 @@ static int pileup_reads_impl(const sx_pileup_reads_batch* b, std::vector<uint16_
     for (uint32_t r = 0; r < b->n_reads; ++r)
     {
         const sx_pileup_read& rd(b->reads[r]);
+        if (rd.flags & SX_PRF_SKIP) continue; // buffered, not piled up (the early returns of pileup_read_segment, :1147 / :1171)
         const unsigned read_size(rd.len);
         const uint8_t* seq(b->seq4 + rd.seq_off);
         const uint8_t* qual(b->qual + rd.qual_off);

@@ -126,7 +126,7 @@ class SxAlignBatch(C.Structure):
 
 # K4 pileup_reads
 SX_SEG_DELETE, SX_SEG_SKIP = 5, 6
-SX_PRF_FWD, SX_PRF_TIER1, SX_PRF_TIER1OR2, SX_PRF_PIN_FIRST, SX_PRF_PIN_SECOND = 1, 2, 4, 8, 16
+SX_PRF_FWD, SX_PRF_TIER1, SX_PRF_TIER1OR2, SX_PRF_PIN_FIRST, SX_PRF_PIN_SECOND, SX_PRF_SKIP = 1, 2, 4, 8, 16, 32
 PILEUP_READ_DT = np.dtype([("seq_off", "<u4"), ("qual_off", "<u4"), ("seg_off", "<u4"), ("pos", "<i4"), ("len", "<u2"), ("mapq", "u1"), ("flags", "u1")])
 
 
@@ -281,6 +281,24 @@ class SxGateBatch(C.Structure):
         ("max_indel_size", C.c_uint32)]
 
 
+class SxWindowBatch(C.Structure):
+    _fields_ = ([(n, C.c_uint32) for n in ("n_regions", "n_reads", "n_keys")] + [(n, C.c_void_p) for n in (
+        "region_read_off", "region_key_off", "keys", "key_hap", "key_ins_off", "key_ins", "realign_begin", "realign_end", "raw_pos", "raw_seg_off", "raw_segs", "read_len",
+        "read_flags", "mapq", "use_key_off", "use_keys", "rec_off", "regions", "seq4", "qual", "ref")] + [
+        ("seq4_bytes", C.c_uint64), ("qual_bytes", C.c_uint64), ("ref_bytes", C.c_uint64), ("qual_bits", C.c_uint32), ("qual_dict", C.c_uint8 * 16),
+        ("ref_begin", C.c_int32), ("report_begin", C.c_int32), ("report_end", C.c_int32), ("cand_snv", C.c_void_p), ("n_cand_snv", C.c_uint32), ("max_read_len", C.c_uint32),
+        ("do_site_gl", C.c_int32), ("is_always_test", C.c_int32), ("enum_opts", SxEnumOpts), ("score_opts", SxScoreIndelsOpts), ("pileup_opts", SxPileupOpts)])
+
+
+class SxWindowOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("gate", "enum_status", "realign_status", "best_pos", "best_seg_off", "best_n_seg", "best_segs")] + [("cap_best_segs", C.c_uint32)] + [
+        (n, C.c_void_p) for n in ("recs", "n_rec")] + [("cols", SxPileupColumns), ("site_gl", C.c_void_p), ("totals", C.c_void_p)]
+
+
+SX_WIN_TOTALS, SX_WIN_N_STAGES = 8, 10
+SX_WIN_STAGE_NAMES = ("prep", "k7g_gates", "k7a_keys", "k7_enumerate", "k7b_link", "k1_score", "k6_score_indels", "k9_choose", "k4_pileup", "k2a_site_gl")
+
+
 class SxGateOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("gate", "in_pos", "in_segs")]
 
@@ -369,6 +387,9 @@ SYMBOLS = [
     ("sx_default_pileup_opts", None, [C.POINTER(SxPileupOpts)]),
     ("sx_pileup_reads", C.c_int, [_P, C.POINTER(SxPileupReadsBatch), C.POINTER(SxPileupColumns)]),
     ("sx_pileup_reads_dev", C.c_int, [_P, C.POINTER(SxPileupReadsBatch), C.POINTER(SxPileupColumns)]),
+    ("sx_default_window_opts", None, [C.POINTER(SxWindowBatch)]),
+    ("sx_process_window_dev", C.c_int, [_P, C.POINTER(SxWindowBatch), C.POINTER(SxWindowOut), _P]),
+    ("sx_last_window_timing", C.c_int, [_P, _P]),
     ("sx_comm_get_unique_id", C.c_int, [_P]),
     ("sx_comm_init", C.c_int, [_P, _P, C.c_int, C.c_int]),
     ("sx_gather_records", C.c_int, [_P, _P, C.c_size_t, _P, C.c_int]),

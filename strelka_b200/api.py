@@ -482,3 +482,89 @@ def _realign_gates(self, gb: B.GateBatch) -> B.GateOut:
 
 
 Context.realign_gates = _realign_gates  # K7g
+
+
+class DevWindow:
+    """sx_process_window_dev on a B.WindowBatch: every input array resident in HBM, every output array the caller may want to read
+    back allocated here (tests download them; bench.py leaves them where they are)."""
+
+    def __init__(self, ctx: "Context", w: "B.WindowBatch", keep_outputs: bool = True, cap_best_segs=None):
+        self.ctx, self.w = ctx, w
+        self.bufs = {}
+        p = {}
+        for name in B.WindowBatch.ARRAYS:
+            arr = w.a.get(name)
+            if arr is None:
+                p[name] = None
+                continue
+            arr = np.ascontiguousarray(arr)
+            self.bufs[name] = DeviceArray(ctx, arr.nbytes + 80).upload(arr)
+            p[name] = self.bufs[name].ptr
+        c = A.SxWindowBatch()
+        ctx.lib.sx_default_window_opts(C.byref(c))
+        c.n_regions, c.n_reads, c.n_keys = w.n_regions, w.n_reads, w.n_keys
+        for name in B.WindowBatch.ARRAYS:
+            if name != "cand_snv":
+                setattr(c, name, p[name])
+        c.cand_snv, c.n_cand_snv = p["cand_snv"], (int(w.a["cand_snv"].size) if w.a.get("cand_snv") is not None else 0)
+        c.seq4_bytes, c.qual_bytes, c.ref_bytes = w.used["seq4"], w.used["qual"], w.used["ref"]
+        c.qual_bits = w.qual_bits
+        c.qual_dict = (C.c_uint8 * 16)(*(w.qual_dict + [0] * (16 - len(w.qual_dict))))
+        c.ref_begin, c.report_begin, c.report_end = w.ref_begin, w.report_begin, w.report_end
+        c.max_read_len, c.do_site_gl = w.max_read_len, 1 if w.do_site_gl else 0
+        if getattr(w, "enum_opts", None) is not None:
+            keep = c.enum_opts.max_alns_per_read
+            c.enum_opts = w.enum_opts
+            c.enum_opts.max_alns_per_read = max(keep, w.enum_opts.max_alns_per_read)
+        self.c = c
+        self.out = A.SxWindowOut()
+        self.obufs = {}
+        n, ns = w.n_reads, w.n_sites
+        if keep_outputs:
+            n_raw = int(w.a["raw_seg_off"][n])
+            self.cap_best = cap_best_segs if cap_best_segs is not None else 64 * n + n_raw + 4096
+            n_slots = int(w.a["rec_off"][n])
+            bases = int(np.asarray(w.a["read_len"][:n], dtype=np.int64).sum()) + 64
+            sizes = {"gate": n + 16, "enum_status": n + 16, "realign_status": n + 16, "best_pos": 4 * n + 16, "best_seg_off": 4 * (n + 2), "best_n_seg": 2 * n + 16,
+                     "best_segs": 4 * self.cap_best + 64, "recs": (n_slots + 1) * A.READ_INDEL_SCORE_DT.itemsize, "n_rec": 4 * n + 16, "site_off": 4 * (ns + 2),
+                     "t2_off": 4 * (ns + 2), "n_spandel": 4 * (ns + 2), "n_submapped": 4 * (ns + 2), "calls": 2 * bases, "t2_calls": 2 * bases,
+                     "site_gl": (ns + 1) * A.DIGT_RESULT_DT.itemsize, "totals": 64}
+            self.obufs = {k: DeviceArray(ctx, v) for k, v in sizes.items()}
+            o, b = self.out, self.obufs
+            for k in ("gate", "enum_status", "realign_status", "best_pos", "best_seg_off", "best_n_seg", "best_segs", "recs", "n_rec", "site_gl", "totals"):
+                setattr(o, k, b[k].ptr)
+            o.cap_best_segs = self.cap_best
+            o.cols = A.SxPileupColumns(b["site_off"].ptr, b["calls"].ptr, b["t2_off"].ptr, b["t2_calls"].ptr, b["n_spandel"].ptr, b["n_submapped"].ptr, bases, bases)
+            self.n_slots = n_slots
+        else:  # only the call records come out; everything else stays in the context's own buffers
+            self.obufs = {"site_gl": DeviceArray(ctx, (ns + 1) * A.DIGT_RESULT_DT.itemsize)}
+            self.out.site_gl = self.obufs["site_gl"].ptr
+        self.totals = np.zeros(A.SX_WIN_TOTALS, np.uint32)
+
+    def run(self):
+        """one pass; returns the per-stage device times (ms)"""
+        ctx = self.ctx
+        ctx._chk(ctx.lib.sx_process_window_dev(ctx.h, C.byref(self.c), C.byref(self.out), self.totals.ctypes.data))
+        ms = np.zeros(A.SX_WIN_N_STAGES, np.float32)
+        ctx.lib.sx_last_window_timing(ctx.h, ms.ctypes.data)
+        return dict(zip(A.SX_WIN_STAGE_NAMES, (float(x) for x in ms)))
+
+    def download(self):
+        """dict of the host copies of every output (keep_outputs only)"""
+        w, b = self.w, self.obufs
+        n, ns = w.n_reads, w.n_sites
+        d = {"gate": b["gate"].download(np.uint8, n), "enum_status": b["enum_status"].download(np.uint8, n), "realign_status": b["realign_status"].download(np.uint8, n),
+             "best_pos": b["best_pos"].download(np.int32, n), "best_seg_off": b["best_seg_off"].download(np.uint32, n + 1), "best_n_seg": b["best_n_seg"].download(np.uint16, n),
+             "n_rec": b["n_rec"].download(np.uint32, n), "recs": b["recs"].download(A.READ_INDEL_SCORE_DT, self.n_slots),
+             "site_off": b["site_off"].download(np.uint32, ns + 1), "t2_off": b["t2_off"].download(np.uint32, ns + 1), "n_spandel": b["n_spandel"].download(np.uint32, ns),
+             "n_submapped": b["n_submapped"].download(np.uint32, ns), "totals": self.totals.copy()}
+        d["best_segs"] = b["best_segs"].download(A.ALN_SEG_DT, int(d["best_seg_off"][n]))
+        d["calls"] = b["calls"].download(np.uint16, int(d["site_off"][ns]))
+        d["t2_calls"] = b["t2_calls"].download(np.uint16, int(d["t2_off"][ns]))
+        if w.do_site_gl:
+            d["site_gl"] = b["site_gl"].download(A.DIGT_RESULT_DT, ns)
+        return d
+
+    def free(self):
+        for x in list(self.bufs.values()) + list(self.obufs.values()):
+            x.free()

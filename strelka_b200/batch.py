@@ -488,7 +488,10 @@ class PileupReadSpec:
 class PileupReadsBatch:
     """Owns the pools of one sx_pileup_reads_batch (reads must be given in pile-up order: ascending position)."""
 
-    def __init__(self, reads: Sequence[PileupReadSpec], ref: str, ref_begin: int, report_begin: int, report_end: int, cand_snv=(), opts=None):
+    def __init__(self, reads: Sequence[PileupReadSpec], ref: str, ref_begin: int, report_begin: int, report_end: int, cand_snv=(), opts=None, buffer_pos=None,
+                 qual_dict=None):
+        """buffer_pos: the read-buffer position of every read (ascending) when the reads' best alignments are not themselves in pile-up
+        order (realigned reads); qual_dict: send the qualities dictionary-coded, two per byte (every quality must be in the dictionary)."""
         self.n_reads = len(reads)
         hdr = np.zeros(len(reads) + 1, dtype=A.PILEUP_READ_DT)
         seq4, qual, segs = bytearray(), bytearray(), []
@@ -503,7 +506,11 @@ class PileupReadsBatch:
             if n & 1:
                 c = np.concatenate([c, np.zeros(1, np.uint8)])
             seq4.extend(((c[0::2] << 4) | c[1::2]).astype(np.uint8).tobytes())
-            qual.extend(np.asarray(r.quals, dtype=np.uint8).tobytes())
+            if qual_dict is None:
+                qual.extend(np.asarray(r.quals, dtype=np.uint8).tobytes())
+            else:
+                qc = np.array([qual_dict.index(int(q)) for q in r.quals] + ([0] if n & 1 else []), dtype=np.uint8)
+                qual.extend(((qc[0::2] << 4) | qc[1::2]).astype(np.uint8).tobytes())
             segs.extend((ln, _PILEUP_KIND[k], 0) for k, ln in r.path)
             span = max(span, sum(ln for k, ln in r.path if k in "MDN"))
         hdr[len(reads)] = (len(seq4), len(qual), len(segs), 0, 0, 0, 0)
@@ -523,6 +530,14 @@ class PileupReadsBatch:
             len(reads), len(segs), A.ptr(self.reads), A.ptr(self.seq4), A.ptr(self.qual), A.ptr(self.segs), A.ptr(self.ref), ref_begin, len(ref),
             report_begin, report_end, A.ptr(self.cand_snv), len(keys), span, int(hdr["len"].max(initial=1)), 0, self.opts,
         )
+        self.buffer_pos = None
+        if buffer_pos is not None:
+            self.buffer_pos = np.ascontiguousarray(list(buffer_pos) + [0], dtype=np.int32)
+            self.c.buffer_pos = A.ptr(self.buffer_pos)
+            self.c.max_pos_shift = int(np.abs(self.buffer_pos[: len(reads)].astype(np.int64) - hdr["pos"][: len(reads)].astype(np.int64)).max(initial=0))
+        if qual_dict is not None:
+            self.c.qual_bits = 4
+            self.c.qual_dict = (C.c_uint8 * 16)(*(list(qual_dict) + [0] * (16 - len(qual_dict))))
 
 
 class PileupColumns:
@@ -1093,3 +1108,52 @@ class GateOut:
             return None
         s0, s1 = int(self._gb.seg_off[r]), int(self._gb.seg_off[r + 1])
         return int(self.in_pos[r]), "".join(f"{int(s['len'])}{AP_CHAR[int(s['kind'])]}" for s in self.in_segs[s0:s1] if not (int(s["kind"]) == A.SX_AP_HARD_CLIP and int(s["len"]) == 0))
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# process_window (sx_process_window_dev): one description of a window of reads for the whole device-resident pass
+# ------------------------------------------------------------------------------------------------------------------------------
+class WindowBatch:
+    """Host arrays of an sx_window_batch.  `a` maps the struct's array fields to numpy arrays; scalars are attributes.  Two ways in:
+    from_enum (a test batch: EnumBatch + the mapper's alignments + its K1 pools, one contig segment) and from_arrays (a generator's output)."""
+
+    ARRAYS = ("region_read_off", "region_key_off", "keys", "key_hap", "key_ins_off", "key_ins", "realign_begin", "realign_end", "raw_pos", "raw_seg_off", "raw_segs",
+              "read_len", "read_flags", "mapq", "use_key_off", "use_keys", "rec_off", "regions", "seq4", "qual", "ref", "cand_snv")
+
+    def __init__(self, a: dict, n_regions: int, n_reads: int, n_keys: int, ref_begin: int, report_begin: int, report_end: int, qual_bits: int = 8, qual_dict=None,
+                 max_read_len: int = 0, do_site_gl: bool = True, used=None):
+        self.a = a
+        self.n_regions, self.n_reads, self.n_keys = n_regions, n_reads, n_keys
+        self.ref_begin, self.report_begin, self.report_end = ref_begin, report_begin, report_end
+        self.qual_bits, self.qual_dict = qual_bits, list(qual_dict or [])
+        self.max_read_len, self.do_site_gl = max_read_len, do_site_gl
+        self.used = used or {"seq4": int(a["seq4"].nbytes), "qual": int(a["qual"].nbytes), "ref": int(a["ref"].nbytes)}
+        self.n_sites = report_end - report_begin
+
+    @classmethod
+    def from_enum(cls, eb: "EnumBatch", gb: "GateBatch", pools: AlignBatch, read_flags=None, mapq=None, report=None, do_site_gl=True):
+        """eb's regions must lie on one contig segment in ascending order with reads in read-buffer order (a single region always does)."""
+        assert pools.fmt == 0 and pools.qual_bits in (0, 4, 8) and pools.n_reads == eb.n_reads and gb.eb is eb
+        n = eb.n_reads
+        reg = pools.regions.copy()
+        ref0, rb0 = int(reg["ref_off"][0]), int(reg["ref_begin"][0])
+        # the pools' reference windows as views of ONE array: window g must start (ref_begin[g] - ref_begin[0]) bytes after window 0
+        for g in range(eb.n_regions):
+            assert int(reg["ref_off"][g]) - ref0 == int(reg["ref_begin"][g]) - rb0, "the regions' reference windows are not views of one contig segment"
+        reg["ref_off"] -= ref0
+        ref = pools.ref[ref0:]
+        n_win = np.diff(eb.region_key_off.astype(np.int64))
+        rec_off = np.concatenate([[0], np.cumsum(np.repeat(n_win, np.diff(eb.region_read_off.astype(np.int64))))]).astype(np.uint32)
+        flags = np.full(n + 1, A.SX_PRF_FWD | A.SX_PRF_TIER1 | A.SX_PRF_TIER1OR2, np.uint8) if read_flags is None else np.ascontiguousarray(read_flags, np.uint8)
+        mq = np.full(n + 1, 60, np.uint8) if mapq is None else np.ascontiguousarray(mapq, np.uint8)
+        a = {"region_read_off": eb.region_read_off, "region_key_off": eb.region_key_off, "keys": eb.keys, "key_hap": eb.key_hap if eb.has_hap else None,
+             "key_ins_off": eb.ins_off, "key_ins": eb.ins_pool, "realign_begin": eb.realign_begin, "realign_end": eb.realign_end, "raw_pos": gb.raw_pos,
+             "raw_seg_off": gb.seg_off, "raw_segs": gb.raw_segs, "read_len": eb.read_len, "read_flags": flags, "mapq": mq, "use_key_off": eb.use_key_off,
+             "use_keys": eb.use_keys, "rec_off": rec_off, "regions": reg, "seq4": pools.seq4, "qual": pools.qual, "ref": ref, "cand_snv": None}
+        if report is None:
+            last = eb.n_regions - 1
+            report = (rb0, int(reg["ref_begin"][last]) + int(reg["ref_len"][last]))
+        w = cls(a, eb.n_regions, n, eb.n_keys, rb0, report[0], report[1], 4 if pools.qual_bits == 4 else 8, pools.qual_dict, int(eb.read_len[:n].max(initial=1)), do_site_gl,
+                {"seq4": pools.used["seq4"], "qual": pools.used["qual"], "ref": int(reg["ref_off"][eb.n_regions - 1]) + int(reg["ref_len"][eb.n_regions - 1])})
+        w.enum_opts = eb.opts
+        return w

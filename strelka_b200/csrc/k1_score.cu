@@ -793,3 +793,15 @@ extern "C" int sx_score_alignments(sx_ctx* ctx, const sx_align_batch* b, double*
     ctx->total_launches += chunks;
     return sx_check_status(ctx, "sx_score_alignments");
 }
+
+// launcher for the device-resident pipeline (sx_pipeline.cu): one 8-byte round trip picks the shared-memory tile, the kernel is only enqueued
+int sx_k1_run_dev(sx_ctx* ctx, const sx_align_batch* d, double* lnp_dev, unsigned* launches)
+{
+    if (d->n_regions == 0) return SX_OK;
+    uint32_t need[2] = {0, 0};
+    int rc = k1_smem_need_dev(ctx, d->regions, 0, d->n_regions, need, d->format);
+    if (rc) return rc;
+    rc = sx_k1_launch(ctx, d, 0, d->n_regions, lnp_dev, need[0], need[1], ctx->s_compute);
+    *launches += 2;
+    return rc;
+}

@@ -794,3 +794,15 @@ extern "C" int sx_dependent_eprob(sx_ctx* ctx, const sx_pileup_batch* b, uint32_
     ctx->total_launches += 1;
     return sx_check_status(ctx, "sx_dependent_eprob");
 }
+
+// launcher for the device-resident pipeline (sx_pipeline.cu): one 4-byte round trip (the deepest column) picks the kernel
+int sx_k2a_run(sx_ctx* ctx, const sx_pileup_batch* d, int is_always_test, sx_digt_result* out_dev, unsigned* launches)
+{
+    if (d->n_sites == 0) return SX_OK;
+    uint32_t max_site = 0;
+    int rc = max_site_dev(ctx, d->site_off, d->n_sites, &max_site);
+    if (rc) return rc;
+    rc = germline_run(ctx, d, is_always_test, out_dev, nullptr, nullptr, max_site);
+    *launches += 2;
+    return rc;
+}

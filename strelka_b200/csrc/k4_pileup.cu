@@ -133,6 +133,7 @@ __global__ void k4_count_kernel(k4_args A, int* __restrict__ d1, int* __restrict
     const sx_pileup_read rd = A.reads[r];
     const int32_t bp = bpos_of(A, r);
     if (r > 0 && bpos_of(A, r - 1) > bp) atomicOr(status, ST_ORDER);
+    if (rd.flags & SX_PRF_SKIP) return;
     const sx_aln_seg* path = A.segs + rd.seg_off;
     const uint32_t as = A.reads[r + 1].seg_off - rd.seg_off;
     if (rd.len > A.Lcap || as > K4_MAX_SEGS)
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_fill_kernel(k4_args A, const
     for (uint32_t r = lo; r < hi; ++r)
     {
         const sx_pileup_read rd = A.reads[r];
-        if (!(rd.flags & SX_PRF_TIER1OR2)) continue; // sub-mapped reads only count (pass 1)
+        if (!(rd.flags & SX_PRF_TIER1OR2) || (rd.flags & SX_PRF_SKIP)) continue; // sub-mapped reads only count (pass 1)
         const uint32_t as = A.reads[r + 1].seg_off - rd.seg_off;
         if (rd.len > A.Lcap || as > K4_MAX_SEGS) continue; // flagged by pass 1
         const sx_aln_seg* path = A.segs + rd.seg_off;
@@ -610,11 +611,10 @@ extern "C" void sx_default_pileup_opts(sx_pileup_opts* o)
     o->reserved_ = 0;
 }
 
-// all pointers (batch arrays and output columns) are device pointers
-extern "C" int sx_pileup_reads_dev(sx_ctx* ctx, const sx_pileup_reads_batch* d, sx_pileup_columns* out)
+// all pointers (batch arrays and output columns) are device pointers; enqueues the three passes (one 8-byte round trip between the scans
+// and the fill checks the capacities) and returns without waiting for the fill
+int sx_k4_run(sx_ctx* ctx, const sx_pileup_reads_batch* d, const sx_pileup_columns* out, unsigned* launches_out)
 {
-    if (!ctx) return SX_ERR_ARG;
-    ctx->timing = sx_timing{};
     if (!d || !out || !out->site_off || !out->t2_off || !out->n_spandel || !out->n_submapped || !out->calls || !out->t2_calls)
         return sx_fail(ctx, SX_ERR_ARG, "sx_pileup_reads_dev: NULL argument");
     if (d->report_end < d->report_begin) return sx_fail(ctx, SX_ERR_ARG, "sx_pileup_reads_dev: empty report range");
@@ -651,7 +651,6 @@ extern "C" int sx_pileup_reads_dev(sx_ctx* ctx, const sx_pileup_reads_batch* d, 
     A.n_sites = n_sites;
     A.opt = d->opts;
 
-    sx_kernel_timer t(ctx);
     // working arrays: the two offset arrays and the two count arrays are scanned in place in the caller's buffers
     int* d1 = reinterpret_cast<int*>(out->site_off);
     int* d2 = reinterpret_cast<int*>(out->t2_off);
@@ -662,7 +661,7 @@ extern "C" int sx_pileup_reads_dev(sx_ctx* ctx, const sx_pileup_reads_batch* d, 
     const uint32_t tiles = (n_sites + 1 + SCAN_TILE - 1) / SCAN_TILE;
     if ((rc = sx_ensure(ctx, 26, (size_t)(n_sites + 1) * 8 + 64, reinterpret_cast<void**>(&s1)))) return rc;
     s2 = s1 + (n_sites + 1);
-    if ((rc = sx_ensure(ctx, 28, (size_t)(n_sites + 1) * 8 + 64, reinterpret_cast<void**>(&b1)))) return rc;
+    if ((rc = sx_ensure(ctx, 64, (size_t)(n_sites + 1) * 8 + 64, reinterpret_cast<void**>(&b1)))) return rc;
     b2 = b1 + (n_sites + 1);
     if ((rc = sx_ensure(ctx, 27, (size_t)tiles * 8 * sizeof(int) + 64, reinterpret_cast<void**>(&tile_sums)))) return rc;
     SX_CUDA(ctx, cudaMemsetAsync(d1, 0, (size_t)(n_sites + 1) * 4, st));
@@ -721,6 +720,18 @@ extern "C" int sx_pileup_reads_dev(sx_ctx* ctx, const sx_pileup_reads_batch* d, 
         SX_CUDA(ctx, cudaGetLastError());
         ++launches;
     }
+    *launches_out += launches;
+    return SX_OK;
+}
+
+extern "C" int sx_pileup_reads_dev(sx_ctx* ctx, const sx_pileup_reads_batch* d, sx_pileup_columns* out)
+{
+    if (!ctx) return SX_ERR_ARG;
+    ctx->timing = sx_timing{};
+    sx_kernel_timer t(ctx);
+    unsigned launches = 0;
+    int rc = sx_k4_run(ctx, d, out, &launches);
+    if (rc) return rc;
     t.stop(launches);
     rc = t.finish();
     if (rc) return rc;

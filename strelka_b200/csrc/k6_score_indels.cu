@@ -283,3 +283,13 @@ extern "C" int sx_score_indels(sx_ctx* ctx, const sx_score_indels_batch* b, cons
     ctx->total_launches += launches;
     return sx_check_status(ctx, "sx_score_indels");
 }
+
+// launcher for the device-resident pipeline (sx_pipeline.cu): one 16-byte round trip sizes the scratch, the kernel itself is only enqueued
+int sx_k6_run(sx_ctx* ctx, const sx_score_indels_batch* d, const double* lnp_dev, const sx_score_indels_out* out_dev, unsigned* launches)
+{
+    if (d->n_reads == 0) return SX_OK;
+    unsigned l(0);
+    const int rc(k6_run(ctx, d, lnp_dev, out_dev, &l));
+    *launches += l;
+    return rc;
+}

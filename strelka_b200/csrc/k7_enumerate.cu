@@ -512,3 +512,12 @@ extern "C" int sx_enumerate_alignments(sx_ctx* ctx, const sx_enum_batch* b, sx_e
     ctx->total_launches += launches;
     return k7_finish(ctx, "sx_enumerate_alignments", out_host->totals);
 }
+
+// asynchronous launcher for the device-resident pipeline (sx_pipeline.cu)
+int sx_k7_run(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsigned* launches)
+{
+    unsigned l(0);
+    const int rc((d->opts.flags & SX_ENUM_F_FAST) ? k7_run_fast(ctx, d, o, &l) : k7_run(ctx, d, o, &l));
+    *launches += l;
+    return rc;
+}

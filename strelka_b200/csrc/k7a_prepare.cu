@@ -336,3 +336,30 @@ extern "C" int sx_alignment_indels(sx_ctx* ctx, const sx_enum_batch* b, const sx
     ctx->total_launches += launches;
     return k7a_finish(ctx, "sx_alignment_indels", out_host->totals);
 }
+
+// ---- asynchronous launchers for the device-resident pipeline (sx_pipeline.cu): everything is enqueued on ctx->s_compute, nothing waits
+int sx_k7g_run(sx_ctx* ctx, const sx_gate_batch* d, const sx_gate_out* o, unsigned* launches)
+{
+    if (d->n_reads == 0) return SX_OK;
+    const unsigned grid((unsigned)std::max(1, std::min<int>((int)((d->n_reads + 127) / 128), ctx->sm_count * 16)));
+    k7g_gates_kernel<<<grid, 128, 0, ctx->s_compute>>>(*d, *o, nullptr);
+    SX_CUDA(ctx, cudaGetLastError());
+    *launches += 1;
+    return SX_OK;
+}
+
+int sx_k7a_run(sx_ctx* ctx, const sx_enum_batch* d, const sx_region* regions, const uint8_t* seq4, const char* ref, const uint32_t* key_ins_off, const char* key_ins,
+               const sx_prep_out* o, unsigned* launches)
+{
+    k7a_view v;
+    v.b = *d;
+    v.regions = regions;
+    v.seq4 = seq4;
+    v.ref = ref;
+    v.key_ins_off = key_ins_off;
+    v.key_ins = key_ins;
+    unsigned l(0);
+    const int rc(k7a_run(ctx, v, o, &l));
+    *launches += l;
+    return rc;
+}

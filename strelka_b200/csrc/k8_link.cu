@@ -301,3 +301,13 @@ extern "C" int sx_link_alignments(sx_ctx* ctx, const sx_enum_batch* b, const sx_
     ctx->total_launches += launches;
     return k8_finish(ctx, "sx_link_alignments", out_host->totals);
 }
+
+// asynchronous launcher for the device-resident pipeline (sx_pipeline.cu)
+int sx_k8_run(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* e, uint32_t n_alns, const uint32_t* key_ins_off, const char* key_ins, const sx_link_out* o,
+              unsigned* launches)
+{
+    unsigned l(0);
+    const int rc(k8_run(ctx, d, e, n_alns, key_ins_off, key_ins, o, &l));
+    *launches += l;
+    return rc;
+}

@@ -224,3 +224,13 @@ extern "C" int sx_choose_realignment(sx_ctx* ctx, const sx_realign_batch* b, con
     ctx->total_launches += launches;
     return k9_finish(ctx, "sx_choose_realignment", out_host->totals);
 }
+
+// asynchronous launcher for the device-resident pipeline (sx_pipeline.cu)
+int sx_k9_run(sx_ctx* ctx, const sx_realign_batch* d, const double* lnp, const sx_realign_out* o, unsigned* launches)
+{
+    if (d->n_reads == 0) return SX_OK;
+    unsigned l(0);
+    const int rc(k9_run(ctx, d, lnp, o, &l));
+    *launches += l;
+    return rc;
+}

@@ -450,6 +450,8 @@ extern "C" void sx_destroy(sx_ctx* ctx)
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->d_status) cudaFree(ctx->d_status);
     for (auto ev : ctx->ev_pool) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_win)
+        if (ev) cudaEventDestroy(ev);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);

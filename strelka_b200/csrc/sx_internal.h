@@ -89,10 +89,12 @@ struct sx_ctx
     std::string err;
     sx_timing timing{};
     uint64_t total_launches = 0;
-    sx_buf buf[64];          // grow-only device arenas, one per logical pool (K7 uses 40..45)
+    sx_buf buf[192];         // grow-only device arenas, one per logical pool (host entries 0..29, K7 family 40..63, K4 64, pipeline 70..)
     void* nccl = nullptr;    // ncclComm_t
     void* nccl_lib = nullptr;
     int rank = 0, world = 1;
+    cudaEvent_t ev_win[16] = {};     // stage boundaries of sx_process_window_dev (created on first use)
+    float win_ms[16] = {};
     cudaStream_t s_comm = nullptr;   // the gather's own stream (created by sx_comm_init)
     cudaEvent_t ev_comm = nullptr;   // compute -> comm ordering
     std::vector<unsigned long long> comm_counts; // per-rank byte counts of the last gather (root: receive offsets)
@@ -139,3 +141,16 @@ struct sx_kernel_timer
 int sx_k1_launch(sx_ctx* ctx, const sx_align_batch* dev, uint32_t region_begin, uint32_t region_end, double* lnp_dev, size_t smem_bytes, size_t smem_fast,
                  cudaStream_t st);
 size_t sx_k1_region_smem(const sx_region* r0, const sx_region* r1, const sx_aln* alns);
+
+// asynchronous stage launchers of the device-resident pipeline (sx_pipeline.cu); each lives beside its kernels
+int sx_k7g_run(sx_ctx* ctx, const sx_gate_batch* d, const sx_gate_out* o, unsigned* launches);
+int sx_k7a_run(sx_ctx* ctx, const sx_enum_batch* d, const sx_region* regions, const uint8_t* seq4, const char* ref, const uint32_t* key_ins_off, const char* key_ins,
+               const sx_prep_out* o, unsigned* launches);
+int sx_k7_run(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsigned* launches);
+int sx_k8_run(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* e, uint32_t n_alns, const uint32_t* key_ins_off, const char* key_ins, const sx_link_out* o,
+              unsigned* launches);
+int sx_k1_run_dev(sx_ctx* ctx, const sx_align_batch* d, double* lnp_dev, unsigned* launches);
+int sx_k6_run(sx_ctx* ctx, const sx_score_indels_batch* d, const double* lnp_dev, const sx_score_indels_out* out_dev, unsigned* launches);
+int sx_k9_run(sx_ctx* ctx, const sx_realign_batch* d, const double* lnp, const sx_realign_out* o, unsigned* launches);
+int sx_k4_run(sx_ctx* ctx, const sx_pileup_reads_batch* d, const sx_pileup_columns* out, unsigned* launches);
+int sx_k2a_run(sx_ctx* ctx, const sx_pileup_batch* d, int is_always_test, sx_digt_result* out_dev, unsigned* launches);

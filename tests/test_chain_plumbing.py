@@ -201,7 +201,7 @@ def chain_vs_realign_and_score_read(ctx, eb, gb, cap_alns_per_read=2048):
         assert int(g_n_rec[r]) == int(r_n_rec[r]), (r, int(g_n_rec[r]), int(r_n_rec[r]))
         assert g_recs[o : o + int(g_n_rec[r])].tobytes() == r_recs[o : o + int(r_n_rec[r])].tobytes(), r
         n_recs += int(r_n_rec[r])
-    chain.free() if hasattr(ctx, "h") and not isinstance(ctx.h, int) else None
+    chain.free()
     return n_real, n_recs, int((ref_status == 2).sum())
 
 

@@ -400,6 +400,38 @@ def test_k4_pileup_reads(ctx, seed, mode):
         assert np.array_equal(w, g), name
 
 
+def _buffer_order_case(rng, packed_quals):
+    """reads whose BEST alignment start differs from their read-buffer position (a realignment moved it, by up to +-25): the batch is in
+    buffer order, the alignments are not sorted."""
+    reads, ref, ref_begin, cand = specgen.random_pileup_reads(rng, n_reads=int(rng.integers(600, 1500)), ref_len=int(rng.integers(900, 3000)))
+    bpos = [int(r.pos) + (int(rng.integers(-25, 26)) if rng.random() < 0.4 else 0) for r in reads]
+    order = np.argsort(np.asarray(bpos), kind="stable")
+    reads, bpos = [reads[i] for i in order], [bpos[i] for i in order]
+    qd = None
+    if packed_quals:
+        qd = sorted({int(q) for r in reads for q in r.quals})
+        if len(qd) > 16:  # bin the qualities into a 16-entry dictionary first
+            qd = qd[:: (len(qd) + 15) // 16][:16]
+            for r in reads:
+                r.quals = [min(qd, key=lambda v: abs(v - int(q))) for q in r.quals]
+    lo, hi = ref_begin + 100, ref_begin + len(ref) - 150
+    return B.PileupReadsBatch(reads, ref, ref_begin, lo, hi, cand, buffer_pos=bpos, qual_dict=qd)
+
+
+@pytest.mark.parametrize("packed", [False, True])
+@pytest.mark.parametrize("seed", range(4))
+def test_k4_pileup_in_read_buffer_order(ctx, seed, packed):
+    """K4 keyed on the read-buffer position (starling_read_buffer.cpp:68-78): columns in the order the reference piles the reads up even
+    where realignments moved the alignment starts past their neighbours'; dictionary-coded qualities."""
+    pb = _buffer_order_case(np.random.default_rng(6300 + seed), packed)
+    assert (np.diff(pb.reads["pos"][: pb.n_reads].astype(np.int64)) < 0).any()  # the alignments themselves are NOT sorted
+    want = reflib.ox_pileup_reads(pb)
+    got = ctx.pileup_reads(pb)
+    assert int(want[0][-1]) > 1000
+    for w, g, name in zip(want, got, ("site_off", "calls", "t2_off", "t2_calls", "n_spandel", "n_submapped")):
+        assert np.array_equal(w, g), name
+
+
 def test_k4_pileup_feeds_k2(ctx):
     """The columns K4 produces are an sx_pileup_batch: K2a on them == K2a on the oracle's columns."""
     rng = np.random.default_rng(6100)

@@ -184,6 +184,31 @@ def test_pileup_reads_columns_match_the_reference(seed, mode):
         assert np.array_equal(w, g), name
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_pileup_reads_in_read_buffer_order_match_the_reference(seed):
+    """The reference piles reads up in read-buffer order while each contributes through its best alignment (realignments move starts):
+    the oracle on a batch in buffer order with unsorted alignments and dictionary-coded qualities == pileup_read_segment driven in that order."""
+    rng = np.random.default_rng(4100 + seed)
+    reads, ref, ref_begin, cand = specgen.random_pileup_reads(rng, n_reads=300)
+    bpos = [int(r.pos) + (int(rng.integers(-25, 26)) if rng.random() < 0.4 else 0) for r in reads]
+    order = np.argsort(np.asarray(bpos), kind="stable")
+    reads, bpos = [reads[i] for i in order], [bpos[i] for i in order]
+    qd = sorted({int(q) for r in reads for q in r.quals})
+    if len(qd) > 16:
+        qd = qd[:: (len(qd) + 15) // 16][:16]
+        for r in reads:
+            r.quals = [min(qd, key=lambda v: abs(v - int(q))) for q in r.quals]
+    lo, hi = ref_begin + 100, ref_begin + len(ref) - 150
+    plain = B.PileupReadsBatch(reads, ref, ref_begin, lo, hi, cand, buffer_pos=bpos)
+    packed = B.PileupReadsBatch(reads, ref, ref_begin, lo, hi, cand, buffer_pos=bpos, qual_dict=qd)
+    want = reflib.ref_pileup_reads(plain)
+    for pb in (plain, packed):
+        for w, g, name in zip(want, reflib.ox_pileup_reads(pb), ("site_off", "calls", "t2_off", "t2_calls", "n_spandel", "n_submapped")):
+            assert np.array_equal(w, g), name
+    for w, g in zip(want, reflib.ref_pileup_reads(packed)):
+        assert np.array_equal(w, g)
+
+
 def test_pileup_bench_workload_matches_the_reference():
     """The K4 leg of bench.py: the oracle and the reference's pileup_read_segment agree on the synthetic read set it times."""
     import ctypes as C

@@ -1,0 +1,49 @@
+"""GPU: sx_process_window_dev -- the whole READ_BUFFER + POST_ALIGN pass of a window, device-resident -- against the reference run stage by
+stage on the same window (tests/window_check.py): realignAndScoreRead, pileup_read_segment in read-buffer order, position_snp_call_pprob_digt.
+Sorts last (it drives every kernel of the chain)."""
+import numpy as np
+import pytest
+
+import reflib
+import specgen
+import window_check as W
+from strelka_b200 import _abi as A
+from strelka_b200 import batch as B
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900, method="thread")]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from strelka_b200.api import Context
+
+    c = Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("block", range(20))
+def test_window_equals_the_reference(ctx, block):
+    """200 seeded batches (plain, clustered / conflicting, phased, dense windows, hard and soft clips, moved starts, over-long deletions,
+    reads the gates turn away), each region a window: per read is_realigned / rseg.realignment segment for segment (hard clips included) and
+    score_indels' records; per window the pile-up columns in read-buffer order and the germline site results."""
+    if not reflib.have_ref():
+        pytest.skip("oracle/_ref/libstrelka_ref.so not built")
+    tot = {"reads": 0, "realigned": 0, "records": 0, "threw": 0, "calls": 0, "sites": 0}
+    for case in range(10 * block, 10 * block + 10):
+        eb = specgen.enum_edge_case(case) if case % 2 else specgen.enum_case(case)
+        raw = specgen.raw_alignments_for(eb, 100 + case)
+        for eb1, gb1 in W.single_region_windows(eb, raw):
+            rng = np.random.default_rng(77000 + case)
+            n = eb1.n_reads
+            # strands, tiers (a few tier2 and sub-mapped reads), mapping qualities and indel error rates vary
+            tier = rng.choice([1, 1, 1, 1, 2, 0], size=n + 1)
+            flags = ((rng.random(n + 1) < 0.5).astype(np.uint8) * A.SX_PRF_FWD) | np.where(tier == 1, A.SX_PRF_TIER1 | A.SX_PRF_TIER1OR2, 0).astype(np.uint8) | np.where(
+                tier == 2, A.SX_PRF_TIER1OR2, 0).astype(np.uint8)
+            eb1.keys["ref_to_indel_lnp"][: eb1.n_keys] = -rng.uniform(5.0, 12.0, eb1.n_keys)
+            eb1.keys["indel_to_ref_lnp"][: eb1.n_keys] = -rng.uniform(5.0, 12.0, eb1.n_keys)
+            mapq = rng.choice([60, 60, 60, 30, 3], size=n + 1).astype(np.uint8)
+            s = W.check_window(ctx, eb1, gb1, read_flags=flags, mapq=mapq)
+            for k in tot:
+                tot[k] += s[k]
+    assert tot["realigned"] > 0 and tot["records"] > 0 and tot["calls"] > 0, tot
