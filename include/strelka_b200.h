@@ -907,7 +907,16 @@ typedef struct sx_window_batch {
     sx_pileup_opts pileup_opts;
 } sx_window_batch;
 
-#define SX_WIN_TOTALS 8 /* alignments, their segments, their keys, K1 segments, insert-pool bytes, best-alignment slots, tier1 calls, tier2 calls */
+#define SX_WIN_TOTALS 10 /* alignments, their segments, their keys, K1 segments, insert-pool bytes, best-alignment slots, tier1 calls, tier2 calls,
+                            variant sites, (reserved) */
+
+/* one call record of the window's site results: a position whose most likely genotype is not the reference's (what leaves the window for
+ * the variant writers; the in-memory analogue of a variants.vcf line, gathered across GPUs by sx_gatherv_records) */
+typedef struct sx_site_call {
+    int32_t pos;
+    uint32_t n_calls;        /* depth of the position's tier1 column */
+    sx_digt_result gl;
+} sx_site_call;
 
 typedef struct sx_window_out { /* device pointers, each may be NULL (capacities count only for non-NULL arrays) */
     uint8_t* gate;               /* [n_reads] SX_GATE_* (sub-mapped reads: 0, align_pos :746) */
@@ -923,6 +932,9 @@ typedef struct sx_window_out { /* device pointers, each may be NULL (capacities 
     sx_pileup_columns cols;      /* each array NULL or caller-allocated with the stated capacities */
     sx_digt_result* site_gl;     /* [report_end - report_begin] */
     uint32_t* totals;            /* [SX_WIN_TOTALS] */
+    sx_site_call* variant_sites; /* [cap_variant_sites] the computed sites with genome.max_gt != ref_gt, ascending position (needs do_site_gl);
+                                    more than the capacity: SX_ERR_CAPACITY, totals[8] says how many */
+    uint32_t cap_variant_sites;
 } sx_window_out;
 
 enum { SX_WIN_ST_PREP = 0, SX_WIN_ST_GATES, SX_WIN_ST_KEYS, SX_WIN_ST_ENUMERATE, SX_WIN_ST_LINK, SX_WIN_ST_SCORE, SX_WIN_ST_SCORE_INDELS, SX_WIN_ST_CHOOSE,
@@ -931,6 +943,10 @@ enum { SX_WIN_ST_PREP = 0, SX_WIN_ST_GATES, SX_WIN_ST_KEYS, SX_WIN_ST_ENUMERATE,
 void sx_default_window_opts(sx_window_batch* b); /* fills enum_opts (max_alns_per_read = 5000), score_opts, pileup_opts, is_always_test = 1 */
 /* SX_ERR_CAPACITY: a caller-provided output array is too small (totals_host, if given, says what the window produced). */
 int sx_process_window_dev(sx_ctx* ctx, const sx_window_batch* batch_dev, sx_window_out* out_dev, uint32_t* totals_host /* [SX_WIN_TOTALS] or NULL */);
+/* the same with HOST arrays in and out: every input array is copied to the device, the pass runs, and every non-NULL output array is copied
+ * back (capacities as above; totals_host says how much of each was produced).  One sx_ctx per host thread: two threads with a context each
+ * overlap one window's transfers with the other's kernels. */
+int sx_process_window(sx_ctx* ctx, const sx_window_batch* batch_host, sx_window_out* out_host, uint32_t* totals_host);
 /* device time of each stage of the most recent sx_process_window_dev on ctx (CUDA events on the compute stream), ms[SX_WIN_N_STAGES] */
 int sx_last_window_timing(const sx_ctx* ctx, float* ms);
 

@@ -70,6 +70,7 @@ DIGT_RESULT_DT = np.dtype(
         ("pad", "<u4"),
     ]
 )
+SITE_CALL_DT = np.dtype([("pos", "<i4"), ("n_calls", "<u4"), ("gl", DIGT_RESULT_DT)])  # sx_site_call, 160 bytes
 SSNV_RESULT_DT = np.dtype(
     [
         ("normal_lhood", "<f4", (30,)),
@@ -292,10 +293,11 @@ class SxWindowBatch(C.Structure):
 
 class SxWindowOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("gate", "enum_status", "realign_status", "best_pos", "best_seg_off", "best_n_seg", "best_segs")] + [("cap_best_segs", C.c_uint32)] + [
-        (n, C.c_void_p) for n in ("recs", "n_rec")] + [("cols", SxPileupColumns), ("site_gl", C.c_void_p), ("totals", C.c_void_p)]
+        (n, C.c_void_p) for n in ("recs", "n_rec")] + [("cols", SxPileupColumns), ("site_gl", C.c_void_p), ("totals", C.c_void_p), ("variant_sites", C.c_void_p),
+                                                       ("cap_variant_sites", C.c_uint32)]
 
 
-SX_WIN_TOTALS, SX_WIN_N_STAGES = 8, 10
+SX_WIN_TOTALS, SX_WIN_N_STAGES = 10, 10
 SX_WIN_STAGE_NAMES = ("prep", "k7g_gates", "k7a_keys", "k7_enumerate", "k7b_link", "k1_score", "k6_score_indels", "k9_choose", "k4_pileup", "k2a_site_gl")
 
 
@@ -389,6 +391,7 @@ SYMBOLS = [
     ("sx_pileup_reads_dev", C.c_int, [_P, C.POINTER(SxPileupReadsBatch), C.POINTER(SxPileupColumns)]),
     ("sx_default_window_opts", None, [C.POINTER(SxWindowBatch)]),
     ("sx_process_window_dev", C.c_int, [_P, C.POINTER(SxWindowBatch), C.POINTER(SxWindowOut), _P]),
+    ("sx_process_window", C.c_int, [_P, C.POINTER(SxWindowBatch), C.POINTER(SxWindowOut), _P]),
     ("sx_last_window_timing", C.c_int, [_P, _P]),
     ("sx_comm_get_unique_id", C.c_int, [_P]),
     ("sx_comm_init", C.c_int, [_P, _P, C.c_int, C.c_int]),

@@ -528,17 +528,20 @@ class DevWindow:
             sizes = {"gate": n + 16, "enum_status": n + 16, "realign_status": n + 16, "best_pos": 4 * n + 16, "best_seg_off": 4 * (n + 2), "best_n_seg": 2 * n + 16,
                      "best_segs": 4 * self.cap_best + 64, "recs": (n_slots + 1) * A.READ_INDEL_SCORE_DT.itemsize, "n_rec": 4 * n + 16, "site_off": 4 * (ns + 2),
                      "t2_off": 4 * (ns + 2), "n_spandel": 4 * (ns + 2), "n_submapped": 4 * (ns + 2), "calls": 2 * bases, "t2_calls": 2 * bases,
-                     "site_gl": (ns + 1) * A.DIGT_RESULT_DT.itemsize, "totals": 64}
+                     "site_gl": (ns + 1) * A.DIGT_RESULT_DT.itemsize, "totals": 64, "variant_sites": (ns // 8 + 1024) * A.SITE_CALL_DT.itemsize}
             self.obufs = {k: DeviceArray(ctx, v) for k, v in sizes.items()}
             o, b = self.out, self.obufs
             for k in ("gate", "enum_status", "realign_status", "best_pos", "best_seg_off", "best_n_seg", "best_segs", "recs", "n_rec", "site_gl", "totals"):
                 setattr(o, k, b[k].ptr)
             o.cap_best_segs = self.cap_best
+            if w.do_site_gl:
+                o.variant_sites, o.cap_variant_sites = b["variant_sites"].ptr, ns // 8 + 1024
             o.cols = A.SxPileupColumns(b["site_off"].ptr, b["calls"].ptr, b["t2_off"].ptr, b["t2_calls"].ptr, b["n_spandel"].ptr, b["n_submapped"].ptr, bases, bases)
             self.n_slots = n_slots
         else:  # only the call records come out; everything else stays in the context's own buffers
-            self.obufs = {"site_gl": DeviceArray(ctx, (ns + 1) * A.DIGT_RESULT_DT.itemsize)}
-            self.out.site_gl = self.obufs["site_gl"].ptr
+            cap_v = ns // 8 + 1024
+            self.obufs = {"variant_sites": DeviceArray(ctx, cap_v * A.SITE_CALL_DT.itemsize)}
+            self.out.variant_sites, self.out.cap_variant_sites = self.obufs["variant_sites"].ptr, cap_v
         self.totals = np.zeros(A.SX_WIN_TOTALS, np.uint32)
 
     def run(self):
@@ -563,6 +566,7 @@ class DevWindow:
         d["t2_calls"] = b["t2_calls"].download(np.uint16, int(d["t2_off"][ns]))
         if w.do_site_gl:
             d["site_gl"] = b["site_gl"].download(A.DIGT_RESULT_DT, ns)
+            d["variant_sites"] = b["variant_sites"].download(A.SITE_CALL_DT, int(self.totals[8]))
         return d
 
     def free(self):

@@ -133,7 +133,7 @@ int k6_run(sx_ctx* ctx, const sx_score_indels_batch* d, const double* lnp_dev, c
     const uint32_t maxA(std::max(1u, h_max[0])), maxE(std::max(1u, std::min(K6_MAX_EVAL, h_max[1])));
     // 128 reads per block when their slices fit a modest tile (several blocks per SM), else 32 reads per block; a block whose
     // slices still do not fit runs on the global arrays
-    const uint32_t smem_limit(48u * 1024u);
+    const uint32_t smem_limit(48u * 1024u - 512u); // (the kernel also has ~100 bytes of static shared memory: the two together must stay under the 48 KB no-opt-in limit)
     const int threads(h_max[2] <= smem_limit ? K6_THREADS : 32);
     const uint32_t smem_bytes(std::min(smem_limit, threads == K6_THREADS ? h_max[2] : h_max[3]));
     int per_sm(1);

@@ -18,7 +18,7 @@
 namespace
 {
 // device status bits the stages raise when one of THEIR capacities is too small (each stage's own file names its bit)
-constexpr int ST_K7_CAP = 1 << 14, ST_K8_CAP = 1 << 17, ST_K7A_CAP = 1 << 18, ST_K9_CAP = 1 << 19;
+constexpr int ST_K8_CAP = 1 << 17, ST_K9_CAP = 1 << 19; // (K7: 1 << 14 and K7a: 1 << 18 are handled by their retry loops through the totals)
 
 struct prep_out
 {
@@ -125,6 +125,92 @@ __global__ void sxp_pileup_reads_kernel(const sx_window_batch b, const prep_out 
     if (max_span) atomicMax(&p.maxima[2], max_span);
 }
 
+// ---- variant-site compaction, order-preserving: per 1024-site chunk a count, an exclusive scan over the chunks, ranked writes
+constexpr uint32_t VC_CHUNK = 1024, VC_THREADS = 256;
+__device__ __forceinline__ bool is_variant_site(const sx_digt_result& g) { return g.is_computed && g.genome.max_gt != g.ref_gt; }
+
+__global__ void __launch_bounds__(VC_THREADS) sxp_variant_count_kernel(const sx_digt_result* __restrict__ gl, const uint32_t n_sites, uint32_t* __restrict__ chunk_cnt)
+{
+    const uint32_t base(blockIdx.x * VC_CHUNK);
+    int total(0);
+    for (uint32_t i = 0; i < VC_CHUNK / VC_THREADS; ++i)
+    {
+        const uint32_t s(base + i * VC_THREADS + threadIdx.x);
+        total += __syncthreads_count(s < n_sites && is_variant_site(gl[s]));
+    }
+    if (threadIdx.x == 0) chunk_cnt[blockIdx.x] = (uint32_t)total;
+}
+
+__global__ void __launch_bounds__(1024) sxp_variant_scan_kernel(uint32_t* __restrict__ chunk_cnt, const uint32_t n_chunks, uint32_t* __restrict__ total_out)
+{
+    __shared__ uint32_t part[1024];
+    const uint32_t per((n_chunks + 1023u) / 1024u), a(threadIdx.x * per), b(min(n_chunks, a + per));
+    uint32_t sum(0);
+    for (uint32_t i = a; i < b; ++i) sum += chunk_cnt[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        uint32_t run(0);
+        for (uint32_t i = 0; i < 1024; ++i)
+        {
+            const uint32_t v(part[i]);
+            part[i] = run;
+            run += v;
+        }
+        *total_out = run;
+    }
+    __syncthreads();
+    uint32_t run(part[threadIdx.x]);
+    for (uint32_t i = a; i < b; ++i)
+    {
+        const uint32_t v(chunk_cnt[i]);
+        chunk_cnt[i] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(VC_THREADS) sxp_variant_write_kernel(const sx_digt_result* __restrict__ gl, const uint32_t* __restrict__ site_off, const uint32_t n_sites,
+                                                                      const int32_t report_begin, const uint32_t* __restrict__ chunk_off, sx_site_call* __restrict__ out,
+                                                                      const uint32_t cap)
+{
+    __shared__ uint32_t warp_cnt[VC_THREADS / 32];
+    __shared__ uint32_t run;
+    if (threadIdx.x == 0) run = chunk_off[blockIdx.x];
+    __syncthreads();
+    const uint32_t base(blockIdx.x * VC_CHUNK), lane(threadIdx.x & 31), wid(threadIdx.x >> 5);
+    for (uint32_t i = 0; i < VC_CHUNK / VC_THREADS; ++i)
+    {
+        const uint32_t s(base + i * VC_THREADS + threadIdx.x);
+        const bool v(s < n_sites && is_variant_site(gl[s]));
+        const unsigned m(__ballot_sync(0xffffffffu, v));
+        if (lane == 0) warp_cnt[wid] = __popc(m);
+        __syncthreads();
+        uint32_t before(run);
+        for (uint32_t k = 0; k < wid; ++k) before += warp_cnt[k];
+        if (v)
+        {
+            const uint32_t at(before + __popc(m & ((1u << lane) - 1u)));
+            if (at < cap)
+            {
+                sx_site_call c;
+                c.pos = report_begin + (int32_t)s;
+                c.n_calls = site_off[s + 1] - site_off[s];
+                c.gl = gl[s];
+                out[at] = c;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            uint32_t t(0);
+            for (uint32_t k = 0; k < VC_THREADS / 32; ++k) t += warp_cnt[k];
+            run += t;
+        }
+        __syncthreads();
+    }
+}
+
 template <typename T> int take(sx_ctx* ctx, int slot, size_t count, T*& p)
 {
     void* q(nullptr);
@@ -188,7 +274,7 @@ extern "C" int sx_process_window_dev(sx_ctx* ctx, const sx_window_batch* b, sx_w
     const uint32_t n_sites((uint32_t)(b->report_end - b->report_begin));
     unsigned launches(0);
     int rc;
-    uint32_t totals[SX_WIN_TOTALS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t totals[SX_WIN_TOTALS] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const int cap_grid(ctx->sm_count * 16);
     const auto grid = [cap_grid](const uint32_t m) { return (unsigned)std::max(1, std::min<int>((int)((m + 127) / 128), cap_grid)); };
     auto mark = [&](int i) { return cudaEventRecord(ctx->ev_win[i], st); };
@@ -550,7 +636,21 @@ extern "C" int sx_process_window_dev(sx_ctx* ctx, const sx_window_batch* b, sx_w
         if ((int64_t)b->report_begin < (int64_t)b->ref_begin || (uint64_t)((int64_t)b->report_end - (int64_t)b->ref_begin) > b->ref_bytes)
             return sx_fail(ctx, SX_ERR_ARG, "sx_process_window_dev: the report range leaves the reference segment");
         if ((rc = sx_k2a_run(ctx, &k2, b->is_always_test, gl, &launches))) return rc;
+        if (out->variant_sites)
+        {
+            const uint32_t n_chunks((n_sites + VC_CHUNK - 1) / VC_CHUNK);
+            uint32_t* chunk_cnt(nullptr);
+            if ((rc = take(ctx, 119, (size_t)n_chunks + 4, chunk_cnt))) return rc;
+            sxp_variant_count_kernel<<<n_chunks, VC_THREADS, 0, st>>>(gl, n_sites, chunk_cnt);
+            sxp_variant_scan_kernel<<<1, 1024, 0, st>>>(chunk_cnt, n_chunks, chunk_cnt + n_chunks);
+            sxp_variant_write_kernel<<<n_chunks, VC_THREADS, 0, st>>>(gl, cols.site_off, n_sites, b->report_begin, chunk_cnt, out->variant_sites, out->cap_variant_sites);
+            SX_CUDA(ctx, cudaGetLastError());
+            launches += 3;
+            SX_CUDA(ctx, cudaMemcpyAsync(&totals[8], chunk_cnt + n_chunks, 4, cudaMemcpyDeviceToHost, st));
+        }
     }
+    else if (out->variant_sites)
+        return sx_fail(ctx, SX_ERR_ARG, "sx_process_window_dev: variant_sites needs do_site_gl");
     SX_CUDA(ctx, mark(SX_WIN_N_STAGES));
     // ---------------------------------------------------------------------------------------------------------------- the end: one wait, the totals, the status
     uint32_t call_totals[2] = {0, 0};
@@ -572,5 +672,147 @@ extern "C" int sx_process_window_dev(sx_ctx* ctx, const sx_window_batch* b, sx_w
     ctx->timing.kernel_ms = sum;
     ctx->timing.launches = launches;
     ctx->total_launches += launches;
+    if (out->variant_sites && totals[8] > out->cap_variant_sites)
+        return sx_fail(ctx, SX_ERR_CAPACITY, "sx_process_window_dev: %u variant sites, cap_variant_sites is %u", totals[8], out->cap_variant_sites);
     return sx_check_status(ctx, "sx_process_window");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// host arrays in, host arrays out
+// ---------------------------------------------------------------------------------------------------------------------------------------
+extern "C" int sx_process_window(sx_ctx* ctx, const sx_window_batch* b, sx_window_out* out, uint32_t* totals_host)
+{
+    if (!ctx) return SX_ERR_ARG;
+    if (!b || !out) return sx_fail(ctx, SX_ERR_ARG, "sx_process_window: NULL argument");
+    if (b->n_reads && (!b->region_read_off || !b->region_key_off || !b->raw_seg_off || !b->use_key_off || !b->rec_off || !b->regions || (b->n_keys && !b->key_ins_off)))
+        return sx_fail(ctx, SX_ERR_ARG, "sx_process_window: NULL array");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st(ctx->s_compute);
+    const uint32_t n(b->n_reads), nr(b->n_regions), nk(b->n_keys);
+    const uint32_t n_sites((uint32_t)(b->report_end - b->report_begin));
+    sx_window_batch d(*b);
+    int rc;
+    int slot(130);
+    float h2d_ms(0), d2h_ms(0);
+    cudaEvent_t e0(ctx->ev_a), e1(ctx->ev_b);
+    SX_CUDA(ctx, cudaEventRecord(e0, st));
+    auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
+        void* p(nullptr);
+        const int r(sx_ensure(ctx, slot++, bytes + 80, &p));
+        if (r) return r;
+        if (bytes && src) SX_CUDA(ctx, cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, st));
+        *dst = p;
+        return SX_OK;
+    };
+#define SX_UPW(field, bytes)                                                                 \
+    if ((rc = up(b->field, (size_t)(bytes), reinterpret_cast<const void**>(&d.field)))) return rc;
+    const size_t n_raw(n ? b->raw_seg_off[n] : 0), n_use(n ? b->use_key_off[n] : 0), ins_bytes(nk ? b->key_ins_off[nk] : 0);
+    SX_UPW(region_read_off, ((size_t)nr + 1) * 4)
+    SX_UPW(region_key_off, ((size_t)nr + 1) * 4)
+    SX_UPW(keys, (size_t)nk * sizeof(sx_indel_key))
+    if (b->key_hap)
+    {
+        SX_UPW(key_hap, (size_t)nk * sizeof(sx_key_hap))
+    }
+    else ++slot;
+    SX_UPW(key_ins_off, ((size_t)nk + 1) * 4)
+    SX_UPW(key_ins, ins_bytes)
+    SX_UPW(realign_begin, (size_t)nr * 4)
+    SX_UPW(realign_end, (size_t)nr * 4)
+    SX_UPW(raw_pos, (size_t)n * 4)
+    SX_UPW(raw_seg_off, ((size_t)n + 1) * 4)
+    SX_UPW(raw_segs, n_raw * sizeof(sx_aln_seg))
+    SX_UPW(read_len, (size_t)n * 2)
+    SX_UPW(read_flags, (size_t)n)
+    SX_UPW(mapq, (size_t)n)
+    SX_UPW(use_key_off, ((size_t)n + 1) * 4)
+    SX_UPW(use_keys, n_use * 2)
+    SX_UPW(rec_off, ((size_t)n + 1) * 4)
+    {
+        const void* p(nullptr);
+        if ((rc = up(b->regions, ((size_t)nr + 1) * sizeof(sx_region), &p))) return rc;
+        d.regions = static_cast<sx_region*>(const_cast<void*>(p));
+    }
+    SX_UPW(seq4, (size_t)b->seq4_bytes)
+    SX_UPW(qual, (size_t)b->qual_bytes)
+    SX_UPW(ref, (size_t)b->ref_bytes)
+    if (b->cand_snv)
+    {
+        SX_UPW(cand_snv, (size_t)b->n_cand_snv * 4)
+    }
+    else ++slot;
+#undef SX_UPW
+    SX_CUDA(ctx, cudaEventRecord(e1, st));
+    // device outputs for whatever the caller wants back
+    sx_window_out o;
+    memset(&o, 0, sizeof(o));
+    const size_t n_slots(n ? b->rec_off[n] : 0);
+    auto want = [&](const void* host, size_t bytes, void** dev) -> int {
+        *dev = nullptr;
+        if (!host) return SX_OK;
+        return sx_ensure(ctx, slot++, bytes + 80, dev);
+    };
+#define SX_WANT(field, bytes)                                                            \
+    if ((rc = want(out->field, (size_t)(bytes), reinterpret_cast<void**>(&o.field)))) return rc;
+    SX_WANT(gate, n)
+    SX_WANT(enum_status, n)
+    SX_WANT(realign_status, n)
+    SX_WANT(best_pos, (size_t)n * 4)
+    SX_WANT(best_seg_off, ((size_t)n + 1) * 4)
+    SX_WANT(best_n_seg, (size_t)n * 2)
+    SX_WANT(best_segs, (size_t)out->cap_best_segs * sizeof(sx_aln_seg))
+    o.cap_best_segs = out->cap_best_segs;
+    SX_WANT(recs, (n_slots + 1) * sizeof(sx_read_indel_score))
+    SX_WANT(n_rec, (size_t)n * 4)
+    SX_WANT(cols.site_off, ((size_t)n_sites + 1) * 4)
+    SX_WANT(cols.t2_off, ((size_t)n_sites + 1) * 4)
+    SX_WANT(cols.n_spandel, (size_t)n_sites * 4)
+    SX_WANT(cols.n_submapped, (size_t)n_sites * 4)
+    SX_WANT(cols.calls, (size_t)out->cols.calls_capacity * 2)
+    SX_WANT(cols.t2_calls, (size_t)out->cols.t2_capacity * 2)
+    o.cols.calls_capacity = out->cols.calls_capacity;
+    o.cols.t2_capacity = out->cols.t2_capacity;
+    SX_WANT(site_gl, (size_t)n_sites * sizeof(sx_digt_result))
+    SX_WANT(variant_sites, (size_t)out->cap_variant_sites * sizeof(sx_site_call))
+    o.cap_variant_sites = out->cap_variant_sites;
+#undef SX_WANT
+    uint32_t totals[SX_WIN_TOTALS];
+    memset(totals, 0, sizeof(totals));
+    rc = sx_process_window_dev(ctx, &d, &o, totals);
+    if (totals_host) memcpy(totals_host, totals, sizeof(totals));
+    if (rc) return rc;
+    const float kernel_ms(ctx->timing.kernel_ms);
+    const uint32_t launches(ctx->timing.launches);
+    cudaEventElapsedTime(&h2d_ms, e0, e1);
+    SX_CUDA(ctx, cudaEventRecord(e0, st));
+    auto down = [&](void* host, const void* dev, size_t bytes) -> int {
+        if (host && dev && bytes) SX_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st));
+        return SX_OK;
+    };
+    if ((rc = down(out->gate, o.gate, n))) return rc;
+    if ((rc = down(out->enum_status, o.enum_status, n))) return rc;
+    if ((rc = down(out->realign_status, o.realign_status, n))) return rc;
+    if ((rc = down(out->best_pos, o.best_pos, (size_t)n * 4))) return rc;
+    if ((rc = down(out->best_seg_off, o.best_seg_off, ((size_t)n + 1) * 4))) return rc;
+    if ((rc = down(out->best_n_seg, o.best_n_seg, (size_t)n * 2))) return rc;
+    if ((rc = down(out->best_segs, o.best_segs, (size_t)totals[5] * sizeof(sx_aln_seg)))) return rc;
+    if ((rc = down(out->recs, o.recs, n_slots * sizeof(sx_read_indel_score)))) return rc;
+    if ((rc = down(out->n_rec, o.n_rec, (size_t)n * 4))) return rc;
+    if ((rc = down(out->cols.site_off, o.cols.site_off, ((size_t)n_sites + 1) * 4))) return rc;
+    if ((rc = down(out->cols.t2_off, o.cols.t2_off, ((size_t)n_sites + 1) * 4))) return rc;
+    if ((rc = down(out->cols.n_spandel, o.cols.n_spandel, (size_t)n_sites * 4))) return rc;
+    if ((rc = down(out->cols.n_submapped, o.cols.n_submapped, (size_t)n_sites * 4))) return rc;
+    if ((rc = down(out->cols.calls, o.cols.calls, (size_t)totals[6] * 2))) return rc;
+    if ((rc = down(out->cols.t2_calls, o.cols.t2_calls, (size_t)totals[7] * 2))) return rc;
+    if ((rc = down(out->site_gl, o.site_gl, (size_t)n_sites * sizeof(sx_digt_result)))) return rc;
+    if ((rc = down(out->variant_sites, o.variant_sites, (size_t)std::min(totals[8], out->cap_variant_sites) * sizeof(sx_site_call)))) return rc;
+    if (out->totals) memcpy(out->totals, totals, sizeof(totals));
+    SX_CUDA(ctx, cudaEventRecord(e1, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&d2h_ms, e0, e1);
+    ctx->timing.kernel_ms = kernel_ms;
+    ctx->timing.h2d_ms = h2d_ms;
+    ctx->timing.d2h_ms = d2h_ms;
+    ctx->timing.launches = launches;
+    return SX_OK;
 }

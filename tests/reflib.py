@@ -468,12 +468,12 @@ def ref_realign_and_score_read(gb: "B.GateBatch", quals: np.ndarray, retain_soft
     segs = np.zeros((n + 1) * max_segs, dtype=A.ALN_SEG_DT)
     err = _err()
     fn = ref().ref_realign_and_score_read_ex
-    fn.argtypes = [C.POINTER(A.SxGateBatch), C.POINTER(A.SxEnumBatch)] + [_P] * 9 + [C.c_int, C.c_int, C.c_double] + [_P] * 4 + [C.c_uint32] + [_P] * 4 + [C.c_char_p, C.c_int]
+    fn.argtypes = [C.POINTER(A.SxGateBatch), C.POINTER(A.SxEnumBatch)] + [_P] * 10 + [C.c_int, C.c_int, C.c_double] + [_P] * 4 + [C.c_uint32] + [_P] * 4 + [C.c_char_p, C.c_int]
     recs = n_rec = None
     if rec_off is not None:
         recs, n_rec = np.zeros(int(rec_off[n]) + 1, A.READ_INDEL_SCORE_DT), np.zeros(n + 1, np.uint32)
     secs = C.c_double(0.0)
-    rc = fn(C.byref(gb.c), C.byref(eb.c) if full_window else None, A.ptr(eb.ins_pool), A.ptr(eb.ins_off), A.ptr(eb.ref_pool), A.ptr(eb.ref_off), A.ptr(eb.ref_begin),
+    rc = fn(C.byref(gb.c), C.byref(eb.c) if full_window else None, A.ptr(eb.ins_pool), A.ptr(eb.ins_off), A.ptr(eb.ref_pool), A.ptr(eb.ref_off), None, A.ptr(eb.ref_begin),
             A.ptr(eb.read_pool), A.ptr(eb.read_off), A.ptr(quals), A.ptr(read_flags), 1 if retain_soft else 0, 1 if is_smoothed else 0, smoothed_range, A.ptr(status),
             A.ptr(pos), A.ptr(nseg), A.ptr(segs), max_segs, A.ptr(rec_off), A.ptr(recs), A.ptr(n_rec), C.addressof(secs), err, 1024)
     if rc != 0:

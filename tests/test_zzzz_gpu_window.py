@@ -47,3 +47,31 @@ def test_window_equals_the_reference(ctx, block):
             for k in tot:
                 tot[k] += s[k]
     assert tot["realigned"] > 0 and tot["records"] > 0 and tot["calls"] > 0, tot
+
+
+@pytest.mark.parametrize("qual_bits,seed", [(4, 1), (8, 2), (4, 3)])
+def test_synthetic_cfg2_window_equals_the_reference(ctx, qual_bits, seed):
+    """bench.py's workload (tools/synth_window.cpp: a contig tiled by candidate loci at 30x, mapper-style alignments) through the one-call pass
+    against the reference's realignAndScoreRead + pileup_read_segment + position_snp_call_pprob_digt on the same arrays: best alignments,
+    score_indels records, columns (in read-buffer order across loci) and site results."""
+    import os
+    import sys
+
+    if not reflib.have_ref():
+        pytest.skip("oracle/_ref/libstrelka_ref.so not built")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import window_workload as WW
+    from strelka_b200.api import DevWindow
+
+    w = WW.make_window(WW.load_synth(), 400, seed, tile=seed, qual_bits=qual_bits, ascii_reads=True)
+    dw = DevWindow(ctx, w)
+    dw.run()
+    d = dw.download()
+    dw.run()  # a second pass over the same buffers (the region records were rewritten by the first)
+    d2 = dw.download()
+    dw.free()
+    res, _secs = WW.reference_pass(w)
+    stats = WW.compare_with_reference(w, d, res)
+    for k in d:
+        assert np.asarray(d[k]).tobytes() == np.asarray(d2[k]).tobytes(), k
+    assert stats["realigned"] > 5000 and stats["records"] > 10000 and stats["variant_sites"] > 50, stats

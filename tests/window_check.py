@@ -44,6 +44,9 @@ def single_region_windows(eb, raw):
         reads, raw1 = [], []
         for r in order:
             seq = bytes(eb.read_pool[int(eb.read_off[r]) : int(eb.read_off[r + 1])]).decode()
+            # '=' and IUPAC codes cannot be piled up (base_to_id ends the reference's process; K4 reports them): such bases become 'N' here --
+            # their handling by the search front is tests/test_enumerate.py's and the chain tests' subject
+            seq = "".join(c if c in "ACGTN" else "N" for c in seq)
             al = (int(eb.in_pos[r]), [(B.AP_CHAR[int(s["kind"])], int(s["len"])) for s in eb.in_segs[int(eb.in_seg_off[r]) : int(eb.in_seg_off[r + 1])]])
             use = [int(x) for x in eb.use_keys[int(eb.use_key_off[r]) : int(eb.use_key_off[r + 1])]]
             reads.append(B.EnumReadSpec(seq, al[0], al[1], use))
@@ -70,54 +73,31 @@ def parse_k4(cig):
     return out
 
 
-def check_window(ctx, eb, gb, pools=None, read_flags=None, mapq=None, quals=None, params=None, report=None):
-    """one window through sx_process_window_dev and through the reference; returns counters.  `quals`: the per-base qualities as the
-    reference harness takes them (one byte per base, reads back to back) -- None: B.read_pools_of's constant 30."""
-    from strelka_b200.api import DevWindow
-
-    pools = pools or B.read_pools_of(eb)
+def reference_window(eb, gb, w, quals=None, params=None):
+    """the window through the reference, stage by stage: per-read (status, best alignment as (pos, cigar in K4 letters), records), the
+    columns and the site results (None when the reference threw on a read: its process would have stopped there)"""
     n = eb.n_reads
-    w = B.WindowBatch.from_enum(eb, gb, pools, read_flags=read_flags, mapq=mapq, report=report)
-    dw = DevWindow(ctx, w)
-    ms = dw.run()
-    d = dw.download()
-    dw.free()
     if quals is None:
         quals = np.full(int(eb.read_off[n]) + 1, 30, np.uint8)
     flags = w.a["read_flags"]
     k6_flags = (flags[: n + 1] & 3).astype(np.uint8)  # SX_SIF_FWD / SX_SIF_TIER1 are SX_PRF_FWD / SX_PRF_TIER1
     submapped = (flags[:n] & A.SX_PRF_TIER1OR2) == 0
     ref_status, want, r_recs, r_n_rec = reflib.ref_realign_and_score_read(gb, quals, read_flags=k6_flags, rec_off=w.a["rec_off"])
-    seg_off, segs = d["best_seg_off"], d["best_segs"]
-    stats = {"reads": n, "realigned": 0, "records": 0, "threw": int((ref_status == 2).sum()), "calls": 0, "sites": 0, "stage_ms": ms}
-    best = []  # getBestAlignment() of every read as the reference has it
+    exp = {"status": ref_status, "want": want, "recs": r_recs, "n_rec": r_n_rec, "submapped": submapped, "best": [], "cols": None, "gl": None}
+    raws = []
     for r in range(n):
-        raw = (int(gb.raw_pos[r]), "".join(f"{int(s['len'])}{B.AP_CHAR[int(s['kind'])]}" for s in gb.raw_segs[int(gb.seg_off[r]) : int(gb.seg_off[r + 1])]).replace("=", "M").replace("X", "M"))
-        got = (int(d["best_pos"][r]), cigar_of(segs[int(seg_off[r]) : int(seg_off[r]) + int(d["best_n_seg"][r])]))
-        if submapped[r]:  # align_pos :746: never handed to realignAndScoreRead
-            assert not (int(d["gate"][r]) & A.SX_GATE_REALIGN) and got == raw, (r, got, raw)
-            best.append(raw)
-            continue
-        if ref_status[r] == 2:
-            best.append(None)
-            continue
-        assert not (int(d["enum_status"][r]) & A.SX_ENUM_ST_LIMIT), (r, "a per-read capacity of the search")
-        if want[r] is None:
-            assert not (int(d["realign_status"][r]) & A.SX_REALIGN_ST_REALIGNED), (r, int(d["realign_status"][r]))
-            assert got == raw, (r, got, raw)
-            best.append(raw)
+        raw_path = [(B.AP_CHAR[int(s["kind"])], int(s["len"])) for s in gb.raw_segs[int(gb.seg_off[r]) : int(gb.seg_off[r + 1])]]
+        raw = (int(gb.raw_pos[r]), "".join(f"{ln}{t}" for t, ln in raw_path).replace("=", "M").replace("X", "M"))
+        raws.append((raw, raw_path))
+        if submapped[r] or (ref_status[r] != 2 and want[r] is None):
+            exp["best"].append(raw)
+        elif ref_status[r] == 2:
+            exp["best"].append(None)
         else:
-            stats["realigned"] += 1
-            ref_al = (want[r][0], want[r][1].replace("=", "M").replace("X", "M"))
-            assert int(d["realign_status"][r]) & A.SX_REALIGN_ST_REALIGNED, (r, int(d["realign_status"][r]), want[r])
-            assert got == ref_al, (r, got, ref_al)
-            best.append(ref_al)
-        o = int(w.a["rec_off"][r])
-        assert int(d["n_rec"][r]) == int(r_n_rec[r]), (r, int(d["n_rec"][r]), int(r_n_rec[r]))
-        assert d["recs"][o : o + int(d["n_rec"][r])].tobytes() == r_recs[o : o + int(r_n_rec[r])].tobytes(), r
-        stats["records"] += int(r_n_rec[r])
-    if stats["threw"]:
-        return stats  # the reference process would have stopped at the throw: no pile-up to compare
+            exp["best"].append((want[r][0], want[r][1].replace("=", "M").replace("X", "M")))
+    exp["raw"] = [x[0] for x in raws]
+    if (ref_status[~submapped] == 2).any():
+        return exp
     # ---- the pile-up: the reference's pileup_read_segment on ITS best alignments, in read-buffer order
     specs, bpos = [], []
     for r in range(n):
@@ -125,12 +105,12 @@ def check_window(ctx, eb, gb, pools=None, read_flags=None, mapq=None, quals=None
         q = quals[int(eb.read_off[r]) : int(eb.read_off[r + 1])]
         f = int(flags[r])
         tier = 1 if f & A.SX_PRF_TIER1 else (2 if f & A.SX_PRF_TIER1OR2 else 0)
-        raw_path = [(B.AP_CHAR[int(s["kind"])], int(s["len"])) for s in gb.raw_segs[int(gb.seg_off[r]) : int(gb.seg_off[r + 1])]]
+        raw_path = raws[r][1]
         bpos.append(buffer_pos_of(int(gb.raw_pos[r]), raw_path))
-        sp = B.PileupReadSpec(B.codes_of(seq), q, best[r][0], parse_k4(best[r][1]), fwd=bool(f & A.SX_PRF_FWD), mapq=int(w.a["mapq"][r]), tier=tier)
+        sp = B.PileupReadSpec(B.codes_of(seq), q, exp["best"][r][0], parse_k4(exp["best"][r][1]), fwd=bool(f & A.SX_PRF_FWD), mapq=int(w.a["mapq"][r]), tier=tier)
         # pileup_read_segment :1145-1148: a read that was not realigned and has no alignment with indels the caller handles is not piled up
-        sp.skip = want[r] is None and not submapped[r] and any(t in "ID" and ln > eb.opts.max_indel_size for t, ln in raw_path[1:-1])
-        sp.skip = sp.skip or (submapped[r] and any(t in "ID" and ln > eb.opts.max_indel_size for t, ln in raw_path[1:-1]))
+        not_realigned = submapped[r] or want[r] is None
+        sp.skip = bool(not_realigned and any(t in "ID" and ln > eb.opts.max_indel_size for t, ln in raw_path[1:-1]))
         specs.append(sp)
     ref_str = bytes(w.a["ref"][: w.used["ref"]]).decode()
     pb = B.PileupReadsBatch(specs, ref_str, w.ref_begin, w.report_begin, w.report_end, buffer_pos=bpos)
@@ -138,17 +118,54 @@ def check_window(ctx, eb, gb, pools=None, read_flags=None, mapq=None, quals=None
         if sp.skip:
             pb.reads["flags"][r] |= A.SX_PRF_SKIP
     cols = reflib.ref_pileup_reads(pb) if reflib.have_ref() else reflib.ox_pileup_reads(pb)
-    got_cols = (d["site_off"], d["calls"], d["t2_off"], d["t2_calls"], d["n_spandel"], d["n_submapped"])
-    for wv, gv, name in zip(cols, got_cols, COL_NAMES):
-        assert np.array_equal(wv, gv), name
-    stats["calls"] = int(cols[0][-1])
-    # ---- per-site germline genotyping on the reference's columns
-    ns = w.n_sites
+    exp["cols"] = cols
     ref_base = np.frombuffer(ref_str[w.report_begin - w.ref_begin : w.report_end - w.ref_begin].encode(), dtype=np.uint8).copy()
     k2 = B.PileupBatch(cols[0].copy(), np.concatenate([cols[1], np.zeros(16, np.uint16)]), ref_base, None)
     params = params or A.default_params()
-    gl = reflib.ref_germline(params, k2, True) if reflib.have_ref() else reflib.ox_germline(params, k2, True)
-    g = d["site_gl"]
+    exp["gl"] = reflib.ref_germline(params, k2, True) if reflib.have_ref() else reflib.ox_germline(params, k2, True)
+    return exp
+
+
+def check_window(ctx, eb, gb, pools=None, read_flags=None, mapq=None, quals=None, params=None, report=None, dry=False):
+    """one window through sx_process_window_dev and through the reference; returns counters.  `quals`: the per-base qualities as the
+    reference harness takes them (one byte per base, reads back to back) -- None: B.read_pools_of's constant 30.  dry: only the reference side."""
+    pools = pools or B.read_pools_of(eb)
+    n = eb.n_reads
+    w = B.WindowBatch.from_enum(eb, gb, pools, read_flags=read_flags, mapq=mapq, report=report)
+    exp = reference_window(eb, gb, w, quals, params)
+    stats = {"reads": n, "realigned": 0, "records": 0, "threw": int((exp["status"] == 2).sum()), "calls": 0, "sites": 0, "stage_ms": {}}
+    if dry:
+        return stats
+    from strelka_b200.api import DevWindow
+
+    dw = DevWindow(ctx, w)
+    stats["stage_ms"] = dw.run()
+    d = dw.download()
+    dw.free()
+    seg_off, segs = d["best_seg_off"], d["best_segs"]
+    for r in range(n):
+        got = (int(d["best_pos"][r]), cigar_of(segs[int(seg_off[r]) : int(seg_off[r]) + int(d["best_n_seg"][r])]))
+        if exp["submapped"][r]:  # align_pos :746: never handed to realignAndScoreRead
+            assert not (int(d["gate"][r]) & A.SX_GATE_REALIGN) and got == exp["raw"][r], (r, got, exp["raw"][r])
+            continue
+        if exp["status"][r] == 2:
+            continue
+        assert not (int(d["enum_status"][r]) & A.SX_ENUM_ST_LIMIT), (r, "a per-read capacity of the search")
+        realigned = exp["want"][r] is not None
+        assert bool(int(d["realign_status"][r]) & A.SX_REALIGN_ST_REALIGNED) == realigned, (r, int(d["realign_status"][r]), exp["want"][r])
+        assert got == exp["best"][r], (r, got, exp["best"][r])
+        stats["realigned"] += int(realigned)
+        o = int(w.a["rec_off"][r])
+        assert int(d["n_rec"][r]) == int(exp["n_rec"][r]), (r, int(d["n_rec"][r]), int(exp["n_rec"][r]))
+        assert d["recs"][o : o + int(d["n_rec"][r])].tobytes() == exp["recs"][o : o + int(exp["n_rec"][r])].tobytes(), r
+        stats["records"] += int(exp["n_rec"][r])
+    if exp["cols"] is None:
+        return stats  # the reference process would have stopped at the throw: no pile-up to compare
+    got_cols = (d["site_off"], d["calls"], d["t2_off"], d["t2_calls"], d["n_spandel"], d["n_submapped"])
+    for wv, gv, name in zip(exp["cols"], got_cols, COL_NAMES):
+        assert np.array_equal(wv, gv), name
+    stats["calls"] = int(exp["cols"][0][-1])
+    gl, g = exp["gl"], d["site_gl"]
     for f in ("ref_gt", "is_computed", "n_used_calls", "phredLoghood"):
         assert np.array_equal(gl[f], g[f]), f
     assert np.array_equal(gl["lhood"].view(np.uint32), g["lhood"].view(np.uint32)), "lhood"
@@ -156,5 +173,5 @@ def check_window(ctx, eb, gb, pools=None, read_flags=None, mapq=None, quals=None
         for f in ("max_gt", "snp_qphred", "max_gt_qphred"):
             assert np.array_equal(gl[rs][f], g[rs][f]), (rs, f)
         assert np.allclose(gl[rs]["ref_pprob"], g[rs]["ref_pprob"], rtol=1e-12, atol=0), (rs, "ref_pprob")
-    stats["sites"] = ns
+    stats["sites"] = w.n_sites
     return stats
