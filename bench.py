@@ -1,18 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- the hot path of Strelka2's per-locus scoring on synthetic BASELINE.json workloads.
+"""bench.py -- Strelka2's per-locus hot path on BASELINE.json's cfg2 ("synthetic 30x germline pileup, 150 bp reads, 1M candidate loci").
 
-One "step" = one pass of the hot path over one batch of candidate loci:
-    K1  score_alignments   every read x every candidate haplotype path of the locus      (+ per-read max epilogue)
-    K2a site_gl_germline   the locus's pileup column -> genotype likelihoods, PLs, posteriors
-    K3  global_align       haplotype-vs-reference DP for the loci that sit in an active region (50 %, 3 haplotypes each)
-At N GPUs the loci shard across ranks with no data-path collective; each step ends with ONE NCCL gather of the per-locus
-call records to rank 0 (weak scaling: per-GPU work is fixed).
+One "step" = one pass of the WHOLE path over the step's candidate loci, from the mapper's alignments to call records:
+    per read    realignAndScoreRead: gates -> candidate-alignment search -> scoreCandidateAlignment of every candidate -> score_indels,
+                choice of rseg.realignment                                   (K7g, K7a, K7, K7b, K1, K6, K9)
+    per read    pileup_read_segment in read-buffer order                     (K4)
+    per site    position_snp_call_pprob_digt, every position (gVCF)         (K2a)
+    per region  GlobalAligner haplotype-vs-reference DP for the loci in an active region (half of them, 3 haplotypes each)   (K3)
+on ONE description of the data (tools/synth_window.cpp: a contig tiled by candidate loci 300 bp apart, 60 reads of 150 bp per locus = 30x,
+mapper-style alignments, 3 candidate alleles per locus), processed window by window (sx_process_window_dev, every intermediate in HBM).
+At N GPUs the windows shard across ranks with no data-path collective; each step ends with ONE NCCL gather (variable block sizes) of the
+variant-site call records to rank 0 (weak scaling: per-GPU work is fixed).
 
     python bench.py [--gpus N --steps K --warmup W]            our arm (CUDA, sm_100a)
-    python bench.py --impl reference [...]                      the CPU arm: the path's CPU implementation on the host cores
+    python bench.py --impl reference [...]                      the CPU arm: the reference's own functions on the host cores, one process per core
+    python bench.py --config cfg2-scoring                       round 1's step (scoring only: K1 + read-max + K2a + K3 on pre-enumerated alignments)
 
-Prints ONE JSON line (see the contract in the task statement): value = candidate loci / s with inputs resident in HBM,
-e2e = the same through the C-ABI with pinned HOST buffers (H2D + kernels + D2H inside the timed region).
+Prints ONE JSON line (see the contract in the task statement): value = candidate loci / s with inputs resident in HBM, e2e = the same through
+the C ABI with pinned HOST arrays (H2D + kernels + D2H inside the timed region).
 """
 from __future__ import annotations
 
@@ -33,11 +38,14 @@ sys.path.insert(0, ROOT)
 from strelka_b200 import _abi as A  # noqa: E402
 from strelka_b200 import batch as B  # noqa: E402
 
-CONFIGS = {
-    # name: (n_loci, depth, read_len, n_haps, description)
+CONFIGS = {  # the scoring-only step's configurations: name: (n_loci, depth, read_len, n_haps, description)
     "cfg2": (1_000_000, 30, 150, 4, "synthetic 30x germline pileup, 150 bp reads, 1M candidate loci, 4 haplotypes/locus"),
     "cfg5": (10_000, 300, 150, 32, "300x high-depth amplicon, 32 haplotypes/locus (regions of 16 reads)"),
     "tiny": (20_000, 30, 150, 4, "cfg2 shape at 20k loci (plumbing)"),
+}
+WHOLE_PATH = {  # the whole-path step: name: (candidate loci per GPU, loci per window, description)
+    "cfg2": (1_000_000, 100_000, "synthetic 30x germline pileup, 150 bp reads, 1M candidate loci (300 bp apart, 3 candidate alleles each): whole path, mapper alignments in, call records out"),
+    "tiny": (20_000, 10_000, "cfg2 shape at 20k loci (plumbing)"),
 }
 
 
@@ -637,25 +645,15 @@ def cpu_pass(ab: B.AlignBatch, pb: B.PileupBatch, gb: B.GaBatch, n_sample_loci: 
     return n, max(busy), ("reference" if use_ref else "port")
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
-    ap.add_argument("--loci", type=int, default=0, help="override the number of candidate loci per GPU")
-    ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-pileup", action="store_true", help="skip the K4 pileup_reads leg (SURVEY 8f1) measured beside the headline step")
-    ap.add_argument("--cpu-sample-loci", type=int, default=0)
-    args = ap.parse_args()
+def scoring_step_main(args):
+    """round 1's step (--config cfg2-scoring / cfg5 / tiny-scoring): K1 + read-max + K2a + K3 on pre-enumerated candidate alignments"""
     assert args.warmup >= 0 and args.steps >= 1
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    n_loci, depth, read_len, n_haps, desc = CONFIGS[args.config]
+    cfg_name = args.config.replace("-scoring", "")
+    n_loci, depth, read_len, n_haps, desc = CONFIGS[cfg_name]
     rpr = 16 if depth > 64 else 0  # deep loci are cut into regions small enough for the K1 fast path's 60 KB of shared memory
     if args.loci:
         n_loci = args.loci
@@ -831,8 +829,8 @@ def main():
         traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch from the committed ncu --set full capture
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            if args.config in tj and n_loci == CONFIGS[args.config][0]:
-                t = tj[args.config]["k1q_score_kernel"]
+            if cfg_name in tj and n_loci == CONFIGS[cfg_name][0]:
+                t = tj[cfg_name]["k1q_score_kernel"]
                 traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
         except Exception:
             pass
@@ -860,7 +858,7 @@ def main():
             line["cpu_baseline"] = {"value": n / t_cpu, "unit": "loci/s", "cores": ncpu, "kind": kind,
                                     "sample": f"first {n} loci of the workload, one pass, {ncpu} host threads, "
                                               + ("oracle/_ref/libstrelka_ref.so (the reference's own functions)" if kind == "reference" else "oracle/liboracle.so")}
-            if not args.no_pileup and args.config != "tiny":
+            if args.legs and cfg_name != "tiny":
                 line["k4_pileup"] = k4_pileup_leg(ctx, peak)
                 ctx.score_alignments_dev(dab)  # the scores K6 consumes: K1's own output buffer, never copied out
                 line["k6_score_indels"] = k6_score_indels_leg(ctx, synth, peak, n_loci, depth, read_len, n_haps, args.seed + 1000 * rank, threads, rpr, dab.out)
@@ -879,6 +877,440 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# host cores this process may really use
+# ----------------------------------------------------------------------------------------------------------------------
+def usable_cpus():
+    """(count, cpu ids to pin to, how it was found).  os.cpu_count() is the machine's; what a container may use is the smaller of its CPU
+    affinity and its cgroup CPU quota (the round-1 CPU arm ran 128 threads under a 16-CPU quota and measured the throttling)."""
+    aff = sorted(os.sched_getaffinity(0))
+    n, how = len(aff), f"affinity {len(aff)}"
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    if quota is not None and quota < n:
+        n, how = max(1, int(quota)), f"cgroup cpu quota {quota:g} (affinity {len(aff)}, machine {os.cpu_count()})"
+    # one hardware thread per physical core first
+    seen, first, rest = set(), [], []
+    for c in aff:
+        try:
+            sib = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
+        except Exception:
+            sib = str(c)
+        (rest if sib in seen else first).append(c)
+        seen.add(sib)
+    ids = (first + rest)[:n]
+    return n, ids, how
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the CPU arm: the reference's own functions, one PROCESS per usable core (its likelihood caches are function-local statics), pinned
+# ----------------------------------------------------------------------------------------------------------------------
+def reference_worker(args):
+    """one worker of the CPU arm: its own window of --worker-loci candidate loci through the reference (tools/window_workload.reference_pass)
+    + its share of the haplotype DP problems; prints one JSON line with the seconds of every pass"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import window_workload as WW
+
+    if args.worker_cpu >= 0:
+        try:
+            os.sched_setaffinity(0, {args.worker_cpu})
+        except Exception:
+            pass
+    synth = WW.load_synth()
+    L = args.worker_loci
+    w = WW.make_window(synth, L, args.seed, tile=1000 + args.worker_index, qual_bits=8, threads=1, ascii_reads=True)
+    n_ga = (L // 2) * 3
+    q_off, r_off = np.zeros(n_ga + 1, np.uint32), np.zeros(n_ga + 1, np.uint32)
+    tot = synth.synth_ga(n_ga, C.c_uint64(args.seed + args.worker_index), 1, C.c_void_p(q_off.ctypes.data), C.c_void_p(r_off.ctypes.data), None, None)
+    query, gref = np.zeros((tot & 0xFFFFFFFF) + 16, np.uint8), np.zeros((tot >> 32) + 16, np.uint8)
+    synth.synth_ga(n_ga, C.c_uint64(args.seed + args.worker_index), 1, C.c_void_p(q_off.ctypes.data), C.c_void_p(r_off.ctypes.data), C.c_void_p(query.ctypes.data), C.c_void_p(gref.ctypes.data))
+    gb = A.SxGaBatch(n_ga, A.ptr(query), A.ptr(gref), A.ptr(q_off), A.ptr(r_off), 24)
+    gres, gcig = np.zeros(max(1, n_ga), A.GA_RESULT_DT), np.zeros((max(1, n_ga), 24), np.uint32)
+    sc = A.SxGaScores(1, -4, -5, -1, -100, -5, 1, 1)
+    rf = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libstrelka_ref.so"))
+    err = C.create_string_buffer(512)
+    passes = []
+    for i in range(args.warmup + args.steps):
+        res, secs = WW.reference_pass(w)
+        t0 = time.perf_counter()
+        rc = rf.ref_global_align(C.byref(sc), C.byref(gb), 0, C.c_void_p(gres.ctypes.data), C.c_void_p(gcig.ctypes.data), err, 512)
+        assert rc == 0, err.value
+        secs["global_align"] = time.perf_counter() - t0
+        if i >= args.warmup:
+            passes.append(secs)
+    print(json.dumps({"worker": args.worker_index, "loci": L, "passes": passes, "realigned": int((res["status"] == 1).sum()), "threw": int((res["status"] == 2).sum())}))
+
+
+def run_reference_workers(n_workers, cpu_ids, loci, steps, warmup, seed, timeout=900):
+    procs = []
+    for i in range(n_workers):
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-worker", "--worker-index", str(i), "--worker-loci", str(loci), "--worker-cpu",
+               str(cpu_ids[i % len(cpu_ids)] if cpu_ids else -1), "--steps", str(steps), "--warmup", str(warmup), "--seed", str(seed)]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))  # (stderr: the reference's theta-file warning, once per options object)
+    outs = []
+    for pr in procs:
+        try:
+            o, _ = pr.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            pr.kill()
+            raise SystemExit("bench.py: a reference worker did not finish")
+        lines = [ln for ln in o.splitlines() if ln.startswith("{")]
+        if pr.returncode != 0 or not lines:
+            raise SystemExit(f"bench.py: a reference worker failed (rc {pr.returncode})")
+        outs.append(json.loads(lines[-1]))
+    return outs
+
+
+PASS_PARTS = ("realign", "pileup", "site_gl", "global_align")
+
+
+def summarize_reference(outs, steps):
+    """per pass the workers run concurrently on distinct cores: a pass lasts as long as its slowest worker"""
+    loci = sum(o["loci"] for o in outs)
+    per_pass = [max(sum(o["passes"][k][p] for p in PASS_PARTS) for o in outs) for k in range(steps)]
+    per_worker = [sum(sum(o["passes"][k][p] for p in PASS_PARTS) for k in range(steps)) / steps for o in outs]
+    t = sum(per_pass)
+    parts = {p: float(np.mean([o["passes"][k][p] for o in outs for k in range(steps)])) for p in PASS_PARTS}
+    return {"loci_per_pass": loci, "seconds": t, "value": loci * steps / t, "per_core_loci_per_s_median": float(np.median([outs[0]["loci"] / x for x in per_worker])),
+            "per_core_loci_per_s_min": float(min(outs[0]["loci"] / x for x in per_worker)), "mean_seconds_per_part": parts, "threw": sum(o["threw"] for o in outs)}
+
+
+def reference_main(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    n_loci, tile_loci, desc = WHOLE_PATH[args.config]
+    n, ids, how = usable_cpus()
+    L = args.cpu_sample_loci or 240
+    outs = run_reference_workers(n, ids, L, args.steps, args.warmup, args.seed)
+    r = summarize_reference(outs, args.steps)
+    if r["per_core_loci_per_s_median"] < 60:
+        raise SystemExit(f"bench.py --impl reference: {r['per_core_loci_per_s_median']:.1f} loci/s per core -- the host cores are oversubscribed or throttled; not a usable baseline")
+    line = {
+        "impl": "reference", "metric": "candidate_loci_per_sec", "value": r["value"], "unit": "loci/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {desc}", "loci_per_step": r["loci_per_pass"], "depth": 30, "read_len": 150, "step": "whole path (realignAndScoreRead + pileup_read_segment + "
+                   "position_snp_call_pprob_digt at every position + GlobalAligner)", "note": "bounded sample of the workload (one window per core); throughput is per locus"},
+        "cpu_baseline": {"value": r["value"], "unit": "loci/s", "cores": n, "kind": "reference", "cores_how": how,
+                         "sample": f"{n} processes x {L} loci x {args.steps} passes, each pinned to one core, oracle/_ref/libstrelka_ref.so (the reference's own functions, timed inside the harness: "
+                                   "the object construction around them is left out)",
+                         "per_core_loci_per_s": {"median": r["per_core_loci_per_s_median"], "min": r["per_core_loci_per_s_min"]}, "mean_seconds_per_part": r["mean_seconds_per_part"]},
+        "e2e": {"value": r["value"], "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm: the whole path, window by window
+# ----------------------------------------------------------------------------------------------------------------------
+def stage_bytes(w, t):
+    """algorithmic bytes of every stage of one window (t: its totals): what the stage must read and write at the least, every array once"""
+    n, nr, nk, ns = w.n_reads, w.n_regions, w.n_keys, w.n_sites
+    nA, nS, nK, k1S, k1I, bestS, calls = (int(x) for x in t[:7])
+    qual = w.used["qual"]
+    raw = n * (4 + 4) + w.n_raw_segs * 4
+    win = nk * A.INDEL_KEY_DT.itemsize + (nr + 1) * 8
+    enum_csr = nA * (4 + 4 + 4 + 2 + 2) + nS * 4 + nK * 2 + n * 5
+    return {
+        "prep": w.used["seq4"] + raw + n * 16,
+        "k7g_gates": raw + win + n * 3 + n * 5 + w.n_raw_segs * 4,
+        "k7a_keys": w.used["seq4"] + w.used["ref"] + raw + win + n * 10,
+        "k7_enumerate": raw + win + n * 12 + enum_csr,
+        "k7b_link": enum_csr + win + nA * 16 + k1S * 4 + k1I + nS * 4,
+        "k1_score": w.used["seq4"] + qual + w.used["ref"] + nr * 48 + nA * 16 + k1S * 4 + k1I + nA * 8,
+        "k6_score_indels": enum_csr + nA * 8 + win + n * 9 + n * 3 * 32 + n * 12,
+        "k9_choose": enum_csr + nA * 8 + raw + win + bestS * 4 + n * 15,
+        "k4_pileup": w.used["seq4"] + qual + w.used["ref"] + bestS * 4 + n * 24 + calls * 2 + ns * 16,
+        "k2a_site_gl": calls * 2 + ns * 5 + ns * A.DIGT_RESULT_DT.itemsize,
+    }
+
+
+def whole_path_main(args):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import window_workload as WW
+    from strelka_b200.api import Context, DevGaBatch, DeviceArray, DevWindow
+
+    assert args.warmup >= 0 and args.steps >= 1
+    rank, local_rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    n_loci, tile_loci, desc = WHOLE_PATH[args.config]
+    if args.loci:
+        n_loci = args.loci
+    tile_loci = min(args.tile_loci or tile_loci, n_loci)
+    n_tiles = (n_loci + tile_loci - 1) // tile_loci
+    n_loci = n_tiles * tile_loci
+    ncpu, cpu_ids, cpu_how = usable_cpus()
+    threads = max(1, ncpu // max(1, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; strelka_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = Context(local_rank)
+    lib = ctx.lib
+    synth = WW.load_synth()
+    alloc = HostAlloc(lib, True)
+    t_gen = time.perf_counter()
+    tiles = [WW.make_window(synth, tile_loci, args.seed + 7919 * rank, tile=t, qual_bits=4, threads=threads, alloc=alloc.array) for t in range(n_tiles)]
+    # K3: 3 haplotypes for half of the loci
+    n_ga = (n_loci // 2) * 3
+    q_off, r_off = alloc.array((n_ga + 1) * 4, np.uint32), alloc.array((n_ga + 1) * 4, np.uint32)
+    tot = synth.synth_ga(n_ga, C.c_uint64(args.seed + rank), threads, C.c_void_p(q_off.ctypes.data), C.c_void_p(r_off.ctypes.data), None, None)
+    query, gref = alloc.array((tot & 0xFFFFFFFF) + 16, np.uint8), alloc.array((tot >> 32) + 16, np.uint8)
+    synth.synth_ga(n_ga, C.c_uint64(args.seed + rank), threads, C.c_void_p(q_off.ctypes.data), C.c_void_p(r_off.ctypes.data), C.c_void_p(query.ctypes.data), C.c_void_p(gref.ctypes.data))
+    gb = B.GaBatch.__new__(B.GaBatch)
+    gb.n, gb.query, gb.ref, gb.query_off, gb.ref_off, gb.max_ops = n_ga, query, gref, q_off[: n_ga + 1], r_off[: n_ga + 1], 24
+    gb.c = A.SxGaBatch(n_ga, A.ptr(query), A.ptr(gref), A.ptr(gb.query_off), A.ptr(gb.ref_off), gb.max_ops)
+    t_gen = time.perf_counter() - t_gen
+    sc = ctx.active_region_scores()
+
+    # inputs resident in HBM before the timed region; the call records of a step land in one buffer, window after window
+    dws = [DevWindow(ctx, w, keep_outputs=False) for w in tiles]
+    dgb = DevGaBatch(ctx, gb)
+    cap_v = sum(d.out.cap_variant_sites for d in dws)
+    d_var = DeviceArray(ctx, cap_v * A.SITE_CALL_DT.itemsize)
+    d_all = DeviceArray(ctx, cap_v * A.SITE_CALL_DT.itemsize * world) if (world > 1 and rank == 0) else None
+    if world > 1:
+        idbuf = torch.zeros(A.SX_NCCL_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            raw = (C.c_ubyte * A.SX_NCCL_ID_BYTES)()
+            ctx._chk(lib.sx_comm_get_unique_id(raw))
+            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+        idbuf = idbuf.cuda()
+        dist.broadcast(idbuf, 0)
+        raw = (C.c_ubyte * A.SX_NCCL_ID_BYTES)(*idbuf.cpu().tolist())
+        ctx._chk(lib.sx_comm_init(ctx.h, raw, rank, world))
+
+    stage_ms = {k: 0.0 for k in A.SX_WIN_STAGE_NAMES + ("k3_global_align",)}
+    totals = np.zeros(A.SX_WIN_TOTALS, np.int64)
+    gather_off = np.zeros(world + 1, np.uint64)
+
+    def step_resident():
+        n_var = 0
+        for d in dws:
+            d.out.variant_sites = d_var.ptr + n_var * A.SITE_CALL_DT.itemsize
+            d.out.cap_variant_sites = cap_v - n_var
+            for k, v in d.run().items():
+                stage_ms[k] += v
+            totals[:] += d.totals
+            n_var += int(d.totals[8])
+        ctx.global_align_dev(sc, dgb)
+        stage_ms["k3_global_align"] += ctx.timing().kernel_ms
+        if world > 1:
+            ctx._chk(lib.sx_gatherv_records(ctx.h, d_var.ptr, n_var * A.SITE_CALL_DT.itemsize, d_all.ptr if d_all else None, (cap_v * A.SITE_CALL_DT.itemsize * world) if d_all else 0,
+                                            gather_off.ctypes.data, 0))
+        return n_var
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    launches0 = ctx.total_launches()
+    for k in stage_ms:
+        stage_ms[k] = 0.0
+    totals[:] = 0
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        n_var_step = step_resident()
+    barrier()
+    dt = time.perf_counter() - t0
+    launches = ctx.total_launches() - launches0
+    step_totals = totals // args.steps
+
+    # end to end: pinned host arrays through the host-array entry, H2D + kernels + D2H inside the timed region.  Two host threads with a context
+    # each take the windows alternately (one window's transfers overlap the other's kernels); the DP batch runs on a third.
+    e2e = None
+    if not args.no_e2e:
+        n_workers = 2 if n_tiles > 1 else 1
+        ctxs = [Context(local_rank) for _ in range(n_workers)]
+        ctx_ga = Context(local_rank)
+        ga_res, ga_cig = alloc.array(gb.n * A.GA_RESULT_DT.itemsize, A.GA_RESULT_DT), alloc.array(gb.n * gb.max_ops * 4, np.uint32)
+        hosts = []
+        for wi in range(n_workers):
+            w0 = tiles[0]
+            n_slots = int(w0.a["rec_off"][w0.n_reads])
+            cap1 = w0.n_sites // 8 + 1024
+            hosts.append({"recs": alloc.array((n_slots + 1) * A.READ_INDEL_SCORE_DT.itemsize, A.READ_INDEL_SCORE_DT), "n_rec": alloc.array((w0.n_reads + 1) * 4, np.uint32),
+                          "var": alloc.array(cap1 * A.SITE_CALL_DT.itemsize, A.SITE_CALL_DT), "cap": cap1, "totals": np.zeros(A.SX_WIN_TOTALS, np.uint32)})
+        batches = []
+        for w in tiles:  # the host-side structs (host pointers) are built once
+            c = A.SxWindowBatch()
+            lib.sx_default_window_opts(C.byref(c))
+            c.n_regions, c.n_reads, c.n_keys = w.n_regions, w.n_reads, w.n_keys
+            for name in B.WindowBatch.ARRAYS:
+                if name != "cand_snv":
+                    setattr(c, name, A.ptr(w.a[name]) if w.a.get(name) is not None else None)
+            c.seq4_bytes, c.qual_bytes, c.ref_bytes = w.used["seq4"], w.used["qual"], w.used["ref"]
+            c.qual_bits = w.qual_bits
+            c.qual_dict = (C.c_uint8 * 16)(*(w.qual_dict + [0] * (16 - len(w.qual_dict))))
+            c.ref_begin, c.report_begin, c.report_end = w.ref_begin, w.report_begin, w.report_end
+            c.max_read_len, c.do_site_gl = w.max_read_len, 1
+            batches.append(c)
+        d2h_step = [0]
+
+        def worker(wi):
+            h, cx = hosts[wi], ctxs[wi]
+            o = A.SxWindowOut()
+            o.recs, o.n_rec, o.variant_sites, o.cap_variant_sites = A.ptr(h["recs"]), A.ptr(h["n_rec"]), A.ptr(h["var"]), h["cap"]
+            for ti in range(wi, n_tiles, n_workers):
+                cx._chk(lib.sx_process_window(cx.h, C.byref(batches[ti]), C.byref(o), h["totals"].ctypes.data))
+                d2h_step[0] += int(tiles[ti].a["rec_off"][tiles[ti].n_reads]) * 32 + tiles[ti].n_reads * 4 + int(h["totals"][8]) * A.SITE_CALL_DT.itemsize
+
+        def step_e2e():
+            d2h_step[0] = 0
+            ths = [threading.Thread(target=worker, args=(wi,)) for wi in range(n_workers)]
+            tg = threading.Thread(target=lambda: ctx_ga._chk(lib.sx_global_align(ctx_ga.h, C.byref(sc), C.byref(gb.c), ga_res.ctypes.data, ga_cig.ctypes.data)))
+            for t in ths + [tg]:
+                t.start()
+            for t in ths + [tg]:
+                t.join()
+
+        for _ in range(min(2, max(1, args.warmup))):
+            step_e2e()
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        dt_e2e = time.perf_counter() - t1
+        h2d = sum(WW.input_bytes(w) for w in tiles) + int(gb.query_off[-1]) + int(gb.ref_off[-1]) + (gb.n + 1) * 8
+        d2h = d2h_step[0] + gb.n * (16 + gb.max_ops * 4)
+        e2e = (dt_e2e, h2d, d2h)
+        for c in ctxs + [ctx_ga]:
+            c.close()
+    clk = clocks.stop() if rank == 0 else None
+
+    if world > 1:
+        tt = torch.tensor([dt, e2e[0] if e2e else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt, dt_e2e_max = tt.tolist()
+        if e2e:
+            e2e = (dt_e2e_max, e2e[1], e2e[2])
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        total_loci = n_loci * world
+        value = total_loci * args.steps / dt
+        per_step = {k: v / args.steps for k, v in stage_ms.items()}
+        # per-stage algorithmic bytes of one step (all windows) and the roofline of the stage that takes longest
+        sb = {}
+        for w in tiles:
+            for k, v in stage_bytes(w, step_totals // n_tiles).items():
+                sb[k] = sb.get(k, 0) + v
+        sb["k3_global_align"] = int(gb.query_off[-1]) + int(gb.ref_off[-1]) + gb.n * (16 + 8)
+        stage_roof = {k: {"ms": per_step[k], "algorithmic_bytes": int(sb[k]), "achieved_gbs": sb[k] / max(per_step[k], 1e-9) / 1e6, "frac": sb[k] / max(per_step[k], 1e-9) / 1e6 / peak}
+                      for k in per_step if k in sb}
+        dom = max((k for k in stage_roof), key=lambda k: per_step[k])
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            if dom in tj and n_loci == WHOLE_PATH[args.config][0]:
+                traffic = tj[dom]["dram_bytes_read"] + tj[dom]["dram_bytes_write"]
+        except Exception:
+            pass
+        cells = sum(int(w.n_reads) for w in tiles) * 0  # (GCUPS is reported by the scoring leg; the whole path is quoted in loci/s)
+        whole_bytes = sum(WW.algorithmic_bytes(w, step_totals // n_tiles) for w in tiles)
+        line = {
+            "metric": "candidate_loci_per_sec", "value": value, "unit": "loci/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {desc}", "loci_per_gpu": n_loci, "windows_per_gpu": n_tiles, "loci_per_window": tile_loci, "reads_per_locus": WW.READS_PER_CELL,
+                       "read_len": WW.READ_LEN, "sites_per_locus": WW.CELL_LEN, "step": "whole path: K7g, K7a, K7, K7b, K1, K6, K9, K4, K2a per window (sx_process_window_dev) + K3",
+                       "parallelism": f"window-shard x{world}, one NCCL gatherv of variant-site records per step" if world > 1 else "single GPU",
+                       "l2": "inputs (%.1f GB per GPU) far exceed the 126 MB L2; no flush needed" % (sum(WW.input_bytes(w) for w in tiles) / 1e9), "gen_seconds": round(t_gen, 1)},
+            "roofline": {"bound": "hbm", "achieved": stage_roof[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stage_roof[dom]["frac"], "traffic": traffic,
+                         "kernel": f"stage {dom} (the longest of the step)", "algorithmic_bytes_per_step": stage_roof[dom]["algorithmic_bytes"], "kernel_ms_per_step": per_step[dom],
+                         "peak_source": peak_src, "whole_step": {"algorithmic_bytes": int(whole_bytes), "achieved_gbs": whole_bytes / (dt / args.steps) / 1e9,
+                                                                 "frac": whole_bytes / (dt / args.steps) / 1e9 / peak}},
+            "stage_roofline": stage_roof,
+            "gpu_launches": launches,
+            "kernel_ms_per_step": per_step,
+            "per_step_totals": {"candidate_alignments": int(step_totals[0]), "k1_segments": int(step_totals[3]), "pileup_calls": int(step_totals[6]), "variant_sites": int(step_totals[8]),
+                                "variant_sites_last_step": int(n_var_step)},
+            "clocks": clk,
+        }
+        if e2e:
+            line["e2e"] = {"value": total_loci * args.steps / e2e[0], "unit": "loci/s", "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2]),
+                           "ms_per_step": 1e3 * e2e[0] / args.steps, "how": "sx_process_window (host arrays in pinned memory) per window, two host threads with a context each; "
+                           "sx_global_align on a third; D2H = score_indels records + variant-site records + DP results"}
+        if world == 1:
+            # the reported CPU baseline: the reference's own functions, one pinned process per usable core, a bounded sample
+            try:
+                outs = run_reference_workers(ncpu, cpu_ids, args.cpu_sample_loci or 160, 2, 1, args.seed, timeout=600)
+                r = summarize_reference(outs, 2)
+                line["cpu_baseline"] = {"value": r["value"], "unit": "loci/s", "cores": ncpu, "kind": "reference", "cores_how": cpu_how,
+                                        "sample": f"{ncpu} processes x {args.cpu_sample_loci or 160} loci x 2 passes (1 warm-up), one pinned process per core, "
+                                                  "oracle/_ref/libstrelka_ref.so (the reference's own realignAndScoreRead, pileup_read_segment, position_snp_call_pprob_digt, GlobalAligner)",
+                                        "per_core_loci_per_s": {"median": r["per_core_loci_per_s_median"], "min": r["per_core_loci_per_s_min"]}, "mean_seconds_per_part": r["mean_seconds_per_part"]}
+            except SystemExit as e:
+                line["cpu_baseline"] = {"error": str(e)}
+            if args.legs:
+                for key, cmd in (("scoring_only_step", [sys.executable, os.path.abspath(__file__), "--config", "cfg2-scoring", "--steps", "5", "--warmup", "3", "--no-legs"]),
+                                 ("k2b_somatic_cfg3", [sys.executable, os.path.join(ROOT, "tools", "site_legs.py"), "k2b", str(peak)]),
+                                 ("k5_indel_gl", [sys.executable, os.path.join(ROOT, "tools", "site_legs.py"), "k5", str(peak)])):
+                    try:
+                        r = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
+                        last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                        line[key] = json.loads(last[-1]) if r.returncode == 0 and last else {"error": (r.stderr or r.stdout)[-600:]}
+                    except Exception as e:  # noqa: BLE001
+                        line[key] = {"error": f"{type(e).__name__}: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-worker"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "tiny", "cfg2-scoring", "cfg5", "tiny-scoring"])
+    ap.add_argument("--loci", type=int, default=0, help="override the number of candidate loci per GPU")
+    ap.add_argument("--tile-loci", type=int, default=0, help="candidate loci per window (whole-path step)")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-legs", dest="legs", action="store_false", help="skip the single-kernel legs measured beside the headline step")
+    ap.add_argument("--cpu-sample-loci", type=int, default=0)
+    ap.add_argument("--worker-index", type=int, default=0)
+    ap.add_argument("--worker-loci", type=int, default=240)
+    ap.add_argument("--worker-cpu", type=int, default=-1)
+    args = ap.parse_args()
+    if args.impl == "reference-worker":
+        return reference_worker(args)
+    if args.config in ("cfg2-scoring", "cfg5", "tiny-scoring"):
+        return scoring_step_main(args)
+    if args.impl == "reference":
+        return reference_main(args)
+    return whole_path_main(args)
 
 
 if __name__ == "__main__":

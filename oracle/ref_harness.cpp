@@ -32,6 +32,7 @@
 #include "starling_common/starling_read_align_score.hh"
 #include "test/starling_base_options_test.hh"
 
+#include <chrono>
 #include <cstring>
 #include <exception>
 #include <memory>
@@ -281,7 +282,15 @@ extern "C" int ref_dependent_eprob(const sx_params* p, const sx_pileup_batch* b,
     }
 }
 
+// secs (may be NULL): accumulates the time inside the reference's own calls per site -- CleanPileupFilter + CleanPileupErrorProb +
+// position_snp_call_pprob_digt, what computeSampleDiploidSiteGenotype's path spends -- leaving out this harness's snp_pos_info filling and
+// its second get_diploid_gt_lhood call (made only to export the float likelihoods)
+extern "C" int ref_site_gl_germline_timed(const sx_params* p, const sx_pileup_batch* b, int is_always_test, sx_digt_result* out, double* secs, char* err, int errlen);
 extern "C" int ref_site_gl_germline(const sx_params* p, const sx_pileup_batch* b, int is_always_test, sx_digt_result* out, char* err, int errlen)
+{
+    return ref_site_gl_germline_timed(p, b, is_always_test, out, nullptr, err, errlen);
+}
+extern "C" int ref_site_gl_germline_timed(const sx_params* p, const sx_pileup_batch* b, int is_always_test, sx_digt_result* out, double* secs, char* err, int errlen)
 {
     try
     {
@@ -297,12 +306,14 @@ extern "C" int ref_site_gl_germline(const sx_params* p, const sx_pileup_batch* b
             sx_digt_result& o(out[s]);
             std::memset(&o, 0, sizeof(o));
             fill_pileup(b, s, pi);
+            const auto t0(std::chrono::steady_clock::now());
             cleaner.CleanPileupFilter(pi, false, cpi);
             cleaner.CleanPileupErrorProb(cpi);
             o.n_used_calls = cpi.usedBasecallCount();
             diploid_genotype dgt;
             dgt.ploidy = b->ploidy ? b->ploidy[s] : 2;
             caller.position_snp_call_pprob_digt(opt, cpi.getExtendedPosInfo(), dgt, is_always_test != 0);
+            if (secs) *secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             o.ref_gt = dgt.ref_gt;
             o.strand_bias = dgt.strand_bias;
             const diploid_genotype::result_set* rsin[2] = {&dgt.genome, &dgt.poly};
@@ -670,8 +681,16 @@ struct PileupReadSegmentTag
 template struct MemberPtrOf<PileupReadSegmentTag, &starling_pos_processor_base::pileup_read_segment>;
 } // namespace
 
+// secs (may be NULL): accumulates the time inside pileup_read_segment itself (the bam_record / starling_read objects around it are this harness's)
+extern "C" int ref_pileup_reads_timed(const sx_pileup_reads_batch* b, uint32_t* site_off, uint16_t* calls, uint64_t calls_cap, uint32_t* t2_off, uint16_t* t2_calls,
+                                      uint64_t t2_cap, uint32_t* n_spandel, uint32_t* n_submapped, double* secs, char* err, int errlen);
 extern "C" int ref_pileup_reads(const sx_pileup_reads_batch* b, uint32_t* site_off, uint16_t* calls, uint64_t calls_cap, uint32_t* t2_off, uint16_t* t2_calls,
                                 uint64_t t2_cap, uint32_t* n_spandel, uint32_t* n_submapped, char* err, int errlen)
+{
+    return ref_pileup_reads_timed(b, site_off, calls, calls_cap, t2_off, t2_calls, t2_cap, n_spandel, n_submapped, nullptr, err, errlen);
+}
+extern "C" int ref_pileup_reads_timed(const sx_pileup_reads_batch* b, uint32_t* site_off, uint16_t* calls, uint64_t calls_cap, uint32_t* t2_off, uint16_t* t2_calls,
+                                      uint64_t t2_cap, uint32_t* n_spandel, uint32_t* n_submapped, double* secs, char* err, int errlen)
 {
     try
     {
@@ -743,7 +762,9 @@ extern "C" int ref_pileup_reads(const sx_pileup_reads_batch* b, uint32_t* site_o
             const MAPLEVEL::index_t lev((rd.flags & SX_PRF_TIER1) ? MAPLEVEL::TIER1_MAPPED : (rd.flags & SX_PRF_TIER1OR2) ? MAPLEVEL::TIER2_MAPPED : MAPLEVEL::SUB_MAPPED);
             sreads.emplace_back(new starling_read(*br, al, lev, r));
             bams.push_back(std::move(br));
+            const auto t0(std::chrono::steady_clock::now());
             (proc.*pileup)(sreads.back()->get_full_segment(), 0);
+            if (secs) *secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         }
         const pos_basecall_buffer& buf(proc.sample(0).basecallBuffer);
         const uint32_t n_sites(static_cast<uint32_t>(b->report_end - b->report_begin));

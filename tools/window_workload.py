@@ -100,8 +100,8 @@ def gate_batch_of(w: B.WindowBatch) -> A.SxGateBatch:
 
 
 def reference_pass(w: B.WindowBatch, params=None, max_segs: int = 16):
-    """The window through the reference, stage by stage; returns (results dict, seconds dict).  Seconds: realign = time inside
-    realignAndScoreRead itself; pileup / site_gl = the whole harness call (object construction included: the reference builds the same objects)."""
+    """The window through the reference, stage by stage; returns (results dict, seconds dict).  Seconds: the time inside the reference's own
+    functions (the harness's object construction around them is not the reference's work and is left out; the *_call entries include it)."""
     rf = _ref_lib()
     assert rf is not None and w.read_ascii is not None, "reference library not built / window made without ascii_reads"
     a, n, ns = w.a, w.n_reads, w.n_sites
@@ -156,10 +156,11 @@ def reference_pass(w: B.WindowBatch, params=None, max_segs: int = 16):
     so, t2o = np.zeros(ns + 1, np.uint32), np.zeros(ns + 1, np.uint32)
     cl, t2c = np.zeros(n * READ_LEN + 16, np.uint16), np.zeros(16, np.uint16)
     sd, sm = np.zeros(ns, np.uint32), np.zeros(ns, np.uint32)
-    fnp = rf.ref_pileup_reads
-    fnp.argtypes = [C.POINTER(A.SxPileupReadsBatch), _P, _P, C.c_uint64, _P, _P, C.c_uint64, _P, _P, C.c_char_p, C.c_int]
+    fnp = rf.ref_pileup_reads_timed
+    fnp.argtypes = [C.POINTER(A.SxPileupReadsBatch), _P, _P, C.c_uint64, _P, _P, C.c_uint64, _P, _P, _P, C.c_char_p, C.c_int]
+    s_pile = C.c_double(0.0)
     t0 = time.perf_counter()
-    rc = fnp(C.byref(pb), A.ptr(so), A.ptr(cl), cl.size, A.ptr(t2o), A.ptr(t2c), t2c.size, A.ptr(sd), A.ptr(sm), err, 1024)
+    rc = fnp(C.byref(pb), A.ptr(so), A.ptr(cl), cl.size, A.ptr(t2o), A.ptr(t2c), t2c.size, A.ptr(sd), A.ptr(sm), C.addressof(s_pile), err, 1024)
     t_pileup = time.perf_counter() - t0
     if rc != 0:
         raise RuntimeError(err.value.decode(errors="replace"))
@@ -168,14 +169,17 @@ def reference_pass(w: B.WindowBatch, params=None, max_segs: int = 16):
     k2 = A.SxPileupBatch(ns, A.ptr(so), A.ptr(cl), None, None, A.ptr(np.ascontiguousarray(ref_base)), None)
     gl = np.zeros(ns, A.DIGT_RESULT_DT)
     params = params or A.default_params()
+    s_gl = C.c_double(0.0)
     t0 = time.perf_counter()
-    rc = rf.ref_site_gl_germline(C.byref(params), C.byref(k2), 1, _P(gl.ctypes.data), err, 1024)
+    rc = rf.ref_site_gl_germline_timed(C.byref(params), C.byref(k2), 1, _P(gl.ctypes.data), _P(C.addressof(s_gl)), err, 1024)
     t_gl = time.perf_counter() - t0
     if rc != 0:
         raise RuntimeError(err.value.decode(errors="replace"))
     res = {"status": status[:n], "best_pos": best_pos, "best_off": best_off, "best_segs": best[: int(best_off[n])], "recs": recs, "n_rec": n_rec[:n], "site_off": so,
            "calls": cl[: int(so[ns])], "t2_off": t2o, "n_spandel": sd, "n_submapped": sm, "site_gl": gl}
-    return res, {"realign": secs.value, "realign_call": t_realign_call, "pileup": t_pileup, "site_gl": t_gl}
+    # seconds inside the reference's own functions (realignAndScoreRead, pileup_read_segment, CleanPileup* + position_snp_call_pprob_digt); the *_call
+    # entries are the whole harness calls, object construction included
+    return res, {"realign": secs.value, "pileup": s_pile.value, "site_gl": s_gl.value, "realign_call": t_realign_call, "pileup_call": t_pileup, "site_gl_call": t_gl}
 
 
 def compare_with_reference(w: B.WindowBatch, d: dict, res: dict):
