@@ -1038,6 +1038,35 @@ def stage_bytes(w, t):
     }
 
 
+def bind_to_gpu_numa(local_rank: int):
+    """Run this rank on the host cores of its GPU's NUMA node BEFORE any pinned memory is allocated or touched: the pinned pages then live on
+    that node, and the H2D / D2H copies of the end-to-end leg do not cross the socket interconnect (round 1's 8-GPU e2e efficiency was 0.65 with
+    unbound generator threads).  Returns a description for the bench line; silently does nothing where the topology is not readable."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        if bus is None:
+            return "pci id not available"
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read())
+        if node < 0:
+            return "single NUMA node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"NUMA node {node} ({len(allowed)} cpus)"
+        return f"NUMA node {node}: no allowed cpu there"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({type(e).__name__})"
+
+
 def whole_path_main(args):
     import torch
     import torch.distributed as dist
@@ -1059,7 +1088,10 @@ def whole_path_main(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; strelka_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else "single rank: not bound"
     if world > 1:
+        ncpu, cpu_ids, cpu_how = usable_cpus()  # (now the node's)
+        threads = max(1, min(threads, ncpu))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = Context(local_rank)
     lib = ctx.lib
@@ -1244,7 +1276,7 @@ def whole_path_main(args):
             "config": {"workload": f"{args.config}: {desc}", "loci_per_gpu": n_loci, "windows_per_gpu": n_tiles, "loci_per_window": tile_loci, "reads_per_locus": WW.READS_PER_CELL,
                        "read_len": WW.READ_LEN, "sites_per_locus": WW.CELL_LEN, "step": "whole path: K7g, K7a, K7, K7b, K1, K6, K9, K4, K2a per window (sx_process_window_dev) + K3",
                        "parallelism": f"window-shard x{world}, one NCCL gatherv of variant-site records per step" if world > 1 else "single GPU",
-                       "l2": "inputs (%.1f GB per GPU) far exceed the 126 MB L2; no flush needed" % (sum(WW.input_bytes(w) for w in tiles) / 1e9), "gen_seconds": round(t_gen, 1)},
+                       "l2": "inputs (%.1f GB per GPU) far exceed the 126 MB L2; no flush needed" % (sum(WW.input_bytes(w) for w in tiles) / 1e9), "gen_seconds": round(t_gen, 1), "host_binding": numa},
             "roofline": {"bound": "hbm", "achieved": stage_roof[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stage_roof[dom]["frac"], "traffic": traffic,
                          "kernel": f"stage {dom} (the longest of the step)", "algorithmic_bytes_per_step": stage_roof[dom]["algorithmic_bytes"], "kernel_ms_per_step": per_step[dom],
                          "peak_source": peak_src, "whole_step": {"algorithmic_bytes": int(whole_bytes), "achieved_gbs": whole_bytes / (dt / args.steps) / 1e9,

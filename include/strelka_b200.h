@@ -902,6 +902,10 @@ typedef struct sx_window_batch {
     uint32_t max_read_len;             /* >= every read_len (0: 1024) */
     int32_t do_site_gl;                /* run K2a on the columns */
     int32_t is_always_test;            /* K2a's is_always_test (the germline caller genotypes every site: 1) */
+    int32_t is_retain_optimal_soft_clipping; /* opt.isRetainOptimalSoftClipping (starling_read_align.cpp:1700-1737; the RNA workflow's
+                                          --retain-optimal-soft-clipping): not accelerated -- nonzero is refused with SX_ERR_UNSUPPORTED, like the RNA
+                                          het-extension model, rather than answered with the DNA behaviour */
+    int32_t reserved_;
     sx_enum_opts enum_opts;
     sx_score_indels_opts score_opts;
     sx_pileup_opts pileup_opts;

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(K7_THREADS) k7_write_kernel(const k7_view v, u
 // which thread got which piece of the log.
 // ---------------------------------------------------------------------------------------------------------------------------
 constexpr uint32_t K7_LOCAL_ALNS = 16, K7_LOCAL_FRAMES = 12;
+constexpr uint32_t K7_MID_ALNS = 96; // per-read capacity of the first arena tier
 constexpr uint32_t K7_LOCAL_BYTES = 6400; // >= k7_scratch_bytes(K7_LOCAL_ALNS, K7_LOCAL_FRAMES); checked in k7_run_fast
 
 struct k7_log
@@ -164,8 +165,16 @@ __device__ __forceinline__ void k7_log_append(const k7_log& L, const k7_scratch&
     L.blob_off[r] = off;
 }
 
+// the reads a tier could not finish: a dense list for the next tier (which thread appends where does not matter: the output is placed by the scan)
+struct k7_retry
+{
+    uint32_t* list1; // [n_reads] reads the local tier passed on
+    uint32_t* list2; // [n_reads] reads the small-arena tier passed on
+    uint32_t* n;     // [2] their counts
+};
+
 __global__ void __launch_bounds__(K7_THREADS) k7_search_local_kernel(const k7_view v, const uint32_t* __restrict__ read_region, uint8_t* __restrict__ status,
-                                                                     uint8_t* __restrict__ tier, const k7_counts c, const k7_log L)
+                                                                     const k7_retry R, const k7_counts c, const k7_log L)
 {
     __align__(16) unsigned char local[K7_LOCAL_BYTES];
     k7_scratch S(k7_scratch_at(local, K7_LOCAL_ALNS, K7_LOCAL_FRAMES, K7_ST_RETRY));
@@ -174,7 +183,6 @@ __global__ void __launch_bounds__(K7_THREADS) k7_search_local_kernel(const k7_vi
     {
         const uint32_t st(k7_enumerate_read(v, read_region[r], r, S));
         const bool retry((st & K7_ST_RETRY) != 0);
-        tier[r] = retry ? 1 : 0;
         uint32_t na(0), ns(0), nk(0);
         if (!retry)
         {
@@ -182,22 +190,32 @@ __global__ void __launch_bounds__(K7_THREADS) k7_search_local_kernel(const k7_vi
             status[r] = (uint8_t)st;
             if (na) k7_log_append(L, S, r);
         }
+        else R.list1[atomicAdd(&R.n[0], 1u)] = r;
         c.aln[r] = na;
         c.seg[r] = ns;
         c.key[r] = nk;
     }
 }
 
+// level 1: the reads of list1 in a modest per-thread arena (most of them need a few dozen alignments); what still does not fit goes to list2.
+// level 2: the reads of list2 with the caller's full per-read capacity (the reference's own bound is 5000 alignments), few threads.
 __global__ void __launch_bounds__(K7_THREADS) k7_search_arena_kernel(const k7_view v, unsigned char* __restrict__ arena, const size_t per_thread, const uint32_t maxA,
                                                                      const uint32_t maxF, const uint32_t* __restrict__ read_region, uint8_t* __restrict__ status,
-                                                                     const uint8_t* __restrict__ tier, const k7_counts c, const k7_log L)
+                                                                     const k7_retry R, const int level, const int pass_on, const k7_counts c, const k7_log L)
 {
     const uint32_t t(blockIdx.x * blockDim.x + threadIdx.x), nthr(gridDim.x * blockDim.x);
-    k7_scratch S(k7_scratch_at(arena + (size_t)t * per_thread, maxA, maxF));
-    for (uint32_t r = t; r < v.b.n_reads; r += nthr)
+    k7_scratch S(k7_scratch_at(arena + (size_t)t * per_thread, maxA, maxF, pass_on ? K7_ST_RETRY : SX_ENUM_ST_LIMIT));
+    const uint32_t* list(level == 1 ? R.list1 : R.list2);
+    const uint32_t cnt(R.n[level - 1]);
+    for (uint32_t i = t; i < cnt; i += nthr)
     {
-        if (!tier[r]) continue;
+        const uint32_t r(list[i]);
         const uint32_t st(k7_enumerate_read(v, read_region[r], r, S));
+        if (st & K7_ST_RETRY) // (only with pass_on)
+        {
+            R.list2[atomicAdd(&R.n[1], 1u)] = r;
+            continue;
+        }
         uint32_t na, ns, nk;
         k7_count(S, st, na, ns, nk);
         status[r] = (uint8_t)st;
@@ -300,12 +318,19 @@ int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsig
     per_sm_local = std::max(1, per_sm_local);
     const size_t n_blocks(((size_t)n + K7_THREADS - 1) / K7_THREADS);
     const size_t blocks_local(std::min<size_t>(n_blocks, (size_t)ctx->sm_count * per_sm_local));
-    // the arena tier sees few reads: a quarter of the device is plenty and keeps the arena small enough for the L2
-    size_t blocks(std::min<size_t>(n_blocks, std::max<size_t>(1, (size_t)ctx->sm_count * per_sm / 4)));
+    // two arena tiers: a modest one (K7_MID_ALNS alignments per read, the whole device) for the reads the local tier passes on, and -- only when the
+    // caller allows more per read -- one with the caller's capacity for the few that still do not fit (few threads: its per-thread scratch is large)
+    const uint32_t maxA1(std::min<uint32_t>(maxA, K7_MID_ALNS));
+    const bool two_levels(maxA > maxA1);
+    const size_t per_thread1((k7_scratch_bytes(maxA1, maxF) + 255) & ~(size_t)255);
+    size_t blocks1(std::min<size_t>(n_blocks, (size_t)ctx->sm_count * per_sm));
     const size_t arena_cap((size_t)1 << 30);
+    while (blocks1 > 1 && blocks1 * K7_THREADS * per_thread1 > arena_cap) blocks1 = (blocks1 + 1) / 2;
+    size_t blocks(std::min<size_t>(n_blocks, std::max<size_t>(1, (size_t)ctx->sm_count * per_sm / 4)));
     while (blocks > 1 && blocks * K7_THREADS * per_thread > arena_cap) blocks = (blocks + 1) / 2;
-    unsigned char* arena(nullptr);
-    if ((rc = sx_ensure(ctx, 40, blocks * K7_THREADS * per_thread, reinterpret_cast<void**>(&arena)))) return rc;
+    unsigned char *arena(nullptr), *arena1(nullptr);
+    if ((rc = sx_ensure(ctx, 40, blocks1 * K7_THREADS * per_thread1, reinterpret_cast<void**>(&arena1)))) return rc;
+    if (two_levels && (rc = sx_ensure(ctx, 65, blocks * K7_THREADS * per_thread, reinterpret_cast<void**>(&arena)))) return rc;
     k7_counts c;
     if ((rc = sx_ensure(ctx, 42, (size_t)n * 4 + 16, reinterpret_cast<void**>(&c.aln)))) return rc;
     if ((rc = sx_ensure(ctx, 43, (size_t)n * 4 + 16, reinterpret_cast<void**>(&c.seg)))) return rc;
@@ -318,19 +343,27 @@ int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsig
     const unsigned long long want_words((unsigned long long)o->cap_alns * 4ull + o->cap_segs + (o->cap_keys + 1ull) / 2ull + 16ull);
     k7_log L;
     L.cap = (uint32_t)std::min<unsigned long long>(want_words, 0xFFFFFFF0ull);
-    uint8_t* tier(nullptr);
+    k7_retry R;
     if ((rc = sx_ensure(ctx, 54, (size_t)L.cap * 4 + 16, reinterpret_cast<void**>(&L.words)))) return rc;
     if ((rc = sx_ensure(ctx, 55, (size_t)n * 4 + 16, reinterpret_cast<void**>(&L.blob_off)))) return rc;
     if ((rc = sx_ensure(ctx, 56, 16, reinterpret_cast<void**>(&L.cursor)))) return rc;
-    if ((rc = sx_ensure(ctx, 57, (size_t)n + 16, reinterpret_cast<void**>(&tier)))) return rc;
+    if ((rc = sx_ensure(ctx, 57, (size_t)n * 4 + 16, reinterpret_cast<void**>(&R.list1)))) return rc;
+    if ((rc = sx_ensure(ctx, 66, (size_t)n * 4 + 16, reinterpret_cast<void**>(&R.list2)))) return rc;
+    if ((rc = sx_ensure(ctx, 67, 16, reinterpret_cast<void**>(&R.n)))) return rc;
     SX_CUDA(ctx, cudaMemsetAsync(L.cursor, 0, 16, st));
+    SX_CUDA(ctx, cudaMemsetAsync(R.n, 0, 16, st));
 
     k7_view v;
     v.b = *d;
-    k7_search_local_kernel<<<(unsigned)blocks_local, K7_THREADS, 0, st>>>(v, read_region, o->status, tier, c, L);
+    k7_search_local_kernel<<<(unsigned)blocks_local, K7_THREADS, 0, st>>>(v, read_region, o->status, R, c, L);
     SX_CUDA(ctx, cudaGetLastError());
-    k7_search_arena_kernel<<<(unsigned)blocks, K7_THREADS, 0, st>>>(v, arena, per_thread, maxA, maxF, read_region, o->status, tier, c, L);
+    k7_search_arena_kernel<<<(unsigned)blocks1, K7_THREADS, 0, st>>>(v, arena1, per_thread1, maxA1, maxF, read_region, o->status, R, 1, two_levels ? 1 : 0, c, L);
     SX_CUDA(ctx, cudaGetLastError());
+    if (two_levels)
+    {
+        k7_search_arena_kernel<<<(unsigned)blocks, K7_THREADS, 0, st>>>(v, arena, per_thread, maxA, maxF, read_region, o->status, R, 2, 0, c, L);
+        SX_CUDA(ctx, cudaGetLastError());
+    }
     k7_scan_tiles<<<n_tiles, K7_SCAN_THREADS, 0, st>>>(n, c.aln, c.seg, c.key, sums, n_tiles);
     SX_CUDA(ctx, cudaGetLastError());
     k7_scan_sums<<<1, K7_SCAN_THREADS, 0, st>>>(sums, n_tiles, totals);
@@ -340,7 +373,7 @@ int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsig
     const int g1(std::max(1, std::min<int>((int)((n + 127) / 128), ctx->sm_count * 16)));
     k7_gather_kernel<<<g1, 128, 0, st>>>(n, c, L, *o, totals);
     SX_CUDA(ctx, cudaGetLastError());
-    *launches = 7;
+    *launches = two_levels ? 8 : 7;
     return SX_OK;
 }
 

@@ -246,6 +246,8 @@ extern "C" void sx_default_window_opts(sx_window_batch* b)
     sx_default_pileup_opts(&b->pileup_opts);
     b->is_always_test = 1;
     b->do_site_gl = 1;
+    b->is_retain_optimal_soft_clipping = 0;
+    b->reserved_ = 0;
 }
 
 extern "C" int sx_last_window_timing(const sx_ctx* ctx, float* ms)
@@ -266,6 +268,8 @@ extern "C" int sx_process_window_dev(sx_ctx* ctx, const sx_window_batch* b, sx_w
                        (b->n_keys && (!b->keys || !b->key_ins_off || !b->key_ins)) || b->n_regions == 0))
         return sx_fail(ctx, SX_ERR_ARG, "sx_process_window_dev: NULL array");
     if (b->qual_bits != 0 && b->qual_bits != 8 && b->qual_bits != 4) return sx_fail(ctx, SX_ERR_ARG, "sx_process_window_dev: qual_bits must be 0, 8 or 4");
+    if (b->is_retain_optimal_soft_clipping)
+        return sx_fail(ctx, SX_ERR_UNSUPPORTED, "sx_process_window_dev: isRetainOptimalSoftClipping (the RNA workflow's soft-clip retention test) is outside the accelerated path");
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st(ctx->s_compute);
     for (int i = 0; i <= SX_WIN_N_STAGES; ++i)

@@ -46,7 +46,7 @@ def test_k7_enumerate_alignments(ctx, case):
     eb.c.opts = eb.opts
     cap = eb.n_reads * 6000 + 64
     got = ctx.enumerate_alignments(eb, cap_alns=cap)
-    assert ctx.timing().launches == 7  # the default launch plan: local tier, arena tier, 3 scan kernels, gather (+ the frame count)
+    assert ctx.timing().launches in (7, 8)  # the default launch plan: frame count, local tier, one or two arena tiers, 3 scan kernels, gather
     _same(reflib.ox_enumerate_alignments(eb, cap_alns=cap), got)
     if case < specgen.ENUM_GOLDEN_CASES:
         gold = np.load(os.path.join(HERE, "golden", "enumerate_ref.npz"))
