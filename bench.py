@@ -1111,11 +1111,21 @@ def whole_path_main(args):
     t_gen = time.perf_counter() - t_gen
     sc = ctx.active_region_scores()
 
-    # inputs resident in HBM before the timed region; the call records of a step land in one buffer, window after window
-    dws = [DevWindow(ctx, w, keep_outputs=False) for w in tiles]
+    # inputs resident in HBM before the timed region.  The windows of a step are independent, and no single stage fills the machine (the search
+    # is latency-bound, the site model issue-bound), so they are processed on `lanes` contexts -- each with its own stream and buffers, one host
+    # thread each -- concurrently; every window's call records land in its own slice of one buffer (slice = the window's capacity), compacted
+    # into gather order by one device-to-device copy per window at the end of the step.
+    lanes = max(1, min(args.lanes, n_tiles))
+    lane_ctx = [ctx] + [Context(local_rank) for _ in range(lanes - 1)]
+    dws = [DevWindow(lane_ctx[i % lanes], w, keep_outputs=False) for i, w in enumerate(tiles)]
     dgb = DevGaBatch(ctx, gb)
-    cap_v = sum(d.out.cap_variant_sites for d in dws)
+    cap_each = [d.out.cap_variant_sites for d in dws]
+    cap_v = sum(cap_each)
+    d_var_raw = DeviceArray(ctx, cap_v * A.SITE_CALL_DT.itemsize)
     d_var = DeviceArray(ctx, cap_v * A.SITE_CALL_DT.itemsize)
+    off_each = np.concatenate([[0], np.cumsum(cap_each)])
+    for i, d in enumerate(dws):
+        d.out.variant_sites = d_var_raw.ptr + int(off_each[i]) * A.SITE_CALL_DT.itemsize
     d_all = DeviceArray(ctx, cap_v * A.SITE_CALL_DT.itemsize * world) if (world > 1 and rank == 0) else None
     if world > 1:
         idbuf = torch.zeros(A.SX_NCCL_ID_BYTES, dtype=torch.uint8)
@@ -1132,17 +1142,37 @@ def whole_path_main(args):
     totals = np.zeros(A.SX_WIN_TOTALS, np.int64)
     gather_off = np.zeros(world + 1, np.uint64)
 
+    lane_ms = [dict() for _ in range(lanes)]
+
+    def lane_work(li):
+        acc = lane_ms[li]
+        for i in range(li, n_tiles, lanes):
+            for k, v in dws[i].run().items():
+                acc[k] = acc.get(k, 0.0) + v
+        if li == lanes - 1:  # the haplotype DP batch rides on the last lane
+            lane_ctx[li].global_align_dev(sc, dgb)
+            acc["k3_global_align"] = acc.get("k3_global_align", 0.0) + lane_ctx[li].timing().kernel_ms
+
     def step_resident():
+        if lanes == 1:
+            lane_work(0)
+        else:
+            ths = [threading.Thread(target=lane_work, args=(li,)) for li in range(lanes)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
         n_var = 0
-        for d in dws:
-            d.out.variant_sites = d_var.ptr + n_var * A.SITE_CALL_DT.itemsize
-            d.out.cap_variant_sites = cap_v - n_var
-            for k, v in d.run().items():
-                stage_ms[k] += v
+        for i, d in enumerate(dws):  # compact the windows' records into one block (gather order = window order)
+            nv = int(d.totals[8])
+            if nv:
+                ctx._chk(lib.sx_memcpy_d2d(ctx.h, d_var.ptr + n_var * A.SITE_CALL_DT.itemsize, d.out.variant_sites, nv * A.SITE_CALL_DT.itemsize))
             totals[:] += d.totals
-            n_var += int(d.totals[8])
-        ctx.global_align_dev(sc, dgb)
-        stage_ms["k3_global_align"] += ctx.timing().kernel_ms
+            n_var += nv
+        for li in range(lanes):
+            for k, v in lane_ms[li].items():
+                stage_ms[k] += v
+            lane_ms[li].clear()
         if world > 1:
             ctx._chk(lib.sx_gatherv_records(ctx.h, d_var.ptr, n_var * A.SITE_CALL_DT.itemsize, d_all.ptr if d_all else None, (cap_v * A.SITE_CALL_DT.itemsize * world) if d_all else 0,
                                             gather_off.ctypes.data, 0))
@@ -1275,6 +1305,8 @@ def whole_path_main(args):
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.config}: {desc}", "loci_per_gpu": n_loci, "windows_per_gpu": n_tiles, "loci_per_window": tile_loci, "reads_per_locus": WW.READS_PER_CELL,
                        "read_len": WW.READ_LEN, "sites_per_locus": WW.CELL_LEN, "step": "whole path: K7g, K7a, K7, K7b, K1, K6, K9, K4, K2a per window (sx_process_window_dev) + K3",
+                       "concurrency": f"{lanes} contexts (own stream + buffers, one host thread each) take the windows in turn; kernel_ms_per_step sums each stage's device time "
+                                      "over the contexts, so the stages add up to more than ms_per_step",
                        "parallelism": f"window-shard x{world}, one NCCL gatherv of variant-site records per step" if world > 1 else "single GPU",
                        "l2": "inputs (%.1f GB per GPU) far exceed the 126 MB L2; no flush needed" % (sum(WW.input_bytes(w) for w in tiles) / 1e9), "gen_seconds": round(t_gen, 1), "host_binding": numa},
             "roofline": {"bound": "hbm", "achieved": stage_roof[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stage_roof[dom]["frac"], "traffic": traffic,
@@ -1328,6 +1360,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "tiny", "cfg2-scoring", "cfg5", "tiny-scoring"])
     ap.add_argument("--loci", type=int, default=0, help="override the number of candidate loci per GPU")
     ap.add_argument("--tile-loci", type=int, default=0, help="candidate loci per window (whole-path step)")
+    ap.add_argument("--lanes", type=int, default=3, help="contexts that process the windows of a step concurrently (whole-path step)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-legs", dest="legs", action="store_false", help="skip the single-kernel legs measured beside the headline step")

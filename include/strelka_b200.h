@@ -88,6 +88,7 @@ void* sx_dev_alloc(sx_ctx* ctx, size_t bytes);
 void sx_dev_free(sx_ctx* ctx, void* p);
 int sx_memcpy_h2d(sx_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int sx_memcpy_d2h(sx_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int sx_memcpy_d2d(sx_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes); /* on ctx's compute stream, asynchronous */
 int sx_synchronize(sx_ctx* ctx);
 
 /* ==========================================================================================

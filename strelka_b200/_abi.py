@@ -357,6 +357,7 @@ SYMBOLS = [
     ("sx_dev_free", None, [_P, _P]),
     ("sx_memcpy_h2d", C.c_int, [_P, _P, _P, C.c_size_t]),
     ("sx_memcpy_d2h", C.c_int, [_P, _P, _P, C.c_size_t]),
+    ("sx_memcpy_d2d", C.c_int, [_P, _P, _P, C.c_size_t]),
     ("sx_synchronize", C.c_int, [_P]),
     ("sx_score_alignments", C.c_int, [_P, C.POINTER(SxAlignBatch), _P]),
     ("sx_score_alignments_dev", C.c_int, [_P, C.POINTER(SxAlignBatch), _P]),

@@ -20,6 +20,7 @@
 #include "sx_stdsort_mirror.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace
 {
@@ -611,6 +612,382 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline4_kernel(const uint
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Twelve sites per warp (round 2).  ncu on the four-site kernel at the whole-path bench's sites (every position of a 30x contig,
+// 99.7 % of them homozygous reference; profiles/r2_whole_path_50k.summary.txt): 3.4e3 warp instructions per site, of which
+//   27 %  the two posterior blocks (calculate_result_set for the genomic and the polymorphic prior), each run on 10 lanes,
+//         one after the other, with the double log10 / exp sequences issued warp-wide;
+//   22 %  the likelihood accumulation, 30 lanes busy with all / fwd-specific / rev-specific sums although the strand-specific
+//         sums are read only at SNP sites (position_snp_call_pprob_digt.cpp:522-533) and only for ONE genotype;
+//   12 %  the (strand x base) grouping: 8 ballot rounds per site, each a loop over the calls;
+//   17 %  the serial per-group phase, 32 (site, group) lanes of which a homozygous site fills 2 of its 8.
+// Here the same arithmetic is laid out so that the lanes are full:
+//   * grouping: with <= 32 calls a lane holds one call and 8 ballots give every group's members and rank;
+//   * the serial phase takes a compacted list of the NON-EMPTY (site, group) pairs of 12 sites, one pair per lane;
+//   * accumulation and posteriors run for THREE sites at once, 10 lanes each (lanes 30, 31 idle): the `all' sums only; the two
+//     strand-specific sums of the called genotype are computed by two lanes, for SNP sites only.
+// Every float sum keeps its order (one lane adds a genotype's terms call by call), so results are bit-identical to the kernels above.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int K2_B12 = 12;
+constexpr int K2_CAP12 = 96; // deepest site this kernel takes (shared memory: 12 sites x cap x 8 bytes per warp)
+
+// calculate_result_set for the 10 lanes [base, base + 10) (sl = lane - base; lanes with sl >= 10 take part in the shuffles only)
+__device__ __forceinline__ rs_out result_set_sub(float lh, const float* lnprior, uint32_t ref_gt, uint32_t base, uint32_t sl)
+{
+    const double pp = (sl < 10) ? static_cast<double>(f_add(lh, lnprior[sl])) : 0.0;
+    double mx = shfl_d(pp, base);
+    uint32_t max_gt = 0;
+#pragma unroll
+    for (int gt = 1; gt < 10; ++gt)
+    {
+        const double v = shfl_d(pp, base + gt);
+        if (v > mx)
+        {
+            mx = v;
+            max_gt = gt;
+        }
+    }
+    const double e = (sl < 10) ? exp(d_sub(pp, mx)) : 0.0;
+    double sum = 0.0;
+#pragma unroll
+    for (int gt = 0; gt < 10; ++gt) sum = d_add(sum, shfl_d(e, base + gt));
+    sum = d_div(1.0, sum);
+    const double p = d_mul(e, sum);
+    double comp = 0.0;
+#pragma unroll
+    for (int gt = 0; gt < 10; ++gt)
+    {
+        const double v = shfl_d(p, base + gt);
+        if (gt != (int)max_gt) comp = d_add(comp, v);
+    }
+    rs_out o;
+    o.max_gt = max_gt;
+    o.ref_pprob = shfl_d(p, base + ref_gt);
+    // the two log10 of a posterior block in ONE pass: sub-lane 0 takes ref_pprob, sub-lane 1 the complement
+    const double arg = (sl == 1) ? comp : o.ref_pprob;
+    const int q = error_prob_to_qphred_d(arg);
+    o.snp_qphred = __shfl_sync(FULL, q, base);
+    o.max_gt_qphred = __shfl_sync(FULL, q, base + 1);
+    return o;
+}
+
+__global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uint32_t* __restrict__ site_off, const uint16_t* __restrict__ calls_g,
+                                                                       const char* __restrict__ ref_base, const uint8_t* __restrict__ ploidy,
+                                                                       uint32_t n_sites, int is_always_test, const sx_tables* __restrict__ tables,
+                                                                       sx_digt_result* __restrict__ out, int* __restrict__ status, uint32_t cap)
+{
+    __shared__ germ_tables T;
+    extern __shared__ __align__(16) unsigned char k2_dyn[];
+    float* const s_val_all = reinterpret_cast<float*>(k2_dyn);
+    uint16_t* const s_calls_all = reinterpret_cast<uint16_t*>(k2_dyn + (size_t)K2_WARPS * K2_B12 * cap * 4);
+    uint16_t* const s_ord_all = s_calls_all + (size_t)K2_WARPS * K2_B12 * cap;
+    __shared__ uint16_t s_gstart[K2_WARPS][K2_B12][10];
+    __shared__ uint16_t s_n[K2_WARPS][K2_B12];
+    __shared__ uint8_t s_pair[K2_WARPS][K2_B12 * 8];
+    for (int i = threadIdx.x; i <= SX_MAX_QSCORE; i += blockDim.x)
+    {
+        T.eprob[i] = tables->g_eprob[i];
+        T.val1[i] = tables->g_val1[i];
+        T.val2[i] = tables->g_val2[i];
+        T.weight[i] = tables->g_weight[i];
+        T.depmin[i] = tables->g_depmin[i];
+    }
+    for (int i = threadIdx.x; i < 200; i += blockDim.x) (&T.lnprior[0][0][0][0])[i] = (&tables->g_lnprior[0][0][0][0])[i];
+    __syncthreads();
+    const float log_one_third = tables->g_log_one_third;
+    const float ln10f = tables->g_ln10f;
+    const float min_vexp = tables->g_min_vexp;
+    const double ssd_no = tables->g_ssd_no_mismatch, ssd_one = tables->g_ssd_one_mismatch;
+    const bool is_dep = tables->g_is_dependent_eprob != 0;
+    const bool is_limit_vexp = tables->g_is_min_vexp != 0;
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t gwarp = blockIdx.x * K2_WARPS + warp, nwarps = gridDim.x * K2_WARPS;
+    const uint32_t sub = lane < 30 ? lane / 10u : 2u, sl = lane - 10u * sub, sbase = 10u * sub; // the three 10-lane blocks of phase C
+
+    for (uint32_t base = gwarp * K2_B12; base < n_sites; base += nwarps * K2_B12)
+    {
+        const uint32_t nb = min((uint32_t)K2_B12, n_sites - base);
+        uint32_t nonref_mask = 0, n_pairs = 0;
+        // ---- phase A, site by site: CleanPileupFilter, initial eprobs, grouping, the list of non-empty groups
+        for (uint32_t s = 0; s < nb; ++s)
+        {
+            uint16_t* w_calls = s_calls_all + (warp * K2_B12 + s) * cap;
+            float* w_val = s_val_all + (warp * K2_B12 + s) * cap;
+            uint16_t* w_ord = s_ord_all + (warp * K2_B12 + s) * cap;
+            const uint32_t site = base + s;
+            const uint32_t c0 = site_off[site], c1 = site_off[site + 1];
+            uint32_t n_raw = c1 - c0;
+            if (n_raw > cap) // the host sizes cap from the deepest site
+            {
+                if (lane == 0) atomicOr(status, 16);
+                n_raw = 0;
+            }
+            const char rb = ref_base[site];
+            const uint32_t ref_gt = rb == 'A' ? 0u : rb == 'C' ? 1u : rb == 'G' ? 2u : rb == 'T' ? 3u : 4u;
+            uint32_t n = 0;
+            bool nonref = false;
+            for (uint32_t b = 0; b < n_raw; b += 32)
+            {
+                const uint32_t i = b + lane;
+                const uint32_t c = i < n_raw ? calls_g[c0 + i] : 0x1000u;
+                const bool keep = !((c >> 12) & 1u);
+                const uint32_t m = __ballot_sync(FULL, keep);
+                if (keep)
+                {
+                    w_calls[n + __popc(m & lt_mask)] = static_cast<uint16_t>(c);
+                    if (((c >> 6) & 15u) != ref_gt) nonref = true;
+                }
+                n += __popc(m);
+            }
+            if (__any_sync(FULL, nonref)) nonref_mask |= 1u << s;
+            __syncwarp();
+            for (uint32_t i = lane; i < n; i += 32) w_val[i] = T.eprob[w_calls[i] & 63u];
+            if (lane == 0) s_n[warp][s] = static_cast<uint16_t>(n);
+            if (is_dep)
+            {
+                // group = is_fwd + 2*base_id over the calls with q >= 3, pileup order kept inside a group (adjust_joint_eprob.cpp:209-232)
+                uint32_t start = 0, my_start = 0, my_size = 0;
+                for (uint32_t b = 0; b < n || b == 0; b += 32)
+                {
+                    const uint32_t i = b + lane;
+                    uint32_t gi = 0xffu;
+                    if (i < n)
+                    {
+                        const uint32_t c = w_calls[i];
+                        if ((c & 63u) >= 3u) gi = ((c >> 10) & 1u) + 2u * ((c >> 6) & 15u);
+                    }
+                    if (n <= 32)
+                    {
+                        // one pass: 8 ballots give members, ranks and sizes
+#pragma unroll
+                        for (uint32_t g = 0; g < 8; ++g)
+                        {
+                            const uint32_t m = __ballot_sync(FULL, gi == g);
+                            if (lane == g)
+                            {
+                                my_start = start;
+                                my_size = __popc(m);
+                            }
+                            if (gi == g) w_ord[start + __popc(m & lt_mask)] = static_cast<uint16_t>(i);
+                            start += __popc(m);
+                        }
+                        break;
+                    }
+                    // deeper sites: sizes first (this chunk's share of every group) ...
+#pragma unroll
+                    for (uint32_t g = 0; g < 8; ++g)
+                    {
+                        const uint32_t m = __ballot_sync(FULL, gi == g);
+                        if (lane == g) my_size += __popc(m);
+                    }
+                }
+                if (n > 32)
+                {
+                    // ... then the starts (exclusive prefix over the 8 groups) and the stable placement, chunk by chunk
+                    uint32_t run = 0;
+#pragma unroll
+                    for (uint32_t g = 0; g < 8; ++g)
+                    {
+                        const uint32_t sz = __shfl_sync(FULL, my_size, g);
+                        if (lane == g) my_start = run;
+                        run += sz;
+                    }
+                    uint32_t cursor = my_start; // lane g: next free slot of group g
+                    for (uint32_t b = 0; b < n; b += 32)
+                    {
+                        const uint32_t i = b + lane;
+                        uint32_t gi = 0xffu;
+                        if (i < n)
+                        {
+                            const uint32_t c = w_calls[i];
+                            if ((c & 63u) >= 3u) gi = ((c >> 10) & 1u) + 2u * ((c >> 6) & 15u);
+                        }
+#pragma unroll
+                        for (uint32_t g = 0; g < 8; ++g)
+                        {
+                            const uint32_t m = __ballot_sync(FULL, gi == g);
+                            const uint32_t cur = __shfl_sync(FULL, cursor, g);
+                            if (gi == g) w_ord[cur + __popc(m & lt_mask)] = static_cast<uint16_t>(i);
+                            if (lane == g) cursor += __popc(m);
+                        }
+                    }
+                }
+                if (lane < 8) s_gstart[warp][s][lane] = static_cast<uint16_t>(my_start);
+                const uint32_t total = __shfl_sync(FULL, my_start + my_size, 7);
+                if (lane == 8) s_gstart[warp][s][8] = static_cast<uint16_t>(total);
+                const uint32_t m8 = __ballot_sync(FULL, lane < 8 && my_size > 0);
+                if (lane < 8 && my_size > 0) s_pair[warp][n_pairs + __popc(m8 & lt_mask)] = static_cast<uint8_t>(s * 8u + lane);
+                n_pairs += __popc(m8);
+            }
+        }
+        __syncwarp();
+        // ---- phase B: one non-empty (site, group) pair per lane -- adjust_icalls_eprob (adjust_joint_eprob.cpp:100-180)
+        if (is_dep)
+        {
+            for (uint32_t p = lane; p < n_pairs; p += 32)
+            {
+                const uint32_t pr = s_pair[warp][p], s = pr >> 3, g = pr & 7u;
+                const uint16_t* w_calls = s_calls_all + (warp * K2_B12 + s) * cap;
+                float* w_val = s_val_all + (warp * K2_B12 + s) * cap;
+                const uint32_t g0 = s_gstart[warp][s][g], sz = s_gstart[warp][s][g + 1] - g0;
+                uint16_t* ic = s_ord_all + (warp * K2_B12 + s) * cap + g0;
+                float num = 0.f, den = 0.f; // :112-127, in pileup order (before the sort)
+                for (uint32_t k = 0; k < sz; ++k)
+                {
+                    const uint32_t c = w_calls[ic[k]];
+                    const float weight = T.weight[c & 63u];
+                    den = f_add(den, weight);
+                    if ((c >> 11) & 1u) num = f_add(num, weight);
+                }
+                float mismatch_frac = 0.f;
+                if (static_cast<double>(den) > 0.) mismatch_frac = f_div(num, den);
+                const float vexp_frac = static_cast<float>(d_add(d_mul(static_cast<double>(f_sub(1.0f, mismatch_frac)), ssd_no), d_mul(static_cast<double>(mismatch_frac), ssd_one)));
+                const QKey key{w_calls};
+                sx_stdsort_desc(ic, sz, key);
+                float vexp = 1.0f;
+                bool is_min_vexp = false;
+                const float step = f_sub(1.0f, vexp_frac);
+                for (uint32_t k = 0; k < sz; ++k)
+                {
+                    const uint32_t idx = ic[k];
+                    const uint32_t q = w_calls[idx] & 63u;
+                    if (!is_min_vexp)
+                    {
+                        w_val[idx] = dependent_eprob(T.eprob[q], vexp);
+                        const float next_vexp = f_mul(vexp, step);
+                        if (is_limit_vexp)
+                        {
+                            is_min_vexp = (next_vexp <= min_vexp);
+                            vexp = (min_vexp < next_vexp) ? next_vexp : min_vexp; // std::max(min_vexp, next_vexp)
+                        }
+                        else
+                        {
+                            vexp = next_vexp;
+                        }
+                    }
+                    else
+                    {
+                        w_val[idx] = T.depmin[q];
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---- val0 of every call of the batch: logf(de) + ln(1/3)  (position_snp_call_pprob_digt.cpp:352)
+        for (uint32_t s = 0; s < nb; ++s)
+        {
+            float* w_val = s_val_all + (warp * K2_B12 + s) * cap;
+            const uint32_t n = s_n[warp][s];
+            for (uint32_t i = lane; i < n; i += 32) w_val[i] = f_add(sx_logf(w_val[i]), log_one_third);
+        }
+        __syncwarp();
+        // ---- phase C, three sites at a time: likelihoods, PLs, posteriors
+        for (uint32_t s0 = 0; s0 < nb; s0 += 3)
+        {
+            const uint32_t s = s0 + sub;
+            const bool have = s < nb;
+            const uint32_t site = have ? base + s : base;
+            const uint16_t* w_calls = s_calls_all + (warp * K2_B12 + (have ? s : 0)) * cap;
+            const float* w_val = s_val_all + (warp * K2_B12 + (have ? s : 0)) * cap;
+            const uint32_t n = have ? s_n[warp][s] : 0u;
+            const char rb = ref_base[site];
+            const uint32_t ref_gt = rb == 'A' ? 0u : rb == 'C' ? 1u : rb == 'G' ? 2u : rb == 'T' ? 3u : 4u;
+            const bool nonref = (nonref_mask >> (have ? s : 0)) & 1u;
+            const bool computed = have && (ref_gt < 4u) && (is_always_test || nonref);
+            sx_digt_result* res = out + site;
+            if (have && !computed && sl < 10)
+            {
+                uint32_t* w = reinterpret_cast<uint32_t*>(res);
+                for (uint32_t i = sl; i < sizeof(sx_digt_result) / 4; i += 10) w[i] = 0u;
+            }
+            __syncwarp();
+            if (have && !computed && sl == 0)
+            {
+                res->ref_gt = (ref_gt < 4u) ? ref_gt : 0u;
+                res->n_used_calls = n;
+            }
+            const bool act = computed && sl < 10;
+            const uint32_t n_act = computed ? n : 0u;
+            const uint32_t n_loop = max(max(__shfl_sync(FULL, n_act, 0), __shfl_sync(FULL, n_act, 10)), __shfl_sync(FULL, n_act, 20));
+            const uint32_t e2_gt = expect2_pack(sl < 10u ? sl : 0u);
+            float lh = 0.f;
+            for (uint32_t i = 0; i < n_loop; ++i)
+            {
+                if (act && i < n)
+                {
+                    const uint32_t c = w_calls[i];
+                    const uint32_t q = c & 63u, obs = (c >> 6) & 3u;
+                    const uint32_t k = (e2_gt >> (2u * obs)) & 3u;
+                    const float v = (k == 0u) ? w_val[i] : (k == 1u) ? T.val1[q] : T.val2[q];
+                    lh = f_add(lh, v);
+                }
+            }
+            const bool haploid = have && ploidy != nullptr && ploidy[site] == 1;
+            const uint32_t gtcount = haploid ? 4u : 10u;
+            float lmax = __shfl_sync(FULL, lh, sbase);
+            for (uint32_t g = 1; g < 10; ++g)
+            {
+                const float v = __shfl_sync(FULL, lh, sbase + g);
+                if (g < gtcount && v > lmax) lmax = v;
+            }
+            uint32_t pl = 0;
+            if (act && sl < gtcount) pl = static_cast<uint32_t>(ln_error_prob_to_qphred_f(f_sub(lh, lmax), ln10f));
+            const uint32_t prg = (ref_gt < 4u) ? ref_gt : 0u;
+            const float* pri = T.lnprior[haploid ? 1 : 0][prg][0];
+            const rs_out genome = result_set_sub(lh, pri, prg, sbase, sl);
+            const rs_out poly = result_set_sub(lh, pri + 10, prg, sbase, sl);
+            // strand bias, SNP sites only: the fwd-specific and rev-specific sums of the called genotype (:522-533), on sub-lanes 0 and 1
+            double strand_bias = 0.0;
+            const bool is_snp = computed && genome.snp_qphred != 0;
+            if (__any_sync(FULL, is_snp))
+            {
+                float ls = 0.f;
+                if (is_snp && sl < 2)
+                {
+                    const uint32_t e2_t = expect2_pack(genome.max_gt), e2_ref = expect2_pack(ref_gt);
+                    for (uint32_t i = 0; i < n; ++i)
+                    {
+                        const uint32_t c = w_calls[i];
+                        const uint32_t q = c & 63u, obs = (c >> 6) & 3u, fwd = (c >> 10) & 1u;
+                        const bool force_ref = ((sl == 0u) != (fwd != 0u)); // sub-lane 0: the fwd-specific sum (reverse-strand calls forced to the reference), 1: rev-specific
+                        const uint32_t k = ((force_ref ? e2_ref : e2_t) >> (2u * obs)) & 3u;
+                        const float v = (k == 0u) ? w_val[i] : (k == 1u) ? T.val1[q] : T.val2[q];
+                        ls = f_add(ls, v);
+                    }
+                }
+                const float lf = __shfl_sync(FULL, ls, sbase), lr = __shfl_sync(FULL, ls, sbase + 1), l0 = __shfl_sync(FULL, lh, sbase + (is_snp ? genome.max_gt : 0u));
+                if (is_snp) strand_bias = static_cast<double>(f_sub((lf < lr) ? lr : lf, l0));
+            }
+            if (act)
+            {
+                res->lhood[sl] = lh;
+                res->phredLoghood[sl] = pl;
+            }
+            if (computed && sl == 0)
+            {
+                res->genome.ref_pprob = genome.ref_pprob;
+                res->genome.max_gt = genome.max_gt;
+                res->genome.snp_qphred = genome.snp_qphred;
+                res->genome.max_gt_qphred = genome.max_gt_qphred;
+                res->genome.pad = 0;
+                res->poly.ref_pprob = poly.ref_pprob;
+                res->poly.max_gt = poly.max_gt;
+                res->poly.snp_qphred = poly.snp_qphred;
+                res->poly.max_gt_qphred = poly.max_gt_qphred;
+                res->poly.pad = 0;
+                res->strand_bias = strand_bias;
+                res->ref_gt = ref_gt;
+                res->is_computed = 1;
+                res->n_used_calls = n;
+                res->pad = 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void k2_max_site_kernel(const uint32_t* __restrict__ site_off, uint32_t n_sites, uint32_t* __restrict__ out)
 {
     uint32_t m = 0;
@@ -635,6 +1012,20 @@ int germline_run(sx_ctx* ctx, const sx_pileup_batch* d, int is_always_test, sx_d
     const int grid = static_cast<int>(std::min<uint32_t>((d->n_sites + K2_WARPS - 1) / K2_WARPS, (uint32_t)ctx->sm_count * 8));
     if (max_site > K2_CAP_BIG)
         return sx_fail(ctx, SX_ERR_UNSUPPORTED, "sx_site_gl_germline: a site holds %u calls; the kernel handles at most %d per site", max_site, K2_CAP_BIG);
+    if (de_dev == nullptr && max_site <= K2_CAP12 && !getenv("SX_K2A_BATCH4"))
+    {
+        // twelve sites per warp: 8 bytes of shared memory per call slot
+        const uint32_t per_cta = K2_WARPS * K2_B12;
+        const uint32_t cap = std::max<uint32_t>(32, (max_site + 31) & ~31u);
+        const size_t smem = (size_t)per_cta * cap * 8;
+        int occ = 4;
+        SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2a_germline12_kernel, K2_WARPS * 32, smem));
+        const int grid12 = static_cast<int>(std::min<uint32_t>((d->n_sites + per_cta - 1) / per_cta, (uint32_t)(ctx->sm_count * std::max(1, occ))));
+        k2a_germline12_kernel<<<grid12, K2_WARPS * 32, smem, ctx->s_compute>>>(d->site_off, d->calls, d->ref_base, d->ploidy, d->n_sites, is_always_test, ctx->d_tables, out_dev,
+                                                                             ctx->d_status, cap);
+        SX_CUDA(ctx, cudaGetLastError());
+        return SX_OK;
+    }
     if (max_site <= K2_CAP_SMEM)
     {
         // every site fits the shared-memory cap: four sites per warp, 8 bytes of shared memory per call slot

@@ -170,8 +170,26 @@ struct k7_retry
 {
     uint32_t* list1; // [n_reads] reads the local tier passed on
     uint32_t* list2; // [n_reads] reads the small-arena tier passed on
-    uint32_t* n;     // [2] their counts
+    uint32_t* n;     // [3] their counts; n[2]: the reads of list0
+    uint32_t* list0; // [n_reads] or NULL: the reads the gates let through (batches with a gate array: about half of a 30x window's reads
+                     // never reach the search, and a thread that returns at once idles while its warp-mates search)
 };
+
+// dense list of the reads that go into the search, in read order within a warp's 32 (neighbouring list entries share their region's window)
+__global__ void k7_active_reads_kernel(const uint32_t n_reads, const uint8_t* __restrict__ gate, uint32_t* __restrict__ list0, uint32_t* __restrict__ count)
+{
+    const uint32_t lane(threadIdx.x & 31u);
+    for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) - lane; b < n_reads; b += gridDim.x * blockDim.x)
+    {
+        const uint32_t r(b + lane);
+        const bool on(r < n_reads && (gate[r] & SX_GATE_REALIGN));
+        const unsigned m(__ballot_sync(0xffffffffu, on));
+        uint32_t at(0);
+        if (lane == 0 && m) at = atomicAdd(count, (uint32_t)__popc(m));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (on) list0[at + __popc(m & ((1u << lane) - 1u))] = r;
+    }
+}
 
 __global__ void __launch_bounds__(K7_THREADS) k7_search_local_kernel(const k7_view v, const uint32_t* __restrict__ read_region, uint8_t* __restrict__ status,
                                                                      const k7_retry R, const k7_counts c, const k7_log L)
@@ -179,8 +197,10 @@ __global__ void __launch_bounds__(K7_THREADS) k7_search_local_kernel(const k7_vi
     __align__(16) unsigned char local[K7_LOCAL_BYTES];
     k7_scratch S(k7_scratch_at(local, K7_LOCAL_ALNS, K7_LOCAL_FRAMES, K7_ST_RETRY));
     const uint32_t t(blockIdx.x * blockDim.x + threadIdx.x), nthr(gridDim.x * blockDim.x);
-    for (uint32_t r = t; r < v.b.n_reads; r += nthr)
+    const uint32_t n_work(R.list0 ? R.n[2] : v.b.n_reads); // (with a list: the counts / status of the other reads were zeroed by the host side)
+    for (uint32_t i = t; i < n_work; i += nthr)
     {
+        const uint32_t r(R.list0 ? R.list0[i] : i);
         const uint32_t st(k7_enumerate_read(v, read_region[r], r, S));
         const bool retry((st & K7_ST_RETRY) != 0);
         uint32_t na(0), ns(0), nk(0);
@@ -352,6 +372,19 @@ int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsig
     if ((rc = sx_ensure(ctx, 67, 16, reinterpret_cast<void**>(&R.n)))) return rc;
     SX_CUDA(ctx, cudaMemsetAsync(L.cursor, 0, 16, st));
     SX_CUDA(ctx, cudaMemsetAsync(R.n, 0, 16, st));
+    R.list0 = nullptr;
+    unsigned extra(0);
+    if (d->gate)
+    {
+        if ((rc = sx_ensure(ctx, 68, (size_t)n * 4 + 16, reinterpret_cast<void**>(&R.list0)))) return rc;
+        SX_CUDA(ctx, cudaMemsetAsync(c.aln, 0, (size_t)n * 4, st));
+        SX_CUDA(ctx, cudaMemsetAsync(c.seg, 0, (size_t)n * 4, st));
+        SX_CUDA(ctx, cudaMemsetAsync(c.key, 0, (size_t)n * 4, st));
+        SX_CUDA(ctx, cudaMemsetAsync(o->status, 0, (size_t)n, st));
+        k7_active_reads_kernel<<<std::max(1, std::min<int>((int)((n + 255) / 256), ctx->sm_count * 8)), 256, 0, st>>>(n, d->gate, R.list0, R.n + 2);
+        SX_CUDA(ctx, cudaGetLastError());
+        extra = 1;
+    }
 
     k7_view v;
     v.b = *d;
@@ -373,7 +406,7 @@ int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsig
     const int g1(std::max(1, std::min<int>((int)((n + 127) / 128), ctx->sm_count * 16)));
     k7_gather_kernel<<<g1, 128, 0, st>>>(n, c, L, *o, totals);
     SX_CUDA(ctx, cudaGetLastError());
-    *launches = two_levels ? 8 : 7;
+    *launches = (two_levels ? 8 : 7) + extra;
     return SX_OK;
 }
 

@@ -554,6 +554,14 @@ extern "C" int sx_memcpy_d2h(sx_ctx* ctx, void* dst_host, const void* src_dev, s
     SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
     return SX_OK;
 }
+extern "C" int sx_memcpy_d2d(sx_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes)
+{
+    if (!ctx) return SX_ERR_ARG;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    SX_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->s_compute));
+    return SX_OK;
+}
+
 extern "C" int sx_synchronize(sx_ctx* ctx)
 {
     SX_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -256,6 +256,31 @@ def test_k2a_site_gl_germline(ctx, seed, depth, always):
     assert np.array_equal(_bits(o_de), _bits(g_de))
 
 
+@pytest.mark.parametrize("seed,depth", [(0, 50.0), (1, 20.0), (2, 33.0)])
+def test_k2a_twelve_sites_per_warp(ctx, seed, depth):
+    """the twelve-sites-per-warp kernel (every site <= 96 cleaned calls: one-ballot grouping up to 32 calls, chunked beyond; compacted
+    (site, group) pairs; three sites per posterior block; strand sums for SNP sites only) on batches that exercise both grouping paths,
+    haploid sites and is_always_test = False: every field against the oracle, bit for bit where the reference is float."""
+    rng = np.random.default_rng(2100 + seed)
+    pb0 = specgen.random_pileups(rng, 6000, depth=depth, max_depth=96)
+    assert int(np.diff(pb0.site_off.astype(np.int64)).max()) <= 96 and int(np.diff(pb0.site_off.astype(np.int64)).max()) > (32 if depth > 25 else 0)
+    pl = np.where(rng.random(pb0.n_sites) < 0.1, 1, 2).astype(np.uint8)
+    pb = B.PileupBatch(pb0.site_off, pb0.calls, pb0.ref_base, pl)
+    p = A.default_params()
+    for always in (True, False):
+        want = reflib.ox_germline(p, pb, always)
+        got = ctx.site_gl_germline(pb, always)
+        for f in ("ref_gt", "is_computed", "n_used_calls", "phredLoghood"):
+            assert np.array_equal(want[f], got[f]), f
+        assert np.array_equal(_bits(want["lhood"]), _bits(got["lhood"]))
+        assert np.array_equal(_bits(want["strand_bias"]), _bits(got["strand_bias"]))
+        assert int((want["strand_bias"] != 0).sum()) > 20
+        for rs in ("genome", "poly"):
+            for f in ("max_gt", "snp_qphred", "max_gt_qphred"):
+                assert np.array_equal(want[rs][f], got[rs][f]), (rs, f)
+            np.testing.assert_allclose(got[rs]["ref_pprob"], want[rs]["ref_pprob"], rtol=1e-12, atol=1e-300)
+
+
 def test_k2a_deep_and_empty_sites(ctx):
     rng = np.random.default_rng(31)
     deep = specgen.random_pileups(rng, 40, depth=900.0, max_depth=3000)  # beyond the shared-memory tile: global scratch path
