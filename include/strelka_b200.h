@@ -105,7 +105,7 @@ int sx_synchronize(sx_ctx* ctx);
  *   region.seq_off, region.qual_off, region.ref_off and the first insert-pool byte of a region
  *   are multiples of 16; the first segment index of a region is a multiple of 4; every pool is
  *   allocated with SX_POOL_SLACK spare bytes after its last used byte.  Violations return
- *   SX_ERR_ALIGNMENT.  The C++ host mirror (strelka_b200/host/sx_read_align.hh) builds
+ *   SX_ERR_ALIGNMENT.  The C++ host mirror (strelka_b200/host/strelka_b200.hh, sx::ReadAlignBatch) builds
  *   conforming batches from reference-shaped objects.
  * ======================================================================================== */
 #define SX_POOL_SLACK 64

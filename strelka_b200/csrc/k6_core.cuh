@@ -707,6 +707,7 @@ K6_HD k6_view k6_rebased(const k6_view& v, const k6_block_plan& p, unsigned char
 
 #define K6_FAST_A 8
 #define K6_FAST_E 4
+#define K6_MID_A 40 /* second local-memory tier: ncu put 20 % of the kernel's instructions on the strided-arena accessor once most reads had > 8 alignments */
 
 /// read r of a block whose view is `lv` (staged or not): find its region among the block's and run the body with the cheapest
 /// scratch that fits
@@ -718,6 +719,11 @@ K6_HD uint32_t k6_score_read_in_block(const k6_view& lv, const k6_block_plan& p,
     if (n_cal <= K6_FAST_A && slots <= K6_FAST_E)
     {
         k6_local_scratch<K6_FAST_A, K6_FAST_E> L;
+        return k6_score_read(lv, g, r, L);
+    }
+    if (n_cal <= K6_MID_A && slots <= K6_FAST_E) // (whole-path windows: 12 candidate alignments per realigned read on average, a few dozen at most)
+    {
+        k6_local_scratch<K6_MID_A, K6_FAST_E> L;
         return k6_score_read(lv, g, r, L);
     }
     return k6_score_read(lv, g, r, S);
