@@ -920,8 +920,9 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
                     const uint32_t c = w_calls[i];
                     const uint32_t q = c & 63u, obs = (c >> 6) & 3u;
                     const uint32_t k = (e2_gt >> (2u * obs)) & 3u;
-                    const float v = (k == 0u) ? w_val[i] : (k == 1u) ? T.val1[q] : T.val2[q];
-                    lh = f_add(lh, v);
+                    // one shared-memory load through a selected ADDRESS (a selected value made three divergent load paths: 16 of 32 lanes, ncu)
+                    const float* src = (k == 0u) ? (w_val + i) : (k == 1u) ? (T.val1 + q) : (T.val2 + q);
+                    lh = f_add(lh, *src);
                 }
             }
             const bool haploid = have && ploidy != nullptr && ploidy[site] == 1;
@@ -953,8 +954,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
                         const uint32_t q = c & 63u, obs = (c >> 6) & 3u, fwd = (c >> 10) & 1u;
                         const bool force_ref = ((sl == 0u) != (fwd != 0u)); // sub-lane 0: the fwd-specific sum (reverse-strand calls forced to the reference), 1: rev-specific
                         const uint32_t k = ((force_ref ? e2_ref : e2_t) >> (2u * obs)) & 3u;
-                        const float v = (k == 0u) ? w_val[i] : (k == 1u) ? T.val1[q] : T.val2[q];
-                        ls = f_add(ls, v);
+                        const float* src = (k == 0u) ? (w_val + i) : (k == 1u) ? (T.val1 + q) : (T.val2 + q);
+                        ls = f_add(ls, *src);
                     }
                 }
                 const float lf = __shfl_sync(FULL, ls, sbase), lr = __shfl_sync(FULL, ls, sbase + 1), l0 = __shfl_sync(FULL, lh, sbase + (is_snp ? genome.max_gt : 0u));

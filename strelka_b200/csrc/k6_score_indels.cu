@@ -17,6 +17,7 @@
 #include "sx_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace
 {
@@ -25,14 +26,28 @@ constexpr int K6_ST_SHIFT = 9; // K6_ST_* bits are reported as ctx status bits 5
 
 // sizes the launch needs: out[0] = max alignments of a read, out[1] = max output slots of a read, out[2] / out[3] = largest staging
 // footprint (k6_plan_block().bytes) of a 128-read / 32-read block
-__global__ void k6_max_kernel(const sx_score_indels_batch b, uint32_t* __restrict__ out)
+// (+ with `list`: the dense list of the reads that HAVE candidate alignments -- out[4] = their count --, in read order within a warp's 32)
+__global__ void k6_max_kernel(const sx_score_indels_batch b, uint32_t* __restrict__ out, uint32_t* __restrict__ list)
 {
     uint32_t mA(0), mS(0), m128(0), m32(0);
-    const uint32_t tid(blockIdx.x * blockDim.x + threadIdx.x), nthr(gridDim.x * blockDim.x);
-    for (uint32_t r = tid; r < b.n_reads; r += nthr)
+    const uint32_t tid(blockIdx.x * blockDim.x + threadIdx.x), nthr(gridDim.x * blockDim.x), lane(threadIdx.x & 31u);
+    for (uint32_t b0 = tid - lane; b0 < b.n_reads; b0 += nthr)
     {
-        mA = max(mA, b.aln_off[r + 1] - b.aln_off[r]);
-        mS = max(mS, b.rec_off[r + 1] - b.rec_off[r]);
+        const uint32_t r(b0 + lane);
+        const uint32_t nc(r < b.n_reads ? b.aln_off[r + 1] - b.aln_off[r] : 0u);
+        if (r < b.n_reads)
+        {
+            mA = max(mA, nc);
+            mS = max(mS, b.rec_off[r + 1] - b.rec_off[r]);
+        }
+        if (list)
+        {
+            const unsigned m(__ballot_sync(0xffffffffu, nc > 0));
+            uint32_t at(0);
+            if (lane == 0 && m) at = atomicAdd(out + 4, (uint32_t)__popc(m));
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (nc > 0) list[at + __popc(m & ((1u << lane) - 1u))] = r;
+        }
     }
     for (uint32_t c = tid; c < (b.n_reads + 31) / 32; c += nthr) // one thread per 32-read block (and per 128-read block)
     {
@@ -93,6 +108,45 @@ __global__ void __launch_bounds__(K6_THREADS) k6_score_kernel(const k6_view v, c
     if (st) atomicOr(status, (int)(st << K6_ST_SHIFT));
 }
 
+// the same per-read body over the dense list of reads that have alignments, on the global arrays (no staging): about half of a 30x window's
+// reads never reach the search, and in the block-staged kernel their threads idle (ncu: 10.9 of 32 lanes) while the staged slices hold the
+// occupancy at 9 warps per SM
+__global__ void __launch_bounds__(K6_THREADS) k6_score_list_kernel(const k6_view v, const k6_scratch S0, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list,
+                                                                  int* __restrict__ status)
+{
+    const uint32_t t(blockIdx.x * blockDim.x + threadIdx.x), nthr(gridDim.x * blockDim.x);
+    k6_scratch S(S0);
+    S.ord.p += t;
+    S.smooth.p += t;
+    S.filt.p += t;
+    S.ev.p += t;
+    S.slot.p += t;
+    S.present.p += t;
+    S.absent.p += t;
+    S.has.p += t;
+    S.alt.p += t;
+    S.pair.p += t;
+    uint32_t st(0);
+    const uint32_t n(*n_list);
+    k6_block_plan whole;
+    whole.g0 = 0;
+    whole.g1 = v.b.n_regions;
+    for (uint32_t i = t; i < n; i += nthr)
+    {
+        const uint32_t r(list[i]);
+        uint32_t lo(0), hi(v.b.n_regions); // the read's region: reads of a region are consecutive
+        while (lo + 1 < hi)
+        {
+            const uint32_t mid((lo + hi) / 2);
+            if (v.b.region_read_off[mid] <= r) lo = mid;
+            else hi = mid;
+        }
+        whole.g0 = lo;
+        st |= k6_score_read_in_block(v, whole, r, S);
+    }
+    if (st) atomicOr(status, (int)(st << K6_ST_SHIFT));
+}
+
 struct k6_layout
 {
     size_t off[10];
@@ -122,10 +176,13 @@ int k6_run(sx_ctx* ctx, const sx_score_indels_batch* d, const double* lnp_dev, c
     // sizes of the launch: the deepest read of the batch decides the scratch, the largest block footprint the shared memory
     uint32_t* d_max(nullptr);
     int rc;
-    if ((rc = sx_ensure(ctx, 29, 16, reinterpret_cast<void**>(&d_max)))) return rc;
-    SX_CUDA(ctx, cudaMemsetAsync(d_max, 0, 16, st));
+    if ((rc = sx_ensure(ctx, 29, 32, reinterpret_cast<void**>(&d_max)))) return rc;
+    SX_CUDA(ctx, cudaMemsetAsync(d_max, 0, 32, st));
+    static const bool use_list(getenv("SX_K6_STAGED") == nullptr); // (SX_K6_STAGED=1: the block-staged kernel, for A/B timing)
+    uint32_t* list(nullptr);
+    if (use_list && (rc = sx_ensure(ctx, 69, (size_t)d->n_reads * 4 + 16, reinterpret_cast<void**>(&list)))) return rc;
     const int grid0(std::max(1, std::min<int>((int)((d->n_reads + 255) / 256), ctx->sm_count * 8)));
-    k6_max_kernel<<<grid0, 256, 0, st>>>(*d, d_max);
+    k6_max_kernel<<<grid0, 256, 0, st>>>(*d, d_max, list);
     SX_CUDA(ctx, cudaGetLastError());
     uint32_t h_max[4] = {0, 0, 0, 0};
     SX_CUDA(ctx, cudaMemcpyAsync(h_max, d_max, 16, cudaMemcpyDeviceToHost, st));
@@ -134,10 +191,11 @@ int k6_run(sx_ctx* ctx, const sx_score_indels_batch* d, const double* lnp_dev, c
     // 128 reads per block when their slices fit a modest tile (several blocks per SM), else 32 reads per block; a block whose
     // slices still do not fit runs on the global arrays
     const uint32_t smem_limit(48u * 1024u - 512u); // (the kernel also has ~100 bytes of static shared memory: the two together must stay under the 48 KB no-opt-in limit)
-    const int threads(h_max[2] <= smem_limit ? K6_THREADS : 32);
-    const uint32_t smem_bytes(std::min(smem_limit, threads == K6_THREADS ? h_max[2] : h_max[3]));
+    const int threads(use_list || h_max[2] <= smem_limit ? K6_THREADS : 32);
+    const uint32_t smem_bytes(use_list ? 0u : std::min(smem_limit, threads == K6_THREADS ? h_max[2] : h_max[3]));
     int per_sm(1);
-    SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k6_score_kernel, threads, smem_bytes));
+    if (use_list) SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k6_score_list_kernel, threads, 0));
+    else SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k6_score_kernel, threads, smem_bytes));
     per_sm = std::max(1, per_sm);
 
     // threads: one per read, up to the resident blocks of every SM; fewer when a deep batch would make the arena too large
@@ -168,7 +226,16 @@ int k6_run(sx_ctx* ctx, const sx_score_indels_batch* d, const double* lnp_dev, c
     v.n_rec = out_dev->n_rec;
     v.max_aln = out_dev->max_aln;
     v.eval_aln = out_dev->eval_aln;
-    k6_score_kernel<<<(unsigned)(T / threads), threads, smem_bytes, st>>>(v, S, smem_bytes, ctx->d_status);
+    if (use_list)
+    {
+        // the reads without alignments answer "no records, no maximum alignment" (what the body writes for them)
+        SX_CUDA(ctx, cudaMemsetAsync(out_dev->n_rec, 0, (size_t)d->n_reads * 4, st));
+        SX_CUDA(ctx, cudaMemsetAsync(out_dev->max_aln, 0xFF, (size_t)d->n_reads * 4, st));
+        SX_CUDA(ctx, cudaMemsetAsync(out_dev->eval_aln, 0xFF, (size_t)d->n_reads * 4, st));
+        k6_score_list_kernel<<<(unsigned)(T / threads), threads, 0, st>>>(v, S, list, d_max + 4, ctx->d_status);
+    }
+    else
+        k6_score_kernel<<<(unsigned)(T / threads), threads, smem_bytes, st>>>(v, S, smem_bytes, ctx->d_status);
     SX_CUDA(ctx, cudaGetLastError());
     *launches = 2;
     return SX_OK;
