@@ -22,6 +22,7 @@
 #include "sx_scan3.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace
 {
@@ -337,6 +338,8 @@ int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsig
     per_sm = std::max(1, per_sm);
     per_sm_local = std::max(1, per_sm_local);
     const size_t n_blocks(((size_t)n + K7_THREADS - 1) / K7_THREADS);
+    // (SX_K7_LOCAL_BLOCKS_PER_SM: tuning knob -- fewer resident threads keep the tier's local-memory scratch closer to the L2's size)
+    if (const char* e = getenv("SX_K7_LOCAL_BLOCKS_PER_SM")) per_sm_local = std::max(1, std::min(per_sm_local, atoi(e)));
     const size_t blocks_local(std::min<size_t>(n_blocks, (size_t)ctx->sm_count * per_sm_local));
     // two arena tiers: a modest one (K7_MID_ALNS alignments per read, the whole device) for the reads the local tier passes on, and -- only when the
     // caller allows more per read -- one with the caller's capacity for the few that still do not fit (few threads: its per-thread scratch is large)
