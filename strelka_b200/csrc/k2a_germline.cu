@@ -629,6 +629,24 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline4_kernel(const uint
 // Every float sum keeps its order (one lane adds a genotype's terms call by call), so results are bit-identical to the kernels above.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int K2_B12 = 12;
+
+// shared-memory loads through 32-bit shared addresses: the accumulation picks one of three arrays per (call, genotype), and a selected
+// C++ pointer made the compiler branch per array (cuobjdump: BSSY / BRA around every load, 16 of 32 lanes active)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ float lds_f32(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+    return v;
+}
+// phase C's view of a call: obs << 14 | q << 3 | fwd  (q << 3 is the byte offset of the call's {val1, val2} pair)
+__device__ __forceinline__ uint32_t k2_repack(uint32_t c) { return (((c >> 6) & 3u) << 14) | ((c & 63u) << 3) | ((c >> 10) & 1u); }
 constexpr int K2_CAP12 = 96; // deepest site this kernel takes (shared memory: 12 sites x cap x 8 bytes per warp)
 
 // calculate_result_set for the 10 lanes [base, base + 10) (sl = lane - base; lanes with sl >= 10 take part in the shuffles only)
@@ -684,11 +702,14 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
     __shared__ uint16_t s_gstart[K2_WARPS][K2_B12][10];
     __shared__ uint16_t s_n[K2_WARPS][K2_B12];
     __shared__ uint8_t s_pair[K2_WARPS][K2_B12 * 8];
+    __shared__ float s_val12[2 * (SX_MAX_QSCORE + 1)]; // {val1[q], val2[q]} side by side: the two tables no longer share a bank
     for (int i = threadIdx.x; i <= SX_MAX_QSCORE; i += blockDim.x)
     {
         T.eprob[i] = tables->g_eprob[i];
         T.val1[i] = tables->g_val1[i];
         T.val2[i] = tables->g_val2[i];
+        s_val12[2 * i] = tables->g_val1[i];
+        s_val12[2 * i + 1] = tables->g_val2[i];
         T.weight[i] = tables->g_weight[i];
         T.depmin[i] = tables->g_depmin[i];
     }
@@ -876,11 +897,17 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
         }
         __syncwarp();
         // ---- val0 of every call of the batch: logf(de) + ln(1/3)  (position_snp_call_pprob_digt.cpp:352)
+        //      (and the calls in phase C's packing: the grouping bits are not needed any more)
         for (uint32_t s = 0; s < nb; ++s)
         {
             float* w_val = s_val_all + (warp * K2_B12 + s) * cap;
+            uint16_t* w_calls = s_calls_all + (warp * K2_B12 + s) * cap;
             const uint32_t n = s_n[warp][s];
-            for (uint32_t i = lane; i < n; i += 32) w_val[i] = f_add(sx_logf(w_val[i]), log_one_third);
+            for (uint32_t i = lane; i < n; i += 32)
+            {
+                w_val[i] = f_add(sx_logf(w_val[i]), log_one_third);
+                w_calls[i] = static_cast<uint16_t>(k2_repack(w_calls[i]));
+            }
         }
         __syncwarp();
         // ---- phase C, three sites at a time: likelihoods, PLs, posteriors
@@ -911,19 +938,20 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
             const bool act = computed && sl < 10;
             const uint32_t n_act = computed ? n : 0u;
             const uint32_t n_loop = max(max(__shfl_sync(FULL, n_act, 0), __shfl_sync(FULL, n_act, 10)), __shfl_sync(FULL, n_act, 20));
-            const uint32_t e2_gt = expect2_pack(sl < 10u ? sl : 0u);
+            // branch-free: every lane loads every step (addresses stay inside the warp's arrays) and the lanes past their site's end add +0.0f,
+            // which leaves a sum that started at +0.0f unchanged bit for bit
+            const uint32_t e2s = expect2_pack(sl < 10u ? sl : 0u) << 2; // expect2 << 2: the table offset of {val1, val2} in bytes
+            const uint32_t a_tab = smem_u32(s_val12) - 4u;
+            const uint32_t n_mine = act ? n : 0u;
+            uint32_t a_c = smem_u32(w_calls), a_v = smem_u32(w_val);
             float lh = 0.f;
-            for (uint32_t i = 0; i < n_loop; ++i)
+#pragma unroll 4
+            for (uint32_t i = 0; i < n_loop; ++i, a_c += 2u, a_v += 4u)
             {
-                if (act && i < n)
-                {
-                    const uint32_t c = w_calls[i];
-                    const uint32_t q = c & 63u, obs = (c >> 6) & 3u;
-                    const uint32_t k = (e2_gt >> (2u * obs)) & 3u;
-                    // one shared-memory load through a selected ADDRESS (a selected value made three divergent load paths: 16 of 32 lanes, ncu)
-                    const float* src = (k == 0u) ? (w_val + i) : (k == 1u) ? (T.val1 + q) : (T.val2 + q);
-                    lh = f_add(lh, *src);
-                }
+                const uint32_t r = lds_u16(a_c);
+                const uint32_t k4 = (e2s >> (r >> 13)) & 12u;
+                const float v = lds_f32(k4 ? a_tab + (r & 0x1f8u) + k4 : a_v);
+                lh = f_add(lh, i < n_mine ? v : 0.f);
             }
             const bool haploid = have && ploidy != nullptr && ploidy[site] == 1;
             const uint32_t gtcount = haploid ? 4u : 10u;
@@ -950,12 +978,11 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
                     const uint32_t e2_t = expect2_pack(genome.max_gt), e2_ref = expect2_pack(ref_gt);
                     for (uint32_t i = 0; i < n; ++i)
                     {
-                        const uint32_t c = w_calls[i];
-                        const uint32_t q = c & 63u, obs = (c >> 6) & 3u, fwd = (c >> 10) & 1u;
+                        const uint32_t r = w_calls[i]; // repacked: obs << 14 | q << 3 | fwd
+                        const uint32_t q = (r >> 3) & 63u, obs = r >> 14, fwd = r & 1u;
                         const bool force_ref = ((sl == 0u) != (fwd != 0u)); // sub-lane 0: the fwd-specific sum (reverse-strand calls forced to the reference), 1: rev-specific
                         const uint32_t k = ((force_ref ? e2_ref : e2_t) >> (2u * obs)) & 3u;
-                        const float* src = (k == 0u) ? (w_val + i) : (k == 1u) ? (T.val1 + q) : (T.val2 + q);
-                        ls = f_add(ls, *src);
+                        ls = f_add(ls, (k == 0u) ? w_val[i] : s_val12[2u * q + k - 1u]);
                     }
                 }
                 const float lf = __shfl_sync(FULL, ls, sbase), lr = __shfl_sync(FULL, ls, sbase + 1), l0 = __shfl_sync(FULL, lh, sbase + (is_snp ? genome.max_gt : 0u));
@@ -1017,7 +1044,10 @@ int germline_run(sx_ctx* ctx, const sx_pileup_batch* d, int is_always_test, sx_d
     {
         // twelve sites per warp: 8 bytes of shared memory per call slot
         const uint32_t per_cta = K2_WARPS * K2_B12;
-        const uint32_t cap = std::max<uint32_t>(32, (max_site + 31) & ~31u);
+        // per-site stride: even, and never a multiple of 16 slots -- phase C reads slot i of three consecutive sites in one instruction, and
+        // a stride of 32 (64) slots put the three float (16-bit) words on one bank (ncu: 58 % of the shared wavefronts were conflicts)
+        uint32_t cap = std::max<uint32_t>(18, (max_site + 1) & ~1u);
+        if (cap % 16 == 0) cap += 2;
         const size_t smem = (size_t)per_cta * cap * 8;
         int occ = 4;
         SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2a_germline12_kernel, K2_WARPS * 32, smem));
