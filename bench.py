@@ -1195,10 +1195,16 @@ def whole_path_main(args):
         clocks.start()
     barrier()
     t0 = time.perf_counter()
+    ctx.timer_mark(0)  # CUDA events on the stream the stages are launched on: the timed region is measured on the device
     for _ in range(args.steps):
         n_var_step = step_resident()
+    ctx.timer_mark(1)
+    dt_dev = ctx.timer_elapsed_ms() / 1e3
     barrier()
-    dt = time.perf_counter() - t0
+    dt_wall = time.perf_counter() - t0
+    # one context: every stage, copy and gather of the step is on that stream, so the event time IS the step (the host clock is kept beside it);
+    # several contexts: the other streams are not between the marks, so the bracketed host clock is the measure
+    dt = dt_dev if lanes == 1 else dt_wall
     launches = ctx.total_launches() - launches0
     step_totals = totals // args.steps
 
@@ -1303,6 +1309,8 @@ def whole_path_main(args):
         line = {
             "metric": "candidate_loci_per_sec", "value": value, "unit": "loci/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "timing": {"how": "CUDA events on the launching stream around the K steps, max over ranks" if lanes == 1 else "host clock between barrier + synchronize, max over ranks",
+                       "device_ms_per_step_rank0": 1e3 * dt_dev / args.steps, "host_clock_ms_per_step_rank0": 1e3 * dt_wall / args.steps},
             "config": {"workload": f"{args.config}: {desc}", "loci_per_gpu": n_loci, "windows_per_gpu": n_tiles, "loci_per_window": tile_loci, "reads_per_locus": WW.READS_PER_CELL,
                        "read_len": WW.READ_LEN, "sites_per_locus": WW.CELL_LEN, "step": "whole path: K7g, K7a, K7, K7b, K1, K6, K9, K4, K2a per window (sx_process_window_dev) + K3",
                        "concurrency": f"{lanes} contexts (own stream + buffers, one host thread each) take the windows in turn; kernel_ms_per_step sums each stage's device time "

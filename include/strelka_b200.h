@@ -90,6 +90,10 @@ int sx_memcpy_h2d(sx_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes
 int sx_memcpy_d2h(sx_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 int sx_memcpy_d2d(sx_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes); /* on ctx's compute stream, asynchronous */
 int sx_synchronize(sx_ctx* ctx);
+/* Device-side timing of a run of entry points: sx_timer_mark(ctx, 0) and (ctx, 1) record CUDA events on ctx's compute stream where they are
+ * called; sx_timer_elapsed_ms waits for mark 1 and returns the device time between the two (host gaps between launches included). */
+int sx_timer_mark(sx_ctx* ctx, int which);
+int sx_timer_elapsed_ms(sx_ctx* ctx, double* ms);
 
 /* ==========================================================================================
  * K1  score_alignments

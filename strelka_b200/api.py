@@ -135,6 +135,16 @@ class Context:
     def total_launches(self) -> int:
         return int(self.lib.sx_total_launches(self.h))
 
+    def timer_mark(self, which: int) -> None:
+        """Record a CUDA event on this context's compute stream (0 = start, 1 = stop)."""
+        self._chk(self.lib.sx_timer_mark(self.h, int(which)))
+
+    def timer_elapsed_ms(self) -> float:
+        """Device time between the two marks (waits for mark 1)."""
+        ms = C.c_double(0.0)
+        self._chk(self.lib.sx_timer_elapsed_ms(self.h, C.byref(ms)))
+        return ms.value
+
     def synchronize(self):
         self._chk(self.lib.sx_synchronize(self.h))
 

@@ -649,46 +649,6 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a)
 __device__ __forceinline__ uint32_t k2_repack(uint32_t c) { return (((c >> 6) & 3u) << 14) | ((c & 63u) << 3) | ((c >> 10) & 1u); }
 constexpr int K2_CAP12 = 96; // deepest site this kernel takes (shared memory: 12 sites x cap x 8 bytes per warp)
 
-// calculate_result_set for the 10 lanes [base, base + 10) (sl = lane - base; lanes with sl >= 10 take part in the shuffles only)
-__device__ __forceinline__ rs_out result_set_sub(float lh, const float* lnprior, uint32_t ref_gt, uint32_t base, uint32_t sl)
-{
-    const double pp = (sl < 10) ? static_cast<double>(f_add(lh, lnprior[sl])) : 0.0;
-    double mx = shfl_d(pp, base);
-    uint32_t max_gt = 0;
-#pragma unroll
-    for (int gt = 1; gt < 10; ++gt)
-    {
-        const double v = shfl_d(pp, base + gt);
-        if (v > mx)
-        {
-            mx = v;
-            max_gt = gt;
-        }
-    }
-    const double e = (sl < 10) ? exp(d_sub(pp, mx)) : 0.0;
-    double sum = 0.0;
-#pragma unroll
-    for (int gt = 0; gt < 10; ++gt) sum = d_add(sum, shfl_d(e, base + gt));
-    sum = d_div(1.0, sum);
-    const double p = d_mul(e, sum);
-    double comp = 0.0;
-#pragma unroll
-    for (int gt = 0; gt < 10; ++gt)
-    {
-        const double v = shfl_d(p, base + gt);
-        if (gt != (int)max_gt) comp = d_add(comp, v);
-    }
-    rs_out o;
-    o.max_gt = max_gt;
-    o.ref_pprob = shfl_d(p, base + ref_gt);
-    // the two log10 of a posterior block in ONE pass: sub-lane 0 takes ref_pprob, sub-lane 1 the complement
-    const double arg = (sl == 1) ? comp : o.ref_pprob;
-    const int q = error_prob_to_qphred_d(arg);
-    o.snp_qphred = __shfl_sync(FULL, q, base);
-    o.max_gt_qphred = __shfl_sync(FULL, q, base + 1);
-    return o;
-}
-
 __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uint32_t* __restrict__ site_off, const uint16_t* __restrict__ calls_g,
                                                                        const char* __restrict__ ref_base, const uint8_t* __restrict__ ploidy,
                                                                        uint32_t n_sites, int is_always_test, const sx_tables* __restrict__ tables,
@@ -702,6 +662,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
     __shared__ uint16_t s_gstart[K2_WARPS][K2_B12][10];
     __shared__ uint16_t s_n[K2_WARPS][K2_B12];
     __shared__ uint8_t s_pair[K2_WARPS][K2_B12 * 8];
+    __shared__ float s_lh[K2_WARPS][K2_B12][10]; // ln P(column | genotype) of the batch's sites, phase C -> phase D
     __shared__ float s_val12[2 * (SX_MAX_QSCORE + 1)]; // {val1[q], val2[q]} side by side: the two tables no longer share a bank
     for (int i = threadIdx.x; i <= SX_MAX_QSCORE; i += blockDim.x)
     {
@@ -769,7 +730,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
             if (is_dep)
             {
                 // group = is_fwd + 2*base_id over the calls with q >= 3, pileup order kept inside a group (adjust_joint_eprob.cpp:209-232)
-                uint32_t start = 0, my_start = 0, my_size = 0;
+                uint32_t my_start = 0, my_size = 0;
                 for (uint32_t b = 0; b < n || b == 0; b += 32)
                 {
                     const uint32_t i = b + lane;
@@ -781,19 +742,24 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
                     }
                     if (n <= 32)
                     {
-                        // one pass: 8 ballots give members, ranks and sizes
+                        // one pass: the three bits of the group id as ballots; a group's members are an AND of the three (or their complements),
+                        // which gives lane g < 8 its group's size and every call its rank (15 % of the kernel went into a ballot + store loop
+                        // over the 8 groups here)
+                        const uint32_t valid = __ballot_sync(FULL, gi < 8u);
+                        const uint32_t b0 = __ballot_sync(FULL, (gi & 1u) != 0u), b1 = __ballot_sync(FULL, (gi & 2u) != 0u), b2 = __ballot_sync(FULL, (gi & 4u) != 0u);
+                        const uint32_t of_lane = valid & ((lane & 1u) ? b0 : ~b0) & ((lane & 2u) ? b1 : ~b1) & ((lane & 4u) ? b2 : ~b2);
+                        const uint32_t of_call = valid & ((gi & 1u) ? b0 : ~b0) & ((gi & 2u) ? b1 : ~b1) & ((gi & 4u) ? b2 : ~b2);
+                        my_size = lane < 8u ? __popc(of_lane) : 0u;
+                        uint32_t incl = my_size;
 #pragma unroll
-                        for (uint32_t g = 0; g < 8; ++g)
+                        for (uint32_t d = 1; d < 8; d <<= 1)
                         {
-                            const uint32_t m = __ballot_sync(FULL, gi == g);
-                            if (lane == g)
-                            {
-                                my_start = start;
-                                my_size = __popc(m);
-                            }
-                            if (gi == g) w_ord[start + __popc(m & lt_mask)] = static_cast<uint16_t>(i);
-                            start += __popc(m);
+                            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                            if (lane >= d) incl += t;
                         }
+                        my_start = incl - my_size;
+                        const uint32_t st = __shfl_sync(FULL, my_start, gi & 7u);
+                        if (gi < 8u) w_ord[st + __popc(of_call & lt_mask)] = static_cast<uint16_t>(i);
                         break;
                     }
                     // deeper sites: sizes first (this chunk's share of every group) ...
@@ -910,7 +876,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
             }
         }
         __syncwarp();
-        // ---- phase C, three sites at a time: likelihoods, PLs, posteriors
+        // ---- phase C, three sites at a time: likelihoods and PLs
+        uint32_t computed_mask = 0;
         for (uint32_t s0 = 0; s0 < nb; s0 += 3)
         {
             const uint32_t s = s0 + sub;
@@ -963,52 +930,109 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
             }
             uint32_t pl = 0;
             if (act && sl < gtcount) pl = static_cast<uint32_t>(ln_error_prob_to_qphred_f(f_sub(lh, lmax), ln10f));
-            const uint32_t prg = (ref_gt < 4u) ? ref_gt : 0u;
-            const float* pri = T.lnprior[haploid ? 1 : 0][prg][0];
-            const rs_out genome = result_set_sub(lh, pri, prg, sbase, sl);
-            const rs_out poly = result_set_sub(lh, pri + 10, prg, sbase, sl);
-            // strand bias, SNP sites only: the fwd-specific and rev-specific sums of the called genotype (:522-533), on sub-lanes 0 and 1
-            double strand_bias = 0.0;
-            const bool is_snp = computed && genome.snp_qphred != 0;
-            if (__any_sync(FULL, is_snp))
-            {
-                float ls = 0.f;
-                if (is_snp && sl < 2)
-                {
-                    const uint32_t e2_t = expect2_pack(genome.max_gt), e2_ref = expect2_pack(ref_gt);
-                    for (uint32_t i = 0; i < n; ++i)
-                    {
-                        const uint32_t r = w_calls[i]; // repacked: obs << 14 | q << 3 | fwd
-                        const uint32_t q = (r >> 3) & 63u, obs = r >> 14, fwd = r & 1u;
-                        const bool force_ref = ((sl == 0u) != (fwd != 0u)); // sub-lane 0: the fwd-specific sum (reverse-strand calls forced to the reference), 1: rev-specific
-                        const uint32_t k = ((force_ref ? e2_ref : e2_t) >> (2u * obs)) & 3u;
-                        ls = f_add(ls, (k == 0u) ? w_val[i] : s_val12[2u * q + k - 1u]);
-                    }
-                }
-                const float lf = __shfl_sync(FULL, ls, sbase), lr = __shfl_sync(FULL, ls, sbase + 1), l0 = __shfl_sync(FULL, lh, sbase + (is_snp ? genome.max_gt : 0u));
-                if (is_snp) strand_bias = static_cast<double>(f_sub((lf < lr) ? lr : lf, l0));
-            }
             if (act)
             {
                 res->lhood[sl] = lh;
                 res->phredLoghood[sl] = pl;
+                s_lh[warp][s][sl] = lh; // the row phase D reads
             }
-            if (computed && sl == 0)
+            const uint32_t cm = __ballot_sync(FULL, computed && sl == 0u); // lanes 0, 10, 20
+            computed_mask |= ((cm & 1u) | ((cm >> 9) & 2u) | ((cm >> 18) & 4u)) << s0;
+        }
+        __syncwarp();
+        // ---- phase D: the posteriors, one (site, prior) pair per lane -- lanes 0-11 the genomic prior of sites 0-11, lanes 12-23 the polymorphic one.
+        //      calculate_result_set is a 10-term reduction with a double exp per term and two double log10: on 10 lanes per site and prior it
+        //      was issued 8 times per batch for the whole warp (27 % / 10 % of the instructions in the two captures); serially per lane it is
+        //      issued once.  Same operations in the same order per (site, prior), so the same bits.
+        {
+            const uint32_t ps = lane < 12u ? lane : lane - 12u;
+            const bool pact = lane < 24u && ps < nb && ((computed_mask >> ps) & 1u);
+            const uint32_t site = base + (pact ? ps : 0u);
+            const char rb = ref_base[site];
+            const uint32_t ref_gt = rb == 'A' ? 0u : rb == 'C' ? 1u : rb == 'G' ? 2u : rb == 'T' ? 3u : 0u;
+            sx_digt_result* res = out + site;
+            rs_out r;
+            r.ref_pprob = 0.0;
+            r.max_gt = 0;
+            r.snp_qphred = 0;
+            r.max_gt_qphred = 0;
+            if (pact)
             {
-                res->genome.ref_pprob = genome.ref_pprob;
-                res->genome.max_gt = genome.max_gt;
-                res->genome.snp_qphred = genome.snp_qphred;
-                res->genome.max_gt_qphred = genome.max_gt_qphred;
-                res->genome.pad = 0;
-                res->poly.ref_pprob = poly.ref_pprob;
-                res->poly.max_gt = poly.max_gt;
-                res->poly.snp_qphred = poly.snp_qphred;
-                res->poly.max_gt_qphred = poly.max_gt_qphred;
-                res->poly.pad = 0;
+                const bool haploid = ploidy != nullptr && ploidy[site] == 1;
+                const float* pri = T.lnprior[haploid ? 1 : 0][ref_gt][0] + (lane < 12u ? 0 : 10);
+                const float* lh10 = s_lh[warp][ps];
+                double e[10];
+                double mx = 0.0;
+#pragma unroll
+                for (int gt = 0; gt < 10; ++gt)
+                {
+                    e[gt] = static_cast<double>(f_add(lh10[gt], pri[gt]));
+                    if (gt == 0 || e[gt] > mx)
+                    {
+                        mx = e[gt];
+                        r.max_gt = gt;
+                    }
+                }
+                double sum = 0.0;
+#pragma unroll
+                for (int gt = 0; gt < 10; ++gt)
+                {
+                    e[gt] = exp(d_sub(e[gt], mx));
+                    sum = d_add(sum, e[gt]);
+                }
+                sum = d_div(1.0, sum);
+                double comp = 0.0;
+#pragma unroll
+                for (int gt = 0; gt < 10; ++gt)
+                {
+                    const double pg = d_mul(e[gt], sum);
+                    if (gt != (int)r.max_gt) comp = d_add(comp, pg);
+                    if (gt == (int)ref_gt) r.ref_pprob = pg;
+                }
+                r.snp_qphred = error_prob_to_qphred_d(r.ref_pprob);
+                r.max_gt_qphred = error_prob_to_qphred_d(comp);
+                sx_digt_result_set* dst = lane < 12u ? &res->genome : &res->poly;
+                dst->ref_pprob = r.ref_pprob;
+                dst->max_gt = r.max_gt;
+                dst->snp_qphred = r.snp_qphred;
+                dst->max_gt_qphred = r.max_gt_qphred;
+                dst->pad = 0;
+            }
+            // strand bias, SNP sites only (rare): the fwd-specific and rev-specific sums of the called genotype (:522-533) on lanes 0 and 1
+            double strand_bias = 0.0;
+            uint32_t snp_mask = __ballot_sync(FULL, pact && lane < 12u && r.snp_qphred != 0);
+            while (snp_mask)
+            {
+                const uint32_t s = __ffs(snp_mask) - 1u;
+                snp_mask &= snp_mask - 1u;
+                const uint32_t tgt = __shfl_sync(FULL, r.max_gt, s);
+                const uint16_t* w_calls = s_calls_all + (warp * K2_B12 + s) * cap;
+                const float* w_val = s_val_all + (warp * K2_B12 + s) * cap;
+                float ls = 0.f;
+                if (lane < 2u)
+                {
+                    const char rbs = ref_base[base + s];
+                    const uint32_t ref_s = rbs == 'A' ? 0u : rbs == 'C' ? 1u : rbs == 'G' ? 2u : 3u;
+                    const uint32_t e2_t = expect2_pack(tgt), e2_ref = expect2_pack(ref_s);
+                    const uint32_t n = s_n[warp][s];
+                    for (uint32_t i = 0; i < n; ++i)
+                    {
+                        const uint32_t c = w_calls[i]; // repacked: obs << 14 | q << 3 | fwd
+                        const uint32_t q = (c >> 3) & 63u, obs = c >> 14, fwd = c & 1u;
+                        const bool force_ref = ((lane == 0u) != (fwd != 0u)); // lane 0: the fwd-specific sum (reverse-strand calls forced to the reference), 1: rev-specific
+                        const uint32_t k = ((force_ref ? e2_ref : e2_t) >> (2u * obs)) & 3u;
+                        ls = f_add(ls, (k == 0u) ? w_val[i] : s_val12[2u * q + k - 1u]);
+                    }
+                }
+                const float lf = __shfl_sync(FULL, ls, 0), lr = __shfl_sync(FULL, ls, 1), l0 = s_lh[warp][s][tgt];
+                if (lane == s) strand_bias = static_cast<double>(f_sub((lf < lr) ? lr : lf, l0));
+            }
+            if (pact && lane < 12u)
+            {
                 res->strand_bias = strand_bias;
                 res->ref_gt = ref_gt;
                 res->is_computed = 1;
-                res->n_used_calls = n;
+                res->n_used_calls = s_n[warp][ps];
                 res->pad = 0;
             }
         }

@@ -33,16 +33,43 @@ __global__ void k7a_read_offsets_kernel(const k7a_view v, unsigned long long* __
     }
 }
 
-__global__ void k7a_count_kernel(const k7a_view v, const unsigned long long* __restrict__ read_byte, const uint32_t* __restrict__ read_region, uint32_t* __restrict__ cnt,
-                                 uint32_t* __restrict__ zero1, uint32_t* __restrict__ zero2, const sx_prep_out o)
+// The reads the gates turned away (about half of a 30x window's) have no keys: with a gate the two passes below run over the DENSE list of the
+// others (full warps instead of 9 of 32 lanes, ncu), and the first pass leaves a read's first K7A_STAGE keys in a staging row so that the second
+// pass copies them instead of walking the read again.
+#define K7A_STAGE 6u
+
+__global__ void k7a_active_reads_kernel(const uint32_t n_reads, const uint8_t* __restrict__ gate, uint32_t* __restrict__ list, uint32_t* __restrict__ count)
 {
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < v.b.n_reads; r += gridDim.x * blockDim.x)
+    const uint32_t lane(threadIdx.x & 31u);
+    for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) - lane; b < n_reads; b += gridDim.x * blockDim.x)
     {
+        const uint32_t r(b + lane);
+        const bool on(r < n_reads && (gate[r] & SX_GATE_REALIGN));
+        const unsigned m(__ballot_sync(0xffffffffu, on));
+        uint32_t at(0);
+        if (lane == 0 && m) at = atomicAdd(count, (uint32_t)__popc(m));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (on) list[at + __popc(m & ((1u << lane) - 1u))] = r;
+    }
+}
+
+// list == NULL: every read (and the per-read defaults are written here); otherwise the listed reads (the defaults were set by the host side)
+__global__ void k7a_count_kernel(const k7a_view v, const unsigned long long* __restrict__ read_byte, const uint32_t* __restrict__ read_region, uint32_t* __restrict__ cnt,
+                                 uint32_t* __restrict__ zero1, uint32_t* __restrict__ zero2, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list,
+                                 uint16_t* __restrict__ stage, const sx_prep_out o)
+{
+    const uint32_t n_work(list ? *n_list : v.b.n_reads);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t r(list ? list[i] : i);
         uint16_t keys[K7A_MAX_KEYS], lead, trail;
-        cnt[r] = k7a_read(v, read_region[r], r, read_byte[r], keys, lead, trail);
-        zero1[r] = zero2[r] = 0;
+        const uint32_t n(k7a_read(v, read_region[r], r, read_byte[r], keys, lead, trail));
+        cnt[r] = n;
+        if (!list) zero1[r] = zero2[r] = 0;
         o.in_lead_key[r] = lead;
         o.in_trail_key[r] = trail;
+        if (stage)
+            for (uint32_t k = 0; k < n && k < K7A_STAGE; ++k) stage[(size_t)r * K7A_STAGE + k] = keys[k];
     }
 }
 
@@ -67,14 +94,23 @@ __global__ void __launch_bounds__(K7_SCAN_THREADS) k7a_finish_kernel(const uint3
 }
 
 __global__ void k7a_write_kernel(const k7a_view v, const unsigned long long* __restrict__ read_byte, const uint32_t* __restrict__ read_region, const uint32_t* __restrict__ off,
-                                 const uint32_t* __restrict__ totals, const sx_prep_out o)
+                                 const uint32_t* __restrict__ totals, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, const uint16_t* __restrict__ stage,
+                                 const sx_prep_out o)
 {
     if (totals[0] > o.cap_keys) return;
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < v.b.n_reads; r += gridDim.x * blockDim.x)
+    const uint32_t n_work(list ? *n_list : v.b.n_reads);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x)
     {
+        const uint32_t r(list ? list[i] : i);
+        const uint32_t at(off[r]), n_known(o.in_key_off[r + 1] - at);
+        if (stage && n_known <= K7A_STAGE)
+        {
+            for (uint32_t k = 0; k < n_known; ++k) o.in_keys[at + k] = stage[(size_t)r * K7A_STAGE + k];
+            continue;
+        }
         uint16_t keys[K7A_MAX_KEYS], lead, trail;
         const uint32_t n(k7a_read(v, read_region[r], r, read_byte[r], keys, lead, trail));
-        for (uint32_t i = 0; i < n; ++i) o.in_keys[off[r] + i] = keys[i];
+        for (uint32_t k = 0; k < n; ++k) o.in_keys[at + k] = keys[k];
     }
 }
 
@@ -116,7 +152,25 @@ int k7a_run(sx_ctx* ctx, const k7a_view& v, const sx_prep_out* o, unsigned* laun
     const auto grid = [cap](const uint32_t m) { return (unsigned)std::max(1, std::min<int>((int)((m + 127) / 128), cap)); };
     k7a_read_offsets_kernel<<<grid(v.b.n_regions), 128, 0, st>>>(v, read_byte, read_region);
     SX_CUDA(ctx, cudaGetLastError());
-    k7a_count_kernel<<<grid(n), 128, 0, st>>>(v, read_byte, read_region, cnt, z1, z2, *o);
+    uint32_t *list(nullptr), *n_list(nullptr);
+    uint16_t* stage(nullptr);
+    unsigned extra(0);
+    if ((rc = sx_ensure(ctx, 39, (size_t)n * K7A_STAGE * 2 + 16, reinterpret_cast<void**>(&stage)))) return rc;
+    if (v.b.gate)
+    {
+        if ((rc = sx_ensure(ctx, 38, ((size_t)n + 4) * 4, reinterpret_cast<void**>(&list)))) return rc;
+        n_list = list + n;
+        SX_CUDA(ctx, cudaMemsetAsync(n_list, 0, 4, st));
+        SX_CUDA(ctx, cudaMemsetAsync(cnt, 0, (size_t)n * 4, st));
+        SX_CUDA(ctx, cudaMemsetAsync(z1, 0, (size_t)n * 4, st));
+        SX_CUDA(ctx, cudaMemsetAsync(z2, 0, (size_t)n * 4, st));
+        SX_CUDA(ctx, cudaMemsetAsync(o->in_lead_key, 0xFF, (size_t)n * 2, st)); // SX_NO_KEY
+        SX_CUDA(ctx, cudaMemsetAsync(o->in_trail_key, 0xFF, (size_t)n * 2, st));
+        k7a_active_reads_kernel<<<std::max(1, std::min<int>((int)((n + 255) / 256), ctx->sm_count * 8)), 256, 0, st>>>(n, v.b.gate, list, n_list);
+        SX_CUDA(ctx, cudaGetLastError());
+        extra = 1;
+    }
+    k7a_count_kernel<<<grid(n), 128, 0, st>>>(v, read_byte, read_region, cnt, z1, z2, list, n_list, stage, *o);
     SX_CUDA(ctx, cudaGetLastError());
     k7_scan_tiles<<<n_tiles, K7_SCAN_THREADS, 0, st>>>(n, cnt, z1, z2, sums, n_tiles);
     SX_CUDA(ctx, cudaGetLastError());
@@ -124,9 +178,9 @@ int k7a_run(sx_ctx* ctx, const k7a_view& v, const sx_prep_out* o, unsigned* laun
     SX_CUDA(ctx, cudaGetLastError());
     k7a_finish_kernel<<<n_tiles, K7_SCAN_THREADS, 0, st>>>(n, cnt, sums, totals, *o, ctx->d_status);
     SX_CUDA(ctx, cudaGetLastError());
-    k7a_write_kernel<<<grid(n), 128, 0, st>>>(v, read_byte, read_region, cnt, totals, *o);
+    k7a_write_kernel<<<grid(n), 128, 0, st>>>(v, read_byte, read_region, cnt, totals, list, n_list, stage, *o);
     SX_CUDA(ctx, cudaGetLastError());
-    *launches = 6;
+    *launches = 6 + extra;
     return SX_OK;
 }
 

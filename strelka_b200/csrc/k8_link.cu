@@ -47,25 +47,45 @@ __global__ void k8_size_kernel(const k8_view v, const uint32_t n_alns, const uin
     if (st) atomicOr(status, (int)(st << K8_ST_SHIFT));
 }
 
-// per region: exclusive offsets of its alignments within the region (in place) and the region's padded totals
+// per region: exclusive offsets of its alignments within the region (in place) and the region's padded totals.  One WARP per region: a region
+// of a 30x window holds a few hundred alignments, and one thread walking them was the whole cost of the link (3.05 of 4.5 ms per 50k loci, ncu)
 __global__ void k8_region_kernel(const k8_view v, uint32_t* __restrict__ seg_n, uint32_t* __restrict__ ins_n, uint32_t* __restrict__ reg_seg,
                                  uint32_t* __restrict__ reg_ins, uint32_t* __restrict__ reg_zero)
 {
-    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < v.b.n_regions; g += gridDim.x * blockDim.x)
+    const uint32_t lane(threadIdx.x & 31u), wpb(blockDim.x >> 5);
+    for (uint32_t g = blockIdx.x * wpb + (threadIdx.x >> 5); g < v.b.n_regions; g += gridDim.x * wpb)
     {
         const uint32_t a0(v.e.aln_off[v.b.region_read_off[g]]), a1(v.e.aln_off[v.b.region_read_off[g + 1]]);
         uint32_t s(0), n(0);
-        for (uint32_t a = a0; a < a1; ++a)
+        for (uint32_t b = a0; b < a1; b += 32)
         {
-            const uint32_t ds(seg_n[a]), dn(ins_n[a]);
-            seg_n[a] = s;
-            ins_n[a] = n;
-            s += ds;
-            n += dn;
+            const uint32_t a(b + lane);
+            const uint32_t ds(a < a1 ? seg_n[a] : 0u), dn(a < a1 ? ins_n[a] : 0u);
+            uint32_t is(ds), in(dn);
+#pragma unroll
+            for (uint32_t d = 1; d < 32; d <<= 1)
+            {
+                const uint32_t t(__shfl_up_sync(0xffffffffu, is, d)), u(__shfl_up_sync(0xffffffffu, in, d));
+                if (lane >= d)
+                {
+                    is += t;
+                    in += u;
+                }
+            }
+            if (a < a1)
+            {
+                seg_n[a] = s + is - ds;
+                ins_n[a] = n + in - dn;
+            }
+            s += __shfl_sync(0xffffffffu, is, 31);
+            n += __shfl_sync(0xffffffffu, in, 31);
         }
-        reg_seg[g] = (s + 7u) & ~7u;
-        reg_ins[g] = (n + 15u) & ~15u;
-        reg_zero[g] = 0;
+        if (lane == 0)
+        {
+            reg_seg[g] = (s + 7u) & ~7u;
+            reg_ins[g] = (n + 15u) & ~15u;
+            reg_zero[g] = 0;
+        }
     }
 }
 
@@ -172,7 +192,7 @@ int k8_run(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* e, const uint
     SX_CUDA(ctx, cudaGetLastError());
     k8_size_kernel<<<grid(n_alns), 128, 0, st>>>(v, n_alns, aln_read, read_region, seg_n, ins_n, ctx->d_status);
     SX_CUDA(ctx, cudaGetLastError());
-    k8_region_kernel<<<grid(nr), 128, 0, st>>>(v, seg_n, ins_n, reg_seg, reg_ins, reg_zero);
+    k8_region_kernel<<<grid((uint32_t)std::min<uint64_t>((uint64_t)nr * 32u, 0xffffff00u)), 128, 0, st>>>(v, seg_n, ins_n, reg_seg, reg_ins, reg_zero);
     SX_CUDA(ctx, cudaGetLastError());
     k7_scan_tiles<<<n_tiles, K7_SCAN_THREADS, 0, st>>>(nr, reg_seg, reg_ins, reg_zero, sums, n_tiles);
     SX_CUDA(ctx, cudaGetLastError());

@@ -452,6 +452,8 @@ extern "C" void sx_destroy(sx_ctx* ctx)
     for (auto ev : ctx->ev_pool) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_win)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_user)
+        if (ev) cudaEventDestroy(ev);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
@@ -559,6 +561,28 @@ extern "C" int sx_memcpy_d2d(sx_ctx* ctx, void* dst_dev, const void* src_dev, si
     if (!ctx) return SX_ERR_ARG;
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
     SX_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->s_compute));
+    return SX_OK;
+}
+
+// Two marks on the compute stream and the device time between them: how a caller times a run of entry points on the device instead of by the
+// host clock (bench.py's timed region).
+extern "C" int sx_timer_mark(sx_ctx* ctx, int which)
+{
+    if (!ctx || which < 0 || which > 1) return SX_ERR_ARG;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->ev_user[which]) SX_CUDA(ctx, cudaEventCreate(&ctx->ev_user[which]));
+    SX_CUDA(ctx, cudaEventRecord(ctx->ev_user[which], ctx->s_compute));
+    return SX_OK;
+}
+extern "C" int sx_timer_elapsed_ms(sx_ctx* ctx, double* ms)
+{
+    if (!ctx || !ms) return SX_ERR_ARG;
+    if (!ctx->ev_user[0] || !ctx->ev_user[1]) return sx_fail(ctx, SX_ERR_ARG, "sx_timer_elapsed_ms: both marks must have been set (sx_timer_mark 0 and 1)");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    SX_CUDA(ctx, cudaEventSynchronize(ctx->ev_user[1]));
+    float f = 0.f;
+    SX_CUDA(ctx, cudaEventElapsedTime(&f, ctx->ev_user[0], ctx->ev_user[1]));
+    *ms = f;
     return SX_OK;
 }
 

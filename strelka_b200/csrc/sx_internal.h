@@ -93,6 +93,7 @@ struct sx_ctx
     void* nccl = nullptr;    // ncclComm_t
     void* nccl_lib = nullptr;
     int rank = 0, world = 1;
+    cudaEvent_t ev_user[2] = {};     // sx_timer_mark
     cudaEvent_t ev_win[16] = {};     // stage boundaries of sx_process_window_dev (created on first use)
     float win_ms[16] = {};
     cudaStream_t s_comm = nullptr;   // the gather's own stream (created by sx_comm_init)
