@@ -138,9 +138,15 @@ __global__ void __launch_bounds__(K7_THREADS) k7_write_kernel(const k7_view v, u
 // records where; after the scan k7_gather_kernel copies every blob to its place in read order -- the output is independent of
 // which thread got which piece of the log.
 // ---------------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t K7_LOCAL_ALNS = 16, K7_LOCAL_FRAMES = 12;
+// The local tier comes in two sizes (SX_K7_LOCAL_ALNS=16|40, default 40): local memory a thread never touches costs nothing but address
+// space, while every read the tier passes on is searched a second time from the start in the slower arena.
+constexpr uint32_t K7_LOCAL_FRAMES = 12;
 constexpr uint32_t K7_MID_ALNS = 96; // per-read capacity of the first arena tier
-constexpr uint32_t K7_LOCAL_BYTES = 6400; // >= k7_scratch_bytes(K7_LOCAL_ALNS, K7_LOCAL_FRAMES); checked in k7_run_fast
+__host__ __device__ constexpr uint32_t k7_local_bytes(const uint32_t alns) // k7_scratch_bytes(alns, K7_LOCAL_FRAMES), as a constant expression (checked in k7_run_fast)
+{
+    return (uint32_t)(((((size_t)K7_MAX_INDELS * 2 + 15) & ~(size_t)15) + ((sizeof(k7_frame) * K7_LOCAL_FRAMES + 15) & ~(size_t)15) +
+                       ((sizeof(k7_cal) * ((size_t)alns + 1) + 15) & ~(size_t)15) + (((size_t)alns * 2 + 15) & ~(size_t)15) + 255) & ~(size_t)255);
+}
 
 struct k7_log
 {
@@ -192,10 +198,11 @@ __global__ void k7_active_reads_kernel(const uint32_t n_reads, const uint8_t* __
     }
 }
 
+template <uint32_t K7_LOCAL_ALNS>
 __global__ void __launch_bounds__(K7_THREADS) k7_search_local_kernel(const k7_view v, const uint32_t* __restrict__ read_region, uint8_t* __restrict__ status,
                                                                      const k7_retry R, const k7_counts c, const k7_log L)
 {
-    __align__(16) unsigned char local[K7_LOCAL_BYTES];
+    __align__(16) unsigned char local[k7_local_bytes(K7_LOCAL_ALNS)];
     k7_scratch S(k7_scratch_at(local, K7_LOCAL_ALNS, K7_LOCAL_FRAMES, K7_ST_RETRY));
     const uint32_t t(blockIdx.x * blockDim.x + threadIdx.x), nthr(gridDim.x * blockDim.x);
     const uint32_t n_work(R.list0 ? R.n[2] : v.b.n_reads); // (with a list: the counts / status of the other reads were zeroed by the host side)
@@ -321,8 +328,11 @@ int k7_run(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsigned* 
 
 int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsigned* launches)
 {
-    static_assert(K7_LOCAL_ALNS < 256 && K7_LOCAL_FRAMES <= K7_MAX_INDELS + 1, "local tier sizes");
-    if (k7_scratch_bytes(K7_LOCAL_ALNS, K7_LOCAL_FRAMES) > K7_LOCAL_BYTES) return sx_fail(ctx, SX_ERR_ARG, "k7: local scratch smaller than its contents");
+    static_assert(K7_LOCAL_FRAMES <= K7_MAX_INDELS + 1, "local tier sizes");
+    bool small_local(false);
+    if (const char* e = getenv("SX_K7_LOCAL_ALNS")) small_local = atoi(e) <= 16;
+    const auto local_kernel(small_local ? k7_search_local_kernel<16> : k7_search_local_kernel<40>);
+    if (k7_scratch_bytes(small_local ? 16 : 40, K7_LOCAL_FRAMES) > k7_local_bytes(small_local ? 16 : 40)) return sx_fail(ctx, SX_ERR_ARG, "k7: local scratch smaller than its contents");
     cudaStream_t st(ctx->s_compute);
     const uint32_t n(d->n_reads);
     const uint32_t maxA(d->opts.max_alns_per_read ? std::min<uint32_t>(d->opts.max_alns_per_read, 65535u) : 64u);
@@ -334,7 +344,7 @@ int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsig
     const size_t per_thread((k7_scratch_bytes(maxA, maxF) + 255) & ~(size_t)255);
     int per_sm(1), per_sm_local(1);
     SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k7_search_arena_kernel, K7_THREADS, 0));
-    SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_local, k7_search_local_kernel, K7_THREADS, 0));
+    SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_local, local_kernel, K7_THREADS, 0));
     per_sm = std::max(1, per_sm);
     per_sm_local = std::max(1, per_sm_local);
     const size_t n_blocks(((size_t)n + K7_THREADS - 1) / K7_THREADS);
@@ -391,7 +401,7 @@ int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsig
 
     k7_view v;
     v.b = *d;
-    k7_search_local_kernel<<<(unsigned)blocks_local, K7_THREADS, 0, st>>>(v, read_region, o->status, R, c, L);
+    local_kernel<<<(unsigned)blocks_local, K7_THREADS, 0, st>>>(v, read_region, o->status, R, c, L);
     SX_CUDA(ctx, cudaGetLastError());
     k7_search_arena_kernel<<<(unsigned)blocks1, K7_THREADS, 0, st>>>(v, arena1, per_thread1, maxA1, maxF, read_region, o->status, R, 1, two_levels ? 1 : 0, c, L);
     SX_CUDA(ctx, cudaGetLastError());
