@@ -1212,7 +1212,7 @@ def whole_path_main(args):
     # each take the windows alternately (one window's transfers overlap the other's kernels); the DP batch runs on a third.
     e2e = None
     if not args.no_e2e:
-        n_workers = 2 if n_tiles > 1 else 1
+        n_workers = max(1, min(args.e2e_workers, n_tiles))
         ctxs = [Context(local_rank) for _ in range(n_workers)]
         ctx_ga = Context(local_rank)
         ga_res, ga_cig = alloc.array(gb.n * A.GA_RESULT_DT.itemsize, A.GA_RESULT_DT), alloc.array(gb.n * gb.max_ops * 4, np.uint32)
@@ -1330,7 +1330,7 @@ def whole_path_main(args):
         }
         if e2e:
             line["e2e"] = {"value": total_loci * args.steps / e2e[0], "unit": "loci/s", "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2]),
-                           "ms_per_step": 1e3 * e2e[0] / args.steps, "how": "sx_process_window (host arrays in pinned memory) per window, two host threads with a context each; "
+                           "ms_per_step": 1e3 * e2e[0] / args.steps, "how": f"sx_process_window (host arrays in pinned memory) per window, {n_workers} host threads with a context each; "
                            "sx_global_align on a third; D2H = score_indels records + variant-site records + DP results"}
         if world == 1:
             # the reported CPU baseline: the reference's own functions, one pinned process per usable core, a bounded sample
@@ -1368,6 +1368,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "tiny", "cfg2-scoring", "cfg5", "tiny-scoring"])
     ap.add_argument("--loci", type=int, default=0, help="override the number of candidate loci per GPU")
     ap.add_argument("--tile-loci", type=int, default=0, help="candidate loci per window (whole-path step)")
+    ap.add_argument("--e2e-workers", type=int, default=2, help="host threads (one context each) of the end-to-end leg")
     ap.add_argument("--lanes", type=int, default=1, help="contexts that process the windows of a step concurrently (whole-path step); measured on a B200: no gain beyond 1 once the stages were tuned")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")

@@ -692,43 +692,28 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
     {
         const uint32_t nb = min((uint32_t)K2_B12, n_sites - base);
         uint32_t nonref_mask = 0, n_pairs = 0;
-        // ---- phase A, site by site: CleanPileupFilter, initial eprobs, grouping, the list of non-empty groups.
-        //      The batch's offsets and reference bases are loaded once (one lane per site) and the first 32 calls of site s + 1 are requested
-        //      before site s is worked on: offset -> calls was a chain of dependent global loads per site (15 % of the stall samples, ncu)
-        const uint32_t b_off = lane <= nb ? site_off[base + lane] : 0u;
-        const char b_ref = lane < nb ? ref_base[base + lane] : 'N';
-        uint32_t c_next = 0x1000u;
-        {
-            const uint32_t c0 = __shfl_sync(FULL, b_off, 0), c1 = __shfl_sync(FULL, b_off, 1);
-            if (lane < c1 - c0 && c1 - c0 <= cap) c_next = calls_g[c0 + lane];
-        }
+        // ---- phase A, site by site: CleanPileupFilter, initial eprobs, grouping, the list of non-empty groups
         for (uint32_t s = 0; s < nb; ++s)
         {
             uint16_t* w_calls = s_calls_all + (warp * K2_B12 + s) * cap;
             float* w_val = s_val_all + (warp * K2_B12 + s) * cap;
             uint16_t* w_ord = s_ord_all + (warp * K2_B12 + s) * cap;
-            const uint32_t c0 = __shfl_sync(FULL, b_off, s), c1 = __shfl_sync(FULL, b_off, s + 1);
+            const uint32_t site = base + s;
+            const uint32_t c0 = site_off[site], c1 = site_off[site + 1];
             uint32_t n_raw = c1 - c0;
             if (n_raw > cap) // the host sizes cap from the deepest site
             {
                 if (lane == 0) atomicOr(status, 16);
                 n_raw = 0;
             }
-            const uint32_t c_first = c_next;
-            c_next = 0x1000u;
-            if (s + 1 < nb)
-            {
-                const uint32_t d0 = c1, d1 = __shfl_sync(FULL, b_off, s + 2);
-                if (lane < d1 - d0 && d1 - d0 <= cap) c_next = calls_g[d0 + lane];
-            }
-            const char rb = static_cast<char>(__shfl_sync(FULL, static_cast<int>(b_ref), s));
+            const char rb = ref_base[site];
             const uint32_t ref_gt = rb == 'A' ? 0u : rb == 'C' ? 1u : rb == 'G' ? 2u : rb == 'T' ? 3u : 4u;
             uint32_t n = 0;
             bool nonref = false;
             for (uint32_t b = 0; b < n_raw; b += 32)
             {
                 const uint32_t i = b + lane;
-                const uint32_t c = b == 0 ? c_first : (i < n_raw ? calls_g[c0 + i] : 0x1000u);
+                const uint32_t c = i < n_raw ? calls_g[c0 + i] : 0x1000u;
                 const bool keep = !((c >> 12) & 1u);
                 const uint32_t m = __ballot_sync(FULL, keep);
                 if (keep)
@@ -1090,6 +1075,7 @@ int germline_run(sx_ctx* ctx, const sx_pileup_batch* d, int is_always_test, sx_d
         const size_t smem = (size_t)per_cta * cap * 8;
         int occ = 4;
         SX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2a_germline12_kernel, K2_WARPS * 32, smem));
+        if (const char* e = getenv("SX_K2A_BLOCKS_PER_SM")) occ = std::max(1, std::min(occ, atoi(e))); // (tuning knob: leave room for another stream's kernels)
         const int grid12 = static_cast<int>(std::min<uint32_t>((d->n_sites + per_cta - 1) / per_cta, (uint32_t)(ctx->sm_count * std::max(1, occ))));
         k2a_germline12_kernel<<<grid12, K2_WARPS * 32, smem, ctx->s_compute>>>(d->site_off, d->calls, d->ref_base, d->ploidy, d->n_sites, is_always_test, ctx->d_tables, out_dev,
                                                                              ctx->d_status, cap);

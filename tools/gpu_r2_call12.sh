@@ -1,0 +1,11 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+step() { local name=$1 secs=$2; shift 2; echo "== $name" | tee -a gpurun_out/r2c12.log; timeout "$secs" "$@" > "gpurun_out/$name.log" 2> "gpurun_out/$name.err"; echo "   exit $?" | tee -a gpurun_out/r2c12.log; }
+step t12_par 900 python -m pytest tests/test_gpu_parity.py -q -x -k "k2a or germline"
+step t12_enum 900 python -m pytest tests/test_zz_gpu_enumerate.py tests/test_zzz_gpu_enumerate_fast.py -q -x
+step t12_window 900 python -m pytest tests/test_zzzz_gpu_window.py -q -x
+step b12_40 600 python bench.py --loci 300000 --steps 2 --warmup 1 --no-legs --no-e2e
+step b12_16 600 env SX_K7_LOCAL_ALNS=16 python bench.py --loci 300000 --steps 2 --warmup 1 --no-legs --no-e2e
+tail -n 3 gpurun_out/t12_*.log
+cat gpurun_out/r2c12.log
