@@ -1304,7 +1304,10 @@ def whole_path_main(args):
                 traffic = tj[dom]["dram_bytes_read"] + tj[dom]["dram_bytes_write"]
         except Exception:
             pass
-        cells = sum(int(w.n_reads) for w in tiles) * 0  # (GCUPS is reported by the scoring leg; the whole path is quoted in loci/s)
+        # cell updates of a step: one per base of every candidate alignment scored (scoreCandidateAlignment walks the read once per alignment)
+        # + 3 states x Q x R per haplotype DP matrix
+        cells_k1 = int(step_totals[0]) * WW.READ_LEN
+        cells_k3 = gb.cells()
         whole_bytes = sum(WW.algorithmic_bytes(w, step_totals // n_tiles) for w in tiles)
         line = {
             "metric": "candidate_loci_per_sec", "value": value, "unit": "loci/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -1323,6 +1326,11 @@ def whole_path_main(args):
                                                                  "frac": whole_bytes / (dt / args.steps) / 1e9 / peak}},
             "stage_roofline": stage_roof,
             "gpu_launches": launches,
+            "gcups": (cells_k1 + cells_k3) * world / (dt / args.steps) / 1e9,
+            "gcups_parts": {"k1_score": cells_k1 / max(per_step["k1_score"], 1e-9) / 1e6, "k3_global_align": cells_k3 / max(per_step["k3_global_align"], 1e-9) / 1e6,
+                            "cells_per_step_per_gpu": {"k1": cells_k1, "k3": cells_k3},
+                            "definition": "k1: candidate alignments x read length (one cell per read base per scored alignment); k3: 3 x Q x R per matrix; "
+                                          "gcups = all cells / step time (the step also enumerates, piles up and genotypes), parts = a kernel's cells / its own time"},
             "kernel_ms_per_step": per_step,
             "per_step_totals": {"candidate_alignments": int(step_totals[0]), "k1_segments": int(step_totals[3]), "pileup_calls": int(step_totals[6]), "variant_sites": int(step_totals[8]),
                                 "variant_sites_last_step": int(n_var_step)},
