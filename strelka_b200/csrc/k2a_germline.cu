@@ -41,6 +41,11 @@ struct QKey // sort_icall_by_eprob's view: quality of call index i
     __device__ __forceinline__ uint32_t operator[](uint32_t i) const { return calls[i] & 63u; }
 };
 
+struct PKey // the same for elements that carry their quality: (q << 7) | call index (the twelve-site kernel: one shared load less per comparison)
+{
+    __device__ __forceinline__ uint32_t operator[](uint32_t packed) const { return packed >> 7; }
+};
+
 __device__ __forceinline__ float dependent_eprob(float eprob, float vexp) // get_dependent_eprob, adjust_joint_eprob.cpp:60-70
 {
     const float val = sx_powf(eprob, vexp);
@@ -718,14 +723,15 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
                 const uint32_t m = __ballot_sync(FULL, keep);
                 if (keep)
                 {
-                    w_calls[n + __popc(m & lt_mask)] = static_cast<uint16_t>(c);
+                    const uint32_t at = n + __popc(m & lt_mask);
+                    w_calls[at] = static_cast<uint16_t>(c);
+                    w_val[at] = T.eprob[c & 63u];
                     if (((c >> 6) & 15u) != ref_gt) nonref = true;
                 }
                 n += __popc(m);
             }
             if (__any_sync(FULL, nonref)) nonref_mask |= 1u << s;
             __syncwarp();
-            for (uint32_t i = lane; i < n; i += 32) w_val[i] = T.eprob[w_calls[i] & 63u];
             if (lane == 0) s_n[warp][s] = static_cast<uint16_t>(n);
             if (is_dep)
             {
@@ -734,11 +740,12 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
                 for (uint32_t b = 0; b < n || b == 0; b += 32)
                 {
                     const uint32_t i = b + lane;
-                    uint32_t gi = 0xffu;
+                    uint32_t gi = 0xffu, cq = 0;
                     if (i < n)
                     {
                         const uint32_t c = w_calls[i];
-                        if ((c & 63u) >= 3u) gi = ((c >> 10) & 1u) + 2u * ((c >> 6) & 15u);
+                        cq = c & 63u;
+                        if (cq >= 3u) gi = ((c >> 10) & 1u) + 2u * ((c >> 6) & 15u);
                     }
                     if (n <= 32)
                     {
@@ -759,7 +766,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
                         }
                         my_start = incl - my_size;
                         const uint32_t st = __shfl_sync(FULL, my_start, gi & 7u);
-                        if (gi < 8u) w_ord[st + __popc(of_call & lt_mask)] = static_cast<uint16_t>(i);
+                        if (gi < 8u) w_ord[st + __popc(of_call & lt_mask)] = static_cast<uint16_t>((cq << 7) | i); // (quality, call index): K2_CAP12 + 2 < 128
                         break;
                     }
                     // deeper sites: sizes first (this chunk's share of every group) ...
@@ -785,18 +792,19 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
                     for (uint32_t b = 0; b < n; b += 32)
                     {
                         const uint32_t i = b + lane;
-                        uint32_t gi = 0xffu;
+                        uint32_t gi = 0xffu, cq = 0;
                         if (i < n)
                         {
                             const uint32_t c = w_calls[i];
-                            if ((c & 63u) >= 3u) gi = ((c >> 10) & 1u) + 2u * ((c >> 6) & 15u);
+                            cq = c & 63u;
+                            if (cq >= 3u) gi = ((c >> 10) & 1u) + 2u * ((c >> 6) & 15u);
                         }
 #pragma unroll
                         for (uint32_t g = 0; g < 8; ++g)
                         {
                             const uint32_t m = __ballot_sync(FULL, gi == g);
                             const uint32_t cur = __shfl_sync(FULL, cursor, g);
-                            if (gi == g) w_ord[cur + __popc(m & lt_mask)] = static_cast<uint16_t>(i);
+                            if (gi == g) w_ord[cur + __popc(m & lt_mask)] = static_cast<uint16_t>((cq << 7) | i);
                             if (lane == g) cursor += __popc(m);
                         }
                     }
@@ -823,7 +831,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
                 float num = 0.f, den = 0.f; // :112-127, in pileup order (before the sort)
                 for (uint32_t k = 0; k < sz; ++k)
                 {
-                    const uint32_t c = w_calls[ic[k]];
+                    const uint32_t c = w_calls[ic[k] & 127u];
                     const float weight = T.weight[c & 63u];
                     den = f_add(den, weight);
                     if ((c >> 11) & 1u) num = f_add(num, weight);
@@ -831,15 +839,14 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
                 float mismatch_frac = 0.f;
                 if (static_cast<double>(den) > 0.) mismatch_frac = f_div(num, den);
                 const float vexp_frac = static_cast<float>(d_add(d_mul(static_cast<double>(f_sub(1.0f, mismatch_frac)), ssd_no), d_mul(static_cast<double>(mismatch_frac), ssd_one)));
-                const QKey key{w_calls};
+                const PKey key{};
                 sx_stdsort_desc(ic, sz, key);
                 float vexp = 1.0f;
                 bool is_min_vexp = false;
                 const float step = f_sub(1.0f, vexp_frac);
                 for (uint32_t k = 0; k < sz; ++k)
                 {
-                    const uint32_t idx = ic[k];
-                    const uint32_t q = w_calls[idx] & 63u;
+                    const uint32_t idx = ic[k] & 127u, q = ic[k] >> 7;
                     if (!is_min_vexp)
                     {
                         w_val[idx] = dependent_eprob(T.eprob[q], vexp);
