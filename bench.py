@@ -1376,7 +1376,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "tiny", "cfg2-scoring", "cfg5", "tiny-scoring"])
     ap.add_argument("--loci", type=int, default=0, help="override the number of candidate loci per GPU")
     ap.add_argument("--tile-loci", type=int, default=0, help="candidate loci per window (whole-path step)")
-    ap.add_argument("--e2e-workers", type=int, default=2, help="host threads (one context each) of the end-to-end leg")
+    ap.add_argument("--e2e-workers", type=int, default=3, help="host threads (one context each) of the end-to-end leg")
     ap.add_argument("--lanes", type=int, default=1, help="contexts that process the windows of a step concurrently (whole-path step); measured on a B200: no gain beyond 1 once the stages were tuned")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
