@@ -567,3 +567,27 @@ def test_k6_rejects_what_the_reference_asserts_on(ctx):
         assert e.value.code == A.SX_ERR_ARG
         sb.aln_keys[0] = k0
     _same_k6(reflib.ox_score_indels(sb, lnp), ctx.score_indels(sb, lnp))  # the context is usable again
+
+
+def test_device_timer_brackets_the_entry_points(ctx):
+    """sx_timer_mark / sx_timer_elapsed_ms (bench.py's timed region): the device time between two marks on the compute stream covers the kernels
+    launched between them; a second pair of marks replaces the first; elapsed before both marks is an error, not a number."""
+    from strelka_b200.api import Context, SxError
+
+    fresh = Context(0)
+    with pytest.raises(SxError):
+        fresh.timer_elapsed_ms()
+    fresh.close()
+    rng = np.random.default_rng(5)
+    pb = specgen.random_pileups(rng, 20000, depth=30.0, max_depth=96)
+    ctx.site_gl_germline(pb, True)  # warm
+    ctx.timer_mark(0)
+    ctx.timer_mark(1)
+    empty = ctx.timer_elapsed_ms()
+    ctx.timer_mark(0)
+    ctx.site_gl_germline(pb, True)
+    k = ctx.timing().kernel_ms
+    ctx.timer_mark(1)
+    ms = ctx.timer_elapsed_ms()
+    assert 0.0 <= empty < 1.0
+    assert ms >= k > 0.0
