@@ -667,7 +667,6 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
     __shared__ uint16_t s_gstart[K2_WARPS][K2_B12][10];
     __shared__ uint16_t s_n[K2_WARPS][K2_B12];
     __shared__ uint8_t s_pair[K2_WARPS][K2_B12 * 8];
-    __shared__ float s_cls[K2_WARPS][K2_B12][3]; // phase C0: the three distinct likelihood sums of a site whose calls all show the reference base
     __shared__ float s_lh[K2_WARPS][K2_B12][10]; // ln P(column | genotype) of the batch's sites, phase C -> phase D
     __shared__ float s_val12[2 * (SX_MAX_QSCORE + 1)]; // {val1[q], val2[q]} side by side: the two tables no longer share a bank
     for (int i = threadIdx.x; i <= SX_MAX_QSCORE; i += blockDim.x)
@@ -697,7 +696,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
     for (uint32_t base = gwarp * K2_B12; base < n_sites; base += nwarps * K2_B12)
     {
         const uint32_t nb = min((uint32_t)K2_B12, n_sites - base);
-        uint32_t nonref_mask = 0, acgt_mask = 0, n_pairs = 0;
+        uint32_t nonref_mask = 0, n_pairs = 0;
         // ---- phase A, site by site: CleanPileupFilter, initial eprobs, grouping, the list of non-empty groups
         for (uint32_t s = 0; s < nb; ++s)
         {
@@ -732,7 +731,6 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
                 n += __popc(m);
             }
             if (__any_sync(FULL, nonref)) nonref_mask |= 1u << s;
-            if (ref_gt < 4u) acgt_mask |= 1u << s;
             __syncwarp();
             if (lane == 0) s_n[warp][s] = static_cast<uint16_t>(n);
             if (is_dep)
@@ -885,35 +883,6 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
             }
         }
         __syncwarp();
-        // ---- phase C0: sites whose calls ALL show the reference base (86 % of a 30x window's positions at 0.5 % base errors).  expect2 of a
-        //      genotype then is the same for every call, so the 10 genotype sums are 3 distinct sums (homozygous reference: the calls' own
-        //      val0; the three hets with the reference: val1[q]; the other six: val2[q]) -- each the same additions in the same order as the
-        //      genotype's own lane would make.  Three lanes per site, ten sites per pass; phase C then only copies them.
-        const uint32_t uni_mask = is_always_test ? (~nonref_mask & acgt_mask & ((1u << nb) - 1u)) : 0u;
-        {
-            const uint32_t a_tab = smem_u32(s_val12) - 4u;
-            for (uint32_t rest = uni_mask; rest;)
-            {
-                const uint32_t j = lane / 3u, cls = lane - 3u * j;
-                const uint32_t s = lane < 30u ? __fns(rest, 0, static_cast<int>(j) + 1) : 0xffffffffu;
-                const bool on = s < 32u;
-                const uint32_t n = on ? s_n[warp][s] : 0u;
-                const uint32_t n_loop = __reduce_max_sync(FULL, n);
-                uint32_t a_c = smem_u32(s_calls_all + (warp * K2_B12 + (on ? s : 0u)) * cap), a_v = smem_u32(s_val_all + (warp * K2_B12 + (on ? s : 0u)) * cap);
-                float sum = 0.f;
-#pragma unroll 4
-                for (uint32_t i = 0; i < n_loop; ++i, a_c += 2u, a_v += 4u)
-                {
-                    const uint32_t r = lds_u16(a_c);
-                    const float v = lds_f32(cls ? a_tab + (r & 0x1f8u) + 4u * cls : a_v);
-                    sum = f_add(sum, i < n ? v : 0.f);
-                }
-                if (on) s_cls[warp][s][cls] = sum;
-                const uint32_t done = min(10u, static_cast<uint32_t>(__popc(rest)));
-                for (uint32_t k = 0; k < done; ++k) rest &= rest - 1u;
-            }
-        }
-        __syncwarp();
         // ---- phase C, three sites at a time: likelihoods and PLs
         uint32_t computed_mask = 0;
         for (uint32_t s0 = 0; s0 < nb; s0 += 3)
@@ -941,14 +910,13 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
                 res->n_used_calls = n;
             }
             const bool act = computed && sl < 10;
-            const bool uniform = have && ((uni_mask >> s) & 1u); // (then computed, and its sums are in s_cls)
-            const uint32_t n_act = (computed && !uniform) ? n : 0u;
+            const uint32_t n_act = computed ? n : 0u;
             const uint32_t n_loop = max(max(__shfl_sync(FULL, n_act, 0), __shfl_sync(FULL, n_act, 10)), __shfl_sync(FULL, n_act, 20));
             // branch-free: every lane loads every step (addresses stay inside the warp's arrays) and the lanes past their site's end add +0.0f,
             // which leaves a sum that started at +0.0f unchanged bit for bit
             const uint32_t e2s = expect2_pack(sl < 10u ? sl : 0u) << 2; // expect2 << 2: the table offset of {val1, val2} in bytes
             const uint32_t a_tab = smem_u32(s_val12) - 4u;
-            const uint32_t n_mine = (act && !uniform) ? n : 0u;
+            const uint32_t n_mine = act ? n : 0u;
             uint32_t a_c = smem_u32(w_calls), a_v = smem_u32(w_val);
             float lh = 0.f;
 #pragma unroll 4
@@ -959,7 +927,6 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
                 const float v = lds_f32(k4 ? a_tab + (r & 0x1f8u) + k4 : a_v);
                 lh = f_add(lh, i < n_mine ? v : 0.f);
             }
-            if (act && uniform) lh = s_cls[warp][s][(expect2_pack(sl) >> (2u * ref_gt)) & 3u];
             const bool haploid = have && ploidy != nullptr && ploidy[site] == 1;
             const uint32_t gtcount = haploid ? 4u : 10u;
             float lmax = __shfl_sync(FULL, lh, sbase);

@@ -198,8 +198,8 @@ __global__ void k7_active_reads_kernel(const uint32_t n_reads, const uint8_t* __
     }
 }
 
-template <uint32_t K7_LOCAL_ALNS>
-__global__ void __launch_bounds__(K7_THREADS) k7_search_local_kernel(const k7_view v, const uint32_t* __restrict__ read_region, uint8_t* __restrict__ status,
+template <uint32_t K7_LOCAL_ALNS, int K7_MIN_BLOCKS>
+__global__ void __launch_bounds__(K7_THREADS, K7_MIN_BLOCKS) k7_search_local_kernel(const k7_view v, const uint32_t* __restrict__ read_region, uint8_t* __restrict__ status,
                                                                      const k7_retry R, const k7_counts c, const k7_log L)
 {
     __align__(16) unsigned char local[k7_local_bytes(K7_LOCAL_ALNS)];
@@ -331,7 +331,13 @@ int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsig
     static_assert(K7_LOCAL_FRAMES <= K7_MAX_INDELS + 1, "local tier sizes");
     bool small_local(false);
     if (const char* e = getenv("SX_K7_LOCAL_ALNS")) small_local = atoi(e) <= 16;
-    const auto local_kernel(small_local ? k7_search_local_kernel<16> : k7_search_local_kernel<40>);
+    // the same kernel compiled for 16 / 24 / 32 resident blocks per SM (64 / 40 / 32 registers; its state lives in local memory, so the smaller
+    // register budgets spill next to nothing): more warps to hide its latency
+    const int min_blocks(getenv("SX_K7_MIN_BLOCKS") ? atoi(getenv("SX_K7_MIN_BLOCKS")) : 24); // measured per 1M loci: 267.6 / 261.5 / 279.0 ms at 16 / 24 / 32
+    const auto local_kernel(small_local ? k7_search_local_kernel<16, 16>
+                            : min_blocks >= 32 ? k7_search_local_kernel<40, 32>
+                            : min_blocks >= 24 ? k7_search_local_kernel<40, 24>
+                                               : k7_search_local_kernel<40, 16>);
     if (k7_scratch_bytes(small_local ? 16 : 40, K7_LOCAL_FRAMES) > k7_local_bytes(small_local ? 16 : 40)) return sx_fail(ctx, SX_ERR_ARG, "k7: local scratch smaller than its contents");
     cudaStream_t st(ctx->s_compute);
     const uint32_t n(d->n_reads);
