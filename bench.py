@@ -1339,7 +1339,7 @@ def whole_path_main(args):
         if e2e:
             line["e2e"] = {"value": total_loci * args.steps / e2e[0], "unit": "loci/s", "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2]),
                            "ms_per_step": 1e3 * e2e[0] / args.steps, "how": f"sx_process_window (host arrays in pinned memory) per window, {n_workers} host threads with a context each; "
-                           "sx_global_align on a third; D2H = score_indels records + variant-site records + DP results"}
+                           "sx_global_align on one more; D2H = score_indels records + variant-site records + DP results"}
         if world == 1:
             # the reported CPU baseline: the reference's own functions, one pinned process per usable core, a bounded sample
             try:
