@@ -1146,6 +1146,8 @@ def whole_path_main(args):
 
     def lane_work(li):
         acc = lane_ms[li]
+        if li and args.lane_offset_ms:  # stagger the contexts so that one's latency-bound stages (K7, K6) run beside the other's issue-bound ones (K2a, K4)
+            time.sleep(li * args.lane_offset_ms / 1e3)
         for i in range(li, n_tiles, lanes):
             for k, v in dws[i].run().items():
                 acc[k] = acc.get(k, 0.0) + v
@@ -1340,7 +1342,7 @@ def whole_path_main(args):
             line["e2e"] = {"value": total_loci * args.steps / e2e[0], "unit": "loci/s", "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2]),
                            "ms_per_step": 1e3 * e2e[0] / args.steps, "how": f"sx_process_window (host arrays in pinned memory) per window, {n_workers} host threads with a context each; "
                            "sx_global_align on one more; D2H = score_indels records + variant-site records + DP results"}
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             # the reported CPU baseline: the reference's own functions, one pinned process per usable core, a bounded sample
             try:
                 outs = run_reference_workers(ncpu, cpu_ids, args.cpu_sample_loci or 160, 2, 1, args.seed, timeout=600)
@@ -1351,6 +1353,7 @@ def whole_path_main(args):
                                         "per_core_loci_per_s": {"median": r["per_core_loci_per_s_median"], "min": r["per_core_loci_per_s_min"]}, "mean_seconds_per_part": r["mean_seconds_per_part"]}
             except SystemExit as e:
                 line["cpu_baseline"] = {"error": str(e)}
+        if world == 1:
             if args.legs:
                 for key, cmd in (("scoring_only_step", [sys.executable, os.path.abspath(__file__), "--config", "cfg2-scoring", "--steps", "5", "--warmup", "3", "--no-legs"]),
                                  ("k2b_somatic_cfg3", [sys.executable, os.path.join(ROOT, "tools", "site_legs.py"), "k2b", str(peak)]),
@@ -1378,8 +1381,10 @@ def main():
     ap.add_argument("--tile-loci", type=int, default=0, help="candidate loci per window (whole-path step)")
     ap.add_argument("--e2e-workers", type=int, default=3, help="host threads (one context each) of the end-to-end leg")
     ap.add_argument("--lanes", type=int, default=1, help="contexts that process the windows of a step concurrently (whole-path step); measured on a B200: no gain beyond 1 once the stages were tuned")
+    ap.add_argument("--lane-offset-ms", type=float, default=0.0, help="delay of context i's first window in a step: i x this (with --lanes > 1)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (tuning runs)")
     ap.add_argument("--no-legs", dest="legs", action="store_false", help="skip the single-kernel legs measured beside the headline step")
     ap.add_argument("--cpu-sample-loci", type=int, default=0)
     ap.add_argument("--worker-index", type=int, default=0)

@@ -654,7 +654,7 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a)
 __device__ __forceinline__ uint32_t k2_repack(uint32_t c) { return (((c >> 6) & 3u) << 14) | ((c & 63u) << 3) | ((c >> 10) & 1u); }
 constexpr int K2_CAP12 = 96; // deepest site this kernel takes (shared memory: 12 sites x cap x 8 bytes per warp)
 
-__global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uint32_t* __restrict__ site_off, const uint16_t* __restrict__ calls_g,
+__global__ void __launch_bounds__(K2_WARPS * 32, 8) k2a_germline12_kernel(const uint32_t* __restrict__ site_off, const uint16_t* __restrict__ calls_g,
                                                                        const char* __restrict__ ref_base, const uint8_t* __restrict__ ploidy,
                                                                        uint32_t n_sites, int is_always_test, const sx_tables* __restrict__ tables,
                                                                        sx_digt_result* __restrict__ out, int* __restrict__ status, uint32_t cap)
@@ -737,48 +737,76 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2a_germline12_kernel(const uin
             {
                 // group = is_fwd + 2*base_id over the calls with q >= 3, pileup order kept inside a group (adjust_joint_eprob.cpp:209-232)
                 uint32_t my_start = 0, my_size = 0;
-                for (uint32_t b = 0; b < n || b == 0; b += 32)
+                if (n <= 64)
                 {
-                    const uint32_t i = b + lane;
-                    uint32_t gi = 0xffu, cq = 0;
-                    if (i < n)
+                    // one or two chunks of 32 calls: the three bits of the group id as ballots; a group's members are an AND of the three (or their
+                    // complements), which gives lane g < 8 its group's size and every call its rank (15 % of the kernel went into a ballot + store loop
+                    // over the 8 groups here).  At 30x about four sites in ten hold 33-64 calls: they take the same path with a second set of ballots,
+                    // the second chunk's members ranked behind the first's (pileup order inside a group).
+                    uint32_t gi0 = 0xffu, cq0 = 0, gi1 = 0xffu, cq1 = 0;
+                    if (lane < n)
                     {
-                        const uint32_t c = w_calls[i];
-                        cq = c & 63u;
-                        if (cq >= 3u) gi = ((c >> 10) & 1u) + 2u * ((c >> 6) & 15u);
+                        const uint32_t c = w_calls[lane];
+                        cq0 = c & 63u;
+                        if (cq0 >= 3u) gi0 = ((c >> 10) & 1u) + 2u * ((c >> 6) & 15u);
                     }
-                    if (n <= 32)
+                    const bool two = n > 32; // warp-uniform
+                    if (two && 32u + lane < n)
                     {
-                        // one pass: the three bits of the group id as ballots; a group's members are an AND of the three (or their complements),
-                        // which gives lane g < 8 its group's size and every call its rank (15 % of the kernel went into a ballot + store loop
-                        // over the 8 groups here)
-                        const uint32_t valid = __ballot_sync(FULL, gi < 8u);
-                        const uint32_t b0 = __ballot_sync(FULL, (gi & 1u) != 0u), b1 = __ballot_sync(FULL, (gi & 2u) != 0u), b2 = __ballot_sync(FULL, (gi & 4u) != 0u);
-                        const uint32_t of_lane = valid & ((lane & 1u) ? b0 : ~b0) & ((lane & 2u) ? b1 : ~b1) & ((lane & 4u) ? b2 : ~b2);
-                        const uint32_t of_call = valid & ((gi & 1u) ? b0 : ~b0) & ((gi & 2u) ? b1 : ~b1) & ((gi & 4u) ? b2 : ~b2);
-                        my_size = lane < 8u ? __popc(of_lane) : 0u;
-                        uint32_t incl = my_size;
-#pragma unroll
-                        for (uint32_t d = 1; d < 8; d <<= 1)
-                        {
-                            const uint32_t t = __shfl_up_sync(FULL, incl, d);
-                            if (lane >= d) incl += t;
-                        }
-                        my_start = incl - my_size;
-                        const uint32_t st = __shfl_sync(FULL, my_start, gi & 7u);
-                        if (gi < 8u) w_ord[st + __popc(of_call & lt_mask)] = static_cast<uint16_t>((cq << 7) | i); // (quality, call index): K2_CAP12 + 2 < 128
-                        break;
+                        const uint32_t c = w_calls[32u + lane];
+                        cq1 = c & 63u;
+                        if (cq1 >= 3u) gi1 = ((c >> 10) & 1u) + 2u * ((c >> 6) & 15u);
                     }
-                    // deeper sites: sizes first (this chunk's share of every group) ...
-#pragma unroll
-                    for (uint32_t g = 0; g < 8; ++g)
+                    const uint32_t v0 = __ballot_sync(FULL, gi0 < 8u);
+                    const uint32_t p0 = __ballot_sync(FULL, (gi0 & 1u) != 0u), p1 = __ballot_sync(FULL, (gi0 & 2u) != 0u), p2 = __ballot_sync(FULL, (gi0 & 4u) != 0u);
+                    const uint32_t of_lane0 = v0 & ((lane & 1u) ? p0 : ~p0) & ((lane & 2u) ? p1 : ~p1) & ((lane & 4u) ? p2 : ~p2);
+                    const uint32_t of_call0 = v0 & ((gi0 & 1u) ? p0 : ~p0) & ((gi0 & 2u) ? p1 : ~p1) & ((gi0 & 4u) ? p2 : ~p2);
+                    const uint32_t size0 = lane < 8u ? __popc(of_lane0) : 0u;
+                    uint32_t of_call1 = 0;
+                    my_size = size0;
+                    if (two)
                     {
-                        const uint32_t m = __ballot_sync(FULL, gi == g);
-                        if (lane == g) my_size += __popc(m);
+                        const uint32_t v1 = __ballot_sync(FULL, gi1 < 8u);
+                        const uint32_t q0 = __ballot_sync(FULL, (gi1 & 1u) != 0u), q1 = __ballot_sync(FULL, (gi1 & 2u) != 0u), q2 = __ballot_sync(FULL, (gi1 & 4u) != 0u);
+                        const uint32_t of_lane1 = v1 & ((lane & 1u) ? q0 : ~q0) & ((lane & 2u) ? q1 : ~q1) & ((lane & 4u) ? q2 : ~q2);
+                        of_call1 = v1 & ((gi1 & 1u) ? q0 : ~q0) & ((gi1 & 2u) ? q1 : ~q1) & ((gi1 & 4u) ? q2 : ~q2);
+                        if (lane < 8u) my_size += __popc(of_lane1);
+                    }
+                    uint32_t incl = my_size;
+#pragma unroll
+                    for (uint32_t d = 1; d < 8; d <<= 1)
+                    {
+                        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                        if (lane >= d) incl += t;
+                    }
+                    my_start = incl - my_size;
+                    const uint32_t st0 = __shfl_sync(FULL, my_start, gi0 & 7u);
+                    if (gi0 < 8u) w_ord[st0 + __popc(of_call0 & lt_mask)] = static_cast<uint16_t>((cq0 << 7) | lane); // (quality, call index): K2_CAP12 + 2 < 128
+                    if (two)
+                    {
+                        const uint32_t st1 = __shfl_sync(FULL, my_start + size0, gi1 & 7u);
+                        if (gi1 < 8u) w_ord[st1 + __popc(of_call1 & lt_mask)] = static_cast<uint16_t>((cq1 << 7) | (32u + lane));
                     }
                 }
-                if (n > 32)
+                else
                 {
+                    // deeper sites: sizes first (every chunk's share of every group) ...
+                    for (uint32_t b = 0; b < n; b += 32)
+                    {
+                        const uint32_t i = b + lane;
+                        uint32_t gi = 0xffu;
+                        if (i < n)
+                        {
+                            const uint32_t c = w_calls[i];
+                            if ((c & 63u) >= 3u) gi = ((c >> 10) & 1u) + 2u * ((c >> 6) & 15u);
+                        }
+#pragma unroll
+                        for (uint32_t g = 0; g < 8; ++g)
+                        {
+                            const uint32_t m = __ballot_sync(FULL, gi == g);
+                            if (lane == g) my_size += __popc(m);
+                        }
+                    }
                     // ... then the starts (exclusive prefix over the 8 groups) and the stable placement, chunk by chunk
                     uint32_t run = 0;
 #pragma unroll

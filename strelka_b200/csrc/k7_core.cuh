@@ -42,7 +42,7 @@ struct k7_path // CandidateAlignment minus its indel set
     uint16_t lead, trail; // window index or SX_NO_KEY
     uint32_t n_seg;
     uint32_t ref_len;     // apath_ref_length of seg[0..n_seg), kept up to date by k7_push_seg (the search asks for it at every call)
-    sx_aln_seg seg[K7_MAX_SEGS]; // kind = SX_AP_*
+    uint32_t seg[K7_MAX_SEGS]; // one word per segment, sx_aln_seg's own bytes: len | kind << 16 | flags << 24 (kind = SX_AP_*); one load / store each
 };
 
 struct k7_cal // one element of the std::set<CandidateAlignment>; the key list sits in front of the (mostly empty) segment array so that an
@@ -130,6 +130,13 @@ struct k7_read // what the search reads of one read and its region
     const sx_enum_opts* opt;
 };
 
+K7_HD uint32_t k7_sw(const unsigned kind, const uint32_t len) { return len | ((uint32_t)kind << 16); }
+K7_HD unsigned k7_sk(const uint32_t w) { return (w >> 16) & 0xFFu; }
+K7_HD uint32_t k7_sl(const uint32_t w) { return w & 0xFFFFu; }
+K7_HD uint32_t k7_seg_load(const sx_aln_seg* a) // (the arrays are 4-byte aligned: device allocations, numpy buffers)
+{
+    return (uint32_t)a->len | ((uint32_t)a->kind << 16) | ((uint32_t)a->flags << 24);
+}
 K7_HD bool k7_is_mismatch(const sx_indel_key& k) { return k.type == SX_INDEL_TYPE_MISMATCH; }
 K7_HD int32_t k7_right(const sx_indel_key& k) { return k.pos + (int32_t)k.del_len; }
 K7_HD bool k7_prim_del(const sx_indel_key& k) { return k.type == SX_INDEL_TYPE_INDEL && k.ins_len == 0 && k.del_len > 0; }
@@ -169,7 +176,7 @@ K7_HD uint32_t k7_ref_length_of(const k7_path& p) // apath_ref_length, align_pat
 {
     uint32_t v(0);
     for (uint32_t i = 0; i < p.n_seg; ++i)
-        if (k7_seg_ref_len(p.seg[i].kind)) v += p.seg[i].len;
+        if (k7_seg_ref_len(k7_sk(p.seg[i]))) v += k7_sl(p.seg[i]);
     return v;
 }
 K7_HD uint32_t k7_ref_length(const k7_path& p) { return p.ref_len; }
@@ -179,8 +186,9 @@ K7_HD uint32_t k7_unaligned_prefix(const k7_path& p) // align_path.cpp:192-201
     uint32_t v(0);
     for (uint32_t i = 0; i < p.n_seg; ++i)
     {
-        if (!k7_seg_unaligned_edge(p.seg[i].kind)) return v;
-        if (k7_seg_read_len(p.seg[i].kind)) v += p.seg[i].len;
+        const uint32_t w(p.seg[i]);
+        if (!k7_seg_unaligned_edge(k7_sk(w))) return v;
+        if (k7_seg_read_len(k7_sk(w))) v += k7_sl(w);
     }
     return v;
 }
@@ -190,8 +198,9 @@ K7_HD uint32_t k7_unaligned_suffix(const k7_path& p) // align_path.cpp:206-215
     uint32_t v(0);
     for (uint32_t i = p.n_seg; i-- > 0;)
     {
-        if (!k7_seg_unaligned_edge(p.seg[i].kind)) return v;
-        if (k7_seg_read_len(p.seg[i].kind)) v += p.seg[i].len;
+        const uint32_t w(p.seg[i]);
+        if (!k7_seg_unaligned_edge(k7_sk(w))) return v;
+        if (k7_seg_read_len(k7_sk(w))) v += k7_sl(w);
     }
     return v;
 }
@@ -202,17 +211,19 @@ K7_HD void k7_soft_clip_range(const k7_path& p, int32_t& b, int32_t& e)
     uint32_t lead(0), trail(0);
     for (uint32_t i = 0; i < p.n_seg; ++i)
     {
-        const unsigned t(p.seg[i].kind);
+        const uint32_t w(p.seg[i]);
+        const unsigned t(k7_sk(w));
         if (t == SX_AP_HARD_CLIP || t == SX_AP_SOFT_CLIP) continue;
         if (t != SX_AP_INSERT) break;
-        lead += p.seg[i].len;
+        lead += k7_sl(w);
     }
     for (uint32_t i = p.n_seg; i-- > 0;)
     {
-        const unsigned t(p.seg[i].kind);
+        const uint32_t w(p.seg[i]);
+        const unsigned t(k7_sk(w));
         if (t == SX_AP_HARD_CLIP || t == SX_AP_SOFT_CLIP) continue;
         if (t != SX_AP_INSERT) break;
-        trail += p.seg[i].len;
+        trail += k7_sl(w);
     }
     b = p.pos - (int32_t)lead;
     e = p.pos + (int32_t)k7_ref_length(p) + (int32_t)trail;
@@ -221,9 +232,7 @@ K7_HD void k7_soft_clip_range(const k7_path& p, int32_t& b, int32_t& e)
 K7_HD bool k7_push_seg(k7_path& p, const unsigned kind, const uint32_t len)
 {
     if (p.n_seg >= K7_MAX_SEGS || len > 0xFFFFu) return false;
-    p.seg[p.n_seg].kind = (uint8_t)kind;
-    p.seg[p.n_seg].len = (uint16_t)len;
-    p.seg[p.n_seg].flags = 0;
+    p.seg[p.n_seg] = k7_sw(kind, len);
     p.n_seg++;
     if (k7_seg_ref_len(kind)) p.ref_len += len;
     return true;
@@ -246,6 +255,14 @@ K7_HD uint32_t k7_present_sorted(const uint16_t* order, const uint32_t n, const 
 
 // make_start_pos_alignment, :393-584.  0 = ok, else SX_ENUM_ST_EXCEPTION (a throw, or an assert the reference would trip) or
 // SX_ENUM_ST_LIMIT
+#define K7_PUSH(kind, len)                                                      \
+    do                                                                          \
+    {                                                                           \
+        const uint32_t k7_len_(len);                                            \
+        if (ns >= K7_MAX_SEGS || k7_len_ > 0xFFFFu) return SX_ENUM_ST_LIMIT;    \
+        cal.seg[ns++] = k7_sw(kind, k7_len_);                                   \
+        if (k7_seg_ref_len(kind)) rl += k7_len_;                                \
+    } while (0)
 K7_HDN uint32_t k7_make_start_pos(const sx_indel_key* win, const int32_t ref_start, const int32_t read_start, const uint32_t read_length, const uint16_t* indels,
                                   const uint32_t n_indels, k7_path& cal)
 {
@@ -253,8 +270,7 @@ K7_HDN uint32_t k7_make_start_pos(const sx_indel_key* win, const int32_t ref_sta
     const bool is_leading_read(read_start != 0);
     cal.pos = ref_start;
     cal.lead = cal.trail = SX_NO_KEY;
-    cal.n_seg = 0;
-    cal.ref_len = 0;
+    uint32_t ns(0), rl(0); // cal.n_seg / cal.ref_len, in registers until the path is complete
     int32_t ref_head(ref_start), read_head(read_start);
     bool prev_mismatch(false);
     for (uint32_t ii = 0; ii < n_indels; ++ii)
@@ -269,16 +285,16 @@ K7_HDN uint32_t k7_make_start_pos(const sx_indel_key* win, const int32_t ref_sta
             if (mismatch) continue;
             if (!is_leading_read) continue;
         }
-        const bool first(cal.n_seg == 0);
+        const bool first(ns == 0);
         if (is_leading_read && first)
         {
             if (ik.pos != ref_start) return SX_ENUM_ST_EXCEPTION;                 // :440-458 "Anomalous condition for indel candidate"
             if (ik.ins_len == 0) return SX_ENUM_ST_EXCEPTION;                     // assert :461 (breakends are not sent)
             if ((int32_t)ik.ins_len < read_start) return SX_ENUM_ST_EXCEPTION;    // assert :466
-            if (!k7_push_seg(cal, SX_AP_INSERT, (uint32_t)read_start)) return SX_ENUM_ST_LIMIT;
+            K7_PUSH(SX_AP_INSERT, (uint32_t)read_start);
             if (ik.del_len > 0)
             {
-                if (!k7_push_seg(cal, SX_AP_DELETE, ik.del_len)) return SX_ENUM_ST_LIMIT;
+                K7_PUSH(SX_AP_DELETE, ik.del_len);
                 ref_head += ik.del_len;
             }
             cal.lead = w;
@@ -296,13 +312,13 @@ K7_HDN uint32_t k7_make_start_pos(const sx_indel_key* win, const int32_t ref_sta
         if (((uint32_t)read_head + match_segment > read_length) || (((uint32_t)read_head + match_segment == read_length) && !k7_prim_del(ik))) break;
         if (match_segment > 0)
         {
-            if (!k7_push_seg(cal, SX_AP_MATCH, match_segment)) return SX_ENUM_ST_LIMIT;
+            K7_PUSH(SX_AP_MATCH, match_segment);
             ref_head += (int32_t)match_segment;
             read_head += (int32_t)match_segment;
         }
         if (mismatch)
         {
-            if (!k7_push_seg(cal, SX_AP_SEQ_MISMATCH, ik.del_len)) return SX_ENUM_ST_LIMIT;
+            K7_PUSH(SX_AP_SEQ_MISMATCH, ik.del_len);
             ref_head += ik.del_len;
             read_head += ik.del_len;
             if (read_head >= (int32_t)read_length) break;
@@ -311,14 +327,14 @@ K7_HDN uint32_t k7_make_start_pos(const sx_indel_key* win, const int32_t ref_sta
         {
             if (ik.del_len > 0)
             {
-                if (!k7_push_seg(cal, SX_AP_DELETE, ik.del_len)) return SX_ENUM_ST_LIMIT;
+                K7_PUSH(SX_AP_DELETE, ik.del_len);
                 ref_head += ik.del_len;
             }
             if (ik.ins_len > 0)
             {
                 const uint32_t max_insert_length(read_length - (uint32_t)read_head);
                 const uint32_t insert_length(ik.ins_len < max_insert_length ? ik.ins_len : max_insert_length);
-                if (!k7_push_seg(cal, SX_AP_INSERT, insert_length)) return SX_ENUM_ST_LIMIT;
+                K7_PUSH(SX_AP_INSERT, insert_length);
                 read_head += (int32_t)insert_length;
                 if (ik.ins_len >= max_insert_length)
                 {
@@ -338,10 +354,14 @@ K7_HDN uint32_t k7_make_start_pos(const sx_indel_key* win, const int32_t ref_sta
     if (read_head > (int32_t)read_length) return SX_ENUM_ST_EXCEPTION; // assert :577
     if (read_head < (int32_t)read_length)
     {
-        if (!k7_push_seg(cal, SX_AP_MATCH, read_length - (uint32_t)read_head)) return SX_ENUM_ST_LIMIT;
+        K7_PUSH(SX_AP_MATCH, read_length - (uint32_t)read_head);
     }
+    cal.n_seg = ns;
+    cal.ref_len = rl;
     return 0;
 }
+
+#undef K7_PUSH
 
 // get_end_pin_start_pos, :593-719
 K7_HDN uint32_t k7_end_pin_start_pos(const sx_indel_key* win, const uint16_t* indels, const uint32_t n_indels, const uint32_t read_length, const int32_t ref_end,
@@ -414,8 +434,10 @@ K7_HD int k7_compare(const k7_cal& a, const k7_cal& b)
     if (a.p.n_seg != b.p.n_seg) return a.p.n_seg < b.p.n_seg ? -1 : 1;
     for (uint32_t i = 0; i < a.p.n_seg; ++i)
     {
-        if (a.p.seg[i].kind != b.p.seg[i].kind) return a.p.seg[i].kind < b.p.seg[i].kind ? -1 : 1;
-        if (a.p.seg[i].len != b.p.seg[i].len) return a.p.seg[i].len < b.p.seg[i].len ? -1 : 1;
+        const uint32_t wa(a.p.seg[i]), wb(b.p.seg[i]); // (flags are always 0 here)
+        if (wa == wb) continue;
+        if (k7_sk(wa) != k7_sk(wb)) return k7_sk(wa) < k7_sk(wb) ? -1 : 1;
+        return k7_sl(wa) < k7_sl(wb) ? -1 : 1;
     }
     const uint32_t m(a.n_keys < b.n_keys ? a.n_keys : b.n_keys);
     for (uint32_t i = 0; i < m; ++i)
@@ -459,18 +481,23 @@ K7_HDN uint32_t k7_emit(const k7_read& R, k7_scratch& S, const k7_frame& f, cons
     if (fcal.lead != SX_NO_KEY && !k7_add_key(c, fcal.lead)) return SX_ENUM_ST_LIMIT;
     if (fcal.trail != SX_NO_KEY && !k7_add_key(c, fcal.trail)) return SX_ENUM_ST_LIMIT;
     // apath_clip_adder, align_path.cpp:515-549
-    c.p.pos = fcal.pos;
-    c.p.lead = fcal.lead;
-    c.p.trail = fcal.trail;
-    c.p.n_seg = 0;
-    c.p.ref_len = 0;
-    bool ok(true);
-    if (R.hc_lead) ok = ok && k7_push_seg(c.p, SX_AP_HARD_CLIP, R.hc_lead);
-    if (R.sc_lead) ok = ok && k7_push_seg(c.p, SX_AP_SOFT_CLIP, R.sc_lead);
-    for (uint32_t i = 0; i < fcal.n_seg; ++i) ok = ok && k7_push_seg(c.p, fcal.seg[i].kind, fcal.seg[i].len);
-    if (R.sc_trail) ok = ok && k7_push_seg(c.p, SX_AP_SOFT_CLIP, R.sc_trail);
-    if (R.hc_trail) ok = ok && k7_push_seg(c.p, SX_AP_HARD_CLIP, R.hc_trail);
-    if (!ok) return SX_ENUM_ST_LIMIT;
+    // (the counters stay in registers: the path is written once, a word per segment; clips carry no reference length)
+    {
+        const uint32_t n_in(fcal.n_seg);
+        const uint32_t extra((R.hc_lead ? 1u : 0u) + (R.sc_lead ? 1u : 0u) + (R.sc_trail ? 1u : 0u) + (R.hc_trail ? 1u : 0u));
+        if (n_in + extra > K7_MAX_SEGS || R.hc_lead > 0xFFFFu || R.sc_lead > 0xFFFFu || R.sc_trail > 0xFFFFu || R.hc_trail > 0xFFFFu) return SX_ENUM_ST_LIMIT;
+        uint32_t m(0);
+        if (R.hc_lead) c.p.seg[m++] = k7_sw(SX_AP_HARD_CLIP, R.hc_lead);
+        if (R.sc_lead) c.p.seg[m++] = k7_sw(SX_AP_SOFT_CLIP, R.sc_lead);
+        for (uint32_t i = 0; i < n_in; ++i) c.p.seg[m++] = fcal.seg[i];
+        if (R.sc_trail) c.p.seg[m++] = k7_sw(SX_AP_SOFT_CLIP, R.sc_trail);
+        if (R.hc_trail) c.p.seg[m++] = k7_sw(SX_AP_HARD_CLIP, R.hc_trail);
+        c.p.pos = fcal.pos;
+        c.p.lead = fcal.lead;
+        c.p.trail = fcal.trail;
+        c.p.n_seg = m;
+        c.p.ref_len = fcal.ref_len;
+    }
     // is_alignment_spanned_by_range, :1455-1459
     if (!(sb >= R.realign_begin && se <= R.realign_end)) return 0;
     // std::set::insert
@@ -919,7 +946,7 @@ K7_HDN uint32_t k7_enumerate_read_raw(const k7_view& v, const uint32_t region, c
         f.cal.lead = b.in_lead_key[r];
         f.cal.trail = b.in_trail_key[r];
         f.cal.n_seg = ns;
-        for (uint32_t i = 0; i < ns; ++i) f.cal.seg[i] = b.in_segs[s0 + i];
+        for (uint32_t i = 0; i < ns; ++i) f.cal.seg[i] = k7_seg_load(b.in_segs + s0 + i);
         f.cal.ref_len = k7_ref_length_of(f.cal);
     }
     // indel set of the exemplar, :1843-1845
@@ -992,17 +1019,17 @@ K7_HDN uint32_t k7_enumerate_read_raw(const k7_view& v, const uint32_t region, c
     uint32_t cal_read_length(read_length);
     {
         const uint32_t ns(f.cal.n_seg);
-        const bool clipped(ns > 0 && (f.cal.seg[0].kind == SX_AP_SOFT_CLIP || f.cal.seg[0].kind == SX_AP_HARD_CLIP ||
-                                      (ns > 1 && (f.cal.seg[ns - 1].kind == SX_AP_SOFT_CLIP || f.cal.seg[ns - 1].kind == SX_AP_HARD_CLIP))));
+        const bool clipped(ns > 0 && (k7_sk(f.cal.seg[0]) == SX_AP_SOFT_CLIP || k7_sk(f.cal.seg[0]) == SX_AP_HARD_CLIP ||
+                                      (ns > 1 && (k7_sk(f.cal.seg[ns - 1]) == SX_AP_SOFT_CLIP || k7_sk(f.cal.seg[ns - 1]) == SX_AP_HARD_CLIP))));
         if (clipped)
         {
             bool is_lead(true);
             uint32_t m(0);
             for (uint32_t i = 0; i < ns; ++i)
             {
-                const sx_aln_seg sg(f.cal.seg[i]);
-                if (sg.kind == SX_AP_HARD_CLIP) (is_lead ? R.hc_lead : R.hc_trail) += sg.len;
-                else if (sg.kind == SX_AP_SOFT_CLIP) (is_lead ? R.sc_lead : R.sc_trail) += sg.len;
+                const uint32_t sg(f.cal.seg[i]);
+                if (k7_sk(sg) == SX_AP_HARD_CLIP) (is_lead ? R.hc_lead : R.hc_trail) += k7_sl(sg);
+                else if (k7_sk(sg) == SX_AP_SOFT_CLIP) (is_lead ? R.sc_lead : R.sc_trail) += k7_sl(sg);
                 else
                 {
                     is_lead = false;
@@ -1058,7 +1085,7 @@ K7_HD void k7_write(const k7_scratch& S, const sx_enum_out& o, const uint32_t a0
         o.aln_trail_key[a] = c.p.trail;
         o.aln_seg_off[a] = s0;
         o.aln_key_off[a] = k0;
-        for (uint32_t j = 0; j < c.p.n_seg; ++j) o.segs[s0 + j] = c.p.seg[j];
+        for (uint32_t j = 0; j < c.p.n_seg; ++j) o.segs[s0 + j] = sx_aln_seg{(uint16_t)k7_sl(c.p.seg[j]), (uint8_t)k7_sk(c.p.seg[j]), (uint8_t)(c.p.seg[j] >> 24)};
         for (uint32_t j = 0; j < c.n_keys; ++j) o.aln_keys[k0 + j] = c.keys[j];
         s0 += c.p.n_seg;
         k0 += c.n_keys;
@@ -1082,7 +1109,7 @@ K7_HD void k7_blob_write(const k7_scratch& S, uint32_t* dst)
         *dst++ = (uint32_t)c.p.pos;
         *dst++ = (uint32_t)c.p.lead | ((uint32_t)c.p.trail << 16);
         *dst++ = c.p.n_seg | (c.n_keys << 8);
-        for (uint32_t j = 0; j < c.p.n_seg; ++j) *dst++ = (uint32_t)c.p.seg[j].len | ((uint32_t)c.p.seg[j].kind << 16) | ((uint32_t)c.p.seg[j].flags << 24);
+        for (uint32_t j = 0; j < c.p.n_seg; ++j) *dst++ = c.p.seg[j];
         for (uint32_t j = 0; j < c.n_keys; j += 2) *dst++ = (uint32_t)c.keys[j] | ((j + 1 < c.n_keys ? (uint32_t)c.keys[j + 1] : 0u) << 16);
     }
 }

@@ -75,7 +75,7 @@ extern "C" int k7core_make_start_pos(const sx_indel_key* win, uint32_t n_win, in
     *lead = cal.lead;
     *trail = cal.trail;
     *n_seg = cal.n_seg;
-    for (uint32_t i = 0; i < cal.n_seg; ++i) segs[i] = cal.seg[i];
+    for (uint32_t i = 0; i < cal.n_seg; ++i) segs[i] = sx_aln_seg{(uint16_t)k7_sl(cal.seg[i]), (uint8_t)k7_sk(cal.seg[i]), (uint8_t)(cal.seg[i] >> 24)};
     return 0;
 }
 
