@@ -1087,6 +1087,12 @@ def whole_path_main(args):
     threads = max(1, ncpu // max(1, world))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; strelka_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    # several ranks share the host's CPU quota (16 CPUs on the GPU boxes): their waiting threads block instead of spinning (see sx_set_host_wait_policy)
+    host_wait = "blocking" if (world > 1 or os.environ.get("SX_BLOCKING_WAIT") == "1") else "spin (driver default)"
+    if host_wait == "blocking":
+        from strelka_b200 import _abi as _A0
+        if _A0.load().sx_set_host_wait_policy(local_rank, 1) != 0:
+            host_wait = "spin (blocking policy refused)"
     torch.cuda.set_device(local_rank)
     numa = bind_to_gpu_numa(local_rank) if world > 1 else "single rank: not bound"
     if world > 1:
@@ -1321,7 +1327,7 @@ def whole_path_main(args):
                        "concurrency": f"{lanes} contexts (own stream + buffers, one host thread each) take the windows in turn; kernel_ms_per_step sums each stage's device time "
                                       "over the contexts, so the stages add up to more than ms_per_step",
                        "parallelism": f"window-shard x{world}, one NCCL gatherv of variant-site records per step" if world > 1 else "single GPU",
-                       "l2": "inputs (%.1f GB per GPU) far exceed the 126 MB L2; no flush needed" % (sum(WW.input_bytes(w) for w in tiles) / 1e9), "gen_seconds": round(t_gen, 1), "host_binding": numa},
+                       "l2": "inputs (%.1f GB per GPU) far exceed the 126 MB L2; no flush needed" % (sum(WW.input_bytes(w) for w in tiles) / 1e9), "gen_seconds": round(t_gen, 1), "host_binding": numa, "host_wait": host_wait},
             "roofline": {"bound": "hbm", "achieved": stage_roof[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stage_roof[dom]["frac"], "traffic": traffic,
                          "kernel": f"stage {dom} (the longest of the step)", "algorithmic_bytes_per_step": stage_roof[dom]["algorithmic_bytes"], "kernel_ms_per_step": per_step[dom],
                          "peak_source": peak_src, "whole_step": {"algorithmic_bytes": int(whole_bytes), "achieved_gbs": whole_bytes / (dt / args.steps) / 1e9,

@@ -76,6 +76,11 @@ typedef struct sx_params {
 void sx_default_params(sx_params* p);
 
 int sx_create(int cuda_device, const sx_params* p, sx_ctx** out);
+/* How this process's host threads wait for `cuda_device` (a runtime knob, not a reference option): blocking = 1 makes every wait of a context on
+ * that device yield the CPU instead of spinning (cudaDeviceScheduleBlockingSync) -- for hosts whose CPU quota is smaller than the number of waiting
+ * threads (8 ranks x several contexts on a 16-CPU cgroup: spinning waiters exhaust the quota and every rank stalls); 0 restores the driver's choice.
+ * Call it before the first sx_create on the device.  Returns SX_OK or SX_ERR_CUDA. */
+int sx_set_host_wait_policy(int cuda_device, int blocking);
 void sx_destroy(sx_ctx* ctx);
 const char* sx_last_error(const sx_ctx* ctx); /* valid until the next call on ctx; ctx may be NULL for create errors */
 int sx_abi_version(void);

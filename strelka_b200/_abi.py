@@ -349,6 +349,7 @@ SYMBOLS = [
     ("sx_default_params", None, [C.POINTER(SxParams)]),
     ("sx_create", C.c_int, [C.c_int, C.POINTER(SxParams), C.POINTER(_P)]),
     ("sx_destroy", None, [_P]),
+    ("sx_set_host_wait_policy", C.c_int, [C.c_int, C.c_int]),
     ("sx_last_error", C.c_char_p, [_P]),
     ("sx_abi_version", C.c_int, []),
     ("sx_host_alloc", _P, [C.c_size_t]),

@@ -198,6 +198,115 @@ __global__ void k7_active_reads_kernel(const uint32_t n_reads, const uint8_t* __
     }
 }
 
+// ---- reads of one shape side by side.  The active list is in read order: a warp's 32 reads are one region's reads at neighbouring positions,
+// and they differ in WHICH of the window's entries they reach -- so their searches have different trees and the warp executes every tree in turn
+// (ncu: 14.5 of 32 lanes active).  A read's shape class = the window entries (first four of its region) its input alignment's range is adjacent
+// to (bp_adjacent: what add_indels_in_range will put into indel_order) + which of them the alignment already contains.  The list is regrouped
+// by class with a block-local counting sort; which thread searches which read does not matter (the output is placed by the scan).
+constexpr uint32_t K7_N_CLASS = 256;
+constexpr int K7_CLS_THREADS = 256, K7_CLS_ITEMS = 4;
+
+__device__ __forceinline__ uint32_t k7_read_class(const sx_enum_batch& b, const uint32_t region, const uint32_t r)
+{
+    const uint32_t k0(b.region_key_off[region]), nw(min(b.region_key_off[region + 1] - k0, 4u));
+    const uint32_t s0(b.in_seg_off[r]), ns(b.in_seg_off[r + 1] - s0);
+    // get_soft_clip_alignment_range of the input alignment (k7_soft_clip_range)
+    uint32_t lead(0), trail(0), ref_len(0);
+    bool in_lead(true);
+    for (uint32_t i = 0; i < ns; ++i)
+    {
+        const unsigned t(b.in_segs[s0 + i].kind);
+        const uint32_t len(b.in_segs[s0 + i].len);
+        if (k7_seg_ref_len(t)) ref_len += len;
+        if (t == SX_AP_HARD_CLIP || t == SX_AP_SOFT_CLIP) continue;
+        if (t == SX_AP_INSERT)
+        {
+            if (in_lead) lead += len;
+            else trail += len;
+        }
+        else
+        {
+            in_lead = false;
+            trail = 0;
+        }
+    }
+    const int32_t eb(b.in_pos[r] - (int32_t)lead), ee(b.in_pos[r] + (int32_t)ref_len + (int32_t)trail);
+    uint32_t cls(0);
+    for (uint32_t k = 0; k < nw; ++k)
+        if (k7_bp_adjacent(eb, ee, b.keys[k0 + k])) cls |= 1u << k;
+    for (uint32_t i = b.in_key_off[r]; i < b.in_key_off[r + 1]; ++i)
+        if (b.in_keys[i] < 4u) cls |= 16u << b.in_keys[i];
+    return cls & (K7_N_CLASS - 1u);
+}
+
+__global__ void __launch_bounds__(K7_CLS_THREADS) k7_class_count_kernel(const k7_view v, const uint32_t* __restrict__ read_region, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list,
+                                                                        uint8_t* __restrict__ cls, uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t s_cnt[K7_N_CLASS];
+    s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t n(*n_list);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t r(list[i]);
+        const uint32_t c(k7_read_class(v.b, read_region[r], r));
+        cls[i] = (uint8_t)c;
+        atomicAdd(&s_cnt[c], 1u);
+    }
+    __syncthreads();
+    if (s_cnt[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(K7_N_CLASS) k7_class_scan_kernel(uint32_t* __restrict__ hist) // hist[c] -> first slot of class c (exclusive prefix sum)
+{
+    __shared__ uint32_t s[K7_N_CLASS];
+    s[threadIdx.x] = hist[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        uint32_t run(0);
+        for (uint32_t c = 0; c < K7_N_CLASS; ++c)
+        {
+            const uint32_t x(s[c]);
+            s[c] = run;
+            run += x;
+        }
+    }
+    __syncthreads();
+    hist[threadIdx.x] = s[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(K7_CLS_THREADS) k7_class_scatter_kernel(const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, const uint8_t* __restrict__ cls,
+                                                                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ out)
+{
+    __shared__ uint32_t s_cnt[K7_N_CLASS], s_base[K7_N_CLASS];
+    const uint32_t n(*n_list);
+    const uint32_t chunk(K7_CLS_THREADS * K7_CLS_ITEMS);
+    for (uint32_t base = blockIdx.x * chunk; base < n; base += gridDim.x * chunk) // (block-uniform)
+    {
+        s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t c[K7_CLS_ITEMS], at[K7_CLS_ITEMS];
+#pragma unroll
+        for (int j = 0; j < K7_CLS_ITEMS; ++j)
+        {
+            const uint32_t i(base + j * K7_CLS_THREADS + threadIdx.x);
+            c[j] = i < n ? cls[i] : 0xffffffffu;
+            at[j] = c[j] != 0xffffffffu ? atomicAdd(&s_cnt[c[j]], 1u) : 0u;
+        }
+        __syncthreads();
+        s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], s_cnt[threadIdx.x]) : 0u;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < K7_CLS_ITEMS; ++j)
+        {
+            const uint32_t i(base + j * K7_CLS_THREADS + threadIdx.x);
+            if (c[j] != 0xffffffffu) out[s_base[c[j]] + at[j]] = list[i];
+        }
+        __syncthreads();
+    }
+}
+
 template <uint32_t K7_LOCAL_ALNS, int K7_MIN_BLOCKS>
 __global__ void __launch_bounds__(K7_THREADS, K7_MIN_BLOCKS) k7_search_local_kernel(const k7_view v, const uint32_t* __restrict__ read_region, uint8_t* __restrict__ status,
                                                                      const k7_retry R, const k7_counts c, const k7_log L)
@@ -407,6 +516,25 @@ int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsig
 
     k7_view v;
     v.b = *d;
+    if (R.list0 && !getenv("SX_K7_NO_CLASS_SORT"))
+    {
+        // the active list regrouped by shape class (see k7_read_class)
+        uint8_t* cls(nullptr);
+        uint32_t *hist(nullptr), *list0b(nullptr);
+        if ((rc = sx_ensure(ctx, 32, (size_t)n + 16, reinterpret_cast<void**>(&cls)))) return rc;
+        if ((rc = sx_ensure(ctx, 33, (size_t)K7_N_CLASS * 4 + 16, reinterpret_cast<void**>(&hist)))) return rc;
+        if ((rc = sx_ensure(ctx, 34, (size_t)n * 4 + 16, reinterpret_cast<void**>(&list0b)))) return rc;
+        SX_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)K7_N_CLASS * 4, st));
+        const int gc(std::max(1, std::min<int>((int)((n + K7_CLS_THREADS * K7_CLS_ITEMS - 1) / (K7_CLS_THREADS * K7_CLS_ITEMS)), ctx->sm_count * 8)));
+        k7_class_count_kernel<<<gc, K7_CLS_THREADS, 0, st>>>(v, read_region, R.list0, R.n + 2, cls, hist);
+        SX_CUDA(ctx, cudaGetLastError());
+        k7_class_scan_kernel<<<1, K7_N_CLASS, 0, st>>>(hist);
+        SX_CUDA(ctx, cudaGetLastError());
+        k7_class_scatter_kernel<<<gc, K7_CLS_THREADS, 0, st>>>(R.list0, R.n + 2, cls, hist, list0b);
+        SX_CUDA(ctx, cudaGetLastError());
+        R.list0 = list0b;
+        extra += 3;
+    }
     local_kernel<<<(unsigned)blocks_local, K7_THREADS, 0, st>>>(v, read_region, o->status, R, c, L);
     SX_CUDA(ctx, cudaGetLastError());
     k7_search_arena_kernel<<<(unsigned)blocks1, K7_THREADS, 0, st>>>(v, arena1, per_thread1, maxA1, maxF, read_region, o->status, R, 1, two_levels ? 1 : 0, c, L);

@@ -381,6 +381,19 @@ void build_tables(const sx_params& p, sx_tables& t)
 }
 } // namespace
 
+extern "C" int sx_set_host_wait_policy(int cuda_device, int blocking)
+{
+    cudaError_t e = cudaSetDevice(cuda_device);
+    if (e == cudaSuccess) e = cudaSetDeviceFlags(blocking ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto);
+    if (e != cudaSuccess)
+    {
+        g_create_err = std::string("sx_set_host_wait_policy: ") + cudaGetErrorString(e);
+        (void)cudaGetLastError();
+        return SX_ERR_CUDA;
+    }
+    return SX_OK;
+}
+
 extern "C" int sx_create(int cuda_device, const sx_params* p, sx_ctx** out)
 {
     if (!p || !out)
