@@ -1087,12 +1087,10 @@ def whole_path_main(args):
     threads = max(1, ncpu // max(1, world))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; strelka_b200 has no CPU fallback (use --impl reference for the CPU arm)")
-    # several ranks share the host's CPU quota (16 CPUs on the GPU boxes): their waiting threads block instead of spinning (see sx_set_host_wait_policy)
-    host_wait = "blocking" if (world > 1 or os.environ.get("SX_BLOCKING_WAIT") == "1") else "spin (driver default)"
-    if host_wait == "blocking":
+    host_wait = "spin (driver default)"
+    if os.environ.get("SX_BLOCKING_WAIT") == "1":  # (A/B knob: blocking waits from the start)
         from strelka_b200 import _abi as _A0
-        if _A0.load().sx_set_host_wait_policy(local_rank, 1) != 0:
-            host_wait = "spin (blocking policy refused)"
+        host_wait = "blocking" if _A0.load().sx_set_host_wait_policy(local_rank, 1) == 0 else "spin (blocking policy refused)"
     torch.cuda.set_device(local_rank)
     numa = bind_to_gpu_numa(local_rank) if world > 1 else "single rank: not bound"
     if world > 1:
@@ -1221,6 +1219,12 @@ def whole_path_main(args):
     e2e = None
     if not args.no_e2e:
         n_workers = max(1, min(args.e2e_workers, n_tiles))
+        # the end-to-end leg keeps n_workers + 1 host threads per rank waiting on the device.  Where the ranks together have more waiting threads
+        # than the job has CPUs (8 ranks x 4 on the GPU boxes' 16-CPU quota) spinning waiters exhaust the quota and every rank stalls: they block instead
+        # (measured on one GPU with CPUs to spare: blocking 321.6 vs spinning 329.4 ms per 300k loci, 0.01 vs 0.68 host CPU seconds per step -- so always)
+        if host_wait.startswith("spin") and os.environ.get("SX_BLOCKING_WAIT") != "0":
+            if lib.sx_set_host_wait_policy(local_rank, 1) == 0:
+                host_wait = "spin for the resident step, blocking for the end-to-end leg"
         ctxs = [Context(local_rank) for _ in range(n_workers)]
         ctx_ga = Context(local_rank)
         ga_res, ga_cig = alloc.array(gb.n * A.GA_RESULT_DT.itemsize, A.GA_RESULT_DT), alloc.array(gb.n * gb.max_ops * 4, np.uint32)
@@ -1267,11 +1271,14 @@ def whole_path_main(args):
         for _ in range(min(2, max(1, args.warmup))):
             step_e2e()
         barrier()
+        cpu0 = os.times()
         t1 = time.perf_counter()
         for _ in range(args.steps):
             step_e2e()
         barrier()
         dt_e2e = time.perf_counter() - t1
+        cpu1 = os.times()
+        e2e_cpu_s = (cpu1.user + cpu1.system - cpu0.user - cpu0.system) / args.steps  # this rank's host CPU seconds per step (spinning waiters show here)
         h2d = sum(WW.input_bytes(w) for w in tiles) + int(gb.query_off[-1]) + int(gb.ref_off[-1]) + (gb.n + 1) * 8
         d2h = d2h_step[0] + gb.n * (16 + gb.max_ops * 4)
         e2e = (dt_e2e, h2d, d2h)
@@ -1347,7 +1354,7 @@ def whole_path_main(args):
         if e2e:
             line["e2e"] = {"value": total_loci * args.steps / e2e[0], "unit": "loci/s", "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2]),
                            "ms_per_step": 1e3 * e2e[0] / args.steps, "how": f"sx_process_window (host arrays in pinned memory) per window, {n_workers} host threads with a context each; "
-                           "sx_global_align on one more; D2H = score_indels records + variant-site records + DP results"}
+                           "sx_global_align on one more; D2H = score_indels records + variant-site records + DP results", "host_cpu_seconds_per_step_rank0": round(e2e_cpu_s, 3)}
         if world == 1 and not args.no_cpu:
             # the reported CPU baseline: the reference's own functions, one pinned process per usable core, a bounded sample
             try:

@@ -14,6 +14,7 @@
 // element-major global arena for deep ones.  Output: one 32-byte record per (read, evaluated indel).  The body is k6_core.cuh.
 
 #include "k6_core.cuh"
+#include "sx_regroup.cuh"
 #include "sx_internal.h"
 
 #include <algorithm>
@@ -232,7 +233,29 @@ int k6_run(sx_ctx* ctx, const sx_score_indels_batch* d, const double* lnp_dev, c
         SX_CUDA(ctx, cudaMemsetAsync(out_dev->n_rec, 0, (size_t)d->n_reads * 4, st));
         SX_CUDA(ctx, cudaMemsetAsync(out_dev->max_aln, 0xFF, (size_t)d->n_reads * 4, st));
         SX_CUDA(ctx, cudaMemsetAsync(out_dev->eval_aln, 0xFF, (size_t)d->n_reads * 4, st));
+        unsigned extra(0);
+        if (!getenv("SX_K6_NO_CLASS_SORT"))
+        {
+            // the list regrouped by class (sx_regroup.cuh) = the read's number of candidate alignments: score_indels loops over the alignments and the
+            // window entries they carry, so warps of reads with equally many alignments stay together
+            uint8_t* cls(nullptr);
+            uint32_t *hist(nullptr), *list2(nullptr);
+            if ((rc = sx_ensure(ctx, 35, (size_t)d->n_reads + 16, reinterpret_cast<void**>(&cls)))) return rc;
+            if ((rc = sx_ensure(ctx, 36, (size_t)SX_RG_CLASSES * 4 + 16, reinterpret_cast<void**>(&hist)))) return rc;
+            if ((rc = sx_ensure(ctx, 37, (size_t)d->n_reads * 4 + 16, reinterpret_cast<void**>(&list2)))) return rc;
+            SX_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)SX_RG_CLASSES * 4, st));
+            const int gc(std::max(1, std::min<int>((int)((d->n_reads + SX_RG_THREADS * SX_RG_ITEMS - 1) / (SX_RG_THREADS * SX_RG_ITEMS)), ctx->sm_count * 8)));
+            sx_regroup_class_by_count_kernel<<<gc, SX_RG_THREADS, 0, st>>>(d->aln_off, list, d_max + 4, cls, hist);
+            sx_regroup_scan_kernel<<<1, SX_RG_CLASSES, 0, st>>>(hist);
+            sx_regroup_scatter_kernel<<<gc, SX_RG_THREADS, 0, st>>>(list, d_max + 4, cls, hist, list2);
+            SX_CUDA(ctx, cudaGetLastError());
+            list = list2;
+            extra = 3;
+        }
         k6_score_list_kernel<<<(unsigned)(T / threads), threads, 0, st>>>(v, S, list, d_max + 4, ctx->d_status);
+        SX_CUDA(ctx, cudaGetLastError());
+        *launches = 2 + extra;
+        return SX_OK;
     }
     else
         k6_score_kernel<<<(unsigned)(T / threads), threads, smem_bytes, st>>>(v, S, smem_bytes, ctx->d_status);

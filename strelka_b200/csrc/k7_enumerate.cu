@@ -19,6 +19,7 @@
 
 #include "k7_core.cuh"
 #include "sx_internal.h"
+#include "sx_regroup.cuh"
 #include "sx_scan3.cuh"
 
 #include <algorithm>
@@ -203,8 +204,8 @@ __global__ void k7_active_reads_kernel(const uint32_t n_reads, const uint8_t* __
 // (ncu: 14.5 of 32 lanes active).  A read's shape class = the window entries (first four of its region) its input alignment's range is adjacent
 // to (bp_adjacent: what add_indels_in_range will put into indel_order) + which of them the alignment already contains.  The list is regrouped
 // by class with a block-local counting sort; which thread searches which read does not matter (the output is placed by the scan).
-constexpr uint32_t K7_N_CLASS = 256;
-constexpr int K7_CLS_THREADS = 256, K7_CLS_ITEMS = 4;
+constexpr uint32_t K7_N_CLASS = SX_RG_CLASSES;
+constexpr int K7_CLS_THREADS = SX_RG_THREADS, K7_CLS_ITEMS = SX_RG_ITEMS;
 
 __device__ __forceinline__ uint32_t k7_read_class(const sx_enum_batch& b, const uint32_t region, const uint32_t r)
 {
@@ -255,56 +256,6 @@ __global__ void __launch_bounds__(K7_CLS_THREADS) k7_class_count_kernel(const k7
     }
     __syncthreads();
     if (s_cnt[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_cnt[threadIdx.x]);
-}
-
-__global__ void __launch_bounds__(K7_N_CLASS) k7_class_scan_kernel(uint32_t* __restrict__ hist) // hist[c] -> first slot of class c (exclusive prefix sum)
-{
-    __shared__ uint32_t s[K7_N_CLASS];
-    s[threadIdx.x] = hist[threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        uint32_t run(0);
-        for (uint32_t c = 0; c < K7_N_CLASS; ++c)
-        {
-            const uint32_t x(s[c]);
-            s[c] = run;
-            run += x;
-        }
-    }
-    __syncthreads();
-    hist[threadIdx.x] = s[threadIdx.x];
-}
-
-__global__ void __launch_bounds__(K7_CLS_THREADS) k7_class_scatter_kernel(const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, const uint8_t* __restrict__ cls,
-                                                                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ out)
-{
-    __shared__ uint32_t s_cnt[K7_N_CLASS], s_base[K7_N_CLASS];
-    const uint32_t n(*n_list);
-    const uint32_t chunk(K7_CLS_THREADS * K7_CLS_ITEMS);
-    for (uint32_t base = blockIdx.x * chunk; base < n; base += gridDim.x * chunk) // (block-uniform)
-    {
-        s_cnt[threadIdx.x] = 0;
-        __syncthreads();
-        uint32_t c[K7_CLS_ITEMS], at[K7_CLS_ITEMS];
-#pragma unroll
-        for (int j = 0; j < K7_CLS_ITEMS; ++j)
-        {
-            const uint32_t i(base + j * K7_CLS_THREADS + threadIdx.x);
-            c[j] = i < n ? cls[i] : 0xffffffffu;
-            at[j] = c[j] != 0xffffffffu ? atomicAdd(&s_cnt[c[j]], 1u) : 0u;
-        }
-        __syncthreads();
-        s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], s_cnt[threadIdx.x]) : 0u;
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < K7_CLS_ITEMS; ++j)
-        {
-            const uint32_t i(base + j * K7_CLS_THREADS + threadIdx.x);
-            if (c[j] != 0xffffffffu) out[s_base[c[j]] + at[j]] = list[i];
-        }
-        __syncthreads();
-    }
 }
 
 template <uint32_t K7_LOCAL_ALNS, int K7_MIN_BLOCKS>
@@ -363,11 +314,15 @@ __global__ void __launch_bounds__(K7_THREADS) k7_search_arena_kernel(const k7_vi
     }
 }
 
-__global__ void k7_gather_kernel(const uint32_t n_reads, const k7_counts c, const k7_log L, const sx_enum_out o, const uint32_t* __restrict__ totals)
+__global__ void k7_gather_kernel(const uint32_t n_reads, const k7_counts c, const k7_log L, const sx_enum_out o, const uint32_t* __restrict__ totals,
+                                 const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list)
 {
     if (totals[0] > o.cap_alns || totals[1] > o.cap_segs || totals[2] > o.cap_keys) return; // reported by k7_scan_finish
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x)
+    // with a list (in read order: the CSR output is written in read order): only the searched reads have a blob
+    const uint32_t n_work(list ? *n_list : n_reads);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x)
     {
+        const uint32_t r(list ? list[i] : i);
         const uint32_t na((r + 1 < n_reads ? c.aln[r + 1] : totals[0]) - c.aln[r]);
         if (na == 0 || L.blob_off[r] == UINT32_MAX) continue;
         k7_blob_gather(L.words + L.blob_off[r], na, o, c.aln[r], c.seg[r], c.key[r]);
@@ -528,9 +483,9 @@ int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsig
         const int gc(std::max(1, std::min<int>((int)((n + K7_CLS_THREADS * K7_CLS_ITEMS - 1) / (K7_CLS_THREADS * K7_CLS_ITEMS)), ctx->sm_count * 8)));
         k7_class_count_kernel<<<gc, K7_CLS_THREADS, 0, st>>>(v, read_region, R.list0, R.n + 2, cls, hist);
         SX_CUDA(ctx, cudaGetLastError());
-        k7_class_scan_kernel<<<1, K7_N_CLASS, 0, st>>>(hist);
+        sx_regroup_scan_kernel<<<1, SX_RG_CLASSES, 0, st>>>(hist);
         SX_CUDA(ctx, cudaGetLastError());
-        k7_class_scatter_kernel<<<gc, K7_CLS_THREADS, 0, st>>>(R.list0, R.n + 2, cls, hist, list0b);
+        sx_regroup_scatter_kernel<<<gc, SX_RG_THREADS, 0, st>>>(R.list0, R.n + 2, cls, hist, list0b);
         SX_CUDA(ctx, cudaGetLastError());
         R.list0 = list0b;
         extra += 3;
@@ -551,7 +506,7 @@ int k7_run_fast(sx_ctx* ctx, const sx_enum_batch* d, const sx_enum_out* o, unsig
     k7_scan_finish<<<n_tiles, K7_SCAN_THREADS, 0, st>>>(n, c, sums, n_tiles, totals, *o, ctx->d_status);
     SX_CUDA(ctx, cudaGetLastError());
     const int g1(std::max(1, std::min<int>((int)((n + 127) / 128), ctx->sm_count * 16)));
-    k7_gather_kernel<<<g1, 128, 0, st>>>(n, c, L, *o, totals);
+    k7_gather_kernel<<<g1, 128, 0, st>>>(n, c, L, *o, totals, nullptr, nullptr); // (every read, in read order: walking the active list instead measured slower, 117 / 126 vs 106 ms per 600k loci in read / class order)
     SX_CUDA(ctx, cudaGetLastError());
     *launches = (two_levels ? 8 : 7) + extra;
     return SX_OK;

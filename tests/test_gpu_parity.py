@@ -509,7 +509,7 @@ def test_k6_score_indels(ctx, case):
         gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "score_indels_ref.npz"))
         assert got[0].tobytes() == gold[f"recs{case}"].tobytes()
         assert np.array_equal(got[1], gold[f"n_rec{case}"]) and np.array_equal(got[2], gold[f"max_aln{case}"])
-    assert ctx.timing().launches == 2
+    assert ctx.timing().launches == 5  # sizes + list, the list regrouped by alignment count (class, scan, scatter), score_indels
 
 
 def test_k6_large_batch_with_deep_reads(ctx):
