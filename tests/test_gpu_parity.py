@@ -425,7 +425,7 @@ def test_k4_pileup_reads(ctx, seed, mode):
         assert np.array_equal(w, g), name
 
 
-def _buffer_order_case(rng, packed_quals):
+def _buffer_order_case(rng, packed_quals, opts=None):
     """reads whose BEST alignment start differs from their read-buffer position (a realignment moved it, by up to +-25): the batch is in
     buffer order, the alignments are not sorted."""
     reads, ref, ref_begin, cand = specgen.random_pileup_reads(rng, n_reads=int(rng.integers(600, 1500)), ref_len=int(rng.integers(900, 3000)))
@@ -440,7 +440,7 @@ def _buffer_order_case(rng, packed_quals):
             for r in reads:
                 r.quals = [min(qd, key=lambda v: abs(v - int(q))) for q in r.quals]
     lo, hi = ref_begin + 100, ref_begin + len(ref) - 150
-    return B.PileupReadsBatch(reads, ref, ref_begin, lo, hi, cand, buffer_pos=bpos, qual_dict=qd)
+    return B.PileupReadsBatch(reads, ref, ref_begin, lo, hi, cand, opts, buffer_pos=bpos, qual_dict=qd)
 
 
 @pytest.mark.parametrize("packed", [False, True])
@@ -450,6 +450,21 @@ def test_k4_pileup_in_read_buffer_order(ctx, seed, packed):
     where realignments moved the alignment starts past their neighbours'; dictionary-coded qualities."""
     pb = _buffer_order_case(np.random.default_rng(6300 + seed), packed)
     assert (np.diff(pb.reads["pos"][: pb.n_reads].astype(np.int64)) < 0).any()  # the alignments themselves are NOT sorted
+    want = reflib.ox_pileup_reads(pb)
+    got = ctx.pileup_reads(pb)
+    assert int(want[0][-1]) > 1000
+    for w, g, name in zip(want, got, ("site_off", "calls", "t2_off", "t2_calls", "n_spandel", "n_submapped")):
+        assert np.array_equal(w, g), name
+
+
+@pytest.mark.parametrize("mode", ["germline", "somatic", "edge"])
+@pytest.mark.parametrize("packed", [False, True])
+def test_k4_gather_plan(ctx, monkeypatch, mode, packed):
+    """K4's second plan for the fill (SX_K4_PLAN=2: k4_bases_kernel, a thread per read, + k4_gather_kernel, a warp per 32 sites) gives the same
+    columns as the oracle -- option modes, reads whose best alignment moved away from their buffer position, dictionary-coded qualities."""
+    monkeypatch.setenv("SX_K4_PLAN", "2")
+    opts = {"germline": None, "somatic": A.SxPileupOpts(1, 0, 20, 3, 1, 10, 0, 0), "edge": A.SxPileupOpts(1, 17, 3, 1, 1, 2, 5, 0)}[mode]
+    pb = _buffer_order_case(np.random.default_rng(6400 + len(mode)), packed, opts)
     want = reflib.ox_pileup_reads(pb)
     got = ctx.pileup_reads(pb)
     assert int(want[0][-1]) > 1000
