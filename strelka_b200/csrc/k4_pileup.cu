@@ -663,30 +663,17 @@ struct k4_segcur
     }
 };
 
-// what a thread of the base pass knows of its read before it walks the bases
-struct k4_rsetup
+__global__ void __launch_bounds__(K4B_THREADS) k4_bases_kernel(k4_args A, k4_rrec* __restrict__ rec, uint16_t* __restrict__ bc, uint32_t Ls,
+                                                               const sx_tables* __restrict__ tables, int* __restrict__ status)
 {
-    sx_pileup_read rd;
-    const sx_aln_seg* path;
-    uint32_t as, first, last; // segments, first / last MATCH segment
-    uint32_t rb, re;          // the preamble's [read_begin, read_end), clipped to the read
-    uint32_t read_size, fs, fs2, delta_size;
-    int32_t site0;            // rd.pos - report_begin
-    int64_t ref0;             // index of the alignment's first reference base in A.ref
-    uint32_t ev[K4B_MAX_EV];  // interior indels: read offset << 16 | length (create_mismatch_filter_map's inc(start, length))
-    uint32_t n_ev;
-    bool isDensity;
-};
-
-// fills S and the gather's record; false = the read contributes nothing (the record says so)
-__device__ __forceinline__ bool k4_read_setup(const k4_args& A, const uint32_t r, k4_rsetup& S, k4_rrec& out, int* __restrict__ status)
-{
-    S.rd = A.reads[r];
-    const sx_pileup_read& rd = S.rd;
+    extern __shared__ __align__(16) uint16_t k4b_P[]; // per thread Lcap + 2 entries: P[i] = mismatches among bases [0, i)
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= A.n_reads) return;
+    uint16_t* P = k4b_P + static_cast<size_t>(threadIdx.x) * (A.Lcap + 2u); // (Lcap % 16 == 0: an odd number of 32-bit words per thread, no bank conflicts)
+    const sx_pileup_read rd = A.reads[r];
     const uint32_t as = A.reads[r + 1].seg_off - rd.seg_off;
     const sx_aln_seg* path = A.segs + rd.seg_off;
-    S.as = as;
-    S.path = path;
+    k4_rrec out;
 #pragma unroll
     for (uint32_t j = 0; j < K4_REC_IV; ++j)
     {
@@ -718,27 +705,25 @@ __device__ __forceinline__ bool k4_read_setup(const k4_args& A, const uint32_t r
             ok = false;
         }
     }
-    S.first = first;
-    S.last = last;
     const uint8_t* gs = A.seq4 + rd.seq_off;
     read_window w;
     w.read_begin = w.read_end = 0;
     if (ok && !read_preamble(A, rd, ref_span, [&](uint32_t i) { return code_at(gs, i); }, w)) ok = false;
-    if (!ok) return false;
+    if (!ok)
+    {
+        rec[r] = out;
+        return;
+    }
     const uint32_t read_size = rd.len;
     const uint32_t rb = w.read_begin, re = min(w.read_end, read_size);
     const uint32_t fs = A.opt.mismatchDensityFilterFlankSize, fs2 = fs * 2;
     const bool isDensity = fs > 0;
+    const uint32_t delta_size = max(1u + fs2, read_size) - fs2;
     const int32_t site0 = static_cast<int32_t>(static_cast<int64_t>(rd.pos) - A.report_begin);
-    S.read_size = read_size;
-    S.rb = rb;
-    S.re = re;
-    S.fs = fs;
-    S.fs2 = fs2;
-    S.isDensity = isDensity;
-    S.delta_size = max(1u + fs2, read_size) - fs2;
-    S.site0 = site0;
-    S.ref0 = static_cast<int64_t>(rd.pos) - A.ref_begin;
+    const int64_t ref0 = static_cast<int64_t>(rd.pos) - A.ref_begin; // index of the alignment's first reference base in A.ref
+    k4_wstream sq;
+    k4_segcur sc;
+    uint32_t ev[K4B_MAX_EV]; // interior indels: read offset << 16 | length (create_mismatch_filter_map's inc(start, length))
     uint32_t n_ev = 0;
     // the path once: the MATCH intervals for the gather, the interior indels for the density map
     {
@@ -777,7 +762,7 @@ __device__ __forceinline__ bool k4_read_setup(const k4_args& A, const uint32_t r
             {
                 if (!edge && (k == SX_SEG_INSERT || k == SX_SEG_DELETE))
                 {
-                    if (n_ev < K4B_MAX_EV) S.ev[n_ev] = (p << 16) | (k == SX_SEG_INSERT ? len : 0u);
+                    if (n_ev < K4B_MAX_EV) ev[n_ev] = (p << 16) | (k == SX_SEG_INSERT ? len : 0u);
                     ++n_ev;
                 }
                 else if (k == SX_SEG_SKIP) atomicOr(status, ST_KIND); // "Can't handle cigar code" in create_mismatch_filter_map
@@ -794,34 +779,6 @@ __device__ __forceinline__ bool k4_read_setup(const k4_args& A, const uint32_t r
         }
         out.n_iv = n_iv | (as << 8) | ((rd.flags & SX_PRF_TIER1) ? 0x80000000u : 0u);
     }
-    S.n_ev = n_ev;
-    return true;
-}
-
-__global__ void __launch_bounds__(K4B_THREADS) k4_bases_kernel(k4_args A, k4_rrec* __restrict__ rec, uint16_t* __restrict__ bc, uint32_t Ls,
-                                                               const sx_tables* __restrict__ tables, int* __restrict__ status)
-{
-    extern __shared__ __align__(16) uint16_t k4b_P[]; // per thread Lcap + 2 entries: P[i] = mismatches among bases [0, i)
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= A.n_reads) return;
-    uint16_t* P = k4b_P + static_cast<size_t>(threadIdx.x) * (A.Lcap + 2u); // (Lcap % 16 == 0: an odd number of 32-bit words per thread, no bank conflicts)
-    k4_rsetup S;
-    k4_rrec out;
-    if (!k4_read_setup(A, r, S, out, status))
-    {
-        rec[r] = out;
-        return;
-    }
-    const sx_pileup_read rd = S.rd;
-    const sx_aln_seg* path = S.path;
-    const uint32_t as = S.as, first = S.first, last = S.last, rb = S.rb, re = S.re, read_size = S.read_size, fs = S.fs, fs2 = S.fs2, delta_size = S.delta_size, n_ev = S.n_ev;
-    const bool isDensity = S.isDensity;
-    const int32_t site0 = S.site0;
-    const int64_t ref0 = S.ref0;
-    const uint32_t* ev = S.ev;
-    const uint8_t* gs = A.seq4 + rd.seq_off;
-    k4_wstream sq;
-    k4_segcur sc;
 // advance the cursor to the segment that holds base q (q ascends by one): warp-divergent only at a lane's own segment boundaries
 #define K4_SEG_ADVANCE(sc, q)                                                         \
     while ((q) >= (sc).seg_end && (sc).i < (sc).as)                                   \
@@ -994,304 +951,7 @@ __global__ void __launch_bounds__(K4B_THREADS) k4_bases_kernel(k4_args A, k4_rre
 #undef K4_SEG_ADVANCE
 }
 
-// ---- the base pass for dictionary-coded qualities (qual_bits 4: the whole-path format), written for instruction count: the generic kernel above
-// spends ~230 instructions per base (nibble streams with a reload test per base, 64-bit literal look-ups, a site test per base).  Here a read is
-// walked in chunks of 8 bases = one 32-bit word of packed bases and one of packed qualities (funnel-shifted out of the aligned words once per
-// chunk), the inner loop over the 8 bases is unrolled (constant shifts, the four 32-bit halves of the 128-bit store are named registers), a
-// segment's usable range [q_lo, q_hi) -- MATCH, inside the preamble's window, on a reportable site -- is set when the cursor enters the segment,
-// and the 16 possible quality results live in 16 bytes of shared memory per thread.
-struct k4_words // 8 packed nibbles per call from a byte array that starts at an arbitrary byte
-{
-    const uint32_t* w32;
-    uint32_t sh;    // 8 * (byte offset of the read's first byte in w32[0])
-    uint32_t w_lo;  // word of the current chunk
-    uint32_t n_w;   // words that hold bytes of this read
-    __device__ __forceinline__ void init(const uint8_t* p, uint32_t n_bytes)
-    {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-        w32 = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
-        sh = 8u * static_cast<uint32_t>(a & 3u);
-        n_w = (static_cast<uint32_t>(a & 3u) + n_bytes + 3u) >> 2;
-        w_lo = n_w ? __ldg(w32) : 0u;
-    }
-    // bytes [4c, 4c + 4) of the read (chunks ascending from 0)
-    __device__ __forceinline__ uint32_t chunk(uint32_t c)
-    {
-        const uint32_t w_hi = (c + 1u < n_w) ? __ldg(w32 + c + 1u) : 0u;
-        const uint32_t v = __funnelshift_r(w_lo, w_hi, sh);
-        w_lo = w_hi;
-        return v;
-    }
-};
-// nibble j (0..7) of a chunk word: byte j / 2, high nibble first
-#define K4_NIB(w, j) (((w) >> (8u * ((j) >> 1) + (((j) & 1u) ? 0u : 4u))) & 15u)
-
-struct k4_cur2 // the segment cursor with the usable range of the current segment
-{
-    uint32_t i, seg_end, rf;
-    uint32_t q_lo, q_hi; // bases of the current segment that count (empty unless it is a MATCH)
-    int32_t rfd;         // MATCH: reference offset of base q = q + rfd
-};
-// enter the segment that holds base q; with_site: the range is also clipped to the reportable sites
-template <bool with_site>
-__device__ __noinline__ void k4_cur2_advance(k4_cur2& c, const uint32_t q, const sx_aln_seg* __restrict__ path, const uint32_t as, const uint32_t rb, const uint32_t re,
-                                                const int32_t site0, const uint32_t n_sites)
-{
-    while (q >= c.seg_end && c.i < as)
-    {
-        const uint32_t k = path[c.i].kind, l = path[c.i].len;
-        ++c.i;
-        if (kind_read(k))
-        {
-            const uint32_t seg_begin = c.seg_end;
-            c.seg_end += l;
-            c.q_lo = c.q_hi = 0;
-            if (k == SX_SEG_MATCH)
-            {
-                c.rfd = static_cast<int32_t>(c.rf) - static_cast<int32_t>(seg_begin);
-                int64_t lo = max(seg_begin, rb), hi = min(c.seg_end, re);
-                if (with_site)
-                {
-                    // site(q) = site0 + q + rfd in [0, n_sites)
-                    const int64_t base = static_cast<int64_t>(site0) + c.rfd;
-                    if (-base > lo) lo = -base;
-                    if (static_cast<int64_t>(n_sites) - base < hi) hi = static_cast<int64_t>(n_sites) - base;
-                }
-                if (lo < hi)
-                {
-                    c.q_lo = static_cast<uint32_t>(lo);
-                    c.q_hi = static_cast<uint32_t>(hi);
-                }
-            }
-        }
-        if (kind_ref(k)) c.rf += l;
-    }
-    if (q >= c.seg_end) c.q_lo = c.q_hi = 0; // (a path shorter than the read)
-}
-
-// interior indels whose window holds index di of the density map (rare: reads with interior indels only)
-__device__ __noinline__ int k4_event_count(const k4_rsetup& S, const uint32_t di)
-{
-    int n = 0;
-    const uint32_t fs2 = S.fs2;
-    if (S.n_ev <= K4B_MAX_EV)
-    {
-        for (uint32_t e = 0; e < S.n_ev; ++e)
-        {
-            const uint32_t st = S.ev[e] >> 16, ln = S.ev[e] & 0xffffu;
-            n += (max(fs2, st) - fs2 <= di && di < st + ln) ? 1 : 0;
-        }
-        return n;
-    }
-    uint32_t p2 = 0;
-    for (uint32_t jj = 0; jj < S.as; ++jj)
-    {
-        const uint32_t k2 = S.path[jj].kind, l2 = S.path[jj].len;
-        if (!((jj < S.first) || (jj > S.last)) && (k2 == SX_SEG_INSERT || k2 == SX_SEG_DELETE))
-        {
-            const uint32_t ln = k2 == SX_SEG_INSERT ? l2 : 0u;
-            n += (max(fs2, p2) - fs2 <= di && di < p2 + ln) ? 1 : 0;
-        }
-        if (kind_read(k2)) p2 += l2;
-    }
-    return n;
-}
-
-// is (site, base id) a registered candidate SNV?  (CandidateSnvBuffer::isCandidateSnvAnySample: such a mismatch is not counted)
-__device__ __noinline__ bool k4_is_cand_snv(const k4_args& A, const int32_t rel, const int id)
-{
-    if (!(id < 4 && rel >= 0 && rel < (1 << 30)) || A.n_cand_snv == 0) return false;
-    const uint32_t key = (static_cast<uint32_t>(rel) << 2) | static_cast<uint32_t>(id);
-    uint32_t l2 = 0, h2 = A.n_cand_snv;
-    while (l2 < h2)
-    {
-        const uint32_t mid = (l2 + h2) >> 1;
-        if (A.cand_snv[mid] < key) l2 = mid + 1;
-        else h2 = mid;
-    }
-    return l2 < A.n_cand_snv && A.cand_snv[l2] == key;
-}
-
-__global__ void __launch_bounds__(K4B_THREADS) k4_bases4_kernel(k4_args A, k4_rrec* __restrict__ rec, uint16_t* __restrict__ bc, uint32_t Ls,
-                                                                const sx_tables* __restrict__ tables, int* __restrict__ status)
-{
-    extern __shared__ __align__(16) uint16_t k4b_P[]; // per thread: Lcap + 2 prefix counts, then 16 quality results (+ padding to an odd number of words)
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= A.n_reads) return;
-    const uint32_t stride16 = A.Lcap + 2u + 12u; // 16-bit entries per thread: (Lcap / 2 + 7) words, odd
-    uint16_t* P = k4b_P + static_cast<size_t>(threadIdx.x) * stride16;
-    uint8_t* qres = reinterpret_cast<uint8_t*>(P + A.Lcap + 2u);
-    k4_rsetup S;
-    k4_rrec out;
-    if (!k4_read_setup(A, r, S, out, status))
-    {
-        rec[r] = out;
-        return;
-    }
-    const sx_aln_seg* path = S.path;
-    const uint32_t as = S.as, rb = S.rb, re = S.re, read_size = S.read_size, fs = S.fs, fs2 = S.fs2, n_ev = S.n_ev;
-    const int32_t site0 = S.site0;
-    const uint32_t n_chunks = (read_size + 7u) >> 3;
-    const uint8_t* gs = A.seq4 + S.rd.seq_off;
-    k4_words sw;
-    k4_cur2 cur;
-    if (S.isDensity)
-    {
-        // create_mismatch_filter_map as counts: P[i] = mismatches (not registered candidate SNVs) among the bases before i, over the whole read
-        sw.init(gs, (read_size + 1u) >> 1);
-        cur.i = cur.seg_end = cur.rf = cur.q_lo = cur.q_hi = 0;
-        cur.rfd = 0;
-        const char* refp = A.ref + S.ref0; // refp[q + rfd] where the index is inside the reference segment
-        const int64_t ref_lo = -S.ref0, ref_hi = static_cast<int64_t>(A.ref_len) - S.ref0; // valid q + rfd
-        uint32_t c = 0;
-        P[0] = 0;
-        for (uint32_t ch = 0; ch < n_chunks; ++ch)
-        {
-            const uint32_t w = sw.chunk(ch);
-#pragma unroll
-            for (uint32_t j = 0; j < 8; ++j)
-            {
-                const uint32_t q = ch * 8u + j;
-                if (q >= cur.seg_end) k4_cur2_advance<false>(cur, q, path, as, rb, re, site0, A.n_sites);
-                if (q - cur.q_lo < cur.q_hi - cur.q_lo)
-                {
-                    const int32_t roff = static_cast<int32_t>(q) + cur.rfd;
-                    const char refc = (roff >= ref_lo && roff < ref_hi) ? refp[roff] : 'N';
-                    const uint32_t code = K4_NIB(w, j);
-                    if (char_of_code(code) != refc)
-                    {
-                        const bool cand = k4_is_cand_snv(A, site0 + roff, static_cast<int>(id_of_code(code)));
-                        if (!cand) ++c;
-                    }
-                }
-                if (q < read_size) P[q + 1u] = static_cast<uint16_t>(c);
-            }
-        }
-    }
-    // the 16 possible quality results: dictionary value -> MAPQ-adjusted value (255 = above the table)
-    const uint32_t adjustedMapq = max(5u, static_cast<uint32_t>(S.rd.mapq));
-    const bool tier1 = S.rd.flags & SX_PRF_TIER1;
-    const uint32_t fwd_bit = (S.rd.flags & SX_PRF_FWD) ? (1u << 10) : 0u;
-    const bool is_mapq_adjust = A.opt.isBasecallQualAdjustedForMapq && adjustedMapq <= 80u;
-    {
-        const uint8_t* mqrow = tables->mappedq[min(adjustedMapq, 90u)];
-        for (uint32_t v = 0; v < 16; ++v)
-        {
-            uint32_t q = A.qual_dict[v];
-            if (is_mapq_adjust) q = q > SX_MAX_QSCORE ? 255u : mqrow[q];
-            qres[v] = static_cast<uint8_t>(q);
-        }
-    }
-    k4_words qw;
-    sw.init(gs, (read_size + 1u) >> 1);
-    qw.init(A.qual + S.rd.qual_off, (read_size + 1u) >> 1);
-    cur.i = cur.seg_end = cur.rf = cur.q_lo = cur.q_hi = 0;
-    cur.rfd = 0;
-    const int max_pass = static_cast<int>(A.opt.mismatchDensityFilterMaxMismatchCount), max_pass2 = A.opt.tier2MismatchDensityFilterMaxMismatchCount;
-    const int min_q = A.opt.minBasecallErrorPhredProb;
-    const bool use_t2 = A.opt.useTier2Evidence != 0;
-    const bool isDensity = S.isDensity;
-    const uint32_t d_last = S.delta_size - 1u, p_last = read_size - 1u;
-    uint4* row = reinterpret_cast<uint4*>(bc + static_cast<size_t>(r) * Ls); // Ls % 16 == 0: 16-byte aligned groups of eight calls
-    for (uint32_t ch = rb >> 3; ch * 8u < re; ++ch)
-    {
-        // (chunks before the preamble's window are skipped: the word readers take any ascending chunk sequence from their state, so re-prime them)
-        if (ch == (rb >> 3) && ch > 0u)
-        {
-            sw.w_lo = ch < sw.n_w ? __ldg(sw.w32 + ch) : 0u;
-            qw.w_lo = ch < qw.n_w ? __ldg(qw.w32 + ch) : 0u;
-        }
-        const uint32_t wseq = sw.chunk(ch), wq = qw.chunk(ch);
-        uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
-#pragma unroll
-        for (uint32_t j = 0; j < 8; ++j)
-        {
-            const uint32_t q = ch * 8u + j;
-            if (q >= cur.seg_end) k4_cur2_advance<true>(cur, q, path, as, rb, re, site0, A.n_sites);
-            uint32_t v16 = 0;
-            if (q - cur.q_lo < cur.q_hi - cur.q_lo)
-            {
-                const uint32_t call_code = K4_NIB(wseq, j);
-                const uint32_t call_id = id_of_code(call_code);
-                if (call_id > 4u) atomicOr(status, ST_BASE);
-                uint32_t qscore = qres[K4_NIB(wq, j)];
-                if (is_mapq_adjust && qscore == 255u)
-                {
-                    atomicOr(status, ST_QUAL);
-                    qscore = 0;
-                }
-                bool is_call_filter = (call_code == 15u) || (static_cast<int>(qscore) < min_q);
-                bool is_tier2_call_filter = is_call_filter, is_neighbor_mismatch = false;
-                if (isDensity)
-                {
-                    const uint32_t di = min(d_last, max(fs, q) - fs); // ddata::get's index
-                    int del = static_cast<int>(P[min(di + fs2, p_last) + 1u]) - static_cast<int>(P[di]);
-                    if (n_ev) del += k4_event_count(S, di);
-                    if (!is_call_filter)
-                    {
-                        is_call_filter = max_pass < del;
-                        is_tier2_call_filter = use_t2 ? (max_pass2 < del) : is_call_filter;
-                    }
-                    const int mis = static_cast<int>(P[q + 1u]) - static_cast<int>(P[q]);
-                    is_neighbor_mismatch = (del - mis) > 0;
-                }
-                const bool current_call_filter = tier1 ? is_call_filter : is_tier2_call_filter;
-                const bool is_tier_specific_filter = tier1 && is_call_filter && !is_tier2_call_filter;
-                v16 = min(qscore, 63u) | (min(call_id, 4u) << 6) | fwd_bit | ((is_neighbor_mismatch ? 1u : 0u) << 11) | ((current_call_filter ? 1u : 0u) << 12) |
-                      ((is_tier_specific_filter ? 1u : 0u) << 13);
-            }
-            const uint32_t half = v16 << (16u * (j & 1u));
-            if (j < 2) o0 |= half;
-            else if (j < 4) o1 |= half;
-            else if (j < 6) o2 |= half;
-            else o3 |= half;
-        }
-        row[ch] = make_uint4(o0, o1, o2, o3); // eight calls per store (positions outside the MATCH segments hold 0: nobody reads them)
-    }
-    rec[r] = out;
-}
-
 constexpr uint32_t K4G_CHUNK = 8; // 32-site blocks per warp: its read range advances with the blocks
-constexpr int K4G_DEPTH = 4;      // reads in flight per warp: their records, then their calls, are loaded together (the walk is latency-bound)
-
-// the read offset of the base a record's read puts on site `si`, or 0xffffffff
-__device__ __forceinline__ uint32_t k4_rec_hit(const k4_args& A, const uint4& lo4, const uint4& hdr, const int32_t si)
-{
-    const uint32_t n_iv = hdr.z & 0xffu;
-    uint32_t hit = 0xffffffffu;
-    if (n_iv == 0u) return hit;
-    if (n_iv <= K4_REC_IV)
-    {
-        const uint32_t d0 = static_cast<uint32_t>(si - static_cast<int32_t>(lo4.x));
-        if (d0 < (lo4.w & 0xffffu)) hit = (hdr.x >> 16) + d0;
-        const uint32_t d1 = static_cast<uint32_t>(si - static_cast<int32_t>(lo4.y));
-        if (n_iv > 1u && d1 < (lo4.w >> 16)) hit = (hdr.y & 0xffffu) + d1;
-        const uint32_t d2 = static_cast<uint32_t>(si - static_cast<int32_t>(lo4.z));
-        if (n_iv > 2u && d2 < (hdr.x & 0xffffu)) hit = (hdr.y >> 16) + d2;
-        return hit;
-    }
-    // more MATCH intervals than a record holds: the path itself
-    const uint32_t rw = lo4.y, rbb = rw & 0xffffu, ree = rw >> 16, ns = (hdr.z >> 8) & 0x7fffffu;
-    const sx_aln_seg* path = A.segs + lo4.z;
-    int32_t ref_head = static_cast<int32_t>(lo4.x);
-    uint32_t read_head = 0;
-    for (uint32_t i = 0; i < ns; ++i)
-    {
-        const uint32_t k = path[i].kind, len = path[i].len;
-        if (k == SX_SEG_MATCH)
-        {
-            const uint32_t a = max(read_head, rbb), e = min(read_head + len, ree);
-            if (a < e)
-            {
-                const uint32_t d = static_cast<uint32_t>(si - (ref_head + static_cast<int32_t>(a - read_head)));
-                if (d < e - a) hit = a + d;
-            }
-        }
-        if (kind_read(k)) read_head += len;
-        if (kind_ref(k)) ref_head += static_cast<int32_t>(len);
-    }
-    return hit;
-}
 
 __global__ void __launch_bounds__(128) k4_gather_kernel(k4_args A, const k4_rrec* __restrict__ rec, const uint16_t* __restrict__ bc, uint32_t Ls, uint32_t reach_back,
                                                         uint32_t reach_fwd, const uint32_t* __restrict__ site_off, const uint32_t* __restrict__ t2_off,
@@ -1309,7 +969,6 @@ __global__ void __launch_bounds__(128) k4_gather_kernel(k4_args A, const k4_rrec
     if (lane == 0) lo = lower_bound_pos(A, static_cast<int64_t>(A.report_begin) + static_cast<int64_t>(b0) * 32 - reach_back);
     lo = __shfl_sync(FULL, lo, 0);
     hi = lo;
-    const uint4* rec4 = reinterpret_cast<const uint4*>(rec);
     for (uint32_t b = b0; b < b1; ++b)
     {
         const int64_t P0 = static_cast<int64_t>(A.report_begin) + static_cast<int64_t>(b) * 32;
@@ -1321,33 +980,58 @@ __global__ void __launch_bounds__(128) k4_gather_kernel(k4_args A, const k4_rrec
         const bool live = s < A.n_sites;
         uint32_t c1 = live ? site_off[s] : 0u, c2 = live ? t2_off[s] : 0u;
         const int32_t si = live ? static_cast<int32_t>(s) : -0x40000000;
-        for (uint32_t r = lo; r < hi; r += K4G_DEPTH)
+        for (uint32_t r = lo; r < hi; ++r)
         {
-            uint4 lo4[K4G_DEPTH], hdr[K4G_DEPTH]; // warp-uniform loads, K4G_DEPTH records (one or two 128-byte lines) in flight
-#pragma unroll
-            for (int j = 0; j < K4G_DEPTH; ++j)
+            const uint4* q4 = reinterpret_cast<const uint4*>(rec + r); // warp-uniform loads
+            const uint4 hdr = q4[1];                                   // len[2] | p_lo[0] << 16, p_lo[1] | p_lo[2] << 16, n_iv, padding
+            const uint32_t n_iv = hdr.z & 0xffu;
+            if (n_iv == 0u) continue;
+            const uint4 lo4 = q4[0]; // site_lo[0..2], len[0] | len[1] << 16
+            uint32_t hit = 0xffffffffu;
+            if (n_iv <= K4_REC_IV)
             {
-                const uint32_t rj = min(r + j, hi - 1u);
-                lo4[j] = rec4[2u * rj];
-                hdr[j] = rec4[2u * rj + 1u];
-                if (r + j >= hi) hdr[j].z = 0u;
-            }
-            uint32_t hit[K4G_DEPTH];
-            uint16_t v[K4G_DEPTH];
-#pragma unroll
-            for (int j = 0; j < K4G_DEPTH; ++j)
-            {
-                hit[j] = k4_rec_hit(A, lo4[j], hdr[j], si);
-                v[j] = 0;
-                if (hit[j] != 0xffffffffu) v[j] = bc[static_cast<size_t>(r + j) * Ls + hit[j]];
-            }
-#pragma unroll
-            for (int j = 0; j < K4G_DEPTH; ++j)
-                if (hit[j] != 0xffffffffu)
+                const uint32_t d0 = static_cast<uint32_t>(si - static_cast<int32_t>(lo4.x));
+                if (d0 < (lo4.w & 0xffffu)) hit = (hdr.x >> 16) + d0;
+                if (n_iv > 1u)
                 {
-                    if (hdr[j].z & 0x80000000u) calls[c1++] = v[j];
-                    else t2_calls[c2++] = v[j];
+                    const uint32_t d1 = static_cast<uint32_t>(si - static_cast<int32_t>(lo4.y));
+                    if (d1 < (lo4.w >> 16)) hit = (hdr.y & 0xffffu) + d1;
+                    if (n_iv > 2u)
+                    {
+                        const uint32_t d2 = static_cast<uint32_t>(si - static_cast<int32_t>(lo4.z));
+                        if (d2 < (hdr.x & 0xffffu)) hit = (hdr.y >> 16) + d2;
+                    }
                 }
+            }
+            else
+            {
+                // more MATCH intervals than a record holds: the path itself
+                const uint32_t rw = lo4.y, rbb = rw & 0xffffu, ree = rw >> 16, ns = (hdr.z >> 8) & 0x7fffffu;
+                const sx_aln_seg* path = A.segs + lo4.z;
+                int32_t ref_head = static_cast<int32_t>(lo4.x);
+                uint32_t read_head = 0;
+                for (uint32_t i = 0; i < ns; ++i)
+                {
+                    const uint32_t k = path[i].kind, len = path[i].len;
+                    if (k == SX_SEG_MATCH)
+                    {
+                        const uint32_t a = max(read_head, rbb), e = min(read_head + len, ree);
+                        if (a < e)
+                        {
+                            const uint32_t d = static_cast<uint32_t>(si - (ref_head + static_cast<int32_t>(a - read_head)));
+                            if (d < e - a) hit = a + d;
+                        }
+                    }
+                    if (kind_read(k)) read_head += len;
+                    if (kind_ref(k)) ref_head += static_cast<int32_t>(len);
+                }
+            }
+            if (hit != 0xffffffffu)
+            {
+                const uint16_t v = bc[static_cast<size_t>(r) * Ls + hit];
+                if (hdr.z & 0x80000000u) calls[c1++] = v;
+                else t2_calls[c2++] = v;
+            }
         }
     }
 }
@@ -1488,14 +1172,7 @@ int sx_k4_run(sx_ctx* ctx, const sx_pileup_reads_batch* d, const sx_pileup_colum
         if ((rc = sx_ensure(ctx, 31, bc_bytes + 64, reinterpret_cast<void**>(&bc)))) return rc;
         const size_t smem = (size_t)K4B_THREADS * (Lcap + 2u) * 2u;
         if (smem > 48 * 1024) SX_CUDA(ctx, cudaFuncSetAttribute(k4_bases_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
-        if (d->qual_bits == 4 && !getenv("SX_K4_GENERIC_BASES"))
-        {
-            const size_t smem4 = (size_t)K4B_THREADS * (Lcap + 2u + 12u) * 2u;
-            if (smem4 > 48 * 1024) SX_CUDA(ctx, cudaFuncSetAttribute(k4_bases4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
-            k4_bases4_kernel<<<(d->n_reads + K4B_THREADS - 1) / K4B_THREADS, K4B_THREADS, smem4, st>>>(A, rec, bc, Lcap, ctx->d_tables, ctx->d_status);
-        }
-        else
-            k4_bases_kernel<<<(d->n_reads + K4B_THREADS - 1) / K4B_THREADS, K4B_THREADS, smem, st>>>(A, rec, bc, Lcap, ctx->d_tables, ctx->d_status);
+        k4_bases_kernel<<<(d->n_reads + K4B_THREADS - 1) / K4B_THREADS, K4B_THREADS, smem, st>>>(A, rec, bc, Lcap, ctx->d_tables, ctx->d_status);
         SX_CUDA(ctx, cudaGetLastError());
         const uint32_t n_warps = ((n_sites + 31u) / 32u + K4G_CHUNK - 1u) / K4G_CHUNK;
         k4_gather_kernel<<<(n_warps + 3u) / 4u, 128, 0, st>>>(A, rec, bc, Lcap, d->max_ref_span + shift, shift, out->site_off, out->t2_off, out->calls, out->t2_calls);
