@@ -56,6 +56,27 @@ class SynthSizes(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_regions", "n_reads", "n_alns", "n_segs", "seq4_bytes", "qual_bytes", "ref_bytes", "ins_bytes", "cells")]
 
 
+def run_threads(fns):
+    """Run the callables on a thread each; an exception in any of them is re-raised here (a worker that died would otherwise just look fast)."""
+    errs = []
+
+    def wrap(f):
+        def g():
+            try:
+                f()
+            except BaseException as e:  # noqa: BLE001
+                errs.append(e)
+        return g
+
+    ths = [threading.Thread(target=wrap(f)) for f in fns]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    if errs:
+        raise errs[0]
+
+
 def load_synth():
     p = os.path.join(ROOT, "tools", "libsx_synth.so")
     if not os.path.exists(p):
@@ -636,11 +657,7 @@ def cpu_pass(ab: B.AlignBatch, pb: B.PileupBatch, gb: B.GaBatch, n_sample_loci: 
                 ox.ox_global_align(C.byref(sc), C.byref(sub), gres.ctypes.data + 16 * ga, gcig.ctypes.data + 4 * gb.max_ops * ga)
             busy[t] = time.perf_counter() - t1
 
-    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
+    run_threads([(lambda t=t: work(t)) for t in range(threads)])
     # the pass is as long as its slowest thread's time inside the scored functions (threads run concurrently on distinct cores)
     return n, max(busy), ("reference" if use_ref else "port")
 
@@ -786,13 +803,9 @@ def scoring_step_main(args):
         ctx_b, ctx_c = Context(local_rank), Context(local_rank)
 
         def step_e2e():
-            tb = threading.Thread(target=lambda: ctx_b.site_gl_germline(pb, True, gl_host))
-            tc = threading.Thread(target=lambda: ctx_c._chk(lib.sx_global_align(ctx_c.h, C.byref(sc), C.byref(gb.c), ga_res.ctypes.data, ga_cig.ctypes.data)))
-            tb.start()
-            tc.start()
-            ctx.score_alignments(ab, lnp_host)
-            tb.join()
-            tc.join()
+            run_threads([lambda: ctx_b.site_gl_germline(pb, True, gl_host),
+                         lambda: ctx_c._chk(lib.sx_global_align(ctx_c.h, C.byref(sc), C.byref(gb.c), ga_res.ctypes.data, ga_cig.ctypes.data)),
+                         lambda: ctx.score_alignments(ab, lnp_host)])
 
         for _ in range(min(2, args.warmup)):
             step_e2e()
@@ -1163,11 +1176,7 @@ def whole_path_main(args):
         if lanes == 1:
             lane_work(0)
         else:
-            ths = [threading.Thread(target=lane_work, args=(li,)) for li in range(lanes)]
-            for t in ths:
-                t.start()
-            for t in ths:
-                t.join()
+            run_threads([(lambda li=li: lane_work(li)) for li in range(lanes)])
         n_var = 0
         for i, d in enumerate(dws):  # compact the windows' records into one block (gather order = window order)
             nv = int(d.totals[8])
@@ -1204,13 +1213,15 @@ def whole_path_main(args):
     ctx.timer_mark(0)  # CUDA events on the stream the stages are launched on: the timed region is measured on the device
     for _ in range(args.steps):
         n_var_step = step_resident()
+    for c in lane_ctx[1:]:  # the other contexts' streams join the timed one: the closing event waits for all of them
+        ctx._chk(lib.sx_stream_join(ctx.h, c.h))
     ctx.timer_mark(1)
     dt_dev = ctx.timer_elapsed_ms() / 1e3
     barrier()
     dt_wall = time.perf_counter() - t0
     # one context: every stage, copy and gather of the step is on that stream, so the event time IS the step (the host clock is kept beside it);
     # several contexts: the other streams are not between the marks, so the bracketed host clock is the measure
-    dt = dt_dev if lanes == 1 else dt_wall
+    dt = dt_dev
     launches = ctx.total_launches() - launches0
     step_totals = totals // args.steps
 
@@ -1261,12 +1272,8 @@ def whole_path_main(args):
 
         def step_e2e():
             d2h_step[0] = 0
-            ths = [threading.Thread(target=worker, args=(wi,)) for wi in range(n_workers)]
-            tg = threading.Thread(target=lambda: ctx_ga._chk(lib.sx_global_align(ctx_ga.h, C.byref(sc), C.byref(gb.c), ga_res.ctypes.data, ga_cig.ctypes.data)))
-            for t in ths + [tg]:
-                t.start()
-            for t in ths + [tg]:
-                t.join()
+            run_threads([(lambda wi=wi: worker(wi)) for wi in range(n_workers)] +
+                        [lambda: ctx_ga._chk(lib.sx_global_align(ctx_ga.h, C.byref(sc), C.byref(gb.c), ga_res.ctypes.data, ga_cig.ctypes.data))])
 
         for _ in range(min(2, max(1, args.warmup))):
             step_e2e()
@@ -1327,7 +1334,8 @@ def whole_path_main(args):
         line = {
             "metric": "candidate_loci_per_sec", "value": value, "unit": "loci/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "timing": {"how": "CUDA events on the launching stream around the K steps, max over ranks" if lanes == 1 else "host clock between barrier + synchronize, max over ranks",
+            "timing": {"how": "CUDA events on the launching stream around the K steps, max over ranks" if lanes == 1 else
+                       f"CUDA events around the K steps on the first of the {lanes} contexts' streams, which the others join before the closing event (sx_stream_join); max over ranks",
                        "device_ms_per_step_rank0": 1e3 * dt_dev / args.steps, "host_clock_ms_per_step_rank0": 1e3 * dt_wall / args.steps},
             "config": {"workload": f"{args.config}: {desc}", "loci_per_gpu": n_loci, "windows_per_gpu": n_tiles, "loci_per_window": tile_loci, "reads_per_locus": WW.READS_PER_CELL,
                        "read_len": WW.READ_LEN, "sites_per_locus": WW.CELL_LEN, "step": "whole path: K7g, K7a, K7, K7b, K1, K6, K9, K4, K2a per window (sx_process_window_dev) + K3",

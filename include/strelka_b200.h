@@ -98,6 +98,9 @@ int sx_synchronize(sx_ctx* ctx);
 /* Device-side timing of a run of entry points: sx_timer_mark(ctx, 0) and (ctx, 1) record CUDA events on ctx's compute stream where they are
  * called; sx_timer_elapsed_ms waits for mark 1 and returns the device time between the two (host gaps between launches included). */
 int sx_timer_mark(sx_ctx* ctx, int which);
+/* Everything enqueued so far on `other`'s compute stream becomes a prerequisite of whatever `waiter` enqueues next (an event on one stream, a
+ * wait on the other; no host synchronisation): lets a caller that runs windows on several contexts close a device-timed region on one of them. */
+int sx_stream_join(sx_ctx* waiter, sx_ctx* other);
 int sx_timer_elapsed_ms(sx_ctx* ctx, double* ms);
 
 /* ==========================================================================================

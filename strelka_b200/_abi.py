@@ -360,6 +360,7 @@ SYMBOLS = [
     ("sx_memcpy_d2h", C.c_int, [_P, _P, _P, C.c_size_t]),
     ("sx_memcpy_d2d", C.c_int, [_P, _P, _P, C.c_size_t]),
     ("sx_timer_mark", C.c_int, [_P, C.c_int]),
+    ("sx_stream_join", C.c_int, [_P, _P]),
     ("sx_timer_elapsed_ms", C.c_int, [_P, C.POINTER(C.c_double)]),
     ("sx_synchronize", C.c_int, [_P]),
     ("sx_score_alignments", C.c_int, [_P, C.POINTER(SxAlignBatch), _P]),

@@ -587,6 +587,20 @@ extern "C" int sx_timer_mark(sx_ctx* ctx, int which)
     SX_CUDA(ctx, cudaEventRecord(ctx->ev_user[which], ctx->s_compute));
     return SX_OK;
 }
+extern "C" int sx_stream_join(sx_ctx* waiter, sx_ctx* other)
+{
+    if (!waiter || !other) return SX_ERR_ARG;
+    if (waiter == other) return SX_OK;
+    if (waiter->device != other->device) return sx_fail(waiter, SX_ERR_ARG, "sx_stream_join: the two contexts are on different devices");
+    SX_CUDA(waiter, cudaSetDevice(waiter->device));
+    cudaEvent_t ev;
+    SX_CUDA(waiter, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, other->s_compute);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(waiter->s_compute, ev, 0);
+    cudaEventDestroy(ev); // (released when the wait has been satisfied)
+    SX_CUDA(waiter, e);
+    return SX_OK;
+}
 extern "C" int sx_timer_elapsed_ms(sx_ctx* ctx, double* ms)
 {
     if (!ctx || !ms) return SX_ERR_ARG;
