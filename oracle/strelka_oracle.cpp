@@ -1332,6 +1332,48 @@ extern "C" int ox_site_gl_somatic(const sx_params* p, const sx_pileup_batch* nor
 extern "C" float ox_logf_restated(float x) { return sx_logf(x); }
 extern "C" float ox_powf_restated(float x, float y) { return sx_powf(x, y); }
 
+// the double-precision mirrors (sx_libm_mirror_d.h) against the live libm, argument by argument: returns the number of arguments whose results
+// differ in any bit (kind 0 exp, 1 log10, 2 log, 3 log1p); *first_bad = the first such argument
+#include "../strelka_b200/csrc/sx_libm_mirror_d.h"
+extern "C" uint64_t ox_libm_d_mirror_check(int kind, const double* xs, uint64_t n, double* first_bad)
+{
+    uint64_t bad(0);
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        const double x(xs[i]);
+        double a, b;
+        if (kind == 0)
+        {
+            a = std::exp(x);
+            b = sx_exp(x);
+        }
+        else if (kind == 1)
+        {
+            a = std::log10(x);
+            b = sx_log10(x);
+        }
+        else if (kind == 2)
+        {
+            a = std::log(x);
+            b = sx_log(x);
+        }
+        else
+        {
+            a = std::log1p(x);
+            b = sx_log1p(x);
+        }
+        uint64_t ua, ub;
+        std::memcpy(&ua, &a, 8);
+        std::memcpy(&ub, &b, 8);
+        if (ua != ub && !(a != a && b != b))
+        {
+            if (!bad && first_bad) *first_bad = x;
+            ++bad;
+        }
+    }
+    return bad;
+}
+
 namespace
 {
 #include "../strelka_b200/csrc/sx_stdsort_mirror.h"

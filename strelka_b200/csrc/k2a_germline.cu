@@ -88,7 +88,7 @@ __device__ __forceinline__ rs_out result_set(float lh, const float* lnprior, uin
             max_gt = gt;
         }
     }
-    const double e = (lane < 10) ? exp(d_sub(pp, mx)) : 0.0;
+    const double e = (lane < 10) ? sx_exp(d_sub(pp, mx)) : 0.0;
     double sum = 0.0;
 #pragma unroll
     for (int gt = 0; gt < 10; ++gt) sum = d_add(sum, shfl_d(e, gt));
@@ -1012,7 +1012,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 8) k2a_germline12_kernel(const 
 #pragma unroll
                 for (int gt = 0; gt < 10; ++gt)
                 {
-                    e[gt] = exp(d_sub(e[gt], mx));
+                    e[gt] = sx_exp(d_sub(e[gt], mx));
                     sum = d_add(sum, e[gt]);
                 }
                 sum = d_div(1.0, sum);

@@ -12,8 +12,10 @@
 // match?, strand?) -- the reference memoises exactly those values in het_ratio_cache; here they are host-built tables
 // (sx_context.cu) staged in shared memory, and each of the 21 normal + 21 tumor + 2x9 strand sums is accumulated by one
 // lane, so the float results are bit-identical.  The posterior (calculate_result_set_grid) is evaluated in double, its
-// exp() terms summed in the reference's loop order.  The nine strand-state likelihoods end in a float log-sum
-// (getLogSum<float>) whose glibc expf/log1pf are not mirrored: they only feed the float strandBias feature (1e-5 rel).
+// exp() terms summed in the reference's loop order; exp / log / log10 are the reference's libm functions restated
+// (sx_libm_mirror_d.h).  The nine strand-state likelihoods end in a float log-sum (getLogSum<float>: expf, then log1p in double
+// below 0.01f or logf), restated the same way, so they and the strandBias feature are the reference's bits as well.
+#include "sx_libm_mirror.h"
 #include "sx_device_util.cuh"
 #include "sx_internal.h"
 
@@ -108,9 +110,12 @@ __device__ __forceinline__ sample_acc accumulate_sample(const som_tables& T, con
     if (strand_lane)
     {
         // *lhood = getLogSum(lhood_fwd, lhood_rev) + ln_one_half  (float; tolerance field, see header)
+        // getLogSum<float> (blt_util/logSumUtil.hh:33-41): std::exp(float) = expf; log1p_switch<float> = boost::math::log1p(float), which promotes to
+        // double and calls log1p, below 0.01f, std::log(1 + x) = logf above -- the reference's libm functions, restated (sx_libm_mirror*.h)
         const float x1 = fmaxf(lh_fwd, lh_rev), x2 = fminf(lh_fwd, lh_rev);
-        const float ls = static_cast<float>(static_cast<double>(x1) + log1p(exp(static_cast<double>(f_sub(x2, x1)))));
-        lh = f_add(ls, ln_one_half);
+        const float e = sx_expf(f_sub(x2, x1));
+        const float l = (fabsf(e) < 0.01f) ? static_cast<float>(sx_log1p(static_cast<double>(e))) : sx_logf(f_add(1.0f, e));
+        lh = f_add(f_add(x1, l), ln_one_half);
     }
     // get_most_frequent_alt_id  (blt_common/snp_pos_info.hh:175-198): first strict maximum over base ids != ref
     uint32_t alt_id = ref_gt, max_count = 0;
@@ -153,13 +158,13 @@ __device__ __forceinline__ void result_set_grid(const som_tables& T, const float
         for (int d = 16; d; d >>= 1) m = fmax(m, __shfl_xor_sync(FULL, m, d));
         max_log_sum = m;
         __syncwarp();
-        if (lane < nt) scratch[lane] = exp(d_sub(l0, max_log_sum));
-        if (lane + 32 < nt) scratch[lane + 32] = exp(d_sub(l1, max_log_sum));
+        if (lane < nt) scratch[lane] = sx_exp(d_sub(l0, max_log_sum));
+        if (lane + 32 < nt) scratch[lane + 32] = sx_exp(d_sub(l1, max_log_sum));
         __syncwarp();
         double sum = 0.0;
         for (uint32_t i = 0; i < nt; ++i) sum = d_add(sum, scratch[i]);
         const double log_genotype_prior = static_cast<double>(T.geno_prior[combo]);
-        log_post_prob[combo] = d_add(d_add(log_genotype_prior, max_log_sum), log(sum));
+        log_post_prob[combo] = d_add(d_add(log_genotype_prior, max_log_sum), sx_log(sum));
         if (log_post_prob[combo] > max_log_prob)
         {
             max_log_prob = log_post_prob[combo];
@@ -168,8 +173,8 @@ __device__ __forceinline__ void result_set_grid(const som_tables& T, const float
     }
     double sum_prob = 0.0;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) sum_prob = d_add(sum_prob, exp(d_sub(log_post_prob[c], max_log_prob)));
-    const double log_sum_prob = log(sum_prob);
+    for (int c = 0; c < 6; ++c) sum_prob = d_add(sum_prob, sx_exp(d_sub(log_post_prob[c], max_log_prob)));
+    const double log_sum_prob = sx_log(sum_prob);
     double min_not_somfrom_sum = INFINITY;
     double nonsom_prob = 0.0;
     rs.ntype = 0;
@@ -181,7 +186,7 @@ __device__ __forceinline__ void result_set_grid(const som_tables& T, const float
 #pragma unroll
         for (uint32_t tgt = 0; tgt < 2; ++tgt)
         {
-            const double pp = exp(d_sub(d_sub(log_post_prob[ngt * 2 + tgt], max_log_prob), log_sum_prob));
+            const double pp = sx_exp(d_sub(d_sub(log_post_prob[ngt * 2 + tgt], max_log_prob), log_sum_prob));
             if (tgt == 0) nonsom_prob = d_add(nonsom_prob, pp);
             else som_prob_given_ngt = d_add(som_prob_given_ngt, pp);
         }

@@ -22,7 +22,7 @@ constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ double log1p_switch_d(double x) // blt_util/math_util.hh:33-47
 {
-    return (fabs(x) < 0.01) ? log1p(x) : log(d_add(1.0, x));
+    return (fabs(x) < 0.01) ? sx_log1p(x) : sx_log(d_add(1.0, x)); // (the reference's libm, bit for bit: sx_libm_mirror_d.h)
 }
 __device__ __forceinline__ double get_log_sum(double x1, double x2) // blt_util/logSumUtil.hh:33-41
 {
@@ -32,7 +32,7 @@ __device__ __forceinline__ double get_log_sum(double x1, double x2) // blt_util/
         x1 = x2;
         x2 = t;
     }
-    return d_add(x1, log1p_switch_d(exp(d_sub(x2, x1))));
+    return d_add(x1, log1p_switch_d(sx_exp(d_sub(x2, x1))));
 }
 
 __global__ void __launch_bounds__(K5_WARPS * 32) k5_indel_gl_kernel(const uint32_t* __restrict__ read_off, const uint32_t* __restrict__ lnp_off,
@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(K5_WARPS * 32) k5_indel_gl_kernel(const uint32
                     if (a < A && total > 0)
                     {
                         const double indel_prob = d_div(indel_path_term, total);
-                        lr[a] = log(d_sub(1.0, indel_prob));
-                        li[a] = log(indel_prob);
+                        lr[a] = sx_log(d_sub(1.0, indel_prob));
+                        li[a] = sx_log(indel_prob);
                     }
                 }
                 if (pl == 1)
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(K5_WARPS * 32) k5_indel_gl_kernel(const uint32
                 for (uint32_t a = 0; a <= SX_INDEL_MAX_ALLELES; ++a)
                     if (a < nfull)
                     {
-                        pm[a] = exp(d_sub(pm[a], mx));
+                        pm[a] = sx_exp(d_sub(pm[a], mx));
                         sum = d_add(sum, pm[a]);
                     }
                 sum = d_div(1.0, sum);

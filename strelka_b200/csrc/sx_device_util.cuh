@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "sx_libm_mirror_d.h"
+
 __device__ __forceinline__ float f_add(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float f_sub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float f_mul(float a, float b) { return __fmul_rn(a, b); }
@@ -22,10 +24,10 @@ __device__ __forceinline__ double shfl_d(double v, int src)
     return __shfl_sync(0xffffffffu, v, src);
 }
 
-// error_prob_to_qphred<double>  blt_util/qscore.hh:40-66 :  floor(-10*max(-307, log10(p)) + 0.5)
+// error_prob_to_qphred<double>  blt_util/qscore.hh:40-66 :  floor(-10*max(-307, log10(p)) + 0.5); log10 = the reference's libm's, bit for bit
 __device__ __forceinline__ int error_prob_to_qphred_d(double prob)
 {
-    const double l = log10(prob);
+    const double l = sx_log10(prob);
     const double m = (-307.0 < l) ? l : -307.0; // std::max(minlog10, l): returns minlog10 unless minlog10 < l
     return static_cast<int>(floor(d_add(d_mul(-10.0, m), 0.5)));
 }

@@ -84,6 +84,32 @@ def test_powf_mirror_matches_libm():
             assert a.view(np.uint32) == b.view(np.uint32), (q, y)
 
 
+def test_double_libm_mirrors_match_libm():
+    """sx_exp / sx_log10 / sx_log / sx_log1p (strelka_b200/csrc/sx_libm_mirror_d.h: what the double epilogues of K2a, K2b and K5 execute on the device) give the bits of
+    the libm the reference is linked against: normalizeLogDistro's exp(x - max) over its whole range incl. the subnormal results and the
+    underflow to 0, error_prob_to_qphred's log10 over (0, 1] down to subnormals and around 1 (the near-1 branch of log)."""
+    lib = reflib.oracle()
+    lib.ox_libm_d_mirror_check.restype = C.c_uint64
+    lib.ox_libm_d_mirror_check.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+    rng = np.random.default_rng(3)
+    n = 2_000_000
+    u = rng.random(n)
+    sets = {
+        0: np.concatenate([-1100.0 * u, -40.0 * rng.random(n), -rng.random(n) * rng.random(n), -745.2 + 80.0 * (rng.random(n) - 0.5), 1440.0 * (rng.random(n) - 0.5),
+                           [0.0, -0.0, 1e-300, -1e-300, -708.0, -709.0, -744.0, -745.0, -745.13, -745.2, -746.0, -1023.9, -1024.0, -1e6, 709.7, 709.8, 710.0, 1024.0, -np.inf]]),
+        1: np.concatenate([u, u * 1e-5, np.ldexp(u, -rng.integers(0, 1074, n).astype(np.int32)), 1.0 - 0.07 * u, 1.0 + 0.07 * u,
+                           [1.0, 0.5, 1e-300, 5e-324, 1e-310, 2.2250738585072014e-308, 0.9375, 1.064697265625, 0.93749999999999989, 1.0646972656249998, 0.0]]),
+        2: np.concatenate([u, np.ldexp(1.0 + u, rng.integers(-1000, 1000, n).astype(np.int32)), 0.93 + 0.14 * u, [1.0, 5e-324, 0.0]]),
+        3: np.concatenate([u, 0.01 * u, np.ldexp(u, -rng.integers(0, 80, n).astype(np.int32)), -0.999999 * u, 1e6 * u, 0.41 + 0.01 * u, -0.30 + 0.02 * u, np.exp(-40.0 * u),
+                           [0.0, -0.0, 1.0, 0.41421356237309503, 0.41421356237309509, -0.29289321881345243, 1e-9, 5.4e-17, 0.5, 3.0, 9007199254740994.0]]),
+    }
+    for kind, xs in sets.items():
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        first = np.zeros(1)
+        bad = lib.ox_libm_d_mirror_check(kind, xs.ctypes.data, len(xs), first.ctypes.data)
+        assert bad == 0, (kind, bad, float(first[0]).hex())
+
+
 def test_stdsort_mirror_matches_libstdcxx():
     lib = reflib.oracle()
     rng = np.random.default_rng(2)
