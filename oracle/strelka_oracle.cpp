@@ -1335,6 +1335,28 @@ extern "C" float ox_powf_restated(float x, float y) { return sx_powf(x, y); }
 // the double-precision mirrors (sx_libm_mirror_d.h) against the live libm, argument by argument: returns the number of arguments whose results
 // differ in any bit (kind 0 exp, 1 log10, 2 log, 3 log1p); *first_bad = the first such argument
 #include "../strelka_b200/csrc/sx_libm_mirror_d.h"
+// sx_expf against the live expf on every stride-th float bit pattern of [start, end]: the number of mismatching arguments
+extern "C" uint64_t ox_expf_mirror_check(uint32_t start, uint32_t end, uint32_t stride, uint32_t* first_bad)
+{
+    uint64_t bad(0);
+    for (uint64_t u = start; u <= (uint64_t)end; u += stride)
+    {
+        const uint32_t v((uint32_t)u);
+        float x;
+        std::memcpy(&x, &v, 4);
+        const float a(std::exp(x)), b(sx_expf(x));
+        uint32_t ua, ub;
+        std::memcpy(&ua, &a, 4);
+        std::memcpy(&ub, &b, 4);
+        if (ua != ub && !(a != a && b != b))
+        {
+            if (!bad && first_bad) *first_bad = v;
+            ++bad;
+        }
+    }
+    return bad;
+}
+
 extern "C" uint64_t ox_libm_d_mirror_check(int kind, const double* xs, uint64_t n, double* first_bad)
 {
     uint64_t bad(0);

@@ -110,6 +110,18 @@ def test_double_libm_mirrors_match_libm():
         assert bad == 0, (kind, bad, float(first[0]).hex())
 
 
+def test_expf_mirror_matches_libm():
+    """sx_expf (the somatic model's float log-sum: getLogSum<float> -> std::exp(float)) == glibc's expf on every 97th float bit pattern and on every
+    17th float of [-104, -2^-20] (the arguments the log-sum produces); all 2^32 patterns were checked once outside the suite (0 mismatches)."""
+    lib = reflib.oracle()
+    lib.ox_expf_mirror_check.restype = C.c_uint64
+    lib.ox_expf_mirror_check.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    first = np.zeros(1, np.uint32)
+    assert lib.ox_expf_mirror_check(5, 0xFFFFFFFF, 97, first.ctypes.data) == 0, hex(int(first[0]))
+    lo, hi = int(np.float32(-(2.0 ** -20)).view(np.uint32)), int(np.float32(-104.0).view(np.uint32))  # negative floats: bit patterns ascend with magnitude
+    assert lo < hi and lib.ox_expf_mirror_check(lo, hi, 17, first.ctypes.data) == 0, hex(int(first[0]))
+
+
 def test_stdsort_mirror_matches_libstdcxx():
     lib = reflib.oracle()
     rng = np.random.default_rng(2)

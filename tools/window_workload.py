@@ -212,7 +212,7 @@ def compare_with_reference(w: B.WindowBatch, d: dict, res: dict):
     for rs in ("genome", "poly"):
         for f in ("max_gt", "snp_qphred", "max_gt_qphred"):
             assert np.array_equal(gl[rs][f], g[rs][f]), (rs, f)
-        assert np.allclose(gl[rs]["ref_pprob"], g[rs]["ref_pprob"], rtol=1e-12, atol=0), (rs, "ref_pprob")
+        assert np.array_equal(np.ascontiguousarray(gl[rs]["ref_pprob"]).view(np.uint64), np.ascontiguousarray(g[rs]["ref_pprob"]).view(np.uint64)), (rs, "ref_pprob")
     if "variant_sites" in d:  # the compacted call records: the computed non-reference sites in position order, each with its record and depth
         sel = np.nonzero((g["is_computed"] != 0) & (g["genome"]["max_gt"] != g["ref_gt"]))[0]
         v = d["variant_sites"]
