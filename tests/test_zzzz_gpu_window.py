@@ -75,3 +75,29 @@ def test_synthetic_cfg2_window_equals_the_reference(ctx, qual_bits, seed):
     for k in d:
         assert np.asarray(d[k]).tobytes() == np.asarray(d2[k]).tobytes(), k
     assert stats["realigned"] > 5000 and stats["records"] > 10000 and stats["variant_sites"] > 50, stats
+
+
+def test_regrouped_work_lists_change_no_output_byte(ctx, monkeypatch):
+    """K7's active list and K6's list are regrouped by class before their kernels run (sx_regroup.cuh); which thread handles which read must not
+    matter: the pass with the regrouping switched off (SX_K7_NO_CLASS_SORT / SX_K6_NO_CLASS_SORT, read at every call) gives the same bytes in
+    every output array -- candidate-alignment CSR (through K9's best alignments and K6's records), columns, site results, variant records."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import window_workload as WW
+    from strelka_b200.api import DevWindow
+
+    w = WW.make_window(WW.load_synth(), 300, 11, tile=2, qual_bits=4, ascii_reads=True)
+    dw = DevWindow(ctx, w)
+    dw.run()
+    d_on = dw.download()
+    monkeypatch.setenv("SX_K7_NO_CLASS_SORT", "1")
+    monkeypatch.setenv("SX_K6_NO_CLASS_SORT", "1")
+    dw.run()
+    d_off = dw.download()
+    dw.free()
+    assert set(d_on) == set(d_off) and len(d_on) > 5
+    for k in d_on:
+        assert np.asarray(d_on[k]).tobytes() == np.asarray(d_off[k]).tobytes(), k
+
