@@ -5,6 +5,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 
 import reflib
 import specgen
@@ -179,3 +180,40 @@ def test_k6_device_body_on_the_host(tmp_path):
             staged_total += int(staged[0])
         total += len(want[0])
     assert total > 1500 and staged_total > 300
+
+
+def test_libm_tables_are_this_libms(tmp_path):
+    """strelka_b200/csrc/sx_libm_mirror_d_tables.inc is what tools/gen_libm_d_tables.py reads out of the libm.so.6 the reference is linked against
+    here (the script refuses another libm build: then the mirror tests above are the ones that matter, and this one is skipped)."""
+    import shutil
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    work = tmp_path / "r"
+    (work / "strelka_b200" / "csrc").mkdir(parents=True)
+    shutil.copy(os.path.join(root, "tools", "gen_libm_d_tables.py"), work / "gen.py")
+    r = subprocess.run([sys.executable, "gen.py"], cwd=work, capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("another libm build: " + (r.stderr or r.stdout).strip()[:200])
+    assert open(work / "strelka_b200" / "csrc" / "sx_libm_mirror_d_tables.inc").read() == open(os.path.join(root, "strelka_b200", "csrc", "sx_libm_mirror_d_tables.inc")).read()
+
+
+def test_bench_worker_failures_fail_the_run():
+    """bench.py runs the windows of the end-to-end leg on worker threads: an exception in one of them must end the run (a worker that had died on an
+    out-of-memory error once made the leg look fast in a tuning run)."""
+    import importlib.util
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    done = []
+    m.run_threads([lambda: done.append(1), lambda: done.append(2)])
+    assert sorted(done) == [1, 2]
+
+    def boom():
+        raise RuntimeError("worker died")
+
+    with pytest.raises(RuntimeError):
+        m.run_threads([lambda: done.append(3), boom])
