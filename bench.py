@@ -807,7 +807,7 @@ def scoring_step_main(args):
                          lambda: ctx_c._chk(lib.sx_global_align(ctx_c.h, C.byref(sc), C.byref(gb.c), ga_res.ctypes.data, ga_cig.ctypes.data)),
                          lambda: ctx.score_alignments(ab, lnp_host)])
 
-        for _ in range(min(2, args.warmup)):
+        for _ in range(min(3, args.warmup)):
             step_e2e()
         barrier()
         t1 = time.perf_counter()
@@ -1275,7 +1275,7 @@ def whole_path_main(args):
             run_threads([(lambda wi=wi: worker(wi)) for wi in range(n_workers)] +
                         [lambda: ctx_ga._chk(lib.sx_global_align(ctx_ga.h, C.byref(sc), C.byref(gb.c), ga_res.ctypes.data, ga_cig.ctypes.data))])
 
-        for _ in range(min(2, max(1, args.warmup))):
+        for _ in range(min(3, max(1, args.warmup))):  # (the resident steps before it have warmed the device; these size the workers' buffers)
             step_e2e()
         barrier()
         cpu0 = os.times()
@@ -1362,7 +1362,8 @@ def whole_path_main(args):
         if e2e:
             line["e2e"] = {"value": total_loci * args.steps / e2e[0], "unit": "loci/s", "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2]),
                            "ms_per_step": 1e3 * e2e[0] / args.steps, "how": f"sx_process_window (host arrays in pinned memory) per window, {n_workers} host threads with a context each; "
-                           "sx_global_align on one more; D2H = score_indels records + variant-site records + DP results", "host_cpu_seconds_per_step_rank0": round(e2e_cpu_s, 3)}
+                           "sx_global_align on one more; D2H = score_indels records + variant-site records + DP results", "host_cpu_seconds_per_step_rank0": round(e2e_cpu_s, 3),
+                           "warmup_steps": min(3, max(1, args.warmup))}
         if world == 1 and not args.no_cpu:
             # the reported CPU baseline: the reference's own functions, one pinned process per usable core, a bounded sample
             try:
